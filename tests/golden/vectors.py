@@ -1,0 +1,80 @@
+"""Literal golden vectors restated by hand from the reference's test files (paths under /root/reference).
+Each entry cites the test it comes from.  DATA ONLY."""
+
+# roaring/roaring_internal_test.go:259-282 TestBitmapCountRange: (start, end, first words, expected)
+BITMAP_COUNT_RANGE = [
+    (0, 1, [1], 1),
+    (2, 7, [0xFFFFFFFFFFFFFF18], 2),
+    (67, 68, [0, 0x8], 1),
+    (1, 68, [0x3, 0x8, 0xF], 2),
+    (1, 258, [0xF, 0x8, 0xA, 0x4, 0xFFFFFFFFFFFFFFFF], 9),
+    (66, 71, [0xF, 0xFFFFFFFFFFFFFF18], 2),
+    (63, 64, [0x8000000000000000], 1),
+]
+
+# roaring_internal_test.go:398-406 TestIntersectionCountArrayRun
+ICOUNT_ARRAY_RUN = [([1, 5, 10, 11, 12], [(2, 10), (12, 13), (15, 16)], 3)]
+
+# roaring_internal_test.go:408-426 TestIntersectionCountBitmapRun: (bitmap words, runs, expected)
+ICOUNT_BITMAP_RUN = [
+    ([1 << 63], [(63, 64)], 1),
+    ([0xF0000001, 0xFF00000000000000, 0xFF000000000000F0, 0x0F0000], [(29, 31), (125, 134), (191, 197), (200, 300)], 14),
+]
+
+# roaring_internal_test.go:428-473 TestIntersectionCountRunRun
+ICOUNT_RUN_RUN = [
+    ([], [(3, 8)], 0),
+    ([(2, 10)], [(3, 8)], 6),
+    ([(2, 10)], [(1, 11)], 9),
+    ([(2, 10)], [(0, 2)], 1),
+    ([(2, 10)], [(1, 10)], 9),
+    ([(2, 10)], [(5, 12)], 6),
+    ([(2, 10)], [(10, 99)], 1),
+    ([(2, 10), (44, 99)], [(12, 14)], 0),
+    ([(2, 10), (12, 13)], [(2, 10), (12, 13)], 11),
+    ([(8, 12), (15, 19)], [(9, 9), (11, 17)], 6),
+]
+
+# roaring_internal_test.go:3793-3813 TestUnmarshalRoaringWithNoErrors (official RoaringBitmap format images)
+OFFICIAL_HEX = [
+    ("3A300000020000000000020001000000180000001E0000000100020003000100", [1, 2, 3, 65537]),
+    ("3B3001000100000900010000000100010009000100", [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 65537]),
+]
+OFFICIAL_FILE = ("bitmapcontainer.roaringbitmap", 10000)
+# roaring_internal_test.go:3839-3853 TestUnmarshalRoaringWithErrors: zero-container images
+OFFICIAL_ZERO_CONTAINER_ERRORS = ["3A30000000000000", "3B30000000000000"]
+PILOSA_EMPTY_OK = "3C30000000000000"
+
+# fragment_internal_test.go:606-916 TestFragment_Range: (values {col: value}, bitDepth, [(op, predicate(s), expected cols)])
+BSI_RANGE_CASES = [
+    ({1000: 382, 2000: 300, 3000: 2818, 4000: 300}, 16, [("==", 300, [2000, 4000]), ("!=", 300, [1000, 3000])]),
+    ({1000: 0, 2000: 1}, 1, [("==", 3, []), ("==", 4, [])]),  # EQOversizeRegression
+    ({1000: 382, 2000: 300, 3000: 2817, 4000: 301, 5000: 1, 6000: 0}, 16, [
+        ("<", 301, [2000, 5000, 6000]), ("<", 300, [5000, 6000]),
+        ("<=", 301, [2000, 4000, 5000, 6000]), ("<=", 300, [2000, 5000, 6000]),
+        (">", 300, [1000, 3000, 4000]), (">", 301, [1000, 3000]),
+        (">=", 300, [1000, 2000, 3000, 4000]), (">=", 301, [1000, 3000, 4000]),
+        ("><", (300, 2817), [1000, 2000, 3000, 4000]), ("><", (301, 2817), [1000, 3000, 4000]),
+        ("><", (301, 2816), [1000, 4000]), ("><", (300, 2816), [1000, 2000, 4000]),
+    ]),
+    ({1: 1}, 1, [("<", 2, [1])]),                      # LTRegression
+    ({1: 3, 2: 0}, 2, [("<", 3, [2])]),                # LTMaxRegression
+    ({1: 0, 2: 1}, 2, [(">", 0, [2])]),                # GTMinRegression
+    ({1: 0, 2: 1}, 2, [(">", 4, [])]),                 # GTOversizeRegression
+    ({1: 0xf0, 2: 0xf1}, 64, [("><", (0xf0, 0xf1), [1, 2])]),  # BetweenCommonBitsRegression
+]
+
+# executor_test.go:1236-1373 set-op end-to-end goldens. Field "general", ShardWidth = 2^20.
+SW = 1 << 20
+EXEC_SETOPS = {
+    # TestExecutor_Execute_Difference: Set(1,general=10) Set(2,general=10) Set(3,general=10) Set(2,general=11) Set(4,general=11)
+    "difference": ({10: [1, 2, 3], 11: [2, 4]}, "Difference(Row(general=10), Row(general=11))", [1, 3]),
+    # TestExecutor_Execute_Intersect: row10 = {1, SW+1, SW+2}, row11 = {1, 2, SW+2}
+    "intersect": ({10: [1, SW + 1, SW + 2], 11: [1, 2, SW + 2]}, "Intersect(Row(general=10), Row(general=11))", [1, SW + 2]),
+    # TestExecutor_Execute_Union: row10 = {0, SW+1, SW+2}, row11 = {2, SW+2}
+    "union": ({10: [0, SW + 1, SW + 2], 11: [2, SW + 2]}, "Union(Row(general=10), Row(general=11))", [0, 2, SW + 1, SW + 2]),
+    # TestExecutor_Execute_Xor: row10 = {0, SW+1, SW+2}, row11 = {2, SW+2}
+    "xor": ({10: [0, SW + 1, SW + 2], 11: [2, SW + 2]}, "Xor(Row(general=10), Row(general=11))", [0, 2, SW + 1]),
+    # TestExecutor_Execute_Count: row10 = {3, SW+1, SW+2} -> Count = 3
+    "count": ({10: [3, SW + 1, SW + 2]}, "Count(Row(general=10))", 3),
+}

@@ -1,0 +1,266 @@
+"""Pins the CPU oracle (oracle/fb_oracle.c) against the reference's own golden vectors and against the naive
+set model.  CPU only."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import naive
+from oracle import oracle as O
+from tests import archetypes as A
+from tests import helpers as H
+from tests.golden import vectors as V
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+TYPES = [O.ARRAY, O.BITMAP, O.RUN]
+
+
+def _apply(op, x, y):
+    if op in ("intersect", "intersectInPlaceWrapper"):
+        return x.intersect(y)
+    if op in ("union", "unionInPlaceWrapper"):
+        return x.union(y)
+    if op in ("difference", "differenceInPlaceWrapper"):
+        return x.difference(y)
+    if op == "xor":
+        return x.xor(y)
+    if op == "flip":
+        return x.flip()
+    raise KeyError(op)
+
+
+@pytest.fixture(scope="module")
+def cts():
+    return {(n, t): A.container(n, t) for n in A.NAMES for t in TYPES}
+
+
+def test_container_combinations_table(cts):
+    """roaring_internal_test.go:2974-3780 — 638 rows x 9 encoding pairs; results compared as sets against
+    the expected archetype (the reference compares in the result's own encoding, i.e. as sets)."""
+    rows = json.load(open(os.path.join(GOLD, "container_combinations.json")))["rows"]
+    assert len(rows) == 638
+    checked = 0
+    for r in rows:
+        exp = A.archetype_values(r["exp"])
+        for tx in TYPES:
+            for ty in TYPES:
+                x = cts[(r["x"], tx)]
+                y = cts[(r["y"], ty)] if r["y"] else None
+                got = _apply(r["op"], x, y)
+                assert got.n == len(exp), (r, tx, ty)
+                assert np.array_equal(got.values(), exp), (r, tx, ty)
+                if r["op"].startswith("intersect"):
+                    assert x.intersection_count(y) == len(exp), (r, tx, ty)
+                checked += 1
+                if not r["y"]:
+                    break
+            if not r["y"]:
+                pass
+    assert checked > 5000
+
+
+def test_bitmap_count_range():
+    for start, end, words, exp in V.BITMAP_COUNT_RANGE:
+        w = np.zeros(1024, dtype=np.uint64)
+        w[: len(words)] = np.array(words, dtype=np.uint64)
+        assert O.Container.bitmap(w).count_range(start, end) == exp
+
+
+def test_intersection_count_vectors():
+    for arr, runs, exp in V.ICOUNT_ARRAY_RUN:
+        assert O.Container.array(arr).intersection_count(O.Container.run(runs)) == exp
+        assert O.Container.run(runs).intersection_count(O.Container.array(arr)) == exp
+    for words, runs, exp in V.ICOUNT_BITMAP_RUN:
+        w = np.zeros(1024, dtype=np.uint64)
+        w[: len(words)] = np.array(words, dtype=np.uint64)
+        assert O.Container.bitmap(w).intersection_count(O.Container.run(runs)) == exp
+    for ra, rb, exp in V.ICOUNT_RUN_RUN:
+        a = O.Container.run(np.array(ra, dtype=np.uint16).reshape(-1, 2))
+        b = O.Container.run(np.array(rb, dtype=np.uint16).reshape(-1, 2))
+        assert a.intersection_count(b) == exp
+        assert a.intersect(b).n == exp
+
+
+def test_official_format_goldens():
+    for hx, bits in V.OFFICIAL_HEX:
+        b = O.Bitmap.from_bytes(bytes.fromhex(hx))
+        assert b.count() == len(bits)
+        assert list(b.slice()) == bits
+    name, count = V.OFFICIAL_FILE
+    b = O.Bitmap.from_bytes(open(os.path.join(GOLD, name), "rb").read())
+    assert b.count() == count
+    for hx in V.OFFICIAL_ZERO_CONTAINER_ERRORS:
+        with pytest.raises(ValueError):
+            O.Bitmap.from_bytes(bytes.fromhex(hx))
+    assert O.Bitmap.from_bytes(bytes.fromhex(V.PILOSA_EMPTY_OK)).count() == 0
+
+
+def test_pilosa_roundtrip_and_canonical_types():
+    rng = np.random.default_rng(5)
+    vals = np.concatenate([
+        rng.choice(1 << 16, 700, replace=False),                      # array
+        (1 << 16) + rng.choice(1 << 16, 30000, replace=False),        # bitmap
+        (2 << 16) + np.arange(100, 9000),                             # run
+        (5 << 16) + np.arange(0, 1 << 16),                            # full -> run{0,65535}
+    ]).astype(np.uint64)
+    b = O.Bitmap.from_values(vals)
+    data = b.to_bytes()
+    # header: cookie 12348, 4 containers; types 1,2,3,3 (optimize(): roaring.go:3412-3426)
+    assert int.from_bytes(data[0:2], "little") == 12348 and int.from_bytes(data[4:8], "little") == 4
+    types = [int.from_bytes(data[8 + 12 * i + 8: 8 + 12 * i + 10], "little") for i in range(4)]
+    assert types == [1, 2, 3, 3]
+    b2 = O.Bitmap.from_bytes(data)
+    assert b2.count() == len(np.unique(vals))
+    assert np.array_equal(b2.slice(), np.unique(vals))
+    assert b2.to_bytes() == data
+
+
+def _rand_container(rng, kind):
+    if kind == 0:
+        return np.sort(rng.choice(1 << 16, int(rng.integers(0, 3000)), replace=False))
+    if kind == 1:
+        return np.sort(rng.choice(1 << 16, int(rng.integers(3000, 60000)), replace=False))
+    out = []
+    v = int(rng.integers(0, 500))
+    while v < (1 << 16):
+        ln = int(rng.geometric(1 / 80.0))
+        out.extend(range(v, min(v + ln, 1 << 16)))
+        v += ln + int(rng.geometric(1 / 120.0))
+    return np.array(out, dtype=np.int64)
+
+
+def test_differential_vs_naive_sets():
+    """naive.go-style differential check over random containers of all 3x3 encodings and all ops"""
+    rng = np.random.default_rng(23)
+    for it in range(60):
+        va, vb = _rand_container(rng, it % 3), _rand_container(rng, (it // 3) % 3)
+        sa, sb = set(va.tolist()), set(vb.tolist())
+        for ta in TYPES:
+            for tb in TYPES:
+                a, b = O.Container.from_values(va, ta), O.Container.from_values(vb, tb)
+                assert a.intersection_count(b) == len(sa & sb)
+                for name, fn, exp in (("and", a.intersect, sa & sb), ("or", a.union, sa | sb),
+                                      ("andnot", a.difference, sa - sb), ("xor", a.xor, sa ^ sb)):
+                    got = fn(b)
+                    assert got.n == len(exp), (name, ta, tb)
+                    assert set(got.values().tolist()) == exp, (name, ta, tb)
+                    assert got.optimized().typ == naive.optimize_type(exp), (name, ta, tb)
+
+
+def test_bitmap_level_ops_and_row_segments():
+    rng = np.random.default_rng(7)
+    a = np.unique(rng.integers(0, 40 << 16, 50000)).astype(np.uint64)
+    b = np.unique(np.concatenate([rng.integers(0, 40 << 16, 30000), np.arange(3 << 16, 5 << 16)])).astype(np.uint64)
+    A_, B_ = O.Bitmap.from_values(a), O.Bitmap.from_values(b)
+    sa, sb = set(a.tolist()), set(b.tolist())
+    assert A_.count() == len(sa)
+    assert set(A_.intersect(B_).slice().tolist()) == sa & sb
+    assert set(A_.union(B_).slice().tolist()) == sa | sb
+    assert set(A_.difference(B_).slice().tolist()) == sa - sb
+    assert set(A_.xor(B_).slice().tolist()) == sa ^ sb
+    assert A_.intersection_count(B_) == len(sa & sb)
+    c = np.unique(rng.integers(0, 40 << 16, 20000)).astype(np.uint64)
+    assert set(A_.union(B_, O.Bitmap.from_values(c)).slice().tolist()) == sa | sb | set(c.tolist())
+
+
+def test_executor_setop_goldens():
+    """executor_test.go:1236-1373 restated through the oracle's Row algebra (fragment.row + Bitmap ops per shard)"""
+    for name, (rows, _q, exp) in V.EXEC_SETOPS.items():
+        frags = H.set_fragments(rows)
+        shards = sorted(frags)
+
+        def row(r):
+            out = O.Bitmap()
+            for s in shards:
+                out = out.union(frags[s].row(r, s))
+            return out
+
+        if name == "count":
+            assert row(10).count() == exp
+            continue
+        a, b = row(10), row(11)
+        got = {"difference": a.difference, "intersect": a.intersect, "union": a.union, "xor": a.xor}[name](b)
+        assert list(got.slice()) == exp, name
+
+
+def _check_bsi(frag, depth, op, pred, exp_cols):
+    if op == "><":
+        got = frag.range_op(op, depth, pred[0], pred[1])
+    else:
+        got = frag.range_op(op, depth, pred)
+    assert list(got.slice()) == sorted(exp_cols), (op, pred)
+
+
+def test_bsi_range_goldens():
+    """fragment_internal_test.go:606-916 TestFragment_Range literal cases"""
+    for values, depth, checks in V.BSI_RANGE_CASES:
+        frag = H.bsi_fragment(values, depth)
+        for op, pred, exp in checks:
+            _check_bsi(frag, depth, op, pred, exp)
+
+
+@pytest.mark.parametrize("signed", [False, True])
+def test_bsi_diagonal_exhaustive(signed):
+    """fragment_internal_test.go:3768-3948 (unsigned) / 4113-4275 (signed): col i holds value i (or i+minVal);
+    every predicate in the checking range for <,<=,>,>=,==,!=,between"""
+    k = 6
+    if signed:
+        lo, hi = 1 - (1 << k), (1 << k) - 1
+        values = {i - lo: i for i in range(lo, hi + 1)}
+        checks = range(2 * lo, 2 * hi)
+    else:
+        values = {i: i for i in range(1 << k)}
+        checks = range(-3, 1 << (k + 1))
+    frag = H.bsi_fragment(values, k)
+    for p in checks:
+        for op, f in (("<", lambda v: v < p), ("<=", lambda v: v <= p), (">", lambda v: v > p),
+                      (">=", lambda v: v >= p), ("==", lambda v: v == p), ("!=", lambda v: v != p)):
+            exp = sorted(c for c, v in values.items() if f(v))
+            assert list(frag.range_op(op, k, p).slice()) == exp, (op, p)
+        for q in (p, p + 1, p + 5, p + 40):
+            exp = sorted(c for c, v in values.items() if p <= v <= q)
+            assert list(frag.range_op("><", k, p, q).slice()) == exp, ("><", p, q)
+
+
+def test_bsi_random_vs_naive():
+    rng = np.random.default_rng(11)
+    depth = 12
+    values = {int(c): int(v) for c, v in zip(rng.choice(200000, 3000, replace=False), rng.integers(-4000, 4000, 3000))}
+    pos = H.bsi_fragment_positions(values, depth)
+    frag = O.Bitmap.from_values(pos)
+    bits = set(pos)
+    for op in ("<", "<=", ">", ">=", "==", "!="):
+        for p in (-5000, -4095, -17, -1, 0, 1, 2, 63, 64, 4095, 4096, 9999):
+            assert set(frag.range_op(op, depth, p).slice().tolist()) == naive.bsi_range(bits, depth, op, p), (op, p)
+    for lo, hi in ((-100, 100), (0, 0), (5, 3000), (-3000, -5), (-9999, 9999), (1, 4095), (1, 4096)):
+        assert set(frag.range_op("><", depth, lo, hi).slice().tolist()) == naive.bsi_range(bits, depth, "><", lo, hi)
+
+
+def test_topk_and_groupby_semantics():
+    """doTopK (executor.go:2705) and groupByIterator (executor.go:8617) restatements vs brute force"""
+    rng = np.random.default_rng(3)
+    SW = H.SW
+    cols = rng.choice(SW, 4000, replace=False)
+    ra, rb = rng.integers(0, 7, 4000), rng.integers(0, 5, 4000)
+    fa = O.Bitmap.from_values([int(r) * SW + int(c) for r, c in zip(ra, cols)])
+    fb = O.Bitmap.from_values([int(r) * SW + int(c) for r, c in zip(rb, cols)])
+    shard = 3
+    filt_cols = set(rng.choice(SW, SW // 3, replace=False).tolist())
+    filt = O.Bitmap.from_values([shard * SW + c for c in filt_cols])
+    rows, cnts = fa.row_counts(shard, None)
+    assert dict(zip(rows.tolist(), cnts.tolist())) == {r: int((ra == r).sum()) for r in range(7) if (ra == r).any()}
+    rows, cnts = fa.row_counts(shard, filt)
+    exp = {r: sum(1 for c, x in zip(cols, ra) if x == r and int(c) in filt_cols) for r in range(7)}
+    assert dict(zip(rows.tolist(), cnts.tolist())) == {r: n for r, n in exp.items() if n}
+    out = O.groupby_shard([fa, fb], shard, [list(range(7)), list(range(5))], None)
+    brute = np.zeros((7, 5), dtype=np.uint64)
+    np.add.at(brute, (ra, rb), 1)
+    assert np.array_equal(out.reshape(7, 5), brute)
+    out = O.groupby_shard([fa, fb], shard, [list(range(7)), list(range(5))], filt)
+    brute = np.zeros((7, 5), dtype=np.uint64)
+    m = np.array([int(c) in filt_cols for c in cols])
+    np.add.at(brute, (ra[m], rb[m]), 1)
+    assert np.array_equal(out.reshape(7, 5), brute)
+    # missing fragment => shard contributes nothing (executor.go:8769-8772)
+    assert O.groupby_shard([fa, None], shard, [list(range(7)), list(range(5))], None).sum() == 0
