@@ -1,0 +1,965 @@
+// libfbgpu host runtime: shard store residency, bitmap-call program compiler, query entry points (C ABI in
+// include/fbgpu.h).  C++17 + CUDA runtime only — no torch types, no CPU fallback: every query runs the
+// sm_100a kernels in kernels.cuh or fails with FBGPU_E_CUDA.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <condition_variable>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <shared_mutex>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/fbgpu.h"
+#include "fbgpu_types.h"
+#include "kernels.cuh"
+
+using namespace fbgpu;
+
+// ------------------------------------------------------------------ errors
+static thread_local std::string g_err;
+static int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CUDA_TRY(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) return fail(FBGPU_E_CUDA, "%s failed: %s (%s:%d)", #x, cudaGetErrorString(_e), __FILE__, __LINE__); } while (0)
+
+extern "C" const char* fbgpu_last_error(void) { return g_err.c_str(); }
+extern "C" int32_t fbgpu_abi_version(void) { return FBGPU_ABI_VERSION; }
+
+// ------------------------------------------------------------------ small device buffer helper
+struct DevBuf {
+    void* p = nullptr; size_t cap = 0;
+    int ensure(size_t n) {
+        if (n <= cap) return 0;
+        size_t nc = std::max(n, cap + cap / 2);
+        nc = (nc + 255) & ~size_t(255);
+        void* q = nullptr;
+        if (cudaMalloc(&q, nc) != cudaSuccess) { cudaGetLastError(); if (cudaMalloc(&q, (n + 255) & ~size_t(255)) != cudaSuccess) return fail(FBGPU_E_NOMEM, "cudaMalloc(%zu) failed", n); nc = (n + 255) & ~size_t(255); }
+        if (p) cudaFree(p);
+        p = q; cap = nc;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+struct PinBuf {
+    void* p = nullptr; size_t cap = 0;
+    int ensure(size_t n) {
+        if (n <= cap) return 0;
+        size_t nc = std::max(n, cap * 2);
+        void* q = nullptr;
+        if (cudaMallocHost(&q, nc) != cudaSuccess) return fail(FBGPU_E_NOMEM, "cudaMallocHost(%zu) failed", nc);
+        if (p) cudaFreeHost(p);
+        p = q; cap = nc;
+        return 0;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+// ------------------------------------------------------------------ NCCL (resolved at run time)
+struct Id128 { char b[128]; };   // ncclUniqueId is passed by value (128 bytes)
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(void*) = nullptr;
+    int (*CommInitRank)(void**, int, Id128, int) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl; static std::once_flag g_nccl_once;
+static bool nccl_load() {
+    std::call_once(g_nccl_once, [] {
+        const char* names[] = { "libnccl.so.2", "libnccl.so" };
+        for (const char* n : names) { g_nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (g_nccl.lib) break; }
+        if (!g_nccl.lib) return;
+        g_nccl.GetUniqueId = (int (*)(void*))dlsym(g_nccl.lib, "ncclGetUniqueId");
+        g_nccl.CommInitRank = (int (*)(void**, int, Id128, int))dlsym(g_nccl.lib, "ncclCommInitRank");
+        g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(g_nccl.lib, "ncclAllReduce");
+        g_nccl.CommDestroy = (int (*)(void*))dlsym(g_nccl.lib, "ncclCommDestroy");
+        g_nccl.GetErrorString = (const char* (*)(int))dlsym(g_nccl.lib, "ncclGetErrorString");
+    });
+    return g_nccl.lib && g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.AllReduce && g_nccl.CommDestroy;
+}
+constexpr int kNcclUint64 = 5, kNcclSum = 0;   // ncclDataType_t / ncclRedOp_t values (nccl.h)
+
+// ------------------------------------------------------------------ context
+struct ViewKey { uint32_t index, field, view; bool operator<(const ViewKey& o) const { return index != o.index ? index < o.index : field != o.field ? field < o.field : view < o.view; } };
+
+struct HostFrag { uint32_t fv; uint64_t shard; bool live; uint32_t row_off, n_rows; uint64_t payload_bytes; uint32_t n_desc; uint32_t n_arr, n_bmp, n_run; };
+
+struct Workspace {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    DevBuf d_in, d_counts, d_bitmaps, d_info, d_emit_units, d_emit, d_rows;
+    PinBuf h_in, h_out;
+    bool busy = false;
+};
+
+struct fbgpu_ctx {
+    int device = 0;
+    int sm_count = 148;
+    // ---- store (host mirrors are the source of truth for metadata; payload lives only in HBM once committed)
+    std::shared_mutex store_mu;
+    std::map<ViewKey, uint32_t> view_ids;
+    std::vector<std::vector<int32_t>> shardmaps;  // per view
+    std::vector<HostFrag> frags;
+    std::vector<FragHdr> h_frags;
+    std::vector<RowEnt> h_rows;
+    std::vector<ContDesc> h_descs;
+    std::vector<uint8_t> staging;        // payload bytes not yet uploaded, destined for [uploaded, uploaded+staging.size())
+    uint64_t uploaded = 0;               // bytes of payload already in HBM
+    bool meta_dirty = false;
+    DevBuf d_payload, d_views, d_shardmap, d_frags, d_rows, d_descs;
+    uint32_t n_views_dev = 0;
+    fbgpu_stats stats{};
+    // ---- execution
+    std::mutex ws_mu; std::condition_variable ws_cv;
+    std::vector<std::unique_ptr<Workspace>> wss;
+    // ---- counters
+    std::mutex cnt_mu; fbgpu_counters counters{};
+    // ---- comm
+    void* comm = nullptr; int n_ranks = 1, rank = 0;
+};
+
+static StoreRef store_ref(fbgpu_ctx* c) {
+    StoreRef s;
+    s.views = (const ViewTab*)c->d_views.p; s.shardmap = (const int32_t*)c->d_shardmap.p; s.frags = (const FragHdr*)c->d_frags.p;
+    s.rows = (const RowEnt*)c->d_rows.p; s.descs = (const ContDesc*)c->d_descs.p; s.payload = (const uint8_t*)c->d_payload.p; s.n_views = c->n_views_dev;
+    return s;
+}
+
+extern "C" int fbgpu_init(int32_t device_ordinal, fbgpu_ctx** out) {
+    if (!out) return fail(FBGPU_E_INVALID, "out is null");
+    int n = 0;
+    CUDA_TRY(cudaGetDeviceCount(&n));
+    if (device_ordinal < 0 || device_ordinal >= n) return fail(FBGPU_E_INVALID, "device ordinal %d out of range (%d devices)", device_ordinal, n);
+    CUDA_TRY(cudaSetDevice(device_ordinal));
+    auto c = new fbgpu_ctx();
+    c->device = device_ordinal;
+    cudaDeviceProp p; CUDA_TRY(cudaGetDeviceProperties(&p, device_ordinal));
+    c->sm_count = p.multiProcessorCount;
+    for (int i = 0; i < 4; i++) {
+        auto w = std::make_unique<Workspace>();
+        CUDA_TRY(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreate(&w->ev0)); CUDA_TRY(cudaEventCreate(&w->ev1));
+        c->wss.push_back(std::move(w));
+    }
+    // opt in to large dynamic shared memory once
+    CUDA_TRY(cudaFuncSetAttribute(eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 17 * 8192));
+    CUDA_TRY(cudaFuncSetAttribute(pair_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairWarps * 8192));
+    CUDA_TRY(cudaFuncSetAttribute(row_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairWarps * 8192));
+    CUDA_TRY(cudaFuncSetAttribute(groupby_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072 + kGbPool * 4 + 8192));
+    *out = c;
+    return FBGPU_OK;
+}
+
+extern "C" void fbgpu_shutdown(fbgpu_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    if (c->comm && nccl_load()) g_nccl.CommDestroy(c->comm);
+    for (auto& w : c->wss) {
+        for (DevBuf* b : { &w->d_in, &w->d_counts, &w->d_bitmaps, &w->d_info, &w->d_emit_units, &w->d_emit, &w->d_rows }) b->release();
+        w->h_in.release(); w->h_out.release();
+        cudaEventDestroy(w->ev0); cudaEventDestroy(w->ev1); cudaStreamDestroy(w->stream);
+    }
+    for (DevBuf* b : { &c->d_payload, &c->d_views, &c->d_shardmap, &c->d_frags, &c->d_rows, &c->d_descs }) b->release();
+    delete c;
+}
+
+struct WsLease {
+    fbgpu_ctx* c; Workspace* w;
+    explicit WsLease(fbgpu_ctx* ctx) : c(ctx), w(nullptr) {
+        std::unique_lock<std::mutex> lk(c->ws_mu);
+        for (;;) { for (auto& x : c->wss) if (!x->busy) { x->busy = true; w = x.get(); return; } c->ws_cv.wait(lk); }
+    }
+    ~WsLease() { { std::lock_guard<std::mutex> lk(c->ws_mu); w->busy = false; } c->ws_cv.notify_one(); }
+};
+
+// ------------------------------------------------------------------ fragment parsing (host)
+static inline uint16_t rd16(const uint8_t* p) { uint16_t v; memcpy(&v, p, 2); return v; }
+static inline uint32_t rd32(const uint8_t* p) { uint32_t v; memcpy(&v, p, 4); return v; }
+static inline uint64_t rd64(const uint8_t* p) { uint64_t v; memcpy(&v, p, 8); return v; }
+
+struct ParsedCont { uint64_t key; uint16_t typ; uint32_t n; uint32_t cnt; const uint8_t* data; bool official_run; };
+
+// Pilosa format: roaring/roaring.go:1984-2029,2124-2178; official: :1942-1980,2194-2260,6943-7006
+static int parse_roaring(const uint8_t* buf, uint64_t len, std::vector<ParsedCont>& out) {
+    out.clear();
+    if (len < 8) return fail(FBGPU_E_FORMAT, "roaring data too small (%llu bytes)", (unsigned long long)len);
+    uint32_t magic = rd16(buf);
+    if (magic == 12348) {
+        if (buf[2] != 0) return fail(FBGPU_E_FORMAT, "unsupported pilosa roaring version %u", buf[2]);
+        uint64_t keys = rd32(buf + 4);
+        if (8 + keys * 16 > len) return fail(FBGPU_E_FORMAT, "header overruns buffer");
+        const uint8_t *hdr = buf + 8, *offs = buf + 8 + keys * 12;
+        uint64_t chunk = 0; uint32_t prev = 0;
+        out.reserve(keys);
+        for (uint64_t i = 0; i < keys; i++) {
+            ParsedCont c{}; c.key = rd64(hdr + i * 12); c.typ = rd16(hdr + i * 12 + 8); c.n = (uint32_t)rd16(hdr + i * 12 + 10) + 1;
+            uint32_t o32 = rd32(offs + i * 4); if (o32 < prev) chunk += 1ull << 32; prev = o32;
+            uint64_t off = chunk + o32;
+            if (c.typ == kArray) { if (off + (uint64_t)c.n * 2 > len) return fail(FBGPU_E_FORMAT, "array container %llu overruns buffer", (unsigned long long)i); c.data = buf + off; }
+            else if (c.typ == kBitmap) { if (off + 8192 > len) return fail(FBGPU_E_FORMAT, "bitmap container %llu overruns buffer", (unsigned long long)i); c.data = buf + off; }
+            else if (c.typ == kRun) {
+                if (off + 2 > len) return fail(FBGPU_E_FORMAT, "run container %llu overruns buffer", (unsigned long long)i);
+                c.cnt = rd16(buf + off); if (off + 2 + (uint64_t)c.cnt * 4 > len) return fail(FBGPU_E_FORMAT, "run container %llu overruns buffer", (unsigned long long)i);
+                c.data = buf + off + 2;
+            } else return fail(FBGPU_E_FORMAT, "container %llu has unknown type %u", (unsigned long long)i, c.typ);
+            if (!out.empty() && out.back().key >= c.key) return fail(FBGPU_E_FORMAT, "container keys not ascending");
+            out.push_back(c);
+        }
+        return 0;
+    }
+    if (magic == 12346 || magic == 12347) {
+        uint64_t keys, pos; const uint8_t* runbits = nullptr; bool have_runs = magic == 12347;
+        if (have_runs) { keys = (uint64_t)rd16(buf + 2) + 1; pos = 4; runbits = buf + pos; pos += (keys + 7) / 8; if (pos > len) return fail(FBGPU_E_FORMAT, "is-run bitmap overruns buffer"); }
+        else { keys = rd32(buf + 4); pos = 8; }
+        if (pos + keys * 4 >= len) return fail(FBGPU_E_FORMAT, "malformed bitmap, key-cardinality slice overruns buffer");
+        const uint8_t* hdr = buf + pos; pos += keys * 4;
+        const uint8_t* offs = nullptr;
+        if (!have_runs) { if (pos + keys * 4 > len) return fail(FBGPU_E_FORMAT, "insufficient data for offsets"); offs = buf + pos; }
+        uint64_t cur = pos;
+        for (uint64_t i = 0; i < keys; i++) {
+            ParsedCont c{}; c.key = rd16(hdr + i * 4); c.n = (uint32_t)rd16(hdr + i * 4 + 2) + 1;
+            bool isrun = have_runs && ((runbits[i / 8] >> (i % 8)) & 1);
+            uint64_t off = offs ? rd32(offs + i * 4) : cur;
+            if (isrun) {
+                if (off + 2 > len) return fail(FBGPU_E_FORMAT, "run container overruns buffer");
+                c.typ = kRun; c.cnt = rd16(buf + off); if (off + 2 + (uint64_t)c.cnt * 4 > len) return fail(FBGPU_E_FORMAT, "run container overruns buffer");
+                c.data = buf + off + 2; c.official_run = true; cur = off + 2 + (uint64_t)c.cnt * 4;
+            } else if (c.n < 4096) { c.typ = kArray; if (off + (uint64_t)c.n * 2 > len) return fail(FBGPU_E_FORMAT, "array container overruns buffer"); c.data = buf + off; cur = off + (uint64_t)c.n * 2; }
+            else { c.typ = kBitmap; if (off + 8192 > len) return fail(FBGPU_E_FORMAT, "bitmap container overruns buffer"); c.data = buf + off; cur = off + 8192; }
+            out.push_back(c);
+        }
+        return 0;
+    }
+    return fail(FBGPU_E_FORMAT, "unknown roaring cookie %u", magic);
+}
+
+static uint32_t view_id_locked(fbgpu_ctx* c, ViewKey k, bool create) {
+    auto it = c->view_ids.find(k);
+    if (it != c->view_ids.end()) return it->second;
+    if (!create) return kNoView;
+    uint32_t id = (uint32_t)c->shardmaps.size();
+    c->view_ids[k] = id; c->shardmaps.emplace_back();
+    return id;
+}
+
+static void drop_locked(fbgpu_ctx* c, uint32_t fv, uint64_t shard) {
+    auto& sm = c->shardmaps[fv];
+    if (shard >= sm.size() || sm[shard] < 0) return;
+    HostFrag& f = c->frags[sm[shard]];
+    f.live = false;
+    c->stats.fragments--; c->stats.containers -= f.n_desc; c->stats.payload_bytes -= f.payload_bytes;
+    c->stats.array_containers -= f.n_arr; c->stats.bitmap_containers -= f.n_bmp; c->stats.run_containers -= f.n_run;
+    sm[shard] = -1;
+    c->meta_dirty = true;
+}
+
+// appends one parsed fragment to the host mirrors + staging (store_mu held exclusively)
+static int add_fragment_locked(fbgpu_ctx* c, uint32_t fv, uint64_t shard, const std::vector<ParsedCont>& cs) {
+    if (shard >= (1ull << 31)) return fail(FBGPU_E_INVALID, "shard %llu too large", (unsigned long long)shard);
+    drop_locked(c, fv, shard);
+    HostFrag hf{}; hf.fv = fv; hf.shard = shard; hf.live = true; hf.row_off = (uint32_t)c->h_rows.size();
+    uint64_t prev_row = ~0ull; bool contiguous = true; uint64_t row0 = 0;
+    for (const ParsedCont& pc : cs) {
+        uint64_t row = pc.key / kSlotsPerRow; int slot = (int)(pc.key % kSlotsPerRow);
+        if (row != prev_row) {
+            if (prev_row == ~0ull) row0 = row; else if (row != prev_row + 1) contiguous = false;
+            RowEnt e{}; e.row = row; e.first_desc = (uint32_t)c->h_descs.size(); e.mask = 0;
+            c->h_rows.push_back(e); prev_row = row; hf.n_rows++;
+        }
+        c->h_rows.back().mask |= (uint16_t)(1u << slot);
+        // stage payload with alignment: bitmaps 128 B, others 16 B
+        uint64_t pos = c->uploaded + c->staging.size();
+        uint64_t align = pc.typ == kBitmap ? 128 : 16;
+        uint64_t apos = (pos + align - 1) & ~(align - 1);
+        uint64_t bytes = pc.typ == kArray ? (uint64_t)pc.n * 2 : pc.typ == kBitmap ? 8192 : (uint64_t)pc.cnt * 4;
+        uint64_t padded = (bytes + 15) & ~15ull;
+        c->staging.resize(c->staging.size() + (apos - pos) + padded, 0);
+        uint8_t* dst = c->staging.data() + (apos - c->uploaded);
+        memcpy(dst, pc.data, bytes);
+        if (pc.typ == kRun && pc.official_run) {     // official format stores (start, length-1): roaring.go:2240-2247
+            uint16_t* r = (uint16_t*)dst; for (uint32_t k = 0; k < pc.cnt; k++) r[2 * k + 1] = (uint16_t)(r[2 * k] + r[2 * k + 1]);
+        }
+        if (apos / 16 > 0xffffffffull) return fail(FBGPU_E_NOMEM, "payload arena exceeds 64 GiB addressable by 32-bit 16 B offsets");
+        ContDesc d{}; d.off16 = (uint32_t)(apos / 16); d.card = pc.n; d.typ = pc.typ; d.cnt = (uint16_t)pc.cnt;
+        c->h_descs.push_back(d);
+        hf.n_desc++; hf.payload_bytes += bytes;
+        if (pc.typ == kArray) hf.n_arr++; else if (pc.typ == kBitmap) hf.n_bmp++; else hf.n_run++;
+    }
+    FragHdr h{}; h.row_off = hf.row_off; h.n_rows = hf.n_rows; h.row0 = row0; h.contiguous = contiguous ? 1u : 0u;
+    int32_t fid = (int32_t)c->frags.size();
+    c->frags.push_back(hf); c->h_frags.push_back(h);
+    auto& sm = c->shardmaps[fv];
+    if (shard >= sm.size()) sm.resize(shard + 1, -1);
+    sm[shard] = fid;
+    c->stats.fragments++; c->stats.containers += hf.n_desc; c->stats.payload_bytes += hf.payload_bytes;
+    c->stats.array_containers += hf.n_arr; c->stats.bitmap_containers += hf.n_bmp; c->stats.run_containers += hf.n_run;
+    c->meta_dirty = true;
+    return 0;
+}
+
+extern "C" int fbgpu_load_fragment(fbgpu_ctx* c, uint32_t index, uint32_t field, uint32_t view, uint64_t shard, const uint8_t* roaring, uint64_t nbytes) {
+    if (!c || !roaring) return fail(FBGPU_E_INVALID, "null argument");
+    std::vector<ParsedCont> cs;
+    int rc = parse_roaring(roaring, nbytes, cs); if (rc) return rc;
+    std::unique_lock<std::shared_mutex> lk(c->store_mu);
+    uint32_t fv = view_id_locked(c, ViewKey{ index, field, view }, true);
+    return add_fragment_locked(c, fv, shard, cs);
+}
+
+extern "C" int fbgpu_load_fragments(fbgpu_ctx* c, uint32_t index, uint32_t field, uint32_t view, const uint64_t* shards, int64_t n,
+                                    const uint8_t* buf, const uint64_t* offsets) {
+    if (!c || !shards || !buf || !offsets || n < 0) return fail(FBGPU_E_INVALID, "null argument");
+    // parse in parallel (validation + container tables), then append serially (memcpy-bound)
+    std::vector<std::vector<ParsedCont>> parsed((size_t)n);
+    std::vector<int> rcs((size_t)n, 0); std::vector<std::string> errs((size_t)n);
+    int nt = (int)std::min<int64_t>(std::max(1u, std::thread::hardware_concurrency()), std::max<int64_t>(1, n / 8));
+    nt = std::min(nt, 32);
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; t++) th.emplace_back([&, t] {
+        for (int64_t i = n * t / nt; i < n * (t + 1) / nt; i++) { rcs[i] = parse_roaring(buf + offsets[i], offsets[i + 1] - offsets[i], parsed[i]); if (rcs[i]) errs[i] = g_err; }
+    });
+    for (auto& t : th) t.join();
+    for (int64_t i = 0; i < n; i++) if (rcs[i]) { g_err = errs[i]; return rcs[i]; }
+    std::unique_lock<std::shared_mutex> lk(c->store_mu);
+    uint32_t fv = view_id_locked(c, ViewKey{ index, field, view }, true);
+    uint64_t total = offsets[n] - offsets[0];
+    c->staging.reserve(c->staging.size() + total + (size_t)n * 4096);
+    for (int64_t i = 0; i < n; i++) { int rc = add_fragment_locked(c, fv, shards[i], parsed[i]); if (rc) return rc; }
+    return 0;
+}
+
+extern "C" int fbgpu_drop_fragment(fbgpu_ctx* c, uint32_t index, uint32_t field, uint32_t view, uint64_t shard) {
+    if (!c) return fail(FBGPU_E_INVALID, "null ctx");
+    std::unique_lock<std::shared_mutex> lk(c->store_mu);
+    uint32_t fv = view_id_locked(c, ViewKey{ index, field, view }, false);
+    if (fv == kNoView) return 0;
+    drop_locked(c, fv, shard);
+    return 0;
+}
+
+// uploads staged payload (append) and refreshes metadata tables; store_mu held exclusively
+static int commit_locked(fbgpu_ctx* c) {
+    if (!c->meta_dirty && c->staging.empty()) return 0;
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaDeviceSynchronize());   // no query may be reading tables we are about to replace (queries hold the shared lock anyway)
+    if (!c->staging.empty()) {
+        uint64_t need = c->uploaded + c->staging.size() + 256;
+        if (need > c->d_payload.cap) {
+            DevBuf nb; size_t want = std::max<size_t>(need, c->d_payload.cap * 2);
+            if (nb.ensure(want)) { if (nb.ensure(need)) return FBGPU_E_NOMEM; }
+            if (c->uploaded) CUDA_TRY(cudaMemcpy(nb.p, c->d_payload.p, c->uploaded, cudaMemcpyDeviceToDevice));
+            c->d_payload.release(); c->d_payload = nb;
+        }
+        CUDA_TRY(cudaMemcpy((uint8_t*)c->d_payload.p + c->uploaded, c->staging.data(), c->staging.size(), cudaMemcpyHostToDevice));
+        c->uploaded += c->staging.size();
+        std::vector<uint8_t>().swap(c->staging);
+    }
+    // flatten shard maps
+    std::vector<ViewTab> views(c->shardmaps.size()); std::vector<int32_t> flat;
+    for (size_t v = 0; v < c->shardmaps.size(); v++) { views[v].shard_off = (uint32_t)flat.size(); views[v].n_shards = (uint32_t)c->shardmaps[v].size(); flat.insert(flat.end(), c->shardmaps[v].begin(), c->shardmaps[v].end()); }
+    auto up = [&](DevBuf& b, const void* src, size_t bytes) -> int {
+        if (b.ensure(std::max<size_t>(bytes, 256))) return FBGPU_E_NOMEM;
+        if (bytes) { cudaError_t e = cudaMemcpy(b.p, src, bytes, cudaMemcpyHostToDevice); if (e != cudaSuccess) return fail(FBGPU_E_CUDA, "metadata upload failed: %s", cudaGetErrorString(e)); }
+        return 0;
+    };
+    int rc;
+    if ((rc = up(c->d_views, views.data(), views.size() * sizeof(ViewTab)))) return rc;
+    if ((rc = up(c->d_shardmap, flat.data(), flat.size() * 4))) return rc;
+    if ((rc = up(c->d_frags, c->h_frags.data(), c->h_frags.size() * sizeof(FragHdr)))) return rc;
+    if ((rc = up(c->d_rows, c->h_rows.data(), c->h_rows.size() * sizeof(RowEnt)))) return rc;
+    if ((rc = up(c->d_descs, c->h_descs.data(), c->h_descs.size() * sizeof(ContDesc)))) return rc;
+    c->n_views_dev = (uint32_t)views.size();
+    c->meta_dirty = false;
+    c->stats.device_bytes = c->d_payload.cap + c->d_views.cap + c->d_shardmap.cap + c->d_frags.cap + c->d_rows.cap + c->d_descs.cap;
+    return 0;
+}
+
+extern "C" int fbgpu_commit(fbgpu_ctx* c) {
+    if (!c) return fail(FBGPU_E_INVALID, "null ctx");
+    std::unique_lock<std::shared_mutex> lk(c->store_mu);
+    return commit_locked(c);
+}
+static int ensure_committed(fbgpu_ctx* c) {
+    { std::shared_lock<std::shared_mutex> lk(c->store_mu); if (!c->meta_dirty && c->staging.empty()) return 0; }
+    return fbgpu_commit(c);
+}
+
+extern "C" int fbgpu_get_stats(fbgpu_ctx* c, fbgpu_stats* out) {
+    if (!c || !out) return fail(FBGPU_E_INVALID, "null argument");
+    std::shared_lock<std::shared_mutex> lk(c->store_mu);
+    *out = c->stats;
+    return 0;
+}
+
+// ------------------------------------------------------------------ program compiler
+// Turns the post-order pql.Call program into stack-machine device ops, mirroring executeBitmapCallShard
+// (executor.go:1782-1816) and, for BSI, fragment.rangeOp's control flow (fragment.go:937-1303).  The only thing
+// dropped is the data-dependent `remaining.Any()` early exit, which cannot change a result.
+struct Node { fbgpu_op op; std::vector<int> kids; };
+
+struct Compiler {
+    fbgpu_ctx* c; uint32_t index;
+    std::vector<DevOp> out; int depth = 0, max_depth = 0;
+    uint32_t fv_of(uint32_t field, uint32_t view) { return view_id_locked(c, ViewKey{ index, field, view }, false); }
+    void emit(uint8_t op, uint32_t fv = kNoView, uint64_t row = 0) {
+        DevOp d{}; d.op = op; d.fv = fv; d.row = row; out.push_back(d);
+        if (op == D_PUSH_ROW || op == D_PUSH_EMPTY) { depth++; max_depth = std::max(max_depth, depth); }
+        else if (op == D_AND || op == D_OR || op == D_ANDNOT || op == D_XOR || op == D_POP) depth--;
+    }
+    static int bitlen(uint64_t x) { return x ? 64 - __builtin_clzll(x) : 0; }
+    static uint64_t ones(uint64_t d) { return d >= 64 ? ~0ull : (1ull << d) - 1; }
+    static uint64_t shl_ones(uint64_t d) { return d >= 64 ? 0 : ~0ull << d; }
+    static uint64_t abs64(int64_t v) { return v > 0 ? (uint64_t)v : v == INT64_MIN ? 9223372036854775808ull : (uint64_t)(-v); }  // fragment.go:952
+
+    // ---- BSI (rows: 0 exists, 1 sign, 2+i bit i; fragment.go:63-65)
+    void range_eq(uint32_t fv, uint64_t depth_, int64_t pred) {                      // fragment.go:963-1003
+        uint64_t up = abs64(pred);
+        if ((uint64_t)bitlen(up) > depth_) { emit(D_PUSH_EMPTY); return; }
+        emit(D_PUSH_ROW, fv, 0);
+        emit(pred < 0 ? D_AND_ROW : D_ANDNOT_ROW, fv, 1);
+        for (int i = (int)depth_ - 1; i >= 0; i--) emit(((up >> i) & 1) ? D_AND_ROW : D_ANDNOT_ROW, fv, 2 + (uint64_t)i);
+    }
+    void range_neq(uint32_t fv, uint64_t d, int64_t pred) { emit(D_PUSH_ROW, fv, 0); range_eq(fv, d, pred); emit(D_ANDNOT); }  // :1005-1022
+    // filter on top of stack -> result on top
+    void lt_unsigned(uint32_t fv, uint64_t d, uint64_t pred, bool eq) {               // :1070-1113
+        if ((uint64_t)bitlen(pred) > d || (pred == ones(d) && eq)) return;
+        if (pred == ones(d) && !eq) {
+            emit(D_PUSH_EMPTY); emit(D_SWAP);
+            for (uint64_t i = 0; i < d; i++) emit(D_ORANDNOT_ROW, fv, 2 + i);
+            emit(D_POP); return;
+        }
+        if (eq) pred++;
+        emit(D_PUSH_EMPTY); emit(D_SWAP);                                              // [matched, remaining]
+        for (int i = (int)d - 1; i >= 0 && pred > 0; i--) {
+            if ((pred >> i) & 1) { emit(D_ORANDNOT_ROW, fv, 2 + (uint64_t)i); pred &= ~(1ull << i); }
+            else emit(D_ANDNOT_ROW, fv, 2 + (uint64_t)i);
+        }
+        emit(D_POP);
+    }
+    void gt_unsigned(uint32_t fv, uint64_t d, uint64_t pred, bool eq) {               // :1157-1205
+        for (;;) {
+            if (pred == 0 && eq) return;
+            if (pred == 0 && !eq) {
+                emit(D_PUSH_EMPTY); emit(D_SWAP);
+                for (uint64_t i = 0; i < d; i++) emit(D_ORAND_ROW, fv, 2 + i);
+                emit(D_POP); return;
+            }
+            if (!eq && (uint64_t)bitlen(pred) > d) { emit(D_POP); emit(D_PUSH_EMPTY); return; }
+            if (eq) { pred--; eq = false; continue; }
+            break;
+        }
+        emit(D_PUSH_EMPTY); emit(D_SWAP);
+        pred |= shl_ones(d);
+        for (int i = (int)d - 1; i >= 0 && pred < ~0ull; i--) {
+            if ((pred >> i) & 1) emit(D_AND_ROW, fv, 2 + (uint64_t)i);
+            else { emit(D_ORAND_ROW, fv, 2 + (uint64_t)i); pred |= 1ull << i; }
+        }
+        emit(D_POP);
+    }
+    void range_lt(uint32_t fv, uint64_t d, int64_t pred, bool eq) {                   // :1024-1067
+        if (pred == 1 && !eq) { pred = 0; eq = true; }
+        uint64_t up = abs64(pred);
+        if (pred == 0 && !eq) { emit(D_PUSH_ROW, fv, 0); emit(D_AND_ROW, fv, 1); }
+        else if (pred == 0 && eq) { emit(D_PUSH_ROW, fv, 0); emit(D_AND_ROW, fv, 1); range_eq(fv, d, 0); emit(D_OR); }
+        else if (pred < 0) { emit(D_PUSH_ROW, fv, 0); emit(D_AND_ROW, fv, 1); gt_unsigned(fv, d, up, eq); }
+        else { emit(D_PUSH_ROW, fv, 0); emit(D_ANDNOT_ROW, fv, 1); lt_unsigned(fv, d, up, eq); emit(D_PUSH_ROW, fv, 0); emit(D_AND_ROW, fv, 1); emit(D_OR); }
+    }
+    void range_gt(uint32_t fv, uint64_t d, int64_t pred, bool eq) {                   // :1115-1155
+        if (pred == -1 && !eq) { pred = 0; eq = true; }
+        uint64_t up = abs64(pred);
+        if (pred == 0 && !eq) { range_neq(fv, d, 0); emit(D_ANDNOT_ROW, fv, 1); }
+        else if (pred == 0 && eq) { emit(D_PUSH_ROW, fv, 0); emit(D_ANDNOT_ROW, fv, 1); }
+        else if (pred >= 0) { emit(D_PUSH_ROW, fv, 0); emit(D_ANDNOT_ROW, fv, 1); gt_unsigned(fv, d, up, eq); }
+        else { emit(D_PUSH_ROW, fv, 0); emit(D_AND_ROW, fv, 1); lt_unsigned(fv, d, up, eq); emit(D_PUSH_ROW, fv, 0); emit(D_ANDNOT_ROW, fv, 1); emit(D_OR); }
+    }
+    void between_unsigned(uint32_t fv, uint64_t d, uint64_t pmin, uint64_t pmax) {     // :1262-1303
+        if (pmax > ones(d)) { gt_unsigned(fv, d, pmin, true); return; }
+        if (pmin == 0) { lt_unsigned(fv, d, pmax, true); return; }
+        int diff = bitlen(pmax ^ pmin);
+        for (int i = (int)d - 1; i >= diff; i--) emit(((pmin >> i) & 1) ? D_AND_ROW : D_ANDNOT_ROW, fv, 2 + (uint64_t)i);
+        uint64_t mask = shl_ones((uint64_t)diff);
+        pmin &= ~mask; pmax &= ~mask;
+        gt_unsigned(fv, (uint64_t)diff, pmin, true);
+        lt_unsigned(fv, (uint64_t)diff, pmax, true);
+    }
+    void range_between(uint32_t fv, uint64_t d, int64_t lo, int64_t hi) {             // :1213-1259
+        uint64_t ulo = abs64(lo), uhi = abs64(hi);
+        if (lo == hi) { range_eq(fv, d, lo); return; }
+        if (lo >= 0) { emit(D_PUSH_ROW, fv, 0); emit(D_ANDNOT_ROW, fv, 1); between_unsigned(fv, d, ulo, uhi); return; }
+        if (hi < 0) { emit(D_PUSH_ROW, fv, 0); emit(D_AND_ROW, fv, 1); between_unsigned(fv, d, uhi, ulo); return; }
+        emit(D_PUSH_ROW, fv, 0); emit(D_ANDNOT_ROW, fv, 1); lt_unsigned(fv, d, uhi, true);
+        emit(D_PUSH_ROW, fv, 0); emit(D_AND_ROW, fv, 1); lt_unsigned(fv, d, ulo, true);
+        emit(D_OR);
+    }
+
+    int gen(const std::vector<Node>& nodes, int id) {
+        const Node& n = nodes[id]; const fbgpu_op& o = n.op;
+        auto is_row_leaf = [&](int k) { return nodes[k].op.opcode == FBGPU_OP_ROW || nodes[k].op.opcode == FBGPU_OP_ALL; };
+        auto leaf_fv = [&](int k) { return fv_of(nodes[k].op.field, nodes[k].op.view); };
+        auto fold = [&](uint8_t fused, uint8_t binop) -> int {
+            int rc = gen(nodes, n.kids[0]); if (rc) return rc;
+            for (size_t k = 1; k < n.kids.size(); k++) {
+                int kid = n.kids[k];
+                if (is_row_leaf(kid)) emit(fused, leaf_fv(kid), nodes[kid].op.a);
+                else { rc = gen(nodes, kid); if (rc) return rc; emit(binop); }
+            }
+            return 0;
+        };
+        switch (o.opcode) {
+            case FBGPU_OP_ROW: case FBGPU_OP_ALL: emit(D_PUSH_ROW, fv_of(o.field, o.view), o.a); return 0;
+            case FBGPU_OP_EMPTY: emit(D_PUSH_EMPTY); return 0;
+            case FBGPU_OP_INTERSECT:
+                if (n.kids.empty()) return fail(FBGPU_E_QUERY, "empty Intersect query is currently not supported");   // executor.go:5362
+                return fold(D_AND_ROW, D_AND);
+            case FBGPU_OP_UNION:
+                if (n.kids.empty()) { emit(D_PUSH_EMPTY); return 0; }                                                  // executor.go:5386
+                return fold(D_OR_ROW, D_OR);
+            case FBGPU_OP_DIFFERENCE:
+                if (n.kids.empty()) return fail(FBGPU_E_QUERY, "empty Difference query is currently not supported");  // executor.go:2955
+                return fold(D_ANDNOT_ROW, D_ANDNOT);
+            case FBGPU_OP_XOR:
+                if (n.kids.empty()) { emit(D_PUSH_EMPTY); return 0; }                                                  // executor.go:5517
+                return fold(D_XOR_ROW, D_XOR);
+            case FBGPU_OP_NOT: {                                                                                        // executor.go:5554-5602
+                if (n.kids.size() != 1) return fail(FBGPU_E_QUERY, "Not() requires a single bitmap input");
+                emit(D_PUSH_ROW, fv_of(o.field, o.view), o.a);
+                int kid = n.kids[0];
+                if (is_row_leaf(kid)) emit(D_ANDNOT_ROW, leaf_fv(kid), nodes[kid].op.a);
+                else { int rc = gen(nodes, kid); if (rc) return rc; emit(D_ANDNOT); }
+                return 0;
+            }
+            case FBGPU_OP_BSI_RANGE: {
+                uint32_t fv = fv_of(o.field, o.view); uint64_t d = o.a;
+                if (d > 64) return fail(FBGPU_E_INVALID, "bit depth %llu > 64", (unsigned long long)d);
+                switch (o.b) {
+                    case FBGPU_CMP_EQ: range_eq(fv, d, o.lo); break;
+                    case FBGPU_CMP_NEQ: range_neq(fv, d, o.lo); break;
+                    case FBGPU_CMP_LT: range_lt(fv, d, o.lo, false); break;
+                    case FBGPU_CMP_LTE: range_lt(fv, d, o.lo, true); break;
+                    case FBGPU_CMP_GT: range_gt(fv, d, o.lo, false); break;
+                    case FBGPU_CMP_GTE: range_gt(fv, d, o.lo, true); break;
+                    case FBGPU_CMP_BETWEEN: range_between(fv, d, o.lo, o.hi); break;
+                    default: return fail(FBGPU_E_INVALID, "invalid range operation %llu", (unsigned long long)o.b);   // ErrInvalidRangeOperation
+                }
+                return 0;
+            }
+        }
+        return fail(FBGPU_E_INVALID, "unknown opcode %u", o.opcode);
+    }
+};
+
+// store_mu must be held (shared) by the caller
+static int compile_program(fbgpu_ctx* c, uint32_t index, const fbgpu_op* ops, int32_t n_ops, std::vector<DevOp>& out, int& depth) {
+    if (n_ops < 0 || (n_ops > 0 && !ops)) return fail(FBGPU_E_INVALID, "bad program");
+    std::vector<Node> nodes; std::vector<int> stack;
+    for (int i = 0; i < n_ops; i++) {
+        Node n; n.op = ops[i];
+        bool nary = n.op.opcode >= FBGPU_OP_INTERSECT && n.op.opcode <= FBGPU_OP_NOT;
+        if (nary) {
+            uint32_t argc = n.op.argc;
+            if (argc > stack.size()) return fail(FBGPU_E_INVALID, "op %d pops %u operands but only %zu available", i, argc, stack.size());
+            n.kids.assign(stack.end() - argc, stack.end()); stack.resize(stack.size() - argc);
+        }
+        nodes.push_back(std::move(n)); stack.push_back((int)nodes.size() - 1);
+    }
+    if (stack.size() != 1) return fail(FBGPU_E_INVALID, "program must leave exactly one result (leaves %zu)", stack.size());
+    Compiler cp{ c, index };
+    int rc = cp.gen(nodes, stack[0]); if (rc) return rc;
+    if (cp.max_depth > 15) return fail(FBGPU_E_INVALID, "program needs operand stack depth %d > 15", cp.max_depth);
+    out.swap(cp.out); depth = std::max(cp.max_depth, 1);
+    return 0;
+}
+
+// ------------------------------------------------------------------ execution helpers
+static void bump(fbgpu_ctx* c, uint64_t launches, float ms) {
+    std::lock_guard<std::mutex> lk(c->cnt_mu);
+    c->counters.kernel_launches += launches; c->counters.queries++; c->counters.last_query_gpu_ms = ms;
+}
+
+static int allreduce_u64(fbgpu_ctx* c, Workspace* w, void* dptr, size_t n) {
+    if (!c->comm) return 0;
+    int r = g_nccl.AllReduce(dptr, dptr, n, kNcclUint64, kNcclSum, c->comm, w->stream);
+    if (r != 0) return fail(FBGPU_E_COMM, "ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+    return 0;
+}
+
+// uploads [DevOp prog | u64 shards] with one H2D copy; returns device pointers
+static int upload_inputs(Workspace* w, const std::vector<DevOp>& prog, const uint64_t* shards, int64_t n_shards, const DevOp** d_prog, const uint64_t** d_shards) {
+    size_t pb = prog.size() * sizeof(DevOp), sb = (size_t)n_shards * 8, tot = pb + sb;
+    if (w->h_in.ensure(tot + 16)) return FBGPU_E_NOMEM;
+    if (w->d_in.ensure(tot + 16)) return FBGPU_E_NOMEM;
+    if (pb) memcpy(w->h_in.p, prog.data(), pb);
+    if (sb) memcpy((uint8_t*)w->h_in.p + pb, shards, sb);
+    if (tot) CUDA_TRY(cudaMemcpyAsync(w->d_in.p, w->h_in.p, tot, cudaMemcpyHostToDevice, w->stream));
+    *d_prog = (const DevOp*)w->d_in.p; *d_shards = (const uint64_t*)((uint8_t*)w->d_in.p + pb);
+    return 0;
+}
+
+static int launch_eval(fbgpu_ctx* c, Workspace* w, const DevOp* d_prog, int n_ops, int depth, const uint64_t* d_shards, long long n_units, EvalOut out) {
+    if (n_units <= 0) return 0;
+    size_t smem = (size_t)(depth + 1) * 8192;
+    int per_sm = std::max(1, (int)std::min<size_t>(8, (220 * 1024) / (smem + 6 * 1024)));
+    long long grid = std::min<long long>(n_units, (long long)c->sm_count * per_sm);
+    eval_kernel<<<(unsigned)grid, kEvalThreads, smem, w->stream>>>(store_ref(c), d_prog, n_ops, depth, d_shards, n_units, out);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------ Count
+extern "C" int fbgpu_count(fbgpu_ctx* c, uint32_t index, const fbgpu_op* ops, int32_t n_ops, const uint64_t* shards, int64_t n_shards,
+                           uint64_t* out_total, uint64_t* out_per_shard) {
+    if (!c || !out_total || n_shards < 0 || (n_shards && !shards)) return fail(FBGPU_E_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    int rc = ensure_committed(c); if (rc) return rc;
+    std::shared_lock<std::shared_mutex> lk(c->store_mu);
+    std::vector<DevOp> prog; int depth = 1;
+    rc = compile_program(c, index, ops, n_ops, prog, depth); if (rc) return rc;
+    WsLease lease(c); Workspace* w = lease.w;
+    const DevOp* d_prog; const uint64_t* d_shards;
+    rc = upload_inputs(w, prog, shards, n_shards, &d_prog, &d_shards); if (rc) return rc;
+    size_t nc = 1 + (out_per_shard ? (size_t)n_shards : 0);
+    if (w->d_counts.ensure(nc * 8)) return FBGPU_E_NOMEM;
+    if (w->h_out.ensure(nc * 8)) return FBGPU_E_NOMEM;
+    CUDA_TRY(cudaMemsetAsync(w->d_counts.p, 0, nc * 8, w->stream));
+    unsigned long long* d_total = (unsigned long long*)w->d_counts.p;
+    unsigned long long* d_per = out_per_shard ? d_total + 1 : nullptr;
+    long long n_units = (long long)n_shards * kSlotsPerRow;
+    CUDA_TRY(cudaEventRecord(w->ev0, w->stream));
+    if (n_units > 0) {
+        // fused Intersect+Count fast path: Count(Intersect(Row, Row))  (executor.go:5357 + row.go:242 + Count)
+        if (prog.size() == 2 && prog[0].op == D_PUSH_ROW && prog[1].op == D_AND_ROW) {
+            long long grid = std::min<long long>((n_units + kPairWarps - 1) / kPairWarps, (long long)c->sm_count * 3);
+            pair_count_kernel<<<(unsigned)grid, kPairWarps * 32, kPairWarps * 8192, w->stream>>>(store_ref(c), prog[0].fv, prog[0].row, prog[1].fv, prog[1].row, d_shards, n_units, d_total, d_per);
+            CUDA_TRY(cudaGetLastError());
+        } else {
+            EvalOut eo{ d_total, d_per, nullptr, nullptr };
+            rc = launch_eval(c, w, d_prog, (int)prog.size(), depth, d_shards, n_units, eo); if (rc) return rc;
+        }
+    }
+    CUDA_TRY(cudaEventRecord(w->ev1, w->stream));
+    rc = allreduce_u64(c, w, d_total, 1); if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(w->h_out.p, w->d_counts.p, nc * 8, cudaMemcpyDeviceToHost, w->stream));
+    CUDA_TRY(cudaStreamSynchronize(w->stream));
+    *out_total = ((uint64_t*)w->h_out.p)[0];
+    if (out_per_shard) memcpy(out_per_shard, (uint64_t*)w->h_out.p + 1, (size_t)n_shards * 8);
+    float ms = 0; cudaEventElapsedTime(&ms, w->ev0, w->ev1);
+    bump(c, n_units > 0 ? 1 : 0, ms);
+    return FBGPU_OK;
+}
+
+// ------------------------------------------------------------------ Row (canonical Pilosa-roaring result)
+static constexpr long long kUnitBatch = 16384;   // 128 MiB of result bitmaps per batch
+
+extern "C" int fbgpu_row(fbgpu_ctx* c, uint32_t index, const fbgpu_op* ops, int32_t n_ops, const uint64_t* shards, int64_t n_shards,
+                         uint8_t* out_buf, uint64_t out_cap, uint64_t* out_len, uint64_t* out_count) {
+    if (!c || !out_len || n_shards < 0 || (n_shards && !shards)) return fail(FBGPU_E_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    int rc = ensure_committed(c); if (rc) return rc;
+    std::shared_lock<std::shared_mutex> lk(c->store_mu);
+    std::vector<DevOp> prog; int depth = 1;
+    rc = compile_program(c, index, ops, n_ops, prog, depth); if (rc) return rc;
+    // Row.Merge concatenates disjoint shard segments (row.go:202); emit in ascending shard order
+    std::vector<uint64_t> sorted(shards, shards + n_shards);
+    std::sort(sorted.begin(), sorted.end());
+    sorted.erase(std::unique(sorted.begin(), sorted.end()), sorted.end());
+    n_shards = (int64_t)sorted.size();
+    WsLease lease(c); Workspace* w = lease.w;
+    const DevOp* d_prog; const uint64_t* d_shards;
+    rc = upload_inputs(w, prog, sorted.data(), n_shards, &d_prog, &d_shards); if (rc) return rc;
+    long long n_units = (long long)n_shards * kSlotsPerRow;
+    struct OutCont { uint64_t key; uint16_t typ; uint32_t n; uint64_t size; std::vector<uint8_t> payload; };
+    std::vector<OutCont> conts; uint64_t total_count = 0; uint64_t launches = 0; float ms_total = 0;
+    for (long long u0 = 0; u0 < n_units; u0 += kUnitBatch) {
+        long long nu = std::min(kUnitBatch, n_units - u0);
+        if (w->d_bitmaps.ensure((size_t)nu * 8192)) return FBGPU_E_NOMEM;
+        if (w->d_info.ensure((size_t)nu * 8)) return FBGPU_E_NOMEM;
+        if (w->h_out.ensure((size_t)nu * 8)) return FBGPU_E_NOMEM;
+        EvalOut eo{ nullptr, nullptr, (uint4*)w->d_bitmaps.p, (uint2*)w->d_info.p };
+        CUDA_TRY(cudaEventRecord(w->ev0, w->stream));
+        rc = launch_eval(c, w, d_prog, (int)prog.size(), depth, d_shards + u0 / kSlotsPerRow, nu, eo); if (rc) return rc;
+        launches++;
+        CUDA_TRY(cudaMemcpyAsync(w->h_out.p, w->d_info.p, (size_t)nu * 8, cudaMemcpyDeviceToHost, w->stream));
+        CUDA_TRY(cudaStreamSynchronize(w->stream));
+        // optimize(): roaring.go:3412-3426
+        std::vector<EmitUnit> emits; uint64_t off = 0; size_t first = conts.size();
+        const uint2* info = (const uint2*)w->h_out.p;
+        for (long long u = 0; u < nu; u++) {
+            uint32_t N = info[u].x, runs = info[u].y;
+            if (!N) continue;
+            uint16_t typ = (runs <= 2048 && runs <= N / 2) ? kRun : (N < 4096 ? kArray : kBitmap);
+            uint64_t size = typ == kRun ? 2 + 4ull * runs : typ == kArray ? 2ull * N : 8192;
+            EmitUnit e{ off, (uint32_t)u, typ };
+            emits.push_back(e);
+            OutCont oc; oc.key = sorted[(u0 + u) / kSlotsPerRow] * kSlotsPerRow + (uint64_t)((u0 + u) % kSlotsPerRow); oc.typ = typ; oc.n = N; oc.size = size;
+            conts.push_back(std::move(oc));
+            off += (size + 15) & ~15ull;
+            total_count += N;
+        }
+        if (!emits.empty()) {
+            if (w->d_emit_units.ensure(emits.size() * sizeof(EmitUnit))) return FBGPU_E_NOMEM;
+            if (w->d_emit.ensure(off)) return FBGPU_E_NOMEM;
+            if (w->h_in.ensure(std::max<size_t>(emits.size() * sizeof(EmitUnit), off))) return FBGPU_E_NOMEM;
+            memcpy(w->h_in.p, emits.data(), emits.size() * sizeof(EmitUnit));
+            CUDA_TRY(cudaMemcpyAsync(w->d_emit_units.p, w->h_in.p, emits.size() * sizeof(EmitUnit), cudaMemcpyHostToDevice, w->stream));
+            int grid = (int)std::min<size_t>(emits.size(), (size_t)c->sm_count * 8);
+            canon_emit_kernel<<<grid, kEvalThreads, 0, w->stream>>>((const uint4*)w->d_bitmaps.p, (const EmitUnit*)w->d_emit_units.p, (int)emits.size(), (uint8_t*)w->d_emit.p);
+            CUDA_TRY(cudaGetLastError()); launches++;
+            CUDA_TRY(cudaStreamSynchronize(w->stream));   // h_in is reused as the D2H landing buffer below
+            CUDA_TRY(cudaMemcpyAsync(w->h_in.p, w->d_emit.p, off, cudaMemcpyDeviceToHost, w->stream));
+            CUDA_TRY(cudaEventRecord(w->ev1, w->stream));
+            CUDA_TRY(cudaStreamSynchronize(w->stream));
+            for (size_t k = 0; k < emits.size(); k++) { OutCont& oc = conts[first + k]; oc.payload.assign((uint8_t*)w->h_in.p + emits[k].offset, (uint8_t*)w->h_in.p + emits[k].offset + oc.size); }
+            float ms = 0; cudaEventElapsedTime(&ms, w->ev0, w->ev1); ms_total += ms;
+        }
+    }
+    bump(c, launches, ms_total);
+    // writeToUnoptimized layout: roaring.go:1738-1817
+    uint64_t need = 8 + conts.size() * 16;
+    for (auto& oc : conts) need += oc.size;
+    *out_len = need;
+    if (out_count) *out_count = total_count;
+    if (need > out_cap || !out_buf) return fail(FBGPU_E_NOSPACE, "output needs %llu bytes", (unsigned long long)need);
+    uint32_t cookie = 12348, cnt = (uint32_t)conts.size();
+    memcpy(out_buf, &cookie, 4); memcpy(out_buf + 4, &cnt, 4);
+    uint8_t *h = out_buf + 8, *offp = out_buf + 8 + conts.size() * 12; uint64_t off = 8 + conts.size() * 16;
+    for (auto& oc : conts) {
+        uint16_t n1 = (uint16_t)(oc.n - 1);
+        memcpy(h, &oc.key, 8); memcpy(h + 8, &oc.typ, 2); memcpy(h + 10, &n1, 2); h += 12;
+        uint32_t o32 = (uint32_t)off; memcpy(offp, &o32, 4); offp += 4;
+        memcpy(out_buf + off, oc.payload.data(), oc.size); off += oc.size;
+    }
+    return FBGPU_OK;
+}
+
+// ------------------------------------------------------------------ per-row counts (TopK / TopN ids)
+// evaluates `filter` for shards [s0, s0+ns) into w->d_bitmaps (16 bitmaps per shard)
+static int eval_filter_batch(fbgpu_ctx* c, Workspace* w, const std::vector<DevOp>& prog, int depth, const DevOp* d_prog, const uint64_t* d_shards, int64_t ns) {
+    if (w->d_bitmaps.ensure((size_t)ns * kSlotsPerRow * 8192)) return FBGPU_E_NOMEM;
+    EvalOut eo{ nullptr, nullptr, (uint4*)w->d_bitmaps.p, nullptr };
+    return launch_eval(c, w, d_prog, (int)prog.size(), depth, d_shards, ns * kSlotsPerRow, eo);
+}
+
+static int row_counts_impl(fbgpu_ctx* c, uint32_t index, uint32_t fv, const std::vector<uint64_t>& rows, const fbgpu_op* filter, int32_t n_filter_ops,
+                           const uint64_t* shards, int64_t n_shards, std::vector<uint64_t>& counts) {
+    counts.assign(rows.size(), 0);
+    if (rows.empty()) return 0;
+    std::vector<DevOp> prog; int depth = 1; int rc;
+    bool have_filter = filter && n_filter_ops > 0;
+    if (have_filter) { rc = compile_program(c, index, filter, n_filter_ops, prog, depth); if (rc) return rc; }
+    WsLease lease(c); Workspace* w = lease.w;
+    const DevOp* d_prog; const uint64_t* d_shards;
+    rc = upload_inputs(w, prog, shards, n_shards, &d_prog, &d_shards); if (rc) return rc;
+    size_t nr = rows.size();
+    if (w->d_rows.ensure(nr * 8) || w->d_counts.ensure(nr * 8) || w->h_out.ensure(nr * 8)) return FBGPU_E_NOMEM;
+    CUDA_TRY(cudaMemcpyAsync(w->d_rows.p, rows.data(), nr * 8, cudaMemcpyHostToDevice, w->stream));
+    CUDA_TRY(cudaMemsetAsync(w->d_counts.p, 0, nr * 8, w->stream));
+    CUDA_TRY(cudaEventRecord(w->ev0, w->stream));
+    uint64_t launches = 0;
+    const int64_t batch = have_filter ? 1024 : n_shards;
+    for (int64_t s0 = 0; s0 < n_shards; s0 += batch) {
+        int64_t ns = std::min(batch, n_shards - s0);
+        if (have_filter) { rc = eval_filter_batch(c, w, prog, depth, d_prog, d_shards + s0, ns); if (rc) return rc; launches++; }
+        long long tasks = (long long)ns * (long long)nr;
+        long long grid = std::min<long long>((tasks + kPairWarps - 1) / kPairWarps, (long long)c->sm_count * 3);
+        row_count_kernel<<<(unsigned)grid, kPairWarps * 32, kPairWarps * 8192, w->stream>>>(store_ref(c), fv, (const uint64_t*)w->d_rows.p, (int)nr, d_shards + s0, ns,
+            have_filter ? (const uint4*)w->d_bitmaps.p : nullptr, (unsigned long long*)w->d_counts.p);
+        CUDA_TRY(cudaGetLastError()); launches++;
+    }
+    CUDA_TRY(cudaEventRecord(w->ev1, w->stream));
+    rc = allreduce_u64(c, w, w->d_counts.p, nr); if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(w->h_out.p, w->d_counts.p, nr * 8, cudaMemcpyDeviceToHost, w->stream));
+    CUDA_TRY(cudaStreamSynchronize(w->stream));
+    memcpy(counts.data(), w->h_out.p, nr * 8);
+    float ms = 0; cudaEventElapsedTime(&ms, w->ev0, w->ev1);
+    bump(c, launches, ms);
+    return 0;
+}
+
+extern "C" int fbgpu_row_counts(fbgpu_ctx* c, uint32_t index, uint32_t field, uint32_t view, const uint64_t* row_ids, int32_t n_rows,
+                                const fbgpu_op* filter, int32_t n_filter_ops, const uint64_t* shards, int64_t n_shards,
+                                uint64_t* out_row_ids, uint64_t* out_counts, int32_t cap, int32_t* out_n) {
+    if (!c || !out_counts || n_shards < 0 || (n_shards && !shards) || n_rows < 0) return fail(FBGPU_E_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    int rc = ensure_committed(c); if (rc) return rc;
+    std::shared_lock<std::shared_mutex> lk(c->store_mu);
+    uint32_t fv = view_id_locked(c, ViewKey{ index, field, view }, false);
+    std::vector<uint64_t> rows, counts;
+    if (row_ids) rows.assign(row_ids, row_ids + n_rows);
+    else {
+        // fragment.rows() (fragment.go:2465-2486): distinct row ids present in the listed shards
+        if (fv != kNoView) for (int64_t s = 0; s < n_shards; s++) {
+            const auto& sm = c->shardmaps[fv];
+            if (shards[s] >= sm.size() || sm[shards[s]] < 0) continue;
+            const HostFrag& f = c->frags[sm[shards[s]]];
+            for (uint32_t k = 0; k < f.n_rows; k++) rows.push_back(c->h_rows[f.row_off + k].row);
+        }
+        std::sort(rows.begin(), rows.end()); rows.erase(std::unique(rows.begin(), rows.end()), rows.end());
+    }
+    rc = row_counts_impl(c, index, fv, rows, filter, n_filter_ops, shards, n_shards, counts); if (rc) return rc;
+    if (row_ids) {
+        if (cap < n_rows) return fail(FBGPU_E_NOSPACE, "cap %d < n_rows %d", cap, n_rows);
+        for (int32_t i = 0; i < n_rows; i++) { out_counts[i] = counts[i]; if (out_row_ids) out_row_ids[i] = rows[i]; }
+        if (out_n) *out_n = n_rows;
+        return FBGPU_OK;
+    }
+    std::vector<size_t> order;
+    for (size_t i = 0; i < rows.size(); i++) if (counts[i]) order.push_back(i);
+    std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return counts[a] != counts[b] ? counts[a] > counts[b] : rows[a] < rows[b]; });
+    int32_t n = (int32_t)std::min<size_t>(order.size(), (size_t)std::max(cap, 0));
+    for (int32_t i = 0; i < n; i++) { if (out_row_ids) out_row_ids[i] = rows[order[i]]; out_counts[i] = counts[order[i]]; }
+    if (out_n) *out_n = n;
+    return FBGPU_OK;
+}
+
+// ------------------------------------------------------------------ GroupBy
+static int groupby2(fbgpu_ctx* c, uint32_t index, uint32_t fvA, const uint64_t* rowsA, int nA, uint32_t fvB, const uint64_t* rowsB, int nB,
+                    const std::vector<fbgpu_op>& filter, const uint64_t* shards, int64_t n_shards, uint64_t* out) {
+    std::vector<DevOp> prog; int depth = 1; int rc;
+    bool have_filter = !filter.empty();
+    if (have_filter) { rc = compile_program(c, index, filter.data(), (int)filter.size(), prog, depth); if (rc) return rc; }
+    WsLease lease(c); Workspace* w = lease.w;
+    const DevOp* d_prog; const uint64_t* d_shards;
+    rc = upload_inputs(w, prog, shards, n_shards, &d_prog, &d_shards); if (rc) return rc;
+    size_t ncnt = (size_t)nA * nB;
+    if (w->d_rows.ensure((size_t)(nA + nB) * 8) || w->d_counts.ensure(ncnt * 8) || w->h_out.ensure(ncnt * 8)) return FBGPU_E_NOMEM;
+    std::vector<uint64_t> rr(rowsA, rowsA + nA); rr.insert(rr.end(), rowsB, rowsB + nB);
+    CUDA_TRY(cudaMemcpyAsync(w->d_rows.p, rr.data(), rr.size() * 8, cudaMemcpyHostToDevice, w->stream));
+    CUDA_TRY(cudaMemsetAsync(w->d_counts.p, 0, ncnt * 8, w->stream));
+    CUDA_TRY(cudaStreamSynchronize(w->stream));   // rr is a local
+    CUDA_TRY(cudaEventRecord(w->ev0, w->stream));
+    uint64_t launches = 0;
+    const int64_t batch = have_filter ? 1024 : n_shards;
+    const size_t smem = 131072 + kGbPool * 4 + 8192;
+    for (int64_t s0 = 0; s0 < n_shards; s0 += batch) {
+        int64_t ns = std::min(batch, n_shards - s0);
+        if (have_filter) { rc = eval_filter_batch(c, w, prog, depth, d_prog, d_shards + s0, ns); if (rc) return rc; launches++; }
+        long long units = (long long)ns * kSlotsPerRow;
+        long long grid = std::min<long long>(units, c->sm_count);
+        groupby_kernel<<<(unsigned)grid, kGbThreads, smem, w->stream>>>(store_ref(c), fvA, (const uint64_t*)w->d_rows.p, nA, fvB, (const uint64_t*)w->d_rows.p + nA, nB,
+            d_shards + s0, units, have_filter ? (const uint4*)w->d_bitmaps.p : nullptr, (unsigned long long*)w->d_counts.p);
+        CUDA_TRY(cudaGetLastError()); launches++;
+    }
+    CUDA_TRY(cudaEventRecord(w->ev1, w->stream));
+    rc = allreduce_u64(c, w, w->d_counts.p, ncnt); if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(w->h_out.p, w->d_counts.p, ncnt * 8, cudaMemcpyDeviceToHost, w->stream));
+    CUDA_TRY(cudaStreamSynchronize(w->stream));
+    memcpy(out, w->h_out.p, ncnt * 8);
+    float ms = 0; cudaEventElapsedTime(&ms, w->ev0, w->ev1);
+    bump(c, launches, ms);
+    return 0;
+}
+
+// n-field GroupBy: peel the leading field on the host, folding Row(f0=r) into the filter (groupByIterator keeps
+// the same prefix intersections per level, executor.go:8829-8835,8861-8867)
+static int groupby_rec(fbgpu_ctx* c, uint32_t index, const uint32_t* fields, const uint32_t* views, int nf, const uint64_t* const* rows, const int32_t* n_rows,
+                       std::vector<fbgpu_op> filter, const uint64_t* shards, int64_t n_shards, uint64_t* out) {
+    if (nf == 1) {
+        uint32_t fv = view_id_locked(c, ViewKey{ index, fields[0], views[0] }, false);
+        std::vector<uint64_t> r(rows[0], rows[0] + n_rows[0]), counts;
+        int rc = row_counts_impl(c, index, fv, r, filter.empty() ? nullptr : filter.data(), (int)filter.size(), shards, n_shards, counts); if (rc) return rc;
+        memcpy(out, counts.data(), counts.size() * 8);
+        return 0;
+    }
+    if (nf == 2) {
+        uint32_t fa = view_id_locked(c, ViewKey{ index, fields[0], views[0] }, false), fb = view_id_locked(c, ViewKey{ index, fields[1], views[1] }, false);
+        return groupby2(c, index, fa, rows[0], n_rows[0], fb, rows[1], n_rows[1], filter, shards, n_shards, out);
+    }
+    size_t sub = 1; for (int i = 1; i < nf; i++) sub *= (size_t)n_rows[i];
+    for (int r = 0; r < n_rows[0]; r++) {
+        std::vector<fbgpu_op> f2 = filter;
+        fbgpu_op ro{}; ro.opcode = FBGPU_OP_ROW; ro.field = fields[0]; ro.view = views[0]; ro.a = rows[0][r];
+        f2.push_back(ro);
+        if (!filter.empty()) { fbgpu_op in{}; in.opcode = FBGPU_OP_INTERSECT; in.argc = 2; f2.push_back(in); }
+        int rc = groupby_rec(c, index, fields + 1, views + 1, nf - 1, rows + 1, n_rows + 1, f2, shards, n_shards, out + (size_t)r * sub); if (rc) return rc;
+    }
+    return 0;
+}
+
+extern "C" int fbgpu_groupby(fbgpu_ctx* c, uint32_t index, const uint32_t* fields, const uint32_t* views, int32_t n_fields, const uint64_t* row_ids_flat, const int32_t* n_rows,
+                             const fbgpu_op* filter, int32_t n_filter_ops, const uint64_t* shards, int64_t n_shards, uint64_t* out_counts) {
+    if (!c || !fields || !views || !row_ids_flat || !n_rows || !out_counts || n_fields < 1 || n_fields > 8 || n_shards < 0 || (n_shards && !shards)) return fail(FBGPU_E_INVALID, "bad argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    int rc = ensure_committed(c); if (rc) return rc;
+    std::shared_lock<std::shared_mutex> lk(c->store_mu);
+    std::vector<const uint64_t*> rows(n_fields); const uint64_t* p = row_ids_flat; size_t total = 1;
+    for (int i = 0; i < n_fields; i++) { if (n_rows[i] < 0 || n_rows[i] > 65535) return fail(FBGPU_E_INVALID, "n_rows[%d]=%d out of range", i, n_rows[i]); rows[i] = p; p += n_rows[i]; total *= (size_t)n_rows[i]; }
+    memset(out_counts, 0, total * 8);
+    if (total == 0) return 0;
+    // executor.go:8769-8772: the kernels treat a shard with a missing fragment as contributing nothing; for the
+    // row_counts path (n_fields == 1) a missing fragment naturally yields zeros.  For n_fields >= 3 the peeled
+    // fields enter through the filter, which is empty on shards without that fragment.
+    std::vector<fbgpu_op> f(filter, filter + (filter ? n_filter_ops : 0));
+    return groupby_rec(c, index, fields, views, n_fields, rows.data(), n_rows, f, shards, n_shards, out_counts);
+}
+
+// ------------------------------------------------------------------ comm
+extern "C" int fbgpu_comm_unique_id(uint8_t id[FBGPU_NCCL_ID_BYTES]) {
+    if (!nccl_load()) return fail(FBGPU_E_COMM, "libnccl.so.2 not loadable: %s", dlerror());
+    int r = g_nccl.GetUniqueId(id);
+    if (r) return fail(FBGPU_E_COMM, "ncclGetUniqueId failed (%d)", r);
+    return 0;
+}
+extern "C" int fbgpu_comm_init(fbgpu_ctx* c, int32_t n_ranks, int32_t rank, const uint8_t id[FBGPU_NCCL_ID_BYTES]) {
+    if (!c || !id || n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(FBGPU_E_INVALID, "bad argument");
+    if (!nccl_load()) return fail(FBGPU_E_COMM, "libnccl.so.2 not loadable");
+    CUDA_TRY(cudaSetDevice(c->device));
+    Id128 u; memcpy(u.b, id, 128);
+    void* comm = nullptr;
+    int r = g_nccl.CommInitRank(&comm, n_ranks, u, rank);
+    if (r) return fail(FBGPU_E_COMM, "ncclCommInitRank failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+    c->comm = comm; c->n_ranks = n_ranks; c->rank = rank;
+    return 0;
+}
+extern "C" int fbgpu_comm_destroy(fbgpu_ctx* c) {
+    if (!c) return fail(FBGPU_E_INVALID, "null ctx");
+    if (c->comm && nccl_load()) { cudaSetDevice(c->device); cudaDeviceSynchronize(); g_nccl.CommDestroy(c->comm); }
+    c->comm = nullptr; c->n_ranks = 1; c->rank = 0;
+    return 0;
+}
+
+extern "C" int fbgpu_get_counters(fbgpu_ctx* c, fbgpu_counters* out) {
+    if (!c || !out) return fail(FBGPU_E_INVALID, "null argument");
+    std::lock_guard<std::mutex> lk(c->cnt_mu);
+    *out = c->counters;
+    return 0;
+}
+extern "C" void* fbgpu_stream(fbgpu_ctx* c) { return c ? (void*)c->wss[0]->stream : nullptr; }
+
+// algorithmic-bytes accounting for bench / DESIGN: payload bytes + 16 B descriptor of every
+// container of the given rows over the given shards
+extern "C" int fbgpu_rows_payload_bytes(fbgpu_ctx* c, uint32_t index, uint32_t field, uint32_t view, const uint64_t* row_ids, int32_t n_rows,
+                                        const uint64_t* shards, int64_t n_shards, uint64_t* out_payload, uint64_t* out_containers) {
+    if (!c || !out_payload || !out_containers) return fail(FBGPU_E_INVALID, "null argument");
+    std::shared_lock<std::shared_mutex> lk(c->store_mu);
+    uint64_t pay = 0, nc = 0;
+    uint32_t fv = view_id_locked(c, ViewKey{ index, field, view }, false);
+    if (fv != kNoView) for (int64_t s = 0; s < n_shards; s++) {
+        const auto& sm = c->shardmaps[fv];
+        if (shards[s] >= sm.size() || sm[shards[s]] < 0) continue;
+        const HostFrag& f = c->frags[sm[shards[s]]];
+        for (uint32_t k = 0; k < f.n_rows; k++) {
+            const RowEnt& e = c->h_rows[f.row_off + k];
+            bool want = row_ids == nullptr;
+            for (int32_t r = 0; !want && r < n_rows; r++) want = row_ids[r] == e.row;
+            if (!want) continue;
+            int n = __builtin_popcount(e.mask);
+            for (int q = 0; q < n; q++) { const ContDesc& d = c->h_descs[e.first_desc + q]; pay += d.typ == kArray ? 2ull * d.card : d.typ == kBitmap ? 8192 : 4ull * d.cnt; nc++; }
+        }
+    }
+    *out_payload = pay; *out_containers = nc;
+    return 0;
+}

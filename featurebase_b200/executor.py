@@ -1,0 +1,342 @@
+"""Host-side mirror of the reference's executor interface for the hot path (executor.go), above the C ABI.
+
+Holder/Index/Field carry just the schema facts the path needs (field type, bsiGroup Base/BitDepth/Min/Max,
+existence tracking); Executor.execute() walks a pql.Call tree exactly like executor.executeCall /
+executeBitmapCallShard do, but instead of mapping a Go closure over shards it compiles each bitmap call into a
+post-order fbgpu_op program and hands the whole shard batch to libfbgpu (one C-ABI call per PQL call).
+
+In a real integration this layer stays in Go; it exists here because the Go toolchain is absent
+and the parity tests should read like the reference's executor tests.  All reference cites are executor.go unless
+noted."""
+import numpy as np
+
+from . import lib as L
+from . import pql
+from . import roaring_io
+
+SHARD_WIDTH = 1 << 20                    # shardwidth/helper.go:13
+VIEW_STANDARD = 0                        # view.go:28 "standard"
+VIEW_BSI = 1                             # view.go:30 "bsig_<field>"
+EXISTENCE_FIELD = "_exists"              # holder.go:33
+
+
+class Field:
+    def __init__(self, fid, name, ftype="set", min=None, max=None, bit_depth=None):
+        self.id, self.name, self.type = fid, name, ftype
+        if ftype == "int":
+            self.min = -(1 << 63) if min is None else int(min)
+            self.max = (1 << 63) - 1 if max is None else int(max)
+            self.base = self.min if self.min > 0 else self.max if self.max < 0 else 0      # bsiBase field.go:2384
+            if bit_depth is None:                                                            # field.go:2502-2512 (data driven)
+                bit_depth = max_bitlen(abs(self.min - self.base), abs(self.max - self.base))
+            self.bit_depth = int(bit_depth)
+
+    # bsiGroup.bitDepthMin / bitDepthMax  field.go:2475-2482
+    def bit_depth_min(self):
+        return self.base - (1 << self.bit_depth) + 1
+
+    def bit_depth_max(self):
+        return self.base + (1 << self.bit_depth) - 1
+
+    def base_value(self, op, value):
+        """bsiGroup.baseValue field.go:2412-2446 -> (baseValue, outOfRange)"""
+        lo, hi = self.bit_depth_min(), self.bit_depth_max()
+        bv = 0
+        if op in (">", ">="):
+            if value > hi:
+                return 0, True
+            if value < lo:
+                bv = lo - self.base - (1 if op == ">" else 0)
+            else:
+                bv = value - self.base
+        elif op in ("<", "<="):
+            if value < lo:
+                return 0, True
+            if value > hi:
+                bv = hi - self.base + (1 if op == "<" else 0)
+            else:
+                bv = value - self.base
+        elif op in ("==", "!="):
+            if value < lo or value > hi:
+                return 0, True
+            bv = value - self.base
+        return bv, False
+
+    def base_value_between(self, lo, hi):
+        """bsiGroup.baseValueBetween field.go:2449-2463"""
+        mn, mx = self.bit_depth_min(), self.bit_depth_max()
+        if hi < mn or lo > mx or hi < lo:
+            return 0, 0, True
+        return max(lo, mn) - self.base, min(hi, mx) - self.base, False
+
+
+def max_bitlen(*vals):
+    return max(int(v).bit_length() for v in vals)
+
+
+class Index:
+    def __init__(self, iid, name, track_existence=True):
+        self.id, self.name, self.track_existence = iid, name, track_existence
+        self.fields = {}
+        self.shards = set()
+        if track_existence:
+            self.fields[EXISTENCE_FIELD] = Field(0, EXISTENCE_FIELD)
+
+    def create_field(self, name, ftype="set", **kw):
+        f = Field(len(self.fields) + (0 if self.track_existence else 1), name, ftype, **kw)
+        self.fields[name] = f
+        return f
+
+
+class Holder:
+    """Schema + residency front end: owns one libfbgpu context."""
+
+    def __init__(self, ctx=None, device=0):
+        self.ctx = ctx or L.Context(device)
+        self.indexes = {}
+        self._pending = {}
+
+    def create_index(self, name, track_existence=True):
+        idx = Index(len(self.indexes), name, track_existence)
+        self.indexes[name] = idx
+        return idx
+
+    def import_roaring(self, index, field, view, shard, data):
+        """API.ImportRoaring analogue: one fragment's Pilosa-roaring bytes (keys row*16+slot)"""
+        idx = self.indexes[index]
+        self.ctx.load_fragment(idx.id, idx.fields[field].id, view, shard, data)
+        idx.shards.add(int(shard))
+
+    # ---- test conveniences mirroring test helpers (hldr.SetBit / SetValue, test/holder.go)
+    def set_bit(self, index, field, row, col):
+        idx = self.indexes[index]
+        shard = col // SHARD_WIDTH
+        self._pending.setdefault((index, field, VIEW_STANDARD, shard), set()).add(row * SHARD_WIDTH + col % SHARD_WIDTH)
+        if idx.track_existence:
+            self._pending.setdefault((index, EXISTENCE_FIELD, VIEW_STANDARD, shard), set()).add(col % SHARD_WIDTH)
+
+    def set_value(self, index, field, col, value):
+        """fragment.setValue fragment.go:619-657: exists row 0, sign row 1, magnitude bits rows 2+i of value-Base"""
+        idx = self.indexes[index]
+        f = idx.fields[field]
+        shard, c = col // SHARD_WIDTH, col % SHARD_WIDTH
+        d = int(value) - f.base
+        if abs(d).bit_length() > f.bit_depth:
+            raise ValueError("value out of bit depth")
+        s = self._pending.setdefault((index, field, VIEW_BSI, shard), set())
+        s.add(c)
+        if d < 0:
+            s.add(1 * SHARD_WIDTH + c)
+        for i in range(f.bit_depth):
+            if (abs(d) >> i) & 1:
+                s.add((2 + i) * SHARD_WIDTH + c)
+        if idx.track_existence:
+            self._pending.setdefault((index, EXISTENCE_FIELD, VIEW_STANDARD, shard), set()).add(c)
+
+    def sync(self):
+        """serialises pending bits per fragment (merged with nothing: test fragments are written once)"""
+        for (index, field, view, shard), bits in self._pending.items():
+            self.import_roaring(index, field, view, shard, roaring_io.encode(np.fromiter(bits, dtype=np.uint64, count=len(bits))))
+        self._pending = {}
+
+
+class RowResult:
+    """pilosa.Row as returned to clients: roaring bytes (absolute keys) + Columns()"""
+
+    def __init__(self, data, count):
+        self.roaring, self.count = data, count
+
+    def columns(self):
+        return roaring_io.decode(self.roaring)
+
+
+class QueryError(Exception):
+    pass
+
+
+class Executor:
+    def __init__(self, holder):
+        self.holder, self.ctx = holder, holder.ctx
+
+    # ------------------------------------------------------------------ entry (executor.Execute :183 / execute :490)
+    def execute(self, index, query, shards=None):
+        idx = self.holder.indexes.get(index)
+        if idx is None:
+            raise QueryError("index not found")
+        calls = pql.parse(query) if isinstance(query, str) else ([query] if isinstance(query, pql.Call) else list(query))
+        if shards is None:
+            shards = sorted(idx.shards)        # idx.AvailableShards :521
+        return [self._execute_call(idx, c, shards) for c in calls]
+
+    # executeCall :679
+    def _execute_call(self, idx, c, shards):
+        try:
+            if c.name == "Count":
+                return self._count(idx, c, shards)
+            if c.name == "TopN":
+                return self._topn(idx, c, shards)
+            if c.name == "TopK":
+                return self._topk(idx, c, shards)
+            if c.name == "GroupBy":
+                return self._groupby(idx, c, shards)
+            if c.name == "Rows":
+                return self._rows(idx, c, shards)
+            ops = self._bitmap_call(idx, c)
+            data, cnt = self.ctx.row(idx.id, ops, shards)
+            return RowResult(data, cnt)
+        except L.FbgpuError as e:
+            if e.code == L.E_QUERY:
+                raise QueryError(str(e)) from e
+            raise
+
+    # ------------------------------------------------------------------ bitmap calls -> post-order program (executeBitmapCallShard :1782)
+    def _bitmap_call(self, idx, c):
+        ops = []
+        self._emit(idx, c, ops)
+        return ops
+
+    def _field(self, idx, name):
+        f = idx.fields.get(name)
+        if f is None:
+            raise QueryError(f"field not found: {name}")       # ErrFieldNotFound
+        return f
+
+    def _emit(self, idx, c, ops):
+        n = c.name
+        if n == "Row":
+            return self._emit_row(idx, c, ops)
+        if n in ("Intersect", "Union", "Difference", "Xor"):
+            for ch in c.children:
+                self._emit(idx, ch, ops)
+            code = {"Intersect": L.OP_INTERSECT, "Union": L.OP_UNION, "Difference": L.OP_DIFFERENCE, "Xor": L.OP_XOR}[n]
+            ops.append(L.Op(code, 0, 0, len(c.children), 0, 0, 0, 0))
+            return
+        if n == "Not":                                           # executeNotShard :5554
+            if len(c.children) != 1:
+                raise QueryError("Not() requires a single bitmap input")
+            if not idx.track_existence:
+                raise QueryError(f"index does not support existence tracking: {idx.name}")
+            self._emit(idx, c.children[0], ops)
+            ops.append(L.Op(L.OP_NOT, idx.fields[EXISTENCE_FIELD].id, VIEW_STANDARD, 1, 0, 0, 0, 0))
+            return
+        if n == "All":                                           # executeAllCallShard :5781
+            if not idx.track_existence:
+                raise QueryError(f"index does not support existence tracking: {idx.name}")
+            ops.append(L.Op(L.OP_ALL, idx.fields[EXISTENCE_FIELD].id, VIEW_STANDARD, 0, 0, 0, 0, 0))
+            return
+        raise QueryError(f"unknown call: {n}")
+
+    def _emit_row(self, idx, c, ops):                            # executeRowShard :5120
+        keys = [k for k in c.args if not k.startswith("_") and k not in ("from", "to")]
+        if len(keys) == 0:
+            raise QueryError("Row(): condition required")
+        if len(keys) > 1:
+            raise QueryError("Row(): too many arguments")
+        name = keys[0]
+        f = self._field(idx, name)
+        v = c.args[name]
+        if f.type == "int" or isinstance(v, pql.Condition):
+            return self._emit_bsi(idx, f, v if isinstance(v, pql.Condition) else pql.Condition("==", v), ops)
+        if f.type == "bool":
+            v = 1 if v else 0                                    # fragment.go:59-60
+        ops.append(L.Op(L.OP_ROW, f.id, VIEW_STANDARD, 0, int(v), 0, 0, 0))
+
+    def _emit_bsi(self, idx, f, cond, ops):                      # executeRowBSIGroupShard :5249-5354
+        if f.type != "int":
+            raise QueryError(f"field {f.name} is not an int field")
+        op, value = cond.op, cond.value
+        not_null = L.Op(L.OP_ROW, f.id, VIEW_BSI, 0, 0, 0, 0, 0)     # frag.notNull fragment.go:1208 == exists row
+        if value is None and op == "!=":
+            ops.append(not_null)
+            return
+        if value is None and op == "==":                        # getNullRowShard :5056: existence \ notNull
+            if not idx.track_existence:
+                raise QueryError(f"index does not support existence tracking: {idx.name}")
+            ops.append(L.Op(L.OP_ALL, idx.fields[EXISTENCE_FIELD].id, VIEW_STANDARD, 0, 0, 0, 0, 0))
+            ops.append(not_null)
+            ops.append(L.Op(L.OP_DIFFERENCE, 0, 0, 2, 0, 0, 0, 0))
+            return
+        if op == "><":
+            if not isinstance(value, (list, tuple)) or len(value) != 2:
+                raise QueryError("Row(): BETWEEN condition requires exactly two integer values")
+            lo, hi, oor = f.base_value_between(int(value[0]), int(value[1]))
+            if oor:
+                ops.append(L.Op(L.OP_EMPTY, 0, 0, 0, 0, 0, 0, 0))
+            elif value[0] <= f.min and value[1] >= f.max:
+                ops.append(not_null)
+            else:
+                ops.append(L.Op(L.OP_BSI_RANGE, f.id, VIEW_BSI, 0, f.bit_depth, L.CMP["><"], lo, hi))
+            return
+        value = int(value)
+        bv, oor = f.base_value(op, value)
+        if oor and op != "!=":
+            ops.append(L.Op(L.OP_EMPTY, 0, 0, 0, 0, 0, 0, 0))
+        elif (op == "<" and value > f.max) or (op == "<=" and value >= f.max) or (op == ">" and value < f.min) or (op == ">=" and value <= f.min):
+            ops.append(not_null)
+        elif oor and op == "!=":
+            ops.append(not_null)
+        else:
+            ops.append(L.Op(L.OP_BSI_RANGE, f.id, VIEW_BSI, 0, f.bit_depth, L.CMP[op], bv, 0))
+
+    # ------------------------------------------------------------------ Count (executeCount :5839)
+    def _count(self, idx, c, shards):
+        if len(c.children) == 0:
+            raise QueryError("Count() requires an input bitmap")
+        if len(c.children) > 1:
+            raise QueryError("Count() only accepts a single bitmap input")
+        return self.ctx.count(idx.id, self._bitmap_call(idx, c.children[0]), shards)
+
+    # ------------------------------------------------------------------ TopN / TopK (exact modes)
+    def _topn(self, idx, c, shards):                             # executeTopN :2779 with ids / second pass semantics
+        f = self._field(idx, c.args["_field"])
+        n = int(c.args.get("n", 0))
+        filt = self._bitmap_call(idx, c.children[0]) if c.children else None
+        ids = c.args.get("ids")
+        if ids is not None:
+            ids = sorted(int(i) for i in ids)
+            counts = self.ctx.row_counts(idx.id, f.id, VIEW_STANDARD, shards, row_ids=ids, filter_ops=filt)
+            pairs = [(i, int(k)) for i, k in zip(ids, counts) if k > 0]
+            pairs.sort(key=lambda p: (-p[1], p[0]))              # Pairs sort desc; ties pinned (count desc, id asc)
+        else:
+            rid, cnt = self.ctx.row_counts(idx.id, f.id, VIEW_STANDARD, shards, filter_ops=filt)
+            pairs = [(int(i), int(k)) for i, k in zip(rid, cnt)]
+        return pairs[:n] if n else pairs
+
+    def _topk(self, idx, c, shards):                             # executeTopK :2357, doTopK :2705
+        f = self._field(idx, c.args["_field"])
+        k = int(c.args.get("k", 0))
+        filt = c.args.get("filter")
+        filt = self._bitmap_call(idx, filt) if isinstance(filt, pql.Call) else None
+        rid, cnt = self.ctx.row_counts(idx.id, f.id, VIEW_STANDARD, shards, filter_ops=filt)
+        pairs = [(int(i), int(n)) for i, n in zip(rid, cnt)]
+        return pairs[:k] if k else pairs
+
+    def _rows(self, idx, c, shards):                             # executeRows :5311 (row ids present)
+        f = self._field(idx, c.args["_field"])
+        rid, _ = self.ctx.row_counts(idx.id, f.id, VIEW_STANDARD, shards)
+        out = sorted(int(r) for r in rid)
+        lim = c.args.get("limit")
+        return out[:lim] if lim else out
+
+    # ------------------------------------------------------------------ GroupBy (executeGroupBy :3176)
+    def _groupby(self, idx, c, shards):
+        if not c.children:
+            raise QueryError("need at least one child call")
+        fields, row_ids = [], []
+        for ch in c.children:
+            if ch.name != "Rows":
+                raise QueryError(f"'{ch.name}' is not a valid child query for GroupBy, must be 'Rows'")
+            f = self._field(idx, ch.args["_field"])
+            fields.append(f)
+            row_ids.append(self._rows(idx, ch, shards))          # pre-pass executeRows :3263-3287
+        filt = c.args.get("filter")
+        filt = self._bitmap_call(idx, filt) if isinstance(filt, pql.Call) else None
+        if any(len(r) == 0 for r in row_ids):
+            return []
+        counts = self.ctx.groupby(idx.id, [f.id for f in fields], [VIEW_STANDARD] * len(fields), row_ids, shards, filter_ops=filt)
+        out = []
+        for flat in np.flatnonzero(counts.reshape(-1)):          # only Count>0, lexicographic (:3960)
+            ix = np.unravel_index(int(flat), counts.shape)
+            out.append(([(f.name, row_ids[k][int(i)]) for k, (f, i) in enumerate(zip(fields, ix))], int(counts[ix])))
+        lim = c.args.get("limit")
+        return out[:lim] if lim else out

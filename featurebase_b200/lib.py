@@ -1,0 +1,214 @@
+"""ctypes binding of libfbgpu.so (include/fbgpu.h).  There is no CPU fallback: if the CUDA library is missing or
+a call fails, an exception is raised."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+OP_ROW, OP_INTERSECT, OP_UNION, OP_DIFFERENCE, OP_XOR, OP_NOT, OP_BSI_RANGE, OP_EMPTY, OP_ALL = range(1, 10)
+CMP = {"==": 1, "!=": 2, "<": 3, "<=": 4, ">": 5, ">=": 6, "><": 7}
+E_INVALID, E_QUERY, E_FORMAT, E_NOSPACE, E_CUDA, E_NOMEM, E_COMM = -1, -2, -3, -4, -5, -6, -7
+
+
+class FbgpuError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"fbgpu error {code}: {msg}")
+        self.code = code
+
+
+class Op(C.Structure):
+    _fields_ = [("opcode", C.c_uint32), ("field", C.c_uint32), ("view", C.c_uint32), ("argc", C.c_uint32),
+                ("a", C.c_uint64), ("b", C.c_uint64), ("lo", C.c_int64), ("hi", C.c_int64)]
+
+
+class Stats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("fragments", "containers", "array_containers", "bitmap_containers",
+                                           "run_containers", "payload_bytes", "device_bytes")]
+
+
+class Counters(C.Structure):
+    _fields_ = [("kernel_launches", C.c_uint64), ("queries", C.c_uint64), ("last_query_gpu_ms", C.c_float),
+                ("reserved", C.c_uint32), ("last_algo_bytes", C.c_uint64)]
+
+
+EXPORTS = ["fbgpu_init", "fbgpu_shutdown", "fbgpu_last_error", "fbgpu_abi_version", "fbgpu_load_fragment",
+           "fbgpu_load_fragments", "fbgpu_drop_fragment", "fbgpu_commit", "fbgpu_get_stats", "fbgpu_count", "fbgpu_row",
+           "fbgpu_row_counts", "fbgpu_groupby", "fbgpu_comm_unique_id", "fbgpu_comm_init", "fbgpu_comm_destroy",
+           "fbgpu_get_counters", "fbgpu_stream", "fbgpu_rows_payload_bytes"]
+
+
+def lib_path():
+    return os.path.join(_HERE, "libfbgpu.so")
+
+
+def load():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    if not os.path.exists(path):
+        raise FileNotFoundError(f"{path} missing: run `python -m featurebase_b200.build` (no CPU fallback exists)")
+    L = C.CDLL(path)
+    vp, u32, u64, i32, i64 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int32, C.c_int64
+    L.fbgpu_init.argtypes, L.fbgpu_init.restype = [i32, C.POINTER(vp)], C.c_int
+    L.fbgpu_shutdown.argtypes, L.fbgpu_shutdown.restype = [vp], None
+    L.fbgpu_last_error.argtypes, L.fbgpu_last_error.restype = [], C.c_char_p
+    L.fbgpu_abi_version.argtypes, L.fbgpu_abi_version.restype = [], i32
+    L.fbgpu_load_fragment.argtypes, L.fbgpu_load_fragment.restype = [vp, u32, u32, u32, u64, vp, u64], C.c_int
+    L.fbgpu_load_fragments.argtypes, L.fbgpu_load_fragments.restype = [vp, u32, u32, u32, vp, i64, vp, vp], C.c_int
+    L.fbgpu_drop_fragment.argtypes, L.fbgpu_drop_fragment.restype = [vp, u32, u32, u32, u64], C.c_int
+    L.fbgpu_commit.argtypes, L.fbgpu_commit.restype = [vp], C.c_int
+    L.fbgpu_get_stats.argtypes, L.fbgpu_get_stats.restype = [vp, C.POINTER(Stats)], C.c_int
+    L.fbgpu_count.argtypes, L.fbgpu_count.restype = [vp, u32, vp, i32, vp, i64, C.POINTER(u64), vp], C.c_int
+    L.fbgpu_row.argtypes, L.fbgpu_row.restype = [vp, u32, vp, i32, vp, i64, vp, u64, C.POINTER(u64), C.POINTER(u64)], C.c_int
+    L.fbgpu_row_counts.argtypes, L.fbgpu_row_counts.restype = [vp, u32, u32, u32, vp, i32, vp, i32, vp, i64, vp, vp, i32, C.POINTER(i32)], C.c_int
+    L.fbgpu_groupby.argtypes, L.fbgpu_groupby.restype = [vp, u32, vp, vp, i32, vp, vp, vp, i32, vp, i64, vp], C.c_int
+    L.fbgpu_comm_unique_id.argtypes, L.fbgpu_comm_unique_id.restype = [vp], C.c_int
+    L.fbgpu_comm_init.argtypes, L.fbgpu_comm_init.restype = [vp, i32, i32, vp], C.c_int
+    L.fbgpu_comm_destroy.argtypes, L.fbgpu_comm_destroy.restype = [vp], C.c_int
+    L.fbgpu_get_counters.argtypes, L.fbgpu_get_counters.restype = [vp, C.POINTER(Counters)], C.c_int
+    L.fbgpu_stream.argtypes, L.fbgpu_stream.restype = [vp], vp
+    L.fbgpu_rows_payload_bytes.argtypes, L.fbgpu_rows_payload_bytes.restype = [vp, u32, u32, u32, vp, i32, vp, i64, C.POINTER(u64), C.POINTER(u64)], C.c_int
+    _LIB = L
+    return L
+
+
+def _u64arr(x):
+    return np.ascontiguousarray(np.asarray(x, dtype=np.uint64))
+
+
+def ops_array(ops):
+    """list of Op / tuples -> ctypes array"""
+    arr = (Op * max(len(ops), 1))()
+    for i, o in enumerate(ops):
+        arr[i] = o
+    return arr
+
+
+class Context:
+    """One fbgpu_ctx (one GPU)."""
+
+    def __init__(self, device=0):
+        self.L = load()
+        self.h = C.c_void_p()
+        self._check(self.L.fbgpu_init(device, C.byref(self.h)))
+
+    def _check(self, rc):
+        if rc != 0:
+            raise FbgpuError(rc, self.L.fbgpu_last_error().decode())
+
+    def close(self):
+        if self.h:
+            self.L.fbgpu_shutdown(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- residency
+    def load_fragment(self, index, field, view, shard, data):
+        data = bytes(data) if not isinstance(data, (bytes, bytearray)) else data
+        buf = (C.c_uint8 * len(data)).from_buffer_copy(data)
+        self._check(self.L.fbgpu_load_fragment(self.h, index, field, view, int(shard), buf, len(data)))
+
+    def load_fragments(self, index, field, view, shards, buf, offsets):
+        """buf: numpy uint8 array or (address, nbytes); offsets: n+1 uint64"""
+        sh, off = _u64arr(shards), _u64arr(offsets)
+        ptr = buf.ctypes.data if isinstance(buf, np.ndarray) else int(buf)
+        self._check(self.L.fbgpu_load_fragments(self.h, index, field, view, sh.ctypes.data, len(sh), ptr, off.ctypes.data))
+
+    def drop_fragment(self, index, field, view, shard):
+        self._check(self.L.fbgpu_drop_fragment(self.h, index, field, view, int(shard)))
+
+    def commit(self):
+        self._check(self.L.fbgpu_commit(self.h))
+
+    def stats(self):
+        s = Stats()
+        self._check(self.L.fbgpu_get_stats(self.h, C.byref(s)))
+        return {n: getattr(s, n) for n, _ in Stats._fields_}
+
+    def counters(self):
+        s = Counters()
+        self._check(self.L.fbgpu_get_counters(self.h, C.byref(s)))
+        return {"kernel_launches": s.kernel_launches, "queries": s.queries, "last_query_gpu_ms": s.last_query_gpu_ms}
+
+    # ---- queries
+    def count(self, index, ops, shards, per_shard=False):
+        sh = _u64arr(shards)
+        arr = ops_array(ops)
+        tot = C.c_uint64(0)
+        per = np.zeros(len(sh), dtype=np.uint64) if per_shard else None
+        self._check(self.L.fbgpu_count(self.h, index, arr, len(ops), sh.ctypes.data, len(sh), C.byref(tot),
+                                       per.ctypes.data if per_shard else None))
+        return (tot.value, per) if per_shard else tot.value
+
+    def row(self, index, ops, shards):
+        """returns (pilosa roaring bytes, count)"""
+        sh = _u64arr(shards)
+        arr = ops_array(ops)
+        need, cnt = C.c_uint64(0), C.c_uint64(0)
+        cap = 1 << 16
+        while True:
+            buf = (C.c_uint8 * cap)()
+            rc = self.L.fbgpu_row(self.h, index, arr, len(ops), sh.ctypes.data, len(sh), buf, cap, C.byref(need), C.byref(cnt))
+            if rc == E_NOSPACE:
+                cap = int(need.value)
+                continue
+            self._check(rc)
+            return bytes(buf[: need.value]), cnt.value
+
+    def row_counts(self, index, field, view, shards, row_ids=None, filter_ops=None, cap=1 << 20):
+        sh = _u64arr(shards)
+        f = ops_array(filter_ops) if filter_ops else None
+        nf = len(filter_ops) if filter_ops else 0
+        n = C.c_int32(0)
+        if row_ids is not None:
+            ids = _u64arr(row_ids)
+            out = np.zeros(len(ids), dtype=np.uint64)
+            self._check(self.L.fbgpu_row_counts(self.h, index, field, view, ids.ctypes.data, len(ids), f, nf, sh.ctypes.data, len(sh),
+                                                None, out.ctypes.data, len(ids), C.byref(n)))
+            return out
+        rid, out = np.zeros(cap, dtype=np.uint64), np.zeros(cap, dtype=np.uint64)
+        self._check(self.L.fbgpu_row_counts(self.h, index, field, view, None, 0, f, nf, sh.ctypes.data, len(sh),
+                                            rid.ctypes.data, out.ctypes.data, cap, C.byref(n)))
+        return rid[: n.value], out[: n.value]
+
+    def groupby(self, index, fields, views, row_ids, shards, filter_ops=None):
+        sh = _u64arr(shards)
+        fl = np.ascontiguousarray(np.asarray(fields, dtype=np.uint32))
+        vw = np.ascontiguousarray(np.asarray(views, dtype=np.uint32))
+        n_rows = np.ascontiguousarray(np.asarray([len(r) for r in row_ids], dtype=np.int32))
+        flat = _u64arr(np.concatenate([np.asarray(r, dtype=np.uint64) for r in row_ids]))
+        out = np.zeros(int(np.prod(n_rows.astype(np.int64))), dtype=np.uint64)
+        f = ops_array(filter_ops) if filter_ops else None
+        nf = len(filter_ops) if filter_ops else 0
+        self._check(self.L.fbgpu_groupby(self.h, index, fl.ctypes.data, vw.ctypes.data, len(fl), flat.ctypes.data, n_rows.ctypes.data,
+                                         f, nf, sh.ctypes.data, len(sh), out.ctypes.data))
+        return out.reshape([int(x) for x in n_rows])
+
+    def rows_payload_bytes(self, index, field, view, shards, row_ids=None):
+        sh = _u64arr(shards)
+        pay, nc = C.c_uint64(0), C.c_uint64(0)
+        if row_ids is None:
+            self._check(self.L.fbgpu_rows_payload_bytes(self.h, index, field, view, None, 0, sh.ctypes.data, len(sh), C.byref(pay), C.byref(nc)))
+        else:
+            ids = _u64arr(row_ids)
+            self._check(self.L.fbgpu_rows_payload_bytes(self.h, index, field, view, ids.ctypes.data, len(ids), sh.ctypes.data, len(sh), C.byref(pay), C.byref(nc)))
+        return pay.value, nc.value
+
+    # ---- comm
+    def comm_unique_id(self):
+        buf = (C.c_uint8 * 128)()
+        self._check(self.L.fbgpu_comm_unique_id(buf))
+        return bytes(buf)
+
+    def comm_init(self, n_ranks, rank, uid):
+        buf = (C.c_uint8 * 128).from_buffer_copy(uid)
+        self._check(self.L.fbgpu_comm_init(self.h, n_ranks, rank, buf))

@@ -1,0 +1,153 @@
+/*
+ * fbgpu.h — C ABI of libfbgpu: a B200-native (sm_100a) roaring-bitmap query executor that replaces the
+ * per-shard inner loop of FeatureBase's executor.go / fragment.go / roaring/.
+ *
+ * The reference has no FFI seam on this path (it is 100 % Go).  Each entry point below names the
+ * reference function(s) whose per-shard map step + reduce it replaces; a Go maintainer binds them through
+ * cgo from executor.mapperLocal (INTEGRATION.md shows the stub).  Paths are relative to /root/reference.
+ *
+ * Conventions: all integers fixed width, little endian; no callbacks; inputs are read-only and never
+ * retained after return (cgo pointer rules); outputs are caller-allocated; return 0 on success or a
+ * negative FBGPU_E_* (maps to Go `error`; every executor function returns (T, error)).  Thread-safe and
+ * re-entrant: any OS thread may call any function on a context (goroutines migrate between threads), the
+ * library sets the CUDA device itself on every call.  One context per GPU; a context owns the contiguous
+ * shard range its caller loads into it.
+ */
+#ifndef FBGPU_H
+#define FBGPU_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FBGPU_ABI_VERSION 1
+
+/* error codes */
+#define FBGPU_OK 0
+#define FBGPU_E_INVALID (-1)  /* bad argument / malformed program                       */
+#define FBGPU_E_QUERY (-2)    /* query the reference rejects (e.g. empty Intersect())    */
+#define FBGPU_E_FORMAT (-3)   /* unreadable roaring data                                 */
+#define FBGPU_E_NOSPACE (-4)  /* output buffer too small; required size reported         */
+#define FBGPU_E_CUDA (-5)     /* CUDA runtime failure (see fbgpu_last_error)             */
+#define FBGPU_E_NOMEM (-6)
+#define FBGPU_E_COMM (-7)     /* NCCL failure / communicator not initialised             */
+
+typedef struct fbgpu_ctx fbgpu_ctx; /* opaque, one per GPU */
+
+/* lifecycle.  device_ordinal is the CUDA ordinal this context owns. */
+int fbgpu_init(int32_t device_ordinal, fbgpu_ctx **out);
+void fbgpu_shutdown(fbgpu_ctx *ctx);
+/* thread-local message of the last failing call on this thread */
+const char *fbgpu_last_error(void);
+int32_t fbgpu_abi_version(void);
+
+/* ---- residency (replaces fragment.row -> tx.OffsetRange -> rbf cursor walk: fragment.go:283-333,
+ *      rbf.go:472, rbf/tx.go:1586-1637; data source = tx.RoaringBitmap / Bitmap.WriteTo bytes, tx.go:85) ----
+ * `roaring` = Pilosa-roaring bytes (cookie 12348, roaring/roaring.go:1738-1817) or official RoaringBitmap
+ * bytes (12346/12347, roaring.go:6943-7006) of ONE fragment with fragment-relative keys row*16+slot
+ * (fragment.go:2780-2782).  index/field/view are caller-assigned ids.  Replaces any previous content of
+ * (index,field,view,shard).  The library copies; the caller keeps ownership of the bytes. */
+int fbgpu_load_fragment(fbgpu_ctx *ctx, uint32_t index, uint32_t field, uint32_t view, uint64_t shard,
+                        const uint8_t *roaring, uint64_t nbytes);
+/* bulk form: n fragments of the same (index,field,view); fragment i is buf[offsets[i], offsets[i+1]) */
+int fbgpu_load_fragments(fbgpu_ctx *ctx, uint32_t index, uint32_t field, uint32_t view,
+                         const uint64_t *shards, int64_t n, const uint8_t *buf, const uint64_t *offsets);
+int fbgpu_drop_fragment(fbgpu_ctx *ctx, uint32_t index, uint32_t field, uint32_t view, uint64_t shard);
+/* pushes pending host-side staging to HBM now (otherwise done lazily by the next query) */
+int fbgpu_commit(fbgpu_ctx *ctx);
+
+typedef struct {
+    uint64_t fragments, containers;
+    uint64_t array_containers, bitmap_containers, run_containers;
+    uint64_t payload_bytes;   /* roaring payload bytes resident in HBM (array 2n, bitmap 8192, run 4r) */
+    uint64_t device_bytes;    /* total HBM held by the store incl. descriptors and padding            */
+} fbgpu_stats;
+int fbgpu_get_stats(fbgpu_ctx *ctx, fbgpu_stats *out);
+
+/* ---- bitmap-call programs (replaces executeBitmapCallShard and its children, executor.go:1782-1816) ----
+ * A program is the post-order walk of the pql.Call tree of one bitmap call. */
+enum {
+    FBGPU_OP_ROW = 1,        /* Row(field=row)         executeRowShard executor.go:5120 ; field,view,a=row id        */
+    FBGPU_OP_INTERSECT = 2,  /* Intersect(c1..cn)      executeIntersectShard :5357 ; argc=n (0 => FBGPU_E_QUERY)      */
+    FBGPU_OP_UNION = 3,      /* Union(c1..cn)          executeUnionShard :5382 ; argc=n (0 => empty row)             */
+    FBGPU_OP_DIFFERENCE = 4, /* Difference(c1..cn)     executeDifferenceShard :2950 ; left fold; argc 0 => E_QUERY    */
+    FBGPU_OP_XOR = 5,        /* Xor(c1..cn)            executeXorShard :5513 ; left fold; argc 0 => empty row         */
+    FBGPU_OP_NOT = 6,        /* Not(c)                 executeNotShard :5554 ; field,view = existence field, a = row  */
+    FBGPU_OP_BSI_RANGE = 7,  /* Row(v <op> k)          executeRowBSIGroupShard :5249 -> fragment.rangeOp fragment.go:937
+                                field,view = bsig view; a = bitDepth; b = FBGPU_CMP_*; lo(,hi) = base-adjusted
+                                predicate(s) exactly as passed to rangeOp/rangeBetween                              */
+    FBGPU_OP_EMPTY = 8,      /* empty row (out-of-range BSI predicate, executor.go:5331)                               */
+    FBGPU_OP_ALL = 9         /* All(): existence row   executeAllCallShard :5781 ; field,view = existence, a = row    */
+};
+enum { FBGPU_CMP_EQ = 1, FBGPU_CMP_NEQ = 2, FBGPU_CMP_LT = 3, FBGPU_CMP_LTE = 4, FBGPU_CMP_GT = 5,
+       FBGPU_CMP_GTE = 6, FBGPU_CMP_BETWEEN = 7 };
+
+typedef struct {
+    uint32_t opcode, field, view, argc;
+    uint64_t a, b;
+    int64_t lo, hi;
+} fbgpu_op; /* 48 bytes */
+
+/* Count(<bitmap call>) over the listed shards (executeCount executor.go:5839-5892: map = per-shard
+ * Row.Count(), reduce = u64 add).  *out_total is the sum over this context's shards, all-reduced over
+ * the communicator when one is attached.  out_per_shard may be NULL, else receives n_shards counts. */
+int fbgpu_count(fbgpu_ctx *ctx, uint32_t index, const fbgpu_op *ops, int32_t n_ops,
+                const uint64_t *shards, int64_t n_shards, uint64_t *out_total, uint64_t *out_per_shard);
+
+/* <bitmap call> returning a Row (mapReduce with Row.Merge, executor.go:1694-1780, row.go:202): writes
+ * Pilosa-roaring bytes with absolute keys shard*16+slot and canonical (optimize()) encodings, i.e. what
+ * Row.Roaring() (row.go:174-180) yields after Optimize.  If out_cap is too small returns FBGPU_E_NOSPACE
+ * and sets *out_len to the needed size.  *out_count receives the row's cardinality (may be NULL). */
+int fbgpu_row(fbgpu_ctx *ctx, uint32_t index, const fbgpu_op *ops, int32_t n_ops,
+              const uint64_t *shards, int64_t n_shards,
+              uint8_t *out_buf, uint64_t out_cap, uint64_t *out_len, uint64_t *out_count);
+
+/* Per-row counts of one field, optionally intersected with a filter program: the exact part of TopN
+ * (fragment.top with explicit ids, fragment.go:1317-1437) and TopK (doTopK executor.go:2705-2746).
+ * row_ids != NULL: counts for exactly those rows (out_counts[i] for row_ids[i]).
+ * row_ids == NULL: all rows present in the field over the shards; writes up to cap (row id, count) pairs with
+ * count > 0 sorted by (count desc, row id asc) — the reference's tie order is unspecified (cache.go:464-482).
+ * Counts are all-reduced over the communicator in the row_ids form. */
+int fbgpu_row_counts(fbgpu_ctx *ctx, uint32_t index, uint32_t field, uint32_t view,
+                     const uint64_t *row_ids, int32_t n_rows,
+                     const fbgpu_op *filter, int32_t n_filter_ops,
+                     const uint64_t *shards, int64_t n_shards,
+                     uint64_t *out_row_ids, uint64_t *out_counts, int32_t cap, int32_t *out_n);
+
+/* GroupBy(Rows(f1), Rows(f2), ..., filter=...) with Count aggregate (executeGroupBy executor.go:3176,
+ * executeGroupByShard :3918, groupByIterator :8617-8934; reduce = mergeGroupCounts :3728).  row_ids_flat holds
+ * the per-field row-id lists concatenated (flat on purpose: cgo forbids nested Go pointers).  out_counts is
+ * the dense count tensor, row-major, rightmost field fastest; the caller emits groups with Count>0 in
+ * lexicographic order (executor.go:3960).  A shard lacking a fragment for any field contributes nothing
+ * (executor.go:8769-8772).  All-reduced over the communicator. */
+int fbgpu_groupby(fbgpu_ctx *ctx, uint32_t index, const uint32_t *fields, const uint32_t *views, int32_t n_fields,
+                  const uint64_t *row_ids_flat, const int32_t *n_rows,
+                  const fbgpu_op *filter, int32_t n_filter_ops,
+                  const uint64_t *shards, int64_t n_shards, uint64_t *out_counts);
+
+/* ---- multi-GPU reduce (replaces the HTTP fan-in of mapReduce/remoteExec, executor.go:6392-6533) ----
+ * One context (process) per GPU; rank 0 creates the id, every rank joins.  When a communicator is attached,
+ * count / row_counts / groupby results are summed with one ncclAllReduce(uint64,sum) on the device before
+ * the single D2H copy.  NCCL is resolved at run time (dlopen libnccl.so.2). */
+#define FBGPU_NCCL_ID_BYTES 128
+int fbgpu_comm_unique_id(uint8_t id[FBGPU_NCCL_ID_BYTES]);
+int fbgpu_comm_init(fbgpu_ctx *ctx, int32_t n_ranks, int32_t rank, const uint8_t id[FBGPU_NCCL_ID_BYTES]);
+int fbgpu_comm_destroy(fbgpu_ctx *ctx);
+
+/* ---- instrumentation (the counters the reference keeps under the roaringstats tag, statsHit()) ---- */
+typedef struct {
+    uint64_t kernel_launches;   /* kernels of this library launched since init       */
+    uint64_t queries;
+    float last_query_gpu_ms;    /* CUDA-event time of the last query's kernels        */
+    uint32_t reserved;
+    uint64_t last_algo_bytes;   /* algorithmic bytes of the last query   */
+} fbgpu_counters;
+int fbgpu_get_counters(fbgpu_ctx *ctx, fbgpu_counters *out);
+/* the CUDA stream queries of the calling thread run on (cudaStream_t), for external event timing */
+void *fbgpu_stream(fbgpu_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,149 @@
+"""Evaluates pql.Call trees with the CPU oracle, shard by shard, following the reference's executor semantics
+(executor.go:1782-1816, 5120-5602, 5839-5892).  TEST INFRASTRUCTURE: the checker for the GPU path."""
+import numpy as np
+
+from featurebase_b200 import executor as X
+from featurebase_b200 import pql
+from oracle import oracle as O
+
+
+class OracleIndex:
+    """fragments[(field name, view)][shard] = oracle Bitmap (fragment-relative keys)"""
+
+    def __init__(self, idx):
+        self.idx = idx
+        self.frags = {}
+
+    def load(self, field, view, shard, data):
+        self.frags.setdefault((field, view), {})[int(shard)] = O.Bitmap.from_bytes(data)
+
+    def frag(self, field, view, shard):
+        return self.frags.get((field, view), {}).get(int(shard))
+
+    def row(self, field, view, row, shard):
+        f = self.frag(field, view, shard)
+        return f.row(row, shard) if f is not None else O.Bitmap()
+
+    def eval_shard(self, c, shard):
+        n = c.name
+        if n == "Row":
+            key = [k for k in c.args if not k.startswith("_")][0]
+            fld = self.idx.fields[key]
+            v = c.args[key]
+            if fld.type == "int" or isinstance(v, pql.Condition):
+                return self._bsi(fld, v if isinstance(v, pql.Condition) else pql.Condition("==", v), shard)
+            return self.row(key, X.VIEW_STANDARD, int(v), shard)
+        if n == "Intersect":
+            if not c.children:
+                raise X.QueryError("empty Intersect query is currently not supported")
+            out = self.eval_shard(c.children[0], shard)
+            for ch in c.children[1:]:
+                out = out.intersect(self.eval_shard(ch, shard))
+            return out
+        if n == "Union":
+            rows = [self.eval_shard(ch, shard) for ch in c.children]
+            if not rows:
+                return O.Bitmap()
+            return rows[0] if len(rows) == 1 else rows[0].union(*rows[1:])
+        if n == "Difference":
+            if not c.children:
+                raise X.QueryError("empty Difference query is currently not supported")
+            out = self.eval_shard(c.children[0], shard)
+            for ch in c.children[1:]:
+                out = out.difference(self.eval_shard(ch, shard))
+            return out
+        if n == "Xor":
+            out = O.Bitmap()
+            for i, ch in enumerate(c.children):
+                r = self.eval_shard(ch, shard)
+                out = r if i == 0 else out.xor(r)
+            return out
+        if n == "Not":
+            ex = self.row(X.EXISTENCE_FIELD, X.VIEW_STANDARD, 0, shard)
+            return ex.difference(self.eval_shard(c.children[0], shard))
+        if n == "All":
+            return self.row(X.EXISTENCE_FIELD, X.VIEW_STANDARD, 0, shard)
+        raise KeyError(n)
+
+    def _bsi(self, fld, cond, shard):
+        frag = self.frag(fld.name, X.VIEW_BSI, shard)
+        op, value = cond.op, cond.value
+        if frag is None:
+            return O.Bitmap()
+        not_null = lambda: frag.row(0, shard)
+        if value is None:
+            if op == "!=":
+                return not_null()
+            return self.row(X.EXISTENCE_FIELD, X.VIEW_STANDARD, 0, shard).difference(not_null())
+        if op == "><":
+            lo, hi, oor = fld.base_value_between(int(value[0]), int(value[1]))
+            if oor:
+                return O.Bitmap()
+            if value[0] <= fld.min and value[1] >= fld.max:
+                return not_null()
+            return frag.range_op("><", fld.bit_depth, lo, hi, shard=shard)
+        value = int(value)
+        bv, oor = fld.base_value(op, value)
+        if oor and op != "!=":
+            return O.Bitmap()
+        if (op == "<" and value > fld.max) or (op == "<=" and value >= fld.max) or (op == ">" and value < fld.min) or (op == ">=" and value <= fld.min):
+            return not_null()
+        if oor and op == "!=":
+            return not_null()
+        return frag.range_op(op, fld.bit_depth, bv, shard=shard)
+
+    def eval_row(self, c, shards):
+        """merged Row over shards (Row.Merge row.go:202) -> oracle Bitmap with absolute keys"""
+        out = O.Bitmap()
+        for s in sorted(shards):
+            out = out.union(self.eval_shard(c, s))
+        return out
+
+    def count(self, c, shards):
+        return sum(self.eval_shard(c, s).count() for s in shards)
+
+
+class Pair:
+    """a GPU Holder/Executor and an oracle index loaded with the same fragments"""
+
+    def __init__(self, name="i", track_existence=True):
+        self.holder = X.Holder()
+        self.idx = self.holder.create_index(name, track_existence)
+        self.ex = X.Executor(self.holder)
+        self.ora = OracleIndex(self.idx)
+        self.name = name
+
+    def field(self, name, ftype="set", **kw):
+        return self.idx.create_field(name, ftype, **kw)
+
+    def load(self, field, view, shard, data):
+        self.holder.import_roaring(self.name, field, view, shard, data)
+        self.ora.load(field, view, shard, data)
+
+    def sync_pending(self):
+        """push Holder.set_bit/set_value staged bits to both sides"""
+        from featurebase_b200 import roaring_io
+        for (index, field, view, shard), bits in self.holder._pending.items():
+            data = roaring_io.encode(np.fromiter(bits, dtype=np.uint64, count=len(bits)))
+            self.load(field, view, shard, data)
+        self.holder._pending = {}
+
+    def shards(self):
+        return sorted(self.idx.shards)
+
+    def check_row(self, q, shards=None):
+        shards = self.shards() if shards is None else shards
+        call = pql.parse(q)[0]
+        got = self.ex.execute(self.name, q, shards)[0]
+        exp = self.ora.eval_row(call, shards)
+        assert got.count == exp.count(), q
+        assert got.roaring == exp.to_bytes(), q      # canonical bytes (Bitmap.WriteTo, roaring.go:1730)
+        return got
+
+    def check_count(self, q, shards=None):
+        shards = self.shards() if shards is None else shards
+        call = pql.parse(q)[0]
+        got = self.ex.execute(self.name, q, shards)[0]
+        exp = self.ora.count(call.children[0], shards)
+        assert got == exp, (q, got, exp)
+        return got
