@@ -15,14 +15,16 @@ def _stale(target, sources):
     return any(os.path.getmtime(s) > t for s in sources if os.path.exists(s))
 
 
-def build_fbgpu(force=False, verbose=False):
+def build_fbgpu(force=False, verbose=False, defines=None, out_name="libfbgpu.so"):
     src = os.path.join(HERE, "csrc", "fbgpu.cu")
     deps = [src, os.path.join(HERE, "csrc", "kernels.cuh"), os.path.join(HERE, "csrc", "fbgpu_types.h"),
             os.path.join(ROOT, "include", "fbgpu.h")]
-    out = os.path.join(HERE, "libfbgpu.so")
+    out = os.path.join(HERE, out_name)
     if force or _stale(out, deps):
         cmd = [NVCC, "-O3", "-std=c++17", "-shared", "-Xcompiler", "-fPIC", "-lineinfo",
                "-gencode", "arch=compute_100a,code=sm_100a", "-o", out, src, "-ldl"]
+        for d in (defines or []):
+            cmd.insert(1, "-D" + d)
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         subprocess.check_call(cmd)

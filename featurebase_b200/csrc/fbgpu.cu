@@ -510,13 +510,22 @@ struct Compiler {
         const Node& n = nodes[id]; const fbgpu_op& o = n.op;
         auto is_row_leaf = [&](int k) { return nodes[k].op.opcode == FBGPU_OP_ROW || nodes[k].op.opcode == FBGPU_OP_ALL; };
         auto leaf_fv = [&](int k) { return fv_of(nodes[k].op.field, nodes[k].op.view); };
-        auto fold = [&](uint8_t fused, uint8_t binop) -> int {
-            int rc = gen(nodes, n.kids[0]); if (rc) return rc;
-            for (size_t k = 1; k < n.kids.size(); k++) {
-                int kid = n.kids[k];
-                if (is_row_leaf(kid)) emit(fused, leaf_fv(kid), nodes[kid].op.a);
-                else { rc = gen(nodes, kid); if (rc) return rc; emit(binop); }
+        // Left fold over the children.  For the commutative/associative ops (and for the subtrahends of Difference)
+        // evaluation order cannot change the result, so complex children are evaluated first and all plain Row
+        // children are applied afterwards as one run of fused row ops, which the kernel executes as a barrier-free batch.
+        auto fold = [&](uint8_t fused, uint8_t binop, bool first_fixed) -> int {
+            std::vector<int> complex_kids, leaf_kids;
+            size_t k0 = 0;
+            int rc;
+            if (first_fixed) { rc = gen(nodes, n.kids[0]); if (rc) return rc; k0 = 1; }
+            for (size_t k = k0; k < n.kids.size(); k++) (is_row_leaf(n.kids[k]) ? leaf_kids : complex_kids).push_back(n.kids[k]);
+            bool have = first_fixed;
+            for (int kid : complex_kids) { rc = gen(nodes, kid); if (rc) return rc; if (have) emit(binop); have = true; }
+            if (!have) {
+                if (fused == D_AND_ROW) { emit(D_PUSH_ROW, leaf_fv(leaf_kids[0]), nodes[leaf_kids[0]].op.a); leaf_kids.erase(leaf_kids.begin()); }
+                else emit(D_PUSH_EMPTY);       // OR / XOR onto an empty bitmap
             }
+            for (int kid : leaf_kids) emit(fused, leaf_fv(kid), nodes[kid].op.a);
             return 0;
         };
         switch (o.opcode) {
@@ -524,16 +533,16 @@ struct Compiler {
             case FBGPU_OP_EMPTY: emit(D_PUSH_EMPTY); return 0;
             case FBGPU_OP_INTERSECT:
                 if (n.kids.empty()) return fail(FBGPU_E_QUERY, "empty Intersect query is currently not supported");   // executor.go:5362
-                return fold(D_AND_ROW, D_AND);
+                return fold(D_AND_ROW, D_AND, false);
             case FBGPU_OP_UNION:
                 if (n.kids.empty()) { emit(D_PUSH_EMPTY); return 0; }                                                  // executor.go:5386
-                return fold(D_OR_ROW, D_OR);
+                return fold(D_OR_ROW, D_OR, false);
             case FBGPU_OP_DIFFERENCE:
                 if (n.kids.empty()) return fail(FBGPU_E_QUERY, "empty Difference query is currently not supported");  // executor.go:2955
-                return fold(D_ANDNOT_ROW, D_ANDNOT);
+                return fold(D_ANDNOT_ROW, D_ANDNOT, true);
             case FBGPU_OP_XOR:
                 if (n.kids.empty()) { emit(D_PUSH_EMPTY); return 0; }                                                  // executor.go:5517
-                return fold(D_XOR_ROW, D_XOR);
+                return fold(D_XOR_ROW, D_XOR, false);
             case FBGPU_OP_NOT: {                                                                                        // executor.go:5554-5602
                 if (n.kids.size() != 1) return fail(FBGPU_E_QUERY, "Not() requires a single bitmap input");
                 emit(D_PUSH_ROW, fv_of(o.field, o.view), o.a);
@@ -612,7 +621,7 @@ static int upload_inputs(Workspace* w, const std::vector<DevOp>& prog, const uin
 static int launch_eval(fbgpu_ctx* c, Workspace* w, const DevOp* d_prog, int n_ops, int depth, const uint64_t* d_shards, long long n_units, EvalOut out) {
     if (n_units <= 0) return 0;
     size_t smem = (size_t)(depth + 1) * 8192;
-    int per_sm = std::max(1, (int)std::min<size_t>(8, (220 * 1024) / (smem + 6 * 1024)));
+    int per_sm = std::max(1, (int)std::min<size_t>(std::min(8, 2048 / kEvalThreads), (220 * 1024) / (smem + 6 * 1024)));
     long long grid = std::min<long long>(n_units, (long long)c->sm_count * per_sm);
     eval_kernel<<<(unsigned)grid, kEvalThreads, smem, w->stream>>>(store_ref(c), d_prog, n_ops, depth, d_shards, n_units, out);
     CUDA_TRY(cudaGetLastError());
@@ -716,7 +725,7 @@ extern "C" int fbgpu_row(fbgpu_ctx* c, uint32_t index, const fbgpu_op* ops, int3
             memcpy(w->h_in.p, emits.data(), emits.size() * sizeof(EmitUnit));
             CUDA_TRY(cudaMemcpyAsync(w->d_emit_units.p, w->h_in.p, emits.size() * sizeof(EmitUnit), cudaMemcpyHostToDevice, w->stream));
             int grid = (int)std::min<size_t>(emits.size(), (size_t)c->sm_count * 8);
-            canon_emit_kernel<<<grid, kEvalThreads, 0, w->stream>>>((const uint4*)w->d_bitmaps.p, (const EmitUnit*)w->d_emit_units.p, (int)emits.size(), (uint8_t*)w->d_emit.p);
+            canon_emit_kernel<<<grid, kEmitThreads, 0, w->stream>>>((const uint4*)w->d_bitmaps.p, (const EmitUnit*)w->d_emit_units.p, (int)emits.size(), (uint8_t*)w->d_emit.p);
             CUDA_TRY(cudaGetLastError()); launches++;
             CUDA_TRY(cudaStreamSynchronize(w->stream));   // h_in is reused as the D2H landing buffer below
             CUDA_TRY(cudaMemcpyAsync(w->h_in.p, w->d_emit.p, off, cudaMemcpyDeviceToHost, w->stream));

@@ -15,7 +15,18 @@
 
 namespace fbgpu {
 
-constexpr int kEvalThreads = 256;
+#ifndef FBGPU_EVAL_THREADS
+#define FBGPU_EVAL_THREADS 256
+#endif
+#ifndef FBGPU_EVAL_MIN_BLOCKS
+#define FBGPU_EVAL_MIN_BLOCKS 7
+#endif
+#ifndef FBGPU_BATCH_UNROLL
+#define FBGPU_BATCH_UNROLL 4
+#endif
+constexpr int kEvalThreads = FBGPU_EVAL_THREADS;          // 256 or 512
+constexpr int kEvalU4PerThread = 512 / kEvalThreads;       // uint4 per thread of an 8 KiB bitmap
+constexpr int kEvalW64PerThread = 1024 / kEvalThreads;     // consecutive u64 words per thread in scans
 constexpr int kResolveChunk = 256;
 
 __device__ __forceinline__ uint4 ldg_nc(const uint4* p) {
@@ -59,7 +70,8 @@ __device__ __forceinline__ Resolved resolve(const StoreRef& st, uint32_t fv, uin
 // CTA-level helpers on 8 KiB shared-memory bitmaps (uint4[512]); thread t owns uint4 t and t+256.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void bm_zero(uint4* d) {
-    d[threadIdx.x] = make_uint4(0, 0, 0, 0); d[threadIdx.x + kEvalThreads] = make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int h = 0; h < kEvalU4PerThread; h++) d[threadIdx.x + h * kEvalThreads] = make_uint4(0, 0, 0, 0);
 }
 // scatter an array container into a bitmap with MODE 0: |=  1: &= ~  2: ^=
 template <int MODE>
@@ -88,7 +100,7 @@ __device__ __forceinline__ void bm_filter_scatter(uint32_t* dst, const uint32_t*
 }
 // Expand a run container into `dst` (overwrites).  Delta bitmap (toggle at start and last+1) followed by a
 // CTA-wide prefix-XOR scan: O(runs + 1024 words), independent of run lengths (runToBitmap roaring.go:3792).
-__device__ __forceinline__ void bm_expand_runs(uint4* dst4, const uint16_t* runs, uint32_t n_runs, uint32_t* warp_par /*[8]*/) {
+__device__ __noinline__ void bm_expand_runs(uint4* dst4, const uint16_t* runs, uint32_t n_runs, uint32_t* warp_par /*[8]*/) {
     bm_zero(dst4);
     __syncthreads();
     uint32_t* d32 = reinterpret_cast<uint32_t*>(dst4);
@@ -100,12 +112,12 @@ __device__ __forceinline__ void bm_expand_runs(uint4* dst4, const uint16_t* runs
         if (e < 65536u) atomicXor(&d32[e >> 5], 1u << (e & 31));
     }
     __syncthreads();
-    // thread t owns u64 words 4t..4t+3
+    // thread t owns kEvalW64PerThread consecutive u64 words
     uint64_t* d64 = reinterpret_cast<uint64_t*>(dst4);
-    uint64_t w[4]; uint32_t carry = 0;
+    uint64_t w[kEvalW64PerThread]; uint32_t carry = 0;
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-        uint64_t x = d64[4 * threadIdx.x + k];
+    for (int k = 0; k < kEvalW64PerThread; k++) {
+        uint64_t x = d64[kEvalW64PerThread * threadIdx.x + k];
         x ^= x << 1; x ^= x << 2; x ^= x << 4; x ^= x << 8; x ^= x << 16; x ^= x << 32;
         if (carry) x = ~x;
         carry = (uint32_t)(x >> 63);
@@ -118,7 +130,7 @@ __device__ __forceinline__ void bm_expand_runs(uint4* dst4, const uint16_t* runs
     __syncthreads();
     for (int k = 0; k < wid; k++) excl ^= warp_par[k];
 #pragma unroll
-    for (int k = 0; k < 4; k++) d64[4 * threadIdx.x + k] = excl ? ~w[k] : w[k];
+    for (int k = 0; k < kEvalW64PerThread; k++) d64[kEvalW64PerThread * threadIdx.x + k] = excl ? ~w[k] : w[k];
     __syncthreads();
 }
 
@@ -127,7 +139,7 @@ enum { K_PUSH = 0, K_OR, K_AND, K_ANDNOT, K_XOR, K_ORAND, K_ORANDNOT };
 // top = f(top, g)   or   below |= top & (~)g   with g streamed from global (bitmap container)
 __device__ __forceinline__ void bm_apply_global(int kind, uint4* top, uint4* below, const uint4* g) {
 #pragma unroll
-    for (int h = 0; h < 2; h++) {
+    for (int h = 0; h < kEvalU4PerThread; h++) {
         int i = threadIdx.x + h * kEvalThreads;
         uint4 x = ldg_nc(g + i);
         switch (kind) {
@@ -143,7 +155,7 @@ __device__ __forceinline__ void bm_apply_global(int kind, uint4* top, uint4* bel
 }
 __device__ __forceinline__ void bm_apply_smem(int kind, uint4* top, uint4* below, const uint4* s) {
 #pragma unroll
-    for (int h = 0; h < 2; h++) {
+    for (int h = 0; h < kEvalU4PerThread; h++) {
         int i = threadIdx.x + h * kEvalThreads;
         uint4 x = s[i];
         switch (kind) {
@@ -158,6 +170,186 @@ __device__ __forceinline__ void bm_apply_smem(int kind, uint4* top, uint4* below
     }
 }
 
+template <int MODE>   // 0: |=   1: &= ~   2: ^=
+__device__ __forceinline__ void smem_bit_op(uint32_t* bm, uint32_t v) {
+    // red.shared (no return value).  `asm volatile` keeps the reductions in program order, which stops ptxas from
+    // hoisting dozens of address/mask computations ahead of them (register pressure decides CTA residency here).
+    uint32_t addr = (uint32_t)__cvta_generic_to_shared(bm + (v >> 5));
+    uint32_t m = 1u << (v & 31);
+    if (MODE == 0) asm volatile("red.shared.or.b32 [%0], %1;" :: "r"(addr), "r"(m) : "memory");
+    else if (MODE == 1) asm volatile("red.shared.and.b32 [%0], %1;" :: "r"(addr), "r"(~m) : "memory");
+    else asm volatile("red.shared.xor.b32 [%0], %1;" :: "r"(addr), "r"(m) : "memory");
+}
+// one warp scatters a whole array container (16-byte loads, 8 elements per lane per step)
+template <int MODE>
+__device__ __forceinline__ void warp_scatter_smem_mode(uint32_t* bm, const uint16_t* arr, uint32_t n, int lane) {
+    const uint4* a4 = reinterpret_cast<const uint4*>(arr);
+    uint32_t n8 = (n + 7) >> 3;
+    for (uint32_t i = lane; i < n8; i += 32) {
+        uint4 v = ldg_nc(a4 + i);
+        uint32_t w[4] = { v.x, v.y, v.z, v.w };
+        uint32_t base = i * 8;
+        if (base + 8 <= n) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) { smem_bit_op<MODE>(bm, w[q] & 0xffffu); smem_bit_op<MODE>(bm, w[q] >> 16); }
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                if (base + 2 * q < n) smem_bit_op<MODE>(bm, w[q] & 0xffffu);
+                if (base + 2 * q + 1 < n) smem_bit_op<MODE>(bm, w[q] >> 16);
+            }
+        }
+    }
+}
+__device__ __forceinline__ void warp_scatter_smem(uint32_t* bm, const uint16_t* arr, uint32_t n, int lane) { warp_scatter_smem_mode<0>(bm, arr, n, lane); }
+// one warp applies a whole bitmap container with word atomics (safe against concurrent warps)
+template <int MODE>
+__device__ __forceinline__ void warp_bitmap_atomic(uint32_t* bm, const uint4* g, int lane) {
+    for (int i = lane; i < 512; i += 32) {
+        uint4 v = ldg_nc(g + i);
+        uint32_t w[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            if (!w[q]) continue;
+            if (MODE == 0) atomicOr(&bm[4 * i + q], w[q]); else if (MODE == 1) atomicAnd(&bm[4 * i + q], ~w[q]); else atomicXor(&bm[4 * i + q], w[q]);
+        }
+    }
+}
+// scatters the (up to) 8 u16 values of one 16-byte chunk; rolled on purpose (keeps register pressure low so
+// that 4+ CTAs stay resident per SM)
+template <int MODE>
+__device__ __forceinline__ void scatter_chunk(uint32_t* bm, uint4 v, uint32_t base, uint32_t n) {
+    uint64_t a = ((uint64_t)v.y << 32) | v.x, b = ((uint64_t)v.w << 32) | v.z;
+    uint32_t cnt = n - base;            // valid elements in this chunk (>= 1)
+    if (cnt >= 8) {
+#pragma unroll 1
+        for (int q = 0; q < 4; q++) { smem_bit_op<MODE>(bm, (uint32_t)a & 0xffffu); smem_bit_op<MODE>(bm, (uint32_t)b & 0xffffu); a >>= 16; b >>= 16; }
+    } else {
+#pragma unroll 1
+        for (uint32_t q = 0; q < cnt; q++) { uint64_t x = q < 4 ? a : b; smem_bit_op<MODE>(bm, (uint32_t)(x >> (16 * (q & 3))) & 0xffffu); }
+    }
+}
+// Batch of commuting row operands (OR / ANDNOT / XOR onto the same target), no barrier in between: the CTA is
+// split into groups of G threads, one group per operand (G*16 B contiguous per load), and every thread keeps four
+// 16-byte loads in flight before it touches shared memory, so the batch is bandwidth- rather than latency-bound.
+template <int MODE>
+__device__ __noinline__ void batch_rows(uint32_t* T32, const Resolved* res, int n) {
+    const int tid = threadIdx.x;
+    int G = kEvalThreads / max(n, 1);
+    G = G >= 32 ? 32 : G <= 1 ? 1 : (1 << (31 - __clz(G)));
+    const int groups = kEvalThreads / G, g = tid & (G - 1);
+    for (int j = tid / G; j < n; j += groups) {
+        const Resolved r = res[j];
+        if (r.ptr == nullptr) continue;
+        if (r.typ == kArray) {
+            const uint4* a4 = reinterpret_cast<const uint4*>(r.ptr);
+            const uint32_t n8 = (r.card + 7) >> 3;
+            for (uint32_t i = g; i < n8; i += FBGPU_BATCH_UNROLL * G) {
+                uint4 v[FBGPU_BATCH_UNROLL];
+#pragma unroll
+                for (int q = 0; q < FBGPU_BATCH_UNROLL; q++) if (i + q * G < n8) v[q] = ldg_nc(a4 + i + q * G);
+#pragma unroll
+                for (int q = 0; q < FBGPU_BATCH_UNROLL; q++) if (i + q * G < n8) scatter_chunk<MODE>(T32, v[q], (i + q * G) * 8, r.card);
+            }
+        } else if (r.typ == kBitmap) {
+            const uint4* g4 = reinterpret_cast<const uint4*>(r.ptr);
+            for (int i = g; i < 512; i += 2 * G) {
+                uint4 v[2];
+#pragma unroll
+                for (int q = 0; q < 2; q++) if (i + q * G < 512) v[q] = ldg_nc(g4 + i + q * G);
+#pragma unroll
+                for (int q = 0; q < 2; q++) if (i + q * G < 512) {
+                    uint32_t w[4] = { v[q].x, v[q].y, v[q].z, v[q].w };
+#pragma unroll
+                    for (int c = 0; c < 4; c++) {
+                        if (!w[c]) continue;
+                        uint32_t* dst = &T32[4 * (i + q * G) + c];
+                        if (MODE == 0) atomicOr(dst, w[c]); else if (MODE == 1) atomicAnd(dst, ~w[c]); else atomicXor(dst, w[c]);
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ---- alternative batch implementations (selected at compile time by FBGPU_BATCH_IMPL)
+template <int MODE>
+__device__ __forceinline__ void scatter_chunk_unrolled(uint32_t* bm, uint4 v, uint32_t base, uint32_t n) {
+    uint32_t w[4] = { v.x, v.y, v.z, v.w };
+    if (base + 8 <= n) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) { smem_bit_op<MODE>(bm, w[q] & 0xffffu); smem_bit_op<MODE>(bm, w[q] >> 16); }
+    } else {
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            if (base + 2 * q < n) smem_bit_op<MODE>(bm, w[q] & 0xffffu);
+            if (base + 2 * q + 1 < n) smem_bit_op<MODE>(bm, w[q] >> 16);
+        }
+    }
+}
+// v1: one warp per operand, plain loop
+template <int MODE>
+__device__ __forceinline__ void batch_rows_v1(uint32_t* T32, const Resolved* res, int n) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int j = wid; j < n; j += kEvalThreads / 32) {
+        const Resolved r = res[j];
+        if (r.ptr == nullptr) continue;
+        if (r.typ == kArray) {
+            const uint4* a4 = reinterpret_cast<const uint4*>(r.ptr);
+            const uint32_t n8 = (r.card + 7) >> 3;
+            for (uint32_t i = lane; i < n8; i += 32) scatter_chunk_unrolled<MODE>(T32, ldg_nc(a4 + i), i * 8, r.card);
+        } else if (r.typ == kBitmap) warp_bitmap_atomic<MODE>(T32, reinterpret_cast<const uint4*>(r.ptr), lane);
+    }
+}
+// v3: one warp per operand, three 16-byte loads per lane in flight and the next operand's loads issued before the
+// current operand is scattered (register double buffering)
+template <int MODE>
+__device__ __forceinline__ void batch_rows_v3(uint32_t* T32, const Resolved* res, int n) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    constexpr int NW = kEvalThreads / 32;
+    uint4 cur[3], nxt[3];
+    Resolved rc; rc.ptr = nullptr; rc.card = 0; rc.typ = 0; rc.cnt = 0;
+    int j = wid;
+    auto issue = [&](const Resolved& r, uint4* buf) {
+        if (r.ptr != nullptr && r.typ == kArray) {
+            const uint4* a4 = reinterpret_cast<const uint4*>(r.ptr);
+            const uint32_t n8 = (r.card + 7) >> 3;
+#pragma unroll
+            for (int q = 0; q < 3; q++) if (lane + 32 * q < n8) buf[q] = ldg_nc(a4 + lane + 32 * q);
+        }
+    };
+    if (j < n) { rc = res[j]; issue(rc, cur); }
+    while (j < n) {
+        Resolved rn; rn.ptr = nullptr; rn.card = 0; rn.typ = 0; rn.cnt = 0;
+        if (j + NW < n) { rn = res[j + NW]; issue(rn, nxt); }
+        if (rc.ptr != nullptr) {
+            if (rc.typ == kArray) {
+                const uint32_t n8 = (rc.card + 7) >> 3;
+#pragma unroll
+                for (int q = 0; q < 3; q++) if (lane + 32 * q < n8) scatter_chunk_unrolled<MODE>(T32, cur[q], (lane + 32 * q) * 8, rc.card);
+                const uint4* a4 = reinterpret_cast<const uint4*>(rc.ptr);
+                for (uint32_t i = lane + 96; i < n8; i += 32) scatter_chunk_unrolled<MODE>(T32, ldg_nc(a4 + i), i * 8, rc.card);
+            } else if (rc.typ == kBitmap) warp_bitmap_atomic<MODE>(T32, reinterpret_cast<const uint4*>(rc.ptr), lane);
+        }
+#pragma unroll
+        for (int q = 0; q < 3; q++) cur[q] = nxt[q];
+        rc = rn; j += NW;
+    }
+}
+#ifndef FBGPU_BATCH_IMPL
+#define FBGPU_BATCH_IMPL 1
+#endif
+template <int MODE>
+__device__ __noinline__ void batch_rows_dispatch(uint32_t* T32, const Resolved* res, int n) {
+#if FBGPU_BATCH_IMPL == 1
+    batch_rows_v1<MODE>(T32, res, n);
+#elif FBGPU_BATCH_IMPL == 2
+    batch_rows<MODE>(T32, res, n);
+#else
+    batch_rows_v3<MODE>(T32, res, n);
+#endif
+}
+
 struct EvalOut {
     unsigned long long* total;      // += count of every unit (may be null)
     unsigned long long* per_shard;  // [n_shards] += (may be null)
@@ -166,7 +358,7 @@ struct EvalOut {
 };
 
 // One CTA per (shard, slot) unit, persistent over units.  Dynamic smem: (depth+1) x 8 KiB.
-__global__ void __launch_bounds__(kEvalThreads)
+__global__ void __launch_bounds__(kEvalThreads, FBGPU_EVAL_MIN_BLOCKS)
 eval_kernel(StoreRef st, const DevOp* __restrict__ prog, int n_ops, int depth,
             const uint64_t* __restrict__ shards, long long n_units, EvalOut out) {
     extern __shared__ uint4 smem4[];
@@ -207,6 +399,27 @@ eval_kernel(StoreRef st, const DevOp* __restrict__ prog, int n_ops, int depth,
                     int kind = opc == D_AND ? K_AND : opc == D_OR ? K_OR : opc == D_ANDNOT ? K_ANDNOT : K_XOR;
                     bm_apply_smem(kind, phys(top - 1), nullptr, phys(top));
                     top--; __syncthreads(); continue;
+                }
+                if (opc == D_OR_ROW || opc == D_ANDNOT_ROW || opc == D_XOR_ROW) {
+                    // maximal run of the same commuting row op inside this chunk
+                    int e = k + 1;
+                    while (e < chunk && prog[base + e].op == opc) e++;
+                    uint4* T = phys(top);
+                    uint32_t* T32 = reinterpret_cast<uint32_t*>(T);
+                    if (opc == D_OR_ROW) batch_rows_dispatch<0>(T32, res + k, e - k);
+                    else if (opc == D_ANDNOT_ROW) batch_rows_dispatch<1>(T32, res + k, e - k);
+                    else batch_rows_dispatch<2>(T32, res + k, e - k);
+                    __syncthreads();
+                    for (int j = k; j < e; j++) {          // run containers: CTA-wide expansion, one at a time
+                        const Resolved r = res[j];
+                        if (r.ptr == nullptr || r.typ != kRun) continue;
+                        uint4* S = phys(depth);
+                        bm_expand_runs(S, reinterpret_cast<const uint16_t*>(r.ptr), r.cnt, warp_tmp);
+                        bm_apply_smem(opc == D_OR_ROW ? K_OR : opc == D_ANDNOT_ROW ? K_ANDNOT : K_XOR, T, nullptr, S);
+                        __syncthreads();
+                    }
+                    k = e - 1;
+                    continue;
                 }
                 // row-operand ops
                 int kind = opc == D_PUSH_ROW ? K_PUSH : opc == D_OR_ROW ? K_OR : opc == D_AND_ROW ? K_AND : opc == D_ANDNOT_ROW ? K_ANDNOT
@@ -258,14 +471,14 @@ eval_kernel(StoreRef st, const DevOp* __restrict__ prog, int n_ops, int depth,
         uint32_t cnt = 0, nruns = 0;
         if (top >= 0) {
             const uint4* R = phys(top);
-            uint4 a = R[tid], b = R[tid + kEvalThreads];
-            cnt = popc4(a) + popc4(b);
-            if (out.bitmaps) { uint4* o = out.bitmaps + (size_t)unit * 512; o[tid] = a; o[tid + kEvalThreads] = b; }
-            if (out.info) {
-                const uint64_t* R64 = reinterpret_cast<const uint64_t*>(R);
+            const uint64_t* R64 = reinterpret_cast<const uint64_t*>(R);
 #pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    int i = tid + h * kEvalThreads;
+            for (int h = 0; h < kEvalU4PerThread; h++) {
+                int i = tid + h * kEvalThreads;
+                uint4 a = R[i];
+                cnt += popc4(a);
+                if (out.bitmaps) out.bitmaps[(size_t)unit * 512 + i] = a;
+                if (out.info) {
 #pragma unroll
                     for (int q = 0; q < 2; q++) {
                         int wi = 2 * i + q;
@@ -276,7 +489,8 @@ eval_kernel(StoreRef st, const DevOp* __restrict__ prog, int n_ops, int depth,
                 }
             }
         } else if (out.bitmaps) {
-            uint4* o = out.bitmaps + (size_t)unit * 512; o[tid] = make_uint4(0, 0, 0, 0); o[tid + kEvalThreads] = make_uint4(0, 0, 0, 0);
+#pragma unroll
+            for (int h = 0; h < kEvalU4PerThread; h++) out.bitmaps[(size_t)unit * 512 + tid + h * kEvalThreads] = make_uint4(0, 0, 0, 0);
         }
         cnt = __reduce_add_sync(0xffffffffu, cnt);
         nruns = __reduce_add_sync(0xffffffffu, nruns);
@@ -320,21 +534,6 @@ __device__ __forceinline__ uint32_t warp_probe_smem(const uint32_t* bm, const ui
         }
     }
     return c;
-}
-__device__ __forceinline__ void warp_scatter_smem(uint32_t* bm, const uint16_t* arr, uint32_t n, int lane) {
-    const uint4* a4 = reinterpret_cast<const uint4*>(arr);
-    uint32_t n8 = (n + 7) >> 3;
-    for (uint32_t i = lane; i < n8; i += 32) {
-        uint4 v = ldg_nc(a4 + i);
-        uint32_t w[4] = { v.x, v.y, v.z, v.w };
-        uint32_t base = i * 8;
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            uint32_t lo = w[q] & 0xffffu, hi = w[q] >> 16;
-            if (base + 2 * q < n) atomicOr(&bm[lo >> 5], 1u << (lo & 31));
-            if (base + 2 * q + 1 < n) atomicOr(&bm[hi >> 5], 1u << (hi & 31));
-        }
-    }
 }
 // per-lane partial count of array elements found in a global-memory bitmap
 __device__ __forceinline__ uint32_t warp_probe_global(const uint32_t* g, const uint16_t* arr, uint32_t n, int lane) {
@@ -510,11 +709,12 @@ row_count_kernel(StoreRef st, uint32_t fv, const uint64_t* __restrict__ row_ids,
 // Canonical emission of result bitmaps (Row results): optimize() roaring.go:3412-3461 decides the encoding
 // on the host from {N, runs}; this kernel writes the payload (array / run / bitmap) at the given offset.
 // ------------------------------------------------------------------------------------------------
+constexpr int kEmitThreads = 256;   // thread t owns u64 words 4t..4t+3
 struct EmitUnit { uint64_t offset; uint32_t unit; uint32_t typ; };
 
-__global__ void __launch_bounds__(kEvalThreads)
+__global__ void __launch_bounds__(kEmitThreads)
 canon_emit_kernel(const uint4* __restrict__ bitmaps, const EmitUnit* __restrict__ units, int n_emit, uint8_t* __restrict__ out) {
-    __shared__ uint32_t wsum[kEvalThreads / 32], wsum2[kEvalThreads / 32];
+    __shared__ uint32_t wsum[kEmitThreads / 32], wsum2[kEmitThreads / 32];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     for (int e = blockIdx.x; e < n_emit; e += gridDim.x) {
         EmitUnit u = units[e];
@@ -522,7 +722,7 @@ canon_emit_kernel(const uint4* __restrict__ bitmaps, const EmitUnit* __restrict_
         if (u.typ == kBitmap) {
             uint4* o = reinterpret_cast<uint4*>(out + u.offset);   // offsets of bitmap payloads are only 2-byte aligned in the
             const uint4* s4 = bitmaps + (size_t)u.unit * 512;      // roaring file; the host keeps emit buffers 16 B aligned per unit
-            o[tid] = s4[tid]; o[tid + kEvalThreads] = s4[tid + kEvalThreads];
+            o[tid] = s4[tid]; o[tid + kEmitThreads] = s4[tid + kEmitThreads];
             continue;
         }
         // thread t owns words 4t..4t+3; compute exclusive prefix of element count (array) or start/end counts (run)
@@ -563,7 +763,7 @@ canon_emit_kernel(const uint4* __restrict__ bitmaps, const EmitUnit* __restrict_
                 v = ends[k]; while (v) { int bit = __ffsll((long long)v) - 1; o16[2 + 2 * (p2++)] = (uint16_t)((4 * tid + k) * 64 + bit); v &= v - 1; }
             }
             __syncthreads();
-            if (tid == kEvalThreads - 1) o16[0] = (uint16_t)p1;
+            if (tid == kEmitThreads - 1) o16[0] = (uint16_t)p1;
         }
     }
 }

@@ -41,7 +41,7 @@ EXPORTS = ["fbgpu_init", "fbgpu_shutdown", "fbgpu_last_error", "fbgpu_abi_versio
 
 
 def lib_path():
-    return os.path.join(_HERE, "libfbgpu.so")
+    return os.environ.get("FBGPU_LIB") or os.path.join(_HERE, "libfbgpu.so")   # FBGPU_LIB: tuning variants only
 
 
 def load():
