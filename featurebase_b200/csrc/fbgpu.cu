@@ -100,7 +100,7 @@ struct HostFrag { uint32_t fv; uint64_t shard; bool live; uint32_t row_off, n_ro
 struct Workspace {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    DevBuf d_in, d_counts, d_bitmaps, d_info, d_emit_units, d_emit, d_rows;
+    DevBuf d_in, d_counts, d_bitmaps, d_info, d_emit_units, d_emit, d_rows, d_aux;
     PinBuf h_in, h_out;
     bool busy = false;
 };
@@ -112,6 +112,7 @@ struct fbgpu_ctx {
     std::shared_mutex store_mu;
     std::map<ViewKey, uint32_t> view_ids;
     std::vector<std::vector<int32_t>> shardmaps;  // per view
+    std::vector<uint64_t> view_arr, view_other;   // per view: live array containers / bitmap+run containers
     std::vector<HostFrag> frags;
     std::vector<FragHdr> h_frags;
     std::vector<RowEnt> h_rows;
@@ -119,7 +120,7 @@ struct fbgpu_ctx {
     std::vector<uint8_t> staging;        // payload bytes not yet uploaded, destined for [uploaded, uploaded+staging.size())
     uint64_t uploaded = 0;               // bytes of payload already in HBM
     bool meta_dirty = false;
-    DevBuf d_payload, d_views, d_shardmap, d_frags, d_rows, d_descs;
+    DevBuf d_payload, d_views, d_shardmap, d_frags, d_rows, d_descs, d_rowtab;
     uint32_t n_views_dev = 0;
     fbgpu_stats stats{};
     // ---- execution
@@ -134,7 +135,7 @@ struct fbgpu_ctx {
 static StoreRef store_ref(fbgpu_ctx* c) {
     StoreRef s;
     s.views = (const ViewTab*)c->d_views.p; s.shardmap = (const int32_t*)c->d_shardmap.p; s.frags = (const FragHdr*)c->d_frags.p;
-    s.rows = (const RowEnt*)c->d_rows.p; s.descs = (const ContDesc*)c->d_descs.p; s.payload = (const uint8_t*)c->d_payload.p; s.n_views = c->n_views_dev;
+    s.rows = (const RowEnt*)c->d_rows.p; s.descs = (const ContDesc*)c->d_descs.p; s.payload = (const uint8_t*)c->d_payload.p; s.rowtab = (const RowTabEnt*)c->d_rowtab.p; s.n_views = c->n_views_dev;
     return s;
 }
 
@@ -156,6 +157,7 @@ extern "C" int fbgpu_init(int32_t device_ordinal, fbgpu_ctx** out) {
     }
     // opt in to large dynamic shared memory once
     CUDA_TRY(cudaFuncSetAttribute(eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 17 * 8192));
+    CUDA_TRY(cudaFuncSetAttribute(eval_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 233472 / 2 - 1024 - 5888));
     CUDA_TRY(cudaFuncSetAttribute(pair_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairWarps * 8192));
     CUDA_TRY(cudaFuncSetAttribute(row_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairWarps * 8192));
     CUDA_TRY(cudaFuncSetAttribute(groupby_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072 + kGbPool * 4 + 8192));
@@ -169,11 +171,11 @@ extern "C" void fbgpu_shutdown(fbgpu_ctx* c) {
     cudaDeviceSynchronize();
     if (c->comm && nccl_load()) g_nccl.CommDestroy(c->comm);
     for (auto& w : c->wss) {
-        for (DevBuf* b : { &w->d_in, &w->d_counts, &w->d_bitmaps, &w->d_info, &w->d_emit_units, &w->d_emit, &w->d_rows }) b->release();
+        for (DevBuf* b : { &w->d_in, &w->d_counts, &w->d_bitmaps, &w->d_info, &w->d_emit_units, &w->d_emit, &w->d_rows, &w->d_aux }) b->release();
         w->h_in.release(); w->h_out.release();
         cudaEventDestroy(w->ev0); cudaEventDestroy(w->ev1); cudaStreamDestroy(w->stream);
     }
-    for (DevBuf* b : { &c->d_payload, &c->d_views, &c->d_shardmap, &c->d_frags, &c->d_rows, &c->d_descs }) b->release();
+    for (DevBuf* b : { &c->d_payload, &c->d_views, &c->d_shardmap, &c->d_frags, &c->d_rows, &c->d_descs, &c->d_rowtab }) b->release();
     delete c;
 }
 
@@ -252,7 +254,7 @@ static uint32_t view_id_locked(fbgpu_ctx* c, ViewKey k, bool create) {
     if (it != c->view_ids.end()) return it->second;
     if (!create) return kNoView;
     uint32_t id = (uint32_t)c->shardmaps.size();
-    c->view_ids[k] = id; c->shardmaps.emplace_back();
+    c->view_ids[k] = id; c->shardmaps.emplace_back(); c->view_arr.push_back(0); c->view_other.push_back(0);
     return id;
 }
 
@@ -263,6 +265,7 @@ static void drop_locked(fbgpu_ctx* c, uint32_t fv, uint64_t shard) {
     f.live = false;
     c->stats.fragments--; c->stats.containers -= f.n_desc; c->stats.payload_bytes -= f.payload_bytes;
     c->stats.array_containers -= f.n_arr; c->stats.bitmap_containers -= f.n_bmp; c->stats.run_containers -= f.n_run;
+    c->view_arr[fv] -= f.n_arr; c->view_other[fv] -= (uint64_t)f.n_bmp + f.n_run;
     sm[shard] = -1;
     c->meta_dirty = true;
 }
@@ -273,6 +276,8 @@ static int add_fragment_locked(fbgpu_ctx* c, uint32_t fv, uint64_t shard, const 
     drop_locked(c, fv, shard);
     HostFrag hf{}; hf.fv = fv; hf.shard = shard; hf.live = true; hf.row_off = (uint32_t)c->h_rows.size();
     uint64_t prev_row = ~0ull; bool contiguous = true; uint64_t row0 = 0;
+    const size_t desc0 = c->h_descs.size();
+    // descriptors: row-major (key order), so that a row's slots are adjacent and rank = popc(mask & below)
     for (const ParsedCont& pc : cs) {
         uint64_t row = pc.key / kSlotsPerRow; int slot = (int)(pc.key % kSlotsPerRow);
         if (row != prev_row) {
@@ -281,7 +286,21 @@ static int add_fragment_locked(fbgpu_ctx* c, uint32_t fv, uint64_t shard, const 
             c->h_rows.push_back(e); prev_row = row; hf.n_rows++;
         }
         c->h_rows.back().mask |= (uint16_t)(1u << slot);
-        // stage payload with alignment: bitmaps 128 B, others 16 B
+        ContDesc d{}; d.off16 = 0; d.card = pc.n; d.typ = pc.typ; d.cnt = (uint16_t)pc.cnt;
+        c->h_descs.push_back(d);
+        uint64_t bytes = pc.typ == kArray ? (uint64_t)pc.n * 2 : pc.typ == kBitmap ? 8192 : (uint64_t)pc.cnt * 4;
+        hf.n_desc++; hf.payload_bytes += bytes;
+        if (pc.typ == kArray) hf.n_arr++; else if (pc.typ == kBitmap) hf.n_bmp++; else hf.n_run++;
+    }
+    // payloads: row-major (key order) by default: a row's 16 containers are contiguous, which is what the common
+    // few-rows-of-many query streams.  FBGPU_LAYOUT_SLOT_MAJOR=1 stores all rows of slot 0, then slot 1, ... so that a
+    // (shard, slot) unit's consecutive rows are adjacent (measured: -20 % on 2-row bitmap queries; profiles/README.md).
+    std::vector<uint32_t> order(cs.size());
+    for (uint32_t i = 0; i < cs.size(); i++) order[i] = i;
+    static const bool slot_major = getenv("FBGPU_LAYOUT_SLOT_MAJOR") != nullptr;   // default: row-major (key order)
+    if (slot_major) std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return cs[a].key % kSlotsPerRow < cs[b].key % kSlotsPerRow; });
+    for (uint32_t i : order) {
+        const ParsedCont& pc = cs[i];
         uint64_t pos = c->uploaded + c->staging.size();
         uint64_t align = pc.typ == kBitmap ? 128 : 16;
         uint64_t apos = (pos + align - 1) & ~(align - 1);
@@ -294,10 +313,7 @@ static int add_fragment_locked(fbgpu_ctx* c, uint32_t fv, uint64_t shard, const 
             uint16_t* r = (uint16_t*)dst; for (uint32_t k = 0; k < pc.cnt; k++) r[2 * k + 1] = (uint16_t)(r[2 * k] + r[2 * k + 1]);
         }
         if (apos / 16 > 0xffffffffull) return fail(FBGPU_E_NOMEM, "payload arena exceeds 64 GiB addressable by 32-bit 16 B offsets");
-        ContDesc d{}; d.off16 = (uint32_t)(apos / 16); d.card = pc.n; d.typ = pc.typ; d.cnt = (uint16_t)pc.cnt;
-        c->h_descs.push_back(d);
-        hf.n_desc++; hf.payload_bytes += bytes;
-        if (pc.typ == kArray) hf.n_arr++; else if (pc.typ == kBitmap) hf.n_bmp++; else hf.n_run++;
+        c->h_descs[desc0 + i].off16 = (uint32_t)(apos / 16);
     }
     FragHdr h{}; h.row_off = hf.row_off; h.n_rows = hf.n_rows; h.row0 = row0; h.contiguous = contiguous ? 1u : 0u;
     int32_t fid = (int32_t)c->frags.size();
@@ -307,6 +323,7 @@ static int add_fragment_locked(fbgpu_ctx* c, uint32_t fv, uint64_t shard, const 
     sm[shard] = fid;
     c->stats.fragments++; c->stats.containers += hf.n_desc; c->stats.payload_bytes += hf.payload_bytes;
     c->stats.array_containers += hf.n_arr; c->stats.bitmap_containers += hf.n_bmp; c->stats.run_containers += hf.n_run;
+    c->view_arr[fv] += hf.n_arr; c->view_other[fv] += (uint64_t)hf.n_bmp + hf.n_run;
     c->meta_dirty = true;
     return 0;
 }
@@ -368,9 +385,23 @@ static int commit_locked(fbgpu_ctx* c) {
         c->uploaded += c->staging.size();
         std::vector<uint8_t>().swap(c->staging);
     }
-    // flatten shard maps
-    std::vector<ViewTab> views(c->shardmaps.size()); std::vector<int32_t> flat;
-    for (size_t v = 0; v < c->shardmaps.size(); v++) { views[v].shard_off = (uint32_t)flat.size(); views[v].n_shards = (uint32_t)c->shardmaps[v].size(); flat.insert(flat.end(), c->shardmaps[v].begin(), c->shardmaps[v].end()); }
+    // flatten shard maps; build the dense (shard,row) directory of every view whose row ids are dense
+    std::vector<ViewTab> views(c->shardmaps.size()); std::vector<int32_t> flat; std::vector<RowTabEnt> rowtab;
+    for (size_t v = 0; v < c->shardmaps.size(); v++) {
+        const auto& sm = c->shardmaps[v];
+        views[v] = ViewTab{}; views[v].shard_off = (uint32_t)flat.size(); views[v].n_shards = (uint32_t)sm.size();
+        flat.insert(flat.end(), sm.begin(), sm.end());
+        uint64_t rmin = ~0ull, rmax = 0, nrows = 0;
+        for (int32_t f : sm) if (f >= 0) { const HostFrag& hf = c->frags[f]; if (!hf.n_rows) continue;
+            rmin = std::min(rmin, c->h_rows[hf.row_off].row); rmax = std::max(rmax, c->h_rows[hf.row_off + hf.n_rows - 1].row); nrows = std::max<uint64_t>(nrows, hf.n_rows); }
+        if (rmin == ~0ull) continue;
+        uint64_t span = rmax - rmin + 1;
+        if (span > 4 * nrows + 64 || span * sm.size() > (64ull << 20) || getenv("FBGPU_NO_ROWTAB")) continue;       // sparse row ids or too large: keep the search chain
+        views[v].rt_rows = (uint32_t)span; views[v].rt_off = rowtab.size(); views[v].rmin = rmin;
+        rowtab.resize(rowtab.size() + span * sm.size(), RowTabEnt{ 0, 0, 0 });
+        for (size_t sh = 0; sh < sm.size(); sh++) if (sm[sh] >= 0) { const HostFrag& hf = c->frags[sm[sh]];
+            for (uint32_t k = 0; k < hf.n_rows; k++) { const RowEnt& e = c->h_rows[hf.row_off + k]; rowtab[views[v].rt_off + sh * span + (e.row - rmin)] = RowTabEnt{ e.first_desc, e.mask, 0 }; } }
+    }
     auto up = [&](DevBuf& b, const void* src, size_t bytes) -> int {
         if (b.ensure(std::max<size_t>(bytes, 256))) return FBGPU_E_NOMEM;
         if (bytes) { cudaError_t e = cudaMemcpy(b.p, src, bytes, cudaMemcpyHostToDevice); if (e != cudaSuccess) return fail(FBGPU_E_CUDA, "metadata upload failed: %s", cudaGetErrorString(e)); }
@@ -382,9 +413,10 @@ static int commit_locked(fbgpu_ctx* c) {
     if ((rc = up(c->d_frags, c->h_frags.data(), c->h_frags.size() * sizeof(FragHdr)))) return rc;
     if ((rc = up(c->d_rows, c->h_rows.data(), c->h_rows.size() * sizeof(RowEnt)))) return rc;
     if ((rc = up(c->d_descs, c->h_descs.data(), c->h_descs.size() * sizeof(ContDesc)))) return rc;
+    if ((rc = up(c->d_rowtab, rowtab.data(), rowtab.size() * sizeof(RowTabEnt)))) return rc;
     c->n_views_dev = (uint32_t)views.size();
     c->meta_dirty = false;
-    c->stats.device_bytes = c->d_payload.cap + c->d_views.cap + c->d_shardmap.cap + c->d_frags.cap + c->d_rows.cap + c->d_descs.cap;
+    c->stats.device_bytes = c->d_payload.cap + c->d_views.cap + c->d_shardmap.cap + c->d_frags.cap + c->d_rows.cap + c->d_descs.cap + c->d_rowtab.cap;
     return 0;
 }
 
@@ -618,12 +650,61 @@ static int upload_inputs(Workspace* w, const std::vector<DevOp>& prog, const uin
     return 0;
 }
 
-static int launch_eval(fbgpu_ctx* c, Workspace* w, const DevOp* d_prog, int n_ops, int depth, const uint64_t* d_shards, long long n_units, EvalOut out) {
+// runs of commuting row ops ([k,e) of D_OR_ROW / D_ANDNOT_ROW / D_XOR_ROW): the staged kernel prefetches them by TMA
+static std::vector<int2> find_batches(const std::vector<DevOp>& prog) {
+    std::vector<int2> b;
+    for (size_t k = 0; k < prog.size();) {
+        uint8_t o = prog[k].op;
+        if (o == D_OR_ROW || o == D_ANDNOT_ROW || o == D_XOR_ROW) { size_t e = k + 1; while (e < prog.size() && prog[e].op == o) e++; b.push_back(make_int2((int)k, (int)e)); k = e; }
+        else k++;
+    }
+    return b;
+}
+
+static int launch_eval(fbgpu_ctx* c, Workspace* w, const std::vector<DevOp>& prog, const DevOp* d_prog, int depth, const uint64_t* d_shards, long long n_units, EvalOut out) {
     if (n_units <= 0) return 0;
+    const int n_ops = (int)prog.size();
+    std::vector<int2> batches = find_batches(prog);
+    size_t staged_rows = 0; for (auto& b : batches) staged_rows += (size_t)(b.y - b.x);
+    // TMA-staged variant: opt-in (FBGPU_STAGED=1) until it beats the direct kernel (profiles/README.md)
+    // Word-parallel kernel for bitmap-heavy programs (BSI plane sweeps, dense rows): chosen when the views the
+    // program references hold few array containers.  Row results (out.info) need cross-slice run counts: not here.
+    if (!out.info && n_ops <= kWpMaxOps && depth <= kWpMaxDepth && !getenv("FBGPU_NO_WORDPAR")) {
+        uint64_t arr = 0, other = 0;
+        for (const DevOp& o : prog) if (o.op >= D_PUSH_ROW && o.op <= D_ORANDNOT_ROW && o.op != D_PUSH_EMPTY && o.fv < c->view_arr.size()) { arr += c->view_arr[o.fv]; other += c->view_other[o.fv]; }
+        if ((other > 0 && arr * 8 <= other) || getenv("FBGPU_FORCE_WORDPAR")) {
+            long long blocks = n_units * 4;
+            long long grid = std::min<long long>(blocks, (long long)c->sm_count * 16);
+            eval_wordpar_kernel<<<(unsigned)grid, kWpThreads, 0, w->stream>>>(store_ref(c), d_prog, n_ops, d_shards, n_units, out);
+            CUDA_TRY(cudaGetLastError());
+            return 0;
+        }
+    }
+    const bool staged = getenv("FBGPU_STAGED") && n_ops <= kStagedMaxOps && staged_rows >= 4;
+    if (w->d_aux.ensure(std::max<size_t>(batches.size(), 1) * sizeof(int2))) return FBGPU_E_NOMEM;
+    if (!batches.empty()) {
+        CUDA_TRY(cudaMemcpyAsync(w->d_aux.p, batches.data(), batches.size() * sizeof(int2), cudaMemcpyHostToDevice, w->stream));
+        CUDA_TRY(cudaStreamSynchronize(w->stream));      // `batches` is a local; tiny copy
+    }
+    if (staged) {
+        // N CTAs per SM (default 2): (depth+1) stack bitmaps + two TMA stages each
+        int ctas = 2;
+        if (const char* e = getenv("FBGPU_STAGE_CTAS")) ctas = std::max(1, std::min(4, atoi(e)));
+        const size_t per_cta = 233472 / ctas - 1024 - 5888;                         // SM smem / N - per-CTA reserve - static smem of the kernel
+        size_t stack = (size_t)(depth + 1) * 8192;
+        if (stack + 2 * 8192 <= per_cta) {
+            uint32_t stg = (uint32_t)(((per_cta - stack) / 2) & ~size_t(127));
+            long long grid = std::min<long long>(n_units, (long long)c->sm_count * ctas);
+            size_t smem = stack + 2 * (size_t)stg;
+            eval_staged_kernel<<<(unsigned)grid, kEvalThreads, smem, w->stream>>>(store_ref(c), d_prog, n_ops, depth, (const int2*)w->d_aux.p, (int)batches.size(), stg, d_shards, n_units, out);
+            CUDA_TRY(cudaGetLastError());
+            return 0;
+        }
+    }
     size_t smem = (size_t)(depth + 1) * 8192;
-    int per_sm = std::max(1, (int)std::min<size_t>(std::min(8, 2048 / kEvalThreads), (220 * 1024) / (smem + 6 * 1024)));
+    int per_sm = std::max(1, (int)std::min<size_t>(std::min(8, 2048 / kEvalThreads), (227 * 1024) / (smem + 3 * 1024 + 512)));
     long long grid = std::min<long long>(n_units, (long long)c->sm_count * per_sm);
-    eval_kernel<<<(unsigned)grid, kEvalThreads, smem, w->stream>>>(store_ref(c), d_prog, n_ops, depth, d_shards, n_units, out);
+    eval_kernel<<<(unsigned)grid, kEvalThreads, smem, w->stream>>>(store_ref(c), d_prog, n_ops, depth, (const int2*)w->d_aux.p, (int)batches.size(), d_shards, n_units, out);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
@@ -656,7 +737,7 @@ extern "C" int fbgpu_count(fbgpu_ctx* c, uint32_t index, const fbgpu_op* ops, in
             CUDA_TRY(cudaGetLastError());
         } else {
             EvalOut eo{ d_total, d_per, nullptr, nullptr };
-            rc = launch_eval(c, w, d_prog, (int)prog.size(), depth, d_shards, n_units, eo); if (rc) return rc;
+            rc = launch_eval(c, w, prog, d_prog, depth, d_shards, n_units, eo); if (rc) return rc;
         }
     }
     CUDA_TRY(cudaEventRecord(w->ev1, w->stream));
@@ -699,7 +780,7 @@ extern "C" int fbgpu_row(fbgpu_ctx* c, uint32_t index, const fbgpu_op* ops, int3
         if (w->h_out.ensure((size_t)nu * 8)) return FBGPU_E_NOMEM;
         EvalOut eo{ nullptr, nullptr, (uint4*)w->d_bitmaps.p, (uint2*)w->d_info.p };
         CUDA_TRY(cudaEventRecord(w->ev0, w->stream));
-        rc = launch_eval(c, w, d_prog, (int)prog.size(), depth, d_shards + u0 / kSlotsPerRow, nu, eo); if (rc) return rc;
+        rc = launch_eval(c, w, prog, d_prog, depth, d_shards + u0 / kSlotsPerRow, nu, eo); if (rc) return rc;
         launches++;
         CUDA_TRY(cudaMemcpyAsync(w->h_out.p, w->d_info.p, (size_t)nu * 8, cudaMemcpyDeviceToHost, w->stream));
         CUDA_TRY(cudaStreamSynchronize(w->stream));
@@ -759,7 +840,7 @@ extern "C" int fbgpu_row(fbgpu_ctx* c, uint32_t index, const fbgpu_op* ops, int3
 static int eval_filter_batch(fbgpu_ctx* c, Workspace* w, const std::vector<DevOp>& prog, int depth, const DevOp* d_prog, const uint64_t* d_shards, int64_t ns) {
     if (w->d_bitmaps.ensure((size_t)ns * kSlotsPerRow * 8192)) return FBGPU_E_NOMEM;
     EvalOut eo{ nullptr, nullptr, (uint4*)w->d_bitmaps.p, nullptr };
-    return launch_eval(c, w, d_prog, (int)prog.size(), depth, d_shards, ns * kSlotsPerRow, eo);
+    return launch_eval(c, w, prog, d_prog, depth, d_shards, ns * kSlotsPerRow, eo);
 }
 
 static int row_counts_impl(fbgpu_ctx* c, uint32_t index, uint32_t fv, const std::vector<uint64_t>& rows, const fbgpu_op* filter, int32_t n_filter_ops,

@@ -8,6 +8,8 @@
 //   frags[f]                       fragment                 -> slice of rows[] (sorted by row id)
 //   rows[frag.row_off + k]         row of a fragment        -> first descriptor + 16-bit slot-presence mask
 //   descs[row.first_desc + rank]   container                -> payload offset, cardinality, encoding
+//   rowtab[view.rt_off + shard*R + (row-rmin)]  dense (shard,row) directory when a view's row ids are dense:
+//                                  shortens the chain to views -> rowtab -> descs (3 dependent loads)
 //   payload[]                      array: u16[n] (16 B aligned) | bitmap: u64[1024] (128 B aligned) |
 //                                  run: {u16 start,u16 last}[r] (16 B aligned)
 //
@@ -48,9 +50,19 @@ struct FragHdr {       // 32 B
     uint64_t pad2;
 };
 
-struct ViewTab {       // 8 B
+struct ViewTab {       // 32 B
     uint32_t shard_off; // into shardmap[]
     uint32_t n_shards;  // shardmap slice covers shards [0, n_shards)
+    uint32_t rt_rows;   // != 0: dense row table present, covering row ids [rmin, rmin + rt_rows)
+    uint32_t pad;
+    uint64_t rt_off;    // into rowtab[]: entry (shard, row) at rt_off + shard * rt_rows + (row - rmin)
+    uint64_t rmin;
+};
+
+struct RowTabEnt {     // 8 B: the (shard,row) directory entry of the dense row table (mask == 0 => row absent in that shard)
+    uint32_t first_desc;
+    uint16_t mask;
+    uint16_t pad;
 };
 
 struct StoreRef {      // passed to kernels by value
@@ -60,6 +72,7 @@ struct StoreRef {      // passed to kernels by value
     const RowEnt* rows;
     const ContDesc* descs;
     const uint8_t* payload;
+    const RowTabEnt* rowtab;
     uint32_t n_views;
 };
 

@@ -19,7 +19,7 @@ namespace fbgpu {
 #define FBGPU_EVAL_THREADS 256
 #endif
 #ifndef FBGPU_EVAL_MIN_BLOCKS
-#define FBGPU_EVAL_MIN_BLOCKS 7
+#define FBGPU_EVAL_MIN_BLOCKS 8
 #endif
 #ifndef FBGPU_BATCH_UNROLL
 #define FBGPU_BATCH_UNROLL 4
@@ -27,7 +27,7 @@ namespace fbgpu {
 constexpr int kEvalThreads = FBGPU_EVAL_THREADS;          // 256 or 512
 constexpr int kEvalU4PerThread = 512 / kEvalThreads;       // uint4 per thread of an 8 KiB bitmap
 constexpr int kEvalW64PerThread = 1024 / kEvalThreads;     // consecutive u64 words per thread in scans
-constexpr int kResolveChunk = 256;
+constexpr int kResolveChunk = 128;
 
 __device__ __forceinline__ uint4 ldg_nc(const uint4* p) {
     uint4 r;
@@ -46,6 +46,14 @@ __device__ __forceinline__ Resolved resolve(const StoreRef& st, uint32_t fv, uin
     if (fv >= st.n_views) return r;
     ViewTab v = st.views[fv];
     if (shard >= v.n_shards) return r;
+    if (v.rt_rows) {                                  // dense (shard,row) directory: views -> rowtab -> descs
+        if (row < v.rmin || row - v.rmin >= v.rt_rows) return r;
+        RowTabEnt e = st.rowtab[v.rt_off + shard * v.rt_rows + (row - v.rmin)];
+        if (!((e.mask >> slot) & 1)) return r;
+        ContDesc d = st.descs[e.first_desc + __popc(e.mask & ((1u << slot) - 1u))];
+        r.ptr = st.payload + (size_t)d.off16 * 16; r.card = d.card; r.typ = d.typ; r.cnt = d.cnt;
+        return r;
+    }
     int f = st.shardmap[v.shard_off + shard];
     if (f < 0) return r;
     FragHdr h = st.frags[f];
@@ -336,6 +344,34 @@ __device__ __forceinline__ void batch_rows_v3(uint32_t* T32, const Resolved* res
         rc = rn; j += NW;
     }
 }
+// v1p: one warp per operand like v1, but flattened over (operand, 512-byte slab) with the next slab's 16-byte load
+// issued before the current slab is scattered, so a warp always has a load in flight while it works shared memory.
+template <int MODE>
+__device__ __forceinline__ void batch_rows_v1p(uint32_t* T32, const Resolved* res, int n) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    constexpr int NW = kEvalThreads / 32;
+    // advance (j, q) to the next array slab owned by this warp; returns false at the end
+    auto first_array = [&](int j) { while (j < n && !(res[j].ptr != nullptr && res[j].typ == kArray)) j += NW; return j; };
+    int j = first_array(wid);
+    uint32_t q = 0;
+    uint4 cur = make_uint4(0, 0, 0, 0), nxt = make_uint4(0, 0, 0, 0);
+    Resolved r; r.ptr = nullptr; r.card = 0; r.typ = 0; r.cnt = 0;
+    if (j < n) { r = res[j]; if (lane < ((r.card + 7) >> 3)) cur = ldg_nc(reinterpret_cast<const uint4*>(r.ptr) + lane); }
+    while (j < n) {
+        const uint32_t n8 = (r.card + 7) >> 3;
+        // next slab
+        int j2 = j; uint32_t q2 = q + 1; Resolved r2 = r;
+        if (q2 * 32 >= n8) { j2 = first_array(j + NW); q2 = 0; if (j2 < n) r2 = res[j2]; }
+        if (j2 < n) { const uint32_t i2 = q2 * 32 + lane; if (i2 < ((r2.card + 7) >> 3)) nxt = ldg_nc(reinterpret_cast<const uint4*>(r2.ptr) + i2); }
+        const uint32_t i = q * 32 + lane;
+        if (i < n8) scatter_chunk_unrolled<MODE>(T32, cur, i * 8, r.card);
+        cur = nxt; j = j2; q = q2; r = r2;
+    }
+    for (int k = wid; k < n; k += NW) {       // bitmap operands of the batch (rare): word atomics
+        const Resolved b = res[k];
+        if (b.ptr != nullptr && b.typ == kBitmap) warp_bitmap_atomic<MODE>(T32, reinterpret_cast<const uint4*>(b.ptr), lane);
+    }
+}
 #ifndef FBGPU_BATCH_IMPL
 #define FBGPU_BATCH_IMPL 1
 #endif
@@ -343,6 +379,8 @@ template <int MODE>
 __device__ __noinline__ void batch_rows_dispatch(uint32_t* T32, const Resolved* res, int n) {
 #if FBGPU_BATCH_IMPL == 1
     batch_rows_v1<MODE>(T32, res, n);
+#elif FBGPU_BATCH_IMPL == 4
+    batch_rows_v1p<MODE>(T32, res, n);
 #elif FBGPU_BATCH_IMPL == 2
     batch_rows<MODE>(T32, res, n);
 #else
@@ -360,6 +398,7 @@ struct EvalOut {
 // One CTA per (shard, slot) unit, persistent over units.  Dynamic smem: (depth+1) x 8 KiB.
 __global__ void __launch_bounds__(kEvalThreads, FBGPU_EVAL_MIN_BLOCKS)
 eval_kernel(StoreRef st, const DevOp* __restrict__ prog, int n_ops, int depth,
+            const int2* __restrict__ batches, int n_batches,
             const uint64_t* __restrict__ shards, long long n_units, EvalOut out) {
     extern __shared__ uint4 smem4[];
     __shared__ Resolved res[kResolveChunk];
@@ -380,16 +419,19 @@ eval_kernel(StoreRef st, const DevOp* __restrict__ prog, int n_ops, int depth,
             map &= ~((15ull << (4 * a)) | (15ull << (4 * b)));
             map |= (pb << (4 * a)) | (pa << (4 * b));
         };
+        int cur_batch = 0;
         for (int base = 0; base < n_ops; base += kResolveChunk) {
             int chunk = min(kResolveChunk, n_ops - base);
             __syncthreads();
+            bool is_run = false;
             if (tid < chunk) {
                 DevOp op = prog[base + tid];
                 Resolved r; r.ptr = nullptr; r.card = 0; r.typ = 0; r.cnt = 0;
                 if (op.op >= D_PUSH_ROW && op.op <= D_ORANDNOT_ROW && op.op != D_PUSH_EMPTY) r = resolve(st, op.fv, shard, op.row, slot);
                 res[tid] = r;
+                is_run = r.ptr != nullptr && r.typ == kRun;
             }
-            __syncthreads();
+            const int has_runs = __syncthreads_or(is_run);
             for (int k = 0; k < chunk; k++) {
                 const uint8_t opc = prog[base + k].op;
                 if (opc == D_PUSH_EMPTY) { top++; bm_zero(phys(top)); __syncthreads(); continue; }
@@ -401,16 +443,16 @@ eval_kernel(StoreRef st, const DevOp* __restrict__ prog, int n_ops, int depth,
                     top--; __syncthreads(); continue;
                 }
                 if (opc == D_OR_ROW || opc == D_ANDNOT_ROW || opc == D_XOR_ROW) {
-                    // maximal run of the same commuting row op inside this chunk
-                    int e = k + 1;
-                    while (e < chunk && prog[base + e].op == opc) e++;
+                    // extent of this batch (host-computed runs of the same commuting row op), clipped to the chunk
+                    while (cur_batch < n_batches && batches[cur_batch].y <= base + k) cur_batch++;
+                    const int e = min(cur_batch < n_batches ? batches[cur_batch].y - base : k + 1, chunk);
                     uint4* T = phys(top);
                     uint32_t* T32 = reinterpret_cast<uint32_t*>(T);
                     if (opc == D_OR_ROW) batch_rows_dispatch<0>(T32, res + k, e - k);
                     else if (opc == D_ANDNOT_ROW) batch_rows_dispatch<1>(T32, res + k, e - k);
                     else batch_rows_dispatch<2>(T32, res + k, e - k);
                     __syncthreads();
-                    for (int j = k; j < e; j++) {          // run containers: CTA-wide expansion, one at a time
+                    if (has_runs) for (int j = k; j < e; j++) {   // run containers: CTA-wide expansion, one at a time
                         const Resolved r = res[j];
                         if (r.ptr == nullptr || r.typ != kRun) continue;
                         uint4* S = phys(depth);
@@ -510,6 +552,388 @@ eval_kernel(StoreRef st, const DevOp* __restrict__ prog, int n_ops, int depth,
 }
 
 // ------------------------------------------------------------------------------------------------
+// eval_staged_kernel: same program machine as eval_kernel, but the operands of every batch (run of commuting
+// OR/ANDNOT/XOR row ops) are first copied into a two-stage shared-memory ring by the TMA engine
+// (cp.async.bulk global->shared, one bulk copy per container, completion on an mbarrier) while the previous
+// sub-batch is being scattered, and the next unit's descriptor chains are walked while the current unit runs.
+// The scatter therefore reads its operands from shared memory and never waits on HBM latency; the only steady
+// state limiter left is shared-memory atomic throughput.
+// ------------------------------------------------------------------------------------------------
+constexpr int kStageOps = 32;          // operands per sub-batch (one bulk copy per lane of warp 0)
+constexpr int kStagedMaxOps = 128;     // programs longer than this use eval_kernel
+
+struct SubBatch { int seq, b, o0, n; uint32_t total, pad; uint32_t off[kStageOps]; uint32_t bytes[kStageOps]; };
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory"); }
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <int MODE>
+__device__ __forceinline__ void stage_scatter(uint32_t* T32, const uint8_t* stage, const SubBatch& S, const Resolved* R) {
+    const int tid = threadIdx.x, n = S.n;
+    int G = kEvalThreads / max(n, 1);
+    G = G >= 32 ? 32 : G <= 1 ? 1 : (1 << (31 - __clz(G)));
+    const int groups = kEvalThreads / G, g = tid & (G - 1);
+    for (int j = tid / G; j < n; j += groups) {
+        const uint32_t sz = S.bytes[j];
+        if (!sz) continue;
+        const Resolved r = R[S.o0 + j];
+        const uint4* src = reinterpret_cast<const uint4*>(stage + S.off[j]);
+        if (r.typ == kArray) {
+            const uint32_t n8 = sz >> 4;
+            for (uint32_t i = g; i < n8; i += G) scatter_chunk_unrolled<MODE>(T32, src[i], i * 8, r.card);
+        } else {
+            for (int i = g; i < 512; i += G) {
+                uint4 v = src[i];
+                uint32_t w[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    if (!w[c]) continue;
+                    uint32_t* dst = &T32[4 * i + c];
+                    if (MODE == 0) atomicOr(dst, w[c]); else if (MODE == 1) atomicAnd(dst, ~w[c]); else atomicXor(dst, w[c]);
+                }
+            }
+        }
+    }
+}
+
+#ifndef FBGPU_STAGED_MIN_BLOCKS
+#define FBGPU_STAGED_MIN_BLOCKS 2
+#endif
+__global__ void __launch_bounds__(kEvalThreads, FBGPU_STAGED_MIN_BLOCKS)
+eval_staged_kernel(StoreRef st, const DevOp* __restrict__ prog, int n_ops, int depth,
+                   const int2* __restrict__ batches, int n_batches, uint32_t stg_bytes,
+                   const uint64_t* __restrict__ shards, long long n_units, EvalOut out) {
+    extern __shared__ uint4 smem4[];
+    __shared__ Resolved res2[2][kStagedMaxOps];
+    __shared__ SubBatch sb[2];
+    __shared__ __align__(8) uint64_t mbar[2];
+    __shared__ int it_seq, it_b, it_o, s_ni;
+    __shared__ uint32_t warp_tmp[kEvalThreads / 32], warp_tmp2[kEvalThreads / 32];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    uint8_t* stage0 = reinterpret_cast<uint8_t*>(smem4 + (size_t)(depth + 1) * 512);
+    const long long n_seq = (n_units - blockIdx.x + gridDim.x - 1) / gridDim.x;   // units of this CTA: blockIdx.x + seq*gridDim.x
+    if (n_seq <= 0) return;
+    if (tid == 0) { mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); it_seq = 0; it_b = 0; it_o = n_batches ? batches[0].x : 0; s_ni = 0; asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    int nc = 0;                       // sub-batches consumed so far (uniform)
+    unsigned long long cta_total = 0;
+
+    auto resolve_unit = [&](long long seq) {
+        if (tid < n_ops) {
+            const long long unit = blockIdx.x + seq * gridDim.x;
+            DevOp op = prog[tid];
+            Resolved r; r.ptr = nullptr; r.card = 0; r.typ = 0; r.cnt = 0;
+            if (op.op >= D_PUSH_ROW && op.op <= D_ORANDNOT_ROW && op.op != D_PUSH_EMPTY) r = resolve(st, op.fv, shards[unit >> 4], op.row, (int)(unit & 15));
+            res2[seq & 1][tid] = r;
+        }
+    };
+    // warp 0: issue sub-batches while a stage is free and descriptors are available (units < avail).
+    // Lane j sizes operand o+j; a warp scan gives the packed stage offsets; one bulk copy per operand.
+    auto pump = [&](long long avail) {
+        for (;;) {
+            const int ni = s_ni;
+            if (ni - nc >= 2) break;
+            const int buf = ni & 1;
+            int seq = it_seq, b = it_b, o = it_o;       // uniform across the warp (read after __syncwarp below)
+            bool found = false;
+            while (seq < avail) {
+                if (b >= n_batches) { seq++; b = 0; o = n_batches ? batches[0].x : 0; continue; }
+                const int2 bt = batches[b];
+                if (o >= bt.y) { b++; if (b < n_batches) o = batches[b].x; continue; }
+                const Resolved* R = res2[seq & 1];
+                const bool in_range = o + lane < bt.y;
+                Resolved r; r.ptr = nullptr; r.card = 0; r.typ = 0; r.cnt = 0;
+                if (in_range) r = R[o + lane];
+                const uint32_t sz = !r.ptr ? 0u : r.typ == kArray ? ((r.card + 7) >> 3) * 16u : r.typ == kBitmap ? 8192u : 0u;
+                uint32_t incl = sz;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { uint32_t x = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += x; }
+                const unsigned bad = __ballot_sync(0xffffffffu, !in_range || (incl > stg_bytes && lane > 0));
+                const int n = bad ? __ffs(bad) - 1 : 32;        // operands taken by this sub-batch (>= 1)
+                const uint32_t total = __shfl_sync(0xffffffffu, incl, n - 1);
+                if (total == 0) { o += n; continue; }            // nothing stageable (absent / run operands)
+                SubBatch& S = sb[buf];
+                if (lane < n) { S.off[lane] = incl - sz; S.bytes[lane] = sz; }
+                if (lane == 0) { S.seq = seq; S.b = b; S.o0 = o; S.n = n; S.total = total; mbar_expect_tx(&mbar[buf], total); }
+                __syncwarp();
+                if (lane < n && sz) tma_bulk_g2s(stage0 + (size_t)buf * stg_bytes + (incl - sz), r.ptr, sz, &mbar[buf]);
+                o += n;
+                found = true;
+                break;
+            }
+            if (lane == 0) { it_seq = seq; it_b = b; it_o = o; if (found) s_ni = ni + 1; }
+            __syncwarp();
+            if (!found) break;
+        }
+    };
+
+    resolve_unit(0);
+    int runs_cur = __syncthreads_or(tid < n_ops && res2[0][tid].typ == kRun && res2[0][tid].ptr != nullptr), runs_next = 0;
+
+    for (long long seq = 0; seq < n_seq; seq++) {
+        const long long unit = blockIdx.x + seq * gridDim.x;
+        const Resolved* res = res2[seq & 1];
+        // descriptors of the next unit are resolved now (the chains overlap with the bulk copies already in flight)
+        if (seq + 1 < n_seq) resolve_unit(seq + 1);
+        runs_next = __syncthreads_or(seq + 1 < n_seq && tid < n_ops && res2[(seq + 1) & 1][tid].typ == kRun && res2[(seq + 1) & 1][tid].ptr != nullptr);
+        const long long avail = min(n_seq, seq + 2);
+        if (wid == 0) pump(avail);
+        uint64_t map = 0xFEDCBA9876543210ull;
+        int top = -1;
+        auto phys = [&](int level) -> uint4* { return smem4 + (size_t)((map >> (4 * level)) & 15u) * 512; };
+        auto swap_levels = [&](int a, int b) {
+            uint64_t pa = (map >> (4 * a)) & 15u, pb = (map >> (4 * b)) & 15u;
+            map &= ~((15ull << (4 * a)) | (15ull << (4 * b)));
+            map |= (pb << (4 * a)) | (pa << (4 * b));
+        };
+        int cur_batch = 0;
+        for (int k = 0; k < n_ops; k++) {
+            const uint8_t opc = prog[k].op;
+            if (opc == D_PUSH_EMPTY) { top++; bm_zero(phys(top)); __syncthreads(); continue; }
+            if (opc == D_SWAP) { swap_levels(top, top - 1); continue; }
+            if (opc == D_POP) { top--; continue; }
+            if (opc >= D_AND && opc <= D_XOR) {
+                int kind = opc == D_AND ? K_AND : opc == D_OR ? K_OR : opc == D_ANDNOT ? K_ANDNOT : K_XOR;
+                bm_apply_smem(kind, phys(top - 1), nullptr, phys(top));
+                top--; __syncthreads(); continue;
+            }
+            if (opc == D_OR_ROW || opc == D_ANDNOT_ROW || opc == D_XOR_ROW) {
+                // this op starts batch `cur_batch` = ops [k, e)
+                const int e = batches[cur_batch].y;
+                uint4* T = phys(top);
+                uint32_t* T32 = reinterpret_cast<uint32_t*>(T);
+                for (;;) {
+                    __syncthreads();                                   // stage info / s_ni written by warp 0 are visible; previous scatter done
+                    const int ni = s_ni;
+                    if (nc >= ni) break;
+                    const int buf = nc & 1;
+                    if (sb[buf].seq != (int)seq || sb[buf].b != cur_batch) break;
+                    if (wid == 0) pump(avail);                         // keep the other stage busy
+                    const uint32_t parity = (uint32_t)(nc >> 1) & 1u;
+                    while (!mbar_try_wait(&mbar[buf], parity)) { }
+                    const uint8_t* stg = stage0 + (size_t)buf * stg_bytes;
+                    if (opc == D_OR_ROW) stage_scatter<0>(T32, stg, sb[buf], res);
+                    else if (opc == D_ANDNOT_ROW) stage_scatter<1>(T32, stg, sb[buf], res);
+                    else stage_scatter<2>(T32, stg, sb[buf], res);
+                    nc++;
+                }
+                if (runs_cur) for (int j = k; j < e; j++) {            // run containers: CTA-wide expansion, one at a time
+                    const Resolved r = res[j];
+                    if (r.ptr == nullptr || r.typ != kRun) continue;
+                    uint4* S = phys(depth);
+                    bm_expand_runs(S, reinterpret_cast<const uint16_t*>(r.ptr), r.cnt, warp_tmp);
+                    bm_apply_smem(opc == D_OR_ROW ? K_OR : opc == D_ANDNOT_ROW ? K_ANDNOT : K_XOR, T, nullptr, S);
+                    __syncthreads();
+                }
+                cur_batch++;
+                k = e - 1;
+                continue;
+            }
+            // single row-operand ops (PUSH_ROW, AND_ROW, ORAND_ROW, ORANDNOT_ROW)
+            int kind = opc == D_PUSH_ROW ? K_PUSH : opc == D_AND_ROW ? K_AND : opc == D_ORAND_ROW ? K_ORAND : K_ORANDNOT;
+            const Resolved r = res[k];
+            if (kind == K_PUSH) top++;
+            uint4* T = phys(top);
+            uint4* B = (kind == K_ORAND || kind == K_ORANDNOT) ? phys(top - 1) : nullptr;
+            if (r.ptr == nullptr) {
+                if (kind == K_PUSH || kind == K_AND) bm_zero(T);
+                else if (kind == K_ORANDNOT) bm_apply_smem(K_OR, B, nullptr, T);
+                __syncthreads();
+            } else if (r.typ == kBitmap) {
+                bm_apply_global(kind, T, B, reinterpret_cast<const uint4*>(r.ptr));
+                __syncthreads();
+            } else if (r.typ == kArray) {
+                const uint16_t* arr = reinterpret_cast<const uint16_t*>(r.ptr);
+                uint32_t* T32 = reinterpret_cast<uint32_t*>(T);
+                if (kind == K_PUSH) { bm_zero(T); __syncthreads(); bm_scatter<0>(T32, arr, r.card); }
+                else if (kind == K_ORAND) bm_filter_scatter(reinterpret_cast<uint32_t*>(B), T32, arr, r.card);
+                else if (kind == K_AND) {
+                    uint4* S = phys(depth);
+                    bm_zero(S); __syncthreads();
+                    bm_filter_scatter(reinterpret_cast<uint32_t*>(S), T32, arr, r.card);
+                    swap_levels(top, depth);
+                } else {
+                    uint4* S = phys(depth);
+                    bm_zero(S); __syncthreads();
+                    bm_scatter<0>(reinterpret_cast<uint32_t*>(S), arr, r.card); __syncthreads();
+                    bm_apply_smem(K_ORANDNOT, T, B, S);
+                }
+                __syncthreads();
+            } else {
+                const uint16_t* runs = reinterpret_cast<const uint16_t*>(r.ptr);
+                if (kind == K_PUSH) bm_expand_runs(T, runs, r.cnt, warp_tmp);
+                else {
+                    uint4* S = phys(depth);
+                    bm_expand_runs(S, runs, r.cnt, warp_tmp);
+                    bm_apply_smem(kind, T, B, S);
+                    __syncthreads();
+                }
+            }
+        }
+        // ---- unit epilogue (same as eval_kernel)
+        uint32_t cnt = 0, nruns = 0;
+        if (top >= 0) {
+            const uint4* R = phys(top);
+            const uint64_t* R64 = reinterpret_cast<const uint64_t*>(R);
+#pragma unroll
+            for (int h = 0; h < kEvalU4PerThread; h++) {
+                int i = tid + h * kEvalThreads;
+                uint4 a = R[i];
+                cnt += popc4(a);
+                if (out.bitmaps) out.bitmaps[(size_t)unit * 512 + i] = a;
+                if (out.info) {
+#pragma unroll
+                    for (int q = 0; q < 2; q++) {
+                        int wi = 2 * i + q;
+                        uint64_t v = R64[wi];
+                        uint64_t prev = wi ? (R64[wi - 1] >> 63) : 0ull;
+                        nruns += __popcll(v & ~((v << 1) | prev));
+                    }
+                }
+            }
+        } else if (out.bitmaps) {
+#pragma unroll
+            for (int h = 0; h < kEvalU4PerThread; h++) out.bitmaps[(size_t)unit * 512 + tid + h * kEvalThreads] = make_uint4(0, 0, 0, 0);
+        }
+        cnt = __reduce_add_sync(0xffffffffu, cnt);
+        nruns = __reduce_add_sync(0xffffffffu, nruns);
+        __syncthreads();
+        if (lane == 0) { warp_tmp[wid] = cnt; warp_tmp2[wid] = nruns; }
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t c = 0, rr = 0;
+#pragma unroll
+            for (int q = 0; q < kEvalThreads / 32; q++) { c += warp_tmp[q]; rr += warp_tmp2[q]; }
+            cta_total += c;
+            if (out.per_shard && c) atomicAdd(&out.per_shard[unit >> 4], (unsigned long long)c);
+            if (out.info) out.info[unit] = make_uint2(c, rr);
+        }
+        runs_cur = runs_next;
+        __syncthreads();
+    }
+    if (tid == 0 && out.total && cta_total) atomicAdd(out.total, cta_total);
+}
+
+// ------------------------------------------------------------------------------------------------
+// eval_wordpar_kernel: word-parallel evaluation for bitmap-heavy programs (BSI plane sweeps, dense rows).
+// Every thread owns ONE 128-bit slice (uint4) of a (shard, slot) stripe and runs the whole program on it with the
+// operand stack in registers: no shared-memory bitmaps, no barriers between ops, and the operands of the next three
+// row ops are already in flight (register prefetch ring) while the current op is applied.  Arrays and runs are
+// handled by a per-thread search for the slice's elements, so any program is valid here; the host only picks this
+// kernel when the referenced views are dominated by bitmap/run containers.
+// ------------------------------------------------------------------------------------------------
+constexpr int kWpThreads = 128;              // 4 CTAs per unit (512 128-bit slices)
+constexpr int kWpMaxOps = 256;
+constexpr int kWpMaxDepth = 4;
+
+__device__ __forceinline__ uint4 wp_slice(const Resolved& r, int i) {
+    if (r.ptr == nullptr) return make_uint4(0, 0, 0, 0);
+    if (r.typ == kBitmap) return ldg_nc(reinterpret_cast<const uint4*>(r.ptr) + i);
+    const uint32_t lo = (uint32_t)i * 128u, hi = lo + 127u;       // value range of this slice
+    uint32_t w[4] = { 0, 0, 0, 0 };
+    if (r.typ == kArray) {
+        const uint16_t* a = reinterpret_cast<const uint16_t*>(r.ptr);
+        uint32_t l = 0, h = r.card;
+        while (l < h) { uint32_t m = (l + h) >> 1; if (__ldg(a + m) < lo) l = m + 1; else h = m; }
+        for (; l < r.card; l++) { uint32_t v = __ldg(a + l); if (v > hi) break; v -= lo; w[v >> 5] |= 1u << (v & 31); }
+    } else {
+        const uint32_t* rr = reinterpret_cast<const uint32_t*>(r.ptr);
+        uint32_t l = 0, h = r.cnt;                                  // first run with last >= lo
+        while (l < h) { uint32_t m = (l + h) >> 1; if ((__ldg(rr + m) >> 16) < lo) l = m + 1; else h = m; }
+        for (; l < r.cnt; l++) {
+            uint32_t v = __ldg(rr + l); uint32_t s0 = v & 0xffffu, l0 = v >> 16;
+            if (s0 > hi) break;
+            uint32_t a0 = max(s0, lo) - lo, b0 = min(l0, hi) - lo;  // inclusive bit range inside the slice
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                uint32_t qa = q * 32, qb = qa + 31;
+                if (b0 < qa || a0 > qb) continue;
+                uint32_t x = max(a0, qa) - qa, y = min(b0, qb) - qa;
+                w[q] |= (0xffffffffu << x) & (0xffffffffu >> (31 - y));
+            }
+        }
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+__global__ void __launch_bounds__(kWpThreads)
+eval_wordpar_kernel(StoreRef st, const DevOp* __restrict__ prog, int n_ops,
+                    const uint64_t* __restrict__ shards, long long n_units, EvalOut out) {
+    __shared__ Resolved res[kWpMaxOps];
+    __shared__ uint8_t opcode[kWpMaxOps];      // bit 7: row op
+    __shared__ uint32_t wsum[kWpThreads / 32];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const long long n_blocks = n_units * 4;
+    for (long long blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
+        const long long unit = blk >> 2;
+        const int i = (int)(blk & 3) * kWpThreads + tid;             // uint4 index inside the stripe
+        __syncthreads();
+        for (int k = tid; k < n_ops; k += kWpThreads) {
+            DevOp op = prog[k];
+            Resolved r; r.ptr = nullptr; r.card = 0; r.typ = 0; r.cnt = 0;
+            const bool row_op = op.op >= D_PUSH_ROW && op.op <= D_ORANDNOT_ROW && op.op != D_PUSH_EMPTY;
+            if (row_op) r = resolve(st, op.fv, shards[unit >> 4], op.row, (int)(unit & 15));
+            res[k] = r; opcode[k] = op.op | (row_op ? 0x80 : 0);
+        }
+        __syncthreads();
+        auto next_row_op = [&](int k) { while (k < n_ops && !(opcode[k] & 0x80)) k++; return k; };
+        // prefetch ring: operands of the next three row ops are in flight while the current one is applied
+        const uint4 z = make_uint4(0, 0, 0, 0);
+        uint4 p0 = z, p1 = z, p2 = z;
+        int kk = next_row_op(0);
+        if (kk < n_ops) { p0 = wp_slice(res[kk], i); kk = next_row_op(kk + 1); }
+        if (kk < n_ops) { p1 = wp_slice(res[kk], i); kk = next_row_op(kk + 1); }
+        if (kk < n_ops) { p2 = wp_slice(res[kk], i); kk = next_row_op(kk + 1); }
+        // operand stack as a shift register: T = top, B = below, S2, S3 deeper (depth <= 4 checked by the host)
+        uint4 T = z, B = z, S2 = z, S3 = z;
+        int depth_now = 0;
+        for (int k = 0; k < n_ops; k++) {
+            const uint8_t oc = opcode[k];
+            const uint8_t opc = oc & 0x7f;
+            if (!(oc & 0x80)) {
+                if (opc == D_PUSH_EMPTY) { S3 = S2; S2 = B; B = T; T = z; depth_now++; }
+                else if (opc == D_SWAP) { uint4 t = T; T = B; B = t; }
+                else if (opc == D_POP) { T = B; B = S2; S2 = S3; depth_now--; }
+                else { T = opc == D_AND ? and4(B, T) : opc == D_OR ? or4(B, T) : opc == D_ANDNOT ? andn4(B, T) : xor4(B, T); B = S2; S2 = S3; depth_now--; }
+                continue;
+            }
+            const uint4 x = p0;
+            p0 = p1; p1 = p2; p2 = z;
+            if (kk < n_ops) { p2 = wp_slice(res[kk], i); kk = next_row_op(kk + 1); }
+            switch (opc) {
+                case D_PUSH_ROW: S3 = S2; S2 = B; B = T; T = x; depth_now++; break;
+                case D_OR_ROW: T = or4(T, x); break;
+                case D_AND_ROW: T = and4(T, x); break;
+                case D_ANDNOT_ROW: T = andn4(T, x); break;
+                case D_XOR_ROW: T = xor4(T, x); break;
+                case D_ORAND_ROW: B = or4(B, and4(T, x)); break;
+                default: B = or4(B, andn4(T, x)); break;             // D_ORANDNOT_ROW
+            }
+        }
+        const uint4 rsl = depth_now > 0 ? T : z;
+        if (out.bitmaps) out.bitmaps[(size_t)unit * 512 + i] = rsl;
+        uint32_t cnt = __reduce_add_sync(0xffffffffu, (uint32_t)popc4(rsl));
+        if (lane == 0) wsum[wid] = cnt;
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t c = 0;
+#pragma unroll
+            for (int q = 0; q < kWpThreads / 32; q++) c += wsum[q];
+            if (c) { if (out.total) atomicAdd(out.total, (unsigned long long)c); if (out.per_shard) atomicAdd(&out.per_shard[unit >> 4], (unsigned long long)c); }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Warp-level intersection count of two located containers; `bm` is the warp's private 8 KiB smem bitmap.
 // Follows the dispatch of intersectionCount (roaring.go:4477-4512) incl. the full/empty short-circuits.
 // ------------------------------------------------------------------------------------------------
@@ -535,38 +959,23 @@ __device__ __forceinline__ uint32_t warp_probe_smem(const uint32_t* bm, const ui
     }
     return c;
 }
-// per-lane partial count of array elements found in a global-memory bitmap
+// per-lane partial count of array elements found in a global-memory bitmap: 16-byte element loads, then the eight
+// word probes of a chunk are issued back to back (independent loads in flight)
 __device__ __forceinline__ uint32_t warp_probe_global(const uint32_t* g, const uint16_t* arr, uint32_t n, int lane) {
+    const uint4* a4 = reinterpret_cast<const uint4*>(arr);
+    const uint32_t n8 = (n + 7) >> 3;
     uint32_t c = 0;
-    for (uint32_t i = lane; i < n; i += 32) { uint32_t v = __ldg(arr + i); c += (__ldg(g + (v >> 5)) >> (v & 31)) & 1u; }
+    for (uint32_t i = lane; i < n8; i += 32) {
+        uint4 v = ldg_nc(a4 + i);
+        uint32_t e[8] = { v.x & 0xffffu, v.x >> 16, v.y & 0xffffu, v.y >> 16, v.z & 0xffffu, v.z >> 16, v.w & 0xffffu, v.w >> 16 };
+        uint32_t w[8];
+        const uint32_t base = i * 8;
+#pragma unroll
+        for (int q = 0; q < 8; q++) w[q] = (base + q < n) ? __ldg(g + (e[q] >> 5)) : 0u;
+#pragma unroll
+        for (int q = 0; q < 8; q++) c += (w[q] >> (e[q] & 31)) & 1u;
+    }
     return c;
-}
-// warp-private run expansion (delta + prefix-xor over 2048 u32 words; lane owns 64 consecutive words)
-__device__ __forceinline__ void warp_expand_runs(uint32_t* bm, const uint16_t* runs, uint32_t n_runs, int lane) {
-    warp_zero(bm, lane);
-    __syncwarp();
-    const uint32_t* r32 = reinterpret_cast<const uint32_t*>(runs);
-    for (uint32_t i = lane; i < n_runs; i += 32) {
-        uint32_t v = __ldg(r32 + i);
-        uint32_t s = v & 0xffffu, e = (v >> 16) + 1;
-        atomicXor(&bm[s >> 5], 1u << (s & 31));
-        if (e < 65536u) atomicXor(&bm[e >> 5], 1u << (e & 31));
-    }
-    __syncwarp();
-    // pass 1: parity of each lane's 64-word block
-    uint32_t par = 0;
-    for (int k = 0; k < 64; k++) par ^= bm[lane * 64 + k];
-    par = __popc(par) & 1u;
-    unsigned b = __ballot_sync(0xffffffffu, par);
-    uint32_t carry = __popc(b & ((1u << lane) - 1u)) & 1u;
-    for (int k = 0; k < 64; k++) {
-        uint32_t x = bm[lane * 64 + k];
-        x ^= x << 1; x ^= x << 2; x ^= x << 4; x ^= x << 8; x ^= x << 16;
-        if (carry) x = ~x;
-        carry = x >> 31;
-        bm[lane * 64 + k] = x;
-    }
-    __syncwarp();
 }
 // per-lane partial: |bitmap(global) ∩ smem bitmap|
 __device__ __forceinline__ uint32_t warp_and_count_gs(const uint4* g, const uint32_t* bm, int lane) {
@@ -586,45 +995,96 @@ __device__ __forceinline__ uint32_t range_count32(const uint32_t* bm, uint32_t s
     return c;
 }
 
+// pairs with a run container on at least one side (kept out of line so the array / bitmap hot paths keep a small
+// register footprint).  Returns the per-lane partial count.
+__device__ __noinline__ uint32_t warp_icount_runs(Resolved a, Resolved b, int lane) {
+    uint32_t c = 0;
+    if (a.typ == kArray) {                                    // array x run: roaring.go:4537
+        // each lane binary-searches its elements in the interval list (no bitmap expansion: O(n log r))
+        const uint16_t* arr = reinterpret_cast<const uint16_t*>(a.ptr);
+        const uint32_t* r32 = reinterpret_cast<const uint32_t*>(b.ptr);
+        for (uint32_t i = lane; i < a.card; i += 32) {
+            uint32_t v = __ldg(arr + i);
+            uint32_t lo = 0, hi = b.cnt;                      // first run with last >= v
+            while (lo < hi) { uint32_t m = (lo + hi) >> 1; if ((__ldg(r32 + m) >> 16) < v) lo = m + 1; else hi = m; }
+            if (lo < b.cnt) c += ((__ldg(r32 + lo) & 0xffffu) <= v);
+        }
+        return c;
+    }
+    if (a.typ == kRun && b.typ != kRun) { Resolved t = a; a = b; b = t; }   // make `b` the run side
+    if (a.typ == kBitmap) {                                   // bitmap x run: roaring.go:4588 (sum of BitmapCountRange per run)
+        const uint32_t* g = reinterpret_cast<const uint32_t*>(a.ptr);
+        const uint32_t* r32 = reinterpret_cast<const uint32_t*>(b.ptr);
+        if (b.cnt >= 32) {                                    // many short runs: one lane per run, range popcount on global words
+            for (uint32_t i = lane; i < b.cnt; i += 32) { uint32_t v = __ldg(r32 + i); c += range_count32(g, v & 0xffffu, v >> 16); }
+        } else {                                              // few long runs: the warp walks each run's words together
+            for (uint32_t i = 0; i < b.cnt; i++) {
+                uint32_t v = __ldg(r32 + i); uint32_t s0 = v & 0xffffu, l0 = v >> 16;
+                for (uint32_t w = (s0 >> 5) + lane; w <= (l0 >> 5); w += 32) {
+                    uint32_t m = 0xffffffffu;
+                    if (w == (s0 >> 5)) m &= 0xffffffffu << (s0 & 31);
+                    if (w == (l0 >> 5)) m &= 0xffffffffu >> (31 - (l0 & 31));
+                    c += __popc(__ldg(g + w) & m);
+                }
+            }
+        }
+        return c;
+    }
+    // run x run: interval overlap, roaring.go:4555
+    if (a.cnt > b.cnt) { Resolved t = a; a = b; b = t; }
+    const uint32_t* ra = reinterpret_cast<const uint32_t*>(a.ptr);
+    const uint32_t* rb = reinterpret_cast<const uint32_t*>(b.ptr);
+    for (uint32_t i = lane; i < a.cnt; i += 32) {
+        uint32_t v = __ldg(ra + i); uint32_t s0 = v & 0xffffu, l0 = v >> 16;
+        uint32_t lo = 0, hi = b.cnt;                          // first run of b with last >= s0
+        while (lo < hi) { uint32_t m = (lo + hi) >> 1; if ((__ldg(rb + m) >> 16) < s0) lo = m + 1; else hi = m; }
+        for (; lo < b.cnt; lo++) {
+            uint32_t u = __ldg(rb + lo); uint32_t s1 = u & 0xffffu, l1 = u >> 16;
+            if (s1 > l0) break;
+            c += min(l0, l1) - max(s0, s1) + 1;
+        }
+    }
+    return c;
+}
+
 // returns the full count (reduced over the warp, valid in all lanes)
 __device__ __forceinline__ uint32_t warp_intersection_count(Resolved a, Resolved b, uint32_t* bm, int lane) {
     if (a.ptr == nullptr || b.ptr == nullptr) return 0;
     if (a.card == kFull) return b.card;                       // roaring.go:4478-4483
     if (b.card == kFull) return a.card;
-    // order so that typ(a) <= typ(b) in {array, bitmap, run} with arrays first
+    // order so that arrays come first
     if (a.typ != kArray && b.typ == kArray) { Resolved t = a; a = b; b = t; }
     uint32_t c = 0;
-    if (a.typ == kArray && b.typ == kArray) {                 // array x array: build the smaller, probe the larger
+    if (a.typ == kRun || b.typ == kRun) c = warp_icount_runs(a, b, lane);
+    else if (a.typ == kArray && b.typ == kArray) {            // array x array: build the smaller, probe the larger
         if (a.card > b.card) { Resolved t = a; a = b; b = t; }
         warp_zero(bm, lane); __syncwarp();
         warp_scatter_smem(bm, reinterpret_cast<const uint16_t*>(a.ptr), a.card, lane); __syncwarp();
         c = warp_probe_smem(bm, reinterpret_cast<const uint16_t*>(b.ptr), b.card, lane); __syncwarp();
-    } else if (a.typ == kArray && b.typ == kBitmap) {         // roaring.go:4596
+    } else if (a.typ == kArray) {                             // array x bitmap: roaring.go:4596
         c = warp_probe_global(reinterpret_cast<const uint32_t*>(b.ptr), reinterpret_cast<const uint16_t*>(a.ptr), a.card, lane);
-    } else if (a.typ == kArray) {                             // array x run: roaring.go:4537
-        warp_expand_runs(bm, reinterpret_cast<const uint16_t*>(b.ptr), b.cnt, lane);
-        c = warp_probe_smem(bm, reinterpret_cast<const uint16_t*>(a.ptr), a.card, lane); __syncwarp();
-    } else if (a.typ == kBitmap && b.typ == kBitmap) {        // roaring.go:4611
+    } else {                                                  // bitmap x bitmap: roaring.go:4611
         const uint4* x = reinterpret_cast<const uint4*>(a.ptr); const uint4* y = reinterpret_cast<const uint4*>(b.ptr);
 #pragma unroll 4
         for (int i = lane; i < 512; i += 32) c += popc4(and4(ldg_nc(x + i), ldg_nc(y + i)));
-    } else {
-        // one side is a run; make it `b`
-        if (a.typ == kRun && b.typ != kRun) { Resolved t = a; a = b; b = t; }
-        warp_expand_runs(bm, reinterpret_cast<const uint16_t*>(b.ptr), b.cnt, lane);
-        if (a.typ == kBitmap) c = warp_and_count_gs(reinterpret_cast<const uint4*>(a.ptr), bm, lane);   // roaring.go:4588
-        else {                                                // run x run: roaring.go:4555
-            const uint32_t* r32 = reinterpret_cast<const uint32_t*>(a.ptr);
-            for (uint32_t i = lane; i < a.cnt; i += 32) { uint32_t v = __ldg(r32 + i); c += range_count32(bm, v & 0xffffu, v >> 16); }
-        }
-        __syncwarp();
     }
     return __reduce_add_sync(0xffffffffu, c);
 }
 
 constexpr int kPairWarps = 8;
 
-// Count(Intersect(Row(fvA,rowA), Row(fvB,rowB))): one warp per (shard, slot) container pair.
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
+// prefetch a container's payload into L2 (one 128-byte line per lane, strided)
+__device__ __forceinline__ void warp_prefetch_container(const Resolved& r, int lane) {
+    if (r.ptr == nullptr) return;
+    const uint32_t bytes = r.typ == kArray ? r.card * 2u : r.typ == kBitmap ? 8192u : (uint32_t)r.cnt * 4u;
+    const uint8_t* p = reinterpret_cast<const uint8_t*>(r.ptr);
+    for (uint32_t off = lane * 128u; off < bytes; off += 32u * 128u) prefetch_l2(p + off);
+}
+
+// Count(Intersect(Row(fvA,rowA), Row(fvB,rowB))): one warp per (shard, slot) container pair.  A warp owns the units
+// w, w+W, w+2W, ...; it walks the descriptor chains of up to 16 of its units at once (lane 2k / 2k+1 = side a / b of
+// unit k), and while unit k is being intersected the payloads of unit k+1 are already being pulled into L2.
 __global__ void __launch_bounds__(kPairWarps * 32)
 pair_count_kernel(StoreRef st, uint32_t fvA, uint64_t rowA, uint32_t fvB, uint64_t rowB,
                   const uint64_t* __restrict__ shards, long long n_units,
@@ -634,23 +1094,36 @@ pair_count_kernel(StoreRef st, uint32_t fvA, uint64_t rowA, uint32_t fvB, uint64
     uint32_t* bm = smem32 + wid * 2048;
     unsigned long long acc = 0;
     const long long stride = (long long)gridDim.x * kPairWarps;
-    for (long long unit = (long long)blockIdx.x * kPairWarps + wid; unit < n_units; unit += stride) {
-        const uint64_t shard = shards[unit >> 4];
-        const int slot = (int)(unit & 15);
-        // lanes 0 and 1 walk the two descriptor chains concurrently, then broadcast
+    for (long long base = (long long)blockIdx.x * kPairWarps + wid; base < n_units; base += stride * 16) {
+        // resolve up to 16 units of this warp concurrently
+        const long long my_unit = base + (long long)(lane >> 1) * stride;
         Resolved r; r.ptr = nullptr; r.card = 0; r.typ = 0; r.cnt = 0;
-        if (lane == 0) r = resolve(st, fvA, shard, rowA, slot);
-        else if (lane == 1) r = resolve(st, fvB, shard, rowB, slot);
-        Resolved a, b;
-        unsigned long long pa = __shfl_sync(0xffffffffu, (unsigned long long)r.ptr, 0), pb = __shfl_sync(0xffffffffu, (unsigned long long)r.ptr, 1);
-        uint32_t meta = ((uint32_t)r.typ << 16) | r.cnt;
-        a.ptr = (const void*)pa; b.ptr = (const void*)pb;
-        a.card = __shfl_sync(0xffffffffu, r.card, 0); b.card = __shfl_sync(0xffffffffu, r.card, 1);
-        uint32_t ma = __shfl_sync(0xffffffffu, meta, 0), mb = __shfl_sync(0xffffffffu, meta, 1);
-        a.typ = ma >> 16; a.cnt = ma & 0xffff; b.typ = mb >> 16; b.cnt = mb & 0xffff;
-        uint32_t c = warp_intersection_count(a, b, bm, lane);
-        acc += c;
-        if (per_shard && c && lane == 0) atomicAdd(&per_shard[unit >> 4], (unsigned long long)c);
+        if (my_unit < n_units) r = (lane & 1) ? resolve(st, fvB, shards[my_unit >> 4], rowB, (int)(my_unit & 15))
+                                              : resolve(st, fvA, shards[my_unit >> 4], rowA, (int)(my_unit & 15));
+        const uint32_t meta = ((uint32_t)r.typ << 16) | r.cnt;
+        auto fetch = [&](int src) {
+            Resolved x;
+            x.ptr = (const void*)__shfl_sync(0xffffffffu, (unsigned long long)r.ptr, src);
+            x.card = __shfl_sync(0xffffffffu, r.card, src);
+            uint32_t m = __shfl_sync(0xffffffffu, meta, src);
+            x.typ = m >> 16; x.cnt = m & 0xffff;
+            return x;
+        };
+        Resolved a = fetch(0), b = fetch(1);
+        for (int k = 0; k < 16; k++) {
+            const long long unit = base + (long long)k * stride;
+            if (unit >= n_units) break;
+            Resolved na, nb; na.ptr = nullptr; nb.ptr = nullptr; na.card = nb.card = 0; na.typ = nb.typ = 0; na.cnt = nb.cnt = 0;
+            if (k + 1 < 16 && unit + stride < n_units) {
+                na = fetch(2 * k + 2); nb = fetch(2 * k + 3);
+                // small (latency-bound) operands only; bitmap pairs are pure streaming and need no help
+                if (na.ptr != nullptr && nb.ptr != nullptr && (na.typ != kBitmap || nb.typ != kBitmap)) { if (na.typ != kBitmap) warp_prefetch_container(na, lane); if (nb.typ != kBitmap) warp_prefetch_container(nb, lane); }
+            }
+            uint32_t c = warp_intersection_count(a, b, bm, lane);
+            acc += c;
+            if (per_shard && c && lane == 0) atomicAdd(&per_shard[unit >> 4], (unsigned long long)c);
+            a = na; b = nb;
+        }
     }
     if (lane == 0 && total && acc) atomicAdd(total, acc);
 }
@@ -793,6 +1266,21 @@ __device__ __forceinline__ void warp_for_each(const Resolved& c, int lane, F f) 
     }
 }
 
+// block-wide exclusive prefix sum of one uint32 per thread (kGbThreads threads); `tmp` holds one word per warp
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* tmp, uint32_t* total) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { uint32_t x = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += x; }
+    __syncthreads();
+    if (lane == 31) tmp[wid] = inc;
+    __syncthreads();
+    uint32_t base = 0, tot = 0;
+    for (int k = 0; k < kGbThreads / 32; k++) { if (k < wid) base += tmp[k]; tot += tmp[k]; }
+    if (total) *total = tot;
+    return base + inc - v;
+}
+
 __global__ void __launch_bounds__(kGbThreads)
 groupby_kernel(StoreRef st, uint32_t fvA, const uint64_t* __restrict__ rowsA, int nA,
                uint32_t fvB, const uint64_t* __restrict__ rowsB, int nB,
@@ -800,124 +1288,141 @@ groupby_kernel(StoreRef st, uint32_t fvA, const uint64_t* __restrict__ rowsA, in
                const uint4* __restrict__ filter_bitmaps /* per unit or null */,
                unsigned long long* counts /* [nA*nB] */) {
     extern __shared__ uint8_t gsm[];
-    uint16_t* head = reinterpret_cast<uint16_t*>(gsm);                       // 128 KiB
-    uint32_t* pool = reinterpret_cast<uint32_t*>(gsm + 131072);              // 64 KiB
-    uint32_t* fbm = reinterpret_cast<uint32_t*>(gsm + 131072 + kGbPool * 4); // 8 KiB (dense a-row / filter scratch)
-    __shared__ uint32_t any_a;
-    __shared__ uint32_t s_need[kGbThreads / 32], s_dense[kGbThreads / 32];
-    __shared__ Resolved dense_c;
+    uint16_t* head = reinterpret_cast<uint16_t*>(gsm);                       // 128 KiB column table
+    uint32_t* pool = reinterpret_cast<uint32_t*>(gsm + 131072);              // 64 KiB chained entries (row<<16 | next)
+    uint32_t* fbm = reinterpret_cast<uint32_t*>(gsm + 131072 + kGbPool * 4); // 8 KiB bitmap (dense a-row)
+    __shared__ Resolved resA[kGbThreads], resB[kGbThreads];
+    __shared__ uint32_t offA[kGbThreads], offB[kGbThreads];
+    __shared__ uint32_t scan_tmp[kGbThreads / 32];
+    __shared__ uint32_t s_any, s_pass_end;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nwarps = kGbThreads / 32;
+
     for (long long unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
         const uint64_t shard = shards[unit >> 4];
         const int slot = (int)(unit & 15);
         const uint32_t* flt = filter_bitmaps ? reinterpret_cast<const uint32_t*>(filter_bitmaps + (size_t)unit * 512) : nullptr;
-        // executor.go:8769-8772: a shard missing either fragment contributes nothing
         __syncthreads();
-        if (tid == 0) {
+        if (tid == 0) {   // executor.go:8769-8772: a shard missing either fragment contributes nothing
             bool ok = fvA < st.n_views && fvB < st.n_views;
             if (ok) { ViewTab va = st.views[fvA], vb = st.views[fvB]; ok = shard < va.n_shards && shard < vb.n_shards && st.shardmap[va.shard_off + shard] >= 0 && st.shardmap[vb.shard_off + shard] >= 0; }
-            any_a = ok ? 1u : 0u;
+            s_any = ok ? 1u : 0u;
         }
         __syncthreads();
-        if (!any_a) continue;
-        int ia = 0;
-        while (ia < nA) {
-            // ---- sparse pass: clear the column table, insert a-rows ia.. in row order until the pool is full or a
-            //      dense row is met.  Pool slots are assigned by a deterministic prefix over the rows' cardinalities.
-            __syncthreads();
-            { uint4* h4 = reinterpret_cast<uint4*>(head); for (int i = tid; i < 8192; i += kGbThreads) h4[i] = make_uint4(0, 0, 0, 0); }
-            __syncthreads();
-            uint32_t pool_base = 0; int pass_end = nA;
-            for (int base = ia; base < nA; base += nwarps) {
-                int i = base + wid;
-                Resolved c; c.ptr = nullptr; c.card = 0; c.typ = 0; c.cnt = 0;
-                if (i < nA) {
-                    if (lane == 0) c = resolve(st, fvA, shard, rowsA[i], slot);
-                    c.ptr = (const void*)__shfl_sync(0xffffffffu, (unsigned long long)c.ptr, 0); c.card = __shfl_sync(0xffffffffu, c.card, 0);
-                    uint32_t m = __shfl_sync(0xffffffffu, ((uint32_t)c.typ << 16) | c.cnt, 0); c.typ = m >> 16; c.cnt = m & 0xffff;
-                }
-                bool is_dense = c.ptr && (c.typ != kArray || c.card >= kGbDenseCard);
-                uint32_t need = (c.ptr && !is_dense) ? c.card : 0u;
-                if (lane == 0) { s_need[wid] = need; s_dense[wid] = is_dense ? 1u : 0u; }
+        if (!s_any) continue;
+
+        for (int a0 = 0; a0 < nA; a0 += kGbThreads) {
+            const int chunkA = min(kGbThreads, nA - a0);
+            // all a-row descriptor chains of this chunk are walked concurrently (one per thread)
+            { Resolved r; r.ptr = nullptr; r.card = 0; r.typ = 0; r.cnt = 0;
+              if (tid < chunkA) r = resolve(st, fvA, shard, rowsA[a0 + tid], slot);
+              __syncthreads(); resA[tid] = r; __syncthreads(); }
+            int ia = 0;
+            while (ia < chunkA) {
+                // ---- sparse pass [ia, pass_end): pool offsets = exclusive prefix over row cardinalities (deterministic)
+                const Resolved mine = resA[tid];
+                const bool in_range = tid >= ia && tid < chunkA;
+                const bool dense = in_range && mine.ptr && (mine.typ != kArray || mine.card >= kGbDenseCard);
+                const uint32_t need = (in_range && mine.ptr && !dense) ? mine.card : 0u;
+                const uint32_t off = block_excl_scan(need, scan_tmp, nullptr);
+                if (tid == 0) s_pass_end = (uint32_t)chunkA;
                 __syncthreads();
-                uint32_t running = pool_base, my_start = 0; int stop_at = -1;
-                for (int w = 0; w < nwarps; w++) {
-                    int idx = base + w; if (idx >= nA) break;
-                    if (s_dense[w] || running + s_need[w] > (uint32_t)kGbPool) { stop_at = idx; break; }
-                    if (w == wid) my_start = running;
-                    running += s_need[w];
-                }
-                bool my_ok = i < nA && (stop_at < 0 || i < stop_at);
-                if (my_ok && need) {
-                    const uint16_t* a = reinterpret_cast<const uint16_t*>(c.ptr);
-                    for (uint32_t k = lane; k < c.card; k += 32) {
-                        uint32_t col = __ldg(a + k);
+                if (in_range && (dense || off + need > (uint32_t)kGbPool)) atomicMin(&s_pass_end, (uint32_t)tid);
+                offA[tid] = off;
+                { uint4* h4 = reinterpret_cast<uint4*>(head); for (int i = tid; i < 8192; i += kGbThreads) h4[i] = make_uint4(0, 0, 0, 0); }
+                __syncthreads();
+                const int pass_end = (int)s_pass_end;
+                {   // flat: one thread per a-element of the pass; the owning row is found by binary search over offA[]
+                    const uint32_t total = pass_end < chunkA ? offA[pass_end] : (offA[chunkA - 1] + ((resA[chunkA - 1].ptr && resA[chunkA - 1].typ == kArray && resA[chunkA - 1].card < kGbDenseCard) ? resA[chunkA - 1].card : 0u));
+                    for (uint32_t e = tid; e < total; e += kGbThreads) {
+                        int lo = ia, hi = pass_end - 1;           // last row i in [ia, pass_end) with offA[i] <= e
+                        while (lo < hi) { int m = (lo + hi + 1) >> 1; if (offA[m] <= e) lo = m; else hi = m - 1; }
+                        const Resolved c = resA[lo];
+                        const uint32_t k = e - offA[lo];
+                        if (!c.ptr || k >= c.card) continue;      // rows without a container have zero width
+                        uint32_t col = __ldg(reinterpret_cast<const uint16_t*>(c.ptr) + k);
                         if (flt && !((__ldg(flt + (col >> 5)) >> (col & 31)) & 1u)) continue;
-                        uint32_t ent = my_start + k + 1;      // 1-based entry index (kGbPool < 65535 fits 16 bits)
+                        uint32_t ent = e + 1;                      // 1-based (kGbPool < 65535 fits 16 bits)
                         unsigned short old = head[col], assumed;
-                        do { assumed = old; pool[ent - 1] = ((uint32_t)i << 16) | assumed; __threadfence_block(); old = atomicCAS(&head[col], assumed, (unsigned short)ent); } while (old != assumed);
+                        do { assumed = old; pool[ent - 1] = ((uint32_t)(a0 + lo) << 16) | assumed; __threadfence_block(); old = atomicCAS(&head[col], assumed, (unsigned short)ent); } while (old != assumed);
                     }
                 }
-                pool_base = running;
                 __syncthreads();
-                if (stop_at >= 0) { pass_end = stop_at; break; }
-            }
-            __syncthreads();
-            const int pass_lo = ia, pass_hi = pass_end;
-            // ---- probe: stream b rows
-            for (int j = wid; j < nB && pass_hi > pass_lo; j += nwarps) {
-                Resolved c; c.ptr = nullptr; c.card = 0; c.typ = 0; c.cnt = 0;
-                if (lane == 0) c = resolve(st, fvB, shard, rowsB[j], slot);
-                c.ptr = (const void*)__shfl_sync(0xffffffffu, (unsigned long long)c.ptr, 0); c.card = __shfl_sync(0xffffffffu, c.card, 0);
-                uint32_t m = __shfl_sync(0xffffffffu, ((uint32_t)c.typ << 16) | c.cnt, 0); c.typ = m >> 16; c.cnt = m & 0xffff;
-                if (!c.ptr) continue;
-                warp_for_each(c, lane, [&](uint32_t col) {
-                    uint32_t ent = head[col];
-                    while (ent) { uint32_t pe = pool[ent - 1]; uint32_t i = pe >> 16; if ((int)i >= pass_lo && (int)i < pass_hi) atomicAdd(&counts[(size_t)i * nB + j], 1ull); ent = pe & 0xffffu; }
-                });
-            }
-            __syncthreads();
-            ia = pass_hi;
-            // ---- dense pass for the row that ended the sparse pass (if it is dense)
-            if (ia < nA) {
-                Resolved c; c.ptr = nullptr; c.card = 0; c.typ = 0; c.cnt = 0;
-                if (tid == 0) { c = resolve(st, fvA, shard, rowsA[ia], slot); }
-                // broadcast through smem
-                if (tid == 0) dense_c = c;
-                __syncthreads();
-                c = dense_c;
-                bool is_dense = c.ptr && (c.typ != kArray || c.card >= kGbDenseCard);
-                if (is_dense) {
-                    // expand into fbm (u32[2048]) and AND with filter
-                    uint4* f4 = reinterpret_cast<uint4*>(fbm);
-                    for (int i = tid; i < 512; i += kGbThreads) f4[i] = make_uint4(0, 0, 0, 0);
-                    __syncthreads();
-                    if (c.typ == kBitmap) { const uint4* g = reinterpret_cast<const uint4*>(c.ptr); for (int i = tid; i < 512; i += kGbThreads) f4[i] = ldg_nc(g + i); }
-                    else if (c.typ == kArray) { const uint16_t* a = reinterpret_cast<const uint16_t*>(c.ptr); for (uint32_t k = tid; k < c.card; k += kGbThreads) { uint32_t v = __ldg(a + k); atomicOr(&fbm[v >> 5], 1u << (v & 31)); } }
-                    else { const uint32_t* r = reinterpret_cast<const uint32_t*>(c.ptr);
-                        for (uint32_t k = wid; k < c.cnt; k += nwarps) { uint32_t v = __ldg(r + k); uint32_t s = v & 0xffffu, l = v >> 16;
-                            for (uint32_t w = (s >> 5) + lane; w <= (l >> 5); w += 32) { uint32_t mask = 0xffffffffu; if (w == (s >> 5)) mask &= 0xffffffffu << (s & 31); if (w == (l >> 5)) mask &= 0xffffffffu >> (31 - (l & 31)); atomicOr(&fbm[w], mask); } } }
-                    __syncthreads();
-                    if (flt) { const uint4* g = reinterpret_cast<const uint4*>(flt); for (int i = tid; i < 512; i += kGbThreads) f4[i] = and4(f4[i], g[i]); __syncthreads(); }
-                    for (int j = wid; j < nB; j += nwarps) {
-                        Resolved b; b.ptr = nullptr; b.card = 0; b.typ = 0; b.cnt = 0;
-                        if (lane == 0) b = resolve(st, fvB, shard, rowsB[j], slot);
-                        b.ptr = (const void*)__shfl_sync(0xffffffffu, (unsigned long long)b.ptr, 0); b.card = __shfl_sync(0xffffffffu, b.card, 0);
-                        uint32_t m = __shfl_sync(0xffffffffu, ((uint32_t)b.typ << 16) | b.cnt, 0); b.typ = m >> 16; b.cnt = m & 0xffff;
-                        if (!b.ptr) continue;
-                        uint32_t cc = 0;
-                        if (b.typ == kArray) cc = warp_probe_smem(fbm, reinterpret_cast<const uint16_t*>(b.ptr), b.card, lane);
-                        else if (b.typ == kBitmap) cc = warp_and_count_gs(reinterpret_cast<const uint4*>(b.ptr), fbm, lane);
-                        else { const uint32_t* r = reinterpret_cast<const uint32_t*>(b.ptr); for (uint32_t k = lane; k < b.cnt; k += 32) { uint32_t v = __ldg(r + k); cc += range_count32(fbm, v & 0xffffu, v >> 16); } }
-                        cc = __reduce_add_sync(0xffffffffu, cc);
-                        if (lane == 0 && cc) atomicAdd(&counts[(size_t)ia * nB + j], (unsigned long long)cc);
+                // ---- probe: stream b rows against the table
+                if (pass_end > ia) {
+                    for (int b0 = 0; b0 < nB; b0 += kGbThreads) {
+                        const int chunkB = min(kGbThreads, nB - b0);
+                        { Resolved r; r.ptr = nullptr; r.card = 0; r.typ = 0; r.cnt = 0;
+                          if (tid < chunkB) r = resolve(st, fvB, shard, rowsB[b0 + tid], slot);
+                          __syncthreads(); resB[tid] = r; __syncthreads(); }
+                        {   // arrays: flat thread-per-element (offsets by block scan); bitmap/run rows: warp loop
+                            const Resolved mb = resB[tid];
+                            const uint32_t nb_ = (tid < chunkB && mb.ptr && mb.typ == kArray) ? mb.card : 0u;
+                            uint32_t totalB = 0;
+                            const uint32_t ob = block_excl_scan(nb_, scan_tmp, &totalB);
+                            __syncthreads();
+                            offB[tid] = ob;
+                            __syncthreads();
+                            for (uint32_t e = tid; e < totalB; e += kGbThreads) {
+                                int lo = 0, hi = chunkB - 1;
+                                while (lo < hi) { int m = (lo + hi + 1) >> 1; if (offB[m] <= e) lo = m; else hi = m - 1; }
+                                const Resolved c = resB[lo];
+                                const uint32_t k = e - offB[lo];
+                                if (!c.ptr || c.typ != kArray || k >= c.card) continue;
+                                uint32_t col = __ldg(reinterpret_cast<const uint16_t*>(c.ptr) + k);
+                                uint32_t ent = head[col];
+                                while (ent) { uint32_t pe = pool[ent - 1]; atomicAdd(&counts[(size_t)(pe >> 16) * nB + (b0 + lo)], 1ull); ent = pe & 0xffffu; }
+                            }
+                        }
+                        for (int j = wid; j < chunkB; j += nwarps) {
+                            const Resolved c = resB[j];
+                            if (!c.ptr || c.typ == kArray) continue;
+                            const int jj = b0 + j;
+                            warp_for_each(c, lane, [&](uint32_t col) {
+                                uint32_t ent = head[col];
+                                while (ent) { uint32_t pe = pool[ent - 1]; atomicAdd(&counts[(size_t)(pe >> 16) * nB + jj], 1ull); ent = pe & 0xffffu; }
+                            });
+                        }
                     }
-                    __syncthreads();
-                    ia++;
+                }
+                __syncthreads();
+                ia = pass_end;
+                // ---- dense pass for the row that ended the sparse pass (bitmap/run container or >= kGbDenseCard elements)
+                if (ia < chunkA) {
+                    const Resolved c = resA[ia];
+                    const bool is_dense = c.ptr && (c.typ != kArray || c.card >= kGbDenseCard);
+                    if (is_dense) {
+                        uint4* f4 = reinterpret_cast<uint4*>(fbm);
+                        for (int i = tid; i < 512; i += kGbThreads) f4[i] = make_uint4(0, 0, 0, 0);
+                        __syncthreads();
+                        if (c.typ == kBitmap) { const uint4* g = reinterpret_cast<const uint4*>(c.ptr); for (int i = tid; i < 512; i += kGbThreads) f4[i] = ldg_nc(g + i); }
+                        else if (c.typ == kArray) { const uint16_t* a = reinterpret_cast<const uint16_t*>(c.ptr); for (uint32_t k = tid; k < c.card; k += kGbThreads) { uint32_t v = __ldg(a + k); atomicOr(&fbm[v >> 5], 1u << (v & 31)); } }
+                        else { const uint32_t* r = reinterpret_cast<const uint32_t*>(c.ptr);
+                            for (uint32_t k = wid; k < c.cnt; k += nwarps) { uint32_t v = __ldg(r + k); uint32_t s0 = v & 0xffffu, l0 = v >> 16;
+                                for (uint32_t w = (s0 >> 5) + lane; w <= (l0 >> 5); w += 32) { uint32_t mask = 0xffffffffu; if (w == (s0 >> 5)) mask &= 0xffffffffu << (s0 & 31); if (w == (l0 >> 5)) mask &= 0xffffffffu >> (31 - (l0 & 31)); atomicOr(&fbm[w], mask); } } }
+                        __syncthreads();
+                        if (flt) { const uint4* g = reinterpret_cast<const uint4*>(flt); for (int i = tid; i < 512; i += kGbThreads) f4[i] = and4(f4[i], g[i]); __syncthreads(); }
+                        for (int b0 = 0; b0 < nB; b0 += kGbThreads) {
+                            const int chunkB = min(kGbThreads, nB - b0);
+                            { Resolved r; r.ptr = nullptr; r.card = 0; r.typ = 0; r.cnt = 0;
+                              if (tid < chunkB) r = resolve(st, fvB, shard, rowsB[b0 + tid], slot);
+                              __syncthreads(); resB[tid] = r; __syncthreads(); }
+                            for (int j = wid; j < chunkB; j += nwarps) {
+                                const Resolved bb = resB[j];
+                                if (!bb.ptr) continue;
+                                uint32_t cc = 0;
+                                if (bb.typ == kArray) cc = warp_probe_smem(fbm, reinterpret_cast<const uint16_t*>(bb.ptr), bb.card, lane);
+                                else if (bb.typ == kBitmap) cc = warp_and_count_gs(reinterpret_cast<const uint4*>(bb.ptr), fbm, lane);
+                                else { const uint32_t* r = reinterpret_cast<const uint32_t*>(bb.ptr); for (uint32_t k = lane; k < bb.cnt; k += 32) { uint32_t v = __ldg(r + k); cc += range_count32(fbm, v & 0xffffu, v >> 16); } }
+                                cc = __reduce_add_sync(0xffffffffu, cc);
+                                if (lane == 0 && cc) atomicAdd(&counts[(size_t)(a0 + ia) * nB + (b0 + j)], (unsigned long long)cc);
+                            }
+                        }
+                        __syncthreads();
+                        ia++;
+                    }
                 }
             }
         }
-        __syncthreads();
     }
 }
 

@@ -48,12 +48,13 @@ def test_container_combinations_table_on_gpu():
     p = Pair(track_existence=False)
     p.field("f")
     types = [O.ARRAY, O.BITMAP, O.RUN]
+    cache = {(n, t): A.container(n, t) for n in A.NAMES for t in types}
     shard_of, s = {}, 0
     for (x, y) in pairs:
         for tx in types:
             for ty in types:
                 frag = O.Bitmap()
-                cx, cy = A.container(x, tx), A.container(y, ty)
+                cx, cy = cache[(x, tx)], cache[(y, ty)]
                 if cx.n:
                     frag.put(0 * 16 + 5, cx)       # row 0, slot 5
                 if cy.n:
@@ -355,3 +356,39 @@ def test_full_size_properties_1024_shards():
         assert int(per[s]) == fr.row(0, s).intersection_count(fr.row(1, s))
     r = ex.execute("i", "Intersect(Row(f=0), Row(f=1))")[0]
     assert r.count == i_ab and len(r.columns()) == i_ab
+
+
+@pytest.mark.parametrize("env", ["FBGPU_FORCE_WORDPAR", "FBGPU_STAGED"])
+def test_alternative_eval_kernels(env, monkeypatch):
+    """the word-parallel kernel (bitmap-heavy programs) and the TMA-staged kernel are normally picked by a heuristic /
+    opt-in; force each one over array, bitmap and run operands, counts and filter bitmaps, and compare with the oracle"""
+    monkeypatch.setenv(env, "1")
+    p = Pair()
+    p.field("f")
+    p.field("v", "int", min=-2000, max=2000)
+    for s in range(3):
+        parts = [D.fragment(9, s, [0, 4, 5, 6], 0.004), D.fragment(9, s, [1], 0.3), D.fragment(9, s, [2], 0.2, mode=1, mean_run=200.0),
+                 D.fragment(9, s, [3], 0.9, mode=1, mean_run=5000.0)]
+        merged = O.Bitmap()
+        for d in parts:
+            merged = merged.union(O.Bitmap.from_bytes(d))
+        p.load("f", X.VIEW_STANDARD, s, merged.to_bytes())
+    rng = np.random.default_rng(5)
+    for col, val in zip(rng.choice(3 * SW, 5000, replace=False), rng.integers(-2000, 2000, 5000)):
+        p.holder.set_value("i", "v", int(col), int(val))
+    p.sync_pending()
+    for q in ("Count(Union(Row(f=0), Row(f=1), Row(f=2), Row(f=4), Row(f=5), Row(f=6)))",
+              "Count(Intersect(Union(Row(f=0), Row(f=4), Row(f=5), Row(f=6), Row(f=2)), Xor(Row(f=1), Row(f=3), Row(f=0), Row(f=4)), Row(f=1)))",
+              "Count(Difference(Row(f=3), Row(f=0), Row(f=2), Row(f=4), Row(f=1)))",
+              "Count(Not(Union(Row(f=0), Row(f=2))))",
+              "Count(Row(v > 17))", "Count(Row(v <= -5))", "Count(Row(v >< [-100, 700]))", "Count(Row(v != 3))"):
+        p.check_count(q)
+    p.check_row("Union(Row(f=0), Row(f=2), Row(f=4), Row(f=5))")
+    # filter bitmaps produced by the alternative kernel feed TopK / GroupBy
+    exp = {}
+    for s in range(3):
+        rows, cnts = p.ora.frag("f", 0, s).row_counts(s, p.ora.eval_shard(__import__("featurebase_b200").pql.parse("Union(Row(f=1), Row(f=2), Row(f=0), Row(f=4))")[0], s))
+        for r, c in zip(rows.tolist(), cnts.tolist()):
+            exp[r] = exp.get(r, 0) + c
+    got = p.ex.execute("i", "TopK(f, k=10, filter=Union(Row(f=1), Row(f=2), Row(f=0), Row(f=4)))")[0]
+    assert got == sorted(exp.items(), key=lambda kv: (-kv[1], kv[0]))

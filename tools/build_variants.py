@@ -3,9 +3,7 @@ import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from featurebase_b200 import build as B
 VARIANTS = {
-    "v1_b6": ["FBGPU_BATCH_IMPL=1", "FBGPU_EVAL_MIN_BLOCKS=6"],
-    "v1_b7": ["FBGPU_BATCH_IMPL=1", "FBGPU_EVAL_MIN_BLOCKS=7"],
-    "v1_b8": ["FBGPU_BATCH_IMPL=1", "FBGPU_EVAL_MIN_BLOCKS=8"],
+    "b7": ["FBGPU_EVAL_MIN_BLOCKS=7"],
 }
 if __name__ == "__main__":
     for name, defs in VARIANTS.items():
