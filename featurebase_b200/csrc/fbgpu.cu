@@ -639,13 +639,18 @@ static int allreduce_u64(fbgpu_ctx* c, Workspace* w, void* dptr, size_t n) {
 }
 
 // uploads [DevOp prog | u64 shards] with one H2D copy; returns device pointers
+static std::vector<int2> find_batches(const std::vector<DevOp>& prog);
 static int upload_inputs(Workspace* w, const std::vector<DevOp>& prog, const uint64_t* shards, int64_t n_shards, const DevOp** d_prog, const uint64_t** d_shards) {
-    size_t pb = prog.size() * sizeof(DevOp), sb = (size_t)n_shards * 8, tot = pb + sb;
+    std::vector<int2> batches = find_batches(prog);
+    size_t pb = prog.size() * sizeof(DevOp), sb = (size_t)n_shards * 8, bb = batches.size() * sizeof(int2), tot = pb + sb + bb;
     if (w->h_in.ensure(tot + 16)) return FBGPU_E_NOMEM;
-    if (w->d_in.ensure(tot + 16)) return FBGPU_E_NOMEM;
+    if (w->d_in.ensure(pb + sb + 16)) return FBGPU_E_NOMEM;
+    if (w->d_aux.ensure(bb + 16)) return FBGPU_E_NOMEM;
     if (pb) memcpy(w->h_in.p, prog.data(), pb);
     if (sb) memcpy((uint8_t*)w->h_in.p + pb, shards, sb);
-    if (tot) CUDA_TRY(cudaMemcpyAsync(w->d_in.p, w->h_in.p, tot, cudaMemcpyHostToDevice, w->stream));
+    if (bb) memcpy((uint8_t*)w->h_in.p + pb + sb, batches.data(), bb);
+    if (pb + sb) CUDA_TRY(cudaMemcpyAsync(w->d_in.p, w->h_in.p, pb + sb, cudaMemcpyHostToDevice, w->stream));
+    if (bb) CUDA_TRY(cudaMemcpyAsync(w->d_aux.p, (uint8_t*)w->h_in.p + pb + sb, bb, cudaMemcpyHostToDevice, w->stream));
     *d_prog = (const DevOp*)w->d_in.p; *d_shards = (const uint64_t*)((uint8_t*)w->d_in.p + pb);
     return 0;
 }
@@ -681,11 +686,8 @@ static int launch_eval(fbgpu_ctx* c, Workspace* w, const std::vector<DevOp>& pro
         }
     }
     const bool staged = getenv("FBGPU_STAGED") && n_ops <= kStagedMaxOps && staged_rows >= 4;
-    if (w->d_aux.ensure(std::max<size_t>(batches.size(), 1) * sizeof(int2))) return FBGPU_E_NOMEM;
-    if (!batches.empty()) {
-        CUDA_TRY(cudaMemcpyAsync(w->d_aux.p, batches.data(), batches.size() * sizeof(int2), cudaMemcpyHostToDevice, w->stream));
-        CUDA_TRY(cudaStreamSynchronize(w->stream));      // `batches` is a local; tiny copy
-    }
+    // the batch table travels in front of the program in the same H2D copy (upload_inputs); see d_batches()
+    const int2* d_batches = reinterpret_cast<const int2*>(w->d_aux.p);
     if (staged) {
         // N CTAs per SM (default 2): (depth+1) stack bitmaps + two TMA stages each
         int ctas = 2;
@@ -696,7 +698,7 @@ static int launch_eval(fbgpu_ctx* c, Workspace* w, const std::vector<DevOp>& pro
             uint32_t stg = (uint32_t)(((per_cta - stack) / 2) & ~size_t(127));
             long long grid = std::min<long long>(n_units, (long long)c->sm_count * ctas);
             size_t smem = stack + 2 * (size_t)stg;
-            eval_staged_kernel<<<(unsigned)grid, kEvalThreads, smem, w->stream>>>(store_ref(c), d_prog, n_ops, depth, (const int2*)w->d_aux.p, (int)batches.size(), stg, d_shards, n_units, out);
+            eval_staged_kernel<<<(unsigned)grid, kEvalThreads, smem, w->stream>>>(store_ref(c), d_prog, n_ops, depth, d_batches, (int)batches.size(), stg, d_shards, n_units, out);
             CUDA_TRY(cudaGetLastError());
             return 0;
         }
@@ -704,7 +706,7 @@ static int launch_eval(fbgpu_ctx* c, Workspace* w, const std::vector<DevOp>& pro
     size_t smem = (size_t)(depth + 1) * 8192;
     int per_sm = std::max(1, (int)std::min<size_t>(std::min(8, 2048 / kEvalThreads), (227 * 1024) / (smem + 3 * 1024 + 512)));
     long long grid = std::min<long long>(n_units, (long long)c->sm_count * per_sm);
-    eval_kernel<<<(unsigned)grid, kEvalThreads, smem, w->stream>>>(store_ref(c), d_prog, n_ops, depth, (const int2*)w->d_aux.p, (int)batches.size(), d_shards, n_units, out);
+    eval_kernel<<<(unsigned)grid, kEvalThreads, smem, w->stream>>>(store_ref(c), d_prog, n_ops, depth, d_batches, (int)batches.size(), d_shards, n_units, out);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }

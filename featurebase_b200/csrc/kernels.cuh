@@ -21,6 +21,9 @@ namespace fbgpu {
 #ifndef FBGPU_EVAL_MIN_BLOCKS
 #define FBGPU_EVAL_MIN_BLOCKS 8
 #endif
+#ifndef FBGPU_BATCH_PREFETCH
+#define FBGPU_BATCH_PREFETCH 0
+#endif
 #ifndef FBGPU_BATCH_UNROLL
 #define FBGPU_BATCH_UNROLL 4
 #endif
@@ -39,6 +42,15 @@ __device__ __forceinline__ uint4 and4(uint4 a, uint4 b) { return make_uint4(a.x 
 __device__ __forceinline__ uint4 or4(uint4 a, uint4 b) { return make_uint4(a.x | b.x, a.y | b.y, a.z | b.z, a.w | b.w); }
 __device__ __forceinline__ uint4 xor4(uint4 a, uint4 b) { return make_uint4(a.x ^ b.x, a.y ^ b.y, a.z ^ b.z, a.w ^ b.w); }
 __device__ __forceinline__ uint4 andn4(uint4 a, uint4 b) { return make_uint4(a.x & ~b.x, a.y & ~b.y, a.z & ~b.z, a.w & ~b.w); }
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
+// prefetch a container's payload into L2 (one 128-byte line per lane, strided)
+__device__ __forceinline__ void warp_prefetch_container(const Resolved& r, int lane) {
+    if (r.ptr == nullptr) return;
+    const uint32_t bytes = r.typ == kArray ? r.card * 2u : r.typ == kBitmap ? 8192u : (uint32_t)r.cnt * 4u;
+    const uint8_t* p = reinterpret_cast<const uint8_t*>(r.ptr);
+    for (uint32_t off = lane * 128u; off < bytes; off += 32u * 128u) prefetch_l2(p + off);
+}
 
 // Locate the container (fv, shard, row, slot).  5 dependent loads; see fbgpu_types.h.
 __device__ __forceinline__ Resolved resolve(const StoreRef& st, uint32_t fv, uint64_t shard, uint64_t row, int slot) {
@@ -299,6 +311,11 @@ __device__ __forceinline__ void scatter_chunk_unrolled(uint32_t* bm, uint4 v, ui
 template <int MODE>
 __device__ __forceinline__ void batch_rows_v1(uint32_t* T32, const Resolved* res, int n) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#if FBGPU_BATCH_PREFETCH
+    // pull every array this warp is going to scatter into L2 first: the sequential per-operand loads below then
+    // see L2 latency instead of HBM latency, at no register cost
+    for (int j = wid; j < n; j += kEvalThreads / 32) { const Resolved r = res[j]; if (r.ptr != nullptr && r.typ == kArray) warp_prefetch_container(r, lane); }
+#endif
     for (int j = wid; j < n; j += kEvalThreads / 32) {
         const Resolved r = res[j];
         if (r.ptr == nullptr) continue;
@@ -942,6 +959,17 @@ __device__ __forceinline__ void warp_zero(uint32_t* bm, int lane) {
 #pragma unroll 4
     for (int i = lane; i < 512; i += 32) b4[i] = make_uint4(0, 0, 0, 0);
 }
+// number of the (up to 8) u16 values of one 16-byte chunk that are set in a shared-memory bitmap
+__device__ __forceinline__ uint32_t probe_chunk(const uint32_t* bm, uint4 v, uint32_t base, uint32_t n) {
+    uint32_t w[4] = { v.x, v.y, v.z, v.w }, c = 0;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        uint32_t lo = w[q] & 0xffffu, hi = w[q] >> 16;
+        if (base + 2 * q < n) c += (bm[lo >> 5] >> (lo & 31)) & 1u;
+        if (base + 2 * q + 1 < n) c += (bm[hi >> 5] >> (hi & 31)) & 1u;
+    }
+    return c;
+}
 // per-lane partial count of array elements found in a shared-memory bitmap
 __device__ __forceinline__ uint32_t warp_probe_smem(const uint32_t* bm, const uint16_t* arr, uint32_t n, int lane) {
     const uint4* a4 = reinterpret_cast<const uint4*>(arr);
@@ -1058,9 +1086,24 @@ __device__ __forceinline__ uint32_t warp_intersection_count(Resolved a, Resolved
     if (a.typ == kRun || b.typ == kRun) c = warp_icount_runs(a, b, lane);
     else if (a.typ == kArray && b.typ == kArray) {            // array x array: build the smaller, probe the larger
         if (a.card > b.card) { Resolved t = a; a = b; b = t; }
+        // all loads of both arrays (up to 768 elements each) are issued before any shared-memory work: one HBM
+        // latency per pair instead of one per 256-element slab
+        const uint4* a4 = reinterpret_cast<const uint4*>(a.ptr); const uint4* b4 = reinterpret_cast<const uint4*>(b.ptr);
+        const uint32_t na8 = (a.card + 7) >> 3, nb8 = (b.card + 7) >> 3;
+        uint4 va[3], vb[3];
+#pragma unroll
+        for (int q = 0; q < 3; q++) if (lane + 32 * q < na8) va[q] = ldg_nc(a4 + lane + 32 * q);
+#pragma unroll
+        for (int q = 0; q < 3; q++) if (lane + 32 * q < nb8) vb[q] = ldg_nc(b4 + lane + 32 * q);
         warp_zero(bm, lane); __syncwarp();
-        warp_scatter_smem(bm, reinterpret_cast<const uint16_t*>(a.ptr), a.card, lane); __syncwarp();
-        c = warp_probe_smem(bm, reinterpret_cast<const uint16_t*>(b.ptr), b.card, lane); __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 3; q++) if (lane + 32 * q < na8) scatter_chunk_unrolled<0>(bm, va[q], (lane + 32 * q) * 8, a.card);
+        for (uint32_t i = lane + 96; i < na8; i += 32) scatter_chunk_unrolled<0>(bm, ldg_nc(a4 + i), i * 8, a.card);
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 3; q++) if (lane + 32 * q < nb8) c += probe_chunk(bm, vb[q], (lane + 32 * q) * 8, b.card);
+        for (uint32_t i = lane + 96; i < nb8; i += 32) c += probe_chunk(bm, ldg_nc(b4 + i), i * 8, b.card);
+        __syncwarp();
     } else if (a.typ == kArray) {                             // array x bitmap: roaring.go:4596
         c = warp_probe_global(reinterpret_cast<const uint32_t*>(b.ptr), reinterpret_cast<const uint16_t*>(a.ptr), a.card, lane);
     } else {                                                  // bitmap x bitmap: roaring.go:4611
@@ -1073,19 +1116,10 @@ __device__ __forceinline__ uint32_t warp_intersection_count(Resolved a, Resolved
 
 constexpr int kPairWarps = 8;
 
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
-// prefetch a container's payload into L2 (one 128-byte line per lane, strided)
-__device__ __forceinline__ void warp_prefetch_container(const Resolved& r, int lane) {
-    if (r.ptr == nullptr) return;
-    const uint32_t bytes = r.typ == kArray ? r.card * 2u : r.typ == kBitmap ? 8192u : (uint32_t)r.cnt * 4u;
-    const uint8_t* p = reinterpret_cast<const uint8_t*>(r.ptr);
-    for (uint32_t off = lane * 128u; off < bytes; off += 32u * 128u) prefetch_l2(p + off);
-}
-
 // Count(Intersect(Row(fvA,rowA), Row(fvB,rowB))): one warp per (shard, slot) container pair.  A warp owns the units
 // w, w+W, w+2W, ...; it walks the descriptor chains of up to 16 of its units at once (lane 2k / 2k+1 = side a / b of
 // unit k), and while unit k is being intersected the payloads of unit k+1 are already being pulled into L2.
-__global__ void __launch_bounds__(kPairWarps * 32)
+__global__ void __launch_bounds__(kPairWarps * 32, 3)
 pair_count_kernel(StoreRef st, uint32_t fvA, uint64_t rowA, uint32_t fvB, uint64_t rowB,
                   const uint64_t* __restrict__ shards, long long n_units,
                   unsigned long long* total, unsigned long long* per_shard) {

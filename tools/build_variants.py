@@ -3,7 +3,7 @@ import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from featurebase_b200 import build as B
 VARIANTS = {
-    "b7": ["FBGPU_EVAL_MIN_BLOCKS=7"],
+    "nopf": ["FBGPU_BATCH_PREFETCH=0"],
 }
 if __name__ == "__main__":
     for name, defs in VARIANTS.items():
