@@ -83,21 +83,35 @@ def config5(args, out):
                  "algorithmic_bytes": int(algo), "achieved_gbs": gbs, "peak_gbs": pk, "peak_source": src, "frac": gbs / pk,
                  "l2_note": f"{n_pairs} row pairs rotated, {n_pairs * algo / 1e6:.0f} MB touched per cycle" + (" (< L2: launch/L2-bound point)" if n_pairs * algo < 126e6 else ""),
                  "containers": {"array": st["array_containers"], "bitmap": st["bitmap_containers"], "run": st["run_containers"]}, "count": int(tot)})
+            if args.batched and mode == 0:
+                # the same Intersect+Count, N independent row pairs fused in one launch (SURVEY §8d "(ii) batched")
+                nb = max(n_pairs, 4)
+                ra, rb = [2 * (k % n_pairs) for k in range(nb)], [2 * (k % n_pairs) + 1 for k in range(nb)]
+                res = {}
+
+                def bstep(i):
+                    res[0] = h.ctx.count_pairs(idx.id, f.id, 0, ra, f.id, 0, rb, shards)
+
+                bms, bmin, bwall = timed(h.ctx, bstep, args.steps)
+                assert int(res[0][0]) == counts[0] and int(res[0].sum()) == sum(counts[k % n_pairs] for k in range(nb))
+                bgbs = nb * algo / (bms * 1e-3) / 1e9
+                out({"config": "5b", "generator": mname, "density": p, "shards": S, "pairs_per_launch": nb, "kernel": "pair_count_kernel (multi-pair)", "ms": bms, "ms_min": bmin, "wall_ms": bwall,
+                     "set_ops_per_sec": nb * S / (bms * 1e-3), "algorithmic_bytes": int(nb * algo), "achieved_gbs": bgbs, "peak_gbs": pk, "peak_source": src, "frac": bgbs / pk,
+                     "l2_note": f"{nb} pairs over {n_pairs} distinct row pairs ({n_pairs * algo / 1e6:.0f} MB distinct data)"})
             h.ctx.close()
 
 
-def config3(args, out):
+def config3(args, out, n_rec=10_000_000, nf=4):
+    """nf fields are rotated between steps so that the touched planes exceed L2 (the 10 M-record config is 42.5 MB)"""
     from featurebase_b200 import datagen as D, executor as X, pql
     from oracle import oracle as O
     from tests.oracle_exec import OracleIndex
     pk, src = peak()
-    n_rec = 10_000_000
     n_sh = (n_rec + SW - 1) // SW
     shards = np.arange(n_sh, dtype=np.uint64)
     h = X.Holder()
     idx = h.create_index("i", track_existence=False)
     ex = X.Executor(h)
-    nf = 4   # rotate 4 fields so the touched planes exceed L2
     ora = OracleIndex(idx)
     for k in range(nf):
         fld = idx.create_field(f"v{k}", "int", min=0, max=(1 << 32) - 1)
@@ -126,7 +140,7 @@ def config3(args, out):
         gbs = algo / (ms * 1e-3) / 1e9
         out({"config": 3, "query": f"Count(Row(v > {kname}))", "records": n_rec, "shards": n_sh, "kernel": "eval_kernel (BSI plane sweep)", "ms": ms, "ms_min": ms_min, "wall_ms": wall,
              "records_per_sec": n_rec / (ms * 1e-3), "algorithmic_bytes": int(algo), "achieved_gbs": gbs, "peak_gbs": pk, "peak_source": src, "frac": gbs / pk,
-             "note": "algorithmic bytes = all 34 planes of the field (upper bound; the sweep stops early when the predicate saturates); 4 fields rotated (> L2)",
+             "note": f"algorithmic bytes = all 34 planes of the field (upper bound; the sweep stops early when the predicate saturates); {nf} field(s) rotated",
              "count": int(tot), "selectivity": tot / n_rec})
     h.ctx.close()
 
@@ -182,6 +196,7 @@ def main():
     ap.add_argument("--shards", type=int, default=1024)
     ap.add_argument("--groupby-shards", type=int, default=512)
     ap.add_argument("--generators", default="uniform,clustered")
+    ap.add_argument("--batched", action="store_true", help="also time the multi-pair launch (config 5b)")
     ap.add_argument("--densities", default="0.0001,0.001,0.01,0.03,0.0625,0.125,0.25,0.5")
     args = ap.parse_args()
 
@@ -189,7 +204,11 @@ def main():
         print(json.dumps(d), flush=True)
 
     for c in args.configs.split(","):
-        {"5": config5, "3": config3, "4": config4}[c.strip()](args, out)
+        c = c.strip()
+        if c == "3L":     # the same BSI query at 256 shards (268 M records, 1.1 GB of planes): shows the kernel away from the launch-bound regime
+            config3(args, out, n_rec=256 * SW, nf=1)
+        else:
+            {"5": config5, "3": config3, "4": config4}[c](args, out)
 
 
 if __name__ == "__main__":

@@ -160,7 +160,7 @@ extern "C" int fbgpu_init(int32_t device_ordinal, fbgpu_ctx** out) {
     CUDA_TRY(cudaFuncSetAttribute(eval_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 233472 / 2 - 1024 - 5888));
     CUDA_TRY(cudaFuncSetAttribute(pair_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairWarps * 8192));
     CUDA_TRY(cudaFuncSetAttribute(row_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairWarps * 8192));
-    CUDA_TRY(cudaFuncSetAttribute(groupby_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072 + kGbPool * 4 + 8192));
+    CUDA_TRY(cudaFuncSetAttribute(groupby_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGbSlots * 4 + 8192));
     *out = c;
     return FBGPU_OK;
 }
@@ -735,15 +735,15 @@ extern "C" int fbgpu_count(fbgpu_ctx* c, uint32_t index, const fbgpu_op* ops, in
         // fused Intersect+Count fast path: Count(Intersect(Row, Row))  (executor.go:5357 + row.go:242 + Count)
         if (prog.size() == 2 && prog[0].op == D_PUSH_ROW && prog[1].op == D_AND_ROW) {
             long long grid = std::min<long long>((n_units + kPairWarps - 1) / kPairWarps, (long long)c->sm_count * 3);
-            pair_count_kernel<<<(unsigned)grid, kPairWarps * 32, kPairWarps * 8192, w->stream>>>(store_ref(c), prog[0].fv, prog[0].row, prog[1].fv, prog[1].row, d_shards, n_units, d_total, d_per);
+            pair_count_kernel<<<(unsigned)grid, kPairWarps * 32, kPairWarps * 8192, w->stream>>>(store_ref(c), prog[0].fv, prog[0].row, prog[1].fv, prog[1].row, nullptr, nullptr, n_units, d_shards, n_units, d_total, d_per, nullptr);
             CUDA_TRY(cudaGetLastError());
         } else {
             EvalOut eo{ d_total, d_per, nullptr, nullptr };
             rc = launch_eval(c, w, prog, d_prog, depth, d_shards, n_units, eo); if (rc) return rc;
         }
     }
+    rc = allreduce_u64(c, w, d_total, 1); if (rc) return rc;     // inside the timed bracket: the collective is part of the step
     CUDA_TRY(cudaEventRecord(w->ev1, w->stream));
-    rc = allreduce_u64(c, w, d_total, 1); if (rc) return rc;
     CUDA_TRY(cudaMemcpyAsync(w->h_out.p, w->d_counts.p, nc * 8, cudaMemcpyDeviceToHost, w->stream));
     CUDA_TRY(cudaStreamSynchronize(w->stream));
     *out_total = ((uint64_t*)w->h_out.p)[0];
@@ -917,6 +917,43 @@ extern "C" int fbgpu_row_counts(fbgpu_ctx* c, uint32_t index, uint32_t field, ui
     return FBGPU_OK;
 }
 
+// ------------------------------------------------------------------ many fused Intersect+Count pairs in one launch
+extern "C" int fbgpu_count_pairs(fbgpu_ctx* c, uint32_t index, uint32_t field_a, uint32_t view_a, const uint64_t* rows_a,
+                                 uint32_t field_b, uint32_t view_b, const uint64_t* rows_b, int32_t n_pairs,
+                                 const uint64_t* shards, int64_t n_shards, uint64_t* out_counts) {
+    if (!c || !rows_a || !rows_b || !out_counts || n_pairs < 0 || n_shards < 0 || (n_shards && !shards)) return fail(FBGPU_E_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    int rc = ensure_committed(c); if (rc) return rc;
+    if (n_pairs == 0) return FBGPU_OK;
+    std::shared_lock<std::shared_mutex> lk(c->store_mu);
+    uint32_t fa = view_id_locked(c, ViewKey{ index, field_a, view_a }, false), fb = view_id_locked(c, ViewKey{ index, field_b, view_b }, false);
+    WsLease lease(c); Workspace* w = lease.w;
+    std::vector<DevOp> none; const DevOp* d_prog; const uint64_t* d_shards;
+    rc = upload_inputs(w, none, shards, n_shards, &d_prog, &d_shards); if (rc) return rc;
+    size_t np = (size_t)n_pairs;
+    if (w->d_rows.ensure(np * 16) || w->d_counts.ensure(np * 8) || w->h_out.ensure(np * 16)) return FBGPU_E_NOMEM;
+    memcpy(w->h_out.p, rows_a, np * 8); memcpy((uint8_t*)w->h_out.p + np * 8, rows_b, np * 8);
+    CUDA_TRY(cudaMemcpyAsync(w->d_rows.p, w->h_out.p, np * 16, cudaMemcpyHostToDevice, w->stream));
+    CUDA_TRY(cudaMemsetAsync(w->d_counts.p, 0, np * 8, w->stream));
+    const long long upp = (long long)n_shards * kSlotsPerRow, n_units = upp * n_pairs;
+    CUDA_TRY(cudaEventRecord(w->ev0, w->stream));
+    if (n_units > 0) {
+        long long grid = std::min<long long>((n_units + kPairWarps - 1) / kPairWarps, (long long)c->sm_count * 3);
+        pair_count_kernel<<<(unsigned)grid, kPairWarps * 32, kPairWarps * 8192, w->stream>>>(store_ref(c), fa, 0, fb, 0, (const uint64_t*)w->d_rows.p, (const uint64_t*)w->d_rows.p + np,
+            upp, d_shards, n_units, nullptr, nullptr, (unsigned long long*)w->d_counts.p);
+        CUDA_TRY(cudaGetLastError());
+    }
+    CUDA_TRY(cudaEventRecord(w->ev1, w->stream));
+    rc = allreduce_u64(c, w, w->d_counts.p, np); if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(w->stream));      // h_out was the H2D source; now reuse it as the D2H landing buffer
+    CUDA_TRY(cudaMemcpyAsync(w->h_out.p, w->d_counts.p, np * 8, cudaMemcpyDeviceToHost, w->stream));
+    CUDA_TRY(cudaStreamSynchronize(w->stream));
+    memcpy(out_counts, w->h_out.p, np * 8);
+    float ms = 0; cudaEventElapsedTime(&ms, w->ev0, w->ev1);
+    bump(c, n_units > 0 ? 1 : 0, ms);
+    return FBGPU_OK;
+}
+
 // ------------------------------------------------------------------ GroupBy
 static int groupby2(fbgpu_ctx* c, uint32_t index, uint32_t fvA, const uint64_t* rowsA, int nA, uint32_t fvB, const uint64_t* rowsB, int nB,
                     const std::vector<fbgpu_op>& filter, const uint64_t* shards, int64_t n_shards, uint64_t* out) {
@@ -935,12 +972,12 @@ static int groupby2(fbgpu_ctx* c, uint32_t index, uint32_t fvA, const uint64_t* 
     CUDA_TRY(cudaEventRecord(w->ev0, w->stream));
     uint64_t launches = 0;
     const int64_t batch = have_filter ? 1024 : n_shards;
-    const size_t smem = 131072 + kGbPool * 4 + 8192;
+    const size_t smem = kGbSlots * 4 + 8192;
     for (int64_t s0 = 0; s0 < n_shards; s0 += batch) {
         int64_t ns = std::min(batch, n_shards - s0);
         if (have_filter) { rc = eval_filter_batch(c, w, prog, depth, d_prog, d_shards + s0, ns); if (rc) return rc; launches++; }
         long long units = (long long)ns * kSlotsPerRow;
-        long long grid = std::min<long long>(units, c->sm_count);
+        long long grid = std::min<long long>(units, (long long)c->sm_count * 4);
         groupby_kernel<<<(unsigned)grid, kGbThreads, smem, w->stream>>>(store_ref(c), fvA, (const uint64_t*)w->d_rows.p, nA, fvB, (const uint64_t*)w->d_rows.p + nA, nB,
             d_shards + s0, units, have_filter ? (const uint4*)w->d_bitmaps.p : nullptr, (unsigned long long*)w->d_counts.p);
         CUDA_TRY(cudaGetLastError()); launches++;

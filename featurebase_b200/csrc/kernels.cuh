@@ -1121,8 +1121,9 @@ constexpr int kPairWarps = 8;
 // unit k), and while unit k is being intersected the payloads of unit k+1 are already being pulled into L2.
 __global__ void __launch_bounds__(kPairWarps * 32, 3)
 pair_count_kernel(StoreRef st, uint32_t fvA, uint64_t rowA, uint32_t fvB, uint64_t rowB,
+                  const uint64_t* __restrict__ rowsA, const uint64_t* __restrict__ rowsB, long long units_per_pair,
                   const uint64_t* __restrict__ shards, long long n_units,
-                  unsigned long long* total, unsigned long long* per_shard) {
+                  unsigned long long* total, unsigned long long* per_shard, unsigned long long* per_pair) {
     extern __shared__ uint32_t smem32[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     uint32_t* bm = smem32 + wid * 2048;
@@ -1130,10 +1131,14 @@ pair_count_kernel(StoreRef st, uint32_t fvA, uint64_t rowA, uint32_t fvB, uint64
     const long long stride = (long long)gridDim.x * kPairWarps;
     for (long long base = (long long)blockIdx.x * kPairWarps + wid; base < n_units; base += stride * 16) {
         // resolve up to 16 units of this warp concurrently
+        // multi-pair form (rowsA != null): unit = pair * units_per_pair + (shard index * 16 + slot)
         const long long my_unit = base + (long long)(lane >> 1) * stride;
         Resolved r; r.ptr = nullptr; r.card = 0; r.typ = 0; r.cnt = 0;
-        if (my_unit < n_units) r = (lane & 1) ? resolve(st, fvB, shards[my_unit >> 4], rowB, (int)(my_unit & 15))
-                                              : resolve(st, fvA, shards[my_unit >> 4], rowA, (int)(my_unit & 15));
+        if (my_unit < n_units) {
+            const long long pr = rowsA ? my_unit / units_per_pair : 0, su = rowsA ? my_unit - pr * units_per_pair : my_unit;
+            r = (lane & 1) ? resolve(st, fvB, shards[su >> 4], rowsA ? rowsB[pr] : rowB, (int)(su & 15))
+                           : resolve(st, fvA, shards[su >> 4], rowsA ? rowsA[pr] : rowA, (int)(su & 15));
+        }
         const uint32_t meta = ((uint32_t)r.typ << 16) | r.cnt;
         auto fetch = [&](int src) {
             Resolved x;
@@ -1155,7 +1160,10 @@ pair_count_kernel(StoreRef st, uint32_t fvA, uint64_t rowA, uint32_t fvB, uint64
             }
             uint32_t c = warp_intersection_count(a, b, bm, lane);
             acc += c;
-            if (per_shard && c && lane == 0) atomicAdd(&per_shard[unit >> 4], (unsigned long long)c);
+            if (c && lane == 0) {
+                if (per_pair) atomicAdd(&per_pair[unit / units_per_pair], (unsigned long long)c);
+                else if (per_shard) atomicAdd(&per_shard[unit >> 4], (unsigned long long)c);
+            }
             a = na; b = nb;
         }
     }
@@ -1276,14 +1284,16 @@ canon_emit_kernel(const uint4* __restrict__ bitmaps, const EmitUnit* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------------
-// GroupBy(Rows(a), Rows(b)) [+ filter]: one CTA per (shard, slot).  Column-keyed join instead of the
-// reference's |A|x|B| nested intersectionCount loop (executor.go:8880-8934): field-a rows are inserted into a
-// 65,536-entry column table in shared memory (chained for multi-valued columns), field-b rows are streamed
-// against it and bump counts[i*nB + j].  Dense (bitmap/run) a-rows take a bitmap pass instead.
-// Shared memory: head[65536] u16 (128 KiB) + pool[kGbPool] u32 (row<<16|next) + 8 KiB bitmap.
+// GroupBy(Rows(a), Rows(b)) [+ filter]: one CTA per (shard, slot).  Column-keyed hash join instead of the
+// reference's |A|x|B| nested intersectionCount loop (executor.go:8880-8934): the elements of field-a rows are inserted
+// as (column, row) entries into an open-addressing table in shared memory (linear probing, duplicates allowed, so
+// multi-valued columns just occupy several slots), field-b rows are streamed against it and bump counts[i*nB + j].
+// Dense (bitmap/run) a-rows take a bitmap pass instead.  Shared memory: 32 KiB table + 8 KiB bitmap => 4 CTAs/SM.
 // ------------------------------------------------------------------------------------------------
 constexpr int kGbThreads = 256;
-constexpr int kGbPool = 16384;          // chained entries per pass (64 KiB)
+constexpr int kGbSlots = 8192;          // open-addressing table slots per CTA (32 KiB)
+constexpr int kGbPool = kGbSlots / 2;   // entries per pass (load factor <= 0.5)
+constexpr uint32_t kGbEmpty = 0xffffffffu;
 constexpr uint32_t kGbDenseCard = 4096; // a-rows at/above this cardinality (or non-array) use the bitmap pass
 
 template <class F>
@@ -1322,9 +1332,8 @@ groupby_kernel(StoreRef st, uint32_t fvA, const uint64_t* __restrict__ rowsA, in
                const uint4* __restrict__ filter_bitmaps /* per unit or null */,
                unsigned long long* counts /* [nA*nB] */) {
     extern __shared__ uint8_t gsm[];
-    uint16_t* head = reinterpret_cast<uint16_t*>(gsm);                       // 128 KiB column table
-    uint32_t* pool = reinterpret_cast<uint32_t*>(gsm + 131072);              // 64 KiB chained entries (row<<16 | next)
-    uint32_t* fbm = reinterpret_cast<uint32_t*>(gsm + 131072 + kGbPool * 4); // 8 KiB bitmap (dense a-row)
+    uint32_t* tab = reinterpret_cast<uint32_t*>(gsm);                        // kGbSlots entries: (column << 16) | row index
+    uint32_t* fbm = reinterpret_cast<uint32_t*>(gsm + kGbSlots * 4);         // 8 KiB bitmap (dense a-row)
     __shared__ Resolved resA[kGbThreads], resB[kGbThreads];
     __shared__ uint32_t offA[kGbThreads], offB[kGbThreads];
     __shared__ uint32_t scan_tmp[kGbThreads / 32];
@@ -1362,7 +1371,7 @@ groupby_kernel(StoreRef st, uint32_t fvA, const uint64_t* __restrict__ rowsA, in
                 __syncthreads();
                 if (in_range && (dense || off + need > (uint32_t)kGbPool)) atomicMin(&s_pass_end, (uint32_t)tid);
                 offA[tid] = off;
-                { uint4* h4 = reinterpret_cast<uint4*>(head); for (int i = tid; i < 8192; i += kGbThreads) h4[i] = make_uint4(0, 0, 0, 0); }
+                { uint4* t4 = reinterpret_cast<uint4*>(tab); for (int i = tid; i < kGbSlots / 4; i += kGbThreads) t4[i] = make_uint4(kGbEmpty, kGbEmpty, kGbEmpty, kGbEmpty); }
                 __syncthreads();
                 const int pass_end = (int)s_pass_end;
                 {   // flat: one thread per a-element of the pass; the owning row is found by binary search over offA[]
@@ -1375,9 +1384,9 @@ groupby_kernel(StoreRef st, uint32_t fvA, const uint64_t* __restrict__ rowsA, in
                         if (!c.ptr || k >= c.card) continue;      // rows without a container have zero width
                         uint32_t col = __ldg(reinterpret_cast<const uint16_t*>(c.ptr) + k);
                         if (flt && !((__ldg(flt + (col >> 5)) >> (col & 31)) & 1u)) continue;
-                        uint32_t ent = e + 1;                      // 1-based (kGbPool < 65535 fits 16 bits)
-                        unsigned short old = head[col], assumed;
-                        do { assumed = old; pool[ent - 1] = ((uint32_t)(a0 + lo) << 16) | assumed; __threadfence_block(); old = atomicCAS(&head[col], assumed, (unsigned short)ent); } while (old != assumed);
+                        const uint32_t ent = (col << 16) | (uint32_t)(a0 + lo);
+                        uint32_t h = (col * 40503u) & (kGbSlots - 1);
+                        while (atomicCAS(&tab[h], kGbEmpty, ent) != kGbEmpty) h = (h + 1) & (kGbSlots - 1);
                     }
                 }
                 __syncthreads();
@@ -1403,8 +1412,11 @@ groupby_kernel(StoreRef st, uint32_t fvA, const uint64_t* __restrict__ rowsA, in
                                 const uint32_t k = e - offB[lo];
                                 if (!c.ptr || c.typ != kArray || k >= c.card) continue;
                                 uint32_t col = __ldg(reinterpret_cast<const uint16_t*>(c.ptr) + k);
-                                uint32_t ent = head[col];
-                                while (ent) { uint32_t pe = pool[ent - 1]; atomicAdd(&counts[(size_t)(pe >> 16) * nB + (b0 + lo)], 1ull); ent = pe & 0xffffu; }
+                                for (uint32_t h = (col * 40503u) & (kGbSlots - 1);; h = (h + 1) & (kGbSlots - 1)) {
+                                    const uint32_t ent = tab[h];
+                                    if (ent == kGbEmpty) break;
+                                    if ((ent >> 16) == col) atomicAdd(&counts[(size_t)(ent & 0xffffu) * nB + (b0 + lo)], 1ull);
+                                }
                             }
                         }
                         for (int j = wid; j < chunkB; j += nwarps) {
@@ -1412,8 +1424,11 @@ groupby_kernel(StoreRef st, uint32_t fvA, const uint64_t* __restrict__ rowsA, in
                             if (!c.ptr || c.typ == kArray) continue;
                             const int jj = b0 + j;
                             warp_for_each(c, lane, [&](uint32_t col) {
-                                uint32_t ent = head[col];
-                                while (ent) { uint32_t pe = pool[ent - 1]; atomicAdd(&counts[(size_t)(pe >> 16) * nB + jj], 1ull); ent = pe & 0xffffu; }
+                                for (uint32_t h = (col * 40503u) & (kGbSlots - 1);; h = (h + 1) & (kGbSlots - 1)) {
+                                    const uint32_t ent = tab[h];
+                                    if (ent == kGbEmpty) break;
+                                    if ((ent >> 16) == col) atomicAdd(&counts[(size_t)(ent & 0xffffu) * nB + jj], 1ull);
+                                }
                             });
                         }
                     }

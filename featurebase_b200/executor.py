@@ -294,7 +294,14 @@ class Executor:
         ids = c.args.get("ids")
         if ids is not None:
             ids = sorted(int(i) for i in ids)
-            counts = self.ctx.row_counts(idx.id, f.id, VIEW_STANDARD, shards, row_ids=ids, filter_ops=filt)
+            src = c.children[0] if c.children else None
+            src_key = [k for k in src.args if not k.startswith("_")] if src is not None and src.name == "Row" else []
+            if src_key and not isinstance(src.args[src_key[0]], pql.Condition) and self._field(idx, src_key[0]).type != "int":
+                # Src is a plain Row: count = Src.intersectionCount(row) per candidate (fragment.go:1367-1372), fused
+                sf = self._field(idx, src_key[0])
+                counts = self.ctx.count_pairs(idx.id, f.id, VIEW_STANDARD, ids, sf.id, VIEW_STANDARD, [int(src.args[src_key[0]])] * len(ids), shards)
+            else:
+                counts = self.ctx.row_counts(idx.id, f.id, VIEW_STANDARD, shards, row_ids=ids, filter_ops=filt)
             pairs = [(i, int(k)) for i, k in zip(ids, counts) if k > 0]
             pairs.sort(key=lambda p: (-p[1], p[0]))              # Pairs sort desc; ties pinned (count desc, id asc)
         else:

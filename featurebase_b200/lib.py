@@ -37,7 +37,7 @@ class Counters(C.Structure):
 EXPORTS = ["fbgpu_init", "fbgpu_shutdown", "fbgpu_last_error", "fbgpu_abi_version", "fbgpu_load_fragment",
            "fbgpu_load_fragments", "fbgpu_drop_fragment", "fbgpu_commit", "fbgpu_get_stats", "fbgpu_count", "fbgpu_row",
            "fbgpu_row_counts", "fbgpu_groupby", "fbgpu_comm_unique_id", "fbgpu_comm_init", "fbgpu_comm_destroy",
-           "fbgpu_get_counters", "fbgpu_stream", "fbgpu_rows_payload_bytes"]
+           "fbgpu_get_counters", "fbgpu_stream", "fbgpu_rows_payload_bytes", "fbgpu_count_pairs"]
 
 
 def lib_path():
@@ -66,6 +66,7 @@ def load():
     L.fbgpu_row.argtypes, L.fbgpu_row.restype = [vp, u32, vp, i32, vp, i64, vp, u64, C.POINTER(u64), C.POINTER(u64)], C.c_int
     L.fbgpu_row_counts.argtypes, L.fbgpu_row_counts.restype = [vp, u32, u32, u32, vp, i32, vp, i32, vp, i64, vp, vp, i32, C.POINTER(i32)], C.c_int
     L.fbgpu_groupby.argtypes, L.fbgpu_groupby.restype = [vp, u32, vp, vp, i32, vp, vp, vp, i32, vp, i64, vp], C.c_int
+    L.fbgpu_count_pairs.argtypes, L.fbgpu_count_pairs.restype = [vp, u32, u32, u32, vp, u32, u32, vp, i32, vp, i64, vp], C.c_int
     L.fbgpu_comm_unique_id.argtypes, L.fbgpu_comm_unique_id.restype = [vp], C.c_int
     L.fbgpu_comm_init.argtypes, L.fbgpu_comm_init.restype = [vp, i32, i32, vp], C.c_int
     L.fbgpu_comm_destroy.argtypes, L.fbgpu_comm_destroy.restype = [vp], C.c_int
@@ -179,6 +180,14 @@ class Context:
         self._check(self.L.fbgpu_row_counts(self.h, index, field, view, None, 0, f, nf, sh.ctypes.data, len(sh),
                                             rid.ctypes.data, out.ctypes.data, cap, C.byref(n)))
         return rid[: n.value], out[: n.value]
+
+    def count_pairs(self, index, field_a, view_a, rows_a, field_b, view_b, rows_b, shards):
+        sh, ra, rb = _u64arr(shards), _u64arr(rows_a), _u64arr(rows_b)
+        assert len(ra) == len(rb)
+        out = np.zeros(len(ra), dtype=np.uint64)
+        self._check(self.L.fbgpu_count_pairs(self.h, index, field_a, view_a, ra.ctypes.data, field_b, view_b, rb.ctypes.data, len(ra),
+                                             sh.ctypes.data, len(sh), out.ctypes.data))
+        return out
 
     def groupby(self, index, fields, views, row_ids, shards, filter_ops=None):
         sh = _u64arr(shards)

@@ -115,6 +115,14 @@ int fbgpu_row_counts(fbgpu_ctx *ctx, uint32_t index, uint32_t field, uint32_t vi
                      const uint64_t *shards, int64_t n_shards,
                      uint64_t *out_row_ids, uint64_t *out_counts, int32_t cap, int32_t *out_n);
 
+/* Many fused Intersect+Count pairs in ONE launch: out_counts[i] = |Row(field_a = rows_a[i]) ∩ Row(field_b = rows_b[i])| over
+ * the shards — the inner loop of fragment.top with a plain-row Src (count = Src.intersectionCount(row) per candidate
+ * row, fragment.go:1367-1372,1416-1420), of the GroupBy leaf (executor.go:8893) and of BenchmarkFragment_IntersectionCount
+ * (fragment_internal_test.go:1461), without materialising anything.  All-reduced over the communicator. */
+int fbgpu_count_pairs(fbgpu_ctx *ctx, uint32_t index, uint32_t field_a, uint32_t view_a, const uint64_t *rows_a,
+                      uint32_t field_b, uint32_t view_b, const uint64_t *rows_b, int32_t n_pairs,
+                      const uint64_t *shards, int64_t n_shards, uint64_t *out_counts);
+
 /* GroupBy(Rows(f1), Rows(f2), ..., filter=...) with Count aggregate (executeGroupBy executor.go:3176,
  * executeGroupByShard :3918, groupByIterator :8617-8934; reduce = mergeGroupCounts :3728).  row_ids_flat holds
  * the per-field row-id lists concatenated (flat on purpose: cgo forbids nested Go pointers).  out_counts is
@@ -144,6 +152,10 @@ typedef struct {
     uint64_t last_algo_bytes;   /* algorithmic bytes of the last query   */
 } fbgpu_counters;
 int fbgpu_get_counters(fbgpu_ctx *ctx, fbgpu_counters *out);
+/* algorithmic-bytes accounting: roaring payload bytes and container count of the given rows (NULL = all
+ * rows) of a field over the shards, from the host-side directory */
+int fbgpu_rows_payload_bytes(fbgpu_ctx *ctx, uint32_t index, uint32_t field, uint32_t view, const uint64_t *row_ids, int32_t n_rows,
+                             const uint64_t *shards, int64_t n_shards, uint64_t *out_payload, uint64_t *out_containers);
 /* the CUDA stream queries of the calling thread run on (cudaStream_t), for external event timing */
 void *fbgpu_stream(fbgpu_ctx *ctx);
 

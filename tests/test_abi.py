@@ -26,7 +26,7 @@ def test_header_symbols_exported(so):
     missing = [s for s in sorted(declared) if not hasattr(dll, s)]
     assert not missing, missing
     assert dll.fbgpu_abi_version() == 1
-    assert set(L.EXPORTS) - {"fbgpu_rows_payload_bytes"} <= declared
+    assert set(L.EXPORTS) <= declared
 
 
 def test_no_oracle_linkage(so):

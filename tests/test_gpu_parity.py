@@ -274,8 +274,12 @@ def test_topk_topn_rowcounts():
     assert p.ex.execute("i", "TopK(f, k=10, filter=Row(g=7))")[0] == order(expf)
     assert p.ex.execute("i", "TopN(f, Row(g=7), n=3)")[0] == order(expf)[:3]
     ids = [0, 3, 11, 99]
-    got = p.ex.execute("i", "TopN(f, Row(g=7), n=5, ids=[0,3,11,99])")[0]
+    got = p.ex.execute("i", "TopN(f, Row(g=7), n=5, ids=[0,3,11,99])")[0]          # plain-Row Src: fused multi-pair kernel
     assert got == order({i: expf[i] for i in ids if expf.get(i)})
+    got = p.ex.execute("i", "TopN(f, Intersect(Row(g=7), Row(g=7)), n=5, ids=[0,3,11,99])")[0]   # general Src: filter bitmaps
+    assert got == order({i: expf[i] for i in ids if expf.get(i)})
+    pc = p.holder.ctx.count_pairs(p.idx.id, p.idx.fields["f"].id, 0, [0, 1, 3, 10, 11, 99, 3], p.idx.fields["g"].id, 0, [7, 7, 7, 7, 7, 7, 8], shards)
+    assert pc.tolist() == [expf.get(r, 0) for r in (0, 1, 3, 10, 11, 99)] + [0]
     assert p.ex.execute("i", "Rows(f)")[0] == sorted(exp)
 
 
@@ -392,3 +396,112 @@ def test_alternative_eval_kernels(env, monkeypatch):
             exp[r] = exp.get(r, 0) + c
     got = p.ex.execute("i", "TopK(f, k=10, filter=Union(Row(f=1), Row(f=2), Row(f=0), Row(f=4)))")[0]
     assert got == sorted(exp.items(), key=lambda kv: (-kv[1], kv[0]))
+
+
+def test_full_size_properties_bsi_and_groupby():
+    """BASELINE config 3 (10 M records, 32-bit BSI) and one GPU's share of config 4 (512 shards, 256 x 256 GroupBy) at
+    full size, checked through size-independent properties: complementary predicates partition the non-null set,
+    monotonicity in k, GroupBy total = number of records = Count(All rows of a), marginals = per-row counts."""
+    h = X.Holder()
+    idx = h.create_index("i", track_existence=False)
+    ex = X.Executor(h)
+    idx.create_field("v", "int", min=0, max=(1 << 32) - 1)
+    n_rec = 10_000_000
+    n_sh = (n_rec + SW - 1) // SW
+    for s in range(n_sh):
+        h.import_roaring("i", "v", X.VIEW_BSI, s, D.bsi_fragment(20, s, min(SW, n_rec - s * SW), 32, 0, (1 << 32) - 1))
+    q = lambda t: ex.execute("i", t)[0]
+    notnull = q("Count(Row(v != null))")
+    assert notnull == n_rec
+    prev = None
+    for k in (0, 1, 12345, 1 << 20, 1 << 31, int(0.99 * (1 << 32)), (1 << 32) - 2):
+        gt, le, eq, ne, ge = q(f"Count(Row(v > {k}))"), q(f"Count(Row(v <= {k}))"), q(f"Count(Row(v == {k}))"), q(f"Count(Row(v != {k}))"), q(f"Count(Row(v >= {k}))")
+        assert gt + le == notnull and eq + ne == notnull and ge == gt + eq
+        assert prev is None or gt <= prev
+        prev = gt
+        assert abs(gt / n_rec - (1 - (k + 1) / (1 << 32))) < 0.002          # uniform values
+    assert q(f"Count(Row(v >< [{1 << 30},{1 << 31}]))") == q(f"Count(Row(v >= {1 << 30}))") - q(f"Count(Row(v > {1 << 31}))")
+
+    idx.create_field("a")
+    idx.create_field("b")
+    S = 512
+    for s in range(S):
+        da, db = D.groupby_fragments(31, 32, s, 100e6 / (4096 * SW), 256, 256)
+        h.import_roaring("i", "a", X.VIEW_STANDARD, s, da)
+        h.import_roaring("i", "b", X.VIEW_STANDARD, s, db)
+    shards = list(range(S))
+    rows = list(range(256))
+    fa, fb = idx.fields["a"], idx.fields["b"]
+    counts = h.ctx.groupby(idx.id, [fa.id, fb.id], [0, 0], [rows, rows], shards)
+    ca = h.ctx.row_counts(idx.id, fa.id, 0, shards, row_ids=rows)
+    cb = h.ctx.row_counts(idx.id, fb.id, 0, shards, row_ids=rows)
+    total = int(counts.sum())
+    assert abs(total - 100e6 / 8) < 0.01 * 100e6 / 8                        # ~12.2 M records on this GPU's share
+    assert total == int(ca.sum()) == int(cb.sum())                          # every record has exactly one a-row and one b-row
+    assert np.array_equal(counts.sum(axis=1), ca) and np.array_equal(counts.sum(axis=0), cb)
+    flt = ex._bitmap_call(idx, __import__("featurebase_b200").pql.parse("Row(b=7)")[0])
+    sub = h.ctx.groupby(idx.id, [fa.id, fb.id], [0, 0], [rows, rows], shards, filter_ops=flt)
+    assert np.array_equal(sub[:, 7], counts[:, 7]) and int(sub.sum()) == int(counts[:, 7].sum())
+
+
+def test_thread_safety_and_api_edges():
+    """The C ABI promises re-entrancy from any thread (goroutines migrate between OS threads): 8 threads issue mixed
+    queries concurrently (ctypes releases the GIL) and must get the sequential answers; plus argument edge cases."""
+    import threading
+    from featurebase_b200 import lib as L
+    p = Pair(track_existence=False)
+    p.field("f")
+    shards = list(range(6))
+    for s in shards:
+        p.load("f", X.VIEW_STANDARD, s, D.fragment(3, s, list(range(8)), 0.02))
+    queries = ["Count(Intersect(Row(f=0), Row(f=1)))", "Count(Union(Row(f=0), Row(f=1), Row(f=2), Row(f=3)))",
+               "Count(Xor(Row(f=4), Row(f=5)))", "Count(Difference(Row(f=6), Row(f=7), Row(f=0)))", "Intersect(Row(f=2), Row(f=3))",
+               "TopK(f, k=4, filter=Row(f=1))"]
+    expect = [p.ex.execute("i", q)[0] for q in queries]
+    expect[4] = expect[4].roaring
+    errors = []
+
+    def worker(tid):
+        try:
+            for it in range(12):
+                k = (tid + it) % len(queries)
+                got = p.ex.execute("i", queries[k])[0]
+                if k == 4:
+                    got = got.roaring
+                if got != expect[k]:
+                    errors.append((tid, it, queries[k]))
+        except Exception as e:  # noqa: BLE001
+            errors.append((tid, repr(e)))
+
+    ths = [threading.Thread(target=worker, args=(t,)) for t in range(8)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    assert not errors, errors[:3]
+    ctx, iid, fid = p.holder.ctx, p.idx.id, p.idx.fields["f"].id
+    row = lambda r: L.Op(L.OP_ROW, fid, 0, 0, r, 0, 0, 0)
+    # empty shard list, unknown field/view/row, duplicate shards in a Row call, malformed programs
+    assert ctx.count(iid, [row(0)], []) == 0
+    assert ctx.count(iid, [L.Op(L.OP_ROW, 999, 0, 0, 0, 0, 0, 0)], shards) == 0
+    assert ctx.count(iid, [row(12345)], shards) == 0
+    assert ctx.count(iid, [row(0)], [77, 78]) == 0
+    one = ctx.row(iid, [row(0)], [2])
+    assert ctx.row(iid, [row(0)], [2, 2, 2]) == one
+    for bad in ([], [row(0), row(1)], [L.Op(L.OP_INTERSECT, 0, 0, 2, 0, 0, 0, 0)], [row(0), L.Op(42, 0, 0, 0, 0, 0, 0, 0)]):
+        with pytest.raises(L.FbgpuError) as ei:
+            ctx.count(iid, bad, shards)
+        assert ei.value.code == L.E_INVALID
+    with pytest.raises(L.FbgpuError) as ei:
+        ctx.count(iid, [L.Op(L.OP_INTERSECT, 0, 0, 0, 0, 0, 0, 0)], shards)
+    assert ei.value.code == L.E_QUERY
+    with pytest.raises(L.FbgpuError) as ei:
+        ctx.load_fragment(iid, fid, 0, 9, b"\x00" * 32)
+    assert ei.value.code == L.E_FORMAT
+    # drop + reload
+    before = ctx.count(iid, [row(0)], shards)
+    ctx.drop_fragment(iid, fid, 0, 3)
+    after = ctx.count(iid, [row(0)], shards)
+    assert after == before - p.ora.row("f", 0, 0, 3).count()
+    ctx.load_fragment(iid, fid, 0, 3, D.fragment(3, 3, list(range(8)), 0.02))
+    assert ctx.count(iid, [row(0)], shards) == before
