@@ -21,12 +21,6 @@ namespace fbgpu {
 #ifndef FBGPU_EVAL_MIN_BLOCKS
 #define FBGPU_EVAL_MIN_BLOCKS 8
 #endif
-#ifndef FBGPU_BATCH_PREFETCH
-#define FBGPU_BATCH_PREFETCH 0
-#endif
-#ifndef FBGPU_BATCH_UNROLL
-#define FBGPU_BATCH_UNROLL 4
-#endif
 constexpr int kEvalThreads = FBGPU_EVAL_THREADS;          // 256 or 512
 constexpr int kEvalU4PerThread = 512 / kEvalThreads;       // uint4 per thread of an 8 KiB bitmap
 constexpr int kEvalW64PerThread = 1024 / kEvalThreads;     // consecutive u64 words per thread in scans
@@ -235,64 +229,6 @@ __device__ __forceinline__ void warp_bitmap_atomic(uint32_t* bm, const uint4* g,
         }
     }
 }
-// scatters the (up to) 8 u16 values of one 16-byte chunk; rolled on purpose (keeps register pressure low so
-// that 4+ CTAs stay resident per SM)
-template <int MODE>
-__device__ __forceinline__ void scatter_chunk(uint32_t* bm, uint4 v, uint32_t base, uint32_t n) {
-    uint64_t a = ((uint64_t)v.y << 32) | v.x, b = ((uint64_t)v.w << 32) | v.z;
-    uint32_t cnt = n - base;            // valid elements in this chunk (>= 1)
-    if (cnt >= 8) {
-#pragma unroll 1
-        for (int q = 0; q < 4; q++) { smem_bit_op<MODE>(bm, (uint32_t)a & 0xffffu); smem_bit_op<MODE>(bm, (uint32_t)b & 0xffffu); a >>= 16; b >>= 16; }
-    } else {
-#pragma unroll 1
-        for (uint32_t q = 0; q < cnt; q++) { uint64_t x = q < 4 ? a : b; smem_bit_op<MODE>(bm, (uint32_t)(x >> (16 * (q & 3))) & 0xffffu); }
-    }
-}
-// Batch of commuting row operands (OR / ANDNOT / XOR onto the same target), no barrier in between: the CTA is
-// split into groups of G threads, one group per operand (G*16 B contiguous per load), and every thread keeps four
-// 16-byte loads in flight before it touches shared memory, so the batch is bandwidth- rather than latency-bound.
-template <int MODE>
-__device__ __noinline__ void batch_rows(uint32_t* T32, const Resolved* res, int n) {
-    const int tid = threadIdx.x;
-    int G = kEvalThreads / max(n, 1);
-    G = G >= 32 ? 32 : G <= 1 ? 1 : (1 << (31 - __clz(G)));
-    const int groups = kEvalThreads / G, g = tid & (G - 1);
-    for (int j = tid / G; j < n; j += groups) {
-        const Resolved r = res[j];
-        if (r.ptr == nullptr) continue;
-        if (r.typ == kArray) {
-            const uint4* a4 = reinterpret_cast<const uint4*>(r.ptr);
-            const uint32_t n8 = (r.card + 7) >> 3;
-            for (uint32_t i = g; i < n8; i += FBGPU_BATCH_UNROLL * G) {
-                uint4 v[FBGPU_BATCH_UNROLL];
-#pragma unroll
-                for (int q = 0; q < FBGPU_BATCH_UNROLL; q++) if (i + q * G < n8) v[q] = ldg_nc(a4 + i + q * G);
-#pragma unroll
-                for (int q = 0; q < FBGPU_BATCH_UNROLL; q++) if (i + q * G < n8) scatter_chunk<MODE>(T32, v[q], (i + q * G) * 8, r.card);
-            }
-        } else if (r.typ == kBitmap) {
-            const uint4* g4 = reinterpret_cast<const uint4*>(r.ptr);
-            for (int i = g; i < 512; i += 2 * G) {
-                uint4 v[2];
-#pragma unroll
-                for (int q = 0; q < 2; q++) if (i + q * G < 512) v[q] = ldg_nc(g4 + i + q * G);
-#pragma unroll
-                for (int q = 0; q < 2; q++) if (i + q * G < 512) {
-                    uint32_t w[4] = { v[q].x, v[q].y, v[q].z, v[q].w };
-#pragma unroll
-                    for (int c = 0; c < 4; c++) {
-                        if (!w[c]) continue;
-                        uint32_t* dst = &T32[4 * (i + q * G) + c];
-                        if (MODE == 0) atomicOr(dst, w[c]); else if (MODE == 1) atomicAnd(dst, ~w[c]); else atomicXor(dst, w[c]);
-                    }
-                }
-            }
-        }
-    }
-}
-
-// ---- alternative batch implementations (selected at compile time by FBGPU_BATCH_IMPL)
 template <int MODE>
 __device__ __forceinline__ void scatter_chunk_unrolled(uint32_t* bm, uint4 v, uint32_t base, uint32_t n) {
     uint32_t w[4] = { v.x, v.y, v.z, v.w };
@@ -307,15 +243,12 @@ __device__ __forceinline__ void scatter_chunk_unrolled(uint32_t* bm, uint4 v, ui
         }
     }
 }
-// v1: one warp per operand, plain loop
+// Batch of commuting row operands (OR / ANDNOT / XOR onto the same target), no barrier in between: warp w takes
+// operands w, w+8, ...; arrays are scattered with red.shared, bitmaps applied with word atomics.  (Tried and slower
+// on B200: 4 loads in flight per thread, register double-buffering, L2 prefetch, TMA staging — profiles/README.md.)
 template <int MODE>
-__device__ __forceinline__ void batch_rows_v1(uint32_t* T32, const Resolved* res, int n) {
+__device__ __forceinline__ void batch_rows(uint32_t* T32, const Resolved* res, int n) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-#if FBGPU_BATCH_PREFETCH
-    // pull every array this warp is going to scatter into L2 first: the sequential per-operand loads below then
-    // see L2 latency instead of HBM latency, at no register cost
-    for (int j = wid; j < n; j += kEvalThreads / 32) { const Resolved r = res[j]; if (r.ptr != nullptr && r.typ == kArray) warp_prefetch_container(r, lane); }
-#endif
     for (int j = wid; j < n; j += kEvalThreads / 32) {
         const Resolved r = res[j];
         if (r.ptr == nullptr) continue;
@@ -326,85 +259,6 @@ __device__ __forceinline__ void batch_rows_v1(uint32_t* T32, const Resolved* res
         } else if (r.typ == kBitmap) warp_bitmap_atomic<MODE>(T32, reinterpret_cast<const uint4*>(r.ptr), lane);
     }
 }
-// v3: one warp per operand, three 16-byte loads per lane in flight and the next operand's loads issued before the
-// current operand is scattered (register double buffering)
-template <int MODE>
-__device__ __forceinline__ void batch_rows_v3(uint32_t* T32, const Resolved* res, int n) {
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    constexpr int NW = kEvalThreads / 32;
-    uint4 cur[3], nxt[3];
-    Resolved rc; rc.ptr = nullptr; rc.card = 0; rc.typ = 0; rc.cnt = 0;
-    int j = wid;
-    auto issue = [&](const Resolved& r, uint4* buf) {
-        if (r.ptr != nullptr && r.typ == kArray) {
-            const uint4* a4 = reinterpret_cast<const uint4*>(r.ptr);
-            const uint32_t n8 = (r.card + 7) >> 3;
-#pragma unroll
-            for (int q = 0; q < 3; q++) if (lane + 32 * q < n8) buf[q] = ldg_nc(a4 + lane + 32 * q);
-        }
-    };
-    if (j < n) { rc = res[j]; issue(rc, cur); }
-    while (j < n) {
-        Resolved rn; rn.ptr = nullptr; rn.card = 0; rn.typ = 0; rn.cnt = 0;
-        if (j + NW < n) { rn = res[j + NW]; issue(rn, nxt); }
-        if (rc.ptr != nullptr) {
-            if (rc.typ == kArray) {
-                const uint32_t n8 = (rc.card + 7) >> 3;
-#pragma unroll
-                for (int q = 0; q < 3; q++) if (lane + 32 * q < n8) scatter_chunk_unrolled<MODE>(T32, cur[q], (lane + 32 * q) * 8, rc.card);
-                const uint4* a4 = reinterpret_cast<const uint4*>(rc.ptr);
-                for (uint32_t i = lane + 96; i < n8; i += 32) scatter_chunk_unrolled<MODE>(T32, ldg_nc(a4 + i), i * 8, rc.card);
-            } else if (rc.typ == kBitmap) warp_bitmap_atomic<MODE>(T32, reinterpret_cast<const uint4*>(rc.ptr), lane);
-        }
-#pragma unroll
-        for (int q = 0; q < 3; q++) cur[q] = nxt[q];
-        rc = rn; j += NW;
-    }
-}
-// v1p: one warp per operand like v1, but flattened over (operand, 512-byte slab) with the next slab's 16-byte load
-// issued before the current slab is scattered, so a warp always has a load in flight while it works shared memory.
-template <int MODE>
-__device__ __forceinline__ void batch_rows_v1p(uint32_t* T32, const Resolved* res, int n) {
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    constexpr int NW = kEvalThreads / 32;
-    // advance (j, q) to the next array slab owned by this warp; returns false at the end
-    auto first_array = [&](int j) { while (j < n && !(res[j].ptr != nullptr && res[j].typ == kArray)) j += NW; return j; };
-    int j = first_array(wid);
-    uint32_t q = 0;
-    uint4 cur = make_uint4(0, 0, 0, 0), nxt = make_uint4(0, 0, 0, 0);
-    Resolved r; r.ptr = nullptr; r.card = 0; r.typ = 0; r.cnt = 0;
-    if (j < n) { r = res[j]; if (lane < ((r.card + 7) >> 3)) cur = ldg_nc(reinterpret_cast<const uint4*>(r.ptr) + lane); }
-    while (j < n) {
-        const uint32_t n8 = (r.card + 7) >> 3;
-        // next slab
-        int j2 = j; uint32_t q2 = q + 1; Resolved r2 = r;
-        if (q2 * 32 >= n8) { j2 = first_array(j + NW); q2 = 0; if (j2 < n) r2 = res[j2]; }
-        if (j2 < n) { const uint32_t i2 = q2 * 32 + lane; if (i2 < ((r2.card + 7) >> 3)) nxt = ldg_nc(reinterpret_cast<const uint4*>(r2.ptr) + i2); }
-        const uint32_t i = q * 32 + lane;
-        if (i < n8) scatter_chunk_unrolled<MODE>(T32, cur, i * 8, r.card);
-        cur = nxt; j = j2; q = q2; r = r2;
-    }
-    for (int k = wid; k < n; k += NW) {       // bitmap operands of the batch (rare): word atomics
-        const Resolved b = res[k];
-        if (b.ptr != nullptr && b.typ == kBitmap) warp_bitmap_atomic<MODE>(T32, reinterpret_cast<const uint4*>(b.ptr), lane);
-    }
-}
-#ifndef FBGPU_BATCH_IMPL
-#define FBGPU_BATCH_IMPL 1
-#endif
-template <int MODE>
-__device__ __noinline__ void batch_rows_dispatch(uint32_t* T32, const Resolved* res, int n) {
-#if FBGPU_BATCH_IMPL == 1
-    batch_rows_v1<MODE>(T32, res, n);
-#elif FBGPU_BATCH_IMPL == 4
-    batch_rows_v1p<MODE>(T32, res, n);
-#elif FBGPU_BATCH_IMPL == 2
-    batch_rows<MODE>(T32, res, n);
-#else
-    batch_rows_v3<MODE>(T32, res, n);
-#endif
-}
-
 struct EvalOut {
     unsigned long long* total;      // += count of every unit (may be null)
     unsigned long long* per_shard;  // [n_shards] += (may be null)
@@ -465,9 +319,9 @@ eval_kernel(StoreRef st, const DevOp* __restrict__ prog, int n_ops, int depth,
                     const int e = min(cur_batch < n_batches ? batches[cur_batch].y - base : k + 1, chunk);
                     uint4* T = phys(top);
                     uint32_t* T32 = reinterpret_cast<uint32_t*>(T);
-                    if (opc == D_OR_ROW) batch_rows_dispatch<0>(T32, res + k, e - k);
-                    else if (opc == D_ANDNOT_ROW) batch_rows_dispatch<1>(T32, res + k, e - k);
-                    else batch_rows_dispatch<2>(T32, res + k, e - k);
+                    if (opc == D_OR_ROW) batch_rows<0>(T32, res + k, e - k);
+                    else if (opc == D_ANDNOT_ROW) batch_rows<1>(T32, res + k, e - k);
+                    else batch_rows<2>(T32, res + k, e - k);
                     __syncthreads();
                     if (has_runs) for (int j = k; j < e; j++) {   // run containers: CTA-wide expansion, one at a time
                         const Resolved r = res[j];

@@ -3,7 +3,8 @@ import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from featurebase_b200 import build as B
 VARIANTS = {
-    "nopf": ["FBGPU_BATCH_PREFETCH=0"],
+    "b7": ["FBGPU_EVAL_MIN_BLOCKS=7"],
+    "t512": ["FBGPU_EVAL_THREADS=512", "FBGPU_EVAL_MIN_BLOCKS=4"],
 }
 if __name__ == "__main__":
     for name, defs in VARIANTS.items():
