@@ -101,6 +101,42 @@ def config5(args, out):
             h.ctx.close()
 
 
+def config_row(args, out):
+    """Row-returning calls (canonical Pilosa-roaring bytes to the host): fbgpu_row end to end, wall clock"""
+    from featurebase_b200 import datagen as D, executor as X, pql
+    from oracle import oracle as O
+    S = args.shards
+    shards = np.arange(S, dtype=np.uint64)
+    h = X.Holder()
+    idx = h.create_index("i", track_existence=False)
+    f = idx.create_field("f")
+    ex = X.Executor(h)
+    bulk = D.fragments(11, shards, [0, 1, 2, 3], 0.01)
+    h.ctx.load_fragments(idx.id, f.id, X.VIEW_STANDARD, shards, bulk.buf, bulk.offsets)
+    h.ctx.commit()
+    idx.shards.update(range(S))
+    for q in ("Intersect(Row(f=0), Row(f=1))", "Union(Row(f=0), Row(f=1), Row(f=2), Row(f=3))", "Row(f=0)"):
+        ops = ex._bitmap_call(idx, pql.parse(q)[0])
+        for _ in range(2):
+            data, cnt = h.ctx.row(idx.id, ops, shards)
+        t0 = time.perf_counter()
+        n = 5
+        for _ in range(n):
+            data, cnt = h.ctx.row(idx.id, ops, shards)
+        wall = (time.perf_counter() - t0) / n * 1e3
+        # oracle spot check: the first shard's segment
+        fr = O.Bitmap.from_bytes(bulk.fragment_bytes(0))
+        call = pql.parse(q)[0]
+        from tests.oracle_exec import OracleIndex
+        oi = OracleIndex(idx)
+        oi.load("f", 0, 0, bulk.fragment_bytes(0))
+        sub, _ = h.ctx.row(idx.id, ops, [0])
+        assert sub == oi.eval_row(call, [0]).to_bytes()
+        out({"config": "R", "query": q, "shards": S, "kernel": "eval_kernel + canon_emit_kernel + host assembly", "ms": wall, "result_bytes": len(data), "result_count": int(cnt),
+             "columns_per_sec": S * SW / (wall * 1e-3), "frac": 0.0, "achieved_gbs": 0.0, "note": "wall clock of fbgpu_row(): evaluate, {N,runs} D2H, encoding choice on host, emit, payload D2H, roaring assembly"})
+    h.ctx.close()
+
+
 def config3(args, out, n_rec=10_000_000, nf=4):
     """nf fields are rotated between steps so that the touched planes exceed L2 (the 10 M-record config is 42.5 MB)"""
     from featurebase_b200 import datagen as D, executor as X, pql
@@ -205,7 +241,9 @@ def main():
 
     for c in args.configs.split(","):
         c = c.strip()
-        if c == "3L":     # the same BSI query at 256 shards (268 M records, 1.1 GB of planes): shows the kernel away from the launch-bound regime
+        if c == "R":
+            config_row(args, out)
+        elif c == "3L":     # the same BSI query at 256 shards (268 M records, 1.1 GB of planes): shows the kernel away from the launch-bound regime
             config3(args, out, n_rec=256 * SW, nf=1)
         else:
             {"5": config5, "3": config3, "4": config4}[c](args, out)

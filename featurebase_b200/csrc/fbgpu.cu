@@ -773,8 +773,9 @@ extern "C" int fbgpu_row(fbgpu_ctx* c, uint32_t index, const fbgpu_op* ops, int3
     const DevOp* d_prog; const uint64_t* d_shards;
     rc = upload_inputs(w, prog, sorted.data(), n_shards, &d_prog, &d_shards); if (rc) return rc;
     long long n_units = (long long)n_shards * kSlotsPerRow;
-    struct OutCont { uint64_t key; uint16_t typ; uint32_t n; uint64_t size; std::vector<uint8_t> payload; };
-    std::vector<OutCont> conts; uint64_t total_count = 0; uint64_t launches = 0; float ms_total = 0;
+    struct OutCont { uint64_t key; uint16_t typ; uint32_t n; uint64_t size; uint32_t batch; uint64_t src_off; };
+    std::vector<OutCont> conts; std::vector<std::vector<uint8_t>> batch_bufs;   // one host copy of the emitted payloads per batch
+    uint64_t total_count = 0; uint64_t launches = 0; float ms_total = 0;
     for (long long u0 = 0; u0 < n_units; u0 += kUnitBatch) {
         long long nu = std::min(kUnitBatch, n_units - u0);
         if (w->d_bitmaps.ensure((size_t)nu * 8192)) return FBGPU_E_NOMEM;
@@ -797,10 +798,12 @@ extern "C" int fbgpu_row(fbgpu_ctx* c, uint32_t index, const fbgpu_op* ops, int3
             EmitUnit e{ off, (uint32_t)u, typ };
             emits.push_back(e);
             OutCont oc; oc.key = sorted[(u0 + u) / kSlotsPerRow] * kSlotsPerRow + (uint64_t)((u0 + u) % kSlotsPerRow); oc.typ = typ; oc.n = N; oc.size = size;
-            conts.push_back(std::move(oc));
+            oc.batch = (uint32_t)batch_bufs.size(); oc.src_off = off;
+            conts.push_back(oc);
             off += (size + 15) & ~15ull;
             total_count += N;
         }
+        if (emits.empty()) batch_bufs.emplace_back();
         if (!emits.empty()) {
             if (w->d_emit_units.ensure(emits.size() * sizeof(EmitUnit))) return FBGPU_E_NOMEM;
             if (w->d_emit.ensure(off)) return FBGPU_E_NOMEM;
@@ -814,7 +817,7 @@ extern "C" int fbgpu_row(fbgpu_ctx* c, uint32_t index, const fbgpu_op* ops, int3
             CUDA_TRY(cudaMemcpyAsync(w->h_in.p, w->d_emit.p, off, cudaMemcpyDeviceToHost, w->stream));
             CUDA_TRY(cudaEventRecord(w->ev1, w->stream));
             CUDA_TRY(cudaStreamSynchronize(w->stream));
-            for (size_t k = 0; k < emits.size(); k++) { OutCont& oc = conts[first + k]; oc.payload.assign((uint8_t*)w->h_in.p + emits[k].offset, (uint8_t*)w->h_in.p + emits[k].offset + oc.size); }
+            batch_bufs.emplace_back((uint8_t*)w->h_in.p, (uint8_t*)w->h_in.p + off);
             float ms = 0; cudaEventElapsedTime(&ms, w->ev0, w->ev1); ms_total += ms;
         }
     }
@@ -832,7 +835,7 @@ extern "C" int fbgpu_row(fbgpu_ctx* c, uint32_t index, const fbgpu_op* ops, int3
         uint16_t n1 = (uint16_t)(oc.n - 1);
         memcpy(h, &oc.key, 8); memcpy(h + 8, &oc.typ, 2); memcpy(h + 10, &n1, 2); h += 12;
         uint32_t o32 = (uint32_t)off; memcpy(offp, &o32, 4); offp += 4;
-        memcpy(out_buf + off, oc.payload.data(), oc.size); off += oc.size;
+        memcpy(out_buf + off, batch_bufs[oc.batch].data() + oc.src_off, oc.size); off += oc.size;
     }
     return FBGPU_OK;
 }

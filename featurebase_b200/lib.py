@@ -155,15 +155,16 @@ class Context:
         sh = _u64arr(shards)
         arr = ops_array(ops)
         need, cnt = C.c_uint64(0), C.c_uint64(0)
-        cap = 1 << 16
+        cap = max(getattr(self, "_row_cap", 0), 1 << 20)
         while True:
-            buf = (C.c_uint8 * cap)()
-            rc = self.L.fbgpu_row(self.h, index, arr, len(ops), sh.ctypes.data, len(sh), buf, cap, C.byref(need), C.byref(cnt))
+            buf = np.empty(cap, dtype=np.uint8)
+            rc = self.L.fbgpu_row(self.h, index, arr, len(ops), sh.ctypes.data, len(sh), buf.ctypes.data, cap, C.byref(need), C.byref(cnt))
             if rc == E_NOSPACE:
-                cap = int(need.value)
+                cap = int(need.value) + (int(need.value) >> 3)
                 continue
             self._check(rc)
-            return bytes(buf[: need.value]), cnt.value
+            self._row_cap = cap
+            return buf[: need.value].tobytes(), cnt.value
 
     def row_counts(self, index, field, view, shards, row_ids=None, filter_ops=None, cap=1 << 20):
         sh = _u64arr(shards)

@@ -1,0 +1,104 @@
+#!/usr/bin/env python3
+"""Regenerates profiles/README.md from the committed measurement files (bench JSON lines, sweep JSONL, ncu summaries)."""
+import csv
+import json
+import os
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+P = os.path.join(ROOT, "profiles")
+
+
+def ncu(name):
+    r = list(csv.reader(open(os.path.join(P, name))))
+    return {h.split(" [")[0]: v for h, v in zip(r[0], r[1])}
+
+
+def main():
+    rows = [json.loads(l) for l in open(os.path.join(P, "r01_sweep.jsonl"))]
+    b = json.load(open(os.path.join(P, "r01_bench.json")))
+    r = json.load(open(os.path.join(P, "r01_bench_reference.json")))
+    ev = ncu("r01_ncu_eval_kernel_summary.csv")
+    tr = json.load(open(os.path.join(P, "traffic.json")))["eval_kernel"]
+    o = []
+    o.append("# profiles/ — round 1 measurements on B200 (sm_100a), one GPU unless noted\n")
+    o.append("All times are CUDA-event durations of the kernels on the library's launching stream (never under a profiler); roofline\n"
+             "denominators are the driver-measured `MEASURED_PEAKS.json` (`hbm_gbs` = 6572 GB/s, \"of measured\"). Algorithmic bytes =\n"
+             "payload of every distinct input container + 16 B per descriptor + mandatory output (SURVEY §8d). Box-to-box spread of the\n"
+             "same binary on this pool is about ±5 % (0.504 / 0.512 / 0.531 ms were seen for the headline kernel on three leases).\n")
+    o.append("## Headline: BASELINE config[1] — 1024 shards x 2^20, 1 %, Count(Intersect(Union(32 rows), Union(32 rows)))\n")
+    o.append("| arm | ms/step | set-ops/s | Count rows/s | columns/s | HBM GB/s (algorithmic) | frac of measured roofline |")
+    o.append("|---|---|---|---|---|---|---|")
+    o.append(f"| ours, kernel (`value`) | {b['ms_per_step']:.4f} | {b['value']:.3e} | {b['count_rows_per_sec']:.3e} | {b['columns_per_sec']:.3e} | {b['roofline']['achieved']:.0f} | {b['roofline']['frac']:.3f} |")
+    o.append(f"| ours, through the C ABI from host buffers (`e2e`) | {b['e2e']['ms_per_step']:.4f} | {b['e2e']['value']:.3e} | | | | |")
+    o.append(f"| CPU restatement of the reference, {r['cpu_baseline']['cores']} host threads (`--impl reference`) | {r['ms_per_step']:.1f} | {r['value']:.3e} | {r['count_rows_per_sec']:.3e} | {r['columns_per_sec']:.3e} | | |")
+    o.append(f"\nkernel/CPU = {b['value'] / r['value']:.0f}x, e2e/CPU = {b['e2e']['value'] / r['value']:.0f}x (a reported baseline, not the target). One-time cold load of the "
+             f"{b['e2e_cold_load']['h2d_bytes'] / 1e9:.2f} GB of fragments (parse + stage + H2D + first query): {b['e2e_cold_load']['ms']:.0f} ms.")
+    o.append(f"DRAM traffic of `eval_kernel` (ncu `dram__bytes_read.sum + dram__bytes_write.sum`): {tr['dram_bytes_per_launch']:,} B per launch vs "
+             f"{tr['algorithmic_bytes_per_launch']:,} algorithmic bytes (x{tr['dram_bytes_per_launch'] / tr['algorithmic_bytes_per_launch']:.3f}): no wasted re-reads. "
+             f"Clocks during the run: {b['clocks']['sm_mhz']:.0f}/{b['clocks']['sm_max_mhz']:.0f} MHz, throttle reasons: {b['clocks']['reasons'] or 'none'}. "
+             f"`gpu_launches` = {b['gpu_launches']} for {b['steps']} steps (one fused kernel per step).")
+    o.append("2 GPUs (weak scaling, 1024 shards per GPU, in-library NCCL sum all-reduce of the count): 0.516 ms/step, 2.50e8 set-ops/s (x1.96 of one GPU on the same lease class); the driver measures N = 1, 2, 4, 8.\n")
+    o.append("## How the headline kernel got here (same workload)\n")
+    o.append("| step | eval kernel ms | frac | what changed | evidence |")
+    o.append("|---|---|---|---|---|")
+    o.append("| first correct version | 1.540 | 0.137 | one op at a time, a barrier per op | `r01_ncu_eval_first_summary.csv`: 977 M warp-instr, barrier + long-scoreboard stalls |")
+    o.append("| barrier-free batches | 0.932 | 0.227 | runs of commuting row ops are scattered warp-per-operand with `red.shared`, no barrier in between | |")
+    o.append("| 7-8 CTAs/SM | 0.728 | 0.291 | `__launch_bounds__(256, 8)` (32 registers), 128-op resolve chunks | |")
+    o.append("| host-computed batch extents, run flag | 0.530 | 0.399 | removed two per-thread op-scan loops = 32 % of all executed instructions (ncu source page) | |")
+    o.append("| dense (shard,row) directory | 0.504 | 0.420 | descriptor chain 5 -> 3 dependent loads | |")
+    o.append(f"| this table's measurement lease | {b['ms_per_step']:.3f} | {b['roofline']['frac']:.3f} | same code | `r01_ncu_eval_kernel_summary.csv`, `r01_launches.csv` |")
+    o.append("| tried, slower: TMA-staged ring (`eval_staged_kernel`, opt-in `FBGPU_STAGED=1`) | 0.748 | 0.283 | `cp.async.bulk` + mbarrier pipeline removes the HBM-latency stall (long-scoreboard 6.6 -> 0.4 per issue) but only 2-3 CTAs fit per SM and the shared-memory atomic pipe is the limiter either way | `r01_ncu_eval_staged_kernel_summary.csv` |")
+    o.append("| tried, slower: 4 loads in flight per thread, register double-buffering, L2 prefetch of the batch | 0.52-2.1 | | extra registers cost CTA residency, which matters more than per-warp MLP here | |")
+    o.append(f"\nWhere the time goes now (ncu): {float(ev['smsp__inst_executed.sum']) / 1e6:.0f} M warp instructions, issue slots {float(ev['smsp__issue_active.avg.pct_of_peak_sustained_active']):.0f} % busy; "
+             f"{float(ev['l1tex__data_pipe_lsu_wavefronts_mem_shared.sum']) / 1e6:.0f} M shared-memory wavefronts ({float(ev['l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed']):.0f} % of the LSU shared pipe's peak, "
+             f"{float(ev['l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum']) / 1e6:.0f} M of them bank conflicts of the random scatter) for 687 M scattered elements; warps active {float(ev['sm__warps_active.avg.pct_of_peak_sustained_active']):.0f} %. "
+             "The kernel is co-limited by shared-memory atomics and issue, not by HBM: 1 %-density data is array-container work; bitmap-container work streams at 82-98 % (below).\n")
+    o.append("## BASELINE config 5 — density sweep, Count(Intersect(Row a, Row b)), 1024 shards (1 B columns), `pair_count_kernel`\n")
+    o.append("`5` = one query per launch (as the executor issues it); `5b` = N independent row pairs fused in one launch through `fbgpu_count_pairs` (SURVEY §8d \"batched\").\n")
+    o.append("| cfg | generator | density | containers (array/bitmap/run) | pairs/launch | ms | GB/s | frac | note |")
+    o.append("|---|---|---|---|---|---|---|---|---|")
+    for d in rows:
+        if d["config"] in (5, "5b"):
+            c = d.get("containers")
+            cs = f"{c['array']}/{c['bitmap']}/{c['run']}" if c else ""
+            o.append(f"| {d['config']} | {d['generator']} | {d['density'] * 100:g} % | {cs} | {d.get('pairs_per_launch', 1)} | {d['ms']:.4f} | {d['achieved_gbs']:.0f} | {d['frac']:.3f} | {d['l2_note']} |")
+    o.append("\nNorth-star acceptance point (1 %, 1 B columns, 43 MB per query): 23 % of roofline for a single query — launch + dependent-load latency bound (even near-empty containers take 17 us) — and 34 % when 7 pairs share a launch, where the shared-memory build/probe of array x array is the limiter. "
+             "Bitmap x bitmap streams at 82 % (single) / 98 % (batched). Clustered data (run containers) is latency-bound at these sizes: 13-135 MB per query.\n")
+    o.append("## BASELINE config 3 — BSI `Count(Row(v > k))`, 32-bit values (`eval_wordpar_kernel`)\n")
+    o.append("| records | query | ms | GB/s | frac | records/s |")
+    o.append("|---|---|---|---|---|---|")
+    for d in rows:
+        if d["config"] == 3:
+            o.append(f"| {d['records']:,} | {d['query']} | {d['ms']:.4f} | {d['achieved_gbs']:.0f} | {d['frac']:.3f} | {d['records_per_sec']:.3e} |")
+    o.append("\nThe 10 M-record config is 42.5 MB of bit planes over 160 (shard, slot) units: launch/latency bound. At 268 M records the word-parallel kernel is bound by its per-op interpretive instruction overhead (34-37 % of roofline). The shared-memory program machine took 0.055-0.065 ms on the 10 M config.\n")
+    o.append("## BASELINE config 4 — GroupBy(Rows(a), Rows(b)) 256 x 256, one GPU's share (512 of 4096 shards)\n")
+    for d in rows:
+        if d["config"] == 4:
+            o.append(f"`groupby_kernel`: {d['ms']:.3f} ms for {d['records']:,} records ({d['records_per_sec']:.3e} records/s, {d['group_counts_per_sec']:.3e} group counts/s, {d['nonzero_groups']} non-zero groups); "
+                     f"algorithmic {d['algorithmic_bytes'] / 1e6:.0f} MB (payload {d['payload_bytes'] / 1e6:.0f} MB) -> {d['achieved_gbs']:.0f} GB/s ({d['frac']:.3f}). "
+                     "Tiny containers (~6 elements) make this descriptor- and latency-bound; the hash-join does work proportional to the records, where the reference does 65,536 IntersectionCount calls per shard. First version (128 KiB direct column table, 1 CTA/SM): 6.9 ms.\n")
+    o.append("## Row-returning calls (`fbgpu_row`, wall clock incl. encoding choice, emission, D2H and roaring assembly), 1024 shards @ 1 %\n")
+    o.append("| query | ms | result bytes | result count |")
+    o.append("|---|---|---|---|")
+    for d in rows:
+        if d["config"] == "R":
+            o.append(f"| `{d['query']}` | {d['ms']:.2f} | {d['result_bytes']:,} | {d['result_count']:,} |")
+    o.append("\nLarge results are dominated by host-side copies of the payload (D2H landing buffer -> per-batch buffer -> caller's buffer); a device-side prefix sum and direct D2H into the caller's buffer are the obvious next step.\n")
+    o.append("## Correctness tooling\n")
+    o.append("`r01_sanitizer_memcheck.log`: compute-sanitizer memcheck over the eval / pair / row-count / groupby / word-parallel / staged kernels (8 GPU tests): 0 errors. `r01_sanitizer_racecheck.log`: racecheck (shared-memory hazards): 0 hazards.\n")
+    o.append("## Files\n")
+    o.append("| file | what |")
+    o.append("|---|---|")
+    for f, w in [("r01_bench.json", "bench.py line (ours), 50 steps, with cpu_baseline and e2e_cold_load"), ("r01_bench_reference.json", "bench.py --impl reference line"),
+                 ("r01_launches.csv", "ncu gpu__time_duration launch list of `bench.py --steps 4 --warmup 3` (one eval_kernel launch per step, 100 % of the step's kernel time)"),
+                 ("r01_ncu_eval_kernel_summary.csv", "ncu --set full summary of eval_kernel (traffic, stalls, occupancy)"), ("traffic.json", "DRAM bytes per launch read by bench.py for `roofline.traffic`"),
+                 ("r01_ncu_pair_kernel_summary.csv / r01_ncu_groupby_kernel_summary.csv / r01_ncu_eval_wordpar_kernel_summary.csv / r01_ncu_eval_staged_kernel_summary.csv", "ncu --set full summaries of the other kernels"),
+                 ("r01_ncu_eval_first_summary.csv / r01_launches_first.csv / r01_bench_first.json / r01_sweep_first.jsonl", "the first correct version, for the before/after record"),
+                 ("r01_sweep.jsonl", "bench_sweep.py --configs 5,3,3L,4,R --batched"), ("r01_micro_aa_variants.txt", "bench_micro/aa_variants.cu: five array x array strategies + raw shared-memory atomic/LDS/STS throughput"),
+                 ("r01_sanitizer_*.log", "compute-sanitizer runs")]:
+        o.append(f"| `{f}` | {w} |")
+    open(os.path.join(P, "README.md"), "w").write("\n".join(o) + "\n")
+
+
+if __name__ == "__main__":
+    main()
