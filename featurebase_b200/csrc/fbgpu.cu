@@ -678,8 +678,8 @@ static int launch_eval(fbgpu_ctx* c, Workspace* w, const std::vector<DevOp>& pro
         uint64_t arr = 0, other = 0;
         for (const DevOp& o : prog) if (o.op >= D_PUSH_ROW && o.op <= D_ORANDNOT_ROW && o.op != D_PUSH_EMPTY && o.fv < c->view_arr.size()) { arr += c->view_arr[o.fv]; other += c->view_other[o.fv]; }
         if ((other > 0 && arr * 8 <= other) || getenv("FBGPU_FORCE_WORDPAR")) {
-            long long blocks = n_units * 4;
-            long long grid = std::min<long long>(blocks, (long long)c->sm_count * 16);
+            long long blocks = n_units * kWpBlocksPerUnit;
+            long long grid = std::min<long long>(blocks, (long long)c->sm_count * std::max(FBGPU_WP_MIN_BLOCKS, 8) * 2);
             eval_wordpar_kernel<<<(unsigned)grid, kWpThreads, 0, w->stream>>>(store_ref(c), d_prog, n_ops, d_shards, n_units, out);
             CUDA_TRY(cudaGetLastError());
             return 0;

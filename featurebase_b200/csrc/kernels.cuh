@@ -702,7 +702,7 @@ eval_staged_kernel(StoreRef st, const DevOp* __restrict__ prog, int n_ops, int d
 // handled by a per-thread search for the slice's elements, so any program is valid here; the host only picks this
 // kernel when the referenced views are dominated by bitmap/run containers.
 // ------------------------------------------------------------------------------------------------
-constexpr int kWpThreads = 128;              // 4 CTAs per unit (512 128-bit slices)
+constexpr int kWpThreads = 128;              // 512 / (128 * slices-per-thread) CTAs per unit
 constexpr int kWpMaxOps = 256;
 constexpr int kWpMaxDepth = 4;
 
@@ -736,63 +736,105 @@ __device__ __forceinline__ uint4 wp_slice(const Resolved& r, int i) {
     return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
-__global__ void __launch_bounds__(kWpThreads)
+#ifndef FBGPU_WP_SLICES
+#define FBGPU_WP_SLICES 1
+#endif
+#ifndef FBGPU_WP_MIN_BLOCKS
+#define FBGPU_WP_MIN_BLOCKS 8
+#endif
+constexpr int kWpSlices = FBGPU_WP_SLICES;       // uint4 slices per thread (slice q of a thread: i0 + q * kWpThreads => coalesced)
+constexpr int kWpBlocksPerUnit = 512 / (kWpThreads * kWpSlices);
+
+struct WpOp { const void* ptr; uint32_t card; uint16_t typ, cnt; uint8_t opc, is_row, pad[6]; };   // pre-decoded op, 24 B
+
+__global__ void __launch_bounds__(kWpThreads, FBGPU_WP_MIN_BLOCKS)
 eval_wordpar_kernel(StoreRef st, const DevOp* __restrict__ prog, int n_ops,
                     const uint64_t* __restrict__ shards, long long n_units, EvalOut out) {
-    __shared__ Resolved res[kWpMaxOps];
-    __shared__ uint8_t opcode[kWpMaxOps];      // bit 7: row op
+    __shared__ WpOp ops[kWpMaxOps];
+    __shared__ uint16_t rowops[kWpMaxOps];     // indices of the row ops, in program order
+    __shared__ int n_rowops;
     __shared__ uint32_t wsum[kWpThreads / 32];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const long long n_blocks = n_units * 4;
+    const long long n_blocks = n_units * kWpBlocksPerUnit;
     for (long long blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
-        const long long unit = blk >> 2;
-        const int i = (int)(blk & 3) * kWpThreads + tid;             // uint4 index inside the stripe
+        const long long unit = blk / kWpBlocksPerUnit;
+        const int i0 = (int)(blk % kWpBlocksPerUnit) * kWpThreads * kWpSlices + tid;
         __syncthreads();
-        for (int k = tid; k < n_ops; k += kWpThreads) {
+        for (int k = tid; k < n_ops; k += kWpThreads) {        // decode + resolve: one op per thread
             DevOp op = prog[k];
             Resolved r; r.ptr = nullptr; r.card = 0; r.typ = 0; r.cnt = 0;
             const bool row_op = op.op >= D_PUSH_ROW && op.op <= D_ORANDNOT_ROW && op.op != D_PUSH_EMPTY;
             if (row_op) r = resolve(st, op.fv, shards[unit >> 4], op.row, (int)(unit & 15));
-            res[k] = r; opcode[k] = op.op | (row_op ? 0x80 : 0);
+            WpOp w; w.ptr = r.ptr; w.card = r.card; w.typ = r.typ; w.cnt = r.cnt; w.opc = op.op; w.is_row = row_op ? 1 : 0;
+            ops[k] = w;
         }
         __syncthreads();
-        auto next_row_op = [&](int k) { while (k < n_ops && !(opcode[k] & 0x80)) k++; return k; };
-        // prefetch ring: operands of the next three row ops are in flight while the current one is applied
+        if (tid == 0) { int n = 0; for (int k = 0; k < n_ops; k++) if (ops[k].is_row) rowops[n++] = (uint16_t)k; n_rowops = n; }
+        __syncthreads();
+        const int nr = n_rowops;
+        auto fetch = [&](uint4* dst, int ri) {
+            const WpOp w = ops[rowops[ri]];
+            if (w.ptr != nullptr && w.typ == kBitmap) {
+#pragma unroll
+                for (int q = 0; q < kWpSlices; q++) dst[q] = ldg_nc(reinterpret_cast<const uint4*>(w.ptr) + i0 + q * kWpThreads);
+            } else {
+                Resolved r; r.ptr = w.ptr; r.card = w.card; r.typ = w.typ; r.cnt = w.cnt;
+#pragma unroll
+                for (int q = 0; q < kWpSlices; q++) dst[q] = wp_slice(r, i0 + q * kWpThreads);
+            }
+        };
         const uint4 z = make_uint4(0, 0, 0, 0);
-        uint4 p0 = z, p1 = z, p2 = z;
-        int kk = next_row_op(0);
-        if (kk < n_ops) { p0 = wp_slice(res[kk], i); kk = next_row_op(kk + 1); }
-        if (kk < n_ops) { p1 = wp_slice(res[kk], i); kk = next_row_op(kk + 1); }
-        if (kk < n_ops) { p2 = wp_slice(res[kk], i); kk = next_row_op(kk + 1); }
+        // prefetch ring: operands of the next three row ops are in flight while the current one is applied
+        uint4 p0[kWpSlices], p1[kWpSlices], p2[kWpSlices];
+#pragma unroll
+        for (int q = 0; q < kWpSlices; q++) { p0[q] = z; p1[q] = z; p2[q] = z; }
+        int ri = 0;
+        if (ri < nr) fetch(p0, ri++);
+        if (ri < nr) fetch(p1, ri++);
+        if (ri < nr) fetch(p2, ri++);
         // operand stack as a shift register: T = top, B = below, S2, S3 deeper (depth <= 4 checked by the host)
-        uint4 T = z, B = z, S2 = z, S3 = z;
+        uint4 T[kWpSlices], B[kWpSlices], S2[kWpSlices], S3[kWpSlices];
+#pragma unroll
+        for (int q = 0; q < kWpSlices; q++) { T[q] = z; B[q] = z; S2[q] = z; S3[q] = z; }
         int depth_now = 0;
         for (int k = 0; k < n_ops; k++) {
-            const uint8_t oc = opcode[k];
-            const uint8_t opc = oc & 0x7f;
-            if (!(oc & 0x80)) {
-                if (opc == D_PUSH_EMPTY) { S3 = S2; S2 = B; B = T; T = z; depth_now++; }
-                else if (opc == D_SWAP) { uint4 t = T; T = B; B = t; }
-                else if (opc == D_POP) { T = B; B = S2; S2 = S3; depth_now--; }
-                else { T = opc == D_AND ? and4(B, T) : opc == D_OR ? or4(B, T) : opc == D_ANDNOT ? andn4(B, T) : xor4(B, T); B = S2; S2 = S3; depth_now--; }
+            const uint8_t opc = ops[k].opc;
+            if (!ops[k].is_row) {
+#pragma unroll
+                for (int q = 0; q < kWpSlices; q++) {
+                    if (opc == D_PUSH_EMPTY) { S3[q] = S2[q]; S2[q] = B[q]; B[q] = T[q]; T[q] = z; }
+                    else if (opc == D_SWAP) { uint4 t = T[q]; T[q] = B[q]; B[q] = t; }
+                    else if (opc == D_POP) { T[q] = B[q]; B[q] = S2[q]; S2[q] = S3[q]; }
+                    else { T[q] = opc == D_AND ? and4(B[q], T[q]) : opc == D_OR ? or4(B[q], T[q]) : opc == D_ANDNOT ? andn4(B[q], T[q]) : xor4(B[q], T[q]); B[q] = S2[q]; S2[q] = S3[q]; }
+                }
+                depth_now += opc == D_PUSH_EMPTY ? 1 : opc == D_SWAP ? 0 : -1;
                 continue;
             }
-            const uint4 x = p0;
-            p0 = p1; p1 = p2; p2 = z;
-            if (kk < n_ops) { p2 = wp_slice(res[kk], i); kk = next_row_op(kk + 1); }
-            switch (opc) {
-                case D_PUSH_ROW: S3 = S2; S2 = B; B = T; T = x; depth_now++; break;
-                case D_OR_ROW: T = or4(T, x); break;
-                case D_AND_ROW: T = and4(T, x); break;
-                case D_ANDNOT_ROW: T = andn4(T, x); break;
-                case D_XOR_ROW: T = xor4(T, x); break;
-                case D_ORAND_ROW: B = or4(B, and4(T, x)); break;
-                default: B = or4(B, andn4(T, x)); break;             // D_ORANDNOT_ROW
+#pragma unroll
+            for (int q = 0; q < kWpSlices; q++) {
+                const uint4 x = p0[q];
+                switch (opc) {
+                    case D_PUSH_ROW: S3[q] = S2[q]; S2[q] = B[q]; B[q] = T[q]; T[q] = x; break;
+                    case D_OR_ROW: T[q] = or4(T[q], x); break;
+                    case D_AND_ROW: T[q] = and4(T[q], x); break;
+                    case D_ANDNOT_ROW: T[q] = andn4(T[q], x); break;
+                    case D_XOR_ROW: T[q] = xor4(T[q], x); break;
+                    case D_ORAND_ROW: B[q] = or4(B[q], and4(T[q], x)); break;
+                    default: B[q] = or4(B[q], andn4(T[q], x)); break;       // D_ORANDNOT_ROW
+                }
+                p0[q] = p1[q]; p1[q] = p2[q]; p2[q] = z;
             }
+            if (opc == D_PUSH_ROW) depth_now++;
+            if (ri < nr) fetch(p2, ri++);
         }
-        const uint4 rsl = depth_now > 0 ? T : z;
-        if (out.bitmaps) out.bitmaps[(size_t)unit * 512 + i] = rsl;
-        uint32_t cnt = __reduce_add_sync(0xffffffffu, (uint32_t)popc4(rsl));
+        uint32_t cnt = 0;
+#pragma unroll
+        for (int q = 0; q < kWpSlices; q++) {
+            const uint4 rsl = depth_now > 0 ? T[q] : z;
+            if (out.bitmaps) out.bitmaps[(size_t)unit * 512 + i0 + q * kWpThreads] = rsl;
+            cnt += (uint32_t)popc4(rsl);
+        }
+        cnt = __reduce_add_sync(0xffffffffu, cnt);
         if (lane == 0) wsum[wid] = cnt;
         __syncthreads();
         if (tid == 0) {

@@ -2,9 +2,9 @@
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from featurebase_b200 import build as B
-VARIANTS = {
-    "b7": ["FBGPU_EVAL_MIN_BLOCKS=7"],
-    "t512": ["FBGPU_EVAL_THREADS=512", "FBGPU_EVAL_MIN_BLOCKS=4"],
+VARIANTS = {   # name -> -D defines; edit freely, outputs featurebase_b200/libfbgpu_<name>.so (select with FBGPU_LIB=...)
+    "eval_b7": ["FBGPU_EVAL_MIN_BLOCKS=7"],
+    "wp2": ["FBGPU_WP_SLICES=2"],
 }
 if __name__ == "__main__":
     for name, defs in VARIANTS.items():
