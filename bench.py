@@ -133,6 +133,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cold", action="store_true", help="also time fragment upload + query (e2e_cold_load)")
     args = ap.parse_args()
+    if int(os.environ.get("LOCAL_RANK", "0")) == 0:
+        import __graft_entry__
+        __graft_entry__.build()          # no-op when libfbgpu.so / datagen / oracle are up to date
     if args.impl == "reference":
         return run_reference(args)
 

@@ -24,3 +24,11 @@ def pytest_collection_modifyitems(config, items):
     for it in items:
         if "gpu" in it.keywords:
             it.add_marker(skip)
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _native_builds():
+    """make sure the in-tree native pieces exist (no-op when they are up to date): libfbgpu.so (nvcc cross-compiles
+    without a GPU), the datagen helper and the CPU oracle"""
+    import __graft_entry__
+    __graft_entry__.build()
