@@ -131,6 +131,7 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--shards-per-gpu", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--reduce", default="p2p", choices=["p2p", "nccl"], help="N>1: fused peer-memory Count merge (default) or ncclAllReduce")
     ap.add_argument("--cold", action="store_true", help="also time fragment upload + query (e2e_cold_load)")
     args = ap.parse_args()
     if int(os.environ.get("LOCAL_RANK", "0")) == 0:
@@ -173,6 +174,10 @@ def main():
         uid = [h.ctx.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         h.ctx.comm_init(world, rank, uid[0])
+        if args.reduce == "p2p":   # fused Count merge over NVLink peer memory (mailboxes mapped through CUDA IPC)
+            handles = [None] * world
+            dist.all_gather_object(handles, h.ctx.comm_p2p_handle())
+            h.ctx.comm_p2p_open(world, rank, handles)
     ops = ex._bitmap_call(idx, pql.parse(query_text())[0].children[0])
     payload, n_cont = h.ctx.rows_payload_bytes(idx.id, fld.id, X.VIEW_STANDARD, shards, ROWS_A + ROWS_B)
     algo_bytes = payload + 16 * n_cont + 8                       # payload + 16 B/descriptor + 8 B count
@@ -203,23 +208,23 @@ def main():
     sync_all()
     wall = time.perf_counter() - t_begin
     launches = h.ctx.counters()["kernel_launches"] - c0
-    # nvidia-smi cannot sample faster than ~10 Hz; when the timed region was shorter than that, keep the identical
-    # step running (untimed) until the sampler has seen the GPU under this load, and say so
-    probe_note = None
-    if wall < 0.5:
-        t_probe = time.perf_counter()
-        while time.perf_counter() - t_probe < 0.7:
-            step()
-        probe_note = "timed region %.0f ms < sampler period: clocks sampled over the timed region plus 0.7 s of the identical step" % (wall * 1e3)
-    clocks = sampler.stop()
-    if probe_note:
-        clocks["note"] = probe_note
     kms = float(np.mean(kernel_ms))
     # max over ranks (device time of the kernels; wall time of the C-ABI calls)
     if world > 1:
         t = torch.tensor([kms, wall], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         kms, wall = float(t[0]), float(t[1])
+    # nvidia-smi cannot sample faster than ~10 Hz; when the timed region was shorter than that, keep the identical
+    # step running (untimed; the SAME number of steps on every rank, the step contains a collective) until the sampler
+    # has seen the GPU under this load, and say so
+    probe_note = None
+    if wall < 0.5:
+        for _ in range(int(0.7 / max(wall / args.steps, 1e-5)) + 1):
+            step()
+        probe_note = "timed region %.0f ms < sampler period: clocks sampled over the timed region plus about 0.7 s of the identical step" % (wall * 1e3)
+    clocks = sampler.stop()
+    if probe_note:
+        clocks["note"] = probe_note
     total_shards = S * world
     set_ops = SET_OPS_PER_SHARD * total_shards
     value = set_ops / (kms * 1e-3)
@@ -259,7 +264,7 @@ def main():
             "ms_per_step": kms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64/u16 integer", "data": "synthetic",
             "config": {"workload": "configs[1]: 1024 shards x 2^20 cols per GPU, 1% density, 64-row Union->Intersect->Count",
                        "query": "Count(Intersect(Union(Row f=0..31),Union(Row f=32..63)))", "shards_per_gpu": S, "total_shards": total_shards,
-                       "density": 0.01, "l2": f"inputs {payload / 1e6:.0f} MB per GPU > 126 MB L2 (no flush needed)", "parallelism": f"shard-range x{world}"},
+                       "density": 0.01, "l2": f"inputs {payload / 1e6:.0f} MB per GPU > 126 MB L2 (no flush needed)", "parallelism": f"shard-range x{world}", "count_merge": (args.reduce if world > 1 else "none")},
             "count_rows_per_sec": total_shards / (kms * 1e-3), "columns_per_sec": total_shards * SW / (kms * 1e-3),
             "check_count": int(expect),
             "e2e": {"value": set_ops / (e2e_ms * 1e-3), "unit": "set-ops/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 8,

@@ -130,6 +130,8 @@ struct fbgpu_ctx {
     std::mutex cnt_mu; fbgpu_counters counters{};
     // ---- comm
     void* comm = nullptr; int n_ranks = 1, rank = 0;
+    // fused peer-memory reduce (Count)
+    Mailbox* mbox = nullptr; Mailbox* peers[kMaxRanks] = {}; DevBuf d_peers; bool p2p = false; unsigned long long epoch = 0; std::mutex coll_mu;
 };
 
 static StoreRef store_ref(fbgpu_ctx* c) {
@@ -723,33 +725,45 @@ extern "C" int fbgpu_count(fbgpu_ctx* c, uint32_t index, const fbgpu_op* ops, in
     WsLease lease(c); Workspace* w = lease.w;
     const DevOp* d_prog; const uint64_t* d_shards;
     rc = upload_inputs(w, prog, shards, n_shards, &d_prog, &d_shards); if (rc) return rc;
-    size_t nc = 1 + (out_per_shard ? (size_t)n_shards : 0);
+    // layout of d_counts: [total][per-shard counts ...][ticket][reduced result]
+    const size_t nper = out_per_shard ? (size_t)n_shards : 0, nc = 1 + nper + 2;
     if (w->d_counts.ensure(nc * 8)) return FBGPU_E_NOMEM;
     if (w->h_out.ensure(nc * 8)) return FBGPU_E_NOMEM;
     CUDA_TRY(cudaMemsetAsync(w->d_counts.p, 0, nc * 8, w->stream));
     unsigned long long* d_total = (unsigned long long*)w->d_counts.p;
     unsigned long long* d_per = out_per_shard ? d_total + 1 : nullptr;
     long long n_units = (long long)n_shards * kSlotsPerRow;
+    // cross-GPU merge of the count: fused into the kernel over peer memory when the mailboxes are mapped, else NCCL
+    std::unique_lock<std::mutex> coll_lk(c->coll_mu, std::defer_lock);
+    FuseReduce fr{};
+    if (c->p2p) {
+        coll_lk.lock();                      // collective queries are issued in the same order on every rank
+        fr.peers = (Mailbox* const*)c->d_peers.p; fr.ticket = (unsigned int*)(d_total + 1 + nper); fr.result = d_total + 1 + nper + 1;
+        fr.epoch = ++c->epoch; fr.rank = c->rank; fr.n_ranks = c->n_ranks;
+    }
     CUDA_TRY(cudaEventRecord(w->ev0, w->stream));
     if (n_units > 0) {
         // fused Intersect+Count fast path: Count(Intersect(Row, Row))  (executor.go:5357 + row.go:242 + Count)
         if (prog.size() == 2 && prog[0].op == D_PUSH_ROW && prog[1].op == D_AND_ROW) {
             long long grid = std::min<long long>((n_units + kPairWarps - 1) / kPairWarps, (long long)c->sm_count * 3);
-            pair_count_kernel<<<(unsigned)grid, kPairWarps * 32, kPairWarps * 8192, w->stream>>>(store_ref(c), prog[0].fv, prog[0].row, prog[1].fv, prog[1].row, nullptr, nullptr, n_units, d_shards, n_units, d_total, d_per, nullptr);
+            pair_count_kernel<<<(unsigned)grid, kPairWarps * 32, kPairWarps * 8192, w->stream>>>(store_ref(c), prog[0].fv, prog[0].row, prog[1].fv, prog[1].row, nullptr, nullptr, n_units, d_shards, n_units, d_total, d_per, nullptr, fr);
             CUDA_TRY(cudaGetLastError());
         } else {
-            EvalOut eo{ d_total, d_per, nullptr, nullptr };
+            EvalOut eo{ d_total, d_per, nullptr, nullptr, fr };
             rc = launch_eval(c, w, prog, d_prog, depth, d_shards, n_units, eo); if (rc) return rc;
         }
+    } else if (c->p2p) {
+        p2p_reduce_only_kernel<<<1, 1, 0, w->stream>>>(fr, d_total);
+        CUDA_TRY(cudaGetLastError());
     }
-    rc = allreduce_u64(c, w, d_total, 1); if (rc) return rc;     // inside the timed bracket: the collective is part of the step
+    if (!c->p2p) { rc = allreduce_u64(c, w, d_total, 1); if (rc) return rc; }   // inside the timed bracket: the collective is part of the step
     CUDA_TRY(cudaEventRecord(w->ev1, w->stream));
     CUDA_TRY(cudaMemcpyAsync(w->h_out.p, w->d_counts.p, nc * 8, cudaMemcpyDeviceToHost, w->stream));
     CUDA_TRY(cudaStreamSynchronize(w->stream));
-    *out_total = ((uint64_t*)w->h_out.p)[0];
+    *out_total = c->p2p ? ((uint64_t*)w->h_out.p)[1 + nper + 1] : ((uint64_t*)w->h_out.p)[0];
     if (out_per_shard) memcpy(out_per_shard, (uint64_t*)w->h_out.p + 1, (size_t)n_shards * 8);
     float ms = 0; cudaEventElapsedTime(&ms, w->ev0, w->ev1);
-    bump(c, n_units > 0 ? 1 : 0, ms);
+    bump(c, (n_units > 0 || c->p2p) ? 1 : 0, ms);
     return FBGPU_OK;
 }
 
@@ -781,7 +795,7 @@ extern "C" int fbgpu_row(fbgpu_ctx* c, uint32_t index, const fbgpu_op* ops, int3
         if (w->d_bitmaps.ensure((size_t)nu * 8192)) return FBGPU_E_NOMEM;
         if (w->d_info.ensure((size_t)nu * 8)) return FBGPU_E_NOMEM;
         if (w->h_out.ensure((size_t)nu * 8)) return FBGPU_E_NOMEM;
-        EvalOut eo{ nullptr, nullptr, (uint4*)w->d_bitmaps.p, (uint2*)w->d_info.p };
+        EvalOut eo{ nullptr, nullptr, (uint4*)w->d_bitmaps.p, (uint2*)w->d_info.p, FuseReduce{} };
         CUDA_TRY(cudaEventRecord(w->ev0, w->stream));
         rc = launch_eval(c, w, prog, d_prog, depth, d_shards + u0 / kSlotsPerRow, nu, eo); if (rc) return rc;
         launches++;
@@ -844,7 +858,7 @@ extern "C" int fbgpu_row(fbgpu_ctx* c, uint32_t index, const fbgpu_op* ops, int3
 // evaluates `filter` for shards [s0, s0+ns) into w->d_bitmaps (16 bitmaps per shard)
 static int eval_filter_batch(fbgpu_ctx* c, Workspace* w, const std::vector<DevOp>& prog, int depth, const DevOp* d_prog, const uint64_t* d_shards, int64_t ns) {
     if (w->d_bitmaps.ensure((size_t)ns * kSlotsPerRow * 8192)) return FBGPU_E_NOMEM;
-    EvalOut eo{ nullptr, nullptr, (uint4*)w->d_bitmaps.p, nullptr };
+    EvalOut eo{ nullptr, nullptr, (uint4*)w->d_bitmaps.p, nullptr, FuseReduce{} };
     return launch_eval(c, w, prog, d_prog, depth, d_shards, ns * kSlotsPerRow, eo);
 }
 
@@ -943,7 +957,7 @@ extern "C" int fbgpu_count_pairs(fbgpu_ctx* c, uint32_t index, uint32_t field_a,
     if (n_units > 0) {
         long long grid = std::min<long long>((n_units + kPairWarps - 1) / kPairWarps, (long long)c->sm_count * 3);
         pair_count_kernel<<<(unsigned)grid, kPairWarps * 32, kPairWarps * 8192, w->stream>>>(store_ref(c), fa, 0, fb, 0, (const uint64_t*)w->d_rows.p, (const uint64_t*)w->d_rows.p + np,
-            upp, d_shards, n_units, nullptr, nullptr, (unsigned long long*)w->d_counts.p);
+            upp, d_shards, n_units, nullptr, nullptr, (unsigned long long*)w->d_counts.p, FuseReduce{});
         CUDA_TRY(cudaGetLastError());
     }
     CUDA_TRY(cudaEventRecord(w->ev1, w->stream));
@@ -1061,6 +1075,35 @@ extern "C" int fbgpu_comm_destroy(fbgpu_ctx* c) {
     if (c->comm && nccl_load()) { cudaSetDevice(c->device); cudaDeviceSynchronize(); g_nccl.CommDestroy(c->comm); }
     c->comm = nullptr; c->n_ranks = 1; c->rank = 0;
     return 0;
+}
+
+// ---- fused peer-memory reduce: mailbox exchange through CUDA IPC (one process per GPU)
+extern "C" int fbgpu_comm_p2p_handle(fbgpu_ctx* c, uint8_t out[64]) {
+    if (!c || !out) return fail(FBGPU_E_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (!c->mbox) { CUDA_TRY(cudaMalloc((void**)&c->mbox, sizeof(Mailbox))); CUDA_TRY(cudaMemset(c->mbox, 0, sizeof(Mailbox))); }
+    cudaIpcMemHandle_t h;
+    CUDA_TRY(cudaIpcGetMemHandle(&h, c->mbox));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    memcpy(out, &h, 64);
+    return FBGPU_OK;
+}
+extern "C" int fbgpu_comm_p2p_open(fbgpu_ctx* c, int32_t n_ranks, int32_t rank, const uint8_t* handles /* n_ranks x 64 */) {
+    if (!c || !handles || n_ranks < 1 || n_ranks > kMaxRanks || rank < 0 || rank >= n_ranks) return fail(FBGPU_E_INVALID, "bad argument");
+    if (!c->mbox) return fail(FBGPU_E_COMM, "call fbgpu_comm_p2p_handle first");
+    CUDA_TRY(cudaSetDevice(c->device));
+    for (int p = 0; p < n_ranks; p++) {
+        if (p == rank) { c->peers[p] = c->mbox; continue; }
+        cudaIpcMemHandle_t h; memcpy(&h, handles + (size_t)p * 64, 64);
+        void* ptr = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) return fail(FBGPU_E_COMM, "cudaIpcOpenMemHandle(rank %d) failed: %s", p, cudaGetErrorString(e));
+        c->peers[p] = (Mailbox*)ptr;
+    }
+    if (c->d_peers.ensure(sizeof(Mailbox*) * kMaxRanks)) return FBGPU_E_NOMEM;
+    CUDA_TRY(cudaMemcpy(c->d_peers.p, c->peers, sizeof(Mailbox*) * kMaxRanks, cudaMemcpyHostToDevice));
+    c->n_ranks = n_ranks; c->rank = rank; c->epoch = 0; c->p2p = true;
+    return FBGPU_OK;
 }
 
 extern "C" int fbgpu_get_counters(fbgpu_ctx* c, fbgpu_counters* out) {

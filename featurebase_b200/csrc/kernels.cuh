@@ -259,11 +259,52 @@ __device__ __forceinline__ void batch_rows(uint32_t* T32, const Resolved* res, i
         } else if (r.typ == kBitmap) warp_bitmap_atomic<MODE>(T32, reinterpret_cast<const uint4*>(r.ptr), lane);
     }
 }
+// ------------------------------------------------------------------------------------------------
+// Fused Count + sum all-reduce over NVLink peer memory (replaces the separate NCCL launch for the 8-byte Count
+// merge, executor.go:5880-5883): every rank owns a Mailbox in its HBM that all peers map through CUDA IPC.  The last
+// CTA of the counting kernel (atomic ticket) stores this rank's total into every peer's mailbox, publishes it with
+// an epoch flag (system-scope fences), then waits for the peers' flags and sums.  Slots are double-buffered by
+// epoch parity: a peer can only reach epoch e+2 after this rank has finished epoch e (it needs our e+1 value).
+// ------------------------------------------------------------------------------------------------
+constexpr int kMaxRanks = 16;
+struct Mailbox { unsigned long long value[2][kMaxRanks]; unsigned long long flag[2][kMaxRanks]; };
+struct FuseReduce {
+    Mailbox* const* peers;          // device array [n_ranks]; peers[rank] is this rank's own mailbox; nullptr => fusion off
+    unsigned int* ticket;           // completion counter of the launch (zeroed by the host)
+    unsigned long long* result;     // receives the reduced total
+    unsigned long long epoch;
+    int rank, n_ranks;
+};
+// called by ONE thread per CTA (or per warp) after its atomicAdd into *total; n_callers = how many will call
+__device__ __forceinline__ void fused_allreduce_tail(const FuseReduce& fr, unsigned long long* total, unsigned int n_callers) {
+    if (fr.peers == nullptr) return;
+    __threadfence();
+    if (atomicAdd(fr.ticket, 1u) != n_callers - 1) return;
+    __threadfence();
+    const unsigned long long mine = *reinterpret_cast<volatile unsigned long long*>(total);
+    const int par = (int)(fr.epoch & 1ull);
+    for (int p = 0; p < fr.n_ranks; p++) *reinterpret_cast<volatile unsigned long long*>(&fr.peers[p]->value[par][fr.rank]) = mine;
+    __threadfence_system();
+    for (int p = 0; p < fr.n_ranks; p++) *reinterpret_cast<volatile unsigned long long*>(&fr.peers[p]->flag[par][fr.rank]) = fr.epoch;
+    __threadfence_system();
+    Mailbox* me = fr.peers[fr.rank];
+    unsigned long long sum = 0;
+    for (int q = 0; q < fr.n_ranks; q++) {
+        while (*reinterpret_cast<volatile unsigned long long*>(&me->flag[par][q]) < fr.epoch) { }
+        __threadfence_system();
+        sum += *reinterpret_cast<volatile unsigned long long*>(&me->value[par][q]);
+    }
+    *fr.result = sum;
+}
+// a rank with nothing to count still has to take part in the exchange
+__global__ void p2p_reduce_only_kernel(FuseReduce fr, unsigned long long* total) { fused_allreduce_tail(fr, total, 1u); }
+
 struct EvalOut {
     unsigned long long* total;      // += count of every unit (may be null)
     unsigned long long* per_shard;  // [n_shards] += (may be null)
     uint4* bitmaps;                 // [n_units][512] result bitmaps (may be null)
     uint2* info;                    // [n_units] {N, runs} (may be null)
+    FuseReduce fr;                  // fused cross-GPU reduce of `total` (fr.peers == nullptr => off)
 };
 
 // One CTA per (shard, slot) unit, persistent over units.  Dynamic smem: (depth+1) x 8 KiB.
@@ -419,7 +460,7 @@ eval_kernel(StoreRef st, const DevOp* __restrict__ prog, int n_ops, int depth,
             if (out.info) out.info[unit] = make_uint2(c, rr);
         }
     }
-    if (tid == 0 && out.total && cta_total) atomicAdd(out.total, cta_total);
+    if (tid == 0 && out.total) { if (cta_total) atomicAdd(out.total, cta_total); fused_allreduce_tail(out.fr, out.total, gridDim.x); }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -691,7 +732,7 @@ eval_staged_kernel(StoreRef st, const DevOp* __restrict__ prog, int n_ops, int d
         runs_cur = runs_next;
         __syncthreads();
     }
-    if (tid == 0 && out.total && cta_total) atomicAdd(out.total, cta_total);
+    if (tid == 0 && out.total) { if (cta_total) atomicAdd(out.total, cta_total); fused_allreduce_tail(out.fr, out.total, gridDim.x); }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -844,6 +885,7 @@ eval_wordpar_kernel(StoreRef st, const DevOp* __restrict__ prog, int n_ops,
             if (c) { if (out.total) atomicAdd(out.total, (unsigned long long)c); if (out.per_shard) atomicAdd(&out.per_shard[unit >> 4], (unsigned long long)c); }
         }
     }
+    if (tid == 0 && out.total) fused_allreduce_tail(out.fr, out.total, gridDim.x);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1019,7 +1061,7 @@ __global__ void __launch_bounds__(kPairWarps * 32, 3)
 pair_count_kernel(StoreRef st, uint32_t fvA, uint64_t rowA, uint32_t fvB, uint64_t rowB,
                   const uint64_t* __restrict__ rowsA, const uint64_t* __restrict__ rowsB, long long units_per_pair,
                   const uint64_t* __restrict__ shards, long long n_units,
-                  unsigned long long* total, unsigned long long* per_shard, unsigned long long* per_pair) {
+                  unsigned long long* total, unsigned long long* per_shard, unsigned long long* per_pair, FuseReduce fr) {
     extern __shared__ uint32_t smem32[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     uint32_t* bm = smem32 + wid * 2048;
@@ -1063,7 +1105,7 @@ pair_count_kernel(StoreRef st, uint32_t fvA, uint64_t rowA, uint32_t fvB, uint64
             a = na; b = nb;
         }
     }
-    if (lane == 0 && total && acc) atomicAdd(total, acc);
+    if (lane == 0 && total) { if (acc) atomicAdd(total, acc); fused_allreduce_tail(fr, total, gridDim.x * kPairWarps); }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -37,7 +37,7 @@ class Counters(C.Structure):
 EXPORTS = ["fbgpu_init", "fbgpu_shutdown", "fbgpu_last_error", "fbgpu_abi_version", "fbgpu_load_fragment",
            "fbgpu_load_fragments", "fbgpu_drop_fragment", "fbgpu_commit", "fbgpu_get_stats", "fbgpu_count", "fbgpu_row",
            "fbgpu_row_counts", "fbgpu_groupby", "fbgpu_comm_unique_id", "fbgpu_comm_init", "fbgpu_comm_destroy",
-           "fbgpu_get_counters", "fbgpu_stream", "fbgpu_rows_payload_bytes", "fbgpu_count_pairs"]
+           "fbgpu_get_counters", "fbgpu_stream", "fbgpu_rows_payload_bytes", "fbgpu_count_pairs", "fbgpu_comm_p2p_handle", "fbgpu_comm_p2p_open"]
 
 
 def lib_path():
@@ -70,6 +70,8 @@ def load():
     L.fbgpu_comm_unique_id.argtypes, L.fbgpu_comm_unique_id.restype = [vp], C.c_int
     L.fbgpu_comm_init.argtypes, L.fbgpu_comm_init.restype = [vp, i32, i32, vp], C.c_int
     L.fbgpu_comm_destroy.argtypes, L.fbgpu_comm_destroy.restype = [vp], C.c_int
+    L.fbgpu_comm_p2p_handle.argtypes, L.fbgpu_comm_p2p_handle.restype = [vp, vp], C.c_int
+    L.fbgpu_comm_p2p_open.argtypes, L.fbgpu_comm_p2p_open.restype = [vp, i32, i32, vp], C.c_int
     L.fbgpu_get_counters.argtypes, L.fbgpu_get_counters.restype = [vp, C.POINTER(Counters)], C.c_int
     L.fbgpu_stream.argtypes, L.fbgpu_stream.restype = [vp], vp
     L.fbgpu_rows_payload_bytes.argtypes, L.fbgpu_rows_payload_bytes.restype = [vp, u32, u32, u32, vp, i32, vp, i64, C.POINTER(u64), C.POINTER(u64)], C.c_int
@@ -222,3 +224,14 @@ class Context:
     def comm_init(self, n_ranks, rank, uid):
         buf = (C.c_uint8 * 128).from_buffer_copy(uid)
         self._check(self.L.fbgpu_comm_init(self.h, n_ranks, rank, buf))
+
+    def comm_p2p_handle(self):
+        buf = (C.c_uint8 * 64)()
+        self._check(self.L.fbgpu_comm_p2p_handle(self.h, buf))
+        return bytes(buf)
+
+    def comm_p2p_open(self, n_ranks, rank, handles):
+        blob = b"".join(handles)
+        assert len(blob) == 64 * n_ranks
+        buf = (C.c_uint8 * len(blob)).from_buffer_copy(blob)
+        self._check(self.L.fbgpu_comm_p2p_open(self.h, n_ranks, rank, buf))

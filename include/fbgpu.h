@@ -142,6 +142,12 @@ int fbgpu_groupby(fbgpu_ctx *ctx, uint32_t index, const uint32_t *fields, const 
 int fbgpu_comm_unique_id(uint8_t id[FBGPU_NCCL_ID_BYTES]);
 int fbgpu_comm_init(fbgpu_ctx *ctx, int32_t n_ranks, int32_t rank, const uint8_t id[FBGPU_NCCL_ID_BYTES]);
 int fbgpu_comm_destroy(fbgpu_ctx *ctx);
+/* Fused Count merge over NVLink peer memory (optional, Count only): every rank exports a small mailbox through CUDA IPC
+ * (fbgpu_comm_p2p_handle), the host exchanges the 64-byte handles (any transport), every rank maps its peers
+ * (fbgpu_comm_p2p_open).  From then on fbgpu_count() sums the per-GPU totals inside the counting kernel itself (last CTA
+ * stores to all peers' mailboxes, waits for theirs) instead of launching a separate all-reduce. */
+int fbgpu_comm_p2p_handle(fbgpu_ctx *ctx, uint8_t out_handle[64]);
+int fbgpu_comm_p2p_open(fbgpu_ctx *ctx, int32_t n_ranks, int32_t rank, const uint8_t *handles /* n_ranks x 64 bytes */);
 
 /* ---- instrumentation (the counters the reference keeps under the roaringstats tag, statsHit()) ---- */
 typedef struct {
