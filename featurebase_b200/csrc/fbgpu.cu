@@ -66,6 +66,22 @@ struct PinBuf {
     void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
 };
 
+// growable host byte buffer without value-initialisation (std::vector::resize would write every byte twice)
+struct RawBuf {
+    uint8_t* p = nullptr; size_t len = 0, cap = 0;
+    bool empty() const { return len == 0; }
+    size_t size() const { return len; }
+    int reserve(size_t n) {
+        if (n <= cap) return 0;
+        size_t nc = std::max(n, cap + cap / 2);
+        uint8_t* q = (uint8_t*)realloc(p, nc);
+        if (!q) return fail(FBGPU_E_NOMEM, "host staging realloc(%zu) failed", nc);
+        p = q; cap = nc; return 0;
+    }
+    void clear_and_free() { free(p); p = nullptr; len = cap = 0; }
+};
+struct PayloadCopy { const uint8_t* src; uint64_t dst; uint32_t bytes, padded; uint16_t typ; uint16_t official_run; uint32_t cnt; };   // dst: offset inside the staging buffer
+
 // ------------------------------------------------------------------ NCCL (resolved at run time)
 struct Id128 { char b[128]; };   // ncclUniqueId is passed by value (128 bytes)
 struct NcclApi {
@@ -117,10 +133,11 @@ struct fbgpu_ctx {
     std::vector<FragHdr> h_frags;
     std::vector<RowEnt> h_rows;
     std::vector<ContDesc> h_descs;
-    std::vector<uint8_t> staging;        // payload bytes not yet uploaded, destined for [uploaded, uploaded+staging.size())
+    RawBuf staging;                      // payload bytes not yet uploaded, destined for [uploaded, uploaded+staging.len)
     uint64_t uploaded = 0;               // bytes of payload already in HBM
     bool meta_dirty = false;
     DevBuf d_payload, d_views, d_shardmap, d_frags, d_rows, d_descs, d_rowtab;
+    PinBuf bounce[2];
     uint32_t n_views_dev = 0;
     fbgpu_stats stats{};
     // ---- execution
@@ -178,6 +195,7 @@ extern "C" void fbgpu_shutdown(fbgpu_ctx* c) {
         cudaEventDestroy(w->ev0); cudaEventDestroy(w->ev1); cudaStreamDestroy(w->stream);
     }
     for (DevBuf* b : { &c->d_payload, &c->d_views, &c->d_shardmap, &c->d_frags, &c->d_rows, &c->d_descs, &c->d_rowtab }) b->release();
+    c->bounce[0].release(); c->bounce[1].release(); c->staging.clear_and_free();
     delete c;
 }
 
@@ -273,7 +291,7 @@ static void drop_locked(fbgpu_ctx* c, uint32_t fv, uint64_t shard) {
 }
 
 // appends one parsed fragment to the host mirrors + staging (store_mu held exclusively)
-static int add_fragment_locked(fbgpu_ctx* c, uint32_t fv, uint64_t shard, const std::vector<ParsedCont>& cs) {
+static int add_fragment_locked(fbgpu_ctx* c, uint32_t fv, uint64_t shard, const std::vector<ParsedCont>& cs, std::vector<PayloadCopy>& copies) {
     if (shard >= (1ull << 31)) return fail(FBGPU_E_INVALID, "shard %llu too large", (unsigned long long)shard);
     drop_locked(c, fv, shard);
     HostFrag hf{}; hf.fv = fv; hf.shard = shard; hf.live = true; hf.row_off = (uint32_t)c->h_rows.size();
@@ -303,18 +321,14 @@ static int add_fragment_locked(fbgpu_ctx* c, uint32_t fv, uint64_t shard, const 
     if (slot_major) std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return cs[a].key % kSlotsPerRow < cs[b].key % kSlotsPerRow; });
     for (uint32_t i : order) {
         const ParsedCont& pc = cs[i];
-        uint64_t pos = c->uploaded + c->staging.size();
+        uint64_t pos = c->uploaded + c->staging.len;
         uint64_t align = pc.typ == kBitmap ? 128 : 16;
         uint64_t apos = (pos + align - 1) & ~(align - 1);
         uint64_t bytes = pc.typ == kArray ? (uint64_t)pc.n * 2 : pc.typ == kBitmap ? 8192 : (uint64_t)pc.cnt * 4;
         uint64_t padded = (bytes + 15) & ~15ull;
-        c->staging.resize(c->staging.size() + (apos - pos) + padded, 0);
-        uint8_t* dst = c->staging.data() + (apos - c->uploaded);
-        memcpy(dst, pc.data, bytes);
-        if (pc.typ == kRun && pc.official_run) {     // official format stores (start, length-1): roaring.go:2240-2247
-            uint16_t* r = (uint16_t*)dst; for (uint32_t k = 0; k < pc.cnt; k++) r[2 * k + 1] = (uint16_t)(r[2 * k] + r[2 * k + 1]);
-        }
         if (apos / 16 > 0xffffffffull) return fail(FBGPU_E_NOMEM, "payload arena exceeds 64 GiB addressable by 32-bit 16 B offsets");
+        c->staging.len += (apos - pos) + padded;            // space is claimed now, bytes are copied by run_copies()
+        copies.push_back(PayloadCopy{ pc.data, apos - c->uploaded, (uint32_t)bytes, (uint32_t)padded, pc.typ, (uint16_t)(pc.official_run ? 1 : 0), pc.cnt });
         c->h_descs[desc0 + i].off16 = (uint32_t)(apos / 16);
     }
     FragHdr h{}; h.row_off = hf.row_off; h.n_rows = hf.n_rows; h.row0 = row0; h.contiguous = contiguous ? 1u : 0u;
@@ -330,13 +344,38 @@ static int add_fragment_locked(fbgpu_ctx* c, uint32_t fv, uint64_t shard, const 
     return 0;
 }
 
+// copies the planned payloads into the staging buffer (possibly on several host threads); store_mu held exclusively
+static int run_copies(fbgpu_ctx* c, const std::vector<PayloadCopy>& copies, int n_threads) {
+    if (c->staging.reserve(c->staging.len + 64)) return FBGPU_E_NOMEM;
+    uint8_t* base = c->staging.p;
+    auto work = [&](size_t lo, size_t hi) {
+        for (size_t i = lo; i < hi; i++) {
+            const PayloadCopy& pc = copies[i];
+            uint8_t* dst = base + pc.dst;
+            memcpy(dst, pc.src, pc.bytes);
+            if (pc.padded > pc.bytes) memset(dst + pc.bytes, 0, pc.padded - pc.bytes);      // zero tail of the last 16-byte chunk
+            if (pc.typ == kRun && pc.official_run) {     // official format stores (start, length-1): roaring.go:2240-2247
+                uint16_t* r = (uint16_t*)dst; for (uint32_t k = 0; k < pc.cnt; k++) r[2 * k + 1] = (uint16_t)(r[2 * k] + r[2 * k + 1]);
+            }
+        }
+    };
+    n_threads = (int)std::min<size_t>(std::max(n_threads, 1), copies.size() / 4096 + 1);
+    if (n_threads <= 1) { work(0, copies.size()); return 0; }
+    std::vector<std::thread> th;
+    for (int t = 0; t < n_threads; t++) th.emplace_back(work, copies.size() * t / n_threads, copies.size() * (t + 1) / n_threads);
+    for (auto& t : th) t.join();
+    return 0;
+}
+
 extern "C" int fbgpu_load_fragment(fbgpu_ctx* c, uint32_t index, uint32_t field, uint32_t view, uint64_t shard, const uint8_t* roaring, uint64_t nbytes) {
     if (!c || !roaring) return fail(FBGPU_E_INVALID, "null argument");
     std::vector<ParsedCont> cs;
     int rc = parse_roaring(roaring, nbytes, cs); if (rc) return rc;
     std::unique_lock<std::shared_mutex> lk(c->store_mu);
     uint32_t fv = view_id_locked(c, ViewKey{ index, field, view }, true);
-    return add_fragment_locked(c, fv, shard, cs);
+    std::vector<PayloadCopy> copies;
+    rc = add_fragment_locked(c, fv, shard, cs, copies); if (rc) return rc;
+    return run_copies(c, copies, 1);
 }
 
 extern "C" int fbgpu_load_fragments(fbgpu_ctx* c, uint32_t index, uint32_t field, uint32_t view, const uint64_t* shards, int64_t n,
@@ -355,10 +394,9 @@ extern "C" int fbgpu_load_fragments(fbgpu_ctx* c, uint32_t index, uint32_t field
     for (int64_t i = 0; i < n; i++) if (rcs[i]) { g_err = errs[i]; return rcs[i]; }
     std::unique_lock<std::shared_mutex> lk(c->store_mu);
     uint32_t fv = view_id_locked(c, ViewKey{ index, field, view }, true);
-    uint64_t total = offsets[n] - offsets[0];
-    c->staging.reserve(c->staging.size() + total + (size_t)n * 4096);
-    for (int64_t i = 0; i < n; i++) { int rc = add_fragment_locked(c, fv, shards[i], parsed[i]); if (rc) return rc; }
-    return 0;
+    std::vector<PayloadCopy> copies;
+    for (int64_t i = 0; i < n; i++) { int rc = add_fragment_locked(c, fv, shards[i], parsed[i], copies); if (rc) return rc; }
+    return run_copies(c, copies, nt);
 }
 
 extern "C" int fbgpu_drop_fragment(fbgpu_ctx* c, uint32_t index, uint32_t field, uint32_t view, uint64_t shard) {
@@ -376,16 +414,35 @@ static int commit_locked(fbgpu_ctx* c) {
     CUDA_TRY(cudaSetDevice(c->device));
     CUDA_TRY(cudaDeviceSynchronize());   // no query may be reading tables we are about to replace (queries hold the shared lock anyway)
     if (!c->staging.empty()) {
-        uint64_t need = c->uploaded + c->staging.size() + 256;
+        uint64_t need = c->uploaded + c->staging.len + 256;
         if (need > c->d_payload.cap) {
             DevBuf nb; size_t want = std::max<size_t>(need, c->d_payload.cap * 2);
             if (nb.ensure(want)) { if (nb.ensure(need)) return FBGPU_E_NOMEM; }
             if (c->uploaded) CUDA_TRY(cudaMemcpy(nb.p, c->d_payload.p, c->uploaded, cudaMemcpyDeviceToDevice));
             c->d_payload.release(); c->d_payload = nb;
         }
-        CUDA_TRY(cudaMemcpy((uint8_t*)c->d_payload.p + c->uploaded, c->staging.data(), c->staging.size(), cudaMemcpyHostToDevice));
-        c->uploaded += c->staging.size();
-        std::vector<uint8_t>().swap(c->staging);
+        // pageable -> HBM through two pinned bounce buffers: the host memcpy of chunk k+1 overlaps the DMA of chunk k
+        {
+            const size_t chunk = 32u << 20, total = c->staging.len;
+            if (total <= (4u << 20)) CUDA_TRY(cudaMemcpy((uint8_t*)c->d_payload.p + c->uploaded, c->staging.p, total, cudaMemcpyHostToDevice));
+            else {
+                if (c->bounce[0].ensure(chunk) || c->bounce[1].ensure(chunk)) return FBGPU_E_NOMEM;
+                cudaStream_t st = c->wss[0]->stream;
+                cudaEvent_t done[2]; CUDA_TRY(cudaEventCreateWithFlags(&done[0], cudaEventDisableTiming)); CUDA_TRY(cudaEventCreateWithFlags(&done[1], cudaEventDisableTiming));
+                int k = 0;
+                for (size_t off = 0; off < total; off += chunk, k ^= 1) {
+                    size_t n = std::min(chunk, total - off);
+                    if (off >= 2 * chunk) CUDA_TRY(cudaEventSynchronize(done[k]));       // bounce buffer k is free again
+                    memcpy(c->bounce[k].p, c->staging.p + off, n);
+                    CUDA_TRY(cudaMemcpyAsync((uint8_t*)c->d_payload.p + c->uploaded + off, c->bounce[k].p, n, cudaMemcpyHostToDevice, st));
+                    CUDA_TRY(cudaEventRecord(done[k], st));
+                }
+                CUDA_TRY(cudaStreamSynchronize(st));
+                cudaEventDestroy(done[0]); cudaEventDestroy(done[1]);
+            }
+        }
+        c->uploaded += c->staging.len;
+        c->staging.clear_and_free();
     }
     // flatten shard maps; build the dense (shard,row) directory of every view whose row ids are dense
     std::vector<ViewTab> views(c->shardmaps.size()); std::vector<int32_t> flat; std::vector<RowTabEnt> rowtab;

@@ -78,3 +78,15 @@ EXEC_SETOPS = {
     # TestExecutor_Execute_Count: row10 = {3, SW+1, SW+2} -> Count = 3
     "count": ({10: [3, SW + 1, SW + 2]}, "Count(Row(general=10))", 3),
 }
+
+# executor_test.go:1758-1809 TestExecutor_ExecuteTopK: bits (row, col); TopK(f, k=2) -> [(10,4),(0,3)]
+TOPK_BITS = [(0, 0), (0, SW + 2), (10, 2), (10, SW), (10, 2 * SW), (10, SW + 1), (20, SW), (0, 1)]
+TOPK_EXPECT = [(10, 4), (0, 3)]
+# executor_test.go:1846-1889 TestExecutor_Execute_TopN: TopN(f, n=2) -> [(0,5),(10,2)]
+TOPN_BITS = [(0, 0), (0, 1), (0, SW), (0, SW + 2), (0, 5 * SW + 100), (10, 0), (10, SW), (20, SW)]
+TOPN_EXPECT = [(0, 5), (10, 2)]
+# executor_test.go:6033-6120 TestExecutor_Execute_GroupBy: Basic / Filter
+GROUPBY_GENERAL = [(10, 0), (10, 1), (10, SW + 1), (11, 2), (11, SW + 2), (12, 2), (12, SW + 2)]
+GROUPBY_SUB = [(100, 0), (100, 1), (100, 3), (100, SW + 1), (110, 2), (110, 0)]
+GROUPBY_BASIC = [((10, 100), 3), ((10, 110), 1), ((11, 110), 1), ((12, 110), 1)]
+GROUPBY_FILTER_GENERAL_10 = [((10, 100), 3), ((10, 110), 1)]

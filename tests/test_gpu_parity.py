@@ -505,3 +505,29 @@ def test_thread_safety_and_api_edges():
     assert after == before - p.ora.row("f", 0, 0, 3).count()
     ctx.load_fragment(iid, fid, 0, 3, D.fragment(3, 3, list(range(8)), 0.02))
     assert ctx.count(iid, [row(0)], shards) == before
+
+
+def test_executor_topk_topn_groupby_goldens_on_gpu():
+    """executor_test.go:1758-1809 (TopK), :1846-1889 (TopN exact), :6033-6120 (GroupBy Basic / Filter / error cases)"""
+    def pair_with(fields_bits):
+        p = Pair()
+        for name, bits in fields_bits.items():
+            p.field(name)
+            for r, c in bits:
+                p.holder.set_bit("i", name, r, c)
+        p.sync_pending()
+        return p
+    p = pair_with({"f": V.TOPK_BITS})
+    assert p.ex.execute("i", "TopK(f, k=2)")[0] == V.TOPK_EXPECT
+    p = pair_with({"f": V.TOPN_BITS, "other": [(0, 0)]})
+    assert p.ex.execute("i", "TopN(f, n=2)")[0] == V.TOPN_EXPECT
+    assert p.ex.execute("i", "TopN(f, Row(other=0), n=5)")[0] == [(0, 1), (10, 1)]
+    p = pair_with({"general": V.GROUPBY_GENERAL, "sub": V.GROUPBY_SUB})
+    fmt = lambda res: [(tuple(r for _, r in g), c) for g, c in res]
+    assert fmt(p.ex.execute("i", "GroupBy(Rows(general), Rows(sub))")[0]) == V.GROUPBY_BASIC
+    assert fmt(p.ex.execute("i", "GroupBy(Rows(general), Rows(sub), filter=Row(general=10))")[0]) == V.GROUPBY_FILTER_GENERAL_10
+    assert fmt(p.ex.execute("i", "GroupBy(Rows(general), Rows(sub), limit=2)")[0]) == V.GROUPBY_BASIC[:2]
+    with pytest.raises(X.QueryError, match="need at least one child call"):
+        p.ex.execute("i", "GroupBy()")
+    with pytest.raises(X.QueryError, match="field not found"):
+        p.ex.execute("i", "GroupBy(Rows(missing))")

@@ -264,3 +264,35 @@ def test_topk_and_groupby_semantics():
     assert np.array_equal(out.reshape(7, 5), brute)
     # missing fragment => shard contributes nothing (executor.go:8769-8772)
     assert O.groupby_shard([fa, None], shard, [list(range(7)), list(range(5))], None).sum() == 0
+
+
+def test_executor_topk_topn_groupby_goldens():
+    """executor_test.go:1758-1809 (TopK), :1846-1889 (TopN), :6033-6120 (GroupBy Basic / Filter) through the oracle's
+    doTopK / groupByIterator restatements, reduced over shards the way the executor does (sum per row id / group)"""
+    def frags(bits):
+        rows = {}
+        for r, c in bits:
+            rows.setdefault(r, []).append(c)
+        return H.set_fragments(rows)
+
+    def topk(bits):
+        tot = {}
+        for s, fr in frags(bits).items():
+            rows, cnts = fr.row_counts(s, None)
+            for r, c in zip(rows.tolist(), cnts.tolist()):
+                tot[r] = tot.get(r, 0) + c
+        return sorted(tot.items(), key=lambda kv: (-kv[1], kv[0]))
+
+    assert topk(V.TOPK_BITS)[:2] == V.TOPK_EXPECT
+    assert topk(V.TOPN_BITS)[:2] == V.TOPN_EXPECT
+    fg, fs = frags(V.GROUPBY_GENERAL), frags(V.GROUPBY_SUB)
+    ra, rb = [10, 11, 12], [100, 110]
+    for filt_row, expect in ((None, V.GROUPBY_BASIC), (10, V.GROUPBY_FILTER_GENERAL_10)):
+        out = np.zeros(6, dtype=np.uint64)
+        for s in sorted(set(fg) | set(fs)):
+            filt = fg[s].row(filt_row, s) if (filt_row is not None and s in fg) else None
+            if filt_row is not None and filt is None:
+                continue
+            O.groupby_shard([fg.get(s), fs.get(s)], s, [ra, rb], filt, out)
+        got = [((ra[i // 2], rb[i % 2]), int(out[i])) for i in range(6) if out[i]]
+        assert got == expect
