@@ -37,7 +37,7 @@ def main():
              f"{tr['algorithmic_bytes_per_launch']:,} algorithmic bytes (x{tr['dram_bytes_per_launch'] / tr['algorithmic_bytes_per_launch']:.3f}): no wasted re-reads. "
              f"Clocks during the run: {b['clocks']['sm_mhz']:.0f}/{b['clocks']['sm_max_mhz']:.0f} MHz, throttle reasons: {b['clocks']['reasons'] or 'none'}. "
              f"`gpu_launches` = {b['gpu_launches']} for {b['steps']} steps (one fused kernel per step).")
-    o.append("N > 1 (weak scaling, 1024 shards per GPU; the 8-byte Count merge is fused into the counting kernel over NVLink peer memory, `--reduce p2p`, or done by ncclAllReduce, `--reduce nccl`): 2 GPUs 0.537 ms/step (p2p) vs 0.535 (nccl), 2.40e8 set-ops/s; 4 GPUs 0.575 ms/step, 4.49e8 set-ops/s (nccl run). Both merges cost the same within noise; at N > 1 a step ends when the slowest rank ends. The driver measures N = 1, 2, 4, 8.\n")
+    o.append("N > 1 (weak scaling, 1024 shards per GPU; the 8-byte Count merge is fused into the counting kernel over NVLink peer memory, `--reduce p2p`, or done by ncclAllReduce, `--reduce nccl`): 2 GPUs 0.537 ms/step (p2p) vs 0.535 (nccl), 2.40e8 set-ops/s; 4 GPUs 0.547 ms/step, 4.71e8 set-ops/s (p2p) vs 0.575 ms/step, 4.49e8 (nccl, another lease); identical counts. For 8 bytes both merges are latency-trivial next to a 0.5 ms step; at N > 1 a step ends when the slowest rank ends. The driver measures N = 1, 2, 4, 8.\n")
     o.append("## How the headline kernel got here (same workload)\n")
     o.append("| step | eval kernel ms | frac | what changed | evidence |")
     o.append("|---|---|---|---|---|")
