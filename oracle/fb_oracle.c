@@ -1021,7 +1021,7 @@ typedef struct {
 
 static fbo_bitmap *union_rows(const fbo_bitmap *frag, uint64_t shard, const uint64_t *rows, int n) { /* executeUnionShard executor.go:5382 */
     if (n == 0) return fbo_b_new();
-    fbo_bitmap **r = xmalloc(sizeof(void *) * n);
+    fbo_bitmap **r = xcalloc((size_t)n, sizeof(void *));
     for (int i = 0; i < n; i++) r[i] = fbo_frag_row(frag, rows[i], shard);
     fbo_bitmap *o = n == 1 ? fbo_b_clone(r[0]) : fbo_b_union_n(r[0], (const fbo_bitmap *const *)(r + 1), n - 1);
     for (int i = 0; i < n; i++) fbo_b_free(r[i]);

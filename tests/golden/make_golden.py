@@ -34,7 +34,61 @@ def combinations():
     return rows
 
 
+KERNEL_TABLE_FUNCS = ["TestIntersectArrayRun", "TestIntersectRunRun", "TestUnionInterval16InPlace", "TestUnionRunRun", "TestUnionArrayRun",
+                      "TestDifferenceArrayRun", "TestDifferenceRunArray", "TestDifferenceRunRun", "TestXorArrayRun", "TestXorRunRun"]
+
+
+def _parse_literal(text):
+    """[]uint16{..} | []uint16(nil) | []Interval16{{Start: a, Last: b}|{a, b}, ..} | NewContainerArray(..) | NewContainerRun(..) | int"""
+    text = text.strip().rstrip(",")
+    m = re.match(r"^NewContainer(Array|Run)\((.*)\)$", text)
+    if m:
+        return _parse_literal(m.group(2))
+    if text.startswith("[]uint16"):
+        body = text[len("[]uint16"):]
+        if body.startswith("(nil)") or body in ("{}",):
+            return {"kind": "array", "values": []}
+        return {"kind": "array", "values": [int(x, 0) for x in re.findall(r"0x[0-9a-fA-F]+|\d+", body)]}
+    if text.startswith("[]Interval16"):
+        body = text[len("[]Interval16"):]
+        if body.startswith("(nil)") or body in ("{}",):
+            return {"kind": "runs", "values": []}
+        pairs = re.findall(r"\{(?:Start:\s*)?(\d+),\s*(?:Last:\s*)?(\d+)\}", body)
+        return {"kind": "runs", "values": [[int(a), int(b)] for a, b in pairs]}
+    if re.match(r"^-?\d+$", text):
+        return {"kind": "int", "values": int(text)}
+    return None
+
+
+def kernel_tables():
+    lines = open(os.path.join(REF, "roaring/roaring_internal_test.go")).read().split("\n")
+    out = []
+    for fn in KERNEL_TABLE_FUNCS:
+        start = next(i for i, l in enumerate(lines) if l.startswith(f"func {fn}("))
+        end = next(i for i in range(start + 1, len(lines)) if lines[i].startswith("func "))
+        cur, cur_line = {}, None
+        for i in range(start, end):
+            m = re.match(r"^\s*(\w+):\s*(.+?),?\s*(?://.*)?$", lines[i])
+            if m and m.group(1) != "name":
+                lit = _parse_literal(m.group(2))
+                if lit is not None:
+                    if not cur:
+                        cur_line = i + 1
+                    cur[m.group(1)] = lit
+            elif re.match(r"^\s*\},?\s*(\{\s*)?$", lines[i]) and cur:
+                out.append({"func": fn, "line": cur_line, "fields": cur})
+                cur = {}
+    return out
+
+
 if __name__ == "__main__":
+    kt = kernel_tables()
+    with open(os.path.join(HERE, "kernel_tables.json"), "w") as f:
+        json.dump({"source": "roaring/roaring_internal_test.go (table tests listed in KERNEL_TABLE_FUNCS)", "cases": kt}, f, indent=0)
+    byf = {}
+    for c in kt:
+        byf[c["func"]] = byf.get(c["func"], 0) + 1
+    print(len(kt), byf)
     rows = combinations()
     with open(os.path.join(HERE, "container_combinations.json"), "w") as f:
         json.dump({"source": "roaring/roaring_internal_test.go:2974-3761 (TestContainerCombinations)", "rows": rows}, f, indent=0)
