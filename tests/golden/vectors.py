@@ -90,3 +90,28 @@ GROUPBY_GENERAL = [(10, 0), (10, 1), (10, SW + 1), (11, 2), (11, SW + 2), (12, 2
 GROUPBY_SUB = [(100, 0), (100, 1), (100, 3), (100, SW + 1), (110, 2), (110, 0)]
 GROUPBY_BASIC = [((10, 100), 3), ((10, 110), 1), ((11, 110), 1), ((12, 110), 1)]
 GROUPBY_FILTER_GENERAL_10 = [((10, 100), 3), ((10, 110), 1)]
+
+# executor_test.go:3007-3289 TestExecutor_Execute_Row_BSIGroup: fields foo in [-990,1000], other/bar int64, edge in [-900,1000];
+# existence tracking on.  (query, expected columns)
+BSI_EXEC_SETUP = {
+    "set": {"f": [(0, 0), (0, SW + 1)]},
+    "int": {"foo": [(50, 20), (SW, 30), (SW + 2, 10), (5 * SW + 100, 20), (SW + 1, 60)], "bar": [(50, 2000)], "other": [(0, 1000)],
+            "edge": [(0, 100), (1, -100)]},
+    "ranges": {"foo": (-990, 1000), "bar": (-(1 << 63), (1 << 63) - 1), "other": (-(1 << 63), (1 << 63) - 1), "edge": (-900, 1000)},
+}
+BSI_EXEC_CASES = [
+    ("Row(other == null)", [1, 50, SW, SW + 1, SW + 2, 5 * SW + 100]),
+    ("Row(foo == 20)", [50, 5 * SW + 100]),
+    ("Row(other != null)", [0]),
+    ("Row(foo != 20)", [SW, SW + 1, SW + 2]),
+    ("Row(other != -20)", [0]),
+    ("Row(foo < 20)", [SW + 2]),
+    ("Row(foo <= 20)", [50, SW + 2, 5 * SW + 100]),
+    ("Row(foo > 20)", [SW, SW + 1]),
+    ("Row(foo >= 20)", [50, SW, SW + 1, 5 * SW + 100]),
+    ("Row(0 <= other <= 1000)", [0]),
+    ("Row(foo == 0)", []),
+    ("Row(foo == 200)", []),
+    ("Row(edge < 200)", [0, 1]),
+    ("Row(edge > -1000)", [0, 1]),
+]

@@ -68,13 +68,13 @@ class OracleIndex:
     def _bsi(self, fld, cond, shard):
         frag = self.frag(fld.name, X.VIEW_BSI, shard)
         op, value = cond.op, cond.value
-        if frag is None:
-            return O.Bitmap()
-        not_null = lambda: frag.row(0, shard)
-        if value is None:
+        not_null = lambda: frag.row(0, shard) if frag is not None else O.Bitmap()
+        if value is None:                       # getNullRowShard / getNonNullRowShard executor.go:5056-5118
             if op == "!=":
                 return not_null()
             return self.row(X.EXISTENCE_FIELD, X.VIEW_STANDARD, 0, shard).difference(not_null())
+        if frag is None:
+            return O.Bitmap()
         if op == "><":
             lo, hi, oor = fld.base_value_between(int(value[0]), int(value[1]))
             if oor:

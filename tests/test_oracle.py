@@ -339,3 +339,37 @@ def test_kernel_table_goldens():
         # symmetric ops must agree with swapped operands
         if op in ("intersect", "union", "xor"):
             assert getattr(b, op)(a).values().tolist() == values(exp)
+
+
+def test_executor_bsi_goldens_through_host_mirror():
+    """executor_test.go:3007-3289: the reference's end-to-end BSI goldens, evaluated as PQL -> host mirror semantics
+    (featurebase_b200/executor.py: null handling, bsiGroup.baseValue clamping, whole-range short cuts) -> oracle BSI."""
+    from featurebase_b200 import executor as X
+    from featurebase_b200 import pql, roaring_io
+    from tests.oracle_exec import OracleIndex
+
+    class NoGpu:                       # the mirror's Holder only needs a residency sink here
+        def load_fragment(self, *a):
+            pass
+
+    h = X.Holder(ctx=NoGpu())
+    idx = h.create_index("i", track_existence=True)
+    idx.create_field("f")
+    for name, (lo, hi) in V.BSI_EXEC_SETUP["ranges"].items():
+        idx.create_field(name, "int", min=lo, max=hi, bit_depth=(63 if hi > (1 << 40) else None))
+    for name, bits in V.BSI_EXEC_SETUP["set"].items():
+        for r, c in bits:
+            h.set_bit("i", name, r, c)
+    for name, vals in V.BSI_EXEC_SETUP["int"].items():
+        for c, v in vals:
+            h.set_value("i", name, c, v)
+    ora = OracleIndex(idx)
+    for (index, field, view, shard), bits in h._pending.items():
+        ora.load(field, view, shard, roaring_io.encode(np.fromiter(bits, dtype=np.uint64, count=len(bits))))
+        idx.shards.add(shard)
+    shards = sorted(idx.shards)
+    for q, exp in V.BSI_EXEC_CASES:
+        got = ora.eval_row(pql.parse(q)[0], shards)
+        assert list(got.slice()) == exp, q
+    with pytest.raises(Exception):
+        X.Executor.__new__(X.Executor)._field(idx, "bad_field")      # ErrFieldNotFound (executor_test.go:3283)
