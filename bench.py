@@ -175,9 +175,20 @@ def main():
         dist.broadcast_object_list(uid, src=0)
         h.ctx.comm_init(world, rank, uid[0])
         if args.reduce == "p2p":   # fused Count merge over NVLink peer memory (mailboxes mapped through CUDA IPC)
-            handles = [None] * world
-            dist.all_gather_object(handles, h.ctx.comm_p2p_handle())
-            h.ctx.comm_p2p_open(world, rank, handles)
+            ok = 1
+            try:
+                handles = [None] * world
+                dist.all_gather_object(handles, h.ctx.comm_p2p_handle())
+                h.ctx.comm_p2p_open(world, rank, handles)
+            except Exception as e:  # noqa: BLE001 — e.g. a peer that cannot be IPC-mapped: every rank falls back together
+                print(f"[rank {rank}] peer-memory merge unavailable ({e}); using ncclAllReduce", file=sys.stderr)
+                ok = 0
+            flag = torch.tensor([ok], device="cuda")
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()) == 0:
+                if ok:
+                    h.ctx.comm_p2p_disable()
+                args.reduce = "nccl"
     ops = ex._bitmap_call(idx, pql.parse(query_text())[0].children[0])
     payload, n_cont = h.ctx.rows_payload_bytes(idx.id, fld.id, X.VIEW_STANDARD, shards, ROWS_A + ROWS_B)
     algo_bytes = payload + 16 * n_cont + 8                       # payload + 16 B/descriptor + 8 B count

@@ -1163,6 +1163,13 @@ extern "C" int fbgpu_comm_p2p_open(fbgpu_ctx* c, int32_t n_ranks, int32_t rank, 
     return FBGPU_OK;
 }
 
+extern "C" int fbgpu_comm_p2p_disable(fbgpu_ctx* c) {      // back to the NCCL merge (mappings stay open; harmless)
+    if (!c) return fail(FBGPU_E_INVALID, "null ctx");
+    std::lock_guard<std::mutex> lk(c->coll_mu);
+    c->p2p = false;
+    return FBGPU_OK;
+}
+
 extern "C" int fbgpu_get_counters(fbgpu_ctx* c, fbgpu_counters* out) {
     if (!c || !out) return fail(FBGPU_E_INVALID, "null argument");
     std::lock_guard<std::mutex> lk(c->cnt_mu);

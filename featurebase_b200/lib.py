@@ -37,7 +37,7 @@ class Counters(C.Structure):
 EXPORTS = ["fbgpu_init", "fbgpu_shutdown", "fbgpu_last_error", "fbgpu_abi_version", "fbgpu_load_fragment",
            "fbgpu_load_fragments", "fbgpu_drop_fragment", "fbgpu_commit", "fbgpu_get_stats", "fbgpu_count", "fbgpu_row",
            "fbgpu_row_counts", "fbgpu_groupby", "fbgpu_comm_unique_id", "fbgpu_comm_init", "fbgpu_comm_destroy",
-           "fbgpu_get_counters", "fbgpu_stream", "fbgpu_rows_payload_bytes", "fbgpu_count_pairs", "fbgpu_comm_p2p_handle", "fbgpu_comm_p2p_open"]
+           "fbgpu_get_counters", "fbgpu_stream", "fbgpu_rows_payload_bytes", "fbgpu_count_pairs", "fbgpu_comm_p2p_handle", "fbgpu_comm_p2p_open", "fbgpu_comm_p2p_disable"]
 
 
 def lib_path():
@@ -72,6 +72,7 @@ def load():
     L.fbgpu_comm_destroy.argtypes, L.fbgpu_comm_destroy.restype = [vp], C.c_int
     L.fbgpu_comm_p2p_handle.argtypes, L.fbgpu_comm_p2p_handle.restype = [vp, vp], C.c_int
     L.fbgpu_comm_p2p_open.argtypes, L.fbgpu_comm_p2p_open.restype = [vp, i32, i32, vp], C.c_int
+    L.fbgpu_comm_p2p_disable.argtypes, L.fbgpu_comm_p2p_disable.restype = [vp], C.c_int
     L.fbgpu_get_counters.argtypes, L.fbgpu_get_counters.restype = [vp, C.POINTER(Counters)], C.c_int
     L.fbgpu_stream.argtypes, L.fbgpu_stream.restype = [vp], vp
     L.fbgpu_rows_payload_bytes.argtypes, L.fbgpu_rows_payload_bytes.restype = [vp, u32, u32, u32, vp, i32, vp, i64, C.POINTER(u64), C.POINTER(u64)], C.c_int
@@ -235,3 +236,6 @@ class Context:
         assert len(blob) == 64 * n_ranks
         buf = (C.c_uint8 * len(blob)).from_buffer_copy(blob)
         self._check(self.L.fbgpu_comm_p2p_open(self.h, n_ranks, rank, buf))
+
+    def comm_p2p_disable(self):
+        self._check(self.L.fbgpu_comm_p2p_disable(self.h))

@@ -148,6 +148,7 @@ int fbgpu_comm_destroy(fbgpu_ctx *ctx);
  * stores to all peers' mailboxes, waits for theirs) instead of launching a separate all-reduce. */
 int fbgpu_comm_p2p_handle(fbgpu_ctx *ctx, uint8_t out_handle[64]);
 int fbgpu_comm_p2p_open(fbgpu_ctx *ctx, int32_t n_ranks, int32_t rank, const uint8_t *handles /* n_ranks x 64 bytes */);
+int fbgpu_comm_p2p_disable(fbgpu_ctx *ctx);   /* fall back to the NCCL merge (e.g. when a peer could not be mapped) */
 
 /* ---- instrumentation (the counters the reference keeps under the roaringstats tag, statsHit()) ---- */
 typedef struct {
