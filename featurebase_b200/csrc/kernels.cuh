@@ -194,28 +194,6 @@ __device__ __forceinline__ void smem_bit_op(uint32_t* bm, uint32_t v) {
     else if (MODE == 1) asm volatile("red.shared.and.b32 [%0], %1;" :: "r"(addr), "r"(~m) : "memory");
     else asm volatile("red.shared.xor.b32 [%0], %1;" :: "r"(addr), "r"(m) : "memory");
 }
-// one warp scatters a whole array container (16-byte loads, 8 elements per lane per step)
-template <int MODE>
-__device__ __forceinline__ void warp_scatter_smem_mode(uint32_t* bm, const uint16_t* arr, uint32_t n, int lane) {
-    const uint4* a4 = reinterpret_cast<const uint4*>(arr);
-    uint32_t n8 = (n + 7) >> 3;
-    for (uint32_t i = lane; i < n8; i += 32) {
-        uint4 v = ldg_nc(a4 + i);
-        uint32_t w[4] = { v.x, v.y, v.z, v.w };
-        uint32_t base = i * 8;
-        if (base + 8 <= n) {
-#pragma unroll
-            for (int q = 0; q < 4; q++) { smem_bit_op<MODE>(bm, w[q] & 0xffffu); smem_bit_op<MODE>(bm, w[q] >> 16); }
-        } else {
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-                if (base + 2 * q < n) smem_bit_op<MODE>(bm, w[q] & 0xffffu);
-                if (base + 2 * q + 1 < n) smem_bit_op<MODE>(bm, w[q] >> 16);
-            }
-        }
-    }
-}
-__device__ __forceinline__ void warp_scatter_smem(uint32_t* bm, const uint16_t* arr, uint32_t n, int lane) { warp_scatter_smem_mode<0>(bm, arr, n, lane); }
 // one warp applies a whole bitmap container with word atomics (safe against concurrent warps)
 template <int MODE>
 __device__ __forceinline__ void warp_bitmap_atomic(uint32_t* bm, const uint4* g, int lane) {
