@@ -1,0 +1,113 @@
+"""OracleCtx: a stand-in for featurebase_b200.lib.Context that interprets the same post-order fbgpu_op programs with
+the CPU oracle.  TEST INFRASTRUCTURE ONLY (`-m "not gpu"` host-logic tests): it lets the host mirror
+(featurebase_b200/executor.py: PQL -> program, baseValue clamping, TopN/TopK/GroupBy reduction) run here, where there
+is no GPU, through exactly the calls it makes on the C ABI.  The opcode semantics follow include/fbgpu.h's table."""
+import numpy as np
+
+from featurebase_b200 import lib as L
+from oracle import oracle as O
+
+_CMP = {v: k for k, v in L.CMP.items()}
+
+
+class OracleCtx:
+    def __init__(self):
+        self.frags = {}                  # (index, field, view) -> {shard: oracle Bitmap}
+        self.programs = []               # every program handed to count()/row(), for assertions on the compile step
+
+    # ---- residency
+    def load_fragment(self, index, field, view, shard, data):
+        self.frags.setdefault((index, field, view), {})[int(shard)] = O.Bitmap.from_bytes(bytes(data))
+
+    def commit(self):
+        pass
+
+    def _frag(self, index, field, view, shard):
+        return self.frags.get((index, field, view), {}).get(int(shard))
+
+    def _row(self, index, field, view, row, shard):
+        f = self._frag(index, field, view, shard)
+        return f.row(int(row), shard) if f is not None else O.Bitmap()
+
+    # ---- program interpreter (one shard)
+    def _eval(self, index, ops, shard):
+        st = []
+        for op in ops:
+            code, argc = op.opcode, op.argc
+            if code == L.OP_ROW or code == L.OP_ALL:
+                st.append(self._row(index, op.field, op.view, op.a, shard))
+            elif code == L.OP_EMPTY:
+                st.append(O.Bitmap())
+            elif code == L.OP_NOT:
+                if argc != 1 or not st:
+                    raise L.FbgpuError(L.E_INVALID, "malformed program")
+                st.append(self._row(index, op.field, op.view, op.a, shard).difference(st.pop()))
+            elif code == L.OP_BSI_RANGE:
+                f = self._frag(index, op.field, op.view, shard)
+                st.append(f.range_op(_CMP[op.b], int(op.a), int(op.lo), int(op.hi), shard=shard) if f is not None else O.Bitmap())
+            elif code in (L.OP_INTERSECT, L.OP_UNION, L.OP_DIFFERENCE, L.OP_XOR):
+                if argc == 0:
+                    if code == L.OP_INTERSECT:
+                        raise L.FbgpuError(L.E_QUERY, "empty Intersect query is currently not supported")
+                    if code == L.OP_DIFFERENCE:
+                        raise L.FbgpuError(L.E_QUERY, "empty Difference query is currently not supported")
+                    st.append(O.Bitmap())
+                    continue
+                if argc > len(st):
+                    raise L.FbgpuError(L.E_INVALID, "malformed program")
+                args = st[len(st) - argc:]
+                del st[len(st) - argc:]
+                out = args[0]
+                for a in args[1:]:
+                    out = {L.OP_INTERSECT: out.intersect, L.OP_UNION: out.union, L.OP_DIFFERENCE: out.difference,
+                           L.OP_XOR: out.xor}[code](a)
+                st.append(out)
+            else:
+                raise L.FbgpuError(L.E_INVALID, "unknown opcode")
+        if len(st) != 1:
+            raise L.FbgpuError(L.E_INVALID, "malformed program")
+        return st[0]
+
+    # ---- queries (signatures of lib.Context)
+    def count(self, index, ops, shards, per_shard=False):
+        self.programs.append(list(ops))
+        per = np.array([self._eval(index, ops, s).count() for s in shards], dtype=np.uint64)
+        return (int(per.sum()), per) if per_shard else int(per.sum())
+
+    def row(self, index, ops, shards):
+        self.programs.append(list(ops))
+        out = O.Bitmap()
+        for s in sorted(int(s) for s in shards):
+            out = out.union(self._eval(index, ops, s))
+        return out.to_bytes(), out.count()
+
+    def row_counts(self, index, field, view, shards, row_ids=None, filter_ops=None, cap=1 << 20):
+        tot = {}
+        for s in shards:
+            f = self._frag(index, field, view, s)
+            if f is None:
+                continue
+            filt = self._eval(index, filter_ops, s) if filter_ops else None
+            rows, cnts = f.row_counts(s, filt)
+            for r, c in zip(rows.tolist(), cnts.tolist()):
+                tot[r] = tot.get(r, 0) + c
+        if row_ids is not None:
+            return np.array([tot.get(int(r), 0) for r in row_ids], dtype=np.uint64)
+        pairs = sorted(((r, c) for r, c in tot.items() if c), key=lambda kv: (-kv[1], kv[0]))[:cap]
+        return (np.array([p[0] for p in pairs], dtype=np.uint64), np.array([p[1] for p in pairs], dtype=np.uint64))
+
+    def count_pairs(self, index, field_a, view_a, rows_a, field_b, view_b, rows_b, shards):
+        out = np.zeros(len(rows_a), dtype=np.uint64)
+        for i, (ra, rb) in enumerate(zip(rows_a, rows_b)):
+            for s in shards:
+                out[i] += self._row(index, field_a, view_a, ra, s).intersection_count(self._row(index, field_b, view_b, rb, s))
+        return out
+
+    def groupby(self, index, fields, views, row_ids, shards, filter_ops=None):
+        shape = [len(r) for r in row_ids]
+        out = np.zeros(int(np.prod(shape)), dtype=np.uint64)
+        for s in shards:
+            frags = [self._frag(index, f, v, s) for f, v in zip(fields, views)]
+            filt = self._eval(index, filter_ops, s) if filter_ops else None
+            O.groupby_shard(frags, s, [list(map(int, r)) for r in row_ids], filt, out)
+        return out.reshape(shape)

@@ -106,8 +106,8 @@ class OracleIndex:
 class Pair:
     """a GPU Holder/Executor and an oracle index loaded with the same fragments"""
 
-    def __init__(self, name="i", track_existence=True):
-        self.holder = X.Holder()
+    def __init__(self, name="i", track_existence=True, ctx=None):
+        self.holder = X.Holder(ctx=ctx)
         self.idx = self.holder.create_index(name, track_existence)
         self.ex = X.Executor(self.holder)
         self.ora = OracleIndex(self.idx)
