@@ -21,6 +21,7 @@
 #include "../../include/fbgpu.h"
 #include "fbgpu_types.h"
 #include "kernels.cuh"
+#include "stripe.h"
 
 using namespace fbgpu;
 
@@ -136,6 +137,7 @@ struct fbgpu_ctx {
     RawBuf staging;                      // payload bytes not yet uploaded, destined for [uploaded, uploaded+staging.len)
     uint64_t uploaded = 0;               // bytes of payload already in HBM
     bool meta_dirty = false;
+    bool stripe_arrays = getenv("FBGPU_ARRAY_STRIPED") != nullptr;   // experimental payload order, see stripe.h (fixed per context)
     DevBuf d_payload, d_views, d_shardmap, d_frags, d_rows, d_descs, d_rowtab;
     PinBuf bounce[2];
     uint32_t n_views_dev = 0;
@@ -352,7 +354,8 @@ static int run_copies(fbgpu_ctx* c, const std::vector<PayloadCopy>& copies, int 
         for (size_t i = lo; i < hi; i++) {
             const PayloadCopy& pc = copies[i];
             uint8_t* dst = base + pc.dst;
-            memcpy(dst, pc.src, pc.bytes);
+            if (pc.typ == kArray && c->stripe_arrays) fbgpu_stripe::stripe_array(pc.src, (uint16_t*)dst, pc.bytes / 2);
+            else memcpy(dst, pc.src, pc.bytes);
             if (pc.padded > pc.bytes) memset(dst + pc.bytes, 0, pc.padded - pc.bytes);      // zero tail of the last 16-byte chunk
             if (pc.typ == kRun && pc.official_run) {     // official format stores (start, length-1): roaring.go:2240-2247
                 uint16_t* r = (uint16_t*)dst; for (uint32_t k = 0; k < pc.cnt; k++) r[2 * k + 1] = (uint16_t)(r[2 * k] + r[2 * k + 1]);
@@ -736,7 +739,8 @@ static int launch_eval(fbgpu_ctx* c, Workspace* w, const std::vector<DevOp>& pro
     if (!out.info && n_ops <= kWpMaxOps && depth <= kWpMaxDepth && !getenv("FBGPU_NO_WORDPAR")) {
         uint64_t arr = 0, other = 0;
         for (const DevOp& o : prog) if (o.op >= D_PUSH_ROW && o.op <= D_ORANDNOT_ROW && o.op != D_PUSH_EMPTY && o.fv < c->view_arr.size()) { arr += c->view_arr[o.fv]; other += c->view_other[o.fv]; }
-        if ((other > 0 && arr * 8 <= other) || getenv("FBGPU_FORCE_WORDPAR")) {
+        // (wp_slice searches sorted arrays: with striped array payloads the kernel is only valid when no arrays are referenced)
+        if (c->stripe_arrays ? (other > 0 && arr == 0) : ((other > 0 && arr * 8 <= other) || getenv("FBGPU_FORCE_WORDPAR") != nullptr)) {
             long long blocks = n_units * kWpBlocksPerUnit;
             long long grid = std::min<long long>(blocks, (long long)c->sm_count * std::max(FBGPU_WP_MIN_BLOCKS, 8) * 2);
             eval_wordpar_kernel<<<(unsigned)grid, kWpThreads, 0, w->stream>>>(store_ref(c), d_prog, n_ops, d_shards, n_units, out);
