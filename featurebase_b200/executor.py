@@ -154,6 +154,24 @@ class QueryError(Exception):
     pass
 
 
+class ValCount:
+    """pilosa.ValCount (executor.go:8425): integer Val + Count; compares equal to a (val, count) tuple"""
+
+    def __init__(self, val=0, count=0):
+        self.val, self.count = int(val), int(count)
+
+    def __eq__(self, o):
+        return (self.val, self.count) == ((o.val, o.count) if isinstance(o, ValCount) else tuple(o))
+
+    def __repr__(self):
+        return f"ValCount(val={self.val}, count={self.count})"
+
+
+def _i64(x):
+    x &= (1 << 64) - 1
+    return x - (1 << 64) if x >> 63 else x
+
+
 class Executor:
     def __init__(self, holder):
         self.holder, self.ctx = holder, holder.ctx
@@ -181,6 +199,10 @@ class Executor:
                 return self._groupby(idx, c, shards)
             if c.name == "Rows":
                 return self._rows(idx, c, shards)
+            if c.name == "Sum":
+                return self._sum(idx, c, shards)
+            if c.name in ("Min", "Max"):
+                return self._minmax(idx, c, shards, c.name)
             ops = self._bitmap_call(idx, c)
             data, cnt = self.ctx.row(idx.id, ops, shards)
             return RowResult(data, cnt)
@@ -324,6 +346,87 @@ class Executor:
         out = sorted(int(r) for r in rid)
         lim = c.args.get("limit")
         return out[:lim] if lim else out
+
+    # ------------------------------------------------------------------ BSI aggregates (executeSum :1119, executeMin :1225, executeMax :1261)
+    # Composed from the library's counting entry points, the way the Go shim would inside executeSumCountShard /
+    # Field.MinForShard: every step is one launch over the whole shard batch.
+    def _agg_setup(self, idx, c, what):
+        name = c.args.get("field", c.args.get("_field"))
+        if name is None:
+            raise QueryError(f"{what}(): field required")
+        if len(c.children) > 1:
+            raise QueryError(f"{what}() only accepts a single bitmap input")
+        f = self._field(idx, name)
+        exists = L.Op(L.OP_ROW, f.id, VIEW_BSI, 0, 0, 0, 0, 0)         # bsiExistsBit fragment.go:44
+        sign = L.Op(L.OP_ROW, f.id, VIEW_BSI, 0, 1, 0, 0, 0)           # bsiSignBit
+        consider = [exists]
+        if c.children:                                                  # filter ∩ exists (filter.go:1133, fragment.go:753-757)
+            consider = self._bitmap_call(idx, c.children[0]) + [exists, L.Op(L.OP_INTERSECT, 0, 0, 2, 0, 0, 0, 0)]
+        return f, consider, sign
+
+    def _sum(self, idx, c, shards):
+        """fragment.sum fragment.go:722 / BitmapBSICountFilter filter.go:1106-1165, reduced by ValCount.Add (:8438):
+        count = |filter ∩ exists|; per value row i the counts under the positive and the negative part of that set;
+        Val = Σ (pos_i - neg_i) << i  +  count * Base (executeSumCountShard :2203-2206), all in wrapping int64."""
+        f, consider, sign = self._agg_setup(idx, c, "Sum")
+        if f.type != "int":
+            return ValCount()                                           # bsig == nil (:2187-2190)
+        count = self.ctx.count(idx.id, consider, shards)
+        if count == 0:
+            return ValCount()                                           # executeSum :1147-1149
+        rows = list(range(2, 2 + f.bit_depth))                          # bsiOffsetBit + i
+        psum = nsum = 0
+        if rows:
+            pos = self.ctx.row_counts(idx.id, f.id, VIEW_BSI, shards, row_ids=rows, filter_ops=consider + [sign, L.Op(L.OP_DIFFERENCE, 0, 0, 2, 0, 0, 0, 0)])
+            neg = self.ctx.row_counts(idx.id, f.id, VIEW_BSI, shards, row_ids=rows, filter_ops=consider + [sign, L.Op(L.OP_INTERSECT, 0, 0, 2, 0, 0, 0, 0)])
+            for i in range(f.bit_depth):
+                psum += int(pos[i]) << i
+                nsum += int(neg[i]) << i
+        return ValCount(_i64(_i64(psum) - _i64(nsum) + count * f.base), count)
+
+    def _sweep_unsigned(self, idx, f, start, n_start, shards, want_max):
+        """fragment.maxUnsigned :841 / minUnsigned :788, run over the whole shard batch at once.  Per shard the reference
+        narrows `filter` bit by bit and the executor keeps the extreme ValCount over shards, adding the counts of
+        equal values (Smaller/Larger :8446,8526); narrowing the union of all shards' columns gives the same extreme
+        value and the same number of columns holding it."""
+        kept, val, cnt = [], 0, n_start
+        for i in range(f.bit_depth - 1, -1, -1):
+            plane = L.Op(L.OP_ROW, f.id, VIEW_BSI, 0, 2 + i, 0, 0, 0)
+            fold = L.Op(L.OP_INTERSECT if want_max else L.OP_DIFFERENCE, 0, 0, len(kept) + 2, 0, 0, 0, 0)
+            n = self.ctx.count(idx.id, start + kept + [plane, fold], shards)
+            if n > 0:                                                   # max: some column has bit i; min: some column lacks it
+                kept.append(plane)
+                cnt = n
+                if want_max:
+                    val += 1 << i
+            elif not want_max:
+                val += 1 << i
+        return val, cnt
+
+    def _minmax(self, idx, c, shards, what):
+        f, consider, sign = self._agg_setup(idx, c, what)
+        if f.type != "int":
+            raise QueryError("bsigroup not found")                      # ErrBSIGroupNotFound field.go:1571
+        n = self.ctx.count(idx.id, consider, shards)
+        if n == 0:
+            return ValCount()                                           # :1252-1254
+        if what == "Min":                                               # fragment.min :752-785
+            neg = consider + [sign, L.Op(L.OP_INTERSECT, 0, 0, 2, 0, 0, 0, 0)]
+            n_neg = self.ctx.count(idx.id, neg, shards)
+            if n_neg > 0:
+                v, cnt = self._sweep_unsigned(idx, f, neg, n_neg, shards, True)
+                v = -v
+            else:
+                v, cnt = self._sweep_unsigned(idx, f, consider, n, shards, False)
+        else:                                                           # fragment.max :811-838
+            pos = consider + [sign, L.Op(L.OP_DIFFERENCE, 0, 0, 2, 0, 0, 0, 0)]
+            n_pos = self.ctx.count(idx.id, pos, shards)
+            if n_pos == 0:
+                v, cnt = self._sweep_unsigned(idx, f, consider, n, shards, False)
+                v = -v
+            else:
+                v, cnt = self._sweep_unsigned(idx, f, pos, n_pos, shards, True)
+        return ValCount(v + f.base, cnt)                                # valCountize field.go:1640
 
     # ------------------------------------------------------------------ GroupBy (executeGroupBy :3176)
     def _groupby(self, idx, c, shards):

@@ -1,6 +1,6 @@
 """Minimal PQL call tree + parser for the hot-path calls (mirror of pql.Call, reference pql/ast.go), so that parity
 tests read like the reference's executor tests.  The full PEG grammar stays in Go; only this subset is needed:
-Row, Intersect, Union, Difference, Xor, Not, All, Count, TopN, TopK, Rows, GroupBy."""
+Row, Intersect, Union, Difference, Xor, Not, All, Count, TopN, TopK, Rows, GroupBy, Sum, Min, Max."""
 import re
 
 
@@ -23,7 +23,7 @@ class Call:
         return f"{self.name}({', '.join(parts)})"
 
 
-_TOK = re.compile(r"\s*(?:(?P<num>-?\d+)|(?P<id>[A-Za-z_][A-Za-z0-9_\-]*)|(?P<op>><|<=|>=|==|!=|[(),=<>\[\]]))")
+_TOK = re.compile(r"\s*(?:(?P<str>\"[^\"]*\"|'[^']*')|(?P<num>-?\d+)|(?P<id>[A-Za-z_][A-Za-z0-9_\-]*)|(?P<op>><|<=|>=|==|!=|[(),=<>\[\]]))")
 
 
 def _tokens(s):
@@ -35,7 +35,9 @@ def _tokens(s):
         if not m:
             raise ValueError(f"PQL syntax error at {pos}: {s[pos:pos + 20]!r}")
         pos = m.end()
-        if m.group("num") is not None:
+        if m.group("str") is not None:
+            out.append(("str", m.group("str")[1:-1]))
+        elif m.group("num") is not None:
             out.append(("num", int(m.group("num"))))
         elif m.group("id") is not None:
             out.append(("id", m.group("id")))
@@ -64,7 +66,7 @@ class _Parser:
 
     def value(self):
         kind, v = self.next()
-        if kind == "num":
+        if kind in ("num", "str"):
             return v
         if kind == "id":
             if v == "null":

@@ -277,6 +277,92 @@ class Bitmap:
             cap = int(n)
 
 
+# ---- BSI aggregates of one fragment (restated with the C oracle's row / set operations; rows 0 exists, 1 sign, 2+i bit i) ----
+_M64 = (1 << 64) - 1
+
+
+def _i64(x):
+    x &= _M64
+    return x - (1 << 64) if x >> 63 else x
+
+
+def bsi_sum(frag, bit_depth, filt=None, shard=0):
+    """fragment.sum fragment.go:722-748 + BitmapBSICountFilter roaring/filter.go:1106-1165: (sum, count) with
+    positive = (filter ∩ exists) minus sign, negative = filter ∩ exists ∩ sign; psum/nsum are uint64 accumulators of
+    count << i, the total is int64(psum) - int64(nsum).  filt is a Bitmap with absolute keys, or None (no filter).
+    The reference walks every value row stored in the fragment; well-formed fragments have none beyond bit_depth."""
+    pos = frag.row(0, shard)
+    if filt is not None:
+        pos = pos.intersect(filt)
+    count = pos.count()
+    sign = frag.row(1, shard)
+    neg = pos.intersect(sign)
+    pos = pos.difference(sign)
+    psum = nsum = 0
+    for i in range(int(bit_depth)):
+        plane = frag.row(2 + i, shard)
+        psum = (psum + (pos.intersection_count(plane) << i)) & _M64
+        nsum = (nsum + (neg.intersection_count(plane) << i)) & _M64
+    return _i64(_i64(psum) - _i64(nsum)), count
+
+
+def _bsi_min_unsigned(frag, filt, bit_depth, shard):
+    """fragment.minUnsigned fragment.go:788-807"""
+    mn, count = 0, filt.count()
+    for i in range(int(bit_depth) - 1, -1, -1):
+        row = filt.difference(frag.row(2 + i, shard))
+        count = row.count()
+        if count > 0:
+            filt = row
+        else:
+            mn += 1 << i
+            if i == 0:
+                count = filt.count()
+    return mn, count
+
+
+def _bsi_max_unsigned(frag, filt, bit_depth, shard):
+    """fragment.maxUnsigned fragment.go:841-860"""
+    mx, count = 0, filt.count()
+    for i in range(int(bit_depth) - 1, -1, -1):
+        row = frag.row(2 + i, shard).intersect(filt)
+        count = row.count()
+        if count > 0:
+            mx += 1 << i
+            filt = row
+        elif i == 0:
+            count = filt.count()
+    return mx, count
+
+
+def bsi_min(frag, bit_depth, filt=None, shard=0):
+    """fragment.min fragment.go:752-785 -> (min, count)"""
+    consider = frag.row(0, shard)
+    if filt is not None:
+        consider = consider.intersect(filt)
+    if consider.count() == 0:
+        return 0, 0
+    neg = frag.row(1, shard).intersect(consider)
+    if neg.any():
+        mx, count = _bsi_max_unsigned(frag, neg, bit_depth, shard)
+        return -mx, count
+    return _bsi_min_unsigned(frag, consider, bit_depth, shard)
+
+
+def bsi_max(frag, bit_depth, filt=None, shard=0):
+    """fragment.max fragment.go:811-838 -> (max, count)"""
+    consider = frag.row(0, shard)
+    if filt is not None:
+        consider = consider.intersect(filt)
+    if not consider.any():
+        return 0, 0
+    pos = consider.difference(frag.row(1, shard))
+    if not pos.any():
+        mn, count = _bsi_min_unsigned(frag, consider, bit_depth, shard)
+        return -mn, count
+    return _bsi_max_unsigned(frag, pos, bit_depth, shard)
+
+
 def groupby_shard(frags, shard, row_ids, filt=None, out=None):
     """frags: list of Bitmap-or-None; row_ids: list of lists; returns dense count array (row-major)."""
     n_rows = np.asarray([len(r) for r in row_ids], dtype=np.int32)

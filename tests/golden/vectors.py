@@ -115,3 +115,34 @@ BSI_EXEC_CASES = [
     ("Row(edge < 200)", [0, 1]),
     ("Row(edge > -1000)", [0, 1]),
 ]
+
+# ---------------------------------------------------------------------------------------------------
+# BSI aggregates.  fragment_internal_test.go:452-521 (TestFragment_Sum: bitDepth 16; the ClearValue step is the same
+# fragment without column 1000) and :524-603 (TestFragment_MinMax).  Entries: (filter columns or None, value, count).
+# ---------------------------------------------------------------------------------------------------
+FRAG_SUM_VALUES = {1000: 382, 2000: 300, 2500: -600, 3000: 2818, 4000: 300}
+FRAG_SUM_CASES = [(None, 382 + 300 - 600 + 2818 + 300, 5), ([2000, 4000, 5000], 300 + 300, 2)]
+FRAG_SUM_CLEARED = (1000, 3800 - 382 - 600, 4)          # after clearValue(1000): sum 2818, count 4
+FRAG_MINMAX_VALUES = {1000: 382, 2000: 300, 3000: 2818, 4000: 300, 5000: 2818, 6000: 2817, 7000: 0}
+FRAG_MIN_CASES = [(None, 0, 1), ([2000, 4000, 5000], 300, 2), ([2000, 4000], 300, 2), ([1], 0, 0), ([1000], 382, 1), ([7000], 0, 1)]
+FRAG_MAX_CASES = [(None, 2818, 2), ([2000, 4000, 5000], 2818, 1), ([2000, 4000], 300, 2), ([1], 0, 0), ([1000], 382, 1), ([7000], 0, 1)]
+
+# executor_test.go:2192-2286 (MinMax WithOffset/Int): field range (min, max), one value set at column 10 -> Min == Max == (value, 1)
+EXEC_MINMAX_OFFSET = [(10, 20, 11), (-10, 20, 11), (-10, 20, -9), (-20, -10, -11)]
+# executor_test.go:2508-2567 (MinMax ColumnID): set field x, int field f in [-1100, 1000]; Min cases :2545-2567.  The Max
+# expectations are the ColumnKey twin's (:2629-2655): same values and filters, columns named by keys instead of ids.
+EXEC_MINMAX_SETUP = {
+    "set": {"x": [(0, 0), (0, 3), (0, SW + 1), (1, 1), (2, SW + 2)]},
+    "int": {"f": [(0, 20), (1, -5), (2, -5), (3, 10), (SW, 30), (SW + 2, 40), (5 * SW + 100, 50), (SW + 1, 60)]},
+    "ranges": {"f": (-1100, 1000)},
+}
+EXEC_MIN_CASES = [("Min(field=f)", (-5, 2)), ("Min(Row(x=0), field=f)", (10, 1)), ("Min(Row(x=1), field=f)", (-5, 1)), ("Min(Row(x=2), field=f)", (40, 1))]
+EXEC_MAX_CASES = [("Max(field=f)", (60, 1)), ("Max(Row(x=0), field=f)", (60, 1)), ("Max(Row(x=1), field=f)", (-5, 1)), ("Max(Row(x=2), field=f)", (40, 1))]
+# executor_test.go:2782-2869 (Sum ColumnID / Integer)
+EXEC_SUM_SETUP = {
+    "set": {"x": [(0, 0), (0, SW + 1)]},
+    "int": {"foo": [(0, 20), (SW, 30), (SW + 2, 40), (5 * SW + 100, 50), (SW + 1, 60)], "bar": [(0, 2000)], "other": [(0, 1000)]},
+    "ranges": {"foo": (-990, 1000), "bar": (-(1 << 63), (1 << 63) - 1), "other": (-(1 << 63), (1 << 63) - 1)},
+}
+EXEC_SUM_CASES = [("Sum(field=foo)", (200, 5)), ('Sum(field="foo")', (200, 5)), ("Sum(foo)", (200, 5)), ("Sum(Row(x=0), field=foo)", (80, 2)),
+                  ("Sum(foo, Row(x=0))", (80, 2)), ("Sum(field=bar)", (2000, 1)), ("Sum(Row(x=1), field=foo)", (0, 0))]

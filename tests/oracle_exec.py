@@ -102,6 +102,36 @@ class OracleIndex:
     def count(self, c, shards):
         return sum(self.eval_shard(c, s).count() for s in shards)
 
+    # ---- BSI aggregates the way the reference runs them: per shard, then reduced (executor.go:1119-1300)
+    def _agg_shards(self, c, shards, fn):
+        name = c.args.get("field", c.args.get("_field"))
+        fld = self.idx.fields[name]
+        for s in shards:
+            filt = self.eval_shard(c.children[0], s) if c.children else None
+            frag = self.frag(name, X.VIEW_BSI, s)
+            if frag is None:
+                yield fld, 0, 0                                  # ValCount{} (executeSumCountShard :2192-2195, field.go:1579-1582)
+                continue
+            v, n = fn(frag, fld.bit_depth, filt, s)
+            yield fld, v, n
+
+    def sum(self, c, shards):
+        val = cnt = 0
+        for fld, v, n in self._agg_shards(c, shards, O.bsi_sum):
+            val += v + n * fld.base                              # :2203-2206, reduced with ValCount.Add :8438
+            cnt += n
+        return (X._i64(val), cnt) if cnt else (0, 0)
+
+    def minmax(self, c, shards, want_max):
+        best = None                                              # ValCount.Smaller / Larger :8446-8470,8526-8550
+        for fld, v, n in self._agg_shards(c, shards, O.bsi_max if want_max else O.bsi_min):
+            cur = (v + fld.base, n) if n else (0, 0)
+            if best is None or best[1] == 0 or (cur[1] > 0 and (cur[0] > best[0] if want_max else cur[0] < best[0])):
+                best = cur
+            elif cur[0] == best[0]:
+                best = (best[0], best[1] + cur[1])
+        return best if best and best[1] else (0, 0)
+
 
 class Pair:
     """a GPU Holder/Executor and an oracle index loaded with the same fragments"""

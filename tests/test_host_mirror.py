@@ -14,6 +14,7 @@ from featurebase_b200 import lib as L
 from tests import oracle_exec
 from tests import test_gpu_parity as G
 from tests import test_zz_gpu_executor_goldens as Z
+from tests import test_zz_gpu_experimental as E
 from tests.oracle_ctx import OracleCtx
 
 
@@ -23,6 +24,7 @@ def oracle_backed(monkeypatch):
         return oracle_exec.Pair(*a, ctx=OracleCtx(), **kw)
     monkeypatch.setattr(G, "Pair", make)
     monkeypatch.setattr(Z, "Pair", make)
+    monkeypatch.setattr(E, "Pair", make)
 
 
 def test_setop_goldens_and_edge_semantics(oracle_backed):
@@ -44,6 +46,13 @@ def test_topk_topn_groupby(oracle_backed):
     G.test_executor_topk_topn_groupby_goldens_on_gpu()
     G.test_topk_topn_rowcounts()
     G.test_groupby_two_and_three_fields()
+
+
+def test_bsi_aggregates(oracle_backed):
+    """Sum / Min / Max: the mirror's whole-batch composition (counts per value row, bit sweep over the batch) against
+    the reference's per-shard evaluation + ValCount reduce, and the literal expectations of executor_test.go"""
+    E.test_bsi_aggregate_goldens()
+    E.test_bsi_aggregates_random()
 
 
 def test_emitted_programs():

@@ -373,3 +373,39 @@ def test_executor_bsi_goldens_through_host_mirror():
         assert list(got.slice()) == exp, q
     with pytest.raises(Exception):
         X.Executor.__new__(X.Executor)._field(idx, "bad_field")      # ErrFieldNotFound (executor_test.go:3283)
+
+
+def test_bsi_aggregate_goldens():
+    """fragment_internal_test.go:452-603: fragment.sum / min / max literal cases (bitDepth 16)"""
+    def filt(cols):
+        return None if cols is None else O.Bitmap.from_values(cols)
+    frag = H.bsi_fragment(V.FRAG_SUM_VALUES, 16)
+    for cols, exp_sum, exp_n in V.FRAG_SUM_CASES:
+        assert O.bsi_sum(frag, 16, filt(cols)) == (exp_sum, exp_n)
+    cleared_col, exp_sum, exp_n = V.FRAG_SUM_CLEARED
+    frag = H.bsi_fragment({c: v for c, v in V.FRAG_SUM_VALUES.items() if c != cleared_col}, 16)
+    assert O.bsi_sum(frag, 16) == (exp_sum, exp_n)
+    frag = H.bsi_fragment(V.FRAG_MINMAX_VALUES, 16)
+    for cols, exp, n in V.FRAG_MIN_CASES:
+        assert O.bsi_min(frag, 16, filt(cols)) == (exp, n), cols
+    for cols, exp, n in V.FRAG_MAX_CASES:
+        assert O.bsi_max(frag, 16, filt(cols)) == (exp, n), cols
+
+
+def test_bsi_aggregates_vs_naive():
+    """random signed values, several shards' worth of filters: sum/min/max restatements against plain Python"""
+    rng = np.random.default_rng(21)
+    for depth, lo, hi in ((12, -4000, 4000), (12, 5, 4000), (12, -4000, -7), (3, -7, 7), (40, -(1 << 39), 1 << 39)):
+        cols = rng.choice(300000, 2500, replace=False)
+        values = {int(c): int(v) for c, v in zip(cols, rng.integers(lo, hi, 2500))}
+        frag = H.bsi_fragment(values, depth)
+        for frac in (None, 0.5, 0.01, 0.0):
+            if frac is None:
+                f, keep = None, set(values)
+            else:
+                pick = rng.choice(300000, int(300000 * frac), replace=False)
+                f, keep = O.Bitmap.from_values(pick), set(values) & set(pick.tolist())
+            vs = [values[c] for c in keep]
+            assert O.bsi_sum(frag, depth, f) == (sum(vs), len(vs))
+            assert O.bsi_min(frag, depth, f) == ((min(vs), vs.count(min(vs))) if vs else (0, 0))
+            assert O.bsi_max(frag, depth, f) == ((max(vs), vs.count(max(vs))) if vs else (0, 0))

@@ -1,12 +1,21 @@
 """Opt-in GPU parity run of EXPERIMENTAL data layouts (not part of the default product path, not yet measured):
 FBGPU_ARRAY_STRIPED=1 permutes array payloads at load time (featurebase_b200/csrc/stripe.h).  Every kernel must give
 bit-identical results on permuted arrays, so the bodies of the regular parity tests are simply re-run with the switch on.
-Skipped unless FBGPU_TEST_EXPERIMENTAL=1 (round 2 turns it on before measuring the layout)."""
+Skipped unless FBGPU_TEST_EXPERIMENTAL=1 (round 2 turns it on before measuring the layout).
+
+Also here until they have had their first GPU run: the BSI aggregates Sum / Min / Max, which the host
+mirror composes from fbgpu_count / fbgpu_row_counts calls.  tests/test_host_mirror.py runs the same bodies on the CPU
+against an oracle-backed context."""
 import os
 
+import numpy as np
 import pytest
 
+from featurebase_b200 import executor as X
+from featurebase_b200 import pql
 from tests import test_gpu_parity as G
+from tests.golden import vectors as V
+from tests.oracle_exec import Pair
 
 pytestmark = [pytest.mark.gpu,
               pytest.mark.skipif(not os.environ.get("FBGPU_TEST_EXPERIMENTAL"), reason="experimental layouts: set FBGPU_TEST_EXPERIMENTAL=1")]
@@ -40,3 +49,83 @@ def test_striped_bsi_topk_groupby(striped):
 @pytest.mark.parametrize("env", ["FBGPU_FORCE_WORDPAR", "FBGPU_STAGED"])
 def test_striped_alternative_kernels(striped, env, monkeypatch):
     G.test_alternative_eval_kernels(env, monkeypatch)       # FORCE_WORDPAR must be ignored for views that hold arrays
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# BSI aggregates (composition of already-verified entry points; bodies shared with tests/test_host_mirror.py)
+# ---------------------------------------------------------------------------------------------------------------
+def _setup(setup):
+    p = Pair(track_existence=True)
+    for name in setup["set"]:
+        p.field(name)
+    for name, (lo, hi) in setup["ranges"].items():
+        p.field(name, "int", min=lo, max=hi, bit_depth=(63 if hi > (1 << 40) else None))
+    for name, bits in setup["set"].items():
+        for r, c in bits:
+            p.holder.set_bit("i", name, r, c)
+    for name, vals in setup["int"].items():
+        for c, v in vals:
+            p.holder.set_value("i", name, c, v)
+    p.sync_pending()
+    return p
+
+
+def _check_agg(p, q, exp=None):
+    """mirror result == reference flow on the oracle (per shard + ValCount reduce) [== literal expectation]"""
+    call = pql.parse(q)[0]
+    got = p.ex.execute("i", q)[0]
+    ref = p.ora.sum(call, p.shards()) if call.name == "Sum" else p.ora.minmax(call, p.shards(), call.name == "Max")
+    assert got == ref, (q, got, ref)
+    if exp is not None:
+        assert got == exp, (q, got, exp)
+    return got
+
+
+def test_bsi_aggregate_goldens():
+    """executor_test.go:2192-2286 (Min/Max with offset bases), :2508-2567,2629-2655 (Min/Max with filters over 3 shards),
+    :2782-2869 (Sum)"""
+    for k, (lo, hi, val) in enumerate(V.EXEC_MINMAX_OFFSET):
+        p = Pair()
+        p.field(f"f{k}", "int", min=lo, max=hi)
+        p.holder.set_value("i", f"f{k}", 10, val)
+        p.sync_pending()
+        for q in (f"Min(field=f{k})", f"Max(field=f{k})", f'Min(field="f{k}")', f"Max(f{k})", f"Sum(f{k})"):
+            _check_agg(p, q, (val, 1))
+    p = _setup(V.EXEC_MINMAX_SETUP)
+    for q, exp in V.EXEC_MIN_CASES + V.EXEC_MAX_CASES:
+        _check_agg(p, q, exp)
+    p = _setup(V.EXEC_SUM_SETUP)
+    for q, exp in V.EXEC_SUM_CASES:
+        _check_agg(p, q, exp)
+    with pytest.raises(X.QueryError, match="field not found"):
+        p.ex.execute("i", "Sum(field=fake)")                      # executor_test.go:2871-2876
+    with pytest.raises(X.QueryError):
+        p.ex.execute("i", "Sum(Row(x=0), Row(x=1), field=foo)")
+    with pytest.raises(X.QueryError):
+        p.ex.execute("i", "Min()")
+
+
+def test_bsi_aggregates_random():
+    """signed / all-negative / all-positive / offset-base fields over several shards, filters of every density"""
+    rng = np.random.default_rng(77)
+    SW = 1 << 20
+    for name, lo, hi, nvals in (("a", -5000, 5000, 6000), ("b", 100, 900, 3000), ("c", -900, -100, 3000), ("d", -3, 3, 500), ("e", -(1 << 40), 1 << 40, 2000)):
+        p = Pair()
+        p.field("x")
+        p.field(name, "int", min=lo, max=hi)
+        cols = rng.choice(4 * SW, nvals, replace=False)
+        for c, v in zip(cols, rng.integers(lo, hi + 1, nvals)):
+            p.holder.set_value("i", name, int(c), int(v))
+        for r, frac in ((0, 0.5), (1, 0.02), (2, 0.0005)):
+            for c in rng.choice(cols, max(1, int(nvals * frac)), replace=False):
+                p.holder.set_bit("i", "x", r, int(c))
+        p.holder.set_bit("i", "x", 3, 4 * SW + 5)                   # a filter row with no valued column
+        p.sync_pending()
+        for agg in ("Sum", "Min", "Max"):
+            _check_agg(p, f"{agg}(field={name})")
+            for r in range(4):
+                _check_agg(p, f"{agg}(Row(x={r}), field={name})")
+            _check_agg(p, f"{agg}(Union(Row(x=1), Row(x=2)), field={name})")
+            _check_agg(p, f"{agg}(Row({name} > 0), field={name})")
+            _check_agg(p, f"{agg}(Row({name} < 0), field={name})")
+        assert _check_agg(p, f"Sum(Row(x=3), field={name})") == (0, 0)
