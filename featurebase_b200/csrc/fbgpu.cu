@@ -22,6 +22,7 @@
 #include "fbgpu_types.h"
 #include "kernels.cuh"
 #include "stripe.h"
+#include "rbf_reader.h"
 
 using namespace fbgpu;
 
@@ -400,6 +401,55 @@ extern "C" int fbgpu_load_fragments(fbgpu_ctx* c, uint32_t index, uint32_t field
     std::vector<PayloadCopy> copies;
     for (int64_t i = 0; i < n; i++) { int rc = add_fragment_locked(c, fv, shards[i], parsed[i], copies); if (rc) return rc; }
     return run_copies(c, copies, nt);
+}
+
+extern "C" int fbgpu_load_rbf(fbgpu_ctx* c, uint32_t index, uint64_t shard, const uint8_t* data, uint64_t data_bytes, const uint8_t* wal, uint64_t wal_bytes,
+                              const char* const* names, const uint32_t* fields, const uint32_t* views, int32_t n_names, int32_t* out_loaded) {
+    if (!c || !data || n_names < 0 || (n_names > 0 && (!names || !fields || !views))) return fail(FBGPU_E_INVALID, "null argument");
+    if (out_loaded) *out_loaded = 0;
+    fbgpu_rbf::File f; std::string err;
+    if (!f.open(data, data_bytes, wal, wal_bytes, err)) return fail(FBGPU_E_FORMAT, "%s", err.c_str());
+    std::vector<fbgpu_rbf::RootRecord> recs;
+    if (!f.root_records(recs, err)) return fail(FBGPU_E_FORMAT, "%s", err.c_str());
+    // walk + validate everything before touching the store, so that a bad file leaves it unchanged
+    struct Found { uint32_t field, view; std::vector<ParsedCont> cs; };
+    std::vector<Found> found;
+    std::vector<fbgpu_rbf::Cell> cells;
+    for (int32_t i = 0; i < n_names; i++) {
+        if (!names[i]) return fail(FBGPU_E_INVALID, "names[%d] is null", i);
+        const fbgpu_rbf::RootRecord* rec = nullptr;
+        for (const auto& r : recs) if (r.name == names[i]) { rec = &r; break; }
+        if (!rec) continue;
+        cells.clear();
+        if (!f.walk(rec->pgno, cells, err)) return fail(FBGPU_E_FORMAT, "%s (bitmap %s)", err.c_str(), names[i]);
+        Found fd{ fields[i], views[i], {} };
+        fd.cs.reserve(cells.size());
+        for (const auto& cl : cells) {
+            if (cl.bit_n == 0) continue;                           // ContainerTypeNone / empty: never written, tolerated
+            ParsedCont pc{}; pc.key = cl.key; pc.data = cl.data; pc.official_run = false; pc.n = cl.bit_n;
+            if (cl.type == fbgpu_rbf::kCellArray) {
+                if (cl.elem_n > 4096) return fail(FBGPU_E_FORMAT, "rbf: array cell with %u elements (bitmap %s)", cl.elem_n, names[i]);   // ArrayMaxSize 4079 rbf.go:39
+                if (cl.elem_n != cl.bit_n) return fail(FBGPU_E_FORMAT, "rbf: array cell with elemN %u != bitN %u (bitmap %s)", cl.elem_n, cl.bit_n, names[i]);
+                pc.typ = kArray;
+            } else if (cl.type == fbgpu_rbf::kCellRLE) {
+                if (cl.elem_n == 0 || cl.elem_n > 2048 || cl.bit_n > 65536) return fail(FBGPU_E_FORMAT, "rbf: bad RLE cell (bitmap %s)", names[i]);   // RLEMaxSize 2039 rbf.go:42
+                pc.typ = kRun; pc.cnt = cl.elem_n;
+            } else {
+                if (cl.bit_n > 65536) return fail(FBGPU_E_FORMAT, "rbf: bad bitmap cell (bitmap %s)", names[i]);
+                pc.typ = kBitmap;
+            }
+            fd.cs.push_back(pc);
+        }
+        found.push_back(std::move(fd));
+    }
+    std::unique_lock<std::shared_mutex> lk(c->store_mu);
+    std::vector<PayloadCopy> copies;
+    for (auto& fd : found) {
+        uint32_t fv = view_id_locked(c, ViewKey{ index, fd.field, fd.view }, true);
+        int rc = add_fragment_locked(c, fv, shard, fd.cs, copies); if (rc) return rc;
+    }
+    if (out_loaded) *out_loaded = (int32_t)found.size();
+    return run_copies(c, copies, 1);
 }
 
 extern "C" int fbgpu_drop_fragment(fbgpu_ctx* c, uint32_t index, uint32_t field, uint32_t view, uint64_t shard) {

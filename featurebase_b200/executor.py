@@ -107,6 +107,21 @@ class Holder:
         self.ctx.load_fragment(idx.id, idx.fields[field].id, view, shard, data)
         idx.shards.add(int(shard))
 
+    def import_rbf(self, index, shard, data, wal=b""):
+        """residency straight from a shard's RBF database bytes: every field/view of this index that the
+        file holds under its rbfName "~field;view<" (rbf.go:504; views "standard" view.go:28 and "bsig_<field>" :30)"""
+        idx = self.indexes[index]
+        names, fields, views = [], [], []
+        for f in idx.fields.values():
+            view = VIEW_BSI if f.type == "int" else VIEW_STANDARD
+            names.append("~%s;%s<" % (f.name, "bsig_" + f.name if view == VIEW_BSI else "standard"))
+            fields.append(f.id)
+            views.append(view)
+        n = self.ctx.load_rbf(idx.id, shard, data, names, fields, views, wal)
+        if n:
+            idx.shards.add(int(shard))
+        return n
+
     # ---- test conveniences mirroring test helpers (hldr.SetBit / SetValue, test/holder.go)
     def set_bit(self, index, field, row, col):
         idx = self.indexes[index]

@@ -60,6 +60,7 @@ def load():
     L.fbgpu_load_fragment.argtypes, L.fbgpu_load_fragment.restype = [vp, u32, u32, u32, u64, vp, u64], C.c_int
     L.fbgpu_load_fragments.argtypes, L.fbgpu_load_fragments.restype = [vp, u32, u32, u32, vp, i64, vp, vp], C.c_int
     L.fbgpu_drop_fragment.argtypes, L.fbgpu_drop_fragment.restype = [vp, u32, u32, u32, u64], C.c_int
+    L.fbgpu_load_rbf.argtypes, L.fbgpu_load_rbf.restype = [vp, u32, u64, vp, u64, vp, u64, vp, vp, vp, i32, C.POINTER(i32)], C.c_int
     L.fbgpu_commit.argtypes, L.fbgpu_commit.restype = [vp], C.c_int
     L.fbgpu_get_stats.argtypes, L.fbgpu_get_stats.restype = [vp, C.POINTER(Stats)], C.c_int
     L.fbgpu_count.argtypes, L.fbgpu_count.restype = [vp, u32, vp, i32, vp, i64, C.POINTER(u64), vp], C.c_int
@@ -126,6 +127,20 @@ class Context:
         sh, off = _u64arr(shards), _u64arr(offsets)
         ptr = buf.ctypes.data if isinstance(buf, np.ndarray) else int(buf)
         self._check(self.L.fbgpu_load_fragments(self.h, index, field, view, sh.ctypes.data, len(sh), ptr, off.ctypes.data))
+
+    def load_rbf(self, index, shard, data, names, fields, views, wal=b""):
+        """one shard's RBF database bytes (+ WAL) -> fragments; names[i] = "~field;view<" maps to (fields[i], views[i]).
+        Returns how many of the names the file held."""
+        data, wal = bytes(data), bytes(wal or b"")
+        dbuf = (C.c_uint8 * max(len(data), 1)).from_buffer_copy(data or b"\0")
+        wbuf = (C.c_uint8 * max(len(wal), 1)).from_buffer_copy(wal or b"\0")
+        cn = (C.c_char_p * max(len(names), 1))(*[n.encode() if isinstance(n, str) else n for n in names])
+        fl = np.ascontiguousarray(np.asarray(fields, dtype=np.uint32))
+        vw = np.ascontiguousarray(np.asarray(views, dtype=np.uint32))
+        n = C.c_int32(0)
+        self._check(self.L.fbgpu_load_rbf(self.h, index, int(shard), C.addressof(dbuf), len(data), C.addressof(wbuf) if wal else None, len(wal),
+                                          C.addressof(cn), fl.ctypes.data, vw.ctypes.data, len(names), C.byref(n)))
+        return n.value
 
     def drop_fragment(self, index, field, view, shard):
         self._check(self.L.fbgpu_drop_fragment(self.h, index, field, view, int(shard)))

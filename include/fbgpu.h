@@ -54,6 +54,17 @@ int fbgpu_load_fragment(fbgpu_ctx *ctx, uint32_t index, uint32_t field, uint32_t
 int fbgpu_load_fragments(fbgpu_ctx *ctx, uint32_t index, uint32_t field, uint32_t view,
                          const uint64_t *shards, int64_t n, const uint8_t *buf, const uint64_t *offsets);
 int fbgpu_drop_fragment(fbgpu_ctx *ctx, uint32_t index, uint32_t field, uint32_t view, uint64_t shard);
+/*  Load the fragments of ONE shard straight from its RBF database, i.e. from the bytes of
+ * `<index>/backends/rbf/<shard>/data` (and, if it is not empty, `wal`) -- one RBF DB holds every field/view of a
+ * shard (dbshard.go:64-71).  Replaces the per-fragment tx.RoaringBitmap().WriteTo re-serialisation: leaf cells (array /
+ * RLE / bitmap page, rbf/rbf.go:489-512) become store containers directly.  names[i] is an RBF bitmap name
+ * "~field;view<" (rbfName rbf.go:504, short_txkey/txkey.go:129); fields[i] / views[i] are the ids the caller uses for
+ * it in programs.  Names that the file does not hold are skipped (a field without data in this shard); *out_loaded
+ * (may be NULL) receives how many were found.  Committed WAL pages override data pages (rbf/tx.go:1269-1273); pages
+ * after the WAL's last meta page are ignored.  The library copies; the caller keeps the buffers. */
+int fbgpu_load_rbf(fbgpu_ctx *ctx, uint32_t index, uint64_t shard, const uint8_t *data, uint64_t data_bytes,
+                   const uint8_t *wal, uint64_t wal_bytes, const char *const *names, const uint32_t *fields,
+                   const uint32_t *views, int32_t n_names, int32_t *out_loaded);
 /* pushes pending host-side staging to HBM now (otherwise done lazily by the next query) */
 int fbgpu_commit(fbgpu_ctx *ctx);
 

@@ -146,3 +146,16 @@ EXEC_SUM_SETUP = {
 }
 EXEC_SUM_CASES = [("Sum(field=foo)", (200, 5)), ('Sum(field="foo")', (200, 5)), ("Sum(foo)", (200, 5)), ("Sum(Row(x=0), field=foo)", (80, 2)),
                   ("Sum(foo, Row(x=0))", (80, 2)), ("Sum(field=bar)", (2000, 1)), ("Sum(Row(x=1), field=foo)", (0, 0))]
+
+# ---------------------------------------------------------------------------------------------------
+# RBF fixtures: the non-zero prefix of every 8 KiB page of rbf/testdata/check/bad-freelist/data and .../bad-bitmap/data
+# (used by rbf/tx_test.go:1280-1305; 4 pages each, the rest of each page is zero).  One bitmap "x" holding the single
+# bit 100 (leaf cell key 0, array, elemN 1, bitN 1).  In "bad-freelist" only the freelist page (2) is damaged (flags 4
+# instead of 2), the bitmap itself is intact; in "bad-bitmap" the bitmap's leaf page (3) carries branch flags.
+# ---------------------------------------------------------------------------------------------------
+RBF_FIXTURE_PAGES = {
+    "bad-freelist": ["ff524246000000000000000400000000000000040000000100000002", "00000001000000010000000000000003000178",
+                     "0000000200000004", "0000000300000002000100100000000000000000000000000100000001000100000064"],
+    "bad-bitmap": ["ff524246000000000000000400000000000000040000000100000002", "00000001000000010000000000000003000178",
+                   "0000000200000002", "0000000300000004000100100000000000000000000000000100000001000100000064"],
+}

@@ -22,6 +22,27 @@ class OracleCtx:
     def commit(self):
         pass
 
+    def load_rbf(self, index, shard, data, names, fields, views, wal=b""):
+        """same contract as lib.Context.load_rbf; the file is read by the product's rbf_reader.h through the g++ harness"""
+        from tests import test_rbf as TR
+        try:
+            found = TR.dump(TR.harness(), bytes(data), bytes(wal or b""))
+        except ValueError as e:
+            raise L.FbgpuError(L.E_FORMAT, str(e))
+        n = 0
+        for name, field, view in zip(names, fields, views):
+            if name not in found:
+                continue
+            vals = [TR.cell_values(*cell) for cell in found[name]]
+            self.frags.setdefault((index, int(field), int(view)), {})[int(shard)] = O.Bitmap.from_values(np.concatenate(vals) if vals else [])
+            n += 1
+        return n
+
+    def stats(self):
+        import struct
+        frs = [b for d in self.frags.values() for b in d.values()]
+        return {"fragments": len(frs), "containers": sum(struct.unpack_from("<I", b.to_bytes(), 4)[0] for b in frs)}
+
     def _frag(self, index, field, view, shard):
         return self.frags.get((index, field, view), {}).get(int(shard))
 

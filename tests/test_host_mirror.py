@@ -55,6 +55,12 @@ def test_bsi_aggregates(oracle_backed):
     E.test_bsi_aggregates_random()
 
 
+def test_rbf_import_plumbing(oracle_backed):
+    """Holder.import_rbf naming ("~field;view<") and the body of the opt-in GPU test, with the RBF bytes read by the
+    product's reader (g++ harness) into an oracle-backed context"""
+    E.test_rbf_loader_matches_fragment_loader()
+
+
 def test_emitted_programs():
     """the exact programs the mirror hands to the C ABI for the BSI short cuts (executor.go:5249-5354)"""
     ctx = OracleCtx()

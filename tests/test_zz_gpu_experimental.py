@@ -129,3 +129,59 @@ def test_bsi_aggregates_random():
             _check_agg(p, f"{agg}(Row({name} > 0), field={name})")
             _check_agg(p, f"{agg}(Row({name} < 0), field={name})")
         assert _check_agg(p, f"Sum(Row(x=3), field={name})") == (0, 0)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# RBF loader: fbgpu_load_rbf must leave the store in a state that answers every query exactly like the
+# same fragments loaded through fbgpu_load_fragment (the reader itself is covered on the CPU by tests/test_rbf.py)
+# ---------------------------------------------------------------------------------------------------------------
+def test_rbf_loader_matches_fragment_loader():
+    from featurebase_b200 import datagen as D
+    from featurebase_b200 import roaring_io
+    from oracle import oracle as O
+    from tests import rbf_writer as W
+    from tests import test_rbf as TR
+
+    a, b = Pair(), Pair()                         # a: Pilosa-roaring path (+ oracle), b: RBF path
+    for p in (a, b):
+        p.field("f")
+        p.field("g")
+        p.field("v", "int", min=-2000, max=2000)
+    rng = np.random.default_rng(8)
+    shards = [0, 3, 4]
+    for s in shards:
+        per_view = {}
+        for k, name in enumerate(("f", "g")):
+            bm, _ = TR._fragment_containers(60 + k, s)
+            per_view[(name, X.VIEW_STANDARD)] = bm.to_bytes()
+        for col, val in zip(rng.choice(1 << 20, 4000, replace=False), rng.integers(-2000, 2001, 4000)):
+            a.holder.set_value("i", "v", s * (1 << 20) + int(col), int(val))
+        for (index, field, view, shard), bits in a.holder._pending.items():
+            per_view[(field, view)] = roaring_io.encode(np.fromiter(bits, dtype=np.uint64, count=len(bits)))
+        a.holder._pending = {}
+        bitmaps = {}
+        for (field, view), data in per_view.items():
+            a.load(field, view, s, data)
+            vname = "standard" if view == X.VIEW_STANDARD else "bsig_" + field
+            bitmaps["~%s;%s<" % (field, vname)] = W.cells_from_pilosa(data)
+        bitmaps["~other;standard<"] = [(0, "array", np.array([1], dtype=np.uint16))]          # a field this index does not know
+        n = b.holder.import_rbf("i", s, W.build(bitmaps))
+        assert n == len(per_view)
+    sa, sb = a.holder.ctx.stats(), b.holder.ctx.stats()
+    assert sa["fragments"] == sb["fragments"]
+    assert sa["containers"] == sb["containers"]   # (RBF turns 4080..4095-element arrays into bitmaps: types may differ, counts not)
+    for q in ("Count(Intersect(Row(f=0), Row(g=1)))", "Count(Union(Row(f=0), Row(f=3), Row(f=5), Row(f=6), Row(f=9), Row(g=40)))",
+              "Count(Xor(Row(f=9), Row(g=9)))", "Count(Difference(Row(f=6), Row(g=5), Row(f=3)))", "Count(Not(Row(f=9)))",
+              "Count(Row(v > 17))", "Count(Row(v >< [-100, 700]))", "Count(Row(v == null))"):
+        assert b.ex.execute("i", q, shards)[0] == a.check_count(q, shards), q
+    for q in ("Union(Row(f=0), Row(f=5), Row(f=9))", "Intersect(Row(f=3), Row(g=6))", "Row(v < -1500)"):
+        ra = a.check_row(q, shards)
+        rb = b.ex.execute("i", q, shards)[0]
+        assert (rb.count, rb.roaring) == (ra.count, ra.roaring), q
+    assert b.ex.execute("i", "TopK(f, k=20)", shards)[0] == a.ex.execute("i", "TopK(f, k=20)", shards)[0]
+    assert b.ex.execute("i", "GroupBy(Rows(f), Rows(g))", shards)[0] == a.ex.execute("i", "GroupBy(Rows(f), Rows(g))", shards)[0]
+    assert b.ex.execute("i", "Sum(field=v)", shards)[0] == a.ex.execute("i", "Sum(field=v)", shards)[0]
+    with pytest.raises(Exception):
+        b.holder.ctx.load_rbf(0, 9, TR.fixture("bad-bitmap"), ["x"], [1], [0])
+    assert b.holder.ctx.load_rbf(0, 9, TR.fixture("bad-freelist"), ["x", "y"], [1, 2], [0, 0]) == 1
+    assert b.holder.ctx.count(0, [X.L.Op(X.L.OP_ROW, 1, 0, 0, 0, 0, 0, 0)], [9]) == 1
