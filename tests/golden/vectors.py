@@ -159,3 +159,34 @@ RBF_FIXTURE_PAGES = {
     "bad-bitmap": ["ff524246000000000000000400000000000000040000000100000002", "00000001000000010000000000000003000178",
                    "0000000200000002", "0000000300000004000100100000000000000000000000000100000001000100000064"],
 }
+
+# ---------------------------------------------------------------------------------------------------
+# fragment.top exact cases (the rank cache holds every row at these sizes).  fragment_internal_test.go:1150-1171 (Top),
+# :1174-1199 (TopN_Intersect, Src = columns 1,2,3), :1202-1249 (TopN_Intersect_Large: row i holds columns 0..i-1 for
+# i < 1000, Src = columns 980..999), :1252-1272 (TopN_IDs), :1513-1537 (Zero_Tanimoto == no threshold).
+# (rows {row: [cols]}, Src columns or None, n, ids or None, expected pairs)
+# ---------------------------------------------------------------------------------------------------
+FRAG_TOP_CASES = [
+    ({100: [1, 3, 200], 101: [1], 102: [1, 2]}, None, 2, None, [(100, 3), (102, 2)]),
+    ({100: [1, 10, 11, 12], 101: [1, 2, 3, 4], 102: [1, 2, 4, 5, 6], 103: [1000, 1001, 1002]}, [1, 2, 3], 3, None, [(101, 3), (102, 2), (100, 1)]),
+    ("large", list(range(980, 1000)), 10, None, [(999 - k, 19 - k) for k in range(10)]),
+    ({100: [1, 2, 3], 101: [4, 5, 6, 7], 102: [8, 9, 10, 11, 12]}, None, 0, [100, 101, 200], [(101, 4), (100, 3)]),
+    ({100: [1, 3, 2, 200], 101: [1, 3], 102: [1, 2, 10, 12]}, [1, 2, 3], 0, None, [(100, 3), (101, 2), (102, 2)]),
+]
+
+# ---------------------------------------------------------------------------------------------------
+# roaring/filter_internal_test.go:24-41 sample fragment: for every slot i in 1..15 the column (i << 16) + i is set in
+# rows 0, i, 2i, ... < 100.  :78-86 TestBaseFilter (all rows 0..99 present), :88-99 TestColumnFilter (rows holding
+# column (i<<16)+i are the multiples of i), :101-114 TestRowsFilter (row set {0,1,2,3} ∩ rows holding column (2<<16)+2 =
+# {0, 2}; limit 1 -> {0}), :116-138 TestRowsUnion (rows 7 ∪ 11 = columns {1<<16+1, 7<<16+7, 11<<16+11}, also in shard 2).
+# ---------------------------------------------------------------------------------------------------
+FILTER_SAMPLE_ROWS = 100
+
+
+def filter_sample_bits():
+    """[(row, column)]"""
+    return [(row, (i << 16) + i) for i in range(1, 16) for row in range(0, FILTER_SAMPLE_ROWS, i)]
+
+
+FILTER_ROWS_UNION = ([7, 11], [(1 << 16) + 1, (7 << 16) + 7, (11 << 16) + 11])
+FILTER_ROWSET = ([0, 1, 2, 3], (2 << 16) + 2, [0, 2])

@@ -55,6 +55,15 @@ def test_bsi_aggregates(oracle_backed):
     E.test_bsi_aggregates_random()
 
 
+def test_fragment_top_goldens(oracle_backed):
+    E.test_fragment_top_goldens()
+    E.test_filter_sample_goldens()
+
+
+def test_bench_archetype_matrix_plumbing(oracle_backed):
+    E.test_bench_archetype_matrix()
+
+
 def test_rbf_import_plumbing(oracle_backed):
     """Holder.import_rbf naming ("~field;view<") and the body of the opt-in GPU test, with the RBF bytes read by the
     product's reader (g++ harness) into an oracle-backed context"""

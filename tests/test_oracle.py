@@ -409,3 +409,47 @@ def test_bsi_aggregates_vs_naive():
             assert O.bsi_sum(frag, depth, f) == (sum(vs), len(vs))
             assert O.bsi_min(frag, depth, f) == ((min(vs), vs.count(min(vs))) if vs else (0, 0))
             assert O.bsi_max(frag, depth, f) == ((max(vs), vs.count(max(vs))) if vs else (0, 0))
+
+
+def test_filter_sample_goldens():
+    """roaring/filter_internal_test.go:78-138 on the oracle's row discovery / filtered row counts / row unions"""
+    SW = H.SW
+    for shard in (0, 2):
+        frag = O.Bitmap.from_values([r * SW + c for r, c in V.filter_sample_bits()])
+        assert frag.rows().tolist() == list(range(V.FILTER_SAMPLE_ROWS))                       # TestBaseFilter
+        for i in range(1, 16):                                                                  # TestColumnFilter
+            rows, cnts = frag.row_counts(shard, O.Bitmap.from_values([shard * SW + (i << 16) + i]))
+            assert sorted(rows.tolist()) == list(range(0, V.FILTER_SAMPLE_ROWS, i)) and set(cnts.tolist()) == {1}
+        rowset, col, exp = V.FILTER_ROWSET                                                      # TestRowsFilter
+        rows, _ = frag.row_counts(shard, O.Bitmap.from_values([shard * SW + col]))
+        assert sorted(set(rows.tolist()) & set(rowset)) == exp
+        ids, cols = V.FILTER_ROWS_UNION                                                         # TestRowsUnion (+ FB-1497 shard offset)
+        u = frag.row(ids[0], shard).union(frag.row(ids[1], shard))
+        assert u.slice().tolist() == [shard * SW + c for c in cols]
+
+
+def test_intersect_variants_property():
+    """roaring_container_test.go:62-88 TestIntersectVariants over the 20 benchmark archetypes (2 draws each, the full
+    matrix): intersect(a, b).N == intersectionCount(a, b); plus every op against plain numpy sets, and the single-word
+    run x bitmap regression of :90-100"""
+    rng = np.random.default_rng(23)
+    cs = [(n, *A.bench_archetype(rng, n)) for n in A.BENCH_NAMES for _ in range(2)]
+    masks = []
+    for _, _, v in cs:
+        m = np.zeros(1 << 16, dtype=bool)
+        m[v] = True
+        masks.append(m)
+    for i, (na, a, _) in enumerate(cs):
+        assert a.n == int(masks[i].sum()), na
+        for j, (nb, b, _) in enumerate(cs):
+            inter = a.intersect(b)
+            cnt = a.intersection_count(b)
+            exp = masks[i] & masks[j]
+            assert inter.n == cnt == int(exp.sum()), (na, nb)
+            assert np.array_equal(inter.values(), np.flatnonzero(exp)), (na, nb)
+            for op, e in (("union", masks[i] | masks[j]), ("difference", masks[i] & ~masks[j]), ("xor", masks[i] ^ masks[j])):
+                got = getattr(a, op)(b)
+                assert got.n == int(e.sum()) and np.array_equal(got.values(), np.flatnonzero(e)), (op, na, nb)
+    w = np.zeros(1024, dtype=np.uint64)
+    w[0] = 0b1001
+    assert O.Container.run(np.array([[1, 2]])).intersection_count(O.Container.bitmap(w)) == 0

@@ -185,3 +185,80 @@ def test_rbf_loader_matches_fragment_loader():
         b.holder.ctx.load_rbf(0, 9, TR.fixture("bad-bitmap"), ["x"], [1], [0])
     assert b.holder.ctx.load_rbf(0, 9, TR.fixture("bad-freelist"), ["x", "y"], [1, 2], [0, 0]) == 1
     assert b.holder.ctx.count(0, [X.L.Op(X.L.OP_ROW, 1, 0, 0, 0, 0, 0, 0)], [9]) == 1
+
+
+def test_fragment_top_goldens():
+    """fragment_internal_test.go:1150-1272,1513-1537 through TopN(f[, Row(src=0)], n=..[, ids=..]) on one shard"""
+    for rows, src, n, ids, exp in V.FRAG_TOP_CASES:
+        p = Pair(track_existence=False)
+        p.field("f")
+        p.field("src")
+        if rows == "large":
+            from oracle import oracle as O
+            pos = np.concatenate([np.uint64(i << 20) + np.arange(i, dtype=np.uint64) for i in range(1, 1000)])
+            p.load("f", X.VIEW_STANDARD, 0, O.Bitmap.from_values(pos).to_bytes())
+        else:
+            for r, cols in rows.items():
+                for c in cols:
+                    p.holder.set_bit("i", "f", r, c)
+        for c in (src or []):
+            p.holder.set_bit("i", "src", 0, c)
+        p.sync_pending()
+        q = "TopN(f" + (", Row(src=0)" if src else "") + (f", n={n}" if n else "") + (", ids=[" + ",".join(map(str, ids)) + "]" if ids else "") + ")"
+        assert p.ex.execute("i", q, [0])[0] == exp, q
+
+
+def test_filter_sample_goldens():
+    """roaring/filter_internal_test.go:78-138 at executor level, shards 0 and 2: Rows(f), rows holding one column (the
+    column filter becomes a one-column filter row), Union of two rows"""
+    SW = 1 << 20
+    p = Pair(track_existence=False)
+    p.field("f")
+    p.field("c")                                        # row i = the single column (i << 16) + i
+    for shard in (0, 2):
+        for r, c in V.filter_sample_bits():
+            p.holder.set_bit("i", "f", r, shard * SW + c)
+        for i in range(1, 16):
+            p.holder.set_bit("i", "c", i, shard * SW + (i << 16) + i)
+    p.sync_pending()
+    assert p.ex.execute("i", "Rows(f)")[0] == list(range(V.FILTER_SAMPLE_ROWS))
+    for shards in ([0], [2], [0, 2]):
+        for i in range(1, 16):
+            got = p.ex.execute("i", f"TopK(f, k=1000, filter=Row(c={i}))", shards)[0]
+            assert sorted(r for r, _ in got) == list(range(0, V.FILTER_SAMPLE_ROWS, i)) and {n for _, n in got} == {len(shards)}
+        ids, cols = V.FILTER_ROWS_UNION
+        got = p.check_row(f"Union(Row(f={ids[0]}), Row(f={ids[1]}))", shards)
+        assert list(got.columns()) == [s * SW + c for s in shards for c in cols]
+    rowset, col, exp = V.FILTER_ROWSET
+    got = p.ex.execute("i", "TopN(f, Row(c=2), ids=[0,1,2,3])", [0])[0]
+    assert sorted(r for r, _ in got) == exp
+
+
+def test_bench_archetype_matrix():
+    """roaring_container_test.go:62-88 shape matrix on the device: the 20 benchmark archetypes (2 draws each) stored in
+    their NAMED encodings (unoptimised Pilosa bytes keep them: a 512-bit bitmap container, a 4096-element array, ...),
+    all 1600 ordered pairs through the fused pair-count kernel, and the four set ops of a diagonal band as Row bytes"""
+    from oracle import oracle as O
+    from tests import archetypes as A
+    rng = np.random.default_rng(23)
+    cs = [(n, *A.bench_archetype(rng, n)) for n in A.BENCH_NAMES for _ in range(2)]
+    shard, slot = 1, 3
+    frag = O.Bitmap()
+    for row, (_, c, v) in enumerate(cs):
+        if len(v):
+            frag.put(row * 16 + slot, c)
+    p = Pair(track_existence=False)
+    p.field("f")
+    p.load("f", X.VIEW_STANDARD, shard, frag.to_bytes(optimize=False))
+    masks = np.zeros((len(cs), 1 << 16), dtype=bool)
+    for i, (_, _, v) in enumerate(cs):
+        masks[i, v] = True
+    ra, rb = np.divmod(np.arange(len(cs) ** 2), len(cs))
+    got = p.holder.ctx.count_pairs(p.idx.id, p.idx.fields["f"].id, 0, ra, p.idx.fields["f"].id, 0, rb, [shard])
+    exp = (masks.astype(np.uint32) @ masks.astype(np.uint32).T).reshape(-1)       # |a ∩ b| for every ordered pair
+    assert np.array_equal(np.asarray(got, dtype=np.int64), exp.astype(np.int64))
+    for i in range(len(cs)):
+        for j in (i, (i + 1) % len(cs), (i + 7) % len(cs), (i + 19) % len(cs)):
+            assert p.check_count(f"Count(Intersect(Row(f={i}), Row(f={j})))", [shard]) == int(exp[i * len(cs) + j])
+            for op in ("Union", "Difference", "Xor"):
+                p.check_row(f"{op}(Row(f={i}), Row(f={j}))", [shard])
