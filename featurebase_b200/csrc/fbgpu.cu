@@ -36,6 +36,12 @@ static int fail(int code, const char* fmt, ...) {
 }
 #define CUDA_TRY(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) return fail(FBGPU_E_CUDA, "%s failed: %s (%s:%d)", #x, cudaGetErrorString(_e), __FILE__, __LINE__); } while (0)
 
+// no C++ exception may cross the C boundary (the caller is cgo): every int-returning entry point is a function-try-block
+#define FBGPU_CATCH \
+    catch (const std::bad_alloc&) { return fail(FBGPU_E_NOMEM, "out of host memory"); } \
+    catch (const std::exception& e) { return fail(FBGPU_E_INVALID, "internal error: %s", e.what()); } \
+    catch (...) { return fail(FBGPU_E_INVALID, "internal error"); }
+
 extern "C" const char* fbgpu_last_error(void) { return g_err.c_str(); }
 extern "C" int32_t fbgpu_abi_version(void) { return FBGPU_ABI_VERSION; }
 
@@ -161,13 +167,14 @@ static StoreRef store_ref(fbgpu_ctx* c) {
     return s;
 }
 
-extern "C" int fbgpu_init(int32_t device_ordinal, fbgpu_ctx** out) {
+extern "C" int fbgpu_init(int32_t device_ordinal, fbgpu_ctx** out) try {
     if (!out) return fail(FBGPU_E_INVALID, "out is null");
     int n = 0;
     CUDA_TRY(cudaGetDeviceCount(&n));
     if (device_ordinal < 0 || device_ordinal >= n) return fail(FBGPU_E_INVALID, "device ordinal %d out of range (%d devices)", device_ordinal, n);
     CUDA_TRY(cudaSetDevice(device_ordinal));
     auto c = new fbgpu_ctx();
+    struct Guard { fbgpu_ctx* c; ~Guard() { if (c) fbgpu_shutdown(c); } } guard{ c };     // a failing step below must not leak the context
     c->device = device_ordinal;
     cudaDeviceProp p; CUDA_TRY(cudaGetDeviceProperties(&p, device_ordinal));
     c->sm_count = p.multiProcessorCount;
@@ -183,9 +190,10 @@ extern "C" int fbgpu_init(int32_t device_ordinal, fbgpu_ctx** out) {
     CUDA_TRY(cudaFuncSetAttribute(pair_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairWarps * 8192));
     CUDA_TRY(cudaFuncSetAttribute(row_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairWarps * 8192));
     CUDA_TRY(cudaFuncSetAttribute(groupby_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGbSlots * 4 + 8192));
+    guard.c = nullptr;
     *out = c;
     return FBGPU_OK;
-}
+} FBGPU_CATCH
 
 extern "C" void fbgpu_shutdown(fbgpu_ctx* c) {
     if (!c) return;
@@ -195,20 +203,27 @@ extern "C" void fbgpu_shutdown(fbgpu_ctx* c) {
     for (auto& w : c->wss) {
         for (DevBuf* b : { &w->d_in, &w->d_counts, &w->d_bitmaps, &w->d_info, &w->d_emit_units, &w->d_emit, &w->d_rows, &w->d_aux }) b->release();
         w->h_in.release(); w->h_out.release();
-        cudaEventDestroy(w->ev0); cudaEventDestroy(w->ev1); cudaStreamDestroy(w->stream);
+        if (w->ev0) cudaEventDestroy(w->ev0);
+        if (w->ev1) cudaEventDestroy(w->ev1);
+        if (w->stream) cudaStreamDestroy(w->stream);
     }
     for (DevBuf* b : { &c->d_payload, &c->d_views, &c->d_shardmap, &c->d_frags, &c->d_rows, &c->d_descs, &c->d_rowtab }) b->release();
     c->bounce[0].release(); c->bounce[1].release(); c->staging.clear_and_free();
+    for (int p = 0; p < kMaxRanks; p++) if (c->peers[p] && c->peers[p] != c->mbox) cudaIpcCloseMemHandle(c->peers[p]);   // peer mailboxes mapped by fbgpu_comm_p2p_open
+    if (c->mbox) cudaFree(c->mbox);
+    c->d_peers.release();
     delete c;
 }
 
 struct WsLease {
     fbgpu_ctx* c; Workspace* w;
+    bool ok = false;        // set on the success path; otherwise the destructor drains the stream, so that work queued
+                            // before an error return cannot still be running when the next query reuses the buffers
     explicit WsLease(fbgpu_ctx* ctx) : c(ctx), w(nullptr) {
         std::unique_lock<std::mutex> lk(c->ws_mu);
         for (;;) { for (auto& x : c->wss) if (!x->busy) { x->busy = true; w = x.get(); return; } c->ws_cv.wait(lk); }
     }
-    ~WsLease() { { std::lock_guard<std::mutex> lk(c->ws_mu); w->busy = false; } c->ws_cv.notify_one(); }
+    ~WsLease() { if (!ok) cudaStreamSynchronize(w->stream); { std::lock_guard<std::mutex> lk(c->ws_mu); w->busy = false; } c->ws_cv.notify_one(); }
 };
 
 // ------------------------------------------------------------------ fragment parsing (host)
@@ -371,7 +386,7 @@ static int run_copies(fbgpu_ctx* c, const std::vector<PayloadCopy>& copies, int 
     return 0;
 }
 
-extern "C" int fbgpu_load_fragment(fbgpu_ctx* c, uint32_t index, uint32_t field, uint32_t view, uint64_t shard, const uint8_t* roaring, uint64_t nbytes) {
+extern "C" int fbgpu_load_fragment(fbgpu_ctx* c, uint32_t index, uint32_t field, uint32_t view, uint64_t shard, const uint8_t* roaring, uint64_t nbytes) try {
     if (!c || !roaring) return fail(FBGPU_E_INVALID, "null argument");
     std::vector<ParsedCont> cs;
     int rc = parse_roaring(roaring, nbytes, cs); if (rc) return rc;
@@ -380,10 +395,10 @@ extern "C" int fbgpu_load_fragment(fbgpu_ctx* c, uint32_t index, uint32_t field,
     std::vector<PayloadCopy> copies;
     rc = add_fragment_locked(c, fv, shard, cs, copies); if (rc) return rc;
     return run_copies(c, copies, 1);
-}
+} FBGPU_CATCH
 
 extern "C" int fbgpu_load_fragments(fbgpu_ctx* c, uint32_t index, uint32_t field, uint32_t view, const uint64_t* shards, int64_t n,
-                                    const uint8_t* buf, const uint64_t* offsets) {
+                                    const uint8_t* buf, const uint64_t* offsets) try {
     if (!c || !shards || !buf || !offsets || n < 0) return fail(FBGPU_E_INVALID, "null argument");
     // parse in parallel (validation + container tables), then append serially (memcpy-bound)
     std::vector<std::vector<ParsedCont>> parsed((size_t)n);
@@ -401,10 +416,10 @@ extern "C" int fbgpu_load_fragments(fbgpu_ctx* c, uint32_t index, uint32_t field
     std::vector<PayloadCopy> copies;
     for (int64_t i = 0; i < n; i++) { int rc = add_fragment_locked(c, fv, shards[i], parsed[i], copies); if (rc) return rc; }
     return run_copies(c, copies, nt);
-}
+} FBGPU_CATCH
 
 extern "C" int fbgpu_load_rbf(fbgpu_ctx* c, uint32_t index, uint64_t shard, const uint8_t* data, uint64_t data_bytes, const uint8_t* wal, uint64_t wal_bytes,
-                              const char* const* names, const uint32_t* fields, const uint32_t* views, int32_t n_names, int32_t* out_loaded) {
+                              const char* const* names, const uint32_t* fields, const uint32_t* views, int32_t n_names, int32_t* out_loaded) try {
     if (!c || !data || n_names < 0 || (n_names > 0 && (!names || !fields || !views))) return fail(FBGPU_E_INVALID, "null argument");
     if (out_loaded) *out_loaded = 0;
     fbgpu_rbf::File f; std::string err;
@@ -450,16 +465,16 @@ extern "C" int fbgpu_load_rbf(fbgpu_ctx* c, uint32_t index, uint64_t shard, cons
     }
     if (out_loaded) *out_loaded = (int32_t)found.size();
     return run_copies(c, copies, 1);
-}
+} FBGPU_CATCH
 
-extern "C" int fbgpu_drop_fragment(fbgpu_ctx* c, uint32_t index, uint32_t field, uint32_t view, uint64_t shard) {
+extern "C" int fbgpu_drop_fragment(fbgpu_ctx* c, uint32_t index, uint32_t field, uint32_t view, uint64_t shard) try {
     if (!c) return fail(FBGPU_E_INVALID, "null ctx");
     std::unique_lock<std::shared_mutex> lk(c->store_mu);
     uint32_t fv = view_id_locked(c, ViewKey{ index, field, view }, false);
     if (fv == kNoView) return 0;
     drop_locked(c, fv, shard);
     return 0;
-}
+} FBGPU_CATCH
 
 // uploads staged payload (append) and refreshes metadata tables; store_mu held exclusively
 static int commit_locked(fbgpu_ctx* c) {
@@ -532,22 +547,29 @@ static int commit_locked(fbgpu_ctx* c) {
     return 0;
 }
 
-extern "C" int fbgpu_commit(fbgpu_ctx* c) {
+extern "C" int fbgpu_commit(fbgpu_ctx* c) try {
     if (!c) return fail(FBGPU_E_INVALID, "null ctx");
     std::unique_lock<std::shared_mutex> lk(c->store_mu);
     return commit_locked(c);
-}
-static int ensure_committed(fbgpu_ctx* c) {
-    { std::shared_lock<std::shared_mutex> lk(c->store_mu); if (!c->meta_dirty && c->staging.empty()) return 0; }
-    return fbgpu_commit(c);
+} FBGPU_CATCH
+// Takes the store's shared lock for a query with the device tables in sync with the host mirrors: the "is anything
+// pending" check and the query run under the SAME lock acquisition, so a load that slips in between a commit and the
+// query cannot leave the query reading host mirrors that are newer than what is in HBM.
+static int lock_committed(fbgpu_ctx* c, std::shared_lock<std::shared_mutex>& lk) {
+    for (;;) {
+        lk = std::shared_lock<std::shared_mutex>(c->store_mu);
+        if (!c->meta_dirty && c->staging.empty()) return 0;
+        lk.unlock();
+        int rc = fbgpu_commit(c); if (rc) return rc;
+    }
 }
 
-extern "C" int fbgpu_get_stats(fbgpu_ctx* c, fbgpu_stats* out) {
+extern "C" int fbgpu_get_stats(fbgpu_ctx* c, fbgpu_stats* out) try {
     if (!c || !out) return fail(FBGPU_E_INVALID, "null argument");
     std::shared_lock<std::shared_mutex> lk(c->store_mu);
     *out = c->stats;
     return 0;
-}
+} FBGPU_CATCH
 
 // ------------------------------------------------------------------ program compiler
 // Turns the post-order pql.Call program into stack-machine device ops, mirroring executeBitmapCallShard
@@ -745,6 +767,9 @@ static void bump(fbgpu_ctx* c, uint64_t launches, float ms) {
 
 static int allreduce_u64(fbgpu_ctx* c, Workspace* w, void* dptr, size_t n) {
     if (!c->comm) return 0;
+    // one communicator, many caller threads: enqueueing must be serialised (and the callers must issue collective
+    // queries in the same order on every rank, like any NCCL program)
+    std::lock_guard<std::mutex> lk(c->coll_mu);
     int r = g_nccl.AllReduce(dptr, dptr, n, kNcclUint64, kNcclSum, c->comm, w->stream);
     if (r != 0) return fail(FBGPU_E_COMM, "ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
     return 0;
@@ -826,11 +851,11 @@ static int launch_eval(fbgpu_ctx* c, Workspace* w, const std::vector<DevOp>& pro
 
 // ------------------------------------------------------------------ Count
 extern "C" int fbgpu_count(fbgpu_ctx* c, uint32_t index, const fbgpu_op* ops, int32_t n_ops, const uint64_t* shards, int64_t n_shards,
-                           uint64_t* out_total, uint64_t* out_per_shard) {
+                           uint64_t* out_total, uint64_t* out_per_shard) try {
     if (!c || !out_total || n_shards < 0 || (n_shards && !shards)) return fail(FBGPU_E_INVALID, "null argument");
     CUDA_TRY(cudaSetDevice(c->device));
-    int rc = ensure_committed(c); if (rc) return rc;
-    std::shared_lock<std::shared_mutex> lk(c->store_mu);
+    std::shared_lock<std::shared_mutex> lk;
+    int rc = lock_committed(c, lk); if (rc) return rc;
     std::vector<DevOp> prog; int depth = 1;
     rc = compile_program(c, index, ops, n_ops, prog, depth); if (rc) return rc;
     WsLease lease(c); Workspace* w = lease.w;
@@ -847,8 +872,10 @@ extern "C" int fbgpu_count(fbgpu_ctx* c, uint32_t index, const fbgpu_op* ops, in
     // cross-GPU merge of the count: fused into the kernel over peer memory when the mailboxes are mapped, else NCCL
     std::unique_lock<std::mutex> coll_lk(c->coll_mu, std::defer_lock);
     FuseReduce fr{};
-    if (c->p2p) {
-        coll_lk.lock();                      // collective queries are issued in the same order on every rank
+    coll_lk.lock();                          // collective queries are issued in the same order on every rank
+    const bool p2p = c->p2p;                 // read once, under the lock fbgpu_comm_p2p_open/_disable take
+    if (!p2p) coll_lk.unlock();
+    if (p2p) {
         fr.peers = (Mailbox* const*)c->d_peers.p; fr.ticket = (unsigned int*)(d_total + 1 + nper); fr.result = d_total + 1 + nper + 1;
         fr.epoch = ++c->epoch; fr.rank = c->rank; fr.n_ranks = c->n_ranks;
     }
@@ -863,30 +890,31 @@ extern "C" int fbgpu_count(fbgpu_ctx* c, uint32_t index, const fbgpu_op* ops, in
             EvalOut eo{ d_total, d_per, nullptr, nullptr, fr };
             rc = launch_eval(c, w, prog, d_prog, depth, d_shards, n_units, eo); if (rc) return rc;
         }
-    } else if (c->p2p) {
+    } else if (p2p) {
         p2p_reduce_only_kernel<<<1, 1, 0, w->stream>>>(fr, d_total);
         CUDA_TRY(cudaGetLastError());
     }
-    if (!c->p2p) { rc = allreduce_u64(c, w, d_total, 1); if (rc) return rc; }   // inside the timed bracket: the collective is part of the step
+    if (!p2p) { rc = allreduce_u64(c, w, d_total, 1); if (rc) return rc; }   // inside the timed bracket: the collective is part of the step
     CUDA_TRY(cudaEventRecord(w->ev1, w->stream));
     CUDA_TRY(cudaMemcpyAsync(w->h_out.p, w->d_counts.p, nc * 8, cudaMemcpyDeviceToHost, w->stream));
     CUDA_TRY(cudaStreamSynchronize(w->stream));
-    *out_total = c->p2p ? ((uint64_t*)w->h_out.p)[1 + nper + 1] : ((uint64_t*)w->h_out.p)[0];
+    *out_total = p2p ? ((uint64_t*)w->h_out.p)[1 + nper + 1] : ((uint64_t*)w->h_out.p)[0];
     if (out_per_shard) memcpy(out_per_shard, (uint64_t*)w->h_out.p + 1, (size_t)n_shards * 8);
     float ms = 0; cudaEventElapsedTime(&ms, w->ev0, w->ev1);
-    bump(c, (n_units > 0 || c->p2p) ? 1 : 0, ms);
+    bump(c, (n_units > 0 || p2p) ? 1 : 0, ms);
+    lease.ok = true;
     return FBGPU_OK;
-}
+} FBGPU_CATCH
 
 // ------------------------------------------------------------------ Row (canonical Pilosa-roaring result)
 static constexpr long long kUnitBatch = 16384;   // 128 MiB of result bitmaps per batch
 
 extern "C" int fbgpu_row(fbgpu_ctx* c, uint32_t index, const fbgpu_op* ops, int32_t n_ops, const uint64_t* shards, int64_t n_shards,
-                         uint8_t* out_buf, uint64_t out_cap, uint64_t* out_len, uint64_t* out_count) {
+                         uint8_t* out_buf, uint64_t out_cap, uint64_t* out_len, uint64_t* out_count) try {
     if (!c || !out_len || n_shards < 0 || (n_shards && !shards)) return fail(FBGPU_E_INVALID, "null argument");
     CUDA_TRY(cudaSetDevice(c->device));
-    int rc = ensure_committed(c); if (rc) return rc;
-    std::shared_lock<std::shared_mutex> lk(c->store_mu);
+    std::shared_lock<std::shared_mutex> lk;
+    int rc = lock_committed(c, lk); if (rc) return rc;
     std::vector<DevOp> prog; int depth = 1;
     rc = compile_program(c, index, ops, n_ops, prog, depth); if (rc) return rc;
     // Row.Merge concatenates disjoint shard segments (row.go:202); emit in ascending shard order
@@ -962,8 +990,9 @@ extern "C" int fbgpu_row(fbgpu_ctx* c, uint32_t index, const fbgpu_op* ops, int3
         uint32_t o32 = (uint32_t)off; memcpy(offp, &o32, 4); offp += 4;
         memcpy(out_buf + off, batch_bufs[oc.batch].data() + oc.src_off, oc.size); off += oc.size;
     }
+    lease.ok = true;
     return FBGPU_OK;
-}
+} FBGPU_CATCH
 
 // ------------------------------------------------------------------ per-row counts (TopK / TopN ids)
 // evaluates `filter` for shards [s0, s0+ns) into w->d_bitmaps (16 bitmaps per shard)
@@ -974,7 +1003,7 @@ static int eval_filter_batch(fbgpu_ctx* c, Workspace* w, const std::vector<DevOp
 }
 
 static int row_counts_impl(fbgpu_ctx* c, uint32_t index, uint32_t fv, const std::vector<uint64_t>& rows, const fbgpu_op* filter, int32_t n_filter_ops,
-                           const uint64_t* shards, int64_t n_shards, std::vector<uint64_t>& counts) {
+                           const uint64_t* shards, int64_t n_shards, std::vector<uint64_t>& counts, bool reduce = true) {
     counts.assign(rows.size(), 0);
     if (rows.empty()) return 0;
     std::vector<DevOp> prog; int depth = 1; int rc;
@@ -1000,22 +1029,24 @@ static int row_counts_impl(fbgpu_ctx* c, uint32_t index, uint32_t fv, const std:
         CUDA_TRY(cudaGetLastError()); launches++;
     }
     CUDA_TRY(cudaEventRecord(w->ev1, w->stream));
-    rc = allreduce_u64(c, w, w->d_counts.p, nr); if (rc) return rc;
+    // every rank must bring the same row list to the collective: only the explicit-ids form is all-reduced (fbgpu.h)
+    if (reduce) { rc = allreduce_u64(c, w, w->d_counts.p, nr); if (rc) return rc; }
     CUDA_TRY(cudaMemcpyAsync(w->h_out.p, w->d_counts.p, nr * 8, cudaMemcpyDeviceToHost, w->stream));
     CUDA_TRY(cudaStreamSynchronize(w->stream));
     memcpy(counts.data(), w->h_out.p, nr * 8);
     float ms = 0; cudaEventElapsedTime(&ms, w->ev0, w->ev1);
     bump(c, launches, ms);
+    lease.ok = true;
     return 0;
 }
 
 extern "C" int fbgpu_row_counts(fbgpu_ctx* c, uint32_t index, uint32_t field, uint32_t view, const uint64_t* row_ids, int32_t n_rows,
                                 const fbgpu_op* filter, int32_t n_filter_ops, const uint64_t* shards, int64_t n_shards,
-                                uint64_t* out_row_ids, uint64_t* out_counts, int32_t cap, int32_t* out_n) {
+                                uint64_t* out_row_ids, uint64_t* out_counts, int32_t cap, int32_t* out_n) try {
     if (!c || !out_counts || n_shards < 0 || (n_shards && !shards) || n_rows < 0) return fail(FBGPU_E_INVALID, "null argument");
     CUDA_TRY(cudaSetDevice(c->device));
-    int rc = ensure_committed(c); if (rc) return rc;
-    std::shared_lock<std::shared_mutex> lk(c->store_mu);
+    std::shared_lock<std::shared_mutex> lk;
+    int rc = lock_committed(c, lk); if (rc) return rc;
     uint32_t fv = view_id_locked(c, ViewKey{ index, field, view }, false);
     std::vector<uint64_t> rows, counts;
     if (row_ids) rows.assign(row_ids, row_ids + n_rows);
@@ -1029,7 +1060,7 @@ extern "C" int fbgpu_row_counts(fbgpu_ctx* c, uint32_t index, uint32_t field, ui
         }
         std::sort(rows.begin(), rows.end()); rows.erase(std::unique(rows.begin(), rows.end()), rows.end());
     }
-    rc = row_counts_impl(c, index, fv, rows, filter, n_filter_ops, shards, n_shards, counts); if (rc) return rc;
+    rc = row_counts_impl(c, index, fv, rows, filter, n_filter_ops, shards, n_shards, counts, row_ids != nullptr); if (rc) return rc;
     if (row_ids) {
         if (cap < n_rows) return fail(FBGPU_E_NOSPACE, "cap %d < n_rows %d", cap, n_rows);
         for (int32_t i = 0; i < n_rows; i++) { out_counts[i] = counts[i]; if (out_row_ids) out_row_ids[i] = rows[i]; }
@@ -1043,17 +1074,17 @@ extern "C" int fbgpu_row_counts(fbgpu_ctx* c, uint32_t index, uint32_t field, ui
     for (int32_t i = 0; i < n; i++) { if (out_row_ids) out_row_ids[i] = rows[order[i]]; out_counts[i] = counts[order[i]]; }
     if (out_n) *out_n = n;
     return FBGPU_OK;
-}
+} FBGPU_CATCH
 
 // ------------------------------------------------------------------ many fused Intersect+Count pairs in one launch
 extern "C" int fbgpu_count_pairs(fbgpu_ctx* c, uint32_t index, uint32_t field_a, uint32_t view_a, const uint64_t* rows_a,
                                  uint32_t field_b, uint32_t view_b, const uint64_t* rows_b, int32_t n_pairs,
-                                 const uint64_t* shards, int64_t n_shards, uint64_t* out_counts) {
+                                 const uint64_t* shards, int64_t n_shards, uint64_t* out_counts) try {
     if (!c || !rows_a || !rows_b || !out_counts || n_pairs < 0 || n_shards < 0 || (n_shards && !shards)) return fail(FBGPU_E_INVALID, "null argument");
     CUDA_TRY(cudaSetDevice(c->device));
-    int rc = ensure_committed(c); if (rc) return rc;
     if (n_pairs == 0) return FBGPU_OK;
-    std::shared_lock<std::shared_mutex> lk(c->store_mu);
+    std::shared_lock<std::shared_mutex> lk;
+    int rc = lock_committed(c, lk); if (rc) return rc;
     uint32_t fa = view_id_locked(c, ViewKey{ index, field_a, view_a }, false), fb = view_id_locked(c, ViewKey{ index, field_b, view_b }, false);
     WsLease lease(c); Workspace* w = lease.w;
     std::vector<DevOp> none; const DevOp* d_prog; const uint64_t* d_shards;
@@ -1079,8 +1110,9 @@ extern "C" int fbgpu_count_pairs(fbgpu_ctx* c, uint32_t index, uint32_t field_a,
     memcpy(out_counts, w->h_out.p, np * 8);
     float ms = 0; cudaEventElapsedTime(&ms, w->ev0, w->ev1);
     bump(c, n_units > 0 ? 1 : 0, ms);
+    lease.ok = true;
     return FBGPU_OK;
-}
+} FBGPU_CATCH
 
 // ------------------------------------------------------------------ GroupBy
 static int groupby2(fbgpu_ctx* c, uint32_t index, uint32_t fvA, const uint64_t* rowsA, int nA, uint32_t fvB, const uint64_t* rowsB, int nB,
@@ -1117,6 +1149,7 @@ static int groupby2(fbgpu_ctx* c, uint32_t index, uint32_t fvA, const uint64_t* 
     memcpy(out, w->h_out.p, ncnt * 8);
     float ms = 0; cudaEventElapsedTime(&ms, w->ev0, w->ev1);
     bump(c, launches, ms);
+    lease.ok = true;
     return 0;
 }
 
@@ -1147,11 +1180,11 @@ static int groupby_rec(fbgpu_ctx* c, uint32_t index, const uint32_t* fields, con
 }
 
 extern "C" int fbgpu_groupby(fbgpu_ctx* c, uint32_t index, const uint32_t* fields, const uint32_t* views, int32_t n_fields, const uint64_t* row_ids_flat, const int32_t* n_rows,
-                             const fbgpu_op* filter, int32_t n_filter_ops, const uint64_t* shards, int64_t n_shards, uint64_t* out_counts) {
+                             const fbgpu_op* filter, int32_t n_filter_ops, const uint64_t* shards, int64_t n_shards, uint64_t* out_counts) try {
     if (!c || !fields || !views || !row_ids_flat || !n_rows || !out_counts || n_fields < 1 || n_fields > 8 || n_shards < 0 || (n_shards && !shards)) return fail(FBGPU_E_INVALID, "bad argument");
     CUDA_TRY(cudaSetDevice(c->device));
-    int rc = ensure_committed(c); if (rc) return rc;
-    std::shared_lock<std::shared_mutex> lk(c->store_mu);
+    std::shared_lock<std::shared_mutex> lk;
+    int rc = lock_committed(c, lk); if (rc) return rc;
     std::vector<const uint64_t*> rows(n_fields); const uint64_t* p = row_ids_flat; size_t total = 1;
     for (int i = 0; i < n_fields; i++) { if (n_rows[i] < 0 || n_rows[i] > 65535) return fail(FBGPU_E_INVALID, "n_rows[%d]=%d out of range", i, n_rows[i]); rows[i] = p; p += n_rows[i]; total *= (size_t)n_rows[i]; }
     memset(out_counts, 0, total * 8);
@@ -1161,16 +1194,16 @@ extern "C" int fbgpu_groupby(fbgpu_ctx* c, uint32_t index, const uint32_t* field
     // fields enter through the filter, which is empty on shards without that fragment.
     std::vector<fbgpu_op> f(filter, filter + (filter ? n_filter_ops : 0));
     return groupby_rec(c, index, fields, views, n_fields, rows.data(), n_rows, f, shards, n_shards, out_counts);
-}
+} FBGPU_CATCH
 
 // ------------------------------------------------------------------ comm
-extern "C" int fbgpu_comm_unique_id(uint8_t id[FBGPU_NCCL_ID_BYTES]) {
+extern "C" int fbgpu_comm_unique_id(uint8_t id[FBGPU_NCCL_ID_BYTES]) try {
     if (!nccl_load()) return fail(FBGPU_E_COMM, "libnccl.so.2 not loadable: %s", dlerror());
     int r = g_nccl.GetUniqueId(id);
     if (r) return fail(FBGPU_E_COMM, "ncclGetUniqueId failed (%d)", r);
     return 0;
-}
-extern "C" int fbgpu_comm_init(fbgpu_ctx* c, int32_t n_ranks, int32_t rank, const uint8_t id[FBGPU_NCCL_ID_BYTES]) {
+} FBGPU_CATCH
+extern "C" int fbgpu_comm_init(fbgpu_ctx* c, int32_t n_ranks, int32_t rank, const uint8_t id[FBGPU_NCCL_ID_BYTES]) try {
     if (!c || !id || n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(FBGPU_E_INVALID, "bad argument");
     if (!nccl_load()) return fail(FBGPU_E_COMM, "libnccl.so.2 not loadable");
     CUDA_TRY(cudaSetDevice(c->device));
@@ -1180,16 +1213,16 @@ extern "C" int fbgpu_comm_init(fbgpu_ctx* c, int32_t n_ranks, int32_t rank, cons
     if (r) return fail(FBGPU_E_COMM, "ncclCommInitRank failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
     c->comm = comm; c->n_ranks = n_ranks; c->rank = rank;
     return 0;
-}
-extern "C" int fbgpu_comm_destroy(fbgpu_ctx* c) {
+} FBGPU_CATCH
+extern "C" int fbgpu_comm_destroy(fbgpu_ctx* c) try {
     if (!c) return fail(FBGPU_E_INVALID, "null ctx");
     if (c->comm && nccl_load()) { cudaSetDevice(c->device); cudaDeviceSynchronize(); g_nccl.CommDestroy(c->comm); }
     c->comm = nullptr; c->n_ranks = 1; c->rank = 0;
     return 0;
-}
+} FBGPU_CATCH
 
 // ---- fused peer-memory reduce: mailbox exchange through CUDA IPC (one process per GPU)
-extern "C" int fbgpu_comm_p2p_handle(fbgpu_ctx* c, uint8_t out[64]) {
+extern "C" int fbgpu_comm_p2p_handle(fbgpu_ctx* c, uint8_t out[64]) try {
     if (!c || !out) return fail(FBGPU_E_INVALID, "null argument");
     CUDA_TRY(cudaSetDevice(c->device));
     if (!c->mbox) { CUDA_TRY(cudaMalloc((void**)&c->mbox, sizeof(Mailbox))); CUDA_TRY(cudaMemset(c->mbox, 0, sizeof(Mailbox))); }
@@ -1198,11 +1231,17 @@ extern "C" int fbgpu_comm_p2p_handle(fbgpu_ctx* c, uint8_t out[64]) {
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
     memcpy(out, &h, 64);
     return FBGPU_OK;
-}
-extern "C" int fbgpu_comm_p2p_open(fbgpu_ctx* c, int32_t n_ranks, int32_t rank, const uint8_t* handles /* n_ranks x 64 */) {
+} FBGPU_CATCH
+extern "C" int fbgpu_comm_p2p_open(fbgpu_ctx* c, int32_t n_ranks, int32_t rank, const uint8_t* handles /* n_ranks x 64 */) try {
     if (!c || !handles || n_ranks < 1 || n_ranks > kMaxRanks || rank < 0 || rank >= n_ranks) return fail(FBGPU_E_INVALID, "bad argument");
     if (!c->mbox) return fail(FBGPU_E_COMM, "call fbgpu_comm_p2p_handle first");
     CUDA_TRY(cudaSetDevice(c->device));
+    std::lock_guard<std::mutex> lk(c->coll_mu);
+    c->p2p = false;
+    for (int p = 0; p < kMaxRanks; p++) {                        // re-open after a membership change: drop the old mappings first
+        if (c->peers[p] && c->peers[p] != c->mbox) cudaIpcCloseMemHandle(c->peers[p]);
+        c->peers[p] = nullptr;
+    }
     for (int p = 0; p < n_ranks; p++) {
         if (p == rank) { c->peers[p] = c->mbox; continue; }
         cudaIpcMemHandle_t h; memcpy(&h, handles + (size_t)p * 64, 64);
@@ -1215,27 +1254,27 @@ extern "C" int fbgpu_comm_p2p_open(fbgpu_ctx* c, int32_t n_ranks, int32_t rank, 
     CUDA_TRY(cudaMemcpy(c->d_peers.p, c->peers, sizeof(Mailbox*) * kMaxRanks, cudaMemcpyHostToDevice));
     c->n_ranks = n_ranks; c->rank = rank; c->epoch = 0; c->p2p = true;
     return FBGPU_OK;
-}
+} FBGPU_CATCH
 
-extern "C" int fbgpu_comm_p2p_disable(fbgpu_ctx* c) {      // back to the NCCL merge (mappings stay open; harmless)
+extern "C" int fbgpu_comm_p2p_disable(fbgpu_ctx* c) try {      // back to the NCCL merge (mappings stay open; harmless)
     if (!c) return fail(FBGPU_E_INVALID, "null ctx");
     std::lock_guard<std::mutex> lk(c->coll_mu);
     c->p2p = false;
     return FBGPU_OK;
-}
+} FBGPU_CATCH
 
-extern "C" int fbgpu_get_counters(fbgpu_ctx* c, fbgpu_counters* out) {
+extern "C" int fbgpu_get_counters(fbgpu_ctx* c, fbgpu_counters* out) try {
     if (!c || !out) return fail(FBGPU_E_INVALID, "null argument");
     std::lock_guard<std::mutex> lk(c->cnt_mu);
     *out = c->counters;
     return 0;
-}
+} FBGPU_CATCH
 extern "C" void* fbgpu_stream(fbgpu_ctx* c) { return c ? (void*)c->wss[0]->stream : nullptr; }
 
 // algorithmic-bytes accounting for bench / DESIGN: payload bytes + 16 B descriptor of every
 // container of the given rows over the given shards
 extern "C" int fbgpu_rows_payload_bytes(fbgpu_ctx* c, uint32_t index, uint32_t field, uint32_t view, const uint64_t* row_ids, int32_t n_rows,
-                                        const uint64_t* shards, int64_t n_shards, uint64_t* out_payload, uint64_t* out_containers) {
+                                        const uint64_t* shards, int64_t n_shards, uint64_t* out_payload, uint64_t* out_containers) try {
     if (!c || !out_payload || !out_containers) return fail(FBGPU_E_INVALID, "null argument");
     std::shared_lock<std::shared_mutex> lk(c->store_mu);
     uint64_t pay = 0, nc = 0;
@@ -1255,4 +1294,4 @@ extern "C" int fbgpu_rows_payload_bytes(fbgpu_ctx* c, uint32_t index, uint32_t f
     }
     *out_payload = pay; *out_containers = nc;
     return 0;
-}
+} FBGPU_CATCH
