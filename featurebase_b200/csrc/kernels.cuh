@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "fbgpu_types.h"
+#include "bitaddr.h"
 
 namespace fbgpu {
 
@@ -207,19 +208,36 @@ __device__ __forceinline__ void warp_bitmap_atomic(uint32_t* bm, const uint4* g,
         }
     }
 }
+// same reduction with the word's byte offset and the bit index given separately (sh: only its low 5 bits are used)
 template <int MODE>
-__device__ __forceinline__ void scatter_chunk_unrolled(uint32_t* bm, uint4 v, uint32_t base, uint32_t n) {
+__device__ __forceinline__ void smem_bit_op_at(uint32_t sbase, uint32_t off, uint32_t sh) {
+    const uint32_t addr = sbase + off;
+    const uint32_t m = 1u << (sh & 31);
+    if (MODE == 0) asm volatile("red.shared.or.b32 [%0], %1;" :: "r"(addr), "r"(m) : "memory");
+    else if (MODE == 1) asm volatile("red.shared.and.b32 [%0], %1;" :: "r"(addr), "r"(~m) : "memory");
+    else asm volatile("red.shared.xor.b32 [%0], %1;" :: "r"(addr), "r"(m) : "memory");
+}
+// scatter the (up to) 8 elements of one 16-byte array chunk; sb = shared-space address of the target bitmap
+template <int MODE>
+__device__ __forceinline__ void scatter_chunk_sb(uint32_t sb, uint4 v, uint32_t base, uint32_t n) {
     uint32_t w[4] = { v.x, v.y, v.z, v.w };
     if (base + 8 <= n) {
 #pragma unroll
-        for (int q = 0; q < 4; q++) { smem_bit_op<MODE>(bm, w[q] & 0xffffu); smem_bit_op<MODE>(bm, w[q] >> 16); }
+        for (int q = 0; q < 4; q++) {            // LOP3 + LEA.HI + SHF.L.W (+ SHF.R for the upper element) + ATOMS, see bitaddr.h
+            smem_bit_op_at<MODE>(sb, word_off_lo(w[q]), w[q]);
+            smem_bit_op_at<MODE>(sb, word_off_hi(w[q]), w[q] >> 16);
+        }
     } else {
 #pragma unroll
         for (int q = 0; q < 4; q++) {
-            if (base + 2 * q < n) smem_bit_op<MODE>(bm, w[q] & 0xffffu);
-            if (base + 2 * q + 1 < n) smem_bit_op<MODE>(bm, w[q] >> 16);
+            if (base + 2 * q < n) smem_bit_op_at<MODE>(sb, word_off_lo(w[q]), w[q]);
+            if (base + 2 * q + 1 < n) smem_bit_op_at<MODE>(sb, word_off_hi(w[q]), w[q] >> 16);
         }
     }
+}
+template <int MODE>
+__device__ __forceinline__ void scatter_chunk_unrolled(uint32_t* bm, uint4 v, uint32_t base, uint32_t n) {
+    scatter_chunk_sb<MODE>((uint32_t)__cvta_generic_to_shared(bm), v, base, n);
 }
 // Batch of commuting row operands (OR / ANDNOT / XOR onto the same target), no barrier in between: warp w takes
 // operands w, w+8, ...; arrays are scattered with red.shared, bitmaps applied with word atomics.  (Tried and slower
@@ -227,13 +245,15 @@ __device__ __forceinline__ void scatter_chunk_unrolled(uint32_t* bm, uint4 v, ui
 template <int MODE>
 __device__ __forceinline__ void batch_rows(uint32_t* T32, const Resolved* res, int n) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t sb = (uint32_t)__cvta_generic_to_shared(T32);
+    asm volatile("" : "+r"(sb));           // keep the shared address live: ptxas otherwise rebuilds it for every chunk
     for (int j = wid; j < n; j += kEvalThreads / 32) {
         const Resolved r = res[j];
         if (r.ptr == nullptr) continue;
         if (r.typ == kArray) {
             const uint4* a4 = reinterpret_cast<const uint4*>(r.ptr);
             const uint32_t n8 = (r.card + 7) >> 3;
-            for (uint32_t i = lane; i < n8; i += 32) scatter_chunk_unrolled<MODE>(T32, ldg_nc(a4 + i), i * 8, r.card);
+            for (uint32_t i = lane; i < n8; i += 32) scatter_chunk_sb<MODE>(sb, ldg_nc(a4 + i), i * 8, r.card);
         } else if (r.typ == kBitmap) warp_bitmap_atomic<MODE>(T32, reinterpret_cast<const uint4*>(r.ptr), lane);
     }
 }
@@ -878,6 +898,15 @@ __device__ __forceinline__ void warp_zero(uint32_t* bm, int lane) {
 // number of the (up to 8) u16 values of one 16-byte chunk that are set in a shared-memory bitmap
 __device__ __forceinline__ uint32_t probe_chunk(const uint32_t* bm, uint4 v, uint32_t base, uint32_t n) {
     uint32_t w[4] = { v.x, v.y, v.z, v.w }, c = 0;
+    if (base + 8 <= n) {                             // full chunk: no per-element bounds, word offsets as in bitaddr.h
+        const char* b8 = reinterpret_cast<const char*>(bm);
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            c += (*reinterpret_cast<const uint32_t*>(b8 + word_off_lo(w[q])) >> (w[q] & 31)) & 1u;
+            c += (*reinterpret_cast<const uint32_t*>(b8 + word_off_hi(w[q])) >> ((w[q] >> 16) & 31)) & 1u;
+        }
+        return c;
+    }
 #pragma unroll
     for (int q = 0; q < 4; q++) {
         uint32_t lo = w[q] & 0xffffu, hi = w[q] >> 16;

@@ -19,6 +19,7 @@ def lib(tmp_path_factory):
     L = C.CDLL(out)
     L.wavefronts.restype = C.c_uint64
     L.worst.restype = C.c_uint32
+    L.word_offset_mismatches.restype = C.c_uint64
     return L
 
 
@@ -69,3 +70,9 @@ def test_wavefront_reduction_uniform(lib):
         ideal += 8 * (n // 256) + min(8, n % 256)
     assert after < 0.45 * before          # measured here: ~0.37
     assert after < 1.35 * ideal
+
+
+def test_word_offset_identity(lib):
+    """csrc/bitaddr.h: 4 * (element >> 5) written as mask + multiply-high (so that ptxas emits LOP3 + LEA.HI) equals the
+    plain form for every lower element and a spread of upper elements, and vice versa"""
+    assert lib.word_offset_mismatches() == 0
