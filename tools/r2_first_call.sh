@@ -1,0 +1,37 @@
+#!/bin/bash
+# First GPU call of round 2 (one gpurun invocation, ~10 GPU-minutes): run everything that was written after round 1's
+# GPU budget was spent, and measure the two pending performance changes.  Results land in gpurun_out/r2_first/.
+#   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/r2_first_call.sh'
+set -u
+out=gpurun_out/r2_first; mkdir -p $out
+python -c "import __graft_entry__ as g; g.build()" > $out/build.log 2>&1
+
+# 1. the regular parity suite (covers the LEA.HI / hoisted-base scatter that is now the default build)
+timeout 900 python -m pytest tests -x -q -m gpu > $out/pytest_gpu.log 2>&1; echo "pytest_gpu rc=$?" >> $out/summary.txt
+
+# 2. opt-in tests: striped arrays, RBF loader, BSI aggregates, fragment.top / filter / archetype goldens
+FBGPU_TEST_EXPERIMENTAL=1 timeout 900 python -m pytest tests/test_zz_gpu_experimental.py -q > $out/pytest_experimental.log 2>&1; echo "pytest_experimental rc=$?" >> $out/summary.txt
+
+# 3. headline bench: default layout vs bank-striped arrays (same build), then the density sweep for both
+bench() { python bench.py --steps 50 --warmup 5 --no-cpu-baseline 2>>$out/bench_err.log | tail -1; }
+echo "default $(bench)" >> $out/bench.jsonl
+echo "striped $(FBGPU_ARRAY_STRIPED=1 bench)" >> $out/bench.jsonl
+python bench_sweep.py --configs 5 --batched --generators uniform > $out/sweep_default.jsonl 2>>$out/bench_err.log
+FBGPU_ARRAY_STRIPED=1 python bench_sweep.py --configs 5 --batched --generators uniform > $out/sweep_striped.jsonl 2>>$out/bench_err.log
+
+# 4. one ncu pass of the headline kernel in both layouts: shared-memory wavefronts / issue utilisation are what changed
+for mode in default striped; do
+  env $( [ $mode = striped ] && echo FBGPU_ARRAY_STRIPED=1 ) ncu --set full --clock-control none -k regex:eval_kernel -c 2 -o $out/eval_$mode \
+      python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $out/ncu_$mode.log 2>&1
+done
+python - <<'PY' >> gpurun_out/r2_first/summary.txt
+import json
+for line in open("gpurun_out/r2_first/bench.jsonl"):
+    name, _, js = line.partition(" ")
+    try:
+        d = json.loads(js)
+        print(name, "ms/step", round(d["ms_per_step"], 4), "frac", round(d["roofline"]["frac"], 4), "count", d.get("check_count"))
+    except Exception as e:
+        print(name, "unparsed:", e)
+PY
+cat $out/summary.txt
