@@ -372,7 +372,8 @@ static int run_copies(fbgpu_ctx* c, const std::vector<PayloadCopy>& copies, int 
             uint8_t* dst = base + pc.dst;
             if (pc.typ == kArray && c->stripe_arrays) fbgpu_stripe::stripe_array(pc.src, (uint16_t*)dst, pc.bytes / 2);
             else memcpy(dst, pc.src, pc.bytes);
-            if (pc.padded > pc.bytes) memset(dst + pc.bytes, 0, pc.padded - pc.bytes);      // zero tail of the last 16-byte chunk
+            if (pc.typ == kArray) fbgpu_stripe::pad_array_tail((uint16_t*)dst, pc.bytes / 2, pc.padded / 2);      // tail of the last 16-byte chunk: copies of the last element (stripe.h)
+            else if (pc.padded > pc.bytes) memset(dst + pc.bytes, 0, pc.padded - pc.bytes);                      // zero tail
             if (pc.typ == kRun && pc.official_run) {     // official format stores (start, length-1): roaring.go:2240-2247
                 uint16_t* r = (uint16_t*)dst; for (uint32_t k = 0; k < pc.cnt; k++) r[2 * k + 1] = (uint16_t)(r[2 * k] + r[2 * k + 1]);
             }

@@ -221,7 +221,9 @@ __device__ __forceinline__ void smem_bit_op_at(uint32_t sbase, uint32_t off, uin
 template <int MODE>
 __device__ __forceinline__ void scatter_chunk_sb(uint32_t sb, uint4 v, uint32_t base, uint32_t n) {
     uint32_t w[4] = { v.x, v.y, v.z, v.w };
-    if (base + 8 <= n) {
+    // OR / AND-NOT: the loader pads the last chunk with copies of the last element (stripe.h pad_array_tail), setting or
+    // clearing a bit twice is harmless, so every chunk takes the unguarded path and the warp never diverges on a tail
+    if (MODE != 2 || base + 8 <= n) {
 #pragma unroll
         for (int q = 0; q < 4; q++) {            // LOP3 + LEA.HI + SHF.L.W (+ SHF.R for the upper element) + ATOMS, see bitaddr.h
             smem_bit_op_at<MODE>(sb, word_off_lo(w[q]), w[q]);

@@ -63,6 +63,14 @@ inline void stripe_array(const void* src_bytes, uint16_t* dst, uint32_t n) {
     }
 }
 
+// Tail padding of an array payload (payloads are stored in whole 16-byte chunks): the slots behind the n-th element repeat
+// the last element instead of holding zeros.  OR-ing / AND-NOT-ing a bit twice is the same as once, so the scatter loops
+// of those two modes run every chunk through the unguarded path (no divergent partial-chunk branch, which cost about a
+// third of the instructions of a ~650-element container); XOR and the counting probes still honour n.
+inline void pad_array_tail(uint16_t* a, uint32_t n, uint32_t padded_elems) {
+    for (uint32_t k = n; k < padded_elems; k++) a[k] = a[n - 1];
+}
+
 // largest number of elements of one instruction group that share a bank (1 = conflict free); test helper
 inline uint32_t worst_group_conflict(const uint16_t* a, uint32_t n) {
     uint32_t worst = 0;

@@ -17,3 +17,9 @@ extern "C" uint64_t word_offset_mismatches() {
         }
     return bad;
 }
+
+// what run_copies() does for one array payload: (striped or plain) copy, then the duplicate tail padding
+extern "C" void load_array(const uint16_t* src, uint16_t* dst, uint32_t n, int striped) {
+    if (striped) fbgpu_stripe::stripe_array(src, dst, n); else memcpy(dst, src, (size_t)n * 2);
+    fbgpu_stripe::pad_array_tail(dst, n, (n + 7) & ~7u);
+}

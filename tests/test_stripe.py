@@ -76,3 +76,19 @@ def test_word_offset_identity(lib):
     """csrc/bitaddr.h: 4 * (element >> 5) written as mask + multiply-high (so that ptxas emits LOP3 + LEA.HI) equals the
     plain form for every lower element and a spread of upper elements, and vice versa"""
     assert lib.word_offset_mismatches() == 0
+
+
+def test_array_tail_padding(lib):
+    """the slots behind the last element of a stored array repeat a VALID element (never a zero that would set bit 0):
+    the OR / AND-NOT scatter runs whole 16-byte chunks unguarded"""
+    rng = np.random.default_rng(9)
+    for n in list(range(1, 40)) + [63, 64, 65, 655, 4079, 4090, 4095, 4096]:
+        for striped in (0, 1):
+            v = np.ascontiguousarray(np.sort(rng.choice(np.arange(1, 65536), n, replace=False)).astype(np.uint16))    # 0 is absent on purpose
+            padded = (n + 7) & ~7
+            d = np.full(padded + 8, 0xDEAD, dtype=np.uint16)
+            lib.load_array(v.ctypes.data, d.ctypes.data, n, striped)
+            assert (d[padded:] == 0xDEAD).all()
+            assert np.array_equal(np.sort(d[:n]), v)
+            assert set(d[n:padded].tolist()) <= {int(d[n - 1])}
+            assert set(np.unique(d[:padded]).tolist()) == set(v.tolist())          # the chunked bit set is exactly the container
