@@ -15,15 +15,11 @@
 
 #include "../../include/fbgpu.h"
 #include "fbgpu_types.h"
+#include "host_error.h"
 
 namespace fbgpu {
 
 using ViewLookup = std::function<uint32_t(uint32_t field, uint32_t view)>;
-struct Error {
-    int code = 0; char msg[512] = { 0 };
-    int set(int c, const char* fmt, ...) { va_list ap; va_start(ap, fmt); vsnprintf(msg, sizeof msg, fmt, ap); va_end(ap); code = c; return c; }
-};
-
 struct Node { fbgpu_op op; std::vector<int> kids; };
 
 struct Compiler {
