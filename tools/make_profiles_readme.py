@@ -49,6 +49,7 @@ def main():
     o.append(f"| this table's measurement lease | {b['ms_per_step']:.3f} | {b['roofline']['frac']:.3f} | same code | `r01_ncu_eval_kernel_summary.csv`, `r01_launches.csv` |")
     o.append("| tried, slower: TMA-staged ring (`eval_staged_kernel`, opt-in `FBGPU_STAGED=1`) | 0.748 | 0.283 | `cp.async.bulk` + mbarrier pipeline removes the HBM-latency stall (long-scoreboard 6.6 -> 0.4 per issue) but only 2-3 CTAs fit per SM and the shared-memory atomic pipe is the limiter either way | `r01_ncu_eval_staged_kernel_summary.csv` |")
     o.append("| tried, slower: 4 loads in flight per thread, register double-buffering, L2 prefetch of the batch | 0.52-2.1 | | extra registers cost CTA residency, which matters more than per-warp MLP here | |")
+    o.append("| after the round's GPU budget was spent (NOT yet timed; `DESIGN.md` §9.1) | ? | ? | array scatter: `LOP3 + LEA.HI` word offsets, shared base kept live, duplicate-padded array tails (no divergent tail path): about 65 + tail -> 43 issued instructions per 8 elements by SASS count, i.e. roughly 378 M -> 230 M warp instructions for this query; opt-in bank-striped array order (`FBGPU_ARRAY_STRIPED=1`) for the wavefront count | `cuobjdump -sass` of the committed build; `tools/r2_first_call.sh` measures both |")
     o.append(f"\nWhere the time goes now (ncu): {float(ev['smsp__inst_executed.sum']) / 1e6:.0f} M warp instructions, issue slots {float(ev['smsp__issue_active.avg.pct_of_peak_sustained_active']):.0f} % busy; "
              f"{float(ev['l1tex__data_pipe_lsu_wavefronts_mem_shared.sum']) / 1e6:.0f} M shared-memory wavefronts ({float(ev['l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed']):.0f} % of the LSU shared pipe's peak, "
              f"{float(ev['l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum']) / 1e6:.0f} M of them bank conflicts of the random scatter) for 687 M scattered elements; warps active {float(ev['sm__warps_active.avg.pct_of_peak_sustained_active']):.0f} %. "
