@@ -90,7 +90,7 @@ struct RawBuf {
     }
     void clear_and_free() { free(p); p = nullptr; len = cap = 0; }
 };
-struct PayloadCopy { const uint8_t* src; uint64_t dst; uint32_t bytes, padded; uint16_t typ; uint16_t official_run; uint32_t cnt; };   // dst: offset inside the staging buffer
+struct PayloadCopy { const uint8_t* src; uint64_t dst; uint32_t bytes, padded; uint16_t typ; uint16_t official_run; uint32_t cnt; uint32_t stripe; };   // dst: offset inside the staging buffer
 
 // ------------------------------------------------------------------ NCCL (resolved at run time)
 struct Id128 { char b[128]; };   // ncclUniqueId is passed by value (128 bytes)
@@ -121,7 +121,7 @@ constexpr int kNcclUint64 = 5, kNcclSum = 0;   // ncclDataType_t / ncclRedOp_t v
 // ------------------------------------------------------------------ context
 struct ViewKey { uint32_t index, field, view; bool operator<(const ViewKey& o) const { return index != o.index ? index < o.index : field != o.field ? field < o.field : view < o.view; } };
 
-struct HostFrag { uint32_t fv; uint64_t shard; bool live; uint32_t row_off, n_rows; uint64_t payload_bytes; uint32_t n_desc; uint32_t n_arr, n_bmp, n_run; };
+struct HostFrag { uint32_t fv; uint64_t shard; bool live; uint32_t row_off, n_rows; uint64_t payload_bytes; uint32_t n_desc; uint32_t n_arr, n_bmp, n_run; uint32_t n_striped; };
 
 struct Workspace {
     cudaStream_t stream = nullptr;
@@ -139,6 +139,7 @@ struct fbgpu_ctx {
     std::map<ViewKey, uint32_t> view_ids;
     std::vector<std::vector<int32_t>> shardmaps;  // per view
     std::vector<uint64_t> view_arr, view_other;   // per view: live array containers / bitmap+run containers
+    std::vector<uint64_t> view_striped;           // per view: live array containers stored in bank-striped order (stripe.h)
     std::vector<HostFrag> frags;
     std::vector<FragHdr> h_frags;
     std::vector<RowEnt> h_rows;
@@ -240,7 +241,7 @@ static uint32_t view_id_locked(fbgpu_ctx* c, ViewKey k, bool create) {
     if (it != c->view_ids.end()) return it->second;
     if (!create) return kNoView;
     uint32_t id = (uint32_t)c->shardmaps.size();
-    c->view_ids[k] = id; c->shardmaps.emplace_back(); c->view_arr.push_back(0); c->view_other.push_back(0);
+    c->view_ids[k] = id; c->shardmaps.emplace_back(); c->view_arr.push_back(0); c->view_other.push_back(0); c->view_striped.push_back(0);
     return id;
 }
 
@@ -251,7 +252,7 @@ static void drop_locked(fbgpu_ctx* c, uint32_t fv, uint64_t shard) {
     f.live = false;
     c->stats.fragments--; c->stats.containers -= f.n_desc; c->stats.payload_bytes -= f.payload_bytes;
     c->stats.array_containers -= f.n_arr; c->stats.bitmap_containers -= f.n_bmp; c->stats.run_containers -= f.n_run;
-    c->view_arr[fv] -= f.n_arr; c->view_other[fv] -= (uint64_t)f.n_bmp + f.n_run;
+    c->view_arr[fv] -= f.n_arr; c->view_other[fv] -= (uint64_t)f.n_bmp + f.n_run; c->view_striped[fv] -= f.n_striped;
     sm[shard] = -1;
     c->meta_dirty = true;
 }
@@ -281,6 +282,10 @@ static int add_fragment_locked(fbgpu_ctx* c, uint32_t fv, uint64_t shard, const 
     // payloads: row-major (key order) by default: a row's 16 containers are contiguous, which is what the common
     // few-rows-of-many query streams.  FBGPU_LAYOUT_SLOT_MAJOR=1 stores all rows of slot 0, then slot 1, ... so that a
     // (shard, slot) unit's consecutive rows are adjacent (measured: -20 % on 2-row bitmap queries; profiles/README.md).
+    // experimental striped order: only for array-dominated fragments, so that bitmap-heavy views (BSI planes) keep every
+    // array sorted and stay eligible for the word-parallel kernel, whose slice search needs sorted arrays
+    const bool stripe = c->stripe_arrays && (uint64_t)hf.n_arr * 8 > (uint64_t)hf.n_bmp + hf.n_run;
+    if (stripe) for (const ParsedCont& pc : cs) if (pc.typ == kArray && pc.n >= fbgpu_stripe::kMinStripe) hf.n_striped++;
     std::vector<uint32_t> order(cs.size());
     for (uint32_t i = 0; i < cs.size(); i++) order[i] = i;
     static const bool slot_major = getenv("FBGPU_LAYOUT_SLOT_MAJOR") != nullptr;   // default: row-major (key order)
@@ -294,7 +299,7 @@ static int add_fragment_locked(fbgpu_ctx* c, uint32_t fv, uint64_t shard, const 
         uint64_t padded = (bytes + 15) & ~15ull;
         if (apos / 16 > 0xffffffffull) return fail(FBGPU_E_NOMEM, "payload arena exceeds 64 GiB addressable by 32-bit 16 B offsets");
         c->staging.len += (apos - pos) + padded;            // space is claimed now, bytes are copied by run_copies()
-        copies.push_back(PayloadCopy{ pc.data, apos - c->uploaded, (uint32_t)bytes, (uint32_t)padded, pc.typ, (uint16_t)(pc.official_run ? 1 : 0), pc.cnt });
+        copies.push_back(PayloadCopy{ pc.data, apos - c->uploaded, (uint32_t)bytes, (uint32_t)padded, pc.typ, (uint16_t)(pc.official_run ? 1 : 0), pc.cnt, stripe ? 1u : 0u });
         c->h_descs[desc0 + i].off16 = (uint32_t)(apos / 16);
     }
     FragHdr h{}; h.row_off = hf.row_off; h.n_rows = hf.n_rows; h.row0 = row0; h.contiguous = contiguous ? 1u : 0u;
@@ -305,7 +310,7 @@ static int add_fragment_locked(fbgpu_ctx* c, uint32_t fv, uint64_t shard, const 
     sm[shard] = fid;
     c->stats.fragments++; c->stats.containers += hf.n_desc; c->stats.payload_bytes += hf.payload_bytes;
     c->stats.array_containers += hf.n_arr; c->stats.bitmap_containers += hf.n_bmp; c->stats.run_containers += hf.n_run;
-    c->view_arr[fv] += hf.n_arr; c->view_other[fv] += (uint64_t)hf.n_bmp + hf.n_run;
+    c->view_arr[fv] += hf.n_arr; c->view_other[fv] += (uint64_t)hf.n_bmp + hf.n_run; c->view_striped[fv] += hf.n_striped;
     c->meta_dirty = true;
     return 0;
 }
@@ -318,7 +323,7 @@ static int run_copies(fbgpu_ctx* c, const std::vector<PayloadCopy>& copies, int 
         for (size_t i = lo; i < hi; i++) {
             const PayloadCopy& pc = copies[i];
             uint8_t* dst = base + pc.dst;
-            if (pc.typ == kArray && c->stripe_arrays) fbgpu_stripe::stripe_array(pc.src, (uint16_t*)dst, pc.bytes / 2);
+            if (pc.typ == kArray && pc.stripe) fbgpu_stripe::stripe_array(pc.src, (uint16_t*)dst, pc.bytes / 2);
             else memcpy(dst, pc.src, pc.bytes);
             if (pc.typ == kArray) fbgpu_stripe::pad_array_tail((uint16_t*)dst, pc.bytes / 2, pc.padded / 2);      // tail of the last 16-byte chunk: copies of the last element (stripe.h)
             else if (pc.padded > pc.bytes) memset(dst + pc.bytes, 0, pc.padded - pc.bytes);                      // zero tail
@@ -582,10 +587,10 @@ static int launch_eval(fbgpu_ctx* c, Workspace* w, const std::vector<DevOp>& pro
     // Word-parallel kernel for bitmap-heavy programs (BSI plane sweeps, dense rows): chosen when the views the
     // program references hold few array containers.  Row results (out.info) need cross-slice run counts: not here.
     if (!out.info && n_ops <= kWpMaxOps && depth <= kWpMaxDepth && !getenv("FBGPU_NO_WORDPAR")) {
-        uint64_t arr = 0, other = 0;
-        for (const DevOp& o : prog) if (o.op >= D_PUSH_ROW && o.op <= D_ORANDNOT_ROW && o.op != D_PUSH_EMPTY && o.fv < c->view_arr.size()) { arr += c->view_arr[o.fv]; other += c->view_other[o.fv]; }
-        // (wp_slice searches sorted arrays: with striped array payloads the kernel is only valid when no arrays are referenced)
-        if (c->stripe_arrays ? (other > 0 && arr == 0) : ((other > 0 && arr * 8 <= other) || getenv("FBGPU_FORCE_WORDPAR") != nullptr)) {
+        uint64_t arr = 0, other = 0, striped = 0;
+        for (const DevOp& o : prog) if (o.op >= D_PUSH_ROW && o.op <= D_ORANDNOT_ROW && o.op != D_PUSH_EMPTY && o.fv < c->view_arr.size()) { arr += c->view_arr[o.fv]; other += c->view_other[o.fv]; striped += c->view_striped[o.fv]; }
+        // (wp_slice searches sorted arrays: a view that holds striped arrays can never take this kernel, forced or not)
+        if (striped == 0 && ((other > 0 && arr * 8 <= other) || getenv("FBGPU_FORCE_WORDPAR") != nullptr)) {
             long long blocks = n_units * kWpBlocksPerUnit;
             long long grid = std::min<long long>(blocks, (long long)c->sm_count * std::max(FBGPU_WP_MIN_BLOCKS, 8) * 2);
             eval_wordpar_kernel<<<(unsigned)grid, kWpThreads, 0, w->stream>>>(store_ref(c), d_prog, n_ops, d_shards, n_units, out);

@@ -4,9 +4,10 @@
 // red.shared (or ld.shared probe) per element.  With the sorted order of the roaring format the 32 lanes of one such
 // instruction hit pseudo-random banks (bank = (v >> 5) & 31): ~3.5 wavefronts per instruction, and the shared-memory
 // pipe is the measured limiter of the headline query (profiles/README.md).  The kernels never use the ORDER of an
-// array's elements (they scatter or probe them; only eval_wordpar_kernel's wp_slice searches, and the host keeps that
-// kernel away from striped arrays), so the loader is free to permute each container such that every group of
-// elements one instruction touches has pairwise distinct banks.
+// array's elements (they scatter or probe them; only eval_wordpar_kernel's wp_slice searches).  So the loader may permute
+// a container such that every group of elements one instruction touches has pairwise distinct banks.  Policy
+// (fbgpu.cu:add_fragment_locked): only fragments dominated by array containers are striped, which leaves bitmap-heavy
+// views (BSI planes) sorted and eligible for the word-parallel kernel; a view holding any striped array never takes it.
 //
 // Access pattern being matched (kernels.cuh: batch_rows / warp_intersection_count -> scatter_chunk_unrolled / probe_chunk):
 // lane L loads the 16-byte chunk i = L + 32 t, i.e. positions 8 i .. 8 i + 7, and issues eight bit operations, the q-th
