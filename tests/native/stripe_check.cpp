@@ -23,3 +23,44 @@ extern "C" void load_array(const uint16_t* src, uint16_t* dst, uint32_t n, int s
     if (striped) fbgpu_stripe::stripe_array(src, dst, n); else memcpy(dst, src, (size_t)n * 2);
     fbgpu_stripe::pad_array_tail(dst, n, (n + 7) & ~7u);
 }
+
+// Line-by-line host model of kernels.cuh:scatter_chunk_sb over a stored array payload (all n8 chunks, as batch_rows /
+// warp_intersection_count issue them): MODE 0 |=, 1 &= ~, 2 ^=.  bm: 2048 words, modified in place.
+static void model_bit_op(int mode, uint32_t* bm, uint32_t off, uint32_t sh) {
+    const uint32_t m = 1u << (sh & 31);
+    uint32_t& w = bm[off / 4];
+    if (mode == 0) w |= m; else if (mode == 1) w &= ~m; else w ^= m;
+}
+extern "C" void model_scatter(int mode, const uint16_t* payload, uint32_t n, uint32_t* bm) {
+    const uint32_t n8 = (n + 7) >> 3;
+    for (uint32_t i = 0; i < n8; i++) {
+        uint32_t w[4]; memcpy(w, payload + 8 * i, 16);
+        const uint32_t base = i * 8;
+        if (mode != 2 || base + 8 <= n) {
+            for (int q = 0; q < 4; q++) { model_bit_op(mode, bm, fbgpu::word_off_lo(w[q]), w[q]); model_bit_op(mode, bm, fbgpu::word_off_hi(w[q]), w[q] >> 16); }
+        } else {
+            for (int q = 0; q < 4; q++) {
+                if (base + 2 * q < n) model_bit_op(mode, bm, fbgpu::word_off_lo(w[q]), w[q]);
+                if (base + 2 * q + 1 < n) model_bit_op(mode, bm, fbgpu::word_off_hi(w[q]), w[q] >> 16);
+            }
+        }
+    }
+}
+// kernels.cuh:probe_chunk over all chunks: number of the n elements set in bm
+extern "C" uint32_t model_probe(const uint16_t* payload, uint32_t n, const uint32_t* bm) {
+    uint32_t c = 0;
+    for (uint32_t i = 0; i < (n + 7) >> 3; i++) {
+        uint32_t w[4]; memcpy(w, payload + 8 * i, 16);
+        const uint32_t base = i * 8;
+        if (base + 8 <= n) {
+            for (int q = 0; q < 4; q++) { c += (bm[fbgpu::word_off_lo(w[q]) / 4] >> (w[q] & 31)) & 1u; c += (bm[fbgpu::word_off_hi(w[q]) / 4] >> ((w[q] >> 16) & 31)) & 1u; }
+        } else {
+            for (int q = 0; q < 4; q++) {
+                uint32_t lo = w[q] & 0xffffu, hi = w[q] >> 16;
+                if (base + 2 * q < n) c += (bm[lo >> 5] >> (lo & 31)) & 1u;
+                if (base + 2 * q + 1 < n) c += (bm[hi >> 5] >> (hi & 31)) & 1u;
+            }
+        }
+    }
+    return c;
+}

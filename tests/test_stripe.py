@@ -92,3 +92,35 @@ def test_array_tail_padding(lib):
             assert np.array_equal(np.sort(d[:n]), v)
             assert set(d[n:padded].tolist()) <= {int(d[n - 1])}
             assert set(np.unique(d[:padded]).tolist()) == set(v.tolist())          # the chunked bit set is exactly the container
+
+
+def test_scatter_and_probe_model_on_stored_payloads(lib):
+    """host model of scatter_chunk_sb / probe_chunk (same helper headers, same control flow) over payloads exactly as the
+    loader stores them (plain or striped order, duplicate-padded tail): OR sets exactly the container, AND-NOT clears
+    exactly it, XOR toggles exactly it, and the probe counts exactly the intersection — for every tail length"""
+    rng = np.random.default_rng(10)
+    lib.model_probe.restype = C.c_uint32
+    for n in list(range(1, 34)) + [63, 64, 65, 100, 655, 1000, 4079, 4095, 4096]:
+        for striped in (0, 1):
+            v = np.ascontiguousarray(np.sort(rng.choice(65536, n, replace=False)).astype(np.uint16))
+            padded = (n + 7) & ~7
+            pay = np.zeros(padded, dtype=np.uint16)
+            lib.load_array(v.ctypes.data, pay.ctypes.data, n, striped)
+            want = np.zeros(65536, dtype=bool)
+            want[v] = True
+            other = rng.random(65536) < 0.3
+            def bits(words):
+                return np.unpackbits(words.view(np.uint8), bitorder="little").astype(bool)
+            def words(mask):
+                return np.packbits(mask, bitorder="little").view(np.uint32).copy()
+            bm = words(other)
+            lib.model_scatter(0, pay.ctypes.data, n, bm.ctypes.data)
+            assert np.array_equal(bits(bm), other | want), (n, striped, "or")
+            bm = words(other)
+            lib.model_scatter(1, pay.ctypes.data, n, bm.ctypes.data)
+            assert np.array_equal(bits(bm), other & ~want), (n, striped, "andnot")
+            bm = words(other)
+            lib.model_scatter(2, pay.ctypes.data, n, bm.ctypes.data)
+            assert np.array_equal(bits(bm), other ^ want), (n, striped, "xor")
+            bm = words(other)
+            assert lib.model_probe(pay.ctypes.data, n, bm.ctypes.data) == int((other & want).sum()), (n, striped, "probe")
