@@ -355,10 +355,17 @@ class Executor:
         pairs = [(int(i), int(n)) for i, n in zip(rid, cnt)]
         return pairs[:k] if k else pairs
 
-    def _rows(self, idx, c, shards):                             # executeRows :5311 (row ids present)
-        f = self._field(idx, c.args["_field"])
-        rid, _ = self.ctx.row_counts(idx.id, f.id, VIEW_STANDARD, shards)
+    def _rows(self, idx, c, shards):                             # executeRows :5311 (row ids present; limit / previous / in)
+        f = self._field(idx, c.args["_field"] if "_field" in c.args else c.args.get("field"))
+        if "column" in c.args or "like" in c.args:
+            raise QueryError("Rows(): column / like arguments are not supported by this mirror")
+        rid, _ = self.ctx.row_counts(idx.id, f.id, VIEW_BSI if f.type == "int" else VIEW_STANDARD, shards)
         out = sorted(int(r) for r in rid)
+        if "in" in c.args:
+            keep = {int(r) for r in c.args["in"]}
+            out = [r for r in out if r in keep]
+        if "previous" in c.args:                                 # rows strictly after `previous` (fragment.rows start = previous + 1)
+            out = [r for r in out if r > int(c.args["previous"])]
         lim = c.args.get("limit")
         return out[:lim] if lim else out
 
@@ -445,23 +452,109 @@ class Executor:
 
     # ------------------------------------------------------------------ GroupBy (executeGroupBy :3176)
     def _groupby(self, idx, c, shards):
+        """The device returns the dense count tensor over the children's row lists; everything after it is the host-side
+        post-processing executeGroupBy does in Go: previous (iterator start, newGroupByIterator :8779-8826), aggregate=Sum
+        (groupByIterator.Next :8893-8911: Count becomes the number of columns holding a value), having (:3388-3406),
+        sort (:3130-3162, 3408-3414), offset / limit (:3441-3459).  Results: (group, count) or (group, count, agg)."""
         if not c.children:
             raise QueryError("need at least one child call")
         fields, row_ids = [], []
         for ch in c.children:
             if ch.name != "Rows":
                 raise QueryError(f"'{ch.name}' is not a valid child query for GroupBy, must be 'Rows'")
-            f = self._field(idx, ch.args["_field"])
+            name = ch.args.get("_field", ch.args.get("field"))
+            f = self._field(idx, name)
             fields.append(f)
-            row_ids.append(self._rows(idx, ch, shards))          # pre-pass executeRows :3263-3287
-        filt = c.args.get("filter")
-        filt = self._bitmap_call(idx, filt) if isinstance(filt, pql.Call) else None
+            pre = pql.Call("Rows", {k: v for k, v in ch.args.items() if k != "previous"})     # previous positions the iterator, it does not drop rows
+            row_ids.append(self._rows(idx, pre, shards))         # pre-pass executeRows :3263-3287
+        filt_call = c.args.get("filter")
+        filt = self._bitmap_call(idx, filt_call) if isinstance(filt_call, pql.Call) else None
+        agg = c.args.get("aggregate")
+        if isinstance(agg, pql.Call) and agg.name != "Sum":
+            raise QueryError(f"aggregate {agg.name} is not supported by this mirror")
         if any(len(r) == 0 for r in row_ids):
             return []
         counts = self.ctx.groupby(idx.id, [f.id for f in fields], [VIEW_STANDARD] * len(fields), row_ids, shards, filter_ops=filt)
+        start = self._groupby_start(c, row_ids)
+        if start is None:
+            return []
+        has_sort, has_having = "sort" in c.args, isinstance(c.args.get("having"), pql.Call)
+        limit = c.args.get("limit") if not (has_sort or has_having) else None       # :3196-3212: no early limit when sorting / filtering
         out = []
-        for flat in np.flatnonzero(counts.reshape(-1)):          # only Count>0, lexicographic (:3960)
+        flat0 = int(np.ravel_multi_index(start, counts.shape))
+        for flat in np.flatnonzero(counts.reshape(-1)):          # only Count > 0, lexicographic (:3960)
+            if flat < flat0:
+                continue
             ix = np.unravel_index(int(flat), counts.shape)
-            out.append(([(f.name, row_ids[k][int(i)]) for k, (f, i) in enumerate(zip(fields, ix))], int(counts[ix])))
+            group = [(f.name, row_ids[k][int(i)]) for k, (f, i) in enumerate(zip(fields, ix))]
+            if isinstance(agg, pql.Call):
+                rows = [pql.Call("Row", {name: rid}) for name, rid in group]
+                if isinstance(filt_call, pql.Call):
+                    rows.append(filt_call)
+                inter = rows[0] if len(rows) == 1 else pql.Call("Intersect", {}, rows)
+                vc = self._sum(idx, pql.Call("Sum", dict(agg.args), [inter]), shards)
+                if vc.count == 0:
+                    continue                                      # ret.Count == 0 => skipped (:8913-8919)
+                out.append((group, vc.count, vc.val))
+            else:
+                out.append((group, int(counts[ix])))
+            if limit and len(out) >= limit and "offset" not in c.args:
+                break
+        if has_having:                                            # Condition(count|sum <op> n)
+            having = c.args["having"]
+            if having.name != "Condition" or len(having.args) != 1:
+                raise QueryError("the only supported having call is Condition() with a single condition")
+            (subj, cond), = having.args.items()
+            if subj not in ("count", "sum"):
+                raise QueryError("Condition() only supports count or sum")
+            pick = (lambda g: g[1]) if subj == "count" else (lambda g: g[2] if len(g) > 2 else 0)
+            out = [g for g in out if _cond_holds(pick(g), cond)]
+        if has_sort:
+            keys = []
+            for part in str(c.args["sort"]).split(","):
+                w = part.split()
+                if not w or w[0] not in ("count", "aggregate", "sum") or len(w) > 2 or (len(w) == 2 and w[1] not in ("asc", "desc")):
+                    raise QueryError(f"invalid sorting directive: '{part.strip()}'")
+                keys.append((1 if w[0] == "count" else 2, len(w) == 2 and w[1] == "asc"))
+            for col, asc in reversed(keys):                       # stable sorts, last key first == sort.Stable on the tuple
+                out.sort(key=lambda g: (g[col] if len(g) > col else 0), reverse=not asc)
+        off = c.args.get("offset")
+        if off is not None and int(off) < len(out):               # (an offset beyond the result is ignored, :3446)
+            out = out[int(off):]
         lim = c.args.get("limit")
         return out[:lim] if lim else out
+
+    def _groupby_start(self, c, row_ids):
+        """position (one index per field) of the first group the iterator yields, or None when `previous` was the last
+        group: newGroupByIterator :8779-8826 on one merged row list per field (the reference seeks per shard)"""
+        n = len(row_ids)
+        pos, ignore = [0] * n, False
+        for i, ch in enumerate(c.children):
+            rows = row_ids[i]
+            prev = ch.args.get("previous")
+            if prev is not None and not ignore:
+                prev = int(prev) + (1 if i == n - 1 else 0)
+                pos[i] = next((k for k, r in enumerate(rows) if r >= prev), len(rows))
+            wrapped = pos[i] >= len(rows)
+            if wrapped:
+                if i == 0:
+                    return None                                   # the first field's iterator does not wrap
+                pos[i] = 0
+            if prev is not None and not ignore and rows[pos[i]] != prev:
+                ignore = True
+            if wrapped:
+                for j in range(i - 1, -1, -1):
+                    pos[j] += 1
+                    if pos[j] < len(row_ids[j]):
+                        break
+                    if j == 0:
+                        return None
+                    pos[j] = 0
+        return pos
+
+
+def _cond_holds(v, cond):
+    op, x = cond.op, cond.value
+    if op == "><":
+        return x[0] <= v <= x[1]
+    return {"==": v == x, "!=": v != x, "<": v < x, "<=": v <= x, ">": v > x, ">=": v >= x}[op]

@@ -190,3 +190,35 @@ def filter_sample_bits():
 
 FILTER_ROWS_UNION = ([7, 11], [(1 << 16) + 1, (7 << 16) + 7, (11 << 16) + 11])
 FILTER_ROWSET = ([0, 1, 2, 3], (2 << 16) + 2, [0, 2])
+
+# ---------------------------------------------------------------------------------------------------
+# executor_test.go:6033-6386 TestExecutor_Execute_GroupBy beyond Basic / Filter: aggregate=Sum (:6121-6129; int field v:
+# column 0 -> 10, 1 -> 100, SW+10 -> 100), previous / limit paging (:6164-6181), "tricky data" (:6194-6201), wrapping
+# iterators (:6203-6258), rows in different shards (:6260-6294, 6321-6331), paging through 64 groups (:6335-6386).
+# Bits are (row, column); results ((row ids...), count[, agg]).
+# ---------------------------------------------------------------------------------------------------
+GB_V_VALUES = [(0, 10), (1, 100), (SW + 10, 100)]
+GB_FIELDS = {
+    "a": [(0, 1), (1, SW + 1)], "b": [(0, SW + 1), (1, 1)],
+    "wa": [(0, 0), (0, 1), (0, 2), (1, 1), (2, 0), (2, 2), (3, 3)],
+    "ma": [(0, 0), (1, SW), (2, 0), (3, SW)],
+    "na": [(0, 0), (0, SW), (1, 0), (1, SW)],
+    "ppa": [(0, 0), (1, 0), (2, 0), (3, 0), (3, 91000), (3, SW), (3, 2 * SW), (3, 3 * SW)],
+}
+for _src, _dsts in (("wa", ("wb", "wc")), ("ma", ("mb",)), ("na", ("nb",)), ("ppa", ("ppb", "ppc"))):
+    for _d in _dsts:
+        GB_FIELDS[_d] = GB_FIELDS[_src]
+GB_CASES = [
+    ("GroupBy(Rows(field=general), Rows(sub))", GROUPBY_BASIC),                                   # BasicLegacy
+    ("GroupBy(Rows(general), Rows(sub), aggregate=Sum(field=v))", [((10, 100), 2, 110), ((10, 110), 1, 10)]),
+    ("GroupBy(Rows(general, previous=10))", [((11,), 2), ((12,), 2)]),
+    ("GroupBy(Rows(general, previous=10), limit=1)", [((11,), 2)]),
+    ("GroupBy(Rows(a), Rows(b), limit=1)", [((0, 1), 1)]),                                           # tricky data
+    ("GroupBy(Rows(wa), Rows(wb), Rows(wc, previous=1), limit=3)", [((0, 0, 2), 2), ((0, 1, 0), 1), ((0, 1, 1), 1)]),
+    ("GroupBy(Rows(wa, previous=3), Rows(wb, previous=3), Rows(wc, previous=3), limit=3)", []),
+    ("GroupBy(Rows(wa), Rows(wb, previous=2), Rows(wc, previous=2), limit=1)", [((1, 0, 0), 1)]),
+    ("GroupBy(Rows(ma), Rows(mb), limit=5)", [((0, 0), 1), ((0, 2), 1), ((1, 1), 1), ((1, 3), 1), ((2, 0), 1)]),
+    ("GroupBy(Rows(ma), Rows(mb, limit=2), limit=5)", [((0, 0), 1), ((1, 1), 1), ((2, 0), 1), ((3, 1), 1)]),
+    ("GroupBy(Rows(na), Rows(nb))", [((0, 0), 2), ((0, 1), 2), ((1, 0), 2), ((1, 1), 2)]),
+]
+GB_PAGING_EXPECT = [((i // 16, (i % 16) // 4, i % 4), 5 if i == 63 else 1) for i in range(64)]

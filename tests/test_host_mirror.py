@@ -60,6 +60,10 @@ def test_fragment_top_goldens(oracle_backed):
     E.test_filter_sample_goldens()
 
 
+def test_groupby_postprocessing_goldens(oracle_backed):
+    E.test_groupby_postprocessing_goldens()
+
+
 def test_bench_archetype_matrix_plumbing(oracle_backed):
     E.test_bench_archetype_matrix()
 
