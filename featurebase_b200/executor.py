@@ -218,6 +218,8 @@ class Executor:
                 return self._sum(idx, c, shards)
             if c.name in ("Min", "Max"):
                 return self._minmax(idx, c, shards, c.name)
+            if c.name == "Percentile":
+                return self._percentile(idx, c, shards)
             ops = self._bitmap_call(idx, c)
             data, cnt = self.ctx.row(idx.id, ops, shards)
             return RowResult(data, cnt)
@@ -449,6 +451,57 @@ class Executor:
             else:
                 v, cnt = self._sweep_unsigned(idx, f, pos, n_pos, shards, True)
         return ValCount(v + f.base, cnt)                                # valCountize field.go:1640
+
+    def _percentile(self, idx, c, shards):
+        """executePercentile :1310-1600 (int fields): total = Count(filter ∩ notNull); the wanted numbers of smaller / larger
+        values; Min and Max under the filter; then a bisection on the value, two Count(Row(f < x) [∩ filter]) style queries
+        per step.  Every step is a whole-batch device query, exactly as every step is a cluster-wide query in the reference.
+        Returns None ("the median of nothing is NULL") or ValCount(value, 1) / the Min / Max ValCount at the ends."""
+        nth = c.args.get("nth")
+        if nth is None:
+            raise QueryError("Percentile(): nth required")
+        if isinstance(nth, bool) or not isinstance(nth, (int, float)):
+            raise QueryError(f"Percentile(): invalid nth='{nth}', should be a number between 0 and 100 inclusive")
+        nth = float(nth)
+        if nth < 0 or nth > 100.0:
+            raise QueryError(f"Percentile(): invalid nth value ({nth}), should be a number between 0 and 100 inclusive")
+        name = c.args.get("field", c.args.get("_field"))
+        if name is None:
+            raise QueryError("Percentile(): field required")
+        f = self._field(idx, name)
+        filt = c.args.get("filter") if isinstance(c.args.get("filter"), pql.Call) else None
+        not_null = pql.Call("Row", {name: pql.Condition("!=", None)})
+
+        def count_of(row_call):
+            inner = row_call if filt is None else pql.Call("Intersect", {}, [row_call, filt])
+            return self._count(idx, pql.Call("Count", {}, [inner]), shards)
+        total = count_of(not_null) if filt is None else self._count(idx, pql.Call("Count", {}, [pql.Call("Intersect", {}, [filt, not_null])]), shards)
+        if total == 0:
+            return None
+        want_less = int(total * nth / 100.0)
+        want_greater = int(total * (100 - nth) / 100.0)
+        kids = [filt] if filt is not None else []
+        mn = ValCount()
+        if want_greater != 0:
+            mn = self._minmax(idx, pql.Call("Min", {"field": name}, kids), shards, "Min")
+            if want_less == 0:
+                return mn
+        mx = self._minmax(idx, pql.Call("Max", {"field": name}, kids), shards, "Max")
+        if want_greater == 0:
+            return mx
+        lo, hi, guess = mn.val, mx.val, mn.val
+        tdiv = lambda a, b: int(a / b) if abs(a) < (1 << 52) else (abs(a) // b) * (1 if a >= 0 else -1)      # Go's truncating division
+        tmod = lambda a, b: a - b * tdiv(a, b)                                                                  # Go's %: sign of the dividend
+        while lo < hi:
+            guess = tdiv(lo, 2) + tdiv(hi, 2) + tdiv(tmod(lo, 2) + tmod(hi, 2), 2)       # overflow-free midpoint (:1493-1497)
+            if count_of(pql.Call("Row", {name: pql.Condition("<", guess)})) > want_less:
+                hi = guess - 1
+                continue
+            if count_of(pql.Call("Row", {name: pql.Condition(">", guess)})) > want_greater:
+                lo = guess + 1
+                continue
+            break
+        return ValCount(guess, 1)
 
     # ------------------------------------------------------------------ GroupBy (executeGroupBy :3176)
     def _groupby(self, idx, c, shards):

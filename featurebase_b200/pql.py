@@ -1,6 +1,6 @@
 """Minimal PQL call tree + parser for the hot-path calls (mirror of pql.Call, reference pql/ast.go), so that parity
 tests read like the reference's executor tests.  The full PEG grammar stays in Go; only this subset is needed:
-Row, Intersect, Union, Difference, Xor, Not, All, Count, TopN, TopK, Rows, GroupBy, Sum, Min, Max."""
+Row, Intersect, Union, Difference, Xor, Not, All, Count, TopN, TopK, Rows, GroupBy, Sum, Min, Max, Percentile."""
 import re
 
 
@@ -23,7 +23,7 @@ class Call:
         return f"{self.name}({', '.join(parts)})"
 
 
-_TOK = re.compile(r"\s*(?:(?P<str>\"[^\"]*\"|'[^']*')|(?P<num>-?\d+)|(?P<id>[A-Za-z_][A-Za-z0-9_\-]*)|(?P<op>><|<=|>=|==|!=|[(),=<>\[\]]))")
+_TOK = re.compile(r"\s*(?:(?P<str>\"[^\"]*\"|'[^']*')|(?P<flt>-?\d+\.\d+)|(?P<num>-?\d+)|(?P<id>[A-Za-z_][A-Za-z0-9_\-]*)|(?P<op>><|<=|>=|==|!=|[(),=<>\[\]]))")
 
 
 def _tokens(s):
@@ -37,6 +37,8 @@ def _tokens(s):
         pos = m.end()
         if m.group("str") is not None:
             out.append(("str", m.group("str")[1:-1]))
+        elif m.group("flt") is not None:
+            out.append(("flt", float(m.group("flt"))))
         elif m.group("num") is not None:
             out.append(("num", int(m.group("num"))))
         elif m.group("id") is not None:
@@ -66,7 +68,7 @@ class _Parser:
 
     def value(self):
         kind, v = self.next()
-        if kind in ("num", "str"):
+        if kind in ("num", "str", "flt"):
             return v
         if kind == "id":
             if v == "null":

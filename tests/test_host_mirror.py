@@ -64,6 +64,10 @@ def test_groupby_postprocessing_goldens(oracle_backed):
     E.test_groupby_postprocessing_goldens()
 
 
+def test_percentile(oracle_backed):
+    E.test_percentile_vs_reference_helper()
+
+
 def test_bench_archetype_matrix_plumbing(oracle_backed):
     E.test_bench_archetype_matrix()
 
