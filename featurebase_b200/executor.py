@@ -13,6 +13,7 @@ import numpy as np
 from . import lib as L
 from . import pql
 from . import roaring_io
+from . import timeq
 
 SHARD_WIDTH = 1 << 20                    # shardwidth/helper.go:13
 VIEW_STANDARD = 0                        # view.go:28 "standard"
@@ -21,8 +22,10 @@ EXISTENCE_FIELD = "_exists"              # holder.go:33
 
 
 class Field:
-    def __init__(self, fid, name, ftype="set", min=None, max=None, bit_depth=None):
+    def __init__(self, fid, name, ftype="set", min=None, max=None, bit_depth=None, quantum=""):
         self.id, self.name, self.type = fid, name, ftype
+        self.quantum = quantum if ftype == "time" else ""       # TimeQuantum "YMDH" (time.go:17)
+        self.view_ids = {"standard": VIEW_STANDARD}              # view name -> the small id used in programs / residency calls
         if ftype == "int":
             self.min = -(1 << 63) if min is None else int(min)
             self.max = (1 << 63) - 1 if max is None else int(max)
@@ -30,6 +33,29 @@ class Field:
             if bit_depth is None:                                                            # field.go:2502-2512 (data driven)
                 bit_depth = max_bitlen(abs(self.min - self.base), abs(self.max - self.base))
             self.bit_depth = int(bit_depth)
+
+    def view_id(self, name, create=False):
+        if name not in self.view_ids:
+            if not create:
+                return None
+            self.view_ids[name] = 2 + sum(1 for v in self.view_ids.values() if v >= 2)      # 0 standard, 1 bsig, 2.. time views
+        return self.view_ids[name]
+
+    def views_by_time_range(self, t_from, t_to):
+        """Field.viewsByTimeRange field.go:1063-1110 -> view names (clamped to the views that exist)"""
+        if not self.quantum:
+            raise QueryError(f"field {self.name} is not a time-field, 'from' and 'to' are not valid options for this field type")
+        if t_from is None and t_to is None:
+            return ["standard"]
+        lo, hi = timeq.min_max_views([v for v in self.view_ids if v != "standard"], self.quantum)
+        if not lo or not hi:
+            return []
+        t_min, t_max = timeq.time_of_view(lo, False), timeq.time_of_view(hi, True)
+        if t_from is None or t_from < t_min:
+            t_from = t_min
+        if t_to is None or t_to > t_max:
+            t_to = t_max
+        return timeq.views_by_time_range("standard", t_from, t_to, self.quantum)
 
     # bsiGroup.bitDepthMin / bitDepthMax  field.go:2475-2482
     def bit_depth_min(self):
@@ -123,10 +149,14 @@ class Holder:
         return n
 
     # ---- test conveniences mirroring test helpers (hldr.SetBit / SetValue, test/holder.go)
-    def set_bit(self, index, field, row, col):
+    def set_bit(self, index, field, row, col, timestamp=None):
         idx = self.indexes[index]
         shard = col // SHARD_WIDTH
         self._pending.setdefault((index, field, VIEW_STANDARD, shard), set()).add(row * SHARD_WIDTH + col % SHARD_WIDTH)
+        if timestamp is not None:                                # Set(col, f=row, timestamp): one more bit per quantum unit view (viewsByTime)
+            f = idx.fields[field]
+            for vname in timeq.views_by_time("standard", timeq.parse_time(timestamp), f.quantum):
+                self._pending.setdefault((index, field, f.view_id(vname, create=True), shard), set()).add(row * SHARD_WIDTH + col % SHARD_WIDTH)
         if idx.track_existence:
             self._pending.setdefault((index, EXISTENCE_FIELD, VIEW_STANDARD, shard), set()).add(col % SHARD_WIDTH)
 
@@ -278,6 +308,22 @@ class Executor:
             return self._emit_bsi(idx, f, v if isinstance(v, pql.Condition) else pql.Condition("==", v), ops)
         if f.type == "bool":
             v = 1 if v else 0                                    # fragment.go:59-60
+        if "from" in c.args or "to" in c.args:                   # :5149-5163, 5209-5241: union of the row over the covering time views
+            try:
+                t_from = timeq.parse_time(c.args["from"]) if "from" in c.args else None
+                t_to = timeq.parse_time(c.args["to"]) if "to" in c.args else None
+            except ValueError as e:
+                raise QueryError(f"parsing time: {e}")
+            ids = [f.view_id(name) for name in f.views_by_time_range(t_from, t_to)]
+            ids = [i for i in ids if i is not None]               # views without a fragment anywhere contribute nothing
+            if not ids:
+                ops.append(L.Op(L.OP_EMPTY, 0, 0, 0, 0, 0, 0, 0))
+                return
+            for i in ids:
+                ops.append(L.Op(L.OP_ROW, f.id, i, 0, int(v), 0, 0, 0))
+            if len(ids) > 1:
+                ops.append(L.Op(L.OP_UNION, 0, 0, len(ids), 0, 0, 0, 0))
+            return
         ops.append(L.Op(L.OP_ROW, f.id, VIEW_STANDARD, 0, int(v), 0, 0, 0))
 
     def _emit_bsi(self, idx, f, cond, ops):                      # executeRowBSIGroupShard :5249-5354

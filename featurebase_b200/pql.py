@@ -23,7 +23,7 @@ class Call:
         return f"{self.name}({', '.join(parts)})"
 
 
-_TOK = re.compile(r"\s*(?:(?P<str>\"[^\"]*\"|'[^']*')|(?P<flt>-?\d+\.\d+)|(?P<num>-?\d+)|(?P<id>[A-Za-z_][A-Za-z0-9_\-]*)|(?P<op>><|<=|>=|==|!=|[(),=<>\[\]]))")
+_TOK = re.compile(r"\s*(?:(?P<str>\"[^\"]*\"|'[^']*')|(?P<ts>\d{4}-\d{2}-\d{2}T\d{2}:\d{2})|(?P<flt>-?\d+\.\d+)|(?P<num>-?\d+)|(?P<id>[A-Za-z_][A-Za-z0-9_\-]*)|(?P<op>><|<=|>=|==|!=|[(),=<>\[\]]))")
 
 
 def _tokens(s):
@@ -37,6 +37,8 @@ def _tokens(s):
         pos = m.end()
         if m.group("str") is not None:
             out.append(("str", m.group("str")[1:-1]))
+        elif m.group("ts") is not None:
+            out.append(("str", m.group("ts")))                    # timestamp literal 2006-01-02T15:04 (from= / to=)
         elif m.group("flt") is not None:
             out.append(("flt", float(m.group("flt"))))
         elif m.group("num") is not None:

@@ -222,3 +222,34 @@ GB_CASES = [
     ("GroupBy(Rows(na), Rows(nb))", [((0, 0), 2), ((0, 1), 2), ((1, 0), 2), ((1, 1), 2)]),
 ]
 GB_PAGING_EXPECT = [((i // 16, (i % 16) // 4, i % 4), 5 if i == 63 else 1) for i in range(64)]
+
+# ---------------------------------------------------------------------------------------------------
+# time_internal_test.go:107-186 TestViewsByTimeRange: (start, end, quantum, views for name "F")
+# ---------------------------------------------------------------------------------------------------
+VIEWS_BY_TIME_RANGE = [
+    ("2000-01-01 00:00", "2002-01-01 00:00", "Y", ["F_2000", "F_2001"]),
+    ("2000-11-01 00:00", "2003-03-01 00:00", "YM", ["F_200011", "F_200012", "F_2001", "F_2002", "F_200301", "F_200302"]),
+    ("2001-10-31 00:00", "2003-04-01 00:00", "YM", ["F_200110", "F_200111", "F_200112", "F_2002", "F_200301", "F_200302", "F_200303"]),
+    ("1999-12-31 00:00", "2000-04-01 00:00", "YM", ["F_199912", "F_200001", "F_200002", "F_200003"]),
+    ("2000-01-31 00:00", "2001-04-01 00:00", "YM", ["F_2000", "F_200101", "F_200102", "F_200103"]),
+    ("2000-11-28 00:00", "2003-03-02 00:00", "YMD", ["F_20001128", "F_20001129", "F_20001130", "F_200012", "F_2001", "F_2002", "F_200301", "F_200302", "F_20030301"]),
+    ("2000-11-28 22:00", "2002-03-01 03:00", "YMDH", ["F_2000112822", "F_2000112823", "F_20001129", "F_20001130", "F_200012", "F_2001", "F_200201", "F_200202",
+                                                       "F_2002030100", "F_2002030101", "F_2002030102"]),
+    ("2000-01-01 00:00", "2000-03-01 00:00", "M", ["F_200001", "F_200002"]),
+    ("2000-11-29 00:00", "2002-02-03 00:00", "MD", ["F_20001129", "F_20001130", "F_200012"] + ["F_2001%02d" % m for m in range(1, 13)] + ["F_200201", "F_20020201", "F_20020202"]),
+    ("2000-11-29 22:00", "2002-03-02 03:00", "MDH", ["F_2000112922", "F_2000112923", "F_20001130", "F_200012"] + ["F_2001%02d" % m for m in range(1, 13)]
+     + ["F_200201", "F_200202", "F_20020301", "F_2002030200", "F_2002030201", "F_2002030202"]),
+    ("2000-01-01 00:00", "2000-01-04 00:00", "D", ["F_20000101", "F_20000102", "F_20000103"]),
+    ("2000-01-01 22:00", "2000-03-01 02:00", "DH", ["F_2000010122", "F_2000010123"] + ["F_200001%02d" % d for d in range(2, 32)] + ["F_200002%02d" % d for d in range(1, 30)]
+     + ["F_2000030100", "F_2000030101"]),
+    ("2000-01-01 00:00", "2000-01-01 02:00", "H", ["F_2000010100", "F_2000010101"]),
+]
+# executor_test.go:470-515 (quantum YMDH) and :982-1010 (quantum YMD): timestamped Set()s of field f, then Row(f=1, from, to)
+TIME_BITS = [(1, 2, "1999-12-31T00:00"), (1, 3, "2000-01-01T00:00"), (1, 4, "2000-01-02T00:00"), (1, 5, "2000-02-01T00:00"), (1, 6, "2001-01-01T00:00"),
+             (1, 7, "2002-01-01T02:00"), (1, 2, "1999-12-30T00:00"), (1, 2, "2002-02-01T00:00"), (10, 2, "2001-01-01T00:00")]
+TIME_ROW_CASES = {
+    "YMDH": [("Row(f=1, from=1999-12-31T00:00, to=2002-01-01T03:00)", [2, 3, 4, 5, 6, 7]), ("Row(f=1, from=1999-12-31T00:00)", [2, 3, 4, 5, 6, 7]),
+             ("Row(f=1, to=2002-01-01T02:00)", [2, 3, 4, 5, 6]), ("Row(f=1, from=946598400, to=1009854000)", [2, 3, 4, 5, 6, 7])],
+    "YMD": [("Row(f=1, from=1999-12-31T00:00, to=2003-01-01T03:00)", [2, 3, 4, 5, 6, 7]), ("Row(f=1, from=2002-01-01T00:00, to=2002-01-02T00:00)", [7]),
+            ("Row(f=10, from=1999-12-31T00:00, to=2003-01-01T03:00)", [2])],
+}

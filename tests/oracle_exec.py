@@ -27,11 +27,20 @@ class OracleIndex:
     def eval_shard(self, c, shard):
         n = c.name
         if n == "Row":
-            key = [k for k in c.args if not k.startswith("_")][0]
+            key = [k for k in c.args if not k.startswith("_") and k not in ("from", "to")][0]
             fld = self.idx.fields[key]
             v = c.args[key]
             if fld.type == "int" or isinstance(v, pql.Condition):
                 return self._bsi(fld, v if isinstance(v, pql.Condition) else pql.Condition("==", v), shard)
+            if "from" in c.args or "to" in c.args:                # executeRowShard :5209-5241: union over the covering time views
+                from featurebase_b200 import timeq
+                names = fld.views_by_time_range(timeq.parse_time(c.args["from"]) if "from" in c.args else None,
+                                                timeq.parse_time(c.args["to"]) if "to" in c.args else None)
+                out = O.Bitmap()
+                for name in names:
+                    if fld.view_id(name) is not None:
+                        out = out.union(self.row(key, fld.view_id(name), int(v), shard))
+                return out
             return self.row(key, X.VIEW_STANDARD, int(v), shard)
         if n == "Intersect":
             if not c.children:

@@ -15,6 +15,7 @@ from tests import oracle_exec
 from tests import test_gpu_parity as G
 from tests import test_zz_gpu_executor_goldens as Z
 from tests import test_zz_gpu_experimental as E
+from tests.golden import vectors as V
 from tests.oracle_ctx import OracleCtx
 
 
@@ -62,6 +63,16 @@ def test_fragment_top_goldens(oracle_backed):
 
 def test_groupby_postprocessing_goldens(oracle_backed):
     E.test_groupby_postprocessing_goldens()
+
+
+def test_time_quantum(oracle_backed):
+    import datetime as dt
+    from featurebase_b200 import timeq
+    for a, b, q, exp in V.VIEWS_BY_TIME_RANGE:                   # time_internal_test.go:107-186, literal
+        got = timeq.views_by_time_range("F", dt.datetime.strptime(a, "%Y-%m-%d %H:%M"), dt.datetime.strptime(b, "%Y-%m-%d %H:%M"), q)
+        assert got == exp, (a, b, q)
+    assert timeq.views_by_time("F", dt.datetime(2000, 1, 2, 3, 4), "YMDH") == ["F_2000", "F_200001", "F_20000102", "F_2000010203"]
+    E.test_time_quantum_rows()
 
 
 def test_percentile(oracle_backed):

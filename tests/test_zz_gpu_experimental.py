@@ -363,3 +363,24 @@ def test_percentile_vs_reference_helper():
     for bad in ("Percentile(field=net_worth)", "Percentile(field=net_worth, nth=101)", "Percentile(nth=5)", "Percentile(field=nope, nth=5)"):
         with pytest.raises(X.QueryError):
             p.ex.execute("i", bad)
+
+
+def test_time_quantum_rows():
+    """executor_test.go:470-515, 982-1010: Row(f=x, from=, to=) over a time field = the union of the row over the views
+    viewsByTimeRange picks (time.go:158-235); the views are ordinary fragments, the union an ordinary program"""
+    for quantum, cases in V.TIME_ROW_CASES.items():
+        p = Pair()
+        p.field("f", "time", quantum=quantum)
+        p.field("plain")
+        for row, col, ts in V.TIME_BITS:
+            p.holder.set_bit("i", "f", row, col, timestamp=ts)
+        p.holder.set_bit("i", "plain", 1, 5)
+        p.sync_pending()
+        for q, exp in cases:
+            got = p.check_row(q)
+            assert [int(c) for c in got.columns()] == exp, (quantum, q)
+        assert [int(c) for c in p.check_row("Row(f=1)").columns()] == [2, 3, 4, 5, 6, 7]          # no range: the standard view
+        assert p.check_count("Count(Intersect(Row(f=1, from=2000-01-01T00:00, to=2001-01-01T00:00), Row(f=1)))") == 3
+        assert p.check_row("Row(f=1, from=2010-01-01T00:00, to=2011-01-01T00:00)").count == 0
+        with pytest.raises(X.QueryError, match="not a time-field"):
+            p.ex.execute("i", "Row(plain=1, from=2000-01-01T00:00)")
