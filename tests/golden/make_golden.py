@@ -55,15 +55,32 @@ def _parse_literal(text):
             return {"kind": "runs", "values": []}
         pairs = re.findall(r"\{(?:Start:\s*)?(\d+),\s*(?:Last:\s*)?(\d+)\}", body)
         return {"kind": "runs", "values": [[int(a), int(b)] for a, b in pairs]}
+    m = re.match(r"^(?:bitmap|Make)(LastBitSet|Full|Empty|OddBitsSet|EvenBitsSet|FirstBitSet)\(\)$", text)
+    if m:                                                        # helper-built bitmaps of roaring_helpers_test.go:77-135: named by archetype
+        name = m.group(1)
+        return {"kind": "archetype", "values": name[0].lower() + name[1:]}
+    m = re.match(r"^MakeBitmap\((.*)\)$", text)
+    if m:
+        return _parse_literal(m.group(1))
+    m = re.match(r"^(?:\[\]uint64|\[bitmapN\]uint64)(.*)$", text)
+    if m:                                                        # leading words of a 1024-word bitmap
+        return {"kind": "bitmap", "values": [int(x, 0) for x in re.findall(r"0x[0-9a-fA-F]+|\d+", m.group(1))]}
     if re.match(r"^-?\d+$", text):
         return {"kind": "int", "values": int(text)}
     return None
 
 
-def kernel_tables():
+# second batch: table tests whose operands include bitmap words / ranges / conversions (same literal-table shape)
+KERNEL_TABLE_FUNCS2 = ["TestIntersectBitmapRunBitmap", "TestIntersectBitmapRunArray", "TestUnionBitmapRun", "TestDifferenceRunBitmap", "TestDifferenceBitmapRun",
+                       "TestDifferenceBitmapArray", "TestDifferenceBitmapBitmap", "TestXorBitmapRun", "TestIntersectArrayBitmap", "TestIntersectionCountArrayBitmap2",
+                       "TestBitmapCountRuns", "TestArrayCountRuns", "TestArrayToBitmap", "TestBitmapToArray", "TestRunToBitmap", "TestBitmapToRun", "TestArrayToRun",
+                       "TestRunToArray", "TestBitmapSetRange", "TestBitmapZeroRange", "TestBitmapXorRange"]
+
+
+def kernel_tables(funcs=None):
     lines = open(os.path.join(REF, "roaring/roaring_internal_test.go")).read().split("\n")
     out = []
-    for fn in KERNEL_TABLE_FUNCS:
+    for fn in (funcs or KERNEL_TABLE_FUNCS):
         start = next(i for i, l in enumerate(lines) if l.startswith(f"func {fn}("))
         end = next(i for i in range(start + 1, len(lines)) if lines[i].startswith("func "))
         cur, cur_line = {}, None
@@ -89,6 +106,13 @@ if __name__ == "__main__":
     for c in kt:
         byf[c["func"]] = byf.get(c["func"], 0) + 1
     print(len(kt), byf)
+    kt2 = kernel_tables(KERNEL_TABLE_FUNCS2)
+    with open(os.path.join(HERE, "kernel_tables2.json"), "w") as f:
+        json.dump({"source": "roaring/roaring_internal_test.go (table tests listed in KERNEL_TABLE_FUNCS2)", "cases": kt2}, f, indent=0)
+    byf = {}
+    for c in kt2:
+        byf[c["func"]] = byf.get(c["func"], 0) + 1
+    print(len(kt2), byf)
     rows = combinations()
     with open(os.path.join(HERE, "container_combinations.json"), "w") as f:
         json.dump({"source": "roaring/roaring_internal_test.go:2974-3761 (TestContainerCombinations)", "rows": rows}, f, indent=0)

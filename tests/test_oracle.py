@@ -453,3 +453,81 @@ def test_intersect_variants_property():
     w = np.zeros(1024, dtype=np.uint64)
     w[0] = 0b1001
     assert O.Container.run(np.array([[1, 2]])).intersection_count(O.Container.bitmap(w)) == 0
+
+
+def test_kernel_table_goldens_bitmap_operands():
+    """99 more literal cases of roaring_internal_test.go table tests whose operands include bitmap words, bit ranges and
+    encoding conversions (TestIntersectBitmapRunBitmap :583, TestIntersectBitmapRunArray :641, TestUnionBitmapRun :1435,
+    TestDifferenceRunBitmap :1652, TestDifferenceBitmapRun :1709, TestDifferenceBitmapArray :1785,
+    TestDifferenceBitmapBitmap :1832, TestXorBitmapRun :2201, TestIntersectArrayBitmap :2766,
+    TestIntersectionCountArrayBitmap2 :305, TestBitmapCountRuns :1469, TestArrayCountRuns :1516, the six conversion
+    tests :1158-1392, TestBitmapSetRange :1122, TestBitmapZeroRange :1394, TestBitmapXorRange :2137), extracted by
+    tests/golden/make_golden.py.  Results are compared as sets, plus N / run counts where the reference states them."""
+    cases = json.load(open(os.path.join(GOLD, "kernel_tables2.json")))["cases"]
+    assert len(cases) == 99
+
+    def cont(lit):
+        if lit["kind"] == "array":
+            return O.Container.array(lit["values"])
+        if lit["kind"] == "runs":
+            return O.Container.run(np.array(lit["values"], dtype=np.uint16).reshape(-1, 2))
+        if lit["kind"] == "archetype":                           # bitmapFull() / bitmapOddBitsSet() / ...: roaring_helpers_test.go:77-135
+            return A.container(lit["values"], O.BITMAP)
+        w = np.zeros(1024, dtype=np.uint64)
+        w[: len(lit["values"])] = np.array(lit["values"], dtype=np.uint64)
+        return O.Container.bitmap(w)
+
+    def values(lit):
+        if lit["kind"] == "array":
+            return sorted(lit["values"])
+        if lit["kind"] == "runs":
+            return [v for s_, l_ in lit["values"] for v in range(s_, l_ + 1)]
+        if lit["kind"] == "archetype":
+            return A.archetype_values(lit["values"]).tolist()
+        return [64 * i + b for i, w in enumerate(lit["values"]) for b in range(64) if (w >> b) & 1]
+
+    binops = {"TestIntersectBitmapRunBitmap": ("intersect", "bitmap", "runs"), "TestIntersectBitmapRunArray": ("intersect", "bitmap", "runs"),
+              "TestUnionBitmapRun": ("union", "bitmap", "runs"), "TestDifferenceRunBitmap": ("difference", "runs", "bitmap"),
+              "TestDifferenceBitmapRun": ("difference", "bitmap", "runs"), "TestDifferenceBitmapArray": ("difference", "bitmap", "array"),
+              "TestDifferenceBitmapBitmap": ("difference", "abitmap", "bbitmap"), "TestXorBitmapRun": ("xor", "bitmap", "runs"),
+              "TestIntersectArrayBitmap": ("intersect", "array", "bitmap")}
+    range_ops = {"TestBitmapSetRange": "union", "TestBitmapZeroRange": "difference", "TestBitmapXorRange": "xor"}
+    conv = {"TestArrayToBitmap": ("array", O.BITMAP), "TestBitmapToArray": ("bitmap", O.ARRAY), "TestRunToBitmap": ("runs", O.BITMAP),
+            "TestBitmapToRun": ("bitmap", O.RUN), "TestArrayToRun": ("array", O.RUN), "TestRunToArray": ("runs", O.ARRAY)}
+    seen = set()
+    for c in cases:
+        fn, f, where = c["func"], c["fields"], (c["func"], c["line"])
+        seen.add(fn)
+        if fn in binops:
+            op, fa, fb = binops[fn]
+            a, b = cont(f[fa]), cont(f[fb])
+            if fn == "TestDifferenceBitmapArray":               # the reference passes test.bitmap[:1]: only the first word (:1823)
+                a = a.intersect(O.Container.run(np.array([[0, 63]], dtype=np.uint16)))
+            got = getattr(a, op)(b)
+            assert got.values().tolist() == values(f["exp"]), where
+            if "expN" in f:
+                assert got.n == f["expN"]["values"], where
+            if op == "intersect":
+                assert a.intersection_count(b) == b.intersection_count(a) == len(values(f["exp"])), where
+        elif fn == "TestIntersectionCountArrayBitmap2":
+            assert cont(f["array"]).intersection_count(cont(f["bitmap"])) == f["exp"]["values"], where
+        elif fn in ("TestBitmapCountRuns", "TestArrayCountRuns"):
+            src = f["bitmap"] if fn == "TestBitmapCountRuns" else f["array"]
+            assert cont(src).count_runs() == f["exp"]["values"], where
+        elif fn in range_ops:
+            a = cont(f["bitmap"])
+            r = O.Container.run(np.array([[f["start"]["values"], f["last"]["values"]]], dtype=np.uint16))
+            got = getattr(a, range_ops[fn])(r)
+            assert got.values().tolist() == values(f["exp"]) and got.n == f["expN"]["values"], where
+        else:
+            field, typ = conv[fn]
+            if field not in f:                                   # TestBitmapToRun :1305-1314 builds two inputs in code (words 1022/1023 set;
+                a = cont(f["exp"]).convert(O.BITMAP)             # getFullBitmap()): they are exactly the bit sets of the expected runs
+            else:
+                a = cont(f[field])
+            got = a.convert(typ)
+            assert got.typ == typ or got.n == 0, where
+            assert got.values().tolist() == values(f["exp"]) == a.values().tolist(), where
+            if f["exp"]["kind"] == "runs":
+                assert a.count_runs() == len(f["exp"]["values"]), where
+    assert seen == set(binops) | set(range_ops) | set(conv) | {"TestIntersectionCountArrayBitmap2", "TestBitmapCountRuns", "TestArrayCountRuns"}
