@@ -253,3 +253,31 @@ TIME_ROW_CASES = {
     "YMD": [("Row(f=1, from=1999-12-31T00:00, to=2003-01-01T03:00)", [2, 3, 4, 5, 6, 7]), ("Row(f=1, from=2002-01-01T00:00, to=2002-01-02T00:00)", [7]),
             ("Row(f=10, from=1999-12-31T00:00, to=2003-01-01T03:00)", [2])],
 }
+
+# ---------------------------------------------------------------------------------------------------
+# roaring/roaring_test.go Bitmap-level literal cases (multi-container operands).  Operand specs: ("vals", [...]),
+# ("range", start, stop, step), ("cat", spec, spec, ...).  (cite, a, b, op, ("count", n) | ("slice", [...]))
+# ---------------------------------------------------------------------------------------------------
+_EVEN10K = ("range", 0, 10000, 2)
+BITMAP_LEVEL_CASES = [
+    ("TestBitmap_Intersection :483", ("vals", [0, 2683177]), ("range", 628, 2683301, 1), "intersect", ("count", 1)),
+    ("TestBitmap_Difference :1041", ("vals", [0, 2683177]), ("range", 628, 2683301, 1), "difference", ("count", 1)),
+    ("TestBitmap_Difference2 :1053", ("vals", [0, 1, 2, 131072, 262144, SW + 5, SW + 7]), ("vals", [2, 3, 100000, 262144, 2 * SW + 1]), "difference",
+     ("slice", [0, 1, 131072, SW + 5, SW + 7])),
+    ("TestBitmap_Difference_Empty :1062", ("vals", [0, 2683177]), ("vals", []), "difference", ("count", 2)),
+    ("TestBitmap_DifferenceArrayArray :1071", ("vals", [0, 4, 8, 12, 16, 20]), ("vals", [1, 3, 6, 9, 12, 15, 18]), "difference", ("count", 5)),
+    ("TestBitmap_DifferenceArrayRun :1080", ("vals", [0, 4, 8, 12, 16, 20, 36, 40, 44]), ("vals", [1, 2, 3, 4, 5, 6, 7, 8, 9, 30, 31, 32, 33, 34, 35, 36]), "difference", ("count", 6)),
+    ("TestBitmap_Union :1091", ("vals", [0, 1000001, 1000002, 1000003]), ("vals", [0, 50000, 1000001, 1000002]), "union", ("count", 5)),
+    ("TestBitmap_Xor_ArrayArray :1143", ("vals", [0, 1000001, 1000002, 1000003]), ("vals", [0, 50000, 1000001, 1000002]), "xor", ("count", 2)),
+    ("TestBitmap_Xor_Empty :1160", ("vals", [0, 50000, 1000001, 1000002]), ("vals", []), "xor", ("count", 4)),
+    ("TestBitmap_Xor_ArrayBitmap :1169", ("vals", [1, 70, 200, 4097, 4098]), _EVEN10K, "xor", ("count", 4999)),
+    ("TestBitmap_Xor_ArrayBitmap :1176 (reverse)", _EVEN10K, ("vals", [1, 70, 200, 4097, 4098]), "xor", ("count", 4999)),
+    ("TestBitmap_Xor_ArrayBitmap :1188 (empty)", _EVEN10K, ("vals", []), "xor", ("count", 5000)),
+    ("TestBitmap_Xor_BitmapBitmap :1199", ("range", 1, 10000, 2), _EVEN10K, "xor", ("count", 10000)),
+    ("TestBitmap_IntersectionCount_ArrayArray :1283", ("vals", [0, 1000001, 1000002, 1000003]), ("vals", [0, 50000, 999998, 999999, 1000000, 1000001, 1000002]), "intersect", ("count", 3)),
+    ("TestBitmap_IntersectionCount_ArrayRun :1295", ("vals", [0, 1000001, 1000002, 1000003]), ("vals", [0, 1, 2, 3, 4, 5, 1000000, 1000002, 1000003, 1000004, 1000005, 1000006]), "intersect", ("count", 3)),
+    ("TestBitmap_IntersectionCount_RunRun :1308", ("vals", [3, 4, 5, 6, 7, 8, 1000001, 1000002, 1000003, 1000004]), ("vals", [0, 1, 2, 3, 4, 5, 1000000, 1000002, 1000003, 1000004, 1000005, 1000006]), "intersect", ("count", 6)),
+    ("TestBitmap_IntersectionCount_BitmapRun :1322", ("range", 3, 1000007, 2), ("vals", [0, 1, 2, 3, 4, 5, 1000000, 1000002, 1000003, 1000004, 1000005, 1000006]), "intersect", ("count", 4)),
+    ("TestBitmap_IntersectionCount_ArrayBitmap :1338", ("vals", [1, 70, 200, 4097, 4098]), ("range", 0, 10001, 2), "intersect", ("count", 3)),
+    ("TestBitmap_IntersectionCount_BitmapBitmap :1353", ("cat", _EVEN10K + (), ("vals", [10000, 1000, 2000])), ("cat", ("range", 1, 10002, 2), ("vals", [1000, 2000])), "intersect", ("count", 2)),
+]

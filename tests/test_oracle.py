@@ -531,3 +531,30 @@ def test_kernel_table_goldens_bitmap_operands():
             if f["exp"]["kind"] == "runs":
                 assert a.count_runs() == len(f["exp"]["values"]), where
     assert seen == set(binops) | set(range_ops) | set(conv) | {"TestIntersectionCountArrayBitmap2", "TestBitmapCountRuns", "TestArrayCountRuns"}
+
+
+def _spec_values(spec):
+    if spec[0] == "vals":
+        return np.array(sorted(set(spec[1])), dtype=np.uint64)
+    if spec[0] == "range":
+        return np.arange(spec[1], spec[2], spec[3], dtype=np.uint64)
+    return np.unique(np.concatenate([_spec_values(s) for s in spec[1:]]))
+
+
+def test_bitmap_level_goldens():
+    """roaring/roaring_test.go Bitmap-level literal cases (tests/golden/vectors.py:BITMAP_LEVEL_CASES): multi-container
+    operands, results as counts or slices; optimised operands (the reference calls Optimize() on several) and plain ones"""
+    for cite, a, b, op, (kind, exp) in V.BITMAP_LEVEL_CASES:
+        for optimise in (False, True):
+            A_, B_ = O.Bitmap.from_values(_spec_values(a)), O.Bitmap.from_values(_spec_values(b))
+            if optimise:
+                A_, B_ = O.Bitmap.from_bytes(A_.to_bytes()), O.Bitmap.from_bytes(B_.to_bytes())
+            got = getattr(A_, op)(B_)
+            if kind == "count":
+                assert got.count() == exp, cite
+            else:
+                assert got.slice().tolist() == exp, cite
+            if op == "intersect":
+                assert A_.intersection_count(B_) == B_.intersection_count(A_) == got.count(), cite
+            if op == "xor":
+                assert got.xor(got).count() == 0, cite

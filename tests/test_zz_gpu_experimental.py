@@ -457,3 +457,28 @@ def test_kernel_table_goldens_on_device():
             tot, per = p.holder.ctx.count(p.idx.id, [X.L.Op(X.L.OP_ROW, p.idx.fields["f"].id, 0, 0, 0, 0, 0, 0), X.L.Op(X.L.OP_ROW, p.idx.fields["f"].id, 0, 0, 1, 0, 0, 0),
                                                      X.L.Op(X.L.OP_INTERSECT, 0, 0, 2, 0, 0, 0, 0)], shards, per_shard=True)
             assert [int(x) for x in per] == [len(expect[k]) for k in shards] and tot == sum(len(expect[k]) for k in shards)
+
+
+def test_bitmap_level_goldens_on_device():
+    """roaring/roaring_test.go Bitmap-level cases: operand a = row 0 of field "a", operand b = row 0 of field "b", values are
+    columns (so the larger cases span three shards); counts through Count(op(...)), slices through the Row bytes"""
+    from tests.test_oracle import _spec_values
+    from oracle import oracle as O
+    names = {"intersect": "Intersect", "difference": "Difference", "union": "Union", "xor": "Xor"}
+    for cite, a, b, op, (kind, exp) in V.BITMAP_LEVEL_CASES:
+        p = Pair(track_existence=False)
+        p.field("a")
+        p.field("b")
+        for fld, spec in (("a", a), ("b", b)):
+            vals = _spec_values(spec)
+            for shard in np.unique(vals >> np.uint64(20)).tolist():
+                part = vals[(vals >> np.uint64(20)) == np.uint64(shard)] & np.uint64((1 << 20) - 1)
+                p.load(fld, X.VIEW_STANDARD, int(shard), O.Bitmap.from_values(part).to_bytes())
+        if not p.idx.shards:
+            continue
+        q = f"{names[op]}(Row(a=0), Row(b=0))"
+        if kind == "count":
+            assert p.check_count(f"Count({q})") == exp, cite
+            assert p.check_row(q).count == exp, cite
+        else:
+            assert [int(c) for c in p.check_row(q).columns()] == exp, cite
