@@ -280,4 +280,12 @@ BITMAP_LEVEL_CASES = [
     ("TestBitmap_IntersectionCount_BitmapRun :1322", ("range", 3, 1000007, 2), ("vals", [0, 1, 2, 3, 4, 5, 1000000, 1000002, 1000003, 1000004, 1000005, 1000006]), "intersect", ("count", 4)),
     ("TestBitmap_IntersectionCount_ArrayBitmap :1338", ("vals", [1, 70, 200, 4097, 4098]), ("range", 0, 10001, 2), "intersect", ("count", 3)),
     ("TestBitmap_IntersectionCount_BitmapBitmap :1353", ("cat", _EVEN10K + (), ("vals", [10000, 1000, 2000])), ("cat", ("range", 1, 10002, 2), ("vals", [1000, 2000])), "intersect", ("count", 2)),
+    # row_test.go: shard-spanning rows (Row.Merge is a union of disjoint-or-equal segments, row.go:202)
+    ("TestRow_Merge #0 row_test.go:21", ("vals", [1, 2, 3, SW + 1, 2 * SW]), ("vals", [3, 4, 5]), "union", ("count", 7)),
+    ("TestRow_Merge #1 row_test.go:26", ("vals", []), ("vals", [2, 66000, 70000, 70001, 70002, 70003, 70004]), "union", ("count", 7)),
+    ("TestRow_Xor row_test.go:46", ("vals", [0, 1, SW]), ("vals", [0, 2 * SW]), "xor", ("slice", [1, SW, 2 * SW])),
+    ("TestRow_Xor (reverse) row_test.go:58", ("vals", [0, 2 * SW]), ("vals", [0, 1, SW]), "xor", ("slice", [1, SW, 2 * SW])),
+    ("TestRow_Union_Segment row_test.go:68", ("vals", [0, 1, SW]), ("vals", [0, 2 * SW]), "union", ("slice", [0, 1, SW, 2 * SW])),
+    ("TestRow_Difference_Segment row_test.go:89", ("vals", [0, 1, SW]), ("vals", [0, 2 * SW]), "difference", ("slice", [1, SW])),
+    ("TestRow_IsEmpty row_test.go:103", ("vals", [0, 2 * SW]), ("vals", [1, SW]), "intersect", ("count", 0)),
 ]
