@@ -289,3 +289,10 @@ BITMAP_LEVEL_CASES = [
     ("TestRow_Difference_Segment row_test.go:89", ("vals", [0, 1, SW]), ("vals", [0, 2 * SW]), "difference", ("slice", [1, SW])),
     ("TestRow_IsEmpty row_test.go:103", ("vals", [0, 2 * SW]), ("vals", [1, SW]), "intersect", ("count", 0)),
 ]
+
+# ---------------------------------------------------------------------------------------------------
+# fragment_internal_test.go TestFragmentPositionsForValue (BSI bit layout: exists row 0, sign row 1, bit i row 2+i):
+# (column, bitDepth, value, positions set).  TestIntLTRegression: value 33 at depth 6, Row(v < 33) is empty.
+# ---------------------------------------------------------------------------------------------------
+BSI_POSITIONS = [(0, 1, 0, [0]), (0, 3, 0, [0]), (1, 3, 0, [1]), (0, 1, 1, [0, 2 * SW]), (0, 4, 10, [0, 3 * SW, 5 * SW]), (0, 5, 10, [0, 3 * SW, 5 * SW])]
+BSI_LT_REGRESSION = (1, 6, 33)

@@ -558,3 +558,25 @@ def test_bitmap_level_goldens():
                 assert A_.intersection_count(B_) == B_.intersection_count(A_) == got.count(), cite
             if op == "xor":
                 assert got.xor(got).count() == 0, cite
+
+
+def test_bsi_layout_goldens():
+    """fragment_internal_test.go TestFragmentPositionsForValue / TestIntLTRegression: the fragment bit layout both test
+    helpers and the host mirror's set_value write, and the LT edge case it was written for"""
+    from featurebase_b200 import executor as X
+
+    class Sink:
+        def load_fragment(self, *a):
+            pass
+    for col, depth, value, exp in V.BSI_POSITIONS:
+        assert sorted(H.bsi_fragment_positions({col: value}, depth)) == exp
+        h = X.Holder(ctx=Sink())
+        idx = h.create_index("i", track_existence=False)
+        idx.create_field("v", "int", min=-(1 << depth) + 1, max=(1 << depth) - 1, bit_depth=depth)
+        h.set_value("i", "v", col, value)
+        (key, bits), = h._pending.items()
+        assert key == ("i", "v", X.VIEW_BSI, 0) and sorted(bits) == exp
+    col, depth, value = V.BSI_LT_REGRESSION
+    frag = H.bsi_fragment({col: value}, depth)
+    assert frag.range_op("<", depth, value).count() == 0
+    assert frag.range_op("<=", depth, value).slice().tolist() == [col]
