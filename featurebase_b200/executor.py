@@ -243,7 +243,7 @@ class Executor:
             if c.name == "GroupBy":
                 return self._groupby(idx, c, shards)
             if c.name == "Rows":
-                return self._rows(idx, c, shards)
+                return self._rows(idx, c, shards, standalone=True)
             if c.name == "Sum":
                 return self._sum(idx, c, shards)
             if c.name in ("Min", "Max"):
@@ -403,8 +403,13 @@ class Executor:
         pairs = [(int(i), int(n)) for i, n in zip(rid, cnt)]
         return pairs[:k] if k else pairs
 
-    def _rows(self, idx, c, shards):                             # executeRows :5311 (row ids present; limit / previous / in)
-        f = self._field(idx, c.args["_field"] if "_field" in c.args else c.args.get("field"))
+    def _rows(self, idx, c, shards, standalone=False):           # executeRows (row ids present; limit / previous / in)
+        name = c.args["_field"] if "_field" in c.args else c.args.get("field")
+        if name is None:
+            raise QueryError("missing field in Rows call")
+        f = self._field(idx, name)
+        if standalone and f.type in ("int", "bool"):
+            raise QueryError(f"{f.type} fields not supported by Rows() query")
         if "column" in c.args or "like" in c.args:
             raise QueryError("Rows(): column / like arguments are not supported by this mirror")
         rid, _ = self.ctx.row_counts(idx.id, f.id, VIEW_BSI if f.type == "int" else VIEW_STANDARD, shards)
@@ -562,6 +567,8 @@ class Executor:
             if ch.name != "Rows":
                 raise QueryError(f"'{ch.name}' is not a valid child query for GroupBy, must be 'Rows'")
             name = ch.args.get("_field", ch.args.get("field"))
+            if name is None:
+                raise QueryError("missing field in Rows call")
             f = self._field(idx, name)
             fields.append(f)
             pre = pql.Call("Rows", {k: v for k, v in ch.args.items() if k != "previous"})     # previous positions the iterator, it does not drop rows

@@ -299,6 +299,19 @@ def test_groupby_postprocessing_goldens():
     assert agg == [((10, 100), 2, 110)]
     with pytest.raises(X.QueryError):
         p.ex.execute("i", 'GroupBy(Rows(general), sort="rowid")')
+    # executor_test.go:5311-5341 TestExecutor_Execute_Rows (the `column=` form needs a column-literal operand: not mirrored)
+    q = Pair()
+    q.field("general")
+    q.field("integer", "int", min=-1000, max=1000)
+    for r, c in [(10, 0), (10, (1 << 20) + 1), (11, 2), (11, (1 << 20) + 2), (12, 2), (12, (1 << 20) + 2), (13, 3)]:
+        q.holder.set_bit("i", "general", r, c)
+    q.sync_pending()
+    for query, exp in (("Rows(general)", [10, 11, 12, 13]), ("Rows(field=general)", [10, 11, 12, 13]), ("Rows(general, limit=2)", [10, 11]),
+                       ("Rows(general, previous=10,limit=2)", [11, 12]), ("Rows(general, in=[11, 13, 99])", [11, 13])):
+        assert q.ex.execute("i", query)[0] == exp, query
+    for bad, msg in (("Rows(integer)", "int fields not supported"), ("GroupBy(Rows())", "missing field in Rows call"), ("Rows(general, column=2)", "not supported")):
+        with pytest.raises(X.QueryError, match=msg):
+            q.ex.execute("i", bad)
 
 
 def test_percentile_vs_reference_helper():
