@@ -19,6 +19,7 @@ SHARD_WIDTH = 1 << 20                    # shardwidth/helper.go:13
 VIEW_STANDARD = 0                        # view.go:28 "standard"
 VIEW_BSI = 1                             # view.go:30 "bsig_<field>"
 EXISTENCE_FIELD = "_exists"              # holder.go:33
+SCRATCH_FIELD = "_embedded"              # mirror-only: holds rows embedded in a query (ConstRow / Precomputed operands)
 
 
 class Field:
@@ -178,6 +179,25 @@ class Holder:
         if idx.track_existence:
             self._pending.setdefault((index, EXISTENCE_FIELD, VIEW_STANDARD, shard), set()).add(c)
 
+    def embed_row(self, index, columns):
+        """A caller-provided operand row (pql ConstRow, or the *Row a Precomputed call carries per shard,
+        executePrecomputedCallShard :5535): stored as the next row of a hidden scratch field, whose touched shards are
+        re-sent through the normal residency call, and then addressed by an ordinary Row op.  Returns (field, row id)."""
+        idx = self.indexes[index]
+        f = idx.fields.get(SCRATCH_FIELD) or idx.create_field(SCRATCH_FIELD)
+        store = self.__dict__.setdefault("_scratch", {}).setdefault(index, {})          # shard -> set of fragment positions
+        row = self.__dict__.setdefault("_scratch_rows", {}).get(index, 0)
+        self._scratch_rows[index] = row + 1
+        touched = set()
+        for col in columns:
+            col = int(col)
+            store.setdefault(col // SHARD_WIDTH, set()).add(row * SHARD_WIDTH + col % SHARD_WIDTH)
+            touched.add(col // SHARD_WIDTH)
+        for shard in touched:
+            bits = store[shard]
+            self.ctx.load_fragment(idx.id, f.id, VIEW_STANDARD, shard, roaring_io.encode(np.fromiter(bits, dtype=np.uint64, count=len(bits))))
+        return f, row
+
     def sync(self):
         """serialises pending bits per fragment (merged with nothing: test fragments are written once)"""
         for (index, field, view, shard), bits in self._pending.items():
@@ -233,6 +253,7 @@ class Executor:
 
     # executeCall :679
     def _execute_call(self, idx, c, shards):
+        self._cur_shards = shards                                # (UnionRows runs its Rows / TopN children over the same shard list)
         try:
             if c.name == "Count":
                 return self._count(idx, c, shards)
@@ -287,6 +308,39 @@ class Executor:
                 raise QueryError(f"index does not support existence tracking: {idx.name}")
             self._emit(idx, c.children[0], ops)
             ops.append(L.Op(L.OP_NOT, idx.fields[EXISTENCE_FIELD].id, VIEW_STANDARD, 1, 0, 0, 0, 0))
+            return
+        if n == "ConstRow":                                      # executeConstRow :5604-5694: the listed columns (∩ existence when tracked)
+            cols = c.args.get("columns")
+            if not isinstance(cols, (list, tuple)):
+                raise QueryError("missing columns list")
+            if not cols:
+                ops.append(L.Op(L.OP_EMPTY, 0, 0, 0, 0, 0, 0, 0))
+                return
+            f, row = self.holder.embed_row(idx.name, cols)
+            ops.append(L.Op(L.OP_ROW, f.id, VIEW_STANDARD, 0, row, 0, 0, 0))
+            if idx.track_existence:
+                ops.append(L.Op(L.OP_ALL, idx.fields[EXISTENCE_FIELD].id, VIEW_STANDARD, 0, 0, 0, 0, 0))
+                ops.append(L.Op(L.OP_INTERSECT, 0, 0, 2, 0, 0, 0, 0))
+            return
+        if n == "UnionRows":                                     # executeUnionRows :5696-5779 -> Union(Row(..), ...) over the children's row ids
+            leaves = []
+            for ch in c.children:
+                if ch.name == "Rows":
+                    fld = self._field(idx, ch.args.get("_field", ch.args.get("field")))
+                    leaves += [(fld, r) for r in self._rows(idx, ch, self._cur_shards, standalone=True)]
+                elif ch.name in ("TopN", "TopK"):
+                    fld = self._field(idx, ch.args["_field"])
+                    pairs = self._topn(idx, ch, self._cur_shards) if ch.name == "TopN" else self._topk(idx, ch, self._cur_shards)
+                    leaves += [(fld, r) for r, _ in pairs]
+                else:
+                    raise QueryError(f"UnionRows doesn't support {ch.name}")
+            if not leaves:
+                ops.append(L.Op(L.OP_EMPTY, 0, 0, 0, 0, 0, 0, 0))
+                return
+            for fld, r in leaves:
+                ops.append(L.Op(L.OP_ROW, fld.id, VIEW_STANDARD, 0, int(r), 0, 0, 0))
+            if len(leaves) > 1:
+                ops.append(L.Op(L.OP_UNION, 0, 0, len(leaves), 0, 0, 0, 0))
             return
         if n == "All":                                           # executeAllCallShard :5781
             if not idx.track_existence:
@@ -410,9 +464,17 @@ class Executor:
         f = self._field(idx, name)
         if standalone and f.type in ("int", "bool"):
             raise QueryError(f"{f.type} fields not supported by Rows() query")
-        if "column" in c.args or "like" in c.args:
-            raise QueryError("Rows(): column / like arguments are not supported by this mirror")
-        rid, _ = self.ctx.row_counts(idx.id, f.id, VIEW_BSI if f.type == "int" else VIEW_STANDARD, shards)
+        if "like" in c.args:
+            raise QueryError("Rows(): like is not supported by this mirror")
+        if "in" in c.args and "column" in c.args:
+            raise QueryError("Rows call with 'in' does not support other arguments")
+        filt = None
+        if "column" in c.args:                                   # rows that hold this column (BitmapColumnFilter roaring/filter.go:118): a one-column filter row
+            col = int(c.args["column"])
+            ef, erow = self.holder.embed_row(idx.name, [col])
+            filt = [L.Op(L.OP_ROW, ef.id, VIEW_STANDARD, 0, erow, 0, 0, 0)]
+            shards = [s for s in shards if s == col // SHARD_WIDTH]
+        rid, _ = self.ctx.row_counts(idx.id, f.id, VIEW_BSI if f.type == "int" else VIEW_STANDARD, shards, filter_ops=filt)
         out = sorted(int(r) for r in rid)
         if "in" in c.args:
             keep = {int(r) for r in c.args["in"]}

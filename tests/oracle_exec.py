@@ -72,6 +72,18 @@ class OracleIndex:
             return ex.difference(self.eval_shard(c.children[0], shard))
         if n == "All":
             return self.row(X.EXISTENCE_FIELD, X.VIEW_STANDARD, 0, shard)
+        if n == "ConstRow":                                      # executeConstRowShard :5674-5694
+            cols = [int(x) for x in c.args["columns"] if int(x) // X.SHARD_WIDTH == shard]
+            out = O.Bitmap.from_values(cols)
+            return out.intersect(self.row(X.EXISTENCE_FIELD, X.VIEW_STANDARD, 0, shard)) if self.idx.track_existence else out
+        if n == "UnionRows":                                     # plain Rows(f) children only: every row of the shard's fragment (fragment.unionRows)
+            out = O.Bitmap()
+            for ch in c.children:
+                assert ch.name == "Rows" and set(ch.args) <= {"_field", "field"}
+                fr = self.frag(ch.args.get("_field", ch.args.get("field")), X.VIEW_STANDARD, shard)
+                for r in (fr.rows().tolist() if fr is not None else []):
+                    out = out.union(fr.row(r, shard))
+            return out
         raise KeyError(n)
 
     def _bsi(self, fld, cond, shard):

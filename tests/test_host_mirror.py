@@ -75,6 +75,10 @@ def test_time_quantum(oracle_backed):
     E.test_time_quantum_rows()
 
 
+def test_embedded_rows(oracle_backed):
+    E.test_embedded_rows_constrow_unionrows()
+
+
 def test_percentile(oracle_backed):
     E.test_percentile_vs_reference_helper()
 

@@ -309,7 +309,8 @@ def test_groupby_postprocessing_goldens():
     for query, exp in (("Rows(general)", [10, 11, 12, 13]), ("Rows(field=general)", [10, 11, 12, 13]), ("Rows(general, limit=2)", [10, 11]),
                        ("Rows(general, previous=10,limit=2)", [11, 12]), ("Rows(general, in=[11, 13, 99])", [11, 13])):
         assert q.ex.execute("i", query)[0] == exp, query
-    for bad, msg in (("Rows(integer)", "int fields not supported"), ("GroupBy(Rows())", "missing field in Rows call"), ("Rows(general, column=2)", "not supported")):
+    for bad, msg in (("Rows(integer)", "int fields not supported"), ("GroupBy(Rows())", "missing field in Rows call"),
+                     ("Rows(general, in=[1, 2], column=3)", "does not support other arguments")):
         with pytest.raises(X.QueryError, match=msg):
             q.ex.execute("i", bad)
 
@@ -495,3 +496,37 @@ def test_bitmap_level_goldens_on_device():
             assert p.check_row(q).count == exp, cite
         else:
             assert [int(c) for c in p.check_row(q).columns()] == exp, cite
+
+
+def test_embedded_rows_constrow_unionrows():
+    """executor_test.go:1195-1234 (ConstRow with / without existence tracking), :7264-7287 (UnionRows over Rows / TopN),
+    :5339-5340 (Rows(f, column=c)); the caller-provided row is an ordinary fragment of a scratch field on the device
+    (what a Precomputed operand becomes, executePrecomputedCallShard :5535)"""
+    SW = 1 << 20
+    for track, exp in ((False, [2, 6, 7]), (True, [2, 6])):
+        p = Pair(track_existence=track)
+        p.field("h")
+        for r, c in ((1, 2), (3, 4), (5, 6)):
+            p.holder.set_bit("i", "h", r, c)
+        p.sync_pending()
+        assert [int(c) for c in p.check_row("ConstRow(columns=[2,6,7])").columns()] == exp
+        assert p.check_count("Count(Intersect(ConstRow(columns=[2,4,9]), Row(h=3)))") == 1
+        assert p.ex.execute("i", "ConstRow(columns=[])")[0].count == 0
+    p = Pair(track_existence=False)
+    p.field("s")
+    for c, r in ((0, 1), (1, 2), (2, 3), (3, 1), (3, 5), (SW + 9, 2)):
+        p.holder.set_bit("i", "s", r, c)
+    p.sync_pending()
+    assert p.ex.execute("i", "Count(UnionRows(TopN(s, n=1)))", [0])[0] == 2         # row 1: columns 0, 3
+    assert p.check_count("Count(UnionRows(Rows(s)))", [0]) == 4
+    assert p.check_count("Count(UnionRows(Rows(s)))") == 5
+    assert [int(c) for c in p.check_row("UnionRows(Rows(s))").columns()] == [0, 1, 2, 3, SW + 9]
+    assert p.ex.execute("i", "Rows(s, column=3)")[0] == [1, 5]
+    assert p.ex.execute("i", f"Rows(s, column={SW + 9})")[0] == [2]
+    assert p.ex.execute("i", "Rows(s, column=77)")[0] == []
+    q = Pair()
+    q.field("general")
+    for r, c in [(10, 0), (10, SW + 1), (11, 2), (11, SW + 2), (12, 2), (12, SW + 2), (13, 3)]:
+        q.holder.set_bit("i", "general", r, c)
+    q.sync_pending()
+    assert q.ex.execute("i", "Rows(general, column=2)")[0] == [11, 12]               # executor_test.go:5339
