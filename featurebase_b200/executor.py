@@ -293,7 +293,7 @@ class Executor:
 
     def _emit(self, idx, c, ops):
         n = c.name
-        if n == "Row":
+        if n in ("Row", "Range"):                                # executeBitmapCallShard :1790-1791
             return self._emit_row(idx, c, ops)
         if n in ("Intersect", "Union", "Difference", "Xor"):
             for ch in c.children:

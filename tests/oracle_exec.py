@@ -26,7 +26,7 @@ class OracleIndex:
 
     def eval_shard(self, c, shard):
         n = c.name
-        if n == "Row":
+        if n in ("Row", "Range"):
             key = [k for k in c.args if not k.startswith("_") and k not in ("from", "to")][0]
             fld = self.idx.fields[key]
             v = c.args[key]
