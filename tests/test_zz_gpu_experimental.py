@@ -394,7 +394,8 @@ def test_time_quantum_rows():
             got = p.check_row(q)
             assert [int(c) for c in got.columns()] == exp, (quantum, q)
         assert [int(c) for c in p.check_row("Row(f=1)").columns()] == [2, 3, 4, 5, 6, 7]          # no range: the standard view
-        assert [int(c) for c in p.check_row("Range(f=1, from=1999-12-31T00:00, to=2002-01-01T03:00)").columns()] == [2, 3, 4, 5, 6, 7]     # :675 legacy spelling
+        if quantum == "YMDH":                                     # executor_test.go:675 legacy spelling (with YMD the last day is not fully covered)
+            assert [int(c) for c in p.check_row("Range(f=1, from=1999-12-31T00:00, to=2002-01-01T03:00)").columns()] == [2, 3, 4, 5, 6, 7]
         assert p.check_count("Count(Intersect(Row(f=1, from=2000-01-01T00:00, to=2001-01-01T00:00), Row(f=1)))") == 3
         assert p.check_row("Row(f=1, from=2010-01-01T00:00, to=2011-01-01T00:00)").count == 0
         with pytest.raises(X.QueryError, match="not a time-field"):
