@@ -281,7 +281,7 @@ static int add_fragment_locked(fbgpu_ctx* c, uint32_t fv, uint64_t shard, const 
     }
     // payloads: row-major (key order) by default: a row's 16 containers are contiguous, which is what the common
     // few-rows-of-many query streams.  FBGPU_LAYOUT_SLOT_MAJOR=1 stores all rows of slot 0, then slot 1, ... so that a
-    // (shard, slot) unit's consecutive rows are adjacent (measured: -20 % on 2-row bitmap queries; profiles/README.md).
+    // (shard, slot) unit's consecutive rows are adjacent (measured: no significant difference; profiles/README.md).
     // experimental striped order: only for array-dominated fragments, so that bitmap-heavy views (BSI planes) keep every
     // array sorted and stay eligible for the word-parallel kernel, whose slice search needs sorted arrays
     const bool stripe = c->stripe_arrays && (uint64_t)hf.n_arr * 8 > (uint64_t)hf.n_bmp + hf.n_run;
