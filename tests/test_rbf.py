@@ -185,3 +185,33 @@ def test_wal_overlay(lib):
     assert dump(lib, b"".join(old), wal + bytes(junk)) == exp
     # a WAL without any meta page commits nothing
     assert dump(lib, b"".join(old), wal[:PAGE]) == dump(lib, b"".join(old))
+
+
+def test_corrupted_and_truncated_files_fail_cleanly(lib):
+    """random byte flips (biased to page headers, cell indexes and cell headers) and truncations: the walker either reports
+    an error or returns cells whose payload views lie inside the file — it must never read out of bounds"""
+    rng = np.random.default_rng(1)
+    _, conts = _fragment_containers(70, 1)
+    data = W.build({"~f;standard<": conts, "~g;standard<": conts[:50]})
+    pages = len(data) // PAGE
+    errors = 0
+    for _ in range(600):
+        b = bytearray(data)
+        for _ in range(int(rng.integers(1, 6))):
+            pg = int(rng.integers(0, pages))
+            off = pg * PAGE + int(rng.choice([rng.integers(0, 64), rng.integers(0, 2048), rng.integers(0, PAGE)]))
+            b[off] = int(rng.integers(0, 256))
+        try:
+            out = dump(lib, bytes(b))
+        except ValueError:
+            errors += 1
+            continue
+        for cells in out.values():
+            for key, typ, elem_n, bit_n, payload in cells:
+                assert len(payload) == (2 * elem_n if typ == W.C_ARRAY else 4 * elem_n if typ == W.C_RLE else PAGE)
+    assert errors > 20
+    for cut in range(0, len(data), 4096):
+        try:
+            dump(lib, data[:cut])
+        except ValueError:
+            pass
