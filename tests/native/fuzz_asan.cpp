@@ -4,6 +4,7 @@
 // touching every byte of every payload view they return.  Any out-of-bounds read aborts under ASan.
 #include "rbf_reader.h"
 #include "roaring_parse.h"
+#include "program_compiler.h"
 #include <cstdio>
 #include <cstdlib>
 #include <random>
@@ -48,6 +49,18 @@ int main(int argc, char** argv) {
                 ok++;
             } else bad++;
         }
+    }
+    for (int it = 0; it < iters * 20; it++) {          // program compiler: arbitrary (mostly malformed) post-order programs
+        int n = (int)(rng() % 12);
+        std::vector<fbgpu_op> ops((size_t)n);
+        for (auto& o : ops) {
+            o.opcode = (uint32_t)(rng() % 12); o.field = (uint32_t)(rng() % 4); o.view = (uint32_t)(rng() % 3); o.argc = (uint32_t)(rng() % 5 == 0 ? rng() : rng() % 4);
+            o.a = rng() % 5 == 0 ? rng() : rng() % 70; o.b = rng() % 9; o.lo = (int64_t)rng() >> (rng() % 64); o.hi = (int64_t)rng() >> (rng() % 64);
+        }
+        std::vector<fbgpu::DevOp> prog; int depth = 0; fbgpu::Error e;
+        fbgpu::ViewLookup lookup = [](uint32_t f, uint32_t v) { return f == 3 ? fbgpu::kNoView : f * 4 + v; };
+        if (fbgpu::compile(ops.data(), n, lookup, prog, depth, e) == 0) { ok++; sink += prog.size() + (uint64_t)depth; if (depth < 1 || depth > 15) { printf("bad depth %d\n", depth); return 1; } }
+        else bad++;
     }
     printf("fuzz_asan done ok=%llu rejected=%llu sink=%llu\n", (unsigned long long)ok, (unsigned long long)bad, (unsigned long long)sink);
     return 0;
