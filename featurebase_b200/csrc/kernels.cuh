@@ -13,6 +13,7 @@
 #include <stdint.h>
 #include "fbgpu_types.h"
 #include "bitaddr.h"
+#include "wp_machine.h"
 
 namespace fbgpu {
 
@@ -826,6 +827,13 @@ eval_wordpar_kernel(StoreRef st, const DevOp* __restrict__ prog, int n_ops,
             }
         };
         const uint4 z = make_uint4(0, 0, 0, 0);
+#if defined(FBGPU_WP_UNROLL3) && FBGPU_WP_SLICES == 1
+        // experimental op loop with fixed register roles (wp_machine.h); same program semantics
+        uint4 T[1];
+        T[0] = wp_run_unrolled<uint4>(n_ops, nr, [&](int k) { return ops[k].opc; }, [&](int k) { return ops[k].is_row != 0; },
+                                      [&](int ri) { return (int)rowops[ri]; }, [&](int ri) { uint4 d[1]; fetch(d, ri); return d[0]; });
+        const int depth_now = 1;                       // (wp_run_unrolled already returns zero for an empty stack)
+#else
         // prefetch ring: operands of the next three row ops are in flight while the current one is applied
         uint4 p0[kWpSlices], p1[kWpSlices], p2[kWpSlices];
 #pragma unroll
@@ -869,6 +877,7 @@ eval_wordpar_kernel(StoreRef st, const DevOp* __restrict__ prog, int n_ops,
             if (opc == D_PUSH_ROW) depth_now++;
             if (ri < nr) fetch(p2, ri++);
         }
+#endif
         uint32_t cnt = 0;
 #pragma unroll
         for (int q = 0; q < kWpSlices; q++) {

@@ -1,0 +1,93 @@
+// Op loop of the word-parallel program machine (eval_wordpar_kernel), restructured to keep every value in a register with a
+// fixed role.  EXPERIMENTAL: compiled into the kernel only with -DFBGPU_WP_UNROLL3 (not measured yet); the default kernel
+// keeps its original loop.  Host-compilable on purpose: tests/test_wp_machine.py checks it on the CPU against a plain
+// stack-machine model for random programs.
+//
+// Why: in the original loop the operand prefetch ring (p0 <- p1 <- p2) rotates and the 4-deep register stack shifts inside
+// one generic loop body, so ptxas emits ~40-60 register moves per op around 4 useful logic instructions (cuobjdump: blocks
+// of IMAD.MOV per switch case) — the "interpretive overhead" profiles/README.md names as that kernel's limiter.  Here the
+// loop walks ROW ops three at a time; ring slot j always serves row op 3t+j, so there is no rotation, and the ops that do
+// move the stack (PUSH_EMPTY / SWAP / POP / binary ops, rare in BSI sweeps) run in a separate small loop between row ops.
+#pragma once
+#include <stdint.h>
+
+#include "bitaddr.h"        // FBGPU_HD
+#include "fbgpu_types.h"
+
+namespace fbgpu {
+
+template <class V>
+struct WpStack {            // T = top, B = below, S2, S3 deeper (the host checks depth <= 4)
+    V T, B, S2, S3; int depth;
+};
+
+template <class V> FBGPU_HD V wp_and(V a, V b) { V r; r.x = a.x & b.x; r.y = a.y & b.y; r.z = a.z & b.z; r.w = a.w & b.w; return r; }
+template <class V> FBGPU_HD V wp_or(V a, V b) { V r; r.x = a.x | b.x; r.y = a.y | b.y; r.z = a.z | b.z; r.w = a.w | b.w; return r; }
+template <class V> FBGPU_HD V wp_xor(V a, V b) { V r; r.x = a.x ^ b.x; r.y = a.y ^ b.y; r.z = a.z ^ b.z; r.w = a.w ^ b.w; return r; }
+template <class V> FBGPU_HD V wp_andn(V a, V b) { V r; r.x = a.x & ~b.x; r.y = a.y & ~b.y; r.z = a.z & ~b.z; r.w = a.w & ~b.w; return r; }
+template <class V> FBGPU_HD V wp_zero() { V r; r.x = 0; r.y = 0; r.z = 0; r.w = 0; return r; }
+
+// ops that take no row operand
+template <class V>
+FBGPU_HD void wp_stack_op(WpStack<V>& s, uint8_t opc) {
+    if (opc == D_PUSH_EMPTY) { s.S3 = s.S2; s.S2 = s.B; s.B = s.T; s.T = wp_zero<V>(); s.depth++; }
+    else if (opc == D_SWAP) { V t = s.T; s.T = s.B; s.B = t; }
+    else if (opc == D_POP) { s.T = s.B; s.B = s.S2; s.S2 = s.S3; s.depth--; }
+    else {
+        s.T = opc == D_AND ? wp_and(s.B, s.T) : opc == D_OR ? wp_or(s.B, s.T) : opc == D_ANDNOT ? wp_andn(s.B, s.T) : wp_xor(s.B, s.T);
+        s.B = s.S2; s.S2 = s.S3; s.depth--;
+    }
+}
+// ops that take a row operand x.  Every case updates T or B in place; PUSH_ROW is executed as PUSH_EMPTY (the only
+// stack shift, kept out of the hot switch) followed by T |= x, so that the switch arms leave all other registers alone
+// and the compiler has nothing to copy where they join.
+template <class V>
+FBGPU_HD void wp_row_op(WpStack<V>& s, uint8_t opc, V x) {
+    if (opc == D_PUSH_ROW) { wp_stack_op(s, D_PUSH_EMPTY); opc = D_OR_ROW; }
+    if (opc == D_ORAND_ROW || opc == D_ORANDNOT_ROW) {
+        if (opc == D_ORANDNOT_ROW) { x.x = ~x.x; x.y = ~x.y; x.z = ~x.z; x.w = ~x.w; }
+        s.B = wp_or(s.B, wp_and(s.T, x));
+    } else if (opc == D_OR_ROW) s.T = wp_or(s.T, x);
+    else if (opc == D_XOR_ROW) s.T = wp_xor(s.T, x);
+    else {                                                          // D_AND_ROW / D_ANDNOT_ROW
+        if (opc == D_ANDNOT_ROW) { x.x = ~x.x; x.y = ~x.y; x.z = ~x.z; x.w = ~x.w; }
+        s.T = wp_and(s.T, x);
+    }
+}
+
+// opc(k): opcode of program op k; is_row(k); rowops[ri]: program index of the ri-th row op; fetch(ri): its operand slice.
+// Returns the top of stack (zero when the program leaves the stack empty).
+template <class V, class OpcAt, class IsRowAt, class RowOpAt, class Fetch>
+FBGPU_HD V wp_run_unrolled(int n_ops, int nr, OpcAt opc_at, IsRowAt is_row_at, RowOpAt rowop_at, Fetch fetch) {
+    WpStack<V> s; s.T = s.B = s.S2 = s.S3 = wp_zero<V>(); s.depth = 0;
+    V p0 = wp_zero<V>(), p1 = p0, p2 = p0;
+    if (0 < nr) p0 = fetch(0);
+    if (1 < nr) p1 = fetch(1);
+    if (2 < nr) p2 = fetch(2);
+    int k = 0;                                         // next program op to execute
+    for (int base = 0; base < nr; base += 3) {
+        {   // row op base+0, operand p0
+            const int kr = rowop_at(base);
+            for (; k < kr; k++) wp_stack_op(s, opc_at(k));
+            wp_row_op(s, opc_at(kr), p0); k = kr + 1;
+            if (base + 3 < nr) p0 = fetch(base + 3);
+        }
+        if (base + 1 < nr) {
+            const int kr = rowop_at(base + 1);
+            for (; k < kr; k++) wp_stack_op(s, opc_at(k));
+            wp_row_op(s, opc_at(kr), p1); k = kr + 1;
+            if (base + 4 < nr) p1 = fetch(base + 4);
+        }
+        if (base + 2 < nr) {
+            const int kr = rowop_at(base + 2);
+            for (; k < kr; k++) wp_stack_op(s, opc_at(k));
+            wp_row_op(s, opc_at(kr), p2); k = kr + 1;
+            if (base + 5 < nr) p2 = fetch(base + 5);
+        }
+    }
+    for (; k < n_ops; k++) wp_stack_op(s, opc_at(k));     // trailing stack ops (and programs without any row op)
+    (void)is_row_at;
+    return s.depth > 0 ? s.T : wp_zero<V>();
+}
+
+}  // namespace fbgpu

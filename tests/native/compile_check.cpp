@@ -12,3 +12,16 @@ extern "C" int compile_ops(const fbgpu_op* ops, int32_t n_ops, fbgpu::DevOp* out
     memcpy(out, prog.data(), prog.size() * sizeof(fbgpu::DevOp));
     return 0;
 }
+
+// featurebase_b200/csrc/wp_machine.h (experimental op loop of the word-parallel kernel) on the host: runs a compiled
+// program over caller-provided 128-bit operand slices (one per row op, in program order) and returns the result slice.
+#include "wp_machine.h"
+struct U4 { uint32_t x, y, z, w; };
+extern "C" void wp_run(const fbgpu::DevOp* prog, int32_t n_ops, const uint32_t* slices /* [n_rowops][4] */, uint32_t out[4]) {
+    std::vector<uint16_t> rowops;
+    auto is_row = [&](int k) { uint8_t o = prog[k].op; return o >= fbgpu::D_PUSH_ROW && o <= fbgpu::D_ORANDNOT_ROW && o != fbgpu::D_PUSH_EMPTY; };
+    for (int k = 0; k < n_ops; k++) if (is_row(k)) rowops.push_back((uint16_t)k);
+    U4 r = fbgpu::wp_run_unrolled<U4>(n_ops, (int)rowops.size(), [&](int k) { return prog[k].op; }, is_row, [&](int ri) { return (int)rowops[ri]; },
+                                      [&](int ri) { U4 v{ slices[4 * ri], slices[4 * ri + 1], slices[4 * ri + 2], slices[4 * ri + 3] }; return v; });
+    out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
+}

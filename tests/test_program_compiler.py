@@ -208,3 +208,85 @@ def test_fold_shape_and_errors(cc):
             compile_ops(cc, bad)
     assert [p[0] for p in compile_ops(cc, [op(L.OP_UNION, argc=0)])[0]] == [D_PUSH_EMPTY]
     assert [p[0] for p in compile_ops(cc, [op(L.OP_XOR, argc=0)])[0]] == [D_PUSH_EMPTY]
+
+
+def test_wordpar_unrolled_loop_matches_stack_model(cc):
+    """csrc/wp_machine.h (the experimental fixed-register op loop of eval_wordpar_kernel, -DFBGPU_WP_UNROLL3) against a plain
+    Python stack machine on 128-bit slices: programs from the real compiler (random call trees with BSI leaves, every
+    comparison at several depths), random operand slices incl. all-zero / all-one rows"""
+    rng = np.random.default_rng(33)
+    M = (1 << 128) - 1
+
+    def model(prog, slices):
+        st, ri = [], 0
+        for op, fv, row in prog:
+            if op in (D_PUSH_ROW, D_OR_ROW, D_AND_ROW, D_ANDNOT_ROW, D_XOR_ROW, D_ORAND_ROW, D_ORANDNOT_ROW):
+                x = slices[ri]
+                ri += 1
+                if op == D_PUSH_ROW:
+                    st.append(x)
+                elif op == D_OR_ROW:
+                    st[-1] |= x
+                elif op == D_AND_ROW:
+                    st[-1] &= x
+                elif op == D_ANDNOT_ROW:
+                    st[-1] &= ~x & M
+                elif op == D_XOR_ROW:
+                    st[-1] ^= x
+                elif op == D_ORAND_ROW:
+                    st[-2] |= st[-1] & x
+                else:
+                    st[-2] |= st[-1] & ~x & M
+            elif op == D_PUSH_EMPTY:
+                st.append(0)
+            elif op == D_SWAP:
+                st[-1], st[-2] = st[-2], st[-1]
+            elif op == D_POP:
+                st.pop()
+            else:
+                b = st.pop()
+                st[-1] = {D_AND: st[-1] & b, D_OR: st[-1] | b, D_ANDNOT: st[-1] & ~b & M, D_XOR: st[-1] ^ b}[op]
+        return st[-1] if st else 0
+
+    def run(prog):
+        n_row = sum(1 for op, _, _ in prog if op in (D_PUSH_ROW, D_OR_ROW, D_AND_ROW, D_ANDNOT_ROW, D_XOR_ROW, D_ORAND_ROW, D_ORANDNOT_ROW))
+        words = rng.integers(0, 1 << 32, (max(n_row, 1), 4), dtype=np.uint64).astype(np.uint32)
+        for k in range(n_row):
+            r = rng.random()
+            if r < 0.1:
+                words[k] = 0
+            elif r < 0.2:
+                words[k] = 0xFFFFFFFF
+        slices = [int(w[0]) | int(w[1]) << 32 | int(w[2]) << 64 | int(w[3]) << 96 for w in words]
+        arr = (DevOp * max(len(prog), 1))()
+        for i, (op, fv, row) in enumerate(prog):
+            arr[i].op, arr[i].fv, arr[i].row = op, fv, row
+        out = (C.c_uint32 * 4)()
+        cc.wp_run(arr, len(prog), np.ascontiguousarray(words).ctypes.data_as(C.c_void_p), out)
+        got = out[0] | out[1] << 32 | out[2] << 64 | out[3] << 96
+        assert got == model(prog, slices), prog
+
+    n = 0
+    for depth in (1, 6, 32, 63):
+        for cmp_name in ("==", "!=", "<", "<=", ">", ">="):
+            for pred in (0, 1, -1, 5, -37, (1 << (depth - 1)), (1 << depth) - 1, -(1 << depth) + 1, 1 << depth):
+                prog, d = compile_ops(cc, [op(L.OP_BSI_RANGE, 2, 1, 0, depth, L.CMP[cmp_name], pred, 0)])
+                if d <= 4:
+                    run(prog)
+                    n += 1
+        for lo, hi in ((0, 5), (-9, 9), (-(1 << depth) + 1, (1 << depth) - 1), (3, 3), (7, 2)):
+            prog, d = compile_ops(cc, [op(L.OP_BSI_RANGE, 2, 1, 0, depth, L.CMP["><"], lo, hi)])
+            if d <= 4:
+                run(prog)
+                n += 1
+    for _ in range(400):
+        try:
+            prog, d = compile_ops(cc, _random_tree(rng, [0, 1, 2], 3))
+        except L.FbgpuError:
+            continue
+        if d <= 4:                                           # kWpMaxDepth
+            run(prog)
+            n += 1
+    run([])                                                  # no ops at all
+    run([(D_PUSH_EMPTY, NO_VIEW, 0)])
+    assert n > 450

@@ -3,9 +3,11 @@ import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from featurebase_b200 import build as B
 VARIANTS = {   # name -> -D defines; edit freely, outputs featurebase_b200/libfbgpu_<name>.so (select with FBGPU_LIB=...)
-    "eval_b7": ["FBGPU_EVAL_MIN_BLOCKS=7"],
-    "wp2": ["FBGPU_WP_SLICES=2"],
+    "wp_unroll3": ["FBGPU_WP_UNROLL3"],          # experimental fixed-register op loop of the word-parallel kernel (csrc/wp_machine.h)
 }
+only = sys.argv[1:]
+if only:
+    VARIANTS = {k: v for k, v in VARIANTS.items() if k in only}
 if __name__ == "__main__":
     for name, defs in VARIANTS.items():
         out = B.build_fbgpu(force=True, defines=defs, out_name=f"libfbgpu_{name}.so")

@@ -19,6 +19,12 @@ echo "striped $(FBGPU_ARRAY_STRIPED=1 bench)" >> $out/bench.jsonl
 python bench_sweep.py --configs 5 --batched --generators uniform > $out/sweep_default.jsonl 2>>$out/bench_err.log
 FBGPU_ARRAY_STRIPED=1 python bench_sweep.py --configs 5 --batched --generators uniform > $out/sweep_striped.jsonl 2>>$out/bench_err.log
 
+# 3b. experimental op loop of the word-parallel kernel (BSI): parity of the BSI tests with the variant library, then config 3
+python tools/build_variants.py wp_unroll3 > $out/build_variants.log 2>&1
+FBGPU_LIB=$PWD/featurebase_b200/libfbgpu_wp_unroll3.so timeout 900 python -m pytest tests/test_gpu_parity.py -q -k "bsi or alternative or executor_goldens" > $out/pytest_wp_unroll3.log 2>&1; echo "pytest_wp_unroll3 rc=$?" >> $out/summary.txt
+python bench_sweep.py --configs 3 > $out/sweep3_default.jsonl 2>>$out/bench_err.log
+FBGPU_LIB=$PWD/featurebase_b200/libfbgpu_wp_unroll3.so python bench_sweep.py --configs 3 > $out/sweep3_wp_unroll3.jsonl 2>>$out/bench_err.log
+
 # 4. one ncu pass of the headline kernel in both layouts: shared-memory wavefronts / issue utilisation are what changed
 for mode in default striped; do
   env $( [ $mode = striped ] && echo FBGPU_ARRAY_STRIPED=1 ) ncu --set full --clock-control none -k regex:eval_kernel -c 2 -o $out/eval_$mode \
