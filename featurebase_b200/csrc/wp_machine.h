@@ -14,6 +14,12 @@
 #include "bitaddr.h"        // FBGPU_HD
 #include "fbgpu_types.h"
 
+#if defined(__CUDACC__)
+#define FBGPU_NO_UNROLL _Pragma("unroll 1")
+#else
+#define FBGPU_NO_UNROLL
+#endif
+
 namespace fbgpu {
 
 template <class V>
@@ -68,24 +74,24 @@ FBGPU_HD V wp_run_unrolled(int n_ops, int nr, OpcAt opc_at, IsRowAt is_row_at, R
     for (int base = 0; base < nr; base += 3) {
         {   // row op base+0, operand p0
             const int kr = rowop_at(base);
-            for (; k < kr; k++) wp_stack_op(s, opc_at(k));
+            FBGPU_NO_UNROLL for (; k < kr; k++) wp_stack_op(s, opc_at(k));
             wp_row_op(s, opc_at(kr), p0); k = kr + 1;
             if (base + 3 < nr) p0 = fetch(base + 3);
         }
         if (base + 1 < nr) {
             const int kr = rowop_at(base + 1);
-            for (; k < kr; k++) wp_stack_op(s, opc_at(k));
+            FBGPU_NO_UNROLL for (; k < kr; k++) wp_stack_op(s, opc_at(k));
             wp_row_op(s, opc_at(kr), p1); k = kr + 1;
             if (base + 4 < nr) p1 = fetch(base + 4);
         }
         if (base + 2 < nr) {
             const int kr = rowop_at(base + 2);
-            for (; k < kr; k++) wp_stack_op(s, opc_at(k));
+            FBGPU_NO_UNROLL for (; k < kr; k++) wp_stack_op(s, opc_at(k));
             wp_row_op(s, opc_at(kr), p2); k = kr + 1;
             if (base + 5 < nr) p2 = fetch(base + 5);
         }
     }
-    for (; k < n_ops; k++) wp_stack_op(s, opc_at(k));     // trailing stack ops (and programs without any row op)
+    FBGPU_NO_UNROLL for (; k < n_ops; k++) wp_stack_op(s, opc_at(k));     // trailing stack ops (and programs without any row op)
     (void)is_row_at;
     return s.depth > 0 ? s.T : wp_zero<V>();
 }
