@@ -271,8 +271,17 @@ class Executor:
                 return self._minmax(idx, c, shards, c.name)
             if c.name == "Percentile":
                 return self._percentile(idx, c, shards)
+            if c.name == "IncludesColumn":                       # executeIncludesColumnCall: is the column in the row?
+                if "column" not in c.args:
+                    raise QueryError("IncludesColumn call must specify a column")
+                if len(c.children) != 1:
+                    raise QueryError("IncludesColumn call must specify a row query")
+                col = int(c.args["column"])
+                ef, erow = self.holder.embed_row(idx.name, [col])
+                ops = self._bitmap_call(idx, c.children[0]) + [L.Op(L.OP_ROW, ef.id, VIEW_STANDARD, 0, erow, 0, 0, 0), L.Op(L.OP_INTERSECT, 0, 0, 2, 0, 0, 0, 0)]
+                return self.ctx.count(idx.id, ops, [col // SHARD_WIDTH]) > 0
             ops = self._bitmap_call(idx, c)
-            data, cnt = self.ctx.row(idx.id, ops, shards)
+            data, cnt = self.ctx.row(idx.id, ops, self._cur_shards)       # (Shift may have carried bits into a further shard)
             return RowResult(data, cnt)
         except L.FbgpuError as e:
             if e.code == L.E_QUERY:
@@ -321,6 +330,19 @@ class Executor:
             if idx.track_existence:
                 ops.append(L.Op(L.OP_ALL, idx.fields[EXISTENCE_FIELD].id, VIEW_STANDARD, 0, 0, 0, 0, 0))
                 ops.append(L.Op(L.OP_INTERSECT, 0, 0, 2, 0, 0, 0, 0))
+            return
+        if n == "Shift":                                         # executeShiftShard (unsupported upstream, row.go Shift): every column + n
+            if len(c.children) != 1:
+                raise QueryError("Shift() requires a single bitmap input")
+            k = int(c.args.get("n", 0))
+            data, _ = self.ctx.row(idx.id, self._bitmap_call(idx, c.children[0]), self._cur_shards)
+            cols = [int(x) + k for x in roaring_io.decode(data)]
+            if not cols:
+                ops.append(L.Op(L.OP_EMPTY, 0, 0, 0, 0, 0, 0, 0))
+                return
+            f, row = self.holder.embed_row(idx.name, cols)       # the shifted row is a caller-provided operand from here on
+            self._cur_shards = sorted(set(self._cur_shards) | {col // SHARD_WIDTH for col in cols})
+            ops.append(L.Op(L.OP_ROW, f.id, VIEW_STANDARD, 0, row, 0, 0, 0))
             return
         if n == "UnionRows":                                     # executeUnionRows :5696-5779 -> Union(Row(..), ...) over the children's row ids
             leaves = []

@@ -77,6 +77,7 @@ def test_time_quantum(oracle_backed):
 
 def test_embedded_rows(oracle_backed):
     E.test_embedded_rows_constrow_unionrows()
+    E.test_shift_and_includes_column()
 
 
 def test_percentile(oracle_backed):

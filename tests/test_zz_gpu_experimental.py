@@ -532,3 +532,38 @@ def test_embedded_rows_constrow_unionrows():
         q.holder.set_bit("i", "general", r, c)
     q.sync_pending()
     assert q.ex.execute("i", "Rows(general, column=2)")[0] == [11, 12]               # executor_test.go:5339
+
+
+def test_shift_and_includes_column():
+    """executor_test.go:6590-6673 (Shift: bit 0, container boundary, shard boundary, nested) and :6678-6706 (IncludesColumn):
+    host-side compositions over Row results / embedded operand rows"""
+    SW = 1 << 20
+
+    def fresh(cols):
+        p = Pair(track_existence=False)
+        p.field("general")
+        for c in cols:
+            p.holder.set_bit("i", "general", 10, c)
+        p.sync_pending()
+        return p
+    cols = lambda p, q: [int(c) for c in p.ex.execute("i", q)[0].columns()]
+    p = fresh([0])
+    assert cols(p, "Shift(Row(general=10), n=1)") == [1]
+    assert cols(p, "Shift(Shift(Row(general=10), n=1), n=1)") == [2]
+    p = fresh([65535])
+    assert cols(p, "Shift(Row(general=10), n=1)") == [65536]
+    p = fresh([1, SW - 1, SW + 1])
+    assert cols(p, "Shift(Row(general=10), n=1)") == [2, SW, SW + 2]
+    assert cols(p, "Shift(Row(general=10), n=2)") == [3, SW + 1, SW + 3]
+    assert cols(p, "Shift(Shift(Row(general=10)))") == [1, SW - 1, SW + 1]
+    p = fresh([SW - 2, SW - 1, SW, SW + 2])
+    assert cols(p, "Shift(Row(general=10), n=1)") == [SW - 1, SW, SW + 1, SW + 3]
+    assert cols(p, "Shift(Shift(Row(general=10), n=1), n=1)") == [SW, SW + 1, SW + 2, SW + 4]
+    assert cols(p, "Intersect(Shift(Row(general=10), n=1), Row(general=10))") == [SW - 1, SW]
+    p = fresh([1, SW, 2 * SW])
+    for col, exp in ((1, True), (2, False), (SW, True), (SW + 1, False), (2 * SW, True), (2 * SW + 1, False)):
+        assert p.ex.execute("i", f"IncludesColumn(Row(general=10), column={col})")[0] is exp
+    with pytest.raises(X.QueryError, match="must specify a column"):
+        p.ex.execute("i", "IncludesColumn(Row(general=10))")
+    with pytest.raises(X.QueryError, match="must specify a row query"):
+        p.ex.execute("i", "IncludesColumn(column=1)")
