@@ -77,3 +77,15 @@ def test_bsigroup_base_value_rules():
     assert f.base_value_between(10, 5)[2]
     g = X.Field(2, "pos", "int", min=100, max=200)
     assert g.base == 100 and g.bit_depth == 7
+
+
+def test_header_is_plain_c():
+    """include/fbgpu.h is what cgo compiles: it must be valid C99 on its own (no C++-isms, every type declared)"""
+    import subprocess
+    import tempfile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with tempfile.TemporaryDirectory() as d:
+        src = os.path.join(d, "h.c")
+        open(src, "w").write('#include "fbgpu.h"\nint main(void) { return sizeof(fbgpu_op) == 48 ? 0 : 1; }\n')
+        subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(root, "include"), src, "-o", os.path.join(d, "h")])
+        assert subprocess.call([os.path.join(d, "h")]) == 0          # the 48-byte op layout INTEGRATION.md's Go struct mirrors
