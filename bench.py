@@ -193,6 +193,8 @@ def main():
     payload, n_cont = h.ctx.rows_payload_bytes(idx.id, fld.id, X.VIEW_STANDARD, shards, ROWS_A + ROWS_B)
     algo_bytes = payload + 16 * n_cont + 8                       # payload + 16 B/descriptor + 8 B count
     h2d_bytes = 48 * len(ops) + 8 * len(shards)                  # fbgpu_op program + shard list (host buffers)
+    ops = X.L.ops_array(ops)                                     # marshal the program once (host memory; still copied H2D by every call)
+    shards = np.ascontiguousarray(np.asarray(shards, dtype=np.uint64))
 
     def step():
         return h.ctx.count(idx.id, ops, shards)

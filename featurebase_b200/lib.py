@@ -86,7 +86,10 @@ def _u64arr(x):
 
 
 def ops_array(ops):
-    """list of Op / tuples -> ctypes array"""
+    """list of Op / tuples -> ctypes array (an array built earlier is passed through: a caller that issues the same program
+    repeatedly keeps it marshalled, like a Go caller holds its []Op)"""
+    if isinstance(ops, C.Array):
+        return ops
     arr = (Op * max(len(ops), 1))()
     for i, o in enumerate(ops):
         arr[i] = o
