@@ -280,8 +280,20 @@ class Executor:
                 ef, erow = self.holder.embed_row(idx.name, [col])
                 ops = self._bitmap_call(idx, c.children[0]) + [L.Op(L.OP_ROW, ef.id, VIEW_STANDARD, 0, erow, 0, 0, 0), L.Op(L.OP_INTERSECT, 0, 0, 2, 0, 0, 0, 0)]
                 return self.ctx.count(idx.id, ops, [col // SHARD_WIDTH]) > 0
+            window = None
+            if c.name == "Limit":                                # executeLimitCall: a column window over the child's row
+                if len(c.children) != 1:
+                    raise QueryError("Limit() requires a single bitmap input")
+                window, c = (int(c.args.get("offset", 0)), c.args.get("limit")), c.children[0]
+            elif c.name == "All" and ("limit" in c.args or "offset" in c.args):      # executeAllCall :5720-5779 with limit / offset
+                window = (int(c.args.get("offset", 0)), c.args.get("limit"))
             ops = self._bitmap_call(idx, c)
             data, cnt = self.ctx.row(idx.id, ops, self._cur_shards)       # (Shift may have carried bits into a further shard)
+            if window is not None:                               # the window is cut from the merged result on the host
+                cols = roaring_io.decode(data)
+                off, lim = window
+                cols = cols[off:] if lim is None else cols[off:off + int(lim)]
+                return RowResult(roaring_io.encode(np.asarray(cols, dtype=np.uint64)), len(cols))
             return RowResult(data, cnt)
         except L.FbgpuError as e:
             if e.code == L.E_QUERY:

@@ -78,6 +78,7 @@ def test_time_quantum(oracle_backed):
 def test_embedded_rows(oracle_backed):
     E.test_embedded_rows_constrow_unionrows()
     E.test_shift_and_includes_column()
+    E.test_all_with_limit_offset()
 
 
 def test_percentile(oracle_backed):

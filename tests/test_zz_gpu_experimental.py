@@ -567,3 +567,25 @@ def test_shift_and_includes_column():
         p.ex.execute("i", "IncludesColumn(Row(general=10))")
     with pytest.raises(X.QueryError, match="must specify a row query"):
         p.ex.execute("i", "IncludesColumn(column=1)")
+
+
+def test_all_with_limit_offset():
+    """executor_test.go:4406-4485 TestExecutor_Execute_All (ColumnID): 105 existence bits spread over the ends of shards 0-2
+    and one in shard 3; All() with every limit / offset window of the reference's table"""
+    SW = 1 << 20
+    n = 105
+    cols = [i + SW - 2 for i in range(n // 2)] + [i + 2 * SW - n + 5 for i in range(n // 2, n - 1)] + [3 * SW + 2]
+    p = Pair(track_existence=True)
+    p.field("f")
+    for c in cols:
+        p.holder.set_bit("i", "f", 10, c)
+    p.sync_pending()
+    assert cols == sorted(cols)
+    cases = [("All()", cols), ("All(limit=1)", cols[:1]), ("All(limit=4)", cols[:4]), ("All(limit=4, offset=4)", cols[4:8]),
+             (f"All(limit=4, offset={n - 5})", cols[n - 5:n - 1]), (f"All(limit=1, offset={n - 2})", cols[n - 2:n - 1]),
+             (f"All(limit=4, offset={n - 2})", cols[n - 2:]), (f"All(limit=4, offset={n + 1})", []), (f"All(limit=2, offset={n - 3})", cols[n - 3:n - 1]),
+             (f"All(limit=2, offset={n - 5})", cols[n - 5:n - 3]), ("All(limit=2, offset=2)", cols[2:4]), ("All(limit=1, offset=1)", cols[1:2]),
+             (f"All(limit={n - 3}, offset=2)", cols[2:n - 1]), ("Limit(Row(f=10), limit=3, offset=50)", cols[50:53])]
+    for q, exp in cases:
+        got = p.ex.execute("i", q)[0]
+        assert got.count == len(exp) and [int(c) for c in got.columns()] == exp, q
