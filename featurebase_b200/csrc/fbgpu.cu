@@ -531,7 +531,11 @@ static int compile_program(fbgpu_ctx* c, uint32_t index, const fbgpu_op* ops, in
     Error err;
     ViewLookup lookup = [c, index](uint32_t field, uint32_t view) { return view_id_locked(c, ViewKey{ index, field, view }, false); };
     int rc = compile(ops, n_ops, lookup, out, depth, err);
-    return rc ? fail(rc, "%s", err.msg) : 0;
+    if (rc) return fail(rc, "%s", err.msg);
+#ifdef FBGPU_WP_UNROLL3
+    expand_push_row(out);          // variant build only: every kernel accepts the rewritten program, the word-parallel loop requires it
+#endif
+    return 0;
 }
 
 // ------------------------------------------------------------------ execution helpers

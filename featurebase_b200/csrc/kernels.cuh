@@ -830,7 +830,7 @@ eval_wordpar_kernel(StoreRef st, const DevOp* __restrict__ prog, int n_ops,
 #if defined(FBGPU_WP_UNROLL3) && FBGPU_WP_SLICES == 1
         // experimental op loop with fixed register roles (wp_machine.h); same program semantics
         uint4 T[1];
-        T[0] = wp_run_unrolled<uint4>(n_ops, nr, [&](int k) { return ops[k].opc; }, [&](int k) { return ops[k].is_row != 0; },
+        T[0] = wp_run_unrolled<uint4, true>(n_ops, nr, [&](int k) { return ops[k].opc; }, [&](int k) { return ops[k].is_row != 0; },
                                       [&](int ri) { return (int)rowops[ri]; }, [&](int ri) { uint4 d[1]; fetch(d, ri); return d[0]; });
         const int depth_now = 1;                       // (wp_run_unrolled already returns zero for an empty stack)
 #else

@@ -207,4 +207,15 @@ inline int compile(const fbgpu_op* ops, int32_t n_ops, const ViewLookup& lookup,
     return 0;
 }
 
+// PUSH_ROW r  ==  PUSH_EMPTY ; OR_ROW r.  Used by the experimental word-parallel op loop (wp_machine.h, -DFBGPU_WP_UNROLL3), whose
+// hot switch then never shifts the register stack.  The operand stack depth is unchanged.
+inline void expand_push_row(std::vector<DevOp>& prog) {
+    std::vector<DevOp> out; out.reserve(prog.size() + 8);
+    for (const DevOp& o : prog) {
+        if (o.op == D_PUSH_ROW) { DevOp e{}; e.op = D_PUSH_EMPTY; e.fv = kNoView; out.push_back(e); DevOp r = o; r.op = D_OR_ROW; out.push_back(r); }
+        else out.push_back(o);
+    }
+    prog.swap(out);
+}
+
 }  // namespace fbgpu

@@ -47,23 +47,23 @@ FBGPU_HD void wp_stack_op(WpStack<V>& s, uint8_t opc) {
 // ops that take a row operand x.  Every case updates T or B in place; PUSH_ROW is executed as PUSH_EMPTY (the only
 // stack shift, kept out of the hot switch) followed by T |= x, so that the switch arms leave all other registers alone
 // and the compiler has nothing to copy where they join.
-template <class V>
+// NO_PUSH: the program was rewritten by expand_push_row() (program_compiler.h) and holds no PUSH_ROW, so the hot switch
+// contains no stack shift at all (otherwise the shift is compiled as ~14 predicated moves that issue on every row op).
+template <bool NO_PUSH, class V>
 FBGPU_HD void wp_row_op(WpStack<V>& s, uint8_t opc, V x) {
-    if (opc == D_PUSH_ROW) { wp_stack_op(s, D_PUSH_EMPTY); opc = D_OR_ROW; }
-    if (opc == D_ORAND_ROW || opc == D_ORANDNOT_ROW) {
-        if (opc == D_ORANDNOT_ROW) { x.x = ~x.x; x.y = ~x.y; x.z = ~x.z; x.w = ~x.w; }
-        s.B = wp_or(s.B, wp_and(s.T, x));
-    } else if (opc == D_OR_ROW) s.T = wp_or(s.T, x);
-    else if (opc == D_XOR_ROW) s.T = wp_xor(s.T, x);
-    else {                                                          // D_AND_ROW / D_ANDNOT_ROW
-        if (opc == D_ANDNOT_ROW) { x.x = ~x.x; x.y = ~x.y; x.z = ~x.z; x.w = ~x.w; }
-        s.T = wp_and(s.T, x);
-    }
+    if (!NO_PUSH && opc == D_PUSH_ROW) { wp_stack_op(s, D_PUSH_EMPTY); opc = D_OR_ROW; }
+    // one expression per arm, each a single three-input LOP3 per word, each updating T or B in place
+    if (opc == D_ORAND_ROW) s.B = wp_or(s.B, wp_and(s.T, x));
+    else if (opc == D_ORANDNOT_ROW) s.B = wp_or(s.B, wp_andn(s.T, x));
+    else if (opc == D_AND_ROW) s.T = wp_and(s.T, x);
+    else if (opc == D_ANDNOT_ROW) s.T = wp_andn(s.T, x);
+    else if (opc == D_OR_ROW) s.T = wp_or(s.T, x);
+    else s.T = wp_xor(s.T, x);                                      // D_XOR_ROW
 }
 
 // opc(k): opcode of program op k; is_row(k); rowops[ri]: program index of the ri-th row op; fetch(ri): its operand slice.
 // Returns the top of stack (zero when the program leaves the stack empty).
-template <class V, class OpcAt, class IsRowAt, class RowOpAt, class Fetch>
+template <class V, bool NO_PUSH = false, class OpcAt, class IsRowAt, class RowOpAt, class Fetch>
 FBGPU_HD V wp_run_unrolled(int n_ops, int nr, OpcAt opc_at, IsRowAt is_row_at, RowOpAt rowop_at, Fetch fetch) {
     WpStack<V> s; s.T = s.B = s.S2 = s.S3 = wp_zero<V>(); s.depth = 0;
     V p0 = wp_zero<V>(), p1 = p0, p2 = p0;
@@ -75,19 +75,19 @@ FBGPU_HD V wp_run_unrolled(int n_ops, int nr, OpcAt opc_at, IsRowAt is_row_at, R
         {   // row op base+0, operand p0
             const int kr = rowop_at(base);
             FBGPU_NO_UNROLL for (; k < kr; k++) wp_stack_op(s, opc_at(k));
-            wp_row_op(s, opc_at(kr), p0); k = kr + 1;
+            wp_row_op<NO_PUSH>(s, opc_at(kr), p0); k = kr + 1;
             if (base + 3 < nr) p0 = fetch(base + 3);
         }
         if (base + 1 < nr) {
             const int kr = rowop_at(base + 1);
             FBGPU_NO_UNROLL for (; k < kr; k++) wp_stack_op(s, opc_at(k));
-            wp_row_op(s, opc_at(kr), p1); k = kr + 1;
+            wp_row_op<NO_PUSH>(s, opc_at(kr), p1); k = kr + 1;
             if (base + 4 < nr) p1 = fetch(base + 4);
         }
         if (base + 2 < nr) {
             const int kr = rowop_at(base + 2);
             FBGPU_NO_UNROLL for (; k < kr; k++) wp_stack_op(s, opc_at(k));
-            wp_row_op(s, opc_at(kr), p2); k = kr + 1;
+            wp_row_op<NO_PUSH>(s, opc_at(kr), p2); k = kr + 1;
             if (base + 5 < nr) p2 = fetch(base + 5);
         }
     }
