@@ -27,8 +27,11 @@ FBGPU_LIB=$PWD/featurebase_b200/libfbgpu_wp_unroll3.so python bench_sweep.py --c
 
 # 4. one ncu pass of the headline kernel in both layouts: shared-memory wavefronts / issue utilisation are what changed
 for mode in default striped; do
-  env $( [ $mode = striped ] && echo FBGPU_ARRAY_STRIPED=1 ) ncu --set full --clock-control none -k regex:eval_kernel -c 2 -o $out/eval_$mode \
+  env $( [ $mode = striped ] && echo FBGPU_ARRAY_STRIPED=1 ) ncu --set full --clock-control none -k regex:eval_kernel -c 1 -f -o $out/eval_$mode \
       python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $out/ncu_$mode.log 2>&1
+  # keep the raw-metrics CSV (small); the .ncu-rep only if it fits the 64 MiB return budget comfortably
+  ncu -i $out/eval_$mode.ncu-rep --page raw --csv > $out/eval_${mode}_raw.csv 2>/dev/null
+  [ "$(stat -c %s $out/eval_$mode.ncu-rep 2>/dev/null || echo 0)" -gt 20000000 ] && rm -f $out/eval_$mode.ncu-rep
 done
 python - <<'PY' >> gpurun_out/r2_first/summary.txt
 import json
