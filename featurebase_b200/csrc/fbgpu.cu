@@ -44,6 +44,10 @@ static int fail(int code, const char* fmt, ...) {
     catch (const std::exception& e) { return fail(FBGPU_E_INVALID, "internal error: %s", e.what()); } \
     catch (...) { return fail(FBGPU_E_INVALID, "internal error"); }
 
+// every entry point that needs the GPU: an inspection-only context (FBGPU_DEVICE_NONE) is refused here, loudly
+#define USE_DEVICE(c) do { if ((c)->inspect_only) return fail(FBGPU_E_CUDA, "this context was created with FBGPU_DEVICE_NONE: it holds no device and answers no query"); \
+                           CUDA_TRY(cudaSetDevice((c)->device)); } while (0)
+
 extern "C" const char* fbgpu_last_error(void) { return g_err.c_str(); }
 extern "C" int32_t fbgpu_abi_version(void) { return FBGPU_ABI_VERSION; }
 
@@ -147,6 +151,8 @@ struct fbgpu_ctx {
     RawBuf staging;                      // payload bytes not yet uploaded, destined for [uploaded, uploaded+staging.len)
     uint64_t uploaded = 0;               // bytes of payload already in HBM
     bool meta_dirty = false;
+    bool inspect_only = false;           // created with FBGPU_DEVICE_NONE: residency + fbgpu_debug_container only, no device, no queries
+    std::vector<ViewTab> t_views; std::vector<int32_t> t_flat; std::vector<RowTabEnt> t_rowtab;   // inspect_only: the tables a commit would upload
     bool stripe_arrays = getenv("FBGPU_ARRAY_STRIPED") != nullptr;   // experimental payload order, see stripe.h (fixed per context)
     DevBuf d_payload, d_views, d_shardmap, d_frags, d_rows, d_descs, d_rowtab;
     PinBuf bounce[2];
@@ -172,6 +178,11 @@ static StoreRef store_ref(fbgpu_ctx* c) {
 
 extern "C" int fbgpu_init(int32_t device_ordinal, fbgpu_ctx** out) try {
     if (!out) return fail(FBGPU_E_INVALID, "out is null");
+    if (device_ordinal == FBGPU_DEVICE_NONE) {          // store inspection without a device (tests): no CUDA call is ever made
+        auto c = new fbgpu_ctx(); c->inspect_only = true; c->device = -1;
+        *out = c;
+        return FBGPU_OK;
+    }
     int n = 0;
     CUDA_TRY(cudaGetDeviceCount(&n));
     if (device_ordinal < 0 || device_ordinal >= n) return fail(FBGPU_E_INVALID, "device ordinal %d out of range (%d devices)", device_ordinal, n);
@@ -200,6 +211,7 @@ extern "C" int fbgpu_init(int32_t device_ordinal, fbgpu_ctx** out) try {
 
 extern "C" void fbgpu_shutdown(fbgpu_ctx* c) {
     if (!c) return;
+    if (c->inspect_only) { c->staging.clear_and_free(); delete c; return; }
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     if (c->comm && nccl_load()) g_nccl.CommDestroy(c->comm);
@@ -431,9 +443,34 @@ extern "C" int fbgpu_drop_fragment(fbgpu_ctx* c, uint32_t index, uint32_t field,
 } FBGPU_CATCH
 
 // uploads staged payload (append) and refreshes metadata tables; store_mu held exclusively
+// flatten shard maps; build the dense (shard,row) directory of every view whose row ids are dense
+static void build_tables(fbgpu_ctx* c, std::vector<ViewTab>& views, std::vector<int32_t>& flat, std::vector<RowTabEnt>& rowtab) {
+    views.assign(c->shardmaps.size(), ViewTab{}); flat.clear(); rowtab.clear();
+    for (size_t v = 0; v < c->shardmaps.size(); v++) {
+        const auto& sm = c->shardmaps[v];
+        views[v] = ViewTab{}; views[v].shard_off = (uint32_t)flat.size(); views[v].n_shards = (uint32_t)sm.size();
+        flat.insert(flat.end(), sm.begin(), sm.end());
+        uint64_t rmin = ~0ull, rmax = 0, nrows = 0;
+        for (int32_t f : sm) if (f >= 0) { const HostFrag& hf = c->frags[f]; if (!hf.n_rows) continue;
+            rmin = std::min(rmin, c->h_rows[hf.row_off].row); rmax = std::max(rmax, c->h_rows[hf.row_off + hf.n_rows - 1].row); nrows = std::max<uint64_t>(nrows, hf.n_rows); }
+        if (rmin == ~0ull) continue;
+        uint64_t span = rmax - rmin + 1;
+        if (span > 4 * nrows + 64 || span * sm.size() > (64ull << 20) || getenv("FBGPU_NO_ROWTAB")) continue;       // sparse row ids or too large: keep the search chain
+        views[v].rt_rows = (uint32_t)span; views[v].rt_off = rowtab.size(); views[v].rmin = rmin;
+        rowtab.resize(rowtab.size() + span * sm.size(), RowTabEnt{ 0, 0, 0 });
+        for (size_t sh = 0; sh < sm.size(); sh++) if (sm[sh] >= 0) { const HostFrag& hf = c->frags[sm[sh]];
+            for (uint32_t k = 0; k < hf.n_rows; k++) { const RowEnt& e = c->h_rows[hf.row_off + k]; rowtab[views[v].rt_off + sh * span + (e.row - rmin)] = RowTabEnt{ e.first_desc, e.mask, 0 }; } }
+    }
+}
+
 static int commit_locked(fbgpu_ctx* c) {
+    if (c->inspect_only) {                  // no device: keep the payload in the staging buffer and the tables on the host
+        build_tables(c, c->t_views, c->t_flat, c->t_rowtab);
+        c->meta_dirty = false;
+        return 0;
+    }
     if (!c->meta_dirty && c->staging.empty()) return 0;
-    CUDA_TRY(cudaSetDevice(c->device));
+    USE_DEVICE(c);
     CUDA_TRY(cudaDeviceSynchronize());   // no query may be reading tables we are about to replace (queries hold the shared lock anyway)
     if (!c->staging.empty()) {
         uint64_t need = c->uploaded + c->staging.len + 256;
@@ -466,23 +503,8 @@ static int commit_locked(fbgpu_ctx* c) {
         c->uploaded += c->staging.len;
         c->staging.clear_and_free();
     }
-    // flatten shard maps; build the dense (shard,row) directory of every view whose row ids are dense
-    std::vector<ViewTab> views(c->shardmaps.size()); std::vector<int32_t> flat; std::vector<RowTabEnt> rowtab;
-    for (size_t v = 0; v < c->shardmaps.size(); v++) {
-        const auto& sm = c->shardmaps[v];
-        views[v] = ViewTab{}; views[v].shard_off = (uint32_t)flat.size(); views[v].n_shards = (uint32_t)sm.size();
-        flat.insert(flat.end(), sm.begin(), sm.end());
-        uint64_t rmin = ~0ull, rmax = 0, nrows = 0;
-        for (int32_t f : sm) if (f >= 0) { const HostFrag& hf = c->frags[f]; if (!hf.n_rows) continue;
-            rmin = std::min(rmin, c->h_rows[hf.row_off].row); rmax = std::max(rmax, c->h_rows[hf.row_off + hf.n_rows - 1].row); nrows = std::max<uint64_t>(nrows, hf.n_rows); }
-        if (rmin == ~0ull) continue;
-        uint64_t span = rmax - rmin + 1;
-        if (span > 4 * nrows + 64 || span * sm.size() > (64ull << 20) || getenv("FBGPU_NO_ROWTAB")) continue;       // sparse row ids or too large: keep the search chain
-        views[v].rt_rows = (uint32_t)span; views[v].rt_off = rowtab.size(); views[v].rmin = rmin;
-        rowtab.resize(rowtab.size() + span * sm.size(), RowTabEnt{ 0, 0, 0 });
-        for (size_t sh = 0; sh < sm.size(); sh++) if (sm[sh] >= 0) { const HostFrag& hf = c->frags[sm[sh]];
-            for (uint32_t k = 0; k < hf.n_rows; k++) { const RowEnt& e = c->h_rows[hf.row_off + k]; rowtab[views[v].rt_off + sh * span + (e.row - rmin)] = RowTabEnt{ e.first_desc, e.mask, 0 }; } }
-    }
+    std::vector<ViewTab> views; std::vector<int32_t> flat; std::vector<RowTabEnt> rowtab;
+    build_tables(c, views, flat, rowtab);
     auto up = [&](DevBuf& b, const void* src, size_t bytes) -> int {
         if (b.ensure(std::max<size_t>(bytes, 256))) return FBGPU_E_NOMEM;
         if (bytes) { cudaError_t e = cudaMemcpy(b.p, src, bytes, cudaMemcpyHostToDevice); if (e != cudaSuccess) return fail(FBGPU_E_CUDA, "metadata upload failed: %s", cudaGetErrorString(e)); }
@@ -510,6 +532,7 @@ extern "C" int fbgpu_commit(fbgpu_ctx* c) try {
 // pending" check and the query run under the SAME lock acquisition, so a load that slips in between a commit and the
 // query cannot leave the query reading host mirrors that are newer than what is in HBM.
 static int lock_committed(fbgpu_ctx* c, std::shared_lock<std::shared_mutex>& lk) {
+    if (c->inspect_only) return fail(FBGPU_E_CUDA, "this context was created with FBGPU_DEVICE_NONE: it holds no device and answers no query");
     for (;;) {
         lk = std::shared_lock<std::shared_mutex>(c->store_mu);
         if (!c->meta_dirty && c->staging.empty()) return 0;
@@ -632,7 +655,7 @@ static int launch_eval(fbgpu_ctx* c, Workspace* w, const std::vector<DevOp>& pro
 extern "C" int fbgpu_count(fbgpu_ctx* c, uint32_t index, const fbgpu_op* ops, int32_t n_ops, const uint64_t* shards, int64_t n_shards,
                            uint64_t* out_total, uint64_t* out_per_shard) try {
     if (!c || !out_total || n_shards < 0 || (n_shards && !shards)) return fail(FBGPU_E_INVALID, "null argument");
-    CUDA_TRY(cudaSetDevice(c->device));
+    USE_DEVICE(c);
     std::shared_lock<std::shared_mutex> lk;
     int rc = lock_committed(c, lk); if (rc) return rc;
     std::vector<DevOp> prog; int depth = 1;
@@ -691,7 +714,7 @@ static constexpr long long kUnitBatch = 16384;   // 128 MiB of result bitmaps pe
 extern "C" int fbgpu_row(fbgpu_ctx* c, uint32_t index, const fbgpu_op* ops, int32_t n_ops, const uint64_t* shards, int64_t n_shards,
                          uint8_t* out_buf, uint64_t out_cap, uint64_t* out_len, uint64_t* out_count) try {
     if (!c || !out_len || n_shards < 0 || (n_shards && !shards)) return fail(FBGPU_E_INVALID, "null argument");
-    CUDA_TRY(cudaSetDevice(c->device));
+    USE_DEVICE(c);
     std::shared_lock<std::shared_mutex> lk;
     int rc = lock_committed(c, lk); if (rc) return rc;
     std::vector<DevOp> prog; int depth = 1;
@@ -823,7 +846,7 @@ extern "C" int fbgpu_row_counts(fbgpu_ctx* c, uint32_t index, uint32_t field, ui
                                 const fbgpu_op* filter, int32_t n_filter_ops, const uint64_t* shards, int64_t n_shards,
                                 uint64_t* out_row_ids, uint64_t* out_counts, int32_t cap, int32_t* out_n) try {
     if (!c || !out_counts || n_shards < 0 || (n_shards && !shards) || n_rows < 0) return fail(FBGPU_E_INVALID, "null argument");
-    CUDA_TRY(cudaSetDevice(c->device));
+    USE_DEVICE(c);
     std::shared_lock<std::shared_mutex> lk;
     int rc = lock_committed(c, lk); if (rc) return rc;
     uint32_t fv = view_id_locked(c, ViewKey{ index, field, view }, false);
@@ -860,7 +883,7 @@ extern "C" int fbgpu_count_pairs(fbgpu_ctx* c, uint32_t index, uint32_t field_a,
                                  uint32_t field_b, uint32_t view_b, const uint64_t* rows_b, int32_t n_pairs,
                                  const uint64_t* shards, int64_t n_shards, uint64_t* out_counts) try {
     if (!c || !rows_a || !rows_b || !out_counts || n_pairs < 0 || n_shards < 0 || (n_shards && !shards)) return fail(FBGPU_E_INVALID, "null argument");
-    CUDA_TRY(cudaSetDevice(c->device));
+    USE_DEVICE(c);
     if (n_pairs == 0) return FBGPU_OK;
     std::shared_lock<std::shared_mutex> lk;
     int rc = lock_committed(c, lk); if (rc) return rc;
@@ -961,7 +984,7 @@ static int groupby_rec(fbgpu_ctx* c, uint32_t index, const uint32_t* fields, con
 extern "C" int fbgpu_groupby(fbgpu_ctx* c, uint32_t index, const uint32_t* fields, const uint32_t* views, int32_t n_fields, const uint64_t* row_ids_flat, const int32_t* n_rows,
                              const fbgpu_op* filter, int32_t n_filter_ops, const uint64_t* shards, int64_t n_shards, uint64_t* out_counts) try {
     if (!c || !fields || !views || !row_ids_flat || !n_rows || !out_counts || n_fields < 1 || n_fields > 8 || n_shards < 0 || (n_shards && !shards)) return fail(FBGPU_E_INVALID, "bad argument");
-    CUDA_TRY(cudaSetDevice(c->device));
+    USE_DEVICE(c);
     std::shared_lock<std::shared_mutex> lk;
     int rc = lock_committed(c, lk); if (rc) return rc;
     std::vector<const uint64_t*> rows(n_fields); const uint64_t* p = row_ids_flat; size_t total = 1;
@@ -985,7 +1008,7 @@ extern "C" int fbgpu_comm_unique_id(uint8_t id[FBGPU_NCCL_ID_BYTES]) try {
 extern "C" int fbgpu_comm_init(fbgpu_ctx* c, int32_t n_ranks, int32_t rank, const uint8_t id[FBGPU_NCCL_ID_BYTES]) try {
     if (!c || !id || n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(FBGPU_E_INVALID, "bad argument");
     if (!nccl_load()) return fail(FBGPU_E_COMM, "libnccl.so.2 not loadable");
-    CUDA_TRY(cudaSetDevice(c->device));
+    USE_DEVICE(c);
     Id128 u; memcpy(u.b, id, 128);
     void* comm = nullptr;
     int r = g_nccl.CommInitRank(&comm, n_ranks, u, rank);
@@ -1003,7 +1026,7 @@ extern "C" int fbgpu_comm_destroy(fbgpu_ctx* c) try {
 // ---- fused peer-memory reduce: mailbox exchange through CUDA IPC (one process per GPU)
 extern "C" int fbgpu_comm_p2p_handle(fbgpu_ctx* c, uint8_t out[64]) try {
     if (!c || !out) return fail(FBGPU_E_INVALID, "null argument");
-    CUDA_TRY(cudaSetDevice(c->device));
+    USE_DEVICE(c);
     if (!c->mbox) { CUDA_TRY(cudaMalloc((void**)&c->mbox, sizeof(Mailbox))); CUDA_TRY(cudaMemset(c->mbox, 0, sizeof(Mailbox))); }
     cudaIpcMemHandle_t h;
     CUDA_TRY(cudaIpcGetMemHandle(&h, c->mbox));
@@ -1014,7 +1037,7 @@ extern "C" int fbgpu_comm_p2p_handle(fbgpu_ctx* c, uint8_t out[64]) try {
 extern "C" int fbgpu_comm_p2p_open(fbgpu_ctx* c, int32_t n_ranks, int32_t rank, const uint8_t* handles /* n_ranks x 64 */) try {
     if (!c || !handles || n_ranks < 1 || n_ranks > kMaxRanks || rank < 0 || rank >= n_ranks) return fail(FBGPU_E_INVALID, "bad argument");
     if (!c->mbox) return fail(FBGPU_E_COMM, "call fbgpu_comm_p2p_handle first");
-    CUDA_TRY(cudaSetDevice(c->device));
+    USE_DEVICE(c);
     std::lock_guard<std::mutex> lk(c->coll_mu);
     c->p2p = false;
     for (int p = 0; p < kMaxRanks; p++) {                        // re-open after a membership change: drop the old mappings first
@@ -1042,13 +1065,37 @@ extern "C" int fbgpu_comm_p2p_disable(fbgpu_ctx* c) try {      // back to the NC
     return FBGPU_OK;
 } FBGPU_CATCH
 
+// ---- store inspection (tests): the container the kernels would find for (index, field, view, shard, row, slot), located by
+// the same resolve() the kernels inline, over the host copies of the tables of an FBGPU_DEVICE_NONE context
+extern "C" int fbgpu_debug_container(fbgpu_ctx* c, uint32_t index, uint32_t field, uint32_t view, uint64_t shard, uint64_t row, int32_t slot,
+                                     uint32_t* out_type, uint32_t* out_card, uint32_t* out_runs, uint8_t* out_payload, uint64_t cap, uint64_t* out_len) try {
+    if (!c || !out_type || !out_card || !out_runs || !out_len || slot < 0 || slot >= kSlotsPerRow) return fail(FBGPU_E_INVALID, "bad argument");
+    if (!c->inspect_only) return fail(FBGPU_E_INVALID, "fbgpu_debug_container needs a context created with FBGPU_DEVICE_NONE");
+    std::unique_lock<std::shared_mutex> lk(c->store_mu);
+    if (c->meta_dirty) { int rc = commit_locked(c); if (rc) return rc; }
+    StoreRef st{};
+    st.views = c->t_views.data(); st.shardmap = c->t_flat.data(); st.frags = c->h_frags.data(); st.rows = c->h_rows.data(); st.descs = c->h_descs.data();
+    st.payload = c->staging.p; st.rowtab = c->t_rowtab.data(); st.n_views = (uint32_t)c->t_views.size();
+    uint32_t fv = view_id_locked(c, ViewKey{ index, field, view }, false);
+    Resolved r = resolve(st, fv, shard, row, slot);
+    *out_type = 0; *out_card = 0; *out_runs = 0; *out_len = 0;
+    if (r.ptr == nullptr) return FBGPU_OK;                      // absent
+    *out_type = r.typ; *out_card = r.card; *out_runs = r.cnt;
+    const uint64_t bytes = r.typ == kArray ? (((uint64_t)r.card * 2 + 15) & ~15ull) : r.typ == kBitmap ? 8192 : (((uint64_t)r.cnt * 4 + 15) & ~15ull);   // padded, as stored
+    *out_len = bytes;
+    if (bytes > cap || !out_payload) return fail(FBGPU_E_NOSPACE, "payload needs %llu bytes", (unsigned long long)bytes);
+    if ((const uint8_t*)r.ptr + bytes > c->staging.p + c->staging.len) return fail(FBGPU_E_INVALID, "descriptor points outside the payload arena");
+    memcpy(out_payload, r.ptr, bytes);
+    return FBGPU_OK;
+} FBGPU_CATCH
+
 extern "C" int fbgpu_get_counters(fbgpu_ctx* c, fbgpu_counters* out) try {
     if (!c || !out) return fail(FBGPU_E_INVALID, "null argument");
     std::lock_guard<std::mutex> lk(c->cnt_mu);
     *out = c->counters;
     return 0;
 } FBGPU_CATCH
-extern "C" void* fbgpu_stream(fbgpu_ctx* c) { return c ? (void*)c->wss[0]->stream : nullptr; }
+extern "C" void* fbgpu_stream(fbgpu_ctx* c) { return c && !c->wss.empty() ? (void*)c->wss[0]->stream : nullptr; }
 
 // algorithmic-bytes accounting for bench / DESIGN: payload bytes + 16 B descriptor of every
 // container of the given rows over the given shards

@@ -14,6 +14,7 @@
 #include "fbgpu_types.h"
 #include "bitaddr.h"
 #include "wp_machine.h"
+#include "resolve.h"
 
 namespace fbgpu {
 
@@ -46,40 +47,6 @@ __device__ __forceinline__ void warp_prefetch_container(const Resolved& r, int l
     const uint32_t bytes = r.typ == kArray ? r.card * 2u : r.typ == kBitmap ? 8192u : (uint32_t)r.cnt * 4u;
     const uint8_t* p = reinterpret_cast<const uint8_t*>(r.ptr);
     for (uint32_t off = lane * 128u; off < bytes; off += 32u * 128u) prefetch_l2(p + off);
-}
-
-// Locate the container (fv, shard, row, slot).  5 dependent loads; see fbgpu_types.h.
-__device__ __forceinline__ Resolved resolve(const StoreRef& st, uint32_t fv, uint64_t shard, uint64_t row, int slot) {
-    Resolved r; r.ptr = nullptr; r.card = 0; r.typ = 0; r.cnt = 0;
-    if (fv >= st.n_views) return r;
-    ViewTab v = st.views[fv];
-    if (shard >= v.n_shards) return r;
-    if (v.rt_rows) {                                  // dense (shard,row) directory: views -> rowtab -> descs
-        if (row < v.rmin || row - v.rmin >= v.rt_rows) return r;
-        RowTabEnt e = st.rowtab[v.rt_off + shard * v.rt_rows + (row - v.rmin)];
-        if (!((e.mask >> slot) & 1)) return r;
-        ContDesc d = st.descs[e.first_desc + __popc(e.mask & ((1u << slot) - 1u))];
-        r.ptr = st.payload + (size_t)d.off16 * 16; r.card = d.card; r.typ = d.typ; r.cnt = d.cnt;
-        return r;
-    }
-    int f = st.shardmap[v.shard_off + shard];
-    if (f < 0) return r;
-    FragHdr h = st.frags[f];
-    uint32_t idx;
-    if (h.contiguous) {
-        if (row < h.row0 || row - h.row0 >= h.n_rows) return r;
-        idx = (uint32_t)(row - h.row0);
-    } else {
-        uint32_t lo = 0, hi = h.n_rows;
-        while (lo < hi) { uint32_t m = (lo + hi) >> 1; if (st.rows[h.row_off + m].row < row) lo = m + 1; else hi = m; }
-        if (lo >= h.n_rows) return r;
-        idx = lo;
-    }
-    RowEnt e = st.rows[h.row_off + idx];
-    if (e.row != row || !((e.mask >> slot) & 1)) return r;
-    ContDesc d = st.descs[e.first_desc + __popc(e.mask & ((1u << slot) - 1u))];
-    r.ptr = st.payload + (size_t)d.off16 * 16; r.card = d.card; r.typ = d.typ; r.cnt = d.cnt;
-    return r;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -11,6 +11,7 @@ _LIB = None
 OP_ROW, OP_INTERSECT, OP_UNION, OP_DIFFERENCE, OP_XOR, OP_NOT, OP_BSI_RANGE, OP_EMPTY, OP_ALL = range(1, 10)
 CMP = {"==": 1, "!=": 2, "<": 3, "<=": 4, ">": 5, ">=": 6, "><": 7}
 E_INVALID, E_QUERY, E_FORMAT, E_NOSPACE, E_CUDA, E_NOMEM, E_COMM = -1, -2, -3, -4, -5, -6, -7
+DEVICE_NONE = -1            # fbgpu_init(FBGPU_DEVICE_NONE): inspection-only context (no device, no queries)
 
 
 class FbgpuError(RuntimeError):
@@ -62,6 +63,8 @@ def load():
     L.fbgpu_drop_fragment.argtypes, L.fbgpu_drop_fragment.restype = [vp, u32, u32, u32, u64], C.c_int
     L.fbgpu_load_rbf.argtypes, L.fbgpu_load_rbf.restype = [vp, u32, u64, vp, u64, vp, u64, vp, vp, vp, i32, C.POINTER(i32)], C.c_int
     L.fbgpu_commit.argtypes, L.fbgpu_commit.restype = [vp], C.c_int
+    L.fbgpu_debug_container.argtypes = [vp, u32, u32, u32, u64, u64, i32, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32), vp, u64, C.POINTER(u64)]
+    L.fbgpu_debug_container.restype = C.c_int
     L.fbgpu_get_stats.argtypes, L.fbgpu_get_stats.restype = [vp, C.POINTER(Stats)], C.c_int
     L.fbgpu_count.argtypes, L.fbgpu_count.restype = [vp, u32, vp, i32, vp, i64, C.POINTER(u64), vp], C.c_int
     L.fbgpu_row.argtypes, L.fbgpu_row.restype = [vp, u32, vp, i32, vp, i64, vp, u64, C.POINTER(u64), C.POINTER(u64)], C.c_int
@@ -144,6 +147,14 @@ class Context:
         self._check(self.L.fbgpu_load_rbf(self.h, index, int(shard), C.addressof(dbuf), len(data), C.addressof(wbuf) if wal else None, len(wal),
                                           C.addressof(cn), fl.ctypes.data, vw.ctypes.data, len(names), C.byref(n)))
         return n.value
+
+    def debug_container(self, index, field, view, shard, row, slot):
+        """inspection-only contexts (Context(DEVICE_NONE)): -> None | (type, card, runs, payload bytes as stored)"""
+        typ, card, runs, n = C.c_uint32(0), C.c_uint32(0), C.c_uint32(0), C.c_uint64(0)
+        buf = np.empty(8192, dtype=np.uint8)
+        self._check(self.L.fbgpu_debug_container(self.h, index, field, view, int(shard), int(row), int(slot), C.byref(typ), C.byref(card), C.byref(runs),
+                                                 buf.ctypes.data, 8192, C.byref(n)))
+        return None if typ.value == 0 else (typ.value, card.value, runs.value, buf[: n.value].tobytes())
 
     def drop_fragment(self, index, field, view, shard):
         self._check(self.L.fbgpu_drop_fragment(self.h, index, field, view, int(shard)))

@@ -35,6 +35,11 @@ extern "C" {
 
 typedef struct fbgpu_ctx fbgpu_ctx; /* opaque, one per GPU */
 
+/* fbgpu_init(FBGPU_DEVICE_NONE, ..) creates an INSPECTION-ONLY context: it touches no device, accepts the residency calls
+ * (load / drop / commit / stats) and fbgpu_debug_container(), and refuses every query with FBGPU_E_CUDA.  It exists so that the
+ * loaders and the store tables can be tested on a machine without a GPU; it is not a CPU execution path. */
+#define FBGPU_DEVICE_NONE (-1)
+
 /* lifecycle.  device_ordinal is the CUDA ordinal this context owns. */
 int fbgpu_init(int32_t device_ordinal, fbgpu_ctx **out);
 void fbgpu_shutdown(fbgpu_ctx *ctx);
@@ -67,6 +72,12 @@ int fbgpu_load_rbf(fbgpu_ctx *ctx, uint32_t index, uint64_t shard, const uint8_t
                    const uint32_t *views, int32_t n_names, int32_t *out_loaded);
 /* pushes pending host-side staging to HBM now (otherwise done lazily by the next query) */
 int fbgpu_commit(fbgpu_ctx *ctx);
+/* Inspection (FBGPU_DEVICE_NONE contexts only): the container the kernels would find for (index, field, view, shard, row,
+ * slot), located by the same resolve() code, with its payload exactly as stored (incl. the padding of the last 16-byte
+ * chunk).  *out_type = 0 when the container is absent, else 1 array / 2 bitmap / 3 run. */
+int fbgpu_debug_container(fbgpu_ctx *ctx, uint32_t index, uint32_t field, uint32_t view, uint64_t shard, uint64_t row,
+                          int32_t slot, uint32_t *out_type, uint32_t *out_card, uint32_t *out_runs,
+                          uint8_t *out_payload, uint64_t cap, uint64_t *out_len);
 
 typedef struct {
     uint64_t fragments, containers;

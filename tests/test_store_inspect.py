@@ -1,0 +1,159 @@
+"""The shard store on a box without a GPU: an inspection-only context (fbgpu_init(FBGPU_DEVICE_NONE)) accepts the
+residency calls and lets fbgpu_debug_container() locate containers with the very resolve() code the kernels inline, over
+the host copies of the tables a commit would upload.  This pins, on the CPU: the fragment reader's hand-over to the store
+builder, the descriptor / row / dense-directory tables, payload placement, array padding and (opt-in) striping, fragment
+replacement and dropping, and fbgpu_load_rbf end to end.  Every query entry point must refuse such a context."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from featurebase_b200 import datagen as D
+from featurebase_b200 import lib as L
+from oracle import oracle as O
+from tests import rbf_writer as W
+from tests import test_rbf as TR
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SW = 1 << 20
+
+
+def container_values(found):
+    typ, card, runs, payload = found
+    if typ == 1:
+        a = np.frombuffer(payload, dtype="<u2")
+        assert len(a) == (card + 7) // 8 * 8 and set(a[card:].tolist()) <= {int(a[card - 1])}       # duplicate-padded tail
+        return np.sort(a[:card]).astype(np.int64)
+    if typ == 2:
+        assert len(payload) == 8192
+        v = np.flatnonzero(np.unpackbits(np.frombuffer(payload, dtype=np.uint8), bitorder="little"))
+        assert len(v) == card
+        return v.astype(np.int64)
+    r = np.frombuffer(payload, dtype="<u2")[: 2 * runs].reshape(-1, 2).astype(np.int64)
+    v = np.concatenate([np.arange(s, l + 1) for s, l in r.tolist()])
+    assert len(v) == card
+    return v
+
+
+def check_fragment(ctx, index, field, view, shard, frag, rows_to_probe):
+    """every (row, slot) of the oracle fragment resolves to exactly its container; absent ones resolve to nothing"""
+    present = set(frag.rows().tolist())
+    n = 0
+    for row in rows_to_probe:
+        bits = frag.row(row, 0).slice() if row in present else np.zeros(0, dtype=np.uint64)
+        for slot in range(16):
+            exp = bits[(bits >> np.uint64(16)) == np.uint64(slot)] & np.uint64(0xFFFF)
+            got = ctx.debug_container(index, field, view, shard, row, slot)
+            if len(exp) == 0:
+                assert got is None, (row, slot)
+            else:
+                assert got is not None, (row, slot)
+                assert np.array_equal(container_values(got), exp.astype(np.int64)), (row, slot)
+                n += 1
+    return n
+
+
+def mixed_fragment(seed, shard, rows=(0, 1, 2, 3, 5, 6, 9, 40)):
+    parts = [D.fragment(seed, shard, [0, 1, 2], 0.01), D.fragment(seed, shard, [3], 0.3), D.fragment(seed, shard, [5], 0.2, mode=1, mean_run=200.0),
+             D.fragment(seed, shard, [6], 0.9, mode=1, mean_run=5000.0), D.fragment(seed, shard, [9], 0.0622), D.fragment(seed, shard, [40], 0.0001)]
+    merged = O.Bitmap()
+    for d in parts:
+        merged = merged.union(O.Bitmap.from_bytes(d))
+    return merged
+
+
+def test_store_tables_and_payloads():
+    ctx = L.Context(L.DEVICE_NONE)
+    frags = {}
+    for shard in (0, 3, 7):
+        frags[shard] = mixed_fragment(11 + shard, shard)
+        ctx.load_fragment(1, 2, 0, shard, frags[shard].to_bytes())
+    # a second view with sparse row ids (search chain instead of the dense directory) and an official-format fragment
+    sparse = O.Bitmap.from_values(np.concatenate([np.uint64(r * SW) + np.arange(0, 70000, 7, dtype=np.uint64) for r in (0, 5, 1000, 123456, 1 << 30)]))
+    ctx.load_fragment(1, 3, 0, 0, sparse.to_bytes())
+    ctx.load_fragment(1, 4, 0, 2, open(os.path.join(ROOT, "tests", "golden", "bitmapcontainer.roaringbitmap"), "rb").read())
+    ctx.commit()
+    st = ctx.stats()
+    assert st["fragments"] == 5
+    total = 0
+    for shard, fr in frags.items():
+        total += check_fragment(ctx, 1, 2, 0, shard, fr, [0, 1, 2, 3, 4, 5, 6, 7, 9, 40, 41])
+    assert total > 300
+    assert check_fragment(ctx, 1, 3, 0, 0, sparse, [0, 1, 5, 999, 1000, 1001, 123456, 1 << 30, (1 << 30) + 1]) == 10
+    official = O.Bitmap.from_bytes(open(os.path.join(ROOT, "tests", "golden", "bitmapcontainer.roaringbitmap"), "rb").read())
+    assert check_fragment(ctx, 1, 4, 0, 2, official, [0, 1]) == 2
+    for args in ((1, 2, 0, 1, 0, 0), (1, 2, 1, 0, 0, 0), (9, 2, 0, 0, 0, 0), (1, 2, 0, 100000, 0, 0)):       # unknown shard / view / index
+        assert ctx.debug_container(*args) is None
+    # replacing and dropping a fragment
+    newer = mixed_fragment(99, 3)
+    ctx.load_fragment(1, 2, 0, 3, newer.to_bytes())
+    assert check_fragment(ctx, 1, 2, 0, 3, newer, [0, 1, 2, 3, 5, 6, 9, 40]) > 80
+    ctx.drop_fragment(1, 2, 0, 0)
+    assert ctx.debug_container(1, 2, 0, 0, 0, 0) is None
+    assert check_fragment(ctx, 1, 2, 0, 7, frags[7], [0, 3, 5]) > 30
+    assert ctx.stats()["fragments"] == 4
+
+
+def test_queries_are_refused_without_a_device():
+    ctx = L.Context(L.DEVICE_NONE)
+    ctx.load_fragment(0, 1, 0, 0, D.fragment(1, 0, [0, 1], 0.01))
+    row = [L.Op(L.OP_ROW, 1, 0, 0, 0, 0, 0, 0)]
+    for call in (lambda: ctx.count(0, row, [0]), lambda: ctx.row(0, row, [0]), lambda: ctx.row_counts(0, 1, 0, [0]),
+                 lambda: ctx.count_pairs(0, 1, 0, [0], 1, 0, [1], [0]), lambda: ctx.groupby(0, [1, 1], [0, 0], [[0], [1]], [0])):
+        with pytest.raises(L.FbgpuError) as e:
+            call()
+        assert e.value.code == L.E_CUDA and "no device" in str(e.value)
+
+
+def test_rbf_loader_end_to_end():
+    ctx = L.Context(L.DEVICE_NONE)
+    bitmaps, frs = {}, {}
+    for k, (name, fid) in enumerate((("~f;standard<", 5), ("~g;standard<", 6))):
+        bm, conts = TR._fragment_containers(30 + k, 7)
+        frs[fid], bitmaps[name] = bm, conts
+    data = W.build(bitmaps)
+    assert ctx.load_rbf(2, 7, data, ["~f;standard<", "~missing;standard<", "~g;standard<"], [5, 8, 6], [0, 0, 0]) == 2
+    for fid, bm in frs.items():
+        assert check_fragment(ctx, 2, fid, 0, 7, bm, [0, 1, 2, 3, 4, 5, 6, 9, 40]) > 100
+    assert ctx.debug_container(2, 8, 0, 7, 0, 0) is None
+    # WAL overlay: the newer content wins
+    bm2, conts2 = TR._fragment_containers(77, 7)
+    wa, wb = W.Writer(), W.Writer()
+    wa.add_bitmap("~f;standard<", bitmaps["~f;standard<"])
+    wb.add_bitmap("~f;standard<", conts2)
+    old, new = wa.finish(1), wb.finish(2)
+    assert ctx.load_rbf(2, 8, b"".join(old), ["~f;standard<"], [5], [0], wal=W.wal_between(old, new, wb.raw)) == 1
+    assert check_fragment(ctx, 2, 5, 0, 8, bm2, [0, 1, 2, 3, 5, 6, 9, 40]) > 100
+    with pytest.raises(L.FbgpuError):
+        ctx.load_rbf(2, 9, TR.fixture("bad-bitmap"), ["x"], [1], [0])
+    assert ctx.debug_container(2, 1, 0, 9, 0, 0) is None                 # a rejected file leaves the store unchanged
+
+
+def test_striped_layout_in_a_subprocess():
+    """FBGPU_ARRAY_STRIPED is read when a context is created: array-dominated fragments are stored permuted (same sets),
+    bitmap-heavy ones keep sorted arrays"""
+    code = r"""
+import sys, numpy as np
+sys.path.insert(0, %r)
+from featurebase_b200 import lib as L, datagen as D
+from oracle import oracle as O
+from tests.test_store_inspect import check_fragment, mixed_fragment
+ctx = L.Context(L.DEVICE_NONE)
+arrays = O.Bitmap.from_bytes(D.fragment(5, 0, [0, 1, 2, 3], 0.01))
+ctx.load_fragment(0, 1, 0, 0, arrays.to_bytes())
+assert check_fragment(ctx, 0, 1, 0, 0, arrays, [0, 1, 2, 3, 4]) == 64
+t, card, runs, payload = ctx.debug_container(0, 1, 0, 0, 0, 0)
+a = np.frombuffer(payload, dtype='<u2')[:card]
+assert t == 1 and not np.all(a[:-1] <= a[1:]), 'array-dominated fragment should be striped'
+dense = mixed_fragment(3, 1, rows=())
+ctx.load_fragment(0, 2, 0, 1, O.Bitmap.from_bytes(D.fragment(6, 1, [0, 1, 2, 3, 4, 5, 6, 7, 8], 0.3)).union(O.Bitmap.from_bytes(D.fragment(6, 1, [9], 0.002))).to_bytes())
+t, card, runs, payload = ctx.debug_container(0, 2, 0, 1, 9, 0)
+a = np.frombuffer(payload, dtype='<u2')[:card]
+assert t == 1 and card >= 64 and np.all(a[:-1] < a[1:]), 'arrays of a bitmap-heavy fragment stay sorted'
+print('striped ok')
+""" % ROOT
+    env = dict(os.environ, FBGPU_ARRAY_STRIPED="1")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd=ROOT, timeout=600)
+    assert out.returncode == 0 and "striped ok" in out.stdout, out.stderr[-3000:]
