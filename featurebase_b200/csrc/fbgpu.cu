@@ -1076,7 +1076,7 @@ extern "C" int fbgpu_debug_container(fbgpu_ctx* c, uint32_t index, uint32_t fiel
     StoreRef st{};
     st.views = c->t_views.data(); st.shardmap = c->t_flat.data(); st.frags = c->h_frags.data(); st.rows = c->h_rows.data(); st.descs = c->h_descs.data();
     st.payload = c->staging.p; st.rowtab = c->t_rowtab.data(); st.n_views = (uint32_t)c->t_views.size();
-    uint32_t fv = view_id_locked(c, ViewKey{ index, field, view }, false);
+    uint32_t fv = index == 0xffffffffu ? field : view_id_locked(c, ViewKey{ index, field, view }, false);   // (index ~0: `field` is a view slot of a compiled program)
     Resolved r = resolve(st, fv, shard, row, slot);
     *out_type = 0; *out_card = 0; *out_runs = 0; *out_len = 0;
     if (r.ptr == nullptr) return FBGPU_OK;                      // absent
@@ -1086,6 +1086,19 @@ extern "C" int fbgpu_debug_container(fbgpu_ctx* c, uint32_t index, uint32_t fiel
     if (bytes > cap || !out_payload) return fail(FBGPU_E_NOSPACE, "payload needs %llu bytes", (unsigned long long)bytes);
     if ((const uint8_t*)r.ptr + bytes > c->staging.p + c->staging.len) return fail(FBGPU_E_INVALID, "descriptor points outside the payload arena");
     memcpy(out_payload, r.ptr, bytes);
+    return FBGPU_OK;
+} FBGPU_CATCH
+
+// the device program the library would run for a post-order fbgpu_op program (records of 16 bytes: u8 op, 3 pad, u32 view slot, u64 row)
+extern "C" int fbgpu_debug_compile(fbgpu_ctx* c, uint32_t index, const fbgpu_op* ops, int32_t n_ops, uint8_t* out, int32_t cap_ops, int32_t* out_n, int32_t* out_depth) try {
+    if (!c || !out_n || !out_depth) return fail(FBGPU_E_INVALID, "null argument");
+    std::shared_lock<std::shared_mutex> lk(c->store_mu);
+    std::vector<DevOp> prog; int depth = 1;
+    int rc = compile_program(c, index, ops, n_ops, prog, depth); if (rc) return rc;
+    *out_n = (int32_t)prog.size(); *out_depth = depth;
+    if ((int32_t)prog.size() > cap_ops || (!out && !prog.empty())) return fail(FBGPU_E_NOSPACE, "program has %zu ops", prog.size());
+    static_assert(sizeof(DevOp) == 16, "DevOp layout");
+    if (!prog.empty()) memcpy(out, prog.data(), prog.size() * sizeof(DevOp));
     return FBGPU_OK;
 } FBGPU_CATCH
 

@@ -65,6 +65,7 @@ def load():
     L.fbgpu_commit.argtypes, L.fbgpu_commit.restype = [vp], C.c_int
     L.fbgpu_debug_container.argtypes = [vp, u32, u32, u32, u64, u64, i32, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32), vp, u64, C.POINTER(u64)]
     L.fbgpu_debug_container.restype = C.c_int
+    L.fbgpu_debug_compile.argtypes, L.fbgpu_debug_compile.restype = [vp, u32, vp, i32, vp, i32, C.POINTER(i32), C.POINTER(i32)], C.c_int
     L.fbgpu_get_stats.argtypes, L.fbgpu_get_stats.restype = [vp, C.POINTER(Stats)], C.c_int
     L.fbgpu_count.argtypes, L.fbgpu_count.restype = [vp, u32, vp, i32, vp, i64, C.POINTER(u64), vp], C.c_int
     L.fbgpu_row.argtypes, L.fbgpu_row.restype = [vp, u32, vp, i32, vp, i64, vp, u64, C.POINTER(u64), C.POINTER(u64)], C.c_int
@@ -155,6 +156,15 @@ class Context:
         self._check(self.L.fbgpu_debug_container(self.h, index, field, view, int(shard), int(row), int(slot), C.byref(typ), C.byref(card), C.byref(runs),
                                                  buf.ctypes.data, 8192, C.byref(n)))
         return None if typ.value == 0 else (typ.value, card.value, runs.value, buf[: n.value].tobytes())
+
+    def debug_compile(self, index, ops):
+        """-> ([(op, view slot, row)], stack depth): the device program for a post-order fbgpu_op program"""
+        arr = ops_array(ops)
+        buf = np.zeros(4096 * 16, dtype=np.uint8)
+        n, depth = C.c_int32(0), C.c_int32(0)
+        self._check(self.L.fbgpu_debug_compile(self.h, index, arr, len(ops), buf.ctypes.data, 4096, C.byref(n), C.byref(depth)))
+        rec = np.frombuffer(buf[: n.value * 16].tobytes(), dtype=np.dtype([("op", "u1"), ("pad", "u1", 3), ("fv", "<u4"), ("row", "<u8")]))
+        return [(int(r["op"]), int(r["fv"]), int(r["row"])) for r in rec], depth.value
 
     def drop_fragment(self, index, field, view, shard):
         self._check(self.L.fbgpu_drop_fragment(self.h, index, field, view, int(shard)))

@@ -172,6 +172,12 @@ int fbgpu_comm_p2p_handle(fbgpu_ctx *ctx, uint8_t out_handle[64]);
 int fbgpu_comm_p2p_open(fbgpu_ctx *ctx, int32_t n_ranks, int32_t rank, const uint8_t *handles /* n_ranks x 64 bytes */);
 int fbgpu_comm_p2p_disable(fbgpu_ctx *ctx);   /* fall back to the NCCL merge (e.g. when a peer could not be mapped) */
 
+/* Inspection (any context): the stack-machine program the library would run for `ops` -- records of 16 bytes {u8 op, u8 pad[3],
+ * u32 view slot, u64 row} (csrc/fbgpu_types.h DevOp); *out_depth = operand stack depth.  With index == 0xffffffff,
+ * fbgpu_debug_container() takes such a view slot in `field`. */
+int fbgpu_debug_compile(fbgpu_ctx *ctx, uint32_t index, const fbgpu_op *ops, int32_t n_ops, uint8_t *out, int32_t cap_ops,
+                        int32_t *out_n, int32_t *out_depth);
+
 /* ---- instrumentation (the counters the reference keeps under the roaringstats tag, statsHit()) ---- */
 typedef struct {
     uint64_t kernel_launches;   /* kernels of this library launched since init       */

@@ -157,3 +157,25 @@ print('striped ok')
     env = dict(os.environ, FBGPU_ARRAY_STRIPED="1")
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd=ROOT, timeout=600)
     assert out.returncode == 0 and "striped ok" in out.stdout, out.stderr[-3000:]
+
+
+def test_executor_bodies_through_library_compiler_and_store(monkeypatch):
+    """the executor-level test bodies once more, with Count / Row answered from the LIBRARY's compiled program and the
+    LIBRARY's store (tests/inspect_ctx.InspectCtx); only the kernels' stack machine is modelled in Python"""
+    from tests import oracle_exec
+    from tests import test_gpu_parity as G
+    from tests import test_zz_gpu_executor_goldens as Z
+    from tests import test_zz_gpu_experimental as E
+    from tests.inspect_ctx import InspectCtx
+
+    def make(*a, **kw):
+        return oracle_exec.Pair(*a, ctx=InspectCtx(), **kw)
+    for mod in (G, Z, E):
+        monkeypatch.setattr(mod, "Pair", make)
+    G.test_executor_goldens_and_edge_semantics()
+    G.test_config1_single_shard_plumbing()
+    G.test_bsi_range_goldens_on_gpu()
+    Z.test_executor_bsi_goldens_on_gpu()
+    E.test_time_quantum_rows()
+    E.test_embedded_rows_constrow_unionrows()
+    E.test_rbf_loader_matches_fragment_loader()
