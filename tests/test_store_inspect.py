@@ -179,3 +179,25 @@ def test_executor_bodies_through_library_compiler_and_store(monkeypatch):
     E.test_time_quantum_rows()
     E.test_embedded_rows_constrow_unionrows()
     E.test_rbf_loader_matches_fragment_loader()
+
+
+def test_algorithmic_byte_accounting():
+    """fbgpu_rows_payload_bytes (the roofline numerator of bench.py) = Σ payload bytes (array 2n, bitmap 8192,
+    run 4r) and the container count of the named rows, checked against the stored containers one by one"""
+    ctx = L.Context(L.DEVICE_NONE)
+    shards = [0, 2, 5]
+    for s in shards:
+        ctx.load_fragment(0, 1, 0, s, mixed_fragment(40 + s, s).to_bytes())
+    for rows in ([0, 1], [3], [5, 6, 9], [0, 1, 2, 3, 5, 6, 9, 40, 77], None):
+        pay = cont = 0
+        for s in shards:
+            for row in (rows if rows is not None else [0, 1, 2, 3, 5, 6, 9, 40]):
+                for slot in range(16):
+                    found = ctx.debug_container(0, 1, 0, s, row, slot)
+                    if found:
+                        typ, card, runs, _ = found
+                        pay += 2 * card if typ == 1 else 8192 if typ == 2 else 4 * runs
+                        cont += 1
+        assert ctx.rows_payload_bytes(0, 1, 0, shards, rows) == (pay, cont), rows
+    assert ctx.rows_payload_bytes(0, 1, 0, [9], [0]) == (0, 0)
+    assert ctx.rows_payload_bytes(0, 7, 0, shards, [0]) == (0, 0)
