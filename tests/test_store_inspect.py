@@ -179,6 +179,15 @@ def test_executor_bodies_through_library_compiler_and_store(monkeypatch):
     E.test_time_quantum_rows()
     E.test_embedded_rows_constrow_unionrows()
     E.test_rbf_loader_matches_fragment_loader()
+    E.test_bsi_aggregate_goldens()
+    E.test_fragment_top_goldens()
+    E.test_filter_sample_goldens()
+    E.test_groupby_postprocessing_goldens()
+    E.test_shift_and_includes_column()
+    E.test_all_with_limit_offset()
+    E.test_kernel_table_goldens_on_device()            # explicit (unoptimised) encodings through the library's reader and store
+    E.test_bitmap_level_goldens_on_device()
+    E.test_bench_archetype_matrix()
 
 
 def test_algorithmic_byte_accounting():

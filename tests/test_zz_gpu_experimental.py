@@ -1,11 +1,11 @@
-"""Opt-in GPU parity run of EXPERIMENTAL data layouts (not part of the default product path, not yet measured):
-FBGPU_ARRAY_STRIPED=1 permutes array payloads at load time (featurebase_b200/csrc/stripe.h).  Every kernel must give
-bit-identical results on permuted arrays, so the bodies of the regular parity tests are simply re-run with the switch on.
-Skipped unless FBGPU_TEST_EXPERIMENTAL=1 (round 2 turns it on before measuring the layout).
+"""Device runs of everything written after round 1's GPU budget was spent.
 
-Also here until they have had their first GPU run: the BSI aggregates Sum / Min / Max, which the host
-mirror composes from fbgpu_count / fbgpu_row_counts calls.  tests/test_host_mirror.py runs the same bodies on the CPU
-against an oracle-backed context."""
+The query-level tests below (BSI aggregates, RBF loader, further reference goldens, GroupBy post-processing, Percentile, time
+views, embedded rows, Shift, All/Limit) use only entry points and kernels whose parity was already green on the GPU; their
+host side — mirror, program compiler, readers, store tables — has been exercised on the CPU through tests/test_host_mirror.py
+(oracle-backed context) and tests/test_store_inspect.py (the library's own compiler and store), so they run by default.
+The bank-striped array payload order (FBGPU_ARRAY_STRIPED=1, csrc/stripe.h) changes the data the kernels read; its tests are
+skipped unless FBGPU_TEST_EXPERIMENTAL=1 until the layout has had its first GPU run (tools/r2_first_call.sh)."""
 import os
 
 import numpy as np
@@ -17,8 +17,9 @@ from tests import test_gpu_parity as G
 from tests.golden import vectors as V
 from tests.oracle_exec import Pair
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(not os.environ.get("FBGPU_TEST_EXPERIMENTAL"), reason="experimental layouts: set FBGPU_TEST_EXPERIMENTAL=1")]
+pytestmark = pytest.mark.gpu
+# opt-in part: the striped payload ORDER changes what the kernels read, so it stays behind a switch until it has run on a GPU once
+experimental = pytest.mark.skipif(not os.environ.get("FBGPU_TEST_EXPERIMENTAL"), reason="experimental layouts: set FBGPU_TEST_EXPERIMENTAL=1")
 
 
 @pytest.fixture
@@ -26,6 +27,7 @@ def striped(monkeypatch):
     monkeypatch.setenv("FBGPU_ARRAY_STRIPED", "1")      # read when a context is created
 
 
+@experimental
 def test_striped_set_ops(striped):
     G.test_config1_single_shard_plumbing()
     G.test_container_combinations_table_on_gpu()
@@ -34,11 +36,13 @@ def test_striped_set_ops(striped):
     G.test_executor_goldens_and_edge_semantics()
 
 
+@experimental
 @pytest.mark.parametrize("mode", [0, 1])
 def test_striped_density_sweep(striped, mode):
     G.test_density_sweep_intersect_count(mode)
 
 
+@experimental
 def test_striped_bsi_topk_groupby(striped):
     G.test_bsi_range_goldens_on_gpu()
     G.test_bsi_uniform_u32_config3_small()
@@ -46,6 +50,7 @@ def test_striped_bsi_topk_groupby(striped):
     G.test_groupby_two_and_three_fields()
 
 
+@experimental
 @pytest.mark.parametrize("env", ["FBGPU_FORCE_WORDPAR", "FBGPU_STAGED"])
 def test_striped_alternative_kernels(striped, env, monkeypatch):
     G.test_alternative_eval_kernels(env, monkeypatch)       # FORCE_WORDPAR must be ignored for views that hold arrays
@@ -466,9 +471,15 @@ def test_kernel_table_goldens_on_device():
         exp = f.get("exp") or f.get("expected")
         expect[k] = [((k * 16 + slot) << 16) + v for v in values(exp)]
     for op, shards in by_op.items():
-        got = p.check_row(f"{op}(Row(f=0), Row(f=1))", shards)              # bytes == oracle canonical bytes, and ...
+        # Sets, not bytes: several of these reference cases use operands with adjacent, unmerged runs ([1,2],[3,4],[5,7]), which
+        # no stored fragment contains.  The reference passes such a container through a one-sided union untouched, whereas the
+        # device always emits the maximal runs of the result set, so the serialised forms legitimately differ there.
+        q = f"{op}(Row(f=0), Row(f=1))"
+        got = p.ex.execute("i", q, shards)[0]
         cols = [int(x) for x in got.columns()]
-        assert cols == [v for k in shards for v in expect[k]], op              # ... == the reference's literal expectations
+        assert cols == [int(x) for x in p.ora.eval_row(pql.parse(q)[0], shards).slice()], op
+        assert cols == [v for k in shards for v in expect[k]], op              # == the reference's literal expectations
+        assert got.count == len(cols)
         if op == "Intersect":
             tot, per = p.holder.ctx.count(p.idx.id, [X.L.Op(X.L.OP_ROW, p.idx.fields["f"].id, 0, 0, 0, 0, 0, 0), X.L.Op(X.L.OP_ROW, p.idx.fields["f"].id, 0, 0, 1, 0, 0, 0),
                                                      X.L.Op(X.L.OP_INTERSECT, 0, 0, 2, 0, 0, 0, 0)], shards, per_shard=True)
