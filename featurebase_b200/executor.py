@@ -271,6 +271,8 @@ class Executor:
                 return self._minmax(idx, c, shards, c.name)
             if c.name == "Percentile":
                 return self._percentile(idx, c, shards)
+            if c.name in ("MinRow", "MaxRow"):
+                return self._minmax_row(idx, c, shards, c.name == "MaxRow")
             if c.name == "IncludesColumn":                       # executeIncludesColumnCall: is the column in the row?
                 if "column" not in c.args:
                     raise QueryError("IncludesColumn call must specify a column")
@@ -598,6 +600,30 @@ class Executor:
             else:
                 v, cnt = self._sweep_unsigned(idx, f, pos, n_pos, shards, True)
         return ValCount(v + f.base, cnt)                                # valCountize field.go:1640
+
+    def _minmax_row(self, idx, c, shards, want_max):
+        """executeMinRow / executeMaxRow :1604-1672 with fragment.minRow / maxRow fragment.go:862-922: the smallest / largest
+        row id that has a bit (under the optional filter).  Per shard the reference reports Count = 1 without a filter, else
+        |row ∩ filter| in that shard, and the reduce keeps the pair of ONE shard (on equal ids the later arrival, so the count
+        is order dependent upstream); here: the last shard, in ascending order, where the row meets the filter.
+        Returns (row id, count), or (0, 0) when nothing qualifies."""
+        name = c.args.get("field", c.args.get("_field"))
+        if not name:
+            raise QueryError(("MaxRow" if want_max else "MinRow") + "(): field required")
+        f = self._field(idx, name)
+        filt = self._bitmap_call(idx, c.children[0]) if c.children else None
+        rid, cnt = self.ctx.row_counts(idx.id, f.id, VIEW_STANDARD, shards, filter_ops=filt)
+        ids = [int(r) for r, n in zip(rid, cnt) if n > 0]
+        if not ids:
+            return (0, 0)
+        best = max(ids) if want_max else min(ids)
+        if filt is None:
+            return (best, 1)
+        for s in sorted(shards, reverse=True):
+            n = int(self.ctx.row_counts(idx.id, f.id, VIEW_STANDARD, [s], row_ids=[best], filter_ops=filt)[0])
+            if n:
+                return (best, n)
+        return (best, 0)
 
     def _percentile(self, idx, c, shards):
         """executePercentile :1310-1600 (int fields): total = Count(filter ∩ notNull); the wanted numbers of smaller / larger

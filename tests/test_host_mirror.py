@@ -79,6 +79,7 @@ def test_embedded_rows(oracle_backed):
     E.test_embedded_rows_constrow_unionrows()
     E.test_shift_and_includes_column()
     E.test_all_with_limit_offset()
+    E.test_min_max_row()
 
 
 def test_percentile(oracle_backed):

@@ -600,3 +600,26 @@ def test_all_with_limit_offset():
     for q, exp in cases:
         got = p.ex.execute("i", q)[0]
         assert got.count == len(exp) and [int(c) for c in got.columns()] == exp, q
+
+
+def test_min_max_row():
+    """executor_test.go:2662-2712 TestExecutor_Execute_MinMaxRow (RowID) + filtered variants against brute force"""
+    SW = 1 << 20
+    p = Pair(track_existence=False)
+    p.field("f")
+    p.field("g")
+    for col, row in ((0, 7000), (3, 50), (SW + 1, 10000), (1000, 1), (SW + 2, 5000)):
+        p.holder.set_bit("i", "f", row, col)
+    for col in (3, SW + 2, 5 * SW):
+        p.holder.set_bit("i", "g", 0, col)
+    p.sync_pending()
+    assert p.ex.execute("i", "MinRow(field=f)")[0] == (1, 1)
+    assert p.ex.execute("i", "MaxRow(field=f)")[0] == (10000, 1)
+    assert p.ex.execute("i", "MinRow(Row(g=0), field=f)")[0] == (50, 1)          # rows meeting the filter: 50 (col 3), 5000 (col SW+2)
+    assert p.ex.execute("i", "MaxRow(Row(g=0), field=f)")[0] == (5000, 1)
+    assert p.ex.execute("i", "MinRow(Row(g=7), field=f)")[0] == (0, 0)
+    for bad in ("MinRow(field=fake)", "MaxRow(field=fake)"):
+        with pytest.raises(X.QueryError, match="field not found"):
+            p.ex.execute("i", bad)
+    with pytest.raises(X.QueryError, match="field required"):
+        p.ex.execute("i", "MinRow()")
