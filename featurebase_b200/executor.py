@@ -232,6 +232,26 @@ class ValCount:
         return f"ValCount(val={self.val}, count={self.count})"
 
 
+class SignedRow:
+    """pilosa.SignedRow executor.go:8225: the distinct values of an int field, as two id sets (Pos: values >= 0, Neg: |v| of
+    the negative ones), Base already added (executeDistinctShardBSI :2125)"""
+
+    def __init__(self, pos=(), neg=()):
+        self.pos, self.neg = sorted(pos), sorted(neg)
+
+    def values(self):
+        return [-v for v in reversed(self.neg)] + list(self.pos)       # SignedRow.ToRows :8253 order
+
+    def count(self):
+        return len(self.pos) + len(self.neg)                            # executeCount :5861
+
+    def __eq__(self, o):
+        return isinstance(o, SignedRow) and (self.pos, self.neg) == (o.pos, o.neg)
+
+    def __repr__(self):
+        return f"SignedRow(pos={self.pos}, neg={self.neg})"
+
+
 def _i64(x):
     x &= (1 << 64) - 1
     return x - (1 << 64) if x >> 63 else x
@@ -273,6 +293,8 @@ class Executor:
                 return self._percentile(idx, c, shards)
             if c.name in ("MinRow", "MaxRow"):
                 return self._minmax_row(idx, c, shards, c.name == "MaxRow")
+            if c.name == "Distinct":
+                return self._distinct(idx, c, shards)
             if c.name == "IncludesColumn":                       # executeIncludesColumnCall: is the column in the row?
                 if "column" not in c.args:
                     raise QueryError("IncludesColumn call must specify a column")
@@ -345,6 +367,15 @@ class Executor:
                 ops.append(L.Op(L.OP_ALL, idx.fields[EXISTENCE_FIELD].id, VIEW_STANDARD, 0, 0, 0, 0, 0))
                 ops.append(L.Op(L.OP_INTERSECT, 0, 0, 2, 0, 0, 0, 0))
             return
+        if n == "Distinct":                                      # handlePreCalls :396-440: the result's ids become a column row (SignedRow: Pos only)
+            res = self._distinct(idx, c, self._cur_shards)
+            cols = res.pos if isinstance(res, SignedRow) else res
+            if not cols:
+                ops.append(L.Op(L.OP_EMPTY, 0, 0, 0, 0, 0, 0, 0))
+                return
+            f, row = self.holder.embed_row(idx.name, cols)
+            ops.append(L.Op(L.OP_ROW, f.id, VIEW_STANDARD, 0, row, 0, 0, 0))
+            return
         if n == "Shift":                                         # executeShiftShard (unsupported upstream, row.go Shift): every column + n
             if len(c.children) != 1:
                 raise QueryError("Shift() requires a single bitmap input")
@@ -399,13 +430,7 @@ class Executor:
         if f.type == "bool":
             v = 1 if v else 0                                    # fragment.go:59-60
         if "from" in c.args or "to" in c.args:                   # :5149-5163, 5209-5241: union of the row over the covering time views
-            try:
-                t_from = timeq.parse_time(c.args["from"]) if "from" in c.args else None
-                t_to = timeq.parse_time(c.args["to"]) if "to" in c.args else None
-            except ValueError as e:
-                raise QueryError(f"parsing time: {e}")
-            ids = [f.view_id(name) for name in f.views_by_time_range(t_from, t_to)]
-            ids = [i for i in ids if i is not None]               # views without a fragment anywhere contribute nothing
+            ids = self._time_view_ids(f, c.args)
             if not ids:
                 ops.append(L.Op(L.OP_EMPTY, 0, 0, 0, 0, 0, 0, 0))
                 return
@@ -415,6 +440,16 @@ class Executor:
                 ops.append(L.Op(L.OP_UNION, 0, 0, len(ids), 0, 0, 0, 0))
             return
         ops.append(L.Op(L.OP_ROW, f.id, VIEW_STANDARD, 0, int(v), 0, 0, 0))
+
+    def _time_view_ids(self, f, args):
+        """ids of the views that cover from= / to= (Field.viewsByTimeRange); views without a fragment anywhere contribute nothing"""
+        try:
+            t_from = timeq.parse_time(args["from"]) if "from" in args else None
+            t_to = timeq.parse_time(args["to"]) if "to" in args else None
+        except ValueError as e:
+            raise QueryError(f"parsing time: {e}")
+        ids = [f.view_id(name) for name in f.views_by_time_range(t_from, t_to)]
+        return [i for i in ids if i is not None]
 
     def _emit_bsi(self, idx, f, cond, ops):                      # executeRowBSIGroupShard :5249-5354
         if f.type != "int":
@@ -459,6 +494,9 @@ class Executor:
             raise QueryError("Count() requires an input bitmap")
         if len(c.children) > 1:
             raise QueryError("Count() only accepts a single bitmap input")
+        if c.children[0].name == "Distinct":                     # PrecallGlobal child: run it and count the result (:5852-5868)
+            res = self._distinct(idx, c.children[0], shards)
+            return res.count() if isinstance(res, SignedRow) else len(res)
         return self.ctx.count(idx.id, self._bitmap_call(idx, c.children[0]), shards)
 
     # ------------------------------------------------------------------ TopN / TopK (exact modes)
@@ -510,8 +548,14 @@ class Executor:
             ef, erow = self.holder.embed_row(idx.name, [col])
             filt = [L.Op(L.OP_ROW, ef.id, VIEW_STANDARD, 0, erow, 0, 0, 0)]
             shards = [s for s in shards if s == col // SHARD_WIDTH]
-        rid, _ = self.ctx.row_counts(idx.id, f.id, VIEW_BSI if f.type == "int" else VIEW_STANDARD, shards, filter_ops=filt)
-        out = sorted(int(r) for r in rid)
+        views = [VIEW_BSI if f.type == "int" else VIEW_STANDARD]
+        if f.quantum and ("from" in c.args or "to" in c.args):    # executeRowsShard :4107-4127: the rows of every covering view, merged
+            views = self._time_view_ids(f, c.args)
+        out = set()
+        for v in views:
+            rid, _ = self.ctx.row_counts(idx.id, f.id, v, shards, filter_ops=filt)
+            out.update(int(r) for r in rid)
+        out = sorted(out)
         if "in" in c.args:
             keep = {int(r) for r in c.args["in"]}
             out = [r for r in out if r in keep]
@@ -625,6 +669,72 @@ class Executor:
                 return (best, n)
         return (best, 0)
 
+    def _distinct(self, idx, c, shards):
+        """executeDistinct :1173 / executeDistinctShard :1820.  Set-like field: the ids of the rows that have a bit (under the
+        optional filter), executeDistinctShardSet :1952 — one row-count launch.  Int field: the set of values present,
+        executeDistinctShardBSI :2034, returned as a SignedRow.  The reference transposes the bit planes column by column;
+        here the value set is found by splitting on bit planes: one row-count launch per node gives |node ∩ plane_i| for
+        every plane, planes that hold none / all of the node's columns fix their bit, the highest mixed plane splits the
+        node.  Launches ~ 2 x distinct values, each over the whole shard batch; meant for low-cardinality fields (a fused
+        extraction kernel is the DESIGN §9 follow-up).  `index=` runs the call on another index (foreign-index joins)."""
+        name = c.args.get("field", c.args.get("_field"))
+        if name is None:
+            raise QueryError("missing field option in Distinct query")
+        if len(c.children) > 1:
+            raise QueryError("Distinct() only accepts a single bitmap input")
+        other = c.args.get("index")
+        if other is not None and other != idx.name:
+            idx = self.holder.indexes.get(other)
+            if idx is None:
+                raise QueryError("index not found")
+            shards = sorted(idx.shards)
+        f = self._field(idx, name)
+        saved, self._cur_shards = self._cur_shards, shards
+        try:
+            filt = self._bitmap_call(idx, c.children[0]) if c.children else None
+        finally:
+            self._cur_shards = saved
+        if f.type != "int":
+            rid, cnt = self.ctx.row_counts(idx.id, f.id, VIEW_STANDARD, shards, filter_ops=filt)
+            return sorted(int(r) for r, n in zip(rid, cnt) if n > 0)
+        exists = L.Op(L.OP_ROW, f.id, VIEW_BSI, 0, 0, 0, 0, 0)
+        sign = L.Op(L.OP_ROW, f.id, VIEW_BSI, 0, 1, 0, 0, 0)
+        consider = [exists] if filt is None else filt + [exists, L.Op(L.OP_INTERSECT, 0, 0, 2, 0, 0, 0, 0)]
+        planes = list(range(2, 2 + f.bit_depth))
+        mags = {}                                                      # sign -> magnitudes
+        for negative in (False, True):
+            root = consider + [sign, L.Op(L.OP_INTERSECT if negative else L.OP_DIFFERENCE, 0, 0, 2, 0, 0, 0, 0)]
+            n_root = self.ctx.count(idx.id, root, shards)
+            found = mags.setdefault(negative, [])
+            stack = [(root, n_root, f.bit_depth - 1, 0)] if n_root else []
+            while stack:
+                node, n, top, val = stack.pop()                        # bits above `top` are decided and folded into `node` / `val`
+                if top < 0:
+                    found.append(val)
+                    continue
+                cnt = self.ctx.row_counts(idx.id, f.id, VIEW_BSI, shards, row_ids=planes[:top + 1], filter_ops=node)
+                split = None
+                for i in range(top, -1, -1):
+                    k = int(cnt[i])
+                    if k == n:
+                        val |= 1 << i
+                    elif k:
+                        split = (i, k)
+                        break
+                if split is None:
+                    found.append(val)
+                    continue
+                i, k = split
+                plane = L.Op(L.OP_ROW, f.id, VIEW_BSI, 0, 2 + i, 0, 0, 0)
+                stack.append((node + [plane, L.Op(L.OP_DIFFERENCE, 0, 0, 2, 0, 0, 0, 0)], n - k, i - 1, val))
+                stack.append((node + [plane, L.Op(L.OP_INTERSECT, 0, 0, 2, 0, 0, 0, 0)], k, i - 1, val | 1 << i))
+        pos, neg = [], []
+        for negative, ms in mags.items():
+            for m in ms:
+                v = (-m if negative else m) + f.base                   # value += offset (:2125)
+                (neg if v < 0 else pos).append(abs(v))
+        return SignedRow(pos, neg)
+
     def _percentile(self, idx, c, shards):
         """executePercentile :1310-1600 (int fields): total = Count(filter ∩ notNull); the wanted numbers of smaller / larger
         values; Min and Max under the filter; then a bisection on the value, two Count(Row(f < x) [∩ filter]) style queries
@@ -684,7 +794,7 @@ class Executor:
         sort (:3130-3162, 3408-3414), offset / limit (:3441-3459).  Results: (group, count) or (group, count, agg)."""
         if not c.children:
             raise QueryError("need at least one child call")
-        fields, row_ids = [], []
+        fields, row_ids, time_args = [], [], []
         for ch in c.children:
             if ch.name != "Rows":
                 raise QueryError(f"'{ch.name}' is not a valid child query for GroupBy, must be 'Rows'")
@@ -695,14 +805,35 @@ class Executor:
             fields.append(f)
             pre = pql.Call("Rows", {k: v for k, v in ch.args.items() if k != "previous"})     # previous positions the iterator, it does not drop rows
             row_ids.append(self._rows(idx, pre, shards))         # pre-pass executeRows :3263-3287
+            time_args.append({k: ch.args[k] for k in ("from", "to") if k in ch.args} if f.quantum else {})
         filt_call = c.args.get("filter")
         filt = self._bitmap_call(idx, filt_call) if isinstance(filt_call, pql.Call) else None
         agg = c.args.get("aggregate")
-        if isinstance(agg, pql.Call) and agg.name != "Sum":
-            raise QueryError(f"aggregate {agg.name} is not supported by this mirror")
+        distinct_agg = False
+        if isinstance(agg, pql.Call):
+            if agg.name == "Count":                              # Count(Distinct(..)) is filled in after the groups are known (:3340-3386);
+                distinct_agg = bool(agg.children) and agg.children[0].name == "Distinct"      # any other Count is the plain count (:8889)
+                agg_distinct, agg = (agg.children[0] if distinct_agg else None), None
+            elif agg.name != "Sum":
+                raise QueryError(f"aggregate {agg.name} is not supported by this mirror")
         if any(len(r) == 0 for r in row_ids):
             return []
-        counts = self.ctx.groupby(idx.id, [f.id for f in fields], [VIEW_STANDARD] * len(fields), row_ids, shards, filter_ops=filt)
+        # what the device groups over: a field's standard view, or — for Rows(f, from=, to=) on a time field — one operand
+        # row per row id holding the union of that row over the covering views (timeFragmentsRowIterator :8755-8768)
+        dev_fields, dev_rows = [], []
+        for f, rows, targs in zip(fields, row_ids, time_args):
+            if not targs:
+                dev_fields.append(f.id)
+                dev_rows.append(rows)
+                continue
+            operands = []
+            for r in rows:
+                data, _ = self.ctx.row(idx.id, self._bitmap_call(idx, pql.Call("Row", {f.name: r, **targs})), shards)
+                sf, srow = self.holder.embed_row(idx.name, roaring_io.decode(data))
+                operands.append(srow)
+            dev_fields.append(sf.id)
+            dev_rows.append(operands)
+        counts = self.ctx.groupby(idx.id, dev_fields, [VIEW_STANDARD] * len(fields), dev_rows, shards, filter_ops=filt)
         start = self._groupby_start(c, row_ids)
         if start is None:
             return []
@@ -716,7 +847,7 @@ class Executor:
             ix = np.unravel_index(int(flat), counts.shape)
             group = [(f.name, row_ids[k][int(i)]) for k, (f, i) in enumerate(zip(fields, ix))]
             if isinstance(agg, pql.Call):
-                rows = [pql.Call("Row", {name: rid}) for name, rid in group]
+                rows = [pql.Call("Row", {name: rid, **targs}) for (name, rid), targs in zip(group, time_args)]
                 if isinstance(filt_call, pql.Call):
                     rows.append(filt_call)
                 inter = rows[0] if len(rows) == 1 else pql.Call("Intersect", {}, rows)
@@ -728,6 +859,18 @@ class Executor:
                 out.append((group, int(counts[ix])))
             if limit and len(out) >= limit and "offset" not in c.args:
                 break
+        if distinct_agg:
+            if not (has_sort or has_having):                      # limits first: the aggregate is expensive per group (:3327-3335)
+                out = self._window(c, out)
+            for k, (group, n) in enumerate(out):                  # Count(Distinct(Intersect(group rows, filter, Distinct's child), field=..)) :3343-3385
+                rows = [pql.Call("Row", {name: rid, **targs}) for (name, rid), targs in zip(group, time_args)]
+                if isinstance(filt_call, pql.Call):
+                    rows.append(filt_call)
+                rows += agg_distinct.children[:1]
+                res = self._distinct(idx, pql.Call("Distinct", dict(agg_distinct.args), [pql.Call("Intersect", {}, rows)]), shards)
+                out[k] = (group, n, res.count() if isinstance(res, SignedRow) else len(res))
+            if not (has_sort or has_having):
+                return out
         if has_having:                                            # Condition(count|sum <op> n)
             having = c.args["having"]
             if having.name != "Condition" or len(having.args) != 1:
@@ -746,6 +889,10 @@ class Executor:
                 keys.append((1 if w[0] == "count" else 2, len(w) == 2 and w[1] == "asc"))
             for col, asc in reversed(keys):                       # stable sorts, last key first == sort.Stable on the tuple
                 out.sort(key=lambda g: (g[col] if len(g) > col else 0), reverse=not asc)
+        return self._window(c, out)
+
+    @staticmethod
+    def _window(c, out):                                          # applyLimitAndOffsetToGroupByResult :3441-3459
         off = c.args.get("offset")
         if off is not None and int(off) < len(out):               # (an offset beyond the result is ignored, :3446)
             out = out[int(off):]

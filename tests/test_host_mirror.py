@@ -82,6 +82,11 @@ def test_embedded_rows(oracle_backed):
     E.test_min_max_row()
 
 
+def test_various_queries(oracle_backed):
+    E.test_various_queries_goldens()
+    E.test_distinct_random()
+
+
 def test_percentile(oracle_backed):
     E.test_percentile_vs_reference_helper()
 

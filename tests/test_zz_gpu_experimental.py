@@ -623,3 +623,135 @@ def test_min_max_row():
             p.ex.execute("i", bad)
     with pytest.raises(X.QueryError, match="field required"):
         p.ex.execute("i", "MinRow()")
+
+
+def test_various_queries_goldens():
+    """executor_test.go:8560-8990 populateTestData / variousQueries with the keys replaced by ids in order of first use (key
+    translation is outside the path): Distinct on set and int fields, Count(Distinct), GroupBy over time-range rows, with
+    filter / aggregate=Sum / aggregate=Count(Distinct) / having / sort / limit / offset.  The users are spread over three
+    shards; userE is alone in the last one."""
+    SW = 1 << 20
+    U = dict(A=1, B=2, C=SW + 3, D=4, E=2 * SW + 5, F=6, G=SW + 7)
+    p = Pair()
+    p.field("likenums")
+    for rid, u in [(1, "A"), (2, "B"), (3, "C"), (4, "D"), (5, "E"), (6, "F"), (7, "A"), (7, "B"), (7, "C"), (7, "D"), (7, "F")]:
+        p.holder.set_bit("i", "likenums", rid, U[u])             # (row 7 leaves userE out, as upstream)
+    p.field("likes")                                              # molecula 1, pilosa 2, pangolin 3, zebra 4, toucan 5, dog 6, icecream 7
+    for rid, u in [(1, "A"), (2, "B"), (3, "C"), (4, "D"), (5, "E"), (6, "F")] + [(7, u) for u in "ABCDEF"]:
+        p.holder.set_bit("i", "likes", rid, U[u])
+    p.field("places", "time", quantum="YM")                       # nairobi 1, paris 2, austin 3, toronto 4, mombasa 5, sydney 6
+    J19, A19, J20 = "2019-01-01T00:00", "2019-08-01T00:00", "2020-01-01T00:00"
+    for rid, u, ts in [(1, "B", J19), (2, "C", J19), (3, "F", J19), (4, "A", J19), (4, "B", A19), (4, "C", A19), (4, "B", J20), (4, "D", J20),
+                       (4, "E", J20), (4, "F", J20), (5, "A", J20), (6, "D", J20), (1, "E", J20)]:
+        p.holder.set_bit("i", "places", rid, U[u], timestamp=ts)
+    p.field("affinity", "int", min=-1000, max=1000)
+    for u, v in dict(A=10, B=-10, C=5, D=-5, E=0).items():
+        p.holder.set_value("i", "affinity", U[u], v)
+    p.field("net_worth", "int", min=-100000000, max=100000000)
+    for u, v in dict(A=1, B=10, C=100, D=1000, E=10000, F=100000).items():
+        p.holder.set_value("i", "net_worth", U[u], v)
+    p.field("zip_code", "int", min=0, max=100000)
+    for u, v in dict(A=78739, B=78739, C=19707, D=19707, E=86753, G=78739).items():
+        p.holder.set_value("i", "zip_code", U[u], v)
+    p.sync_pending()
+    run = lambda q: p.ex.execute("i", q)[0]
+    gb = lambda q: [tuple(r for _, r in g[0]) + tuple(g[1:]) for g in run(q)]
+    Y19, ALL = "from='2019-01-01T00:00', to='2019-12-31T23:59'", "from='2019-01-01T00:00', to='2020-12-31T23:59'"
+    NOT_C = "filter=Not(Intersect(Row(likes=3), Row(likes=7)))"
+    assert gb(f"GroupBy(Rows(places, {ALL}))") == [(1, 2), (2, 1), (3, 1), (4, 6), (5, 1), (6, 1)]
+    assert gb("GroupBy(Rows(places, from='2019-01-01T00:00', to='2019-02-01T00:00'))") == [(1, 1), (2, 1), (3, 1), (4, 1)]
+    assert gb(f"GroupBy(Rows(places, {Y19}))") == [(1, 1), (2, 1), (3, 1), (4, 3)]
+    assert gb(f"GroupBy(Rows(places, {Y19}), {NOT_C})") == [(1, 1), (3, 1), (4, 2)]
+    assert gb(f"GroupBy(Rows(places, {Y19}), {NOT_C}, aggregate=Sum(field=net_worth))") == [(1, 1, 10), (3, 1, 100000), (4, 2, 11)]
+    assert run(f"Rows(places, {ALL})") == [1, 2, 3, 4, 5, 6]
+    assert run(f"Rows(places, {Y19})") == [1, 2, 3, 4]
+    assert run("Rows(places, from='2019-01-01T00:00', to='2019-02-01T00:00')") == [1, 2, 3, 4]
+    assert run("Count(All())") == 7
+    assert run("Count(Distinct(field=likenums))") == 7
+    assert run("Distinct(field=likenums)") == [1, 2, 3, 4, 5, 6, 7]
+    assert run("Count(Distinct(field=likes))") == 7
+    d = run("Distinct(field=affinity)")
+    assert (d.pos, d.neg, d.values()) == ([0, 5, 10], [5, 10], [-10, -5, 0, 5, 10])
+    assert run("Count(Distinct(field=affinity))") == 5
+    assert run("Distinct(Row(affinity>=0),field=affinity)") == X.SignedRow([0, 5, 10], [])
+    assert run("Count(Distinct(Row(affinity>=0),field=affinity))") == 3
+    assert run("Distinct(Row(affinity<0),field=likes)") == [2, 4, 7]
+    assert run("Distinct(Row(affinity>0),field=likes)") == [1, 3, 7]
+    assert run("Distinct(Row(likenums=1),field=likes)") == [1, 7]
+    for q in ("Distinct(field=likes)", "Distinct(All(),field=likes)", "Distinct(field=likes )"):
+        assert run(q) == [1, 2, 3, 4, 5, 6, 7], q
+    assert gb("GroupBy(Rows(field=likes))") == [(1, 1), (2, 1), (3, 1), (4, 1), (5, 1), (6, 1), (7, 6)]
+    assert gb("GroupBy(Rows(field=likes), aggregate=Sum(field=net_worth), limit=2, having=Condition(sum>10))") == [(3, 1, 100), (4, 1, 1000)]
+    assert gb("GroupBy(Rows(field=likes), having=Condition(count>5))") == [(7, 6)]
+    assert gb("GroupBy(Rows(field=likes), filter=Row(affinity>-7))") == [(1, 1), (3, 1), (4, 1), (5, 1), (7, 4)]
+    CD = "aggregate=Count(Distinct(field=zip_code))"
+    assert gb(f"GroupBy(Rows(field=likes), {CD})") == [(1, 1, 1), (2, 1, 1), (3, 1, 1), (4, 1, 1), (5, 1, 1), (6, 1, 0), (7, 6, 3)]
+    assert gb(f"GroupBy(Rows(field=likes), {CD}, having=Condition(sum>2))") == [(7, 6, 3)]
+    assert gb(f"GroupBy(Rows(field=likes), filter=Row(affinity>-11), {CD})") == [(1, 1, 1), (2, 1, 1), (3, 1, 1), (4, 1, 1), (5, 1, 1), (7, 5, 3)]
+    assert gb("GroupBy(Rows(field=likes), filter=Row(affinity>-11), aggregate=Count(Distinct(Row(affinity>-7), field=zip_code)))") == \
+        [(1, 1, 1), (2, 1, 0), (3, 1, 1), (4, 1, 1), (5, 1, 1), (7, 5, 3)]
+    assert gb('GroupBy(Rows(field=likes), sort="count desc")') == [(7, 6), (1, 1), (2, 1), (3, 1), (4, 1), (5, 1), (6, 1)]
+    SUM = 'aggregate=Sum(field=net_worth), sort="aggregate desc, count asc"'
+    full = [(7, 6, 111111), (6, 1, 100000), (5, 1, 10000), (4, 1, 1000), (3, 1, 100), (2, 1, 10), (1, 1, 1)]
+    assert gb(f"GroupBy(Rows(field=likes), {SUM})") == full
+    assert gb(f"GroupBy(Rows(field=likes), {SUM}, limit=3)") == full[:3]
+    assert gb(f"GroupBy(Rows(field=likes), {SUM},limit=3,offset=2)") == full[2:5]
+    # TestExecutor_Execute_Distinct / BareDistinct (executor_test.go:5945-5977, 7175-7207): a foreign-index join through Distinct(index=)
+    h = p.holder
+    par, ch = h.create_index("parent"), h.create_index("child")
+    par.create_field("general")
+    for row, cols in ((1, (1, 2, 3)), (2, (21, 22, 23)), (SW, (1, 21))):
+        for c in cols:
+            h.set_bit("parent", "general", row, c)
+    ch.create_field("parent_id", "int", min=0, max=(1 << 28) - 1)
+    ch.create_field("parent_set_id")
+    ch.create_field("color")                                      # red 1, blue 2
+    for col, parent, color in ((1, 1, 1), (2, 2, 2), (SW, 1, 2), (4, 21, 1)):
+        h.set_value("child", "parent_id", col, parent)
+        h.set_bit("child", "parent_set_id", parent, col)
+        h.set_bit("child", "color", color, col)
+    h.sync()
+    ex = X.Executor(h)
+    assert ex.execute("child", "Distinct(index=child, field=parent_id)")[0] == X.SignedRow([1, 2, 21], [])
+    assert ex.execute("child", "Distinct(field=parent_set_id)")[0] == [1, 2, 21]
+    assert ex.execute("child", "Distinct(Row(parent_id=3), field=parent_id)")[0] == X.SignedRow()
+    for fld in ("parent_id", "parent_set_id"):
+        got = ex.execute("parent", f"Intersect(Row(general={SW}), Distinct(Row(color=2), index=child, field={fld}))")[0]
+        assert [int(c) for c in got.columns()] == [1], fld
+    with pytest.raises(X.QueryError, match="missing field option"):
+        ex.execute("child", "Distinct(Row(color=2))")
+
+
+def test_distinct_random():
+    """Distinct over int fields (zero, positive and negative Base; values on both sides of zero; with and without a filter) and
+    set fields against a direct enumeration of the imported values"""
+    SW = 1 << 20
+    rng = np.random.default_rng(77)
+    for lo, hi, n_vals in ((-300, 300, 40), (1000, 90000, 25), (-5000, -10, 30), (0, 1, 2), (-(1 << 40), 1 << 40, 12)):
+        p = Pair()
+        p.field("v", "int", min=lo, max=hi)
+        p.field("s")
+        pool = [int(x) for x in rng.integers(lo, hi, size=n_vals, endpoint=True)] + [lo, hi]
+        cols = rng.choice(3 * SW, size=400, replace=False)
+        vals = {}
+        for c in cols.tolist():
+            vals[c] = pool[int(rng.integers(len(pool)))]
+            p.holder.set_value("i", "v", c, vals[c])
+            p.holder.set_bit("i", "s", int(rng.integers(0, 9)) * 1000, c)
+        for c in rng.choice(3 * SW, size=100, replace=False).tolist():           # columns without a value
+            p.holder.set_bit("i", "s", 3, c)
+        p.sync_pending()
+        members = {}
+        for r in [k * 1000 for k in range(9)] + [3]:
+            members[r] = {int(c) for c in p.ex.execute("i", f"Row(s={r})")[0].columns()}
+        def expect(keep):
+            seen = {vals[c] for c in vals if keep(c)}
+            return X.SignedRow([v for v in seen if v >= 0], [-v for v in seen if v < 0])
+        assert p.ex.execute("i", "Distinct(field=v)")[0] == expect(lambda c: True), (lo, hi)
+        assert p.ex.execute("i", "Count(Distinct(field=v))")[0] == expect(lambda c: True).count()
+        for r in (0, 4000, 3):
+            assert p.ex.execute("i", f"Distinct(Row(s={r}), field=v)")[0] == expect(lambda c: c in members[r]), (lo, hi, r)
+        mid = (lo + hi) // 2
+        assert p.ex.execute("i", f"Distinct(Row(v > {mid}), field=v)")[0] == expect(lambda c: vals[c] > mid), (lo, hi)
+        assert p.ex.execute("i", f"Distinct(Row(v < {mid}), field=s)")[0] == sorted(r for r in members if any(c in vals and vals[c] < mid for c in members[r]))
+        assert p.ex.execute("i", "Distinct(Row(s=12345), field=v)")[0] == X.SignedRow()
