@@ -1219,6 +1219,20 @@ constexpr int kGbSlots = 8192;          // open-addressing table slots per CTA (
 constexpr int kGbPool = kGbSlots / 2;   // entries per pass (load factor <= 0.5)
 constexpr uint32_t kGbEmpty = 0xffffffffu;
 constexpr uint32_t kGbDenseCard = 4096; // a-rows at/above this cardinality (or non-array) use the bitmap pass
+constexpr uint32_t kGbSmallCard = 32;   // kFast: arrays up to this cardinality are walked by one thread each
+
+// one thread walks a small array container, 8 elements per 16-byte load (array payloads start 16-byte aligned and are
+// allocated in 16-byte units, so the last load stays inside the container's allocation; elements past card are skipped)
+template <class F>
+__device__ __forceinline__ void thread_for_each_small(const Resolved& c, F f) {
+    const uint4* p = reinterpret_cast<const uint4*>(c.ptr);
+    for (uint32_t k0 = 0; k0 < c.card; k0 += 8) {
+        const uint4 v = ldg_nc(p + (k0 >> 3));
+        const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+        for (int q = 0; q < 8; q++) if (k0 + q < c.card) f((w[q >> 1] >> ((q & 1) * 16)) & 0xffffu);
+    }
+}
 
 template <class F>
 __device__ __forceinline__ void warp_for_each(const Resolved& c, int lane, F f) {
@@ -1249,6 +1263,12 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* tmp, u
     return base + inc - v;
 }
 
+// kFast (opt-in, FBGPU_GROUPBY_FAST=1, not yet run on a GPU): when every a-row container of the chunk is a small array
+// (<= kGbSmallCard elements) and they fit one pass, each thread inserts its own row's elements straight from a 16-byte
+// load — no offset scan, no per-element binary search; small b-row arrays are probed the same way; the fragment check is
+// done by every thread instead of thread 0 + two barriers, and the b-row descriptors of the first chunk are fetched
+// together with the a-rows so that the two dependent-load chains overlap.  kFast == false is the measured kernel.
+template <bool kFast>
 __global__ void __launch_bounds__(kGbThreads)
 groupby_kernel(StoreRef st, uint32_t fvA, const uint64_t* __restrict__ rowsA, int nA,
                uint32_t fvB, const uint64_t* __restrict__ rowsB, int nB,
@@ -1268,6 +1288,12 @@ groupby_kernel(StoreRef st, uint32_t fvA, const uint64_t* __restrict__ rowsA, in
         const uint64_t shard = shards[unit >> 4];
         const int slot = (int)(unit & 15);
         const uint32_t* flt = filter_bitmaps ? reinterpret_cast<const uint32_t*>(filter_bitmaps + (size_t)unit * 512) : nullptr;
+        int resB_chunk = -1;          // kFast: first b-row of the chunk resB[] holds for this unit (-1: none)
+        if (kFast) {      // same test, made by every thread (uniform; the loads are broadcasts) — no barrier
+            bool ok = fvA < st.n_views && fvB < st.n_views;
+            if (ok) { ViewTab va = st.views[fvA], vb = st.views[fvB]; ok = shard < va.n_shards && shard < vb.n_shards && st.shardmap[va.shard_off + shard] >= 0 && st.shardmap[vb.shard_off + shard] >= 0; }
+            if (!ok) continue;
+        } else {
         __syncthreads();
         if (tid == 0) {   // executor.go:8769-8772: a shard missing either fragment contributes nothing
             bool ok = fvA < st.n_views && fvB < st.n_views;
@@ -1276,15 +1302,46 @@ groupby_kernel(StoreRef st, uint32_t fvA, const uint64_t* __restrict__ rowsA, in
         }
         __syncthreads();
         if (!s_any) continue;
+        }
 
         for (int a0 = 0; a0 < nA; a0 += kGbThreads) {
             const int chunkA = min(kGbThreads, nA - a0);
             // all a-row descriptor chains of this chunk are walked concurrently (one per thread)
+            bool fastA = false;
+            if (kFast) {
+                Resolved r, rb; r.ptr = nullptr; r.card = 0; r.typ = 0; r.cnt = 0; rb = r;
+                const bool fetchB = resB_chunk != 0;               // (uniform)
+                if (tid < chunkA) r = resolve(st, fvA, shard, rowsA[a0 + tid], slot);
+                if (fetchB && tid < min(kGbThreads, nB)) rb = resolve(st, fvB, shard, rowsB[tid], slot);
+                const bool small = !r.ptr || (r.typ == kArray && r.card <= kGbSmallCard);
+                __syncthreads();                                   // previous readers of resA / resB / the table are done
+                resA[tid] = r;
+                if (fetchB) { resB[tid] = rb; resB_chunk = 0; }
+                uint32_t total = 0;
+                block_excl_scan(small ? r.card : 0u, scan_tmp, &total);       // (barriers inside: resA / resB are visible after it)
+                fastA = __syncthreads_and(small) && total <= (uint32_t)kGbPool;
+            } else
             { Resolved r; r.ptr = nullptr; r.card = 0; r.typ = 0; r.cnt = 0;
               if (tid < chunkA) r = resolve(st, fvA, shard, rowsA[a0 + tid], slot);
               __syncthreads(); resA[tid] = r; __syncthreads(); }
             int ia = 0;
             while (ia < chunkA) {
+                int pass_end;
+                if (kFast && fastA) {
+                    // ---- the whole chunk in one pass, one thread per a-row
+                    { uint4* t4 = reinterpret_cast<uint4*>(tab); for (int i = tid; i < kGbSlots / 4; i += kGbThreads) t4[i] = make_uint4(kGbEmpty, kGbEmpty, kGbEmpty, kGbEmpty); }
+                    __syncthreads();
+                    const Resolved c = resA[tid];
+                    if (tid < chunkA && c.ptr)
+                        thread_for_each_small(c, [&](uint32_t col) {
+                            if (flt && !((__ldg(flt + (col >> 5)) >> (col & 31)) & 1u)) return;
+                            const uint32_t ent = (col << 16) | (uint32_t)(a0 + tid);
+                            uint32_t h = (col * 40503u) & (kGbSlots - 1);
+                            while (atomicCAS(&tab[h], kGbEmpty, ent) != kGbEmpty) h = (h + 1) & (kGbSlots - 1);
+                        });
+                    pass_end = chunkA;
+                    __syncthreads();
+                } else {
                 // ---- sparse pass [ia, pass_end): pool offsets = exclusive prefix over row cardinalities (deterministic)
                 const Resolved mine = resA[tid];
                 const bool in_range = tid >= ia && tid < chunkA;
@@ -1297,7 +1354,7 @@ groupby_kernel(StoreRef st, uint32_t fvA, const uint64_t* __restrict__ rowsA, in
                 offA[tid] = off;
                 { uint4* t4 = reinterpret_cast<uint4*>(tab); for (int i = tid; i < kGbSlots / 4; i += kGbThreads) t4[i] = make_uint4(kGbEmpty, kGbEmpty, kGbEmpty, kGbEmpty); }
                 __syncthreads();
-                const int pass_end = (int)s_pass_end;
+                pass_end = (int)s_pass_end;
                 {   // flat: one thread per a-element of the pass; the owning row is found by binary search over offA[]
                     const uint32_t total = pass_end < chunkA ? offA[pass_end] : (offA[chunkA - 1] + ((resA[chunkA - 1].ptr && resA[chunkA - 1].typ == kArray && resA[chunkA - 1].card < kGbDenseCard) ? resA[chunkA - 1].card : 0u));
                     for (uint32_t e = tid; e < total; e += kGbThreads) {
@@ -1314,13 +1371,31 @@ groupby_kernel(StoreRef st, uint32_t fvA, const uint64_t* __restrict__ rowsA, in
                     }
                 }
                 __syncthreads();
+                }
                 // ---- probe: stream b rows against the table
                 if (pass_end > ia) {
                     for (int b0 = 0; b0 < nB; b0 += kGbThreads) {
                         const int chunkB = min(kGbThreads, nB - b0);
+                        if (!(kFast && resB_chunk == b0))
                         { Resolved r; r.ptr = nullptr; r.card = 0; r.typ = 0; r.cnt = 0;
                           if (tid < chunkB) r = resolve(st, fvB, shard, rowsB[b0 + tid], slot);
-                          __syncthreads(); resB[tid] = r; __syncthreads(); }
+                          __syncthreads(); resB[tid] = r; __syncthreads(); resB_chunk = b0; }
+                        bool fastB = false;
+                        if (kFast) {      // every array of the chunk small: one thread per b-row, straight from its 16-byte loads
+                            const Resolved mb = resB[tid];
+                            fastB = __syncthreads_and(!(tid < chunkB) || !mb.ptr || mb.typ != kArray || mb.card <= kGbSmallCard) != 0;
+                            if (fastB && tid < chunkB && mb.ptr && mb.typ == kArray) {
+                                unsigned long long* cj = counts + (b0 + tid);
+                                thread_for_each_small(mb, [&](uint32_t col) {
+                                    for (uint32_t h = (col * 40503u) & (kGbSlots - 1);; h = (h + 1) & (kGbSlots - 1)) {
+                                        const uint32_t ent = tab[h];
+                                        if (ent == kGbEmpty) break;
+                                        if ((ent >> 16) == col) atomicAdd(cj + (size_t)(ent & 0xffffu) * nB, 1ull);
+                                    }
+                                });
+                            }
+                        }
+                        if (!fastB)
                         {   // arrays: flat thread-per-element (offsets by block scan); bitmap/run rows: warp loop
                             const Resolved mb = resB[tid];
                             const uint32_t nb_ = (tid < chunkB && mb.ptr && mb.typ == kArray) ? mb.card : 0u;
@@ -1378,7 +1453,7 @@ groupby_kernel(StoreRef st, uint32_t fvA, const uint64_t* __restrict__ rowsA, in
                             const int chunkB = min(kGbThreads, nB - b0);
                             { Resolved r; r.ptr = nullptr; r.card = 0; r.typ = 0; r.cnt = 0;
                               if (tid < chunkB) r = resolve(st, fvB, shard, rowsB[b0 + tid], slot);
-                              __syncthreads(); resB[tid] = r; __syncthreads(); }
+                              __syncthreads(); resB[tid] = r; __syncthreads(); resB_chunk = b0; }
                             for (int j = wid; j < chunkB; j += nwarps) {
                                 const Resolved bb = resB[j];
                                 if (!bb.ptr) continue;

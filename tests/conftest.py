@@ -18,7 +18,7 @@ def pytest_collection_modifyitems(config, items):
         have = torch.cuda.is_available()
     except Exception:
         have = False
-    if have:
+    if have or os.environ.get("FBGPU_TEST_ON_EMULATOR"):      # tests/test_emu_kernels.py re-runs gpu-marked bodies on the CPU kernel interpreter
         return
     skip = pytest.mark.skip(reason="no CUDA device")
     for it in items:

@@ -755,3 +755,40 @@ def test_distinct_random():
         assert p.ex.execute("i", f"Distinct(Row(v > {mid}), field=v)")[0] == expect(lambda c: vals[c] > mid), (lo, hi)
         assert p.ex.execute("i", f"Distinct(Row(v < {mid}), field=s)")[0] == sorted(r for r in members if any(c in vals and vals[c] < mid for c in members[r]))
         assert p.ex.execute("i", "Distinct(Row(s=12345), field=v)")[0] == X.SignedRow()
+
+
+def test_groupby_kernel_pass_shapes():
+    """GroupBy over shapes chosen for groupby_kernel's passes: 300 x 270 rows (two a-chunks, two b-chunks) of tiny array
+    containers, a bitmap a-row and a bitmap b-row (dense / warp passes), with and without a filter, either field order —
+    the dense count tensor against the oracle's nested-loop restatement.  (Also run with FBGPU_GROUPBY_FAST=1 by
+    tests/test_emu_kernels.py and tools/r2_first_call.sh.)"""
+    from oracle import oracle as O
+    SW = 1 << 20
+    rng = np.random.default_rng(5)
+    p = Pair(track_existence=False)
+    for n in ("a", "b", "f"):
+        p.field(n)
+    for c in rng.choice(2 * SW, size=6000, replace=False).tolist():
+        p.holder.set_bit("i", "a", int(rng.integers(0, 300)), c)
+        p.holder.set_bit("i", "b", int(rng.integers(0, 270)), c)
+        if c & 1:
+            p.holder.set_bit("i", "f", 1, c)
+    for c in range(70000, 79000):                                  # bitmap containers: a row 7 and b row 11, slot 1 of shard 0
+        p.holder.set_bit("i", "a", 7, c)
+        if c % 3:
+            p.holder.set_bit("i", "b", 11, c)
+    for c in range(SW + 5, SW + 45):                               # an a-row container of 40 elements: above the thread-per-row limit
+        p.holder.set_bit("i", "a", 299, c)
+        p.holder.set_bit("i", "b", c % 270, c)
+    p.sync_pending()
+    rows = {"a": list(range(300)), "b": list(range(270))}
+    for fields, filt in ((("a", "b"), None), (("a", "b"), "Row(f=1)"), (("b", "a"), None), (("b", "a"), "Row(f=1)")):
+        call = pql.parse(filt)[0] if filt else None
+        ids = [rows[f] for f in fields]
+        exp = np.zeros(len(ids[0]) * len(ids[1]), dtype=np.uint64)
+        for s in p.shards():
+            O.groupby_shard([p.ora.frag(f, 0, s) for f in fields], s, ids, p.ora.eval_shard(call, s) if call is not None else None, exp)
+        got = p.holder.ctx.groupby(p.idx.id, [p.idx.fields[f].id for f in fields], [X.VIEW_STANDARD] * 2, ids, p.shards(),
+                                   filter_ops=p.ex._bitmap_call(p.idx, call) if call is not None else None)
+        assert np.array_equal(np.asarray(got).reshape(-1), exp), (fields, filt)
+        assert int(exp.sum()) > 3000

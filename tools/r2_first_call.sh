@@ -25,6 +25,11 @@ FBGPU_LIB=$PWD/featurebase_b200/libfbgpu_wp_unroll3.so timeout 900 python -m pyt
 python bench_sweep.py --configs 3 > $out/sweep3_default.jsonl 2>>$out/bench_err.log
 FBGPU_LIB=$PWD/featurebase_b200/libfbgpu_wp_unroll3.so python bench_sweep.py --configs 3 > $out/sweep3_wp_unroll3.jsonl 2>>$out/bench_err.log
 
+# 3c. thread-per-row GroupBy passes (groupby_kernel<true>, FBGPU_GROUPBY_FAST=1): parity of every GroupBy test, then config 4 A/B
+FBGPU_GROUPBY_FAST=1 timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_zz_gpu_experimental.py -q -k "groupby or various_queries" > $out/pytest_groupby_fast.log 2>&1; echo "pytest_groupby_fast rc=$?" >> $out/summary.txt
+python bench_sweep.py --configs 4 > $out/sweep4_default.jsonl 2>>$out/bench_err.log
+FBGPU_GROUPBY_FAST=1 python bench_sweep.py --configs 4 > $out/sweep4_groupby_fast.jsonl 2>>$out/bench_err.log
+
 # 4. one ncu pass of the headline kernel in both layouts: shared-memory wavefronts / issue utilisation are what changed
 for mode in default striped; do
   env $( [ $mode = striped ] && echo FBGPU_ARRAY_STRIPED=1 ) ncu --set full --clock-control none -k regex:eval_kernel -c 1 -f -o $out/eval_$mode \
