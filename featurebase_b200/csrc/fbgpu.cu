@@ -797,6 +797,74 @@ extern "C" int fbgpu_row(fbgpu_ctx* c, uint32_t index, const fbgpu_op* ops, int3
     return FBGPU_OK;
 } FBGPU_CATCH
 
+// ------------------------------------------------------------------ Columns (Row.Columns(): ascending ids, with executeLimitCall's window)
+extern "C" int fbgpu_columns(fbgpu_ctx* c, uint32_t index, const fbgpu_op* ops, int32_t n_ops, const uint64_t* shards, int64_t n_shards,
+                             uint64_t offset, int64_t limit, uint64_t* out_cols, uint64_t cap, uint64_t* out_n, uint64_t* out_total) try {
+    if (!c || !out_n || n_shards < 0 || (n_shards && !shards) || (cap && !out_cols)) return fail(FBGPU_E_INVALID, "null argument");
+    USE_DEVICE(c);
+    std::shared_lock<std::shared_mutex> lk;
+    int rc = lock_committed(c, lk); if (rc) return rc;
+    std::vector<DevOp> prog; int depth = 1;
+    rc = compile_program(c, index, ops, n_ops, prog, depth); if (rc) return rc;
+    std::vector<uint64_t> sorted(shards, shards + n_shards);
+    std::sort(sorted.begin(), sorted.end());
+    sorted.erase(std::unique(sorted.begin(), sorted.end()), sorted.end());
+    n_shards = (int64_t)sorted.size();
+    WsLease lease(c); Workspace* w = lease.w;
+    const DevOp* d_prog; const uint64_t* d_shards;
+    rc = upload_inputs(w, prog, sorted.data(), n_shards, &d_prog, &d_shards); if (rc) return rc;
+    const long long n_units = (long long)n_shards * kSlotsPerRow;
+    const uint64_t win_end = limit < 0 ? ~0ull : (offset + (uint64_t)limit < offset ? ~0ull : offset + (uint64_t)limit);
+    uint64_t seen = 0, written = 0, launches = 0; float ms_total = 0;
+    for (long long u0 = 0; u0 < n_units; u0 += kUnitBatch) {
+        const long long nu = std::min(kUnitBatch, n_units - u0);
+        if (w->d_bitmaps.ensure((size_t)nu * 8192) || w->d_info.ensure((size_t)nu * 8) || w->h_out.ensure((size_t)nu * 8)) return FBGPU_E_NOMEM;
+        EvalOut eo{ nullptr, nullptr, (uint4*)w->d_bitmaps.p, (uint2*)w->d_info.p, FuseReduce{} };
+        CUDA_TRY(cudaEventRecord(w->ev0, w->stream));
+        rc = launch_eval(c, w, prog, d_prog, depth, d_shards + u0 / kSlotsPerRow, nu, eo); if (rc) return rc;
+        launches++;
+        CUDA_TRY(cudaMemcpyAsync(w->h_out.p, w->d_info.p, (size_t)nu * 8, cudaMemcpyDeviceToHost, w->stream));
+        CUDA_TRY(cudaStreamSynchronize(w->stream));
+        const uint2* info = (const uint2*)w->h_out.p;
+        std::vector<ColUnit> units; uint64_t batch_out = 0;
+        for (long long u = 0; u < nu; u++) {
+            const uint64_t N = info[u].x;
+            if (!N) continue;
+            const uint64_t lo = std::max(seen, offset), hi = std::min(seen + N, win_end);    // the unit's ranks are [seen, seen + N)
+            if (hi > lo) {
+                ColUnit cu{};
+                cu.out_off = batch_out; cu.unit = (uint32_t)u; cu.first = (uint32_t)(lo - seen); cu.last = (uint32_t)(hi - seen);
+                cu.col_base = (sorted[(u0 + u) / kSlotsPerRow] << 20) + (uint64_t)((u0 + u) % kSlotsPerRow) * 65536ull;
+                units.push_back(cu);
+                batch_out += hi - lo;
+            }
+            seen += N;
+        }
+        if (batch_out && written + batch_out <= cap) {
+            const size_t ub = units.size() * sizeof(ColUnit);
+            if (w->d_emit_units.ensure(ub) || w->d_emit.ensure(batch_out * 8) || w->h_in.ensure(std::max<size_t>(ub, batch_out * 8))) return FBGPU_E_NOMEM;
+            memcpy(w->h_in.p, units.data(), ub);
+            CUDA_TRY(cudaMemcpyAsync(w->d_emit_units.p, w->h_in.p, ub, cudaMemcpyHostToDevice, w->stream));
+            const int grid = (int)std::min<size_t>(units.size(), (size_t)c->sm_count * 8);
+            columns_emit_kernel<<<grid, kEmitThreads, 0, w->stream>>>((const uint4*)w->d_bitmaps.p, (const ColUnit*)w->d_emit_units.p, (int)units.size(), (unsigned long long*)w->d_emit.p);
+            CUDA_TRY(cudaGetLastError()); launches++;
+            CUDA_TRY(cudaStreamSynchronize(w->stream));   // h_in is reused as the D2H landing buffer below
+            CUDA_TRY(cudaMemcpyAsync(w->h_in.p, w->d_emit.p, batch_out * 8, cudaMemcpyDeviceToHost, w->stream));
+            CUDA_TRY(cudaEventRecord(w->ev1, w->stream));
+            CUDA_TRY(cudaStreamSynchronize(w->stream));
+            memcpy(out_cols + written, w->h_in.p, batch_out * 8);
+            float ms = 0; cudaEventElapsedTime(&ms, w->ev0, w->ev1); ms_total += ms;
+        }
+        written += batch_out;                              // (past cap: counted, not written)
+    }
+    bump(c, launches, ms_total);
+    *out_n = written;
+    if (out_total) *out_total = seen;
+    lease.ok = true;
+    if (written > cap) return fail(FBGPU_E_NOSPACE, "output needs room for %llu column ids", (unsigned long long)written);
+    return FBGPU_OK;
+} FBGPU_CATCH
+
 // ------------------------------------------------------------------ per-row counts (TopK / TopN ids)
 // evaluates `filter` for shards [s0, s0+ns) into w->d_bitmaps (16 bitmaps per shard)
 static int eval_filter_batch(fbgpu_ctx* c, Workspace* w, const std::vector<DevOp>& prog, int depth, const DevOp* d_prog, const uint64_t* d_shards, int64_t ns) {

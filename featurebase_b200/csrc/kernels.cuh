@@ -1207,6 +1207,43 @@ canon_emit_kernel(const uint4* __restrict__ bitmaps, const EmitUnit* __restrict_
     }
 }
 
+// Column-id expansion of result bitmaps (Row.Columns row.go:471): one CTA per non-empty unit; thread t owns u64 words
+// 4t..4t+3, a block scan of the popcounts gives each thread its output position, every set bit becomes one u64 id.
+// `first` / `last` clip the unit to the caller's [offset, offset+limit) window (element ranks inside the unit).
+struct ColUnit { uint64_t out_off; uint64_t col_base; uint32_t unit; uint32_t first; uint32_t last; uint32_t pad; };
+
+__global__ void __launch_bounds__(kEmitThreads)
+columns_emit_kernel(const uint4* __restrict__ bitmaps, const ColUnit* __restrict__ units, int n_units, unsigned long long* __restrict__ out) {
+    __shared__ uint32_t wsum[kEmitThreads / 32];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    for (int e = blockIdx.x; e < n_units; e += gridDim.x) {
+        const ColUnit u = units[e];
+        const uint64_t* src = reinterpret_cast<const uint64_t*>(bitmaps + (size_t)u.unit * 512);
+        uint64_t w[4]; uint32_t c = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) { w[k] = src[4 * tid + k]; c += __popcll(w[k]); }
+        uint32_t inc = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { uint32_t x = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += x; }
+        __syncthreads();                                   // (wsum of the previous unit has been read)
+        if (lane == 31) wsum[wid] = inc;
+        __syncthreads();
+        uint32_t base = 0;
+        for (int k = 0; k < wid; k++) base += wsum[k];
+        uint32_t rank = base + inc - c;                    // rank of this thread's first element inside the unit
+        if (rank >= u.last || rank + c <= u.first) continue;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            uint64_t v = w[k];
+            while (v) {
+                const int bit = __ffsll((long long)v) - 1;
+                if (rank >= u.first && rank < u.last) out[u.out_off + (rank - u.first)] = u.col_base + (uint64_t)((4 * tid + k) * 64 + bit);
+                rank++; v &= v - 1;
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // GroupBy(Rows(a), Rows(b)) [+ filter]: one CTA per (shard, slot).  Column-keyed hash join instead of the
 // reference's |A|x|B| nested intersectionCount loop (executor.go:8880-8934): the elements of field-a rows are inserted

@@ -125,6 +125,16 @@ int fbgpu_row(fbgpu_ctx *ctx, uint32_t index, const fbgpu_op *ops, int32_t n_ops
               const uint64_t *shards, int64_t n_shards,
               uint8_t *out_buf, uint64_t out_cap, uint64_t *out_len, uint64_t *out_count);
 
+/* <bitmap call> returning the row's column ids (Row.Columns(), row.go:471, what Extract / Limit / API row responses
+ * iterate): ascending absolute column ids (shard * 2^20 + position), expanded on the device from the result bitmaps, so
+ * a caller that wants ids does not have to decode roaring containers.  Skips the first `offset` columns and writes at
+ * most `limit` (limit < 0: no limit) — executeLimitCall's window.  *out_n = columns written, *out_total = the row's
+ * cardinality before the window (may be NULL).  FBGPU_E_NOSPACE when cap is smaller than the window; *out_n then holds
+ * the needed capacity. */
+int fbgpu_columns(fbgpu_ctx *ctx, uint32_t index, const fbgpu_op *ops, int32_t n_ops,
+                  const uint64_t *shards, int64_t n_shards, uint64_t offset, int64_t limit,
+                  uint64_t *out_cols, uint64_t cap, uint64_t *out_n, uint64_t *out_total);
+
 /* Per-row counts of one field, optionally intersected with a filter program: the exact part of TopN
  * (fragment.top with explicit ids, fragment.go:1317-1437) and TopK (doTopK executor.go:2705-2746).
  * row_ids != NULL: counts for exactly those rows (out_counts[i] for row_ids[i]).

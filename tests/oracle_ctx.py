@@ -102,6 +102,13 @@ class OracleCtx:
             out = out.union(self._eval(index, ops, s))
         return out.to_bytes(), out.count()
 
+
+    def columns(self, index, ops, shards, offset=0, limit=None):
+        from featurebase_b200 import roaring_io
+        data, n = self.row(index, ops, shards)
+        cols = np.asarray(roaring_io.decode(data), dtype=np.uint64)
+        return (cols[offset:] if limit is None else cols[offset:offset + limit]), n
+
     def row_counts(self, index, field, view, shards, row_ids=None, filter_ops=None, cap=1 << 20):
         tot = {}
         for s in shards:

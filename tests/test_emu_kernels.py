@@ -9,8 +9,9 @@ What it does give: the scatter / probe / program-loop / group-by code paths writ
 (and the opt-in ones: striped array order, thread-per-row GroupBy, the unrolled word-parallel loop) have executed, statement
 by statement, against the oracle and the reference's goldens.
 
-Default run: everything gpu-marked except the 1024-shard property tests, the staged (TMA) kernel and four bodies that take
-minutes each when interpreted (≈1.5 min in all).  FBGPU_EMU_FULL=1 adds those four (≈7 min)."""
+Default run: everything gpu-marked except the staged (TMA) kernel and the bodies that take a minute or more each when
+interpreted (≈1.5 min in all).  FBGPU_EMU_FULL=1 adds those: the 1024-shard property tests, the reference's 638 x 9
+combination table (plain and striped), Percentile, the random aggregates (≈9 min)."""
 import hashlib
 import os
 import subprocess
@@ -58,8 +59,8 @@ def run_on_emulator(args, env=None, defines=(), timeout=1500):
     return tail
 
 
-NOT_HUGE = "not full_size and not STAGED"          # 1024-shard property tests: device only; the staged kernel is TMA / mbarrier PTX
-SLOW = " and not container_combinations and not striped_set_ops and not percentile and not aggregates_random"      # minutes each when interpreted
+NOT_HUGE = "not STAGED"                            # the staged kernel is TMA / mbarrier PTX: device only
+SLOW = " and not full_size and not container_combinations and not striped_set_ops and not percentile and not aggregates_random"      # a minute or more each when interpreted
 
 
 def test_default_kernels_parity():
@@ -82,7 +83,8 @@ def test_striped_array_order():
 def test_groupby_thread_per_row_variant():
     """FBGPU_GROUPBY_FAST=1 (groupby_kernel<true>): the GroupBy goldens and parity tests, and the shapes built for its passes
     (tiny arrays -> thread-per-row; a bitmap row / a 40-element row -> fallback inside the same kernel; two chunks per side; filter)"""
-    run_on_emulator(["tests/test_gpu_parity.py", "tests/test_zz_gpu_experimental.py", "-k", "(groupby or various_queries) and not full_size and not striped"], env={"FBGPU_GROUPBY_FAST": "1"})
+    run_on_emulator(["tests/test_gpu_parity.py", "tests/test_zz_gpu_experimental.py", "-k", "(groupby or various_queries) and not striped" + ("" if FULL else " and not full_size")],
+                    env={"FBGPU_GROUPBY_FAST": "1"})
 
 
 def test_wordpar_unrolled_loop_variant():

@@ -85,6 +85,7 @@ def test_embedded_rows(oracle_backed):
 def test_various_queries(oracle_backed):
     E.test_various_queries_goldens()
     E.test_distinct_random()
+    E.test_columns_entry_point()
 
 
 def test_percentile(oracle_backed):

@@ -792,3 +792,105 @@ def test_groupby_kernel_pass_shapes():
                                    filter_ops=p.ex._bitmap_call(p.idx, call) if call is not None else None)
         assert np.array_equal(np.asarray(got).reshape(-1), exp), (fields, filt)
         assert int(exp.sum()) > 3000
+
+
+def _random_call(rng, depth):
+    """a random bitmap call over the fields of test_random_call_trees_differential (PQL text)"""
+    if depth == 0 or rng.random() < 0.3:
+        r = rng.random()
+        if r < 0.7:
+            return f"Row(m={int(rng.integers(0, 9))})"             # rows 0..6 exist (array / bitmap / run / mixed), 7..8 do not
+        if r < 0.8:
+            return "All()"
+        if r < 0.9:
+            op = ["<", "<=", ">", ">=", "==", "!="][int(rng.integers(0, 6))]
+            return f"Row(v {op} {int(rng.integers(-700, 700))})"
+        lo = int(rng.integers(-700, 600))
+        return f"Row(v >< [{lo}, {lo + int(rng.integers(0, 500))}])"
+    kind = ["Intersect", "Union", "Difference", "Xor", "Not"][int(rng.integers(0, 5))]
+    if kind == "Not":
+        return f"Not({_random_call(rng, depth - 1)})"
+    return f"{kind}({', '.join(_random_call(rng, depth - 1) for _ in range(int(rng.integers(1, 6))))})"
+
+
+def test_random_call_trees_differential():
+    """random call trees (n-ary set ops, Not, All, BSI comparisons as leaves; up to 4 levels) over rows of every encoding —
+    sparse arrays, ~4000-element arrays at the array/bitmap boundary, bitmaps, short and long runs, a row mixing all three
+    per slot — Row bytes and Count against the oracle on three shards"""
+    import featurebase_b200.datagen as D
+    from oracle import oracle as O
+    rng = np.random.default_rng(int(os.environ.get("FBGPU_FUZZ_SEED", "2024")))
+    p = Pair()
+    p.field("m")
+    p.field("v", "int", min=-600, max=600)
+    for s in (0, 1, 4):
+        parts = [D.fragment(9, s, [0], 0.004), D.fragment(9, s, [1], 0.0615), D.fragment(9, s, [2], 0.3), D.fragment(9, s, [3], 0.2, mode=1, mean_run=200.0),
+                 D.fragment(9, s, [4], 0.9, mode=1, mean_run=5000.0), D.fragment(9, s, [5], 0.02, mode=1, mean_run=3.0)]
+        merged = O.Bitmap()
+        for d in parts:
+            merged = merged.union(O.Bitmap.from_bytes(d))
+        mixed = []                                                 # row 6: slot k takes its container from row k % 5
+        for k in range(16):
+            src = merged.row(k % 5, s)
+            cols = roaring_values(src)
+            cols = cols[(cols % (1 << 20)) // 65536 == k]
+            mixed.append(np.uint64(6 << 20) + (cols % np.uint64(1 << 20)))
+        merged = merged.union(O.Bitmap.from_values(np.concatenate(mixed)))
+        p.load("m", X.VIEW_STANDARD, s, merged.to_bytes())
+        p.load("v", X.VIEW_BSI, s, D.bsi_fragment(12, s, 300000, p.idx.fields["v"].bit_depth, -600, 600, base=0, null_frac=0.2))
+        p.load(X.EXISTENCE_FIELD, X.VIEW_STANDARD, s, D.fragment(13, s, [0], 0.7))
+    n_checked = 0
+    for i in range(int(os.environ.get("FBGPU_FUZZ_TREES", "120"))):
+        q = _random_call(rng, 3)
+        try:
+            if i % 2:
+                p.check_row(q)
+            else:
+                p.check_count(f"Count({q})")
+            n_checked += 1
+        except X.QueryError as e:                                  # both sides refuse the same calls (empty Intersect(), > 15 operands deep)
+            assert "not supported" in str(e) or "stack depth" in str(e), (q, e)
+    assert n_checked > 80
+
+
+def roaring_values(bm):
+    from featurebase_b200 import roaring_io
+    return np.asarray(roaring_io.decode(bm.to_bytes()), dtype=np.uint64)
+
+
+def test_columns_entry_point():
+    """fbgpu_columns: the row's ascending column ids straight from the device (Row.Columns row.go:471) with executeLimitCall's
+    offset / limit window, against the decoded Row result and the oracle — rows of every encoding, windows that start and
+    end inside containers, across containers and across shards, an empty row, a too-small buffer"""
+    import featurebase_b200.datagen as D
+    from featurebase_b200 import lib as L
+    from featurebase_b200 import roaring_io
+    from oracle import oracle as O
+    p = Pair(track_existence=False)
+    p.field("m")
+    for s in (0, 2, 3):
+        merged = O.Bitmap()
+        for d in (D.fragment(9, s, [0], 0.004), D.fragment(9, s, [1], 0.3), D.fragment(9, s, [2], 0.2, mode=1, mean_run=200.0)):
+            merged = merged.union(O.Bitmap.from_bytes(d))
+        p.load("m", X.VIEW_STANDARD, s, merged.to_bytes())
+    ctx = p.holder.ctx
+    for q in ("Row(m=0)", "Row(m=1)", "Row(m=2)", "Union(Row(m=0), Row(m=2))", "Difference(Row(m=1), Row(m=2))", "Row(m=7)"):
+        ops = p.ex._bitmap_call(p.idx, pql.parse(q)[0])
+        want = np.asarray(roaring_io.decode(p.check_row(q).roaring), dtype=np.uint64)
+        cols, total = ctx.columns(p.idx.id, ops, p.shards())
+        assert total == len(want) and np.array_equal(cols, want), q
+        n = len(want)
+        for off, lim in ((0, 1), (0, 10), (5, 0), (n // 3, 1000), (max(n - 3, 0), 10), (n, 5), (n + 9, 5), (70000, 70000), (1, None)):
+            cols, total = ctx.columns(p.idx.id, ops, p.shards(), offset=off, limit=lim)
+            assert total == n and np.array_equal(cols, want[off:] if lim is None else want[off:off + lim]), (q, off, lim)
+        cols, _ = ctx.columns(p.idx.id, ops, [3, 0])                       # shard list order does not matter, subsets do
+        assert np.array_equal(cols, want[(want >> np.uint64(20) == 0) | (want >> np.uint64(20) == 3)])
+    if isinstance(ctx, L.Context):                                         # the C ABI's too-small-buffer contract
+        import ctypes as C
+        ops = L.ops_array(p.ex._bitmap_call(p.idx, pql.parse("Row(m=1)")[0]))
+        sh = np.asarray(p.shards(), dtype=np.uint64)
+        n, tot, buf = C.c_uint64(0), C.c_uint64(0), np.empty(10, dtype=np.uint64)
+        rc = ctx.L.fbgpu_columns(ctx.h, p.idx.id, ops, len(ops), sh.ctypes.data, len(sh), 0, -1, buf.ctypes.data, 10, C.byref(n), C.byref(tot))
+        assert rc == L.E_NOSPACE and n.value == tot.value > 10
+        rc = ctx.L.fbgpu_columns(ctx.h, p.idx.id, ops, len(ops), sh.ctypes.data, len(sh), 3, 10, buf.ctypes.data, 10, C.byref(n), None)
+        assert rc == 0 and n.value == 10
