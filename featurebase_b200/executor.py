@@ -527,9 +527,29 @@ class Executor:
         k = int(c.args.get("k", 0))
         filt = c.args.get("filter")
         filt = self._bitmap_call(idx, filt) if isinstance(filt, pql.Call) else None
+        targs = {a: c.args[a] for a in ("from", "to") if a in c.args} if f.quantum else {}
+        if targs:                                                # executeTopKShardTime :2506-2533 / mergerator :2570: a row is the union of
+            rows = self._rows(idx, pql.Call("Rows", {"_field": f.name, **targs}), shards)      # itself over the covering views
+            if not rows:
+                return []
+            sf, operands = self._time_rows_as_operands(idx, f, rows, targs, shards)
+            cnt = self.ctx.row_counts(idx.id, sf.id, VIEW_STANDARD, shards, row_ids=operands, filter_ops=filt)
+            pairs = sorted(((r, int(n)) for r, n in zip(rows, cnt) if n), key=lambda kv: (-kv[1], kv[0]))
+            return pairs[:k] if k else pairs
         rid, cnt = self.ctx.row_counts(idx.id, f.id, VIEW_STANDARD, shards, filter_ops=filt)
         pairs = [(int(i), int(n)) for i, n in zip(rid, cnt)]
         return pairs[:k] if k else pairs
+
+    def _time_rows_as_operands(self, idx, f, rows, targs, shards):
+        """Rows of a time field restricted to from= / to=, made addressable by the single-view kernels: each row's union over
+        the covering views (timeFragmentsRowIterator :8755-8768, mergerator :2570) is evaluated once and stored as an operand
+        row of the scratch field.  Returns (scratch field, operand row ids in the order of `rows`)."""
+        operands = []
+        for r in rows:
+            data, _ = self.ctx.row(idx.id, self._bitmap_call(idx, pql.Call("Row", {f.name: r, **targs})), shards)
+            sf, srow = self.holder.embed_row(idx.name, roaring_io.decode(data))
+            operands.append(srow)
+        return sf, operands
 
     def _rows(self, idx, c, shards, standalone=False):           # executeRows (row ids present; limit / previous / in)
         name = c.args["_field"] if "_field" in c.args else c.args.get("field")
@@ -826,11 +846,7 @@ class Executor:
                 dev_fields.append(f.id)
                 dev_rows.append(rows)
                 continue
-            operands = []
-            for r in rows:
-                data, _ = self.ctx.row(idx.id, self._bitmap_call(idx, pql.Call("Row", {f.name: r, **targs})), shards)
-                sf, srow = self.holder.embed_row(idx.name, roaring_io.decode(data))
-                operands.append(srow)
+            sf, operands = self._time_rows_as_operands(idx, f, rows, targs, shards)
             dev_fields.append(sf.id)
             dev_rows.append(operands)
         counts = self.ctx.groupby(idx.id, dev_fields, [VIEW_STANDARD] * len(fields), dev_rows, shards, filter_ops=filt)

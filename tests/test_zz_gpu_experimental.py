@@ -794,6 +794,27 @@ def test_groupby_kernel_pass_shapes():
         assert int(exp.sum()) > 3000
 
 
+def test_topk_time_range():
+    """executor_test.go:1811-1843 TestExecutor_Execute_TopK_Time: TopK over a time range counts a row's union over the covering
+    views (column 0 is set on two days and counts once), plus a filter and k"""
+    p = Pair()
+    p.field("f", "time", quantum="YMD")
+    p.field("g")
+    for col, row, ts in ((0, 0, "2016-01-02T00:00"), (0, 1, "2016-01-02T00:00"), (0, 0, "2016-01-03T00:00"), (1, 0, "2016-01-10T00:00"),
+                         (100000000, 2, "2016-02-02T00:00"), (200000000, 3, "2015-01-02T00:00")):
+        p.holder.set_bit("i", "f", row, col, timestamp=ts)
+    p.holder.set_bit("i", "g", 5, 1)
+    p.holder.set_bit("i", "g", 5, 100000000)
+    p.sync_pending()
+    run = lambda q: p.ex.execute("i", q)[0]
+    assert run("TopK(f, k=3, from=2016-01-01T00:00, to=2016-01-11T00:00)") == [(0, 2), (1, 1)]
+    assert run("TopK(f, k=1, from=2016-01-01T00:00, to=2016-01-11T00:00)") == [(0, 2)]
+    assert run("TopK(f, from=2016-01-01T00:00, to=2016-03-01T00:00)") == [(0, 2), (1, 1), (2, 1)]
+    assert run("TopK(f, from=2016-01-01T00:00, to=2016-03-01T00:00, filter=Row(g=5))") == [(0, 1), (2, 1)]
+    assert run("TopK(f, from=2017-01-01T00:00, to=2017-03-01T00:00)") == []
+    assert run("TopK(f, k=3)") == [(0, 2), (1, 1), (2, 1)]                        # no range: the standard view
+
+
 def _random_call(rng, depth):
     """a random bitmap call over the fields of test_random_call_trees_differential (PQL text)"""
     if depth == 0 or rng.random() < 0.3:
