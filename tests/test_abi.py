@@ -39,6 +39,18 @@ def test_no_oracle_linkage(so):
             assert "oracle" not in src.replace("# oracle", ""), f
 
 
+def test_no_kernel_interpreter_in_product(so):
+    """tests/emu/ (the CPU kernel interpreter) is test infrastructure: nothing the product ships may name it, and the shipped
+    library is the nvcc build (it carries sm_100a device code, the interpreted build carries none)"""
+    data = open(so, "rb").read()
+    assert b"fbgpu_emu_switch" not in data and b"kernel emulation" not in data and b".nv_fatbin" in data
+    for sub in ("featurebase_b200", os.path.join("featurebase_b200", "csrc"), "include", "."):
+        for f in os.listdir(os.path.join(ROOT, sub)):
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(ROOT, sub, f)).read()
+                assert "tests/emu" not in src and "FBGPU_EMU" not in src and "libfbgpu_emu" not in src, f
+
+
 def test_init_without_gpu_fails_loudly(so):
     import torch
     if torch.cuda.is_available():
