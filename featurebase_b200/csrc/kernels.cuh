@@ -1019,7 +1019,9 @@ __device__ __forceinline__ uint32_t warp_intersection_count(Resolved a, Resolved
         for (int q = 0; q < 3; q++) if (lane + 32 * q < na8) va[q] = ldg_nc(a4 + lane + 32 * q);
 #pragma unroll
         for (int q = 0; q < 3; q++) if (lane + 32 * q < nb8) vb[q] = ldg_nc(b4 + lane + 32 * q);
+#ifndef FBGPU_PAIR_UNSCATTER
         warp_zero(bm, lane); __syncwarp();
+#endif
 #pragma unroll
         for (int q = 0; q < 3; q++) if (lane + 32 * q < na8) scatter_chunk_unrolled<0>(bm, va[q], (lane + 32 * q) * 8, a.card);
         for (uint32_t i = lane + 96; i < na8; i += 32) scatter_chunk_unrolled<0>(bm, ldg_nc(a4 + i), i * 8, a.card);
@@ -1028,6 +1030,15 @@ __device__ __forceinline__ uint32_t warp_intersection_count(Resolved a, Resolved
         for (int q = 0; q < 3; q++) if (lane + 32 * q < nb8) c += probe_chunk(bm, vb[q], (lane + 32 * q) * 8, b.card);
         for (uint32_t i = lane + 96; i < nb8; i += 32) c += probe_chunk(bm, ldg_nc(b4 + i), i * 8, b.card);
         __syncwarp();
+#ifdef FBGPU_PAIR_UNSCATTER
+        // (experimental, not yet timed) the bitmap is all-zero on entry — the callers clear it once per warp — and the bits of
+        // `a` are taken out again here from the chunks still in registers: <= 3 and-not reductions per lane for a ~650-element
+        // array instead of 16 16-byte stores per lane to wipe 8 KiB, the larger share of this path's shared-memory traffic
+#pragma unroll
+        for (int q = 0; q < 3; q++) if (lane + 32 * q < na8) scatter_chunk_unrolled<1>(bm, va[q], (lane + 32 * q) * 8, a.card);
+        for (uint32_t i = lane + 96; i < na8; i += 32) scatter_chunk_unrolled<1>(bm, ldg_nc(a4 + i), i * 8, a.card);
+        __syncwarp();
+#endif
     } else if (a.typ == kArray) {                             // array x bitmap: roaring.go:4596
         c = warp_probe_global(reinterpret_cast<const uint32_t*>(b.ptr), reinterpret_cast<const uint16_t*>(a.ptr), a.card, lane);
     } else {                                                  // bitmap x bitmap: roaring.go:4611
@@ -1051,6 +1062,9 @@ pair_count_kernel(StoreRef st, uint32_t fvA, uint64_t rowA, uint32_t fvB, uint64
     extern __shared__ uint32_t smem32[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     uint32_t* bm = smem32 + wid * 2048;
+#ifdef FBGPU_PAIR_UNSCATTER
+    warp_zero(bm, lane); __syncwarp();
+#endif
     unsigned long long acc = 0;
     const long long stride = (long long)gridDim.x * kPairWarps;
     for (long long base = (long long)blockIdx.x * kPairWarps + wid; base < n_units; base += stride * 16) {

@@ -92,6 +92,14 @@ def test_wordpar_unrolled_loop_variant():
     run_on_emulator(["tests/test_gpu_parity.py", "-k", "bsi_range or bsi_uniform or FORCE_WORDPAR or bsi_diagonal"], defines=("FBGPU_WP_UNROLL3",), timeout=3000)
 
 
+def test_pair_count_unscatter_variant():
+    """-DFBGPU_PAIR_UNSCATTER: pair_count_kernel clears the a-side bits after the probe instead of wiping its 8 KiB bitmap per
+    pair — every test that reaches the fused Intersect+Count / count-pairs path, in the sorted and the striped array order"""
+    sel = "config1 or density_sweep or mixed_encoding or topk or executor_goldens or thread_safety" + (" or full_size_properties_1024" if FULL else "")
+    run_on_emulator(["tests/test_gpu_parity.py", "tests/test_zz_gpu_experimental.py", "-k", sel + " or fragment_top"], defines=("FBGPU_PAIR_UNSCATTER",), timeout=3000)
+    run_on_emulator(["tests/test_zz_gpu_experimental.py", "-k", "striped_density_sweep"], defines=("FBGPU_PAIR_UNSCATTER",), env={"FBGPU_TEST_EXPERIMENTAL": "1"}, timeout=3000)
+
+
 def test_interpreter_reports_divergent_barriers():
     """the interpreter's own checks: a barrier only part of a block reaches is reported (not silently passed), full-mask warp
     primitives see every lane, and shared-memory reductions land where the 32-bit shared address says"""

@@ -25,6 +25,13 @@ FBGPU_LIB=$PWD/featurebase_b200/libfbgpu_wp_unroll3.so timeout 900 python -m pyt
 python bench_sweep.py --configs 3 > $out/sweep3_default.jsonl 2>>$out/bench_err.log
 FBGPU_LIB=$PWD/featurebase_b200/libfbgpu_wp_unroll3.so python bench_sweep.py --configs 3 > $out/sweep3_wp_unroll3.jsonl 2>>$out/bench_err.log
 
+# 3b'. pair_count_kernel without the per-pair 8 KiB wipe (-DFBGPU_PAIR_UNSCATTER): parity, then the density sweep in both array orders
+python tools/build_variants.py pair_unscatter >> $out/build_variants.log 2>&1
+PU=$PWD/featurebase_b200/libfbgpu_pair_unscatter.so
+FBGPU_LIB=$PU timeout 900 python -m pytest tests/test_gpu_parity.py -q -k "config1 or density_sweep or mixed_encoding or topk or executor_goldens or full_size_properties_1024" > $out/pytest_pair_unscatter.log 2>&1; echo "pytest_pair_unscatter rc=$?" >> $out/summary.txt
+FBGPU_LIB=$PU python bench_sweep.py --configs 5 --batched --generators uniform > $out/sweep_pair_unscatter.jsonl 2>>$out/bench_err.log
+FBGPU_LIB=$PU FBGPU_ARRAY_STRIPED=1 python bench_sweep.py --configs 5 --batched --generators uniform > $out/sweep_pair_unscatter_striped.jsonl 2>>$out/bench_err.log
+
 # 3c. thread-per-row GroupBy passes (groupby_kernel<true>, FBGPU_GROUPBY_FAST=1): parity of every GroupBy test, then config 4 A/B
 FBGPU_GROUPBY_FAST=1 timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_zz_gpu_experimental.py -q -k "groupby or various_queries" > $out/pytest_groupby_fast.log 2>&1; echo "pytest_groupby_fast rc=$?" >> $out/summary.txt
 python bench_sweep.py --configs 4 > $out/sweep4_default.jsonl 2>>$out/bench_err.log
