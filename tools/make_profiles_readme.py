@@ -85,6 +85,17 @@ def main():
         if d["config"] == "R":
             o.append(f"| `{d['query']}` | {d['ms']:.2f} | {d['result_bytes']:,} | {d['result_count']:,} |")
     o.append("\nLarge results are dominated by host-side copies of the payload (D2H landing buffer -> per-batch buffer -> caller's buffer); a device-side prefix sum and direct D2H into the caller's buffer are the obvious next step.\n")
+    o.append("## Written after the GPU budget was spent: no timing yet (round 2's first call, `tools/r2_first_call.sh`, measures each)\n")
+    o.append("Kernel logic of every row has run against the oracle on the CPU kernel interpreter (`tests/emu/`, `tests/test_emu_kernels.py`); the default build's other kernels are byte-identical SASS to the measured ones.\n")
+    o.append("| change | switch | targets | expectation (model, not a measurement) |")
+    o.append("|---|---|---|---|")
+    o.append("| array scatter: LOP3 + LEA.HI word offsets, shared base kept live, duplicate-padded tails | default build | config 1/2 `eval_kernel` (issue slots 61 % busy) | 65 + tail -> 43 issued instructions per 8 elements |")
+    o.append("| bank-striped array payload order | `FBGPU_ARRAY_STRIPED=1` | every scatter / probe of array containers (`eval_kernel`, `pair_count_kernel`) | random banks cost ~4 shared-memory wavefronts per warp instruction (`r01_micro_aa_variants.txt`: 7.8 lane-ops/clk/SM); striped ~1.2 (host model, `tests/test_stripe.py`) |")
+    o.append("| no per-pair 8 KiB wipe in array x array counting | `-DFBGPU_PAIR_UNSCATTER` (`libfbgpu_pair_unscatter.so`) | config 5 at <= 3 % density (north-star point) | 64 of ~210 wavefronts per pair; with the striped order ~63 in all |")
+    o.append("| three-ops-per-iteration word-parallel loop | `-DFBGPU_WP_UNROLL3` (`libfbgpu_wp_unroll3.so`) | config 3 `eval_wordpar_kernel` (interpretive overhead) | ~12 instructions per op + operand fetch instead of 80-100 |")
+    o.append("| thread-per-row GroupBy passes | `FBGPU_GROUPBY_FAST=1` | config 4 `groupby_kernel` (25.8 k warp instructions per unit) | ~9x fewer instructions per unit; then latency-bound |")
+    o.append("| `fbgpu_columns` / `columns_emit_kernel`, `fbgpu_load_rbf`, host-mirror compositions (Sum / Min / Max / Percentile / Distinct / MinRow / time ranges) | new entry points / host code | SURVEY §8(f) rows | functional only |")
+    o.append("")
     o.append("## Correctness tooling\n")
     o.append("`r01_sanitizer_memcheck.log`: compute-sanitizer memcheck over the eval / pair / row-count / groupby / word-parallel / staged kernels (8 GPU tests): 0 errors. `r01_sanitizer_racecheck.log`: racecheck (shared-memory hazards): 0 hazards.\n")
     o.append("## Files\n")
