@@ -19,6 +19,7 @@
 
 #include <dlfcn.h>
 #include <stdarg.h>
+#include <sys/mman.h>
 
 #include <algorithm>
 #include <chrono>
@@ -324,9 +325,34 @@ static inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) {
     p->totalGlobalMem = 8ull << 30; p->multiProcessorCount = 3; p->major = 10; p->minor = 0; p->sharedMemPerBlockOptin = emu::kDynSmem; p->sharedMemPerMultiprocessor = emu::kDynSmem; p->l2CacheSize = 1 << 20; p->clockRate = 1000000;
     return cudaSuccess;
 }
-static inline cudaError_t cudaMalloc(void** p, size_t n) { *p = aligned_alloc(256, (n + 255) & ~(size_t)255); if (!*p) return cudaErrorMemoryAllocation; memset(*p, 0xA5, n); return cudaSuccess; }
+// "Device" allocations end flush against an inaccessible page (size rounded up to 16 bytes, the granularity the kernels'
+// vector loads rely on), so a kernel or a copy that runs past the end of a buffer faults at once — the interpreter's
+// stand-in for compute-sanitizer's memcheck on over-runs.  Contents start as 0xA5 garbage, like fresh device memory.
+namespace emu {
+struct Allocs { std::mutex mu; std::unordered_map<void*, std::pair<void*, size_t>> m; };
+inline Allocs g_allocs;
+}
+static inline cudaError_t cudaMalloc(void** p, size_t n) {
+    const size_t page = 4096, body = (std::max<size_t>(n, 1) + 15) & ~(size_t)15, len = ((body + page - 1) / page + 1) * page;
+    char* base = (char*)mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    if (base == (char*)MAP_FAILED) return cudaErrorMemoryAllocation;
+    mprotect(base + len - page, page, PROT_NONE);
+    *p = base + len - page - body;
+    memset(*p, 0xA5, body);
+    std::lock_guard<std::mutex> lk(emu::g_allocs.mu);
+    emu::g_allocs.m[*p] = std::make_pair((void*)base, len);
+    return cudaSuccess;
+}
 template <class T> static inline cudaError_t cudaMalloc(T** p, size_t n) { return cudaMalloc((void**)p, n); }
-static inline cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
+static inline cudaError_t cudaFree(void* p) {
+    if (!p) return cudaSuccess;
+    std::lock_guard<std::mutex> lk(emu::g_allocs.mu);
+    auto it = emu::g_allocs.m.find(p);
+    if (it == emu::g_allocs.m.end()) emu::die("cudaFree of a pointer cudaMalloc did not return");
+    munmap(it->second.first, it->second.second);
+    emu::g_allocs.m.erase(it);
+    return cudaSuccess;
+}
 static inline cudaError_t cudaMallocHost(void** p, size_t n) { *p = aligned_alloc(256, (n + 255) & ~(size_t)255); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
 template <class T> static inline cudaError_t cudaMallocHost(T** p, size_t n) { return cudaMallocHost((void**)p, n); }
 static inline cudaError_t cudaFreeHost(void* p) { free(p); return cudaSuccess; }

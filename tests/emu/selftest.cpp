@@ -53,6 +53,15 @@ int main(int argc, char** argv) {
         emu::launch(dim3(1), dim3(64), 0, [&] { diverge_kernel(g_out); });
         return 0;
     }
+    if (argc > 1 && !strcmp(argv[1], "overrun")) {                // device buffers end at a guard page: reading past the (16-byte rounded) end faults
+        unsigned char* d = nullptr;
+        cudaMalloc(&d, 100);
+        volatile unsigned char ok = d[111]; (void)ok;             // inside the rounded size
+        puts("in bounds ok"); fflush(stdout);
+        volatile unsigned char bad = d[112]; (void)bad;
+        puts("not reached");
+        return 0;
+    }
     const int T = 256;
     emu::launch(dim3(3), dim3(T), T * 4, [&] { scan_kernel(g_out, 200); });
     for (unsigned b = 0; b < 3; b++) {

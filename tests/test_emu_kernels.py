@@ -102,7 +102,8 @@ def test_pair_count_unscatter_variant():
 
 def test_interpreter_reports_divergent_barriers():
     """the interpreter's own checks: a barrier only part of a block reaches is reported (not silently passed), full-mask warp
-    primitives see every lane, and shared-memory reductions land where the 32-bit shared address says"""
+    primitives see every lane, shared-memory reductions land where the 32-bit shared address says, and a read past the end of
+    a device buffer faults"""
     src = os.path.join(EMU, "selftest.cpp")
     exe = os.path.join(EMU, "_build", "selftest")
     os.makedirs(os.path.dirname(exe), exist_ok=True)
@@ -110,3 +111,5 @@ def test_interpreter_reports_divergent_barriers():
     assert subprocess.run([exe, "ok"], stdout=subprocess.PIPE, text=True).stdout.strip() == "selftest ok"
     r = subprocess.run([exe, "diverge"], stderr=subprocess.PIPE, text=True)
     assert r.returncode != 0 and "deadlock" in r.stderr
+    r = subprocess.run([exe, "overrun"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode < 0 and "in bounds ok" in r.stdout and "not reached" not in r.stdout      # killed by SIGSEGV at the guard page
