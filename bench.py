@@ -277,7 +277,8 @@ def main():
             "ms_per_step": kms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64/u16 integer", "data": "synthetic",
             "config": {"workload": "configs[1]: 1024 shards x 2^20 cols per GPU, 1% density, 64-row Union->Intersect->Count",
                        "query": "Count(Intersect(Union(Row f=0..31),Union(Row f=32..63)))", "shards_per_gpu": S, "total_shards": total_shards,
-                       "density": 0.01, "l2": f"inputs {payload / 1e6:.0f} MB per GPU > 126 MB L2 (no flush needed)", "parallelism": f"shard-range x{world}", "count_merge": (args.reduce if world > 1 else "none")},
+                       "density": 0.01, "l2": (f"inputs {payload / 1e6:.0f} MB per GPU > 126 MB L2 (no flush needed)" if payload > 126e6 else
+                                                   f"inputs {payload / 1e6:.0f} MB per GPU fit the 126 MB L2: NOT a valid bench size (use the default --shards-per-gpu)"), "parallelism": f"shard-range x{world}", "count_merge": (args.reduce if world > 1 else "none")},
             "count_rows_per_sec": total_shards / (kms * 1e-3), "columns_per_sec": total_shards * SW / (kms * 1e-3),
             "check_count": int(expect),
             "e2e": {"value": set_ops / (e2e_ms * 1e-3), "unit": "set-ops/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 8,

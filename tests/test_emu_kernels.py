@@ -100,6 +100,38 @@ def test_pair_count_unscatter_variant():
     run_on_emulator(["tests/test_zz_gpu_experimental.py", "-k", "striped_density_sweep"], defines=("FBGPU_PAIR_UNSCATTER",), env={"FBGPU_TEST_EXPERIMENTAL": "1"}, timeout=3000)
 
 
+def test_bench_main_runs_against_interpreted_library():
+    """bench.py's own main() (GPU arm) on 8 shards with torch.cuda's device calls stubbed (tests/emu/bench_shim.py): the JSON
+    line carries every key of the contract and the count agrees with the oracle-checked value for this data; the timings are
+    meaningless.  Guards edits to bench.py made while no device was reachable."""
+    import json
+    e = dict(os.environ, FBGPU_LIB=emu_lib())
+    r = subprocess.run([sys.executable, os.path.join(EMU, "bench_shim.py"), "--steps", "2", "--warmup", "1", "--shards-per-gpu", "8", "--no-cpu-baseline"],
+                       cwd=ROOT, env=e, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "config",
+              "e2e", "gpu_launches", "clocks", "roofline"):
+        assert k in d, k
+    assert d["warmup"] >= 3 and d["gpu_launches"] == 2 and d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] == 8
+    assert set(d["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"} and "NOT a valid bench size" in d["config"]["l2"]
+    # the same query through the oracle-backed mirror
+    sys.path.insert(0, ROOT)
+    import bench
+    from featurebase_b200 import datagen as D
+    from oracle import oracle as O
+    exp = 0
+    for s in range(8):
+        fr = O.Bitmap.from_bytes(D.fragment(bench.FIELD_SEED_ID, s, bench.ROWS_A + bench.ROWS_B, 0.01))
+        a, b = O.Bitmap(), O.Bitmap()
+        for rr in bench.ROWS_A:
+            a = a.union(fr.row(rr, s))
+        for rr in bench.ROWS_B:
+            b = b.union(fr.row(rr, s))
+        exp += a.intersect(b).count()
+    assert d["check_count"] == exp > 0
+
+
 def test_interpreter_reports_divergent_barriers():
     """the interpreter's own checks: a barrier only part of a block reaches is reported (not silently passed), full-mask warp
     primitives see every lane, shared-memory reductions land where the 32-bit shared address says, and a read past the end of
