@@ -797,15 +797,14 @@ extern "C" int fbgpu_row(fbgpu_ctx* c, uint32_t index, const fbgpu_op* ops, int3
     return FBGPU_OK;
 } FBGPU_CATCH
 
-// ------------------------------------------------------------------ Columns (Row.Columns(): ascending ids, with executeLimitCall's window)
-extern "C" int fbgpu_columns(fbgpu_ctx* c, uint32_t index, const fbgpu_op* ops, int32_t n_ops, const uint64_t* shards, int64_t n_shards,
-                             uint64_t offset, int64_t limit, uint64_t* out_cols, uint64_t cap, uint64_t* out_n, uint64_t* out_total) try {
-    if (!c || !out_n || n_shards < 0 || (n_shards && !shards) || (cap && !out_cols)) return fail(FBGPU_E_INVALID, "null argument");
-    USE_DEVICE(c);
-    std::shared_lock<std::shared_mutex> lk;
-    int rc = lock_committed(c, lk); if (rc) return rc;
+// ------------------------------------------------------------------ Columns (Row.Columns(): ascending ids, with executeLimitCall's window) / Extract
+// shared body: evaluate the row into per-unit bitmaps, cut the [offset, offset+limit) window into per-unit rank ranges, expand
+// the column ids on the device and — for Extract — gather the BSI planes of `fv_vals` for exactly those columns
+static int columns_impl(fbgpu_ctx* c, uint32_t index, const fbgpu_op* ops, int32_t n_ops, const uint64_t* shards, int64_t n_shards,
+                        uint64_t offset, int64_t limit, bool want_vals, uint32_t fv_vals, int depth_vals,
+                        uint64_t* out_cols, int64_t* out_vals, uint64_t cap, uint64_t* out_n, uint64_t* out_total) {
     std::vector<DevOp> prog; int depth = 1;
-    rc = compile_program(c, index, ops, n_ops, prog, depth); if (rc) return rc;
+    int rc = compile_program(c, index, ops, n_ops, prog, depth); if (rc) return rc;
     std::vector<uint64_t> sorted(shards, shards + n_shards);
     std::sort(sorted.begin(), sorted.end());
     sorted.erase(std::unique(sorted.begin(), sorted.end()), sorted.end());
@@ -841,18 +840,28 @@ extern "C" int fbgpu_columns(fbgpu_ctx* c, uint32_t index, const fbgpu_op* ops, 
             seen += N;
         }
         if (batch_out && written + batch_out <= cap) {
-            const size_t ub = units.size() * sizeof(ColUnit);
-            if (w->d_emit_units.ensure(ub) || w->d_emit.ensure(batch_out * 8) || w->h_in.ensure(std::max<size_t>(ub, batch_out * 8))) return FBGPU_E_NOMEM;
+            const size_t ub = units.size() * sizeof(ColUnit), ob = batch_out * 8 * (want_vals ? 2 : 1);
+            if (w->d_emit_units.ensure(ub) || w->d_emit.ensure(ob) || w->h_in.ensure(std::max<size_t>(ub, ob))) return FBGPU_E_NOMEM;
             memcpy(w->h_in.p, units.data(), ub);
             CUDA_TRY(cudaMemcpyAsync(w->d_emit_units.p, w->h_in.p, ub, cudaMemcpyHostToDevice, w->stream));
             const int grid = (int)std::min<size_t>(units.size(), (size_t)c->sm_count * 8);
-            columns_emit_kernel<<<grid, kEmitThreads, 0, w->stream>>>((const uint4*)w->d_bitmaps.p, (const ColUnit*)w->d_emit_units.p, (int)units.size(), (unsigned long long*)w->d_emit.p);
+            unsigned long long* d_cols = (unsigned long long*)w->d_emit.p; unsigned long long* d_vals = d_cols + batch_out;
+            columns_emit_kernel<<<grid, kEmitThreads, 0, w->stream>>>((const uint4*)w->d_bitmaps.p, (const ColUnit*)w->d_emit_units.p, (int)units.size(), d_cols);
             CUDA_TRY(cudaGetLastError()); launches++;
+            if (want_vals) {
+                CUDA_TRY(cudaMemsetAsync(d_vals, 0, batch_out * 8, w->stream));
+                extract_values_kernel<<<grid, kExtractThreads, 0, w->stream>>>(store_ref(c), fv_vals, depth_vals, (const uint4*)w->d_bitmaps.p, (const ColUnit*)w->d_emit_units.p, (int)units.size(), d_vals);
+                CUDA_TRY(cudaGetLastError()); launches++;
+            }
             CUDA_TRY(cudaStreamSynchronize(w->stream));   // h_in is reused as the D2H landing buffer below
-            CUDA_TRY(cudaMemcpyAsync(w->h_in.p, w->d_emit.p, batch_out * 8, cudaMemcpyDeviceToHost, w->stream));
+            CUDA_TRY(cudaMemcpyAsync(w->h_in.p, w->d_emit.p, ob, cudaMemcpyDeviceToHost, w->stream));
             CUDA_TRY(cudaEventRecord(w->ev1, w->stream));
             CUDA_TRY(cudaStreamSynchronize(w->stream));
             memcpy(out_cols + written, w->h_in.p, batch_out * 8);
+            if (want_vals) {                               // sign-magnitude (bit 63 = sign row) -> int64
+                const uint64_t* raw = (const uint64_t*)w->h_in.p + batch_out;
+                for (uint64_t i = 0; i < batch_out; i++) { const int64_t m = (int64_t)(raw[i] & ~(1ull << 63)); out_vals[written + i] = (raw[i] >> 63) ? -m : m; }
+            }
             float ms = 0; cudaEventElapsedTime(&ms, w->ev0, w->ev1); ms_total += ms;
         }
         written += batch_out;                              // (past cap: counted, not written)
@@ -861,8 +870,34 @@ extern "C" int fbgpu_columns(fbgpu_ctx* c, uint32_t index, const fbgpu_op* ops, 
     *out_n = written;
     if (out_total) *out_total = seen;
     lease.ok = true;
-    if (written > cap) return fail(FBGPU_E_NOSPACE, "output needs room for %llu column ids", (unsigned long long)written);
+    if (written > cap) return fail(FBGPU_E_NOSPACE, "output needs room for %llu columns", (unsigned long long)written);
     return FBGPU_OK;
+}
+
+extern "C" int fbgpu_columns(fbgpu_ctx* c, uint32_t index, const fbgpu_op* ops, int32_t n_ops, const uint64_t* shards, int64_t n_shards,
+                             uint64_t offset, int64_t limit, uint64_t* out_cols, uint64_t cap, uint64_t* out_n, uint64_t* out_total) try {
+    if (!c || !out_n || n_shards < 0 || (n_shards && !shards) || (cap && !out_cols)) return fail(FBGPU_E_INVALID, "null argument");
+    USE_DEVICE(c);
+    std::shared_lock<std::shared_mutex> lk;
+    int rc = lock_committed(c, lk); if (rc) return rc;
+    return columns_impl(c, index, ops, n_ops, shards, n_shards, offset, limit, false, 0, 0, out_cols, nullptr, cap, out_n, out_total);
+} FBGPU_CATCH
+
+extern "C" int fbgpu_extract(fbgpu_ctx* c, uint32_t index, const fbgpu_op* ops, int32_t n_ops, uint32_t field, uint32_t view, int32_t bit_depth,
+                             const uint64_t* shards, int64_t n_shards, uint64_t offset, int64_t limit,
+                             uint64_t* out_cols, int64_t* out_vals, uint64_t cap, uint64_t* out_n, uint64_t* out_total) try {
+    if (!c || !out_n || n_shards < 0 || (n_shards && !shards) || (cap && (!out_cols || !out_vals)) || n_ops < 0 || (n_ops && !ops)) return fail(FBGPU_E_INVALID, "null argument");
+    if (bit_depth < 0 || bit_depth > 63) return fail(FBGPU_E_INVALID, "bit depth %d outside 0..63", bit_depth);
+    USE_DEVICE(c);
+    std::shared_lock<std::shared_mutex> lk;
+    int rc = lock_committed(c, lk); if (rc) return rc;
+    // the row: <filter> ∩ exists (bsiExistsBit, row 0 of the bsig_ view; fragment.go:44)
+    std::vector<fbgpu_op> full(ops, ops + n_ops);
+    fbgpu_op ex{}; ex.opcode = FBGPU_OP_ROW; ex.field = field; ex.view = view; ex.a = 0;
+    full.push_back(ex);
+    if (n_ops) { fbgpu_op in{}; in.opcode = FBGPU_OP_INTERSECT; in.argc = 2; full.push_back(in); }
+    const uint32_t fv = view_id_locked(c, ViewKey{ index, field, view }, false);
+    return columns_impl(c, index, full.data(), (int32_t)full.size(), shards, n_shards, offset, limit, true, fv, bit_depth, out_cols, out_vals, cap, out_n, out_total);
 } FBGPU_CATCH
 
 // ------------------------------------------------------------------ per-row counts (TopK / TopN ids)

@@ -1258,6 +1258,80 @@ columns_emit_kernel(const uint4* __restrict__ bitmaps, const ColUnit* __restrict
     }
 }
 
+// Bit-sliced values of the columns of a result row (the bulk form of fragment.value fragment.go:585-617, what Extract and
+// executeDistinctShardBSI :2034 transpose column by column): one CTA per non-empty unit.  The unit's base bitmap
+// (filter ∩ exists, produced by eval_kernel) is staged in shared memory with a per-word rank table; warp w then walks the
+// planes w, w+8, ... — sign row 1 and magnitude rows 2..depth+1 of the BSI view — each container read once, in its own
+// encoding, and every base column found in plane b gets bit b (sign: bit 63) or-ed into its output slot
+// out[out_off + rank - first].  Ranks match columns_emit_kernel, so the two outputs line up.
+constexpr int kExtractThreads = 256;
+__global__ void __launch_bounds__(kExtractThreads)
+extract_values_kernel(StoreRef st, uint32_t fv, int depth, const uint4* __restrict__ bitmaps, const ColUnit* __restrict__ units, int n_units,
+                      unsigned long long* __restrict__ out) {
+    __shared__ __align__(16) uint64_t base[1024];
+    __shared__ uint32_t rank0[1024];            // number of base bits before word i
+    __shared__ uint32_t wsum[kExtractThreads / 32];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nwarps = kExtractThreads / 32;
+    for (int e = blockIdx.x; e < n_units; e += gridDim.x) {
+        const ColUnit u = units[e];
+        const uint64_t* src = reinterpret_cast<const uint64_t*>(bitmaps + (size_t)u.unit * 512);
+        __syncthreads();                                   // the previous unit's readers are done
+        uint64_t w[4]; uint32_t c = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) { w[k] = src[4 * tid + k]; base[4 * tid + k] = w[k]; c += __popcll(w[k]); }
+        uint32_t inc = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { uint32_t x = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += x; }
+        if (lane == 31) wsum[wid] = inc;
+        __syncthreads();
+        uint32_t r = inc - c;
+        for (int k = 0; k < wid; k++) r += wsum[k];
+#pragma unroll
+        for (int k = 0; k < 4; k++) { rank0[4 * tid + k] = r; r += __popcll(w[k]); }
+        __syncthreads();
+        const uint64_t shard = u.col_base >> 20; const int slot = (int)((u.col_base >> 16) & 15);
+        // or `flag` into the slot of base column v (a column outside the base or outside the window is skipped)
+        auto hit = [&](uint32_t v, unsigned long long flag) {
+            const uint64_t bw = base[v >> 6];
+            if (!((bw >> (v & 63)) & 1ull)) return;
+            const uint32_t rk = rank0[v >> 6] + __popcll(bw & ((1ull << (v & 63)) - 1ull));
+            if (rk >= u.first && rk < u.last) atomicOr(&out[u.out_off + (rk - u.first)], flag);
+        };
+        for (int pl = wid; pl < depth + 1; pl += nwarps) {                 // pl 0: sign row 1; pl 1..depth: value rows 2..depth+1
+            Resolved rc; rc.ptr = nullptr; rc.card = 0; rc.typ = 0; rc.cnt = 0;
+            if (lane == 0) rc = resolve(st, fv, shard, (uint64_t)(pl + 1), slot);
+            const void* ptr = (const void*)__shfl_sync(0xffffffffu, (unsigned long long)rc.ptr, 0);
+            const uint32_t card = __shfl_sync(0xffffffffu, rc.card, 0);
+            const uint32_t meta = __shfl_sync(0xffffffffu, ((uint32_t)rc.typ << 16) | rc.cnt, 0);
+            if (ptr == nullptr) continue;
+            const unsigned long long flag = pl == 0 ? (1ull << 63) : (1ull << (pl - 1));
+            const uint32_t typ = meta >> 16, cnt = meta & 0xffffu;
+            if (typ == kArray) {
+                const uint16_t* a = reinterpret_cast<const uint16_t*>(ptr);
+                for (uint32_t i = lane; i < card; i += 32) hit((uint32_t)__ldg(a + i), flag);
+            } else if (typ == kBitmap) {
+                const uint64_t* g = reinterpret_cast<const uint64_t*>(ptr);
+                for (int i = lane; i < 1024; i += 32) {
+                    uint64_t v = __ldg(g + i) & base[i];
+                    while (v) { const int bit = __ffsll((long long)v) - 1; hit((uint32_t)(i * 64 + bit), flag); v &= v - 1; }
+                }
+            } else {
+                const uint32_t* r32 = reinterpret_cast<const uint32_t*>(ptr);
+                for (uint32_t k = 0; k < cnt; k++) {                      // the warp walks each interval's words together
+                    const uint32_t iv = __ldg(r32 + k), s0 = iv & 0xffffu, l0 = iv >> 16;
+                    for (uint32_t i = (s0 >> 6) + lane; i <= (l0 >> 6); i += 32) {
+                        uint64_t m = ~0ull;
+                        if (i == (s0 >> 6)) m &= ~0ull << (s0 & 63);
+                        if (i == (l0 >> 6)) m &= ~0ull >> (63 - (l0 & 63));
+                        uint64_t v = base[i] & m;
+                        while (v) { const int bit = __ffsll((long long)v) - 1; hit(i * 64 + (uint32_t)bit, flag); v &= v - 1; }
+                    }
+                }
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // GroupBy(Rows(a), Rows(b)) [+ filter]: one CTA per (shard, slot).  Column-keyed hash join instead of the
 // reference's |A|x|B| nested intersectionCount loop (executor.go:8880-8934): the elements of field-a rows are inserted

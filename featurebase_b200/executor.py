@@ -693,10 +693,9 @@ class Executor:
         """executeDistinct :1173 / executeDistinctShard :1820.  Set-like field: the ids of the rows that have a bit (under the
         optional filter), executeDistinctShardSet :1952 — one row-count launch.  Int field: the set of values present,
         executeDistinctShardBSI :2034, returned as a SignedRow.  The reference transposes the bit planes column by column;
-        here the value set is found by splitting on bit planes: one row-count launch per node gives |node ∩ plane_i| for
-        every plane, planes that hold none / all of the node's columns fix their bit, the highest mixed plane splits the
-        node.  Launches ~ 2 x distinct values, each over the whole shard batch; meant for low-cardinality fields (a fused
-        extraction kernel is the DESIGN §9 follow-up).  `index=` runs the call on another index (foreign-index joins)."""
+        the library does that on the device (fbgpu_extract: the values of the columns of filter ∩ not-null, gathered from the
+        planes in one pass) and the distinct set is taken from the value vector.  `index=` runs the call on another index
+        (foreign-index joins)."""
         name = c.args.get("field", c.args.get("_field"))
         if name is None:
             raise QueryError("missing field option in Distinct query")
@@ -717,42 +716,11 @@ class Executor:
         if f.type != "int":
             rid, cnt = self.ctx.row_counts(idx.id, f.id, VIEW_STANDARD, shards, filter_ops=filt)
             return sorted(int(r) for r, n in zip(rid, cnt) if n > 0)
-        exists = L.Op(L.OP_ROW, f.id, VIEW_BSI, 0, 0, 0, 0, 0)
-        sign = L.Op(L.OP_ROW, f.id, VIEW_BSI, 0, 1, 0, 0, 0)
-        consider = [exists] if filt is None else filt + [exists, L.Op(L.OP_INTERSECT, 0, 0, 2, 0, 0, 0, 0)]
-        planes = list(range(2, 2 + f.bit_depth))
-        mags = {}                                                      # sign -> magnitudes
-        for negative in (False, True):
-            root = consider + [sign, L.Op(L.OP_INTERSECT if negative else L.OP_DIFFERENCE, 0, 0, 2, 0, 0, 0, 0)]
-            n_root = self.ctx.count(idx.id, root, shards)
-            found = mags.setdefault(negative, [])
-            stack = [(root, n_root, f.bit_depth - 1, 0)] if n_root else []
-            while stack:
-                node, n, top, val = stack.pop()                        # bits above `top` are decided and folded into `node` / `val`
-                if top < 0:
-                    found.append(val)
-                    continue
-                cnt = self.ctx.row_counts(idx.id, f.id, VIEW_BSI, shards, row_ids=planes[:top + 1], filter_ops=node)
-                split = None
-                for i in range(top, -1, -1):
-                    k = int(cnt[i])
-                    if k == n:
-                        val |= 1 << i
-                    elif k:
-                        split = (i, k)
-                        break
-                if split is None:
-                    found.append(val)
-                    continue
-                i, k = split
-                plane = L.Op(L.OP_ROW, f.id, VIEW_BSI, 0, 2 + i, 0, 0, 0)
-                stack.append((node + [plane, L.Op(L.OP_DIFFERENCE, 0, 0, 2, 0, 0, 0, 0)], n - k, i - 1, val))
-                stack.append((node + [plane, L.Op(L.OP_INTERSECT, 0, 0, 2, 0, 0, 0, 0)], k, i - 1, val | 1 << i))
-        pos, neg = [], []
-        for negative, ms in mags.items():
-            for m in ms:
-                v = (-m if negative else m) + f.base                   # value += offset (:2125)
-                (neg if v < 0 else pos).append(abs(v))
+        _, vals, _ = self.ctx.extract(idx.id, f.id, VIEW_BSI, min(f.bit_depth, 63), shards, filter_ops=filt)
+        pos, neg = set(), set()
+        for m in np.unique(vals).tolist():
+            v = int(m) + f.base                                        # value += offset (:2125)
+            (neg if v < 0 else pos).add(abs(v))
         return SignedRow(pos, neg)
 
     def _percentile(self, idx, c, shards):

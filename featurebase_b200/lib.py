@@ -38,7 +38,7 @@ class Counters(C.Structure):
 EXPORTS = ["fbgpu_init", "fbgpu_shutdown", "fbgpu_last_error", "fbgpu_abi_version", "fbgpu_load_fragment",
            "fbgpu_load_fragments", "fbgpu_drop_fragment", "fbgpu_commit", "fbgpu_get_stats", "fbgpu_count", "fbgpu_row",
            "fbgpu_row_counts", "fbgpu_groupby", "fbgpu_comm_unique_id", "fbgpu_comm_init", "fbgpu_comm_destroy",
-           "fbgpu_get_counters", "fbgpu_stream", "fbgpu_rows_payload_bytes", "fbgpu_count_pairs", "fbgpu_columns", "fbgpu_comm_p2p_handle", "fbgpu_comm_p2p_open", "fbgpu_comm_p2p_disable"]
+           "fbgpu_get_counters", "fbgpu_stream", "fbgpu_rows_payload_bytes", "fbgpu_count_pairs", "fbgpu_columns", "fbgpu_extract", "fbgpu_comm_p2p_handle", "fbgpu_comm_p2p_open", "fbgpu_comm_p2p_disable"]
 
 
 def lib_path():
@@ -70,6 +70,8 @@ def load():
     L.fbgpu_count.argtypes, L.fbgpu_count.restype = [vp, u32, vp, i32, vp, i64, C.POINTER(u64), vp], C.c_int
     L.fbgpu_row.argtypes, L.fbgpu_row.restype = [vp, u32, vp, i32, vp, i64, vp, u64, C.POINTER(u64), C.POINTER(u64)], C.c_int
     L.fbgpu_columns.argtypes, L.fbgpu_columns.restype = [vp, u32, vp, i32, vp, i64, u64, i64, vp, u64, C.POINTER(u64), C.POINTER(u64)], C.c_int
+    L.fbgpu_extract.argtypes = [vp, u32, vp, i32, u32, u32, i32, vp, i64, u64, i64, vp, vp, u64, C.POINTER(u64), C.POINTER(u64)]
+    L.fbgpu_extract.restype = C.c_int
     L.fbgpu_row_counts.argtypes, L.fbgpu_row_counts.restype = [vp, u32, u32, u32, vp, i32, vp, i32, vp, i64, vp, vp, i32, C.POINTER(i32)], C.c_int
     L.fbgpu_groupby.argtypes, L.fbgpu_groupby.restype = [vp, u32, vp, vp, i32, vp, vp, vp, i32, vp, i64, vp], C.c_int
     L.fbgpu_count_pairs.argtypes, L.fbgpu_count_pairs.restype = [vp, u32, u32, u32, vp, u32, u32, vp, i32, vp, i64, vp], C.c_int
@@ -227,6 +229,24 @@ class Context:
             if limit is None:
                 self._col_cap = cap
             return buf[: n.value].copy(), total.value
+
+    def extract(self, index, field, view, bit_depth, shards, filter_ops=None, offset=0, limit=None):
+        """(column ids, int64 values relative to the field's Base, number of columns with a value under the filter): the int
+        field's values for the columns of <filter> ∩ not-null, ascending by column, gathered from the bit planes on the device"""
+        sh = _u64arr(shards)
+        arr = ops_array(filter_ops) if filter_ops else None
+        nf = len(filter_ops) if filter_ops else 0
+        n, total = C.c_uint64(0), C.c_uint64(0)
+        cap = max(getattr(self, "_col_cap", 0), 1 << 16) if limit is None else max(int(limit), 1)
+        while True:
+            cols, vals = np.empty(cap, dtype=np.uint64), np.empty(cap, dtype=np.int64)
+            rc = self.L.fbgpu_extract(self.h, index, arr, nf, field, view, int(bit_depth), sh.ctypes.data, len(sh), int(offset), -1 if limit is None else int(limit),
+                                      cols.ctypes.data, vals.ctypes.data, cap, C.byref(n), C.byref(total))
+            if rc == E_NOSPACE:
+                cap = int(n.value)
+                continue
+            self._check(rc)
+            return cols[: n.value].copy(), vals[: n.value].copy(), total.value
 
     def row_counts(self, index, field, view, shards, row_ids=None, filter_ops=None, cap=1 << 20):
         sh = _u64arr(shards)

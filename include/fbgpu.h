@@ -135,6 +135,16 @@ int fbgpu_columns(fbgpu_ctx *ctx, uint32_t index, const fbgpu_op *ops, int32_t n
                   const uint64_t *shards, int64_t n_shards, uint64_t offset, int64_t limit,
                   uint64_t *out_cols, uint64_t cap, uint64_t *out_n, uint64_t *out_total);
 
+/* Values of an int field for the columns of a row: the bulk form of fragment.value (fragment.go:585-617) that Extract
+ * (executor.go executeExtract) and Distinct on int fields (executeDistinctShardBSI :2034) are built on.  The row is
+ * <filter program> ∩ not-null(field) (n_ops == 0: every column that has a value); for its columns, in ascending order and
+ * inside the offset / limit window, out_cols[i] receives the column id and out_vals[i] the stored sign-magnitude value as
+ * an int64, i.e. value - bsiGroup.Base (the caller adds Base, field.go:1640).  `view` is the field's bsig_ view,
+ * bit_depth <= 63 its current depth.  Same capacity contract as fbgpu_columns. */
+int fbgpu_extract(fbgpu_ctx *ctx, uint32_t index, const fbgpu_op *ops, int32_t n_ops, uint32_t field, uint32_t view, int32_t bit_depth,
+                  const uint64_t *shards, int64_t n_shards, uint64_t offset, int64_t limit,
+                  uint64_t *out_cols, int64_t *out_vals, uint64_t cap, uint64_t *out_n, uint64_t *out_total);
+
 /* Per-row counts of one field, optionally intersected with a filter program: the exact part of TopN
  * (fragment.top with explicit ids, fragment.go:1317-1437) and TopK (doTopK executor.go:2705-2746).
  * row_ids != NULL: counts for exactly those rows (out_counts[i] for row_ids[i]).

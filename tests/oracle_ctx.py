@@ -109,6 +109,29 @@ class OracleCtx:
         cols = np.asarray(roaring_io.decode(data), dtype=np.uint64)
         return (cols[offset:] if limit is None else cols[offset:offset + limit]), n
 
+    def extract(self, index, field, view, bit_depth, shards, filter_ops=None, offset=0, limit=None):
+        from featurebase_b200 import roaring_io
+        cols, vals = [], []
+        for s in sorted(set(int(x) for x in shards)):
+            f = self._frag(index, field, view, s)
+            if f is None:
+                continue
+            plane = lambda r: np.asarray(roaring_io.decode(f.row(r, s).to_bytes()), dtype=np.uint64)
+            keep = f.row(0, s)
+            if filter_ops:
+                keep = keep.intersect(self._eval(index, filter_ops, s))
+            c = np.asarray(roaring_io.decode(keep.to_bytes()), dtype=np.uint64)
+            v = np.zeros(len(c), dtype=np.int64)
+            for b in range(bit_depth):
+                v |= np.isin(c, plane(2 + b)).astype(np.int64) << b
+            v = np.where(np.isin(c, plane(1)), -v, v)
+            cols.append(c)
+            vals.append(v)
+        cols = np.concatenate(cols) if cols else np.zeros(0, dtype=np.uint64)
+        vals = np.concatenate(vals) if vals else np.zeros(0, dtype=np.int64)
+        end = None if limit is None else offset + limit
+        return cols[offset:end], vals[offset:end], len(cols)
+
     def row_counts(self, index, field, view, shards, row_ids=None, filter_ops=None, cap=1 << 20):
         tot = {}
         for s in shards:

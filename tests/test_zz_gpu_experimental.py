@@ -625,138 +625,6 @@ def test_min_max_row():
         p.ex.execute("i", "MinRow()")
 
 
-def test_various_queries_goldens():
-    """executor_test.go:8560-8990 populateTestData / variousQueries with the keys replaced by ids in order of first use (key
-    translation is outside the path): Distinct on set and int fields, Count(Distinct), GroupBy over time-range rows, with
-    filter / aggregate=Sum / aggregate=Count(Distinct) / having / sort / limit / offset.  The users are spread over three
-    shards; userE is alone in the last one."""
-    SW = 1 << 20
-    U = dict(A=1, B=2, C=SW + 3, D=4, E=2 * SW + 5, F=6, G=SW + 7)
-    p = Pair()
-    p.field("likenums")
-    for rid, u in [(1, "A"), (2, "B"), (3, "C"), (4, "D"), (5, "E"), (6, "F"), (7, "A"), (7, "B"), (7, "C"), (7, "D"), (7, "F")]:
-        p.holder.set_bit("i", "likenums", rid, U[u])             # (row 7 leaves userE out, as upstream)
-    p.field("likes")                                              # molecula 1, pilosa 2, pangolin 3, zebra 4, toucan 5, dog 6, icecream 7
-    for rid, u in [(1, "A"), (2, "B"), (3, "C"), (4, "D"), (5, "E"), (6, "F")] + [(7, u) for u in "ABCDEF"]:
-        p.holder.set_bit("i", "likes", rid, U[u])
-    p.field("places", "time", quantum="YM")                       # nairobi 1, paris 2, austin 3, toronto 4, mombasa 5, sydney 6
-    J19, A19, J20 = "2019-01-01T00:00", "2019-08-01T00:00", "2020-01-01T00:00"
-    for rid, u, ts in [(1, "B", J19), (2, "C", J19), (3, "F", J19), (4, "A", J19), (4, "B", A19), (4, "C", A19), (4, "B", J20), (4, "D", J20),
-                       (4, "E", J20), (4, "F", J20), (5, "A", J20), (6, "D", J20), (1, "E", J20)]:
-        p.holder.set_bit("i", "places", rid, U[u], timestamp=ts)
-    p.field("affinity", "int", min=-1000, max=1000)
-    for u, v in dict(A=10, B=-10, C=5, D=-5, E=0).items():
-        p.holder.set_value("i", "affinity", U[u], v)
-    p.field("net_worth", "int", min=-100000000, max=100000000)
-    for u, v in dict(A=1, B=10, C=100, D=1000, E=10000, F=100000).items():
-        p.holder.set_value("i", "net_worth", U[u], v)
-    p.field("zip_code", "int", min=0, max=100000)
-    for u, v in dict(A=78739, B=78739, C=19707, D=19707, E=86753, G=78739).items():
-        p.holder.set_value("i", "zip_code", U[u], v)
-    p.sync_pending()
-    run = lambda q: p.ex.execute("i", q)[0]
-    gb = lambda q: [tuple(r for _, r in g[0]) + tuple(g[1:]) for g in run(q)]
-    Y19, ALL = "from='2019-01-01T00:00', to='2019-12-31T23:59'", "from='2019-01-01T00:00', to='2020-12-31T23:59'"
-    NOT_C = "filter=Not(Intersect(Row(likes=3), Row(likes=7)))"
-    assert gb(f"GroupBy(Rows(places, {ALL}))") == [(1, 2), (2, 1), (3, 1), (4, 6), (5, 1), (6, 1)]
-    assert gb("GroupBy(Rows(places, from='2019-01-01T00:00', to='2019-02-01T00:00'))") == [(1, 1), (2, 1), (3, 1), (4, 1)]
-    assert gb(f"GroupBy(Rows(places, {Y19}))") == [(1, 1), (2, 1), (3, 1), (4, 3)]
-    assert gb(f"GroupBy(Rows(places, {Y19}), {NOT_C})") == [(1, 1), (3, 1), (4, 2)]
-    assert gb(f"GroupBy(Rows(places, {Y19}), {NOT_C}, aggregate=Sum(field=net_worth))") == [(1, 1, 10), (3, 1, 100000), (4, 2, 11)]
-    assert run(f"Rows(places, {ALL})") == [1, 2, 3, 4, 5, 6]
-    assert run(f"Rows(places, {Y19})") == [1, 2, 3, 4]
-    assert run("Rows(places, from='2019-01-01T00:00', to='2019-02-01T00:00')") == [1, 2, 3, 4]
-    assert run("Count(All())") == 7
-    assert run("Count(Distinct(field=likenums))") == 7
-    assert run("Distinct(field=likenums)") == [1, 2, 3, 4, 5, 6, 7]
-    assert run("Count(Distinct(field=likes))") == 7
-    d = run("Distinct(field=affinity)")
-    assert (d.pos, d.neg, d.values()) == ([0, 5, 10], [5, 10], [-10, -5, 0, 5, 10])
-    assert run("Count(Distinct(field=affinity))") == 5
-    assert run("Distinct(Row(affinity>=0),field=affinity)") == X.SignedRow([0, 5, 10], [])
-    assert run("Count(Distinct(Row(affinity>=0),field=affinity))") == 3
-    assert run("Distinct(Row(affinity<0),field=likes)") == [2, 4, 7]
-    assert run("Distinct(Row(affinity>0),field=likes)") == [1, 3, 7]
-    assert run("Distinct(Row(likenums=1),field=likes)") == [1, 7]
-    for q in ("Distinct(field=likes)", "Distinct(All(),field=likes)", "Distinct(field=likes )"):
-        assert run(q) == [1, 2, 3, 4, 5, 6, 7], q
-    assert gb("GroupBy(Rows(field=likes))") == [(1, 1), (2, 1), (3, 1), (4, 1), (5, 1), (6, 1), (7, 6)]
-    assert gb("GroupBy(Rows(field=likes), aggregate=Sum(field=net_worth), limit=2, having=Condition(sum>10))") == [(3, 1, 100), (4, 1, 1000)]
-    assert gb("GroupBy(Rows(field=likes), having=Condition(count>5))") == [(7, 6)]
-    assert gb("GroupBy(Rows(field=likes), filter=Row(affinity>-7))") == [(1, 1), (3, 1), (4, 1), (5, 1), (7, 4)]
-    CD = "aggregate=Count(Distinct(field=zip_code))"
-    assert gb(f"GroupBy(Rows(field=likes), {CD})") == [(1, 1, 1), (2, 1, 1), (3, 1, 1), (4, 1, 1), (5, 1, 1), (6, 1, 0), (7, 6, 3)]
-    assert gb(f"GroupBy(Rows(field=likes), {CD}, having=Condition(sum>2))") == [(7, 6, 3)]
-    assert gb(f"GroupBy(Rows(field=likes), filter=Row(affinity>-11), {CD})") == [(1, 1, 1), (2, 1, 1), (3, 1, 1), (4, 1, 1), (5, 1, 1), (7, 5, 3)]
-    assert gb("GroupBy(Rows(field=likes), filter=Row(affinity>-11), aggregate=Count(Distinct(Row(affinity>-7), field=zip_code)))") == \
-        [(1, 1, 1), (2, 1, 0), (3, 1, 1), (4, 1, 1), (5, 1, 1), (7, 5, 3)]
-    assert gb('GroupBy(Rows(field=likes), sort="count desc")') == [(7, 6), (1, 1), (2, 1), (3, 1), (4, 1), (5, 1), (6, 1)]
-    SUM = 'aggregate=Sum(field=net_worth), sort="aggregate desc, count asc"'
-    full = [(7, 6, 111111), (6, 1, 100000), (5, 1, 10000), (4, 1, 1000), (3, 1, 100), (2, 1, 10), (1, 1, 1)]
-    assert gb(f"GroupBy(Rows(field=likes), {SUM})") == full
-    assert gb(f"GroupBy(Rows(field=likes), {SUM}, limit=3)") == full[:3]
-    assert gb(f"GroupBy(Rows(field=likes), {SUM},limit=3,offset=2)") == full[2:5]
-    # TestExecutor_Execute_Distinct / BareDistinct (executor_test.go:5945-5977, 7175-7207): a foreign-index join through Distinct(index=)
-    h = p.holder
-    par, ch = h.create_index("parent"), h.create_index("child")
-    par.create_field("general")
-    for row, cols in ((1, (1, 2, 3)), (2, (21, 22, 23)), (SW, (1, 21))):
-        for c in cols:
-            h.set_bit("parent", "general", row, c)
-    ch.create_field("parent_id", "int", min=0, max=(1 << 28) - 1)
-    ch.create_field("parent_set_id")
-    ch.create_field("color")                                      # red 1, blue 2
-    for col, parent, color in ((1, 1, 1), (2, 2, 2), (SW, 1, 2), (4, 21, 1)):
-        h.set_value("child", "parent_id", col, parent)
-        h.set_bit("child", "parent_set_id", parent, col)
-        h.set_bit("child", "color", color, col)
-    h.sync()
-    ex = X.Executor(h)
-    assert ex.execute("child", "Distinct(index=child, field=parent_id)")[0] == X.SignedRow([1, 2, 21], [])
-    assert ex.execute("child", "Distinct(field=parent_set_id)")[0] == [1, 2, 21]
-    assert ex.execute("child", "Distinct(Row(parent_id=3), field=parent_id)")[0] == X.SignedRow()
-    for fld in ("parent_id", "parent_set_id"):
-        got = ex.execute("parent", f"Intersect(Row(general={SW}), Distinct(Row(color=2), index=child, field={fld}))")[0]
-        assert [int(c) for c in got.columns()] == [1], fld
-    with pytest.raises(X.QueryError, match="missing field option"):
-        ex.execute("child", "Distinct(Row(color=2))")
-
-
-def test_distinct_random():
-    """Distinct over int fields (zero, positive and negative Base; values on both sides of zero; with and without a filter) and
-    set fields against a direct enumeration of the imported values"""
-    SW = 1 << 20
-    rng = np.random.default_rng(77)
-    for lo, hi, n_vals in ((-300, 300, 40), (1000, 90000, 25), (-5000, -10, 30), (0, 1, 2), (-(1 << 40), 1 << 40, 12)):
-        p = Pair()
-        p.field("v", "int", min=lo, max=hi)
-        p.field("s")
-        pool = [int(x) for x in rng.integers(lo, hi, size=n_vals, endpoint=True)] + [lo, hi]
-        cols = rng.choice(3 * SW, size=400, replace=False)
-        vals = {}
-        for c in cols.tolist():
-            vals[c] = pool[int(rng.integers(len(pool)))]
-            p.holder.set_value("i", "v", c, vals[c])
-            p.holder.set_bit("i", "s", int(rng.integers(0, 9)) * 1000, c)
-        for c in rng.choice(3 * SW, size=100, replace=False).tolist():           # columns without a value
-            p.holder.set_bit("i", "s", 3, c)
-        p.sync_pending()
-        members = {}
-        for r in [k * 1000 for k in range(9)] + [3]:
-            members[r] = {int(c) for c in p.ex.execute("i", f"Row(s={r})")[0].columns()}
-        def expect(keep):
-            seen = {vals[c] for c in vals if keep(c)}
-            return X.SignedRow([v for v in seen if v >= 0], [-v for v in seen if v < 0])
-        assert p.ex.execute("i", "Distinct(field=v)")[0] == expect(lambda c: True), (lo, hi)
-        assert p.ex.execute("i", "Count(Distinct(field=v))")[0] == expect(lambda c: True).count()
-        for r in (0, 4000, 3):
-            assert p.ex.execute("i", f"Distinct(Row(s={r}), field=v)")[0] == expect(lambda c: c in members[r]), (lo, hi, r)
-        mid = (lo + hi) // 2
-        assert p.ex.execute("i", f"Distinct(Row(v > {mid}), field=v)")[0] == expect(lambda c: vals[c] > mid), (lo, hi)
-        assert p.ex.execute("i", f"Distinct(Row(v < {mid}), field=s)")[0] == sorted(r for r in members if any(c in vals and vals[c] < mid for c in members[r]))
-        assert p.ex.execute("i", "Distinct(Row(s=12345), field=v)")[0] == X.SignedRow()
-
-
 def test_groupby_kernel_pass_shapes():
     """GroupBy over shapes chosen for groupby_kernel's passes: 300 x 270 rows (two a-chunks, two b-chunks) of tiny array
     containers, a bitmap a-row and a bitmap b-row (dense / warp passes), with and without a filter, either field order —
@@ -915,3 +783,187 @@ def test_columns_entry_point():
         assert rc == L.E_NOSPACE and n.value == tot.value > 10
         rc = ctx.L.fbgpu_columns(ctx.h, p.idx.id, ops, len(ops), sh.ctypes.data, len(sh), 3, 10, buf.ctypes.data, 10, C.byref(n), None)
         assert rc == 0 and n.value == 10
+
+
+def test_extract_entry_point():
+    """fbgpu_extract: an int field's values for the columns of filter ∩ not-null, gathered from the bit planes on the device
+    (the bulk fragment.value, fragment.go:585-617).  Planes of every encoding: uniform values (bitmap / array planes), a
+    contiguous block of equal values (run planes), negative values, a Base other than zero, nulls, windows, an empty filter."""
+    import featurebase_b200.datagen as D
+    SW = 1 << 20
+    p = Pair()
+    p.field("u", "int", min=-40000, max=40000)
+    p.field("w", "int", min=1000, max=9000)                        # Base 1000
+    p.field("g")
+    depth = p.idx.fields["u"].bit_depth
+    want_u, want_w = {}, {}
+    for s in (0, 2):
+        p.load("u", X.VIEW_BSI, s, D.bsi_fragment(21, s, 200000, depth, -40000, 40000, base=0, null_frac=0.3))
+        for col in range(200000):
+            v = D.bsi_value(21, s, col, -40000, 40000, null_frac=0.3)
+            if v is not None:
+                want_u[s * SW + col] = v
+    for col in range(3 * SW + 100, 3 * SW + 9000):                 # run planes: a block of equal values, then a ramp
+        want_w[col] = 4097 if col < 3 * SW + 5000 else 1000 + (col % 8000)
+        p.holder.set_value("i", "w", col, want_w[col])
+    p.field("z", "int", min=-200000, max=200000)                   # array planes: scattered columns, small values, a few large ones
+    want_z = {}
+    for k, col in enumerate(np.random.default_rng(8).choice(2 * SW, size=20000, replace=False).tolist()):
+        want_z[col] = (70000 + k % 1000) * (-1 if k % 100 == 0 else 1) if k % 50 == 0 else k % 6
+        p.holder.set_value("i", "z", col, want_z[col])
+    for col in list(want_u)[::7] + list(want_w)[::3] + list(want_z)[::2]:
+        p.holder.set_bit("i", "g", 1, col)
+    p.sync_pending()
+    ctx, idx = p.holder.ctx, p.idx
+    g_cols = {int(c) for c in p.ex.execute("i", "Row(g=1)")[0].columns()}
+    for name, want in (("u", want_u), ("w", want_w), ("z", want_z)):
+        f = idx.fields[name]
+        keys = np.array(sorted(want), dtype=np.uint64)
+        cols, vals, total = ctx.extract(idx.id, f.id, X.VIEW_BSI, f.bit_depth, p.shards())
+        assert total == len(keys) and np.array_equal(cols, keys)
+        assert np.array_equal(vals + f.base, np.array([want[int(c)] for c in keys], dtype=np.int64)), name
+        filt = p.ex._bitmap_call(idx, pql.parse("Row(g=1)")[0])
+        fk = np.array([c for c in keys.tolist() if c in g_cols], dtype=np.uint64)
+        cols, vals, total = ctx.extract(idx.id, f.id, X.VIEW_BSI, f.bit_depth, p.shards(), filter_ops=filt)
+        assert total == len(fk) and np.array_equal(cols, fk) and np.array_equal(vals + f.base, np.array([want[int(c)] for c in fk], dtype=np.int64)), name
+        for off, lim in ((0, 5), (len(fk) // 2, 4000), (len(fk) - 2, 10), (len(fk) + 3, 4)):
+            cols, vals, total = ctx.extract(idx.id, f.id, X.VIEW_BSI, f.bit_depth, p.shards(), filter_ops=filt, offset=off, limit=lim)
+            assert total == len(fk) and np.array_equal(cols, fk[off:off + lim]) and np.array_equal(vals + f.base, np.array([want[int(c)] for c in fk[off:off + lim]], dtype=np.int64))
+        cols, vals, total = ctx.extract(idx.id, f.id, X.VIEW_BSI, f.bit_depth, p.shards(), filter_ops=p.ex._bitmap_call(idx, pql.parse("Row(g=9)")[0]))
+        assert total == 0 and len(cols) == 0 and len(vals) == 0
+    # Sum / Min / Max cross-check: the aggregates composed from counts agree with the extracted values
+    vc = p.ex.execute("i", "Sum(field=u)")[0]
+    assert (vc.val, vc.count) == (sum(want_u.values()), len(want_u))
+    assert p.ex.execute("i", "Min(field=w)")[0].val == min(want_w.values()) and p.ex.execute("i", "Max(field=u)")[0].val == max(want_u.values())
+
+
+def test_various_queries_goldens():
+    """executor_test.go:8560-8990 populateTestData / variousQueries with the keys replaced by ids in order of first use (key
+    translation is outside the path): Distinct on set and int fields, Count(Distinct), GroupBy over time-range rows, with
+    filter / aggregate=Sum / aggregate=Count(Distinct) / having / sort / limit / offset.  The users are spread over three
+    shards; userE is alone in the last one."""
+    SW = 1 << 20
+    U = dict(A=1, B=2, C=SW + 3, D=4, E=2 * SW + 5, F=6, G=SW + 7)
+    p = Pair()
+    p.field("likenums")
+    for rid, u in [(1, "A"), (2, "B"), (3, "C"), (4, "D"), (5, "E"), (6, "F"), (7, "A"), (7, "B"), (7, "C"), (7, "D"), (7, "F")]:
+        p.holder.set_bit("i", "likenums", rid, U[u])             # (row 7 leaves userE out, as upstream)
+    p.field("likes")                                              # molecula 1, pilosa 2, pangolin 3, zebra 4, toucan 5, dog 6, icecream 7
+    for rid, u in [(1, "A"), (2, "B"), (3, "C"), (4, "D"), (5, "E"), (6, "F")] + [(7, u) for u in "ABCDEF"]:
+        p.holder.set_bit("i", "likes", rid, U[u])
+    p.field("places", "time", quantum="YM")                       # nairobi 1, paris 2, austin 3, toronto 4, mombasa 5, sydney 6
+    J19, A19, J20 = "2019-01-01T00:00", "2019-08-01T00:00", "2020-01-01T00:00"
+    for rid, u, ts in [(1, "B", J19), (2, "C", J19), (3, "F", J19), (4, "A", J19), (4, "B", A19), (4, "C", A19), (4, "B", J20), (4, "D", J20),
+                       (4, "E", J20), (4, "F", J20), (5, "A", J20), (6, "D", J20), (1, "E", J20)]:
+        p.holder.set_bit("i", "places", rid, U[u], timestamp=ts)
+    p.field("affinity", "int", min=-1000, max=1000)
+    for u, v in dict(A=10, B=-10, C=5, D=-5, E=0).items():
+        p.holder.set_value("i", "affinity", U[u], v)
+    p.field("net_worth", "int", min=-100000000, max=100000000)
+    for u, v in dict(A=1, B=10, C=100, D=1000, E=10000, F=100000).items():
+        p.holder.set_value("i", "net_worth", U[u], v)
+    p.field("zip_code", "int", min=0, max=100000)
+    for u, v in dict(A=78739, B=78739, C=19707, D=19707, E=86753, G=78739).items():
+        p.holder.set_value("i", "zip_code", U[u], v)
+    p.sync_pending()
+    run = lambda q: p.ex.execute("i", q)[0]
+    gb = lambda q: [tuple(r for _, r in g[0]) + tuple(g[1:]) for g in run(q)]
+    Y19, ALL = "from='2019-01-01T00:00', to='2019-12-31T23:59'", "from='2019-01-01T00:00', to='2020-12-31T23:59'"
+    NOT_C = "filter=Not(Intersect(Row(likes=3), Row(likes=7)))"
+    assert gb(f"GroupBy(Rows(places, {ALL}))") == [(1, 2), (2, 1), (3, 1), (4, 6), (5, 1), (6, 1)]
+    assert gb("GroupBy(Rows(places, from='2019-01-01T00:00', to='2019-02-01T00:00'))") == [(1, 1), (2, 1), (3, 1), (4, 1)]
+    assert gb(f"GroupBy(Rows(places, {Y19}))") == [(1, 1), (2, 1), (3, 1), (4, 3)]
+    assert gb(f"GroupBy(Rows(places, {Y19}), {NOT_C})") == [(1, 1), (3, 1), (4, 2)]
+    assert gb(f"GroupBy(Rows(places, {Y19}), {NOT_C}, aggregate=Sum(field=net_worth))") == [(1, 1, 10), (3, 1, 100000), (4, 2, 11)]
+    assert run(f"Rows(places, {ALL})") == [1, 2, 3, 4, 5, 6]
+    assert run(f"Rows(places, {Y19})") == [1, 2, 3, 4]
+    assert run("Rows(places, from='2019-01-01T00:00', to='2019-02-01T00:00')") == [1, 2, 3, 4]
+    assert run("Count(All())") == 7
+    assert run("Count(Distinct(field=likenums))") == 7
+    assert run("Distinct(field=likenums)") == [1, 2, 3, 4, 5, 6, 7]
+    assert run("Count(Distinct(field=likes))") == 7
+    d = run("Distinct(field=affinity)")
+    assert (d.pos, d.neg, d.values()) == ([0, 5, 10], [5, 10], [-10, -5, 0, 5, 10])
+    assert run("Count(Distinct(field=affinity))") == 5
+    assert run("Distinct(Row(affinity>=0),field=affinity)") == X.SignedRow([0, 5, 10], [])
+    assert run("Count(Distinct(Row(affinity>=0),field=affinity))") == 3
+    assert run("Distinct(Row(affinity<0),field=likes)") == [2, 4, 7]
+    assert run("Distinct(Row(affinity>0),field=likes)") == [1, 3, 7]
+    assert run("Distinct(Row(likenums=1),field=likes)") == [1, 7]
+    for q in ("Distinct(field=likes)", "Distinct(All(),field=likes)", "Distinct(field=likes )"):
+        assert run(q) == [1, 2, 3, 4, 5, 6, 7], q
+    assert gb("GroupBy(Rows(field=likes))") == [(1, 1), (2, 1), (3, 1), (4, 1), (5, 1), (6, 1), (7, 6)]
+    assert gb("GroupBy(Rows(field=likes), aggregate=Sum(field=net_worth), limit=2, having=Condition(sum>10))") == [(3, 1, 100), (4, 1, 1000)]
+    assert gb("GroupBy(Rows(field=likes), having=Condition(count>5))") == [(7, 6)]
+    assert gb("GroupBy(Rows(field=likes), filter=Row(affinity>-7))") == [(1, 1), (3, 1), (4, 1), (5, 1), (7, 4)]
+    CD = "aggregate=Count(Distinct(field=zip_code))"
+    assert gb(f"GroupBy(Rows(field=likes), {CD})") == [(1, 1, 1), (2, 1, 1), (3, 1, 1), (4, 1, 1), (5, 1, 1), (6, 1, 0), (7, 6, 3)]
+    assert gb(f"GroupBy(Rows(field=likes), {CD}, having=Condition(sum>2))") == [(7, 6, 3)]
+    assert gb(f"GroupBy(Rows(field=likes), filter=Row(affinity>-11), {CD})") == [(1, 1, 1), (2, 1, 1), (3, 1, 1), (4, 1, 1), (5, 1, 1), (7, 5, 3)]
+    assert gb("GroupBy(Rows(field=likes), filter=Row(affinity>-11), aggregate=Count(Distinct(Row(affinity>-7), field=zip_code)))") == \
+        [(1, 1, 1), (2, 1, 0), (3, 1, 1), (4, 1, 1), (5, 1, 1), (7, 5, 3)]
+    assert gb('GroupBy(Rows(field=likes), sort="count desc")') == [(7, 6), (1, 1), (2, 1), (3, 1), (4, 1), (5, 1), (6, 1)]
+    SUM = 'aggregate=Sum(field=net_worth), sort="aggregate desc, count asc"'
+    full = [(7, 6, 111111), (6, 1, 100000), (5, 1, 10000), (4, 1, 1000), (3, 1, 100), (2, 1, 10), (1, 1, 1)]
+    assert gb(f"GroupBy(Rows(field=likes), {SUM})") == full
+    assert gb(f"GroupBy(Rows(field=likes), {SUM}, limit=3)") == full[:3]
+    assert gb(f"GroupBy(Rows(field=likes), {SUM},limit=3,offset=2)") == full[2:5]
+    # TestExecutor_Execute_Distinct / BareDistinct (executor_test.go:5945-5977, 7175-7207): a foreign-index join through Distinct(index=)
+    h = p.holder
+    par, ch = h.create_index("parent"), h.create_index("child")
+    par.create_field("general")
+    for row, cols in ((1, (1, 2, 3)), (2, (21, 22, 23)), (SW, (1, 21))):
+        for c in cols:
+            h.set_bit("parent", "general", row, c)
+    ch.create_field("parent_id", "int", min=0, max=(1 << 28) - 1)
+    ch.create_field("parent_set_id")
+    ch.create_field("color")                                      # red 1, blue 2
+    for col, parent, color in ((1, 1, 1), (2, 2, 2), (SW, 1, 2), (4, 21, 1)):
+        h.set_value("child", "parent_id", col, parent)
+        h.set_bit("child", "parent_set_id", parent, col)
+        h.set_bit("child", "color", color, col)
+    h.sync()
+    ex = X.Executor(h)
+    assert ex.execute("child", "Distinct(index=child, field=parent_id)")[0] == X.SignedRow([1, 2, 21], [])
+    assert ex.execute("child", "Distinct(field=parent_set_id)")[0] == [1, 2, 21]
+    assert ex.execute("child", "Distinct(Row(parent_id=3), field=parent_id)")[0] == X.SignedRow()
+    for fld in ("parent_id", "parent_set_id"):
+        got = ex.execute("parent", f"Intersect(Row(general={SW}), Distinct(Row(color=2), index=child, field={fld}))")[0]
+        assert [int(c) for c in got.columns()] == [1], fld
+    with pytest.raises(X.QueryError, match="missing field option"):
+        ex.execute("child", "Distinct(Row(color=2))")
+
+
+def test_distinct_random():
+    """Distinct over int fields (zero, positive and negative Base; values on both sides of zero; with and without a filter) and
+    set fields against a direct enumeration of the imported values"""
+    SW = 1 << 20
+    rng = np.random.default_rng(77)
+    for lo, hi, n_vals in ((-300, 300, 40), (1000, 90000, 25), (-5000, -10, 30), (0, 1, 2), (-(1 << 40), 1 << 40, 12)):
+        p = Pair()
+        p.field("v", "int", min=lo, max=hi)
+        p.field("s")
+        pool = [int(x) for x in rng.integers(lo, hi, size=n_vals, endpoint=True)] + [lo, hi]
+        cols = rng.choice(3 * SW, size=400, replace=False)
+        vals = {}
+        for c in cols.tolist():
+            vals[c] = pool[int(rng.integers(len(pool)))]
+            p.holder.set_value("i", "v", c, vals[c])
+            p.holder.set_bit("i", "s", int(rng.integers(0, 9)) * 1000, c)
+        for c in rng.choice(3 * SW, size=100, replace=False).tolist():           # columns without a value
+            p.holder.set_bit("i", "s", 3, c)
+        p.sync_pending()
+        members = {}
+        for r in [k * 1000 for k in range(9)] + [3]:
+            members[r] = {int(c) for c in p.ex.execute("i", f"Row(s={r})")[0].columns()}
+        def expect(keep):
+            seen = {vals[c] for c in vals if keep(c)}
+            return X.SignedRow([v for v in seen if v >= 0], [-v for v in seen if v < 0])
+        assert p.ex.execute("i", "Distinct(field=v)")[0] == expect(lambda c: True), (lo, hi)
+        assert p.ex.execute("i", "Count(Distinct(field=v))")[0] == expect(lambda c: True).count()
+        for r in (0, 4000, 3):
+            assert p.ex.execute("i", f"Distinct(Row(s={r}), field=v)")[0] == expect(lambda c: c in members[r]), (lo, hi, r)
+        mid = (lo + hi) // 2
+        assert p.ex.execute("i", f"Distinct(Row(v > {mid}), field=v)")[0] == expect(lambda c: vals[c] > mid), (lo, hi)
+        assert p.ex.execute("i", f"Distinct(Row(v < {mid}), field=s)")[0] == sorted(r for r in members if any(c in vals and vals[c] < mid for c in members[r]))
+        assert p.ex.execute("i", "Distinct(Row(s=12345), field=v)")[0] == X.SignedRow()
