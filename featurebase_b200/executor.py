@@ -295,6 +295,8 @@ class Executor:
                 return self._minmax_row(idx, c, shards, c.name == "MaxRow")
             if c.name == "Distinct":
                 return self._distinct(idx, c, shards)
+            if c.name == "Extract":
+                return self._extract(idx, c, shards)
             if c.name == "IncludesColumn":                       # executeIncludesColumnCall: is the column in the row?
                 if "column" not in c.args:
                     raise QueryError("IncludesColumn call must specify a column")
@@ -722,6 +724,65 @@ class Executor:
             v = int(m) + f.base                                        # value += offset (:2125)
             (neg if v < 0 else pos).add(abs(v))
         return SignedRow(pos, neg)
+
+    def _extract(self, idx, c, shards):
+        """executeExtract :4711 / executeExtractShard :4758: the table {column -> per-field cell} for the columns of the first
+        child.  The column list and the int cells come from the device (fbgpu_columns, fbgpu_extract: value + Base, None
+        when the column has no value); a set / time cell is the ascending list of the field's rows that hold the column, a
+        mutex cell the single such row (None if none), a bool cell True / False / None — one column expansion of
+        filter ∩ Row(field=r) per row of the field.  Keys, decimals and timestamps are translation layers above the path.
+        Returns {"fields": [(name, type)], "columns": [(column id, [cell, ...])]}."""
+        if not c.children:
+            raise QueryError("missing column filter in Extract")
+        filt_call = c.children[0]
+        if filt_call.name == "Sort":
+            raise QueryError("Extract(Sort(..)) is not supported by this mirror")
+        win = (0, None)
+        if filt_call.name == "Limit":                            # Extract(Limit(x, limit=, offset=), ...): the window is cut on the device
+            if len(filt_call.children) != 1:
+                raise QueryError("Limit() requires a single bitmap input")
+            win, filt_call = (int(filt_call.args.get("offset", 0)), filt_call.args.get("limit")), filt_call.children[0]
+        fields = []
+        for ch in c.children[1:]:                                # extractFieldsFromRowsCalls :4670-4708
+            if ch.name != "Rows":
+                raise QueryError(f"child call of Extract is {ch.name} but expected Rows")
+            name = ch.args.get("_field", ch.args.get("field"))
+            if name is None:
+                raise QueryError("missing field in Rows call")
+            fields.append(self._field(idx, name))
+        filt = self._bitmap_call(idx, filt_call)
+        cols, _ = self.ctx.columns(idx.id, filt, shards, offset=win[0], limit=win[1])
+        cols = [int(x) for x in cols]
+        pos = {col: i for i, col in enumerate(cols)}
+        if win != (0, None) and cols:                            # cells are only needed for the window: narrow the filter to it
+            ef, erow = self.holder.embed_row(idx.name, cols)
+            filt = [L.Op(L.OP_ROW, ef.id, VIEW_STANDARD, 0, erow, 0, 0, 0)]
+        table = [[None] * len(fields) for _ in cols]
+        types = []
+        for k, f in enumerate(fields):
+            if f.type == "int":
+                types.append("int64")
+                vc, vv, _ = self.ctx.extract(idx.id, f.id, VIEW_BSI, min(f.bit_depth, 63), shards, filter_ops=filt)
+                for col, v in zip(vc.tolist(), vv.tolist()):
+                    if col in pos:
+                        table[pos[col]][k] = int(v) + f.base
+                continue
+            multi = f.type in ("set", "time")
+            types.append("[]uint64" if multi else "bool" if f.type == "bool" else "uint64")
+            if multi:
+                for row in table:
+                    row[k] = []
+            rid, _ = self.ctx.row_counts(idx.id, f.id, VIEW_STANDARD, shards, filter_ops=filt)
+            for r in sorted(int(x) for x in rid):
+                ops = filt + [L.Op(L.OP_ROW, f.id, VIEW_STANDARD, 0, r, 0, 0, 0), L.Op(L.OP_INTERSECT, 0, 0, 2, 0, 0, 0, 0)]
+                for col in self.ctx.columns(idx.id, ops, shards)[0].tolist():
+                    if col not in pos:
+                        continue
+                    if multi:
+                        table[pos[col]][k].append(r)
+                    elif table[pos[col]][k] is None:
+                        table[pos[col]][k] = (r == 1) if f.type == "bool" else r
+        return {"fields": [(f.name, t) for f, t in zip(fields, types)], "columns": list(zip(cols, table))}
 
     def _percentile(self, idx, c, shards):
         """executePercentile :1310-1600 (int fields): total = Count(filter ∩ notNull); the wanted numbers of smaller / larger

@@ -87,6 +87,7 @@ def test_various_queries(oracle_backed):
     E.test_distinct_random()
     E.test_columns_entry_point()
     E.test_extract_entry_point()
+    E.test_extract_table_golden()
     E.test_topk_time_range()
 
 

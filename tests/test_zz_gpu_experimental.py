@@ -837,6 +837,45 @@ def test_extract_entry_point():
     assert p.ex.execute("i", "Min(field=w)")[0].val == min(want_w.values()) and p.ex.execute("i", "Max(field=u)")[0].val == max(want_u.values())
 
 
+def test_extract_table_golden():
+    """executor_test.go:4940-5182 TestExecutor_Execute_Extract without the key / decimal / timestamp columns (translation layers):
+    set, mutex, time, int and bool cells for every existing column, incl. a column whose only bit was cleared"""
+    SW = 1 << 20
+    p = Pair()
+    p.field("set")
+    p.field("mutex", "mutex")
+    p.field("time", "time", quantum="YMDH")
+    p.field("bsint", "int", min=-100, max=100)
+    p.field("bool", "bool")
+    for row, col in ((0, 1), (0, 2), (3, 1), (4, 1), (4, 4 * SW)):
+        p.holder.set_bit("i", "set", row, col)
+    p.holder._pending.setdefault(("i", X.EXISTENCE_FIELD, X.VIEW_STANDARD, 1), set()).add(0)       # Set(SW, set=5) then Clear(): the column stays
+    for row, col in ((0, 1), (0, 2), (4, 4 * SW)):
+        p.holder.set_bit("i", "mutex", row, col)
+    for col, row, ts in ((0, 1, "2016-01-01T00:00"), (1, 2, "2017-01-01T00:00"), (3, 3, "2018-01-01T00:00")):
+        p.holder.set_bit("i", "time", row, col, timestamp=ts)
+    for col, v in ((0, 1), (1, -1), (3, 2)):
+        p.holder.set_value("i", "bsint", col, v)
+    for col, v in ((0, True), (1, False), (3, True)):
+        p.holder.set_bit("i", "bool", 1 if v else 0, col)
+    p.sync_pending()
+    got = p.ex.execute("i", "Extract(All(), Rows(set), Rows(mutex), Rows(time), Rows(bsint), Rows(bool))")[0]
+    assert got["fields"] == [("set", "[]uint64"), ("mutex", "uint64"), ("time", "[]uint64"), ("bsint", "int64"), ("bool", "bool")]
+    assert got["columns"] == [
+        (0, [[], None, [1], 1, True]),
+        (1, [[0, 3, 4], 0, [2], -1, False]),
+        (2, [[0], 0, [], None, None]),
+        (3, [[], None, [3], 2, True]),
+        (SW, [[], None, [], None, None]),
+        (4 * SW, [[4], 4, [], None, None]),
+    ]
+    assert p.ex.execute("i", "Extract(Limit(All(), limit=2, offset=1), Rows(set), Rows(bsint))")[0]["columns"] == [(1, [[0, 3, 4], -1]), (2, [[0], None])]
+    assert p.ex.execute("i", "Extract(Row(set=4), Rows(mutex))")[0]["columns"] == [(1, [0]), (4 * SW, [4])]
+    assert p.ex.execute("i", "Extract(Row(set=9), Rows(mutex))")[0]["columns"] == []
+    with pytest.raises(X.QueryError, match="missing column filter"):
+        p.ex.execute("i", "Extract()")
+
+
 def test_various_queries_goldens():
     """executor_test.go:8560-8990 populateTestData / variousQueries with the keys replaced by ids in order of first use (key
     translation is outside the path): Distinct on set and int fields, Count(Distinct), GroupBy over time-range rows, with
