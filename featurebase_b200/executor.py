@@ -852,6 +852,10 @@ class Executor:
                 raise QueryError("missing field in Rows call")
             f = self._field(idx, name)
             fields.append(f)
+            if f.type == "int":                                  # groups of an int field are its values (FieldRow.Value, :8740-8750), ascending
+                row_ids.append(self._distinct(idx, pql.Call("Distinct", {"field": f.name}), shards).values())
+                time_args.append(None)
+                continue
             pre = pql.Call("Rows", {k: v for k, v in ch.args.items() if k != "previous"})     # previous positions the iterator, it does not drop rows
             row_ids.append(self._rows(idx, pre, shards))         # pre-pass executeRows :3263-3287
             time_args.append({k: ch.args[k] for k in ("from", "to") if k in ch.args} if f.quantum else {})
@@ -871,11 +875,11 @@ class Executor:
         # row per row id holding the union of that row over the covering views (timeFragmentsRowIterator :8755-8768)
         dev_fields, dev_rows = [], []
         for f, rows, targs in zip(fields, row_ids, time_args):
-            if not targs:
+            if targs is not None and not targs:
                 dev_fields.append(f.id)
                 dev_rows.append(rows)
                 continue
-            sf, operands = self._time_rows_as_operands(idx, f, rows, targs, shards)
+            sf, operands = self._time_rows_as_operands(idx, f, rows, targs or {}, shards)      # (int field: Row(f == value) per value)
             dev_fields.append(sf.id)
             dev_rows.append(operands)
         counts = self.ctx.groupby(idx.id, dev_fields, [VIEW_STANDARD] * len(fields), dev_rows, shards, filter_ops=filt)
@@ -892,7 +896,7 @@ class Executor:
             ix = np.unravel_index(int(flat), counts.shape)
             group = [(f.name, row_ids[k][int(i)]) for k, (f, i) in enumerate(zip(fields, ix))]
             if isinstance(agg, pql.Call):
-                rows = [pql.Call("Row", {name: rid, **targs}) for (name, rid), targs in zip(group, time_args)]
+                rows = [pql.Call("Row", {name: rid, **(targs or {})}) for (name, rid), targs in zip(group, time_args)]
                 if isinstance(filt_call, pql.Call):
                     rows.append(filt_call)
                 inter = rows[0] if len(rows) == 1 else pql.Call("Intersect", {}, rows)
@@ -908,7 +912,7 @@ class Executor:
             if not (has_sort or has_having):                      # limits first: the aggregate is expensive per group (:3327-3335)
                 out = self._window(c, out)
             for k, (group, n) in enumerate(out):                  # Count(Distinct(Intersect(group rows, filter, Distinct's child), field=..)) :3343-3385
-                rows = [pql.Call("Row", {name: rid, **targs}) for (name, rid), targs in zip(group, time_args)]
+                rows = [pql.Call("Row", {name: rid, **(targs or {})}) for (name, rid), targs in zip(group, time_args)]
                 if isinstance(filt_call, pql.Call):
                     rows.append(filt_call)
                 rows += agg_distinct.children[:1]

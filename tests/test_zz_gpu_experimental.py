@@ -947,6 +947,11 @@ def test_various_queries_goldens():
     assert gb(f"GroupBy(Rows(field=likes), {SUM})") == full
     assert gb(f"GroupBy(Rows(field=likes), {SUM}, limit=3)") == full[:3]
     assert gb(f"GroupBy(Rows(field=likes), {SUM},limit=3,offset=2)") == full[2:5]
+    # groups of an int field are its values (executor_test.go:8980-8990), alone and next to a set field
+    assert gb("GroupBy(Rows(field=affinity), aggregate=Count(Distinct(field=zip_code)))") == [(-10, 1, 1), (-5, 1, 1), (0, 1, 1), (5, 1, 1), (10, 1, 1)]
+    assert gb("GroupBy(Rows(field=affinity))") == [(-10, 1), (-5, 1), (0, 1), (5, 1), (10, 1)]
+    assert gb("GroupBy(Rows(field=zip_code), Rows(field=likes))") == [(19707, 3, 1), (19707, 4, 1), (19707, 7, 2), (78739, 1, 1), (78739, 2, 1), (78739, 7, 2), (86753, 5, 1), (86753, 7, 1)]
+    assert gb("GroupBy(Rows(field=zip_code), aggregate=Sum(field=net_worth))") == [(19707, 2, 1100), (78739, 2, 11), (86753, 1, 10000)]
     # TestExecutor_Execute_Distinct / BareDistinct (executor_test.go:5945-5977, 7175-7207): a foreign-index join through Distinct(index=)
     h = p.holder
     par, ch = h.create_index("parent"), h.create_index("child")
