@@ -3,6 +3,10 @@
 // sm_100a kernels in kernels.cuh or fails with FBGPU_E_CUDA.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
@@ -432,6 +436,33 @@ extern "C" int fbgpu_load_rbf(fbgpu_ctx* c, uint32_t index, uint64_t shard, cons
     }
     if (out_loaded) *out_loaded = (int32_t)found.size();
     return run_copies(c, copies, 1);
+} FBGPU_CATCH
+
+// read-only mapping of one file; empty / missing files map to (nullptr, 0) with ok() still true when `optional`
+struct MappedFile {
+    const uint8_t* p = nullptr; uint64_t n = 0; bool good = false;
+    MappedFile(const std::string& path, bool optional) {
+        int fd = open(path.c_str(), O_RDONLY | O_CLOEXEC);
+        if (fd < 0) { good = optional; return; }
+        struct stat st;
+        if (fstat(fd, &st) == 0 && st.st_size > 0) {
+            void* m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+            if (m != MAP_FAILED) { p = (const uint8_t*)m; n = (uint64_t)st.st_size; good = true; }
+        } else good = optional;
+        close(fd);
+    }
+    ~MappedFile() { if (p) munmap((void*)p, (size_t)n); }
+    MappedFile(const MappedFile&) = delete; MappedFile& operator=(const MappedFile&) = delete;
+};
+
+extern "C" int fbgpu_load_rbf_dir(fbgpu_ctx* c, uint32_t index, uint64_t shard, const char* dir, const char* const* names, const uint32_t* fields,
+                                  const uint32_t* views, int32_t n_names, int32_t* out_loaded) try {
+    if (!c || !dir) return fail(FBGPU_E_INVALID, "null argument");
+    const std::string d(dir);
+    MappedFile data(d + "/data", false), wal(d + "/wal", true);
+    if (!data.good) return fail(FBGPU_E_FORMAT, "rbf: cannot map %s/data", dir);
+    if (!wal.good) return fail(FBGPU_E_FORMAT, "rbf: cannot map %s/wal", dir);
+    return fbgpu_load_rbf(c, index, shard, data.p, data.n, wal.p, wal.n, names, fields, views, n_names, out_loaded);
 } FBGPU_CATCH
 
 extern "C" int fbgpu_drop_fragment(fbgpu_ctx* c, uint32_t index, uint32_t field, uint32_t view, uint64_t shard) try {

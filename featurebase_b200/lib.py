@@ -38,7 +38,7 @@ class Counters(C.Structure):
 EXPORTS = ["fbgpu_init", "fbgpu_shutdown", "fbgpu_last_error", "fbgpu_abi_version", "fbgpu_load_fragment",
            "fbgpu_load_fragments", "fbgpu_drop_fragment", "fbgpu_commit", "fbgpu_get_stats", "fbgpu_count", "fbgpu_row",
            "fbgpu_row_counts", "fbgpu_groupby", "fbgpu_comm_unique_id", "fbgpu_comm_init", "fbgpu_comm_destroy",
-           "fbgpu_get_counters", "fbgpu_stream", "fbgpu_rows_payload_bytes", "fbgpu_count_pairs", "fbgpu_columns", "fbgpu_extract", "fbgpu_comm_p2p_handle", "fbgpu_comm_p2p_open", "fbgpu_comm_p2p_disable"]
+           "fbgpu_get_counters", "fbgpu_stream", "fbgpu_rows_payload_bytes", "fbgpu_count_pairs", "fbgpu_columns", "fbgpu_extract", "fbgpu_load_rbf", "fbgpu_load_rbf_dir", "fbgpu_comm_p2p_handle", "fbgpu_comm_p2p_open", "fbgpu_comm_p2p_disable"]
 
 
 def lib_path():
@@ -62,6 +62,7 @@ def load():
     L.fbgpu_load_fragments.argtypes, L.fbgpu_load_fragments.restype = [vp, u32, u32, u32, vp, i64, vp, vp], C.c_int
     L.fbgpu_drop_fragment.argtypes, L.fbgpu_drop_fragment.restype = [vp, u32, u32, u32, u64], C.c_int
     L.fbgpu_load_rbf.argtypes, L.fbgpu_load_rbf.restype = [vp, u32, u64, vp, u64, vp, u64, vp, vp, vp, i32, C.POINTER(i32)], C.c_int
+    L.fbgpu_load_rbf_dir.argtypes, L.fbgpu_load_rbf_dir.restype = [vp, u32, u64, C.c_char_p, vp, vp, vp, i32, C.POINTER(i32)], C.c_int
     L.fbgpu_commit.argtypes, L.fbgpu_commit.restype = [vp], C.c_int
     L.fbgpu_debug_container.argtypes = [vp, u32, u32, u32, u64, u64, i32, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32), vp, u64, C.POINTER(u64)]
     L.fbgpu_debug_container.restype = C.c_int
@@ -150,6 +151,15 @@ class Context:
         n = C.c_int32(0)
         self._check(self.L.fbgpu_load_rbf(self.h, index, int(shard), C.addressof(dbuf), len(data), C.addressof(wbuf) if wal else None, len(wal),
                                           C.addressof(cn), fl.ctypes.data, vw.ctypes.data, len(names), C.byref(n)))
+        return n.value
+
+    def load_rbf_dir(self, index, shard, path, names, fields, views):
+        """same as load_rbf, the library mapping `<path>/data` (+ `<path>/wal`) itself"""
+        cn = (C.c_char_p * max(len(names), 1))(*[n.encode() if isinstance(n, str) else n for n in names])
+        fl = np.ascontiguousarray(np.asarray(fields, dtype=np.uint32))
+        vw = np.ascontiguousarray(np.asarray(views, dtype=np.uint32))
+        n = C.c_int32(0)
+        self._check(self.L.fbgpu_load_rbf_dir(self.h, index, int(shard), os.fsencode(path), C.addressof(cn), fl.ctypes.data, vw.ctypes.data, len(names), C.byref(n)))
         return n.value
 
     def debug_container(self, index, field, view, shard, row, slot):

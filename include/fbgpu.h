@@ -70,6 +70,11 @@ int fbgpu_drop_fragment(fbgpu_ctx *ctx, uint32_t index, uint32_t field, uint32_t
 int fbgpu_load_rbf(fbgpu_ctx *ctx, uint32_t index, uint64_t shard, const uint8_t *data, uint64_t data_bytes,
                    const uint8_t *wal, uint64_t wal_bytes, const char *const *names, const uint32_t *fields,
                    const uint32_t *views, int32_t n_names, int32_t *out_loaded);
+/* Same, with the library mapping the files itself (read-only mmap of `<dir>/data` and, when present and non-empty,
+ * `<dir>/wal`): the caller hands over the shard's RBF directory instead of reading it into its own memory first.  The
+ * mappings are released before the call returns.  FBGPU_E_FORMAT when `data` cannot be opened or mapped. */
+int fbgpu_load_rbf_dir(fbgpu_ctx *ctx, uint32_t index, uint64_t shard, const char *dir, const char *const *names,
+                       const uint32_t *fields, const uint32_t *views, int32_t n_names, int32_t *out_loaded);
 /* pushes pending host-side staging to HBM now (otherwise done lazily by the next query) */
 int fbgpu_commit(fbgpu_ctx *ctx);
 /* Inspection (FBGPU_DEVICE_NONE contexts only): the container the kernels would find for (index, field, view, shard, row,

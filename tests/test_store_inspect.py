@@ -129,6 +129,24 @@ def test_rbf_loader_end_to_end():
     with pytest.raises(L.FbgpuError):
         ctx.load_rbf(2, 9, TR.fixture("bad-bitmap"), ["x"], [1], [0])
     assert ctx.debug_container(2, 1, 0, 9, 0, 0) is None                 # a rejected file leaves the store unchanged
+    # the same two databases from a shard directory the library maps itself (<dir>/data, <dir>/wal; wal absent or empty is fine)
+    import tempfile
+    with tempfile.TemporaryDirectory() as tmp:
+        for sub, d, w in (("a", data, None), ("b", b"".join(old), W.wal_between(old, new, wb.raw)), ("c", data, b"")):
+            os.makedirs(os.path.join(tmp, sub))
+            open(os.path.join(tmp, sub, "data"), "wb").write(d)
+            if w is not None:
+                open(os.path.join(tmp, sub, "wal"), "wb").write(w)
+        assert ctx.load_rbf_dir(2, 17, os.path.join(tmp, "a"), ["~f;standard<", "~g;standard<"], [5, 6], [0, 0]) == 2
+        assert ctx.load_rbf_dir(2, 18, os.path.join(tmp, "b"), ["~f;standard<"], [5], [0]) == 1
+        assert ctx.load_rbf_dir(2, 19, os.path.join(tmp, "c"), ["~g;standard<"], [6], [0]) == 1
+        with pytest.raises(L.FbgpuError, match="cannot map"):
+            ctx.load_rbf_dir(2, 20, os.path.join(tmp, "nope"), ["~f;standard<"], [5], [0])
+    for shard, fid, want in ((17, 5, frs[5]), (17, 6, frs[6]), (19, 6, frs[6])):
+        got = {r: [ctx.debug_container(2, fid, 0, shard, r, sl) for sl in range(16)] for r in (0, 1, 2, 3)}
+        ref = {r: [ctx.debug_container(2, fid, 0, 7, r, sl) for sl in range(16)] for r in (0, 1, 2, 3)}
+        assert got == ref and any(x is not None for row in got.values() for x in row)      # (the file's keys are fragment-relative: same containers under any shard id)
+    assert [ctx.debug_container(2, 5, 0, 18, r, 3) for r in range(6)] == [ctx.debug_container(2, 5, 0, 8, r, 3) for r in range(6)]
 
 
 def test_striped_layout_in_a_subprocess():
