@@ -36,6 +36,9 @@ FBGPU_LIB=$PU FBGPU_ARRAY_STRIPED=1 python bench_sweep.py --configs 5 --batched 
 FBGPU_GROUPBY_FAST=1 timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_zz_gpu_experimental.py -q -k "groupby or various_queries" > $out/pytest_groupby_fast.log 2>&1; echo "pytest_groupby_fast rc=$?" >> $out/summary.txt
 python bench_sweep.py --configs 4 > $out/sweep4_default.jsonl 2>>$out/bench_err.log
 FBGPU_GROUPBY_FAST=1 python bench_sweep.py --configs 4 > $out/sweep4_groupby_fast.jsonl 2>>$out/bench_err.log
+# (payloads of one slot's rows adjacent: tiny containers of a unit then share cache lines)
+FBGPU_LAYOUT_SLOT_MAJOR=1 python bench_sweep.py --configs 4 > $out/sweep4_slot_major.jsonl 2>>$out/bench_err.log
+FBGPU_LAYOUT_SLOT_MAJOR=1 FBGPU_GROUPBY_FAST=1 python bench_sweep.py --configs 4 > $out/sweep4_groupby_fast_slot_major.jsonl 2>>$out/bench_err.log
 
 # 4. one ncu pass of the headline kernel in both layouts: shared-memory wavefronts / issue utilisation are what changed
 for mode in default striped; do
