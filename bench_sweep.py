@@ -5,6 +5,7 @@
             (fused pair_count_kernel); row pairs are rotated between steps so that the touched data exceeds L2.
   config 3: BSI Count(Row(v > k)) over 10 M records, 32-bit values (eval_kernel plane sweep).
   config 4: GroupBy(Rows(a), Rows(b)) 256 x 256 over this GPU's share (512 shards) of 100 M records / 4096 shards.
+  config X: fbgpu_columns / fbgpu_extract (device-side column-id and int-value expansion), wall clock; R: fbgpu_row.
 Every point is spot-checked against the CPU oracle on a few shards (the checker, not the thing measured)."""
 import argparse
 import json
@@ -137,6 +138,50 @@ def config_row(args, out):
     h.ctx.close()
 
 
+def config_extract(args, out):
+    """Column-id and value expansion on the device: fbgpu_columns over a 1 % row, fbgpu_extract over a 32-bit int field
+    (10 M records), wall clock through the C ABI; every result is checked against the data generator"""
+    from featurebase_b200 import datagen as D, executor as X, pql, roaring_io
+    S = args.shards
+    shards = np.arange(S, dtype=np.uint64)
+    h = X.Holder()
+    idx = h.create_index("i", track_existence=False)
+    f = idx.create_field("f")
+    v = idx.create_field("v", "int", min=0, max=(1 << 32) - 1)
+    ex = X.Executor(h)
+    bulk = D.fragments(11, shards, [0, 1], 0.01)
+    h.ctx.load_fragments(idx.id, f.id, X.VIEW_STANDARD, shards, bulk.buf, bulk.offsets)
+    n_rec = min(10_000_000, S * SW)
+    n_sh = (n_rec + SW - 1) // SW
+    for s in range(n_sh):
+        h.ctx.load_fragment(idx.id, v.id, X.VIEW_BSI, s, D.bsi_fragment(12, s, min(SW, n_rec - s * SW), 32, 0, (1 << 32) - 1))
+    h.ctx.commit()
+    idx.shards.update(range(S))
+
+    def timed(fn, n=5):
+        for _ in range(2):
+            r = fn()
+        t0 = time.perf_counter()
+        for _ in range(n):
+            r = fn()
+        return r, (time.perf_counter() - t0) / n * 1e3
+
+    ops = ex._bitmap_call(idx, pql.parse("Union(Row(f=0), Row(f=1))")[0])
+    (cols, total), wall = timed(lambda: h.ctx.columns(idx.id, ops, shards))
+    want = roaring_io.decode(h.ctx.row(idx.id, ops, shards)[0])
+    assert total == len(want) and np.array_equal(cols, np.asarray(want, dtype=np.uint64))
+    out({"config": "X", "query": "columns of Union(Row(f=0), Row(f=1)) at 1 %", "shards": S, "kernel": "eval_kernel + columns_emit_kernel", "ms": wall, "columns": int(total),
+         "columns_per_sec": float(total) / (wall * 1e-3), "frac": 0.0, "achieved_gbs": 0.0, "note": "wall clock of fbgpu_columns(): evaluate, N per unit D2H, expand ids on the device, ids D2H"})
+    bsh = np.arange(n_sh, dtype=np.uint64)
+    (c2, vals, tot2), wall = timed(lambda: h.ctx.extract(idx.id, v.id, X.VIEW_BSI, 32, bsh), n=3)
+    assert tot2 == n_rec and len(c2) == n_rec
+    for i in (0, 1, n_rec // 2, n_rec - 1):
+        assert int(vals[i]) == D.bsi_value(12, int(c2[i]) // SW, int(c2[i]) % SW, 0, (1 << 32) - 1)
+    out({"config": "X", "query": "values of a 32-bit int field, all records", "records": n_rec, "kernel": "eval_kernel + columns_emit_kernel + extract_values_kernel", "ms": wall,
+         "records_per_sec": n_rec / (wall * 1e-3), "frac": 0.0, "achieved_gbs": 0.0, "note": "wall clock of fbgpu_extract(): 34 planes read once, 16 B per record D2H"})
+    h.ctx.close()
+
+
 def config3(args, out, n_rec=10_000_000, nf=4):
     """nf fields are rotated between steps so that the touched planes exceed L2 (the 10 M-record config is 42.5 MB)"""
     from featurebase_b200 import datagen as D, executor as X, pql
@@ -243,6 +288,8 @@ def main():
         c = c.strip()
         if c == "R":
             config_row(args, out)
+        elif c == "X":
+            config_extract(args, out)
         elif c == "3L":     # the same BSI query at 256 shards (268 M records, 1.1 GB of planes): shows the kernel away from the launch-bound regime
             config3(args, out, n_rec=256 * SW, nf=1)
         else:

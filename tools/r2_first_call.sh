@@ -40,6 +40,9 @@ FBGPU_GROUPBY_FAST=1 python bench_sweep.py --configs 4 > $out/sweep4_groupby_fas
 FBGPU_LAYOUT_SLOT_MAJOR=1 python bench_sweep.py --configs 4 > $out/sweep4_slot_major.jsonl 2>>$out/bench_err.log
 FBGPU_LAYOUT_SLOT_MAJOR=1 FBGPU_GROUPBY_FAST=1 python bench_sweep.py --configs 4 > $out/sweep4_groupby_fast_slot_major.jsonl 2>>$out/bench_err.log
 
+# 3d. the two result-expansion kernels (fbgpu_columns / fbgpu_extract): first timing, checked against the generator inside the script
+python bench_sweep.py --configs X,R > $out/sweep_columns_extract.jsonl 2>>$out/bench_err.log
+
 # 4. one ncu pass of the headline kernel in both layouts: shared-memory wavefronts / issue utilisation are what changed
 for mode in default striped; do
   env $( [ $mode = striped ] && echo FBGPU_ARRAY_STRIPED=1 ) ncu --set full --clock-control none -k regex:eval_kernel -c 1 -f -o $out/eval_$mode \
