@@ -94,6 +94,9 @@ def config5(args, out):
                     res[0] = h.ctx.count_pairs(idx.id, f.id, 0, ra, f.id, 0, rb, shards)
 
                 bms, bmin, bwall = timed(h.ctx, bstep, args.steps)
+                for k in range(n_pairs):                         # (fewer timed steps than row pairs: count the ones the rotation did not reach)
+                    if k not in counts:
+                        counts[k] = h.ctx.count(idx.id, progs[k], shards)
                 assert int(res[0][0]) == counts[0] and int(res[0].sum()) == sum(counts[k % n_pairs] for k in range(nb))
                 bgbs = nb * algo / (bms * 1e-3) / 1e9
                 out({"config": "5b", "generator": mname, "density": p, "shards": S, "pairs_per_launch": nb, "kernel": "pair_count_kernel (multi-pair)", "ms": bms, "ms_min": bmin, "wall_ms": bwall,

@@ -132,6 +132,18 @@ def test_bench_main_runs_against_interpreted_library():
     assert d["check_count"] == exp > 0
 
 
+def test_bench_sweep_runs_against_interpreted_library():
+    """bench_sweep.py (configs 5 / 5b / 4 / X / R at 2 shards, one step) incl. its own checks against the oracle and the data
+    generator — guards the script the round-2 first call runs; timings meaningless"""
+    import json
+    e = dict(os.environ, FBGPU_LIB=emu_lib())
+    r = subprocess.run([sys.executable, "bench_sweep.py", "--configs", "5,4,X,R", "--shards", "2", "--groupby-shards", "2", "--steps", "1", "--densities", "0.01",
+                        "--generators", "uniform,clustered", "--batched"], cwd=ROOT, env=e, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    rows = [json.loads(l) for l in r.stdout.strip().splitlines()]
+    assert [str(d["config"]) for d in rows] == ["5", "5b", "5", "4", "X", "X", "R", "R", "R"]
+
+
 def test_interpreter_reports_divergent_barriers():
     """the interpreter's own checks: a barrier only part of a block reaches is reported (not silently passed), full-mask warp
     primitives see every lane, shared-memory reductions land where the 32-bit shared address says, and a read past the end of
