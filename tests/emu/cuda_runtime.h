@@ -8,8 +8,8 @@
 // (__syncthreads*, or the implicit warp barrier inside a *_sync primitive) and are resumed when every live thread of the
 // block / warp has arrived.  A barrier that can never complete (divergent __syncthreads, a lane missing from a full-mask
 // shuffle) is reported as a deadlock and aborts.  Atomics are plain read-modify-writes (one fibre runs at a time), so data
-// races are NOT detected — compute-sanitizer on the GPU does that (profiles/r01_sanitizer_*.log).  Dynamic shared memory
-// is re-poisoned for every block.
+// races are NOT detected — compute-sanitizer on the GPU does that (profiles/r01_sanitizer_*.log).  Shared memory, static
+// and dynamic, is re-poisoned for every block; device allocations start as garbage and end at a guard page.
 //
 // tests/emu/make_emu_source.py rewrites, in a scratch copy of the sources, the three constructs g++ cannot parse:
 // kernel<<<...>>>(...) launches, `extern __shared__ T name[];`, and inline PTX (each known statement is mapped to the
@@ -48,7 +48,11 @@
 #define __forceinline__ inline __attribute__((always_inline))
 #define __noinline__ __attribute__((noinline))
 #define __launch_bounds__(...)
-#define __shared__ static
+// static shared memory goes into one named section so that launch() can poison all of it before every block: real shared
+// memory is not zero at block start, a kernel that reads a __shared__ variable before writing it must not pass here
+#define __shared__ static __attribute__((section("fbgpu_smem")))
+extern "C" char __start_fbgpu_smem[] __attribute__((weak, visibility("hidden")));
+extern "C" char __stop_fbgpu_smem[] __attribute__((weak, visibility("hidden")));
 #define __constant__ static
 
 struct uint2 { uint32_t x, y; };
@@ -221,6 +225,7 @@ inline void launch(dim3 grid, dim3 block, size_t smem, const std::function<void(
     for (unsigned b = 0; b < grid.x; b++) {
         s.bid = dim3(b); s.alive = T; s.arrived = 0; s.bar_gen = 0; s.red_cnt[0] = s.red_cnt[1] = 0;
         memset(g_dyn, 0xCD, smem ? smem : 16);
+        if (__start_fbgpu_smem && __stop_fbgpu_smem > __start_fbgpu_smem) memset(__start_fbgpu_smem, 0xCD, (size_t)(__stop_fbgpu_smem - __start_fbgpu_smem));
         for (int w = 0; w < W; w++) { s.warps[w] = Warp(); s.warps[w].alive = std::min(32, T - 32 * w); }
         for (int t = 0; t < T; t++) {
             Fiber& f = s.fibers[t];
