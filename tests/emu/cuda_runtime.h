@@ -129,6 +129,8 @@ struct State {
     int red_cnt[2] = { 0, 0 };
     const std::function<void()>* body = nullptr;
     unsigned long long launches = 0, switches = 0;
+    int order = 0; unsigned salt = 12345u;
+    State() { const char* e = getenv("FBGPU_EMU_ORDER"); order = !e ? 0 : !strcmp(e, "reverse") ? 1 : !strcmp(e, "random") ? 2 : 0; }
 };
 inline State g_state;                                  // (one per library image)
 alignas(128) inline uint8_t g_dyn[kDynSmem];           // dynamic shared memory; lives in .bss next to the `__shared__` statics
@@ -235,7 +237,11 @@ inline void launch(dim3 grid, dim3 block, size_t smem, const std::function<void(
         int left = T, idle_scans = 0;
         while (left > 0) {
             bool ran = false;
-            for (int t = 0; t < T; t++) {
+            for (int k = 0; k < T; k++) {
+                // FBGPU_EMU_ORDER=reverse|random: the order in which runnable threads get the CPU between barriers.  Results
+                // must not depend on it; a missing barrier between a producer and a consumer phase usually does.
+                const int t = s.order == 1 ? T - 1 - k : (s.order == 2 && (T & (T - 1)) == 0) ? (int)((k * 2654435761u + s.salt) % (unsigned)T) : k;   // (odd multiplier: a permutation of a power-of-two block)
+                if (s.order == 2 && k == T - 1) s.salt = s.salt * 1664525u + 1013904223u;
                 Fiber& f = s.fibers[t];
                 if (!runnable(s, f)) continue;
                 s.cur = &f; ran = true;

@@ -100,6 +100,20 @@ def test_pair_count_unscatter_variant():
     run_on_emulator(["tests/test_zz_gpu_experimental.py", "-k", "striped_density_sweep"], defines=("FBGPU_PAIR_UNSCATTER",), env={"FBGPU_TEST_EXPERIMENTAL": "1"}, timeout=3000)
 
 
+@pytest.mark.parametrize("order", ["reverse", "random"])
+def test_results_do_not_depend_on_thread_order(order):
+    """the same parity tests with the interpreter handing the CPU to runnable threads in reverse / pseudo-random order
+    between barriers (FBGPU_EMU_ORDER): a missing barrier between a producer and a consumer phase shows up as a
+    different result under one of the orders"""
+    if order == "reverse" and not FULL:
+        pytest.skip("reverse order: FBGPU_EMU_FULL=1 (the default suite runs the pseudo-random order)")
+    sel = NOT_HUGE + SLOW + " and not thread_safety and not bsi_diagonal"
+    run_on_emulator(["tests/test_gpu_parity.py", "tests/test_zz_gpu_experimental.py", "-k", sel + " and not striped"], env={"FBGPU_EMU_ORDER": order, "FBGPU_GROUPBY_FAST": "1"}, timeout=3000)
+    if FULL:
+        run_on_emulator(["tests/test_gpu_parity.py", "-k", "groupby or density_sweep or mixed_encoding"], env={"FBGPU_EMU_ORDER": order}, timeout=3000)
+        run_on_emulator(["tests/test_zz_gpu_experimental.py", "-k", "striped_density_sweep or striped_bsi"], env={"FBGPU_EMU_ORDER": order, "FBGPU_TEST_EXPERIMENTAL": "1"}, timeout=3000)
+
+
 def test_bench_main_runs_against_interpreted_library():
     """bench.py's own main() (GPU arm) on 8 shards with torch.cuda's device calls stubbed (tests/emu/bench_shim.py): the JSON
     line carries every key of the contract and the count agrees with the oracle-checked value for this data; the timings are
