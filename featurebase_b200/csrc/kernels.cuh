@@ -1332,6 +1332,92 @@ extract_values_kernel(StoreRef st, uint32_t fv, int depth, const uint4* __restri
     }
 }
 
+// Min / Max of an int field over a row (fragment.min / max fragment.go:752-838 with minUnsigned :788 / maxUnsigned :841),
+// one CTA per (shard, slot) unit, every plane container read once.  The unit's `consider` bitmap (filter ∩ exists, produced
+// by eval_kernel) is split by the sign row; the side that decides the answer is narrowed plane by plane from the top bit:
+// largest magnitude keeps R ∩ plane when that is non-empty (bit = 1), smallest magnitude keeps R \ plane when that is
+// non-empty (bit = 0).  What is left are the columns holding the extreme value: out = {has, signed value, count} per unit.
+// Narrowing a unit on its own is sound because the reduce over units is the executor's ValCount reduce (Smaller / Larger
+// executor.go:8446-8560: keep the extreme value, add the counts of equal values), done by the host over the unit results.
+struct MinMaxUnit { long long val; unsigned long long cnt; };       // cnt == 0: the unit holds no column of the row
+
+__global__ void __launch_bounds__(kEvalThreads)
+bsi_minmax_kernel(StoreRef st, uint32_t fv, int depth, const uint4* __restrict__ consider, const uint64_t* __restrict__ shards, long long n_units, int want_max,
+                  MinMaxUnit* __restrict__ out) {
+    __shared__ __align__(16) uint4 X[512];
+    __shared__ Resolved s_res;
+    __shared__ uint32_t warp_tmp[kEvalThreads / 32];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    // plane `row` of the unit as a bitmap: this thread's two uint4 (bitmap containers are read straight from global memory,
+    // arrays / runs are expanded into X first; an absent container is empty)
+    auto load_plane = [&](uint64_t shard, int slot, uint64_t row, uint4 x[kEvalU4PerThread]) {
+        __syncthreads();                                   // X and s_res of the previous plane are no longer read
+        if (tid == 0) s_res = resolve(st, fv, shard, row, slot);
+        __syncthreads();
+        const Resolved r = s_res;
+        if (r.ptr == nullptr) {
+#pragma unroll
+            for (int h = 0; h < kEvalU4PerThread; h++) x[h] = make_uint4(0, 0, 0, 0);
+        } else if (r.typ == kBitmap) {
+#pragma unroll
+            for (int h = 0; h < kEvalU4PerThread; h++) x[h] = ldg_nc(reinterpret_cast<const uint4*>(r.ptr) + tid + h * kEvalThreads);
+        } else {
+            if (r.typ == kArray) { bm_zero(X); __syncthreads(); bm_scatter<0>(reinterpret_cast<uint32_t*>(X), reinterpret_cast<const uint16_t*>(r.ptr), r.card); __syncthreads(); }
+            else bm_expand_runs(X, reinterpret_cast<const uint16_t*>(r.ptr), r.cnt, warp_tmp);
+#pragma unroll
+            for (int h = 0; h < kEvalU4PerThread; h++) x[h] = X[tid + h * kEvalThreads];
+        }
+    };
+    auto any4 = [](const uint4 v[kEvalU4PerThread]) { uint32_t o = 0;
+#pragma unroll
+        for (int h = 0; h < kEvalU4PerThread; h++) o |= v[h].x | v[h].y | v[h].z | v[h].w;
+        return o != 0; };
+    for (long long unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+        const uint64_t shard = shards[unit >> 4];
+        const int slot = (int)(unit & 15);
+        uint4 a[kEvalU4PerThread], x[kEvalU4PerThread], pos[kEvalU4PerThread], neg[kEvalU4PerThread];
+#pragma unroll
+        for (int h = 0; h < kEvalU4PerThread; h++) a[h] = consider[(size_t)unit * 512 + tid + h * kEvalThreads];
+        if (!__syncthreads_or(any4(a))) { if (tid == 0) { out[unit].val = 0; out[unit].cnt = 0; } continue; }
+        load_plane(shard, slot, 1, x);                      // bsiSignBit
+#pragma unroll
+        for (int h = 0; h < kEvalU4PerThread; h++) { pos[h] = andn4(a[h], x[h]); neg[h] = and4(a[h], x[h]); }
+        const int has_pos = __syncthreads_or(any4(pos)), has_neg = __syncthreads_or(any4(neg));
+        // which side decides, and in which direction its magnitude is narrowed (fragment.go:760-784, 819-837)
+        const bool use_neg = want_max ? !has_pos : has_neg != 0;
+        const bool largest = want_max ? !use_neg : use_neg;  // max: largest positive, else smallest |negative|; min: largest |negative|, else smallest positive
+        uint4 r[kEvalU4PerThread];
+#pragma unroll
+        for (int h = 0; h < kEvalU4PerThread; h++) r[h] = use_neg ? neg[h] : pos[h];
+        unsigned long long mag = 0;
+        for (int i = depth - 1; i >= 0; i--) {
+            load_plane(shard, slot, (uint64_t)(2 + i), x);
+            uint4 t[kEvalU4PerThread];
+#pragma unroll
+            for (int h = 0; h < kEvalU4PerThread; h++) t[h] = largest ? and4(r[h], x[h]) : andn4(r[h], x[h]);
+            const int some = __syncthreads_or(any4(t));
+            if (some) {
+#pragma unroll
+                for (int h = 0; h < kEvalU4PerThread; h++) r[h] = t[h];
+            }
+            if ((some != 0) == largest) mag |= 1ull << i;   // largest: bit set when kept; smallest: bit set when no column lacks it
+        }
+        uint32_t c = 0;
+#pragma unroll
+        for (int h = 0; h < kEvalU4PerThread; h++) c += popc4(r[h]);
+        c = __reduce_add_sync(0xffffffffu, c);
+        __syncthreads();
+        if (lane == 0) warp_tmp[wid] = c;
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t n = 0;
+            for (int k = 0; k < kEvalThreads / 32; k++) n += warp_tmp[k];
+            out[unit].val = use_neg ? -(long long)mag : (long long)mag;
+            out[unit].cnt = n;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // GroupBy(Rows(a), Rows(b)) [+ filter]: one CTA per (shard, slot).  Column-keyed hash join instead of the
 // reference's |A|x|B| nested intersectionCount loop (executor.go:8880-8934): the elements of field-a rows are inserted

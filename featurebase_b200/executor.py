@@ -623,49 +623,23 @@ class Executor:
                 nsum += int(neg[i]) << i
         return ValCount(_i64(_i64(psum) - _i64(nsum) + count * f.base), count)
 
-    def _sweep_unsigned(self, idx, f, start, n_start, shards, want_max):
-        """fragment.maxUnsigned :841 / minUnsigned :788, run over the whole shard batch at once.  Per shard the reference
-        narrows `filter` bit by bit and the executor keeps the extreme ValCount over shards, adding the counts of
-        equal values (Smaller/Larger :8446,8526); narrowing the union of all shards' columns gives the same extreme
-        value and the same number of columns holding it."""
-        kept, val, cnt = [], 0, n_start
-        for i in range(f.bit_depth - 1, -1, -1):
-            plane = L.Op(L.OP_ROW, f.id, VIEW_BSI, 0, 2 + i, 0, 0, 0)
-            fold = L.Op(L.OP_INTERSECT if want_max else L.OP_DIFFERENCE, 0, 0, len(kept) + 2, 0, 0, 0, 0)
-            n = self.ctx.count(idx.id, start + kept + [plane, fold], shards)
-            if n > 0:                                                   # max: some column has bit i; min: some column lacks it
-                kept.append(plane)
-                cnt = n
-                if want_max:
-                    val += 1 << i
-            elif not want_max:
-                val += 1 << i
-        return val, cnt
-
     def _minmax(self, idx, c, shards, what):
-        f, consider, sign = self._agg_setup(idx, c, what)
+        """executeMin :1225 / executeMax :1261 over fragment.min / max (fragment.go:752-838): one library call — the row
+        (filter ∩ not-null) is evaluated once and the bit planes are walked once per (shard, slot) unit on the device, the
+        per-unit extremes are merged as ValCount.Smaller / Larger do (:8446-8560)."""
+        name = c.args.get("field", c.args.get("_field"))
+        if name is None:
+            raise QueryError(f"{what}(): field required")
+        if len(c.children) > 1:
+            raise QueryError(f"{what}() only accepts a single bitmap input")
+        f = self._field(idx, name)
         if f.type != "int":
             raise QueryError("bsigroup not found")                      # ErrBSIGroupNotFound field.go:1571
-        n = self.ctx.count(idx.id, consider, shards)
+        filt = self._bitmap_call(idx, c.children[0]) if c.children else None
+        v, n = self.ctx.bsi_minmax(idx.id, f.id, VIEW_BSI, min(f.bit_depth, 63), shards, what == "Max", filter_ops=filt)
         if n == 0:
             return ValCount()                                           # :1252-1254
-        if what == "Min":                                               # fragment.min :752-785
-            neg = consider + [sign, L.Op(L.OP_INTERSECT, 0, 0, 2, 0, 0, 0, 0)]
-            n_neg = self.ctx.count(idx.id, neg, shards)
-            if n_neg > 0:
-                v, cnt = self._sweep_unsigned(idx, f, neg, n_neg, shards, True)
-                v = -v
-            else:
-                v, cnt = self._sweep_unsigned(idx, f, consider, n, shards, False)
-        else:                                                           # fragment.max :811-838
-            pos = consider + [sign, L.Op(L.OP_DIFFERENCE, 0, 0, 2, 0, 0, 0, 0)]
-            n_pos = self.ctx.count(idx.id, pos, shards)
-            if n_pos == 0:
-                v, cnt = self._sweep_unsigned(idx, f, consider, n, shards, False)
-                v = -v
-            else:
-                v, cnt = self._sweep_unsigned(idx, f, pos, n_pos, shards, True)
-        return ValCount(v + f.base, cnt)                                # valCountize field.go:1640
+        return ValCount(v + f.base, n)                                  # valCountize field.go:1640
 
     def _minmax_row(self, idx, c, shards, want_max):
         """executeMinRow / executeMaxRow :1604-1672 with fragment.minRow / maxRow fragment.go:862-922: the smallest / largest

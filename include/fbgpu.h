@@ -150,6 +150,15 @@ int fbgpu_extract(fbgpu_ctx *ctx, uint32_t index, const fbgpu_op *ops, int32_t n
                   const uint64_t *shards, int64_t n_shards, uint64_t offset, int64_t limit,
                   uint64_t *out_cols, int64_t *out_vals, uint64_t cap, uint64_t *out_n, uint64_t *out_total);
 
+/* Min / Max of an int field over a row (executeMin :1225 / executeMax :1261, fragment.min / max fragment.go:752-838): the row
+ * is <filter program> ∩ not-null(field) (n_ops == 0: every column with a value).  *out_val receives the extreme stored
+ * value, i.e. value - bsiGroup.Base (the caller adds Base), *out_count how many columns hold it — the reference's ValCount;
+ * *out_count == 0 when the row is empty.  One evaluation of the row plus one pass over the bit planes, every plane container
+ * read once (the composition from fbgpu_count calls re-reads the planes it has kept).  Not reduced over the communicator:
+ * the caller merges per-node ValCounts as it does today (ValCount.Smaller / Larger executor.go:8446-8560). */
+int fbgpu_bsi_minmax(fbgpu_ctx *ctx, uint32_t index, const fbgpu_op *ops, int32_t n_ops, uint32_t field, uint32_t view, int32_t bit_depth,
+                     const uint64_t *shards, int64_t n_shards, int32_t want_max, int64_t *out_val, uint64_t *out_count);
+
 /* Per-row counts of one field, optionally intersected with a filter program: the exact part of TopN
  * (fragment.top with explicit ids, fragment.go:1317-1437) and TopK (doTopK executor.go:2705-2746).
  * row_ids != NULL: counts for exactly those rows (out_counts[i] for row_ids[i]).

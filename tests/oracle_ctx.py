@@ -132,6 +132,13 @@ class OracleCtx:
         end = None if limit is None else offset + limit
         return cols[offset:end], vals[offset:end], len(cols)
 
+    def bsi_minmax(self, index, field, view, bit_depth, shards, want_max, filter_ops=None):
+        _, vals, _ = self.extract(index, field, view, bit_depth, shards, filter_ops=filter_ops)
+        if len(vals) == 0:
+            return 0, 0
+        v = int(vals.max() if want_max else vals.min())
+        return v, int((vals == v).sum())
+
     def row_counts(self, index, field, view, shards, row_ids=None, filter_ops=None, cap=1 << 20):
         tot = {}
         for s in shards:
