@@ -978,6 +978,52 @@ extern "C" int fbgpu_bsi_minmax(fbgpu_ctx* c, uint32_t index, const fbgpu_op* op
     return FBGPU_OK;
 } FBGPU_CATCH
 
+extern "C" int fbgpu_bsi_sum(fbgpu_ctx* c, uint32_t index, const fbgpu_op* ops, int32_t n_ops, uint32_t field, uint32_t view, int32_t bit_depth,
+                             const uint64_t* shards, int64_t n_shards, int64_t* out_sum, uint64_t* out_count) try {
+    if (!c || !out_sum || !out_count || n_shards < 0 || (n_shards && !shards) || n_ops < 0 || (n_ops && !ops)) return fail(FBGPU_E_INVALID, "null argument");
+    if (bit_depth < 0 || bit_depth > 63) return fail(FBGPU_E_INVALID, "bit depth %d outside 0..63", bit_depth);
+    USE_DEVICE(c);
+    std::shared_lock<std::shared_mutex> lk;
+    int rc = lock_committed(c, lk); if (rc) return rc;
+    *out_sum = 0; *out_count = 0;
+    std::vector<fbgpu_op> full(ops, ops + n_ops);
+    fbgpu_op ex{}; ex.opcode = FBGPU_OP_ROW; ex.field = field; ex.view = view; ex.a = 0;
+    full.push_back(ex);
+    if (n_ops) { fbgpu_op in{}; in.opcode = FBGPU_OP_INTERSECT; in.argc = 2; full.push_back(in); }
+    std::vector<DevOp> prog; int depth = 1;
+    rc = compile_program(c, index, full.data(), (int32_t)full.size(), prog, depth); if (rc) return rc;
+    const uint32_t fv = view_id_locked(c, ViewKey{ index, field, view }, false);
+    WsLease lease(c); Workspace* w = lease.w;
+    const DevOp* d_prog; const uint64_t* d_shards;
+    rc = upload_inputs(w, prog, shards, n_shards, &d_prog, &d_shards); if (rc) return rc;
+    const long long n_units = (long long)n_shards * kSlotsPerRow;
+    const size_t n_acc = 1 + 2 * (size_t)bit_depth;
+    if (w->d_counts.ensure(n_acc * 8) || w->h_out.ensure(n_acc * 8)) return FBGPU_E_NOMEM;
+    CUDA_TRY(cudaMemsetAsync(w->d_counts.p, 0, n_acc * 8, w->stream));
+    uint64_t launches = 0;
+    CUDA_TRY(cudaEventRecord(w->ev0, w->stream));
+    for (long long u0 = 0; u0 < n_units; u0 += kUnitBatch) {
+        const long long nu = std::min(kUnitBatch, n_units - u0);
+        if (w->d_bitmaps.ensure((size_t)nu * 8192)) return FBGPU_E_NOMEM;
+        EvalOut eo{ nullptr, nullptr, (uint4*)w->d_bitmaps.p, nullptr, FuseReduce{} };
+        rc = launch_eval(c, w, prog, d_prog, depth, d_shards + u0 / kSlotsPerRow, nu, eo); if (rc) return rc;
+        const long long grid = std::min<long long>(nu, (long long)c->sm_count * 8);
+        bsi_sum_kernel<<<(unsigned)grid, kEvalThreads, 0, w->stream>>>(store_ref(c), fv, bit_depth, (const uint4*)w->d_bitmaps.p, d_shards + u0 / kSlotsPerRow, nu, (unsigned long long*)w->d_counts.p);
+        CUDA_TRY(cudaGetLastError()); launches += 2;
+    }
+    CUDA_TRY(cudaEventRecord(w->ev1, w->stream));
+    CUDA_TRY(cudaMemcpyAsync(w->h_out.p, w->d_counts.p, n_acc * 8, cudaMemcpyDeviceToHost, w->stream));
+    CUDA_TRY(cudaStreamSynchronize(w->stream));
+    const uint64_t* acc = (const uint64_t*)w->h_out.p;
+    uint64_t sum = 0;                                       // wrapping, like the reference's int64 arithmetic
+    for (int i = 0; i < bit_depth; i++) sum += (acc[1 + 2 * i] - acc[2 + 2 * i]) << i;
+    *out_sum = (int64_t)sum; *out_count = acc[0];
+    float ms = 0; cudaEventElapsedTime(&ms, w->ev0, w->ev1);
+    bump(c, launches, ms);
+    lease.ok = true;
+    return FBGPU_OK;
+} FBGPU_CATCH
+
 // ------------------------------------------------------------------ per-row counts (TopK / TopN ids)
 // evaluates `filter` for shards [s0, s0+ns) into w->d_bitmaps (16 bitmaps per shard)
 static int eval_filter_batch(fbgpu_ctx* c, Workspace* w, const std::vector<DevOp>& prog, int depth, const DevOp* d_prog, const uint64_t* d_shards, int64_t ns) {

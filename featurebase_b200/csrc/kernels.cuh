@@ -1339,6 +1339,36 @@ extract_values_kernel(StoreRef st, uint32_t fv, int depth, const uint4* __restri
 // non-empty (bit = 0).  What is left are the columns holding the extreme value: out = {has, signed value, count} per unit.
 // Narrowing a unit on its own is sound because the reduce over units is the executor's ValCount reduce (Smaller / Larger
 // executor.go:8446-8560: keep the extreme value, add the counts of equal values), done by the host over the unit results.
+// plane `row` of the BSI view `fv` for one (shard, slot) unit as a bitmap, returned as this thread's kEvalU4PerThread uint4
+// (CTA-wide call, kEvalThreads threads): bitmap containers are read straight from global memory, arrays / runs are expanded
+// into the shared buffer X first, an absent container is empty.  s_res / warp_tmp are CTA-shared scratch.
+__device__ __forceinline__ void unit_load_plane(const StoreRef& st, uint32_t fv, uint64_t shard, int slot, uint64_t row,
+                                                uint4* X, Resolved* s_res, uint32_t* warp_tmp, uint4 x[kEvalU4PerThread]) {
+    const int tid = threadIdx.x;
+    __syncthreads();                                       // X and s_res of the previous plane are no longer read
+    if (tid == 0) *s_res = resolve(st, fv, shard, row, slot);
+    __syncthreads();
+    const Resolved r = *s_res;
+    if (r.ptr == nullptr) {
+#pragma unroll
+        for (int h = 0; h < kEvalU4PerThread; h++) x[h] = make_uint4(0, 0, 0, 0);
+    } else if (r.typ == kBitmap) {
+#pragma unroll
+        for (int h = 0; h < kEvalU4PerThread; h++) x[h] = ldg_nc(reinterpret_cast<const uint4*>(r.ptr) + tid + h * kEvalThreads);
+    } else {
+        if (r.typ == kArray) { bm_zero(X); __syncthreads(); bm_scatter<0>(reinterpret_cast<uint32_t*>(X), reinterpret_cast<const uint16_t*>(r.ptr), r.card); __syncthreads(); }
+        else bm_expand_runs(X, reinterpret_cast<const uint16_t*>(r.ptr), r.cnt, warp_tmp);
+#pragma unroll
+        for (int h = 0; h < kEvalU4PerThread; h++) x[h] = X[tid + h * kEvalThreads];
+    }
+}
+__device__ __forceinline__ bool any_u4(const uint4 v[kEvalU4PerThread]) {
+    uint32_t o = 0;
+#pragma unroll
+    for (int h = 0; h < kEvalU4PerThread; h++) o |= v[h].x | v[h].y | v[h].z | v[h].w;
+    return o != 0;
+}
+
 struct MinMaxUnit { long long val; unsigned long long cnt; };       // cnt == 0: the unit holds no column of the row
 
 __global__ void __launch_bounds__(kEvalThreads)
@@ -1348,41 +1378,17 @@ bsi_minmax_kernel(StoreRef st, uint32_t fv, int depth, const uint4* __restrict__
     __shared__ Resolved s_res;
     __shared__ uint32_t warp_tmp[kEvalThreads / 32];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    // plane `row` of the unit as a bitmap: this thread's two uint4 (bitmap containers are read straight from global memory,
-    // arrays / runs are expanded into X first; an absent container is empty)
-    auto load_plane = [&](uint64_t shard, int slot, uint64_t row, uint4 x[kEvalU4PerThread]) {
-        __syncthreads();                                   // X and s_res of the previous plane are no longer read
-        if (tid == 0) s_res = resolve(st, fv, shard, row, slot);
-        __syncthreads();
-        const Resolved r = s_res;
-        if (r.ptr == nullptr) {
-#pragma unroll
-            for (int h = 0; h < kEvalU4PerThread; h++) x[h] = make_uint4(0, 0, 0, 0);
-        } else if (r.typ == kBitmap) {
-#pragma unroll
-            for (int h = 0; h < kEvalU4PerThread; h++) x[h] = ldg_nc(reinterpret_cast<const uint4*>(r.ptr) + tid + h * kEvalThreads);
-        } else {
-            if (r.typ == kArray) { bm_zero(X); __syncthreads(); bm_scatter<0>(reinterpret_cast<uint32_t*>(X), reinterpret_cast<const uint16_t*>(r.ptr), r.card); __syncthreads(); }
-            else bm_expand_runs(X, reinterpret_cast<const uint16_t*>(r.ptr), r.cnt, warp_tmp);
-#pragma unroll
-            for (int h = 0; h < kEvalU4PerThread; h++) x[h] = X[tid + h * kEvalThreads];
-        }
-    };
-    auto any4 = [](const uint4 v[kEvalU4PerThread]) { uint32_t o = 0;
-#pragma unroll
-        for (int h = 0; h < kEvalU4PerThread; h++) o |= v[h].x | v[h].y | v[h].z | v[h].w;
-        return o != 0; };
     for (long long unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
         const uint64_t shard = shards[unit >> 4];
         const int slot = (int)(unit & 15);
         uint4 a[kEvalU4PerThread], x[kEvalU4PerThread], pos[kEvalU4PerThread], neg[kEvalU4PerThread];
 #pragma unroll
         for (int h = 0; h < kEvalU4PerThread; h++) a[h] = consider[(size_t)unit * 512 + tid + h * kEvalThreads];
-        if (!__syncthreads_or(any4(a))) { if (tid == 0) { out[unit].val = 0; out[unit].cnt = 0; } continue; }
-        load_plane(shard, slot, 1, x);                      // bsiSignBit
+        if (!__syncthreads_or(any_u4(a))) { if (tid == 0) { out[unit].val = 0; out[unit].cnt = 0; } continue; }
+        unit_load_plane(st, fv, shard, slot, 1, X, &s_res, warp_tmp, x);                      // bsiSignBit
 #pragma unroll
         for (int h = 0; h < kEvalU4PerThread; h++) { pos[h] = andn4(a[h], x[h]); neg[h] = and4(a[h], x[h]); }
-        const int has_pos = __syncthreads_or(any4(pos)), has_neg = __syncthreads_or(any4(neg));
+        const int has_pos = __syncthreads_or(any_u4(pos)), has_neg = __syncthreads_or(any_u4(neg));
         // which side decides, and in which direction its magnitude is narrowed (fragment.go:760-784, 819-837)
         const bool use_neg = want_max ? !has_pos : has_neg != 0;
         const bool largest = want_max ? !use_neg : use_neg;  // max: largest positive, else smallest |negative|; min: largest |negative|, else smallest positive
@@ -1391,11 +1397,11 @@ bsi_minmax_kernel(StoreRef st, uint32_t fv, int depth, const uint4* __restrict__
         for (int h = 0; h < kEvalU4PerThread; h++) r[h] = use_neg ? neg[h] : pos[h];
         unsigned long long mag = 0;
         for (int i = depth - 1; i >= 0; i--) {
-            load_plane(shard, slot, (uint64_t)(2 + i), x);
+            unit_load_plane(st, fv, shard, slot, (uint64_t)(2 + i), X, &s_res, warp_tmp, x);
             uint4 t[kEvalU4PerThread];
 #pragma unroll
             for (int h = 0; h < kEvalU4PerThread; h++) t[h] = largest ? and4(r[h], x[h]) : andn4(r[h], x[h]);
-            const int some = __syncthreads_or(any4(t));
+            const int some = __syncthreads_or(any_u4(t));
             if (some) {
 #pragma unroll
                 for (int h = 0; h < kEvalU4PerThread; h++) r[h] = t[h];
@@ -1414,6 +1420,52 @@ bsi_minmax_kernel(StoreRef st, uint32_t fv, int depth, const uint4* __restrict__
             for (int k = 0; k < kEvalThreads / 32; k++) n += warp_tmp[k];
             out[unit].val = use_neg ? -(long long)mag : (long long)mag;
             out[unit].cnt = n;
+        }
+    }
+}
+
+// Sum of an int field over a row (fragment.sum fragment.go:722-750 / BitmapBSICountFilter roaring/filter.go:1106-1165), same
+// walk: acc[0] += |consider|, acc[1 + 2 i] += |positives ∩ plane i|, acc[2 + 2 i] += |negatives ∩ plane i| — the host forms
+// Σ (pos_i - neg_i) << i.  One CTA per (shard, slot) unit, every plane container read once.
+__global__ void __launch_bounds__(kEvalThreads)
+bsi_sum_kernel(StoreRef st, uint32_t fv, int depth, const uint4* __restrict__ consider, const uint64_t* __restrict__ shards, long long n_units,
+               unsigned long long* __restrict__ acc /* [1 + 2 * depth], zeroed by the host */) {
+    __shared__ __align__(16) uint4 X[512];
+    __shared__ Resolved s_res;
+    __shared__ uint32_t warp_tmp[kEvalThreads / 32];
+    __shared__ uint32_t wp[kEvalThreads / 32], wn[kEvalThreads / 32];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    // CTA-wide sums of two per-thread counts; thread 0 adds them to acc[k], acc[k + 1] (k + 1 skipped when negative)
+    auto add2 = [&](uint32_t p, uint32_t n, int kp, int kn) {
+        p = __reduce_add_sync(0xffffffffu, p); n = __reduce_add_sync(0xffffffffu, n);
+        __syncthreads();
+        if (lane == 0) { wp[wid] = p; wn[wid] = n; }
+        __syncthreads();
+        if (tid == 0) {
+            unsigned long long sp = 0, sn = 0;
+            for (int k = 0; k < kEvalThreads / 32; k++) { sp += wp[k]; sn += wn[k]; }
+            if (sp) atomicAdd(&acc[kp], sp);
+            if (sn && kn >= 0) atomicAdd(&acc[kn], sn);
+        }
+    };
+    for (long long unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+        const uint64_t shard = shards[unit >> 4];
+        const int slot = (int)(unit & 15);
+        uint4 a[kEvalU4PerThread], x[kEvalU4PerThread], pos[kEvalU4PerThread], neg[kEvalU4PerThread];
+#pragma unroll
+        for (int h = 0; h < kEvalU4PerThread; h++) a[h] = consider[(size_t)unit * 512 + tid + h * kEvalThreads];
+        if (!__syncthreads_or(any_u4(a))) continue;
+        unit_load_plane(st, fv, shard, slot, 1, X, &s_res, warp_tmp, x);       // bsiSignBit
+        uint32_t ca = 0;
+#pragma unroll
+        for (int h = 0; h < kEvalU4PerThread; h++) { pos[h] = andn4(a[h], x[h]); neg[h] = and4(a[h], x[h]); ca += (uint32_t)popc4(a[h]); }
+        add2(ca, 0u, 0, -1);
+        for (int i = 0; i < depth; i++) {
+            unit_load_plane(st, fv, shard, slot, (uint64_t)(2 + i), X, &s_res, warp_tmp, x);
+            uint32_t cp = 0, cn = 0;
+#pragma unroll
+            for (int h = 0; h < kEvalU4PerThread; h++) { cp += (uint32_t)popc4(and4(pos[h], x[h])); cn += (uint32_t)popc4(and4(neg[h], x[h])); }
+            add2(cp, cn, 1 + 2 * i, 2 + 2 * i);
         }
     }
 }

@@ -589,39 +589,23 @@ class Executor:
     # ------------------------------------------------------------------ BSI aggregates (executeSum :1119, executeMin :1225, executeMax :1261)
     # Composed from the library's counting entry points, the way the Go shim would inside executeSumCountShard /
     # Field.MinForShard: every step is one launch over the whole shard batch.
-    def _agg_setup(self, idx, c, what):
+    def _sum(self, idx, c, shards):
+        """executeSum :1119 over fragment.sum (fragment.go:722) / BitmapBSICountFilter (filter.go:1106-1165), reduced by
+        ValCount.Add (:8438): one library call — the row (filter ∩ not-null) is evaluated once, the planes are walked once,
+        Val = Σ (pos_i - neg_i) << i  +  count * Base (executeSumCountShard :2203-2206), all in wrapping int64."""
         name = c.args.get("field", c.args.get("_field"))
         if name is None:
-            raise QueryError(f"{what}(): field required")
+            raise QueryError("Sum(): field required")
         if len(c.children) > 1:
-            raise QueryError(f"{what}() only accepts a single bitmap input")
+            raise QueryError("Sum() only accepts a single bitmap input")
         f = self._field(idx, name)
-        exists = L.Op(L.OP_ROW, f.id, VIEW_BSI, 0, 0, 0, 0, 0)         # bsiExistsBit fragment.go:44
-        sign = L.Op(L.OP_ROW, f.id, VIEW_BSI, 0, 1, 0, 0, 0)           # bsiSignBit
-        consider = [exists]
-        if c.children:                                                  # filter ∩ exists (filter.go:1133, fragment.go:753-757)
-            consider = self._bitmap_call(idx, c.children[0]) + [exists, L.Op(L.OP_INTERSECT, 0, 0, 2, 0, 0, 0, 0)]
-        return f, consider, sign
-
-    def _sum(self, idx, c, shards):
-        """fragment.sum fragment.go:722 / BitmapBSICountFilter filter.go:1106-1165, reduced by ValCount.Add (:8438):
-        count = |filter ∩ exists|; per value row i the counts under the positive and the negative part of that set;
-        Val = Σ (pos_i - neg_i) << i  +  count * Base (executeSumCountShard :2203-2206), all in wrapping int64."""
-        f, consider, sign = self._agg_setup(idx, c, "Sum")
         if f.type != "int":
             return ValCount()                                           # bsig == nil (:2187-2190)
-        count = self.ctx.count(idx.id, consider, shards)
+        filt = self._bitmap_call(idx, c.children[0]) if c.children else None
+        total, count = self.ctx.bsi_sum(idx.id, f.id, VIEW_BSI, min(f.bit_depth, 63), shards, filter_ops=filt)
         if count == 0:
             return ValCount()                                           # executeSum :1147-1149
-        rows = list(range(2, 2 + f.bit_depth))                          # bsiOffsetBit + i
-        psum = nsum = 0
-        if rows:
-            pos = self.ctx.row_counts(idx.id, f.id, VIEW_BSI, shards, row_ids=rows, filter_ops=consider + [sign, L.Op(L.OP_DIFFERENCE, 0, 0, 2, 0, 0, 0, 0)])
-            neg = self.ctx.row_counts(idx.id, f.id, VIEW_BSI, shards, row_ids=rows, filter_ops=consider + [sign, L.Op(L.OP_INTERSECT, 0, 0, 2, 0, 0, 0, 0)])
-            for i in range(f.bit_depth):
-                psum += int(pos[i]) << i
-                nsum += int(neg[i]) << i
-        return ValCount(_i64(_i64(psum) - _i64(nsum) + count * f.base), count)
+        return ValCount(_i64(total + count * f.base), count)
 
     def _minmax(self, idx, c, shards, what):
         """executeMin :1225 / executeMax :1261 over fragment.min / max (fragment.go:752-838): one library call — the row

@@ -38,7 +38,7 @@ class Counters(C.Structure):
 EXPORTS = ["fbgpu_init", "fbgpu_shutdown", "fbgpu_last_error", "fbgpu_abi_version", "fbgpu_load_fragment",
            "fbgpu_load_fragments", "fbgpu_drop_fragment", "fbgpu_commit", "fbgpu_get_stats", "fbgpu_count", "fbgpu_row",
            "fbgpu_row_counts", "fbgpu_groupby", "fbgpu_comm_unique_id", "fbgpu_comm_init", "fbgpu_comm_destroy",
-           "fbgpu_get_counters", "fbgpu_stream", "fbgpu_rows_payload_bytes", "fbgpu_count_pairs", "fbgpu_columns", "fbgpu_extract", "fbgpu_load_rbf", "fbgpu_load_rbf_dir", "fbgpu_bsi_minmax", "fbgpu_comm_p2p_handle", "fbgpu_comm_p2p_open", "fbgpu_comm_p2p_disable"]
+           "fbgpu_get_counters", "fbgpu_stream", "fbgpu_rows_payload_bytes", "fbgpu_count_pairs", "fbgpu_columns", "fbgpu_extract", "fbgpu_load_rbf", "fbgpu_load_rbf_dir", "fbgpu_bsi_minmax", "fbgpu_bsi_sum", "fbgpu_comm_p2p_handle", "fbgpu_comm_p2p_open", "fbgpu_comm_p2p_disable"]
 
 
 def lib_path():
@@ -75,6 +75,7 @@ def load():
     L.fbgpu_extract.restype = C.c_int
     L.fbgpu_bsi_minmax.argtypes = [vp, u32, vp, i32, u32, u32, i32, vp, i64, i32, C.POINTER(C.c_int64), C.POINTER(u64)]
     L.fbgpu_bsi_minmax.restype = C.c_int
+    L.fbgpu_bsi_sum.argtypes, L.fbgpu_bsi_sum.restype = [vp, u32, vp, i32, u32, u32, i32, vp, i64, C.POINTER(C.c_int64), C.POINTER(u64)], C.c_int
     L.fbgpu_row_counts.argtypes, L.fbgpu_row_counts.restype = [vp, u32, u32, u32, vp, i32, vp, i32, vp, i64, vp, vp, i32, C.POINTER(i32)], C.c_int
     L.fbgpu_groupby.argtypes, L.fbgpu_groupby.restype = [vp, u32, vp, vp, i32, vp, vp, vp, i32, vp, i64, vp], C.c_int
     L.fbgpu_count_pairs.argtypes, L.fbgpu_count_pairs.restype = [vp, u32, u32, u32, vp, u32, u32, vp, i32, vp, i64, vp], C.c_int
@@ -268,6 +269,15 @@ class Context:
         self._check(self.L.fbgpu_bsi_minmax(self.h, index, arr, len(filter_ops) if filter_ops else 0, field, view, int(bit_depth), sh.ctypes.data, len(sh),
                                             1 if want_max else 0, C.byref(val), C.byref(cnt)))
         return val.value, cnt.value
+
+    def bsi_sum(self, index, field, view, bit_depth, shards, filter_ops=None):
+        """(Σ stored values = Σ (value - Base) in wrapping int64, number of columns) over <filter> ∩ not-null"""
+        sh = _u64arr(shards)
+        arr = ops_array(filter_ops) if filter_ops else None
+        tot, cnt = C.c_int64(0), C.c_uint64(0)
+        self._check(self.L.fbgpu_bsi_sum(self.h, index, arr, len(filter_ops) if filter_ops else 0, field, view, int(bit_depth), sh.ctypes.data, len(sh),
+                                         C.byref(tot), C.byref(cnt)))
+        return tot.value, cnt.value
 
     def row_counts(self, index, field, view, shards, row_ids=None, filter_ops=None, cap=1 << 20):
         sh = _u64arr(shards)

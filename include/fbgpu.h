@@ -159,6 +159,13 @@ int fbgpu_extract(fbgpu_ctx *ctx, uint32_t index, const fbgpu_op *ops, int32_t n
 int fbgpu_bsi_minmax(fbgpu_ctx *ctx, uint32_t index, const fbgpu_op *ops, int32_t n_ops, uint32_t field, uint32_t view, int32_t bit_depth,
                      const uint64_t *shards, int64_t n_shards, int32_t want_max, int64_t *out_val, uint64_t *out_count);
 
+/* Sum of an int field over a row (executeSum :1119, fragment.sum fragment.go:722-750): *out_count = |<filter> ∩ not-null|,
+ * *out_sum = Σ (stored value) over those columns in wrapping int64 arithmetic, i.e. Σ (value - Base); the caller adds
+ * count * Base (executeSumCountShard :2203-2206).  One evaluation of the row, one pass over the planes.  Per-node result,
+ * like fbgpu_bsi_minmax (ValCount.Add merges nodes). */
+int fbgpu_bsi_sum(fbgpu_ctx *ctx, uint32_t index, const fbgpu_op *ops, int32_t n_ops, uint32_t field, uint32_t view, int32_t bit_depth,
+                  const uint64_t *shards, int64_t n_shards, int64_t *out_sum, uint64_t *out_count);
+
 /* Per-row counts of one field, optionally intersected with a filter program: the exact part of TopN
  * (fragment.top with explicit ids, fragment.go:1317-1437) and TopK (doTopK executor.go:2705-2746).
  * row_ids != NULL: counts for exactly those rows (out_counts[i] for row_ids[i]).

@@ -132,6 +132,12 @@ class OracleCtx:
         end = None if limit is None else offset + limit
         return cols[offset:end], vals[offset:end], len(cols)
 
+    def bsi_sum(self, index, field, view, bit_depth, shards, filter_ops=None):
+        _, vals, _ = self.extract(index, field, view, bit_depth, shards, filter_ops=filter_ops)
+        t = int(vals.astype(object).sum()) if len(vals) else 0
+        t &= (1 << 64) - 1
+        return (t - (1 << 64) if t >> 63 else t), len(vals)
+
     def bsi_minmax(self, index, field, view, bit_depth, shards, want_max, filter_ops=None):
         _, vals, _ = self.extract(index, field, view, bit_depth, shards, filter_ops=filter_ops)
         if len(vals) == 0:

@@ -163,57 +163,6 @@ def test_bench_archetype_matrix():
                 p.check_row(f"{op}(Row(f={i}), Row(f={j}))", [shard])
 
 
-def test_groupby_postprocessing_goldens():
-    """executor_test.go:6087-6386: aggregate=Sum, previous / limit paging, wrapping iterators, rows spread over shards — the
-    dense count tensor comes from the device, the rest is the mirror's host-side post-processing"""
-    p = Pair()
-    fields = {"general": V.GROUPBY_GENERAL, "sub": V.GROUPBY_SUB, **V.GB_FIELDS}
-    for name, bits in fields.items():
-        p.field(name)
-        for r, c in bits:
-            p.holder.set_bit("i", name, r, c)
-    p.field("v", "int", min=0, max=1000)
-    for c, val in V.GB_V_VALUES:
-        p.holder.set_value("i", "v", c, val)
-    p.sync_pending()
-    fmt = lambda res: [(tuple(r for _, r in g[0]),) + tuple(g[1:]) for g in res]
-    for q, exp in V.GB_CASES:
-        assert fmt(p.ex.execute("i", q)[0]) == exp, q
-    got = fmt(p.ex.execute("i", "GroupBy(Rows(ppa), Rows(ppb), Rows(ppc), limit=3)")[0])
-    total = list(got)
-    while len(total) < 64:
-        a, b, c = got[-1][0]
-        got = fmt(p.ex.execute("i", f"GroupBy(Rows(ppa, previous={a}), Rows(ppb, previous={b}), Rows(ppc, previous={c}), limit=3)")[0])
-        assert got, "paging stalled"
-        total += got
-    assert total == V.GB_PAGING_EXPECT
-    # having / sort / offset (executeGroupBy :3388-3421, applyLimitAndOffsetToGroupByResult :3441-3459)
-    base = fmt(p.ex.execute("i", "GroupBy(Rows(general), Rows(sub))")[0])
-    assert fmt(p.ex.execute("i", "GroupBy(Rows(general), Rows(sub), having=Condition(count > 1))")[0]) == [g for g in base if g[1] > 1]
-    assert fmt(p.ex.execute("i", 'GroupBy(Rows(general), Rows(sub), sort="count asc")')[0]) == sorted(base, key=lambda g: g[1])
-    assert fmt(p.ex.execute("i", 'GroupBy(Rows(general), Rows(sub), sort="count desc", limit=1)')[0]) == [base[0]]
-    assert fmt(p.ex.execute("i", "GroupBy(Rows(general), Rows(sub), offset=1, limit=2)")[0]) == base[1:3]
-    assert fmt(p.ex.execute("i", "GroupBy(Rows(general), Rows(sub), offset=9)")[0]) == base
-    agg = fmt(p.ex.execute("i", 'GroupBy(Rows(general), Rows(sub), aggregate=Sum(field=v), having=Condition(sum > 50))')[0])
-    assert agg == [((10, 100), 2, 110)]
-    with pytest.raises(X.QueryError):
-        p.ex.execute("i", 'GroupBy(Rows(general), sort="rowid")')
-    # executor_test.go:5311-5341 TestExecutor_Execute_Rows (the `column=` form needs a column-literal operand: not mirrored)
-    q = Pair()
-    q.field("general")
-    q.field("integer", "int", min=-1000, max=1000)
-    for r, c in [(10, 0), (10, (1 << 20) + 1), (11, 2), (11, (1 << 20) + 2), (12, 2), (12, (1 << 20) + 2), (13, 3)]:
-        q.holder.set_bit("i", "general", r, c)
-    q.sync_pending()
-    for query, exp in (("Rows(general)", [10, 11, 12, 13]), ("Rows(field=general)", [10, 11, 12, 13]), ("Rows(general, limit=2)", [10, 11]),
-                       ("Rows(general, previous=10,limit=2)", [11, 12]), ("Rows(general, in=[11, 13, 99])", [11, 13])):
-        assert q.ex.execute("i", query)[0] == exp, query
-    for bad, msg in (("Rows(integer)", "int fields not supported"), ("GroupBy(Rows())", "missing field in Rows call"),
-                     ("Rows(general, in=[1, 2], column=3)", "does not support other arguments")):
-        with pytest.raises(X.QueryError, match=msg):
-            q.ex.execute("i", bad)
-
-
 def test_time_quantum_rows():
     """executor_test.go:470-515, 982-1010: Row(f=x, from=, to=) over a time field = the union of the row over the views
     viewsByTimeRange picks (time.go:158-235); the views are ordinary fragments, the union an ordinary program"""
@@ -575,6 +524,57 @@ def test_random_call_trees_differential():
 def roaring_values(bm):
     from featurebase_b200 import roaring_io
     return np.asarray(roaring_io.decode(bm.to_bytes()), dtype=np.uint64)
+
+
+def test_groupby_postprocessing_goldens():
+    """executor_test.go:6087-6386: aggregate=Sum, previous / limit paging, wrapping iterators, rows spread over shards — the
+    dense count tensor comes from the device, the rest is the mirror's host-side post-processing"""
+    p = Pair()
+    fields = {"general": V.GROUPBY_GENERAL, "sub": V.GROUPBY_SUB, **V.GB_FIELDS}
+    for name, bits in fields.items():
+        p.field(name)
+        for r, c in bits:
+            p.holder.set_bit("i", name, r, c)
+    p.field("v", "int", min=0, max=1000)
+    for c, val in V.GB_V_VALUES:
+        p.holder.set_value("i", "v", c, val)
+    p.sync_pending()
+    fmt = lambda res: [(tuple(r for _, r in g[0]),) + tuple(g[1:]) for g in res]
+    for q, exp in V.GB_CASES:
+        assert fmt(p.ex.execute("i", q)[0]) == exp, q
+    got = fmt(p.ex.execute("i", "GroupBy(Rows(ppa), Rows(ppb), Rows(ppc), limit=3)")[0])
+    total = list(got)
+    while len(total) < 64:
+        a, b, c = got[-1][0]
+        got = fmt(p.ex.execute("i", f"GroupBy(Rows(ppa, previous={a}), Rows(ppb, previous={b}), Rows(ppc, previous={c}), limit=3)")[0])
+        assert got, "paging stalled"
+        total += got
+    assert total == V.GB_PAGING_EXPECT
+    # having / sort / offset (executeGroupBy :3388-3421, applyLimitAndOffsetToGroupByResult :3441-3459)
+    base = fmt(p.ex.execute("i", "GroupBy(Rows(general), Rows(sub))")[0])
+    assert fmt(p.ex.execute("i", "GroupBy(Rows(general), Rows(sub), having=Condition(count > 1))")[0]) == [g for g in base if g[1] > 1]
+    assert fmt(p.ex.execute("i", 'GroupBy(Rows(general), Rows(sub), sort="count asc")')[0]) == sorted(base, key=lambda g: g[1])
+    assert fmt(p.ex.execute("i", 'GroupBy(Rows(general), Rows(sub), sort="count desc", limit=1)')[0]) == [base[0]]
+    assert fmt(p.ex.execute("i", "GroupBy(Rows(general), Rows(sub), offset=1, limit=2)")[0]) == base[1:3]
+    assert fmt(p.ex.execute("i", "GroupBy(Rows(general), Rows(sub), offset=9)")[0]) == base
+    agg = fmt(p.ex.execute("i", 'GroupBy(Rows(general), Rows(sub), aggregate=Sum(field=v), having=Condition(sum > 50))')[0])
+    assert agg == [((10, 100), 2, 110)]
+    with pytest.raises(X.QueryError):
+        p.ex.execute("i", 'GroupBy(Rows(general), sort="rowid")')
+    # executor_test.go:5311-5341 TestExecutor_Execute_Rows (the `column=` form needs a column-literal operand: not mirrored)
+    q = Pair()
+    q.field("general")
+    q.field("integer", "int", min=-1000, max=1000)
+    for r, c in [(10, 0), (10, (1 << 20) + 1), (11, 2), (11, (1 << 20) + 2), (12, 2), (12, (1 << 20) + 2), (13, 3)]:
+        q.holder.set_bit("i", "general", r, c)
+    q.sync_pending()
+    for query, exp in (("Rows(general)", [10, 11, 12, 13]), ("Rows(field=general)", [10, 11, 12, 13]), ("Rows(general, limit=2)", [10, 11]),
+                       ("Rows(general, previous=10,limit=2)", [11, 12]), ("Rows(general, in=[11, 13, 99])", [11, 13])):
+        assert q.ex.execute("i", query)[0] == exp, query
+    for bad, msg in (("Rows(integer)", "int fields not supported"), ("GroupBy(Rows())", "missing field in Rows call"),
+                     ("Rows(general, in=[1, 2], column=3)", "does not support other arguments")):
+        with pytest.raises(X.QueryError, match=msg):
+            q.ex.execute("i", bad)
 
 
 def test_columns_entry_point():

@@ -94,7 +94,7 @@ def main():
     o.append("| no per-pair 8 KiB wipe in array x array counting | `-DFBGPU_PAIR_UNSCATTER` (`libfbgpu_pair_unscatter.so`) | config 5 at <= 3 % density (north-star point) | 64 of ~210 wavefronts per pair; with the striped order ~63 in all |")
     o.append("| three-ops-per-iteration word-parallel loop | `-DFBGPU_WP_UNROLL3` (`libfbgpu_wp_unroll3.so`) | config 3 `eval_wordpar_kernel` (interpretive overhead) | ~12 instructions per op + operand fetch instead of 80-100 |")
     o.append("| thread-per-row GroupBy passes | `FBGPU_GROUPBY_FAST=1` | config 4 `groupby_kernel` (25.8 k warp instructions per unit) | ~9x fewer instructions per unit; then latency-bound |")
-    o.append("| `fbgpu_columns` / `columns_emit_kernel`, `fbgpu_extract` / `extract_values_kernel`, `fbgpu_bsi_minmax` / `bsi_minmax_kernel`, `fbgpu_load_rbf`, host-mirror compositions (Sum / Min / Max / Percentile / Distinct / MinRow / time ranges) | new entry points / host code | SURVEY §8(f) rows | functional only |")
+    o.append("| `fbgpu_columns` / `columns_emit_kernel`, `fbgpu_extract` / `extract_values_kernel`, `fbgpu_bsi_sum` / `fbgpu_bsi_minmax` (`bsi_sum_kernel`, `bsi_minmax_kernel`), `fbgpu_load_rbf`, host-mirror compositions (Sum / Min / Max / Percentile / Distinct / MinRow / time ranges) | new entry points / host code | SURVEY §8(f) rows | functional only |")
     o.append("")
     o.append("## Correctness tooling\n")
     o.append("`r01_sanitizer_memcheck.log`: compute-sanitizer memcheck over the eval / pair / row-count / groupby / word-parallel / staged kernels (8 GPU tests): 0 errors. `r01_sanitizer_racecheck.log`: racecheck (shared-memory hazards): 0 hazards.\n")
