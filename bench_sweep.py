@@ -182,6 +182,17 @@ def config_extract(args, out):
         assert int(vals[i]) == D.bsi_value(12, int(c2[i]) // SW, int(c2[i]) % SW, 0, (1 << 32) - 1)
     out({"config": "X", "query": "values of a 32-bit int field, all records", "records": n_rec, "kernel": "eval_kernel + columns_emit_kernel + extract_values_kernel", "ms": wall,
          "records_per_sec": n_rec / (wall * 1e-3), "frac": 0.0, "achieved_gbs": 0.0, "note": "wall clock of fbgpu_extract(): 34 planes read once, 16 B per record D2H"})
+    # the one-pass aggregates, cross-checked against the extracted value vector
+    (tot, cnt), wall = timed(lambda: h.ctx.bsi_sum(idx.id, v.id, X.VIEW_BSI, 32, bsh))
+    assert cnt == n_rec and tot == int(vals.astype(object).sum())
+    out({"config": "X", "query": "Sum(field=v), 32-bit, all records", "records": n_rec, "kernel": "eval_kernel + bsi_sum_kernel", "ms": wall, "records_per_sec": n_rec / (wall * 1e-3),
+         "frac": 0.0, "achieved_gbs": 0.0, "note": "wall clock of fbgpu_bsi_sum()"})
+    for want_max in (False, True):
+        (val, n), wall = timed(lambda: h.ctx.bsi_minmax(idx.id, v.id, X.VIEW_BSI, 32, bsh, want_max))
+        ref = int(vals.max() if want_max else vals.min())
+        assert (val, n) == (ref, int((vals == ref).sum()))
+        out({"config": "X", "query": ("Max" if want_max else "Min") + "(field=v), 32-bit, all records", "records": n_rec, "kernel": "eval_kernel + bsi_minmax_kernel", "ms": wall,
+             "records_per_sec": n_rec / (wall * 1e-3), "frac": 0.0, "achieved_gbs": 0.0, "note": "wall clock of fbgpu_bsi_minmax()"})
     h.ctx.close()
 
 
