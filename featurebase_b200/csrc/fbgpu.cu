@@ -129,7 +129,9 @@ constexpr int kNcclUint64 = 5, kNcclSum = 0;   // ncclDataType_t / ncclRedOp_t v
 // ------------------------------------------------------------------ context
 struct ViewKey { uint32_t index, field, view; bool operator<(const ViewKey& o) const { return index != o.index ? index < o.index : field != o.field ? field < o.field : view < o.view; } };
 
-struct HostFrag { uint32_t fv; uint64_t shard; bool live; uint32_t row_off, n_rows; uint64_t payload_bytes; uint32_t n_desc; uint32_t n_arr, n_bmp, n_run; uint32_t n_striped; };
+struct HostFrag { uint32_t fv; uint64_t shard; bool live; uint32_t row_off, n_rows; uint64_t payload_bytes; uint32_t n_desc; uint32_t n_arr, n_bmp, n_run; uint32_t n_striped;
+                  uint64_t desc_off = 0;               // its descriptors are h_descs[desc_off, desc_off + n_desc)
+                  uint64_t arena_off = 0, arena_len = 0; };   // its payloads (with their alignment gaps) are arena bytes [arena_off, arena_off + arena_len)
 
 struct Workspace {
     cudaStream_t stream = nullptr;
@@ -154,6 +156,7 @@ struct fbgpu_ctx {
     std::vector<ContDesc> h_descs;
     RawBuf staging;                      // payload bytes not yet uploaded, destined for [uploaded, uploaded+staging.len)
     uint64_t uploaded = 0;               // bytes of payload already in HBM
+    uint64_t dead_arena = 0;             // arena bytes of replaced / dropped fragments (reclaimed by compact_locked)
     bool meta_dirty = false;
     bool inspect_only = false;           // created with FBGPU_DEVICE_NONE: residency + fbgpu_debug_container only, no device, no queries
     std::vector<ViewTab> t_views; std::vector<int32_t> t_flat; std::vector<RowTabEnt> t_rowtab;   // inspect_only: the tables a commit would upload
@@ -267,6 +270,7 @@ static void drop_locked(fbgpu_ctx* c, uint32_t fv, uint64_t shard) {
     if (shard >= sm.size() || sm[shard] < 0) return;
     HostFrag& f = c->frags[sm[shard]];
     f.live = false;
+    c->dead_arena += f.arena_len; c->stats.dead_bytes = c->dead_arena;
     c->stats.fragments--; c->stats.containers -= f.n_desc; c->stats.payload_bytes -= f.payload_bytes;
     c->stats.array_containers -= f.n_arr; c->stats.bitmap_containers -= f.n_bmp; c->stats.run_containers -= f.n_run;
     c->view_arr[fv] -= f.n_arr; c->view_other[fv] -= (uint64_t)f.n_bmp + f.n_run; c->view_striped[fv] -= f.n_striped;
@@ -278,7 +282,8 @@ static void drop_locked(fbgpu_ctx* c, uint32_t fv, uint64_t shard) {
 static int add_fragment_locked(fbgpu_ctx* c, uint32_t fv, uint64_t shard, const std::vector<ParsedCont>& cs, std::vector<PayloadCopy>& copies) {
     if (shard >= (1ull << 31)) return fail(FBGPU_E_INVALID, "shard %llu too large", (unsigned long long)shard);
     drop_locked(c, fv, shard);
-    HostFrag hf{}; hf.fv = fv; hf.shard = shard; hf.live = true; hf.row_off = (uint32_t)c->h_rows.size();
+    HostFrag hf{}; hf.fv = fv; hf.shard = shard; hf.live = true; hf.row_off = (uint32_t)c->h_rows.size(); hf.desc_off = c->h_descs.size();
+    hf.arena_off = c->uploaded + c->staging.len;
     uint64_t prev_row = ~0ull; bool contiguous = true; uint64_t row0 = 0;
     const size_t desc0 = c->h_descs.size();
     // descriptors: row-major (key order), so that a row's slots are adjacent and rank = popc(mask & below)
@@ -319,6 +324,7 @@ static int add_fragment_locked(fbgpu_ctx* c, uint32_t fv, uint64_t shard, const 
         copies.push_back(PayloadCopy{ pc.data, apos - c->uploaded, (uint32_t)bytes, (uint32_t)padded, pc.typ, (uint16_t)(pc.official_run ? 1 : 0), pc.cnt, stripe ? 1u : 0u });
         c->h_descs[desc0 + i].off16 = (uint32_t)(apos / 16);
     }
+    hf.arena_len = c->uploaded + c->staging.len - hf.arena_off;
     FragHdr h{}; h.row_off = hf.row_off; h.n_rows = hf.n_rows; h.row0 = row0; h.contiguous = contiguous ? 1u : 0u;
     int32_t fid = (int32_t)c->frags.size();
     c->frags.push_back(hf); c->h_frags.push_back(h);
@@ -555,10 +561,58 @@ static int commit_locked(fbgpu_ctx* c) {
     return 0;
 }
 
+// Reclaims what replaced / dropped fragments left behind (store_mu held exclusively; everything pending is committed first):
+// live fragments are copied device-to-device into a fresh arena in their current order, each keeping its offset modulo 128 so
+// that every container keeps its alignment, and the host mirrors (fragment headers, row entries, descriptors, shard maps)
+// are rebuilt without the dead entries.  Write batches re-send whole fragments, so without this the
+// arena of a long-running node would only grow.
+static int compact_locked(fbgpu_ctx* c) {
+    int rc = commit_locked(c); if (rc) return rc;
+    if (c->inspect_only) return 0;                         // (no device arena: the staging buffer is the store)
+    if (c->dead_arena == 0) return 0;
+    USE_DEVICE(c);
+    CUDA_TRY(cudaDeviceSynchronize());
+    std::vector<HostFrag> frags; std::vector<FragHdr> hfr; std::vector<RowEnt> rows; std::vector<ContDesc> descs;
+    struct Move { uint64_t from, to, len; };
+    std::vector<Move> moves; uint64_t cur = 0;
+    for (auto& sm : c->shardmaps) std::fill(sm.begin(), sm.end(), -1);
+    for (size_t fid = 0; fid < c->frags.size(); fid++) {
+        HostFrag f = c->frags[fid];
+        if (!f.live) continue;
+        FragHdr h = c->h_frags[fid];
+        const uint64_t to = ((cur + 127) & ~127ull) + (f.arena_off & 127ull);
+        const int64_t d16 = ((int64_t)to - (int64_t)f.arena_off) / 16;         // both are 16-byte aligned
+        const uint64_t desc_new = descs.size(), row_new = rows.size();
+        for (uint32_t r = 0; r < f.n_rows; r++) { RowEnt e = c->h_rows[f.row_off + r]; e.first_desc = (uint32_t)(e.first_desc - f.desc_off + desc_new); rows.push_back(e); }
+        for (uint32_t k = 0; k < f.n_desc; k++) { ContDesc d = c->h_descs[f.desc_off + k]; d.off16 = (uint32_t)((int64_t)d.off16 + d16); descs.push_back(d); }
+        moves.push_back(Move{ f.arena_off, to, f.arena_len });
+        f.row_off = (uint32_t)row_new; f.desc_off = desc_new; f.arena_off = to; h.row_off = (uint32_t)row_new;
+        c->shardmaps[f.fv][f.shard] = (int32_t)frags.size();
+        frags.push_back(f); hfr.push_back(h);
+        cur = to + f.arena_len;
+    }
+    DevBuf nb;
+    if (nb.ensure(cur + 256)) return FBGPU_E_NOMEM;
+    for (const Move& m : moves) if (m.len) CUDA_TRY(cudaMemcpy((uint8_t*)nb.p + m.to, (const uint8_t*)c->d_payload.p + m.from, m.len, cudaMemcpyDeviceToDevice));
+    c->d_payload.release(); c->d_payload = nb;
+    c->frags.swap(frags); c->h_frags.swap(hfr); c->h_rows.swap(rows); c->h_descs.swap(descs);
+    c->uploaded = cur; c->dead_arena = 0; c->stats.dead_bytes = 0;
+    c->meta_dirty = true;
+    return commit_locked(c);                               // tables for the new layout
+}
+
 extern "C" int fbgpu_commit(fbgpu_ctx* c) try {
     if (!c) return fail(FBGPU_E_INVALID, "null ctx");
     std::unique_lock<std::shared_mutex> lk(c->store_mu);
+    // a node that keeps re-sending fragments compacts on its own once the dead share is large (never reached by small stores)
+    if (!c->inspect_only && c->dead_arena >= (256ull << 20) && c->dead_arena * 2 >= c->uploaded + c->staging.len) return compact_locked(c);
     return commit_locked(c);
+} FBGPU_CATCH
+
+extern "C" int fbgpu_compact(fbgpu_ctx* c) try {
+    if (!c) return fail(FBGPU_E_INVALID, "null ctx");
+    std::unique_lock<std::shared_mutex> lk(c->store_mu);
+    return compact_locked(c);
 } FBGPU_CATCH
 // Takes the store's shared lock for a query with the device tables in sync with the host mirrors: the "is anything
 // pending" check and the query run under the SAME lock acquisition, so a load that slips in between a commit and the

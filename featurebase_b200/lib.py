@@ -27,7 +27,7 @@ class Op(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("fragments", "containers", "array_containers", "bitmap_containers",
-                                           "run_containers", "payload_bytes", "device_bytes")]
+                                           "run_containers", "payload_bytes", "device_bytes", "dead_bytes")]
 
 
 class Counters(C.Structure):
@@ -38,7 +38,7 @@ class Counters(C.Structure):
 EXPORTS = ["fbgpu_init", "fbgpu_shutdown", "fbgpu_last_error", "fbgpu_abi_version", "fbgpu_load_fragment",
            "fbgpu_load_fragments", "fbgpu_drop_fragment", "fbgpu_commit", "fbgpu_get_stats", "fbgpu_count", "fbgpu_row",
            "fbgpu_row_counts", "fbgpu_groupby", "fbgpu_comm_unique_id", "fbgpu_comm_init", "fbgpu_comm_destroy",
-           "fbgpu_get_counters", "fbgpu_stream", "fbgpu_rows_payload_bytes", "fbgpu_count_pairs", "fbgpu_columns", "fbgpu_extract", "fbgpu_load_rbf", "fbgpu_load_rbf_dir", "fbgpu_bsi_minmax", "fbgpu_bsi_sum", "fbgpu_comm_p2p_handle", "fbgpu_comm_p2p_open", "fbgpu_comm_p2p_disable"]
+           "fbgpu_get_counters", "fbgpu_stream", "fbgpu_rows_payload_bytes", "fbgpu_count_pairs", "fbgpu_columns", "fbgpu_extract", "fbgpu_load_rbf", "fbgpu_load_rbf_dir", "fbgpu_bsi_minmax", "fbgpu_bsi_sum", "fbgpu_compact", "fbgpu_comm_p2p_handle", "fbgpu_comm_p2p_open", "fbgpu_comm_p2p_disable"]
 
 
 def lib_path():
@@ -64,6 +64,7 @@ def load():
     L.fbgpu_load_rbf.argtypes, L.fbgpu_load_rbf.restype = [vp, u32, u64, vp, u64, vp, u64, vp, vp, vp, i32, C.POINTER(i32)], C.c_int
     L.fbgpu_load_rbf_dir.argtypes, L.fbgpu_load_rbf_dir.restype = [vp, u32, u64, C.c_char_p, vp, vp, vp, i32, C.POINTER(i32)], C.c_int
     L.fbgpu_commit.argtypes, L.fbgpu_commit.restype = [vp], C.c_int
+    L.fbgpu_compact.argtypes, L.fbgpu_compact.restype = [vp], C.c_int
     L.fbgpu_debug_container.argtypes = [vp, u32, u32, u32, u64, u64, i32, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32), vp, u64, C.POINTER(u64)]
     L.fbgpu_debug_container.restype = C.c_int
     L.fbgpu_debug_compile.argtypes, L.fbgpu_debug_compile.restype = [vp, u32, vp, i32, vp, i32, C.POINTER(i32), C.POINTER(i32)], C.c_int
@@ -187,6 +188,10 @@ class Context:
 
     def commit(self):
         self._check(self.L.fbgpu_commit(self.h))
+
+    def compact(self):
+        """reclaim the arena space of replaced / dropped fragments (stats()["dead_bytes"])"""
+        self._check(self.L.fbgpu_compact(self.h))
 
     def stats(self):
         s = Stats()

@@ -77,6 +77,10 @@ int fbgpu_load_rbf_dir(fbgpu_ctx *ctx, uint32_t index, uint64_t shard, const cha
                        const uint32_t *fields, const uint32_t *views, int32_t n_names, int32_t *out_loaded);
 /* pushes pending host-side staging to HBM now (otherwise done lazily by the next query) */
 int fbgpu_commit(fbgpu_ctx *ctx);
+/* Replacing or dropping a fragment leaves its old payload in the arena.  fbgpu_compact() commits what is pending, then
+ * copies the live fragments into a fresh arena (device to device) and rebuilds the tables; fbgpu_commit() does the same on
+ * its own once at least 256 MiB and half of the arena are dead.  Blocks queries for the duration, like a commit. */
+int fbgpu_compact(fbgpu_ctx *ctx);
 /* Inspection (FBGPU_DEVICE_NONE contexts only): the container the kernels would find for (index, field, view, shard, row,
  * slot), located by the same resolve() code, with its payload exactly as stored (incl. the padding of the last 16-byte
  * chunk).  *out_type = 0 when the container is absent, else 1 array / 2 bitmap / 3 run. */
@@ -89,6 +93,7 @@ typedef struct {
     uint64_t array_containers, bitmap_containers, run_containers;
     uint64_t payload_bytes;   /* roaring payload bytes resident in HBM (array 2n, bitmap 8192, run 4r) */
     uint64_t device_bytes;    /* total HBM held by the store incl. descriptors and padding            */
+    uint64_t dead_bytes;      /* arena bytes of replaced / dropped fragments, reclaimed by fbgpu_compact */
 } fbgpu_stats;
 int fbgpu_get_stats(fbgpu_ctx *ctx, fbgpu_stats *out);
 

@@ -17,7 +17,10 @@ class OracleCtx:
 
     # ---- residency
     def load_fragment(self, index, field, view, shard, data):
-        self.frags.setdefault((index, field, view), {})[int(shard)] = O.Bitmap.from_bytes(bytes(data))
+        slot = self.frags.setdefault((index, field, view), {})
+        if int(shard) in slot:                               # (a replaced fragment leaves its bytes behind, as in the library's arena)
+            self._dead = getattr(self, "_dead", 0) + 2 * len(bytes(data))
+        slot[int(shard)] = O.Bitmap.from_bytes(bytes(data))
 
     def commit(self):
         pass
@@ -41,7 +44,19 @@ class OracleCtx:
     def stats(self):
         import struct
         frs = [b for d in self.frags.values() for b in d.values()]
-        return {"fragments": len(frs), "containers": sum(struct.unpack_from("<I", b.to_bytes(), 4)[0] for b in frs)}
+        payload = 0
+        for b in frs:
+            raw = b.to_bytes()
+            n = struct.unpack_from("<I", raw, 4)[0]
+            for i in range(n):
+                _, typ, n1 = struct.unpack_from("<QHH", raw, 8 + 12 * i)
+                off = struct.unpack_from("<I", raw, 8 + 12 * n + 4 * i)[0]
+                payload += 2 * (n1 + 1) if typ == 1 else 8192 if typ == 2 else 4 * struct.unpack_from("<H", raw, off)[0]
+        return {"fragments": len(frs), "containers": sum(struct.unpack_from("<I", b.to_bytes(), 4)[0] for b in frs), "payload_bytes": payload,
+                "dead_bytes": getattr(self, "_dead", 0), "device_bytes": 0}
+
+    def compact(self):
+        self._dead = 0
 
     def _frag(self, index, field, view, shard):
         return self.frags.get((index, field, view), {}).get(int(shard))

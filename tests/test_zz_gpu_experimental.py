@@ -1011,3 +1011,51 @@ def test_percentile_vs_reference_helper():
     for bad in ("Percentile(field=net_worth)", "Percentile(field=net_worth, nth=101)", "Percentile(nth=5)", "Percentile(field=nope, nth=5)"):
         with pytest.raises(X.QueryError):
             p.ex.execute("i", bad)
+
+
+def test_arena_compaction():
+    """fbgpu_compact: fragments are replaced and dropped (dead arena bytes grow), queries stay right before and after the live
+    fragments are moved into a fresh arena, further loads land behind them, and the dead bytes are gone"""
+    import featurebase_b200.datagen as D
+    from oracle import oracle as O
+    p = Pair(track_existence=False)
+    p.field("m")
+    p.field("n")
+    ctx = p.holder.ctx
+
+    def frag(seed, s):
+        b = O.Bitmap()
+        for d in (D.fragment(seed, s, [0, 1], 0.004), D.fragment(seed, s, [2], 0.3), D.fragment(seed, s, [3], 0.2, mode=1, mean_run=200.0)):
+            b = b.union(O.Bitmap.from_bytes(d))
+        return b.to_bytes()
+
+    def check():
+        for q in ("Intersect(Row(m=0), Row(n=1))", "Union(Row(m=2), Row(n=3), Row(m=1))", "Difference(Row(n=2), Row(m=3))", "Xor(Row(m=0), Row(m=3))"):
+            p.check_row(q)
+            p.check_count(f"Count({q})")
+        assert p.ex.execute("i", "TopK(m, k=3)")[0] == sorted(((r, p.ora.count(pql.parse(f"Row(m={r})")[0], p.shards())) for r in range(4)), key=lambda kv: (-kv[1], kv[0]))[:3]
+
+    for s in range(4):
+        p.load("m", X.VIEW_STANDARD, s, frag(40, s))
+        p.load("n", X.VIEW_STANDARD, s, frag(41, s))
+    check()
+    assert ctx.stats()["dead_bytes"] == 0
+    for rnd in range(3):                                           # write batches: the same fragments re-sent with new content
+        for s in (0, 2, 3):
+            p.load("m", X.VIEW_STANDARD, s, frag(50 + rnd, s))
+        p.load("n", X.VIEW_STANDARD, 1, frag(60 + rnd, 1))
+    check()
+    before = ctx.stats()
+    assert before["dead_bytes"] > before["payload_bytes"]           # three generations of garbage behind the live data
+    ctx.compact()
+    after = ctx.stats()
+    assert after["dead_bytes"] == 0 and after["payload_bytes"] == before["payload_bytes"] and after["containers"] == before["containers"]
+    if hasattr(ctx, "L"):                                          # (the real library: the arena shrank)
+        assert after["device_bytes"] < before["device_bytes"]
+    check()
+    p.load("m", X.VIEW_STANDARD, 5, frag(70, 5))                    # loads after a compaction append behind the moved data
+    p.load("n", X.VIEW_STANDARD, 0, frag(71, 0))
+    check()
+    ctx.compact()
+    ctx.compact()                                                  # nothing dead: a no-op
+    check()
