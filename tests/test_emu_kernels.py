@@ -27,8 +27,8 @@ sys.path.insert(0, EMU)
 FULL = bool(os.environ.get("FBGPU_EMU_FULL"))
 
 
-def emu_lib(defines=()):
-    """build (once per source state) the interpreted library for the given -D list"""
+def emu_lib(defines=(), flags=()):
+    """build (once per source state) the interpreted library for the given -D list (+ extra compiler flags)"""
     import make_emu_source
     csrc = os.path.join(ROOT, "featurebase_b200", "csrc")
     srcs = [os.path.join(csrc, n) for n in sorted(os.listdir(csrc))] + [os.path.join(EMU, "cuda_runtime.h"), os.path.join(EMU, "make_emu_source.py"),
@@ -36,13 +36,13 @@ def emu_lib(defines=()):
     h = hashlib.sha1()
     for p in srcs:
         h.update(open(p, "rb").read())
-    h.update(" ".join(defines).encode())
+    h.update(" ".join(list(defines) + list(flags)).encode())
     out_dir = os.path.join(EMU, "_build", h.hexdigest()[:16])
     lib = os.path.join(out_dir, "libfbgpu_emu.so")
     if not os.path.exists(lib):
         make_emu_source.main(out_dir)
         cmd = ["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-I", EMU, "-o", lib + ".tmp", os.path.join(out_dir, "fbgpu.cpp"), "-ldl", "-lpthread"]
-        cmd += ["-D" + d for d in defines]
+        cmd += ["-D" + d for d in defines] + list(flags)
         subprocess.check_call(cmd)
         os.replace(lib + ".tmp", lib)
     return lib
@@ -112,6 +112,22 @@ def test_results_do_not_depend_on_thread_order(order):
     if FULL:
         run_on_emulator(["tests/test_gpu_parity.py", "-k", "groupby or density_sweep or mixed_encoding"], env={"FBGPU_EMU_ORDER": order}, timeout=3000)
         run_on_emulator(["tests/test_zz_gpu_experimental.py", "-k", "striped_density_sweep or striped_bsi"], env={"FBGPU_EMU_ORDER": order, "FBGPU_TEST_EXPERIMENTAL": "1"}, timeout=3000)
+
+
+def test_interpreted_library_under_ubsan():
+    """kernels and host code compiled with -fsanitize=undefined (shifts, signed overflow, misaligned vector accesses, bad
+    enum / bool loads abort): the parity tests, the striped order, the GroupBy variant and the threaded API test"""
+    if not FULL:
+        pytest.skip("UBSAN build: FBGPU_EMU_FULL=1")
+    lib = emu_lib(flags=("-O1", "-g", "-fsanitize=undefined", "-fno-sanitize-recover=undefined"))
+    rt = subprocess.run(["g++", "-print-file-name=libubsan.so"], stdout=subprocess.PIPE, text=True).stdout.strip()
+    base = dict(os.environ, FBGPU_LIB=lib, FBGPU_TEST_ON_EMULATOR="1", LD_PRELOAD=rt, UBSAN_OPTIONS="print_stacktrace=1:halt_on_error=1")
+    base.pop("FBGPU_EMU_FULL", None)
+    for extra, sel in (({}, NOT_HUGE + SLOW + " and not striped"),
+                       ({"FBGPU_ARRAY_STRIPED": "1", "FBGPU_GROUPBY_FAST": "1", "FBGPU_TEST_EXPERIMENTAL": "1"}, "(striped or groupby or density_sweep) and " + NOT_HUGE + SLOW)):
+        r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider", "tests/test_gpu_parity.py", "tests/test_zz_gpu_experimental.py", "-k", sel],
+                           cwd=ROOT, env=dict(base, **extra), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=3000)
+        assert r.returncode == 0 and " passed" in r.stdout, r.stdout[-3000:]
 
 
 def test_bench_main_runs_against_interpreted_library():
