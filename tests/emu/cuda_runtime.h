@@ -50,9 +50,15 @@
 #define __launch_bounds__(...)
 // static shared memory goes into one named section so that launch() can poison all of it before every block: real shared
 // memory is not zero at block start, a kernel that reads a __shared__ variable before writing it must not pass here
+#ifdef FBGPU_EMU_PLAIN_SHARED            // AddressSanitizer build: ordinary statics get red zones (ASAN leaves named sections alone)
+#define __shared__ static
+static char* const __start_fbgpu_smem = nullptr;
+static char* const __stop_fbgpu_smem = nullptr;
+#else
 #define __shared__ static __attribute__((section("fbgpu_smem")))
 extern "C" char __start_fbgpu_smem[] __attribute__((weak, visibility("hidden")));
 extern "C" char __stop_fbgpu_smem[] __attribute__((weak, visibility("hidden")));
+#endif
 #define __constant__ static
 
 struct uint2 { uint32_t x, y; };

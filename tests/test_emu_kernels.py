@@ -114,14 +114,18 @@ def test_results_do_not_depend_on_thread_order(order):
         run_on_emulator(["tests/test_zz_gpu_experimental.py", "-k", "striped_density_sweep or striped_bsi"], env={"FBGPU_EMU_ORDER": order, "FBGPU_TEST_EXPERIMENTAL": "1"}, timeout=3000)
 
 
-def test_interpreted_library_under_ubsan():
-    """kernels and host code compiled with -fsanitize=undefined (shifts, signed overflow, misaligned vector accesses, bad
-    enum / bool loads abort): the parity tests, the striped order, the GroupBy variant and the threaded API test"""
+@pytest.mark.parametrize("san", ["undefined", "address"])
+def test_interpreted_library_under_sanitizers(san):
+    """kernels and host code compiled with -fsanitize=undefined (shifts, signed overflow, misaligned vector accesses abort)
+    or -fsanitize=address (out-of-bounds on `__shared__` statics — plain red-zoned globals in that build —, on host
+    vectors and on thread stacks): the parity tests, the striped order, the GroupBy variant, the threaded API test"""
     if not FULL:
-        pytest.skip("UBSAN build: FBGPU_EMU_FULL=1")
-    lib = emu_lib(flags=("-O1", "-g", "-fsanitize=undefined", "-fno-sanitize-recover=undefined"))
-    rt = subprocess.run(["g++", "-print-file-name=libubsan.so"], stdout=subprocess.PIPE, text=True).stdout.strip()
-    base = dict(os.environ, FBGPU_LIB=lib, FBGPU_TEST_ON_EMULATOR="1", LD_PRELOAD=rt, UBSAN_OPTIONS="print_stacktrace=1:halt_on_error=1")
+        pytest.skip("sanitizer builds: FBGPU_EMU_FULL=1")
+    flags = ("-O1", "-g", "-fsanitize=undefined", "-fno-sanitize-recover=undefined") if san == "undefined" else ("-O1", "-g", "-fsanitize=address")
+    lib = emu_lib(defines=() if san == "undefined" else ("FBGPU_EMU_PLAIN_SHARED",), flags=flags)
+    rt = subprocess.run(["g++", "-print-file-name=" + ("libubsan.so" if san == "undefined" else "libasan.so")], stdout=subprocess.PIPE, text=True).stdout.strip()
+    base = dict(os.environ, FBGPU_LIB=lib, FBGPU_TEST_ON_EMULATOR="1", LD_PRELOAD=rt, UBSAN_OPTIONS="print_stacktrace=1:halt_on_error=1",
+                ASAN_OPTIONS="detect_leaks=0:halt_on_error=1")
     base.pop("FBGPU_EMU_FULL", None)
     for extra, sel in (({}, NOT_HUGE + SLOW + " and not striped"),
                        ({"FBGPU_ARRAY_STRIPED": "1", "FBGPU_GROUPBY_FAST": "1", "FBGPU_TEST_EXPERIMENTAL": "1"}, "(striped or groupby or density_sweep) and " + NOT_HUGE + SLOW)):
