@@ -297,6 +297,8 @@ class Executor:
                 return self._distinct(idx, c, shards)
             if c.name == "Extract":
                 return self._extract(idx, c, shards)
+            if c.name == "Sort":
+                return self._sort(idx, c, shards)
             if c.name == "IncludesColumn":                       # executeIncludesColumnCall: is the column in the row?
                 if "column" not in c.args:
                     raise QueryError("IncludesColumn call must specify a column")
@@ -693,8 +695,9 @@ class Executor:
         if not c.children:
             raise QueryError("missing column filter in Extract")
         filt_call = c.children[0]
-        if filt_call.name == "Sort":
-            raise QueryError("Extract(Sort(..)) is not supported by this mirror")
+        sorted_cols = None
+        if filt_call.name == "Sort":                             # Extract(Sort(..), ..): rows in the sort's order (ExtractedIDMatrixSorted :9610)
+            sorted_cols = [col for col, _ in self._sort(idx, filt_call, shards)]
         win = (0, None)
         if filt_call.name == "Limit":                            # Extract(Limit(x, limit=, offset=), ...): the window is cut on the device
             if len(filt_call.children) != 1:
@@ -708,9 +711,12 @@ class Executor:
             if name is None:
                 raise QueryError("missing field in Rows call")
             fields.append(self._field(idx, name))
-        filt = self._bitmap_call(idx, filt_call)
-        cols, _ = self.ctx.columns(idx.id, filt, shards, offset=win[0], limit=win[1])
-        cols = [int(x) for x in cols]
+        if sorted_cols is None:
+            filt = self._bitmap_call(idx, filt_call)
+            cols, _ = self.ctx.columns(idx.id, filt, shards, offset=win[0], limit=win[1])
+            cols = [int(x) for x in cols]
+        else:
+            cols, filt, win = sorted_cols, [], (1, None)         # (cells for exactly these columns: the narrowed filter below)
         pos = {col: i for i, col in enumerate(cols)}
         if win != (0, None) and cols:                            # cells are only needed for the window: narrow the filter to it
             ef, erow = self.holder.embed_row(idx.name, cols)
@@ -741,6 +747,36 @@ class Executor:
                     elif table[pos[col]][k] is None:
                         table[pos[col]][k] = (r == 1) if f.type == "bool" else r
         return {"fields": [(f.name, t) for f, t in zip(fields, types)], "columns": list(zip(cols, table))}
+
+    def _sort(self, idx, c, shards):
+        """executeSort :9321 / executeSortShard :9387: the columns of the child row ordered by a field's value — int (values from
+        fbgpu_extract), bool (falses then trues), mutex (by row id) — ascending or `sort-desc`, then offset / limit.  The
+        reference merges per-shard lists in arrival order, so its order among equal values is unspecified; here ties keep
+        ascending column order.  Returns [(column, value)]."""
+        name = c.args.get("field", c.args.get("_field"))
+        if name is None:
+            raise QueryError("getting field: Sort(): field required")
+        if len(c.children) != 1:
+            raise QueryError("Sort() requires a single bitmap input")
+        f = self._field(idx, name)
+        desc = bool(c.args.get("sort-desc", False))
+        filt = self._bitmap_call(idx, c.children[0])
+        if f.type == "int":
+            cols, vals, _ = self.ctx.extract(idx.id, f.id, VIEW_BSI, min(f.bit_depth, 63), shards, filter_ops=filt)
+            kvs = [(int(col), int(v) + f.base) for col, v in zip(cols.tolist(), vals.tolist())]
+        elif f.type in ("bool", "mutex"):
+            kvs = []
+            rid, _ = self.ctx.row_counts(idx.id, f.id, VIEW_STANDARD, shards, filter_ops=filt)
+            for r in sorted(int(x) for x in rid):
+                ops = filt + [L.Op(L.OP_ROW, f.id, VIEW_STANDARD, 0, r, 0, 0, 0), L.Op(L.OP_INTERSECT, 0, 0, 2, 0, 0, 0, 0)]
+                kvs += [(int(col), (r == 1) if f.type == "bool" else r) for col in self.ctx.columns(idx.id, ops, shards)[0].tolist()]
+        else:
+            raise QueryError(f"Sort of field type {f.type} not implemented yet")
+        kvs.sort(key=lambda kv: (-kv[1] if desc else kv[1], kv[0]))
+        off = int(c.args.get("offset", 0))
+        kvs = kvs[off:]
+        lim = c.args.get("limit")
+        return kvs[:int(lim)] if lim is not None else kvs
 
     def _percentile(self, idx, c, shards):
         """executePercentile :1310-1600 (int fields): total = Count(filter ∩ notNull); the wanted numbers of smaller / larger

@@ -88,6 +88,7 @@ def test_various_queries(oracle_backed):
     E.test_columns_entry_point()
     E.test_extract_entry_point()
     E.test_extract_table_golden()
+    E.test_sort_goldens()
     E.test_topk_time_range()
     E.test_arena_compaction()
 

@@ -706,6 +706,32 @@ def test_extract_table_golden():
         p.ex.execute("i", "Extract()")
 
 
+def test_sort_goldens():
+    """executor_test.go:4298-4390 TestExecutor_Sort (the key-translated mutex replaced by an id mutex): Sort by an int / bool /
+    mutex field with limit, offset and sort-desc, alone and as Extract's column source"""
+    p = Pair()
+    p.field("bsint", "int")
+    p.field("bool", "bool")
+    p.field("mutex", "mutex")
+    for col, v in enumerate((1, -1, 2, -2, 3, 4)):
+        p.holder.set_value("i", "bsint", col, v)
+    for col, v in enumerate((True, False, False, True, False, True)):
+        p.holder.set_bit("i", "bool", 1 if v else 0, col)
+    for col, r in enumerate((8, 26, 18, 16, 23, 9)):              # "h", "xyzzy", "ra", "plugh", "wl", "ig" by first letter
+        p.holder.set_bit("i", "mutex", r, col)
+    p.sync_pending()
+    run = lambda q: p.ex.execute("i", q)[0]
+    assert run("Extract(Sort(Row(bsint > 1), field = bsint, limit = 2, offset = 1), Rows(bsint))") == {"fields": [("bsint", "int64")], "columns": [(4, [3]), (5, [4])]}
+    assert run("Extract(Sort(Row(bsint < -1), field = bool, limit = 1, sort-desc = true), Rows(bool))") == {"fields": [("bool", "bool")], "columns": [(3, [True])]}
+    assert run("Extract(Sort(All(), field = mutex, limit = 1), Rows(mutex))") == {"fields": [("mutex", "uint64")], "columns": [(0, [8])]}
+    assert run("Sort(All(), field=bsint)") == [(3, -2), (1, -1), (0, 1), (2, 2), (4, 3), (5, 4)]
+    assert run("Sort(All(), field=bsint, sort-desc=true, limit=3)") == [(5, 4), (4, 3), (2, 2)]
+    assert run("Sort(All(), field=bool)") == [(1, False), (2, False), (4, False), (0, True), (3, True), (5, True)]
+    assert run("Sort(Row(bsint > 0), field=mutex, sort-desc=true)") == [(4, 23), (2, 18), (5, 9), (0, 8)]
+    with pytest.raises(X.QueryError, match="not implemented"):
+        p.ex.execute("i", "Sort(All(), field=_exists)")
+
+
 def test_various_queries_goldens():
     """executor_test.go:8560-8990 populateTestData / variousQueries with the keys replaced by ids in order of first use (key
     translation is outside the path): Distinct on set and int fields, Count(Distinct), GroupBy over time-range rows, with
