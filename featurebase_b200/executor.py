@@ -299,6 +299,25 @@ class Executor:
                 return self._extract(idx, c, shards)
             if c.name == "Sort":
                 return self._sort(idx, c, shards)
+            if c.name == "FieldValue":                           # executeFieldValueCall :943: the int value of one column, ValCount(value, 1)
+                name = c.args.get("field")
+                if not name:
+                    raise QueryError("field required")
+                if c.args.get("column") in (None, ""):
+                    raise QueryError("column required")
+                f = self._field(idx, name)
+                if f.type != "int":
+                    raise QueryError(f"field {name} is not an int field")
+                col = int(c.args["column"])
+                ef, erow = self.holder.embed_row(idx.name, [col])
+                _, vals, n = self.ctx.extract(idx.id, f.id, VIEW_BSI, min(f.bit_depth, 63), [col // SHARD_WIDTH],
+                                              filter_ops=[L.Op(L.OP_ROW, ef.id, VIEW_STANDARD, 0, erow, 0, 0, 0)])
+                return ValCount(int(vals[0]) + f.base, 1) if n else ValCount()
+            if c.name == "Options":                              # executeOptionsCall :869: shards=[..] narrows the shard list of the child call
+                if len(c.children) != 1:
+                    raise QueryError("Options() requires a single child call")
+                sh = c.args.get("shards")
+                return self._execute_call(idx, c.children[0], shards if sh is None else sorted(int(x) for x in sh))
             if c.name == "IncludesColumn":                       # executeIncludesColumnCall: is the column in the row?
                 if "column" not in c.args:
                     raise QueryError("IncludesColumn call must specify a column")

@@ -89,6 +89,7 @@ def test_various_queries(oracle_backed):
     E.test_extract_entry_point()
     E.test_extract_table_golden()
     E.test_sort_goldens()
+    E.test_field_value_and_options()
     E.test_topk_time_range()
     E.test_arena_compaction()
 

@@ -732,6 +732,31 @@ def test_sort_goldens():
         p.ex.execute("i", "Sort(All(), field=_exists)")
 
 
+def test_field_value_and_options():
+    """executor_test.go:4066-4123 FieldValue (int cases) and :820-830 Options(shards=)"""
+    SW = 1 << 20
+    p = Pair()
+    p.field("f", "int", min=-1100, max=1000)
+    p.field("s")
+    for col, v in ((1, 3), (2, -4), (SW + 1, 3)):
+        p.holder.set_value("i", "f", col, v)
+    for col in (100, SW, 2 * SW):
+        p.holder.set_bit("i", "s", 10, col)
+    p.sync_pending()
+    run = lambda q: p.ex.execute("i", q)[0]
+    for q, exp in (("FieldValue(field=f, column=1)", 3), ("FieldValue(field=f, column=2)", -4), (f"FieldValue(field=f, column={SW + 1})", 3)):
+        vc = run(q)
+        assert (vc.val, vc.count) == (exp, 1), q
+    vc = run("FieldValue(field=f, column=7)")
+    assert (vc.val, vc.count) == (0, 0)
+    for q, msg in (("FieldValue()", "field required"), ("FieldValue(field=f)", "column required")):
+        with pytest.raises(X.QueryError, match=msg):
+            run(q)
+    assert [int(c) for c in run("Options(Row(s=10), shards=[0, 2])").columns()] == [100, 2 * SW]
+    assert run("Options(Count(Row(s=10)), shards=[1])") == 1
+    assert [int(c) for c in run("Options(Row(s=10))").columns()] == [100, SW, 2 * SW]
+
+
 def test_various_queries_goldens():
     """executor_test.go:8560-8990 populateTestData / variousQueries with the keys replaced by ids in order of first use (key
     translation is outside the path): Distinct on set and int fields, Count(Distinct), GroupBy over time-range rows, with
