@@ -1,7 +1,8 @@
 #!/bin/bash
-# First GPU call of round 2 (one gpurun invocation, ~10 GPU-minutes): run everything that was written after round 1's
-# GPU budget was spent, and measure the two pending performance changes.  Results land in gpurun_out/r2_first/.
-#   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/r2_first_call.sh'
+# First GPU call of round 2 (one gpurun invocation, about 25 GPU-minutes): run everything that was written after round 1's
+# GPU budget was spent, and measure every pending performance change (one A/B each).  Results land in gpurun_out/r2_first/.
+#   /usr/local/graft/bin/gpurun --timeout 2700 -- 'bash tools/r2_first_call.sh'
+# If the budget is tight, the sections are independent: comment out from the bottom up.
 set -u
 out=gpurun_out/r2_first; mkdir -p $out
 python -c "import __graft_entry__ as g; g.build()" > $out/build.log 2>&1
