@@ -507,6 +507,13 @@ def test_random_call_trees_differential():
         p.load("m", X.VIEW_STANDARD, s, merged.to_bytes())
         p.load("v", X.VIEW_BSI, s, D.bsi_fragment(12, s, 300000, p.idx.fields["v"].bit_depth, -600, 600, base=0, null_frac=0.2))
         p.load(X.EXISTENCE_FIELD, X.VIEW_STANDARD, s, D.fragment(13, s, [0], 0.7))
+    from tests.oracle_ctx import OracleCtx
+    twin = OracleCtx()                                             # the same fragments, for the value-level entry points
+    vf = p.idx.fields["v"]
+    for s in (0, 1, 4):
+        twin.load_fragment(p.idx.id, vf.id, X.VIEW_BSI, s, p.ora.frag("v", X.VIEW_BSI, s).to_bytes())
+        twin.load_fragment(p.idx.id, p.idx.fields["m"].id, X.VIEW_STANDARD, s, p.ora.frag("m", X.VIEW_STANDARD, s).to_bytes())
+        twin.load_fragment(p.idx.id, p.idx.fields[X.EXISTENCE_FIELD].id, X.VIEW_STANDARD, s, p.ora.frag(X.EXISTENCE_FIELD, X.VIEW_STANDARD, s).to_bytes())
     n_checked = 0
     for i in range(int(os.environ.get("FBGPU_FUZZ_TREES", "120"))):
         q = _random_call(rng, 3)
@@ -516,6 +523,14 @@ def test_random_call_trees_differential():
             else:
                 p.check_count(f"Count({q})")
             n_checked += 1
+            if i % 8 == 0:                                         # the row as a filter of the value-level entry points
+                ops = p.ex._bitmap_call(p.idx, pql.parse(q)[0])
+                args = (p.idx.id, vf.id, X.VIEW_BSI, vf.bit_depth, p.shards())
+                got, exp = p.holder.ctx.extract(*args, filter_ops=ops), twin.extract(*args, filter_ops=ops)
+                assert got[2] == exp[2] and np.array_equal(got[0], exp[0]) and np.array_equal(got[1], exp[1]), q
+                assert p.holder.ctx.bsi_sum(*args, filter_ops=ops) == twin.bsi_sum(*args, filter_ops=ops), q
+                for want_max in (False, True):
+                    assert p.holder.ctx.bsi_minmax(*args, want_max, filter_ops=ops) == twin.bsi_minmax(*args, want_max, filter_ops=ops), q
         except X.QueryError as e:                                  # both sides refuse the same calls (empty Intersect(), > 15 operands deep)
             assert "not supported" in str(e) or "stack depth" in str(e), (q, e)
     assert n_checked > 80
