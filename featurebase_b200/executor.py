@@ -8,6 +8,8 @@ post-order fbgpu_op program and hands the whole shard batch to libfbgpu (one C-A
 In a real integration this layer stays in Go; it exists here because the Go toolchain is absent
 and the parity tests should read like the reference's executor tests.  All reference cites are executor.go unless
 noted."""
+import math
+
 import numpy as np
 
 from . import lib as L
@@ -525,11 +527,22 @@ class Executor:
     # ------------------------------------------------------------------ TopN / TopK (exact modes)
     def _topn(self, idx, c, shards):                             # executeTopN :2779 with ids / second pass semantics
         f = self._field(idx, c.args["_field"])
+        if f.type in ("int", "decimal", "timestamp"):            # executeTopNShard :2876
+            raise QueryError(f'cannot compute TopN() on integer, decimal, or timestamp field: "{f.name}"')
+        if len(c.children) > 1:
+            raise QueryError("TopN() can only have one input bitmap")
         n = int(c.args.get("n", 0))
+        thr = int(c.args.get("threshold", 0)) or 1               # defaultMinThreshold = 1 (:2917-2919)
+        tan = int(c.args.get("tanimotoThreshold", 0))
+        if tan > 100:
+            raise QueryError("Tanimoto Threshold is from 1 to 100 only")
         filt = self._bitmap_call(idx, c.children[0]) if c.children else None
         ids = c.args.get("ids")
         if ids is not None:
             ids = sorted(int(i) for i in ids)
+        if thr > 1 or (tan > 0 and filt is not None):            # per-shard cut-offs of fragment.top (fragment.go:1329-1388)
+            pairs = self._topn_cutoffs(idx, f, filt, ids, thr, tan, shards)
+        elif ids is not None:
             src = c.children[0] if c.children else None
             src_key = [k for k in src.args if not k.startswith("_")] if src is not None and src.name == "Row" else []
             if src_key and not isinstance(src.args[src_key[0]], pql.Condition) and self._field(idx, src_key[0]).type != "int":
@@ -543,7 +556,46 @@ class Executor:
         else:
             rid, cnt = self.ctx.row_counts(idx.id, f.id, VIEW_STANDARD, shards, filter_ops=filt)
             pairs = [(int(i), int(k)) for i, k in zip(rid, cnt)]
+        if ids is not None:                                      # explicit ids: the result is never truncated (:2802-2807, fragment.go:1325)
+            return pairs
         return pairs[:n] if n else pairs
+
+    def _topn_cutoffs(self, idx, f, filt, ids, thr, tan, shards):
+        """TopN with threshold= / tanimotoThreshold=: fragment.top applies its cut-offs per shard — on the row's own count `cnt`
+        in that shard, then on `count` = |Src ∩ row| there (MinThreshold :1357-1362,1384-1388; Tanimoto band and coefficient
+        :1329-1338,1351-1356,1378-1383) — and only what passes is summed across shards (Pairs.Add, executeTopNShards :2845).
+        So the counts are fetched shard by shard from the same entry points (a slow path: one fbgpu_row_counts call, two with
+        a Src, per shard; the Src counts of all shards come from one fbgpu_count).  Candidates: `ids`, else every row of the
+        field (what the internal second pass asks for when the first pass missed nothing)."""
+        if ids is None:
+            rid, _ = self.ctx.row_counts(idx.id, f.id, VIEW_STANDARD, shards)
+            ids = sorted(int(r) for r in rid)
+        if not ids:
+            return []
+        use_tan = tan > 0 and filt is not None
+        src_counts = self.ctx.count(idx.id, filt, shards, per_shard=True)[1] if use_tan else None
+        total = np.zeros(len(ids), dtype=np.uint64)
+        for k, s in enumerate(shards):
+            cnt = np.asarray(self.ctx.row_counts(idx.id, f.id, VIEW_STANDARD, [s], row_ids=ids), dtype=np.uint64)
+            if not cnt.any():
+                continue
+            count = np.asarray(self.ctx.row_counts(idx.id, f.id, VIEW_STANDARD, [s], row_ids=ids, filter_ops=filt), dtype=np.uint64) if filt is not None else cnt
+            for j in range(len(ids)):
+                cj, kj = int(cnt[j]), int(count[j])
+                if cj == 0 or kj == 0:
+                    continue
+                if use_tan:
+                    sc = int(src_counts[k])
+                    if float(cj) <= float(sc * tan) / 100 or float(cj) >= float(sc * 100) / float(tan):
+                        continue
+                    if math.ceil(float(kj * 100) / float(cj + sc - kj)) <= float(tan):
+                        continue
+                elif cj < thr or kj < thr:
+                    continue
+                total[j] += np.uint64(kj)
+        pairs = [(i, int(k)) for i, k in zip(ids, total) if k > 0]
+        pairs.sort(key=lambda p: (-p[1], p[0]))
+        return pairs
 
     def _topk(self, idx, c, shards):                             # executeTopK :2357, doTopK :2705
         f = self._field(idx, c.args["_field"])

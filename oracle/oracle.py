@@ -363,6 +363,60 @@ def bsi_max(frag, bit_depth, filt=None, shard=0):
     return _bsi_max_unsigned(frag, pos, bit_depth, shard)
 
 
+def fragment_top(frag, shard=0, n=0, src=None, row_ids=None, min_threshold=0, tanimoto_threshold=0):
+    """fragment.top (fragment.go:1317-1437) over one fragment whose rank cache holds every row (the exact case, SURVEY
+    Appendix D): candidates = rows with a non-zero count, largest first (topBitmapPairs :1439-1480; ties pinned id ascending);
+    cut-offs on the row's own count `cnt` and on `count` = |Src ∩ row| by MinThreshold or by the Tanimoto band / coefficient
+    (:1329-1338, 1351-1362, 1378-1388); the first N pairs go to a min-heap, later rows only while their `cnt` can still
+    beat the smallest kept count (:1401-1421).  Returns [(row, count)], count descending, ties id ascending."""
+    import heapq
+    import math
+    rows, cnts = frag.row_counts(shard)
+    pairs = [(int(r), int(c)) for r, c in zip(rows.tolist(), cnts.tolist()) if c > 0]
+    if row_ids is not None and len(row_ids) > 0:
+        have = dict(pairs)
+        pairs = [(int(r), have[int(r)]) for r in row_ids if int(r) in have]
+        n = 0                                                    # :1325-1327 ids given: no truncation
+    pairs.sort(key=lambda p: (-p[1], p[0]))
+    tan = 0
+    src_count = 0
+    if tanimoto_threshold > 0 and src is not None:
+        tan = int(tanimoto_threshold)
+        src_count = src.count()
+        min_tan = float(src_count * tan) / 100
+        max_tan = float(src_count * 100) / float(tan)
+    heap = []                                                    # pairHeap: min-heap on Count (cache.go:395-431)
+    for row, cnt in pairs:
+        if tan > 0:
+            if float(cnt) <= min_tan or float(cnt) >= max_tan:
+                continue
+        elif cnt < min_threshold:
+            continue
+        if n == 0 or len(heap) < n:
+            count = cnt
+            if src is not None:
+                count = src.intersection_count(frag.row(row, shard))
+            if count == 0:
+                continue
+            if tan > 0:
+                if math.ceil(float(count * 100) / float(cnt + src_count - count)) <= float(tan):
+                    continue
+            elif count < min_threshold:
+                continue
+            heapq.heappush(heap, (count, row))
+            if n > 0 and len(heap) == n and src is None:
+                break
+            continue
+        threshold = heap[0][0]
+        if threshold < min_threshold or cnt < threshold:
+            break
+        count = src.intersection_count(frag.row(row, shard))
+        if count < threshold:
+            continue
+        heapq.heappush(heap, (count, row))
+    return sorted(((r, c) for c, r in heap), key=lambda p: (-p[1], p[0]))
+
+
 def groupby_shard(frags, shard, row_ids, filt=None, out=None):
     """frags: list of Bitmap-or-None; row_ids: list of lists; returns dense count array (row-major)."""
     n_rows = np.asarray([len(r) for r in row_ids], dtype=np.int32)

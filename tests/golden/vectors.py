@@ -174,6 +174,20 @@ FRAG_TOP_CASES = [
     ({100: [1, 3, 2, 200], 101: [1, 3], 102: [1, 2, 10, 12]}, [1, 2, 3], 0, None, [(100, 3), (101, 2), (102, 2)]),
 ]
 
+# fragment.top with cut-offs: fragment_internal_test.go:1490-1511 (TestFragment_Tanimoto: threshold 50, Src = columns 1,2,3 ->
+# rows 100 (coefficient 75) and 101 (67) stay, 102 (40) goes) and :1514-1537 (threshold 0 == no cut-off).  The MinThreshold
+# rows are worked from fragment.go:1357-1362,1384-1388 on the same bits (cnt = 4, 2, 4; |Src ∩ row| = 3, 2, 2).
+# (rows, Src columns or None, n, ids or None, MinThreshold, TanimotoThreshold, expected pairs)
+FRAG_TOP_THRESHOLD_ROWS = {100: [1, 3, 2, 200], 101: [1, 3], 102: [1, 2, 10, 12]}
+FRAG_TOP_THRESHOLD_CASES = [
+    (FRAG_TOP_THRESHOLD_ROWS, [1, 2, 3], 0, None, 0, 50, [(100, 3), (101, 2)]),
+    (FRAG_TOP_THRESHOLD_ROWS, [1, 2, 3], 0, None, 0, 0, [(100, 3), (101, 2), (102, 2)]),
+    (FRAG_TOP_THRESHOLD_ROWS, None, 0, None, 3, 0, [(100, 4), (102, 4)]),                 # cnt < MinThreshold: row 101 out
+    (FRAG_TOP_THRESHOLD_ROWS, [1, 2, 3], 0, None, 3, 0, [(100, 3)]),                      # 101 out on cnt, 102 out on |Src ∩ row| = 2
+    (FRAG_TOP_THRESHOLD_ROWS, [1, 2, 3], 0, [100, 101, 102], 2, 0, [(100, 3), (101, 2), (102, 2)]),
+    (FRAG_TOP_THRESHOLD_ROWS, None, 0, None, 0, 50, [(100, 4), (102, 4), (101, 2)]),      # Tanimoto without Src: ignored (:1333)
+]
+
 # ---------------------------------------------------------------------------------------------------
 # roaring/filter_internal_test.go:24-41 sample fragment: for every slot i in 1..15 the column (i << 16) + i is set in
 # rows 0, i, 2i, ... < 100.  :78-86 TestBaseFilter (all rows 0..99 present), :88-99 TestColumnFilter (rows holding

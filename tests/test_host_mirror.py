@@ -58,6 +58,8 @@ def test_bsi_aggregates(oracle_backed):
 
 def test_fragment_top_goldens(oracle_backed):
     E.test_fragment_top_goldens()
+    E.test_topn_cutoff_goldens()
+    E.test_topn_cutoffs_random()
     E.test_filter_sample_goldens()
 
 

@@ -411,6 +411,42 @@ def test_bsi_aggregates_vs_naive():
             assert O.bsi_max(frag, depth, f) == ((max(vs), vs.count(max(vs))) if vs else (0, 0))
 
 
+def _top_fragment(rows):
+    if rows == "large":
+        pos = np.concatenate([np.uint64(i << 20) + np.arange(i, dtype=np.uint64) for i in range(1, 1000)])
+    else:
+        pos = np.array([(r << 20) + c for r, cols in rows.items() for c in cols], dtype=np.uint64)
+    return O.Bitmap.from_values(pos)
+
+
+def test_fragment_top_goldens():
+    """fragment.top restatement (oracle.fragment_top) against fragment_internal_test.go:1150-1272 (Top / TopN_Intersect /
+    TopN_Intersect_Large / TopN_IDs) and :1490-1537 (Tanimoto, Zero_Tanimoto), plus MinThreshold rows worked by hand"""
+    for rows, src, n, ids, exp in V.FRAG_TOP_CASES:
+        got = O.fragment_top(_top_fragment(rows), 0, n=n, src=O.Bitmap.from_values(src) if src else None, row_ids=ids)
+        assert got == exp, (rows if rows == "large" else sorted(rows), src, n, ids, got)
+    for rows, src, n, ids, thr, tan, exp in V.FRAG_TOP_THRESHOLD_CASES:
+        got = O.fragment_top(_top_fragment(rows), 0, n=n, src=O.Bitmap.from_values(src) if src else None, row_ids=ids,
+                             min_threshold=thr, tanimoto_threshold=tan)
+        assert got == exp, (src, n, ids, thr, tan, got)
+
+
+def test_fragment_top_heap_truncation():
+    """N > 0 with a Src: the first N candidates (by the row's own count) seed the heap, a later row enters only if its own count
+    and its intersection reach the smallest kept count, and the walk stops at the first row whose own count is below it
+    (fragment.go:1401-1421) -- so the result may hold more than N pairs, and a row with a small own count is never looked at."""
+    rows = {1: list(range(0, 10)), 2: list(range(5, 14)), 3: list(range(20, 28)), 4: [0, 1, 2, 3, 4, 5, 6], 5: [0, 1]}
+    src = O.Bitmap.from_values(list(range(0, 7)))
+    fr = _top_fragment(rows)
+    # candidates by own count: 1 (10), 2 (9), 3 (8), 4 (7), 5 (2).  n = 2: heap = {1: 7, 2: 2}; row 3: cnt 8 >= 2, count 0 < 2 skip;
+    # row 4: cnt 7 >= 2, count 7 >= 2 pushed; row 5: cnt 2 >= 2, count 2 >= 2 pushed
+    assert O.fragment_top(fr, 0, n=2, src=src) == [(1, 7), (4, 7), (2, 2), (5, 2)]
+    # n = 1: heap = {1: 7}; rows 2, 3: count < 7 skipped; row 4: cnt 7 >= 7, count 7 pushed; row 5: cnt 2 < 7 -> stop
+    assert O.fragment_top(fr, 0, n=1, src=src) == [(1, 7), (4, 7)]
+    # no Src: stops as soon as N pairs are in
+    assert O.fragment_top(fr, 0, n=3) == [(1, 10), (2, 9), (3, 8)]
+
+
 def test_filter_sample_goldens():
     """roaring/filter_internal_test.go:78-138 on the oracle's row discovery / filtered row counts / row unions"""
     SW = H.SW

@@ -199,6 +199,7 @@ def test_executor_bodies_through_library_compiler_and_store(monkeypatch):
     E.test_rbf_loader_matches_fragment_loader()
     E.test_bsi_aggregate_goldens()
     E.test_fragment_top_goldens()
+    E.test_topn_cutoff_goldens()
     E.test_filter_sample_goldens()
     E.test_groupby_postprocessing_goldens()
     E.test_shift_and_includes_column()
