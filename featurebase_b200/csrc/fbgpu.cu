@@ -161,6 +161,10 @@ struct fbgpu_ctx {
     bool inspect_only = false;           // created with FBGPU_DEVICE_NONE: residency + fbgpu_debug_container only, no device, no queries
     std::vector<ViewTab> t_views; std::vector<int32_t> t_flat; std::vector<RowTabEnt> t_rowtab;   // inspect_only: the tables a commit would upload
     bool stripe_arrays = getenv("FBGPU_ARRAY_STRIPED") != nullptr;   // experimental payload order, see stripe.h (fixed per context)
+    // (shard, slot) units whose result bitmaps are materialised per launch by the row-returning / aggregate / filtered entry
+    // points: 16384 units = 1024 shards = 128 MiB of workspace per lease.  FBGPU_UNIT_BATCH (a multiple of 16, fixed per
+    // context) trades workspace for launches; the tests set it small to walk the multi-batch paths with a handful of shards.
+    long long unit_batch = [] { const char* e = getenv("FBGPU_UNIT_BATCH"); const long long n = e ? atoll(e) : 0; return n >= 16 ? (n / 16) * 16 : 16384ll; }();
     DevBuf d_payload, d_views, d_shardmap, d_frags, d_rows, d_descs, d_rowtab;
     PinBuf bounce[2];
     uint32_t n_views_dev = 0;
@@ -795,8 +799,6 @@ extern "C" int fbgpu_count(fbgpu_ctx* c, uint32_t index, const fbgpu_op* ops, in
 } FBGPU_CATCH
 
 // ------------------------------------------------------------------ Row (canonical Pilosa-roaring result)
-static constexpr long long kUnitBatch = 16384;   // 128 MiB of result bitmaps per batch
-
 extern "C" int fbgpu_row(fbgpu_ctx* c, uint32_t index, const fbgpu_op* ops, int32_t n_ops, const uint64_t* shards, int64_t n_shards,
                          uint8_t* out_buf, uint64_t out_cap, uint64_t* out_len, uint64_t* out_count) try {
     if (!c || !out_len || n_shards < 0 || (n_shards && !shards)) return fail(FBGPU_E_INVALID, "null argument");
@@ -816,9 +818,13 @@ extern "C" int fbgpu_row(fbgpu_ctx* c, uint32_t index, const fbgpu_op* ops, int3
     long long n_units = (long long)n_shards * kSlotsPerRow;
     struct OutCont { uint64_t key; uint16_t typ; uint32_t n; uint64_t size; uint32_t batch; uint64_t src_off; };
     std::vector<OutCont> conts; std::vector<std::vector<uint8_t>> batch_bufs;   // one host copy of the emitted payloads per batch
+    // a single batch (<= 1024 shards, the usual call) needs no such copy: its payloads are assembled straight from the pinned
+    // D2H landing buffer, which stays leased until this function returns
+    const bool single_batch = n_units <= c->unit_batch;
+    const uint8_t* single_src = nullptr;
     uint64_t total_count = 0; uint64_t launches = 0; float ms_total = 0;
-    for (long long u0 = 0; u0 < n_units; u0 += kUnitBatch) {
-        long long nu = std::min(kUnitBatch, n_units - u0);
+    for (long long u0 = 0; u0 < n_units; u0 += c->unit_batch) {
+        long long nu = std::min(c->unit_batch, n_units - u0);
         if (w->d_bitmaps.ensure((size_t)nu * 8192)) return FBGPU_E_NOMEM;
         if (w->d_info.ensure((size_t)nu * 8)) return FBGPU_E_NOMEM;
         if (w->h_out.ensure((size_t)nu * 8)) return FBGPU_E_NOMEM;
@@ -858,7 +864,8 @@ extern "C" int fbgpu_row(fbgpu_ctx* c, uint32_t index, const fbgpu_op* ops, int3
             CUDA_TRY(cudaMemcpyAsync(w->h_in.p, w->d_emit.p, off, cudaMemcpyDeviceToHost, w->stream));
             CUDA_TRY(cudaEventRecord(w->ev1, w->stream));
             CUDA_TRY(cudaStreamSynchronize(w->stream));
-            batch_bufs.emplace_back((uint8_t*)w->h_in.p, (uint8_t*)w->h_in.p + off);
+            if (single_batch) { single_src = (const uint8_t*)w->h_in.p; batch_bufs.emplace_back(); }
+            else batch_bufs.emplace_back((uint8_t*)w->h_in.p, (uint8_t*)w->h_in.p + off);
             float ms = 0; cudaEventElapsedTime(&ms, w->ev0, w->ev1); ms_total += ms;
         }
     }
@@ -868,15 +875,34 @@ extern "C" int fbgpu_row(fbgpu_ctx* c, uint32_t index, const fbgpu_op* ops, int3
     for (auto& oc : conts) need += oc.size;
     *out_len = need;
     if (out_count) *out_count = total_count;
+    if (need > 0xffffffffull) return fail(FBGPU_E_INVALID, "result of %llu bytes exceeds the 32-bit container offsets of the Pilosa roaring format (roaring.go:1790-1800); query fewer shards per call", (unsigned long long)need);
     if (need > out_cap || !out_buf) return fail(FBGPU_E_NOSPACE, "output needs %llu bytes", (unsigned long long)need);
     uint32_t cookie = 12348, cnt = (uint32_t)conts.size();
     memcpy(out_buf, &cookie, 4); memcpy(out_buf + 4, &cnt, 4);
+    // header + offset table serially (12 + 4 bytes per container); the payload copies are split over a few host threads when
+    // the result is large (one thread moves ~10 GB/s; an 85 MB union of rows otherwise spends most of its time here)
     uint8_t *h = out_buf + 8, *offp = out_buf + 8 + conts.size() * 12; uint64_t off = 8 + conts.size() * 16;
-    for (auto& oc : conts) {
+    std::vector<uint64_t> dst_off(conts.size());
+    for (size_t i = 0; i < conts.size(); i++) {
+        const OutCont& oc = conts[i];
         uint16_t n1 = (uint16_t)(oc.n - 1);
         memcpy(h, &oc.key, 8); memcpy(h + 8, &oc.typ, 2); memcpy(h + 10, &n1, 2); h += 12;
         uint32_t o32 = (uint32_t)off; memcpy(offp, &o32, 4); offp += 4;
-        memcpy(out_buf + off, batch_bufs[oc.batch].data() + oc.src_off, oc.size); off += oc.size;
+        dst_off[i] = off; off += oc.size;
+    }
+    auto copy_range = [&](size_t lo, size_t hi) {
+        for (size_t i = lo; i < hi; i++) {
+            const OutCont& oc = conts[i];
+            const uint8_t* src = single_batch ? single_src : batch_bufs[oc.batch].data();
+            memcpy(out_buf + dst_off[i], src + oc.src_off, oc.size);
+        }
+    };
+    const int n_threads = (int)std::min<uint64_t>({ (uint64_t)std::max(1u, std::thread::hardware_concurrency()), 8ull, need / (8ull << 20) + 1 });
+    if (n_threads <= 1) copy_range(0, conts.size());
+    else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < n_threads; t++) th.emplace_back(copy_range, conts.size() * t / n_threads, conts.size() * (t + 1) / n_threads);
+        for (auto& t : th) t.join();
     }
     lease.ok = true;
     return FBGPU_OK;
@@ -900,8 +926,8 @@ static int columns_impl(fbgpu_ctx* c, uint32_t index, const fbgpu_op* ops, int32
     const long long n_units = (long long)n_shards * kSlotsPerRow;
     const uint64_t win_end = limit < 0 ? ~0ull : (offset + (uint64_t)limit < offset ? ~0ull : offset + (uint64_t)limit);
     uint64_t seen = 0, written = 0, launches = 0; float ms_total = 0;
-    for (long long u0 = 0; u0 < n_units; u0 += kUnitBatch) {
-        const long long nu = std::min(kUnitBatch, n_units - u0);
+    for (long long u0 = 0; u0 < n_units; u0 += c->unit_batch) {
+        const long long nu = std::min(c->unit_batch, n_units - u0);
         if (w->d_bitmaps.ensure((size_t)nu * 8192) || w->d_info.ensure((size_t)nu * 8) || w->h_out.ensure((size_t)nu * 8)) return FBGPU_E_NOMEM;
         EvalOut eo{ nullptr, nullptr, (uint4*)w->d_bitmaps.p, (uint2*)w->d_info.p, FuseReduce{} };
         CUDA_TRY(cudaEventRecord(w->ev0, w->stream));
@@ -1006,8 +1032,8 @@ extern "C" int fbgpu_bsi_minmax(fbgpu_ctx* c, uint32_t index, const fbgpu_op* op
     rc = upload_inputs(w, prog, shards, n_shards, &d_prog, &d_shards); if (rc) return rc;
     const long long n_units = (long long)n_shards * kSlotsPerRow;
     bool have = false; int64_t best = 0; uint64_t best_n = 0; uint64_t launches = 0; float ms_total = 0;
-    for (long long u0 = 0; u0 < n_units; u0 += kUnitBatch) {
-        const long long nu = std::min(kUnitBatch, n_units - u0);
+    for (long long u0 = 0; u0 < n_units; u0 += c->unit_batch) {
+        const long long nu = std::min(c->unit_batch, n_units - u0);
         if (w->d_bitmaps.ensure((size_t)nu * 8192) || w->d_counts.ensure((size_t)nu * sizeof(MinMaxUnit)) || w->h_out.ensure((size_t)nu * sizeof(MinMaxUnit))) return FBGPU_E_NOMEM;
         EvalOut eo{ nullptr, nullptr, (uint4*)w->d_bitmaps.p, nullptr, FuseReduce{} };
         CUDA_TRY(cudaEventRecord(w->ev0, w->stream));
@@ -1056,8 +1082,8 @@ extern "C" int fbgpu_bsi_sum(fbgpu_ctx* c, uint32_t index, const fbgpu_op* ops, 
     CUDA_TRY(cudaMemsetAsync(w->d_counts.p, 0, n_acc * 8, w->stream));
     uint64_t launches = 0;
     CUDA_TRY(cudaEventRecord(w->ev0, w->stream));
-    for (long long u0 = 0; u0 < n_units; u0 += kUnitBatch) {
-        const long long nu = std::min(kUnitBatch, n_units - u0);
+    for (long long u0 = 0; u0 < n_units; u0 += c->unit_batch) {
+        const long long nu = std::min(c->unit_batch, n_units - u0);
         if (w->d_bitmaps.ensure((size_t)nu * 8192)) return FBGPU_E_NOMEM;
         EvalOut eo{ nullptr, nullptr, (uint4*)w->d_bitmaps.p, nullptr, FuseReduce{} };
         rc = launch_eval(c, w, prog, d_prog, depth, d_shards + u0 / kSlotsPerRow, nu, eo); if (rc) return rc;
@@ -1102,7 +1128,7 @@ static int row_counts_impl(fbgpu_ctx* c, uint32_t index, uint32_t fv, const std:
     CUDA_TRY(cudaMemsetAsync(w->d_counts.p, 0, nr * 8, w->stream));
     CUDA_TRY(cudaEventRecord(w->ev0, w->stream));
     uint64_t launches = 0;
-    const int64_t batch = have_filter ? 1024 : n_shards;
+    const int64_t batch = have_filter ? c->unit_batch / kSlotsPerRow : n_shards;
     for (int64_t s0 = 0; s0 < n_shards; s0 += batch) {
         int64_t ns = std::min(batch, n_shards - s0);
         if (have_filter) { rc = eval_filter_batch(c, w, prog, depth, d_prog, d_shards + s0, ns); if (rc) return rc; launches++; }
@@ -1215,7 +1241,7 @@ static int groupby2(fbgpu_ctx* c, uint32_t index, uint32_t fvA, const uint64_t* 
     CUDA_TRY(cudaStreamSynchronize(w->stream));   // rr is a local
     CUDA_TRY(cudaEventRecord(w->ev0, w->stream));
     uint64_t launches = 0;
-    const int64_t batch = have_filter ? 1024 : n_shards;
+    const int64_t batch = have_filter ? c->unit_batch / kSlotsPerRow : n_shards;
     const size_t smem = kGbSlots * 4 + 8192;
     for (int64_t s0 = 0; s0 < n_shards; s0 += batch) {
         int64_t ns = std::min(batch, n_shards - s0);

@@ -2,6 +2,7 @@
 a call fails, an exception is raised."""
 import ctypes as C
 import os
+import threading
 
 import numpy as np
 
@@ -12,6 +13,9 @@ OP_ROW, OP_INTERSECT, OP_UNION, OP_DIFFERENCE, OP_XOR, OP_NOT, OP_BSI_RANGE, OP_
 CMP = {"==": 1, "!=": 2, "<": 3, "<=": 4, ">": 5, ">=": 6, "><": 7}
 E_INVALID, E_QUERY, E_FORMAT, E_NOSPACE, E_CUDA, E_NOMEM, E_COMM = -1, -2, -3, -4, -5, -6, -7
 DEVICE_NONE = -1            # fbgpu_init(FBGPU_DEVICE_NONE): inspection-only context (no device, no queries)
+
+
+_row_tls = threading.local()
 
 
 class FbgpuError(RuntimeError):
@@ -213,21 +217,29 @@ class Context:
                                        per.ctypes.data if per_shard else None))
         return (tot.value, per) if per_shard else tot.value
 
-    def row(self, index, ops, shards):
-        """returns (pilosa roaring bytes, count)"""
+    def row_into(self, index, ops, shards, buf):
+        """fbgpu_row into a caller-owned uint8 array (what a Go caller with a reused buffer does): returns (bytes needed, count,
+        fits) — when `fits` is False nothing was written and `buf` must be at least `bytes needed` long"""
         sh = _u64arr(shards)
         arr = ops_array(ops)
         need, cnt = C.c_uint64(0), C.c_uint64(0)
-        cap = max(getattr(self, "_row_cap", 0), 1 << 20)
+        rc = self.L.fbgpu_row(self.h, index, arr, len(ops), sh.ctypes.data, len(sh), buf.ctypes.data, len(buf), C.byref(need), C.byref(cnt))
+        if rc == E_NOSPACE:
+            return need.value, cnt.value, False
+        self._check(rc)
+        return need.value, cnt.value, True
+
+    def row(self, index, ops, shards):
+        """returns (pilosa roaring bytes, count)"""
+        tls = _row_tls                                           # output buffer kept across calls, one per calling thread
+        buf = getattr(tls, "buf", None)                          # (its pages stay mapped; the library is re-entrant, a shared buffer is not)
+        if buf is None:
+            buf = tls.buf = np.empty(1 << 20, dtype=np.uint8)
         while True:
-            buf = np.empty(cap, dtype=np.uint8)
-            rc = self.L.fbgpu_row(self.h, index, arr, len(ops), sh.ctypes.data, len(sh), buf.ctypes.data, cap, C.byref(need), C.byref(cnt))
-            if rc == E_NOSPACE:
-                cap = int(need.value) + (int(need.value) >> 3)
-                continue
-            self._check(rc)
-            self._row_cap = cap
-            return buf[: need.value].tobytes(), cnt.value
+            need, cnt, fits = self.row_into(index, ops, shards, buf)
+            if fits:
+                return buf[:need].tobytes(), cnt
+            buf = tls.buf = np.empty(int(need) + (int(need) >> 3), dtype=np.uint8)
 
     def columns(self, index, ops, shards, offset=0, limit=None):
         """ascending column ids of the row (Row.Columns()), expanded on the device; offset / limit = executeLimitCall's window.

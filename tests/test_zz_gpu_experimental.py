@@ -1186,3 +1186,40 @@ def test_arena_compaction():
     ctx.compact()
     ctx.compact()                                                  # nothing dead: a no-op
     check()
+
+
+def test_multi_batch_paths(monkeypatch):
+    """FBGPU_UNIT_BATCH=16 (read when a context is created): one shard per launch, so the batch loops of fbgpu_row (payloads of
+    several batches assembled behind one header), fbgpu_columns / fbgpu_extract (a window that starts in one batch and ends in
+    another), fbgpu_bsi_sum / fbgpu_bsi_minmax (accumulators and the ValCount merge across batches) and the filtered
+    fbgpu_row_counts / fbgpu_groupby passes run with a handful of shards instead of more than 1024"""
+    monkeypatch.setenv("FBGPU_UNIT_BATCH", "16")
+    G.test_executor_goldens_and_edge_semantics()
+    G.test_topk_topn_rowcounts()
+    G.test_groupby_two_and_three_fields()
+    test_columns_entry_point()
+    test_extract_entry_point()
+    test_bsi_aggregate_goldens()
+    test_filter_sample_goldens()
+    test_topn_cutoffs_random()
+
+
+def test_row_result_threaded_assembly():
+    """a Row result above 8 MiB (72 shards of bitmap containers): fbgpu_row splits the payload copies into the caller's buffer over
+    several host threads; the bytes must still be the canonical serialisation.  Also with two batches behind one header."""
+    import featurebase_b200.datagen as D
+    for env in (None, "640"):                            # 640 units = 40 shards per batch
+        if env:
+            os.environ["FBGPU_UNIT_BATCH"] = env
+        try:
+            p = Pair(track_existence=False)
+            p.field("f")
+            shards = list(range(72))
+            bulk = D.fragments(5, np.asarray(shards, dtype=np.uint64), [0, 1], 0.5)
+            for s in shards:
+                p.load("f", X.VIEW_STANDARD, s, bulk.fragment_bytes(s))
+            got = p.check_row("Row(f=0)")
+            assert len(got.roaring) > (9 << 20)
+            p.check_row("Intersect(Row(f=0), Row(f=1))")
+        finally:
+            os.environ.pop("FBGPU_UNIT_BATCH", None)

@@ -84,7 +84,7 @@ def main():
     for d in rows:
         if d["config"] == "R":
             o.append(f"| `{d['query']}` | {d['ms']:.2f} | {d['result_bytes']:,} | {d['result_count']:,} |")
-    o.append("\nLarge results are dominated by host-side copies of the payload (D2H landing buffer -> per-batch buffer -> caller's buffer); a device-side prefix sum and direct D2H into the caller's buffer are the obvious next step.\n")
+    o.append("\nThese three were timed through the Python wrapper with a fresh output array per call: most of the time on large results was host-side — page faults of the fresh array and of a per-batch vector, and three passes over the payload (D2H landing buffer -> per-batch buffer -> caller's buffer -> `tobytes`).  Changed since, **not yet re-timed**: a single-batch call (<= 1024 shards) assembles straight from the pinned landing buffer into the caller's buffer, the payload copies of results above 8 MiB are split over up to 8 host threads, and `bench_sweep.py` config R now times `fbgpu_row` into a reused caller-owned buffer (what a Go caller does).  A device-side pack and D2H straight into a registered caller buffer are the next step.\n")
     o.append("## Written after the GPU budget was spent: no timing yet (round 2's first call, `tools/r2_first_call.sh`, measures each)\n")
     o.append("Kernel logic of every row has run against the oracle on the CPU kernel interpreter (`tests/emu/`, `tests/test_emu_kernels.py`); the default build's other kernels are byte-identical SASS to the measured ones.\n")
     o.append("| change | switch | targets | expectation (model, not a measurement) |")
