@@ -505,6 +505,18 @@ static void build_tables(fbgpu_ctx* c, std::vector<ViewTab>& views, std::vector<
     }
 }
 
+// memcpy split over a few host threads (one core moves ~10 GB/s, well below what the H2D DMA behind it takes)
+static void par_memcpy(void* dst, const void* src, size_t n) {
+    const int nt = (int)std::min<size_t>({ (size_t)std::max(1u, std::thread::hardware_concurrency()), (size_t)4, n / (4u << 20) + 1 });
+    if (nt <= 1) { memcpy(dst, src, n); return; }
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; t++) {
+        const size_t lo = (n * t / nt) & ~size_t(63), hi = t + 1 == nt ? n : (n * (t + 1) / nt) & ~size_t(63);
+        th.emplace_back([=] { memcpy((uint8_t*)dst + lo, (const uint8_t*)src + lo, hi - lo); });
+    }
+    for (auto& t : th) t.join();
+}
+
 static int commit_locked(fbgpu_ctx* c) {
     if (c->inspect_only) {                  // no device: keep the payload in the staging buffer and the tables on the host
         build_tables(c, c->t_views, c->t_flat, c->t_rowtab);
@@ -534,7 +546,7 @@ static int commit_locked(fbgpu_ctx* c) {
                 for (size_t off = 0; off < total; off += chunk, k ^= 1) {
                     size_t n = std::min(chunk, total - off);
                     if (off >= 2 * chunk) CUDA_TRY(cudaEventSynchronize(done[k]));       // bounce buffer k is free again
-                    memcpy(c->bounce[k].p, c->staging.p + off, n);
+                    par_memcpy(c->bounce[k].p, c->staging.p + off, n);
                     CUDA_TRY(cudaMemcpyAsync((uint8_t*)c->d_payload.p + c->uploaded + off, c->bounce[k].p, n, cudaMemcpyHostToDevice, st));
                     CUDA_TRY(cudaEventRecord(done[k], st));
                 }
@@ -579,7 +591,8 @@ static int compact_locked(fbgpu_ctx* c) {
     std::vector<HostFrag> frags; std::vector<FragHdr> hfr; std::vector<RowEnt> rows; std::vector<ContDesc> descs;
     struct Move { uint64_t from, to, len; };
     std::vector<Move> moves; uint64_t cur = 0;
-    for (auto& sm : c->shardmaps) std::fill(sm.begin(), sm.end(), -1);
+    auto maps = c->shardmaps;                              // (built aside: an allocation failure below must leave the store as it was)
+    for (auto& sm : maps) std::fill(sm.begin(), sm.end(), -1);
     for (size_t fid = 0; fid < c->frags.size(); fid++) {
         HostFrag f = c->frags[fid];
         if (!f.live) continue;
@@ -591,7 +604,7 @@ static int compact_locked(fbgpu_ctx* c) {
         for (uint32_t k = 0; k < f.n_desc; k++) { ContDesc d = c->h_descs[f.desc_off + k]; d.off16 = (uint32_t)((int64_t)d.off16 + d16); descs.push_back(d); }
         moves.push_back(Move{ f.arena_off, to, f.arena_len });
         f.row_off = (uint32_t)row_new; f.desc_off = desc_new; f.arena_off = to; h.row_off = (uint32_t)row_new;
-        c->shardmaps[f.fv][f.shard] = (int32_t)frags.size();
+        maps[f.fv][f.shard] = (int32_t)frags.size();
         frags.push_back(f); hfr.push_back(h);
         cur = to + f.arena_len;
     }
@@ -599,7 +612,7 @@ static int compact_locked(fbgpu_ctx* c) {
     if (nb.ensure(cur + 256)) return FBGPU_E_NOMEM;
     for (const Move& m : moves) if (m.len) CUDA_TRY(cudaMemcpy((uint8_t*)nb.p + m.to, (const uint8_t*)c->d_payload.p + m.from, m.len, cudaMemcpyDeviceToDevice));
     c->d_payload.release(); c->d_payload = nb;
-    c->frags.swap(frags); c->h_frags.swap(hfr); c->h_rows.swap(rows); c->h_descs.swap(descs);
+    c->frags.swap(frags); c->h_frags.swap(hfr); c->h_rows.swap(rows); c->h_descs.swap(descs); c->shardmaps.swap(maps);
     c->uploaded = cur; c->dead_arena = 0; c->stats.dead_bytes = 0;
     c->meta_dirty = true;
     return commit_locked(c);                               // tables for the new layout
