@@ -310,3 +310,55 @@ BITMAP_LEVEL_CASES = [
 # ---------------------------------------------------------------------------------------------------
 BSI_POSITIONS = [(0, 1, 0, [0]), (0, 3, 0, [0]), (1, 3, 0, [1]), (0, 1, 1, [0, 2 * SW]), (0, 4, 10, [0, 3 * SW, 5 * SW]), (0, 5, 10, [0, 3 * SW, 5 * SW])]
 BSI_LT_REGRESSION = (1, 6, 33)
+
+
+# ---------------------------------------------------------------------------------------------------
+# Mixed-encoding container cases of roaring_internal_test.go that are not table tests (so not in kernel_tables*.json).
+# Operand specs: ("array", [values]) / ("run", [(start, last), ...]) / ("bitmap", [first words]).
+# (cite, op, a, b, expected values, encoding the reference reads the result through: "array" / "run" / "bitmap" / None)
+# ---------------------------------------------------------------------------------------------------
+_UM_A, _UM_B, _UM_R = ("array", [1, 4, 5, 7, 10, 11, 12]), ("bitmap", [0x3]), ("run", [(5, 10)])
+_IM_A, _IM_B, _IM_C = ("run", [(5, 10)]), ("array", [1, 4, 5, 7, 10, 11, 12]), ("bitmap", [0x60])
+_DM_A, _DM_B, _DM_C, _DM_D = ("run", [(5, 10)]), ("array", [0, 2, 4, 6, 8, 10, 12]), ("bitmap", [0x64]), ("array", [1, 3, 5, 7, 9, 11, 12])
+MIXED_CONTAINER_CASES = [
+    # TestUnionMixed :694-735 (results compared as arrays after conversion: encoding not asserted)
+    (":712 run-array", "union", _UM_R, _UM_A, [1, 4, 5, 6, 7, 8, 9, 10, 11, 12], None),
+    (":713 array-run", "union", _UM_A, _UM_R, [1, 4, 5, 6, 7, 8, 9, 10, 11, 12], None),
+    (":714 run-run", "union", _UM_R, _UM_R, [5, 6, 7, 8, 9, 10], None),
+    (":716 bitmap-run", "union", _UM_B, _UM_R, [0, 1, 5, 6, 7, 8, 9, 10], None),
+    (":717 run-bitmap", "union", _UM_R, _UM_B, [0, 1, 5, 6, 7, 8, 9, 10], None),
+    (":718 array-bitmap", "union", _UM_A, _UM_B, [0, 1, 4, 5, 7, 10, 11, 12], None),
+    # TestIntersectMixed :918-955
+    (":923", "intersect", _IM_A, _IM_B, [5, 7, 10], "array"),
+    (":927", "intersect", _IM_B, _IM_A, [5, 7, 10], "array"),
+    (":931", "intersect", _IM_A, _IM_A, [5, 6, 7, 8, 9, 10], "run"),
+    (":936", "intersect", _IM_C, _IM_A, [5, 6], "array"),
+    (":941", "intersect", _IM_A, _IM_C, [5, 6], "array"),
+    (":946", "intersect", _IM_B, _IM_C, [5], "array"),
+    (":950", "intersect", _IM_C, _IM_B, [5], "array"),
+    # TestDifferenceMixed :956-1022
+    (":965", "difference", _DM_A, _DM_B, [5, 7, 9], "array"),
+    (":971", "difference", _DM_B, _DM_A, [0, 2, 4, 12], "array"),
+    (":976", "difference", _DM_A, _DM_A, [], None),
+    (":981", "difference", _DM_C, _DM_A, [2], "bitmap"),
+    (":986", "difference", _DM_A, _DM_C, [7, 8, 9, 10], "run"),
+    (":991", "difference", _DM_B, _DM_C, [0, 4, 8, 10, 12], "array"),
+    (":996", "difference", _DM_C, _DM_B, [5], "array"),
+    (":1001", "difference", _DM_B, _DM_B, [], None),
+    (":1006", "difference", _DM_C, _DM_C, [], None),
+    (":1011", "difference", _DM_D, _DM_B, [1, 3, 5, 7, 9, 11], "array"),
+    (":1016", "difference", _DM_B, _DM_D, [0, 2, 4, 6, 8, 10], "array"),
+    # TestXorRunRun1 :2026-2037
+    (":2029", "xor", ("run", [(4, 10)]), ("run", [(5, 10)]), [4], "array"),
+    (":2033", "xor", ("run", [(5, 10)]), ("run", [(4, 10)]), [4], "array"),
+]
+# TestIntersectionCountArrayBitmap3 :284-304 (full containers through bitmap / run encodings: |a ∩ b| = 65536 every way) and
+# TestDifferenceInPlace_N :4316-4323 (full run \ full bitmap is empty)
+FULL_CONTAINER_ENCODINGS = [("bitmap", "bitmap"), ("bitmap", "run"), ("run", "bitmap"), ("run", "run")]
+# TestRunCountRange :144-236: (runs, start, end, expected count of [start, end)); the last run list must count 3 runs
+RUN_COUNT_RANGE = [
+    ([], 2, 9, 0), ([(5, 7)], 2, 9, 3),
+    ([(5, 11)], 4, 8, 3), ([(5, 11)], 5, 8, 3), ([(5, 11)], 6, 8, 2), ([(5, 11)], 3, 9, 4), ([(5, 11)], 9, 14, 3), ([(5, 11)], 8, 10, 2),
+    ([(5, 11)], 8, 11, 3), ([(5, 11)], 8, 12, 4), ([(5, 11)], 5, 12, 7), ([(5, 11)], 5, 11, 6),
+    ([(5, 11), (17, 19)], 1, 22, 10), ([(5, 11), (13, 14), (17, 19)], 6, 18, 9),
+]

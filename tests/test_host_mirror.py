@@ -103,6 +103,7 @@ def test_percentile(oracle_backed):
 def test_bench_archetype_matrix_plumbing(oracle_backed):
     E.test_bench_archetype_matrix()
     E.test_kernel_table_goldens_on_device()
+    E.test_mixed_container_goldens_on_device()
     E.test_bitmap_level_goldens_on_device()
 
 

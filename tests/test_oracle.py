@@ -447,6 +447,43 @@ def test_fragment_top_heap_truncation():
     assert O.fragment_top(fr, 0, n=3) == [(1, 10), (2, 9), (3, 8)]
 
 
+def _spec_container(spec):
+    kind, lit = spec
+    if kind == "array":
+        return O.Container.array(lit)
+    if kind == "run":
+        return O.Container.run(np.array(lit, dtype=np.uint16).reshape(-1, 2))
+    w = np.zeros(1024, dtype=np.uint64)
+    w[: len(lit)] = np.array(lit, dtype=np.uint64)
+    return O.Container.bitmap(w)
+
+
+def test_mixed_container_goldens():
+    """TestUnionMixed / TestIntersectMixed / TestDifferenceMixed / TestXorRunRun1 (roaring_internal_test.go:694-735, 918-1022,
+    2026-2037): values, and the encoding of the result where the reference reads it through an encoding-specific accessor"""
+    typ = {"array": O.ARRAY, "run": O.RUN, "bitmap": O.BITMAP}
+    for cite, op, a, b, exp, enc in V.MIXED_CONTAINER_CASES:
+        res = getattr(_spec_container(a), op)(_spec_container(b))
+        assert res.values().tolist() == exp and res.n == len(exp), (cite, op)
+        if enc is not None:
+            assert res.typ == typ[enc], (cite, op, res.typ)
+        assert _spec_container(a).intersection_count(_spec_container(b)) == len(set(_spec_container(a).values().tolist()) & set(_spec_container(b).values().tolist()))
+
+
+def test_full_container_and_run_count_range_goldens():
+    """TestIntersectionCountArrayBitmap3 :284-304, TestDifferenceInPlace_N :4316-4323, TestRunCountRange :144-236"""
+    full = {"bitmap": O.Container.bitmap(np.full(1024, 0xFFFFFFFFFFFFFFFF, dtype=np.uint64)), "run": O.Container.run(np.array([[0, 65535]], dtype=np.uint16))}
+    for ea, eb in V.FULL_CONTAINER_ENCODINGS:
+        a, b = full[ea], full[eb]
+        res = a.intersect(b)
+        assert res.n == 65536 and a.intersection_count(b) == 65536
+        assert a.difference(b).n == 0
+    for runs, start, end, exp in V.RUN_COUNT_RANGE:
+        c = O.Container.run(np.array(runs, dtype=np.uint16).reshape(-1, 2))
+        assert c.count_range(start, end) == exp, (runs, start, end)
+    assert O.Container.run(np.array(V.RUN_COUNT_RANGE[-1][0], dtype=np.uint16)).count_runs() == 3
+
+
 def test_filter_sample_goldens():
     """roaring/filter_internal_test.go:78-138 on the oracle's row discovery / filtered row counts / row unions"""
     SW = H.SW

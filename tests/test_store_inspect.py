@@ -213,6 +213,7 @@ def test_executor_bodies_through_library_compiler_and_store(monkeypatch):
     E.test_sort_goldens()
     E.test_field_value_and_options()
     E.test_topk_time_range()
+    E.test_mixed_container_goldens_on_device()
     E.test_kernel_table_goldens_on_device()            # explicit (unoptimised) encodings through the library's reader and store
     E.test_bitmap_level_goldens_on_device()
     E.test_bench_archetype_matrix()

@@ -326,6 +326,40 @@ def test_kernel_table_goldens_on_device():
             assert [int(x) for x in per] == [len(expect[k]) for k in shards] and tot == sum(len(expect[k]) for k in shards)
 
 
+def test_mixed_container_goldens_on_device():
+    """TestUnionMixed / TestIntersectMixed / TestDifferenceMixed / TestXorRunRun1 and the full-container cases
+    (roaring_internal_test.go:284-304, 694-735, 918-1022, 2026-2037, 4316-4323) on the device: case k lives in shard k as rows 0
+    and 1 of one field in the encodings the reference test builds (unoptimised Pilosa bytes keep them); one query per operation"""
+    from oracle import oracle as O
+    from tests.test_oracle import _spec_container
+    names = {"union": "Union", "intersect": "Intersect", "difference": "Difference", "xor": "Xor"}
+    full = {"bitmap": ("bitmap", [0xFFFFFFFFFFFFFFFF] * 1024), "run": ("run", [(0, 65535)])}
+    cases = [(op, a, b, exp) for _, op, a, b, exp, _ in V.MIXED_CONTAINER_CASES]
+    for ea, eb in V.FULL_CONTAINER_ENCODINGS:
+        cases.append(("intersect", full[ea], full[eb], list(range(65536))))
+        cases.append(("difference", full[ea], full[eb], []))
+    p = Pair(track_existence=False)
+    p.field("f")
+    slot, by_op, expect = 9, {}, {}
+    for k, (op, a, b, exp) in enumerate(cases):
+        frag = O.Bitmap()
+        frag.put(0 * 16 + slot, _spec_container(a))
+        frag.put(1 * 16 + slot, _spec_container(b))
+        p.load("f", X.VIEW_STANDARD, k, frag.to_bytes(optimize=False))
+        by_op.setdefault(op, []).append(k)
+        expect[k] = [((k * 16 + slot) << 16) + v for v in exp]
+    fid = p.idx.fields["f"].id
+    for op, shards in by_op.items():
+        got = p.check_row(f"{names[op]}(Row(f=0), Row(f=1))", shards)           # canonical bytes == the oracle's
+        assert [int(x) for x in got.columns()] == [v for k in shards for v in expect[k]], op
+        if op == "intersect":
+            prog = [X.L.Op(X.L.OP_ROW, fid, 0, 0, 0, 0, 0, 0), X.L.Op(X.L.OP_ROW, fid, 0, 0, 1, 0, 0, 0), X.L.Op(X.L.OP_INTERSECT, 0, 0, 2, 0, 0, 0, 0)]
+            tot, per = p.holder.ctx.count(p.idx.id, prog, shards, per_shard=True)
+            assert [int(x) for x in per] == [len(expect[k]) for k in shards] and tot == sum(len(expect[k]) for k in shards)
+            pairs = p.holder.ctx.count_pairs(p.idx.id, fid, 0, [0], fid, 0, [1], shards)      # the fused Intersect+Count kernel
+            assert int(pairs[0]) == tot
+
+
 def test_bitmap_level_goldens_on_device():
     """roaring/roaring_test.go Bitmap-level cases: operand a = row 0 of field "a", operand b = row 0 of field "b", values are
     columns (so the larger cases span three shards); counts through Count(op(...)), slices through the Row bytes"""
