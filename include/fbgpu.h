@@ -40,7 +40,8 @@ typedef struct fbgpu_ctx fbgpu_ctx; /* opaque, one per GPU */
  * loaders and the store tables can be tested on a machine without a GPU; it is not a CPU execution path. */
 #define FBGPU_DEVICE_NONE (-1)
 
-/* lifecycle.  device_ordinal is the CUDA ordinal this context owns. */
+/* lifecycle (what Holder.Open / Holder.Close are to the fragments of a node, holder.go:432, 614): one context per GPU,
+ * created once per process.  device_ordinal is the CUDA ordinal this context owns. */
 int fbgpu_init(int32_t device_ordinal, fbgpu_ctx **out);
 void fbgpu_shutdown(fbgpu_ctx *ctx);
 /* thread-local message of the last failing call on this thread */
@@ -55,9 +56,11 @@ int32_t fbgpu_abi_version(void);
  * (index,field,view,shard).  The library copies; the caller keeps ownership of the bytes. */
 int fbgpu_load_fragment(fbgpu_ctx *ctx, uint32_t index, uint32_t field, uint32_t view, uint64_t shard,
                         const uint8_t *roaring, uint64_t nbytes);
-/* bulk form: n fragments of the same (index,field,view); fragment i is buf[offsets[i], offsets[i+1]) */
+/* bulk form (the shape of API.ImportRoaringShard's per-view payloads, api.go:1647; fragment.importRoaringOverwrite
+ * fragment.go:2196): n fragments of the same (index,field,view); fragment i is buf[offsets[i], offsets[i+1]) */
 int fbgpu_load_fragments(fbgpu_ctx *ctx, uint32_t index, uint32_t field, uint32_t view,
                          const uint64_t *shards, int64_t n, const uint8_t *buf, const uint64_t *offsets);
+/* view.deleteFragment (view.go:405): the fragment no longer answers queries; its arena space is reclaimed by fbgpu_compact */
 int fbgpu_drop_fragment(fbgpu_ctx *ctx, uint32_t index, uint32_t field, uint32_t view, uint64_t shard);
 /*  Load the fragments of ONE shard straight from its RBF database, i.e. from the bytes of
  * `<index>/backends/rbf/<shard>/data` (and, if it is not empty, `wal`) -- one RBF DB holds every field/view of a
@@ -75,7 +78,8 @@ int fbgpu_load_rbf(fbgpu_ctx *ctx, uint32_t index, uint64_t shard, const uint8_t
  * mappings are released before the call returns.  FBGPU_E_FORMAT when `data` cannot be opened or mapped. */
 int fbgpu_load_rbf_dir(fbgpu_ctx *ctx, uint32_t index, uint64_t shard, const char *dir, const char *const *names,
                        const uint32_t *fields, const uint32_t *views, int32_t n_names, int32_t *out_loaded);
-/* pushes pending host-side staging to HBM now (otherwise done lazily by the next query) */
+/* pushes pending host-side staging to HBM now (otherwise done lazily by the next query): the point at which loaded
+ * fragments become visible to queries, as RBFTx.Commit (rbf.go:189) is for writes in the reference */
 int fbgpu_commit(fbgpu_ctx *ctx);
 /* Replacing or dropping a fragment leaves its old payload in the arena.  fbgpu_compact() commits what is pending, then
  * copies the live fragments into a fresh arena (device to device) and rebuilds the tables; fbgpu_commit() does the same on
