@@ -26,8 +26,10 @@ def _worker(rank, world, port, q):
     n_shards = 12
     lo, hi = cluster.shard_range(rank, world, n_shards)
     mine = np.arange(lo, hi, dtype=np.uint64)
+    g = idx.create_field("g")
     for s in mine:
         h.import_roaring("i", "f", X.VIEW_STANDARD, int(s), D.fragment(1, int(s), [0, 1, 2, 3], 0.02))
+        h.import_roaring("i", "g", X.VIEW_STANDARD, int(s), D.fragment(2, int(s), [0, 1, 2], 0.05))
     row = lambda r: L.Op(L.OP_ROW, f.id, 0, 0, r, 0, 0, 0)
     pair = [row(0), row(1), L.Op(L.OP_INTERSECT, 0, 0, 2, 0, 0, 0, 0)]
     union = [row(0), row(1), row(2), row(3), L.Op(L.OP_UNION, 0, 0, 4, 0, 0, 0, 0)]
@@ -38,6 +40,10 @@ def _worker(rank, world, port, q):
     h.ctx.comm_init(world, rank, uid[0])
     out["nccl_pair"] = h.ctx.count(idx.id, pair, mine)
     out["nccl_union"] = h.ctx.count(idx.id, union, mine)
+    # count VECTORS are summed by the same ncclAllReduce(uint64, sum): TopN / TopK over explicit ids, GroupBy (BASELINE config 4's merge)
+    out["nccl_row_counts"] = [int(x) for x in h.ctx.row_counts(idx.id, f.id, 0, mine, row_ids=[0, 1, 2, 3, 9])]
+    out["nccl_row_counts_filtered"] = [int(x) for x in h.ctx.row_counts(idx.id, f.id, 0, mine, row_ids=[0, 1, 2, 3], filter_ops=[L.Op(L.OP_ROW, g.id, 0, 0, 1, 0, 0, 0)])]
+    out["nccl_groupby"] = [int(x) for x in np.asarray(h.ctx.groupby(idx.id, [f.id, g.id], [0, 0], [[0, 1, 2, 3], [0, 1, 2]], mine)).reshape(-1)]
     # 2. fused peer-memory path
     handles = [None] * world
     dist.all_gather_object(handles, h.ctx.comm_p2p_handle())
@@ -72,9 +78,15 @@ def test_fused_count_allreduce_two_gpus():
         p.join(timeout=60)
         assert p.exitcode == 0
     pair_tot, union_tot, pair_r0 = 0, 0, 0
+    rc, rcf, gb = np.zeros(5, dtype=np.uint64), np.zeros(4, dtype=np.uint64), np.zeros(12, dtype=np.uint64)
     for s in range(12):
         fr = O.Bitmap.from_bytes(D.fragment(1, s, [0, 1, 2, 3], 0.02))
+        gr = O.Bitmap.from_bytes(D.fragment(2, s, [0, 1, 2], 0.05))
         r = [fr.row(k, s) for k in range(4)]
+        for k in range(4):
+            rc[k] += np.uint64(r[k].count())
+            rcf[k] += np.uint64(r[k].intersection_count(gr.row(1, s)))
+        gb += O.groupby_shard([fr, gr], s, [[0, 1, 2, 3], [0, 1, 2]])
         c = r[0].intersection_count(r[1])
         pair_tot += c
         if s < cluster.shard_range(0, 2, 12)[1]:
@@ -83,6 +95,8 @@ def test_fused_count_allreduce_two_gpus():
     for rank in (0, 1):
         o = res[rank]
         assert o["nccl_pair"] == pair_tot and o["nccl_union"] == union_tot
+        assert o["nccl_row_counts"] == [int(x) for x in rc] and o["nccl_row_counts_filtered"] == [int(x) for x in rcf]
+        assert o["nccl_groupby"] == [int(x) for x in gb]
         for it in range(5):
             assert o[f"p2p_pair_{it}"] == pair_tot and o[f"p2p_union_{it}"] == union_tot
         assert o["p2p_rank0_only"] == pair_r0

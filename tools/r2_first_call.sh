@@ -13,6 +13,9 @@ timeout 900 python -m pytest tests -x -q -m gpu > $out/pytest_gpu.log 2>&1; echo
 # 2. opt-in tests: striped arrays, RBF loader, BSI aggregates, fragment.top / filter / archetype goldens
 FBGPU_TEST_EXPERIMENTAL=1 timeout 900 python -m pytest tests/test_zz_gpu_experimental.py -q > $out/pytest_experimental.log 2>&1; echo "pytest_experimental rc=$?" >> $out/summary.txt
 
+# 2b. (only when the call was made with `gpurun --gpus 2`) the two-GPU test: fused Count merge, ncclAllReduce of count vectors (TopN ids / GroupBy)
+[ "$(nvidia-smi -L | wc -l)" -ge 2 ] && { timeout 600 python -m pytest tests/test_gpu_multi.py -q > $out/pytest_multi.log 2>&1; echo "pytest_multi rc=$?" >> $out/summary.txt; }
+
 # 3. headline bench: default layout vs bank-striped arrays (same build), then the density sweep for both
 bench() { python bench.py --steps 50 --warmup 5 --no-cpu-baseline 2>>$out/bench_err.log | tail -1; }
 echo "default $(bench)" >> $out/bench.jsonl
