@@ -213,7 +213,8 @@ extern "C" int fbgpu_init(int32_t device_ordinal, fbgpu_ctx** out) try {
     CUDA_TRY(cudaFuncSetAttribute(eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 17 * 8192));
     CUDA_TRY(cudaFuncSetAttribute(eval_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 233472 / 2 - 1024 - 5888));
     CUDA_TRY(cudaFuncSetAttribute(pair_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairWarps * 8192));
-    CUDA_TRY(cudaFuncSetAttribute(row_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairWarps * 8192));
+    CUDA_TRY(cudaFuncSetAttribute(row_count_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairWarps * 8192));
+    CUDA_TRY(cudaFuncSetAttribute(row_count_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairWarps * 8192));
     CUDA_TRY(cudaFuncSetAttribute(groupby_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGbSlots * 4 + 8192));
     CUDA_TRY(cudaFuncSetAttribute(groupby_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGbSlots * 4 + 8192));
     guard.c = nullptr;
@@ -1126,8 +1127,8 @@ static int eval_filter_batch(fbgpu_ctx* c, Workspace* w, const std::vector<DevOp
 }
 
 static int row_counts_impl(fbgpu_ctx* c, uint32_t index, uint32_t fv, const std::vector<uint64_t>& rows, const fbgpu_op* filter, int32_t n_filter_ops,
-                           const uint64_t* shards, int64_t n_shards, std::vector<uint64_t>& counts, bool reduce = true) {
-    counts.assign(rows.size(), 0);
+                           const uint64_t* shards, int64_t n_shards, std::vector<uint64_t>& counts, bool reduce = true, bool per_shard = false) {
+    counts.assign(rows.size() * (per_shard ? (size_t)n_shards : 1), 0);
     if (rows.empty()) return 0;
     std::vector<DevOp> prog; int depth = 1; int rc;
     bool have_filter = filter && n_filter_ops > 0;
@@ -1136,9 +1137,10 @@ static int row_counts_impl(fbgpu_ctx* c, uint32_t index, uint32_t fv, const std:
     const DevOp* d_prog; const uint64_t* d_shards;
     rc = upload_inputs(w, prog, shards, n_shards, &d_prog, &d_shards); if (rc) return rc;
     size_t nr = rows.size();
-    if (w->d_rows.ensure(nr * 8) || w->d_counts.ensure(nr * 8) || w->h_out.ensure(nr * 8)) return FBGPU_E_NOMEM;
+    const size_t n_out = counts.size();                     // nr, or n_shards x nr (per_shard: one row of the matrix per listed shard)
+    if (w->d_rows.ensure(nr * 8) || w->d_counts.ensure(n_out * 8) || w->h_out.ensure(n_out * 8)) return FBGPU_E_NOMEM;
     CUDA_TRY(cudaMemcpyAsync(w->d_rows.p, rows.data(), nr * 8, cudaMemcpyHostToDevice, w->stream));
-    CUDA_TRY(cudaMemsetAsync(w->d_counts.p, 0, nr * 8, w->stream));
+    CUDA_TRY(cudaMemsetAsync(w->d_counts.p, 0, n_out * 8, w->stream));
     CUDA_TRY(cudaEventRecord(w->ev0, w->stream));
     uint64_t launches = 0;
     const int64_t batch = have_filter ? c->unit_batch / kSlotsPerRow : n_shards;
@@ -1147,16 +1149,20 @@ static int row_counts_impl(fbgpu_ctx* c, uint32_t index, uint32_t fv, const std:
         if (have_filter) { rc = eval_filter_batch(c, w, prog, depth, d_prog, d_shards + s0, ns); if (rc) return rc; launches++; }
         long long tasks = (long long)ns * (long long)nr;
         long long grid = std::min<long long>((tasks + kPairWarps - 1) / kPairWarps, (long long)c->sm_count * 3);
-        row_count_kernel<<<(unsigned)grid, kPairWarps * 32, kPairWarps * 8192, w->stream>>>(store_ref(c), fv, (const uint64_t*)w->d_rows.p, (int)nr, d_shards + s0, ns,
-            have_filter ? (const uint4*)w->d_bitmaps.p : nullptr, (unsigned long long*)w->d_counts.p);
+        if (per_shard)
+            row_count_kernel<true><<<(unsigned)grid, kPairWarps * 32, kPairWarps * 8192, w->stream>>>(store_ref(c), fv, (const uint64_t*)w->d_rows.p, (int)nr, d_shards + s0, ns,
+                have_filter ? (const uint4*)w->d_bitmaps.p : nullptr, (unsigned long long*)w->d_counts.p + (size_t)s0 * nr);
+        else
+            row_count_kernel<false><<<(unsigned)grid, kPairWarps * 32, kPairWarps * 8192, w->stream>>>(store_ref(c), fv, (const uint64_t*)w->d_rows.p, (int)nr, d_shards + s0, ns,
+                have_filter ? (const uint4*)w->d_bitmaps.p : nullptr, (unsigned long long*)w->d_counts.p);
         CUDA_TRY(cudaGetLastError()); launches++;
     }
     CUDA_TRY(cudaEventRecord(w->ev1, w->stream));
     // every rank must bring the same row list to the collective: only the explicit-ids form is all-reduced (fbgpu.h)
-    if (reduce) { rc = allreduce_u64(c, w, w->d_counts.p, nr); if (rc) return rc; }
-    CUDA_TRY(cudaMemcpyAsync(w->h_out.p, w->d_counts.p, nr * 8, cudaMemcpyDeviceToHost, w->stream));
+    if (reduce && !per_shard) { rc = allreduce_u64(c, w, w->d_counts.p, nr); if (rc) return rc; }
+    CUDA_TRY(cudaMemcpyAsync(w->h_out.p, w->d_counts.p, n_out * 8, cudaMemcpyDeviceToHost, w->stream));
     CUDA_TRY(cudaStreamSynchronize(w->stream));
-    memcpy(counts.data(), w->h_out.p, nr * 8);
+    memcpy(counts.data(), w->h_out.p, n_out * 8);
     float ms = 0; cudaEventElapsedTime(&ms, w->ev0, w->ev1);
     bump(c, launches, ms);
     lease.ok = true;
@@ -1196,6 +1202,21 @@ extern "C" int fbgpu_row_counts(fbgpu_ctx* c, uint32_t index, uint32_t field, ui
     int32_t n = (int32_t)std::min<size_t>(order.size(), (size_t)std::max(cap, 0));
     for (int32_t i = 0; i < n; i++) { if (out_row_ids) out_row_ids[i] = rows[order[i]]; out_counts[i] = counts[order[i]]; }
     if (out_n) *out_n = n;
+    return FBGPU_OK;
+} FBGPU_CATCH
+
+// per-shard counts of explicit rows: out_counts[s * n_rows + i] = |Row(row_ids[i]) [∩ filter]| in shards[s]
+extern "C" int fbgpu_row_counts_per_shard(fbgpu_ctx* c, uint32_t index, uint32_t field, uint32_t view, const uint64_t* row_ids, int32_t n_rows,
+                                          const fbgpu_op* filter, int32_t n_filter_ops, const uint64_t* shards, int64_t n_shards, uint64_t* out_counts) try {
+    if (!c || !out_counts || !row_ids || n_rows < 0 || n_shards < 0 || (n_shards && !shards) || n_filter_ops < 0 || (n_filter_ops && !filter)) return fail(FBGPU_E_INVALID, "null argument");
+    if (n_rows == 0 || n_shards == 0) return FBGPU_OK;
+    USE_DEVICE(c);
+    std::shared_lock<std::shared_mutex> lk;
+    int rc = lock_committed(c, lk); if (rc) return rc;
+    const uint32_t fv = view_id_locked(c, ViewKey{ index, field, view }, false);
+    std::vector<uint64_t> rows(row_ids, row_ids + n_rows), counts;
+    rc = row_counts_impl(c, index, fv, rows, filter, n_filter_ops, shards, n_shards, counts, false, true); if (rc) return rc;
+    memcpy(out_counts, counts.data(), counts.size() * 8);
     return FBGPU_OK;
 } FBGPU_CATCH
 

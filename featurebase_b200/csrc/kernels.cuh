@@ -1126,11 +1126,14 @@ __device__ __forceinline__ uint32_t warp_count_vs_global_bitmap(Resolved a, cons
     return __reduce_add_sync(0xffffffffu, c);
 }
 
+// kPerShard: out_counts is the [n_shards][n_rows] matrix of per-shard counts (what fragment.top's per-shard cut-offs need,
+// fragment.go:1329-1388) instead of the [n_rows] vector summed over the shards; every (shard, row) task then owns its slot.
+template <bool kPerShard>
 __global__ void __launch_bounds__(kPairWarps * 32)
 row_count_kernel(StoreRef st, uint32_t fv, const uint64_t* __restrict__ row_ids, int n_rows,
                  const uint64_t* __restrict__ shards, long long n_shards,
                  const uint4* __restrict__ filter_bitmaps /* [n_shards*16][512] or null */,
-                 unsigned long long* out_counts /* [n_rows] */) {
+                 unsigned long long* out_counts /* [n_rows], or [n_shards][n_rows] */) {
     extern __shared__ uint32_t smem32[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     uint32_t* bm = smem32 + wid * 2048;
@@ -1154,7 +1157,7 @@ row_count_kernel(StoreRef st, uint32_t fv, const uint64_t* __restrict__ row_ids,
             if (!filter_bitmaps) acc += a.card;
             else acc += warp_count_vs_global_bitmap(a, reinterpret_cast<const uint32_t*>(filter_bitmaps + ((size_t)si * 16 + s) * 512), bm, lane);
         }
-        if (lane == 0 && acc) atomicAdd(&out_counts[ri], acc);
+        if (lane == 0 && acc) { if (kPerShard) out_counts[(size_t)si * n_rows + ri] = acc; else atomicAdd(&out_counts[ri], acc); }
     }
 }
 

@@ -564,8 +564,8 @@ class Executor:
         """TopN with threshold= / tanimotoThreshold=: fragment.top applies its cut-offs per shard — on the row's own count `cnt`
         in that shard, then on `count` = |Src ∩ row| there (MinThreshold :1357-1362,1384-1388; Tanimoto band and coefficient
         :1329-1338,1351-1356,1378-1383) — and only what passes is summed across shards (Pairs.Add, executeTopNShards :2845).
-        So the counts are fetched shard by shard from the same entry points (a slow path: one fbgpu_row_counts call, two with
-        a Src, per shard; the Src counts of all shards come from one fbgpu_count).  Candidates: `ids`, else every row of the
+        So the counts are fetched as [shard][row] matrices (fbgpu_row_counts_per_shard: one launch for the rows' own counts, one
+        more with the Src as filter; the Src counts of all shards come from one fbgpu_count).  Candidates: `ids`, else every row of the
         field (what the internal second pass asks for when the first pass missed nothing)."""
         if ids is None:
             rid, _ = self.ctx.row_counts(idx.id, f.id, VIEW_STANDARD, shards)
@@ -575,11 +575,12 @@ class Executor:
         use_tan = tan > 0 and filt is not None
         src_counts = self.ctx.count(idx.id, filt, shards, per_shard=True)[1] if use_tan else None
         total = np.zeros(len(ids), dtype=np.uint64)
-        for k, s in enumerate(shards):
-            cnt = np.asarray(self.ctx.row_counts(idx.id, f.id, VIEW_STANDARD, [s], row_ids=ids), dtype=np.uint64)
+        cnt_m = self.ctx.row_counts_per_shard(idx.id, f.id, VIEW_STANDARD, shards, ids)
+        count_m = self.ctx.row_counts_per_shard(idx.id, f.id, VIEW_STANDARD, shards, ids, filter_ops=filt) if filt is not None else cnt_m
+        for k in range(len(shards)):
+            cnt, count = cnt_m[k], count_m[k]
             if not cnt.any():
                 continue
-            count = np.asarray(self.ctx.row_counts(idx.id, f.id, VIEW_STANDARD, [s], row_ids=ids, filter_ops=filt), dtype=np.uint64) if filt is not None else cnt
             for j in range(len(ids)):
                 cj, kj = int(cnt[j]), int(count[j])
                 if cj == 0 or kj == 0:

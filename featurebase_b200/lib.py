@@ -41,7 +41,7 @@ class Counters(C.Structure):
 
 EXPORTS = ["fbgpu_init", "fbgpu_shutdown", "fbgpu_last_error", "fbgpu_abi_version", "fbgpu_load_fragment",
            "fbgpu_load_fragments", "fbgpu_drop_fragment", "fbgpu_commit", "fbgpu_get_stats", "fbgpu_count", "fbgpu_row",
-           "fbgpu_row_counts", "fbgpu_groupby", "fbgpu_comm_unique_id", "fbgpu_comm_init", "fbgpu_comm_destroy",
+           "fbgpu_row_counts", "fbgpu_row_counts_per_shard", "fbgpu_groupby", "fbgpu_comm_unique_id", "fbgpu_comm_init", "fbgpu_comm_destroy",
            "fbgpu_get_counters", "fbgpu_stream", "fbgpu_rows_payload_bytes", "fbgpu_count_pairs", "fbgpu_columns", "fbgpu_extract", "fbgpu_load_rbf", "fbgpu_load_rbf_dir", "fbgpu_bsi_minmax", "fbgpu_bsi_sum", "fbgpu_compact", "fbgpu_comm_p2p_handle", "fbgpu_comm_p2p_open", "fbgpu_comm_p2p_disable"]
 
 
@@ -82,6 +82,7 @@ def load():
     L.fbgpu_bsi_minmax.restype = C.c_int
     L.fbgpu_bsi_sum.argtypes, L.fbgpu_bsi_sum.restype = [vp, u32, vp, i32, u32, u32, i32, vp, i64, C.POINTER(C.c_int64), C.POINTER(u64)], C.c_int
     L.fbgpu_row_counts.argtypes, L.fbgpu_row_counts.restype = [vp, u32, u32, u32, vp, i32, vp, i32, vp, i64, vp, vp, i32, C.POINTER(i32)], C.c_int
+    L.fbgpu_row_counts_per_shard.argtypes, L.fbgpu_row_counts_per_shard.restype = [vp, u32, u32, u32, vp, i32, vp, i32, vp, i64, vp], C.c_int
     L.fbgpu_groupby.argtypes, L.fbgpu_groupby.restype = [vp, u32, vp, vp, i32, vp, vp, vp, i32, vp, i64, vp], C.c_int
     L.fbgpu_count_pairs.argtypes, L.fbgpu_count_pairs.restype = [vp, u32, u32, u32, vp, u32, u32, vp, i32, vp, i64, vp], C.c_int
     L.fbgpu_comm_unique_id.argtypes, L.fbgpu_comm_unique_id.restype = [vp], C.c_int
@@ -311,6 +312,15 @@ class Context:
         self._check(self.L.fbgpu_row_counts(self.h, index, field, view, None, 0, f, nf, sh.ctypes.data, len(sh),
                                             rid.ctypes.data, out.ctypes.data, cap, C.byref(n)))
         return rid[: n.value], out[: n.value]
+
+    def row_counts_per_shard(self, index, field, view, shards, row_ids, filter_ops=None):
+        """[len(shards), len(row_ids)] matrix of per-shard counts (fbgpu_row_counts_per_shard)"""
+        sh, ids = _u64arr(shards), _u64arr(row_ids)
+        f = ops_array(filter_ops) if filter_ops else None
+        out = np.zeros((len(sh), len(ids)), dtype=np.uint64)
+        self._check(self.L.fbgpu_row_counts_per_shard(self.h, index, field, view, ids.ctypes.data, len(ids), f, len(filter_ops) if filter_ops else 0,
+                                                      sh.ctypes.data, len(sh), out.ctypes.data))
+        return out
 
     def count_pairs(self, index, field_a, view_a, rows_a, field_b, view_b, rows_b, shards):
         sh, ra, rb = _u64arr(shards), _u64arr(rows_a), _u64arr(rows_b)

@@ -186,6 +186,14 @@ int fbgpu_row_counts(fbgpu_ctx *ctx, uint32_t index, uint32_t field, uint32_t vi
                      const fbgpu_op *filter, int32_t n_filter_ops,
                      const uint64_t *shards, int64_t n_shards,
                      uint64_t *out_row_ids, uint64_t *out_counts, int32_t cap, int32_t *out_n);
+/* The same counts kept apart per shard, for explicit rows: out_counts[s * n_rows + i] = |Row(row_ids[i]) [∩ filter]| in
+ * shards[s] (a shard without the fragment gives zeros).  fragment.top applies its MinThreshold / Tanimoto cut-offs to each
+ * shard's own counts before Pairs.Add sums them (fragment.go:1329-1388, executeTopNShards executor.go:2831-2866), so TopN
+ * with threshold= / tanimotoThreshold= needs this matrix, not the reduced vector.  Never all-reduced: a shard belongs to
+ * one rank. */
+int fbgpu_row_counts_per_shard(fbgpu_ctx *ctx, uint32_t index, uint32_t field, uint32_t view,
+                               const uint64_t *row_ids, int32_t n_rows, const fbgpu_op *filter, int32_t n_filter_ops,
+                               const uint64_t *shards, int64_t n_shards, uint64_t *out_counts);
 
 /* Many fused Intersect+Count pairs in ONE launch: out_counts[i] = |Row(field_a = rows_a[i]) ∩ Row(field_b = rows_b[i])| over
  * the shards — the inner loop of fragment.top with a plain-row Src (count = Src.intersectionCount(row) per candidate

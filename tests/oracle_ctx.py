@@ -175,6 +175,9 @@ class OracleCtx:
         pairs = sorted(((r, c) for r, c in tot.items() if c), key=lambda kv: (-kv[1], kv[0]))[:cap]
         return (np.array([p[0] for p in pairs], dtype=np.uint64), np.array([p[1] for p in pairs], dtype=np.uint64))
 
+    def row_counts_per_shard(self, index, field, view, shards, row_ids, filter_ops=None):
+        return np.stack([self.row_counts(index, field, view, [s], row_ids=row_ids, filter_ops=filter_ops) for s in shards]) if len(shards) else np.zeros((0, len(row_ids)), dtype=np.uint64)
+
     def count_pairs(self, index, field_a, view_a, rows_a, field_b, view_b, rows_b, shards):
         out = np.zeros(len(rows_a), dtype=np.uint64)
         for i, (ra, rb) in enumerate(zip(rows_a, rows_b)):

@@ -60,6 +60,7 @@ def test_fragment_top_goldens(oracle_backed):
     E.test_fragment_top_goldens()
     E.test_topn_cutoff_goldens()
     E.test_topn_cutoffs_random()
+    E.test_row_counts_per_shard_entry_point()
     E.test_filter_sample_goldens()
 
 

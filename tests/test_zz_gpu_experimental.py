@@ -1222,6 +1222,40 @@ def test_arena_compaction():
     check()
 
 
+def test_row_counts_per_shard_entry_point():
+    """fbgpu_row_counts_per_shard (row_count_kernel<true>): the [shard][row] matrix against per-shard oracle counts — rows of
+    every encoding, a filter program, a shard without the fragment, a row id the field does not hold, a repeated shard; its
+    column sums are what fbgpu_row_counts returns"""
+    import featurebase_b200.datagen as D
+    from oracle import oracle as O
+    p = Pair(track_existence=False)
+    p.field("m")
+    p.field("flt")
+    for s in (0, 2, 3):
+        merged = O.Bitmap()
+        for d in (D.fragment(9, s, [0], 0.004), D.fragment(9, s, [1], 0.3), D.fragment(9, s, [2], 0.2, mode=1, mean_run=200.0), D.fragment(9, s, [5], 0.02)):
+            merged = merged.union(O.Bitmap.from_bytes(d))
+        p.load("m", X.VIEW_STANDARD, s, merged.to_bytes())
+        if s != 3:
+            p.load("flt", X.VIEW_STANDARD, s, D.fragment(4, s, [0, 1], 0.1))
+    ctx, mid = p.holder.ctx, p.idx.fields["m"].id
+    ids, shards = [0, 1, 2, 5, 77], [3, 0, 1, 2, 0]
+    filt_call = pql.parse("Union(Row(flt=0), Row(flt=1))")[0]
+    for call in (None, filt_call):
+        ops = p.ex._bitmap_call(p.idx, call) if call is not None else None
+        got = ctx.row_counts_per_shard(p.idx.id, mid, X.VIEW_STANDARD, shards, ids, filter_ops=ops)
+        assert got.shape == (len(shards), len(ids))
+        for k, s in enumerate(shards):
+            fr = p.ora.frag("m", X.VIEW_STANDARD, s)
+            filt = p.ora.eval_shard(call, s) if call is not None else None
+            for j, r in enumerate(ids):
+                row = fr.row(r, s) if fr is not None else O.Bitmap()
+                assert int(got[k, j]) == (row.count() if filt is None else row.intersection_count(filt)), (s, r, call is not None)
+        uniq = [0, 2, 3]
+        total = ctx.row_counts(p.idx.id, mid, X.VIEW_STANDARD, uniq, row_ids=ids, filter_ops=ops)
+        assert [int(x) for x in total] == [int(x) for x in ctx.row_counts_per_shard(p.idx.id, mid, X.VIEW_STANDARD, uniq, ids, filter_ops=ops).sum(axis=0)]
+
+
 def test_multi_batch_paths(monkeypatch):
     """FBGPU_UNIT_BATCH=16 (read when a context is created): one shard per launch, so the batch loops of fbgpu_row (payloads of
     several batches assembled behind one header), fbgpu_columns / fbgpu_extract (a window that starts in one batch and ends in
@@ -1236,6 +1270,7 @@ def test_multi_batch_paths(monkeypatch):
     test_bsi_aggregate_goldens()
     test_filter_sample_goldens()
     test_topn_cutoffs_random()
+    test_row_counts_per_shard_entry_point()
 
 
 def test_row_result_threaded_assembly():
