@@ -86,6 +86,7 @@ def main():
             o.append(f"| `{d['query']}` | {d['ms']:.2f} | {d['result_bytes']:,} | {d['result_count']:,} |")
     o.append("\nThese three were timed through the Python wrapper with a fresh output array per call: most of the time on large results was host-side — page faults of the fresh array and of a per-batch vector, and three passes over the payload (D2H landing buffer -> per-batch buffer -> caller's buffer -> `tobytes`).  Changed since, **not yet re-timed**: a single-batch call (<= 1024 shards) assembles straight from the pinned landing buffer into the caller's buffer, the payload copies of results above 8 MiB are split over up to 8 host threads, and `bench_sweep.py` config R now times `fbgpu_row` into a reused caller-owned buffer (what a Go caller does).  A device-side pack and D2H straight into a registered caller buffer are the next step.\n")
     o.append("## Written after the GPU budget was spent: no timing yet (round 2's first call, `tools/r2_first_call.sh`, measures each)\n")
+    o.append('Which kernels of the current build are, instruction for instruction, the ones that ran on the device (`python tools/sass_diff.py 5f6bb73`, the last round-1 commit that was on a B200; no GPU needed): **identical** — `eval_wordpar_kernel`, `canon_emit_kernel`, `groupby_kernel<false>`, `row_count_kernel<false>`, `p2p_reduce_only_kernel`; **changed** (array scatter / probe instruction cuts, §9.1 of DESIGN.md) — `eval_kernel` 3384 -> 2920 instructions, `pair_count_kernel` 3064 -> 2864, `eval_staged_kernel` (opt-in); **new** — `columns_emit_kernel`, `extract_values_kernel`, `bsi_sum_kernel`, `bsi_minmax_kernel`, `row_count_kernel<true>`, `groupby_kernel<true>` (opt-in).\n')
     o.append("Kernel logic of every row has run against the oracle on the CPU kernel interpreter (`tests/emu/`, `tests/test_emu_kernels.py`); the default build's other kernels are byte-identical SASS to the measured ones.\n")
     o.append("| change | switch | targets | expectation (model, not a measurement) |")
     o.append("|---|---|---|---|")
