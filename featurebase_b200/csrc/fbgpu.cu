@@ -1215,8 +1215,13 @@ extern "C" int fbgpu_row_counts_per_shard(fbgpu_ctx* c, uint32_t index, uint32_t
     int rc = lock_committed(c, lk); if (rc) return rc;
     const uint32_t fv = view_id_locked(c, ViewKey{ index, field, view }, false);
     std::vector<uint64_t> rows(row_ids, row_ids + n_rows), counts;
-    rc = row_counts_impl(c, index, fv, rows, filter, n_filter_ops, shards, n_shards, counts, false, true); if (rc) return rc;
-    memcpy(out_counts, counts.data(), counts.size() * 8);
+    // the matrix is produced in blocks of shards so that the device / pinned buffers stay below 512 MiB however many rows are asked for
+    const int64_t block = std::max<int64_t>(1, (int64_t)((64ull << 20) / (uint64_t)n_rows));
+    for (int64_t s0 = 0; s0 < n_shards; s0 += block) {
+        const int64_t ns = std::min(block, n_shards - s0);
+        rc = row_counts_impl(c, index, fv, rows, filter, n_filter_ops, shards + s0, ns, counts, false, true); if (rc) return rc;
+        memcpy(out_counts + (size_t)s0 * n_rows, counts.data(), counts.size() * 8);
+    }
     return FBGPU_OK;
 } FBGPU_CATCH
 
