@@ -539,7 +539,7 @@ class Executor:
         filt = self._bitmap_call(idx, c.children[0]) if c.children else None
         ids = c.args.get("ids")
         if ids is not None:
-            ids = sorted(int(i) for i in ids)
+            ids = sorted(int(i) for i in ids) or None              # an empty list is "no ids" (len(opt.RowIDs) > 0, fragment.go:1325)
         if thr > 1 or (tan > 0 and filt is not None):            # per-shard cut-offs of fragment.top (fragment.go:1329-1388)
             pairs = self._topn_cutoffs(idx, f, filt, ids, thr, tan, shards)
         elif ids is not None:

@@ -131,6 +131,7 @@ def test_topn_cutoff_goldens():
             p.ex.execute("i", q, [0])
     # explicit ids: n does not truncate (executeTopN :2802-2807, fragment.go:1325-1327)
     assert p.ex.execute("i", "TopN(f, n=1, ids=[100,101,102])", [0])[0] == [(100, 4), (102, 4), (101, 2)]
+    assert p.ex.execute("i", "TopN(f, n=1, ids=[])", [0])[0] == [(100, 4)]                       # an empty id list is no id list
 
 
 def test_topn_cutoffs_random():
