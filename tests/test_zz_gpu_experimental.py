@@ -107,68 +107,6 @@ def test_fragment_top_goldens():
         assert p.ex.execute("i", q, [0])[0] == exp, q
 
 
-def test_topn_cutoff_goldens():
-    """threshold= / tanimotoThreshold= through TopN on one shard: fragment_internal_test.go:1490-1537 and the MinThreshold rows of
-    tests/golden/vectors.py; argument errors of executeTopNShard :2876,2893,2921"""
-    for rows, src, n, ids, thr, tan, exp in V.FRAG_TOP_THRESHOLD_CASES:
-        p = Pair(track_existence=False)
-        p.field("f")
-        p.field("src")
-        for r, cols in rows.items():
-            for c in cols:
-                p.holder.set_bit("i", "f", r, c)
-        for c in (src or []):
-            p.holder.set_bit("i", "src", 0, c)
-        p.sync_pending()
-        q = ("TopN(f" + (", Row(src=0)" if src else "") + (f", n={n}" if n else "") + (", ids=[" + ",".join(map(str, ids)) + "]" if ids else "")
-             + (f", threshold={thr}" if thr else "") + (f", tanimotoThreshold={tan}" if tan else "") + ")")
-        assert p.ex.execute("i", q, [0])[0] == exp, q
-    p.field("v", "int", min=0, max=100)
-    for q, msg in (("TopN(f, Row(src=0), tanimotoThreshold=101)", "Tanimoto Threshold is from 1 to 100 only"),
-                   ("TopN(f, Row(src=0), Row(src=0), n=1)", "TopN() can only have one input bitmap"),
-                   ("TopN(v, n=1)", "cannot compute TopN() on integer, decimal, or timestamp field")):
-        with pytest.raises(X.QueryError, match=msg.replace("(", r"\(").replace(")", r"\)")):
-            p.ex.execute("i", q, [0])
-    # explicit ids: n does not truncate (executeTopN :2802-2807, fragment.go:1325-1327)
-    assert p.ex.execute("i", "TopN(f, n=1, ids=[100,101,102])", [0])[0] == [(100, 4), (102, 4), (101, 2)]
-    assert p.ex.execute("i", "TopN(f, n=1, ids=[])", [0])[0] == [(100, 4)]                       # an empty id list is no id list
-
-
-def test_topn_cutoffs_random():
-    """several shards, random rows: the mirror's per-shard cut-offs == fragment.top per shard (oracle.fragment_top with the
-    candidate ids) summed by Pairs.Add and sorted (executeTopNShards :2831-2866)"""
-    from oracle import oracle as O
-    rng = np.random.default_rng(77)
-    SW = 1 << 20
-    p = Pair(track_existence=False)
-    p.field("f")
-    p.field("src")
-    shards = [0, 1, 3]
-    for s in shards:
-        for r in range(12):
-            k = int(rng.integers(0, 60))
-            for c in rng.choice(400, size=k, replace=False):
-                p.holder.set_bit("i", "f", r, s * SW + int(c))
-        for c in rng.choice(400, size=int(rng.integers(20, 200)), replace=False):
-            p.holder.set_bit("i", "src", 0, s * SW + int(c))
-    p.sync_pending()
-    src_call = pql.parse("Row(src=0)")[0]
-    for with_src in (False, True):
-        for thr, tan in ((2, 0), (8, 0), (25, 0), (0, 1), (0, 10), (0, 35), (0, 100), (4, 20)):
-            for ids in (None, [0, 3, 5, 7, 11, 40]):
-                want = {}
-                for s in shards:
-                    fr = p.ora.frag("f", X.VIEW_STANDARD, s)
-                    src = p.ora.eval_shard(src_call, s) if with_src else None
-                    cand = ids if ids is not None else [int(r) for r in fr.rows()]
-                    for r, k in O.fragment_top(fr, s, src=src, row_ids=cand, min_threshold=thr or 1, tanimoto_threshold=tan):
-                        want[r] = want.get(r, 0) + k
-                exp = sorted(want.items(), key=lambda kv: (-kv[1], kv[0]))
-                q = ("TopN(f" + (", Row(src=0)" if with_src else "") + (", ids=[" + ",".join(map(str, ids)) + "]" if ids else "")
-                     + (f", threshold={thr}" if thr else "") + (f", tanimotoThreshold={tan}" if tan else "") + ")")
-                assert p.ex.execute("i", q, shards)[0] == exp, q
-
-
 def test_filter_sample_goldens():
     """roaring/filter_internal_test.go:78-138 at executor level, shards 0 and 2: Rows(f), rows holding one column (the
     column filter becomes a one-column filter row), Union of two rows"""
@@ -1223,6 +1161,88 @@ def test_arena_compaction():
     check()
 
 
+def test_row_result_threaded_assembly():
+    """a Row result above 8 MiB (72 shards of bitmap containers): fbgpu_row splits the payload copies into the caller's buffer over
+    several host threads; the bytes must still be the canonical serialisation.  Also with two batches behind one header."""
+    import featurebase_b200.datagen as D
+    for env in (None, "640"):                            # 640 units = 40 shards per batch
+        if env:
+            os.environ["FBGPU_UNIT_BATCH"] = env
+        try:
+            p = Pair(track_existence=False)
+            p.field("f")
+            shards = list(range(72))
+            bulk = D.fragments(5, np.asarray(shards, dtype=np.uint64), [0, 1], 0.5)
+            for s in shards:
+                p.load("f", X.VIEW_STANDARD, s, bulk.fragment_bytes(s))
+            got = p.check_row("Row(f=0)")
+            assert len(got.roaring) > (9 << 20)
+            p.check_row("Intersect(Row(f=0), Row(f=1))")
+        finally:
+            os.environ.pop("FBGPU_UNIT_BATCH", None)
+
+def test_topn_cutoff_goldens():
+    """threshold= / tanimotoThreshold= through TopN on one shard: fragment_internal_test.go:1490-1537 and the MinThreshold rows of
+    tests/golden/vectors.py; argument errors of executeTopNShard :2876,2893,2921"""
+    for rows, src, n, ids, thr, tan, exp in V.FRAG_TOP_THRESHOLD_CASES:
+        p = Pair(track_existence=False)
+        p.field("f")
+        p.field("src")
+        for r, cols in rows.items():
+            for c in cols:
+                p.holder.set_bit("i", "f", r, c)
+        for c in (src or []):
+            p.holder.set_bit("i", "src", 0, c)
+        p.sync_pending()
+        q = ("TopN(f" + (", Row(src=0)" if src else "") + (f", n={n}" if n else "") + (", ids=[" + ",".join(map(str, ids)) + "]" if ids else "")
+             + (f", threshold={thr}" if thr else "") + (f", tanimotoThreshold={tan}" if tan else "") + ")")
+        assert p.ex.execute("i", q, [0])[0] == exp, q
+    p.field("v", "int", min=0, max=100)
+    for q, msg in (("TopN(f, Row(src=0), tanimotoThreshold=101)", "Tanimoto Threshold is from 1 to 100 only"),
+                   ("TopN(f, Row(src=0), Row(src=0), n=1)", "TopN() can only have one input bitmap"),
+                   ("TopN(v, n=1)", "cannot compute TopN() on integer, decimal, or timestamp field")):
+        with pytest.raises(X.QueryError, match=msg.replace("(", r"\(").replace(")", r"\)")):
+            p.ex.execute("i", q, [0])
+    # explicit ids: n does not truncate (executeTopN :2802-2807, fragment.go:1325-1327)
+    assert p.ex.execute("i", "TopN(f, n=1, ids=[100,101,102])", [0])[0] == [(100, 4), (102, 4), (101, 2)]
+    assert p.ex.execute("i", "TopN(f, n=1, ids=[])", [0])[0] == [(100, 4)]                       # an empty id list is no id list
+
+
+def test_topn_cutoffs_random():
+    """several shards, random rows: the mirror's per-shard cut-offs == fragment.top per shard (oracle.fragment_top with the
+    candidate ids) summed by Pairs.Add and sorted (executeTopNShards :2831-2866)"""
+    from oracle import oracle as O
+    rng = np.random.default_rng(77)
+    SW = 1 << 20
+    p = Pair(track_existence=False)
+    p.field("f")
+    p.field("src")
+    shards = [0, 1, 3]
+    for s in shards:
+        for r in range(12):
+            k = int(rng.integers(0, 60))
+            for c in rng.choice(400, size=k, replace=False):
+                p.holder.set_bit("i", "f", r, s * SW + int(c))
+        for c in rng.choice(400, size=int(rng.integers(20, 200)), replace=False):
+            p.holder.set_bit("i", "src", 0, s * SW + int(c))
+    p.sync_pending()
+    src_call = pql.parse("Row(src=0)")[0]
+    for with_src in (False, True):
+        for thr, tan in ((2, 0), (8, 0), (25, 0), (0, 1), (0, 10), (0, 35), (0, 100), (4, 20)):
+            for ids in (None, [0, 3, 5, 7, 11, 40]):
+                want = {}
+                for s in shards:
+                    fr = p.ora.frag("f", X.VIEW_STANDARD, s)
+                    src = p.ora.eval_shard(src_call, s) if with_src else None
+                    cand = ids if ids is not None else [int(r) for r in fr.rows()]
+                    for r, k in O.fragment_top(fr, s, src=src, row_ids=cand, min_threshold=thr or 1, tanimoto_threshold=tan):
+                        want[r] = want.get(r, 0) + k
+                exp = sorted(want.items(), key=lambda kv: (-kv[1], kv[0]))
+                q = ("TopN(f" + (", Row(src=0)" if with_src else "") + (", ids=[" + ",".join(map(str, ids)) + "]" if ids else "")
+                     + (f", threshold={thr}" if thr else "") + (f", tanimotoThreshold={tan}" if tan else "") + ")")
+                assert p.ex.execute("i", q, shards)[0] == exp, q
+
+
 def test_row_counts_per_shard_entry_point():
     """fbgpu_row_counts_per_shard (row_count_kernel<true>): the [shard][row] matrix against per-shard oracle counts — rows of
     every encoding, a filter program, a shard without the fragment, a row id the field does not hold, a repeated shard; its
@@ -1272,24 +1292,3 @@ def test_multi_batch_paths(monkeypatch):
     test_filter_sample_goldens()
     test_topn_cutoffs_random()
     test_row_counts_per_shard_entry_point()
-
-
-def test_row_result_threaded_assembly():
-    """a Row result above 8 MiB (72 shards of bitmap containers): fbgpu_row splits the payload copies into the caller's buffer over
-    several host threads; the bytes must still be the canonical serialisation.  Also with two batches behind one header."""
-    import featurebase_b200.datagen as D
-    for env in (None, "640"):                            # 640 units = 40 shards per batch
-        if env:
-            os.environ["FBGPU_UNIT_BATCH"] = env
-        try:
-            p = Pair(track_existence=False)
-            p.field("f")
-            shards = list(range(72))
-            bulk = D.fragments(5, np.asarray(shards, dtype=np.uint64), [0, 1], 0.5)
-            for s in shards:
-                p.load("f", X.VIEW_STANDARD, s, bulk.fragment_bytes(s))
-            got = p.check_row("Row(f=0)")
-            assert len(got.roaring) > (9 << 20)
-            p.check_row("Intersect(Row(f=0), Row(f=1))")
-        finally:
-            os.environ.pop("FBGPU_UNIT_BATCH", None)
