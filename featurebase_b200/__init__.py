@@ -5,5 +5,14 @@ lib.py     ctypes binding (no CPU fallback)
 executor.py / pql.py / roaring_io.py   host-side mirror of the reference's executor interface for this path
 datagen.py synthetic fragments (tests, bench)
 """
-from . import lib  # noqa: F401
-from .lib import Context, FbgpuError  # noqa: F401
+import importlib
+
+_LAZY = {"lib": None, "Context": "lib", "FbgpuError": "lib"}
+
+
+def __getattr__(name):
+    # lazy: importing the package (e.g. for datagen in the CPU reference arm of bench.py) must not touch the CUDA binding
+    if name in _LAZY:
+        mod = importlib.import_module(".lib", __name__)
+        return mod if _LAZY[name] is None else getattr(mod, name)
+    raise AttributeError(name)

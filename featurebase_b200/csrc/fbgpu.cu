@@ -748,7 +748,7 @@ static int launch_eval(fbgpu_ctx* c, Workspace* w, const std::vector<DevOp>& pro
         }
     }
     size_t smem = (size_t)(depth + 1) * 8192;
-    int per_sm = std::max(1, (int)std::min<size_t>(std::min(8, 2048 / kEvalThreads), (227 * 1024) / (smem + 3 * 1024 + 512)));
+    int per_sm = std::max(1, (int)std::min<size_t>(std::min(FBGPU_EVAL_MIN_BLOCKS, 2048 / kEvalThreads), (227 * 1024) / (smem + 3 * 1024 + 512)));
     long long grid = std::min<long long>(n_units, (long long)c->sm_count * per_sm);
     eval_kernel<<<(unsigned)grid, kEvalThreads, smem, w->stream>>>(store_ref(c), d_prog, n_ops, depth, d_batches, (int)batches.size(), d_shards, n_units, out);
     CUDA_TRY(cudaGetLastError());

@@ -213,19 +213,34 @@ __device__ __forceinline__ void scatter_chunk_unrolled(uint32_t* bm, uint4 v, ui
 // Batch of commuting row operands (OR / ANDNOT / XOR onto the same target), no barrier in between: warp w takes
 // operands w, w+8, ...; arrays are scattered with red.shared, bitmaps applied with word atomics.  (Tried and slower
 // on B200: 4 loads in flight per thread, register double-buffering, L2 prefetch, TMA staging — profiles/README.md.)
+static_assert(sizeof(Resolved) == 16, "batch_rows reads a Resolved with one 16-byte shared load");
+#ifndef FBGPU_EVAL_DEEP
+#define FBGPU_EVAL_DEEP 3
+#endif
 template <int MODE>
 __device__ __forceinline__ void batch_rows(uint32_t* T32, const Resolved* res, int n) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     uint32_t sb = (uint32_t)__cvta_generic_to_shared(T32);
     asm volatile("" : "+r"(sb));           // keep the shared address live: ptxas otherwise rebuilds it for every chunk
     for (int j = wid; j < n; j += kEvalThreads / 32) {
-        const Resolved r = res[j];
-        if (r.ptr == nullptr) continue;
-        if (r.typ == kArray) {
-            const uint4* a4 = reinterpret_cast<const uint4*>(r.ptr);
-            const uint32_t n8 = (r.card + 7) >> 3;
-            for (uint32_t i = lane; i < n8; i += 32) scatter_chunk_sb<MODE>(sb, ldg_nc(a4 + i), i * 8, r.card);
-        } else if (r.typ == kBitmap) warp_bitmap_atomic<MODE>(T32, reinterpret_cast<const uint4*>(r.ptr), lane);
+        const uint4 raw = *reinterpret_cast<const uint4*>(res + j);        // one LDS.128: {ptr lo, ptr hi, card, typ | cnt << 16}
+        const uint4* a4 = reinterpret_cast<const uint4*>(((unsigned long long)raw.y << 32) | raw.x);
+        if (a4 == nullptr) continue;
+        const uint32_t typ = raw.w & 0xffffu;
+        if (typ == kArray) {
+            const uint32_t card = raw.z, n8 = (card + 7) >> 3;
+            // the first FBGPU_EVAL_DEEP chunks of the lane are all in flight before the first reduction is issued: a ~650-element
+            // container is 82 chunks = at most 3 per lane, so its whole payload costs the warp ONE exposed HBM latency instead of
+            // three (ncu round 2: 42 % of the stall samples sat on the single load of the old one-chunk loop)
+            // (the loads are unconditional — index clamped to the last chunk — so that no register of v[] is ever undefined:
+            // predicated loads made ptxas park the chunks in local memory)
+            uint4 v[FBGPU_EVAL_DEEP];
+#pragma unroll
+            for (int q = 0; q < FBGPU_EVAL_DEEP; q++) v[q] = ldg_nc(a4 + min((uint32_t)lane + 32u * q, n8 - 1u));
+#pragma unroll
+            for (int q = 0; q < FBGPU_EVAL_DEEP; q++) if (lane + 32 * q < n8) scatter_chunk_sb<MODE>(sb, v[q], (lane + 32 * q) * 8, card);
+            for (uint32_t i = lane + 32 * FBGPU_EVAL_DEEP; i < n8; i += 32) scatter_chunk_sb<MODE>(sb, ldg_nc(a4 + i), i * 8, card);
+        } else if (typ == kBitmap) warp_bitmap_atomic<MODE>(T32, a4, lane);
     }
 }
 // ------------------------------------------------------------------------------------------------
@@ -282,7 +297,7 @@ eval_kernel(StoreRef st, const DevOp* __restrict__ prog, int n_ops, int depth,
             const int2* __restrict__ batches, int n_batches,
             const uint64_t* __restrict__ shards, long long n_units, EvalOut out) {
     extern __shared__ uint4 smem4[];
-    __shared__ Resolved res[kResolveChunk];
+    __shared__ __align__(16) Resolved res[kResolveChunk];
     __shared__ uint32_t warp_tmp[kEvalThreads / 32];
     __shared__ uint32_t warp_tmp2[kEvalThreads / 32];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;

@@ -525,7 +525,7 @@ fbo_container *fbo_flip(const fbo_container *a) {
 fbo_bitmap *fbo_b_new(void) { return xcalloc(1, sizeof(fbo_bitmap)); }
 void fbo_b_free(fbo_bitmap *b) {
     if (!b) return;
-    for (int64_t i = 0; i < b->n; i++) fbo_c_free(b->cs[i]);
+    if (!b->view) for (int64_t i = 0; i < b->n; i++) fbo_c_free(b->cs[i]);
     free(b->keys); free(b->cs); free(b);
 }
 static void b_reserve(fbo_bitmap *b, int64_t need) {
@@ -641,6 +641,19 @@ fbo_bitmap *fbo_b_union(const fbo_bitmap *a, const fbo_bitmap *b) {
     }
     return o;
 }
+/* Container.unionInPlace into a bitmap target: unionBitmapArrayInPlace roaring.go:5440 (sets the bits), unionBitmapBitmapInPlace
+ * :5473 (ORs the words), unionBitmapRunInPlace :5222 (bitmapSetRangeIgnoreN per run) */
+static void c_or_into_words(const fbo_container *c, uint64_t *acc) {
+    if (!c || c->n == 0) return;
+    if (c->typ == FBO_ARRAY) { const uint16_t *a = ARR(c); for (int i = 0; i < c->len; i++) acc[a[i] >> 6] |= 1ull << (a[i] & 63); return; }
+    if (c->typ == FBO_BITMAP) { const uint64_t *w = BMP(c); for (int q = 0; q < 1024; q++) acc[q] |= w[q]; return; }
+    for (int i = 0; i < c->len; i++) {
+        uint32_t s = RUN(c)[i].start, l = RUN(c)[i].last, ws = s >> 6, wl = l >> 6;
+        uint64_t ms = ~0ull << (s & 63), ml = ~0ull >> (63 - (l & 63));
+        if (ws == wl) acc[ws] |= ms & ml;
+        else { acc[ws] |= ms; for (uint32_t k = ws + 1; k < wl; k++) acc[k] = ~0ull; acc[wl] |= ml; }
+    }
+}
 /* n-ary Bitmap.Union -> unionInPlace roaring.go:1272-1284,1410-1561.  Per key: any full => fullContainer;
  * single source => reuse; expectedN >= 512 => accumulate in a bitmap container, popcount once (Repair :1560);
  * else left-fold union(). */
@@ -650,7 +663,7 @@ fbo_bitmap *fbo_b_union_n(const fbo_bitmap *a, const fbo_bitmap *const *others, 
     const fbo_bitmap **src = xmalloc(sizeof(void *) * total); int64_t *pos = xcalloc(total, sizeof(int64_t));
     src[0] = a; for (int i = 0; i < n; i++) src[i + 1] = others[i];
     fbo_bitmap *o = fbo_b_new();
-    uint64_t acc[1024], w[1024];
+    uint64_t acc[1024];
     for (;;) {
         uint64_t key = ~0ull; int have = 0;
         for (int s = 0; s < total; s++) if (pos[s] < src[s]->n) { uint64_t k = src[s]->keys[pos[s]]; if (!have || k < key) { key = k; have = 1; } }
@@ -665,11 +678,9 @@ fbo_bitmap *fbo_b_union_n(const fbo_bitmap *a, const fbo_bitmap *const *others, 
         if (full) res = full_container();
         else if (cnt == 1) res = fbo_c_clone(only);
         else if (cnt > 1 && expected >= 512) {
-            memset(acc, 0, sizeof acc);
-            for (int s = 0; s < total; s++) if (pos[s] < src[s]->n && src[s]->keys[pos[s]] == key) {
-                fbo_c_to_words(src[s]->cs[pos[s]], w); for (int q = 0; q < 1024; q++) acc[q] |= w[q];
-            }
-            res = fbo_c_bitmap(acc);
+            memset(acc, 0, sizeof acc);          /* NewContainerBitmapN(nil, 0), then Container.unionInPlace per source */
+            for (int s = 0; s < total; s++) if (pos[s] < src[s]->n && src[s]->keys[pos[s]] == key) c_or_into_words(src[s]->cs[pos[s]], acc);
+            res = fbo_c_bitmap(acc);             /* Repair :1560: one popcount per target container */
         } else if (cnt > 1) {
             for (int s = 0; s < total; s++) if (pos[s] < src[s]->n && src[s]->keys[pos[s]] == key) {
                 fbo_container *u = fbo_union(res, src[s]->cs[pos[s]]); fbo_c_free(res); res = u;
@@ -712,6 +723,15 @@ fbo_bitmap *fbo_b_offset_range(const fbo_bitmap *b, uint64_t offset, uint64_t st
     uint64_t off = offset >> 16, hi0 = start >> 16, hi1 = end >> 16;
     int64_t i = b_search(b, hi0); if (i < 0) i = -(i + 1);
     for (; i < b->n && b->keys[i] < hi1; i++) if (fbo_c_n(b->cs[i]) > 0) b_append(o, off + (b->keys[i] - hi0), fbo_c_clone(b->cs[i]));
+    return o;
+}
+
+/* the same range as a view: keys re-based, containers borrowed (what the storage layer returns: frozen containers) */
+static fbo_bitmap *b_offset_range_view(const fbo_bitmap *b, uint64_t offset, uint64_t start, uint64_t end) {
+    fbo_bitmap *o = fbo_b_new(); o->view = 1;
+    uint64_t off = offset >> 16, hi0 = start >> 16, hi1 = end >> 16;
+    int64_t i = b_search(b, hi0); if (i < 0) i = -(i + 1);
+    for (; i < b->n && b->keys[i] < hi1; i++) if (fbo_c_n(b->cs[i]) > 0) b_append(o, off + (b->keys[i] - hi0), b->cs[i]);
     return o;
 }
 
@@ -829,8 +849,16 @@ static uint64_t abs_i64(int64_t v) { /* absInt64 fragment.go:952-961 */
 static uint64_t all_ones(uint64_t depth) { return depth >= 64 ? ~0ull : (1ull << depth) - 1; } /* Go: 1<<64 == 0 */
 static uint64_t shl_ones(uint64_t depth) { return depth >= 64 ? 0 : ~0ull << depth; }
 
+fbo_bitmap *fbo_frag_row_view(const fbo_bitmap *frag, uint64_t row, uint64_t shard) {
+    if (!frag) return fbo_b_new();
+    return b_offset_range_view(frag, shard << FBO_SHARD_WIDTH_EXP, row << FBO_SHARD_WIDTH_EXP, (row + 1) << FBO_SHARD_WIDTH_EXP);
+}
+
+/* rows inside rangeOp / groupBy are only ever read (every op builds a fresh result), so they are fetched as views; a view
+ * that would leave one of these functions as its RESULT is cloned first (own_result) */
 typedef struct { const fbo_bitmap *frag; uint64_t shard; } fctx;
-static fbo_bitmap *frow(const fctx *f, uint64_t r) { return fbo_frag_row(f->frag, r, f->shard); }
+static fbo_bitmap *frow(const fctx *f, uint64_t r) { return fbo_frag_row_view(f->frag, r, f->shard); }
+static fbo_bitmap *own_result(fbo_bitmap *b) { if (b && b->view) { fbo_bitmap *o = fbo_b_clone(b); fbo_b_free(b); return o; } return b; }
 #define OWN2(expr, a, b) ({ fbo_bitmap *_r = (expr); fbo_b_free(a); fbo_b_free(b); _r; })
 
 static fbo_bitmap *range_eq(const fctx *f, uint64_t depth, int64_t pred) { /* rangeEQ fragment.go:963-1003 */
@@ -954,13 +982,13 @@ fbo_bitmap *fbo_frag_range_op(const fbo_bitmap *frag, uint64_t shard, int op, ui
     fctx f = { frag, shard };
     if (!frag) return fbo_b_new();
     switch (op) {
-    case FBO_OP_EQ: return range_eq(&f, depth, pred);
-    case FBO_OP_NEQ: return range_neq(&f, depth, pred);
-    case FBO_OP_LT: return range_lt(&f, depth, pred, 0);
-    case FBO_OP_LTE: return range_lt(&f, depth, pred, 1);
-    case FBO_OP_GT: return range_gt(&f, depth, pred, 0);
-    case FBO_OP_GTE: return range_gt(&f, depth, pred, 1);
-    case FBO_OP_BETWEEN: return range_between(&f, depth, pred, pmax);
+    case FBO_OP_EQ: return own_result(range_eq(&f, depth, pred));
+    case FBO_OP_NEQ: return own_result(range_neq(&f, depth, pred));
+    case FBO_OP_LT: return own_result(range_lt(&f, depth, pred, 0));
+    case FBO_OP_LTE: return own_result(range_lt(&f, depth, pred, 1));
+    case FBO_OP_GT: return own_result(range_gt(&f, depth, pred, 0));
+    case FBO_OP_GTE: return own_result(range_gt(&f, depth, pred, 1));
+    case FBO_OP_BETWEEN: return own_result(range_between(&f, depth, pred, pmax));
     }
     return NULL;
 }
@@ -992,14 +1020,14 @@ int64_t fbo_frag_rows(const fbo_bitmap *frag, uint64_t *rows, int64_t cap) {
 static void gb_rec(const fbo_bitmap *const *frags, int nf, uint64_t shard, const uint64_t *const *ids, const int32_t *n_rows,
                    int level, const fbo_bitmap *prefix, uint64_t *out, uint64_t base) {
     for (int r = 0; r < n_rows[level]; r++) {
-        fbo_bitmap *row = fbo_frag_row(frags[level], ids[level][r], shard);
+        fbo_bitmap *row = fbo_frag_row_view(frags[level], ids[level][r], shard);
         uint64_t idx = base * (uint64_t)n_rows[level] + (uint64_t)r;
         if (level == nf - 1) {
             out[idx] += prefix ? fbo_b_intersection_count(row, prefix) : fbo_b_count(row);
         } else {
-            fbo_bitmap *cur = prefix ? fbo_b_intersect(row, prefix) : fbo_b_clone(row);
+            fbo_bitmap *cur = prefix ? fbo_b_intersect(row, prefix) : row;   /* level 0 without a filter walks the row itself :8829 */
             if (fbo_b_any(cur)) gb_rec(frags, nf, shard, ids, n_rows, level + 1, cur, out, idx); /* nextAtIdx skips empty rows :8869 */
-            fbo_b_free(cur);
+            if (cur != row) fbo_b_free(cur);
         }
         fbo_b_free(row);
     }
@@ -1013,46 +1041,3 @@ int fbo_groupby_shard(const fbo_bitmap *const *frags, int nf, uint64_t shard, co
     return 0;
 }
 
-/* ------------------------------------------------------------------ multi-threaded CPU baseline */
-typedef struct {
-    const fbo_bitmap *const *frags; const uint64_t *shards; int64_t lo, hi;
-    const uint64_t *ra; int na; const uint64_t *rb; int nb; uint64_t total;
-} bench_arg;
-
-static fbo_bitmap *union_rows(const fbo_bitmap *frag, uint64_t shard, const uint64_t *rows, int n) { /* executeUnionShard executor.go:5382 */
-    if (n == 0) return fbo_b_new();
-    fbo_bitmap **r = xcalloc((size_t)n, sizeof(void *));
-    for (int i = 0; i < n; i++) r[i] = fbo_frag_row(frag, rows[i], shard);
-    fbo_bitmap *o = n == 1 ? fbo_b_clone(r[0]) : fbo_b_union_n(r[0], (const fbo_bitmap *const *)(r + 1), n - 1);
-    for (int i = 0; i < n; i++) fbo_b_free(r[i]);
-    free(r);
-    return o;
-}
-static void *bench_worker(void *p) {
-    bench_arg *a = p; uint64_t t = 0;
-    for (int64_t s = a->lo; s < a->hi; s++) {
-        fbo_bitmap *ua = union_rows(a->frags[s], a->shards[s], a->ra, a->na);
-        fbo_bitmap *ub = union_rows(a->frags[s], a->shards[s], a->rb, a->nb);
-        fbo_bitmap *x = fbo_b_intersect(ua, ub);          /* executeIntersectShard executor.go:5357 */
-        t += fbo_b_count(x);                              /* executeCount executor.go:5871-5877 */
-        fbo_b_free(ua); fbo_b_free(ub); fbo_b_free(x);
-    }
-    a->total = t;
-    return NULL;
-}
-uint64_t fbo_bench_union_intersect_count(const fbo_bitmap *const *frags, const uint64_t *shards, int64_t n_shards,
-                                         const uint64_t *rows_a, int na, const uint64_t *rows_b, int nb, int n_threads, double *seconds) {
-    if (n_threads < 1) n_threads = 1;
-    pthread_t *th = xmalloc(sizeof(pthread_t) * n_threads); bench_arg *args = xcalloc(n_threads, sizeof(bench_arg));
-    struct timespec t0, t1; clock_gettime(CLOCK_MONOTONIC, &t0);
-    for (int t = 0; t < n_threads; t++) {
-        args[t] = (bench_arg){ frags, shards, n_shards * t / n_threads, n_shards * (t + 1) / n_threads, rows_a, na, rows_b, nb, 0 };
-        pthread_create(&th[t], NULL, bench_worker, &args[t]);
-    }
-    uint64_t total = 0;
-    for (int t = 0; t < n_threads; t++) { pthread_join(th[t], NULL); total += args[t].total; }
-    clock_gettime(CLOCK_MONOTONIC, &t1);
-    if (seconds) *seconds = (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
-    free(th); free(args);
-    return total;
-}

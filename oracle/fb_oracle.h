@@ -50,6 +50,8 @@ typedef struct fbo_bitmap {
     int64_t cap;
     uint64_t *keys;
     fbo_container **cs;
+    int32_t view; /* != 0: cs[] are borrowed from another bitmap (frozen containers handed out by fragment.row,
+                   * fragment.go:283-333 / rbf tx.OffsetRange): fbo_b_free leaves them alone; a view is read-only */
 } fbo_bitmap;
 
 /* ---- containers ---- */
@@ -133,13 +135,36 @@ int fbo_groupby_shard(const fbo_bitmap *const *frags, int n_fields, uint64_t sha
                       const uint64_t *row_ids_flat, const int32_t *n_rows,
                       const fbo_bitmap *filter, uint64_t *out_counts);
 
-/* ---- multi-threaded CPU baseline helpers (bench.py --impl reference / cpu_baseline) ----
- * Count(Intersect(Union(rows a..), Union(rows b..))) over n_shards fragments, one thread per
- * shard statically partitioned (mapperLocal + task.Pool model, executor.go:6742-6812).
- * frags[s] is the fragment of shard shards[s]. Returns total count; *seconds = wall time. */
-uint64_t fbo_bench_union_intersect_count(const fbo_bitmap *const *frags, const uint64_t *shards, int64_t n_shards,
-                                         const uint64_t *rows_a, int na, const uint64_t *rows_b, int nb,
-                                         int n_threads, double *seconds);
+/* fragment.row as the reference hands it out: a Bitmap over the fragment's own (frozen) containers, no payload copy
+ * (fragment.go:283-333, rbf/tx.go:1586-1637).  Read-only; free with fbo_b_free. */
+fbo_bitmap *fbo_frag_row_view(const fbo_bitmap *frag, uint64_t row, uint64_t shard);
+
+/* ---- multi-threaded CPU baseline (bench.py --impl reference / cpu_baseline; fb_bench.c) ----
+ * The worker pool is created ONCE (threads pinned round-robin to the host cores) and reused by every call: the
+ * reference's task.Pool workers are long-lived goroutines (executor.go:6742-6812), so thread creation is not part of a
+ * query.  Shards are handed out dynamically in small blocks (what mapperLocal's job channel does).  Rows are fetched as
+ * views (no container cloning).  Every bench call returns its wall time through *seconds. */
+typedef struct fbo_pool fbo_pool;
+fbo_pool *fbo_pool_create(int n_threads);
+void fbo_pool_destroy(fbo_pool *p);
+int fbo_pool_threads(const fbo_pool *p);
+/* Count(Intersect(Union(rows a..), Union(rows b..))): frags[s] is the fragment of shard shards[s] (executeUnionShard
+ * executor.go:5382 -> Row.Union row.go:288 -> unionInPlace roaring.go:1410; executeIntersectShard :5357; Count :5871) */
+uint64_t fbo_bench_union_intersect_count(fbo_pool *p, const fbo_bitmap *const *frags, const uint64_t *shards, int64_t n_shards,
+                                         const uint64_t *rows_a, int na, const uint64_t *rows_b, int nb, double *seconds);
+/* n_pairs queries Count(Intersect(Row(a_k), Row(b_k))) over the same fragments; materialise != 0: the executor's path
+ * (Row.Intersect materialises, then Count sums N; executor.go:5357,5871); 0: Bitmap.IntersectionCount (roaring.go:928).
+ * out_counts[k] += the count of pair k (may be NULL). */
+uint64_t fbo_bench_pair_counts(fbo_pool *p, const fbo_bitmap *const *frags, const uint64_t *shards, int64_t n_shards,
+                               const uint64_t *rows_a, const uint64_t *rows_b, int n_pairs, int materialise,
+                               uint64_t *out_counts, double *seconds);
+/* Count(Row(v <op> predicate)) over BSI fragments: fragment.rangeOp (fragment.go:937-1303) + Count */
+uint64_t fbo_bench_range_count(fbo_pool *p, const fbo_bitmap *const *frags, const uint64_t *shards, int64_t n_shards,
+                               int op, uint64_t bit_depth, int64_t predicate, int64_t predicate_max, double *seconds);
+/* GroupBy over n_fields set fields: frags[f * n_shards + s]; out_counts dense, summed over the shards (mergeGroupCounts
+ * executor.go:3728); groupByIterator executor.go:8617-8934 */
+int fbo_bench_groupby(fbo_pool *p, const fbo_bitmap *const *frags, int n_fields, const uint64_t *shards, int64_t n_shards,
+                      const uint64_t *row_ids_flat, const int32_t *n_rows, uint64_t *out_counts, double *seconds);
 
 void fbo_free(void *p);
 

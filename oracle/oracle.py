@@ -23,8 +23,8 @@ OPS = {"==": OP_EQ, "!=": OP_NEQ, "<": OP_LT, "<=": OP_LTE, ">": OP_GT, ">=": OP
 
 def build(force=False):
     so = os.path.join(_HERE, "libfboracle.so")
-    src = os.path.join(_HERE, "fb_oracle.c")
-    if force or not os.path.exists(so) or (os.path.exists(src) and os.path.getmtime(so) < os.path.getmtime(src)):
+    srcs = [os.path.join(_HERE, f) for f in ("fb_oracle.c", "fb_bench.c", "fb_oracle.h")]
+    if force or not os.path.exists(so) or any(os.path.exists(x) and os.path.getmtime(so) < os.path.getmtime(x) for x in srcs):
         subprocess.check_call(["make", "-C", _HERE, "libfboracle.so"], stdout=subprocess.DEVNULL)
     return so
 
@@ -56,7 +56,12 @@ def lib():
             "fbo_frag_row_counts": (i64, [vp, u64, vp, vp, vp, i64]),
             "fbo_frag_rows": (i64, [vp, vp, i64]),
             "fbo_groupby_shard": (C.c_int, [vp, C.c_int, u64, vp, vp, vp, vp]),
-            "fbo_bench_union_intersect_count": (u64, [vp, vp, i64, vp, C.c_int, vp, C.c_int, C.c_int, vp]),
+            "fbo_frag_row_view": (vp, [vp, u64, u64]),
+            "fbo_pool_create": (vp, [C.c_int]), "fbo_pool_destroy": (None, [vp]), "fbo_pool_threads": (C.c_int, [vp]),
+            "fbo_bench_union_intersect_count": (u64, [vp, vp, vp, i64, vp, C.c_int, vp, C.c_int, vp]),
+            "fbo_bench_pair_counts": (u64, [vp, vp, vp, i64, vp, vp, C.c_int, C.c_int, vp, vp]),
+            "fbo_bench_range_count": (u64, [vp, vp, vp, i64, C.c_int, u64, i64, i64, vp]),
+            "fbo_bench_groupby": (C.c_int, [vp, vp, C.c_int, vp, i64, vp, vp, vp, vp]),
         }
         for name, (res, args) in sig.items():
             f = getattr(L, name)
@@ -430,13 +435,71 @@ def groupby_shard(frags, shard, row_ids, filt=None, out=None):
     return out
 
 
-def bench_union_intersect_count(frags, shards, rows_a, rows_b, n_threads):
+class Pool:
+    """Long-lived pinned worker threads of the CPU baseline (fb_bench.c): created once, reused by every bench call."""
+
+    def __init__(self, n_threads=None):
+        self.n = int(n_threads or os.cpu_count() or 1)
+        self.ptr = lib().fbo_pool_create(self.n)
+
+    def close(self):
+        if self.ptr:
+            lib().fbo_pool_destroy(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _frag_array(frags):
+    return (C.c_void_p * len(frags))(*[(f.ptr if f is not None else None) for f in frags])
+
+
+def _u64(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.uint64))
+
+
+def bench_union_intersect_count(pool, frags, shards, rows_a, rows_b):
     """CPU baseline: Count(Intersect(Union(rows_a), Union(rows_b))) over the given fragments. Returns (count, seconds)."""
-    arr = (C.c_void_p * len(frags))(*[f.ptr for f in frags])
-    sh = np.ascontiguousarray(np.asarray(shards, dtype=np.uint64))
-    ra = np.ascontiguousarray(np.asarray(rows_a, dtype=np.uint64))
-    rb = np.ascontiguousarray(np.asarray(rows_b, dtype=np.uint64))
+    arr, sh, ra, rb = _frag_array(frags), _u64(shards), _u64(rows_a), _u64(rows_b)
     secs = C.c_double(0)
-    tot = lib().fbo_bench_union_intersect_count(arr, sh.ctypes.data, len(frags), ra.ctypes.data, len(ra),
-                                                rb.ctypes.data, len(rb), int(n_threads), C.byref(secs))
+    tot = lib().fbo_bench_union_intersect_count(pool.ptr, arr, sh.ctypes.data, len(frags), ra.ctypes.data, len(ra),
+                                                rb.ctypes.data, len(rb), C.byref(secs))
     return int(tot), secs.value
+
+
+def bench_pair_counts(pool, frags, shards, rows_a, rows_b, materialise=True):
+    """CPU baseline: Count(Intersect(Row(a_k), Row(b_k))) for every pair k. Returns (per-pair counts, seconds)."""
+    arr, sh, ra, rb = _frag_array(frags), _u64(shards), _u64(rows_a), _u64(rows_b)
+    out = np.zeros(len(ra), dtype=np.uint64)
+    secs = C.c_double(0)
+    tot = lib().fbo_bench_pair_counts(pool.ptr, arr, sh.ctypes.data, len(frags), ra.ctypes.data, rb.ctypes.data, len(ra),
+                                      1 if materialise else 0, out.ctypes.data, C.byref(secs))
+    assert int(tot) == int(out.sum())
+    return out, secs.value
+
+
+def bench_range_count(pool, frags, shards, op, bit_depth, predicate, predicate_max=0):
+    """CPU baseline: Count(Row(v <op> predicate)) over BSI fragments. Returns (count, seconds)."""
+    arr, sh = _frag_array(frags), _u64(shards)
+    secs = C.c_double(0)
+    tot = lib().fbo_bench_range_count(pool.ptr, arr, sh.ctypes.data, len(frags), OPS[op] if isinstance(op, str) else int(op),
+                                      int(bit_depth), int(predicate), int(predicate_max), C.byref(secs))
+    return int(tot), secs.value
+
+
+def bench_groupby(pool, frags_per_field, shards, row_ids):
+    """CPU baseline: GroupBy over set fields; frags_per_field[f][s]. Returns (dense counts, seconds)."""
+    nf, ns = len(frags_per_field), len(shards)
+    flat_frags = [f for per in frags_per_field for f in per]
+    arr, sh = _frag_array(flat_frags), _u64(shards)
+    n_rows = np.asarray([len(r) for r in row_ids], dtype=np.int32)
+    flat = _u64(np.concatenate([np.asarray(r, dtype=np.uint64) for r in row_ids]))
+    out = np.zeros(int(np.prod(n_rows)), dtype=np.uint64)
+    secs = C.c_double(0)
+    rc = lib().fbo_bench_groupby(pool.ptr, arr, nf, sh.ctypes.data, ns, flat.ctypes.data, n_rows.ctypes.data, out.ctypes.data, C.byref(secs))
+    assert rc == 0
+    return out, secs.value
