@@ -17,7 +17,7 @@ def _stale(target, sources):
 
 def build_fbgpu(force=False, verbose=False, defines=None, out_name="libfbgpu.so"):
     src = os.path.join(HERE, "csrc", "fbgpu.cu")
-    deps = [src, os.path.join(HERE, "csrc", "kernels.cuh"), os.path.join(HERE, "csrc", "fbgpu_types.h"), os.path.join(HERE, "csrc", "stripe.h"), os.path.join(HERE, "csrc", "rbf_reader.h"), os.path.join(HERE, "csrc", "bitaddr.h"), os.path.join(HERE, "csrc", "program_compiler.h"), os.path.join(HERE, "csrc", "roaring_parse.h"), os.path.join(HERE, "csrc", "host_error.h"), os.path.join(HERE, "csrc", "wp_machine.h"), os.path.join(HERE, "csrc", "resolve.h"),
+    deps = [src, os.path.join(HERE, "csrc", "kernels.cuh"), os.path.join(HERE, "csrc", "fbgpu_types.h"), os.path.join(HERE, "csrc", "stripe.h"), os.path.join(HERE, "csrc", "rbf_reader.h"), os.path.join(HERE, "csrc", "bitaddr.h"), os.path.join(HERE, "csrc", "program_compiler.h"), os.path.join(HERE, "csrc", "roaring_parse.h"), os.path.join(HERE, "csrc", "host_error.h"), os.path.join(HERE, "csrc", "wp_machine.h"), os.path.join(HERE, "csrc", "resolve.h"), os.path.join(HERE, "csrc", "node.h"),
             os.path.join(ROOT, "include", "fbgpu.h")]
     out = os.path.join(HERE, out_name)
     if force or _stale(out, deps):

@@ -17,6 +17,9 @@
 #include <memory>
 #include <mutex>
 #include <shared_mutex>
+#include <atomic>
+#include <deque>
+#include <functional>
 #include <string>
 #include <thread>
 #include <unordered_map>
@@ -177,7 +180,9 @@ struct fbgpu_ctx {
     // ---- comm
     void* comm = nullptr; int n_ranks = 1, rank = 0;
     // fused peer-memory reduce (Count)
-    Mailbox* mbox = nullptr; Mailbox* peers[kMaxRanks] = {}; DevBuf d_peers; bool p2p = false; unsigned long long epoch = 0; std::mutex coll_mu;
+    Mailbox* mbox = nullptr; Mailbox* peers[kMaxRanks] = {}; DevBuf d_peers; bool p2p = false; bool peers_local = false; unsigned long long epoch = 0; std::mutex coll_mu;
+    // bound of the in-kernel wait for one peer's count (FBGPU_P2P_TIMEOUT_MS, default 2000 ms at ~2 GHz)
+    long long p2p_timeout_cycles = [] { const char* e = getenv("FBGPU_P2P_TIMEOUT_MS"); const long long ms = e ? atoll(e) : 2000; return (ms > 0 ? ms : 2000) * 2000000ll; }();
 };
 
 static StoreRef store_ref(fbgpu_ctx* c) {
@@ -237,7 +242,7 @@ extern "C" void fbgpu_shutdown(fbgpu_ctx* c) {
     }
     for (DevBuf* b : { &c->d_payload, &c->d_views, &c->d_shardmap, &c->d_frags, &c->d_rows, &c->d_descs, &c->d_rowtab }) b->release();
     c->bounce[0].release(); c->bounce[1].release(); c->staging.clear_and_free();
-    for (int p = 0; p < kMaxRanks; p++) if (c->peers[p] && c->peers[p] != c->mbox) cudaIpcCloseMemHandle(c->peers[p]);   // peer mailboxes mapped by fbgpu_comm_p2p_open
+    for (int p = 0; p < kMaxRanks; p++) if (c->peers[p] && c->peers[p] != c->mbox && !c->peers_local) cudaIpcCloseMemHandle(c->peers[p]);   // peer mailboxes mapped by fbgpu_comm_p2p_open
     if (c->mbox) cudaFree(c->mbox);
     c->d_peers.release();
     delete c;
@@ -283,9 +288,49 @@ static void drop_locked(fbgpu_ctx* c, uint32_t fv, uint64_t shard) {
     c->meta_dirty = true;
 }
 
-// appends one parsed fragment to the host mirrors + staging (store_mu held exclusively)
-static int add_fragment_locked(fbgpu_ctx* c, uint32_t fv, uint64_t shard, const std::vector<ParsedCont>& cs, std::vector<PayloadCopy>& copies) {
-    if (shard >= (1ull << 31)) return fail(FBGPU_E_INVALID, "shard %llu too large", (unsigned long long)shard);
+// A load is all-or-nothing: the entry points open a StoreTxn before the first mutation; unless commit() is reached
+// (every fragment appended AND every payload copied), its destructor puts the host mirrors back exactly as they were —
+// vector lengths, the claimed staging space, statistics, the shard-map entries and the liveness of replaced fragments.
+// store_mu is held exclusively for the whole life of the object.
+struct StoreTxn {
+    fbgpu_ctx* c;
+    size_t n_rows, n_descs, n_frags, n_hfrags; uint64_t staging_len, dead_arena; fbgpu_stats stats; bool meta_dirty;
+    std::vector<uint64_t> view_arr, view_other, view_striped;
+    struct Undo { uint32_t fv; uint64_t shard; int32_t old_fid; size_t old_size; };
+    std::vector<Undo> undo;
+    bool done = false;
+    explicit StoreTxn(fbgpu_ctx* ctx) : c(ctx), n_rows(ctx->h_rows.size()), n_descs(ctx->h_descs.size()), n_frags(ctx->frags.size()), n_hfrags(ctx->h_frags.size()),
+        staging_len(ctx->staging.len), dead_arena(ctx->dead_arena), stats(ctx->stats), meta_dirty(ctx->meta_dirty),
+        view_arr(ctx->view_arr), view_other(ctx->view_other), view_striped(ctx->view_striped) {}
+    void note(uint32_t fv, uint64_t shard) {
+        auto& sm = c->shardmaps[fv];
+        undo.push_back(Undo{ fv, shard, shard < sm.size() ? sm[shard] : -1, sm.size() });
+    }
+    void commit() { done = true; }
+    ~StoreTxn() {
+        if (done) return;
+        for (size_t k = undo.size(); k-- > 0;) {
+            const Undo& u = undo[k]; auto& sm = c->shardmaps[u.fv];
+            if (sm.size() > u.old_size) sm.resize(u.old_size);
+            if (u.shard < sm.size()) sm[u.shard] = u.old_fid;
+            if (u.old_fid >= 0) c->frags[(size_t)u.old_fid].live = true;
+        }
+        c->h_rows.resize(n_rows); c->h_descs.resize(n_descs); c->frags.resize(n_frags); c->h_frags.resize(n_hfrags);
+        c->staging.len = staging_len; c->dead_arena = dead_arena; c->stats = stats; c->meta_dirty = meta_dirty;
+        // (views created by the failed call stay, empty: resize the snapshots up to the current number of views)
+        view_arr.resize(c->view_arr.size(), 0); view_other.resize(c->view_other.size(), 0); view_striped.resize(c->view_striped.size(), 0);
+        c->view_arr = view_arr; c->view_other = view_other; c->view_striped = view_striped;
+    }
+};
+
+// Shard ids index the dense per-view shard maps: the accepted range is bounded so that one stray id cannot make a load allocate
+// gigabytes of map (the reference's shard space is sparse; 2^24 shards = 1.7e13 columns per index is far past its deployments).
+constexpr uint64_t kMaxShard = 1ull << 24;
+
+// appends one parsed fragment to the host mirrors + staging (store_mu held exclusively, inside a StoreTxn)
+static int add_fragment_locked(fbgpu_ctx* c, StoreTxn& txn, uint32_t fv, uint64_t shard, const std::vector<ParsedCont>& cs, std::vector<PayloadCopy>& copies) {
+    if (shard >= kMaxShard) return fail(FBGPU_E_INVALID, "shard %llu too large (limit %llu)", (unsigned long long)shard, (unsigned long long)kMaxShard);
+    txn.note(fv, shard);
     drop_locked(c, fv, shard);
     HostFrag hf{}; hf.fv = fv; hf.shard = shard; hf.live = true; hf.row_off = (uint32_t)c->h_rows.size(); hf.desc_off = c->h_descs.size();
     hf.arena_off = c->uploaded + c->staging.len;
@@ -375,8 +420,11 @@ extern "C" int fbgpu_load_fragment(fbgpu_ctx* c, uint32_t index, uint32_t field,
     std::unique_lock<std::shared_mutex> lk(c->store_mu);
     uint32_t fv = view_id_locked(c, ViewKey{ index, field, view }, true);
     std::vector<PayloadCopy> copies;
-    rc = add_fragment_locked(c, fv, shard, cs, copies); if (rc) return rc;
-    return run_copies(c, copies, 1);
+    StoreTxn txn(c);
+    rc = add_fragment_locked(c, txn, fv, shard, cs, copies); if (rc) return rc;
+    rc = run_copies(c, copies, 1); if (rc) return rc;
+    txn.commit();
+    return FBGPU_OK;
 } FBGPU_CATCH
 
 extern "C" int fbgpu_load_fragments(fbgpu_ctx* c, uint32_t index, uint32_t field, uint32_t view, const uint64_t* shards, int64_t n,
@@ -396,8 +444,11 @@ extern "C" int fbgpu_load_fragments(fbgpu_ctx* c, uint32_t index, uint32_t field
     std::unique_lock<std::shared_mutex> lk(c->store_mu);
     uint32_t fv = view_id_locked(c, ViewKey{ index, field, view }, true);
     std::vector<PayloadCopy> copies;
-    for (int64_t i = 0; i < n; i++) { int rc = add_fragment_locked(c, fv, shards[i], parsed[i], copies); if (rc) return rc; }
-    return run_copies(c, copies, nt);
+    StoreTxn txn(c);
+    for (int64_t i = 0; i < n; i++) { int rc = add_fragment_locked(c, txn, fv, shards[i], parsed[i], copies); if (rc) return rc; }
+    int rc = run_copies(c, copies, nt); if (rc) return rc;
+    txn.commit();
+    return FBGPU_OK;
 } FBGPU_CATCH
 
 extern "C" int fbgpu_load_rbf(fbgpu_ctx* c, uint32_t index, uint64_t shard, const uint8_t* data, uint64_t data_bytes, const uint8_t* wal, uint64_t wal_bytes,
@@ -441,12 +492,15 @@ extern "C" int fbgpu_load_rbf(fbgpu_ctx* c, uint32_t index, uint64_t shard, cons
     }
     std::unique_lock<std::shared_mutex> lk(c->store_mu);
     std::vector<PayloadCopy> copies;
+    StoreTxn txn(c);
     for (auto& fd : found) {
         uint32_t fv = view_id_locked(c, ViewKey{ index, fd.field, fd.view }, true);
-        int rc = add_fragment_locked(c, fv, shard, fd.cs, copies); if (rc) return rc;
+        int rc = add_fragment_locked(c, txn, fv, shard, fd.cs, copies); if (rc) return rc;
     }
+    int rc = run_copies(c, copies, 1); if (rc) return rc;
+    txn.commit();
     if (out_loaded) *out_loaded = (int32_t)found.size();
-    return run_copies(c, copies, 1);
+    return FBGPU_OK;
 } FBGPU_CATCH
 
 // read-only mapping of one file; empty / missing files map to (nullptr, 0) with ok() still true when `optional`
@@ -767,8 +821,8 @@ extern "C" int fbgpu_count(fbgpu_ctx* c, uint32_t index, const fbgpu_op* ops, in
     WsLease lease(c); Workspace* w = lease.w;
     const DevOp* d_prog; const uint64_t* d_shards;
     rc = upload_inputs(w, prog, shards, n_shards, &d_prog, &d_shards); if (rc) return rc;
-    // layout of d_counts: [total][per-shard counts ...][ticket][reduced result]
-    const size_t nper = out_per_shard ? (size_t)n_shards : 0, nc = 1 + nper + 2;
+    // layout of d_counts: [total][per-shard counts ...][ticket][reduced result][error]
+    const size_t nper = out_per_shard ? (size_t)n_shards : 0, nc = 1 + nper + 3;
     if (w->d_counts.ensure(nc * 8)) return FBGPU_E_NOMEM;
     if (w->h_out.ensure(nc * 8)) return FBGPU_E_NOMEM;
     CUDA_TRY(cudaMemsetAsync(w->d_counts.p, 0, nc * 8, w->stream));
@@ -783,7 +837,8 @@ extern "C" int fbgpu_count(fbgpu_ctx* c, uint32_t index, const fbgpu_op* ops, in
     if (!p2p) coll_lk.unlock();
     if (p2p) {
         fr.peers = (Mailbox* const*)c->d_peers.p; fr.ticket = (unsigned int*)(d_total + 1 + nper); fr.result = d_total + 1 + nper + 1;
-        fr.epoch = ++c->epoch; fr.rank = c->rank; fr.n_ranks = c->n_ranks;
+        fr.error = (unsigned int*)(d_total + 1 + nper + 2);
+        fr.epoch = ++c->epoch; fr.rank = c->rank; fr.n_ranks = c->n_ranks; fr.timeout_cycles = c->p2p_timeout_cycles;
     }
     CUDA_TRY(cudaEventRecord(w->ev0, w->stream));
     if (n_units > 0) {
@@ -804,6 +859,11 @@ extern "C" int fbgpu_count(fbgpu_ctx* c, uint32_t index, const fbgpu_op* ops, in
     CUDA_TRY(cudaEventRecord(w->ev1, w->stream));
     CUDA_TRY(cudaMemcpyAsync(w->h_out.p, w->d_counts.p, nc * 8, cudaMemcpyDeviceToHost, w->stream));
     CUDA_TRY(cudaStreamSynchronize(w->stream));
+    if (p2p && ((uint64_t*)w->h_out.p)[1 + nper + 2] != 0) {
+        lease.ok = true;                     // the stream is drained; the exchange state is not: the caller re-opens the peers
+        return fail(FBGPU_E_COMM, "rank %d did not publish its count for exchange %llu in time (peer dead, or the ranks issued their collective queries in different orders); re-open with fbgpu_comm_p2p_open",
+                    (int)((uint64_t*)w->h_out.p)[1 + nper + 2] - 1, (unsigned long long)fr.epoch);
+    }
     *out_total = p2p ? ((uint64_t*)w->h_out.p)[1 + nper + 1] : ((uint64_t*)w->h_out.p)[0];
     if (out_per_shard) memcpy(out_per_shard, (uint64_t*)w->h_out.p + 1, (size_t)n_shards * 8);
     float ms = 0; cudaEventElapsedTime(&ms, w->ev0, w->ev1);
@@ -1389,9 +1449,10 @@ extern "C" int fbgpu_comm_p2p_open(fbgpu_ctx* c, int32_t n_ranks, int32_t rank, 
     std::lock_guard<std::mutex> lk(c->coll_mu);
     c->p2p = false;
     for (int p = 0; p < kMaxRanks; p++) {                        // re-open after a membership change: drop the old mappings first
-        if (c->peers[p] && c->peers[p] != c->mbox) cudaIpcCloseMemHandle(c->peers[p]);
+        if (c->peers[p] && c->peers[p] != c->mbox && !c->peers_local) cudaIpcCloseMemHandle(c->peers[p]);
         c->peers[p] = nullptr;
     }
+    c->peers_local = false;
     for (int p = 0; p < n_ranks; p++) {
         if (p == rank) { c->peers[p] = c->mbox; continue; }
         cudaIpcMemHandle_t h; memcpy(&h, handles + (size_t)p * 64, 64);
@@ -1402,6 +1463,11 @@ extern "C" int fbgpu_comm_p2p_open(fbgpu_ctx* c, int32_t n_ranks, int32_t rank, 
     }
     if (c->d_peers.ensure(sizeof(Mailbox*) * kMaxRanks)) return FBGPU_E_NOMEM;
     CUDA_TRY(cudaMemcpy(c->d_peers.p, c->peers, sizeof(Mailbox*) * kMaxRanks, cudaMemcpyHostToDevice));
+    // a re-open restarts the exchange numbering: flags left by the previous membership must not satisfy a new wait.  Every rank
+    // clears its OWN mailbox here; the caller separates fbgpu_comm_p2p_open from the first query by a barrier (all ranks opened).
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemset(c->mbox, 0, sizeof(Mailbox)));
+    CUDA_TRY(cudaDeviceSynchronize());
     c->n_ranks = n_ranks; c->rank = rank; c->epoch = 0; c->p2p = true;
     return FBGPU_OK;
 } FBGPU_CATCH
@@ -1482,3 +1548,6 @@ extern "C" int fbgpu_rows_payload_bytes(fbgpu_ctx* c, uint32_t index, uint32_t f
     *out_payload = pay; *out_containers = nc;
     return 0;
 } FBGPU_CATCH
+
+// ------------------------------------------------------------------ all GPUs of one process behind one handle
+#include "node.h"

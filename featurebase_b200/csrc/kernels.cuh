@@ -256,7 +256,9 @@ struct FuseReduce {
     Mailbox* const* peers;          // device array [n_ranks]; peers[rank] is this rank's own mailbox; nullptr => fusion off
     unsigned int* ticket;           // completion counter of the launch (zeroed by the host)
     unsigned long long* result;     // receives the reduced total
+    unsigned int* error;            // set to 1 + the rank that never published (bounded wait); zeroed by the host
     unsigned long long epoch;
+    long long timeout_cycles;       // bound of the wait for one peer, in SM clock cycles
     int rank, n_ranks;
 };
 // called by ONE thread per CTA (or per warp) after its atomicAdd into *total; n_callers = how many will call
@@ -274,7 +276,13 @@ __device__ __forceinline__ void fused_allreduce_tail(const FuseReduce& fr, unsig
     Mailbox* me = fr.peers[fr.rank];
     unsigned long long sum = 0;
     for (int q = 0; q < fr.n_ranks; q++) {
-        while (*reinterpret_cast<volatile unsigned long long*>(&me->flag[par][q]) < fr.epoch) { }
+        // exact match: a slot of this parity holds e-2 (or 0) until the peer publishes e; anything else is a protocol error and
+        // runs into the same bound.  The wait is bounded: a dead or diverged peer must not hang the GPU (the host turns the
+        // error word into FBGPU_E_COMM).
+        const long long t0 = clock64();
+        while (*reinterpret_cast<volatile unsigned long long*>(&me->flag[par][q]) != fr.epoch) {
+            if (clock64() - t0 > fr.timeout_cycles) { *fr.error = 1u + (unsigned int)q; *fr.result = ~0ull; __threadfence_system(); return; }
+        }
         __threadfence_system();
         sum += *reinterpret_cast<volatile unsigned long long*>(&me->value[par][q]);
     }

@@ -42,7 +42,10 @@ class Counters(C.Structure):
 EXPORTS = ["fbgpu_init", "fbgpu_shutdown", "fbgpu_last_error", "fbgpu_abi_version", "fbgpu_load_fragment",
            "fbgpu_load_fragments", "fbgpu_drop_fragment", "fbgpu_commit", "fbgpu_get_stats", "fbgpu_count", "fbgpu_row",
            "fbgpu_row_counts", "fbgpu_row_counts_per_shard", "fbgpu_groupby", "fbgpu_comm_unique_id", "fbgpu_comm_init", "fbgpu_comm_destroy",
-           "fbgpu_get_counters", "fbgpu_stream", "fbgpu_rows_payload_bytes", "fbgpu_count_pairs", "fbgpu_columns", "fbgpu_extract", "fbgpu_load_rbf", "fbgpu_load_rbf_dir", "fbgpu_bsi_minmax", "fbgpu_bsi_sum", "fbgpu_compact", "fbgpu_comm_p2p_handle", "fbgpu_comm_p2p_open", "fbgpu_comm_p2p_disable"]
+           "fbgpu_get_counters", "fbgpu_stream", "fbgpu_rows_payload_bytes", "fbgpu_count_pairs", "fbgpu_columns", "fbgpu_extract", "fbgpu_load_rbf", "fbgpu_load_rbf_dir", "fbgpu_bsi_minmax", "fbgpu_bsi_sum", "fbgpu_compact", "fbgpu_comm_p2p_handle", "fbgpu_comm_p2p_open", "fbgpu_comm_p2p_disable",
+           "fbgpu_comm_p2p_open_local", "fbgpu_node_init", "fbgpu_node_shutdown", "fbgpu_node_devices", "fbgpu_node_owner", "fbgpu_node_ctx", "fbgpu_node_load_fragment",
+           "fbgpu_node_load_fragments", "fbgpu_node_load_rbf_dir", "fbgpu_node_drop_fragment", "fbgpu_node_commit", "fbgpu_node_get_stats", "fbgpu_node_count", "fbgpu_node_row",
+           "fbgpu_node_count_pairs", "fbgpu_node_row_counts", "fbgpu_node_groupby", "fbgpu_node_bsi_sum", "fbgpu_node_bsi_minmax"]
 
 
 def lib_path():
@@ -94,6 +97,17 @@ def load():
     L.fbgpu_get_counters.argtypes, L.fbgpu_get_counters.restype = [vp, C.POINTER(Counters)], C.c_int
     L.fbgpu_stream.argtypes, L.fbgpu_stream.restype = [vp], vp
     L.fbgpu_rows_payload_bytes.argtypes, L.fbgpu_rows_payload_bytes.restype = [vp, u32, u32, u32, vp, i32, vp, i64, C.POINTER(u64), C.POINTER(u64)], C.c_int
+    L.fbgpu_comm_p2p_open_local.argtypes, L.fbgpu_comm_p2p_open_local.restype = [vp, i32], C.c_int
+    # fbgpu_node_*: the fbgpu_* signature of the same name with the node handle in place of the context
+    L.fbgpu_node_init.argtypes, L.fbgpu_node_init.restype = [vp, i32, u64, C.POINTER(vp)], C.c_int
+    L.fbgpu_node_shutdown.argtypes, L.fbgpu_node_shutdown.restype = [vp], None
+    L.fbgpu_node_devices.argtypes, L.fbgpu_node_devices.restype = [vp], i32
+    L.fbgpu_node_owner.argtypes, L.fbgpu_node_owner.restype = [vp, u64], i32
+    L.fbgpu_node_ctx.argtypes, L.fbgpu_node_ctx.restype = [vp, i32], vp
+    for name in ("load_fragment", "load_fragments", "load_rbf_dir", "drop_fragment", "commit", "get_stats", "count", "row", "count_pairs", "groupby", "bsi_sum", "bsi_minmax"):
+        src, dst = getattr(L, "fbgpu_" + name), getattr(L, "fbgpu_node_" + name)
+        dst.argtypes, dst.restype = src.argtypes, src.restype
+    L.fbgpu_node_row_counts.argtypes, L.fbgpu_node_row_counts.restype = [vp, u32, u32, u32, vp, i32, vp, i32, vp, i64, vp], C.c_int
     _LIB = L
     return L
 
@@ -376,3 +390,65 @@ class Context:
 
     def comm_p2p_disable(self):
         self._check(self.L.fbgpu_comm_p2p_disable(self.h))
+
+
+class _NodeCalls:
+    """routes Context's `self.L.fbgpu_<call>` to `fbgpu_node_<call>` where the node has that call"""
+
+    def __init__(self, real):
+        self._real = real
+
+    def __getattr__(self, name):
+        if name.startswith("fbgpu_") and not name.startswith("fbgpu_node_") and hasattr(self._real, "fbgpu_node_" + name[6:]):
+            return getattr(self._real, "fbgpu_node_" + name[6:])
+        return getattr(self._real, name)
+
+
+class Node(Context):
+    """fbgpu_node: every GPU of this process behind one handle.  Residency and query methods are Context's, fanned out over
+    the devices by the library; shard s lives on device slot (s // shard_block) % len(devices)."""
+
+    def __init__(self, devices, shard_block):
+        real = load()
+        self.L = _NodeCalls(real)
+        self.h = C.c_void_p()
+        devs = (C.c_int32 * len(devices))(*[int(d) for d in devices])
+        self._check(real.fbgpu_node_init(devs, len(devices), int(shard_block), C.byref(self.h)))
+        self.n_devices = len(devices)
+
+    def close(self):
+        if self.h:
+            self.L.fbgpu_node_shutdown(self.h)
+            self.h = C.c_void_p()
+
+    def owner(self, shard):
+        return int(self.L.fbgpu_node_owner(self.h, int(shard)))
+
+    def device_counters(self, slot):
+        s = Counters()
+        self._check(self.L._real.fbgpu_get_counters(self.L.fbgpu_node_ctx(self.h, slot), C.byref(s)))
+        return {"kernel_launches": s.kernel_launches, "queries": s.queries, "last_query_gpu_ms": s.last_query_gpu_ms}
+
+    def counters(self):
+        per = [self.device_counters(i) for i in range(self.n_devices)]
+        return {"kernel_launches": sum(p["kernel_launches"] for p in per), "queries": sum(p["queries"] for p in per),
+                "last_query_gpu_ms": max(p["last_query_gpu_ms"] for p in per)}
+
+    def row_counts(self, index, field, view, shards, row_ids=None, filter_ops=None, cap=1 << 20):
+        if row_ids is None:
+            raise NotImplementedError("fbgpu_node_row_counts takes explicit row ids (TopN(ids=..) / TopK candidates)")
+        sh, ids = _u64arr(shards), _u64arr(row_ids)
+        f = ops_array(filter_ops) if filter_ops else None
+        out = np.zeros(len(ids), dtype=np.uint64)
+        self._check(self.L.fbgpu_node_row_counts(self.h, index, field, view, ids.ctypes.data, len(ids), f, len(filter_ops) if filter_ops else 0,
+                                                 sh.ctypes.data, len(sh), out.ctypes.data))
+        return out
+
+
+def p2p_open_local(contexts):
+    """wire the Count mailboxes of contexts living in this process to each other (fbgpu_comm_p2p_open_local)"""
+    L = load()
+    arr = (C.c_void_p * len(contexts))(*[c.h for c in contexts])
+    rc = L.fbgpu_comm_p2p_open_local(arr, len(contexts))
+    if rc != 0:
+        raise FbgpuError(rc, L.fbgpu_last_error().decode())

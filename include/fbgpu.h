@@ -230,6 +230,56 @@ int fbgpu_comm_p2p_handle(fbgpu_ctx *ctx, uint8_t out_handle[64]);
 int fbgpu_comm_p2p_open(fbgpu_ctx *ctx, int32_t n_ranks, int32_t rank, const uint8_t *handles /* n_ranks x 64 bytes */);
 int fbgpu_comm_p2p_disable(fbgpu_ctx *ctx);   /* fall back to the NCCL merge (e.g. when a peer could not be mapped) */
 
+/* In-process form of the same exchange: the contexts of ONE process (one per GPU, one caller thread each) are wired to each
+ * other through peer access instead of CUDA IPC.  ctxs[r] becomes rank r. */
+int fbgpu_comm_p2p_open_local(fbgpu_ctx *const *ctxs, int32_t n_ranks);
+/* The wait for a peer's count inside the kernel is bounded (FBGPU_P2P_TIMEOUT_MS, default 2000): a peer that died, or ranks
+ * that issued their collective queries in different orders, make fbgpu_count() return FBGPU_E_COMM instead of hanging the GPU.
+ * The multi-process forms keep NCCL's precondition: every rank issues its collective queries in the same order, from one thread
+ * at a time.  A process whose threads query concurrently (FeatureBase: executor.go:6449-6533) uses fbgpu_node below. */
+
+/* ---- every GPU of one process behind one handle (SURVEY §8(b) fbgpu_init(device_ordinals, n); replaces mapReduce's local
+ *      fan-out + reduce, executor.go:6449-6533, 6742-6812) ----
+ * A node owns one context per listed device.  Shard s lives on device slot (s / shard_block) % n_devices: contiguous blocks of
+ * shard_block shards per GPU (shard_block = ceil(total shards / n_devices) gives one range per GPU).  Every
+ * fbgpu_node_* query takes the caller's whole shard list, runs each device's share concurrently on that device (own worker
+ * thread, stream and workspace per call) and merges the per-device results on the host with the reference's reducers (u64
+ * add: Count executor.go:5880, Pairs.Add cache.go:464, mergeGroupCounts executor.go:3728; Row.Merge row.go:202).  Any number
+ * of threads may call concurrently; calls never share result buffers, and a failure on one device fails only that call.
+ * The same device ordinal may be listed more than once (two contexts on one GPU; used by the tests). */
+typedef struct fbgpu_node fbgpu_node;
+int fbgpu_node_init(const int32_t *device_ordinals, int32_t n_devices, uint64_t shard_block, fbgpu_node **out);
+void fbgpu_node_shutdown(fbgpu_node *node);
+int32_t fbgpu_node_devices(const fbgpu_node *node);
+int32_t fbgpu_node_owner(const fbgpu_node *node, uint64_t shard);      /* device slot that holds the shard */
+fbgpu_ctx *fbgpu_node_ctx(fbgpu_node *node, int32_t slot);             /* the slot's context (stats, counters); owned by the node */
+int fbgpu_node_load_fragment(fbgpu_node *node, uint32_t index, uint32_t field, uint32_t view, uint64_t shard,
+                             const uint8_t *roaring, uint64_t nbytes);
+int fbgpu_node_load_fragments(fbgpu_node *node, uint32_t index, uint32_t field, uint32_t view,
+                              const uint64_t *shards, int64_t n, const uint8_t *buf, const uint64_t *offsets);
+int fbgpu_node_load_rbf_dir(fbgpu_node *node, uint32_t index, uint64_t shard, const char *dir, const char *const *names,
+                            const uint32_t *fields, const uint32_t *views, int32_t n_names, int32_t *out_loaded);
+int fbgpu_node_drop_fragment(fbgpu_node *node, uint32_t index, uint32_t field, uint32_t view, uint64_t shard);
+int fbgpu_node_commit(fbgpu_node *node);
+int fbgpu_node_get_stats(fbgpu_node *node, fbgpu_stats *out);           /* summed over the devices */
+/* same contracts as the fbgpu_* calls of the same name, over all devices */
+int fbgpu_node_count(fbgpu_node *node, uint32_t index, const fbgpu_op *ops, int32_t n_ops,
+                     const uint64_t *shards, int64_t n_shards, uint64_t *out_total, uint64_t *out_per_shard);
+int fbgpu_node_row(fbgpu_node *node, uint32_t index, const fbgpu_op *ops, int32_t n_ops,
+                   const uint64_t *shards, int64_t n_shards, uint8_t *out_buf, uint64_t out_cap, uint64_t *out_len, uint64_t *out_count);
+int fbgpu_node_count_pairs(fbgpu_node *node, uint32_t index, uint32_t field_a, uint32_t view_a, const uint64_t *rows_a,
+                           uint32_t field_b, uint32_t view_b, const uint64_t *rows_b, int32_t n_pairs,
+                           const uint64_t *shards, int64_t n_shards, uint64_t *out_counts);
+int fbgpu_node_row_counts(fbgpu_node *node, uint32_t index, uint32_t field, uint32_t view, const uint64_t *row_ids, int32_t n_rows,
+                          const fbgpu_op *filter, int32_t n_filter_ops, const uint64_t *shards, int64_t n_shards, uint64_t *out_counts);
+int fbgpu_node_groupby(fbgpu_node *node, uint32_t index, const uint32_t *fields, const uint32_t *views, int32_t n_fields,
+                       const uint64_t *row_ids_flat, const int32_t *n_rows, const fbgpu_op *filter, int32_t n_filter_ops,
+                       const uint64_t *shards, int64_t n_shards, uint64_t *out_counts);
+int fbgpu_node_bsi_sum(fbgpu_node *node, uint32_t index, const fbgpu_op *ops, int32_t n_ops, uint32_t field, uint32_t view, int32_t bit_depth,
+                       const uint64_t *shards, int64_t n_shards, int64_t *out_sum, uint64_t *out_count);
+int fbgpu_node_bsi_minmax(fbgpu_node *node, uint32_t index, const fbgpu_op *ops, int32_t n_ops, uint32_t field, uint32_t view, int32_t bit_depth,
+                          const uint64_t *shards, int64_t n_shards, int32_t want_max, int64_t *out_val, uint64_t *out_count);
+
 /* Inspection (any context): the stack-machine program the library would run for `ops` -- records of 16 bytes {u8 op, u8 pad[3],
  * u32 view slot, u64 row} (csrc/fbgpu_types.h DevOp); *out_depth = operand stack depth.  With index == 0xffffffff,
  * fbgpu_debug_container() takes such a view slot in `field`. */

@@ -15,6 +15,7 @@
 // kernel<<<...>>>(...) launches, `extern __shared__ T name[];`, and inline PTX (each known statement is mapped to the
 // emu:: function below; an unknown one becomes emu::unsupported()).
 #pragma once
+#include <time.h>
 #include <ucontext.h>
 
 #include <dlfcn.h>
@@ -296,6 +297,7 @@ static inline unsigned __reduce_and_sync(unsigned, unsigned v) { return (unsigne
 static inline unsigned __reduce_max_sync(unsigned, unsigned v) { return (unsigned)emu::warp_fold(v, [](uint64_t a, uint64_t b) { return a > b ? a : b; }); }
 static inline unsigned __reduce_min_sync(unsigned, unsigned v) { return (unsigned)emu::warp_fold(v, [](uint64_t a, uint64_t b) { return a < b ? a : b; }); }
 
+static inline long long clock64() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return (long long)ts.tv_sec * 1000000000ll + ts.tv_nsec; }   // "cycles" = ns
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __popcll(unsigned long long v) { return __builtin_popcountll(v); }
 static inline int __ffs(int v) { return __builtin_ffs(v); }
@@ -326,7 +328,7 @@ template <class T> static inline T atomicCAS(T* p, EMU_V(T) c, EMU_V(T) v) { T o
 typedef int cudaError_t;
 typedef struct emuStream* cudaStream_t;
 typedef struct emuEvent { std::chrono::steady_clock::time_point t; }* cudaEvent_t;
-enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2, cudaErrorNotSupported = 801 };
+enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2, cudaErrorPeerAccessAlreadyEnabled = 704, cudaErrorNotSupported = 801 };
 enum cudaMemcpyKind { cudaMemcpyHostToHost, cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice, cudaMemcpyDefault };
 enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2, cudaIpcMemLazyEnablePeerAccess = 1 };
 enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
@@ -391,3 +393,5 @@ template <class F> static inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAtt
 static inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t*, void*) { return cudaErrorNotSupported; }
 static inline cudaError_t cudaIpcOpenMemHandle(void**, cudaIpcMemHandle_t, unsigned) { return cudaErrorNotSupported; }
 static inline cudaError_t cudaIpcCloseMemHandle(void*) { return cudaErrorNotSupported; }
+static inline cudaError_t cudaDeviceCanAccessPeer(int* can, int, int) { *can = 1; return cudaSuccess; }
+static inline cudaError_t cudaDeviceEnablePeerAccess(int, unsigned) { return cudaSuccess; }

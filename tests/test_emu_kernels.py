@@ -75,6 +75,12 @@ def test_query_level_bodies_on_interpreted_kernels():
     run_on_emulator(["tests/test_zz_gpu_experimental.py", "-k", NOT_HUGE + " and not striped" + ("" if FULL else SLOW)], timeout=3000)
 
 
+def test_node_fan_out_and_merge():
+    """fbgpu_node (all devices of one process behind one handle): routing by shard owner, per-device fan-out on worker threads,
+    host merge of counts / vectors / Row images, concurrent callers — two contexts stand in for two devices"""
+    run_on_emulator(["tests/test_gpu_node.py"], timeout=3000)
+
+
 def test_striped_array_order():
     """FBGPU_ARRAY_STRIPED=1: the loader's bank-striped element order under every kernel that reads array payloads"""
     run_on_emulator(["tests/test_zz_gpu_experimental.py", "-k", "striped and " + NOT_HUGE + ("" if FULL else SLOW)], env={"FBGPU_TEST_EXPERIMENTAL": "1"}, timeout=3000)

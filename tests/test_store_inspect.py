@@ -239,3 +239,30 @@ def test_algorithmic_byte_accounting():
         assert ctx.rows_payload_bytes(0, 1, 0, shards, rows) == (pay, cont), rows
     assert ctx.rows_payload_bytes(0, 1, 0, [9], [0]) == (0, 0)
     assert ctx.rows_payload_bytes(0, 7, 0, shards, [0]) == (0, 0)
+
+
+def test_failed_batch_load_leaves_the_store_unchanged():
+    """a batch load that fails half way (here: a shard id past the accepted range) must not leave the earlier fragments
+    of the batch live with unwritten payloads, nor drop the fragments they were about to replace."""
+    from featurebase_b200 import datagen as D
+    from featurebase_b200 import lib as L
+    ctx = L.Context(L.DEVICE_NONE)
+    old = D.fragment(7, 0, [0, 1], 0.01)
+    ctx.load_fragment(0, 0, 0, 0, old)
+    before = ctx.stats()
+    kept = ctx.debug_container(0, 0, 0, 0, 0, 3)
+    assert kept is not None
+    new0, new1 = D.fragment(8, 0, [0, 1, 2], 0.02), D.fragment(8, 1, [0], 0.02)
+    buf = np.frombuffer(new0 + new1, dtype=np.uint8)
+    offs = np.array([0, len(new0), len(new0) + len(new1)], dtype=np.uint64)
+    with pytest.raises(L.FbgpuError):
+        ctx.load_fragments(0, 0, 0, np.array([0, 1 << 40], dtype=np.uint64), buf, offs)
+    after = ctx.stats()
+    assert after == before
+    assert ctx.debug_container(0, 0, 0, 0, 0, 3) == kept          # the replaced fragment is live again, payload intact
+    assert ctx.debug_container(0, 0, 0, 0, 2, 0) is None           # nothing of the failed batch is visible
+    # and the store still accepts the same data once the bad shard id is gone
+    ctx.load_fragments(0, 0, 0, np.array([0, 1], dtype=np.uint64), buf, offs)
+    assert ctx.debug_container(0, 0, 0, 0, 2, 0) is not None
+    assert ctx.debug_container(0, 0, 0, 1, 0, 0) is not None
+    ctx.close()
