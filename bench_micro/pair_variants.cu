@@ -11,6 +11,7 @@
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <thread>
 #include <vector>
 #include <cuda_runtime.h>
@@ -220,6 +221,266 @@ __global__ void __launch_bounds__(T) c3_rot(const uint16_t* data, const int* len
   if ((tid & 31) == 0 && total) atomicAdd(out, (unsigned long long)total);
 }
 
+
+// ---- w5: two-part layout.  Part 1 = one element per distinct 32-bit bitmap word (plain STS of the bit, no atomic needed on an
+// all-zero bitmap), part 2 = the other elements of shared words (ATOMS.OR after part 1).  Clearing = STS 0 to the part-1 words
+// (every touched word has exactly one part-1 element): no 8 KiB wipe, no atomic un-scatter.  Both parts are bank-striped and
+// padded to whole chunks with copies of their last element.  len1[c] / len2[c] = elements of part 1 / 2.
+__device__ __forceinline__ void sts(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(addr), "r"(v) : "memory"); }
+template <bool CLEAR> __device__ __forceinline__ void store8(uint32_t sb, uint4 v) {
+  uint32_t w[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    sts(sb + off_lo(w[q]), CLEAR ? 0u : (1u << (w[q] & 31)));
+    sts(sb + off_hi(w[q]), CLEAR ? 0u : (1u << ((w[q] >> 16) & 31)));
+  }
+}
+template <int WARPS, bool PREFETCH>
+__global__ void __launch_bounds__(WARPS * 32) w5_split(const uint16_t* data, const int* len1, const int* len2, int n_pairs, unsigned long long* out) {
+  extern __shared__ __align__(128) uint32_t smem[];
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t* bm = smem + wid * 2048; const uint32_t sb = (uint32_t)__cvta_generic_to_shared(bm);
+  for (int i = lane; i < 512; i += 32) ((uint4*)bm)[i] = make_uint4(0, 0, 0, 0);
+  __syncwarp();
+  unsigned total = 0;
+  const int stride = gridDim.x * WARPS;
+  int w = blockIdx.x * WARPS + wid;
+  uint4 va[3], vb[3]; uint32_t a1 = 0, a2 = 0, b1 = 0, b2 = 0;
+  auto load = [&](int p, uint4* xa, uint4* xb, uint32_t& la1, uint32_t& la2, uint32_t& lb1, uint32_t& lb2) {
+    const uint4* A = (const uint4*)(data + (size_t)(2 * p) * STRIDE); const uint4* B = (const uint4*)(data + (size_t)(2 * p + 1) * STRIDE);
+    la1 = len1[2 * p]; la2 = len2[2 * p]; lb1 = len1[2 * p + 1]; lb2 = len2[2 * p + 1];
+    const uint32_t na8 = ((la1 + 7) >> 3) + ((la2 + 7) >> 3), nb8 = ((lb1 + 7) >> 3) + ((lb2 + 7) >> 3);
+#pragma unroll
+    for (int q = 0; q < 3; q++) xa[q] = ldg_nc(A + min((uint32_t)lane + 32 * q, na8 - 1));
+#pragma unroll
+    for (int q = 0; q < 3; q++) xb[q] = ldg_nc(B + min((uint32_t)lane + 32 * q, nb8 - 1));
+  };
+  if (PREFETCH && w < n_pairs) load(w, va, vb, a1, a2, b1, b2);
+  for (; w < n_pairs; w += stride) {
+    uint4 xa[3], xb[3]; uint32_t la1, la2, lb1, lb2;
+    if (PREFETCH) {
+#pragma unroll
+      for (int q = 0; q < 3; q++) { xa[q] = va[q]; xb[q] = vb[q]; }
+      la1 = a1; la2 = a2; lb1 = b1; lb2 = b2;
+      if (w + stride < n_pairs) load(w + stride, va, vb, a1, a2, b1, b2);
+    } else load(w, xa, xb, la1, la2, lb1, lb2);
+    const uint32_t ca1 = (la1 + 7) >> 3, ca = ca1 + ((la2 + 7) >> 3), cb1 = (lb1 + 7) >> 3, cb = cb1 + ((lb2 + 7) >> 3);
+#pragma unroll
+    for (int q = 0; q < 3; q++) if (lane + 32 * q < ca1) store8<false>(sb, xa[q]);
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 3; q++) { const uint32_t i = lane + 32 * q; if (i >= ca1 && i < ca) scatter8<0>(sb, xa[q]); }
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 3; q++) {
+      const uint32_t i = lane + 32 * q;
+      if (i < cb1) total += probe8(sb, xb[q], i * 8, lb1);
+      else if (i < cb) total += probe8(sb, xb[q], (i - cb1) * 8, lb2);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 3; q++) if (lane + 32 * q < ca1) store8<true>(sb, xa[q]);
+    __syncwarp();
+  }
+  total = __reduce_add_sync(0xffffffff, total);
+  if (lane == 0) atomicAdd(out, (unsigned long long)total);
+}
+
+
+// ---- w6: w1 (wipe) + next pair prefetched + unguarded chunks (tails padded with copies of the last element; the probe's over-count
+// of a padded tail is taken out again by one extra lookup of the last element) + probe hits collected by a funnel shift.
+// MULHI: the two offset computations go through IMAD.HI with a register multiplier (fma pipe) instead of LEA.HI (alu pipe).
+template <bool MULHI> __device__ __forceinline__ uint32_t o_lo(uint32_t w, uint32_t m29) { return MULHI ? __umulhi(w & 0xffe0u, m29) : off_lo(w); }
+template <bool MULHI> __device__ __forceinline__ uint32_t o_hi(uint32_t w, uint32_t m13) { return MULHI ? __umulhi(w & 0xffe00000u, m13) : off_hi(w); }
+template <int WARPS, bool MULHI>
+__global__ void __launch_bounds__(WARPS * 32) w6_tuned(const uint16_t* data, const int* len, int n_pairs, unsigned long long* out, uint32_t m29, uint32_t m13) {
+  extern __shared__ __align__(128) uint32_t smem[];
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t* bm = smem + wid * 2048; const uint32_t sb = (uint32_t)__cvta_generic_to_shared(bm);
+  unsigned total = 0;
+  const int stride = gridDim.x * WARPS;
+  int w = blockIdx.x * WARPS + wid;
+  uint4 va[3], vb[3]; uint32_t na = 0, nb = 0;
+  auto load = [&](int p, uint4* xa, uint4* xb, uint32_t& la, uint32_t& lb) {
+    const uint4* A = (const uint4*)(data + (size_t)(2 * p) * STRIDE); const uint4* B = (const uint4*)(data + (size_t)(2 * p + 1) * STRIDE);
+    la = len[2 * p]; lb = len[2 * p + 1];
+    const uint32_t na8 = (la + 7) >> 3, nb8 = (lb + 7) >> 3;
+#pragma unroll
+    for (int q = 0; q < 3; q++) xa[q] = ldg_nc(A + min((uint32_t)lane + 32 * q, na8 - 1));
+#pragma unroll
+    for (int q = 0; q < 3; q++) xb[q] = ldg_nc(B + min((uint32_t)lane + 32 * q, nb8 - 1));
+  };
+  if (w < n_pairs) load(w, va, vb, na, nb);
+  for (; w < n_pairs; w += stride) {
+    uint4 xa[3], xb[3];
+#pragma unroll
+    for (int q = 0; q < 3; q++) { xa[q] = va[q]; xb[q] = vb[q]; }
+    const uint32_t la = na, lb = nb;
+    const uint32_t last_b = __ldg(data + (size_t)(2 * w + 1) * STRIDE + lb - 1);      // (the product keeps it in the descriptor)
+    if (w + stride < n_pairs) load(w + stride, va, vb, na, nb);
+    const uint32_t na8 = (la + 7) >> 3, nb8 = (lb + 7) >> 3;
+#pragma unroll 4
+    for (int i = lane; i < 512; i += 32) ((uint4*)bm)[i] = make_uint4(0, 0, 0, 0);
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 3; q++) if (lane + 32 * q < na8) {
+      uint32_t x[4] = { xa[q].x, xa[q].y, xa[q].z, xa[q].w };
+#pragma unroll
+      for (int k = 0; k < 4; k++) { bit_op<0>(sb, o_lo<MULHI>(x[k], m29), x[k]); bit_op<0>(sb, o_hi<MULHI>(x[k], m13), x[k] >> 16); }
+    }
+    __syncwarp();
+    uint32_t hits = 0;      // one bit per probed element (<= 24 per lane)
+#pragma unroll
+    for (int q = 0; q < 3; q++) if (lane + 32 * q < nb8) {
+      uint32_t x[4] = { xb[q].x, xb[q].y, xb[q].z, xb[q].w };
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        uint32_t t0 = lds(sb + o_lo<MULHI>(x[k], m29)) >> (x[k] & 31), t1 = lds(sb + o_hi<MULHI>(x[k], m13)) >> ((x[k] >> 16) & 31);
+        hits = __funnelshift_l(t0 << 31, hits, 1);      // hits = (hits << 1) | bit
+        hits = __funnelshift_l(t1 << 31, hits, 1);
+      }
+    }
+    total += __popc(hits);
+    if (lane == 0) { const uint32_t pad = (8 - (lb & 7)) & 7; total -= pad * ((lds(sb + ((last_b >> 5) << 2)) >> (last_b & 31)) & 1u); }
+    __syncwarp();
+  }
+  total = __reduce_add_sync(0xffffffff, total);
+  if (lane == 0) atomicAdd(out, (unsigned long long)total);
+}
+
+
+// ---- w8: half-range passes.  Every container is stored as [values < 32768][values >= 32768], each half bank-striped for 8-byte
+// pieces (4 elements per lane and round) and padded to whole pieces.  A warp intersects a pair in two passes over a 4 KiB bitmap:
+// half the shared memory per warp => twice the pairs in flight per SM (the 8 KiB form is bounded to 27 warps by 227 KiB).
+template <int E>
+static void stripe_generic(const uint16_t* src, uint16_t* dst, uint32_t n) {      // host: as fbgpu_stripe::stripe_array, E elements per lane-chunk
+  if (n == 0) return;
+  std::vector<std::vector<uint16_t>> bank(32);
+  for (uint32_t i = 0; i < n; i++) bank[(src[i] >> 5) & 31].push_back(src[i]);
+  std::vector<size_t> pos(32, 0);
+  const uint32_t per_round = 32 * E, rounds = (n + per_round - 1) / per_round;
+  for (uint32_t t = 0; t < rounds; t++) for (uint32_t q = 0; q < (uint32_t)E; q++) {
+    uint32_t base = per_round * t + q; if (base >= n) continue;
+    uint32_t m = (n - base + E - 1) / E; if (m > 32) m = 32;
+    int order[32]; for (int b = 0; b < 32; b++) order[b] = b;
+    std::sort(order, order + 32, [&](int a, int b) { return bank[a].size() - pos[a] > bank[b].size() - pos[b]; });
+    uint32_t lane = 0;
+    while (lane < m) for (int k = 0; k < 32 && lane < m; k++) { int b = order[k]; if (pos[b] >= bank[b].size()) continue; dst[base + E * lane] = bank[b][pos[b]++]; lane++; }
+  }
+}
+__device__ __forceinline__ uint2 ldg_nc2(const uint2* p) { uint2 r; asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p)); return r; }
+__device__ __forceinline__ uint32_t h_lo(uint32_t w) { return __umulhi(w & 0x7fe0u, 1u << 29); }
+__device__ __forceinline__ uint32_t h_hi(uint32_t w) { return __umulhi(w & 0x7fe00000u, 1u << 13); }
+template <int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB) w8_half(const uint16_t* data, const int* len_lo, const int* len_hi, int n_pairs, unsigned long long* out) {
+  extern __shared__ __align__(128) uint32_t smem[];
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t* bm = smem + wid * 1024; const uint32_t sb = (uint32_t)__cvta_generic_to_shared(bm);
+  unsigned total = 0;
+  const int stride = gridDim.x * WARPS;
+  for (int w = blockIdx.x * WARPS + wid; w < n_pairs; w += stride) {
+    const uint16_t* A = data + (size_t)(2 * w) * STRIDE; const uint16_t* B = data + (size_t)(2 * w + 1) * STRIDE;
+    const uint32_t al = len_lo[2 * w], ah = len_hi[2 * w], bl = len_lo[2 * w + 1], bh = len_hi[2 * w + 1];
+    const uint32_t alp = (al + 3) & ~3u, blp = (bl + 3) & ~3u;
+    uint2 xa[2][3], xb[2][3];
+    const uint32_t pa[2] = { (al + 3) >> 2, (ah + 3) >> 2 }, pb[2] = { (bl + 3) >> 2, (bh + 3) >> 2 };
+    const uint2* Ap[2] = { (const uint2*)A, (const uint2*)(A + alp) }; const uint2* Bp[2] = { (const uint2*)B, (const uint2*)(B + blp) };
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+#pragma unroll
+      for (int q = 0; q < 3; q++) { xa[h][q] = ldg_nc2(Ap[h] + min((uint32_t)lane + 32 * q, max(pa[h], 1u) - 1)); xb[h][q] = ldg_nc2(Bp[h] + min((uint32_t)lane + 32 * q, max(pb[h], 1u) - 1)); }
+    }
+    const uint32_t nb_[2] = { bl, bh };
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+#pragma unroll 4
+      for (int i = lane; i < 256; i += 32) ((uint4*)bm)[i] = make_uint4(0, 0, 0, 0);
+      __syncwarp();
+#pragma unroll
+      for (int q = 0; q < 3; q++) if (lane + 32 * q < pa[h]) {
+        const uint32_t x[2] = { xa[h][q].x, xa[h][q].y };
+#pragma unroll
+        for (int k = 0; k < 2; k++) { bit_op<0>(sb, h_lo(x[k]), x[k]); bit_op<0>(sb, h_hi(x[k]), x[k] >> 16); }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int q = 0; q < 3; q++) if (lane + 32 * q < pb[h]) {
+        const uint32_t x[2] = { xb[h][q].x, xb[h][q].y }; const uint32_t base = (lane + 32 * q) * 4;
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+          if (base + 2 * k < nb_[h]) total += (lds(sb + h_lo(x[k])) >> (x[k] & 31)) & 1u;
+          if (base + 2 * k + 1 < nb_[h]) total += (lds(sb + h_hi(x[k])) >> ((x[k] >> 16) & 31)) & 1u;
+        }
+      }
+      __syncwarp();
+    }
+  }
+  total = __reduce_add_sync(0xffffffff, total);
+  if (lane == 0) atomicAdd(out, (unsigned long long)total);
+}
+
+
+// ---- w9: no wipe, no atomic un-scatter: the shared-memory addresses computed for the scatter stay in registers and the same
+// words are set back to zero with plain stores after the probe (0 ALU work, ~1/2 of the wipe's shared-memory wavefronts).
+template <int WARPS, int MINB, bool PREFETCH>
+__global__ void __launch_bounds__(WARPS * 32, MINB) w9_keepaddr(const uint16_t* data, const int* len, int n_pairs, unsigned long long* out) {
+  extern __shared__ __align__(128) uint32_t smem[];
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t* bm = smem + wid * 2048; const uint32_t sb = (uint32_t)__cvta_generic_to_shared(bm);
+  for (int i = lane; i < 512; i += 32) ((uint4*)bm)[i] = make_uint4(0, 0, 0, 0);
+  __syncwarp();
+  unsigned total = 0;
+  const int stride = gridDim.x * WARPS;
+  int w = blockIdx.x * WARPS + wid;
+  uint4 va[3], vb[3]; uint32_t na = 0, nb = 0;
+  auto load = [&](int p, uint4* xa, uint4* xb, uint32_t& la, uint32_t& lb) {
+    const uint4* A = (const uint4*)(data + (size_t)(2 * p) * STRIDE); const uint4* B = (const uint4*)(data + (size_t)(2 * p + 1) * STRIDE);
+    la = len[2 * p]; lb = len[2 * p + 1];
+    const uint32_t na8 = (la + 7) >> 3, nb8 = (lb + 7) >> 3;
+#pragma unroll
+    for (int q = 0; q < 3; q++) xa[q] = ldg_nc(A + min((uint32_t)lane + 32 * q, na8 - 1));
+#pragma unroll
+    for (int q = 0; q < 3; q++) xb[q] = ldg_nc(B + min((uint32_t)lane + 32 * q, nb8 - 1));
+  };
+  if (PREFETCH && w < n_pairs) load(w, va, vb, na, nb);
+  for (; w < n_pairs; w += stride) {
+    uint4 xa[3], xb[3]; uint32_t la, lb;
+    if (PREFETCH) {
+#pragma unroll
+      for (int q = 0; q < 3; q++) { xa[q] = va[q]; xb[q] = vb[q]; }
+      la = na; lb = nb;
+    } else load(w, xa, xb, la, lb);
+    const uint32_t na8 = (la + 7) >> 3, nb8 = (lb + 7) >> 3;
+    uint32_t addr[3][8];
+#pragma unroll
+    for (int q = 0; q < 3; q++) {
+      const uint32_t x[4] = { xa[q].x, xa[q].y, xa[q].z, xa[q].w };
+#pragma unroll
+      for (int k = 0; k < 4; k++) { addr[q][2 * k] = sb + off_lo(x[k]); addr[q][2 * k + 1] = sb + off_hi(x[k]); }
+      if (lane + 32 * q < na8) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          asm volatile("red.shared.or.b32 [%0], %1;" :: "r"(addr[q][2 * k]), "r"(1u << (x[k] & 31)) : "memory");
+          asm volatile("red.shared.or.b32 [%0], %1;" :: "r"(addr[q][2 * k + 1]), "r"(1u << ((x[k] >> 16) & 31)) : "memory");
+        }
+      }
+    }
+    if (PREFETCH && w + stride < n_pairs) load(w + stride, va, vb, na, nb);
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 3; q++) if (lane + 32 * q < nb8) total += probe8(sb, xb[q], (lane + 32 * q) * 8, lb);
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 3; q++) if (lane + 32 * q < na8) {
+#pragma unroll
+      for (int k = 0; k < 8; k++) sts(addr[q][k], 0u);
+    }
+    __syncwarp();
+  }
+  total = __reduce_add_sync(0xffffffff, total);
+  if (lane == 0) atomicAdd(out, (unsigned long long)total);
+}
+
 template <typename F> float timeit(F f, int reps) {
   cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
   f(); CK(cudaDeviceSynchronize());
@@ -257,6 +518,48 @@ int main(int argc, char** argv) {
   }
   CK(cudaMemcpy(data, h.data(), bytes_all, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(sdata, hs.data(), bytes_all, cudaMemcpyHostToDevice));
+  // two-part layout (w5): from the SORTED data before padding matters (h still holds n valid sorted elements + padded tail)
+  std::vector<uint16_t> h2(bytes_all / 2, 0); std::vector<int> l1(n_cont), l2(n_cont);
+  {
+    int nt = std::max(1u, std::thread::hardware_concurrency()); std::vector<std::thread> th;
+    for (int t = 0; t < nt; t++) th.emplace_back([&, t] {
+      std::vector<uint16_t> p1(4096), p2(4096);
+      for (int c = t; c < n_cont; c += nt) {
+        const uint16_t* src = h.data() + (size_t)c * STRIDE; uint16_t* dst = h2.data() + (size_t)c * STRIDE; int n = hl[c];
+        int n1 = 0, n2 = 0; int prevw = -1;
+        for (int i = 0; i < n; i++) { int wd = src[i] >> 5; if (wd != prevw) { p1[n1++] = src[i]; prevw = wd; } else p2[n2++] = src[i]; }
+        int c1 = (n1 + 7) / 8 * 8, c2 = (n2 + 7) / 8 * 8;
+        if (c1 + c2 > STRIDE) { n2 = std::max(0, std::min(n2, STRIDE - c1 - 8)); c2 = (n2 + 7) / 8 * 8; }
+        if (n1) { fbgpu_stripe::stripe_array(p1.data(), dst, n1); fbgpu_stripe::pad_array_tail(dst, n1, c1); }
+        if (n2) { fbgpu_stripe::stripe_array(p2.data(), dst + c1, n2); fbgpu_stripe::pad_array_tail(dst + c1, n2, c2); }
+        l1[c] = n1; l2[c] = n2;
+      }
+    });
+    for (auto& x : th) x.join();
+  }
+  std::vector<uint16_t> h3(bytes_all / 2, 0); std::vector<int> llo(n_cont), lhi(n_cont);
+  {
+    int nt = std::max(1u, std::thread::hardware_concurrency()); std::vector<std::thread> th;
+    for (int t = 0; t < nt; t++) th.emplace_back([&, t] {
+      for (int c = t; c < n_cont; c += nt) {
+        const uint16_t* src = h.data() + (size_t)c * STRIDE; uint16_t* dst = h3.data() + (size_t)c * STRIDE; int n = hl[c];
+        int nlo = 0; while (nlo < n && src[nlo] < 32768) nlo++;
+        int nhi = n - nlo, plo = (nlo + 3) / 4 * 4, phi = (nhi + 3) / 4 * 4;
+        if (plo + phi > STRIDE) { nhi = std::max(0, STRIDE - plo - 4); phi = (nhi + 3) / 4 * 4; }
+        stripe_generic<4>(src, dst, nlo); for (int k = nlo; k < plo; k++) dst[k] = dst[nlo - 1];
+        stripe_generic<4>(src + nlo, dst + plo, nhi); for (int k = nhi; k < phi; k++) dst[plo + k] = dst[plo + nhi - 1];
+        llo[c] = nlo; lhi[c] = nhi;
+      }
+    });
+    for (auto& x : th) x.join();
+  }
+  uint16_t* data3; int *dlo, *dhi;
+  CK(cudaMalloc(&data3, bytes_all)); CK(cudaMalloc(&dlo, n_cont * 4)); CK(cudaMalloc(&dhi, n_cont * 4));
+  CK(cudaMemcpy(data3, h3.data(), bytes_all, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dlo, llo.data(), n_cont * 4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dhi, lhi.data(), n_cont * 4, cudaMemcpyHostToDevice));
+  uint16_t* data2; int *dl1, *dl2;
+  CK(cudaMalloc(&data2, bytes_all)); CK(cudaMalloc(&dl1, n_cont * 4)); CK(cudaMalloc(&dl2, n_cont * 4));
+  CK(cudaMemcpy(data2, h2.data(), bytes_all, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dl1, l1.data(), n_cont * 4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dl2, l2.data(), n_cont * 4, cudaMemcpyHostToDevice));
+  { double s1 = 0, s2 = 0; for (int c = 0; c < n_cont; c++) { s1 += l1[c]; s2 += l2[c]; } printf("two-part layout: part1 %.1f  part2 %.1f elements per container\n", s1 / n_cont, s2 / n_cont); }
   double elems = 0, wf_sorted = 0, wf_striped = 0; for (int x : hl) elems += x;
   for (int c = 0; c < std::min(n_cont, 4096); c++) { wf_sorted += fbgpu_stripe::total_wavefronts(h.data() + (size_t)c * STRIDE, hl[c]); wf_striped += fbgpu_stripe::total_wavefronts(hs.data() + (size_t)c * STRIDE, hl[c]); }
   double bytes = elems * 2;
@@ -269,6 +572,48 @@ int main(int argc, char** argv) {
     printf("%-34s %8.3f ms  %8.1f GB/s  frac %.3f  %6.1f clk/pair/SM  count=%llu\n", name, ms, bytes / ms / 1e6, bytes / ms / 1e6 / 6572.0, ms * 1e-3 * 1.92e9 * sms / n_pairs, hc);
   };
 #define RUN(NAME, DATA, CALL) if (!filter || strstr(NAME, filter)) { CK(cudaMemset(out, 0, 8)); const uint16_t* D = DATA; float ms = timeit([&] { CALL; }, 3); CK(cudaGetLastError()); report(NAME, ms); }
+  for (int W : { 8, 9 }) for (int pf = 0; pf < 2; pf++) {
+    char nm[128]; snprintf(nm, sizeof nm, "w5 split %dw x3 %s", W, pf ? "prefetch" : "direct");
+    if (W == 8) { auto k = pf ? w5_split<8, true> : w5_split<8, false>; cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 8192); RUN(nm, data2, (k<<<sms * 3, 8 * 32, 8 * 8192>>>(D, dl1, dl2, n_pairs, out))); }
+    else { auto k = pf ? w5_split<9, true> : w5_split<9, false>; cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 9 * 8192); RUN(nm, data2, (k<<<sms * 3, 9 * 32, 9 * 8192>>>(D, dl1, dl2, n_pairs, out))); }
+  }
+  { char nm[128]; snprintf(nm, sizeof nm, "w5 split 4w x6 prefetch"); auto k = w5_split<4, true>; cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 8192); RUN(nm, data2, (k<<<sms * 6, 4 * 32, 4 * 8192>>>(D, dl1, dl2, n_pairs, out))); }
+  { char nm[128]; snprintf(nm, sizeof nm, "w5 split 7w x4 prefetch"); auto k = w5_split<7, true>; cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 7 * 8192); RUN(nm, data2, (k<<<sms * 4, 7 * 32, 7 * 8192>>>(D, dl1, dl2, n_pairs, out))); }
+  {
+    char nm[128];
+    { auto k = w8_half<16, 3>; cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 4096);
+      snprintf(nm, sizeof nm, "w8 half 16w x3"); RUN(nm, data3, (k<<<sms * 3, 16 * 32, 16 * 4096>>>(D, dlo, dhi, n_pairs, out))); }
+    { auto k = w8_half<8, 6>; cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 4096);
+      snprintf(nm, sizeof nm, "w8 half 8w x6"); RUN(nm, data3, (k<<<sms * 6, 8 * 32, 8 * 4096>>>(D, dlo, dhi, n_pairs, out))); }
+    { auto k = w8_half<8, 5>; cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 4096);
+      snprintf(nm, sizeof nm, "w8 half 8w x5"); RUN(nm, data3, (k<<<sms * 5, 8 * 32, 8 * 4096>>>(D, dlo, dhi, n_pairs, out))); }
+    { auto k = w8_half<8, 4>; cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 4096);
+      snprintf(nm, sizeof nm, "w8 half 8w x4"); RUN(nm, data3, (k<<<sms * 4, 8 * 32, 8 * 4096>>>(D, dlo, dhi, n_pairs, out))); }
+  }
+  {
+    char nm[128];
+    { auto k = w9_keepaddr<8, 3, false>; cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 8192);
+      snprintf(nm, sizeof nm, "w9 keepaddr 8w x3 direct striped"); RUN(nm, sdata, (k<<<sms * 3, 8 * 32, 8 * 8192>>>(D, len, n_pairs, out))); }
+    { auto k = w9_keepaddr<8, 3, true>; cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 8192);
+      snprintf(nm, sizeof nm, "w9 keepaddr 8w x3 prefetch striped"); RUN(nm, sdata, (k<<<sms * 3, 8 * 32, 8 * 8192>>>(D, len, n_pairs, out))); }
+    { auto k = w9_keepaddr<9, 3, false>; cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 9 * 8192);
+      snprintf(nm, sizeof nm, "w9 keepaddr 9w x3 direct striped"); RUN(nm, sdata, (k<<<sms * 3, 9 * 32, 9 * 8192>>>(D, len, n_pairs, out))); }
+    { auto k = w9_keepaddr<9, 3, true>; cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 9 * 8192);
+      snprintf(nm, sizeof nm, "w9 keepaddr 9w x3 prefetch striped"); RUN(nm, sdata, (k<<<sms * 3, 9 * 32, 9 * 8192>>>(D, len, n_pairs, out))); }
+    { auto k = w9_keepaddr<9, 3, false>;
+      snprintf(nm, sizeof nm, "w9 keepaddr 9w x3 direct sorted"); RUN(nm, data, (k<<<sms * 3, 9 * 32, 9 * 8192>>>(D, len, n_pairs, out))); }
+  }
+  {
+    uint32_t m29 = 1u << 29, m13 = 1u << 13; char nm[128];
+    { constexpr int W = 8; auto k = w6_tuned<W, false>; cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, W * 8192);
+      snprintf(nm, sizeof nm, "w6 tuned 8w x3 striped"); RUN(nm, sdata, (k<<<sms * 3, W * 32, W * 8192>>>(D, len, n_pairs, out, m29, m13))); }
+    { constexpr int W = 8; auto k = w6_tuned<W, true>; cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, W * 8192);
+      snprintf(nm, sizeof nm, "w6 tuned mulhi 8w x3 striped"); RUN(nm, sdata, (k<<<sms * 3, W * 32, W * 8192>>>(D, len, n_pairs, out, m29, m13))); }
+    { constexpr int W = 9; auto k = w6_tuned<W, false>; cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, W * 8192);
+      snprintf(nm, sizeof nm, "w6 tuned 9w x3 striped"); RUN(nm, sdata, (k<<<sms * 3, W * 32, W * 8192>>>(D, len, n_pairs, out, m29, m13))); }
+    { constexpr int W = 9; auto k = w6_tuned<W, true>; cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, W * 8192);
+      snprintf(nm, sizeof nm, "w6 tuned mulhi 9w x3 striped"); RUN(nm, sdata, (k<<<sms * 3, W * 32, W * 8192>>>(D, len, n_pairs, out, m29, m13))); }
+  }
   for (int layout = 0; layout < 2; layout++) {
     const uint16_t* D0 = layout ? sdata : data; const char* L = layout ? "striped" : "sorted ";
     char nm[128];

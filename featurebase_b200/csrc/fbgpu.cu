@@ -163,7 +163,7 @@ struct fbgpu_ctx {
     bool meta_dirty = false;
     bool inspect_only = false;           // created with FBGPU_DEVICE_NONE: residency + fbgpu_debug_container only, no device, no queries
     std::vector<ViewTab> t_views; std::vector<int32_t> t_flat; std::vector<RowTabEnt> t_rowtab;   // inspect_only: the tables a commit would upload
-    bool stripe_arrays = getenv("FBGPU_ARRAY_STRIPED") != nullptr;   // experimental payload order, see stripe.h (fixed per context)
+    bool stripe_arrays = getenv("FBGPU_ARRAY_SORTED") == nullptr;    // bank-striped array payload order (stripe.h) unless FBGPU_ARRAY_SORTED=1 (fixed per context)
     // (shard, slot) units whose result bitmaps are materialised per launch by the row-returning / aggregate / filtered entry
     // points: 16384 units = 1024 shards = 128 MiB of workspace per lease.  FBGPU_UNIT_BATCH (a multiple of 16, fixed per
     // context) trades workspace for launches; the tests set it small to walk the multi-batch paths with a handful of shards.
@@ -809,6 +809,12 @@ static int launch_eval(fbgpu_ctx* c, Workspace* w, const std::vector<DevOp>& pro
     return 0;
 }
 
+// the usual shard list is a contiguous range (a node's share): kernels then compute the shard id instead of loading it
+static bool contiguous_shards(const uint64_t* shards, int64_t n) {
+    for (int64_t i = 1; i < n; i++) if (shards[i] != shards[0] + (uint64_t)i) return false;
+    return n > 0;
+}
+
 // ------------------------------------------------------------------ Count
 extern "C" int fbgpu_count(fbgpu_ctx* c, uint32_t index, const fbgpu_op* ops, int32_t n_ops, const uint64_t* shards, int64_t n_shards,
                            uint64_t* out_total, uint64_t* out_per_shard) try {
@@ -845,7 +851,8 @@ extern "C" int fbgpu_count(fbgpu_ctx* c, uint32_t index, const fbgpu_op* ops, in
         // fused Intersect+Count fast path: Count(Intersect(Row, Row))  (executor.go:5357 + row.go:242 + Count)
         if (prog.size() == 2 && prog[0].op == D_PUSH_ROW && prog[1].op == D_AND_ROW) {
             long long grid = std::min<long long>((n_units + kPairWarps - 1) / kPairWarps, (long long)c->sm_count * 3);
-            pair_count_kernel<<<(unsigned)grid, kPairWarps * 32, kPairWarps * 8192, w->stream>>>(store_ref(c), prog[0].fv, prog[0].row, prog[1].fv, prog[1].row, nullptr, nullptr, n_units, d_shards, n_units, d_total, d_per, nullptr, fr);
+            pair_count_kernel<<<(unsigned)grid, kPairWarps * 32, kPairWarps * 8192, w->stream>>>(store_ref(c), prog[0].fv, prog[0].row, prog[1].fv, prog[1].row, nullptr, nullptr, n_units,
+                contiguous_shards(shards, n_shards) ? nullptr : d_shards, n_shards ? shards[0] : 0, n_units, d_total, d_per, nullptr, fr);
             CUDA_TRY(cudaGetLastError());
         } else {
             EvalOut eo{ d_total, d_per, nullptr, nullptr, fr };
@@ -1308,7 +1315,7 @@ extern "C" int fbgpu_count_pairs(fbgpu_ctx* c, uint32_t index, uint32_t field_a,
     if (n_units > 0) {
         long long grid = std::min<long long>((n_units + kPairWarps - 1) / kPairWarps, (long long)c->sm_count * 3);
         pair_count_kernel<<<(unsigned)grid, kPairWarps * 32, kPairWarps * 8192, w->stream>>>(store_ref(c), fa, 0, fb, 0, (const uint64_t*)w->d_rows.p, (const uint64_t*)w->d_rows.p + np,
-            upp, d_shards, n_units, nullptr, nullptr, (unsigned long long*)w->d_counts.p, FuseReduce{});
+            upp, contiguous_shards(shards, n_shards) ? nullptr : d_shards, n_shards ? shards[0] : 0, n_units, nullptr, nullptr, (unsigned long long*)w->d_counts.p, FuseReduce{});
         CUDA_TRY(cudaGetLastError());
     }
     CUDA_TRY(cudaEventRecord(w->ev1, w->stream));

@@ -22,7 +22,7 @@ namespace fbgpu {
 #define FBGPU_EVAL_THREADS 256
 #endif
 #ifndef FBGPU_EVAL_MIN_BLOCKS
-#define FBGPU_EVAL_MIN_BLOCKS 8
+#define FBGPU_EVAL_MIN_BLOCKS 6      // 40 registers: room for three chunk loads in flight per lane (round 2: 0.39 -> 0.35 ms on the headline query vs 8 CTAs / 32 registers)
 #endif
 constexpr int kEvalThreads = FBGPU_EVAL_THREADS;          // 256 or 512
 constexpr int kEvalU4PerThread = 512 / kEvalThreads;       // uint4 per thread of an 8 KiB bitmap
@@ -1022,7 +1022,12 @@ __device__ __noinline__ uint32_t warp_icount_runs(Resolved a, Resolved b, int la
     return c;
 }
 
-// returns the full count (reduced over the warp, valid in all lanes)
+// shared-memory store of a zero word / probe of one bit at an absolute shared address
+__device__ __forceinline__ void sts_zero(uint32_t addr) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(addr), "r"(0u) : "memory"); }
+__device__ __forceinline__ void red_or_at(uint32_t addr, uint32_t m) { asm volatile("red.shared.or.b32 [%0], %1;" :: "r"(addr), "r"(m) : "memory"); }
+
+// returns the full count (reduced over the warp, valid in all lanes).  `bm` is the warp's private 8 KiB bitmap and is ALL ZERO on
+// entry and on exit (the kernel clears it once per warp): no path below pays an 8 KiB wipe per pair.
 __device__ __forceinline__ uint32_t warp_intersection_count(Resolved a, Resolved b, uint32_t* bm, int lane) {
     if (a.ptr == nullptr || b.ptr == nullptr) return 0;
     if (a.card == kFull) return b.card;                       // roaring.go:4478-4483
@@ -1033,35 +1038,49 @@ __device__ __forceinline__ uint32_t warp_intersection_count(Resolved a, Resolved
     if (a.typ == kRun || b.typ == kRun) c = warp_icount_runs(a, b, lane);
     else if (a.typ == kArray && b.typ == kArray) {            // array x array: build the smaller, probe the larger
         if (a.card > b.card) { Resolved t = a; a = b; b = t; }
-        // all loads of both arrays (up to 768 elements each) are issued before any shared-memory work: one HBM
-        // latency per pair instead of one per 256-element slab
+        // Round-2 shape (bench_micro/pair_variants.cu w9, profiles/README.md): all chunks of both arrays (up to 768 elements each) are
+        // loaded before any shared-memory work; the shared addresses computed for the scatter of `a` STAY IN REGISTERS, and after the
+        // probe the same words are set back to zero with plain stores — no 8 KiB wipe (64 shared-memory wavefronts per pair) and no
+        // second round of address arithmetic (the ALU pipe is the co-limiter of this path: IADD3/LOP3/SHF issue every 2nd cycle).
         const uint4* a4 = reinterpret_cast<const uint4*>(a.ptr); const uint4* b4 = reinterpret_cast<const uint4*>(b.ptr);
         const uint32_t na8 = (a.card + 7) >> 3, nb8 = (b.card + 7) >> 3;
+        const uint32_t sb = (uint32_t)__cvta_generic_to_shared(bm);
         uint4 va[3], vb[3];
 #pragma unroll
-        for (int q = 0; q < 3; q++) if (lane + 32 * q < na8) va[q] = ldg_nc(a4 + lane + 32 * q);
+        for (int q = 0; q < 3; q++) va[q] = ldg_nc(a4 + min((uint32_t)lane + 32u * q, na8 - 1u));     // clamped, unconditional: no undefined register
 #pragma unroll
-        for (int q = 0; q < 3; q++) if (lane + 32 * q < nb8) vb[q] = ldg_nc(b4 + lane + 32 * q);
-#ifndef FBGPU_PAIR_UNSCATTER
-        warp_zero(bm, lane); __syncwarp();
-#endif
+        for (int q = 0; q < 3; q++) vb[q] = ldg_nc(b4 + min((uint32_t)lane + 32u * q, nb8 - 1u));
+        uint32_t addr[3][8];
 #pragma unroll
-        for (int q = 0; q < 3; q++) if (lane + 32 * q < na8) scatter_chunk_unrolled<0>(bm, va[q], (lane + 32 * q) * 8, a.card);
-        for (uint32_t i = lane + 96; i < na8; i += 32) scatter_chunk_unrolled<0>(bm, ldg_nc(a4 + i), i * 8, a.card);
+        for (int q = 0; q < 3; q++) {
+            const uint32_t x[4] = { va[q].x, va[q].y, va[q].z, va[q].w };
+#pragma unroll
+            for (int k = 0; k < 4; k++) { addr[q][2 * k] = sb + word_off_lo(x[k]); addr[q][2 * k + 1] = sb + word_off_hi(x[k]); }
+            if (lane + 32 * q < na8) {          // (array tails are padded with copies of the last element: setting a bit twice is harmless)
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    red_or_at(addr[q][2 * k], 1u << (x[k] & 31));
+                    red_or_at(addr[q][2 * k + 1], 1u << ((x[k] >> 16) & 31));
+                }
+            }
+        }
+        for (uint32_t i = lane + 96; i < na8; i += 32) scatter_chunk_unrolled<0>(bm, ldg_nc(a4 + i), i * 8, a.card);      // > 768 elements: rare
         __syncwarp();
 #pragma unroll
         for (int q = 0; q < 3; q++) if (lane + 32 * q < nb8) c += probe_chunk(bm, vb[q], (lane + 32 * q) * 8, b.card);
         for (uint32_t i = lane + 96; i < nb8; i += 32) c += probe_chunk(bm, ldg_nc(b4 + i), i * 8, b.card);
         __syncwarp();
-#ifdef FBGPU_PAIR_UNSCATTER
-        // (experimental, not yet timed) the bitmap is all-zero on entry — the callers clear it once per warp — and the bits of
-        // `a` are taken out again here from the chunks still in registers: <= 3 and-not reductions per lane for a ~650-element
-        // array instead of 16 16-byte stores per lane to wipe 8 KiB, the larger share of this path's shared-memory traffic
 #pragma unroll
-        for (int q = 0; q < 3; q++) if (lane + 32 * q < na8) scatter_chunk_unrolled<1>(bm, va[q], (lane + 32 * q) * 8, a.card);
-        for (uint32_t i = lane + 96; i < na8; i += 32) scatter_chunk_unrolled<1>(bm, ldg_nc(a4 + i), i * 8, a.card);
+        for (int q = 0; q < 3; q++) if (lane + 32 * q < na8) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) sts_zero(addr[q][k]);
+        }
+        for (uint32_t i = lane + 96; i < na8; i += 32) {     // the words of the chunks past the register window: addresses recomputed
+            const uint4 v = ldg_nc(a4 + i); const uint32_t x[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+            for (int k = 0; k < 4; k++) { sts_zero(sb + word_off_lo(x[k])); sts_zero(sb + word_off_hi(x[k])); }
+        }
         __syncwarp();
-#endif
     } else if (a.typ == kArray) {                             // array x bitmap: roaring.go:4596
         c = warp_probe_global(reinterpret_cast<const uint32_t*>(b.ptr), reinterpret_cast<const uint16_t*>(a.ptr), a.card, lane);
     } else {                                                  // bitmap x bitmap: roaring.go:4611
@@ -1080,14 +1099,12 @@ constexpr int kPairWarps = 8;
 __global__ void __launch_bounds__(kPairWarps * 32, 3)
 pair_count_kernel(StoreRef st, uint32_t fvA, uint64_t rowA, uint32_t fvB, uint64_t rowB,
                   const uint64_t* __restrict__ rowsA, const uint64_t* __restrict__ rowsB, long long units_per_pair,
-                  const uint64_t* __restrict__ shards, long long n_units,
+                  const uint64_t* __restrict__ shards, uint64_t shard0, long long n_units,
                   unsigned long long* total, unsigned long long* per_shard, unsigned long long* per_pair, FuseReduce fr) {
-    extern __shared__ uint32_t smem32[];
+    extern __shared__ __align__(128) uint32_t smem32[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     uint32_t* bm = smem32 + wid * 2048;
-#ifdef FBGPU_PAIR_UNSCATTER
-    warp_zero(bm, lane); __syncwarp();
-#endif
+    warp_zero(bm, lane); __syncwarp();          // the only full clear: warp_intersection_count leaves the bitmap all-zero again
     unsigned long long acc = 0;
     const long long stride = (long long)gridDim.x * kPairWarps;
     for (long long base = (long long)blockIdx.x * kPairWarps + wid; base < n_units; base += stride * 16) {
@@ -1097,8 +1114,10 @@ pair_count_kernel(StoreRef st, uint32_t fvA, uint64_t rowA, uint32_t fvB, uint64
         Resolved r; r.ptr = nullptr; r.card = 0; r.typ = 0; r.cnt = 0;
         if (my_unit < n_units) {
             const long long pr = rowsA ? my_unit / units_per_pair : 0, su = rowsA ? my_unit - pr * units_per_pair : my_unit;
-            r = (lane & 1) ? resolve(st, fvB, shards[su >> 4], rowsA ? rowsB[pr] : rowB, (int)(su & 15))
-                           : resolve(st, fvA, shards[su >> 4], rowsA ? rowsA[pr] : rowA, (int)(su & 15));
+            // shards == nullptr: the caller's list is the contiguous range shard0, shard0 + 1, ... (one dependent load less)
+            const uint64_t shard = shards ? shards[su >> 4] : shard0 + (uint64_t)(su >> 4);
+            r = (lane & 1) ? resolve(st, fvB, shard, rowsA ? rowsB[pr] : rowB, (int)(su & 15))
+                           : resolve(st, fvA, shard, rowsA ? rowsA[pr] : rowA, (int)(su & 15));
         }
         const uint32_t meta = ((uint32_t)r.typ << 16) | r.cnt;
         auto fetch = [&](int src) {
@@ -1157,7 +1176,7 @@ row_count_kernel(StoreRef st, uint32_t fv, const uint64_t* __restrict__ row_ids,
                  const uint64_t* __restrict__ shards, long long n_shards,
                  const uint4* __restrict__ filter_bitmaps /* [n_shards*16][512] or null */,
                  unsigned long long* out_counts /* [n_rows], or [n_shards][n_rows] */) {
-    extern __shared__ uint32_t smem32[];
+    extern __shared__ __align__(128) uint32_t smem32[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     uint32_t* bm = smem32 + wid * 2048;
     const long long n_tasks = n_shards * (long long)n_rows;

@@ -84,6 +84,7 @@ ASM = [
     (r'asm volatile\("red\.shared\.and\.b32 \[%0\], %1;" :: "r"\((\w+)\), "r"\(([^()]+)\) : "memory"\);', r"emu::red_and(\1, \2);"),
     (r'asm volatile\("red\.shared\.xor\.b32 \[%0\], %1;" :: "r"\((\w+)\), "r"\(([^()]+)\) : "memory"\);', r"emu::red_xor(\1, \2);"),
     (r'asm volatile\("" : "\+r"\((\w+)\)\);', r"(void)\1;"),
+    (r'asm volatile\("st\.shared\.u32 \[%0\], %1;" :: "r"\((\w+)\), "r"\(([^()]+)\) : "memory"\);', r"emu::sts_u32(\1, \2);"),
 ]
 
 
@@ -107,7 +108,7 @@ def main(out_dir):
             continue
         s = open(os.path.join(CSRC, name)).read()
         s, n_launch = rewrite_launches(s)
-        s, n_dyn = re.subn(r"extern\s+__shared__\s+(\w+)\s+(\w+)\[\];", r"\1* \2 = reinterpret_cast<\1*>(emu::g_dyn);", s)
+        s, n_dyn = re.subn(r"extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?(\w+)\s+(\w+)\[\];", r"\1* \2 = reinterpret_cast<\1*>(emu::g_dyn);", s)
         s, n_asm, n_unsup = rewrite_asm(s)
         s = s.replace('#include "../../include/fbgpu.h"', f'#include "{os.path.join(ROOT, "include", "fbgpu.h")}"')
         out = name[:-3] + ".cpp" if name.endswith(".cu") else name

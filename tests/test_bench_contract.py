@@ -43,4 +43,6 @@ def test_gpu_arm_reports_the_contract_keys():
     for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "config",
                 "roofline", "e2e", "gpu_launches", "clocks"):
         assert key in keys, key
-    assert 'line["cpu_baseline"] = cpu' in src                     # added on rank 0 at N=1 unless --no-cpu-baseline
+    assert 'line["cpu_baseline"] = cpu_rec' in src                 # added on rank 0 at N=1 unless --no-cpu-baseline
+    for key in ('"parity_ok"', '"north_star"', '"config4"', '"config3"'):   # driver-visible parity + the sub-records of the other BASELINE configs
+        assert key in src, key

@@ -6,12 +6,12 @@ gpu-marked parity tests are then re-run against that library in a child process.
 never loads it (featurebase_b200/lib.py loads libfbgpu.so; FBGPU_LIB is the tuning-variant override the child uses), it
 proves nothing about speed, memory-model races or the PTX the rewrites replace, and the device run stays the parity gate.
 What it does give: the scatter / probe / program-loop / group-by code paths written after the round's GPU budget was spent
-(and the opt-in ones: striped array order, thread-per-row GroupBy, the unrolled word-parallel loop) have executed, statement
+(and the opt-in ones: sorted array order, thread-per-row GroupBy, the unrolled word-parallel loop) have executed, statement
 by statement, against the oracle and the reference's goldens.
 
 Default run: everything gpu-marked except the staged (TMA) kernel and the bodies that take a minute or more each when
 interpreted (≈1.5 min in all).  FBGPU_EMU_FULL=1 adds those: the 1024-shard property tests, the reference's 638 x 9
-combination table (plain and striped), Percentile, the random aggregates (≈9 min)."""
+combination table (in both array orders), Percentile, the random aggregates (≈9 min)."""
 import hashlib
 import os
 import subprocess
@@ -60,7 +60,7 @@ def run_on_emulator(args, env=None, defines=(), timeout=1500):
 
 
 NOT_HUGE = "not STAGED"                            # the staged kernel is TMA / mbarrier PTX: device only
-SLOW = " and not full_size and not container_combinations and not striped_set_ops and not percentile and not aggregates_random"      # a minute or more each when interpreted
+SLOW = " and not full_size and not container_combinations and not sorted_order_set_ops and not percentile and not aggregates_random"      # a minute or more each when interpreted
 
 
 def test_default_kernels_parity():
@@ -72,7 +72,7 @@ def test_default_kernels_parity():
 def test_query_level_bodies_on_interpreted_kernels():
     """the query-level tests written after the GPU budget ran out (aggregates, RBF loader, Distinct, time views, GroupBy
     pass shapes, ...) — on a GPU box these are plain gpu tests"""
-    run_on_emulator(["tests/test_zz_gpu_experimental.py", "-k", NOT_HUGE + " and not striped" + ("" if FULL else SLOW)], timeout=3000)
+    run_on_emulator(["tests/test_zz_gpu_experimental.py", "-k", NOT_HUGE + " and not sorted_order" + ("" if FULL else SLOW)], timeout=3000)
 
 
 def test_node_fan_out_and_merge():
@@ -81,29 +81,21 @@ def test_node_fan_out_and_merge():
     run_on_emulator(["tests/test_gpu_node.py"], timeout=3000)
 
 
-def test_striped_array_order():
-    """FBGPU_ARRAY_STRIPED=1: the loader's bank-striped element order under every kernel that reads array payloads"""
-    run_on_emulator(["tests/test_zz_gpu_experimental.py", "-k", "striped and " + NOT_HUGE + ("" if FULL else SLOW)], env={"FBGPU_TEST_EXPERIMENTAL": "1"}, timeout=3000)
+def test_sorted_array_order():
+    """FBGPU_ARRAY_SORTED=1: the reference's sorted element order (the default is the bank-striped one) under every kernel that reads array payloads"""
+    run_on_emulator(["tests/test_zz_gpu_experimental.py", "-k", "sorted_order and " + NOT_HUGE + ("" if FULL else SLOW)], env={"FBGPU_TEST_EXPERIMENTAL": "1"}, timeout=3000)
 
 
 def test_groupby_thread_per_row_variant():
     """FBGPU_GROUPBY_FAST=1 (groupby_kernel<true>): the GroupBy goldens and parity tests, and the shapes built for its passes
     (tiny arrays -> thread-per-row; a bitmap row / a 40-element row -> fallback inside the same kernel; two chunks per side; filter)"""
-    run_on_emulator(["tests/test_gpu_parity.py", "tests/test_zz_gpu_experimental.py", "-k", "(groupby or various_queries) and not striped" + ("" if FULL else " and not full_size")],
+    run_on_emulator(["tests/test_gpu_parity.py", "tests/test_zz_gpu_experimental.py", "-k", "(groupby or various_queries) and not sorted_order" + ("" if FULL else " and not full_size")],
                     env={"FBGPU_GROUPBY_FAST": "1"})
 
 
 def test_wordpar_unrolled_loop_variant():
     """-DFBGPU_WP_UNROLL3 (wp_machine.h): the 3-ops-per-iteration word-parallel loop on BSI programs"""
     run_on_emulator(["tests/test_gpu_parity.py", "-k", "bsi_range or bsi_uniform or FORCE_WORDPAR or bsi_diagonal"], defines=("FBGPU_WP_UNROLL3",), timeout=3000)
-
-
-def test_pair_count_unscatter_variant():
-    """-DFBGPU_PAIR_UNSCATTER: pair_count_kernel clears the a-side bits after the probe instead of wiping its 8 KiB bitmap per
-    pair — every test that reaches the fused Intersect+Count / count-pairs path, in the sorted and the striped array order"""
-    sel = "config1 or density_sweep or mixed_encoding or topk or executor_goldens or thread_safety" + (" or full_size_properties_1024" if FULL else "")
-    run_on_emulator(["tests/test_gpu_parity.py", "tests/test_zz_gpu_experimental.py", "-k", sel + " or fragment_top"], defines=("FBGPU_PAIR_UNSCATTER",), timeout=3000)
-    run_on_emulator(["tests/test_zz_gpu_experimental.py", "-k", "striped_density_sweep"], defines=("FBGPU_PAIR_UNSCATTER",), env={"FBGPU_TEST_EXPERIMENTAL": "1"}, timeout=3000)
 
 
 @pytest.mark.parametrize("order", ["reverse", "random"])
@@ -114,17 +106,17 @@ def test_results_do_not_depend_on_thread_order(order):
     if order == "reverse" and not FULL:
         pytest.skip("reverse order: FBGPU_EMU_FULL=1 (the default suite runs the pseudo-random order)")
     sel = NOT_HUGE + SLOW + " and not thread_safety and not bsi_diagonal"
-    run_on_emulator(["tests/test_gpu_parity.py", "tests/test_zz_gpu_experimental.py", "-k", sel + " and not striped"], env={"FBGPU_EMU_ORDER": order, "FBGPU_GROUPBY_FAST": "1"}, timeout=3000)
+    run_on_emulator(["tests/test_gpu_parity.py", "tests/test_zz_gpu_experimental.py", "-k", sel + " and not sorted_order"], env={"FBGPU_EMU_ORDER": order, "FBGPU_GROUPBY_FAST": "1"}, timeout=3000)
     if FULL:
         run_on_emulator(["tests/test_gpu_parity.py", "-k", "groupby or density_sweep or mixed_encoding"], env={"FBGPU_EMU_ORDER": order}, timeout=3000)
-        run_on_emulator(["tests/test_zz_gpu_experimental.py", "-k", "striped_density_sweep or striped_bsi"], env={"FBGPU_EMU_ORDER": order, "FBGPU_TEST_EXPERIMENTAL": "1"}, timeout=3000)
+        run_on_emulator(["tests/test_zz_gpu_experimental.py", "-k", "sorted_order_density_sweep or sorted_order_bsi"], env={"FBGPU_EMU_ORDER": order, "FBGPU_TEST_EXPERIMENTAL": "1"}, timeout=3000)
 
 
 @pytest.mark.parametrize("san", ["undefined", "address"])
 def test_interpreted_library_under_sanitizers(san):
     """kernels and host code compiled with -fsanitize=undefined (shifts, signed overflow, misaligned vector accesses abort)
     or -fsanitize=address (out-of-bounds on `__shared__` statics — plain red-zoned globals in that build —, on host
-    vectors and on thread stacks): the parity tests, the striped order, the GroupBy variant, the threaded API test"""
+    vectors and on thread stacks): the parity tests, the sorted order, the GroupBy variant, the threaded API test"""
     if not FULL:
         pytest.skip("sanitizer builds: FBGPU_EMU_FULL=1")
     flags = ("-O1", "-g", "-fsanitize=undefined", "-fno-sanitize-recover=undefined") if san == "undefined" else ("-O1", "-g", "-fsanitize=address")
@@ -133,8 +125,8 @@ def test_interpreted_library_under_sanitizers(san):
     base = dict(os.environ, FBGPU_LIB=lib, FBGPU_TEST_ON_EMULATOR="1", LD_PRELOAD=rt, UBSAN_OPTIONS="print_stacktrace=1:halt_on_error=1",
                 ASAN_OPTIONS="detect_leaks=0:halt_on_error=1")
     base.pop("FBGPU_EMU_FULL", None)
-    for extra, sel in (({}, NOT_HUGE + SLOW + " and not striped"),
-                       ({"FBGPU_ARRAY_STRIPED": "1", "FBGPU_GROUPBY_FAST": "1", "FBGPU_TEST_EXPERIMENTAL": "1"}, "(striped or groupby or density_sweep) and " + NOT_HUGE + SLOW)):
+    for extra, sel in (({}, NOT_HUGE + SLOW + " and not sorted_order"),
+                       ({"FBGPU_ARRAY_SORTED": "1", "FBGPU_GROUPBY_FAST": "1", "FBGPU_TEST_EXPERIMENTAL": "1"}, "(sorted_order or groupby or density_sweep) and " + NOT_HUGE + SLOW)):
         r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider", "tests/test_gpu_parity.py", "tests/test_zz_gpu_experimental.py", "-k", sel],
                            cwd=ROOT, env=dict(base, **extra), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=3000)
         assert r.returncode == 0 and " passed" in r.stdout, r.stdout[-3000:]
@@ -146,7 +138,7 @@ def test_bench_main_runs_against_interpreted_library():
     meaningless.  Guards edits to bench.py made while no device was reachable."""
     import json
     e = dict(os.environ, FBGPU_LIB=emu_lib())
-    r = subprocess.run([sys.executable, os.path.join(EMU, "bench_shim.py"), "--steps", "2", "--warmup", "1", "--shards-per-gpu", "8", "--no-cpu-baseline"],
+    r = subprocess.run([sys.executable, os.path.join(EMU, "bench_shim.py"), "--steps", "2", "--warmup", "1", "--shards-per-gpu", "8", "--no-cpu-baseline", "--no-extras"],
                        cwd=ROOT, env=e, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=900)
     assert r.returncode == 0, r.stderr[-2000:]
     d = json.loads(r.stdout.strip().splitlines()[-1])

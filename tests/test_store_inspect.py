@@ -150,8 +150,8 @@ def test_rbf_loader_end_to_end():
 
 
 def test_striped_layout_in_a_subprocess():
-    """FBGPU_ARRAY_STRIPED is read when a context is created: array-dominated fragments are stored permuted (same sets),
-    bitmap-heavy ones keep sorted arrays"""
+    """the default payload order: array-dominated fragments are stored bank-striped (same sets), bitmap-heavy ones keep sorted
+    arrays; FBGPU_ARRAY_SORTED=1 (read when a context is created) keeps every array sorted"""
     code = r"""
 import sys, numpy as np
 sys.path.insert(0, %r)
@@ -172,7 +172,8 @@ a = np.frombuffer(payload, dtype='<u2')[:card]
 assert t == 1 and card >= 64 and np.all(a[:-1] < a[1:]), 'arrays of a bitmap-heavy fragment stay sorted'
 print('striped ok')
 """ % ROOT
-    env = dict(os.environ, FBGPU_ARRAY_STRIPED="1")
+    env = dict(os.environ)
+    env.pop("FBGPU_ARRAY_SORTED", None)
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd=ROOT, timeout=600)
     assert out.returncode == 0 and "striped ok" in out.stdout, out.stderr[-3000:]
 

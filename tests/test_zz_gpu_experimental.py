@@ -4,8 +4,9 @@ The query-level tests below (BSI aggregates, RBF loader, further reference golde
 views, embedded rows, Shift, All/Limit) use only entry points and kernels whose parity was already green on the GPU; their
 host side — mirror, program compiler, readers, store tables — has been exercised on the CPU through tests/test_host_mirror.py
 (oracle-backed context) and tests/test_store_inspect.py (the library's own compiler and store), so they run by default.
-The bank-striped array payload order (FBGPU_ARRAY_STRIPED=1, csrc/stripe.h) changes the data the kernels read; its tests are
-skipped unless FBGPU_TEST_EXPERIMENTAL=1 until the layout has had its first GPU run (tools/r2_first_call.sh)."""
+Array payloads are stored in the bank-sorted_order order by default since round 2 (csrc/stripe.h); FBGPU_ARRAY_SORTED=1 keeps the
+reference's sorted order.  The *sorted_order* tests re-run the parity bodies under that switch (FBGPU_TEST_EXPERIMENTAL=1: they
+repeat the long tables)."""
 import os
 
 import numpy as np
@@ -18,17 +19,17 @@ from tests.golden import vectors as V
 from tests.oracle_exec import Pair
 
 pytestmark = pytest.mark.gpu
-# opt-in part: the striped payload ORDER changes what the kernels read, so it stays behind a switch until it has run on a GPU once
+# opt-in part: the parity bodies once more in the other array payload order
 experimental = pytest.mark.skipif(not os.environ.get("FBGPU_TEST_EXPERIMENTAL"), reason="experimental layouts: set FBGPU_TEST_EXPERIMENTAL=1")
 
 
 @pytest.fixture
-def striped(monkeypatch):
-    monkeypatch.setenv("FBGPU_ARRAY_STRIPED", "1")      # read when a context is created
+def sorted_order(monkeypatch):
+    monkeypatch.setenv("FBGPU_ARRAY_SORTED", "1")      # read when a context is created
 
 
 @experimental
-def test_striped_set_ops(striped):
+def test_sorted_order_set_ops(sorted_order):
     G.test_config1_single_shard_plumbing()
     G.test_container_combinations_table_on_gpu()
     G.test_mixed_encoding_pairs()
@@ -38,12 +39,12 @@ def test_striped_set_ops(striped):
 
 @experimental
 @pytest.mark.parametrize("mode", [0, 1])
-def test_striped_density_sweep(striped, mode):
+def test_sorted_order_density_sweep(sorted_order, mode):
     G.test_density_sweep_intersect_count(mode)
 
 
 @experimental
-def test_striped_bsi_topk_groupby(striped):
+def test_sorted_order_bsi_topk_groupby(sorted_order):
     G.test_bsi_range_goldens_on_gpu()
     G.test_bsi_uniform_u32_config3_small()
     G.test_topk_topn_rowcounts()
@@ -52,7 +53,7 @@ def test_striped_bsi_topk_groupby(striped):
 
 @experimental
 @pytest.mark.parametrize("env", ["FBGPU_FORCE_WORDPAR", "FBGPU_STAGED"])
-def test_striped_alternative_kernels(striped, env, monkeypatch):
+def test_sorted_order_alternative_kernels(sorted_order, env, monkeypatch):
     G.test_alternative_eval_kernels(env, monkeypatch)       # FORCE_WORDPAR must be ignored for views that hold arrays
 
 

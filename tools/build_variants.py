@@ -6,7 +6,7 @@ VARIANTS = {   # name -> -D defines; edit freely, outputs featurebase_b200/libfb
     "wp_unroll3": ["FBGPU_WP_UNROLL3"],          # experimental fixed-register op loop of the word-parallel kernel (csrc/wp_machine.h)
     "pair_unscatter": ["FBGPU_PAIR_UNSCATTER"],
     "eval_deep1": ["FBGPU_EVAL_DEEP=1"],                                  # round-1 scatter loop: one chunk load in flight per lane
-    "eval_mb6": ["FBGPU_EVAL_MIN_BLOCKS=6"],                              # 40 registers, 6 CTAs / SM
+    "eval_mb8": ["FBGPU_EVAL_MIN_BLOCKS=8"],                              # round-1 shape: 32 registers, 8 CTAs / SM
     "eval_mb5": ["FBGPU_EVAL_MIN_BLOCKS=5"],                              # 48 registers, 5 CTAs / SM
     "eval_mb6_deep4": ["FBGPU_EVAL_MIN_BLOCKS=6", "FBGPU_EVAL_DEEP=4"],  # pair_count_kernel array x array: clear the a-side bits after the probe instead of wiping 8 KiB per pair
 }
