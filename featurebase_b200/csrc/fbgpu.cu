@@ -222,6 +222,7 @@ extern "C" int fbgpu_init(int32_t device_ordinal, fbgpu_ctx** out) try {
     CUDA_TRY(cudaFuncSetAttribute(row_count_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairWarps * 8192));
     CUDA_TRY(cudaFuncSetAttribute(groupby_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGbSlots * 4 + 8192));
     CUDA_TRY(cudaFuncSetAttribute(groupby_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGbSlots * 4 + 8192));
+    CUDA_TRY(cudaFuncSetAttribute(groupby_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGsWarps * kGsSlots * 4));
     guard.c = nullptr;
     *out = c;
     return FBGPU_OK;
@@ -713,8 +714,8 @@ static int compile_program(fbgpu_ctx* c, uint32_t index, const fbgpu_op* ops, in
     ViewLookup lookup = [c, index](uint32_t field, uint32_t view) { return view_id_locked(c, ViewKey{ index, field, view }, false); };
     int rc = compile(ops, n_ops, lookup, out, depth, err);
     if (rc) return fail(rc, "%s", err.msg);
-#ifdef FBGPU_WP_UNROLL3
-    expand_push_row(out);          // variant build only: every kernel accepts the rewritten program, the word-parallel loop requires it
+#ifndef FBGPU_WP_LEGACY_LOOP
+    expand_push_row(out);          // every kernel accepts the rewritten program; the word-parallel op loop (wp_machine.h) requires it
 #endif
     return 0;
 }
@@ -816,8 +817,9 @@ static bool contiguous_shards(const uint64_t* shards, int64_t n) {
 }
 
 // ------------------------------------------------------------------ Count
-extern "C" int fbgpu_count(fbgpu_ctx* c, uint32_t index, const fbgpu_op* ops, int32_t n_ops, const uint64_t* shards, int64_t n_shards,
-                           uint64_t* out_total, uint64_t* out_per_shard) try {
+// collective == false: this context's shards only — no cross-GPU merge (fbgpu_any's early exit must not desynchronise the ranks)
+static int count_impl(fbgpu_ctx* c, uint32_t index, const fbgpu_op* ops, int32_t n_ops, const uint64_t* shards, int64_t n_shards,
+                      uint64_t* out_total, uint64_t* out_per_shard, bool collective) {
     if (!c || !out_total || n_shards < 0 || (n_shards && !shards)) return fail(FBGPU_E_INVALID, "null argument");
     USE_DEVICE(c);
     std::shared_lock<std::shared_mutex> lk;
@@ -839,7 +841,7 @@ extern "C" int fbgpu_count(fbgpu_ctx* c, uint32_t index, const fbgpu_op* ops, in
     std::unique_lock<std::mutex> coll_lk(c->coll_mu, std::defer_lock);
     FuseReduce fr{};
     coll_lk.lock();                          // collective queries are issued in the same order on every rank
-    const bool p2p = c->p2p;                 // read once, under the lock fbgpu_comm_p2p_open/_disable take
+    const bool p2p = c->p2p && collective;   // read once, under the lock fbgpu_comm_p2p_open/_disable take
     if (!p2p) coll_lk.unlock();
     if (p2p) {
         fr.peers = (Mailbox* const*)c->d_peers.p; fr.ticket = (unsigned int*)(d_total + 1 + nper); fr.result = d_total + 1 + nper + 1;
@@ -862,7 +864,7 @@ extern "C" int fbgpu_count(fbgpu_ctx* c, uint32_t index, const fbgpu_op* ops, in
         p2p_reduce_only_kernel<<<1, 1, 0, w->stream>>>(fr, d_total);
         CUDA_TRY(cudaGetLastError());
     }
-    if (!p2p) { rc = allreduce_u64(c, w, d_total, 1); if (rc) return rc; }   // inside the timed bracket: the collective is part of the step
+    if (!p2p && collective) { rc = allreduce_u64(c, w, d_total, 1); if (rc) return rc; }   // inside the timed bracket: the collective is part of the step
     CUDA_TRY(cudaEventRecord(w->ev1, w->stream));
     CUDA_TRY(cudaMemcpyAsync(w->h_out.p, w->d_counts.p, nc * 8, cudaMemcpyDeviceToHost, w->stream));
     CUDA_TRY(cudaStreamSynchronize(w->stream));
@@ -877,7 +879,14 @@ extern "C" int fbgpu_count(fbgpu_ctx* c, uint32_t index, const fbgpu_op* ops, in
     bump(c, (n_units > 0 || p2p) ? 1 : 0, ms);
     lease.ok = true;
     return FBGPU_OK;
+}
+extern "C" int fbgpu_count(fbgpu_ctx* c, uint32_t index, const fbgpu_op* ops, int32_t n_ops, const uint64_t* shards, int64_t n_shards,
+                           uint64_t* out_total, uint64_t* out_per_shard) try {
+    return count_impl(c, index, ops, n_ops, shards, n_shards, out_total, out_per_shard, true);
 } FBGPU_CATCH
+static int fbgpu_count_local(fbgpu_ctx* c, uint32_t index, const fbgpu_op* ops, int32_t n_ops, const uint64_t* shards, int64_t n_shards, uint64_t* out_total) {
+    return count_impl(c, index, ops, n_ops, shards, n_shards, out_total, nullptr, false);
+}
 
 // ------------------------------------------------------------------ Row (canonical Pilosa-roaring result)
 extern "C" int fbgpu_row(fbgpu_ctx* c, uint32_t index, const fbgpu_op* ops, int32_t n_ops, const uint64_t* shards, int64_t n_shards,
@@ -1330,6 +1339,50 @@ extern "C" int fbgpu_count_pairs(fbgpu_ctx* c, uint32_t index, uint32_t field_a,
     return FBGPU_OK;
 } FBGPU_CATCH
 
+// container-pair-type histogram of Count(Intersect(Row a, Row b)) (statsHit analogue, roaring.go:4477-4614)
+extern "C" int fbgpu_pair_types(fbgpu_ctx* c, uint32_t index, uint32_t field_a, uint32_t view_a, uint64_t row_a, uint32_t field_b, uint32_t view_b, uint64_t row_b,
+                                const uint64_t* shards, int64_t n_shards, uint64_t out_hist[16]) try {
+    if (!c || !out_hist || n_shards < 0 || (n_shards && !shards)) return fail(FBGPU_E_INVALID, "null argument");
+    USE_DEVICE(c);
+    memset(out_hist, 0, 16 * 8);
+    if (n_shards == 0) return FBGPU_OK;
+    std::shared_lock<std::shared_mutex> lk;
+    int rc = lock_committed(c, lk); if (rc) return rc;
+    const uint32_t fa = view_id_locked(c, ViewKey{ index, field_a, view_a }, false), fb = view_id_locked(c, ViewKey{ index, field_b, view_b }, false);
+    WsLease lease(c); Workspace* w = lease.w;
+    std::vector<DevOp> none; const DevOp* d_prog; const uint64_t* d_shards;
+    rc = upload_inputs(w, none, shards, n_shards, &d_prog, &d_shards); if (rc) return rc;
+    if (w->d_counts.ensure(16 * 8) || w->h_out.ensure(16 * 8)) return FBGPU_E_NOMEM;
+    CUDA_TRY(cudaMemsetAsync(w->d_counts.p, 0, 16 * 8, w->stream));
+    const long long n_units = (long long)n_shards * kSlotsPerRow;
+    const long long grid = std::min<long long>((n_units + 255) / 256, (long long)c->sm_count * 4);
+    pair_types_kernel<<<(unsigned)grid, 256, 0, w->stream>>>(store_ref(c), fa, row_a, fb, row_b, d_shards, n_units, (unsigned long long*)w->d_counts.p);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(w->h_out.p, w->d_counts.p, 16 * 8, cudaMemcpyDeviceToHost, w->stream));
+    CUDA_TRY(cudaStreamSynchronize(w->stream));
+    memcpy(out_hist, w->h_out.p, 16 * 8);
+    bump(c, 1, 0.f);
+    lease.ok = true;
+    return FBGPU_OK;
+} FBGPU_CATCH
+
+// Row.Any() of a bitmap call (row.go:258; the early exit of intersectionAny, roaring.go:4266-4408, lifted to shard granularity):
+// the shards are evaluated in blocks of growing size and the walk stops at the first block whose count is not zero, so a row that
+// has any column in its first shards costs one small launch instead of a pass over every shard.
+extern "C" int fbgpu_any(fbgpu_ctx* c, uint32_t index, const fbgpu_op* ops, int32_t n_ops, const uint64_t* shards, int64_t n_shards, int32_t* out_any) try {
+    if (!c || !out_any || n_shards < 0 || (n_shards && !shards)) return fail(FBGPU_E_INVALID, "null argument");
+    *out_any = 0;
+    uint64_t cnt = 0;
+    if (n_shards == 0) return fbgpu_count(c, index, ops, n_ops, shards, 0, &cnt, nullptr);      // (still validates the program)
+    int64_t block = 8;
+    for (int64_t s0 = 0; s0 < n_shards; s0 += block, block *= 8) {
+        const int64_t ns = std::min(block, n_shards - s0);
+        int rc = fbgpu_count_local(c, index, ops, n_ops, shards + s0, ns, &cnt); if (rc) return rc;
+        if (cnt) { *out_any = 1; return FBGPU_OK; }
+    }
+    return FBGPU_OK;
+} FBGPU_CATCH
+
 // ------------------------------------------------------------------ GroupBy
 static int groupby2(fbgpu_ctx* c, uint32_t index, uint32_t fvA, const uint64_t* rowsA, int nA, uint32_t fvB, const uint64_t* rowsB, int nB,
                     const std::vector<fbgpu_op>& filter, const uint64_t* shards, int64_t n_shards, uint64_t* out) {
@@ -1354,9 +1407,23 @@ static int groupby2(fbgpu_ctx* c, uint32_t index, uint32_t fvA, const uint64_t* 
         if (have_filter) { rc = eval_filter_batch(c, w, prog, depth, d_prog, d_shards + s0, ns); if (rc) return rc; launches++; }
         long long units = (long long)ns * kSlotsPerRow;
         long long grid = std::min<long long>(units, (long long)c->sm_count * 4);
-        static const bool gb_fast = getenv("FBGPU_GROUPBY_FAST") != nullptr;    // experimental thread-per-row passes (kernels.cuh), first GPU run pending
-        (gb_fast ? groupby_kernel<true> : groupby_kernel<false>)<<<(unsigned)grid, kGbThreads, smem, w->stream>>>(store_ref(c), fvA, (const uint64_t*)w->d_rows.p, nA, fvB, (const uint64_t*)w->d_rows.p + nA, nB,
-            d_shards + s0, units, have_filter ? (const uint4*)w->d_bitmaps.p : nullptr, (unsigned long long*)w->d_counts.p);
+        static const bool gb_fast = getenv("FBGPU_GROUPBY_FAST") != nullptr;    // thread-per-row passes of the CTA kernel (kernels.cuh)
+        static const bool gb_cta_only = getenv("FBGPU_GROUPBY_CTA") != nullptr; // round-1 path only: one CTA per unit
+        auto cta_kernel = gb_fast ? groupby_kernel<true> : groupby_kernel<false>;
+        if (!gb_cta_only && units < (1ll << 31)) {
+            // warp-per-unit kernel first; the units it declines (an a-row that is not a small array) are listed for the CTA kernel
+            if (w->d_emit_units.ensure((size_t)(units + 1) * 4)) return FBGPU_E_NOMEM;
+            unsigned int* d_fb = (unsigned int*)w->d_emit_units.p;
+            CUDA_TRY(cudaMemsetAsync(d_fb, 0, 4, w->stream));
+            long long sgrid = std::min<long long>((units + kGsWarps - 1) / kGsWarps, (long long)c->sm_count * 3);
+            groupby_small_kernel<<<(unsigned)sgrid, kGsWarps * 32, kGsWarps * kGsSlots * 4, w->stream>>>(store_ref(c), fvA, (const uint64_t*)w->d_rows.p, nA, fvB, (const uint64_t*)w->d_rows.p + nA, nB,
+                d_shards + s0, units, have_filter ? (const uint4*)w->d_bitmaps.p : nullptr, (unsigned long long*)w->d_counts.p, d_fb);
+            CUDA_TRY(cudaGetLastError()); launches++;
+            cta_kernel<<<(unsigned)grid, kGbThreads, smem, w->stream>>>(store_ref(c), fvA, (const uint64_t*)w->d_rows.p, nA, fvB, (const uint64_t*)w->d_rows.p + nA, nB,
+                d_shards + s0, units, have_filter ? (const uint4*)w->d_bitmaps.p : nullptr, (unsigned long long*)w->d_counts.p, d_fb);
+        } else
+        cta_kernel<<<(unsigned)grid, kGbThreads, smem, w->stream>>>(store_ref(c), fvA, (const uint64_t*)w->d_rows.p, nA, fvB, (const uint64_t*)w->d_rows.p + nA, nB,
+            d_shards + s0, units, have_filter ? (const uint4*)w->d_bitmaps.p : nullptr, (unsigned long long*)w->d_counts.p, nullptr);
         CUDA_TRY(cudaGetLastError()); launches++;
     }
     CUDA_TRY(cudaEventRecord(w->ev1, w->stream));

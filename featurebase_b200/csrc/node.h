@@ -166,6 +166,19 @@ extern "C" int fbgpu_node_count(fbgpu_node* n, uint32_t index, const fbgpu_op* o
     return FBGPU_OK;
 } FBGPU_CATCH
 
+// Row.Any(): every device walks its own shards with the early exit; the answers are OR-ed
+extern "C" int fbgpu_node_any(fbgpu_node* n, uint32_t index, const fbgpu_op* ops, int32_t n_ops, const uint64_t* shards, int64_t n_shards, int32_t* out_any) try {
+    if (!n || !out_any || n_shards < 0 || (n_shards && !shards)) return fail(FBGPU_E_INVALID, "null argument");
+    NodeSplit sp = node_split(n, shards, n_shards);
+    std::vector<int> devs = node_owners(sp);
+    if (devs.empty()) devs.push_back(0);
+    std::vector<int32_t> any(n->ctx.size(), 0);
+    int rc = node_fan_out(n, devs, [&](int d) { auto& s = sp.shards[(size_t)d]; return fbgpu_any(n->ctx[(size_t)d], index, ops, n_ops, s.data(), (int64_t)s.size(), &any[(size_t)d]); });
+    if (rc) return rc;
+    *out_any = 0; for (int d : devs) *out_any |= any[(size_t)d];
+    return FBGPU_OK;
+} FBGPU_CATCH
+
 // element-wise sum of per-device u64 vectors into out (out is overwritten)
 static void node_sum(const std::vector<int>& devs, const std::vector<std::vector<uint64_t>>& part, uint64_t* out, size_t len) {
     memset(out, 0, len * 8);

@@ -207,7 +207,7 @@ inline int compile(const fbgpu_op* ops, int32_t n_ops, const ViewLookup& lookup,
     return 0;
 }
 
-// PUSH_ROW r  ==  PUSH_EMPTY ; OR_ROW r.  Used by the experimental word-parallel op loop (wp_machine.h, -DFBGPU_WP_UNROLL3), whose
+// PUSH_ROW r  ==  PUSH_EMPTY ; OR_ROW r.  Used by the word-parallel op loop (wp_machine.h), whose
 // hot switch then never shifts the register stack.  The operand stack depth is unchanged.
 inline void expand_push_row(std::vector<DevOp>& prog) {
     std::vector<DevOp> out; out.reserve(prog.size() + 8);

@@ -1,6 +1,5 @@
 // Op loop of the word-parallel program machine (eval_wordpar_kernel), restructured to keep every value in a register with a
-// fixed role.  EXPERIMENTAL: compiled into the kernel only with -DFBGPU_WP_UNROLL3 (not measured yet); the default kernel
-// keeps its original loop.  Host-compilable on purpose: tests/test_wp_machine.py checks it on the CPU against a plain
+// fixed role.  The default since round 2 (-DFBGPU_WP_LEGACY_LOOP restores the original rotating-ring loop).  Host-compilable on purpose: tests/test_wp_machine.py checks it on the CPU against a plain
 // stack-machine model for random programs.
 //
 // Why: in the original loop the operand prefetch ring (p0 <- p1 <- p2) rotates and the 4-deep register stack shifts inside
@@ -62,33 +61,32 @@ FBGPU_HD void wp_row_op(WpStack<V>& s, uint8_t opc, V x) {
 }
 
 // opc(k): opcode of program op k; is_row(k); rowops[ri]: program index of the ri-th row op; fetch(ri): its operand slice.
-// Returns the top of stack (zero when the program leaves the stack empty).
-template <class V, bool NO_PUSH = false, class OpcAt, class IsRowAt, class RowOpAt, class Fetch>
+// Returns the top of stack (zero when the program leaves the stack empty).  R = operand slices in flight per thread: ring slot j
+// always serves row op R*t + j, so the ring never rotates.  (Round 2: R = 3 took BASELINE config 3 from 35 to 22 us; the 10 M-record
+// config is latency-bound — 34 plane loads per thread — so the default ring is deeper.)
+#ifndef FBGPU_WP_RING
+#define FBGPU_WP_RING 6
+#endif
+template <class V, bool NO_PUSH = false, int R = FBGPU_WP_RING, class OpcAt, class IsRowAt, class RowOpAt, class Fetch>
 FBGPU_HD V wp_run_unrolled(int n_ops, int nr, OpcAt opc_at, IsRowAt is_row_at, RowOpAt rowop_at, Fetch fetch) {
     WpStack<V> s; s.T = s.B = s.S2 = s.S3 = wp_zero<V>(); s.depth = 0;
-    V p0 = wp_zero<V>(), p1 = p0, p2 = p0;
-    if (0 < nr) p0 = fetch(0);
-    if (1 < nr) p1 = fetch(1);
-    if (2 < nr) p2 = fetch(2);
+    V p[R];
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (int j = 0; j < R; j++) { p[j] = wp_zero<V>(); if (j < nr) p[j] = fetch(j); }
     int k = 0;                                         // next program op to execute
-    for (int base = 0; base < nr; base += 3) {
-        {   // row op base+0, operand p0
-            const int kr = rowop_at(base);
-            FBGPU_NO_UNROLL for (; k < kr; k++) wp_stack_op(s, opc_at(k));
-            wp_row_op<NO_PUSH>(s, opc_at(kr), p0); k = kr + 1;
-            if (base + 3 < nr) p0 = fetch(base + 3);
-        }
-        if (base + 1 < nr) {
-            const int kr = rowop_at(base + 1);
-            FBGPU_NO_UNROLL for (; k < kr; k++) wp_stack_op(s, opc_at(k));
-            wp_row_op<NO_PUSH>(s, opc_at(kr), p1); k = kr + 1;
-            if (base + 4 < nr) p1 = fetch(base + 4);
-        }
-        if (base + 2 < nr) {
-            const int kr = rowop_at(base + 2);
-            FBGPU_NO_UNROLL for (; k < kr; k++) wp_stack_op(s, opc_at(k));
-            wp_row_op<NO_PUSH>(s, opc_at(kr), p2); k = kr + 1;
-            if (base + 5 < nr) p2 = fetch(base + 5);
+    for (int base = 0; base < nr; base += R) {
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+        for (int j = 0; j < R; j++) {
+            if (base + j < nr) {
+                const int kr = rowop_at(base + j);
+                FBGPU_NO_UNROLL for (; k < kr; k++) wp_stack_op(s, opc_at(k));
+                wp_row_op<NO_PUSH>(s, opc_at(kr), p[j]); k = kr + 1;
+                if (base + j + R < nr) p[j] = fetch(base + j + R);
+            }
         }
     }
     FBGPU_NO_UNROLL for (; k < n_ops; k++) wp_stack_op(s, opc_at(k));     // trailing stack ops (and programs without any row op)

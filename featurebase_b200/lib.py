@@ -43,6 +43,7 @@ EXPORTS = ["fbgpu_init", "fbgpu_shutdown", "fbgpu_last_error", "fbgpu_abi_versio
            "fbgpu_load_fragments", "fbgpu_drop_fragment", "fbgpu_commit", "fbgpu_get_stats", "fbgpu_count", "fbgpu_row",
            "fbgpu_row_counts", "fbgpu_row_counts_per_shard", "fbgpu_groupby", "fbgpu_comm_unique_id", "fbgpu_comm_init", "fbgpu_comm_destroy",
            "fbgpu_get_counters", "fbgpu_stream", "fbgpu_rows_payload_bytes", "fbgpu_count_pairs", "fbgpu_columns", "fbgpu_extract", "fbgpu_load_rbf", "fbgpu_load_rbf_dir", "fbgpu_bsi_minmax", "fbgpu_bsi_sum", "fbgpu_compact", "fbgpu_comm_p2p_handle", "fbgpu_comm_p2p_open", "fbgpu_comm_p2p_disable",
+           "fbgpu_any", "fbgpu_pair_types", "fbgpu_node_any",
            "fbgpu_comm_p2p_open_local", "fbgpu_node_init", "fbgpu_node_shutdown", "fbgpu_node_devices", "fbgpu_node_owner", "fbgpu_node_ctx", "fbgpu_node_load_fragment",
            "fbgpu_node_load_fragments", "fbgpu_node_load_rbf_dir", "fbgpu_node_drop_fragment", "fbgpu_node_commit", "fbgpu_node_get_stats", "fbgpu_node_count", "fbgpu_node_row",
            "fbgpu_node_count_pairs", "fbgpu_node_row_counts", "fbgpu_node_groupby", "fbgpu_node_bsi_sum", "fbgpu_node_bsi_minmax"]
@@ -97,14 +98,19 @@ def load():
     L.fbgpu_get_counters.argtypes, L.fbgpu_get_counters.restype = [vp, C.POINTER(Counters)], C.c_int
     L.fbgpu_stream.argtypes, L.fbgpu_stream.restype = [vp], vp
     L.fbgpu_rows_payload_bytes.argtypes, L.fbgpu_rows_payload_bytes.restype = [vp, u32, u32, u32, vp, i32, vp, i64, C.POINTER(u64), C.POINTER(u64)], C.c_int
+    if os.environ.get("FBGPU_LIB") and not hasattr(L, "fbgpu_node_init"):      # an older tuning build (A/B runs only): round-1 entry points only
+        _LIB = L
+        return L
     L.fbgpu_comm_p2p_open_local.argtypes, L.fbgpu_comm_p2p_open_local.restype = [vp, i32], C.c_int
+    L.fbgpu_any.argtypes, L.fbgpu_any.restype = [vp, u32, vp, i32, vp, i64, C.POINTER(i32)], C.c_int
+    L.fbgpu_pair_types.argtypes, L.fbgpu_pair_types.restype = [vp, u32, u32, u32, u64, u32, u32, u64, vp, i64, vp], C.c_int
     # fbgpu_node_*: the fbgpu_* signature of the same name with the node handle in place of the context
     L.fbgpu_node_init.argtypes, L.fbgpu_node_init.restype = [vp, i32, u64, C.POINTER(vp)], C.c_int
     L.fbgpu_node_shutdown.argtypes, L.fbgpu_node_shutdown.restype = [vp], None
     L.fbgpu_node_devices.argtypes, L.fbgpu_node_devices.restype = [vp], i32
     L.fbgpu_node_owner.argtypes, L.fbgpu_node_owner.restype = [vp, u64], i32
     L.fbgpu_node_ctx.argtypes, L.fbgpu_node_ctx.restype = [vp, i32], vp
-    for name in ("load_fragment", "load_fragments", "load_rbf_dir", "drop_fragment", "commit", "get_stats", "count", "row", "count_pairs", "groupby", "bsi_sum", "bsi_minmax"):
+    for name in ("load_fragment", "load_fragments", "load_rbf_dir", "drop_fragment", "commit", "get_stats", "count", "any", "row", "count_pairs", "groupby", "bsi_sum", "bsi_minmax"):
         src, dst = getattr(L, "fbgpu_" + name), getattr(L, "fbgpu_node_" + name)
         dst.argtypes, dst.restype = src.argtypes, src.restype
     L.fbgpu_node_row_counts.argtypes, L.fbgpu_node_row_counts.restype = [vp, u32, u32, u32, vp, i32, vp, i32, vp, i64, vp], C.c_int
@@ -231,6 +237,21 @@ class Context:
         self._check(self.L.fbgpu_count(self.h, index, arr, len(ops), sh.ctypes.data, len(sh), C.byref(tot),
                                        per.ctypes.data if per_shard else None))
         return (tot.value, per) if per_shard else tot.value
+
+    def any(self, index, ops, shards):
+        """Row.Any(): True as soon as one block of shards holds a column of the row (fbgpu_any, early exit by shard blocks)"""
+        sh = _u64arr(shards)
+        arr = ops_array(ops)
+        out = C.c_int32(0)
+        self._check(self.L.fbgpu_any(self.h, index, arr, len(ops), sh.ctypes.data, len(sh), C.byref(out)))
+        return bool(out.value)
+
+    def pair_types(self, index, field_a, view_a, row_a, field_b, view_b, row_b, shards):
+        """4 x 4 histogram of container type pairs (0 absent, 1 array, 2 bitmap, 3 run) of Count(Intersect(Row a, Row b))"""
+        sh = _u64arr(shards)
+        out = np.zeros(16, dtype=np.uint64)
+        self._check(self.L.fbgpu_pair_types(self.h, index, field_a, view_a, int(row_a), field_b, view_b, int(row_b), sh.ctypes.data, len(sh), out.ctypes.data))
+        return out.reshape(4, 4)
 
     def row_into(self, index, ops, shards, buf):
         """fbgpu_row into a caller-owned uint8 array (what a Go caller with a reused buffer does): returns (bytes needed, count,

@@ -131,6 +131,12 @@ typedef struct {
 int fbgpu_count(fbgpu_ctx *ctx, uint32_t index, const fbgpu_op *ops, int32_t n_ops,
                 const uint64_t *shards, int64_t n_shards, uint64_t *out_total, uint64_t *out_per_shard);
 
+/* Row.Any() of a bitmap call (row.go:258; roaring.go:4266-4408 intersectionAny lifted to shard granularity): *out_any = 1 as soon
+ * as one block of shards holds a column.  Shards are evaluated in blocks of growing size (8, 64, 512, ...), so a non-empty row
+ * costs one small launch.  Local to this context: never merged across GPUs (fbgpu_node_any walks the devices itself). */
+int fbgpu_any(fbgpu_ctx *ctx, uint32_t index, const fbgpu_op *ops, int32_t n_ops,
+              const uint64_t *shards, int64_t n_shards, int32_t *out_any);
+
 /* <bitmap call> returning a Row (mapReduce with Row.Merge, executor.go:1694-1780, row.go:202): writes
  * Pilosa-roaring bytes with absolute keys shard*16+slot and canonical (optimize()) encodings, i.e. what
  * Row.Roaring() (row.go:174-180) yields after Optimize.  If out_cap is too small returns FBGPU_E_NOSPACE
@@ -203,6 +209,12 @@ int fbgpu_count_pairs(fbgpu_ctx *ctx, uint32_t index, uint32_t field_a, uint32_t
                       uint32_t field_b, uint32_t view_b, const uint64_t *rows_b, int32_t n_pairs,
                       const uint64_t *shards, int64_t n_shards, uint64_t *out_counts);
 
+/* Which of the nine container-pair kernels Count(Intersect(Row a, Row b)) exercises and how often: out_hist[4 * ta + tb] = number
+ * of (shard, slot) units whose a / b containers have types ta / tb (0 absent, 1 array, 2 bitmap, 3 run).  The reference keeps
+ * the same information as statsHit("intersectionCount/...") counters (roaring.go:4477-4614).  Computed on the device. */
+int fbgpu_pair_types(fbgpu_ctx *ctx, uint32_t index, uint32_t field_a, uint32_t view_a, uint64_t row_a,
+                     uint32_t field_b, uint32_t view_b, uint64_t row_b, const uint64_t *shards, int64_t n_shards, uint64_t out_hist[16]);
+
 /* GroupBy(Rows(f1), Rows(f2), ..., filter=...) with Count aggregate (executeGroupBy executor.go:3176,
  * executeGroupByShard :3918, groupByIterator :8617-8934; reduce = mergeGroupCounts :3728).  row_ids_flat holds
  * the per-field row-id lists concatenated (flat on purpose: cgo forbids nested Go pointers).  out_counts is
@@ -265,6 +277,8 @@ int fbgpu_node_get_stats(fbgpu_node *node, fbgpu_stats *out);           /* summe
 /* same contracts as the fbgpu_* calls of the same name, over all devices */
 int fbgpu_node_count(fbgpu_node *node, uint32_t index, const fbgpu_op *ops, int32_t n_ops,
                      const uint64_t *shards, int64_t n_shards, uint64_t *out_total, uint64_t *out_per_shard);
+int fbgpu_node_any(fbgpu_node *node, uint32_t index, const fbgpu_op *ops, int32_t n_ops,
+                   const uint64_t *shards, int64_t n_shards, int32_t *out_any);
 int fbgpu_node_row(fbgpu_node *node, uint32_t index, const fbgpu_op *ops, int32_t n_ops,
                    const uint64_t *shards, int64_t n_shards, uint8_t *out_buf, uint64_t out_cap, uint64_t *out_len, uint64_t *out_count);
 int fbgpu_node_count_pairs(fbgpu_node *node, uint32_t index, uint32_t field_a, uint32_t view_a, const uint64_t *rows_a,

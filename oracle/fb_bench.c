@@ -54,7 +54,7 @@ static void *pool_worker(void *a) {
     }
 }
 
-fbo_pool *fbo_pool_create(int n_threads) {
+fbo_pool *fbo_pool_create2(int n_threads, int pin) {
     if (n_threads < 1) n_threads = 1;
     fbo_pool *p = calloc(1, sizeof *p);
     if (!p) return NULL;
@@ -66,10 +66,11 @@ fbo_pool *fbo_pool_create(int n_threads) {
     for (int t = 0; t < n_threads; t++) {
         worker_arg *wa = malloc(sizeof *wa); wa->p = p; wa->id = t;
         pthread_create(&p->th[t], NULL, pool_worker, wa);
-        if (n_allowed > 0) { cpu_set_t one; CPU_ZERO(&one); CPU_SET(cpus[t % n_allowed], &one); pthread_setaffinity_np(p->th[t], sizeof one, &one); }
+        if (pin && n_allowed > 0) { cpu_set_t one; CPU_ZERO(&one); CPU_SET(cpus[t % n_allowed], &one); pthread_setaffinity_np(p->th[t], sizeof one, &one); }
     }
     return p;
 }
+fbo_pool *fbo_pool_create(int n_threads) { return fbo_pool_create2(n_threads, 1); }
 void fbo_pool_destroy(fbo_pool *p) {
     if (!p) return;
     pthread_mutex_lock(&p->mu); p->quit = 1; pthread_cond_broadcast(&p->cv_start); pthread_mutex_unlock(&p->mu);

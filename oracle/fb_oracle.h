@@ -145,7 +145,8 @@ fbo_bitmap *fbo_frag_row_view(const fbo_bitmap *frag, uint64_t row, uint64_t sha
  * query.  Shards are handed out dynamically in small blocks (what mapperLocal's job channel does).  Rows are fetched as
  * views (no container cloning).  Every bench call returns its wall time through *seconds. */
 typedef struct fbo_pool fbo_pool;
-fbo_pool *fbo_pool_create(int n_threads);
+fbo_pool *fbo_pool_create(int n_threads);            /* pinned round-robin to the allowed CPUs */
+fbo_pool *fbo_pool_create2(int n_threads, int pin);  /* pin == 0: the OS places the threads */
 void fbo_pool_destroy(fbo_pool *p);
 int fbo_pool_threads(const fbo_pool *p);
 /* Count(Intersect(Union(rows a..), Union(rows b..))): frags[s] is the fragment of shard shards[s] (executeUnionShard

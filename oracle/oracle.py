@@ -57,7 +57,7 @@ def lib():
             "fbo_frag_rows": (i64, [vp, vp, i64]),
             "fbo_groupby_shard": (C.c_int, [vp, C.c_int, u64, vp, vp, vp, vp]),
             "fbo_frag_row_view": (vp, [vp, u64, u64]),
-            "fbo_pool_create": (vp, [C.c_int]), "fbo_pool_destroy": (None, [vp]), "fbo_pool_threads": (C.c_int, [vp]),
+            "fbo_pool_create": (vp, [C.c_int]), "fbo_pool_create2": (vp, [C.c_int, C.c_int]), "fbo_pool_destroy": (None, [vp]), "fbo_pool_threads": (C.c_int, [vp]),
             "fbo_bench_union_intersect_count": (u64, [vp, vp, vp, i64, vp, C.c_int, vp, C.c_int, vp]),
             "fbo_bench_pair_counts": (u64, [vp, vp, vp, i64, vp, vp, C.c_int, C.c_int, vp, vp]),
             "fbo_bench_range_count": (u64, [vp, vp, vp, i64, C.c_int, u64, i64, i64, vp]),
@@ -438,9 +438,10 @@ def groupby_shard(frags, shard, row_ids, filt=None, out=None):
 class Pool:
     """Long-lived pinned worker threads of the CPU baseline (fb_bench.c): created once, reused by every bench call."""
 
-    def __init__(self, n_threads=None):
-        self.n = int(n_threads or os.cpu_count() or 1)
-        self.ptr = lib().fbo_pool_create(self.n)
+    def __init__(self, n_threads=None, pin=True):
+        self.n = int(n_threads or len(os.sched_getaffinity(0)) or 1)
+        self.pin = bool(pin)
+        self.ptr = lib().fbo_pool_create2(self.n, 1 if pin else 0)
 
     def close(self):
         if self.ptr:

@@ -110,6 +110,12 @@ class OracleCtx:
         per = np.array([self._eval(index, ops, s).count() for s in shards], dtype=np.uint64)
         return (int(per.sum()), per) if per_shard else int(per.sum())
 
+    def any(self, index, ops, shards):
+        if len(shards) == 0:
+            self._eval(index, ops, 0)                       # the program is still validated
+            return False
+        return any(self._eval(index, ops, s).count() > 0 for s in shards)
+
     def row(self, index, ops, shards):
         self.programs.append(list(ops))
         out = O.Bitmap()

@@ -93,9 +93,11 @@ def test_groupby_thread_per_row_variant():
                     env={"FBGPU_GROUPBY_FAST": "1"})
 
 
-def test_wordpar_unrolled_loop_variant():
-    """-DFBGPU_WP_UNROLL3 (wp_machine.h): the 3-ops-per-iteration word-parallel loop on BSI programs"""
-    run_on_emulator(["tests/test_gpu_parity.py", "-k", "bsi_range or bsi_uniform or FORCE_WORDPAR or bsi_diagonal"], defines=("FBGPU_WP_UNROLL3",), timeout=3000)
+def test_wordpar_loop_variants():
+    """the word-parallel op loop (wp_machine.h) with another ring depth, and the round-1 rotating-ring loop (-DFBGPU_WP_LEGACY_LOOP),
+    on the BSI programs (the default build's loop runs in test_default_kernels_parity)"""
+    run_on_emulator(["tests/test_gpu_parity.py", "-k", "bsi_range or bsi_uniform or FORCE_WORDPAR or bsi_diagonal"], defines=("FBGPU_WP_RING=3",), timeout=3000)
+    run_on_emulator(["tests/test_gpu_parity.py", "-k", "bsi_range or bsi_uniform or FORCE_WORDPAR"], defines=("FBGPU_WP_LEGACY_LOOP",), timeout=3000)
 
 
 @pytest.mark.parametrize("order", ["reverse", "random"])

@@ -68,6 +68,7 @@ def _queries(shards):
     q.append(("groupby", lambda c: np.asarray(c.groupby(0, [F, G], [0, 0], [list(range(6)), list(range(4))], shards)).reshape(-1).tolist()))
     q.append(("groupby_filtered", lambda c: np.asarray(c.groupby(0, [F, G], [0, 0], [[0, 2, 4], [1, 3]], some, filter_ops=[_row(F, 1)])).reshape(-1).tolist()))
     q.append(("bsi_count", lambda c: c.count(0, [L.Op(L.OP_BSI_RANGE, V, 7, 0, 12, L.CMP[">"], 100, 0)], shards)))
+    q.append(("any", lambda c: (c.any(0, [_row(F, 5)], shards), c.any(0, [_row(F, 77)], shards), c.any(0, [_row(F, 0), _row(G, 0), _nary(L.OP_INTERSECT, 2)], some))))
     q.append(("row", lambda c: c.row(0, [_row(F, 0), _row(G, 3), _nary(L.OP_UNION, 2)], shards)))
     q.append(("row_some", lambda c: c.row(0, [_row(F, 2), _row(F, 3), _nary(L.OP_INTERSECT, 2)], some)))
     return q

@@ -531,3 +531,46 @@ def test_executor_topk_topn_groupby_goldens_on_gpu():
         p.ex.execute("i", "GroupBy()")
     with pytest.raises(X.QueryError, match="field not found"):
         p.ex.execute("i", "GroupBy(Rows(missing))")
+
+
+def test_any_early_exit_and_pair_type_histogram():
+    """fbgpu_any (Row.Any, row.go:258 — early exit by shard blocks) and fbgpu_pair_types (the statsHit analogue: which of the nine
+    container-pair kernels a Count(Intersect(Row, Row)) exercises, roaring.go:4477-4614)"""
+    import struct
+    from featurebase_b200 import lib as L
+    p = Pair(track_existence=False)
+    f = p.field("f")
+    n_sh, frags = 40, {}
+    for s in range(n_sh):
+        # row 0 only exists from shard 30 on; rows 1 / 2: uniform and clustered data so that arrays, bitmaps and runs all occur
+        rows = ([0] if s >= 30 else []) + [1, 2]
+        data = D.fragment(41, s, rows, 0.3 if s % 3 == 0 else 0.01, mode=s % 2)
+        p.load("f", X.VIEW_STANDARD, s, data)
+        frags[s] = data
+    shards = list(range(n_sh))
+    ctx, idx = p.ex.ctx, p.idx
+    row = lambda r: L.Op(L.OP_ROW, f.id, 0, 0, r, 0, 0, 0)
+    q = [row(0), row(1), L.Op(L.OP_INTERSECT, 0, 0, 2, 0, 0, 0, 0)]
+    launches0 = ctx.counters()["kernel_launches"]
+    assert ctx.any(idx.id, [row(1)], shards) is True
+    assert ctx.counters()["kernel_launches"] - launches0 == 1                   # found in the first block of 8 shards
+    assert ctx.any(idx.id, [row(0)], shards[:30]) is False                      # absent: every block was looked at
+    assert ctx.any(idx.id, [row(0)], shards) is True
+    assert ctx.any(idx.id, q, shards) == (ctx.count(idx.id, q, shards) > 0)
+    assert ctx.any(idx.id, [row(7)], shards) is False
+    with pytest.raises(L.FbgpuError):
+        ctx.any(idx.id, [L.Op(L.OP_INTERSECT, 0, 0, 0, 0, 0, 0, 0)], shards[:0])
+    # expected histogram from the container tables of the loaded images (type per key; key = row * 16 + slot)
+    want = np.zeros((4, 4), dtype=np.uint64)
+    for s in shards:
+        raw = frags[s]
+        n = struct.unpack_from("<I", raw, 4)[0]
+        typ = {}
+        for i in range(n):
+            key, t, _ = struct.unpack_from("<QHH", raw, 8 + 12 * i)
+            typ[key] = t
+        for slot in range(16):
+            want[typ.get(1 * 16 + slot, 0), typ.get(2 * 16 + slot, 0)] += 1
+    got = ctx.pair_types(idx.id, f.id, 0, 1, f.id, 0, 2, shards)
+    assert np.array_equal(got, want), (got, want)
+    assert int(got.sum()) == 16 * n_sh and (got > 0).sum() >= 3                 # several of the nine kernels are exercised

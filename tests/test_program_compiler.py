@@ -211,7 +211,7 @@ def test_fold_shape_and_errors(cc):
 
 
 def test_wordpar_unrolled_loop_matches_stack_model(cc):
-    """csrc/wp_machine.h (the experimental fixed-register op loop of eval_wordpar_kernel, -DFBGPU_WP_UNROLL3) against a plain
+    """csrc/wp_machine.h (the fixed-register op loop of eval_wordpar_kernel) against a plain
     Python stack machine on 128-bit slices: programs from the real compiler (random call trees with BSI leaves, every
     comparison at several depths), random operand slices incl. all-zero / all-one rows"""
     rng = np.random.default_rng(33)

@@ -3,7 +3,9 @@ import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from featurebase_b200 import build as B
 VARIANTS = {   # name -> -D defines; edit freely, outputs featurebase_b200/libfbgpu_<name>.so (select with FBGPU_LIB=...)
-    "wp_unroll3": ["FBGPU_WP_UNROLL3"],          # experimental fixed-register op loop of the word-parallel kernel (csrc/wp_machine.h)
+    "wp_ring3": ["FBGPU_WP_RING=3"],             # word-parallel op loop with 3 operand slices in flight (the round-2 first measurement)
+    "wp_ring8": ["FBGPU_WP_RING=8"],
+    "wp_legacy": ["FBGPU_WP_LEGACY_LOOP"],       # round-1 rotating-ring loop
     "pair_unscatter": ["FBGPU_PAIR_UNSCATTER"],
     "eval_deep1": ["FBGPU_EVAL_DEEP=1"],                                  # round-1 scatter loop: one chunk load in flight per lane
     "eval_mb8": ["FBGPU_EVAL_MIN_BLOCKS=8"],                              # round-1 shape: 32 registers, 8 CTAs / SM
