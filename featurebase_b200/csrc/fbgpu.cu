@@ -132,9 +132,14 @@ constexpr int kNcclUint64 = 5, kNcclSum = 0;   // ncclDataType_t / ncclRedOp_t v
 // ------------------------------------------------------------------ context
 struct ViewKey { uint32_t index, field, view; bool operator<(const ViewKey& o) const { return index != o.index ? index < o.index : field != o.field ? field < o.field : view < o.view; } };
 
+struct Extent { uint64_t off, len; };
 struct HostFrag { uint32_t fv; uint64_t shard; bool live; uint32_t row_off, n_rows; uint64_t payload_bytes; uint32_t n_desc; uint32_t n_arr, n_bmp, n_run; uint32_t n_striped;
                   uint64_t desc_off = 0;               // its descriptors are h_descs[desc_off, desc_off + n_desc)
-                  uint64_t arena_off = 0, arena_len = 0; };   // its payloads (with their alignment gaps) are arena bytes [arena_off, arena_off + arena_len)
+                  uint64_t arena_off = 0, arena_len = 0;      // the payloads it brought (with their alignment gaps) are arena bytes [arena_off, arena_off + arena_len)
+                  // a fragment produced by fbgpu_apply_containers keeps the untouched containers of its predecessor where they are:
+                  std::vector<Extent> inherited;       // arena extents taken over from the predecessors (theirs to free with this fragment)
+                  uint64_t hole_bytes = 0;             // bytes inside those extents no descriptor points at any more (already counted in dead_arena)
+                  bool stripe_policy = false; };       // arrays of this fragment are stored bank-striped (decided at its first load, kept by updates)
 
 struct Workspace {
     cudaStream_t stream = nullptr;
@@ -161,6 +166,12 @@ struct fbgpu_ctx {
     uint64_t uploaded = 0;               // bytes of payload already in HBM
     uint64_t dead_arena = 0;             // arena bytes of replaced / dropped fragments (reclaimed by compact_locked)
     bool meta_dirty = false;
+    // incremental commit: the host tables t_* are kept between commits; a commit after a few loads / drops / container updates patches the
+    // entries of the touched (view, shard) pairs and uploads the tails of the append-only mirrors instead of rebuilding and re-sending everything
+    bool tables_valid = false;            // t_views / t_flat / t_rowtab describe the mirrors except for `dirty_shards`
+    bool dev_tables_valid = false;        // the device tables equal the host tables as of the last commit
+    std::vector<std::pair<uint32_t, uint64_t>> dirty_shards;
+    size_t dev_rows = 0, dev_descs = 0, dev_frags = 0;   // prefix of h_rows / h_descs / h_frags already in HBM
     bool inspect_only = false;           // created with FBGPU_DEVICE_NONE: residency + fbgpu_debug_container only, no device, no queries
     std::vector<ViewTab> t_views; std::vector<int32_t> t_flat; std::vector<RowTabEnt> t_rowtab;   // inspect_only: the tables a commit would upload
     bool stripe_arrays = getenv("FBGPU_ARRAY_SORTED") == nullptr;    // bank-striped array payload order (stripe.h) unless FBGPU_ARRAY_SORTED=1 (fixed per context)
@@ -276,17 +287,22 @@ static uint32_t view_id_locked(fbgpu_ctx* c, ViewKey k, bool create) {
     return id;
 }
 
-static void drop_locked(fbgpu_ctx* c, uint32_t fv, uint64_t shard) {
+// `successor_keeps_arena`: the fragment is being superseded by fbgpu_apply_containers — its arena extents go to the new fragment
+static void drop_locked(fbgpu_ctx* c, uint32_t fv, uint64_t shard, bool successor_keeps_arena = false) {
     auto& sm = c->shardmaps[fv];
     if (shard >= sm.size() || sm[shard] < 0) return;
     HostFrag& f = c->frags[sm[shard]];
     f.live = false;
-    c->dead_arena += f.arena_len; c->stats.dead_bytes = c->dead_arena;
+    if (!successor_keeps_arena) {
+        uint64_t own = f.arena_len; for (const Extent& e : f.inherited) own += e.len;
+        c->dead_arena += own - f.hole_bytes; c->stats.dead_bytes = c->dead_arena;
+    }
     c->stats.fragments--; c->stats.containers -= f.n_desc; c->stats.payload_bytes -= f.payload_bytes;
     c->stats.array_containers -= f.n_arr; c->stats.bitmap_containers -= f.n_bmp; c->stats.run_containers -= f.n_run;
     c->view_arr[fv] -= f.n_arr; c->view_other[fv] -= (uint64_t)f.n_bmp + f.n_run; c->view_striped[fv] -= f.n_striped;
     sm[shard] = -1;
     c->meta_dirty = true;
+    c->dirty_shards.emplace_back(fv, shard);
 }
 
 // A load is all-or-nothing: the entry points open a StoreTxn before the first mutation; unless commit() is reached
@@ -321,6 +337,7 @@ struct StoreTxn {
         // (views created by the failed call stay, empty: resize the snapshots up to the current number of views)
         view_arr.resize(c->view_arr.size(), 0); view_other.resize(c->view_other.size(), 0); view_striped.resize(c->view_striped.size(), 0);
         c->view_arr = view_arr; c->view_other = view_other; c->view_striped = view_striped;
+        c->tables_valid = false;            // (dirty_shards may name pairs of the undone call: the next commit rebuilds the tables)
     }
 };
 
@@ -328,47 +345,63 @@ struct StoreTxn {
 // gigabytes of map (the reference's shard space is sparse; 2^24 shards = 1.7e13 columns per index is far past its deployments).
 constexpr uint64_t kMaxShard = 1ull << 24;
 
-// appends one parsed fragment to the host mirrors + staging (store_mu held exclusively, inside a StoreTxn)
-static int add_fragment_locked(fbgpu_ctx* c, StoreTxn& txn, uint32_t fv, uint64_t shard, const std::vector<ParsedCont>& cs, std::vector<PayloadCopy>& copies) {
+static inline uint64_t cont_bytes(uint16_t typ, uint32_t n, uint32_t cnt) { return typ == kArray ? (uint64_t)n * 2 : typ == kBitmap ? 8192 : (uint64_t)cnt * 4; }
+
+// one container of a fragment being appended: a parsed one (payload to be copied), or one kept from the predecessor fragment
+// (descriptor copied, payload stays where it is in the arena)
+struct FragItem { uint64_t key; const ParsedCont* pc; ContDesc kept; };
+
+// appends one fragment to the host mirrors + staging (store_mu held exclusively, inside a StoreTxn).  `pred` != null: the fragment
+// supersedes *pred (fbgpu_apply_containers): it takes over pred's arena extents, `new_holes` more bytes of them are unreferenced now
+static int add_items_locked(fbgpu_ctx* c, StoreTxn& txn, uint32_t fv, uint64_t shard, const std::vector<FragItem>& items, std::vector<PayloadCopy>& copies,
+                            const HostFrag* pred, uint64_t new_holes) {
     if (shard >= kMaxShard) return fail(FBGPU_E_INVALID, "shard %llu too large (limit %llu)", (unsigned long long)shard, (unsigned long long)kMaxShard);
     txn.note(fv, shard);
-    drop_locked(c, fv, shard);
     HostFrag hf{}; hf.fv = fv; hf.shard = shard; hf.live = true; hf.row_off = (uint32_t)c->h_rows.size(); hf.desc_off = c->h_descs.size();
+    if (pred) {             // (read before drop_locked / push_back: `pred` points into c->frags)
+        hf.inherited = pred->inherited;
+        if (pred->arena_len) hf.inherited.push_back(Extent{ pred->arena_off, pred->arena_len });
+        hf.hole_bytes = pred->hole_bytes + new_holes; hf.stripe_policy = pred->stripe_policy;
+        c->dead_arena += new_holes; c->stats.dead_bytes = c->dead_arena;
+    }
+    drop_locked(c, fv, shard, pred != nullptr);
     hf.arena_off = c->uploaded + c->staging.len;
     uint64_t prev_row = ~0ull; bool contiguous = true; uint64_t row0 = 0;
     const size_t desc0 = c->h_descs.size();
     // descriptors: row-major (key order), so that a row's slots are adjacent and rank = popc(mask & below)
-    for (const ParsedCont& pc : cs) {
-        uint64_t row = pc.key / kSlotsPerRow; int slot = (int)(pc.key % kSlotsPerRow);
+    for (const FragItem& it : items) {
+        uint64_t row = it.key / kSlotsPerRow; int slot = (int)(it.key % kSlotsPerRow);
         if (row != prev_row) {
             if (prev_row == ~0ull) row0 = row; else if (row != prev_row + 1) contiguous = false;
             RowEnt e{}; e.row = row; e.first_desc = (uint32_t)c->h_descs.size(); e.mask = 0;
             c->h_rows.push_back(e); prev_row = row; hf.n_rows++;
         }
         c->h_rows.back().mask |= (uint16_t)(1u << slot);
-        ContDesc d{}; d.off16 = 0; d.card = pc.n; d.typ = pc.typ; d.cnt = (uint16_t)pc.cnt;
+        ContDesc d = it.kept;
+        if (it.pc) { d = ContDesc{}; d.off16 = 0; d.card = it.pc->n; d.typ = it.pc->typ; d.cnt = (uint16_t)it.pc->cnt; }
         c->h_descs.push_back(d);
-        uint64_t bytes = pc.typ == kArray ? (uint64_t)pc.n * 2 : pc.typ == kBitmap ? 8192 : (uint64_t)pc.cnt * 4;
-        hf.n_desc++; hf.payload_bytes += bytes;
-        if (pc.typ == kArray) hf.n_arr++; else if (pc.typ == kBitmap) hf.n_bmp++; else hf.n_run++;
+        hf.n_desc++; hf.payload_bytes += cont_bytes(d.typ, d.card, d.cnt);
+        if (d.typ == kArray) hf.n_arr++; else if (d.typ == kBitmap) hf.n_bmp++; else hf.n_run++;
     }
     // payloads: row-major (key order) by default: a row's 16 containers are contiguous, which is what the common
     // few-rows-of-many query streams.  FBGPU_LAYOUT_SLOT_MAJOR=1 stores all rows of slot 0, then slot 1, ... so that a
     // (shard, slot) unit's consecutive rows are adjacent (measured: no significant difference; profiles/README.md).
-    // experimental striped order: only for array-dominated fragments, so that bitmap-heavy views (BSI planes) keep every
+    // striped order: only for array-dominated fragments, so that bitmap-heavy views (BSI planes) keep every
     // array sorted and stay eligible for the word-parallel kernel, whose slice search needs sorted arrays
-    const bool stripe = c->stripe_arrays && (uint64_t)hf.n_arr * 8 > (uint64_t)hf.n_bmp + hf.n_run;
-    if (stripe) for (const ParsedCont& pc : cs) if (pc.typ == kArray && pc.n >= fbgpu_stripe::kMinStripe) hf.n_striped++;
-    std::vector<uint32_t> order(cs.size());
-    for (uint32_t i = 0; i < cs.size(); i++) order[i] = i;
+    if (!pred) hf.stripe_policy = c->stripe_arrays && (uint64_t)hf.n_arr * 8 > (uint64_t)hf.n_bmp + hf.n_run;
+    const bool stripe = hf.stripe_policy;
+    if (stripe) for (size_t i = 0; i < items.size(); i++) { const ContDesc& d = c->h_descs[desc0 + i]; if (d.typ == kArray && d.card >= fbgpu_stripe::kMinStripe) hf.n_striped++; }
+    std::vector<uint32_t> order(items.size());
+    for (uint32_t i = 0; i < items.size(); i++) order[i] = i;
     static const bool slot_major = getenv("FBGPU_LAYOUT_SLOT_MAJOR") != nullptr;   // default: row-major (key order)
-    if (slot_major) std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return cs[a].key % kSlotsPerRow < cs[b].key % kSlotsPerRow; });
+    if (slot_major) std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return items[a].key % kSlotsPerRow < items[b].key % kSlotsPerRow; });
     for (uint32_t i : order) {
-        const ParsedCont& pc = cs[i];
+        if (!items[i].pc) continue;                             // kept: its descriptor already points at the payload
+        const ParsedCont& pc = *items[i].pc;
         uint64_t pos = c->uploaded + c->staging.len;
         uint64_t align = pc.typ == kBitmap ? 128 : 16;
         uint64_t apos = (pos + align - 1) & ~(align - 1);
-        uint64_t bytes = pc.typ == kArray ? (uint64_t)pc.n * 2 : pc.typ == kBitmap ? 8192 : (uint64_t)pc.cnt * 4;
+        uint64_t bytes = cont_bytes(pc.typ, pc.n, pc.cnt);
         uint64_t padded = (bytes + 15) & ~15ull;
         if (apos / 16 > 0xffffffffull) return fail(FBGPU_E_NOMEM, "payload arena exceeds 64 GiB addressable by 32-bit 16 B offsets");
         c->staging.len += (apos - pos) + padded;            // space is claimed now, bytes are copied by run_copies()
@@ -378,15 +411,21 @@ static int add_fragment_locked(fbgpu_ctx* c, StoreTxn& txn, uint32_t fv, uint64_
     hf.arena_len = c->uploaded + c->staging.len - hf.arena_off;
     FragHdr h{}; h.row_off = hf.row_off; h.n_rows = hf.n_rows; h.row0 = row0; h.contiguous = contiguous ? 1u : 0u;
     int32_t fid = (int32_t)c->frags.size();
-    c->frags.push_back(hf); c->h_frags.push_back(h);
-    auto& sm = c->shardmaps[fv];
-    if (shard >= sm.size()) sm.resize(shard + 1, -1);
-    sm[shard] = fid;
     c->stats.fragments++; c->stats.containers += hf.n_desc; c->stats.payload_bytes += hf.payload_bytes;
     c->stats.array_containers += hf.n_arr; c->stats.bitmap_containers += hf.n_bmp; c->stats.run_containers += hf.n_run;
     c->view_arr[fv] += hf.n_arr; c->view_other[fv] += (uint64_t)hf.n_bmp + hf.n_run; c->view_striped[fv] += hf.n_striped;
+    c->frags.push_back(std::move(hf)); c->h_frags.push_back(h);
+    auto& sm = c->shardmaps[fv];
+    if (shard >= sm.size()) sm.resize(shard + 1, -1);
+    sm[shard] = fid;
     c->meta_dirty = true;
+    c->dirty_shards.emplace_back(fv, shard);
     return 0;
+}
+static int add_fragment_locked(fbgpu_ctx* c, StoreTxn& txn, uint32_t fv, uint64_t shard, const std::vector<ParsedCont>& cs, std::vector<PayloadCopy>& copies) {
+    std::vector<FragItem> items(cs.size());
+    for (size_t i = 0; i < cs.size(); i++) items[i] = FragItem{ cs[i].key, &cs[i], ContDesc{} };
+    return add_items_locked(c, txn, fv, shard, items, copies, nullptr, 0);
 }
 
 // copies the planned payloads into the staging buffer (possibly on several host threads); store_mu held exclusively
@@ -540,6 +579,71 @@ extern "C" int fbgpu_drop_fragment(fbgpu_ctx* c, uint32_t index, uint32_t field,
     return 0;
 } FBGPU_CATCH
 
+// ------------------------------------------------------------------ incremental refresh (the write path's mirror)
+// fbgpu_apply_containers: what a committed write transaction did to ONE fragment, container by container — the mirror of
+// Tx.PutContainer / Tx.RemoveContainer (tx.go:91-96, rbf/tx.go:791-860) collected over the transaction.  `roaring` holds only
+// the containers that were written (each REPLACES the container under its key, or adds it), `removed_keys` the keys that were
+// deleted.  Untouched containers keep their payload where it is in HBM: the call costs the bytes of the changed containers plus the
+// fragment's row / descriptor entries, not a re-send of the fragment (fbgpu_load_fragment).  The replaced payloads become holes that
+// fbgpu_compact reclaims container by container.  A fragment that is not resident yet is created from the written containers.
+extern "C" int fbgpu_apply_containers(fbgpu_ctx* c, uint32_t index, uint32_t field, uint32_t view, uint64_t shard, const uint8_t* roaring, uint64_t nbytes,
+                                      const uint64_t* removed_keys, int64_t n_removed) try {
+    if (!c || n_removed < 0 || (n_removed && !removed_keys) || (nbytes && !roaring)) return fail(FBGPU_E_INVALID, "null argument");
+    std::vector<ParsedCont> put;
+    if (nbytes) { int rc = parse_roaring(roaring, nbytes, put); if (rc) return rc; }
+    for (size_t i = 1; i < put.size(); i++) if (put[i - 1].key >= put[i].key) return fail(FBGPU_E_FORMAT, "container keys not ascending");
+    std::vector<uint64_t> removed(removed_keys, removed_keys + n_removed);
+    std::sort(removed.begin(), removed.end());
+    removed.erase(std::unique(removed.begin(), removed.end()), removed.end());
+    for (const ParsedCont& pc : put) if (std::binary_search(removed.begin(), removed.end(), pc.key)) return fail(FBGPU_E_INVALID, "container key %llu is both written and removed", (unsigned long long)pc.key);
+    std::unique_lock<std::shared_mutex> lk(c->store_mu);
+    uint32_t fv = view_id_locked(c, ViewKey{ index, field, view }, true);
+    std::vector<PayloadCopy> copies;
+    StoreTxn txn(c);
+    const auto& sm = c->shardmaps[fv];
+    const int32_t old_fid = shard < sm.size() ? sm[shard] : -1;
+    std::vector<FragItem> items;
+    uint64_t holes = 0;
+    if (old_fid >= 0) {
+        const HostFrag& of = c->frags[(size_t)old_fid];
+        items.reserve((size_t)of.n_desc + put.size());
+        size_t pi = 0;
+        auto flush_put = [&](uint64_t below) { while (pi < put.size() && put[pi].key < below) { items.push_back(FragItem{ put[pi].key, &put[pi], ContDesc{} }); pi++; } };
+        for (uint32_t r = 0; r < of.n_rows; r++) {
+            const RowEnt e = c->h_rows[of.row_off + r];
+            uint32_t rank = 0;
+            for (int slot = 0; slot < kSlotsPerRow; slot++) {
+                if (!((e.mask >> slot) & 1)) continue;
+                const ContDesc d = c->h_descs[e.first_desc + rank++];
+                const uint64_t key = e.row * kSlotsPerRow + (uint64_t)slot;
+                flush_put(key);
+                const bool replaced = pi < put.size() && put[pi].key == key;
+                if (replaced || std::binary_search(removed.begin(), removed.end(), key)) {
+                    holes += (cont_bytes(d.typ, d.card, d.cnt) + 15) & ~15ull;
+                    if (replaced) { items.push_back(FragItem{ key, &put[pi], ContDesc{} }); pi++; }
+                } else items.push_back(FragItem{ key, nullptr, d });
+            }
+        }
+        while (pi < put.size()) { items.push_back(FragItem{ put[pi].key, &put[pi], ContDesc{} }); pi++; }
+    } else {
+        items.reserve(put.size());
+        for (const ParsedCont& pc : put) items.push_back(FragItem{ pc.key, &pc, ContDesc{} });
+    }
+    int rc;
+    if (items.empty()) {                         // every container is gone: the fragment is dropped (its arena becomes dead space)
+        if (old_fid >= 0) { txn.note(fv, shard); drop_locked(c, fv, shard); }
+        rc = 0;
+    } else {
+        HostFrag pred_copy; const HostFrag* pred = nullptr;
+        if (old_fid >= 0) { pred_copy = c->frags[(size_t)old_fid]; pred = &pred_copy; }
+        rc = add_items_locked(c, txn, fv, shard, items, copies, pred, holes);
+    }
+    if (rc) return rc;
+    rc = run_copies(c, copies, 1); if (rc) return rc;
+    txn.commit();
+    return FBGPU_OK;
+} FBGPU_CATCH
+
 // uploads staged payload (append) and refreshes metadata tables; store_mu held exclusively
 // flatten shard maps; build the dense (shard,row) directory of every view whose row ids are dense
 static void build_tables(fbgpu_ctx* c, std::vector<ViewTab>& views, std::vector<int32_t>& flat, std::vector<RowTabEnt>& rowtab) {
@@ -573,9 +677,58 @@ static void par_memcpy(void* dst, const void* src, size_t n) {
     for (auto& t : th) t.join();
 }
 
+// Brings the host tables t_views / t_flat / t_rowtab up to date.  Full rebuild, or — when only a few (view, shard) pairs changed and
+// none of them changes a table's geometry (a new view, a shard past the view's map, a row outside the dense directory's range) —
+// a patch of those pairs' entries.  `patched` receives the patched pairs (empty after a full rebuild).
+static bool refresh_tables(fbgpu_ctx* c, std::vector<std::pair<uint32_t, uint64_t>>& patched) {
+    patched.clear();
+    bool full = !c->tables_valid || c->dirty_shards.size() > 512 || c->t_views.size() != c->shardmaps.size();
+    if (!full) {
+        std::sort(c->dirty_shards.begin(), c->dirty_shards.end());
+        c->dirty_shards.erase(std::unique(c->dirty_shards.begin(), c->dirty_shards.end()), c->dirty_shards.end());
+        for (const auto& ds : c->dirty_shards) {
+            const uint32_t fv = ds.first; const uint64_t shard = ds.second;
+            const ViewTab& v = c->t_views[fv]; const auto& sm = c->shardmaps[fv];
+            if (sm.size() != v.n_shards || shard >= v.n_shards) { full = true; break; }
+            const int32_t fid = sm[shard];
+            if (v.rt_rows && fid >= 0) {
+                const HostFrag& hf = c->frags[(size_t)fid];
+                if (hf.n_rows && (c->h_rows[hf.row_off].row < v.rmin || c->h_rows[hf.row_off + hf.n_rows - 1].row - v.rmin >= v.rt_rows)) { full = true; break; }
+            }       // (a view without a dense directory stays correct through the search chain; it only gets one at the next full rebuild)
+        }
+    }
+    if (full) { build_tables(c, c->t_views, c->t_flat, c->t_rowtab); c->tables_valid = true; c->dirty_shards.clear(); c->stats.full_commits++; return true; }
+    c->stats.patch_commits++;
+    for (const auto& ds : c->dirty_shards) {
+        const uint32_t fv = ds.first; const uint64_t shard = ds.second;
+        const ViewTab& v = c->t_views[fv];
+        const int32_t fid = c->shardmaps[fv][shard];
+        c->t_flat[v.shard_off + shard] = fid;
+        if (v.rt_rows) {
+            RowTabEnt* slice = c->t_rowtab.data() + v.rt_off + shard * v.rt_rows;
+            std::fill(slice, slice + v.rt_rows, RowTabEnt{ 0, 0, 0 });
+            if (fid >= 0) { const HostFrag& hf = c->frags[(size_t)fid];
+                for (uint32_t k = 0; k < hf.n_rows; k++) { const RowEnt& e = c->h_rows[hf.row_off + k]; slice[e.row - v.rmin] = RowTabEnt{ e.first_desc, e.mask, 0 }; } }
+        }
+    }
+    patched.swap(c->dirty_shards); c->dirty_shards.clear();
+    return false;
+}
+
+// grows a device table to hold `need` bytes, keeping its first `keep` bytes (DevBuf::ensure alone would drop them)
+static int grow_keeping(DevBuf& b, size_t need, size_t keep) {
+    if (need <= b.cap) return 0;
+    DevBuf nb;
+    if (nb.ensure(std::max(need, b.cap + b.cap / 2))) return FBGPU_E_NOMEM;
+    if (keep && b.p) { cudaError_t e = cudaMemcpy(nb.p, b.p, keep, cudaMemcpyDeviceToDevice); if (e != cudaSuccess) { nb.release(); return fail(FBGPU_E_CUDA, "table copy failed: %s", cudaGetErrorString(e)); } }
+    b.release(); b = nb;
+    return 0;
+}
+
 static int commit_locked(fbgpu_ctx* c) {
+    std::vector<std::pair<uint32_t, uint64_t>> patched;
     if (c->inspect_only) {                  // no device: keep the payload in the staging buffer and the tables on the host
-        build_tables(c, c->t_views, c->t_flat, c->t_rowtab);
+        if (c->meta_dirty || !c->tables_valid) refresh_tables(c, patched);
         c->meta_dirty = false;
         return 0;
     }
@@ -613,21 +766,45 @@ static int commit_locked(fbgpu_ctx* c) {
         c->uploaded += c->staging.len;
         c->staging.clear_and_free();
     }
-    std::vector<ViewTab> views; std::vector<int32_t> flat; std::vector<RowTabEnt> rowtab;
-    build_tables(c, views, flat, rowtab);
+    const bool full = refresh_tables(c, patched) || !c->dev_tables_valid;
+    auto h2d = [&](void* dst, const void* src, size_t bytes) -> int {
+        if (!bytes) return 0;
+        cudaError_t e = cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice);
+        return e == cudaSuccess ? 0 : fail(FBGPU_E_CUDA, "metadata upload failed: %s", cudaGetErrorString(e));
+    };
     auto up = [&](DevBuf& b, const void* src, size_t bytes) -> int {
         if (b.ensure(std::max<size_t>(bytes, 256))) return FBGPU_E_NOMEM;
-        if (bytes) { cudaError_t e = cudaMemcpy(b.p, src, bytes, cudaMemcpyHostToDevice); if (e != cudaSuccess) return fail(FBGPU_E_CUDA, "metadata upload failed: %s", cudaGetErrorString(e)); }
-        return 0;
+        return h2d(b.p, src, bytes);
     };
     int rc;
-    if ((rc = up(c->d_views, views.data(), views.size() * sizeof(ViewTab)))) return rc;
-    if ((rc = up(c->d_shardmap, flat.data(), flat.size() * 4))) return rc;
-    if ((rc = up(c->d_frags, c->h_frags.data(), c->h_frags.size() * sizeof(FragHdr)))) return rc;
-    if ((rc = up(c->d_rows, c->h_rows.data(), c->h_rows.size() * sizeof(RowEnt)))) return rc;
-    if ((rc = up(c->d_descs, c->h_descs.data(), c->h_descs.size() * sizeof(ContDesc)))) return rc;
-    if ((rc = up(c->d_rowtab, rowtab.data(), rowtab.size() * sizeof(RowTabEnt)))) return rc;
-    c->n_views_dev = (uint32_t)views.size();
+    c->dev_tables_valid = false;            // (a failure below leaves the device tables in an unknown state: the next commit re-sends them)
+    if (full) {
+        if ((rc = up(c->d_views, c->t_views.data(), c->t_views.size() * sizeof(ViewTab)))) return rc;
+        if ((rc = up(c->d_shardmap, c->t_flat.data(), c->t_flat.size() * 4))) return rc;
+        if ((rc = up(c->d_frags, c->h_frags.data(), c->h_frags.size() * sizeof(FragHdr)))) return rc;
+        if ((rc = up(c->d_rows, c->h_rows.data(), c->h_rows.size() * sizeof(RowEnt)))) return rc;
+        if ((rc = up(c->d_descs, c->h_descs.data(), c->h_descs.size() * sizeof(ContDesc)))) return rc;
+        if ((rc = up(c->d_rowtab, c->t_rowtab.data(), c->t_rowtab.size() * sizeof(RowTabEnt)))) return rc;
+    } else {
+        // append-only mirrors: only their new tails travel; then the patched directory entries
+        auto tail = [&](DevBuf& b, const void* base, size_t have, size_t now, size_t elem) -> int {
+            int r = grow_keeping(b, std::max<size_t>(now * elem, 256), have * elem); if (r) return r;
+            return h2d((uint8_t*)b.p + have * elem, (const uint8_t*)base + have * elem, (now - have) * elem);
+        };
+        if ((rc = tail(c->d_frags, c->h_frags.data(), c->dev_frags, c->h_frags.size(), sizeof(FragHdr)))) return rc;
+        if ((rc = tail(c->d_rows, c->h_rows.data(), c->dev_rows, c->h_rows.size(), sizeof(RowEnt)))) return rc;
+        if ((rc = tail(c->d_descs, c->h_descs.data(), c->dev_descs, c->h_descs.size(), sizeof(ContDesc)))) return rc;
+        for (const auto& ds : patched) {
+            const ViewTab& v = c->t_views[ds.first];
+            const size_t fi = (size_t)v.shard_off + ds.second;
+            if ((rc = h2d((int32_t*)c->d_shardmap.p + fi, c->t_flat.data() + fi, 4))) return rc;
+            if (v.rt_rows) { const size_t ri = (size_t)v.rt_off + ds.second * v.rt_rows;
+                if ((rc = h2d((RowTabEnt*)c->d_rowtab.p + ri, c->t_rowtab.data() + ri, (size_t)v.rt_rows * sizeof(RowTabEnt)))) return rc; }
+        }
+    }
+    c->dev_frags = c->h_frags.size(); c->dev_rows = c->h_rows.size(); c->dev_descs = c->h_descs.size();
+    c->dev_tables_valid = true;
+    c->n_views_dev = (uint32_t)c->t_views.size();
     c->meta_dirty = false;
     c->stats.device_bytes = c->d_payload.cap + c->d_views.cap + c->d_shardmap.cap + c->d_frags.cap + c->d_rows.cap + c->d_descs.cap + c->d_rowtab.cap;
     return 0;
@@ -647,30 +824,59 @@ static int compact_locked(fbgpu_ctx* c) {
     std::vector<HostFrag> frags; std::vector<FragHdr> hfr; std::vector<RowEnt> rows; std::vector<ContDesc> descs;
     struct Move { uint64_t from, to, len; };
     std::vector<Move> moves; uint64_t cur = 0;
+    std::vector<ArenaMove> gathers;                        // container-granular moves of fragments that hold holes (fbgpu_apply_containers)
     auto maps = c->shardmaps;                              // (built aside: an allocation failure below must leave the store as it was)
     for (auto& sm : maps) std::fill(sm.begin(), sm.end(), -1);
     for (size_t fid = 0; fid < c->frags.size(); fid++) {
         HostFrag f = c->frags[fid];
         if (!f.live) continue;
         FragHdr h = c->h_frags[fid];
-        const uint64_t to = ((cur + 127) & ~127ull) + (f.arena_off & 127ull);
-        const int64_t d16 = ((int64_t)to - (int64_t)f.arena_off) / 16;         // both are 16-byte aligned
         const uint64_t desc_new = descs.size(), row_new = rows.size();
         for (uint32_t r = 0; r < f.n_rows; r++) { RowEnt e = c->h_rows[f.row_off + r]; e.first_desc = (uint32_t)(e.first_desc - f.desc_off + desc_new); rows.push_back(e); }
-        for (uint32_t k = 0; k < f.n_desc; k++) { ContDesc d = c->h_descs[f.desc_off + k]; d.off16 = (uint32_t)((int64_t)d.off16 + d16); descs.push_back(d); }
-        moves.push_back(Move{ f.arena_off, to, f.arena_len });
-        f.row_off = (uint32_t)row_new; f.desc_off = desc_new; f.arena_off = to; h.row_off = (uint32_t)row_new;
+        if (f.inherited.empty() && f.hole_bytes == 0) {    // one extent, no hole: moved as a block, every container keeps its offset modulo 128
+            const uint64_t to = ((cur + 127) & ~127ull) + (f.arena_off & 127ull);
+            const int64_t d16 = ((int64_t)to - (int64_t)f.arena_off) / 16;         // both are 16-byte aligned
+            for (uint32_t k = 0; k < f.n_desc; k++) { ContDesc d = c->h_descs[f.desc_off + k]; d.off16 = (uint32_t)((int64_t)d.off16 + d16); descs.push_back(d); }
+            moves.push_back(Move{ f.arena_off, to, f.arena_len });
+            f.arena_off = to;
+            cur = to + f.arena_len;
+        } else {                                           // updated fragment: its live containers are gathered one by one, the holes stay behind
+            const uint64_t start = (cur + 15) & ~15ull;
+            cur = start;
+            for (uint32_t k = 0; k < f.n_desc; k++) {
+                ContDesc d = c->h_descs[f.desc_off + k];
+                const uint64_t align = d.typ == kBitmap ? 128 : 16, to = (cur + align - 1) & ~(align - 1);
+                const uint64_t padded = (cont_bytes(d.typ, d.card, d.cnt) + 15) & ~15ull;
+                gathers.push_back(ArenaMove{ d.off16, (uint32_t)(to / 16), (uint32_t)(padded / 16), 0u });
+                d.off16 = (uint32_t)(to / 16); descs.push_back(d);
+                cur = to + padded;
+            }
+            f.arena_off = start; f.arena_len = cur - start; f.inherited.clear(); f.hole_bytes = 0;
+        }
+        f.row_off = (uint32_t)row_new; f.desc_off = desc_new; h.row_off = (uint32_t)row_new;
         maps[f.fv][f.shard] = (int32_t)frags.size();
-        frags.push_back(f); hfr.push_back(h);
-        cur = to + f.arena_len;
+        frags.push_back(std::move(f)); hfr.push_back(h);
     }
+    if (cur / 16 > 0xffffffffull) return fail(FBGPU_E_NOMEM, "payload arena exceeds 64 GiB addressable by 32-bit 16 B offsets");
     DevBuf nb;
     if (nb.ensure(cur + 256)) return FBGPU_E_NOMEM;
     for (const Move& m : moves) if (m.len) CUDA_TRY(cudaMemcpy((uint8_t*)nb.p + m.to, (const uint8_t*)c->d_payload.p + m.from, m.len, cudaMemcpyDeviceToDevice));
+    if (!gathers.empty()) {
+        DevBuf d_mv;
+        if (d_mv.ensure(gathers.size() * sizeof(ArenaMove))) { nb.release(); return FBGPU_E_NOMEM; }
+        cudaError_t e = cudaMemcpy(d_mv.p, gathers.data(), gathers.size() * sizeof(ArenaMove), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) {
+            const unsigned grid = (unsigned)std::min<size_t>((gathers.size() + 7) / 8, (size_t)c->sm_count * 16);
+            arena_gather_kernel<<<grid, 256>>>((const uint4*)c->d_payload.p, (uint4*)nb.p, (const ArenaMove*)d_mv.p, (long long)gathers.size());
+            e = cudaGetLastError(); if (e == cudaSuccess) e = cudaDeviceSynchronize();
+        }
+        d_mv.release();
+        if (e != cudaSuccess) { nb.release(); return fail(FBGPU_E_CUDA, "arena gather failed: %s", cudaGetErrorString(e)); }
+    }
     c->d_payload.release(); c->d_payload = nb;
     c->frags.swap(frags); c->h_frags.swap(hfr); c->h_rows.swap(rows); c->h_descs.swap(descs); c->shardmaps.swap(maps);
     c->uploaded = cur; c->dead_arena = 0; c->stats.dead_bytes = 0;
-    c->meta_dirty = true;
+    c->meta_dirty = true; c->tables_valid = false; c->dev_tables_valid = false;
     return commit_locked(c);                               // tables for the new layout
 }
 

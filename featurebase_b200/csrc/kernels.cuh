@@ -917,6 +917,19 @@ __device__ __forceinline__ uint32_t probe_chunk(const uint32_t* bm, uint4 v, uin
     }
     return c;
 }
+// the same for a chunk whose eight slots may all be probed (tail slots hold copies of the array's last element, stripe.h
+// pad_array_tail; the caller takes the copies out of the count again): no bounds, no divergent partial-chunk path
+__device__ __forceinline__ uint32_t probe_chunk_full(const uint32_t* bm, uint4 v) {
+    const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+    const char* b8 = reinterpret_cast<const char*>(bm);
+    uint32_t c = 0;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        c += (*reinterpret_cast<const uint32_t*>(b8 + word_off_lo(w[q])) >> (w[q] & 31)) & 1u;
+        c += (*reinterpret_cast<const uint32_t*>(b8 + word_off_hi(w[q])) >> ((w[q] >> 16) & 31)) & 1u;
+    }
+    return c;
+}
 // per-lane partial count of array elements found in a shared-memory bitmap
 __device__ __forceinline__ uint32_t warp_probe_smem(const uint32_t* bm, const uint16_t* arr, uint32_t n, int lane) {
     const uint4* a4 = reinterpret_cast<const uint4*>(arr);
@@ -1066,9 +1079,20 @@ __device__ __forceinline__ uint32_t warp_intersection_count(Resolved a, Resolved
         }
         for (uint32_t i = lane + 96; i < na8; i += 32) scatter_chunk_unrolled<0>(bm, ldg_nc(a4 + i), i * 8, a.card);      // > 768 elements: rare
         __syncwarp();
+        // every chunk of `b` is probed whole: the slots behind its last element hold copies of that element (pad_array_tail), and
+        // the copies are taken out of the count below.  (The guarded partial-chunk path made the warp run ~100 extra instructions
+        // for the ONE lane holding the tail — a third of the pair's instruction count.)
 #pragma unroll
-        for (int q = 0; q < 3; q++) if (lane + 32 * q < nb8) c += probe_chunk(bm, vb[q], (lane + 32 * q) * 8, b.card);
-        for (uint32_t i = lane + 96; i < nb8; i += 32) c += probe_chunk(bm, ldg_nc(b4 + i), i * 8, b.card);
+        for (int q = 0; q < 3; q++) if (lane + 32 * q < nb8) c += probe_chunk_full(bm, vb[q]);
+        for (uint32_t i = lane + 96; i < nb8; i += 32) c += probe_chunk_full(bm, ldg_nc(b4 + i));
+        const uint32_t pads = nb8 * 8u - b.card;                      // 0..7 copies of b's last element were probed too (warp-uniform)
+        if (pads) {
+            const uint32_t ql = (nb8 - 1u) >> 5;                       // the chunk holding them: register window slot ql of lane (nb8-1) & 31
+            uint32_t wl = ql == 0 ? vb[0].w : ql == 1 ? vb[1].w : vb[2].w;
+            wl = __shfl_sync(0xffffffffu, wl, (int)((nb8 - 1u) & 31u)) >> 16;
+            if (ql > 2) wl = __ldg(reinterpret_cast<const uint16_t*>(b.ptr) + b.card - 1);
+            if (lane == 0) c -= pads * ((bm[wl >> 5] >> (wl & 31)) & 1u);
+        }
         __syncwarp();
 #pragma unroll
         for (int q = 0; q < 3; q++) if (lane + 32 * q < na8) {
@@ -1950,6 +1974,20 @@ groupby_small_kernel(StoreRef st, uint32_t fvA, const uint64_t* __restrict__ row
             __syncwarp();
         }
         if (!small_ok && lane == 0) { const unsigned int k = atomicAdd(&fallback[0], 1u); fallback[1 + k] = (unsigned int)unit; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// arena_gather_kernel (fbgpu_compact): copies containers one by one from the old payload arena into the new one — one warp per
+// container, 16 bytes per lane and step.  Used for fragments that fbgpu_apply_containers left with holes.
+// ------------------------------------------------------------------------------------------------
+struct ArenaMove { uint32_t from16, to16, len16, pad; };
+__global__ void __launch_bounds__(256)
+arena_gather_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, const ArenaMove* __restrict__ mv, long long n) {
+    const int lane = threadIdx.x & 31;
+    for (long long i = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); i < n; i += (long long)gridDim.x * 8) {
+        const ArenaMove m = mv[i];
+        for (uint32_t k = lane; k < m.len16; k += 32) dst[(size_t)m.to16 + k] = src[(size_t)m.from16 + k];
     }
 }
 

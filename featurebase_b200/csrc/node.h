@@ -130,6 +130,11 @@ extern "C" int fbgpu_node_drop_fragment(fbgpu_node* n, uint32_t index, uint32_t 
     if (!n) return fail(FBGPU_E_INVALID, "null node");
     return fbgpu_drop_fragment(n->ctx[(size_t)n->owner(shard)], index, field, view, shard);
 } FBGPU_CATCH
+extern "C" int fbgpu_node_apply_containers(fbgpu_node* n, uint32_t index, uint32_t field, uint32_t view, uint64_t shard, const uint8_t* roaring, uint64_t nbytes,
+                                           const uint64_t* removed_keys, int64_t n_removed) try {
+    if (!n) return fail(FBGPU_E_INVALID, "null node");
+    return fbgpu_apply_containers(n->ctx[(size_t)n->owner(shard)], index, field, view, shard, roaring, nbytes, removed_keys, n_removed);
+} FBGPU_CATCH
 extern "C" int fbgpu_node_commit(fbgpu_node* n) try {
     if (!n) return fail(FBGPU_E_INVALID, "null node");
     return node_fan_out(n, node_all(n), [&](int d) { return fbgpu_commit(n->ctx[(size_t)d]); });
@@ -141,6 +146,7 @@ extern "C" int fbgpu_node_get_stats(fbgpu_node* n, fbgpu_stats* out) try {
         fbgpu_stats s{}; int rc = fbgpu_get_stats(c, &s); if (rc) return rc;
         out->fragments += s.fragments; out->containers += s.containers; out->array_containers += s.array_containers; out->bitmap_containers += s.bitmap_containers;
         out->run_containers += s.run_containers; out->payload_bytes += s.payload_bytes; out->device_bytes += s.device_bytes; out->dead_bytes += s.dead_bytes;
+        out->full_commits += s.full_commits; out->patch_commits += s.patch_commits;
     }
     return FBGPU_OK;
 } FBGPU_CATCH

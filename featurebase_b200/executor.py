@@ -136,6 +136,13 @@ class Holder:
         self.ctx.load_fragment(idx.id, idx.fields[field].id, view, shard, data)
         idx.shards.add(int(shard))
 
+    def apply_containers(self, index, field, view, shard, data=b"", removed_keys=()):
+        """a committed write transaction's container changes to one fragment (Tx.PutContainer / RemoveContainer, tx.go:91-96): `data`
+        holds only the written containers, removed_keys the deleted ones; untouched containers stay where they are in HBM"""
+        idx = self.indexes[index]
+        self.ctx.apply_containers(idx.id, idx.fields[field].id, view, shard, data, removed_keys)
+        idx.shards.add(int(shard))
+
     def import_rbf(self, index, shard, data, wal=b""):
         """residency straight from a shard's RBF database bytes: every field/view of this index that the
         file holds under its rbfName "~field;view<" (rbf.go:504; views "standard" view.go:28 and "bsig_<field>" :30)"""

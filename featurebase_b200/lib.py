@@ -31,7 +31,7 @@ class Op(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("fragments", "containers", "array_containers", "bitmap_containers",
-                                           "run_containers", "payload_bytes", "device_bytes", "dead_bytes")]
+                                           "run_containers", "payload_bytes", "device_bytes", "dead_bytes", "full_commits", "patch_commits")]
 
 
 class Counters(C.Structure):
@@ -43,7 +43,7 @@ EXPORTS = ["fbgpu_init", "fbgpu_shutdown", "fbgpu_last_error", "fbgpu_abi_versio
            "fbgpu_load_fragments", "fbgpu_drop_fragment", "fbgpu_commit", "fbgpu_get_stats", "fbgpu_count", "fbgpu_row",
            "fbgpu_row_counts", "fbgpu_row_counts_per_shard", "fbgpu_groupby", "fbgpu_comm_unique_id", "fbgpu_comm_init", "fbgpu_comm_destroy",
            "fbgpu_get_counters", "fbgpu_stream", "fbgpu_rows_payload_bytes", "fbgpu_count_pairs", "fbgpu_columns", "fbgpu_extract", "fbgpu_load_rbf", "fbgpu_load_rbf_dir", "fbgpu_bsi_minmax", "fbgpu_bsi_sum", "fbgpu_compact", "fbgpu_comm_p2p_handle", "fbgpu_comm_p2p_open", "fbgpu_comm_p2p_disable",
-           "fbgpu_any", "fbgpu_pair_types", "fbgpu_node_any",
+           "fbgpu_any", "fbgpu_pair_types", "fbgpu_node_any", "fbgpu_apply_containers", "fbgpu_node_apply_containers",
            "fbgpu_comm_p2p_open_local", "fbgpu_node_init", "fbgpu_node_shutdown", "fbgpu_node_devices", "fbgpu_node_owner", "fbgpu_node_ctx", "fbgpu_node_load_fragment",
            "fbgpu_node_load_fragments", "fbgpu_node_load_rbf_dir", "fbgpu_node_drop_fragment", "fbgpu_node_commit", "fbgpu_node_get_stats", "fbgpu_node_count", "fbgpu_node_row",
            "fbgpu_node_count_pairs", "fbgpu_node_row_counts", "fbgpu_node_groupby", "fbgpu_node_bsi_sum", "fbgpu_node_bsi_minmax"]
@@ -69,6 +69,8 @@ def load():
     L.fbgpu_load_fragment.argtypes, L.fbgpu_load_fragment.restype = [vp, u32, u32, u32, u64, vp, u64], C.c_int
     L.fbgpu_load_fragments.argtypes, L.fbgpu_load_fragments.restype = [vp, u32, u32, u32, vp, i64, vp, vp], C.c_int
     L.fbgpu_drop_fragment.argtypes, L.fbgpu_drop_fragment.restype = [vp, u32, u32, u32, u64], C.c_int
+    L.fbgpu_apply_containers.argtypes, L.fbgpu_apply_containers.restype = [vp, u32, u32, u32, u64, vp, u64, vp, i64], C.c_int
+    L.fbgpu_node_apply_containers.argtypes, L.fbgpu_node_apply_containers.restype = [vp, u32, u32, u32, u64, vp, u64, vp, i64], C.c_int
     L.fbgpu_load_rbf.argtypes, L.fbgpu_load_rbf.restype = [vp, u32, u64, vp, u64, vp, u64, vp, vp, vp, i32, C.POINTER(i32)], C.c_int
     L.fbgpu_load_rbf_dir.argtypes, L.fbgpu_load_rbf_dir.restype = [vp, u32, u64, C.c_char_p, vp, vp, vp, i32, C.POINTER(i32)], C.c_int
     L.fbgpu_commit.argtypes, L.fbgpu_commit.restype = [vp], C.c_int
@@ -210,6 +212,14 @@ class Context:
 
     def drop_fragment(self, index, field, view, shard):
         self._check(self.L.fbgpu_drop_fragment(self.h, index, field, view, int(shard)))
+
+    def apply_containers(self, index, field, view, shard, data=b"", removed_keys=()):
+        """incremental refresh of one fragment: `data` = roaring bytes of ONLY the written containers, removed_keys = deleted keys"""
+        data = bytes(data or b"")
+        buf = (C.c_uint8 * max(len(data), 1)).from_buffer_copy(data or b"\0")
+        rk = _u64arr(list(removed_keys))
+        self._check(self.L.fbgpu_apply_containers(self.h, index, field, view, int(shard), buf if data else None, len(data),
+                                                  rk.ctypes.data if len(rk) else None, len(rk)))
 
     def commit(self):
         self._check(self.L.fbgpu_commit(self.h))

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define FBGPU_ABI_VERSION 1
+#define FBGPU_ABI_VERSION 2
 
 /* error codes */
 #define FBGPU_OK 0
@@ -62,6 +62,18 @@ int fbgpu_load_fragments(fbgpu_ctx *ctx, uint32_t index, uint32_t field, uint32_
                          const uint64_t *shards, int64_t n, const uint8_t *buf, const uint64_t *offsets);
 /* view.deleteFragment (view.go:405): the fragment no longer answers queries; its arena space is reclaimed by fbgpu_compact */
 int fbgpu_drop_fragment(fbgpu_ctx *ctx, uint32_t index, uint32_t field, uint32_t view, uint64_t shard);
+/* Incremental refresh: what ONE committed write transaction did to ONE fragment, container by container -- the mirror of the
+ * Tx.PutContainer / Tx.RemoveContainer calls of the transaction (tx.go:91-96, rbf/tx.go:791-860; the writes reach them through
+ * fragment.setBit / importRoaring / ImportRoaringBits, fragment.go:2196, rbf/tx.go:1819).  `roaring` (may be NULL / 0 bytes) holds
+ * ONLY the containers that were written, under their fragment-relative keys: each replaces the container stored under its key, or
+ * adds it.  removed_keys lists the keys whose containers were deleted.  Containers the transaction did not touch keep their payload
+ * where it is in HBM, so the call moves the changed containers' bytes plus the fragment's row / descriptor entries -- not the
+ * fragment (fbgpu_load_fragment re-sends it whole); the next fbgpu_commit patches the tables of the touched (view, shard) pairs
+ * instead of rebuilding them.  Replaced payloads become holes (fbgpu_stats.dead_bytes) that fbgpu_compact reclaims.  A fragment
+ * that is not resident yet is created from the written containers; one whose last container is removed is dropped.  A key that
+ * is both written and removed is FBGPU_E_INVALID.  All-or-nothing like the loads. */
+int fbgpu_apply_containers(fbgpu_ctx *ctx, uint32_t index, uint32_t field, uint32_t view, uint64_t shard,
+                           const uint8_t *roaring, uint64_t nbytes, const uint64_t *removed_keys, int64_t n_removed);
 /*  Load the fragments of ONE shard straight from its RBF database, i.e. from the bytes of
  * `<index>/backends/rbf/<shard>/data` (and, if it is not empty, `wal`) -- one RBF DB holds every field/view of a
  * shard (dbshard.go:64-71).  Replaces the per-fragment tx.RoaringBitmap().WriteTo re-serialisation: leaf cells (array /
@@ -97,7 +109,9 @@ typedef struct {
     uint64_t array_containers, bitmap_containers, run_containers;
     uint64_t payload_bytes;   /* roaring payload bytes resident in HBM (array 2n, bitmap 8192, run 4r) */
     uint64_t device_bytes;    /* total HBM held by the store incl. descriptors and padding            */
-    uint64_t dead_bytes;      /* arena bytes of replaced / dropped fragments, reclaimed by fbgpu_compact */
+    uint64_t dead_bytes;      /* arena bytes of replaced / dropped fragments and containers, reclaimed by fbgpu_compact */
+    uint64_t full_commits;    /* commits that rebuilt (and re-sent) every lookup table                                */
+    uint64_t patch_commits;   /* commits that patched the touched (view, shard) entries and sent only those + the new tails */
 } fbgpu_stats;
 int fbgpu_get_stats(fbgpu_ctx *ctx, fbgpu_stats *out);
 
@@ -272,6 +286,8 @@ int fbgpu_node_load_fragments(fbgpu_node *node, uint32_t index, uint32_t field, 
 int fbgpu_node_load_rbf_dir(fbgpu_node *node, uint32_t index, uint64_t shard, const char *dir, const char *const *names,
                             const uint32_t *fields, const uint32_t *views, int32_t n_names, int32_t *out_loaded);
 int fbgpu_node_drop_fragment(fbgpu_node *node, uint32_t index, uint32_t field, uint32_t view, uint64_t shard);
+int fbgpu_node_apply_containers(fbgpu_node *node, uint32_t index, uint32_t field, uint32_t view, uint64_t shard,
+                                const uint8_t *roaring, uint64_t nbytes, const uint64_t *removed_keys, int64_t n_removed);
 int fbgpu_node_commit(fbgpu_node *node);
 int fbgpu_node_get_stats(fbgpu_node *node, fbgpu_stats *out);           /* summed over the devices */
 /* same contracts as the fbgpu_* calls of the same name, over all devices */

@@ -22,6 +22,21 @@ class OracleCtx:
             self._dead = getattr(self, "_dead", 0) + 2 * len(bytes(data))
         slot[int(shard)] = O.Bitmap.from_bytes(bytes(data))
 
+    def apply_containers(self, index, field, view, shard, data=b"", removed_keys=()):
+        slot = self.frags.setdefault((index, field, view), {})
+        cur = slot.get(int(shard))
+        vals = cur.slice() if cur is not None else np.zeros(0, dtype=np.uint64)
+        put = O.Bitmap.from_bytes(bytes(data)).slice() if data else np.zeros(0, dtype=np.uint64)
+        gone = np.concatenate([np.unique(put >> np.uint64(16)), np.asarray(list(removed_keys), dtype=np.uint64)])
+        if len(set(np.unique(put >> np.uint64(16)).tolist()) & set(int(k) for k in removed_keys)):
+            raise L.FbgpuError(L.E_INVALID, "container key both written and removed")
+        self._dead = getattr(self, "_dead", 0) + 1
+        vals = np.sort(np.concatenate([vals[~np.isin(vals >> np.uint64(16), gone)], put]))
+        if len(vals):
+            slot[int(shard)] = O.Bitmap.from_values(vals)
+        else:
+            slot.pop(int(shard), None)
+
     def commit(self):
         pass
 

@@ -171,6 +171,18 @@ class Pair:
         self.holder.import_roaring(self.name, field, view, shard, data)
         self.ora.load(field, view, shard, data)
 
+    def apply(self, field, view, shard, put_values=(), removed_keys=()):
+        """incremental refresh on both sides: put_values = fragment-relative bit positions of the WRITTEN containers (whole containers),
+        removed_keys = deleted container keys; the product gets only the delta, the oracle the resulting fragment"""
+        put = np.sort(np.asarray(put_values, dtype=np.uint64))
+        data = O.Bitmap.from_values(put).to_bytes() if len(put) else b""
+        self.holder.apply_containers(self.name, field, view, shard, data, list(removed_keys))
+        cur = self.ora.frag(field, view, shard)
+        vals = cur.slice() if cur is not None else np.zeros(0, dtype=np.uint64)
+        gone = np.concatenate([np.unique(put >> np.uint64(16)), np.asarray(list(removed_keys), dtype=np.uint64)])
+        vals = np.sort(np.concatenate([vals[~np.isin(vals >> np.uint64(16), gone)], put]))
+        self.ora.frags.setdefault((field, view), {})[int(shard)] = O.Bitmap.from_values(vals)
+
     def sync_pending(self):
         """push Holder.set_bit/set_value staged bits to both sides"""
         from featurebase_b200 import roaring_io

@@ -25,7 +25,7 @@ def test_header_symbols_exported(so):
     dll = ctypes.CDLL(so)
     missing = [s for s in sorted(declared) if not hasattr(dll, s)]
     assert not missing, missing
-    assert dll.fbgpu_abi_version() == 1
+    assert dll.fbgpu_abi_version() == 2
     assert set(L.EXPORTS) <= declared
 
 

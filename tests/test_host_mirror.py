@@ -95,6 +95,7 @@ def test_various_queries(oracle_backed):
     E.test_field_value_and_options()
     E.test_topk_time_range()
     E.test_arena_compaction()
+    E.test_incremental_container_refresh()
 
 
 def test_percentile(oracle_backed):

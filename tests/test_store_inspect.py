@@ -250,9 +250,9 @@ def test_failed_batch_load_leaves_the_store_unchanged():
     ctx = L.Context(L.DEVICE_NONE)
     old = D.fragment(7, 0, [0, 1], 0.01)
     ctx.load_fragment(0, 0, 0, 0, old)
-    before = ctx.stats()
     kept = ctx.debug_container(0, 0, 0, 0, 0, 3)
     assert kept is not None
+    before = ctx.stats()
     new0, new1 = D.fragment(8, 0, [0, 1, 2], 0.02), D.fragment(8, 1, [0], 0.02)
     buf = np.frombuffer(new0 + new1, dtype=np.uint8)
     offs = np.array([0, len(new0), len(new0) + len(new1)], dtype=np.uint64)
@@ -267,3 +267,80 @@ def test_failed_batch_load_leaves_the_store_unchanged():
     assert ctx.debug_container(0, 0, 0, 0, 2, 0) is not None
     assert ctx.debug_container(0, 0, 0, 1, 0, 0) is not None
     ctx.close()
+
+
+def _container_bitmap(frag, keys):
+    """roaring bytes of ONLY the containers `keys` of an oracle fragment (what a write transaction's PutContainer calls carry)"""
+    vals = frag.slice()
+    sel = vals[np.isin(vals >> np.uint64(16), np.asarray(sorted(keys), dtype=np.uint64))]
+    return O.Bitmap.from_values(sel).to_bytes()
+
+
+def test_apply_containers_incremental_refresh():
+    """fbgpu_apply_containers (Tx.PutContainer / RemoveContainer mirror): written containers replace / add, removed keys vanish, untouched
+    containers keep their payload in place; small updates are committed by patching the tables, not by rebuilding them."""
+    rng = np.random.default_rng(5)
+    ctx = L.Context(L.DEVICE_NONE)
+    rows = [0, 1, 2, 3, 4, 5, 6, 7, 9, 40, 41]
+    frags = {s: mixed_fragment(21 + s, s) for s in (0, 1, 2)}
+    for s, fr in frags.items():
+        ctx.load_fragment(1, 2, 0, s, fr.to_bytes())
+    ctx.commit()
+    st0 = ctx.stats()
+    assert st0["full_commits"] == 1 and st0["patch_commits"] == 0
+    model = {s: fr.slice() for s, fr in frags.items()}
+    for step in range(6):
+        s = int(rng.integers(0, 3))
+        cur = model[s]
+        keys = np.unique(cur >> np.uint64(16))
+        written = set(int(k) for k in rng.choice(keys, size=min(4, len(keys)), replace=False))
+        written |= {int(rng.integers(0, 16)) + 16 * int(r) for r in rng.choice([1, 8, 40, 41, 42], size=2)}       # keys in existing and in new rows
+        removed = set(int(k) for k in rng.choice(keys, size=3, replace=False)) - written
+        new_vals = []
+        for k in sorted(written):
+            kind = int(rng.integers(0, 3))
+            n = [int(rng.integers(1, 300)), int(rng.integers(5000, 30000)), 65536][kind]
+            lo = rng.choice(65536, size=n, replace=False) if n < 65536 else np.arange(65536)
+            if kind == 2:
+                lo = np.arange(int(rng.integers(0, 1000)), int(rng.integers(30000, 65536)))                        # one long run
+            new_vals.append((np.uint64(k) << np.uint64(16)) | np.sort(lo).astype(np.uint64))
+        new_vals = np.concatenate(new_vals)
+        keep = cur[~np.isin(cur >> np.uint64(16), np.asarray(sorted(written | removed), dtype=np.uint64))]
+        model[s] = np.sort(np.concatenate([keep, new_vals]))
+        ctx.apply_containers(1, 2, 0, s, O.Bitmap.from_values(new_vals).to_bytes(), sorted(removed))
+        want = O.Bitmap.from_values(model[s])
+        assert check_fragment(ctx, 1, 2, 0, s, want, rows + [8, 42]) > 50
+        for other in (0, 1, 2):                                                                                   # the neighbours are untouched
+            if other != s:
+                assert check_fragment(ctx, 1, 2, 0, other, O.Bitmap.from_values(model[other]), [0, 3, 9]) > 10
+    st = ctx.stats()
+    assert st["fragments"] == 3 and st["dead_bytes"] > 0
+    # rows 41 / 42 lie past the dense directory's range the first time they appear (full rebuild); every later update is a patch
+    assert st["patch_commits"] >= 3 and st["full_commits"] <= 3, st
+    assert st["payload_bytes"] == sum(_payload_bytes(O.Bitmap.from_values(model[s])) for s in model)
+    # a key both written and removed, and a malformed delta, change nothing
+    before = ctx.stats()
+    with pytest.raises(L.FbgpuError):
+        ctx.apply_containers(1, 2, 0, 0, _container_bitmap(O.Bitmap.from_values(model[0]), [0]), [0])
+    with pytest.raises(L.FbgpuError):
+        ctx.apply_containers(1, 2, 0, 0, b"\x3c\x30\x00\x00\xff\xff\xff\x7f", [])
+    after = ctx.stats()
+    assert {k: v for k, v in after.items() if 'commits' not in k} == {k: v for k, v in before.items() if 'commits' not in k}
+    # removing every container drops the fragment; applying to a shard that is not resident creates it
+    keys0 = np.unique(model[0] >> np.uint64(16)).tolist()
+    ctx.apply_containers(1, 2, 0, 0, b"", keys0)
+    assert ctx.stats()["fragments"] == 2 and ctx.debug_container(1, 2, 0, 0, 0, 0) is None
+    fresh = mixed_fragment(77, 5)
+    ctx.apply_containers(1, 2, 0, 5, fresh.to_bytes(), [123456])
+    assert check_fragment(ctx, 1, 2, 0, 5, fresh, rows) > 80
+
+
+def _payload_bytes(bm):
+    data = bm.to_bytes()
+    n = int(np.frombuffer(data[4:8], dtype="<u4")[0])
+    hdr = np.frombuffer(data[8:8 + 12 * n], dtype=np.dtype([("key", "<u8"), ("typ", "<u2"), ("n1", "<u2")]))
+    tot = int(2 * (hdr["n1"][hdr["typ"] == 1].astype(np.int64) + 1).sum()) + 8192 * int((hdr["typ"] == 2).sum())
+    for j in np.nonzero(hdr["typ"] == 3)[0]:
+        off = int(np.frombuffer(data[8 + 12 * n + 4 * j: 12 + 12 * n + 4 * j], dtype="<u4")[0])
+        tot += 4 * int(np.frombuffer(data[off:off + 2], dtype="<u2")[0])
+    return tot

@@ -13,6 +13,7 @@ import numpy as np
 import pytest
 
 from featurebase_b200 import executor as X
+from featurebase_b200 import lib as L
 from featurebase_b200 import pql
 from tests import test_gpu_parity as G
 from tests.golden import vectors as V
@@ -1159,6 +1160,66 @@ def test_arena_compaction():
     check()
     ctx.compact()
     ctx.compact()                                                  # nothing dead: a no-op
+    check()
+
+
+def test_incremental_container_refresh():
+    """fbgpu_apply_containers on the device: a fragment's containers are replaced / added / removed one write batch after the other
+    (bytes moved = the delta), queries are right after every batch, the commits are table patches, and fbgpu_compact gathers the
+    live containers of the holed fragments one by one (arena_gather_kernel) without changing any result"""
+    import featurebase_b200.datagen as D
+    from oracle import oracle as O
+    rng = np.random.default_rng(17)
+    p = Pair(track_existence=False)
+    p.field("m")
+    p.field("n")
+    ctx = p.holder.ctx
+
+    def frag(seed, s):
+        b = O.Bitmap()
+        for d in (D.fragment(seed, s, [0, 1], 0.004), D.fragment(seed, s, [2], 0.3), D.fragment(seed, s, [3], 0.2, mode=1, mean_run=200.0)):
+            b = b.union(O.Bitmap.from_bytes(d))
+        return b.to_bytes()
+
+    def check():
+        for q in ("Intersect(Row(m=0), Row(n=1))", "Union(Row(m=2), Row(n=3), Row(m=1), Row(m=4))", "Difference(Row(n=2), Row(m=3))", "Xor(Row(m=0), Row(m=3))"):
+            p.check_row(q)
+            p.check_count(f"Count({q})")
+        got = p.ex.execute("i", "TopK(m, k=4)")[0]
+        assert got == sorted(((r, p.ora.count(pql.parse(f"Row(m={r})")[0], p.shards())) for r in range(6)), key=lambda kv: (-kv[1], kv[0]))[:4]
+
+    for s in range(4):
+        p.load("m", X.VIEW_STANDARD, s, frag(40, s))
+        p.load("n", X.VIEW_STANDARD, s, frag(41, s))
+    check()
+    base = ctx.stats()
+    for rnd in range(5):
+        s = int(rng.integers(0, 4))
+        keys = np.unique(p.ora.frag("m", X.VIEW_STANDARD, s).slice() >> np.uint64(16))
+        written = sorted(set(int(k) for k in rng.choice(keys, size=3, replace=False)) | {16 * 4 + int(rng.integers(0, 16)), int(rng.integers(0, 64))})   # row 4 is new
+        removed = sorted(set(int(k) for k in rng.choice(keys, size=2, replace=False)) - set(written))
+        put = []
+        for k in written:
+            n = int(rng.choice([7, 300, 5000, 40000]))
+            put.append((np.uint64(k) << np.uint64(16)) | np.sort(rng.choice(65536, size=n, replace=False)).astype(np.uint64))
+        p.apply("m", X.VIEW_STANDARD, s, np.concatenate(put), removed)
+        if rnd == 2:                                                # a batch for the other field and a removal-only batch in the same commit
+            p.apply("n", X.VIEW_STANDARD, 1, (np.uint64(16 * 1 + 3) << np.uint64(16)) | np.arange(0, 60000, 3, dtype=np.uint64), [])
+            p.apply("n", X.VIEW_STANDARD, 2, [], [int(np.unique(p.ora.frag("n", X.VIEW_STANDARD, 2).slice() >> np.uint64(16))[0])])
+        check()
+    st = ctx.stats()
+    assert st["fragments"] == base["fragments"] and st["dead_bytes"] > 0
+    if hasattr(ctx, "L"):                                          # (the real library) row 4 is new to the dense directory once; the rest are patches
+        assert st["patch_commits"] - base["patch_commits"] >= 3, (base, st)
+    ctx.compact()
+    after = ctx.stats()
+    assert after["dead_bytes"] == 0 and after["payload_bytes"] == st["payload_bytes"] and after["containers"] == st["containers"]
+    check()
+    p.apply("m", X.VIEW_STANDARD, 0, (np.uint64(5 * 16) << np.uint64(16)) | np.arange(100, dtype=np.uint64), [])      # updates after a compaction
+    p.apply("m", X.VIEW_STANDARD, 9, (np.uint64(1 * 16 + 2) << np.uint64(16)) | np.arange(0, 65536, 2, dtype=np.uint64), [])   # a shard that was not resident
+    check()
+    with pytest.raises(L.FbgpuError):
+        p.holder.apply_containers("i", "m", X.VIEW_STANDARD, 0, O.Bitmap.from_values(np.arange(10, dtype=np.uint64)).to_bytes(), [0])
     check()
 
 
