@@ -8,6 +8,7 @@ columns/s, HBM GB/s vs the measured roofline.  The same JSON line carries sub-re
 each with its own roofline fraction, CPU baseline and parity check against the CPU port:
     north_star   configs[4] at the acceptance point: Count(Intersect(Row, Row)) at 1 %, 1 B columns per GPU — one query per
                  launch (rotating over 32 row pairs = 1.4 GB) and 32 pairs fused in one launch
+    density_sweep  configs[4] around it: 0.01 % .. 50 % uniform and two clustered (run-container) points, same two forms, on every rank
     config3      BSI Count(Row(v > 2^31)) over 10 M records (rank 0)
     config4      GroupBy(Rows(a), Rows(b)) 256 x 256, 512 shards per GPU, ncclAllReduce of the 512 KiB count tensor at N > 1
 
@@ -142,10 +143,10 @@ class CpuArm:
             times.append(secs)
         return count, times
 
-    def pairs(self, frags, shards, reps, materialise=True):
+    def pairs(self, frags, shards, reps, materialise=True, rows_a=None, rows_b=None):
         times, counts = [], None
         for _ in range(reps):
-            counts, secs = self.O.bench_pair_counts(self.pool, frags, shards, PAIRS_A, PAIRS_B, materialise)
+            counts, secs = self.O.bench_pair_counts(self.pool, frags, shards, rows_a or PAIRS_A, rows_b or PAIRS_B, materialise)
             times.append(secs)
         return counts, times
 
@@ -223,12 +224,12 @@ def timed_calls(ctx, fn, steps, warmup):
     return float(np.mean(ms)), float(np.min(ms)), wall
 
 
-def north_star(h, idx, fld, shards, cpu, frags, peak, world, dist, torch, steps):
-    """BASELINE configs[4] at its acceptance point (1 %, 1 B columns per GPU): (i) one Count(Intersect(Row, Row)) per launch,
-    (ii) the 32 row pairs of the field fused in one launch"""
+def pair_record(h, idx, fld, shards, rows_a, rows_b, label, cpu, frags, peak, world, dist, torch, steps):
+    """Count(Intersect(Row a_k, Row b_k)) over this rank's shards: (i) one query per launch, rotating over the row pairs, (ii) all pairs
+    fused in one launch.  Parity of every pair's count against the CPU port over ALL shards (all ranks)."""
     from featurebase_b200 import executor as X, lib as L
     ctx = h.ctx
-    progs = [[L.Op(L.OP_ROW, fld.id, 0, 0, a, 0, 0, 0), L.Op(L.OP_ROW, fld.id, 0, 0, b, 0, 0, 0), L.Op(L.OP_INTERSECT, 0, 0, 2, 0, 0, 0, 0)] for a, b in zip(PAIRS_A, PAIRS_B)]
+    progs = [[L.Op(L.OP_ROW, fld.id, 0, 0, a, 0, 0, 0), L.Op(L.OP_ROW, fld.id, 0, 0, b, 0, 0, 0), L.Op(L.OP_INTERSECT, 0, 0, 2, 0, 0, 0, 0)] for a, b in zip(rows_a, rows_b)]
     progs = [L.ops_array(p) for p in progs]
     n_pairs = len(progs)
     single = {}
@@ -241,24 +242,37 @@ def north_star(h, idx, fld, shards, cpu, frags, peak, world, dist, torch, steps)
     batched = {}
 
     def fused(i):
-        batched[0] = ctx.count_pairs(idx.id, fld.id, 0, PAIRS_A, fld.id, 0, PAIRS_B, shards)
+        batched[0] = ctx.count_pairs(idx.id, fld.id, 0, rows_a, fld.id, 0, rows_b, shards)
 
     b_ms, b_min, b_wall = timed_calls(ctx, fused, max(steps, 10), 3)
-    pay, nc = ctx.rows_payload_bytes(idx.id, fld.id, X.VIEW_STANDARD, shards, PAIRS_A + PAIRS_B)
+    pay, nc = ctx.rows_payload_bytes(idx.id, fld.id, X.VIEW_STANDARD, shards, list(rows_a) + list(rows_b))
     algo_all = pay + 16 * nc + 8 * n_pairs
     algo_one = algo_all / n_pairs
     got = np.asarray(batched[0], dtype=np.uint64)
     got_single = np.array([single[k] for k in range(n_pairs)], dtype=np.uint64)
-    rec = {"query": "Count(Intersect(Row(f=2k), Row(f=2k+1))), 1 %% density, %d shards x 2^20 columns per GPU" % len(shards),
+    names = ("absent", "array", "bitmap", "run")      # device-side analogue of the reference's statsHit("intersectionCount/...") counters
+    hm = ctx.pair_types(idx.id, fld.id, 0, rows_a[0], fld.id, 0, rows_b[0], shards)
+    hist = {"%s x %s" % (names[i], names[j]): int(hm[i][j]) for i in range(4) for j in range(4) if hm[i][j]}
+    l2 = "%.2f GB touched per cycle (> L2)" % (algo_all / 1e9) if algo_all > 126e6 else "%.0f MB touched per cycle: fits the 126 MB L2 — a launch / L2-bound point, not an HBM one" % (algo_all / 1e6)
+    rec = {"query": "Count(Intersect(Row(f=a), Row(f=b))), %s, %d shards x 2^20 columns per GPU" % (label, len(shards)),
            "single": {"ms": s_ms, "ms_min": s_min, "e2e_ms": s_wall, "gbs": algo_one / (s_ms * 1e-3) / 1e9, "frac": algo_one / (s_ms * 1e-3) / 1e9 / peak,
                       "algorithmic_bytes": int(algo_one), "launches_timed": n_single,
-                      "note": "one fused pair_count_kernel launch per query, CUDA events around each launch; the %d row pairs are rotated: %.2f GB touched per cycle (> L2)" % (n_pairs, algo_all / 1e9)},
+                      "note": "one fused pair_count_kernel launch per query, CUDA events around each launch; the %d row pairs are rotated: %s" % (n_pairs, l2)},
            "batched": {"ms": b_ms, "ms_min": b_min, "e2e_ms": b_wall, "pairs_per_launch": n_pairs, "gbs": algo_all / (b_ms * 1e-3) / 1e9, "frac": algo_all / (b_ms * 1e-3) / 1e9 / peak,
                        "algorithmic_bytes": int(algo_all), "note": "fbgpu_count_pairs: %d independent row pairs in one launch" % n_pairs},
-           "set_ops_per_sec_single": len(shards) * world / (s_ms * 1e-3), "set_ops_per_sec_batched": n_pairs * len(shards) * world / (b_ms * 1e-3)}
+           "set_ops_per_sec_single": len(shards) * world / (s_ms * 1e-3), "set_ops_per_sec_batched": n_pairs * len(shards) * world / (b_ms * 1e-3),
+           "container_pair_types_pair0": hist}
+    if world > 1:
+        t = torch.tensor([s_ms, b_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)                  # max over ranks, like the headline
+        for key, v in (("single", float(t[0])), ("batched", float(t[1]))):
+            by = algo_one if key == "single" else algo_all
+            rec[key].update({"ms": v, "gbs": by / (v * 1e-3) / 1e9, "frac": by / (v * 1e-3) / 1e9 / peak})
+        rec["set_ops_per_sec_single"] = len(shards) * world / (float(t[0]) * 1e-3)
+        rec["set_ops_per_sec_batched"] = n_pairs * len(shards) * world / (float(t[1]) * 1e-3)
     if cpu is not None:
         # parity: every pair's count against the CPU port over ALL shards of this rank (IntersectionCount form), then the executor-path timing
-        want, _ = cpu.pairs(frags, shards, 1, materialise=False)
+        want, _ = cpu.pairs(frags, shards, 1, materialise=False, rows_a=rows_a, rows_b=rows_b)
         if world > 1:                    # (the GPU counts are already merged across ranks by the library: fused exchange / ncclAllReduce)
             t = torch.tensor(np.asarray(want, dtype=np.int64), device="cuda")
             dist.all_reduce(t)
@@ -266,11 +280,41 @@ def north_star(h, idx, fld, shards, cpu, frags, peak, world, dist, torch, steps)
         rec["parity_ok"] = bool(np.array_equal(got, want) and np.array_equal(got_single, want))
         rec["counts_sum"] = int(got.sum())
         if world == 1:
-            _, ptimes = cpu.pairs(frags, shards, 3, materialise=True)
+            _, ptimes = cpu.pairs(frags, shards, 3, materialise=True, rows_a=rows_a, rows_b=rows_b)
             psec = float(np.median(ptimes))
             rec["cpu_baseline"] = {"value": n_pairs * len(shards) / psec, "unit": "set-ops/s", "cores": cpu.threads, "kind": "port", "ms": psec * 1e3,
                                    "sample": "the %d pairs over all %d shards, 3 reps, median; executor path (Row.Intersect materialises, Count sums N)" % (n_pairs, len(shards))}
     return rec
+
+
+def north_star(h, idx, fld, shards, cpu, frags, peak, world, dist, torch, steps):
+    """BASELINE configs[4] at its acceptance point (1 %, 1 B columns per GPU)"""
+    return pair_record(h, idx, fld, shards, PAIRS_A, PAIRS_B, "1 % density (uniform)", cpu, frags, peak, world, dist, torch, steps)
+
+
+SWEEP_POINTS = [(0.0001, 0, 8), (0.001, 0, 8), (0.1, 0, 2), (0.5, 0, 2), (0.01, 1, 8), (0.2, 1, 2)]   # (density, generator mode, row pairs); 1 % uniform = north_star
+
+
+def density_sweep(h, idx, rank, S, cpu, peak, world, dist, torch, steps):
+    """BASELINE configs[4]: the density sweep around the acceptance point (array / bitmap / run container mixes), on every rank's own
+    shard range — at N GPUs this is the sweep `at 1, 2, 4, 8 GPUs` the north star asks for.  One field per point in the headline's
+    context (same communicator); each point is parity-checked against the CPU port like the north-star record."""
+    from featurebase_b200 import datagen as D, executor as X
+    shards = np.arange(rank * S, (rank + 1) * S, dtype=np.uint64)
+    out = []
+    for k, (p, mode, n_pairs) in enumerate(SWEEP_POINTS):
+        fld = idx.create_field("d%d" % k)
+        rows = list(range(2 * n_pairs))
+        bulk = D.fragments(40 + k, shards, rows, p, mode=mode, mean_run=64.0)
+        h.ctx.load_fragments(idx.id, fld.id, X.VIEW_STANDARD, shards, bulk.buf, bulk.offsets)
+        h.ctx.commit()
+        frags = cpu.fragments(bulk, S) if cpu is not None else None
+        label = "%g %% density (%s)" % (p * 100, "uniform" if mode == 0 else "clustered, mean run 64")
+        rec = pair_record(h, idx, fld, shards, rows[0::2], rows[1::2], label, cpu, frags, peak, world, dist, torch, max(steps // 2, 8))
+        rec.update({"density": p, "generator": "uniform" if mode == 0 else "clustered"})
+        out.append(rec)
+        del bulk, frags
+    return out
 
 
 def config3(cpu, peak, steps, local):
@@ -384,6 +428,8 @@ def main():
     ap.add_argument("--shards-per-gpu", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU port (parity check and cpu_baseline records)")
     ap.add_argument("--no-extras", action="store_true", help="headline only (skip the north_star / config3 / config4 sub-records)")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the density_sweep sub-record (six more fields are generated and loaded)")
+    ap.add_argument("--extras", default="north_star,density_sweep,config3,config4", help="which sub-records to produce (comma list)")
     ap.add_argument("--reduce", default="p2p", choices=["p2p", "nccl"], help="N>1: fused peer-memory Count merge (default) or ncclAllReduce")
     ap.add_argument("--cold", action="store_true", help="also time fragment upload + query (e2e_cold_load)")
     args = ap.parse_args()
@@ -546,14 +592,19 @@ def main():
                        "sample": f"all {S} shards x 5 reps (median {sec * 1e3:.1f} ms); " + cpu.note}
 
     extras = {}
-    if not args.no_extras:
+    want = set() if args.no_extras else set(args.extras.split(","))
+    if args.no_sweep:
+        want.discard("density_sweep")
+    if "north_star" in want:
         extras["north_star"] = north_star(h, idx, fld, shards, cpu, frags, peak, world, dist, torch, args.steps)
-        frags = None
+    frags = None
+    if "density_sweep" in want:
+        extras["density_sweep"] = density_sweep(h, idx, rank, S, cpu, peak, world, dist, torch, args.steps)
     h.ctx.close()
     del bulk
-    if not args.no_extras:
-        if rank == 0 and world == 1:
-            extras["config3"] = config3(cpu, peak, args.steps, local)
+    if "config3" in want and rank == 0 and world == 1:
+        extras["config3"] = config3(cpu, peak, args.steps, local)
+    if "config4" in want:
         extras["config4"] = config4(cpu, peak, args.steps, local, rank, world, dist, torch, new_uid)
 
     if rank == 0:

@@ -166,6 +166,24 @@ def test_bench_main_runs_against_interpreted_library():
     assert d["check_count"] == exp > 0
 
 
+def test_bench_sub_records_run_against_interpreted_library():
+    """bench.py's north_star and density_sweep sub-records on 4 shards, CPU port included: every point's parity_ok (GPU arm's counts,
+    single and batched, against the CPU port over all shards) must hold — these are the checks the driver sees at full size"""
+    import json
+    e = dict(os.environ, FBGPU_LIB=emu_lib())
+    r = subprocess.run([sys.executable, os.path.join(EMU, "bench_shim.py"), "--steps", "2", "--warmup", "1", "--shards-per-gpu", "4", "--extras", "north_star,density_sweep"],
+                       cwd=ROOT, env=e, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=1500)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    assert d["parity_ok"] is True and d["north_star"]["parity_ok"] is True and d["north_star"]["counts_sum"] > 0
+    assert len(d["density_sweep"]) == 6
+    for rec in d["density_sweep"]:
+        assert rec["parity_ok"] is True, rec["query"]
+        assert rec["container_pair_types_pair0"] and "cpu_baseline" in rec
+    kinds = set(k for rec in d["density_sweep"] for k in rec["container_pair_types_pair0"])
+    assert {"array x array", "bitmap x bitmap"} <= kinds and any("run" in k for k in kinds), kinds
+
+
 def test_bench_sweep_runs_against_interpreted_library():
     """bench_sweep.py (configs 5 / 5b / 4 / X / R at 2 shards, one step) incl. its own checks against the oracle and the data
     generator — guards the script the round-2 first call runs; timings meaningless"""
