@@ -179,6 +179,10 @@ struct fbgpu_ctx {
     // points: 16384 units = 1024 shards = 128 MiB of workspace per lease.  FBGPU_UNIT_BATCH (a multiple of 16, fixed per
     // context) trades workspace for launches; the tests set it small to walk the multi-batch paths with a handful of shards.
     long long unit_batch = [] { const char* e = getenv("FBGPU_UNIT_BATCH"); const long long n = e ? atoll(e) : 0; return n >= 16 ? (n / 16) * 16 : 16384ll; }();
+    bool count_fallbacks = getenv("FBGPU_COUNT_FALLBACKS") != nullptr;
+    std::atomic<uint64_t> counters_pair_launches{0};      // Count(Intersect(Row, Row)) queries that took the fused pair kernel
+    // pair_count_kernel: how many of a warp's units ahead the operands are prefetched into L2 (FBGPU_PAIR_PF, 1..15)
+    int pair_pf_depth = [] { const char* e = getenv("FBGPU_PAIR_PF"); const int n = e ? atoi(e) : 4; return n < 1 ? 1 : n > 15 ? 15 : n; }();
     DevBuf d_payload, d_views, d_shardmap, d_frags, d_rows, d_descs, d_rowtab;
     PinBuf bounce[2];
     uint32_t n_views_dev = 0;
@@ -1057,10 +1061,15 @@ static int count_impl(fbgpu_ctx* c, uint32_t index, const fbgpu_op* ops, int32_t
     CUDA_TRY(cudaEventRecord(w->ev0, w->stream));
     if (n_units > 0) {
         // fused Intersect+Count fast path: Count(Intersect(Row, Row))  (executor.go:5357 + row.go:242 + Count)
-        if (prog.size() == 2 && prog[0].op == D_PUSH_ROW && prog[1].op == D_AND_ROW) {
+        // (the compiled form of Row is PUSH_ROW, or PUSH_EMPTY ; OR_ROW after expand_push_row)
+        const DevOp* pa = nullptr; const DevOp* pb = nullptr;
+        if (prog.size() == 2 && prog[0].op == D_PUSH_ROW && prog[1].op == D_AND_ROW) { pa = &prog[0]; pb = &prog[1]; }
+        else if (prog.size() == 3 && prog[0].op == D_PUSH_EMPTY && prog[1].op == D_OR_ROW && prog[2].op == D_AND_ROW) { pa = &prog[1]; pb = &prog[2]; }
+        if (pa && !getenv("FBGPU_NO_PAIR_KERNEL")) {
             long long grid = std::min<long long>((n_units + kPairWarps - 1) / kPairWarps, (long long)c->sm_count * 3);
-            pair_count_kernel<<<(unsigned)grid, kPairWarps * 32, kPairWarps * 8192, w->stream>>>(store_ref(c), prog[0].fv, prog[0].row, prog[1].fv, prog[1].row, nullptr, nullptr, n_units,
-                contiguous_shards(shards, n_shards) ? nullptr : d_shards, n_shards ? shards[0] : 0, n_units, d_total, d_per, nullptr, fr);
+            c->counters_pair_launches++;
+            pair_count_kernel<<<(unsigned)grid, kPairWarps * 32, kPairWarps * 8192, w->stream>>>(store_ref(c), pa->fv, pa->row, pb->fv, pb->row, nullptr, nullptr, n_units,
+                contiguous_shards(shards, n_shards) ? nullptr : d_shards, n_shards ? shards[0] : 0, n_units, d_total, d_per, nullptr, fr, c->pair_pf_depth);
             CUDA_TRY(cudaGetLastError());
         } else {
             EvalOut eo{ d_total, d_per, nullptr, nullptr, fr };
@@ -1530,7 +1539,7 @@ extern "C" int fbgpu_count_pairs(fbgpu_ctx* c, uint32_t index, uint32_t field_a,
     if (n_units > 0) {
         long long grid = std::min<long long>((n_units + kPairWarps - 1) / kPairWarps, (long long)c->sm_count * 3);
         pair_count_kernel<<<(unsigned)grid, kPairWarps * 32, kPairWarps * 8192, w->stream>>>(store_ref(c), fa, 0, fb, 0, (const uint64_t*)w->d_rows.p, (const uint64_t*)w->d_rows.p + np,
-            upp, contiguous_shards(shards, n_shards) ? nullptr : d_shards, n_shards ? shards[0] : 0, n_units, nullptr, nullptr, (unsigned long long*)w->d_counts.p, FuseReduce{});
+            upp, contiguous_shards(shards, n_shards) ? nullptr : d_shards, n_shards ? shards[0] : 0, n_units, nullptr, nullptr, (unsigned long long*)w->d_counts.p, FuseReduce{}, c->pair_pf_depth);
         CUDA_TRY(cudaGetLastError());
     }
     CUDA_TRY(cudaEventRecord(w->ev1, w->stream));
@@ -1605,7 +1614,7 @@ static int groupby2(fbgpu_ctx* c, uint32_t index, uint32_t fvA, const uint64_t* 
     CUDA_TRY(cudaMemsetAsync(w->d_counts.p, 0, ncnt * 8, w->stream));
     CUDA_TRY(cudaStreamSynchronize(w->stream));   // rr is a local
     CUDA_TRY(cudaEventRecord(w->ev0, w->stream));
-    uint64_t launches = 0;
+    uint64_t launches = 0, fb_units = 0, all_units = 0;
     const int64_t batch = have_filter ? c->unit_batch / kSlotsPerRow : n_shards;
     const size_t smem = kGbSlots * 4 + 8192;
     for (int64_t s0 = 0; s0 < n_shards; s0 += batch) {
@@ -1627,6 +1636,12 @@ static int groupby2(fbgpu_ctx* c, uint32_t index, uint32_t fvA, const uint64_t* 
             CUDA_TRY(cudaGetLastError()); launches++;
             cta_kernel<<<(unsigned)grid, kGbThreads, smem, w->stream>>>(store_ref(c), fvA, (const uint64_t*)w->d_rows.p, nA, fvB, (const uint64_t*)w->d_rows.p + nA, nB,
                 d_shards + s0, units, have_filter ? (const uint4*)w->d_bitmaps.p : nullptr, (unsigned long long*)w->d_counts.p, d_fb);
+            if (c->count_fallbacks) {          // FBGPU_COUNT_FALLBACKS=1 (tests, tuning): how many units the warp kernel declined; costs a stream sync per batch
+                unsigned int n_fb = 0;
+                CUDA_TRY(cudaMemcpyAsync(&n_fb, d_fb, 4, cudaMemcpyDeviceToHost, w->stream)); CUDA_TRY(cudaStreamSynchronize(w->stream));
+                fb_units += n_fb;
+            }
+            all_units += (uint64_t)units;
         } else
         cta_kernel<<<(unsigned)grid, kGbThreads, smem, w->stream>>>(store_ref(c), fvA, (const uint64_t*)w->d_rows.p, nA, fvB, (const uint64_t*)w->d_rows.p + nA, nB,
             d_shards + s0, units, have_filter ? (const uint4*)w->d_bitmaps.p : nullptr, (unsigned long long*)w->d_counts.p, nullptr);
@@ -1639,6 +1654,7 @@ static int groupby2(fbgpu_ctx* c, uint32_t index, uint32_t fvA, const uint64_t* 
     memcpy(out, w->h_out.p, ncnt * 8);
     float ms = 0; cudaEventElapsedTime(&ms, w->ev0, w->ev1);
     bump(c, launches, ms);
+    { std::lock_guard<std::mutex> lk2(c->cnt_mu); c->counters.groupby_units += all_units; c->counters.groupby_fallback_units += fb_units; }
     lease.ok = true;
     return 0;
 }
@@ -1800,6 +1816,7 @@ extern "C" int fbgpu_get_counters(fbgpu_ctx* c, fbgpu_counters* out) try {
     if (!c || !out) return fail(FBGPU_E_INVALID, "null argument");
     std::lock_guard<std::mutex> lk(c->cnt_mu);
     *out = c->counters;
+    out->pair_kernel_queries = (uint32_t)c->counters_pair_launches.load();
     return 0;
 } FBGPU_CATCH
 extern "C" void* fbgpu_stream(fbgpu_ctx* c) { return c && !c->wss.empty() ? (void*)c->wss[0]->stream : nullptr; }

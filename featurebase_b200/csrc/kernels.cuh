@@ -179,8 +179,7 @@ __device__ __forceinline__ void warp_bitmap_atomic(uint32_t* bm, const uint4* g,
 }
 // same reduction with the word's byte offset and the bit index given separately (sh: only its low 5 bits are used)
 template <int MODE>
-__device__ __forceinline__ void smem_bit_op_at(uint32_t sbase, uint32_t off, uint32_t sh) {
-    const uint32_t addr = sbase + off;
+__device__ __forceinline__ void smem_bit_op_at(uint32_t addr, uint32_t sh) {
     const uint32_t m = 1u << (sh & 31);
     if (MODE == 0) asm volatile("red.shared.or.b32 [%0], %1;" :: "r"(addr), "r"(m) : "memory");
     else if (MODE == 1) asm volatile("red.shared.and.b32 [%0], %1;" :: "r"(addr), "r"(~m) : "memory");
@@ -188,27 +187,27 @@ __device__ __forceinline__ void smem_bit_op_at(uint32_t sbase, uint32_t off, uin
 }
 // scatter the (up to) 8 elements of one 16-byte array chunk; sb = shared-space address of the target bitmap
 template <int MODE>
-__device__ __forceinline__ void scatter_chunk_sb(uint32_t sb, uint4 v, uint32_t base, uint32_t n) {
+__device__ __forceinline__ void scatter_chunk_sb(smem_base_t sb, uint4 v, uint32_t base, uint32_t n) {
     uint32_t w[4] = { v.x, v.y, v.z, v.w };
     // OR / AND-NOT: the loader pads the last chunk with copies of the last element (stripe.h pad_array_tail), setting or
     // clearing a bit twice is harmless, so every chunk takes the unguarded path and the warp never diverges on a tail
     if (MODE != 2 || base + 8 <= n) {
 #pragma unroll
         for (int q = 0; q < 4; q++) {            // LOP3 + LEA.HI + SHF.L.W (+ SHF.R for the upper element) + ATOMS, see bitaddr.h
-            smem_bit_op_at<MODE>(sb, word_off_lo(w[q]), w[q]);
-            smem_bit_op_at<MODE>(sb, word_off_hi(w[q]), w[q] >> 16);
+            smem_bit_op_at<MODE>(word_addr_lo(sb, w[q]), w[q]);
+            smem_bit_op_at<MODE>(word_addr_hi(sb, w[q]), upper16(w[q]));
         }
     } else {
 #pragma unroll
         for (int q = 0; q < 4; q++) {
-            if (base + 2 * q < n) smem_bit_op_at<MODE>(sb, word_off_lo(w[q]), w[q]);
-            if (base + 2 * q + 1 < n) smem_bit_op_at<MODE>(sb, word_off_hi(w[q]), w[q] >> 16);
+            if (base + 2 * q < n) smem_bit_op_at<MODE>(word_addr_lo(sb, w[q]), w[q]);
+            if (base + 2 * q + 1 < n) smem_bit_op_at<MODE>(word_addr_hi(sb, w[q]), w[q] >> 16);
         }
     }
 }
 template <int MODE>
 __device__ __forceinline__ void scatter_chunk_unrolled(uint32_t* bm, uint4 v, uint32_t base, uint32_t n) {
-    scatter_chunk_sb<MODE>((uint32_t)__cvta_generic_to_shared(bm), v, base, n);
+    scatter_chunk_sb<MODE>(smem_base((uint32_t)__cvta_generic_to_shared(bm)), v, base, n);
 }
 // Batch of commuting row operands (OR / ANDNOT / XOR onto the same target), no barrier in between: warp w takes
 // operands w, w+8, ...; arrays are scattered with red.shared, bitmaps applied with word atomics.  (Tried and slower
@@ -220,8 +219,8 @@ static_assert(sizeof(Resolved) == 16, "batch_rows reads a Resolved with one 16-b
 template <int MODE>
 __device__ __forceinline__ void batch_rows(uint32_t* T32, const Resolved* res, int n) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    uint32_t sb = (uint32_t)__cvta_generic_to_shared(T32);
-    asm volatile("" : "+r"(sb));           // keep the shared address live: ptxas otherwise rebuilds it for every chunk
+    smem_base_t sb = smem_base((uint32_t)__cvta_generic_to_shared(T32));
+    pin_base(sb);                          // keep the shared address live: ptxas otherwise rebuilds it for every chunk
     for (int j = wid; j < n; j += kEvalThreads / 32) {
         const uint4 raw = *reinterpret_cast<const uint4*>(res + j);        // one LDS.128: {ptr lo, ptr hi, card, typ | cnt << 16}
         const uint4* a4 = reinterpret_cast<const uint4*>(((unsigned long long)raw.y << 32) | raw.x);
@@ -898,14 +897,15 @@ __device__ __forceinline__ void warp_zero(uint32_t* bm, int lane) {
     for (int i = lane; i < 512; i += 32) b4[i] = make_uint4(0, 0, 0, 0);
 }
 // number of the (up to 8) u16 values of one 16-byte chunk that are set in a shared-memory bitmap
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
 __device__ __forceinline__ uint32_t probe_chunk(const uint32_t* bm, uint4 v, uint32_t base, uint32_t n) {
     uint32_t w[4] = { v.x, v.y, v.z, v.w }, c = 0;
-    if (base + 8 <= n) {                             // full chunk: no per-element bounds, word offsets as in bitaddr.h
-        const char* b8 = reinterpret_cast<const char*>(bm);
+    if (base + 8 <= n) {                             // full chunk: no per-element bounds, word addresses as in bitaddr.h
+        const smem_base_t sb = smem_base((uint32_t)__cvta_generic_to_shared(bm));
 #pragma unroll
         for (int q = 0; q < 4; q++) {
-            c += (*reinterpret_cast<const uint32_t*>(b8 + word_off_lo(w[q])) >> (w[q] & 31)) & 1u;
-            c += (*reinterpret_cast<const uint32_t*>(b8 + word_off_hi(w[q])) >> ((w[q] >> 16) & 31)) & 1u;
+            c += (lds_u32(word_addr_lo(sb, w[q])) >> (w[q] & 31)) & 1u;
+            c += (lds_u32(word_addr_hi(sb, w[q])) >> (upper16(w[q]) & 31)) & 1u;
         }
         return c;
     }
@@ -919,14 +919,13 @@ __device__ __forceinline__ uint32_t probe_chunk(const uint32_t* bm, uint4 v, uin
 }
 // the same for a chunk whose eight slots may all be probed (tail slots hold copies of the array's last element, stripe.h
 // pad_array_tail; the caller takes the copies out of the count again): no bounds, no divergent partial-chunk path
-__device__ __forceinline__ uint32_t probe_chunk_full(const uint32_t* bm, uint4 v) {
+__device__ __forceinline__ uint32_t probe_chunk_full(smem_base_t sb, uint4 v) {
     const uint32_t w[4] = { v.x, v.y, v.z, v.w };
-    const char* b8 = reinterpret_cast<const char*>(bm);
     uint32_t c = 0;
 #pragma unroll
     for (int q = 0; q < 4; q++) {
-        c += (*reinterpret_cast<const uint32_t*>(b8 + word_off_lo(w[q])) >> (w[q] & 31)) & 1u;
-        c += (*reinterpret_cast<const uint32_t*>(b8 + word_off_hi(w[q])) >> ((w[q] >> 16) & 31)) & 1u;
+        c += (lds_u32(word_addr_lo(sb, w[q])) >> (w[q] & 31)) & 1u;
+        c += (lds_u32(word_addr_hi(sb, w[q])) >> (upper16(w[q]) & 31)) & 1u;
     }
     return c;
 }
@@ -1057,7 +1056,9 @@ __device__ __forceinline__ uint32_t warp_intersection_count(Resolved a, Resolved
         // second round of address arithmetic (the ALU pipe is the co-limiter of this path: IADD3/LOP3/SHF issue every 2nd cycle).
         const uint4* a4 = reinterpret_cast<const uint4*>(a.ptr); const uint4* b4 = reinterpret_cast<const uint4*>(b.ptr);
         const uint32_t na8 = (a.card + 7) >> 3, nb8 = (b.card + 7) >> 3;
-        const uint32_t sb = (uint32_t)__cvta_generic_to_shared(bm);
+        const uint32_t sb32 = (uint32_t)__cvta_generic_to_shared(bm);
+        smem_base_t sb = smem_base(sb32);
+        pin_base(sb);
         uint4 va[3], vb[3];
 #pragma unroll
         for (int q = 0; q < 3; q++) va[q] = ldg_nc(a4 + min((uint32_t)lane + 32u * q, na8 - 1u));     // clamped, unconditional: no undefined register
@@ -1068,12 +1069,12 @@ __device__ __forceinline__ uint32_t warp_intersection_count(Resolved a, Resolved
         for (int q = 0; q < 3; q++) {
             const uint32_t x[4] = { va[q].x, va[q].y, va[q].z, va[q].w };
 #pragma unroll
-            for (int k = 0; k < 4; k++) { addr[q][2 * k] = sb + word_off_lo(x[k]); addr[q][2 * k + 1] = sb + word_off_hi(x[k]); }
+            for (int k = 0; k < 4; k++) { addr[q][2 * k] = word_addr_lo(sb, x[k]); addr[q][2 * k + 1] = word_addr_hi(sb, x[k]); }
             if (lane + 32 * q < na8) {          // (array tails are padded with copies of the last element: setting a bit twice is harmless)
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
                     red_or_at(addr[q][2 * k], 1u << (x[k] & 31));
-                    red_or_at(addr[q][2 * k + 1], 1u << ((x[k] >> 16) & 31));
+                    red_or_at(addr[q][2 * k + 1], 1u << (upper16(x[k]) & 31));
                 }
             }
         }
@@ -1083,8 +1084,8 @@ __device__ __forceinline__ uint32_t warp_intersection_count(Resolved a, Resolved
         // the copies are taken out of the count below.  (The guarded partial-chunk path made the warp run ~100 extra instructions
         // for the ONE lane holding the tail — a third of the pair's instruction count.)
 #pragma unroll
-        for (int q = 0; q < 3; q++) if (lane + 32 * q < nb8) c += probe_chunk_full(bm, vb[q]);
-        for (uint32_t i = lane + 96; i < nb8; i += 32) c += probe_chunk_full(bm, ldg_nc(b4 + i));
+        for (int q = 0; q < 3; q++) if (lane + 32 * q < nb8) c += probe_chunk_full(sb, vb[q]);
+        for (uint32_t i = lane + 96; i < nb8; i += 32) c += probe_chunk_full(sb, ldg_nc(b4 + i));
         const uint32_t pads = nb8 * 8u - b.card;                      // 0..7 copies of b's last element were probed too (warp-uniform)
         if (pads) {
             const uint32_t ql = (nb8 - 1u) >> 5;                       // the chunk holding them: register window slot ql of lane (nb8-1) & 31
@@ -1102,7 +1103,7 @@ __device__ __forceinline__ uint32_t warp_intersection_count(Resolved a, Resolved
         for (uint32_t i = lane + 96; i < na8; i += 32) {     // the words of the chunks past the register window: addresses recomputed
             const uint4 v = ldg_nc(a4 + i); const uint32_t x[4] = { v.x, v.y, v.z, v.w };
 #pragma unroll
-            for (int k = 0; k < 4; k++) { sts_zero(sb + word_off_lo(x[k])); sts_zero(sb + word_off_hi(x[k])); }
+            for (int k = 0; k < 4; k++) { sts_zero(word_addr_lo(sb, x[k])); sts_zero(word_addr_hi(sb, x[k])); }
         }
         __syncwarp();
     } else if (a.typ == kArray) {                             // array x bitmap: roaring.go:4596
@@ -1124,7 +1125,7 @@ __global__ void __launch_bounds__(kPairWarps * 32, 3)
 pair_count_kernel(StoreRef st, uint32_t fvA, uint64_t rowA, uint32_t fvB, uint64_t rowB,
                   const uint64_t* __restrict__ rowsA, const uint64_t* __restrict__ rowsB, long long units_per_pair,
                   const uint64_t* __restrict__ shards, uint64_t shard0, long long n_units,
-                  unsigned long long* total, unsigned long long* per_shard, unsigned long long* per_pair, FuseReduce fr) {
+                  unsigned long long* total, unsigned long long* per_shard, unsigned long long* per_pair, FuseReduce fr, int pf_depth) {
     extern __shared__ __align__(128) uint32_t smem32[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     uint32_t* bm = smem32 + wid * 2048;
@@ -1153,15 +1154,21 @@ pair_count_kernel(StoreRef st, uint32_t fvA, uint64_t rowA, uint32_t fvB, uint64
             return x;
         };
         Resolved a = fetch(0), b = fetch(1);
+        // L2 prefetch of the operands of the units `pf_depth` ahead (the first pf_depth - 1 right away): a warp's units are processed
+        // one after the other, so without it every unit pays an HBM round trip of its own; with it the payload of a whole round is on
+        // its way while the first unit is intersected.  Small (latency-bound) operands only: bitmap pairs are pure streaming.
+        auto prefetch_unit = [&](int j) {
+            if (j >= 16 || base + (long long)j * stride >= n_units) return;
+            const Resolved pa = fetch(2 * j), pb = fetch(2 * j + 1);
+            if (pa.ptr != nullptr && pb.ptr != nullptr && (pa.typ != kBitmap || pb.typ != kBitmap)) { if (pa.typ != kBitmap) warp_prefetch_container(pa, lane); if (pb.typ != kBitmap) warp_prefetch_container(pb, lane); }
+        };
+        for (int j = 1; j < pf_depth; j++) prefetch_unit(j);
         for (int k = 0; k < 16; k++) {
             const long long unit = base + (long long)k * stride;
             if (unit >= n_units) break;
             Resolved na, nb; na.ptr = nullptr; nb.ptr = nullptr; na.card = nb.card = 0; na.typ = nb.typ = 0; na.cnt = nb.cnt = 0;
-            if (k + 1 < 16 && unit + stride < n_units) {
-                na = fetch(2 * k + 2); nb = fetch(2 * k + 3);
-                // small (latency-bound) operands only; bitmap pairs are pure streaming and need no help
-                if (na.ptr != nullptr && nb.ptr != nullptr && (na.typ != kBitmap || nb.typ != kBitmap)) { if (na.typ != kBitmap) warp_prefetch_container(na, lane); if (nb.typ != kBitmap) warp_prefetch_container(nb, lane); }
-            }
+            prefetch_unit(k + pf_depth);
+            if (k + 1 < 16 && unit + stride < n_units) { na = fetch(2 * k + 2); nb = fetch(2 * k + 3); }
             uint32_t c = warp_intersection_count(a, b, bm, lane);
             acc += c;
             if (c && lane == 0) {

@@ -36,7 +36,8 @@ class Stats(C.Structure):
 
 class Counters(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("queries", C.c_uint64), ("last_query_gpu_ms", C.c_float),
-                ("reserved", C.c_uint32), ("last_algo_bytes", C.c_uint64)]
+                ("pair_kernel_queries", C.c_uint32), ("last_algo_bytes", C.c_uint64),
+                ("groupby_units", C.c_uint64), ("groupby_fallback_units", C.c_uint64)]
 
 
 EXPORTS = ["fbgpu_init", "fbgpu_shutdown", "fbgpu_last_error", "fbgpu_abi_version", "fbgpu_load_fragment",
@@ -236,7 +237,8 @@ class Context:
     def counters(self):
         s = Counters()
         self._check(self.L.fbgpu_get_counters(self.h, C.byref(s)))
-        return {"kernel_launches": s.kernel_launches, "queries": s.queries, "last_query_gpu_ms": s.last_query_gpu_ms}
+        return {"kernel_launches": s.kernel_launches, "queries": s.queries, "last_query_gpu_ms": s.last_query_gpu_ms, "pair_kernel_queries": s.pair_kernel_queries,
+                "groupby_units": s.groupby_units, "groupby_fallback_units": s.groupby_fallback_units}
 
     # ---- queries
     def count(self, index, ops, shards, per_shard=False):

@@ -321,8 +321,10 @@ typedef struct {
     uint64_t kernel_launches;   /* kernels of this library launched since init       */
     uint64_t queries;
     float last_query_gpu_ms;    /* CUDA-event time of the last query's kernels        */
-    uint32_t reserved;
+    uint32_t pair_kernel_queries; /* Count(Intersect(Row, Row)) queries answered by the fused pair_count_kernel (low 32 bits) */
     uint64_t last_algo_bytes;   /* algorithmic bytes of the last query   */
+    uint64_t groupby_units;     /* (shard, slot) units of GroupBy queries so far ...                          */
+    uint64_t groupby_fallback_units; /* ... and how many of them the warp-per-unit kernel handed to the CTA kernel */
 } fbgpu_counters;
 int fbgpu_get_counters(fbgpu_ctx *ctx, fbgpu_counters *out);
 /* algorithmic-bytes accounting: roaring payload bytes and container count of the given rows (NULL = all

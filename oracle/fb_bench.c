@@ -100,7 +100,7 @@ typedef struct { uint64_t v; char pad[56]; } padded_u64;   /* one cache line per
 typedef struct {
     const fbo_bitmap *const *frags; const uint64_t *shards;
     const uint64_t *ra; int na; const uint64_t *rb; int nb;
-    padded_u64 *tot;
+    padded_u64 *tot; uint64_t *per_shard;   /* per_shard: optional [n_shards] output, one writer per entry */
 } uic_arg;
 
 static fbo_bitmap *union_rows(const fbo_bitmap *frag, uint64_t shard, const uint64_t *rows, int n) { /* executeUnionShard executor.go:5382 */
@@ -118,17 +118,29 @@ static void uic_job(void *p, int64_t s, int w) {
     fbo_bitmap *ua = union_rows(a->frags[s], a->shards[s], a->ra, a->na);
     fbo_bitmap *ub = union_rows(a->frags[s], a->shards[s], a->rb, a->nb);
     fbo_bitmap *x = fbo_b_intersect(ua, ub);          /* executeIntersectShard executor.go:5357 */
-    a->tot[w].v += fbo_b_count(x);                    /* executeCount executor.go:5871-5877 */
+    const uint64_t c = fbo_b_count(x);                /* executeCount executor.go:5871-5877 */
+    a->tot[w].v += c;
+    if (a->per_shard) a->per_shard[s] = c;
     fbo_b_free(ua); fbo_b_free(ub); fbo_b_free(x);
 }
 uint64_t fbo_bench_union_intersect_count(fbo_pool *p, const fbo_bitmap *const *frags, const uint64_t *shards, int64_t n_shards,
                                          const uint64_t *rows_a, int na, const uint64_t *rows_b, int nb, double *seconds) {
     padded_u64 *tot = calloc((size_t)p->n, sizeof *tot);
-    uic_arg a = { frags, shards, rows_a, na, rows_b, nb, tot };
+    uic_arg a = { frags, shards, rows_a, na, rows_b, nb, tot, NULL };
     double sec = pool_run(p, uic_job, &a, n_shards);
     uint64_t total = 0; for (int t = 0; t < p->n; t++) total += tot[t].v;
     free(tot);
     if (seconds) *seconds = sec;
+    return total;
+}
+/* the same query with the per-shard counts kept (full-size parity tests compare EVERY shard with the device's per-shard vector) */
+uint64_t fbo_bench_union_intersect_per_shard(fbo_pool *p, const fbo_bitmap *const *frags, const uint64_t *shards, int64_t n_shards,
+                                             const uint64_t *rows_a, int na, const uint64_t *rows_b, int nb, uint64_t *per_shard) {
+    padded_u64 *tot = calloc((size_t)p->n, sizeof *tot);
+    uic_arg a = { frags, shards, rows_a, na, rows_b, nb, tot, per_shard };
+    pool_run(p, uic_job, &a, n_shards);
+    uint64_t total = 0; for (int t = 0; t < p->n; t++) total += tot[t].v;
+    free(tot);
     return total;
 }
 

@@ -156,6 +156,8 @@ uint64_t fbo_bench_union_intersect_count(fbo_pool *p, const fbo_bitmap *const *f
 /* n_pairs queries Count(Intersect(Row(a_k), Row(b_k))) over the same fragments; materialise != 0: the executor's path
  * (Row.Intersect materialises, then Count sums N; executor.go:5357,5871); 0: Bitmap.IntersectionCount (roaring.go:928).
  * out_counts[k] += the count of pair k (may be NULL). */
+uint64_t fbo_bench_union_intersect_per_shard(fbo_pool *p, const fbo_bitmap *const *frags, const uint64_t *shards, int64_t n_shards,
+                                             const uint64_t *rows_a, int na, const uint64_t *rows_b, int nb, uint64_t *per_shard);
 uint64_t fbo_bench_pair_counts(fbo_pool *p, const fbo_bitmap *const *frags, const uint64_t *shards, int64_t n_shards,
                                const uint64_t *rows_a, const uint64_t *rows_b, int n_pairs, int materialise,
                                uint64_t *out_counts, double *seconds);

@@ -59,6 +59,7 @@ def lib():
             "fbo_frag_row_view": (vp, [vp, u64, u64]),
             "fbo_pool_create": (vp, [C.c_int]), "fbo_pool_create2": (vp, [C.c_int, C.c_int]), "fbo_pool_destroy": (None, [vp]), "fbo_pool_threads": (C.c_int, [vp]),
             "fbo_bench_union_intersect_count": (u64, [vp, vp, vp, i64, vp, C.c_int, vp, C.c_int, vp]),
+            "fbo_bench_union_intersect_per_shard": (u64, [vp, vp, vp, i64, vp, C.c_int, vp, C.c_int, vp]),
             "fbo_bench_pair_counts": (u64, [vp, vp, vp, i64, vp, vp, C.c_int, C.c_int, vp, vp]),
             "fbo_bench_range_count": (u64, [vp, vp, vp, i64, C.c_int, u64, i64, i64, vp]),
             "fbo_bench_groupby": (C.c_int, [vp, vp, C.c_int, vp, i64, vp, vp, vp, vp]),
@@ -470,6 +471,15 @@ def bench_union_intersect_count(pool, frags, shards, rows_a, rows_b):
     tot = lib().fbo_bench_union_intersect_count(pool.ptr, arr, sh.ctypes.data, len(frags), ra.ctypes.data, len(ra),
                                                 rb.ctypes.data, len(rb), C.byref(secs))
     return int(tot), secs.value
+
+
+def union_intersect_per_shard(pool, frags, shards, rows_a, rows_b):
+    """Count(Intersect(Union(rows_a), Union(rows_b))) of EVERY shard (threaded). Returns the per-shard vector."""
+    arr, sh, ra, rb = _frag_array(frags), _u64(shards), _u64(rows_a), _u64(rows_b)
+    per = np.zeros(len(frags), dtype=np.uint64)
+    tot = lib().fbo_bench_union_intersect_per_shard(pool.ptr, arr, sh.ctypes.data, len(frags), ra.ctypes.data, len(ra), rb.ctypes.data, len(rb), per.ctypes.data)
+    assert int(tot) == int(per.sum())
+    return per
 
 
 def bench_pair_counts(pool, frags, shards, rows_a, rows_b, materialise=True):

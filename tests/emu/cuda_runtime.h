@@ -268,6 +268,7 @@ inline uint32_t* sptr(uint32_t a) { return (uint32_t*)(smem_base() + a); }
 inline void red_or(uint32_t a, uint32_t m) { *sptr(a) |= m; }
 inline void red_and(uint32_t a, uint32_t m) { *sptr(a) &= m; }
 inline void sts_u32(uint32_t a, uint32_t v) { *sptr(a) = v; }
+inline uint32_t lds_u32(uint32_t a) { return *sptr(a); }
 inline void red_xor(uint32_t a, uint32_t m) { *sptr(a) ^= m; }
 
 }  // namespace emu

@@ -84,6 +84,8 @@ ASM = [
     (r'asm volatile\("red\.shared\.and\.b32 \[%0\], %1;" :: "r"\((\w+)\), "r"\(([^()]+)\) : "memory"\);', r"emu::red_and(\1, \2);"),
     (r'asm volatile\("red\.shared\.xor\.b32 \[%0\], %1;" :: "r"\((\w+)\), "r"\(([^()]+)\) : "memory"\);', r"emu::red_xor(\1, \2);"),
     (r'asm volatile\("" : "\+r"\((\w+)\)\);', r"(void)\1;"),
+    (r'asm volatile\("" : "\+l"\((\w+)\)\);', r"(void)\1;"),
+    (r'asm volatile\("ld\.shared\.u32 %0, \[%1\];" : "=r"\((\w+)\) : "r"\((\w+)\)\);', r"\1 = emu::lds_u32(\2);"),
     (r'asm volatile\("st\.shared\.u32 \[%0\], %1;" :: "r"\((\w+)\), "r"\(([^()]+)\) : "memory"\);', r"emu::sts_u32(\1, \2);"),
 ]
 

@@ -25,8 +25,12 @@ def test_config1_single_shard_plumbing():
     p = Pair()
     p.field("f")
     p.load("f", X.VIEW_STANDARD, 0, D.fragment(1, 0, [0, 1], 0.01))
+    before = p.holder.ctx.counters().get("pair_kernel_queries", 0)
     n = p.check_count("Count(Intersect(Row(f=0), Row(f=1)))")
     assert 40 < n < 200
+    # the north-star query shape must reach the fused pair_count_kernel (round 2 lost it for a while to a program rewrite: 97 us
+    # instead of 17 us per query, with every result still right)
+    assert p.holder.ctx.counters()["pair_kernel_queries"] == before + 1
     r = p.check_row("Intersect(Row(f=0), Row(f=1))")
     assert r.count == n
     p.check_count("Count(Row(f=0))")
@@ -442,6 +446,59 @@ def test_full_size_properties_bsi_and_groupby():
     flt = ex._bitmap_call(idx, __import__("featurebase_b200").pql.parse("Row(b=7)")[0])
     sub = h.ctx.groupby(idx.id, [fa.id, fb.id], [0, 0], [rows, rows], shards, filter_ops=flt)
     assert np.array_equal(sub[:, 7], counts[:, 7]) and int(sub.sum()) == int(counts[:, 7].sum())
+
+
+def test_full_size_every_shard_against_the_cpu_port():
+    """BASELINE config[1] and config[3] at their full sizes, every unit compared (not sampled): the headline 64-row
+    Union->Intersect->Count per-shard vector of all 1024 shards, and the complete 256 x 256 GroupBy tensor over all 4096 shards of
+    config 4, against the CPU port run on the host's cores (threaded C restatement: groupByIterator's nested loop, executor.go:8617)."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench as B
+    if os.environ.get("FBGPU_TEST_ON_EMULATOR"):
+        pytest.skip("full BASELINE sizes: device only")
+    pool = O.Pool()
+    # ---- config[1]
+    S = 1024
+    shards = np.arange(S, dtype=np.uint64)
+    h = X.Holder()
+    idx = h.create_index("i", track_existence=False)
+    fld = idx.create_field("f")
+    ex = X.Executor(h)
+    bulk = B.gen_headline(shards)
+    h.ctx.load_fragments(idx.id, fld.id, X.VIEW_STANDARD, shards, bulk.buf, bulk.offsets)
+    idx.shards.update(range(S))
+    ops = ex._bitmap_call(idx, __import__("featurebase_b200").pql.parse(B.query_text())[0].children[0])
+    tot, per = h.ctx.count(idx.id, ops, shards, per_shard=True)
+    frags = [O.Bitmap.from_bytes(bulk.fragment_bytes(i)) for i in range(S)]
+    want = O.union_intersect_per_shard(pool, frags, shards, B.ROWS_A, B.ROWS_B)
+    assert np.array_equal(np.asarray(per, dtype=np.uint64), want) and tot == int(want.sum()) > 0
+    # the 32 north-star pairs: every pair's count over all shards, fused and one by one
+    pw, _ = O.bench_pair_counts(pool, frags, shards, B.PAIRS_A, B.PAIRS_B, materialise=False)
+    got = h.ctx.count_pairs(idx.id, fld.id, 0, B.PAIRS_A, fld.id, 0, B.PAIRS_B, shards)
+    assert np.array_equal(np.asarray(got, dtype=np.uint64), pw)
+    h.ctx.close()
+    del frags, bulk
+    # ---- config[3]: all 4096 shards on this one GPU
+    S = 4096
+    h = X.Holder()
+    idx = h.create_index("g", track_existence=False)
+    fa, fb = idx.create_field("a"), idx.create_field("b")
+    fr_a, fr_b = [], []
+    for s in range(S):
+        da, db = D.groupby_fragments(31, 32, s, 100e6 / (4096 * SW), 256, 256)
+        h.import_roaring("g", "a", X.VIEW_STANDARD, s, da)
+        h.import_roaring("g", "b", X.VIEW_STANDARD, s, db)
+        fr_a.append(O.Bitmap.from_bytes(da))
+        fr_b.append(O.Bitmap.from_bytes(db))
+    rows = list(range(256))
+    shards = np.arange(S, dtype=np.uint64)
+    counts = h.ctx.groupby(idx.id, [fa.id, fb.id], [0, 0], [rows, rows], shards)
+    want, _ = O.bench_groupby(pool, [fr_a, fr_b], shards, [rows, rows])
+    assert np.array_equal(np.asarray(counts, dtype=np.uint64).reshape(-1), want)
+    assert abs(int(want.sum()) - 100e6) < 0.01 * 100e6
+    h.ctx.close()
+    pool.close()
 
 
 def test_thread_safety_and_api_edges():

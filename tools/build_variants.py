@@ -3,6 +3,7 @@ import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from featurebase_b200 import build as B
 VARIANTS = {   # name -> -D defines; edit freely, outputs featurebase_b200/libfbgpu_<name>.so (select with FBGPU_LIB=...)
+    "addr_alu": ["FBGPU_ADDR_ALU"],              # scatter / probe word addresses with shifts / LEA on the ALU pipe (the round-1 form) instead of IMAD.HI
     "wp_ring3": ["FBGPU_WP_RING=3"],             # word-parallel op loop with 3 operand slices in flight (the round-2 first measurement)
     "wp_ring8": ["FBGPU_WP_RING=8"],
     "wp_legacy": ["FBGPU_WP_LEGACY_LOOP"],       # round-1 rotating-ring loop
