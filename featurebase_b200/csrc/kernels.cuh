@@ -779,6 +779,16 @@ constexpr int kWpBlocksPerUnit = 512 / (kWpThreads * kWpSlices);
 
 struct WpOp { const void* ptr; uint32_t card; uint16_t typ, cnt; uint8_t opc, is_row, pad[6]; };   // pre-decoded op, 24 B
 
+#ifndef FBGPU_WP_ASYNC_DEPTH
+#define FBGPU_WP_ASYNC_DEPTH 8
+#endif
+constexpr int kWpAsyncDepth = FBGPU_WP_ASYNC_DEPTH;       // ring slots per thread: depth - 1 operand slices in flight
+__device__ __forceinline__ void cp_async_16(uint4* dst_smem, const uint4* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
 __global__ void __launch_bounds__(kWpThreads, FBGPU_WP_MIN_BLOCKS)
 eval_wordpar_kernel(StoreRef st, const DevOp* __restrict__ prog, int n_ops,
                     const uint64_t* __restrict__ shards, long long n_units, EvalOut out) {
@@ -786,6 +796,9 @@ eval_wordpar_kernel(StoreRef st, const DevOp* __restrict__ prog, int n_ops,
     __shared__ uint16_t rowops[kWpMaxOps];     // indices of the row ops, in program order
     __shared__ int n_rowops;
     __shared__ uint32_t wsum[kWpThreads / 32];
+#if !defined(FBGPU_WP_LEGACY_LOOP) && FBGPU_WP_SLICES == 1 && !defined(FBGPU_WP_REG_RING)
+    __shared__ __align__(16) uint4 wp_ring[kWpAsyncDepth][kWpThreads];
+#endif
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const long long n_blocks = n_units * kWpBlocksPerUnit;
     for (long long blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
@@ -801,7 +814,17 @@ eval_wordpar_kernel(StoreRef st, const DevOp* __restrict__ prog, int n_ops,
             ops[k] = w;
         }
         __syncthreads();
-        if (tid == 0) { int n = 0; for (int k = 0; k < n_ops; k++) if (ops[k].is_row) rowops[n++] = (uint16_t)k; n_rowops = n; }
+        if (wid == 0) {                        // positions of the row ops: ballot scan, 32 ops per step (was a serial loop of one thread)
+            int n = 0;
+            for (int base = 0; base < n_ops; base += 32) {
+                const int k = base + lane;
+                const bool is = k < n_ops && ops[k].is_row != 0;
+                const unsigned m = __ballot_sync(0xffffffffu, is);
+                if (is) rowops[n + __popc(m & ((1u << lane) - 1u))] = (uint16_t)k;
+                n += __popc(m);
+            }
+            if (lane == 0) n_rowops = n;
+        }
         __syncthreads();
         const int nr = n_rowops;
         auto fetch = [&](uint4* dst, int ri) {
@@ -816,8 +839,35 @@ eval_wordpar_kernel(StoreRef st, const DevOp* __restrict__ prog, int n_ops,
             }
         };
         const uint4 z = make_uint4(0, 0, 0, 0);
-#if !defined(FBGPU_WP_LEGACY_LOOP) && FBGPU_WP_SLICES == 1
-        // experimental op loop with fixed register roles (wp_machine.h); same program semantics
+#if !defined(FBGPU_WP_LEGACY_LOOP) && FBGPU_WP_SLICES == 1 && !defined(FBGPU_WP_REG_RING)
+        // Operand ring in shared memory, filled by cp.async (LDGSTS): every thread copies ITS 16-byte slice of the next kWpAsyncDepth - 1
+        // row operands into its own ring slots — no registers and no scoreboard entry per load in flight (the register ring of
+        // wp_run_unrolled stalled on shared scoreboards beyond 3 loads: 22 us at depth 3, 30 us at depth 6 for BASELINE config 3),
+        // no barrier (a slot is written and read by the same thread), and the depth is a shared-memory size, not a register count.
+        // One commit group per row op, empty when the operand is absent or not a bitmap (its slice is computed into the slot right
+        // away), so that `wait_group depth - 1` at row op ri always means "group ri has landed".
+        auto issue = [&](int ri) {
+            if (ri < nr) {
+                const WpOp w = ops[rowops[ri]];
+                uint4* slot = &wp_ring[ri % kWpAsyncDepth][tid];
+                if (w.ptr != nullptr && w.typ == kBitmap) cp_async_16(slot, reinterpret_cast<const uint4*>(w.ptr) + i0);
+                else { Resolved r; r.ptr = w.ptr; r.card = w.card; r.typ = w.typ; r.cnt = w.cnt; *slot = wp_slice(r, i0); }
+            }
+            cp_async_commit();
+        };
+        for (int ri = 0; ri < kWpAsyncDepth - 1; ri++) issue(ri);
+        uint4 T[1];
+        T[0] = wp_run_unrolled<uint4, true, 1>(n_ops, nr, [&](int k) { return ops[k].opc; }, [&](int k) { return ops[k].is_row != 0; },
+                                         [&](int ri) { return (int)rowops[ri]; },
+                                         [&](int ri) {      // called once per row op, in order, after the previous operand has been consumed
+                                             issue(ri + kWpAsyncDepth - 1);          // into the slot the previous row op was read from
+                                             cp_async_wait_group<kWpAsyncDepth - 1>();
+                                             return wp_ring[ri % kWpAsyncDepth][tid];
+                                         });
+        cp_async_wait_group<0>();
+        const int depth_now = 1;                       // (wp_run_unrolled already returns zero for an empty stack)
+#elif !defined(FBGPU_WP_LEGACY_LOOP) && FBGPU_WP_SLICES == 1
+        // op loop with fixed register roles and a register operand ring (wp_machine.h); same program semantics
         uint4 T[1];
         T[0] = wp_run_unrolled<uint4, true>(n_ops, nr, [&](int k) { return ops[k].opc; }, [&](int k) { return ops[k].is_row != 0; },
                                       [&](int ri) { return (int)rowops[ri]; }, [&](int ri) { uint4 d[1]; fetch(d, ri); return d[0]; });

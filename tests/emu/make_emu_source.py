@@ -85,6 +85,9 @@ ASM = [
     (r'asm volatile\("red\.shared\.xor\.b32 \[%0\], %1;" :: "r"\((\w+)\), "r"\(([^()]+)\) : "memory"\);', r"emu::red_xor(\1, \2);"),
     (r'asm volatile\("" : "\+r"\((\w+)\)\);', r"(void)\1;"),
     (r'asm volatile\("" : "\+l"\((\w+)\)\);', r"(void)\1;"),
+    (r'asm volatile\("cp\.async\.cg\.shared\.global \[%0\], \[%1\], 16;" :: "r"\(\(uint32_t\)__cvta_generic_to_shared\(dst_smem\)\), "l"\(src\) : "memory"\);', r"*dst_smem = *src;"),
+    (r'asm volatile\("cp\.async\.commit_group;" ::: "memory"\);', r"(void)0;"),
+    (r'asm volatile\("cp\.async\.wait_group %0;" :: "n"\(N\) : "memory"\);', r"(void)0;"),
     (r'asm volatile\("ld\.shared\.u32 %0, \[%1\];" : "=r"\((\w+)\) : "r"\((\w+)\)\);', r"\1 = emu::lds_u32(\2);"),
     (r'asm volatile\("st\.shared\.u32 \[%0\], %1;" :: "r"\((\w+)\), "r"\(([^()]+)\) : "memory"\);', r"emu::sts_u32(\1, \2);"),
 ]

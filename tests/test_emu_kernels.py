@@ -94,9 +94,10 @@ def test_groupby_thread_per_row_variant():
 
 
 def test_wordpar_loop_variants():
-    """the word-parallel op loop (wp_machine.h) with another ring depth, and the round-1 rotating-ring loop (-DFBGPU_WP_LEGACY_LOOP),
-    on the BSI programs (the default build's loop runs in test_default_kernels_parity)"""
-    run_on_emulator(["tests/test_gpu_parity.py", "-k", "bsi_range or bsi_uniform or FORCE_WORDPAR or bsi_diagonal"], defines=("FBGPU_WP_RING=3",), timeout=3000)
+    """the word-parallel op loop (wp_machine.h) with its register operand ring (-DFBGPU_WP_REG_RING), a shallower cp.async ring, and the
+    round-1 rotating-ring loop (-DFBGPU_WP_LEGACY_LOOP), on the BSI programs (the default build's cp.async ring runs in test_default_kernels_parity)"""
+    run_on_emulator(["tests/test_gpu_parity.py", "-k", "bsi_range or bsi_uniform or FORCE_WORDPAR or bsi_diagonal"], defines=("FBGPU_WP_REG_RING", "FBGPU_WP_RING=3"), timeout=3000)
+    run_on_emulator(["tests/test_gpu_parity.py", "-k", "bsi_range or bsi_uniform or FORCE_WORDPAR"], defines=("FBGPU_WP_ASYNC_DEPTH=3",), timeout=3000)
     run_on_emulator(["tests/test_gpu_parity.py", "-k", "bsi_range or bsi_uniform or FORCE_WORDPAR"], defines=("FBGPU_WP_LEGACY_LOOP",), timeout=3000)
 
 

@@ -4,8 +4,10 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from featurebase_b200 import build as B
 VARIANTS = {   # name -> -D defines; edit freely, outputs featurebase_b200/libfbgpu_<name>.so (select with FBGPU_LIB=...)
     "addr_alu": ["FBGPU_ADDR_ALU"],              # scatter / probe word addresses with shifts / LEA on the ALU pipe (the round-1 form) instead of IMAD.HI
-    "wp_ring3": ["FBGPU_WP_RING=3"],             # word-parallel op loop with 3 operand slices in flight (the round-2 first measurement)
-    "wp_ring8": ["FBGPU_WP_RING=8"],
+    "wp_reg3": ["FBGPU_WP_REG_RING", "FBGPU_WP_RING=3"],   # word-parallel op loop with a REGISTER ring of 3 operand slices (22 us on config 3 in the round-2 first measurement)
+    "wp_reg6": ["FBGPU_WP_REG_RING", "FBGPU_WP_RING=6"],   # register ring of 6 (30 us: the default of call 5)
+    "wp_async4": ["FBGPU_WP_ASYNC_DEPTH=4"],               # cp.async shared-memory ring (default depth 8)
+    "wp_async16": ["FBGPU_WP_ASYNC_DEPTH=16"],
     "wp_legacy": ["FBGPU_WP_LEGACY_LOOP"],       # round-1 rotating-ring loop
     "pair_unscatter": ["FBGPU_PAIR_UNSCATTER"],
     "eval_deep1": ["FBGPU_EVAL_DEEP=1"],                                  # round-1 scatter loop: one chunk load in flight per lane
