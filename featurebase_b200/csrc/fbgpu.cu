@@ -238,6 +238,7 @@ extern "C" int fbgpu_init(int32_t device_ordinal, fbgpu_ctx** out) try {
     CUDA_TRY(cudaFuncSetAttribute(groupby_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGbSlots * 4 + 8192));
     CUDA_TRY(cudaFuncSetAttribute(groupby_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGbSlots * 4 + 8192));
     CUDA_TRY(cudaFuncSetAttribute(groupby_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGsWarps * kGsSlots * 4));
+    CUDA_TRY(cudaFuncSetAttribute(groupby_shard_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGhSlots * 4));
     guard.c = nullptr;
     *out = c;
     return FBGPU_OK;
@@ -1599,6 +1600,25 @@ extern "C" int fbgpu_any(fbgpu_ctx* c, uint32_t index, const fbgpu_op* ops, int3
 } FBGPU_CATCH
 
 // ------------------------------------------------------------------ GroupBy
+// Slots per CTA of groupby_shard_kernel (16, 8, 4, 2 or 1), or 0 when the fields are not its shape: picked so that a group of
+// slots of field a holds about 12 k columns (the table takes 20 k), from the cardinality of a sample of the listed shards' fragments.
+static int groupby_slots_per_group(fbgpu_ctx* c, uint32_t fvA, uint32_t fvB, const uint64_t* shards, int64_t n) {
+    if (fvA >= c->shardmaps.size() || fvB >= c->shardmaps.size() || n <= 0) return 0;
+    if (c->view_other[fvA] * 8 > c->view_arr[fvA] || c->view_other[fvB] * 8 > c->view_arr[fvB]) return 0;     // bitmap / run heavy: the per-slot kernels
+    const auto& sm = c->shardmaps[fvA];
+    uint64_t elems = 0, seen = 0;
+    const int64_t step = std::max<int64_t>(1, n / 64);
+    for (int64_t i = 0; i < n; i += step) {
+        const uint64_t sh = shards[i];
+        if (sh >= sm.size() || sm[sh] < 0) continue;
+        elems += c->frags[(size_t)sm[sh]].payload_bytes / 2; seen++;
+    }
+    if (!seen) return 16;
+    const uint64_t avg = elems / seen;                       // columns of field a per shard (all its rows: an upper bound for a row subset)
+    for (int spg = 16; spg >= 1; spg >>= 1) if (avg * (uint64_t)spg / 16 <= 12000) return spg;
+    return 0;
+}
+
 static int groupby2(fbgpu_ctx* c, uint32_t index, uint32_t fvA, const uint64_t* rowsA, int nA, uint32_t fvB, const uint64_t* rowsB, int nB,
                     const std::vector<fbgpu_op>& filter, const uint64_t* shards, int64_t n_shards, uint64_t* out) {
     std::vector<DevOp> prog; int depth = 1; int rc;
@@ -1624,8 +1644,28 @@ static int groupby2(fbgpu_ctx* c, uint32_t index, uint32_t fvA, const uint64_t* 
         long long grid = std::min<long long>(units, (long long)c->sm_count * 4);
         static const bool gb_fast = getenv("FBGPU_GROUPBY_FAST") != nullptr;    // thread-per-row passes of the CTA kernel (kernels.cuh)
         static const bool gb_cta_only = getenv("FBGPU_GROUPBY_CTA") != nullptr; // round-1 path only: one CTA per unit
+        static const bool gb_small = getenv("FBGPU_GROUPBY_SMALL") != nullptr;   // warp-per-(shard, slot) kernel instead of the CTA-per-(shard, slot group) one
         auto cta_kernel = gb_fast ? groupby_kernel<true> : groupby_kernel<false>;
-        if (!gb_cta_only && units < (1ll << 31)) {
+        const int spg = (gb_cta_only || gb_small) ? 0 : groupby_slots_per_group(c, fvA, fvB, shards + s0, ns);
+        if (spg > 0 && units < (1ll << 31)) {
+            // one CTA per (shard, group of `spg` slots): contiguous descriptor / payload reads; declined units go to the CTA kernel
+            if (w->d_emit_units.ensure((size_t)(units + 1) * 4)) return FBGPU_E_NOMEM;
+            unsigned int* d_fb = (unsigned int*)w->d_emit_units.p;
+            CUDA_TRY(cudaMemsetAsync(d_fb, 0, 4, w->stream));
+            const long long hunits = ns * (kSlotsPerRow / spg);
+            const long long hgrid = std::min<long long>(hunits, (long long)c->sm_count);
+            groupby_shard_kernel<<<(unsigned)hgrid, kGhThreads, kGhSlots * 4, w->stream>>>(store_ref(c), fvA, (const uint64_t*)w->d_rows.p, nA, fvB, (const uint64_t*)w->d_rows.p + nA, nB,
+                d_shards + s0, ns, spg, have_filter ? (const uint4*)w->d_bitmaps.p : nullptr, (unsigned long long*)w->d_counts.p, d_fb);
+            CUDA_TRY(cudaGetLastError()); launches++;
+            cta_kernel<<<(unsigned)grid, kGbThreads, smem, w->stream>>>(store_ref(c), fvA, (const uint64_t*)w->d_rows.p, nA, fvB, (const uint64_t*)w->d_rows.p + nA, nB,
+                d_shards + s0, units, have_filter ? (const uint4*)w->d_bitmaps.p : nullptr, (unsigned long long*)w->d_counts.p, d_fb);
+            if (c->count_fallbacks) {
+                unsigned int n_fb = 0;
+                CUDA_TRY(cudaMemcpyAsync(&n_fb, d_fb, 4, cudaMemcpyDeviceToHost, w->stream)); CUDA_TRY(cudaStreamSynchronize(w->stream));
+                fb_units += n_fb;
+            }
+            all_units += (uint64_t)units;
+        } else if (!gb_cta_only && units < (1ll << 31)) {
             // warp-per-unit kernel first; the units it declines (an a-row that is not a small array) are listed for the CTA kernel
             if (w->d_emit_units.ensure((size_t)(units + 1) * 4)) return FBGPU_E_NOMEM;
             unsigned int* d_fb = (unsigned int*)w->d_emit_units.p;

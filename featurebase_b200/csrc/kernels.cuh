@@ -2035,6 +2035,159 @@ groupby_small_kernel(StoreRef st, uint32_t fvA, const uint64_t* __restrict__ row
 }
 
 // ------------------------------------------------------------------------------------------------
+// groupby_shard_kernel (round 2): the column-keyed join of GroupBy(Rows(a), Rows(b)) for the shape BASELINE config 4 has — hundreds of
+// rows per field, a handful of columns per container — with one CTA per (shard, GROUP OF SLOTS) instead of per (shard, slot).
+// The work of such a query is the descriptor walk (16 B of descriptor for ~12 B of payload).  Per (shard, slot) a unit reads one
+// descriptor out of every row's 16 (a 16-byte read every 256 bytes, and the same for the payload); per group of `spg` adjacent slots
+// thread e = row * spg + slot reads descriptor e and payload chunk e of a contiguous run: whole 128-byte lines, every byte used.
+// Table: kGhSlots x u32 in shared memory (128 KiB, one CTA of 1024 threads per SM), entry = (slot-in-group << 28) | (column << 12) |
+// a-row index in the chunk, linear probing.  A unit goes to `fallback` (-> groupby_kernel per (shard, slot)) before anything is
+// counted when an a- or b-row container is not an array, an a-row holds more than kGhMaxCard columns, or the group holds more entries
+// than 5/8 of the table.
+// ------------------------------------------------------------------------------------------------
+constexpr int kGhThreads = 1024;
+constexpr int kGhItems = 2;                       // containers per thread and pass
+constexpr int kGhSlots = 32768;                   // 128 KiB
+constexpr uint32_t kGhMaxEntries = kGhSlots / 8 * 5;
+constexpr uint32_t kGhMaxCard = 512;
+
+__device__ __forceinline__ uint32_t gh_hash(uint32_t key) { return (key * 2654435761u) >> 17; }   // 15 bits
+
+__global__ void __launch_bounds__(kGhThreads, 1)
+groupby_shard_kernel(StoreRef st, uint32_t fvA, const uint64_t* __restrict__ rowsA, int nA,
+                     uint32_t fvB, const uint64_t* __restrict__ rowsB, int nB,
+                     const uint64_t* __restrict__ shards, long long n_shards, int spg /* slots per group: 1, 2, 4, 8 or 16 */,
+                     const uint4* __restrict__ filter_bitmaps /* per (shard, slot) unit or null */,
+                     unsigned long long* counts /* [nA*nB] */, unsigned int* fallback /* [0] = n, then (shard index * 16 + slot) units */) {
+    extern __shared__ __align__(16) uint32_t gh_tab[];
+    __shared__ uint32_t red[kGhThreads / 32];
+    __shared__ uint32_t s_tot;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int groups = kSlotsPerRow / spg;
+    const int rows_per_pass = (kGhThreads * kGhItems) / spg;         // rows of a field one pass covers (<= 2048: 12-bit row index)
+    const long long n_units = n_shards * groups;
+    for (long long unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+        const long long si = unit / groups;
+        const int g = (int)(unit - si * groups);
+        const uint64_t shard = shards[si];
+        {   // executor.go:8769-8772: a shard missing either fragment contributes nothing (uniform test, broadcast loads)
+            bool ok = fvA < st.n_views && fvB < st.n_views;
+            if (ok) { const ViewTab va = st.views[fvA], vb = st.views[fvB]; ok = shard < va.n_shards && shard < vb.n_shards && st.shardmap[va.shard_off + shard] >= 0 && st.shardmap[vb.shard_off + shard] >= 0; }
+            if (!ok) continue;
+        }
+        // item e of a pass = (row e / spg of the chunk, slot g * spg + e % spg)
+        auto load_items = [&](uint32_t fv, const uint64_t* rows, int r0, int n, Resolved (&it)[kGhItems]) {
+#pragma unroll
+            for (int k = 0; k < kGhItems; k++) {
+                const int e = tid + k * kGhThreads, i = e / spg;
+                it[k].ptr = nullptr; it[k].card = 0; it[k].typ = 0; it[k].cnt = 0;
+                if (i < n) it[k] = resolve(st, fv, shard, rows[r0 + i], g * spg + (e - i * spg));
+            }
+        };
+        auto block_sum_or = [&](uint32_t v, bool flag, uint32_t& total) -> bool {      // sum of v and OR of flag over the CTA
+            v = __reduce_add_sync(0xffffffffu, v);
+            __syncthreads();                                    // (previous readers of red / s_tot are done)
+            if (lane == 0) red[wid] = v;
+            const int any = __syncthreads_or(flag ? 1 : 0);
+            if (wid == 0) { uint32_t t = red[lane]; t = __reduce_add_sync(0xffffffffu, t); if (lane == 0) s_tot = t; }
+            __syncthreads();
+            total = s_tot;
+            return any != 0;
+        };
+        // ---- pass 0: nothing may be counted for a unit that ends up in the fallback list, so every a- and b-row of the group is
+        // looked at first when a side needs several passes (a single pass per side is checked on the fly, without extra reads)
+        bool decline = false;
+        const bool multiA = nA > rows_per_pass, multiB = nB > rows_per_pass;
+        if (multiA || multiB) {
+            for (int side = 0; side < 2 && !decline; side++) {
+                const int n = side ? nB : nA;
+                for (int r0 = 0; r0 < n && !decline; r0 += rows_per_pass) {
+                    Resolved it[kGhItems];
+                    load_items(side ? fvB : fvA, side ? rowsB : rowsA, r0, min(rows_per_pass, n - r0), it);
+                    uint32_t cnt = 0; bool bad = false;
+#pragma unroll
+                    for (int k = 0; k < kGhItems; k++) if (it[k].ptr) { bad |= it[k].typ != kArray || (!side && it[k].card > kGhMaxCard); cnt += it[k].card; }
+                    uint32_t tot;
+                    if (block_sum_or(cnt, bad, tot) || (!side && tot > kGhMaxEntries)) decline = true;
+                }
+            }
+        }
+        for (int a0 = 0; a0 < nA && !decline; a0 += rows_per_pass) {
+            const int chunkA = min(rows_per_pass, nA - a0);
+            Resolved ra[kGhItems], rb[kGhItems];
+            load_items(fvA, rowsA, a0, chunkA, ra);
+            if (!multiB) load_items(fvB, rowsB, 0, nB, rb);       // (its descriptor chains run while the a-rows are inserted)
+            uint4 va[kGhItems], vb[kGhItems];                 // first 16-byte chunk of every container, in flight before the first barrier
+            uint32_t cnt = 0; bool bad = false;
+#pragma unroll
+            for (int k = 0; k < kGhItems; k++) {
+                va[k] = vb[k] = make_uint4(0, 0, 0, 0);
+                if (ra[k].ptr) { bad |= ra[k].typ != kArray || ra[k].card > kGhMaxCard; cnt += ra[k].card; if (ra[k].typ == kArray) va[k] = ldg_nc(reinterpret_cast<const uint4*>(ra[k].ptr)); }
+                if (!multiB && rb[k].ptr) { bad |= rb[k].typ != kArray; if (rb[k].typ == kArray) vb[k] = ldg_nc(reinterpret_cast<const uint4*>(rb[k].ptr)); }
+            }
+            uint32_t tot;
+            const bool any_bad = block_sum_or(cnt, bad, tot);
+            if (!multiA && !multiB && (any_bad || tot > kGhMaxEntries)) { decline = true; break; }      // (multi-pass sides were vetted in pass 0)
+            if (tot == 0) continue;
+            {   uint4* t4 = reinterpret_cast<uint4*>(gh_tab);
+#pragma unroll 4
+                for (int k = tid; k < kGhSlots / 4; k += kGhThreads) t4[k] = make_uint4(kGbEmpty, kGbEmpty, kGbEmpty, kGbEmpty); }
+            __syncthreads();
+            // ---- insert the a-rows
+#pragma unroll
+            for (int k = 0; k < kGhItems; k++) {
+                if (!ra[k].ptr) continue;
+                const int e = tid + k * kGhThreads, i = e / spg, sl = e - i * spg;
+                const uint32_t* flt = filter_bitmaps ? reinterpret_cast<const uint32_t*>(filter_bitmaps + ((size_t)si * kSlotsPerRow + g * spg + sl) * 512) : nullptr;
+                const uint4* p = reinterpret_cast<const uint4*>(ra[k].ptr);
+                for (uint32_t k0 = 0; k0 < ra[k].card; k0 += 8) {
+                    const uint4 v = k0 ? ldg_nc(p + (k0 >> 3)) : va[k];
+                    const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+                    for (int q = 0; q < 8; q++) {
+                        if (k0 + q >= ra[k].card) break;
+                        const uint32_t col = (w[q >> 1] >> ((q & 1) * 16)) & 0xffffu;
+                        if (flt && !((__ldg(flt + (col >> 5)) >> (col & 31)) & 1u)) continue;
+                        const uint32_t key = ((uint32_t)sl << 16) | col, ent = (key << 12) | (uint32_t)i;
+                        uint32_t h = gh_hash(key);
+                        while (atomicCAS(&gh_tab[h], kGbEmpty, ent) != kGbEmpty) h = (h + 1) & (kGhSlots - 1);
+                    }
+                }
+            }
+            __syncthreads();
+            // ---- probe with the b-rows
+            for (int b0 = 0; b0 < nB; b0 += rows_per_pass) {
+                const int chunkB = min(rows_per_pass, nB - b0);
+                if (multiB) load_items(fvB, rowsB, b0, chunkB, rb);
+#pragma unroll
+                for (int k = 0; k < kGhItems; k++) {
+                    if (!rb[k].ptr) continue;
+                    const int e = tid + k * kGhThreads, i = e / spg, sl = e - i * spg;
+                    unsigned long long* cj = counts + (size_t)a0 * nB + (b0 + i);
+                    const uint4* p = reinterpret_cast<const uint4*>(rb[k].ptr);
+                    for (uint32_t k0 = 0; k0 < rb[k].card; k0 += 8) {
+                        const uint4 v = (k0 || multiB) ? ldg_nc(p + (k0 >> 3)) : vb[k];
+                        const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+                        for (int q = 0; q < 8; q++) {
+                            if (k0 + q >= rb[k].card) break;
+                            const uint32_t key = ((uint32_t)sl << 16) | ((w[q >> 1] >> ((q & 1) * 16)) & 0xffffu);
+                            for (uint32_t h = gh_hash(key);; h = (h + 1) & (kGhSlots - 1)) {
+                                const uint32_t ent = gh_tab[h];
+                                if (ent == kGbEmpty) break;
+                                if ((ent >> 12) == key) atomicAdd(cj + (size_t)(ent & 0xfffu) * nB, 1ull);
+                            }
+                        }
+                    }
+                }
+            }
+            __syncthreads();                                     // the table is cleared for the next a-chunk
+        }
+        if (decline && tid < spg) { const unsigned int k = atomicAdd(&fallback[0], 1u); fallback[1 + k] = (unsigned int)(si * kSlotsPerRow + g * spg + tid); }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // arena_gather_kernel (fbgpu_compact): copies containers one by one from the old payload arena into the new one — one warp per
 // container, 16 bytes per lane and step.  Used for fragments that fbgpu_apply_containers left with holes.
 // ------------------------------------------------------------------------------------------------

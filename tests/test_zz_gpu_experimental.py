@@ -477,6 +477,46 @@ def test_groupby_kernel_pass_shapes():
         assert int(exp.sum()) > 3000
 
 
+def test_groupby_slot_groups(monkeypatch):
+    """groupby_shard_kernel with several slots per CTA (denser fields -> 4 slots per group instead of 16), one group whose columns
+    overflow the shared-memory table (declined before anything is counted -> groupby_kernel takes its four (shard, slot) units), a
+    row subset, and a filter: the dense count tensor against the oracle's nested loop, and the fallback counter says what ran where"""
+    from oracle import oracle as O
+    monkeypatch.setenv("FBGPU_COUNT_FALLBACKS", "1")
+    SW = 1 << 20
+    rng = np.random.default_rng(11)
+    p = Pair(track_existence=False)
+    for n in ("a", "b", "f"):
+        p.field(n)
+    cols = {0: rng.choice(SW, size=40000, replace=False), 1: np.concatenate([rng.choice(4 * 65536, size=26000, replace=False), 4 * 65536 + rng.choice(12 * 65536, size=14000, replace=False)]) + SW}
+    frs = {"a": {}, "b": {}, "f": {}}
+    for s, cc in cols.items():
+        ra, rb = rng.integers(0, 64, size=len(cc)), rng.integers(0, 50, size=len(cc))
+        rel = cc.astype(np.uint64) - np.uint64(s * SW)
+        frs["a"][s] = np.sort(ra.astype(np.uint64) * np.uint64(SW) + rel)
+        frs["b"][s] = np.sort(rb.astype(np.uint64) * np.uint64(SW) + rel)
+        frs["f"][s] = np.sort(np.uint64(1 * SW) + rel[rel % np.uint64(3) != 0])
+    from featurebase_b200 import roaring_io
+    for f in frs:
+        for s, bits in frs[f].items():
+            p.load(f, X.VIEW_STANDARD, s, roaring_io.encode(bits))
+    ids = [list(range(64)), list(range(0, 50, 2)) + [49, 77]]
+    for filt in (None, "Row(f=1)"):
+        call = pql.parse(filt)[0] if filt else None
+        exp = np.zeros(len(ids[0]) * len(ids[1]), dtype=np.uint64)
+        for s in p.shards():
+            O.groupby_shard([p.ora.frag(f, 0, s) for f in ("a", "b")], s, ids, p.ora.eval_shard(call, s) if call is not None else None, exp)
+        before = p.holder.ctx.counters()
+        got = p.holder.ctx.groupby(p.idx.id, [p.idx.fields["a"].id, p.idx.fields["b"].id], [X.VIEW_STANDARD] * 2, ids, p.shards(),
+                                   filter_ops=p.ex._bitmap_call(p.idx, call) if call is not None else None)
+        assert np.array_equal(np.asarray(got).reshape(-1), exp), filt
+        assert int(exp.sum()) > 20000
+        after = p.holder.ctx.counters()
+        if "groupby_fallback_units" in after and not os.environ.get("FBGPU_GROUPBY_CTA") and not os.environ.get("FBGPU_GROUPBY_SMALL"):
+            assert after["groupby_units"] - before["groupby_units"] == 32
+            assert after["groupby_fallback_units"] - before["groupby_fallback_units"] == 4, (filt, before, after)   # (the crowded group of shard 1; decided on cardinalities, before the filter)
+
+
 def test_topk_time_range():
     """executor_test.go:1811-1843 TestExecutor_Execute_TopK_Time: TopK over a time range counts a row's union over the covering
     views (column 0 is set on two days and counts once), plus a filter and k"""
