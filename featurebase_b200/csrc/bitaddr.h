@@ -20,18 +20,18 @@ FBGPU_HD uint32_t mulhi_u32(uint32_t a, uint32_t b) {
 #endif
 }
 // Pipe balance (B200: the integer ALU pipe — LOP3 / SHF / LEA / IADD3 — and the FMA pipe — IMAD — each issue every second cycle per
-// SM sub-partition): the scatter / probe loops are ALU-pipe bound (ncu round 2: alu 63 % busy, fma 7 %).  With the multipliers
-// read from constant memory ptxas cannot strength-reduce the multiply-high into LEA.HI / SHF, so the two word addresses and the
-// `>> 16` of the upper element become IMAD.HI on the idle FMA pipe, with the bitmap's shared-memory base riding along as the
-// 64-bit addend (base << 32): per 8 elements 28 -> 16 ALU-pipe instructions + 12 FMA-pipe ones, same issue count.
-// -DFBGPU_ADDR_ALU restores the shift / LEA forms.
+// SM sub-partition): the scatter / probe loops are ALU-pipe bound (ncu round 2: alu 63 % busy, fma 7 %).  -DFBGPU_ADDR_IMAD moves
+// the two word addresses and the `>> 16` of the upper element to IMAD.HI on the FMA pipe (multipliers read from constant memory so
+// that ptxas cannot strength-reduce them, the bitmap's shared-memory base riding along as the 64-bit addend).  MEASURED SLOWER
+// (bench_micro/pipe_rates.cu: IMAD.HI issues every 4.3 cycles per sub-partition, LEA.HI / SHF / IMAD-low every 2.2; headline query
+// 0.381 ms against 0.352 ms), so the shift / LEA forms are the default and the IMAD form is kept only as the record of the experiment.
 // w = (hi << 16) | lo.  4 * (lo >> 5)  and  4 * (hi >> 5)
 FBGPU_HD uint32_t word_off_lo(uint32_t w) { return mulhi_u32(w & 0xffe0u, 1u << 29); }
 FBGPU_HD uint32_t word_off_hi(uint32_t w) { return mulhi_u32(w & 0xffe00000u, 1u << 13); }
-#if defined(__CUDACC__) && !defined(FBGPU_ADDR_ALU)
+#if defined(__CUDACC__) && defined(FBGPU_ADDR_IMAD)
 __constant__ uint32_t c_mul29 = 1u << 29, c_mul13 = 1u << 13, c_mul16 = 1u << 16;
 #endif
-#if defined(__CUDA_ARCH__) && !defined(FBGPU_ADDR_ALU)
+#if defined(__CUDA_ARCH__) && defined(FBGPU_ADDR_IMAD)
 typedef uint64_t smem_base_t;                        // shared-space address of a bitmap, kept in the upper half of a register pair
 __device__ __forceinline__ smem_base_t smem_base(uint32_t sb) { return (uint64_t)sb << 32; }
 __device__ __forceinline__ uint32_t word_addr_lo(smem_base_t b, uint32_t w) { return (uint32_t)(((uint64_t)(w & 0xffe0u) * c_mul29 + b) >> 32); }

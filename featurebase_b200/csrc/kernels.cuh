@@ -1090,7 +1090,9 @@ __device__ __forceinline__ void red_or_at(uint32_t addr, uint32_t m) { asm volat
 
 // returns the full count (reduced over the warp, valid in all lanes).  `bm` is the warp's private 8 KiB bitmap and is ALL ZERO on
 // entry and on exit (the kernel clears it once per warp): no path below pays an 8 KiB wipe per pair.
-__device__ __forceinline__ uint32_t warp_intersection_count(Resolved a, Resolved b, uint32_t* bm, int lane) {
+// `sa` / `sb_` : when not null, the first 96 chunks of a / b already sit in shared memory (cp.async staging of pair_count_kernel), lane L's
+// chunks at [L + 32 q]; the array x array path then reads them from there instead of from global memory.
+__device__ __forceinline__ uint32_t warp_intersection_count(Resolved a, Resolved b, uint32_t* bm, int lane, const uint4* sa = nullptr, const uint4* sb_ = nullptr) {
     if (a.ptr == nullptr || b.ptr == nullptr) return 0;
     if (a.card == kFull) return b.card;                       // roaring.go:4478-4483
     if (b.card == kFull) return a.card;
@@ -1099,7 +1101,7 @@ __device__ __forceinline__ uint32_t warp_intersection_count(Resolved a, Resolved
     uint32_t c = 0;
     if (a.typ == kRun || b.typ == kRun) c = warp_icount_runs(a, b, lane);
     else if (a.typ == kArray && b.typ == kArray) {            // array x array: build the smaller, probe the larger
-        if (a.card > b.card) { Resolved t = a; a = b; b = t; }
+        if (a.card > b.card) { Resolved t = a; a = b; b = t; const uint4* ts = sa; sa = sb_; sb_ = ts; }
         // Round-2 shape (bench_micro/pair_variants.cu w9, profiles/README.md): all chunks of both arrays (up to 768 elements each) are
         // loaded before any shared-memory work; the shared addresses computed for the scatter of `a` STAY IN REGISTERS, and after the
         // probe the same words are set back to zero with plain stores — no 8 KiB wipe (64 shared-memory wavefronts per pair) and no
@@ -1110,10 +1112,15 @@ __device__ __forceinline__ uint32_t warp_intersection_count(Resolved a, Resolved
         smem_base_t sb = smem_base(sb32);
         pin_base(sb);
         uint4 va[3], vb[3];
+        if (sa != nullptr) {                    // staged (warp-uniform): slots past the array's last chunk hold stale bytes, never used below
 #pragma unroll
-        for (int q = 0; q < 3; q++) va[q] = ldg_nc(a4 + min((uint32_t)lane + 32u * q, na8 - 1u));     // clamped, unconditional: no undefined register
+            for (int q = 0; q < 3; q++) { va[q] = sa[lane + 32 * q]; vb[q] = sb_[lane + 32 * q]; }
+        } else {
 #pragma unroll
-        for (int q = 0; q < 3; q++) vb[q] = ldg_nc(b4 + min((uint32_t)lane + 32u * q, nb8 - 1u));
+            for (int q = 0; q < 3; q++) va[q] = ldg_nc(a4 + min((uint32_t)lane + 32u * q, na8 - 1u));     // clamped, unconditional: no undefined register
+#pragma unroll
+            for (int q = 0; q < 3; q++) vb[q] = ldg_nc(b4 + min((uint32_t)lane + 32u * q, nb8 - 1u));
+        }
         uint32_t addr[3][8];
 #pragma unroll
         for (int q = 0; q < 3; q++) {
@@ -1160,29 +1167,46 @@ __device__ __forceinline__ uint32_t warp_intersection_count(Resolved a, Resolved
         c = warp_probe_global(reinterpret_cast<const uint32_t*>(b.ptr), reinterpret_cast<const uint16_t*>(a.ptr), a.card, lane);
     } else {                                                  // bitmap x bitmap: roaring.go:4611
         const uint4* x = reinterpret_cast<const uint4*>(a.ptr); const uint4* y = reinterpret_cast<const uint4*>(b.ptr);
-#pragma unroll 4
+#pragma unroll 8
         for (int i = lane; i < 512; i += 32) c += popc4(and4(ldg_nc(x + i), ldg_nc(y + i)));
     }
     return __reduce_add_sync(0xffffffffu, c);
 }
 
-constexpr int kPairWarps = 8;
+constexpr int kPairWarps = 8;           // row_count_kernel
+#ifndef FBGPU_PAIR_WARPS
+#define FBGPU_PAIR_WARPS 13
+#endif
+#ifndef FBGPU_PAIR_BUFS
+#define FBGPU_PAIR_BUFS 3
+#endif
+constexpr int kPcWarps = FBGPU_PAIR_WARPS;                  // warps of a pair_count_kernel CTA (one CTA per SM)
+constexpr int kPcBufs = FBGPU_PAIR_BUFS;                    // staging buffers per warp: kPcBufs - 1 container pairs in flight behind the one being intersected
+constexpr int kPcStageChunks = 96;                          // 16-byte chunks per side and buffer: arrays of up to 768 elements are staged
+constexpr int kPcWarpBytes = 8192 + kPcBufs * 2 * kPcStageChunks * 16;
+static_assert(kPcWarps * kPcWarpBytes <= 232448, "pair_count_kernel: shared memory per CTA");
 
 // Count(Intersect(Row(fvA,rowA), Row(fvB,rowB))): one warp per (shard, slot) container pair.  A warp owns the units
-// w, w+W, w+2W, ...; it walks the descriptor chains of up to 16 of its units at once (lane 2k / 2k+1 = side a / b of
-// unit k), and while unit k is being intersected the payloads of unit k+1 are already being pulled into L2.
-__global__ void __launch_bounds__(kPairWarps * 32, 3)
+// w, w+W, w+2W, ...; it walks the descriptor chains of up to 16 of its units at once (lane 2k / 2k+1 = side a / b of unit k).
+// Round 2: the array payloads of the next kPcBufs - 1 units are copied into the warp's shared-memory staging buffers by cp.async
+// while the current unit is intersected — the bytes in flight per SM no longer depend on registers or on how many warps are between
+// their load and their compute phase (ncu round 2: 24 resident warps x 3 KB each only during their wait could not cover the loaded
+// HBM latency; the kernel ran at 0.42 of the roofline with the ALU pipe 38 % busy).  One CTA of kPcWarps warps per SM; per warp an
+// 8 KiB bitmap + kPcBufs x 3 KiB of staging.  Lane L copies and later reads the chunks L, L+32, L+64 of either side itself, so the
+// staged data needs no cross-lane synchronisation.  Operands that are not two arrays of at most 768 elements are read directly.
+__global__ void __launch_bounds__(kPcWarps * 32, 1)
 pair_count_kernel(StoreRef st, uint32_t fvA, uint64_t rowA, uint32_t fvB, uint64_t rowB,
                   const uint64_t* __restrict__ rowsA, const uint64_t* __restrict__ rowsB, long long units_per_pair,
                   const uint64_t* __restrict__ shards, uint64_t shard0, long long n_units,
-                  unsigned long long* total, unsigned long long* per_shard, unsigned long long* per_pair, FuseReduce fr, int pf_depth) {
+                  unsigned long long* total, unsigned long long* per_shard, unsigned long long* per_pair, FuseReduce fr) {
     extern __shared__ __align__(128) uint32_t smem32[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    uint32_t* bm = smem32 + wid * 2048;
+    uint32_t* bm = smem32 + (size_t)wid * (kPcWarpBytes / 4);
+    uint4* stage = reinterpret_cast<uint4*>(bm + 2048);       // [kPcBufs][2][kPcStageChunks]
     warp_zero(bm, lane); __syncwarp();          // the only full clear: warp_intersection_count leaves the bitmap all-zero again
     unsigned long long acc = 0;
-    const long long stride = (long long)gridDim.x * kPairWarps;
-    for (long long base = (long long)blockIdx.x * kPairWarps + wid; base < n_units; base += stride * 16) {
+    const long long stride = (long long)gridDim.x * kPcWarps;
+    for (long long base = (long long)blockIdx.x * kPcWarps + wid; base < n_units; base += stride * 16) {
         // resolve up to 16 units of this warp concurrently
         // multi-pair form (rowsA != null): unit = pair * units_per_pair + (shard index * 16 + slot)
         const long long my_unit = base + (long long)(lane >> 1) * stride;
@@ -1203,32 +1227,47 @@ pair_count_kernel(StoreRef st, uint32_t fvA, uint64_t rowA, uint32_t fvB, uint64
             x.typ = m >> 16; x.cnt = m & 0xffff;
             return x;
         };
-        Resolved a = fetch(0), b = fetch(1);
-        // L2 prefetch of the operands of the units `pf_depth` ahead (the first pf_depth - 1 right away): a warp's units are processed
-        // one after the other, so without it every unit pays an HBM round trip of its own; with it the payload of a whole round is on
-        // its way while the first unit is intersected.  Small (latency-bound) operands only: bitmap pairs are pure streaming.
-        auto prefetch_unit = [&](int j) {
-            if (j >= 16 || base + (long long)j * stride >= n_units) return;
-            const Resolved pa = fetch(2 * j), pb = fetch(2 * j + 1);
-            if (pa.ptr != nullptr && pb.ptr != nullptr && (pa.typ != kBitmap || pb.typ != kBitmap)) { if (pa.typ != kBitmap) warp_prefetch_container(pa, lane); if (pb.typ != kBitmap) warp_prefetch_container(pb, lane); }
+        auto stageable = [](const Resolved& x, const Resolved& y) {
+            return x.ptr != nullptr && y.ptr != nullptr && x.typ == kArray && y.typ == kArray && x.card <= kPcStageChunks * 8u && y.card <= kPcStageChunks * 8u;
         };
-        for (int j = 1; j < pf_depth; j++) prefetch_unit(j);
+        // unit j of this round -> staging buffer j % kPcBufs; always one commit group per unit, so that `wait_group kPcBufs - 1` in
+        // iteration k means "the copies of unit k have landed"
+        auto stage_unit = [&](int j) {
+            if (j < 16 && base + (long long)j * stride < n_units) {
+                const Resolved pa = fetch(2 * j), pb = fetch(2 * j + 1);
+                if (stageable(pa, pb)) {
+                    uint4* dst = stage + (size_t)(j % kPcBufs) * 2 * kPcStageChunks;
+                    const uint4* ga = reinterpret_cast<const uint4*>(pa.ptr); const uint4* gb = reinterpret_cast<const uint4*>(pb.ptr);
+                    const uint32_t na8 = (pa.card + 7) >> 3, nb8 = (pb.card + 7) >> 3;
+#pragma unroll
+                    for (int q = 0; q < 3; q++) {
+                        if (lane + 32 * q < na8) cp_async_16(dst + lane + 32 * q, ga + lane + 32 * q);
+                        if (lane + 32 * q < nb8) cp_async_16(dst + kPcStageChunks + lane + 32 * q, gb + lane + 32 * q);
+                    }
+                }
+            }
+            cp_async_commit();
+        };
+        for (int j = 0; j < kPcBufs - 1; j++) stage_unit(j);
         for (int k = 0; k < 16; k++) {
             const long long unit = base + (long long)k * stride;
             if (unit >= n_units) break;
-            Resolved na, nb; na.ptr = nullptr; nb.ptr = nullptr; na.card = nb.card = 0; na.typ = nb.typ = 0; na.cnt = nb.cnt = 0;
-            prefetch_unit(k + pf_depth);
-            if (k + 1 < 16 && unit + stride < n_units) { na = fetch(2 * k + 2); nb = fetch(2 * k + 3); }
-            uint32_t c = warp_intersection_count(a, b, bm, lane);
+            stage_unit(k + kPcBufs - 1);                      // into the buffer unit k - 1 was read from
+            cp_async_wait_group<kPcBufs - 1>();
+            const Resolved a = fetch(2 * k), b = fetch(2 * k + 1);
+            const bool st_ok = stageable(a, b);
+            const uint4* sbuf = stage + (size_t)(k % kPcBufs) * 2 * kPcStageChunks;
+            uint32_t c = warp_intersection_count(a, b, bm, lane, st_ok ? sbuf : nullptr, st_ok ? sbuf + kPcStageChunks : nullptr);
             acc += c;
             if (c && lane == 0) {
                 if (per_pair) atomicAdd(&per_pair[unit / units_per_pair], (unsigned long long)c);
                 else if (per_shard) atomicAdd(&per_shard[unit >> 4], (unsigned long long)c);
             }
-            a = na; b = nb;
         }
+        cp_async_wait_group<0>();
+        __syncwarp();
     }
-    if (lane == 0 && total) { if (acc) atomicAdd(total, acc); fused_allreduce_tail(fr, total, gridDim.x * kPairWarps); }
+    if (lane == 0 && total) { if (acc) atomicAdd(total, acc); fused_allreduce_tail(fr, total, gridDim.x * kPcWarps); }
 }
 
 // Container-pair-type histogram of a Count(Intersect(Row, Row)) query: hist[4 * ta + tb] += 1 per (shard, slot) unit, t = 0 absent,
