@@ -179,7 +179,6 @@ struct fbgpu_ctx {
     // points: 16384 units = 1024 shards = 128 MiB of workspace per lease.  FBGPU_UNIT_BATCH (a multiple of 16, fixed per
     // context) trades workspace for launches; the tests set it small to walk the multi-batch paths with a handful of shards.
     long long unit_batch = [] { const char* e = getenv("FBGPU_UNIT_BATCH"); const long long n = e ? atoll(e) : 0; return n >= 16 ? (n / 16) * 16 : 16384ll; }();
-    bool count_fallbacks = getenv("FBGPU_COUNT_FALLBACKS") != nullptr;
     std::atomic<uint64_t> counters_pair_launches{0};      // Count(Intersect(Row, Row)) queries that took the fused pair kernel
     DevBuf d_payload, d_views, d_shardmap, d_frags, d_rows, d_descs, d_rowtab;
     PinBuf bounce[2];
@@ -235,7 +234,6 @@ extern "C" int fbgpu_init(int32_t device_ordinal, fbgpu_ctx** out) try {
     CUDA_TRY(cudaFuncSetAttribute(row_count_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairWarps * 8192));
     CUDA_TRY(cudaFuncSetAttribute(groupby_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGbSlots * 4 + 8192));
     CUDA_TRY(cudaFuncSetAttribute(groupby_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGbSlots * 4 + 8192));
-    CUDA_TRY(cudaFuncSetAttribute(groupby_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGsWarps * kGsSlots * 4));
     CUDA_TRY(cudaFuncSetAttribute(groupby_shard_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGhSlots * 4));
     guard.c = nullptr;
     *out = c;
@@ -1642,11 +1640,12 @@ static int groupby2(fbgpu_ctx* c, uint32_t index, uint32_t fvA, const uint64_t* 
         long long grid = std::min<long long>(units, (long long)c->sm_count * 4);
         static const bool gb_fast = getenv("FBGPU_GROUPBY_FAST") != nullptr;    // thread-per-row passes of the CTA kernel (kernels.cuh)
         static const bool gb_cta_only = getenv("FBGPU_GROUPBY_CTA") != nullptr; // round-1 path only: one CTA per unit
-        static const bool gb_small = getenv("FBGPU_GROUPBY_SMALL") != nullptr;   // warp-per-(shard, slot) kernel instead of the CTA-per-(shard, slot group) one
         auto cta_kernel = gb_fast ? groupby_kernel<true> : groupby_kernel<false>;
-        const int spg = (gb_cta_only || gb_small) ? 0 : groupby_slots_per_group(c, fvA, fvB, shards + s0, ns);
+        const int spg = gb_cta_only ? 0 : groupby_slots_per_group(c, fvA, fvB, shards + s0, ns);
         if (spg > 0 && units < (1ll << 31)) {
-            // one CTA per (shard, group of `spg` slots): contiguous descriptor / payload reads; declined units go to the CTA kernel
+            // one CTA per (shard, group of `spg` slots): contiguous descriptor / payload reads.  The units it declines are listed for
+            // the CTA kernel, which is launched only when the list is not empty (its launch alone costs ~60 us on B200 next to a
+            // kernel with another shared-memory carve-out: profiles/README.md) — the 4-byte count is read back first.
             if (w->d_emit_units.ensure((size_t)(units + 1) * 4)) return FBGPU_E_NOMEM;
             unsigned int* d_fb = (unsigned int*)w->d_emit_units.p;
             CUDA_TRY(cudaMemsetAsync(d_fb, 0, 4, w->stream));
@@ -1655,37 +1654,26 @@ static int groupby2(fbgpu_ctx* c, uint32_t index, uint32_t fvA, const uint64_t* 
             groupby_shard_kernel<<<(unsigned)hgrid, kGhThreads, kGhSlots * 4, w->stream>>>(store_ref(c), fvA, (const uint64_t*)w->d_rows.p, nA, fvB, (const uint64_t*)w->d_rows.p + nA, nB,
                 d_shards + s0, ns, spg, have_filter ? (const uint4*)w->d_bitmaps.p : nullptr, (unsigned long long*)w->d_counts.p, d_fb);
             CUDA_TRY(cudaGetLastError()); launches++;
-            cta_kernel<<<(unsigned)grid, kGbThreads, smem, w->stream>>>(store_ref(c), fvA, (const uint64_t*)w->d_rows.p, nA, fvB, (const uint64_t*)w->d_rows.p + nA, nB,
-                d_shards + s0, units, have_filter ? (const uint4*)w->d_bitmaps.p : nullptr, (unsigned long long*)w->d_counts.p, d_fb);
-            if (c->count_fallbacks) {
-                unsigned int n_fb = 0;
-                CUDA_TRY(cudaMemcpyAsync(&n_fb, d_fb, 4, cudaMemcpyDeviceToHost, w->stream)); CUDA_TRY(cudaStreamSynchronize(w->stream));
-                fb_units += n_fb;
+            CUDA_TRY(cudaEventRecord(w->ev1, w->stream));
+            unsigned int* h_fb = (unsigned int*)w->h_in.p;          // (pinned; upload_inputs sized it, its content is in flight no longer: the stream was synchronised above)
+            CUDA_TRY(cudaMemcpyAsync(h_fb, d_fb, 4, cudaMemcpyDeviceToHost, w->stream));
+            CUDA_TRY(cudaStreamSynchronize(w->stream));
+            const unsigned int n_fb = *h_fb;
+            if (n_fb) {
+                cta_kernel<<<(unsigned)std::min<long long>(n_fb, grid), kGbThreads, smem, w->stream>>>(store_ref(c), fvA, (const uint64_t*)w->d_rows.p, nA, fvB, (const uint64_t*)w->d_rows.p + nA, nB,
+                    d_shards + s0, units, have_filter ? (const uint4*)w->d_bitmaps.p : nullptr, (unsigned long long*)w->d_counts.p, d_fb);
+                CUDA_TRY(cudaGetLastError()); launches++;
+                CUDA_TRY(cudaEventRecord(w->ev1, w->stream));
             }
-            all_units += (uint64_t)units;
-        } else if (!gb_cta_only && units < (1ll << 31)) {
-            // warp-per-unit kernel first; the units it declines (an a-row that is not a small array) are listed for the CTA kernel
-            if (w->d_emit_units.ensure((size_t)(units + 1) * 4)) return FBGPU_E_NOMEM;
-            unsigned int* d_fb = (unsigned int*)w->d_emit_units.p;
-            CUDA_TRY(cudaMemsetAsync(d_fb, 0, 4, w->stream));
-            long long sgrid = std::min<long long>((units + kGsWarps - 1) / kGsWarps, (long long)c->sm_count * 3);
-            groupby_small_kernel<<<(unsigned)sgrid, kGsWarps * 32, kGsWarps * kGsSlots * 4, w->stream>>>(store_ref(c), fvA, (const uint64_t*)w->d_rows.p, nA, fvB, (const uint64_t*)w->d_rows.p + nA, nB,
-                d_shards + s0, units, have_filter ? (const uint4*)w->d_bitmaps.p : nullptr, (unsigned long long*)w->d_counts.p, d_fb);
+            fb_units += n_fb; all_units += (uint64_t)units;
+        } else {
+            cta_kernel<<<(unsigned)grid, kGbThreads, smem, w->stream>>>(store_ref(c), fvA, (const uint64_t*)w->d_rows.p, nA, fvB, (const uint64_t*)w->d_rows.p + nA, nB,
+                d_shards + s0, units, have_filter ? (const uint4*)w->d_bitmaps.p : nullptr, (unsigned long long*)w->d_counts.p, nullptr);
             CUDA_TRY(cudaGetLastError()); launches++;
-            cta_kernel<<<(unsigned)grid, kGbThreads, smem, w->stream>>>(store_ref(c), fvA, (const uint64_t*)w->d_rows.p, nA, fvB, (const uint64_t*)w->d_rows.p + nA, nB,
-                d_shards + s0, units, have_filter ? (const uint4*)w->d_bitmaps.p : nullptr, (unsigned long long*)w->d_counts.p, d_fb);
-            if (c->count_fallbacks) {          // FBGPU_COUNT_FALLBACKS=1 (tests, tuning): how many units the warp kernel declined; costs a stream sync per batch
-                unsigned int n_fb = 0;
-                CUDA_TRY(cudaMemcpyAsync(&n_fb, d_fb, 4, cudaMemcpyDeviceToHost, w->stream)); CUDA_TRY(cudaStreamSynchronize(w->stream));
-                fb_units += n_fb;
-            }
-            all_units += (uint64_t)units;
-        } else
-        cta_kernel<<<(unsigned)grid, kGbThreads, smem, w->stream>>>(store_ref(c), fvA, (const uint64_t*)w->d_rows.p, nA, fvB, (const uint64_t*)w->d_rows.p + nA, nB,
-            d_shards + s0, units, have_filter ? (const uint4*)w->d_bitmaps.p : nullptr, (unsigned long long*)w->d_counts.p, nullptr);
-        CUDA_TRY(cudaGetLastError()); launches++;
+            CUDA_TRY(cudaEventRecord(w->ev1, w->stream));
+        }
     }
-    CUDA_TRY(cudaEventRecord(w->ev1, w->stream));
+    if (n_shards <= 0) CUDA_TRY(cudaEventRecord(w->ev1, w->stream));
     rc = allreduce_u64(c, w, w->d_counts.p, ncnt); if (rc) return rc;
     CUDA_TRY(cudaMemcpyAsync(w->h_out.p, w->d_counts.p, ncnt * 8, cudaMemcpyDeviceToHost, w->stream));
     CUDA_TRY(cudaStreamSynchronize(w->stream));

@@ -1728,7 +1728,7 @@ groupby_kernel(StoreRef st, uint32_t fvA, const uint64_t* __restrict__ rowsA, in
     __shared__ uint32_t s_any, s_pass_end;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nwarps = kGbThreads / 32;
 
-    const long long n_work = unit_list ? (long long)unit_list[0] : n_units;     // the units groupby_small_kernel left for this kernel
+    const long long n_work = unit_list ? (long long)unit_list[0] : n_units;     // the units groupby_shard_kernel left for this kernel
     for (long long wi = blockIdx.x; wi < n_work; wi += gridDim.x) {
         const long long unit = unit_list ? (long long)unit_list[1 + wi] : wi;
         const uint64_t shard = shards[unit >> 4];
@@ -1917,159 +1917,6 @@ groupby_kernel(StoreRef st, uint32_t fvA, const uint64_t* __restrict__ rowsA, in
                 }
             }
         }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// groupby_small_kernel (round 2): the same column-keyed join, ONE WARP per (shard, slot) unit, for the shape BASELINE config 4
-// has — hundreds of rows per field whose containers hold a handful of columns each.  groupby_kernel gives such a unit a whole
-// CTA and eight barriers; its time is the sum of ~6 dependent HBM latencies per unit with 4 units in flight per SM (ncu round 1:
-// 0.042 of roofline, issue 48 %).  Here a unit costs no barrier at all, 12 units are in flight per SM, a lane walks the
-// descriptor chains of its 8 rows back to back (8 chains in flight per lane) and then their 16-byte chunks.
-//   table: kGsSlots x u32 per warp in shared memory, entry = (column << 16) | a-row index, linear probing, load <= 1/2.
-// A unit whose a-rows are not all array containers of at most kGsMaxCard columns, or hold more entries than half the table, is
-// not touched: its index goes to `fallback` and groupby_kernel processes that list afterwards (same stream).
-// ------------------------------------------------------------------------------------------------
-constexpr int kGsWarps = 4;
-constexpr int kGsSlots = 4096;           // 16 KiB per warp
-constexpr uint32_t kGsMaxCard = 64;      // longer a-rows: the CTA kernel's passes are the better shape
-constexpr int kGsRowsPerLane = 8;        // 256 rows per chunk of a field's row list
-
-__global__ void __launch_bounds__(kGsWarps * 32)
-groupby_small_kernel(StoreRef st, uint32_t fvA, const uint64_t* __restrict__ rowsA, int nA,
-                     uint32_t fvB, const uint64_t* __restrict__ rowsB, int nB,
-                     const uint64_t* __restrict__ shards, long long n_units,
-                     const uint4* __restrict__ filter_bitmaps /* per unit or null */,
-                     unsigned long long* counts /* [nA*nB] */, unsigned int* fallback /* [0] = n, then unit indices */) {
-    extern __shared__ __align__(16) uint32_t gs_smem[];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    uint32_t* tab = gs_smem + (size_t)wid * kGsSlots;
-    const long long stride = (long long)gridDim.x * kGsWarps;
-    for (long long unit = (long long)blockIdx.x * kGsWarps + wid; unit < n_units; unit += stride) {
-        const uint64_t shard = shards[unit >> 4];
-        const int slot = (int)(unit & 15);
-        {   // executor.go:8769-8772: a shard missing either fragment contributes nothing (uniform test, broadcast loads)
-            bool ok = fvA < st.n_views && fvB < st.n_views;
-            if (ok) { const ViewTab va = st.views[fvA], vb = st.views[fvB]; ok = shard < va.n_shards && shard < vb.n_shards && st.shardmap[va.shard_off + shard] >= 0 && st.shardmap[vb.shard_off + shard] >= 0; }
-            if (!ok) continue;
-        }
-        const uint32_t* flt = filter_bitmaps ? reinterpret_cast<const uint32_t*>(filter_bitmaps + (size_t)unit * 512) : nullptr;
-        // ---- pass 0 (only when the a-row list has several chunks): every a-row must fit the small path before anything is counted
-        bool small_ok = true;
-        if (nA > 32 * kGsRowsPerLane) {
-            for (int a0 = 0; a0 < nA && small_ok; a0 += 32 * kGsRowsPerLane) {
-                uint32_t tot = 0; bool bad = false;
-#pragma unroll
-                for (int j = 0; j < kGsRowsPerLane; j++) {
-                    const int i = a0 + lane + 32 * j;
-                    if (i < nA) { const Resolved r = resolve(st, fvA, shard, rowsA[i], slot); if (r.ptr) { bad |= r.typ != kArray || r.card > kGsMaxCard; tot += r.card; } }
-                }
-                tot = __reduce_add_sync(0xffffffffu, tot);
-                if (__any_sync(0xffffffffu, bad) || tot > (uint32_t)kGsSlots / 2) small_ok = false;
-            }
-        }
-        for (int a0 = 0; a0 < nA && small_ok; a0 += 32 * kGsRowsPerLane) {
-            // ---- a-rows of this chunk: 8 descriptor chains per lane, issued back to back
-            Resolved ra[kGsRowsPerLane];
-            uint32_t tot = 0; bool bad = false;
-#pragma unroll
-            for (int j = 0; j < kGsRowsPerLane; j++) {
-                const int i = a0 + lane + 32 * j;
-                ra[j].ptr = nullptr; ra[j].card = 0; ra[j].typ = 0; ra[j].cnt = 0;
-                if (i < nA) ra[j] = resolve(st, fvA, shard, rowsA[i], slot);
-                if (ra[j].ptr) { bad |= ra[j].typ != kArray || ra[j].card > kGsMaxCard; tot += ra[j].card; }
-            }
-            tot = __reduce_add_sync(0xffffffffu, tot);
-            if (__any_sync(0xffffffffu, bad) || tot > (uint32_t)kGsSlots / 2) { small_ok = false; break; }   // (single-chunk lists are tested here, before any count)
-            if (tot == 0) continue;
-            {   uint4* t4 = reinterpret_cast<uint4*>(tab);
-#pragma unroll 4
-                for (int k = lane; k < kGsSlots / 4; k += 32) t4[k] = make_uint4(kGbEmpty, kGbEmpty, kGbEmpty, kGbEmpty); }
-            __syncwarp();
-            // ---- insert: first 16-byte chunks of all 8 rows in flight, then the (rare) longer tails
-            uint4 va[kGsRowsPerLane];
-#pragma unroll
-            for (int j = 0; j < kGsRowsPerLane; j++) if (ra[j].ptr) va[j] = ldg_nc(reinterpret_cast<const uint4*>(ra[j].ptr));
-#pragma unroll
-            for (int j = 0; j < kGsRowsPerLane; j++) {
-                if (!ra[j].ptr) continue;
-                const uint32_t rowi = (uint32_t)(a0 + lane + 32 * j);
-                const uint4* p = reinterpret_cast<const uint4*>(ra[j].ptr);
-                for (uint32_t k0 = 0; k0 < ra[j].card; k0 += 8) {
-                    const uint4 v = k0 ? ldg_nc(p + (k0 >> 3)) : va[j];
-                    const uint32_t w[4] = { v.x, v.y, v.z, v.w };
-#pragma unroll
-                    for (int q = 0; q < 8; q++) {
-                        if (k0 + q >= ra[j].card) break;
-                        const uint32_t col = (w[q >> 1] >> ((q & 1) * 16)) & 0xffffu;
-                        if (flt && !((__ldg(flt + (col >> 5)) >> (col & 31)) & 1u)) continue;
-                        const uint32_t ent = (col << 16) | rowi;
-                        uint32_t h = (col * 40503u) & (kGsSlots - 1);
-                        while (atomicCAS(&tab[h], kGbEmpty, ent) != kGbEmpty) h = (h + 1) & (kGsSlots - 1);
-                    }
-                }
-            }
-            __syncwarp();
-            // ---- probe: b-rows in chunks of 256, any container type
-            for (int b0 = 0; b0 < nB; b0 += 32 * kGsRowsPerLane) {
-                Resolved rb[kGsRowsPerLane];
-#pragma unroll
-                for (int j = 0; j < kGsRowsPerLane; j++) {
-                    const int i = b0 + lane + 32 * j;
-                    rb[j].ptr = nullptr; rb[j].card = 0; rb[j].typ = 0; rb[j].cnt = 0;
-                    if (i < nB) rb[j] = resolve(st, fvB, shard, rowsB[i], slot);
-                }
-                uint4 vb[kGsRowsPerLane];
-#pragma unroll
-                for (int j = 0; j < kGsRowsPerLane; j++) if (rb[j].ptr && rb[j].typ == kArray) vb[j] = ldg_nc(reinterpret_cast<const uint4*>(rb[j].ptr));
-                bool big = false;
-#pragma unroll
-                for (int j = 0; j < kGsRowsPerLane; j++) {
-                    if (!rb[j].ptr) continue;
-                    if (rb[j].typ != kArray) { big = true; continue; }
-                    unsigned long long* cj = counts + (b0 + lane + 32 * j);
-                    const uint4* p = reinterpret_cast<const uint4*>(rb[j].ptr);
-                    for (uint32_t k0 = 0; k0 < rb[j].card; k0 += 8) {
-                        const uint4 v = k0 ? ldg_nc(p + (k0 >> 3)) : vb[j];
-                        const uint32_t w[4] = { v.x, v.y, v.z, v.w };
-#pragma unroll
-                        for (int q = 0; q < 8; q++) {
-                            if (k0 + q >= rb[j].card) break;
-                            const uint32_t col = (w[q >> 1] >> ((q & 1) * 16)) & 0xffffu;
-                            for (uint32_t h = (col * 40503u) & (kGsSlots - 1);; h = (h + 1) & (kGsSlots - 1)) {
-                                const uint32_t ent = tab[h];
-                                if (ent == kGbEmpty) break;
-                                if ((ent >> 16) == col) atomicAdd(cj + (size_t)(ent & 0xffffu) * nB, 1ull);
-                            }
-                        }
-                    }
-                }
-                // bitmap / run b-rows of the chunk: the whole warp walks each one
-                unsigned bigmask = __ballot_sync(0xffffffffu, big);
-                while (bigmask) {
-                    const int src = __ffs(bigmask) - 1; bigmask &= bigmask - 1;
-#pragma unroll
-                    for (int j = 0; j < kGsRowsPerLane; j++) {
-                        Resolved c;
-                        c.ptr = (const void*)__shfl_sync(0xffffffffu, (unsigned long long)rb[j].ptr, src);
-                        c.card = __shfl_sync(0xffffffffu, rb[j].card, src);
-                        const uint32_t meta = __shfl_sync(0xffffffffu, ((uint32_t)rb[j].typ << 16) | rb[j].cnt, src);
-                        c.typ = meta >> 16; c.cnt = meta & 0xffff;
-                        if (!c.ptr || c.typ == kArray) continue;
-                        const int jj = b0 + src + 32 * j;
-                        warp_for_each(c, lane, [&](uint32_t col) {
-                            for (uint32_t h = (col * 40503u) & (kGsSlots - 1);; h = (h + 1) & (kGsSlots - 1)) {
-                                const uint32_t ent = tab[h];
-                                if (ent == kGbEmpty) break;
-                                if ((ent >> 16) == col) atomicAdd(&counts[(size_t)(ent & 0xffffu) * nB + jj], 1ull);
-                            }
-                        });
-                    }
-                }
-            }
-            __syncwarp();
-        }
-        if (!small_ok && lane == 0) { const unsigned int k = atomicAdd(&fallback[0], 1u); fallback[1 + k] = (unsigned int)unit; }
     }
 }
 

@@ -477,12 +477,11 @@ def test_groupby_kernel_pass_shapes():
         assert int(exp.sum()) > 3000
 
 
-def test_groupby_slot_groups(monkeypatch):
+def test_groupby_slot_groups():
     """groupby_shard_kernel with several slots per CTA (denser fields -> 4 slots per group instead of 16), one group whose columns
     overflow the shared-memory table (declined before anything is counted -> groupby_kernel takes its four (shard, slot) units), a
     row subset, and a filter: the dense count tensor against the oracle's nested loop, and the fallback counter says what ran where"""
     from oracle import oracle as O
-    monkeypatch.setenv("FBGPU_COUNT_FALLBACKS", "1")
     SW = 1 << 20
     rng = np.random.default_rng(11)
     p = Pair(track_existence=False)
@@ -512,7 +511,7 @@ def test_groupby_slot_groups(monkeypatch):
         assert np.array_equal(np.asarray(got).reshape(-1), exp), filt
         assert int(exp.sum()) > 20000
         after = p.holder.ctx.counters()
-        if "groupby_fallback_units" in after and not os.environ.get("FBGPU_GROUPBY_CTA") and not os.environ.get("FBGPU_GROUPBY_SMALL"):
+        if "groupby_fallback_units" in after and not os.environ.get("FBGPU_GROUPBY_CTA"):
             assert after["groupby_units"] - before["groupby_units"] == 32
             assert after["groupby_fallback_units"] - before["groupby_fallback_units"] == 4, (filt, before, after)   # (the crowded group of shard 1; decided on cardinalities, before the filter)
 
