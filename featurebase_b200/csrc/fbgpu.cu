@@ -179,6 +179,7 @@ struct fbgpu_ctx {
     // points: 16384 units = 1024 shards = 128 MiB of workspace per lease.  FBGPU_UNIT_BATCH (a multiple of 16, fixed per
     // context) trades workspace for launches; the tests set it small to walk the multi-batch paths with a handful of shards.
     long long unit_batch = [] { const char* e = getenv("FBGPU_UNIT_BATCH"); const long long n = e ? atoll(e) : 0; return n >= 16 ? (n / 16) * 16 : 16384ll; }();
+    int pair_ctas_per_sm = 2;             // resident CTAs of pair_count_kernel per SM (occupancy query at init)
     std::atomic<uint64_t> counters_pair_launches{0};      // Count(Intersect(Row, Row)) queries that took the fused pair kernel
     DevBuf d_payload, d_views, d_shardmap, d_frags, d_rows, d_descs, d_rowtab;
     PinBuf bounce[2];
@@ -229,12 +230,13 @@ extern "C" int fbgpu_init(int32_t device_ordinal, fbgpu_ctx** out) try {
     // opt in to large dynamic shared memory once
     CUDA_TRY(cudaFuncSetAttribute(eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 17 * 8192));
     CUDA_TRY(cudaFuncSetAttribute(eval_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 233472 / 2 - 1024 - 5888));
-    CUDA_TRY(cudaFuncSetAttribute(pair_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPcWarps * kPcWarpBytes));
+    CUDA_TRY(cudaFuncSetAttribute(pair_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPcTeams * 8192));
     CUDA_TRY(cudaFuncSetAttribute(row_count_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairWarps * 8192));
     CUDA_TRY(cudaFuncSetAttribute(row_count_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairWarps * 8192));
     CUDA_TRY(cudaFuncSetAttribute(groupby_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGbSlots * 4 + 8192));
     CUDA_TRY(cudaFuncSetAttribute(groupby_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGbSlots * 4 + 8192));
     CUDA_TRY(cudaFuncSetAttribute(groupby_shard_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGhSlots * 4));
+    { int nb = 0; if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, pair_count_kernel, kPcTeams * 64, kPcTeams * 8192) == cudaSuccess && nb > 0) c->pair_ctas_per_sm = nb; }
     guard.c = nullptr;
     *out = c;
     return FBGPU_OK;
@@ -1063,9 +1065,9 @@ static int count_impl(fbgpu_ctx* c, uint32_t index, const fbgpu_op* ops, int32_t
         if (prog.size() == 2 && prog[0].op == D_PUSH_ROW && prog[1].op == D_AND_ROW) { pa = &prog[0]; pb = &prog[1]; }
         else if (prog.size() == 3 && prog[0].op == D_PUSH_EMPTY && prog[1].op == D_OR_ROW && prog[2].op == D_AND_ROW) { pa = &prog[1]; pb = &prog[2]; }
         if (pa && !getenv("FBGPU_NO_PAIR_KERNEL")) {
-            long long grid = std::min<long long>((n_units + kPcWarps - 1) / kPcWarps, (long long)c->sm_count);
+            long long grid = std::min<long long>((n_units + kPcTeams - 1) / kPcTeams, (long long)c->sm_count * c->pair_ctas_per_sm);
             c->counters_pair_launches++;
-            pair_count_kernel<<<(unsigned)grid, kPcWarps * 32, kPcWarps * kPcWarpBytes, w->stream>>>(store_ref(c), pa->fv, pa->row, pb->fv, pb->row, nullptr, nullptr, n_units,
+            pair_count_kernel<<<(unsigned)grid, kPcTeams * 64, kPcTeams * 8192, w->stream>>>(store_ref(c), pa->fv, pa->row, pb->fv, pb->row, nullptr, nullptr, n_units,
                 contiguous_shards(shards, n_shards) ? nullptr : d_shards, n_shards ? shards[0] : 0, n_units, d_total, d_per, nullptr, fr);
             CUDA_TRY(cudaGetLastError());
         } else {
@@ -1534,8 +1536,8 @@ extern "C" int fbgpu_count_pairs(fbgpu_ctx* c, uint32_t index, uint32_t field_a,
     const long long upp = (long long)n_shards * kSlotsPerRow, n_units = upp * n_pairs;
     CUDA_TRY(cudaEventRecord(w->ev0, w->stream));
     if (n_units > 0) {
-        long long grid = std::min<long long>((n_units + kPcWarps - 1) / kPcWarps, (long long)c->sm_count);
-        pair_count_kernel<<<(unsigned)grid, kPcWarps * 32, kPcWarps * kPcWarpBytes, w->stream>>>(store_ref(c), fa, 0, fb, 0, (const uint64_t*)w->d_rows.p, (const uint64_t*)w->d_rows.p + np,
+        long long grid = std::min<long long>((n_units + kPcTeams - 1) / kPcTeams, (long long)c->sm_count * c->pair_ctas_per_sm);
+        pair_count_kernel<<<(unsigned)grid, kPcTeams * 64, kPcTeams * 8192, w->stream>>>(store_ref(c), fa, 0, fb, 0, (const uint64_t*)w->d_rows.p, (const uint64_t*)w->d_rows.p + np,
             upp, contiguous_shards(shards, n_shards) ? nullptr : d_shards, n_shards ? shards[0] : 0, n_units, nullptr, nullptr, (unsigned long long*)w->d_counts.p, FuseReduce{});
         CUDA_TRY(cudaGetLastError());
     }

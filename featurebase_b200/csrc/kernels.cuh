@@ -1087,127 +1087,128 @@ __device__ __noinline__ uint32_t warp_icount_runs(Resolved a, Resolved b, int la
 // shared-memory store of a zero word / probe of one bit at an absolute shared address
 __device__ __forceinline__ void sts_zero(uint32_t addr) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(addr), "r"(0u) : "memory"); }
 __device__ __forceinline__ void red_or_at(uint32_t addr, uint32_t m) { asm volatile("red.shared.or.b32 [%0], %1;" :: "r"(addr), "r"(m) : "memory"); }
+__device__ __forceinline__ uint2 ldg_nc64(const uint2* p) {
+    uint2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
+}
+// barrier of one two-warp team (named barrier `id`, 64 threads)
+__device__ __forceinline__ void team_barrier(int id) { __syncwarp(); asm volatile("bar.sync %0, 64;" :: "r"(id) : "memory"); }
 
-// returns the full count (reduced over the warp, valid in all lanes).  `bm` is the warp's private 8 KiB bitmap and is ALL ZERO on
-// entry and on exit (the kernel clears it once per warp): no path below pays an 8 KiB wipe per pair.
-// `sa` / `sb_` : when not null, the first 96 chunks of a / b already sit in shared memory (cp.async staging of pair_count_kernel), lane L's
-// chunks at [L + 32 q]; the array x array path then reads them from there instead of from global memory.
-__device__ __forceinline__ uint32_t warp_intersection_count(Resolved a, Resolved b, uint32_t* bm, int lane, const uint4* sa = nullptr, const uint4* sb_ = nullptr) {
+constexpr int kPairWarps = 8;           // row_count_kernel
+#ifndef FBGPU_PAIR_TEAMS
+#define FBGPU_PAIR_TEAMS 8
+#endif
+#ifndef FBGPU_PAIR_MIN_BLOCKS
+#define FBGPU_PAIR_MIN_BLOCKS 2
+#endif
+constexpr int kPcTeams = FBGPU_PAIR_TEAMS;                  // two-warp teams per CTA of pair_count_kernel, one 8 KiB bitmap each
+
+// Intersection count of two located containers by a TEAM of two warps sharing one 8 KiB shared-memory bitmap (`bm`, all zero on entry
+// and on exit).  Follows the dispatch of intersectionCount (roaring.go:4477-4512) incl. the full/empty short-circuits.  Returns this
+// WARP's share of the count (reduced over the warp, valid in all lanes); the team's count is the sum of both warps' values.
+// array x array (roaring.go:4514): both warps visit the same 16-byte chunks lane L <-> chunks L, L+32, L+64 — warp `half` takes the
+// half-th 8 bytes (4 elements) of each, so that one instruction still touches exactly the elements of one bank-striped group (stripe.h):
+// scatter the smaller array, team barrier, probe with the larger, team barrier, store zeros over the words this warp set, team barrier.
+// Why two warps per bitmap: the path is bound by how many warps an SM holds (ncu round 2: 24 one-warp-per-bitmap warps issue 47 % of the
+// cycles, 16 with their payloads already staged in shared memory issue 50 %, the ALU pipe 38-47 % busy) and 8 KiB per warp caps that at
+// 24-27; halving the bitmap per warp doubles the resident warps at the same per-element work.
+__device__ __forceinline__ uint32_t team_intersection_count(Resolved a, Resolved b, uint32_t* bm, int lane, int half, int bar_id) {
     if (a.ptr == nullptr || b.ptr == nullptr) return 0;
-    if (a.card == kFull) return b.card;                       // roaring.go:4478-4483
-    if (b.card == kFull) return a.card;
+    if (a.card == kFull) return half ? 0u : b.card;           // roaring.go:4478-4483
+    if (b.card == kFull) return half ? 0u : a.card;
     // order so that arrays come first
     if (a.typ != kArray && b.typ == kArray) { Resolved t = a; a = b; b = t; }
     uint32_t c = 0;
-    if (a.typ == kRun || b.typ == kRun) c = warp_icount_runs(a, b, lane);
+    if (a.typ == kRun || b.typ == kRun) { if (half == 0) c = warp_icount_runs(a, b, lane); }
     else if (a.typ == kArray && b.typ == kArray) {            // array x array: build the smaller, probe the larger
-        if (a.card > b.card) { Resolved t = a; a = b; b = t; const uint4* ts = sa; sa = sb_; sb_ = ts; }
-        // Round-2 shape (bench_micro/pair_variants.cu w9, profiles/README.md): all chunks of both arrays (up to 768 elements each) are
-        // loaded before any shared-memory work; the shared addresses computed for the scatter of `a` STAY IN REGISTERS, and after the
-        // probe the same words are set back to zero with plain stores — no 8 KiB wipe (64 shared-memory wavefronts per pair) and no
-        // second round of address arithmetic (the ALU pipe is the co-limiter of this path: IADD3/LOP3/SHF issue every 2nd cycle).
-        const uint4* a4 = reinterpret_cast<const uint4*>(a.ptr); const uint4* b4 = reinterpret_cast<const uint4*>(b.ptr);
+        if (a.card > b.card) { Resolved t = a; a = b; b = t; }
+        const uint2* a2 = reinterpret_cast<const uint2*>(a.ptr) + half; const uint2* b2 = reinterpret_cast<const uint2*>(b.ptr) + half;
         const uint32_t na8 = (a.card + 7) >> 3, nb8 = (b.card + 7) >> 3;
-        const uint32_t sb32 = (uint32_t)__cvta_generic_to_shared(bm);
-        smem_base_t sb = smem_base(sb32);
+        smem_base_t sb = smem_base((uint32_t)__cvta_generic_to_shared(bm));
         pin_base(sb);
-        uint4 va[3], vb[3];
-        if (sa != nullptr) {                    // staged (warp-uniform): slots past the array's last chunk hold stale bytes, never used below
+        uint2 va[3], vb[3];
 #pragma unroll
-            for (int q = 0; q < 3; q++) { va[q] = sa[lane + 32 * q]; vb[q] = sb_[lane + 32 * q]; }
-        } else {
+        for (int q = 0; q < 3; q++) va[q] = ldg_nc64(a2 + 2u * min((uint32_t)lane + 32u * q, na8 - 1u));     // clamped, unconditional: no undefined register
 #pragma unroll
-            for (int q = 0; q < 3; q++) va[q] = ldg_nc(a4 + min((uint32_t)lane + 32u * q, na8 - 1u));     // clamped, unconditional: no undefined register
-#pragma unroll
-            for (int q = 0; q < 3; q++) vb[q] = ldg_nc(b4 + min((uint32_t)lane + 32u * q, nb8 - 1u));
-        }
-        uint32_t addr[3][8];
+        for (int q = 0; q < 3; q++) vb[q] = ldg_nc64(b2 + 2u * min((uint32_t)lane + 32u * q, nb8 - 1u));
+        // every chunk of `b` is probed whole: the slots behind its last element hold copies of that element (pad_array_tail), which
+        // are taken out of the count again below — no divergent partial-chunk path
+        const uint32_t pads = nb8 * 8u - b.card;              // 0..7 (team-uniform)
+        uint32_t last = 0;
+        if (pads && half == 0) last = __ldg(reinterpret_cast<const uint16_t*>(b.ptr) + b.card - 1);
+        uint32_t addr[3][4];
 #pragma unroll
         for (int q = 0; q < 3; q++) {
-            const uint32_t x[4] = { va[q].x, va[q].y, va[q].z, va[q].w };
-#pragma unroll
-            for (int k = 0; k < 4; k++) { addr[q][2 * k] = word_addr_lo(sb, x[k]); addr[q][2 * k + 1] = word_addr_hi(sb, x[k]); }
+            addr[q][0] = word_addr_lo(sb, va[q].x); addr[q][1] = word_addr_hi(sb, va[q].x);
+            addr[q][2] = word_addr_lo(sb, va[q].y); addr[q][3] = word_addr_hi(sb, va[q].y);
             if (lane + 32 * q < na8) {          // (array tails are padded with copies of the last element: setting a bit twice is harmless)
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    red_or_at(addr[q][2 * k], 1u << (x[k] & 31));
-                    red_or_at(addr[q][2 * k + 1], 1u << (upper16(x[k]) & 31));
-                }
+                red_or_at(addr[q][0], 1u << (va[q].x & 31)); red_or_at(addr[q][1], 1u << (upper16(va[q].x) & 31));
+                red_or_at(addr[q][2], 1u << (va[q].y & 31)); red_or_at(addr[q][3], 1u << (upper16(va[q].y) & 31));
             }
         }
-        for (uint32_t i = lane + 96; i < na8; i += 32) scatter_chunk_unrolled<0>(bm, ldg_nc(a4 + i), i * 8, a.card);      // > 768 elements: rare
-        __syncwarp();
-        // every chunk of `b` is probed whole: the slots behind its last element hold copies of that element (pad_array_tail), and
-        // the copies are taken out of the count below.  (The guarded partial-chunk path made the warp run ~100 extra instructions
-        // for the ONE lane holding the tail — a third of the pair's instruction count.)
-#pragma unroll
-        for (int q = 0; q < 3; q++) if (lane + 32 * q < nb8) c += probe_chunk_full(sb, vb[q]);
-        for (uint32_t i = lane + 96; i < nb8; i += 32) c += probe_chunk_full(sb, ldg_nc(b4 + i));
-        const uint32_t pads = nb8 * 8u - b.card;                      // 0..7 copies of b's last element were probed too (warp-uniform)
-        if (pads) {
-            const uint32_t ql = (nb8 - 1u) >> 5;                       // the chunk holding them: register window slot ql of lane (nb8-1) & 31
-            uint32_t wl = ql == 0 ? vb[0].w : ql == 1 ? vb[1].w : vb[2].w;
-            wl = __shfl_sync(0xffffffffu, wl, (int)((nb8 - 1u) & 31u)) >> 16;
-            if (ql > 2) wl = __ldg(reinterpret_cast<const uint16_t*>(b.ptr) + b.card - 1);
-            if (lane == 0) c -= pads * ((bm[wl >> 5] >> (wl & 31)) & 1u);
+        for (uint32_t i = lane + 96; i < na8; i += 32) {      // > 768 elements: rare
+            const uint2 v = ldg_nc64(a2 + 2u * i);
+            red_or_at(word_addr_lo(sb, v.x), 1u << (v.x & 31)); red_or_at(word_addr_hi(sb, v.x), 1u << (upper16(v.x) & 31));
+            red_or_at(word_addr_lo(sb, v.y), 1u << (v.y & 31)); red_or_at(word_addr_hi(sb, v.y), 1u << (upper16(v.y) & 31));
         }
-        __syncwarp();
+        team_barrier(bar_id);
+        auto probe2 = [&](uint2 v) {
+            return ((lds_u32(word_addr_lo(sb, v.x)) >> (v.x & 31)) & 1u) + ((lds_u32(word_addr_hi(sb, v.x)) >> (upper16(v.x) & 31)) & 1u)
+                 + ((lds_u32(word_addr_lo(sb, v.y)) >> (v.y & 31)) & 1u) + ((lds_u32(word_addr_hi(sb, v.y)) >> (upper16(v.y) & 31)) & 1u);
+        };
 #pragma unroll
-        for (int q = 0; q < 3; q++) if (lane + 32 * q < na8) {
+        for (int q = 0; q < 3; q++) if (lane + 32 * q < nb8) c += probe2(vb[q]);
+        for (uint32_t i = lane + 96; i < nb8; i += 32) c += probe2(ldg_nc64(b2 + 2u * i));
+        if (pads && half == 0 && lane == 0) c -= pads * ((bm[last >> 5] >> (last & 31)) & 1u);
+        team_barrier(bar_id);
 #pragma unroll
-            for (int k = 0; k < 8; k++) sts_zero(addr[q][k]);
-        }
+        for (int q = 0; q < 3; q++) if (lane + 32 * q < na8) { sts_zero(addr[q][0]); sts_zero(addr[q][1]); sts_zero(addr[q][2]); sts_zero(addr[q][3]); }
         for (uint32_t i = lane + 96; i < na8; i += 32) {     // the words of the chunks past the register window: addresses recomputed
-            const uint4 v = ldg_nc(a4 + i); const uint32_t x[4] = { v.x, v.y, v.z, v.w };
-#pragma unroll
-            for (int k = 0; k < 4; k++) { sts_zero(word_addr_lo(sb, x[k])); sts_zero(word_addr_hi(sb, x[k])); }
+            const uint2 v = ldg_nc64(a2 + 2u * i);
+            sts_zero(word_addr_lo(sb, v.x)); sts_zero(word_addr_hi(sb, v.x)); sts_zero(word_addr_lo(sb, v.y)); sts_zero(word_addr_hi(sb, v.y));
         }
-        __syncwarp();
-    } else if (a.typ == kArray) {                             // array x bitmap: roaring.go:4596
-        c = warp_probe_global(reinterpret_cast<const uint32_t*>(b.ptr), reinterpret_cast<const uint16_t*>(a.ptr), a.card, lane);
-    } else {                                                  // bitmap x bitmap: roaring.go:4611
+        team_barrier(bar_id);
+    } else if (a.typ == kArray) {                             // array x bitmap: roaring.go:4596 — the warps take alternate chunks
+        const uint32_t* g = reinterpret_cast<const uint32_t*>(b.ptr);
+        const uint4* a4 = reinterpret_cast<const uint4*>(a.ptr);
+        const uint32_t n8 = (a.card + 7) >> 3;
+        for (uint32_t i = lane + 32u * half; i < n8; i += 64) {
+            const uint4 v = ldg_nc(a4 + i);
+            const uint32_t e[8] = { v.x & 0xffffu, v.x >> 16, v.y & 0xffffu, v.y >> 16, v.z & 0xffffu, v.z >> 16, v.w & 0xffffu, v.w >> 16 };
+            uint32_t w[8];
+#pragma unroll
+            for (int q = 0; q < 8; q++) w[q] = (i * 8 + q < a.card) ? __ldg(g + (e[q] >> 5)) : 0u;
+#pragma unroll
+            for (int q = 0; q < 8; q++) c += (w[q] >> (e[q] & 31)) & 1u;
+        }
+    } else {                                                  // bitmap x bitmap: roaring.go:4611 — each warp one half of the words
         const uint4* x = reinterpret_cast<const uint4*>(a.ptr); const uint4* y = reinterpret_cast<const uint4*>(b.ptr);
 #pragma unroll 8
-        for (int i = lane; i < 512; i += 32) c += popc4(and4(ldg_nc(x + i), ldg_nc(y + i)));
+        for (int i = lane + 32 * half; i < 512; i += 64) c += popc4(and4(ldg_nc(x + i), ldg_nc(y + i)));
     }
     return __reduce_add_sync(0xffffffffu, c);
 }
 
-constexpr int kPairWarps = 8;           // row_count_kernel
-#ifndef FBGPU_PAIR_WARPS
-#define FBGPU_PAIR_WARPS 13
-#endif
-#ifndef FBGPU_PAIR_BUFS
-#define FBGPU_PAIR_BUFS 3
-#endif
-constexpr int kPcWarps = FBGPU_PAIR_WARPS;                  // warps of a pair_count_kernel CTA (one CTA per SM)
-constexpr int kPcBufs = FBGPU_PAIR_BUFS;                    // staging buffers per warp: kPcBufs - 1 container pairs in flight behind the one being intersected
-constexpr int kPcStageChunks = 96;                          // 16-byte chunks per side and buffer: arrays of up to 768 elements are staged
-constexpr int kPcWarpBytes = 8192 + kPcBufs * 2 * kPcStageChunks * 16;
-static_assert(kPcWarps * kPcWarpBytes <= 232448, "pair_count_kernel: shared memory per CTA");
-
-// Count(Intersect(Row(fvA,rowA), Row(fvB,rowB))): one warp per (shard, slot) container pair.  A warp owns the units
-// w, w+W, w+2W, ...; it walks the descriptor chains of up to 16 of its units at once (lane 2k / 2k+1 = side a / b of unit k).
-// Round 2: the array payloads of the next kPcBufs - 1 units are copied into the warp's shared-memory staging buffers by cp.async
-// while the current unit is intersected — the bytes in flight per SM no longer depend on registers or on how many warps are between
-// their load and their compute phase (ncu round 2: 24 resident warps x 3 KB each only during their wait could not cover the loaded
-// HBM latency; the kernel ran at 0.42 of the roofline with the ALU pipe 38 % busy).  One CTA of kPcWarps warps per SM; per warp an
-// 8 KiB bitmap + kPcBufs x 3 KiB of staging.  Lane L copies and later reads the chunks L, L+32, L+64 of either side itself, so the
-// staged data needs no cross-lane synchronisation.  Operands that are not two arrays of at most 768 elements are read directly.
-__global__ void __launch_bounds__(kPcWarps * 32, 1)
+// Count(Intersect(Row(fvA,rowA), Row(fvB,rowB))): one two-warp TEAM per (shard, slot) container pair.  A team owns the units
+// t, t+T, t+2T, ...; both of its warps walk the descriptor chains of up to 16 of the team's units at once (lane 2k / 2k+1 = side a / b
+// of unit k; the second warp's loads hit the lines the first one pulled in), then intersect them one after the other.
+__global__ void __launch_bounds__(kPcTeams * 64, FBGPU_PAIR_MIN_BLOCKS)
 pair_count_kernel(StoreRef st, uint32_t fvA, uint64_t rowA, uint32_t fvB, uint64_t rowB,
                   const uint64_t* __restrict__ rowsA, const uint64_t* __restrict__ rowsB, long long units_per_pair,
                   const uint64_t* __restrict__ shards, uint64_t shard0, long long n_units,
                   unsigned long long* total, unsigned long long* per_shard, unsigned long long* per_pair, FuseReduce fr) {
     extern __shared__ __align__(128) uint32_t smem32[];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    uint32_t* bm = smem32 + (size_t)wid * (kPcWarpBytes / 4);
-    uint4* stage = reinterpret_cast<uint4*>(bm + 2048);       // [kPcBufs][2][kPcStageChunks]
-    warp_zero(bm, lane); __syncwarp();          // the only full clear: warp_intersection_count leaves the bitmap all-zero again
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, team = wid >> 1, half = wid & 1, bar_id = 1 + team;
+    uint32_t* bm = smem32 + team * 2048;
+    {   uint4* b4 = reinterpret_cast<uint4*>(bm);          // the only full clear: team_intersection_count leaves the bitmap all-zero again
+#pragma unroll 4
+        for (int i = lane + 32 * half; i < 512; i += 64) b4[i] = make_uint4(0, 0, 0, 0); }
+    team_barrier(bar_id);
     unsigned long long acc = 0;
-    const long long stride = (long long)gridDim.x * kPcWarps;
-    for (long long base = (long long)blockIdx.x * kPcWarps + wid; base < n_units; base += stride * 16) {
-        // resolve up to 16 units of this warp concurrently
+    const long long stride = (long long)gridDim.x * kPcTeams;
+    for (long long base = (long long)blockIdx.x * kPcTeams + team; base < n_units; base += stride * 16) {
+        // resolve up to 16 units of this team concurrently
         // multi-pair form (rowsA != null): unit = pair * units_per_pair + (shard index * 16 + slot)
         const long long my_unit = base + (long long)(lane >> 1) * stride;
         Resolved r; r.ptr = nullptr; r.card = 0; r.typ = 0; r.cnt = 0;
@@ -1227,47 +1228,19 @@ pair_count_kernel(StoreRef st, uint32_t fvA, uint64_t rowA, uint32_t fvB, uint64
             x.typ = m >> 16; x.cnt = m & 0xffff;
             return x;
         };
-        auto stageable = [](const Resolved& x, const Resolved& y) {
-            return x.ptr != nullptr && y.ptr != nullptr && x.typ == kArray && y.typ == kArray && x.card <= kPcStageChunks * 8u && y.card <= kPcStageChunks * 8u;
-        };
-        // unit j of this round -> staging buffer j % kPcBufs; always one commit group per unit, so that `wait_group kPcBufs - 1` in
-        // iteration k means "the copies of unit k have landed"
-        auto stage_unit = [&](int j) {
-            if (j < 16 && base + (long long)j * stride < n_units) {
-                const Resolved pa = fetch(2 * j), pb = fetch(2 * j + 1);
-                if (stageable(pa, pb)) {
-                    uint4* dst = stage + (size_t)(j % kPcBufs) * 2 * kPcStageChunks;
-                    const uint4* ga = reinterpret_cast<const uint4*>(pa.ptr); const uint4* gb = reinterpret_cast<const uint4*>(pb.ptr);
-                    const uint32_t na8 = (pa.card + 7) >> 3, nb8 = (pb.card + 7) >> 3;
-#pragma unroll
-                    for (int q = 0; q < 3; q++) {
-                        if (lane + 32 * q < na8) cp_async_16(dst + lane + 32 * q, ga + lane + 32 * q);
-                        if (lane + 32 * q < nb8) cp_async_16(dst + kPcStageChunks + lane + 32 * q, gb + lane + 32 * q);
-                    }
-                }
-            }
-            cp_async_commit();
-        };
-        for (int j = 0; j < kPcBufs - 1; j++) stage_unit(j);
         for (int k = 0; k < 16; k++) {
             const long long unit = base + (long long)k * stride;
             if (unit >= n_units) break;
-            stage_unit(k + kPcBufs - 1);                      // into the buffer unit k - 1 was read from
-            cp_async_wait_group<kPcBufs - 1>();
             const Resolved a = fetch(2 * k), b = fetch(2 * k + 1);
-            const bool st_ok = stageable(a, b);
-            const uint4* sbuf = stage + (size_t)(k % kPcBufs) * 2 * kPcStageChunks;
-            uint32_t c = warp_intersection_count(a, b, bm, lane, st_ok ? sbuf : nullptr, st_ok ? sbuf + kPcStageChunks : nullptr);
+            const uint32_t c = team_intersection_count(a, b, bm, lane, half, bar_id);
             acc += c;
             if (c && lane == 0) {
                 if (per_pair) atomicAdd(&per_pair[unit / units_per_pair], (unsigned long long)c);
                 else if (per_shard) atomicAdd(&per_shard[unit >> 4], (unsigned long long)c);
             }
         }
-        cp_async_wait_group<0>();
-        __syncwarp();
     }
-    if (lane == 0 && total) { if (acc) atomicAdd(total, acc); fused_allreduce_tail(fr, total, gridDim.x * kPcWarps); }
+    if (lane == 0 && total) { if (acc) atomicAdd(total, acc); fused_allreduce_tail(fr, total, gridDim.x * kPcTeams * 2); }
 }
 
 // Container-pair-type histogram of a Count(Intersect(Row, Row)) query: hist[4 * ta + tb] += 1 per (shard, slot) unit, t = 0 absent,
