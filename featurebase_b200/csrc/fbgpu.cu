@@ -235,7 +235,7 @@ extern "C" int fbgpu_init(int32_t device_ordinal, fbgpu_ctx** out) try {
     CUDA_TRY(cudaFuncSetAttribute(row_count_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairWarps * 8192));
     CUDA_TRY(cudaFuncSetAttribute(groupby_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGbSlots * 4 + 8192));
     CUDA_TRY(cudaFuncSetAttribute(groupby_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGbSlots * 4 + 8192));
-    CUDA_TRY(cudaFuncSetAttribute(groupby_shard_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGhSlots * 4));
+    CUDA_TRY(cudaFuncSetAttribute(groupby_shard_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGhSmemBytes));
     { int nb = 0; if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, pair_count_kernel, kPcTeams * 64, kPcTeams * 8192) == cudaSuccess && nb > 0) c->pair_ctas_per_sm = nb; }
     guard.c = nullptr;
     *out = c;
@@ -1653,7 +1653,7 @@ static int groupby2(fbgpu_ctx* c, uint32_t index, uint32_t fvA, const uint64_t* 
             CUDA_TRY(cudaMemsetAsync(d_fb, 0, 4, w->stream));
             const long long hunits = ns * (kSlotsPerRow / spg);
             const long long hgrid = std::min<long long>(hunits, (long long)c->sm_count);
-            groupby_shard_kernel<<<(unsigned)hgrid, kGhThreads, kGhSlots * 4, w->stream>>>(store_ref(c), fvA, (const uint64_t*)w->d_rows.p, nA, fvB, (const uint64_t*)w->d_rows.p + nA, nB,
+            groupby_shard_kernel<<<(unsigned)hgrid, kGhThreads, kGhSmemBytes, w->stream>>>(store_ref(c), fvA, (const uint64_t*)w->d_rows.p, nA, fvB, (const uint64_t*)w->d_rows.p + nA, nB,
                 d_shards + s0, ns, spg, have_filter ? (const uint4*)w->d_bitmaps.p : nullptr, (unsigned long long*)w->d_counts.p, d_fb);
             CUDA_TRY(cudaGetLastError()); launches++;
             CUDA_TRY(cudaEventRecord(w->ev1, w->stream));

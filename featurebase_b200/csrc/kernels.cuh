@@ -734,7 +734,16 @@ eval_staged_kernel(StoreRef st, const DevOp* __restrict__ prog, int n_ops, int d
 // handled by a per-thread search for the slice's elements, so any program is valid here; the host only picks this
 // kernel when the referenced views are dominated by bitmap/run containers.
 // ------------------------------------------------------------------------------------------------
+// FBGPU_WP_WIDE (default, with the cp.async operand ring): a thread owns 32 bytes (two adjacent 128-bit slices) instead of 16, in CTAs
+// of 64 threads — the same 2 KiB per CTA and row op, but the program loop's per-op overhead (ring bookkeeping, op decode, branches:
+// ~32 of the ~36 instructions per op and thread; the kernel issued 43 % of its cycles with DRAM 30 % busy) is paid once per 32 bytes.
+#if !defined(FBGPU_WP_LEGACY_LOOP) && !defined(FBGPU_WP_REG_RING) && !defined(FBGPU_WP_NARROW)
+#define FBGPU_WP_WIDE 1
+constexpr int kWpThreads = 64;
+#else
 constexpr int kWpThreads = 128;              // 512 / (128 * slices-per-thread) CTAs per unit
+#endif
+struct __align__(16) WpV32 { unsigned long long x, y, z, w; };      // 32 bytes of a stripe; member-wise bit ops (wp_machine.h)
 constexpr int kWpMaxOps = 256;
 constexpr int kWpMaxDepth = 4;
 
@@ -775,7 +784,11 @@ __device__ __forceinline__ uint4 wp_slice(const Resolved& r, int i) {
 #define FBGPU_WP_MIN_BLOCKS 8
 #endif
 constexpr int kWpSlices = FBGPU_WP_SLICES;       // uint4 slices per thread (slice q of a thread: i0 + q * kWpThreads => coalesced)
+#if defined(FBGPU_WP_WIDE)
+constexpr int kWpBlocksPerUnit = 512 / (kWpThreads * 2);
+#else
 constexpr int kWpBlocksPerUnit = 512 / (kWpThreads * kWpSlices);
+#endif
 
 struct WpOp { const void* ptr; uint32_t card; uint16_t typ, cnt; uint8_t opc, is_row, pad[6]; };   // pre-decoded op, 24 B
 
@@ -796,14 +809,20 @@ eval_wordpar_kernel(StoreRef st, const DevOp* __restrict__ prog, int n_ops,
     __shared__ uint16_t rowops[kWpMaxOps];     // indices of the row ops, in program order
     __shared__ int n_rowops;
     __shared__ uint32_t wsum[kWpThreads / 32];
-#if !defined(FBGPU_WP_LEGACY_LOOP) && FBGPU_WP_SLICES == 1 && !defined(FBGPU_WP_REG_RING)
+#if defined(FBGPU_WP_WIDE)
+    __shared__ __align__(16) WpV32 wp_ring[kWpAsyncDepth][kWpThreads];
+#elif !defined(FBGPU_WP_LEGACY_LOOP) && FBGPU_WP_SLICES == 1 && !defined(FBGPU_WP_REG_RING)
     __shared__ __align__(16) uint4 wp_ring[kWpAsyncDepth][kWpThreads];
 #endif
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const long long n_blocks = n_units * kWpBlocksPerUnit;
     for (long long blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
         const long long unit = blk / kWpBlocksPerUnit;
+#if defined(FBGPU_WP_WIDE)
+        const int i0 = (int)(blk % kWpBlocksPerUnit) * kWpThreads * 2 + 2 * tid;       // the thread's two adjacent uint4 slices: i0, i0 + 1
+#else
         const int i0 = (int)(blk % kWpBlocksPerUnit) * kWpThreads * kWpSlices + tid;
+#endif
         __syncthreads();
         for (int k = tid; k < n_ops; k += kWpThreads) {        // decode + resolve: one op per thread
             DevOp op = prog[k];
@@ -839,7 +858,30 @@ eval_wordpar_kernel(StoreRef st, const DevOp* __restrict__ prog, int n_ops,
             }
         };
         const uint4 z = make_uint4(0, 0, 0, 0);
-#if !defined(FBGPU_WP_LEGACY_LOOP) && FBGPU_WP_SLICES == 1 && !defined(FBGPU_WP_REG_RING)
+#if defined(FBGPU_WP_WIDE)
+        // Operand ring in shared memory, filled by cp.async (see the 16-byte form below); 32 bytes per thread and row op
+        auto issue = [&](int ri) {
+            if (ri < nr) {
+                const WpOp w = ops[rowops[ri]];
+                uint4* slot = reinterpret_cast<uint4*>(&wp_ring[ri % kWpAsyncDepth][tid]);
+                if (w.ptr != nullptr && w.typ == kBitmap) { const uint4* g = reinterpret_cast<const uint4*>(w.ptr) + i0; cp_async_16(slot, g); cp_async_16(slot + 1, g + 1); }
+                else { Resolved r; r.ptr = w.ptr; r.card = w.card; r.typ = w.typ; r.cnt = w.cnt; slot[0] = wp_slice(r, i0); slot[1] = wp_slice(r, i0 + 1); }
+            }
+            cp_async_commit();
+        };
+        for (int ri = 0; ri < kWpAsyncDepth - 1; ri++) issue(ri);
+        const WpV32 T32 = wp_run_unrolled<WpV32, true, 1>(n_ops, nr, [&](int k) { return ops[k].opc; }, [&](int k) { return ops[k].is_row != 0; },
+                                         [&](int ri) { return (int)rowops[ri]; },
+                                         [&](int ri) {      // called once per row op, in order, after the previous operand has been consumed
+                                             issue(ri + kWpAsyncDepth - 1);          // into the slot the previous row op was read from
+                                             cp_async_wait_group<kWpAsyncDepth - 1>();
+                                             return wp_ring[ri % kWpAsyncDepth][tid];
+                                         });
+        cp_async_wait_group<0>();
+        uint4 T[2];
+        T[0] = make_uint4((uint32_t)T32.x, (uint32_t)(T32.x >> 32), (uint32_t)T32.y, (uint32_t)(T32.y >> 32));
+        T[1] = make_uint4((uint32_t)T32.z, (uint32_t)(T32.z >> 32), (uint32_t)T32.w, (uint32_t)(T32.w >> 32));
+#elif !defined(FBGPU_WP_LEGACY_LOOP) && FBGPU_WP_SLICES == 1 && !defined(FBGPU_WP_REG_RING)
         // Operand ring in shared memory, filled by cp.async (LDGSTS): every thread copies ITS 16-byte slice of the next kWpAsyncDepth - 1
         // row operands into its own ring slots — no registers and no scoreboard entry per load in flight (the register ring of
         // wp_run_unrolled stalled on shared scoreboards beyond 3 loads: 22 us at depth 3, 30 us at depth 6 for BASELINE config 3),
@@ -918,12 +960,20 @@ eval_wordpar_kernel(StoreRef st, const DevOp* __restrict__ prog, int n_ops,
         }
 #endif
         uint32_t cnt = 0;
+#if defined(FBGPU_WP_WIDE)
+#pragma unroll
+        for (int q = 0; q < 2; q++) {                   // (wp_run_unrolled already returns zero for an empty stack)
+            if (out.bitmaps) out.bitmaps[(size_t)unit * 512 + i0 + q] = T[q];
+            cnt += (uint32_t)popc4(T[q]);
+        }
+#else
 #pragma unroll
         for (int q = 0; q < kWpSlices; q++) {
             const uint4 rsl = depth_now > 0 ? T[q] : z;
             if (out.bitmaps) out.bitmaps[(size_t)unit * 512 + i0 + q * kWpThreads] = rsl;
             cnt += (uint32_t)popc4(rsl);
         }
+#endif
         cnt = __reduce_add_sync(0xffffffffu, cnt);
         if (lane == 0) wsum[wid] = cnt;
         __syncthreads();
@@ -1909,8 +1959,22 @@ constexpr int kGhItems = 2;                       // containers per thread and p
 constexpr int kGhSlots = 32768;                   // 128 KiB
 constexpr uint32_t kGhMaxEntries = kGhSlots / 8 * 5;
 constexpr uint32_t kGhMaxCard = 512;
+constexpr int kGhStage = 512;                     // entries of a warp's staging list (2 KiB per warp, 64 KiB per CTA)
+constexpr size_t kGhSmemBytes = (size_t)kGhSlots * 4 + (size_t)(kGhThreads / 32) * kGhStage * 4;
 
 __device__ __forceinline__ uint32_t gh_hash(uint32_t key) { return (key * 2654435761u) >> 17; }   // 15 bits
+
+// resolve() with the view's table entry already in registers (one unit looks up hundreds of rows of the same two views)
+__device__ __forceinline__ Resolved gh_resolve(const StoreRef& st, const ViewTab& v, uint32_t fv, uint64_t shard, uint64_t row, int slot) {
+    if (v.rt_rows == 0) return resolve(st, fv, shard, row, slot);          // sparse row ids: the search chain
+    Resolved r; r.ptr = nullptr; r.card = 0; r.typ = 0; r.cnt = 0;
+    if (row < v.rmin || row - v.rmin >= v.rt_rows) return r;
+    const RowTabEnt e = st.rowtab[v.rt_off + shard * v.rt_rows + (row - v.rmin)];
+    if (!((e.mask >> slot) & 1)) return r;
+    const ContDesc d = st.descs[e.first_desc + __popc(e.mask & ((1u << slot) - 1u))];
+    r.ptr = st.payload + (size_t)d.off16 * 16; r.card = d.card; r.typ = d.typ; r.cnt = d.cnt;
+    return r;
+}
 
 __global__ void __launch_bounds__(kGhThreads, 1)
 groupby_shard_kernel(StoreRef st, uint32_t fvA, const uint64_t* __restrict__ rowsA, int nA,
@@ -1922,25 +1986,25 @@ groupby_shard_kernel(StoreRef st, uint32_t fvA, const uint64_t* __restrict__ row
     __shared__ uint32_t red[kGhThreads / 32];
     __shared__ uint32_t s_tot;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int groups = kSlotsPerRow / spg;
-    const int rows_per_pass = (kGhThreads * kGhItems) / spg;         // rows of a field one pass covers (<= 2048: 12-bit row index)
+    uint32_t* stg = gh_tab + kGhSlots + wid * kGhStage;              // this warp's staging list
+    const int groups = kSlotsPerRow / spg, spg_sh = 31 - __clz(spg);
+    const int rows_per_pass = (kGhThreads * kGhItems) >> spg_sh;     // rows of a field one pass covers (<= 2048: 12-bit row index)
     const long long n_units = n_shards * groups;
     for (long long unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
         const long long si = unit / groups;
         const int g = (int)(unit - si * groups);
         const uint64_t shard = shards[si];
-        {   // executor.go:8769-8772: a shard missing either fragment contributes nothing (uniform test, broadcast loads)
-            bool ok = fvA < st.n_views && fvB < st.n_views;
-            if (ok) { const ViewTab va = st.views[fvA], vb = st.views[fvB]; ok = shard < va.n_shards && shard < vb.n_shards && st.shardmap[va.shard_off + shard] >= 0 && st.shardmap[vb.shard_off + shard] >= 0; }
-            if (!ok) continue;
-        }
+        if (fvA >= st.n_views || fvB >= st.n_views) continue;
+        const ViewTab vwA = st.views[fvA], vwB = st.views[fvB];
+        // executor.go:8769-8772: a shard missing either fragment contributes nothing (uniform test, broadcast loads)
+        if (!(shard < vwA.n_shards && shard < vwB.n_shards && st.shardmap[vwA.shard_off + shard] >= 0 && st.shardmap[vwB.shard_off + shard] >= 0)) continue;
         // item e of a pass = (row e / spg of the chunk, slot g * spg + e % spg)
-        auto load_items = [&](uint32_t fv, const uint64_t* rows, int r0, int n, Resolved (&it)[kGhItems]) {
+        auto load_items = [&](const ViewTab& vw, uint32_t fv, const uint64_t* rows, int r0, int n, Resolved (&it)[kGhItems]) {
 #pragma unroll
             for (int k = 0; k < kGhItems; k++) {
-                const int e = tid + k * kGhThreads, i = e / spg;
+                const int e = tid + k * kGhThreads, i = e >> spg_sh;
                 it[k].ptr = nullptr; it[k].card = 0; it[k].typ = 0; it[k].cnt = 0;
-                if (i < n) it[k] = resolve(st, fv, shard, rows[r0 + i], g * spg + (e - i * spg));
+                if (i < n) it[k] = gh_resolve(st, vw, fv, shard, rows[r0 + i], g * spg + (e & (spg - 1)));
             }
         };
         auto block_sum_or = [&](uint32_t v, bool flag, uint32_t& total) -> bool {      // sum of v and OR of flag over the CTA
@@ -1953,6 +2017,48 @@ groupby_shard_kernel(StoreRef st, uint32_t fvA, const uint64_t* __restrict__ row
             total = s_tot;
             return any != 0;
         };
+        // Elements of this lane's containers -> entries ((slot-in-group << 16 | column) << 12) | row index in the pass.  The warp's
+        // entries are first written to its staging list at consecutive positions (a warp scan of the cardinalities), then every lane
+        // takes entries lane, lane + 32, ...: the hash-table work is spread evenly whatever the containers' sizes are (walking its
+        // own containers, a lane was busy 16 of 32 slots on average: cardinalities of ~6 +- 2.4).  A warp whose containers hold more
+        // than kGhStage elements walks them directly.
+        auto for_each_entry = [&](const Resolved (&it)[kGhItems], const uint4 (&first)[kGhItems], bool first_valid, auto&& fn) {
+            uint32_t mine = 0;
+#pragma unroll
+            for (int k = 0; k < kGhItems; k++) if (it[k].ptr) mine += it[k].card;
+            uint32_t inc = mine;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += x; }
+            const uint32_t tot = __shfl_sync(0xffffffffu, inc, 31);
+            const bool staged = tot <= (uint32_t)kGhStage;
+            uint32_t pos = inc - mine;
+#pragma unroll
+            for (int k = 0; k < kGhItems; k++) {
+                if (!it[k].ptr) continue;
+                const int e = tid + k * kGhThreads, i = e >> spg_sh, sl = e & (spg - 1);
+                const uint32_t hi = ((uint32_t)sl << 28) | (uint32_t)i;
+                const uint32_t* flt = filter_bitmaps ? reinterpret_cast<const uint32_t*>(filter_bitmaps + ((size_t)si * kSlotsPerRow + g * spg + sl) * 512) : nullptr;
+                const uint4* p = reinterpret_cast<const uint4*>(it[k].ptr);
+                for (uint32_t k0 = 0; k0 < it[k].card; k0 += 8) {
+                    const uint4 v = (k0 == 0 && first_valid) ? first[k] : ldg_nc(p + (k0 >> 3));
+                    const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+                    const uint32_t m = min(8u, it[k].card - k0);
+#pragma unroll
+                    for (uint32_t q = 0; q < 8; q++) {
+                        if (q >= m) break;
+                        const uint32_t col = (w[q >> 1] >> ((q & 1) * 16)) & 0xffffu;
+                        uint32_t ent = hi | (col << 12);
+                        if (flt && !((__ldg(flt + (col >> 5)) >> (col & 31)) & 1u)) ent = kGbEmpty;
+                        if (staged) stg[pos++] = ent; else if (ent != kGbEmpty) fn(ent);
+                    }
+                }
+            }
+            if (staged) {
+                __syncwarp();
+                for (uint32_t x = lane; x < tot; x += 32) { const uint32_t ent = stg[x]; if (ent != kGbEmpty) fn(ent); }
+                __syncwarp();
+            }
+        };
         // ---- pass 0: nothing may be counted for a unit that ends up in the fallback list, so every a- and b-row of the group is
         // looked at first when a side needs several passes (a single pass per side is checked on the fly, without extra reads)
         bool decline = false;
@@ -1962,7 +2068,7 @@ groupby_shard_kernel(StoreRef st, uint32_t fvA, const uint64_t* __restrict__ row
                 const int n = side ? nB : nA;
                 for (int r0 = 0; r0 < n && !decline; r0 += rows_per_pass) {
                     Resolved it[kGhItems];
-                    load_items(side ? fvB : fvA, side ? rowsB : rowsA, r0, min(rows_per_pass, n - r0), it);
+                    load_items(side ? vwB : vwA, side ? fvB : fvA, side ? rowsB : rowsA, r0, min(rows_per_pass, n - r0), it);
                     uint32_t cnt = 0; bool bad = false;
 #pragma unroll
                     for (int k = 0; k < kGhItems; k++) if (it[k].ptr) { bad |= it[k].typ != kArray || (!side && it[k].card > kGhMaxCard); cnt += it[k].card; }
@@ -1974,8 +2080,8 @@ groupby_shard_kernel(StoreRef st, uint32_t fvA, const uint64_t* __restrict__ row
         for (int a0 = 0; a0 < nA && !decline; a0 += rows_per_pass) {
             const int chunkA = min(rows_per_pass, nA - a0);
             Resolved ra[kGhItems], rb[kGhItems];
-            load_items(fvA, rowsA, a0, chunkA, ra);
-            if (!multiB) load_items(fvB, rowsB, 0, nB, rb);       // (its descriptor chains run while the a-rows are inserted)
+            load_items(vwA, fvA, rowsA, a0, chunkA, ra);
+            if (!multiB) load_items(vwB, fvB, rowsB, 0, nB, rb);       // (its descriptor chains run while the a-rows are inserted)
             uint4 va[kGhItems], vb[kGhItems];                 // first 16-byte chunk of every container, in flight before the first barrier
             uint32_t cnt = 0; bool bad = false;
 #pragma unroll
@@ -1993,52 +2099,23 @@ groupby_shard_kernel(StoreRef st, uint32_t fvA, const uint64_t* __restrict__ row
                 for (int k = tid; k < kGhSlots / 4; k += kGhThreads) t4[k] = make_uint4(kGbEmpty, kGbEmpty, kGbEmpty, kGbEmpty); }
             __syncthreads();
             // ---- insert the a-rows
-#pragma unroll
-            for (int k = 0; k < kGhItems; k++) {
-                if (!ra[k].ptr) continue;
-                const int e = tid + k * kGhThreads, i = e / spg, sl = e - i * spg;
-                const uint32_t* flt = filter_bitmaps ? reinterpret_cast<const uint32_t*>(filter_bitmaps + ((size_t)si * kSlotsPerRow + g * spg + sl) * 512) : nullptr;
-                const uint4* p = reinterpret_cast<const uint4*>(ra[k].ptr);
-                for (uint32_t k0 = 0; k0 < ra[k].card; k0 += 8) {
-                    const uint4 v = k0 ? ldg_nc(p + (k0 >> 3)) : va[k];
-                    const uint32_t w[4] = { v.x, v.y, v.z, v.w };
-#pragma unroll
-                    for (int q = 0; q < 8; q++) {
-                        if (k0 + q >= ra[k].card) break;
-                        const uint32_t col = (w[q >> 1] >> ((q & 1) * 16)) & 0xffffu;
-                        if (flt && !((__ldg(flt + (col >> 5)) >> (col & 31)) & 1u)) continue;
-                        const uint32_t key = ((uint32_t)sl << 16) | col, ent = (key << 12) | (uint32_t)i;
-                        uint32_t h = gh_hash(key);
-                        while (atomicCAS(&gh_tab[h], kGbEmpty, ent) != kGbEmpty) h = (h + 1) & (kGhSlots - 1);
-                    }
-                }
-            }
+            for_each_entry(ra, va, true, [&](uint32_t ent) {
+                uint32_t h = gh_hash(ent >> 12);
+                while (atomicCAS(&gh_tab[h], kGbEmpty, ent) != kGbEmpty) h = (h + 1) & (kGhSlots - 1);
+            });
             __syncthreads();
             // ---- probe with the b-rows
             for (int b0 = 0; b0 < nB; b0 += rows_per_pass) {
-                const int chunkB = min(rows_per_pass, nB - b0);
-                if (multiB) load_items(fvB, rowsB, b0, chunkB, rb);
-#pragma unroll
-                for (int k = 0; k < kGhItems; k++) {
-                    if (!rb[k].ptr) continue;
-                    const int e = tid + k * kGhThreads, i = e / spg, sl = e - i * spg;
-                    unsigned long long* cj = counts + (size_t)a0 * nB + (b0 + i);
-                    const uint4* p = reinterpret_cast<const uint4*>(rb[k].ptr);
-                    for (uint32_t k0 = 0; k0 < rb[k].card; k0 += 8) {
-                        const uint4 v = (k0 || multiB) ? ldg_nc(p + (k0 >> 3)) : vb[k];
-                        const uint32_t w[4] = { v.x, v.y, v.z, v.w };
-#pragma unroll
-                        for (int q = 0; q < 8; q++) {
-                            if (k0 + q >= rb[k].card) break;
-                            const uint32_t key = ((uint32_t)sl << 16) | ((w[q >> 1] >> ((q & 1) * 16)) & 0xffffu);
-                            for (uint32_t h = gh_hash(key);; h = (h + 1) & (kGhSlots - 1)) {
-                                const uint32_t ent = gh_tab[h];
-                                if (ent == kGbEmpty) break;
-                                if ((ent >> 12) == key) atomicAdd(cj + (size_t)(ent & 0xfffu) * nB, 1ull);
-                            }
-                        }
+                if (multiB) load_items(vwB, fvB, rowsB, b0, min(rows_per_pass, nB - b0), rb);
+                unsigned long long* cb = counts + (size_t)a0 * nB + b0;
+                for_each_entry(rb, vb, !multiB, [&](uint32_t ent) {
+                    const uint32_t key = ent >> 12;
+                    for (uint32_t h = gh_hash(key);; h = (h + 1) & (kGhSlots - 1)) {
+                        const uint32_t t = gh_tab[h];
+                        if (t == kGbEmpty) break;
+                        if ((t >> 12) == key) atomicAdd(cb + (size_t)(t & 0xfffu) * nB + (ent & 0xfffu), 1ull);
                     }
-                }
+                });
             }
             __syncthreads();                                     // the table is cleared for the next a-chunk
         }
