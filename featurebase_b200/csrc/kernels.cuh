@@ -40,6 +40,20 @@ __device__ __forceinline__ uint4 or4(uint4 a, uint4 b) { return make_uint4(a.x |
 __device__ __forceinline__ uint4 xor4(uint4 a, uint4 b) { return make_uint4(a.x ^ b.x, a.y ^ b.y, a.z ^ b.z, a.w ^ b.w); }
 __device__ __forceinline__ uint4 andn4(uint4 a, uint4 b) { return make_uint4(a.x & ~b.x, a.y & ~b.y, a.z & ~b.z, a.w & ~b.w); }
 
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
+// L2 prefetch of what resolve() will read for (fv, shard, row, slot): stage 1 = the dense row-table entry, stage 2 (a while later,
+// reading that entry — by then an L2 hit) = the container descriptor.  eval_kernel issues them for the unit the CTA takes NEXT while it
+// works on the current one, so that the next unit's two dependent directory loads hit L2 instead of HBM.
+__device__ __forceinline__ void resolve_prefetch(const StoreRef& st, uint32_t fv, uint64_t shard, uint64_t row, int slot, bool stage2) {
+    if (fv >= st.n_views) return;
+    const ViewTab v = st.views[fv];
+    if (shard >= v.n_shards || !v.rt_rows || row < v.rmin || row - v.rmin >= v.rt_rows) return;
+    const RowTabEnt* ep = st.rowtab + (v.rt_off + shard * v.rt_rows + (row - v.rmin));
+    if (!stage2) { prefetch_l2(ep); return; }
+    const RowTabEnt e = *ep;
+    if ((e.mask >> slot) & 1) prefetch_l2(st.descs + (e.first_desc + __popc(e.mask & ((1u << slot) - 1u))));
+}
+
 // ------------------------------------------------------------------------------------------------
 // CTA-level helpers on 8 KiB shared-memory bitmaps (uint4[512]); thread t owns uint4 t and t+256.
 // ------------------------------------------------------------------------------------------------
@@ -326,6 +340,12 @@ eval_kernel(StoreRef st, const DevOp* __restrict__ prog, int n_ops, int depth,
                 is_run = r.ptr != nullptr && r.typ == kRun;
             }
             const int has_runs = __syncthreads_or(is_run);
+#ifndef FBGPU_EVAL_NO_DIRPF
+            if (base == 0 && tid < chunk && unit + gridDim.x < n_units) {     // directory entries of the unit this CTA takes next: on their way to L2
+                const DevOp op = prog[tid]; const long long nu = unit + gridDim.x;
+                if (op.op >= D_PUSH_ROW && op.op <= D_ORANDNOT_ROW && op.op != D_PUSH_EMPTY) resolve_prefetch(st, op.fv, shards[nu >> 4], op.row, (int)(nu & 15), false);
+            }
+#endif
             for (int k = 0; k < chunk; k++) {
                 const uint8_t opc = prog[base + k].op;
                 if (opc == D_PUSH_EMPTY) { top++; bm_zero(phys(top)); __syncthreads(); continue; }
@@ -404,6 +424,12 @@ eval_kernel(StoreRef st, const DevOp* __restrict__ prog, int n_ops, int depth,
             }
         }
         // ---- unit epilogue: popcount (+ optional bitmap / run statistics for canonical emission)
+#ifndef FBGPU_EVAL_NO_DIRPF
+        if (tid < min(n_ops, kResolveChunk) && unit + gridDim.x < n_units) {      // stage 2 for the next unit: its descriptors
+            const DevOp op = prog[tid]; const long long nu = unit + gridDim.x;
+            if (op.op >= D_PUSH_ROW && op.op <= D_ORANDNOT_ROW && op.op != D_PUSH_EMPTY) resolve_prefetch(st, op.fv, shards[nu >> 4], op.row, (int)(nu & 15), true);
+        }
+#endif
         uint32_t cnt = 0, nruns = 0;
         if (top >= 0) {
             const uint4* R = phys(top);

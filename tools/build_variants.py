@@ -3,6 +3,7 @@ import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from featurebase_b200 import build as B
 VARIANTS = {   # name -> -D defines; edit freely, outputs featurebase_b200/libfbgpu_<name>.so (select with FBGPU_LIB=...)
+    "eval_nopf": ["FBGPU_EVAL_NO_DIRPF"],       # eval_kernel without the L2 prefetch of the next unit's directory entries
     "addr_imad": ["FBGPU_ADDR_IMAD"],            # scatter / probe word addresses with IMAD.HI on the FMA pipe (measured slower: IMAD.HI is half rate)
     "wp_reg3": ["FBGPU_WP_REG_RING", "FBGPU_WP_RING=3"],   # word-parallel op loop with a REGISTER ring of 3 operand slices (22 us on config 3 in the round-2 first measurement)
     "wp_reg6": ["FBGPU_WP_REG_RING", "FBGPU_WP_RING=6"],   # register ring of 6 (30 us: the default of call 5)
