@@ -38,6 +38,32 @@ def test_config1_single_shard_plumbing():
     p.check_row("Row(f=1)")
 
 
+def test_pair_kernel_padded_array_tails():
+    """Count(Intersect(Row, Row)) on arrays whose last 16-byte chunk is padded (1..17, 63..65 elements), with the LAST element present on
+    both sides: the fused pair kernel probes the pad copies too and must take them out again — in the right warp of its two-warp team and
+    in 64-bit arithmetic (a per-warp share of the count can be negative).  One query per launch and all row pairs in one launch."""
+    from featurebase_b200 import lib as L
+    p = Pair(track_existence=False)
+    p.field("f")
+    sizes = list(range(1, 18)) + [63, 64, 65, 255, 257]
+    bits = []
+    for k, n in enumerate(sizes):
+        cols = np.arange(n, dtype=np.uint64) * np.uint64(3) + np.uint64(5)            # row 2k: n columns
+        other = np.concatenate([cols[-1:], cols[: n // 2], np.arange(n, dtype=np.uint64) * np.uint64(3) + np.uint64(70000 + 6)])   # row 2k+1 shares the last one and a few more
+        for r, cc in ((2 * k, cols), (2 * k + 1, np.unique(other))):
+            bits.append(np.uint64(r * SW) + cc)
+            bits.append(np.uint64(r * SW) + cc + np.uint64(3 * 65536))               # a second slot with the same pattern
+    p.load("f", X.VIEW_STANDARD, 0, roaring_io.encode(np.sort(np.concatenate(bits))))
+    fid = p.idx.fields["f"].id
+    for k, n in enumerate(sizes):
+        for a, b in ((2 * k, 2 * k + 1), (2 * k + 1, 2 * k), (2 * k, 2 * k)):
+            got = p.check_count(f"Count(Intersect(Row(f={a}), Row(f={b})))")
+            assert got == (2 * n if a == b else 2 * (1 + n // 2)), (n, a, b, got)
+    ra, rb = [2 * k for k in range(len(sizes))], [2 * k + 1 for k in range(len(sizes))]
+    got = p.holder.ctx.count_pairs(p.idx.id, fid, 0, ra, fid, 0, rb, [0])
+    assert [int(x) for x in got] == [2 * (1 + n // 2) for n in sizes]
+
+
 def test_container_combinations_table_on_gpu():
     """The reference's TestContainerCombinations table (roaring_internal_test.go:2974-3780) evaluated by the CUDA
     kernels: one shard per (x, y, enc_x, enc_y); ops intersect/union/difference/xor; results as sets AND as
