@@ -1961,7 +1961,7 @@ constexpr int kGhItems = 2;                       // containers per thread and p
 constexpr int kGhSlots = 32768;                   // 128 KiB
 constexpr uint32_t kGhMaxEntries = kGhSlots / 8 * 5;
 constexpr uint32_t kGhMaxCard = 512;
-constexpr int kGhStage = 512;                     // entries of a warp's staging list (2 KiB per warp, 64 KiB per CTA)
+constexpr int kGhStage = 32 * kGhItems * 8;       // entries of a warp's staging list: 8 per container (2 KiB per warp, 64 KiB per CTA)
 constexpr size_t kGhSmemBytes = (size_t)kGhSlots * 4 + (size_t)(kGhThreads / 32) * kGhStage * 4;
 
 __device__ __forceinline__ uint32_t gh_hash(uint32_t key) { return (key * 2654435761u) >> 17; }   // 15 bits
@@ -1986,7 +1986,7 @@ groupby_shard_kernel(StoreRef st, uint32_t fvA, const uint64_t* __restrict__ row
                      unsigned long long* counts /* [nA*nB] */, unsigned int* fallback /* [0] = n, then (shard index * 16 + slot) units */) {
     extern __shared__ __align__(16) uint32_t gh_tab[];
     __shared__ uint32_t red[kGhThreads / 32];
-    __shared__ uint32_t s_tot;
+    __shared__ uint32_t s_tot, s_dups;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     uint32_t* stg = gh_tab + kGhSlots + wid * kGhStage;              // this warp's staging list
     const int groups = kSlotsPerRow / spg, spg_sh = 31 - __clz(spg);
@@ -2019,46 +2019,50 @@ groupby_shard_kernel(StoreRef st, uint32_t fvA, const uint64_t* __restrict__ row
             total = s_tot;
             return any != 0;
         };
-        // Elements of this lane's containers -> entries ((slot-in-group << 16 | column) << 12) | row index in the pass.  The warp's
-        // entries are first written to its staging list at consecutive positions (a warp scan of the cardinalities), then every lane
-        // takes entries lane, lane + 32, ...: the hash-table work is spread evenly whatever the containers' sizes are (walking its
-        // own containers, a lane was busy 16 of 32 slots on average: cardinalities of ~6 +- 2.4).  A warp whose containers hold more
-        // than kGhStage elements walks them directly.
+        // Elements of this lane's containers -> entries ((slot-in-group << 16 | column) << 12) | row index in the pass.  The first 16-byte
+        // chunk (8 elements) of every container goes to a fixed place in the warp's staging list — 8 entries per container, EMPTY behind
+        // its last element, two 16-byte stores, no scan and no per-element branch — and the warp then takes the 512 slots 32 at a time:
+        // the hash-table work is spread over the lanes whatever the containers' sizes are (walking its own containers, a lane was
+        // busy 16 of 32 slots on average: cardinalities of ~6 +- 2.4).  Elements past a container's 8th are walked by its lane.
         auto for_each_entry = [&](const Resolved (&it)[kGhItems], const uint4 (&first)[kGhItems], bool first_valid, auto&& fn) {
-            uint32_t mine = 0;
-#pragma unroll
-            for (int k = 0; k < kGhItems; k++) if (it[k].ptr) mine += it[k].card;
-            uint32_t inc = mine;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += x; }
-            const uint32_t tot = __shfl_sync(0xffffffffu, inc, 31);
-            const bool staged = tot <= (uint32_t)kGhStage;
-            uint32_t pos = inc - mine;
 #pragma unroll
             for (int k = 0; k < kGhItems; k++) {
-                if (!it[k].ptr) continue;
+                uint32_t e8[8];
+#pragma unroll
+                for (int q = 0; q < 8; q++) e8[q] = kGbEmpty;
+                if (it[k].ptr) {
+                    const int e = tid + k * kGhThreads, i = e >> spg_sh, sl = e & (spg - 1);
+                    const uint32_t hi = ((uint32_t)sl << 28) | (uint32_t)i;
+                    const uint32_t* flt = filter_bitmaps ? reinterpret_cast<const uint32_t*>(filter_bitmaps + ((size_t)si * kSlotsPerRow + g * spg + sl) * 512) : nullptr;
+                    const uint4 v = first_valid ? first[k] : ldg_nc(reinterpret_cast<const uint4*>(it[k].ptr));
+                    const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+                    for (int q = 0; q < 8; q++) {
+                        const uint32_t col = (w[q >> 1] >> ((q & 1) * 16)) & 0xffffu;
+                        bool keep = (uint32_t)q < it[k].card;
+                        if (flt && keep) keep = ((__ldg(flt + (col >> 5)) >> (col & 31)) & 1u) != 0;
+                        if (keep) e8[q] = hi | (col << 12);
+                    }
+                }
+                uint4* dst = reinterpret_cast<uint4*>(stg + (lane * kGhItems + k) * 8);
+                dst[0] = make_uint4(e8[0], e8[1], e8[2], e8[3]); dst[1] = make_uint4(e8[4], e8[5], e8[6], e8[7]);
+            }
+            __syncwarp();
+#pragma unroll 4
+            for (int x = lane; x < kGhStage; x += 32) { const uint32_t ent = stg[x]; if (ent != kGbEmpty) fn(ent); }
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < kGhItems; k++) {           // containers of more than 8 elements: the rest, by the owning lane
+                if (!it[k].ptr || it[k].card <= 8) continue;
                 const int e = tid + k * kGhThreads, i = e >> spg_sh, sl = e & (spg - 1);
                 const uint32_t hi = ((uint32_t)sl << 28) | (uint32_t)i;
                 const uint32_t* flt = filter_bitmaps ? reinterpret_cast<const uint32_t*>(filter_bitmaps + ((size_t)si * kSlotsPerRow + g * spg + sl) * 512) : nullptr;
-                const uint4* p = reinterpret_cast<const uint4*>(it[k].ptr);
-                for (uint32_t k0 = 0; k0 < it[k].card; k0 += 8) {
-                    const uint4 v = (k0 == 0 && first_valid) ? first[k] : ldg_nc(p + (k0 >> 3));
-                    const uint32_t w[4] = { v.x, v.y, v.z, v.w };
-                    const uint32_t m = min(8u, it[k].card - k0);
-#pragma unroll
-                    for (uint32_t q = 0; q < 8; q++) {
-                        if (q >= m) break;
-                        const uint32_t col = (w[q >> 1] >> ((q & 1) * 16)) & 0xffffu;
-                        uint32_t ent = hi | (col << 12);
-                        if (flt && !((__ldg(flt + (col >> 5)) >> (col & 31)) & 1u)) ent = kGbEmpty;
-                        if (staged) stg[pos++] = ent; else if (ent != kGbEmpty) fn(ent);
-                    }
+                const uint16_t* p = reinterpret_cast<const uint16_t*>(it[k].ptr);
+                for (uint32_t j = 8; j < it[k].card; j++) {
+                    const uint32_t col = __ldg(p + j);
+                    if (flt && !((__ldg(flt + (col >> 5)) >> (col & 31)) & 1u)) continue;
+                    fn(hi | (col << 12));
                 }
-            }
-            if (staged) {
-                __syncwarp();
-                for (uint32_t x = lane; x < tot; x += 32) { const uint32_t ent = stg[x]; if (ent != kGbEmpty) fn(ent); }
-                __syncwarp();
             }
         };
         // ---- pass 0: nothing may be counted for a unit that ends up in the fallback list, so every a- and b-row of the group is
@@ -2099,13 +2103,20 @@ groupby_shard_kernel(StoreRef st, uint32_t fvA, const uint64_t* __restrict__ row
             {   uint4* t4 = reinterpret_cast<uint4*>(gh_tab);
 #pragma unroll 4
                 for (int k = tid; k < kGhSlots / 4; k += kGhThreads) t4[k] = make_uint4(kGbEmpty, kGbEmpty, kGbEmpty, kGbEmpty); }
+            if (tid == 0) s_dups = 0;
             __syncthreads();
-            // ---- insert the a-rows
+            // ---- insert the a-rows (and notice whether any column sits in two of them: only then a probe has to walk past its first hit)
             for_each_entry(ra, va, true, [&](uint32_t ent) {
                 uint32_t h = gh_hash(ent >> 12);
-                while (atomicCAS(&gh_tab[h], kGbEmpty, ent) != kGbEmpty) h = (h + 1) & (kGhSlots - 1);
+                for (;;) {
+                    const uint32_t prev = atomicCAS(&gh_tab[h], kGbEmpty, ent);
+                    if (prev == kGbEmpty) break;
+                    if ((prev >> 12) == (ent >> 12)) s_dups = 1u;
+                    h = (h + 1) & (kGhSlots - 1);
+                }
             });
             __syncthreads();
+            const bool dups = s_dups != 0;
             // ---- probe with the b-rows
             for (int b0 = 0; b0 < nB; b0 += rows_per_pass) {
                 if (multiB) load_items(vwB, fvB, rowsB, b0, min(rows_per_pass, nB - b0), rb);
@@ -2115,7 +2126,7 @@ groupby_shard_kernel(StoreRef st, uint32_t fvA, const uint64_t* __restrict__ row
                     for (uint32_t h = gh_hash(key);; h = (h + 1) & (kGhSlots - 1)) {
                         const uint32_t t = gh_tab[h];
                         if (t == kGbEmpty) break;
-                        if ((t >> 12) == key) atomicAdd(cb + (size_t)(t & 0xfffu) * nB + (ent & 0xfffu), 1ull);
+                        if ((t >> 12) == key) { atomicAdd(cb + ((t & 0xfffu) * (uint32_t)nB + (ent & 0xfffu)), 1ull); if (!dups) break; }
                     }
                 });
             }

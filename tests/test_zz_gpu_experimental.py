@@ -492,7 +492,8 @@ def test_groupby_slot_groups():
     for s, cc in cols.items():
         ra, rb = rng.integers(0, 64, size=len(cc)), rng.integers(0, 50, size=len(cc))
         rel = cc.astype(np.uint64) - np.uint64(s * SW)
-        frs["a"][s] = np.sort(ra.astype(np.uint64) * np.uint64(SW) + rel)
+        dup = rel[:3000]                                                     # 3000 columns sit in TWO a-rows: a probe must not stop at its first hit
+        frs["a"][s] = np.sort(np.concatenate([ra.astype(np.uint64) * np.uint64(SW) + rel, ((ra[:3000] + 1) % 64).astype(np.uint64) * np.uint64(SW) + dup]))
         frs["b"][s] = np.sort(rb.astype(np.uint64) * np.uint64(SW) + rel)
         frs["f"][s] = np.sort(np.uint64(1 * SW) + rel[rel % np.uint64(3) != 0])
     from featurebase_b200 import roaring_io
