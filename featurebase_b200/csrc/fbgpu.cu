@@ -230,13 +230,13 @@ extern "C" int fbgpu_init(int32_t device_ordinal, fbgpu_ctx** out) try {
     // opt in to large dynamic shared memory once
     CUDA_TRY(cudaFuncSetAttribute(eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 17 * 8192));
     CUDA_TRY(cudaFuncSetAttribute(eval_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 233472 / 2 - 1024 - 5888));
-    CUDA_TRY(cudaFuncSetAttribute(pair_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPcTeams * 8192));
+    CUDA_TRY(cudaFuncSetAttribute(pair_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPcWarps * 8192));
     CUDA_TRY(cudaFuncSetAttribute(row_count_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairWarps * 8192));
     CUDA_TRY(cudaFuncSetAttribute(row_count_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairWarps * 8192));
     CUDA_TRY(cudaFuncSetAttribute(groupby_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGbSlots * 4 + 8192));
     CUDA_TRY(cudaFuncSetAttribute(groupby_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGbSlots * 4 + 8192));
     CUDA_TRY(cudaFuncSetAttribute(groupby_shard_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGhSmemBytes));
-    { int nb = 0; if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, pair_count_kernel, kPcTeams * 64, kPcTeams * 8192) == cudaSuccess && nb > 0) c->pair_ctas_per_sm = nb; }
+    { int nb = 0; if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, pair_count_kernel, kPcWarps * 32, kPcWarps * 8192) == cudaSuccess && nb > 0) c->pair_ctas_per_sm = nb; }
     guard.c = nullptr;
     *out = c;
     return FBGPU_OK;
@@ -343,6 +343,10 @@ struct StoreTxn {
         c->tables_valid = false;            // (dirty_shards may name pairs of the undone call: the next commit rebuilds the tables)
     }
 };
+
+// Bytes kept allocated behind the last payload byte of the arena: pair_count_kernel loads three 16-byte chunks per lane of a small array
+// without looking at its length (up to 1.5 KiB past a one-chunk array) and only USES the chunks the array has.
+constexpr uint64_t kArenaSlack = 4096;
 
 // Shard ids index the dense per-view shard maps: the accepted range is bounded so that one stray id cannot make a load allocate
 // gigabytes of map (the reference's shard space is sparse; 2^24 shards = 1.7e13 columns per index is far past its deployments).
@@ -739,7 +743,7 @@ static int commit_locked(fbgpu_ctx* c) {
     USE_DEVICE(c);
     CUDA_TRY(cudaDeviceSynchronize());   // no query may be reading tables we are about to replace (queries hold the shared lock anyway)
     if (!c->staging.empty()) {
-        uint64_t need = c->uploaded + c->staging.len + 256;
+        uint64_t need = c->uploaded + c->staging.len + kArenaSlack;
         if (need > c->d_payload.cap) {
             DevBuf nb; size_t want = std::max<size_t>(need, c->d_payload.cap * 2);
             if (nb.ensure(want)) { if (nb.ensure(need)) return FBGPU_E_NOMEM; }
@@ -862,7 +866,7 @@ static int compact_locked(fbgpu_ctx* c) {
     }
     if (cur / 16 > 0xffffffffull) return fail(FBGPU_E_NOMEM, "payload arena exceeds 64 GiB addressable by 32-bit 16 B offsets");
     DevBuf nb;
-    if (nb.ensure(cur + 256)) return FBGPU_E_NOMEM;
+    if (nb.ensure(cur + kArenaSlack)) return FBGPU_E_NOMEM;
     for (const Move& m : moves) if (m.len) CUDA_TRY(cudaMemcpy((uint8_t*)nb.p + m.to, (const uint8_t*)c->d_payload.p + m.from, m.len, cudaMemcpyDeviceToDevice));
     if (!gathers.empty()) {
         DevBuf d_mv;
@@ -1065,9 +1069,9 @@ static int count_impl(fbgpu_ctx* c, uint32_t index, const fbgpu_op* ops, int32_t
         if (prog.size() == 2 && prog[0].op == D_PUSH_ROW && prog[1].op == D_AND_ROW) { pa = &prog[0]; pb = &prog[1]; }
         else if (prog.size() == 3 && prog[0].op == D_PUSH_EMPTY && prog[1].op == D_OR_ROW && prog[2].op == D_AND_ROW) { pa = &prog[1]; pb = &prog[2]; }
         if (pa && !getenv("FBGPU_NO_PAIR_KERNEL")) {
-            long long grid = std::min<long long>((n_units + kPcTeams - 1) / kPcTeams, (long long)c->sm_count * c->pair_ctas_per_sm);
+            long long grid = std::min<long long>((n_units + kPcWarps - 1) / kPcWarps, (long long)c->sm_count * c->pair_ctas_per_sm);
             c->counters_pair_launches++;
-            pair_count_kernel<<<(unsigned)grid, kPcTeams * 64, kPcTeams * 8192, w->stream>>>(store_ref(c), pa->fv, pa->row, pb->fv, pb->row, nullptr, nullptr, n_units,
+            pair_count_kernel<<<(unsigned)grid, kPcWarps * 32, kPcWarps * 8192, w->stream>>>(store_ref(c), pa->fv, pa->row, pb->fv, pb->row, nullptr, nullptr, n_units,
                 contiguous_shards(shards, n_shards) ? nullptr : d_shards, n_shards ? shards[0] : 0, n_units, d_total, d_per, nullptr, fr);
             CUDA_TRY(cudaGetLastError());
         } else {
@@ -1536,8 +1540,8 @@ extern "C" int fbgpu_count_pairs(fbgpu_ctx* c, uint32_t index, uint32_t field_a,
     const long long upp = (long long)n_shards * kSlotsPerRow, n_units = upp * n_pairs;
     CUDA_TRY(cudaEventRecord(w->ev0, w->stream));
     if (n_units > 0) {
-        long long grid = std::min<long long>((n_units + kPcTeams - 1) / kPcTeams, (long long)c->sm_count * c->pair_ctas_per_sm);
-        pair_count_kernel<<<(unsigned)grid, kPcTeams * 64, kPcTeams * 8192, w->stream>>>(store_ref(c), fa, 0, fb, 0, (const uint64_t*)w->d_rows.p, (const uint64_t*)w->d_rows.p + np,
+        long long grid = std::min<long long>((n_units + kPcWarps - 1) / kPcWarps, (long long)c->sm_count * c->pair_ctas_per_sm);
+        pair_count_kernel<<<(unsigned)grid, kPcWarps * 32, kPcWarps * 8192, w->stream>>>(store_ref(c), fa, 0, fb, 0, (const uint64_t*)w->d_rows.p, (const uint64_t*)w->d_rows.p + np,
             upp, contiguous_shards(shards, n_shards) ? nullptr : d_shards, n_shards ? shards[0] : 0, n_units, nullptr, nullptr, (unsigned long long*)w->d_counts.p, FuseReduce{});
         CUDA_TRY(cudaGetLastError());
     }

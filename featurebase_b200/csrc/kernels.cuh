@@ -40,20 +40,6 @@ __device__ __forceinline__ uint4 or4(uint4 a, uint4 b) { return make_uint4(a.x |
 __device__ __forceinline__ uint4 xor4(uint4 a, uint4 b) { return make_uint4(a.x ^ b.x, a.y ^ b.y, a.z ^ b.z, a.w ^ b.w); }
 __device__ __forceinline__ uint4 andn4(uint4 a, uint4 b) { return make_uint4(a.x & ~b.x, a.y & ~b.y, a.z & ~b.z, a.w & ~b.w); }
 
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
-// L2 prefetch of what resolve() will read for (fv, shard, row, slot): stage 1 = the dense row-table entry, stage 2 (a while later,
-// reading that entry — by then an L2 hit) = the container descriptor.  eval_kernel issues them for the unit the CTA takes NEXT while it
-// works on the current one, so that the next unit's two dependent directory loads hit L2 instead of HBM.
-__device__ __forceinline__ void resolve_prefetch(const StoreRef& st, uint32_t fv, uint64_t shard, uint64_t row, int slot, bool stage2) {
-    if (fv >= st.n_views) return;
-    const ViewTab v = st.views[fv];
-    if (shard >= v.n_shards || !v.rt_rows || row < v.rmin || row - v.rmin >= v.rt_rows) return;
-    const RowTabEnt* ep = st.rowtab + (v.rt_off + shard * v.rt_rows + (row - v.rmin));
-    if (!stage2) { prefetch_l2(ep); return; }
-    const RowTabEnt e = *ep;
-    if ((e.mask >> slot) & 1) prefetch_l2(st.descs + (e.first_desc + __popc(e.mask & ((1u << slot) - 1u))));
-}
-
 // ------------------------------------------------------------------------------------------------
 // CTA-level helpers on 8 KiB shared-memory bitmaps (uint4[512]); thread t owns uint4 t and t+256.
 // ------------------------------------------------------------------------------------------------
@@ -340,12 +326,6 @@ eval_kernel(StoreRef st, const DevOp* __restrict__ prog, int n_ops, int depth,
                 is_run = r.ptr != nullptr && r.typ == kRun;
             }
             const int has_runs = __syncthreads_or(is_run);
-#ifndef FBGPU_EVAL_NO_DIRPF
-            if (base == 0 && tid < chunk && unit + gridDim.x < n_units) {     // directory entries of the unit this CTA takes next: on their way to L2
-                const DevOp op = prog[tid]; const long long nu = unit + gridDim.x;
-                if (op.op >= D_PUSH_ROW && op.op <= D_ORANDNOT_ROW && op.op != D_PUSH_EMPTY) resolve_prefetch(st, op.fv, shards[nu >> 4], op.row, (int)(nu & 15), false);
-            }
-#endif
             for (int k = 0; k < chunk; k++) {
                 const uint8_t opc = prog[base + k].op;
                 if (opc == D_PUSH_EMPTY) { top++; bm_zero(phys(top)); __syncthreads(); continue; }
@@ -424,12 +404,6 @@ eval_kernel(StoreRef st, const DevOp* __restrict__ prog, int n_ops, int depth,
             }
         }
         // ---- unit epilogue: popcount (+ optional bitmap / run statistics for canonical emission)
-#ifndef FBGPU_EVAL_NO_DIRPF
-        if (tid < min(n_ops, kResolveChunk) && unit + gridDim.x < n_units) {      // stage 2 for the next unit: its descriptors
-            const DevOp op = prog[tid]; const long long nu = unit + gridDim.x;
-            if (op.op >= D_PUSH_ROW && op.op <= D_ORANDNOT_ROW && op.op != D_PUSH_EMPTY) resolve_prefetch(st, op.fv, shards[nu >> 4], op.row, (int)(nu & 15), true);
-        }
-#endif
         uint32_t cnt = 0, nruns = 0;
         if (top >= 0) {
             const uint4* R = phys(top);
@@ -1070,36 +1044,33 @@ __device__ __forceinline__ uint2 ldg_nc64(const uint2* p) {
     asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
     return r;
 }
-// barrier of one two-warp team (named barrier `id`, 64 threads)
-__device__ __forceinline__ void team_barrier(int id) { __syncwarp(); asm volatile("bar.sync %0, 64;" :: "r"(id) : "memory"); }
-
 constexpr int kPairWarps = 8;           // row_count_kernel
-#ifndef FBGPU_PAIR_TEAMS
-#define FBGPU_PAIR_TEAMS 8
+#ifndef FBGPU_PAIR_WARPS
+#define FBGPU_PAIR_WARPS 9
 #endif
 #ifndef FBGPU_PAIR_MIN_BLOCKS
-#define FBGPU_PAIR_MIN_BLOCKS 2
+#define FBGPU_PAIR_MIN_BLOCKS 3
 #endif
-constexpr int kPcTeams = FBGPU_PAIR_TEAMS;                  // two-warp teams per CTA of pair_count_kernel, one 8 KiB bitmap each
-constexpr int kPcPairSlots = 1024;                          // row pairs per launch whose counts are summed in shared memory first
+constexpr int kPcWarps = FBGPU_PAIR_WARPS;                  // warps per CTA of pair_count_kernel, one 8 KiB bitmap each (27 per SM)
+constexpr int kPcPairSlots = 256;                           // row pairs per launch whose counts are summed in shared memory first
+constexpr uint32_t kPcFastCard = 768;                       // arrays up to this size take the register-window path (3 chunks per lane)
 
-// Pairs with a run container on at least one side, by a two-warp team (`tl` = lane index inside the team, 0..63); returns the per-lane
-// partial count.  The searched interval list (<= 2048 runs = 8 KiB) is first copied into the team's shared-memory words, so the
-// per-element / per-run binary searches are ~30-cycle shared-memory loads instead of dependent global loads (ncu round 2: run x run
-// at 20 % clustered density took 92 us for 13 MB — six rounds of an eight-deep chain of L2 round trips per warp and pair); the words
-// are zeroed again before returning.
-__device__ __noinline__ uint32_t team_icount_runs(Resolved a, Resolved b, uint32_t* bm, int tl, int bar_id) {
+// Pairs with a run container on at least one side; returns the per-lane partial count.  The searched interval list (<= 2048 runs =
+// 8 KiB) is first copied into the warp's shared-memory words, so the per-element / per-run binary searches are ~30-cycle shared-memory
+// loads instead of dependent global loads (ncu round 2: run x run at 20 % clustered density took 92 us for 13 MB — six rounds of an
+// eight-deep chain of L2 round trips per warp and pair; 41 us with the list in shared memory); the words are zeroed again before returning.
+__device__ __noinline__ uint32_t warp_icount_runs(Resolved a, Resolved b, uint32_t* bm, int lane) {
     uint32_t c = 0;
     if (a.typ == kRun && b.typ != kRun) { Resolved t = a; a = b; b = t; }   // make `b` a run side
     if (a.typ == kBitmap) {                                   // bitmap x run: roaring.go:4588 (sum of BitmapCountRange per run), global words
         const uint32_t* g = reinterpret_cast<const uint32_t*>(a.ptr);
         const uint32_t* r32 = reinterpret_cast<const uint32_t*>(b.ptr);
         if (b.cnt >= 32) {                                    // many short runs: one lane per run
-            for (uint32_t i = tl; i < b.cnt; i += 64) { uint32_t v = __ldg(r32 + i); c += range_count32(g, v & 0xffffu, v >> 16); }
-        } else {                                              // few long runs: the team walks each run's words together
+            for (uint32_t i = lane; i < b.cnt; i += 32) { uint32_t v = __ldg(r32 + i); c += range_count32(g, v & 0xffffu, v >> 16); }
+        } else {                                              // few long runs: the warp walks each run's words together
             for (uint32_t i = 0; i < b.cnt; i++) {
                 uint32_t v = __ldg(r32 + i); uint32_t s0 = v & 0xffffu, l0 = v >> 16;
-                for (uint32_t w = (s0 >> 5) + tl; w <= (l0 >> 5); w += 64) {
+                for (uint32_t w = (s0 >> 5) + lane; w <= (l0 >> 5); w += 32) {
                     uint32_t m = 0xffffffffu;
                     if (w == (s0 >> 5)) m &= 0xffffffffu << (s0 & 31);
                     if (w == (l0 >> 5)) m &= 0xffffffffu >> (31 - (l0 & 31));
@@ -1111,147 +1082,124 @@ __device__ __noinline__ uint32_t team_icount_runs(Resolved a, Resolved b, uint32
     }
     if (a.typ == kRun && a.cnt > b.cnt) { Resolved t = a; a = b; b = t; }   // run x run: search the longer list
     const uint32_t* rb = reinterpret_cast<const uint32_t*>(b.ptr);
-    for (uint32_t i = tl; i < b.cnt; i += 64) bm[i] = __ldg(rb + i);
-    team_barrier(bar_id);
+    // (stored fragments hold at most 2048 runs per container — optimize() turns longer lists into bitmaps — but a hand-built
+    // container may carry up to 32768: those are searched where they are, in global memory)
+    const bool staged = b.cnt <= 2048u;
+    if (staged) { for (uint32_t i = lane; i < b.cnt; i += 32) bm[i] = __ldg(rb + i); }
+    __syncwarp();
+    auto run_at = [&](uint32_t m) { return staged ? bm[m] : __ldg(rb + m); };
     if (a.typ == kArray) {                                    // array x run: roaring.go:4537
         const uint16_t* arr = reinterpret_cast<const uint16_t*>(a.ptr);
-        for (uint32_t i = tl; i < a.card; i += 64) {
+        for (uint32_t i = lane; i < a.card; i += 32) {
             const uint32_t v = __ldg(arr + i);
             uint32_t lo = 0, hi = b.cnt;                      // first run with last >= v
-            while (lo < hi) { uint32_t m = (lo + hi) >> 1; if ((bm[m] >> 16) < v) lo = m + 1; else hi = m; }
-            if (lo < b.cnt) c += ((bm[lo] & 0xffffu) <= v);
+            while (lo < hi) { uint32_t m = (lo + hi) >> 1; if ((run_at(m) >> 16) < v) lo = m + 1; else hi = m; }
+            if (lo < b.cnt) c += ((run_at(lo) & 0xffffu) <= v);
         }
     } else {                                                  // run x run: interval overlap, roaring.go:4555
         const uint32_t* ra = reinterpret_cast<const uint32_t*>(a.ptr);
-        for (uint32_t i = tl; i < a.cnt; i += 64) {
+        for (uint32_t i = lane; i < a.cnt; i += 32) {
             const uint32_t v = __ldg(ra + i); const uint32_t s0 = v & 0xffffu, l0 = v >> 16;
             uint32_t lo = 0, hi = b.cnt;                      // first run of b with last >= s0
-            while (lo < hi) { uint32_t m = (lo + hi) >> 1; if ((bm[m] >> 16) < s0) lo = m + 1; else hi = m; }
+            while (lo < hi) { uint32_t m = (lo + hi) >> 1; if ((run_at(m) >> 16) < s0) lo = m + 1; else hi = m; }
             for (; lo < b.cnt; lo++) {
-                const uint32_t u = bm[lo]; const uint32_t s1 = u & 0xffffu, l1 = u >> 16;
+                const uint32_t u = run_at(lo); const uint32_t s1 = u & 0xffffu, l1 = u >> 16;
                 if (s1 > l0) break;
                 c += min(l0, l1) - max(s0, s1) + 1;
             }
         }
     }
-    team_barrier(bar_id);
-    for (uint32_t i = tl; i < b.cnt; i += 64) bm[i] = 0;
-    team_barrier(bar_id);
+    __syncwarp();
+    if (staged) { for (uint32_t i = lane; i < b.cnt; i += 32) bm[i] = 0; }
+    __syncwarp();
     return c;
 }
 
-// Intersection count of two located containers by a TEAM of two warps sharing one 8 KiB shared-memory bitmap (`bm`, all zero on entry
-// and on exit).  Follows the dispatch of intersectionCount (roaring.go:4477-4512) incl. the full/empty short-circuits.  Returns this
-// WARP's share of the count (reduced over the warp, valid in all lanes); the team's count is the sum of both warps' values.
-// array x array (roaring.go:4514): both warps visit the same 16-byte chunks lane L <-> chunks L, L+32, L+64 — warp `half` takes the
-// half-th 8 bytes (4 elements) of each, so that one instruction still touches exactly the elements of one bank-striped group (stripe.h):
-// scatter the smaller array, team barrier, probe with the larger, team barrier, store zeros over the words this warp set, team barrier.
-// Why two warps per bitmap: the path is bound by how many warps an SM holds (ncu round 2: 24 one-warp-per-bitmap warps issue 47 % of the
-// cycles, 16 with their payloads already staged in shared memory issue 50 %, the ALU pipe 38-47 % busy) and 8 KiB per warp caps that at
-// 24-27; halving the bitmap per warp doubles the resident warps at the same per-element work.
-__device__ __forceinline__ uint32_t team_intersection_count(Resolved a, Resolved b, uint32_t* bm, int lane, int half, int bar_id) {
+// Every pair that is not two arrays of at most kPcFastCard elements (kept out of line: the hot path is the inline code of the kernel).
+// Follows the dispatch of intersectionCount (roaring.go:4477-4512) incl. the full/empty short-circuits.  `bm` is all zero on entry
+// and on exit.  Returns the count (reduced over the warp, valid in all lanes).
+__device__ __noinline__ uint32_t warp_intersection_count_generic(Resolved a, Resolved b, uint32_t* bm, int lane) {
     if (a.ptr == nullptr || b.ptr == nullptr) return 0;
-    if (a.card == kFull) return half ? 0u : b.card;           // roaring.go:4478-4483
-    if (b.card == kFull) return half ? 0u : a.card;
-    // order so that arrays come first
-    if (a.typ != kArray && b.typ == kArray) { Resolved t = a; a = b; b = t; }
+    if (a.card == kFull) return b.card;                       // roaring.go:4478-4483
+    if (b.card == kFull) return a.card;
+    if (a.typ != kArray && b.typ == kArray) { Resolved t = a; a = b; b = t; }      // arrays first
     uint32_t c = 0;
-    if (a.typ == kRun || b.typ == kRun) c = team_icount_runs(a, b, bm, lane + 32 * half, bar_id);
-    else if (a.typ == kArray && b.typ == kArray) {            // array x array: build the smaller, probe the larger
+    if (a.typ == kRun || b.typ == kRun) c = warp_icount_runs(a, b, bm, lane);
+    else if (a.typ == kArray && b.typ == kArray) {            // long arrays (> kPcFastCard): scatter the smaller, probe the larger, chunk by chunk
         if (a.card > b.card) { Resolved t = a; a = b; b = t; }
-        const uint2* a2 = reinterpret_cast<const uint2*>(a.ptr) + half; const uint2* b2 = reinterpret_cast<const uint2*>(b.ptr) + half;
+        const uint4* a4 = reinterpret_cast<const uint4*>(a.ptr); const uint4* b4 = reinterpret_cast<const uint4*>(b.ptr);
         const uint32_t na8 = (a.card + 7) >> 3, nb8 = (b.card + 7) >> 3;
-        smem_base_t sb = smem_base((uint32_t)__cvta_generic_to_shared(bm));
-        pin_base(sb);
-        uint2 va[3], vb[3];
+        const smem_base_t sb = smem_base((uint32_t)__cvta_generic_to_shared(bm));
+        for (uint32_t i = lane; i < na8; i += 32) scatter_chunk_sb<0>(sb, ldg_nc(a4 + i), i * 8, a.card);
+        __syncwarp();
+        for (uint32_t i = lane; i < nb8; i += 32) {           // whole chunks: the pad copies of b's last element are taken out below
+            const uint4 v = ldg_nc(b4 + i); const uint32_t w[4] = { v.x, v.y, v.z, v.w };
 #pragma unroll
-        for (int q = 0; q < 3; q++) va[q] = ldg_nc64(a2 + 2u * min((uint32_t)lane + 32u * q, na8 - 1u));     // clamped, unconditional: no undefined register
-#pragma unroll
-        for (int q = 0; q < 3; q++) vb[q] = ldg_nc64(b2 + 2u * min((uint32_t)lane + 32u * q, nb8 - 1u));
-        // every chunk of `b` is probed whole: the slots behind its last element hold copies of that element (pad_array_tail), which
-        // are taken out of the count again below — no divergent partial-chunk path
-        const uint32_t pads = nb8 * 8u - b.card;              // 0..7 (team-uniform)
-        uint32_t last = 0;
-        if (pads && half == 0) last = __ldg(reinterpret_cast<const uint16_t*>(b.ptr) + b.card - 1);
-        uint32_t addr[3][4];
-#pragma unroll
-        for (int q = 0; q < 3; q++) {
-            addr[q][0] = word_addr_lo(sb, va[q].x); addr[q][1] = word_addr_hi(sb, va[q].x);
-            addr[q][2] = word_addr_lo(sb, va[q].y); addr[q][3] = word_addr_hi(sb, va[q].y);
-            if (lane + 32 * q < na8) {          // (array tails are padded with copies of the last element: setting a bit twice is harmless)
-                red_or_at(addr[q][0], 1u << (va[q].x & 31)); red_or_at(addr[q][1], 1u << (upper16(va[q].x) & 31));
-                red_or_at(addr[q][2], 1u << (va[q].y & 31)); red_or_at(addr[q][3], 1u << (upper16(va[q].y) & 31));
+            for (int q = 0; q < 4; q++) {
+                c += (lds_u32(word_addr_lo(sb, w[q])) >> (w[q] & 31)) & 1u;
+                c += (lds_u32(word_addr_hi(sb, w[q])) >> (upper16(w[q]) & 31)) & 1u;
             }
         }
-        for (uint32_t i = lane + 96; i < na8; i += 32) {      // > 768 elements: rare
-            const uint2 v = ldg_nc64(a2 + 2u * i);
-            red_or_at(word_addr_lo(sb, v.x), 1u << (v.x & 31)); red_or_at(word_addr_hi(sb, v.x), 1u << (upper16(v.x) & 31));
-            red_or_at(word_addr_lo(sb, v.y), 1u << (v.y & 31)); red_or_at(word_addr_hi(sb, v.y), 1u << (upper16(v.y) & 31));
+        const uint32_t pads = nb8 * 8u - b.card;
+        if (pads && lane == 0) { const uint32_t last = __ldg(reinterpret_cast<const uint16_t*>(b.ptr) + b.card - 1); c -= pads * ((bm[last >> 5] >> (last & 31)) & 1u); }
+        __syncwarp();
+        for (uint32_t i = lane; i < na8; i += 32) {
+            const uint4 v = ldg_nc(a4 + i); const uint32_t x[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+            for (int k = 0; k < 4; k++) { sts_zero(word_addr_lo(sb, x[k])); sts_zero(word_addr_hi(sb, x[k])); }
         }
-        team_barrier(bar_id);
-        auto probe2 = [&](uint2 v) {
-            return ((lds_u32(word_addr_lo(sb, v.x)) >> (v.x & 31)) & 1u) + ((lds_u32(word_addr_hi(sb, v.x)) >> (upper16(v.x) & 31)) & 1u)
-                 + ((lds_u32(word_addr_lo(sb, v.y)) >> (v.y & 31)) & 1u) + ((lds_u32(word_addr_hi(sb, v.y)) >> (upper16(v.y) & 31)) & 1u);
-        };
-#pragma unroll
-        for (int q = 0; q < 3; q++) if (lane + 32 * q < nb8) c += probe2(vb[q]);
-        for (uint32_t i = lane + 96; i < nb8; i += 32) c += probe2(ldg_nc64(b2 + 2u * i));
-        if (pads && half == 0 && lane == 0) c -= pads * ((bm[last >> 5] >> (last & 31)) & 1u);
-        team_barrier(bar_id);
-#pragma unroll
-        for (int q = 0; q < 3; q++) if (lane + 32 * q < na8) { sts_zero(addr[q][0]); sts_zero(addr[q][1]); sts_zero(addr[q][2]); sts_zero(addr[q][3]); }
-        for (uint32_t i = lane + 96; i < na8; i += 32) {     // the words of the chunks past the register window: addresses recomputed
-            const uint2 v = ldg_nc64(a2 + 2u * i);
-            sts_zero(word_addr_lo(sb, v.x)); sts_zero(word_addr_hi(sb, v.x)); sts_zero(word_addr_lo(sb, v.y)); sts_zero(word_addr_hi(sb, v.y));
-        }
-        team_barrier(bar_id);
-    } else if (a.typ == kArray) {                             // array x bitmap: roaring.go:4596 — the warps take alternate chunks
-        const uint32_t* g = reinterpret_cast<const uint32_t*>(b.ptr);
-        const uint4* a4 = reinterpret_cast<const uint4*>(a.ptr);
-        const uint32_t n8 = (a.card + 7) >> 3;
-        for (uint32_t i = lane + 32u * half; i < n8; i += 64) {
-            const uint4 v = ldg_nc(a4 + i);
-            const uint32_t e[8] = { v.x & 0xffffu, v.x >> 16, v.y & 0xffffu, v.y >> 16, v.z & 0xffffu, v.z >> 16, v.w & 0xffffu, v.w >> 16 };
-            uint32_t w[8];
-#pragma unroll
-            for (int q = 0; q < 8; q++) w[q] = (i * 8 + q < a.card) ? __ldg(g + (e[q] >> 5)) : 0u;
-#pragma unroll
-            for (int q = 0; q < 8; q++) c += (w[q] >> (e[q] & 31)) & 1u;
-        }
-    } else {                                                  // bitmap x bitmap: roaring.go:4611 — each warp one half of the words
+        __syncwarp();
+    } else if (a.typ == kArray) {                             // array x bitmap: roaring.go:4596
+        c = warp_probe_global(reinterpret_cast<const uint32_t*>(b.ptr), reinterpret_cast<const uint16_t*>(a.ptr), a.card, lane);
+    } else {                                                  // bitmap x bitmap: roaring.go:4611
         const uint4* x = reinterpret_cast<const uint4*>(a.ptr); const uint4* y = reinterpret_cast<const uint4*>(b.ptr);
 #pragma unroll 8
-        for (int i = lane + 32 * half; i < 512; i += 64) c += popc4(and4(ldg_nc(x + i), ldg_nc(y + i)));
+        for (int i = lane; i < 512; i += 32) c += popc4(and4(ldg_nc(x + i), ldg_nc(y + i)));
     }
     return __reduce_add_sync(0xffffffffu, c);
 }
 
-// Count(Intersect(Row(fvA,rowA), Row(fvB,rowB))): one two-warp TEAM per (shard, slot) container pair.  A team owns the units
-// t, t+T, t+2T, ...; both of its warps walk the descriptor chains of up to 16 of the team's units at once (lane 2k / 2k+1 = side a / b
-// of unit k; the second warp's loads hit the lines the first one pulled in), then intersect them one after the other.
-__global__ void __launch_bounds__(kPcTeams * 64, FBGPU_PAIR_MIN_BLOCKS)
+// Count(Intersect(Row(fvA,rowA), Row(fvB,rowB))): one warp per (shard, slot) container pair, a warp-private 8 KiB bitmap in shared
+// memory.  A warp owns the units w, w+W, w+2W, ...; it walks the descriptor chains of up to 16 of its units at once (lane 2k / 2k+1 =
+// side a / b of unit k) and classifies them lane-parallel: for two arrays of at most 768 elements — the shape of the 1 % acceptance
+// point — lane 2k ends up holding the SMALLER array (scattered), lane 2k+1 the larger (probed), so that the per-unit code has no
+// dispatch left: six shuffles, six 16-byte loads per lane, scatter / probe / clear out of a register window.
+// The path is bound by the integer ALU pipe (LOP3 / LEA / SHF issue every second cycle per sub-partition; ncu round 2: 69 % busy at
+// 0.38 of the HBM roofline with 435 ALU instructions per pair, of which ~205 are the scatter and probe arithmetic itself): every
+// instruction that is not per-element work was taken out of the per-unit loop.
+__global__ void __launch_bounds__(kPcWarps * 32, FBGPU_PAIR_MIN_BLOCKS)
 pair_count_kernel(StoreRef st, uint32_t fvA, uint64_t rowA, uint32_t fvB, uint64_t rowB,
                   const uint64_t* __restrict__ rowsA, const uint64_t* __restrict__ rowsB, long long units_per_pair,
                   const uint64_t* __restrict__ shards, uint64_t shard0, long long n_units,
                   unsigned long long* total, unsigned long long* per_shard, unsigned long long* per_pair, FuseReduce fr) {
     extern __shared__ __align__(128) uint32_t smem32[];
-    // per-pair counts of this CTA (multi-pair form): summed here with shared-memory atomics and added to the global vector once per
-    // CTA and pair at the end.  One global atomicAdd per unit onto per_pair[pair] put ~16 k same-address atomics per pair and launch
-    // on one L2 slice: 0.5 ms of the 0.5 ms the 32-pair launch took in every kernel variant measured before this was found.
+    // per-pair counts of this CTA (multi-pair form): summed here and added to the global vector once per CTA and pair at the end —
+    // one global atomicAdd per unit onto per_pair[pair] was ~16 k same-address atomics per pair and launch on one L2 slice
     __shared__ unsigned long long s_pair[kPcPairSlots];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, team = wid >> 1, half = wid & 1, bar_id = 1 + team;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const long long n_pairs = per_pair ? (n_units + units_per_pair - 1) / units_per_pair : 0;
     const bool pairs_in_smem = per_pair && n_pairs <= kPcPairSlots;
     if (pairs_in_smem) { for (int i = threadIdx.x; i < (int)n_pairs; i += blockDim.x) s_pair[i] = 0; __syncthreads(); }
-    uint32_t* bm = smem32 + team * 2048;
-    {   uint4* b4 = reinterpret_cast<uint4*>(bm);          // the only full clear: team_intersection_count leaves the bitmap all-zero again
+    uint32_t* bm = smem32 + wid * 2048;
+    {   uint4* b4 = reinterpret_cast<uint4*>(bm);          // the only full clear: every path leaves the bitmap all-zero again
 #pragma unroll 4
-        for (int i = lane + 32 * half; i < 512; i += 64) b4[i] = make_uint4(0, 0, 0, 0); }
-    team_barrier(bar_id);
-    unsigned long long acc = 0;
-    const long long stride = (long long)gridDim.x * kPcTeams;
-    for (long long base = (long long)blockIdx.x * kPcTeams + team; base < n_units; base += stride * 16) {
-        // resolve up to 16 units of this team concurrently
+        for (int i = lane; i < 512; i += 32) b4[i] = make_uint4(0, 0, 0, 0); }
+    __syncwarp();
+    smem_base_t sb = smem_base((uint32_t)__cvta_generic_to_shared(bm));
+    pin_base(sb);
+    unsigned long long acc = 0, run_sum = 0;               // run_sum: count of the current pair index / shard, flushed when it changes
+    long long run_key = -1;
+    auto flush = [&]() {
+        if (run_key >= 0 && run_sum && lane == 0) {
+            if (pairs_in_smem) atomicAdd(&s_pair[run_key], run_sum);
+            else if (per_pair) atomicAdd(&per_pair[run_key], run_sum);
+            else atomicAdd(&per_shard[run_key], run_sum);
+        }
+        run_sum = 0;
+    };
+    const long long stride = (long long)gridDim.x * kPcWarps;
+    for (long long base = (long long)blockIdx.x * kPcWarps + wid; base < n_units; base += stride * 16) {
+        // ---- resolve up to 16 units of this warp concurrently
         // multi-pair form (rowsA != null): unit = pair * units_per_pair + (shard index * 16 + slot)
         const long long my_unit = base + (long long)(lane >> 1) * stride;
         Resolved r; r.ptr = nullptr; r.card = 0; r.typ = 0; r.cnt = 0;
@@ -1262,37 +1210,108 @@ pair_count_kernel(StoreRef st, uint32_t fvA, uint64_t rowA, uint32_t fvB, uint64
             r = (lane & 1) ? resolve(st, fvB, shard, rowsA ? rowsB[pr] : rowB, (int)(su & 15))
                            : resolve(st, fvA, shard, rowsA ? rowsA[pr] : rowA, (int)(su & 15));
         }
+        // ---- classify lane-parallel; for the fast class put the smaller array into the even lane
         const uint32_t meta = ((uint32_t)r.typ << 16) | r.cnt;
-        auto fetch = [&](int src) {
-            Resolved x;
-            x.ptr = (const void*)__shfl_sync(0xffffffffu, (unsigned long long)r.ptr, src);
-            x.card = __shfl_sync(0xffffffffu, r.card, src);
-            uint32_t m = __shfl_sync(0xffffffffu, meta, src);
-            x.typ = m >> 16; x.cnt = m & 0xffff;
-            return x;
-        };
-        long long pr = per_pair ? base / units_per_pair : 0, pr_rem = per_pair ? base - pr * units_per_pair : 0;     // pair index of unit k, kept incrementally
+        unsigned long long my_ptr = (unsigned long long)r.ptr; uint32_t my_card = r.card;
+        {
+            const uint32_t o_card = __shfl_xor_sync(0xffffffffu, r.card, 1), o_meta = __shfl_xor_sync(0xffffffffu, meta, 1);
+            const unsigned long long o_ptr = __shfl_xor_sync(0xffffffffu, my_ptr, 1);
+            const bool fast = my_ptr != 0 && o_ptr != 0 && r.typ == kArray && (o_meta >> 16) == kArray && r.card <= kPcFastCard && o_card <= kPcFastCard;
+            const bool absent = my_ptr == 0 || o_ptr == 0;
+            const uint32_t even_card = (lane & 1) ? o_card : r.card, odd_card = (lane & 1) ? r.card : o_card;
+            if (fast && even_card > odd_card) { my_ptr = o_ptr; my_card = o_card; }        // swap the two lanes' containers
+            my_card |= fast ? (1u << 20) : absent ? 0u : (2u << 20);                          // bits 20..21: 0 absent, 1 fast, 2 generic
+        }
+        long long pr = per_pair ? base / units_per_pair : 0, pr_rem = per_pair ? base - pr * units_per_pair : 0;     // pair index of unit k, kept incrementally (one division per round)
         for (int k = 0; k < 16; k++) {
             const long long unit = base + (long long)k * stride;
             if (unit >= n_units) break;
-            const Resolved a = fetch(2 * k), b = fetch(2 * k + 1);
-            // this warp's share of the count; it can be "negative" (the pad correction of a pair is applied in warp 0 only), so it is
-            // sign-extended before it is added to a 64-bit sum
-            const unsigned long long c = (unsigned long long)(long long)(int32_t)team_intersection_count(a, b, bm, lane, half, bar_id);
-            acc += c;
-            if (c && lane == 0) {
-                if (pairs_in_smem) atomicAdd(&s_pair[pr], c);
-                else if (per_pair) atomicAdd(&per_pair[pr], c);
-                else if (per_shard) atomicAdd(&per_shard[unit >> 4], c);
+            const uint32_t ca = __shfl_sync(0xffffffffu, my_card, 2 * k), cb = __shfl_sync(0xffffffffu, my_card, 2 * k + 1);
+            uint32_t c = 0;
+            if ((ca >> 20) == 1u) {
+                // ---- two small arrays: a (even lane) is scattered, b probed; lane L owns chunks L, L+32, L+64 of both
+                const uint4* a4 = reinterpret_cast<const uint4*>(__shfl_sync(0xffffffffu, my_ptr, 2 * k)) + lane;
+                const uint4* b4 = reinterpret_cast<const uint4*>(__shfl_sync(0xffffffffu, my_ptr, 2 * k + 1)) + lane;
+                const uint32_t card_b = cb & 0xfffffu, na8 = ((ca & 0xfffffu) + 7) >> 3, nb8 = (card_b + 7) >> 3;
+                // (chunks past an array's end are loaded too — the arena ends with 4 KiB of slack — and never used)
+                const uint4 va0 = ldg_nc(a4), va1 = ldg_nc(a4 + 32), va2 = ldg_nc(a4 + 64);
+                const uint4 vb0 = ldg_nc(b4), vb1 = ldg_nc(b4 + 32), vb2 = ldg_nc(b4 + 64);
+                const bool pa0 = (uint32_t)lane < na8, pa1 = (uint32_t)lane + 32 < na8, pa2 = (uint32_t)lane + 64 < na8;
+                uint32_t addr[3][8];
+                auto scatter = [&](const uint4& v, uint32_t (&ad)[8], bool on) {
+                    const uint32_t x[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+                    for (int q = 0; q < 4; q++) { ad[2 * q] = word_addr_lo(sb, x[q]); ad[2 * q + 1] = word_addr_hi(sb, x[q]); }
+                    if (on) {       // (array tails are padded with copies of the last element: setting a bit twice is harmless)
+#pragma unroll
+                        for (int q = 0; q < 4; q++) { red_or_at(ad[2 * q], 1u << (x[q] & 31)); red_or_at(ad[2 * q + 1], 1u << (upper16(x[q]) & 31)); }
+                    }
+                };
+                scatter(va0, addr[0], pa0); scatter(va1, addr[1], pa1); scatter(va2, addr[2], pa2);
+                __syncwarp();
+                // every chunk of b is probed whole: the slots behind its last element hold copies of that element (pad_array_tail),
+                // which are taken out of the count again below — no divergent partial-chunk path
+                auto probe = [&](const uint4& v) {
+                    const uint32_t x[4] = { v.x, v.y, v.z, v.w };
+                    uint32_t n = 0;
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        n += (lds_u32(word_addr_lo(sb, x[q])) >> (x[q] & 31)) & 1u;
+                        n += (lds_u32(word_addr_hi(sb, x[q])) >> (upper16(x[q]) & 31)) & 1u;
+                    }
+                    return n;
+                };
+                if ((uint32_t)lane < nb8) c += probe(vb0);
+                if ((uint32_t)lane + 32 < nb8) c += probe(vb1);
+                if ((uint32_t)lane + 64 < nb8) c += probe(vb2);
+                const uint32_t pads = nb8 * 8u - card_b;              // 0..7 copies of b's last element were probed too (warp-uniform)
+                if (pads) {
+                    const uint32_t ql = (nb8 - 1u) >> 5;               // the chunk holding them: register window slot ql of lane (nb8 - 1) & 31
+                    uint32_t wl = ql == 0 ? vb0.w : ql == 1 ? vb1.w : vb2.w;
+                    wl = __shfl_sync(0xffffffffu, wl, (int)((nb8 - 1u) & 31u)) >> 16;
+                    if (lane == 0) c -= pads * ((bm[wl >> 5] >> (wl & 31)) & 1u);
+                }
+                __syncwarp();
+                if (pa0) {
+#pragma unroll
+                    for (int q = 0; q < 8; q++) sts_zero(addr[0][q]);
+                }
+                if (pa1) {
+#pragma unroll
+                    for (int q = 0; q < 8; q++) sts_zero(addr[1][q]);
+                }
+                if (pa2) {
+#pragma unroll
+                    for (int q = 0; q < 8; q++) sts_zero(addr[2][q]);
+                }
+                __syncwarp();
+                c = __reduce_add_sync(0xffffffffu, c);
+            } else if ((ca >> 20) == 2u) {
+                auto fetch = [&](int src) {     // the original container of lane `src` (the generic class is never swapped)
+                    Resolved x;
+                    x.ptr = (const void*)__shfl_sync(0xffffffffu, (unsigned long long)r.ptr, src);
+                    x.card = __shfl_sync(0xffffffffu, r.card, src);
+                    const uint32_t m = __shfl_sync(0xffffffffu, meta, src);
+                    x.typ = m >> 16; x.cnt = m & 0xffff;
+                    return x;
+                };
+                c = warp_intersection_count_generic(fetch(2 * k), fetch(2 * k + 1), bm, lane);
             }
-            if (per_pair) { pr_rem += stride; while (pr_rem >= units_per_pair) { pr_rem -= units_per_pair; pr++; } }
+            acc += c;
+            if (per_pair || per_shard) {                    // (uniform) sums per pair index / per shard: consecutive units mostly share the key
+                const long long key = per_pair ? pr : (unit >> 4);
+                if (key != run_key) { flush(); run_key = key; }
+                run_sum += c;
+                if (per_pair) { pr_rem += stride; while (pr_rem >= units_per_pair) { pr_rem -= units_per_pair; pr++; } }
+            }
         }
     }
+    if (per_pair || per_shard) flush();
     if (pairs_in_smem) {
         __syncthreads();
         for (int i = threadIdx.x; i < (int)n_pairs; i += blockDim.x) { const unsigned long long v = s_pair[i]; if (v) atomicAdd(&per_pair[i], v); }
     }
-    if (lane == 0 && total) { if (acc) atomicAdd(total, acc); fused_allreduce_tail(fr, total, gridDim.x * kPcTeams * 2); }
+    if (lane == 0 && total) { if (acc) atomicAdd(total, acc); fused_allreduce_tail(fr, total, gridDim.x * kPcWarps); }
 }
 
 // Container-pair-type histogram of a Count(Intersect(Row, Row)) query: hist[4 * ta + tb] += 1 per (shard, slot) unit, t = 0 absent,

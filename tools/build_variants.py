@@ -3,14 +3,13 @@ import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from featurebase_b200 import build as B
 VARIANTS = {   # name -> -D defines; edit freely, outputs featurebase_b200/libfbgpu_<name>.so (select with FBGPU_LIB=...)
-    "eval_nopf": ["FBGPU_EVAL_NO_DIRPF"],       # eval_kernel without the L2 prefetch of the next unit's directory entries
     "addr_imad": ["FBGPU_ADDR_IMAD"],            # scatter / probe word addresses with IMAD.HI on the FMA pipe (measured slower: IMAD.HI is half rate)
     "wp_reg3": ["FBGPU_WP_REG_RING", "FBGPU_WP_RING=3"],   # word-parallel op loop with a REGISTER ring of 3 operand slices (22 us on config 3 in the round-2 first measurement)
     "wp_reg6": ["FBGPU_WP_REG_RING", "FBGPU_WP_RING=6"],   # register ring of 6 (30 us: the default of call 5)
     "wp_narrow": ["FBGPU_WP_NARROW"],                      # cp.async ring with 16 bytes per thread, 128 threads per CTA (19 us on config 3; default: 32 bytes, 64 threads)
     "wp_async4": ["FBGPU_WP_ASYNC_DEPTH=4"],               # cp.async shared-memory ring (default depth 8)
-    "pair_mb3": ["FBGPU_PAIR_MIN_BLOCKS=3"],               # pair_count_kernel: 3 CTAs of 8 teams per SM (42 registers) instead of 2 (64)
-    "pair_t4": ["FBGPU_PAIR_TEAMS=4", "FBGPU_PAIR_MIN_BLOCKS=4"],   # 4 CTAs of 4 teams
+    "pair_w8": ["FBGPU_PAIR_WARPS=8"],                     # pair_count_kernel: 3 CTAs of 8 warps per SM (default 9)
+    "pair_w13b2": ["FBGPU_PAIR_WARPS=13", "FBGPU_PAIR_MIN_BLOCKS=2"],   # 2 CTAs of 13 warps
     "wp_legacy": ["FBGPU_WP_LEGACY_LOOP"],       # round-1 rotating-ring loop
     "pair_unscatter": ["FBGPU_PAIR_UNSCATTER"],
     "eval_deep1": ["FBGPU_EVAL_DEEP=1"],                                  # round-1 scatter loop: one chunk load in flight per lane
