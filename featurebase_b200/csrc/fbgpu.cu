@@ -1603,7 +1603,7 @@ extern "C" int fbgpu_any(fbgpu_ctx* c, uint32_t index, const fbgpu_op* ops, int3
 
 // ------------------------------------------------------------------ GroupBy
 // Slots per CTA of groupby_shard_kernel (16, 8, 4, 2 or 1), or 0 when the fields are not its shape: picked so that a group of
-// slots of field a holds about 12 k columns (the table takes 20 k), from the cardinality of a sample of the listed shards' fragments.
+// slots of field a holds about 12 k columns (3/5 of what the table takes), from the cardinality of a sample of the listed shards' fragments.
 static int groupby_slots_per_group(fbgpu_ctx* c, uint32_t fvA, uint32_t fvB, const uint64_t* shards, int64_t n) {
     if (fvA >= c->shardmaps.size() || fvB >= c->shardmaps.size() || n <= 0) return 0;
     if (c->view_other[fvA] * 8 > c->view_arr[fvA] || c->view_other[fvB] * 8 > c->view_arr[fvB]) return 0;     // bitmap / run heavy: the per-slot kernels
@@ -1617,7 +1617,7 @@ static int groupby_slots_per_group(fbgpu_ctx* c, uint32_t fvA, uint32_t fvB, con
     }
     if (!seen) return 16;
     const uint64_t avg = elems / seen;                       // columns of field a per shard (all its rows: an upper bound for a row subset)
-    for (int spg = 16; spg >= 1; spg >>= 1) if (avg * (uint64_t)spg / 16 <= 12000) return spg;
+    for (int spg = 16; spg >= 1; spg >>= 1) if (avg * (uint64_t)spg / 16 <= (uint64_t)kGhMaxEntries * 3 / 5) return spg;
     return 0;
 }
 
@@ -1656,7 +1656,7 @@ static int groupby2(fbgpu_ctx* c, uint32_t index, uint32_t fvA, const uint64_t* 
             unsigned int* d_fb = (unsigned int*)w->d_emit_units.p;
             CUDA_TRY(cudaMemsetAsync(d_fb, 0, 4, w->stream));
             const long long hunits = ns * (kSlotsPerRow / spg);
-            const long long hgrid = std::min<long long>(hunits, (long long)c->sm_count);
+            const long long hgrid = std::min<long long>(hunits, (long long)c->sm_count * (1024 / kGhThreads));
             groupby_shard_kernel<<<(unsigned)hgrid, kGhThreads, kGhSmemBytes, w->stream>>>(store_ref(c), fvA, (const uint64_t*)w->d_rows.p, nA, fvB, (const uint64_t*)w->d_rows.p + nA, nB,
                 d_shards + s0, ns, spg, have_filter ? (const uint4*)w->d_bitmaps.p : nullptr, (unsigned long long*)w->d_counts.p, d_fb);
             CUDA_TRY(cudaGetLastError()); launches++;

@@ -1053,6 +1053,10 @@ constexpr int kPairWarps = 8;           // row_count_kernel
 #endif
 constexpr int kPcWarps = FBGPU_PAIR_WARPS;                  // warps per CTA of pair_count_kernel, one 8 KiB bitmap each (27 per SM)
 constexpr int kPcPairSlots = 256;                           // row pairs per launch whose counts are summed in shared memory first
+#ifndef FBGPU_PAIR_BM_UNROLL
+#define FBGPU_PAIR_BM_UNROLL 8
+#endif
+constexpr int kPcBmUnroll = FBGPU_PAIR_BM_UNROLL;           // bitmap x bitmap: pairs of 16-byte loads in flight per lane
 constexpr uint32_t kPcFastCard = 768;                       // arrays up to this size take the register-window path (3 chunks per lane)
 
 // Pairs with a run container on at least one side; returns the per-lane partial count.  The searched interval list (<= 2048 runs =
@@ -1153,7 +1157,7 @@ __device__ __noinline__ uint32_t warp_intersection_count_generic(Resolved a, Res
         c = warp_probe_global(reinterpret_cast<const uint32_t*>(b.ptr), reinterpret_cast<const uint16_t*>(a.ptr), a.card, lane);
     } else {                                                  // bitmap x bitmap: roaring.go:4611
         const uint4* x = reinterpret_cast<const uint4*>(a.ptr); const uint4* y = reinterpret_cast<const uint4*>(b.ptr);
-#pragma unroll 8
+#pragma unroll kPcBmUnroll
         for (int i = lane; i < 512; i += 32) c += popc4(and4(ldg_nc(x + i), ldg_nc(y + i)));
     }
     return __reduce_add_sync(0xffffffffu, c);
@@ -1228,6 +1232,12 @@ pair_count_kernel(StoreRef st, uint32_t fvA, uint64_t rowA, uint32_t fvB, uint64
             if (unit >= n_units) break;
             const uint32_t ca = __shfl_sync(0xffffffffu, my_card, 2 * k), cb = __shfl_sync(0xffffffffu, my_card, 2 * k + 1);
             uint32_t c = 0;
+#ifndef FBGPU_PAIR_NO_PF
+            if (k < 15) {       // the NEXT unit's payloads on their way to L2 while this one is intersected: lanes 0-11 / 16-27 one 128-byte line each
+                const unsigned long long np = __shfl_sync(0xffffffffu, my_ptr, 2 * k + 2 + (lane >> 4));
+                if (np != 0 && (lane & 15) < 12) asm volatile("prefetch.global.L2 [%0];" :: "l"(np + (unsigned long long)(lane & 15) * 128ull));
+            }
+#endif
             if ((ca >> 20) == 1u) {
                 // ---- two small arrays: a (even lane) is scattered, b probed; lane L owns chunks L, L+32, L+64 of both
                 const uint4* a4 = reinterpret_cast<const uint4*>(__shfl_sync(0xffffffffu, my_ptr, 2 * k)) + lane;
@@ -1975,15 +1985,17 @@ groupby_kernel(StoreRef st, uint32_t fvA, const uint64_t* __restrict__ rowsA, in
 // counted when an a- or b-row container is not an array, an a-row holds more than kGhMaxCard columns, or the group holds more entries
 // than 5/8 of the table.
 // ------------------------------------------------------------------------------------------------
-constexpr int kGhThreads = 1024;
+#ifndef FBGPU_GH_THREADS
+#define FBGPU_GH_THREADS 1024
+#endif
+constexpr int kGhThreads = FBGPU_GH_THREADS;      // 1024 (one CTA per SM) or 512 (two)
 constexpr int kGhItems = 2;                       // containers per thread and pass
-constexpr int kGhSlots = 32768;                   // 128 KiB
+constexpr int kGhSlots = kGhThreads * 32;         // 128 KiB (64 KiB)
 constexpr uint32_t kGhMaxEntries = kGhSlots / 8 * 5;
 constexpr uint32_t kGhMaxCard = 512;
-constexpr int kGhStage = 32 * kGhItems * 8;       // entries of a warp's staging list: 8 per container (2 KiB per warp, 64 KiB per CTA)
-constexpr size_t kGhSmemBytes = (size_t)kGhSlots * 4 + (size_t)(kGhThreads / 32) * kGhStage * 4;
+constexpr size_t kGhSmemBytes = (size_t)kGhSlots * 4;
 
-__device__ __forceinline__ uint32_t gh_hash(uint32_t key) { return (key * 2654435761u) >> 17; }   // 15 bits
+__device__ __forceinline__ uint32_t gh_hash(uint32_t key) { return (key * 2654435761u) >> (kGhThreads == 1024 ? 17 : 18); }   // log2(kGhSlots) bits
 
 // resolve() with the view's table entry already in registers (one unit looks up hundreds of rows of the same two views)
 __device__ __forceinline__ Resolved gh_resolve(const StoreRef& st, const ViewTab& v, uint32_t fv, uint64_t shard, uint64_t row, int slot) {
@@ -1997,7 +2009,7 @@ __device__ __forceinline__ Resolved gh_resolve(const StoreRef& st, const ViewTab
     return r;
 }
 
-__global__ void __launch_bounds__(kGhThreads, 1)
+__global__ void __launch_bounds__(kGhThreads, 1024 / kGhThreads)
 groupby_shard_kernel(StoreRef st, uint32_t fvA, const uint64_t* __restrict__ rowsA, int nA,
                      uint32_t fvB, const uint64_t* __restrict__ rowsB, int nB,
                      const uint64_t* __restrict__ shards, long long n_shards, int spg /* slots per group: 1, 2, 4, 8 or 16 */,
@@ -2007,7 +2019,6 @@ groupby_shard_kernel(StoreRef st, uint32_t fvA, const uint64_t* __restrict__ row
     __shared__ uint32_t red[kGhThreads / 32];
     __shared__ uint32_t s_tot, s_dups;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    uint32_t* stg = gh_tab + kGhSlots + wid * kGhStage;              // this warp's staging list
     const int groups = kSlotsPerRow / spg, spg_sh = 31 - __clz(spg);
     const int rows_per_pass = (kGhThreads * kGhItems) >> spg_sh;     // rows of a field one pass covers (<= 2048: 12-bit row index)
     const long long n_units = n_shards * groups;
@@ -2033,54 +2044,33 @@ groupby_shard_kernel(StoreRef st, uint32_t fvA, const uint64_t* __restrict__ row
             __syncthreads();                                    // (previous readers of red / s_tot are done)
             if (lane == 0) red[wid] = v;
             const int any = __syncthreads_or(flag ? 1 : 0);
-            if (wid == 0) { uint32_t t = red[lane]; t = __reduce_add_sync(0xffffffffu, t); if (lane == 0) s_tot = t; }
+            if (wid == 0) { uint32_t t = lane < kGhThreads / 32 ? red[lane] : 0u; t = __reduce_add_sync(0xffffffffu, t); if (lane == 0) s_tot = t; }
             __syncthreads();
             total = s_tot;
             return any != 0;
         };
-        // Elements of this lane's containers -> entries ((slot-in-group << 16 | column) << 12) | row index in the pass.  The first 16-byte
-        // chunk (8 elements) of every container goes to a fixed place in the warp's staging list — 8 entries per container, EMPTY behind
-        // its last element, two 16-byte stores, no scan and no per-element branch — and the warp then takes the 512 slots 32 at a time:
-        // the hash-table work is spread over the lanes whatever the containers' sizes are (walking its own containers, a lane was
-        // busy 16 of 32 slots on average: cardinalities of ~6 +- 2.4).  Elements past a container's 8th are walked by its lane.
+        // Elements of this lane's containers -> entries ((slot-in-group << 16 | column) << 12) | row index in the pass, walked by the
+        // lane itself.  (Two ways of spreading the entries over the warp first — a scan + compacted staging list, and fixed 8-entry
+        // slots per container in shared memory — were measured and were slower, 0.34 and 0.44 ms against 0.25 ms on BASELINE config 4:
+        // the extra stores, loads and the divergent validity test cost more than the idle lanes they fill.)
         auto for_each_entry = [&](const Resolved (&it)[kGhItems], const uint4 (&first)[kGhItems], bool first_valid, auto&& fn) {
 #pragma unroll
             for (int k = 0; k < kGhItems; k++) {
-                uint32_t e8[8];
-#pragma unroll
-                for (int q = 0; q < 8; q++) e8[q] = kGbEmpty;
-                if (it[k].ptr) {
-                    const int e = tid + k * kGhThreads, i = e >> spg_sh, sl = e & (spg - 1);
-                    const uint32_t hi = ((uint32_t)sl << 28) | (uint32_t)i;
-                    const uint32_t* flt = filter_bitmaps ? reinterpret_cast<const uint32_t*>(filter_bitmaps + ((size_t)si * kSlotsPerRow + g * spg + sl) * 512) : nullptr;
-                    const uint4 v = first_valid ? first[k] : ldg_nc(reinterpret_cast<const uint4*>(it[k].ptr));
-                    const uint32_t w[4] = { v.x, v.y, v.z, v.w };
-#pragma unroll
-                    for (int q = 0; q < 8; q++) {
-                        const uint32_t col = (w[q >> 1] >> ((q & 1) * 16)) & 0xffffu;
-                        bool keep = (uint32_t)q < it[k].card;
-                        if (flt && keep) keep = ((__ldg(flt + (col >> 5)) >> (col & 31)) & 1u) != 0;
-                        if (keep) e8[q] = hi | (col << 12);
-                    }
-                }
-                uint4* dst = reinterpret_cast<uint4*>(stg + (lane * kGhItems + k) * 8);
-                dst[0] = make_uint4(e8[0], e8[1], e8[2], e8[3]); dst[1] = make_uint4(e8[4], e8[5], e8[6], e8[7]);
-            }
-            __syncwarp();
-#pragma unroll 4
-            for (int x = lane; x < kGhStage; x += 32) { const uint32_t ent = stg[x]; if (ent != kGbEmpty) fn(ent); }
-            __syncwarp();
-#pragma unroll
-            for (int k = 0; k < kGhItems; k++) {           // containers of more than 8 elements: the rest, by the owning lane
-                if (!it[k].ptr || it[k].card <= 8) continue;
+                if (!it[k].ptr) continue;
                 const int e = tid + k * kGhThreads, i = e >> spg_sh, sl = e & (spg - 1);
                 const uint32_t hi = ((uint32_t)sl << 28) | (uint32_t)i;
                 const uint32_t* flt = filter_bitmaps ? reinterpret_cast<const uint32_t*>(filter_bitmaps + ((size_t)si * kSlotsPerRow + g * spg + sl) * 512) : nullptr;
-                const uint16_t* p = reinterpret_cast<const uint16_t*>(it[k].ptr);
-                for (uint32_t j = 8; j < it[k].card; j++) {
-                    const uint32_t col = __ldg(p + j);
-                    if (flt && !((__ldg(flt + (col >> 5)) >> (col & 31)) & 1u)) continue;
-                    fn(hi | (col << 12));
+                const uint4* p = reinterpret_cast<const uint4*>(it[k].ptr);
+                for (uint32_t k0 = 0; k0 < it[k].card; k0 += 8) {
+                    const uint4 v = (k0 == 0 && first_valid) ? first[k] : ldg_nc(p + (k0 >> 3));
+                    const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+                    for (int q = 0; q < 8; q++) {
+                        if (k0 + q >= it[k].card) break;
+                        const uint32_t col = (w[q >> 1] >> ((q & 1) * 16)) & 0xffffu;
+                        if (flt && !((__ldg(flt + (col >> 5)) >> (col & 31)) & 1u)) continue;
+                        fn(hi | (col << 12));
+                    }
                 }
             }
         };
