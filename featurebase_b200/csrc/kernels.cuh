@@ -1046,12 +1046,12 @@ __device__ __forceinline__ uint2 ldg_nc64(const uint2* p) {
 }
 constexpr int kPairWarps = 8;           // row_count_kernel
 #ifndef FBGPU_PAIR_WARPS
-#define FBGPU_PAIR_WARPS 9
+#define FBGPU_PAIR_WARPS 8
 #endif
 #ifndef FBGPU_PAIR_MIN_BLOCKS
 #define FBGPU_PAIR_MIN_BLOCKS 3
 #endif
-constexpr int kPcWarps = FBGPU_PAIR_WARPS;                  // warps per CTA of pair_count_kernel, one 8 KiB bitmap each (27 per SM)
+constexpr int kPcWarps = FBGPU_PAIR_WARPS;                  // warps per CTA of pair_count_kernel, one 8 KiB bitmap each; 3 CTAs per SM (8 warps measured faster than 9: 0.395 vs 0.407 ms)
 constexpr int kPcPairSlots = 256;                           // row pairs per launch whose counts are summed in shared memory first
 #ifndef FBGPU_PAIR_BM_UNROLL
 #define FBGPU_PAIR_BM_UNROLL 8
@@ -1991,23 +1991,11 @@ groupby_kernel(StoreRef st, uint32_t fvA, const uint64_t* __restrict__ rowsA, in
 constexpr int kGhThreads = FBGPU_GH_THREADS;      // 1024 (one CTA per SM) or 512 (two)
 constexpr int kGhItems = 2;                       // containers per thread and pass
 constexpr int kGhSlots = kGhThreads * 32;         // 128 KiB (64 KiB)
+constexpr size_t kGhSmemBytes = (size_t)kGhSlots * 4;
 constexpr uint32_t kGhMaxEntries = kGhSlots / 8 * 5;
 constexpr uint32_t kGhMaxCard = 512;
-constexpr size_t kGhSmemBytes = (size_t)kGhSlots * 4;
 
 __device__ __forceinline__ uint32_t gh_hash(uint32_t key) { return (key * 2654435761u) >> (kGhThreads == 1024 ? 17 : 18); }   // log2(kGhSlots) bits
-
-// resolve() with the view's table entry already in registers (one unit looks up hundreds of rows of the same two views)
-__device__ __forceinline__ Resolved gh_resolve(const StoreRef& st, const ViewTab& v, uint32_t fv, uint64_t shard, uint64_t row, int slot) {
-    if (v.rt_rows == 0) return resolve(st, fv, shard, row, slot);          // sparse row ids: the search chain
-    Resolved r; r.ptr = nullptr; r.card = 0; r.typ = 0; r.cnt = 0;
-    if (row < v.rmin || row - v.rmin >= v.rt_rows) return r;
-    const RowTabEnt e = st.rowtab[v.rt_off + shard * v.rt_rows + (row - v.rmin)];
-    if (!((e.mask >> slot) & 1)) return r;
-    const ContDesc d = st.descs[e.first_desc + __popc(e.mask & ((1u << slot) - 1u))];
-    r.ptr = st.payload + (size_t)d.off16 * 16; r.card = d.card; r.typ = d.typ; r.cnt = d.cnt;
-    return r;
-}
 
 __global__ void __launch_bounds__(kGhThreads, 1024 / kGhThreads)
 groupby_shard_kernel(StoreRef st, uint32_t fvA, const uint64_t* __restrict__ rowsA, int nA,
@@ -2017,26 +2005,27 @@ groupby_shard_kernel(StoreRef st, uint32_t fvA, const uint64_t* __restrict__ row
                      unsigned long long* counts /* [nA*nB] */, unsigned int* fallback /* [0] = n, then (shard index * 16 + slot) units */) {
     extern __shared__ __align__(16) uint32_t gh_tab[];
     __shared__ uint32_t red[kGhThreads / 32];
-    __shared__ uint32_t s_tot, s_dups;
+    __shared__ uint32_t s_tot;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int groups = kSlotsPerRow / spg, spg_sh = 31 - __clz(spg);
-    const int rows_per_pass = (kGhThreads * kGhItems) >> spg_sh;     // rows of a field one pass covers (<= 2048: 12-bit row index)
+    const int groups = kSlotsPerRow / spg;
+    const int rows_per_pass = (kGhThreads * kGhItems) / spg;         // rows of a field one pass covers (<= 2048: 12-bit row index)
     const long long n_units = n_shards * groups;
     for (long long unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
         const long long si = unit / groups;
         const int g = (int)(unit - si * groups);
         const uint64_t shard = shards[si];
-        if (fvA >= st.n_views || fvB >= st.n_views) continue;
-        const ViewTab vwA = st.views[fvA], vwB = st.views[fvB];
-        // executor.go:8769-8772: a shard missing either fragment contributes nothing (uniform test, broadcast loads)
-        if (!(shard < vwA.n_shards && shard < vwB.n_shards && st.shardmap[vwA.shard_off + shard] >= 0 && st.shardmap[vwB.shard_off + shard] >= 0)) continue;
+        {   // executor.go:8769-8772: a shard missing either fragment contributes nothing (uniform test, broadcast loads)
+            bool ok = fvA < st.n_views && fvB < st.n_views;
+            if (ok) { const ViewTab va = st.views[fvA], vb = st.views[fvB]; ok = shard < va.n_shards && shard < vb.n_shards && st.shardmap[va.shard_off + shard] >= 0 && st.shardmap[vb.shard_off + shard] >= 0; }
+            if (!ok) continue;
+        }
         // item e of a pass = (row e / spg of the chunk, slot g * spg + e % spg)
-        auto load_items = [&](const ViewTab& vw, uint32_t fv, const uint64_t* rows, int r0, int n, Resolved (&it)[kGhItems]) {
+        auto load_items = [&](uint32_t fv, const uint64_t* rows, int r0, int n, Resolved (&it)[kGhItems]) {
 #pragma unroll
             for (int k = 0; k < kGhItems; k++) {
-                const int e = tid + k * kGhThreads, i = e >> spg_sh;
+                const int e = tid + k * kGhThreads, i = e / spg;
                 it[k].ptr = nullptr; it[k].card = 0; it[k].typ = 0; it[k].cnt = 0;
-                if (i < n) it[k] = gh_resolve(st, vw, fv, shard, rows[r0 + i], g * spg + (e & (spg - 1)));
+                if (i < n) it[k] = resolve(st, fv, shard, rows[r0 + i], g * spg + (e - i * spg));
             }
         };
         auto block_sum_or = [&](uint32_t v, bool flag, uint32_t& total) -> bool {      // sum of v and OR of flag over the CTA
@@ -2049,31 +2038,6 @@ groupby_shard_kernel(StoreRef st, uint32_t fvA, const uint64_t* __restrict__ row
             total = s_tot;
             return any != 0;
         };
-        // Elements of this lane's containers -> entries ((slot-in-group << 16 | column) << 12) | row index in the pass, walked by the
-        // lane itself.  (Two ways of spreading the entries over the warp first — a scan + compacted staging list, and fixed 8-entry
-        // slots per container in shared memory — were measured and were slower, 0.34 and 0.44 ms against 0.25 ms on BASELINE config 4:
-        // the extra stores, loads and the divergent validity test cost more than the idle lanes they fill.)
-        auto for_each_entry = [&](const Resolved (&it)[kGhItems], const uint4 (&first)[kGhItems], bool first_valid, auto&& fn) {
-#pragma unroll
-            for (int k = 0; k < kGhItems; k++) {
-                if (!it[k].ptr) continue;
-                const int e = tid + k * kGhThreads, i = e >> spg_sh, sl = e & (spg - 1);
-                const uint32_t hi = ((uint32_t)sl << 28) | (uint32_t)i;
-                const uint32_t* flt = filter_bitmaps ? reinterpret_cast<const uint32_t*>(filter_bitmaps + ((size_t)si * kSlotsPerRow + g * spg + sl) * 512) : nullptr;
-                const uint4* p = reinterpret_cast<const uint4*>(it[k].ptr);
-                for (uint32_t k0 = 0; k0 < it[k].card; k0 += 8) {
-                    const uint4 v = (k0 == 0 && first_valid) ? first[k] : ldg_nc(p + (k0 >> 3));
-                    const uint32_t w[4] = { v.x, v.y, v.z, v.w };
-#pragma unroll
-                    for (int q = 0; q < 8; q++) {
-                        if (k0 + q >= it[k].card) break;
-                        const uint32_t col = (w[q >> 1] >> ((q & 1) * 16)) & 0xffffu;
-                        if (flt && !((__ldg(flt + (col >> 5)) >> (col & 31)) & 1u)) continue;
-                        fn(hi | (col << 12));
-                    }
-                }
-            }
-        };
         // ---- pass 0: nothing may be counted for a unit that ends up in the fallback list, so every a- and b-row of the group is
         // looked at first when a side needs several passes (a single pass per side is checked on the fly, without extra reads)
         bool decline = false;
@@ -2083,7 +2047,7 @@ groupby_shard_kernel(StoreRef st, uint32_t fvA, const uint64_t* __restrict__ row
                 const int n = side ? nB : nA;
                 for (int r0 = 0; r0 < n && !decline; r0 += rows_per_pass) {
                     Resolved it[kGhItems];
-                    load_items(side ? vwB : vwA, side ? fvB : fvA, side ? rowsB : rowsA, r0, min(rows_per_pass, n - r0), it);
+                    load_items(side ? fvB : fvA, side ? rowsB : rowsA, r0, min(rows_per_pass, n - r0), it);
                     uint32_t cnt = 0; bool bad = false;
 #pragma unroll
                     for (int k = 0; k < kGhItems; k++) if (it[k].ptr) { bad |= it[k].typ != kArray || (!side && it[k].card > kGhMaxCard); cnt += it[k].card; }
@@ -2095,8 +2059,8 @@ groupby_shard_kernel(StoreRef st, uint32_t fvA, const uint64_t* __restrict__ row
         for (int a0 = 0; a0 < nA && !decline; a0 += rows_per_pass) {
             const int chunkA = min(rows_per_pass, nA - a0);
             Resolved ra[kGhItems], rb[kGhItems];
-            load_items(vwA, fvA, rowsA, a0, chunkA, ra);
-            if (!multiB) load_items(vwB, fvB, rowsB, 0, nB, rb);       // (its descriptor chains run while the a-rows are inserted)
+            load_items(fvA, rowsA, a0, chunkA, ra);
+            if (!multiB) load_items(fvB, rowsB, 0, nB, rb);       // (its descriptor chains run while the a-rows are inserted)
             uint4 va[kGhItems], vb[kGhItems];                 // first 16-byte chunk of every container, in flight before the first barrier
             uint32_t cnt = 0; bool bad = false;
 #pragma unroll
@@ -2112,32 +2076,54 @@ groupby_shard_kernel(StoreRef st, uint32_t fvA, const uint64_t* __restrict__ row
             {   uint4* t4 = reinterpret_cast<uint4*>(gh_tab);
 #pragma unroll 4
                 for (int k = tid; k < kGhSlots / 4; k += kGhThreads) t4[k] = make_uint4(kGbEmpty, kGbEmpty, kGbEmpty, kGbEmpty); }
-            if (tid == 0) s_dups = 0;
             __syncthreads();
-            // ---- insert the a-rows (and notice whether any column sits in two of them: only then a probe has to walk past its first hit)
-            for_each_entry(ra, va, true, [&](uint32_t ent) {
-                uint32_t h = gh_hash(ent >> 12);
-                for (;;) {
-                    const uint32_t prev = atomicCAS(&gh_tab[h], kGbEmpty, ent);
-                    if (prev == kGbEmpty) break;
-                    if ((prev >> 12) == (ent >> 12)) s_dups = 1u;
-                    h = (h + 1) & (kGhSlots - 1);
+            // ---- insert the a-rows
+#pragma unroll
+            for (int k = 0; k < kGhItems; k++) {
+                if (!ra[k].ptr) continue;
+                const int e = tid + k * kGhThreads, i = e / spg, sl = e - i * spg;
+                const uint32_t* flt = filter_bitmaps ? reinterpret_cast<const uint32_t*>(filter_bitmaps + ((size_t)si * kSlotsPerRow + g * spg + sl) * 512) : nullptr;
+                const uint4* p = reinterpret_cast<const uint4*>(ra[k].ptr);
+                for (uint32_t k0 = 0; k0 < ra[k].card; k0 += 8) {
+                    const uint4 v = k0 ? ldg_nc(p + (k0 >> 3)) : va[k];
+                    const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+                    for (int q = 0; q < 8; q++) {
+                        if (k0 + q >= ra[k].card) break;
+                        const uint32_t col = (w[q >> 1] >> ((q & 1) * 16)) & 0xffffu;
+                        if (flt && !((__ldg(flt + (col >> 5)) >> (col & 31)) & 1u)) continue;
+                        const uint32_t key = ((uint32_t)sl << 16) | col, ent = (key << 12) | (uint32_t)i;
+                        uint32_t h = gh_hash(key);
+                        while (atomicCAS(&gh_tab[h], kGbEmpty, ent) != kGbEmpty) h = (h + 1) & (kGhSlots - 1);
+                    }
                 }
-            });
+            }
             __syncthreads();
-            const bool dups = s_dups != 0;
             // ---- probe with the b-rows
             for (int b0 = 0; b0 < nB; b0 += rows_per_pass) {
-                if (multiB) load_items(vwB, fvB, rowsB, b0, min(rows_per_pass, nB - b0), rb);
-                unsigned long long* cb = counts + (size_t)a0 * nB + b0;
-                for_each_entry(rb, vb, !multiB, [&](uint32_t ent) {
-                    const uint32_t key = ent >> 12;
-                    for (uint32_t h = gh_hash(key);; h = (h + 1) & (kGhSlots - 1)) {
-                        const uint32_t t = gh_tab[h];
-                        if (t == kGbEmpty) break;
-                        if ((t >> 12) == key) { atomicAdd(cb + ((t & 0xfffu) * (uint32_t)nB + (ent & 0xfffu)), 1ull); if (!dups) break; }
+                const int chunkB = min(rows_per_pass, nB - b0);
+                if (multiB) load_items(fvB, rowsB, b0, chunkB, rb);
+#pragma unroll
+                for (int k = 0; k < kGhItems; k++) {
+                    if (!rb[k].ptr) continue;
+                    const int e = tid + k * kGhThreads, i = e / spg, sl = e - i * spg;
+                    unsigned long long* cj = counts + (size_t)a0 * nB + (b0 + i);
+                    const uint4* p = reinterpret_cast<const uint4*>(rb[k].ptr);
+                    for (uint32_t k0 = 0; k0 < rb[k].card; k0 += 8) {
+                        const uint4 v = (k0 || multiB) ? ldg_nc(p + (k0 >> 3)) : vb[k];
+                        const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+                        for (int q = 0; q < 8; q++) {
+                            if (k0 + q >= rb[k].card) break;
+                            const uint32_t key = ((uint32_t)sl << 16) | ((w[q >> 1] >> ((q & 1) * 16)) & 0xffffu);
+                            for (uint32_t h = gh_hash(key);; h = (h + 1) & (kGhSlots - 1)) {
+                                const uint32_t ent = gh_tab[h];
+                                if (ent == kGbEmpty) break;
+                                if ((ent >> 12) == key) atomicAdd(cj + (size_t)(ent & 0xfffu) * nB, 1ull);
+                            }
+                        }
                     }
-                });
+                }
             }
             __syncthreads();                                     // the table is cleared for the next a-chunk
         }

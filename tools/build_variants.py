@@ -11,7 +11,8 @@ VARIANTS = {   # name -> -D defines; edit freely, outputs featurebase_b200/libfb
     "wp_reg6": ["FBGPU_WP_REG_RING", "FBGPU_WP_RING=6"],   # register ring of 6 (30 us: the default of call 5)
     "wp_narrow": ["FBGPU_WP_NARROW"],                      # cp.async ring with 16 bytes per thread, 128 threads per CTA (19 us on config 3; default: 32 bytes, 64 threads)
     "wp_async4": ["FBGPU_WP_ASYNC_DEPTH=4"],               # cp.async shared-memory ring (default depth 8)
-    "pair_w8": ["FBGPU_PAIR_WARPS=8"],                     # pair_count_kernel: 3 CTAs of 8 warps per SM (default 9)
+    "pair_w9": ["FBGPU_PAIR_WARPS=9"],                     # pair_count_kernel: 3 CTAs of 9 warps per SM (default 8)
+    "pair_w7": ["FBGPU_PAIR_WARPS=7"],
     "pair_w13b2": ["FBGPU_PAIR_WARPS=13", "FBGPU_PAIR_MIN_BLOCKS=2"],   # 2 CTAs of 13 warps
     "wp_legacy": ["FBGPU_WP_LEGACY_LOOP"],       # round-1 rotating-ring loop
     "pair_unscatter": ["FBGPU_PAIR_UNSCATTER"],
