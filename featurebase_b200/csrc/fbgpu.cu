@@ -1603,7 +1603,7 @@ extern "C" int fbgpu_any(fbgpu_ctx* c, uint32_t index, const fbgpu_op* ops, int3
 
 // ------------------------------------------------------------------ GroupBy
 // Slots per CTA of groupby_shard_kernel (16, 8, 4, 2 or 1), or 0 when the fields are not its shape: picked so that a group of
-// slots of field a holds about 12 k columns (3/5 of what the table takes), from the cardinality of a sample of the listed shards' fragments.
+// slots of field a holds at most ~8 k columns (2/5 of what the table takes), from the cardinality of a sample of the listed shards' fragments.
 static int groupby_slots_per_group(fbgpu_ctx* c, uint32_t fvA, uint32_t fvB, const uint64_t* shards, int64_t n) {
     if (fvA >= c->shardmaps.size() || fvB >= c->shardmaps.size() || n <= 0) return 0;
     if (c->view_other[fvA] * 8 > c->view_arr[fvA] || c->view_other[fvB] * 8 > c->view_arr[fvB]) return 0;     // bitmap / run heavy: the per-slot kernels
@@ -1617,7 +1617,10 @@ static int groupby_slots_per_group(fbgpu_ctx* c, uint32_t fvA, uint32_t fvB, con
     }
     if (!seen) return 16;
     const uint64_t avg = elems / seen;                       // columns of field a per shard (all its rows: an upper bound for a row subset)
-    for (int spg = 16; spg >= 1; spg >>= 1) if (avg * (uint64_t)spg / 16 <= (uint64_t)kGhMaxEntries * 3 / 5) return spg;
+    // (measured on BASELINE config 4, 24.4 k columns per shard: 4 slots per group = 6.1 k entries, table 19 % full: 0.25 ms; 8 slots = 12.2 k
+    // entries, 37 % full: 0.44 ms — longer probe walks and half as many units to balance over the SMs)
+    static const uint64_t target = [] { const char* e = getenv("FBGPU_GH_TARGET"); const long long n = e ? atoll(e) : 0; return (uint64_t)(n > 0 ? n : (long long)kGhMaxEntries * 2 / 5); }();
+    for (int spg = 16; spg >= 1; spg >>= 1) if (avg * (uint64_t)spg / 16 <= std::min<uint64_t>(target, kGhMaxEntries * 3 / 5)) return spg;
     return 0;
 }
 

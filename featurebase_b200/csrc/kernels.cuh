@@ -1056,6 +1056,10 @@ constexpr int kPcPairSlots = 256;                           // row pairs per lau
 #ifndef FBGPU_PAIR_BM_UNROLL
 #define FBGPU_PAIR_BM_UNROLL 8
 #endif
+#ifndef FBGPU_PAIR_PF_DIST
+#define FBGPU_PAIR_PF_DIST 1
+#endif
+constexpr int kPcPfDist = FBGPU_PAIR_PF_DIST;               // how many units ahead the payload lines are prefetched into L2
 constexpr int kPcBmUnroll = FBGPU_PAIR_BM_UNROLL;           // bitmap x bitmap: pairs of 16-byte loads in flight per lane
 constexpr uint32_t kPcFastCard = 768;                       // arrays up to this size take the register-window path (3 chunks per lane)
 
@@ -1227,16 +1231,25 @@ pair_count_kernel(StoreRef st, uint32_t fvA, uint64_t rowA, uint32_t fvB, uint64
             my_card |= fast ? (1u << 20) : absent ? 0u : (2u << 20);                          // bits 20..21: 0 absent, 1 fast, 2 generic
         }
         long long pr = per_pair ? base / units_per_pair : 0, pr_rem = per_pair ? base - pr * units_per_pair : 0;     // pair index of unit k, kept incrementally (one division per round)
-        for (int k = 0; k < 16; k++) {
-            const long long unit = base + (long long)k * stride;
-            if (unit >= n_units) break;
+        // lanes 0-11 / 16-27 prefetch one 128-byte line each of unit j's two containers (up to 1.5 KiB per side)
+        auto prefetch_unit = [&](int j) {
+            if (j < 16) {
+                const unsigned long long np = __shfl_sync(0xffffffffu, my_ptr, 2 * j + (lane >> 4));
+                if (np != 0 && (lane & 15) < 12) asm volatile("prefetch.global.L2 [%0];" :: "l"(np + (unsigned long long)(lane & 15) * 128ull));
+            }
+        };
+#ifndef FBGPU_PAIR_NO_PF
+#pragma unroll
+        for (int j = 1; j < kPcPfDist; j++) prefetch_unit(j);
+#endif
+        const int n_k = (int)min((long long)16, (n_units - base + stride - 1) / stride);      // units of this round (one division per round instead of a 64-bit compare per unit)
+        long long unit = base - stride;
+        for (int k = 0; k < n_k; k++) {
+            unit += stride;
             const uint32_t ca = __shfl_sync(0xffffffffu, my_card, 2 * k), cb = __shfl_sync(0xffffffffu, my_card, 2 * k + 1);
             uint32_t c = 0;
 #ifndef FBGPU_PAIR_NO_PF
-            if (k < 15) {       // the NEXT unit's payloads on their way to L2 while this one is intersected: lanes 0-11 / 16-27 one 128-byte line each
-                const unsigned long long np = __shfl_sync(0xffffffffu, my_ptr, 2 * k + 2 + (lane >> 4));
-                if (np != 0 && (lane & 15) < 12) asm volatile("prefetch.global.L2 [%0];" :: "l"(np + (unsigned long long)(lane & 15) * 128ull));
-            }
+            prefetch_unit(k + kPcPfDist);       // payloads of a later unit on their way to L2 while this one is intersected
 #endif
             if ((ca >> 20) == 1u) {
                 // ---- two small arrays: a (even lane) is scattered, b probed; lane L owns chunks L, L+32, L+64 of both

@@ -478,8 +478,8 @@ def test_groupby_kernel_pass_shapes():
 
 
 def test_groupby_slot_groups():
-    """groupby_shard_kernel with several slots per CTA (denser fields -> 4 slots per group instead of 16), one group whose columns
-    overflow the shared-memory table (declined before anything is counted -> groupby_kernel takes its four (shard, slot) units), a
+    """groupby_shard_kernel with several slots per CTA (denser fields -> 2 slots per group instead of 16), one group whose columns
+    overflow the shared-memory table (declined before anything is counted -> groupby_kernel takes its two (shard, slot) units), a
     row subset, and a filter: the dense count tensor against the oracle's nested loop, and the fallback counter says what ran where"""
     from oracle import oracle as O
     SW = 1 << 20
@@ -487,7 +487,7 @@ def test_groupby_slot_groups():
     p = Pair(track_existence=False)
     for n in ("a", "b", "f"):
         p.field(n)
-    cols = {0: rng.choice(SW, size=40000, replace=False), 1: np.concatenate([rng.choice(4 * 65536, size=26000, replace=False), 4 * 65536 + rng.choice(12 * 65536, size=14000, replace=False)]) + SW}
+    cols = {0: rng.choice(SW, size=40000, replace=False), 1: np.concatenate([rng.choice(2 * 65536, size=24000, replace=False), 2 * 65536 + rng.choice(14 * 65536, size=16000, replace=False)]) + SW}
     frs = {"a": {}, "b": {}, "f": {}}
     for s, cc in cols.items():
         ra, rb = rng.integers(0, 64, size=len(cc)), rng.integers(0, 50, size=len(cc))
@@ -514,7 +514,7 @@ def test_groupby_slot_groups():
         after = p.holder.ctx.counters()
         if "groupby_fallback_units" in after and not os.environ.get("FBGPU_GROUPBY_CTA"):
             assert after["groupby_units"] - before["groupby_units"] == 32
-            assert after["groupby_fallback_units"] - before["groupby_fallback_units"] == 4, (filt, before, after)   # (the crowded group of shard 1; decided on cardinalities, before the filter)
+            assert after["groupby_fallback_units"] - before["groupby_fallback_units"] == 2, (filt, before, after)   # (the crowded slots 0-1 of shard 1; decided on cardinalities, before the filter)
 
 
 def test_topk_time_range():

@@ -13,6 +13,7 @@ VARIANTS = {   # name -> -D defines; edit freely, outputs featurebase_b200/libfb
     "wp_async4": ["FBGPU_WP_ASYNC_DEPTH=4"],               # cp.async shared-memory ring (default depth 8)
     "pair_w9": ["FBGPU_PAIR_WARPS=9"],                     # pair_count_kernel: 3 CTAs of 9 warps per SM (default 8)
     "pair_w7": ["FBGPU_PAIR_WARPS=7"],
+    "pair_pf3": ["FBGPU_PAIR_PF_DIST=3"],                  # L2 prefetch three units ahead (default 1)
     "pair_w13b2": ["FBGPU_PAIR_WARPS=13", "FBGPU_PAIR_MIN_BLOCKS=2"],   # 2 CTAs of 13 warps
     "wp_legacy": ["FBGPU_WP_LEGACY_LOOP"],       # round-1 rotating-ring loop
     "pair_unscatter": ["FBGPU_PAIR_UNSCATTER"],
