@@ -25,12 +25,14 @@ def test_config1_single_shard_plumbing():
     p = Pair()
     p.field("f")
     p.load("f", X.VIEW_STANDARD, 0, D.fragment(1, 0, [0, 1], 0.01))
-    before = p.holder.ctx.counters().get("pair_kernel_queries", 0)
+    real = hasattr(p.holder.ctx, "counters")                       # (the oracle-backed stand-in of the host-logic tests has no kernels)
+    before = p.holder.ctx.counters().get("pair_kernel_queries", 0) if real else 0
     n = p.check_count("Count(Intersect(Row(f=0), Row(f=1)))")
     assert 40 < n < 200
     # the north-star query shape must reach the fused pair_count_kernel (round 2 lost it for a while to a program rewrite: 97 us
     # instead of 17 us per query, with every result still right)
-    assert p.holder.ctx.counters()["pair_kernel_queries"] == before + 1
+    if real:
+        assert p.holder.ctx.counters()["pair_kernel_queries"] == before + 1
     r = p.check_row("Intersect(Row(f=0), Row(f=1))")
     assert r.count == n
     p.check_count("Count(Row(f=0))")
