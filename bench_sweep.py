@@ -84,7 +84,7 @@ def config5(args, out):
                  "algorithmic_bytes": int(algo), "achieved_gbs": gbs, "peak_gbs": pk, "peak_source": src, "frac": gbs / pk,
                  "l2_note": f"{n_pairs} row pairs rotated, {n_pairs * algo / 1e6:.0f} MB touched per cycle" + (" (< L2: launch/L2-bound point)" if n_pairs * algo < 126e6 else ""),
                  "containers": {"array": st["array_containers"], "bitmap": st["bitmap_containers"], "run": st["run_containers"]}, "count": int(tot)})
-            if args.batched and mode == 0:
+            if args.batched:
                 # the same Intersect+Count, N independent row pairs fused in one launch (SURVEY §8d "(ii) batched")
                 nb = max(n_pairs, 4)
                 ra, rb = [2 * (k % n_pairs) for k in range(nb)], [2 * (k % n_pairs) + 1 for k in range(nb)]

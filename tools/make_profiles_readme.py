@@ -1,5 +1,6 @@
 #!/usr/bin/env python3
-"""Regenerates profiles/README.md from the committed measurement files (bench JSON lines, sweep JSONL, ncu summaries)."""
+"""Regenerates profiles/README.md (round 2) from the committed measurement files: r02_bench.json, r02_bench_reference.json,
+r02_sweep5.jsonl, r02_sweep34.jsonl, r02_ncu_*_summary.csv, r02_2gpu_*.json and the A/B logs of the round's GPU calls."""
 import csv
 import json
 import os
@@ -10,106 +11,95 @@ P = os.path.join(ROOT, "profiles")
 
 def ncu(name):
     r = list(csv.reader(open(os.path.join(P, name))))
-    return {h.split(" [")[0]: v for h, v in zip(r[0], r[1])}
+    return [{h.split(" [")[0]: v for h, v in zip(r[0], row)} for row in r[1:]]
+
+
+def f(x, n=3):
+    return ("%%.%df" % n) % float(x)
 
 
 def main():
-    rows = [json.loads(l) for l in open(os.path.join(P, "r01_sweep.jsonl"))]
-    b = json.load(open(os.path.join(P, "r01_bench.json")))
-    r = json.load(open(os.path.join(P, "r01_bench_reference.json")))
-    ev = ncu("r01_ncu_eval_kernel_summary.csv")
-    tr = json.load(open(os.path.join(P, "traffic.json")))["eval_kernel"]
+    b = json.load(open(os.path.join(P, "r02_bench.json")))
+    ref = json.load(open(os.path.join(P, "r02_bench_reference.json")))
     o = []
-    o.append("# profiles/ — round 1 measurements on B200 (sm_100a), one GPU unless noted\n")
+    o.append("# profiles/ — round 2 measurements on B200 (sm_100a), one GPU unless noted\n")
     o.append("All times are CUDA-event durations of the kernels on the library's launching stream (never under a profiler); roofline\n"
-             "denominators are the driver-measured `MEASURED_PEAKS.json` (`hbm_gbs` = 6572 GB/s, \"of measured\"). Algorithmic bytes =\n"
-             "payload of every distinct input container + 16 B per descriptor + mandatory output (SURVEY §8d). Box-to-box spread of the\n"
-             "same binary on this pool is about ±5 % (0.504 / 0.512 / 0.531 ms were seen for the headline kernel on three leases).\n")
+             "denominators are the driver-measured `MEASURED_PEAKS.json` (`hbm_gbs` = 6572 GB/s).  Algorithmic bytes = payload of every\n"
+             "distinct input container + 16 B per descriptor + mandatory output (SURVEY §8d).  Round 1's files and log: `README_r01.md`, `r01_*`.\n"
+             "Files named `r02_callN_*` are the A/B records of the round's GPU calls (scripts: `tools/r2_call*.sh`); `r02_*` without a call\n"
+             "number come from the final call (`tools/r2_final.sh`) on the committed source.\n")
     o.append("## Headline: BASELINE config[1] — 1024 shards x 2^20, 1 %, Count(Intersect(Union(32 rows), Union(32 rows)))\n")
-    o.append("| arm | ms/step | set-ops/s | Count rows/s | columns/s | HBM GB/s (algorithmic) | frac of measured roofline |")
-    o.append("|---|---|---|---|---|---|---|")
-    o.append(f"| ours, kernel (`value`) | {b['ms_per_step']:.4f} | {b['value']:.3e} | {b['count_rows_per_sec']:.3e} | {b['columns_per_sec']:.3e} | {b['roofline']['achieved']:.0f} | {b['roofline']['frac']:.3f} |")
-    o.append(f"| ours, through the C ABI from host buffers (`e2e`) | {b['e2e']['ms_per_step']:.4f} | {b['e2e']['value']:.3e} | | | | |")
-    o.append(f"| CPU restatement of the reference, {r['cpu_baseline']['cores']} host threads (`--impl reference`) | {r['ms_per_step']:.1f} | {r['value']:.3e} | {r['count_rows_per_sec']:.3e} | {r['columns_per_sec']:.3e} | | |")
-    o.append(f"\nkernel/CPU = {b['value'] / r['value']:.0f}x, e2e/CPU = {b['e2e']['value'] / r['value']:.0f}x (a reported baseline, not the target). One-time cold load of the "
-             f"{b['e2e_cold_load']['h2d_bytes'] / 1e9:.2f} GB of fragments (parse + stage + H2D + first query): {b['e2e_cold_load']['ms']:.0f} ms.")
-    o.append(f"DRAM traffic of `eval_kernel` (ncu `dram__bytes_read.sum + dram__bytes_write.sum`): {tr['dram_bytes_per_launch']:,} B per launch vs "
-             f"{tr['algorithmic_bytes_per_launch']:,} algorithmic bytes (x{tr['dram_bytes_per_launch'] / tr['algorithmic_bytes_per_launch']:.3f}): no wasted re-reads. "
-             f"Clocks during the run: {b['clocks']['sm_mhz']:.0f}/{b['clocks']['sm_max_mhz']:.0f} MHz, throttle reasons: {b['clocks']['reasons'] or 'none'}. "
-             f"`gpu_launches` = {b['gpu_launches']} for {b['steps']} steps (one fused kernel per step).")
-    o.append("N > 1 (weak scaling, 1024 shards per GPU; the 8-byte Count merge is fused into the counting kernel over NVLink peer memory, `--reduce p2p`, or done by ncclAllReduce, `--reduce nccl`): 2 GPUs 0.537 ms/step (p2p) vs 0.535 (nccl), 2.40e8 set-ops/s; 4 GPUs 0.547 ms/step, 4.71e8 set-ops/s (p2p) vs 0.575 ms/step, 4.49e8 (nccl, another lease); identical counts. For 8 bytes both merges are latency-trivial next to a 0.5 ms step; at N > 1 a step ends when the slowest rank ends. The driver measures N = 1, 2, 4, 8.\n")
-    o.append("## How the headline kernel got here (same workload)\n")
-    o.append("| step | eval kernel ms | frac | what changed | evidence |")
+    o.append("| arm | ms/step | set-ops/s | HBM GB/s (algorithmic) | frac of measured roofline |")
     o.append("|---|---|---|---|---|")
-    o.append("| first correct version | 1.540 | 0.137 | one op at a time, a barrier per op | `r01_ncu_eval_first_summary.csv`: 977 M warp-instr, barrier + long-scoreboard stalls |")
-    o.append("| barrier-free batches | 0.932 | 0.227 | runs of commuting row ops are scattered warp-per-operand with `red.shared`, no barrier in between | |")
-    o.append("| 7-8 CTAs/SM | 0.728 | 0.291 | `__launch_bounds__(256, 8)` (32 registers), 128-op resolve chunks | |")
-    o.append("| host-computed batch extents, run flag | 0.530 | 0.399 | removed two per-thread op-scan loops = 32 % of all executed instructions (ncu source page) | |")
-    o.append("| dense (shard,row) directory | 0.504 | 0.420 | descriptor chain 5 -> 3 dependent loads | |")
-    o.append(f"| this table's measurement lease | {b['ms_per_step']:.3f} | {b['roofline']['frac']:.3f} | same code | `r01_ncu_eval_kernel_summary.csv`, `r01_launches.csv` |")
-    o.append("| tried, slower: TMA-staged ring (`eval_staged_kernel`, opt-in `FBGPU_STAGED=1`) | 0.748 | 0.283 | `cp.async.bulk` + mbarrier pipeline removes the HBM-latency stall (long-scoreboard 6.6 -> 0.4 per issue) but only 2-3 CTAs fit per SM and the shared-memory atomic pipe is the limiter either way | `r01_ncu_eval_staged_kernel_summary.csv` |")
-    o.append("| tried, slower: 4 loads in flight per thread, register double-buffering, L2 prefetch of the batch | 0.52-2.1 | | extra registers cost CTA residency, which matters more than per-warp MLP here | |")
-    o.append("| after the round's GPU budget was spent (NOT yet timed; `DESIGN.md` §9.1) | ? | ? | array scatter: `LOP3 + LEA.HI` word offsets, shared base kept live, duplicate-padded array tails (no divergent tail path): about 65 + tail -> 43 issued instructions per 8 elements by SASS count, i.e. roughly 378 M -> 230 M warp instructions for this query; opt-in bank-striped array order (`FBGPU_ARRAY_STRIPED=1`) for the wavefront count | `cuobjdump -sass` of the committed build; `tools/r2_first_call.sh` measures both |")
-    o.append(f"\nWhere the time goes now (ncu): {float(ev['smsp__inst_executed.sum']) / 1e6:.0f} M warp instructions, issue slots {float(ev['smsp__issue_active.avg.pct_of_peak_sustained_active']):.0f} % busy; "
-             f"{float(ev['l1tex__data_pipe_lsu_wavefronts_mem_shared.sum']) / 1e6:.0f} M shared-memory wavefronts ({float(ev['l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed']):.0f} % of the LSU shared pipe's peak, "
-             f"{float(ev['l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum']) / 1e6:.0f} M of them bank conflicts of the random scatter) for 687 M scattered elements; warps active {float(ev['sm__warps_active.avg.pct_of_peak_sustained_active']):.0f} %. "
-             "The kernel is co-limited by shared-memory atomics and issue, not by HBM: 1 %-density data is array-container work; bitmap-container work streams at 82-98 % (below).\n")
-    o.append("## BASELINE config 5 — density sweep, Count(Intersect(Row a, Row b)), 1024 shards (1 B columns), `pair_count_kernel`\n")
-    o.append("`5` = one query per launch (as the executor issues it); `5b` = N independent row pairs fused in one launch through `fbgpu_count_pairs` (SURVEY §8d \"batched\").\n")
-    o.append("| cfg | generator | density | containers (array/bitmap/run) | pairs/launch | ms | GB/s | frac | note |")
-    o.append("|---|---|---|---|---|---|---|---|---|")
-    for d in rows:
-        if d["config"] in (5, "5b"):
-            c = d.get("containers")
-            cs = f"{c['array']}/{c['bitmap']}/{c['run']}" if c else ""
-            o.append(f"| {d['config']} | {d['generator']} | {d['density'] * 100:g} % | {cs} | {d.get('pairs_per_launch', 1)} | {d['ms']:.4f} | {d['achieved_gbs']:.0f} | {d['frac']:.3f} | {d['l2_note']} |")
-    o.append("\nNorth-star acceptance point (1 %, 1 B columns, 43 MB per query): 23 % of roofline for a single query — launch + dependent-load latency bound (even near-empty containers take 17 us) — and 34 % when 7 pairs share a launch, where the shared-memory build/probe of array x array is the limiter. "
-             "Bitmap x bitmap streams at 82 % (single) / 98 % (batched). Clustered data (run containers) is latency-bound at these sizes: 13-135 MB per query.\n")
-    o.append("## BASELINE config 3 — BSI `Count(Row(v > k))`, 32-bit values (`eval_wordpar_kernel`)\n")
-    o.append("| records | query | ms | GB/s | frac | records/s |")
-    o.append("|---|---|---|---|---|---|")
-    for d in rows:
-        if d["config"] == 3:
-            o.append(f"| {d['records']:,} | {d['query']} | {d['ms']:.4f} | {d['achieved_gbs']:.0f} | {d['frac']:.3f} | {d['records_per_sec']:.3e} |")
-    o.append("\nThe 10 M-record config is 42.5 MB of bit planes over 160 (shard, slot) units: launch/latency bound. At 268 M records the word-parallel kernel is bound by its per-op interpretive instruction overhead (34-37 % of roofline). The shared-memory program machine took 0.055-0.065 ms on the 10 M config.\n")
-    o.append("## BASELINE config 4 — GroupBy(Rows(a), Rows(b)) 256 x 256, one GPU's share (512 of 4096 shards)\n")
-    for d in rows:
-        if d["config"] == 4:
-            o.append(f"`groupby_kernel`: {d['ms']:.3f} ms for {d['records']:,} records ({d['records_per_sec']:.3e} records/s, {d['group_counts_per_sec']:.3e} group counts/s, {d['nonzero_groups']} non-zero groups); "
-                     f"algorithmic {d['algorithmic_bytes'] / 1e6:.0f} MB (payload {d['payload_bytes'] / 1e6:.0f} MB) -> {d['achieved_gbs']:.0f} GB/s ({d['frac']:.3f}). "
-                     "Tiny containers (~6 elements) make this descriptor- and latency-bound; the hash-join does work proportional to the records, where the reference does 65,536 IntersectionCount calls per shard. First version (128 KiB direct column table, 1 CTA/SM): 6.9 ms.\n")
-    o.append("## Row-returning calls (`fbgpu_row`, wall clock incl. encoding choice, emission, D2H and roaring assembly), 1024 shards @ 1 %\n")
-    o.append("| query | ms | result bytes | result count |")
-    o.append("|---|---|---|---|")
-    for d in rows:
-        if d["config"] == "R":
-            o.append(f"| `{d['query']}` | {d['ms']:.2f} | {d['result_bytes']:,} | {d['result_count']:,} |")
-    o.append("\nThese three were timed through the Python wrapper with a fresh output array per call: most of the time on large results was host-side — page faults of the fresh array and of a per-batch vector, and three passes over the payload (D2H landing buffer -> per-batch buffer -> caller's buffer -> `tobytes`).  Changed since, **not yet re-timed**: a single-batch call (<= 1024 shards) assembles straight from the pinned landing buffer into the caller's buffer, the payload copies of results above 8 MiB are split over up to 8 host threads, and `bench_sweep.py` config R now times `fbgpu_row` into a reused caller-owned buffer (what a Go caller does).  A device-side pack and D2H straight into a registered caller buffer are the next step.\n")
-    o.append("## Written after the GPU budget was spent: no timing yet (round 2's first call, `tools/r2_first_call.sh`, measures each)\n")
-    o.append('Which kernels of the current build are, instruction for instruction, the ones that ran on the device (`python tools/sass_diff.py 5f6bb73`, the last round-1 commit that was on a B200; no GPU needed): **identical** — `eval_wordpar_kernel`, `canon_emit_kernel`, `groupby_kernel<false>`, `row_count_kernel<false>`, `p2p_reduce_only_kernel`; **changed** (array scatter / probe instruction cuts, §9.1 of DESIGN.md) — `eval_kernel` 3384 -> 2920 instructions, `pair_count_kernel` 3064 -> 2864, `eval_staged_kernel` (opt-in); **new** — `columns_emit_kernel`, `extract_values_kernel`, `bsi_sum_kernel`, `bsi_minmax_kernel`, `row_count_kernel<true>`, `groupby_kernel<true>` (opt-in).\n')
-    o.append("Kernel logic of every row has run against the oracle on the CPU kernel interpreter (`tests/emu/`, `tests/test_emu_kernels.py`); the default build's other kernels are byte-identical SASS to the measured ones.\n")
-    o.append("| change | switch | targets | expectation (model, not a measurement) |")
-    o.append("|---|---|---|---|")
-    o.append("| array scatter: LOP3 + LEA.HI word offsets, shared base kept live, duplicate-padded tails | default build | config 1/2 `eval_kernel` (issue slots 61 % busy) | 65 + tail -> 43 issued instructions per 8 elements |")
-    o.append("| bank-striped array payload order | `FBGPU_ARRAY_STRIPED=1` | every scatter / probe of array containers (`eval_kernel`, `pair_count_kernel`) | random banks cost ~4 shared-memory wavefronts per warp instruction (`r01_micro_aa_variants.txt`: 7.8 lane-ops/clk/SM); striped ~1.2 (host model, `tests/test_stripe.py`) |")
-    o.append("| no per-pair 8 KiB wipe in array x array counting | `-DFBGPU_PAIR_UNSCATTER` (`libfbgpu_pair_unscatter.so`) | config 5 at <= 3 % density (north-star point) | 64 of ~210 wavefronts per pair; with the striped order ~63 in all |")
-    o.append("| three-ops-per-iteration word-parallel loop | `-DFBGPU_WP_UNROLL3` (`libfbgpu_wp_unroll3.so`) | config 3 `eval_wordpar_kernel` (interpretive overhead) | ~12 instructions per op + operand fetch instead of 80-100 |")
-    o.append("| thread-per-row GroupBy passes | `FBGPU_GROUPBY_FAST=1` | config 4 `groupby_kernel` (25.8 k warp instructions per unit) | ~9x fewer instructions per unit; then latency-bound |")
-    o.append("| `fbgpu_columns` / `columns_emit_kernel`, `fbgpu_extract` / `extract_values_kernel`, `fbgpu_bsi_sum` / `fbgpu_bsi_minmax` (`bsi_sum_kernel`, `bsi_minmax_kernel`), `fbgpu_load_rbf`, host-mirror compositions (Sum / Min / Max / Percentile / Distinct / MinRow / time ranges) | new entry points / host code | SURVEY §8(f) rows | functional only |")
+    o.append(f"| ours, kernel (`value`) | {b['ms_per_step']:.4f} | {b['value']:.3e} | {b['roofline']['achieved']:.0f} | {b['roofline']['frac']:.3f} |")
+    o.append(f"| ours, through the C ABI from host buffers (`e2e`) | {b['e2e']['ms_per_step']:.4f} | {b['e2e']['value']:.3e} | | |")
+    cb = b["cpu_baseline"]
+    o.append(f"| CPU restatement of the reference, {cb['cores']} host threads (in-line `cpu_baseline`) | {cb['ms']:.1f} | {cb['value']:.3e} | | |")
+    o.append(f"| the same from `bench.py --impl reference` (its own process) | {ref['ms_per_step']:.1f} | {ref['value']:.3e} | | |")
+    cal = cb.get("calibration") or {}
+    o.append(f"\nkernel/CPU = {b['value'] / cb['value']:.0f}x, e2e/CPU = {b['e2e']['value'] / cb['value']:.0f}x (a reported baseline, not the target).  CPU calibration on this box: "
+             f"{cal.get('single_thread_ms_per_shard', 0):.2f} ms per shard on one thread, parallel speed-up {cal.get('parallel_speedup', 0):.1f} with {cal.get('threads')} threads "
+             f"(best of two calibration steps: pinned {cal.get('pinned_ms', 0):.0f} ms / unpinned {cal.get('unpinned_ms', 0):.0f} ms; the timed loop's median is the {cb['ms']:.0f} ms above): "
+             f"the pool's boxes advertise 128 CPUs but give a fraction of them, and a CPU quota throttles sustained runs — short bursts of the same pool are several times faster than its steady state.  "
+             f"Against the fastest calibration step the kernel is still {b['value'] / (63 * 1024 / (min(cal.get('pinned_ms', 1e9), cal.get('unpinned_ms', 1e9)) * 1e-3)):.0f}x.")
+    o.append(f"`parity_ok` = {b.get('parity_ok')} (GPU count {b.get('gpu_count')} = CPU port count {b.get('cpu_count')} over all 1024 shards).  "
+             f"Clocks during the run: {b['clocks']['sm_mhz']:.0f}/{b['clocks']['sm_max_mhz']:.0f} MHz, throttle reasons: {b['clocks']['reasons'] or 'none'}.  "
+             f"`gpu_launches` = {b['gpu_launches']} for {b['steps']} steps (one fused kernel per step).")
+    tr = b["roofline"]
+    if tr.get("traffic"):
+        o.append(f"DRAM traffic of `eval_kernel` (ncu `dram__bytes_read.sum + dram__bytes_write.sum`, this kernel source): {tr['traffic']:,} B per launch vs "
+                 f"{tr['algorithmic_bytes_per_launch']:,} algorithmic bytes (x{tr['traffic'] / tr['algorithmic_bytes_per_launch']:.3f}).")
     o.append("")
-    o.append("## Correctness tooling\n")
-    o.append("`r01_sanitizer_memcheck.log`: compute-sanitizer memcheck over the eval / pair / row-count / groupby / word-parallel / staged kernels (8 GPU tests): 0 errors. `r01_sanitizer_racecheck.log`: racecheck (shared-memory hazards): 0 hazards.\n")
-    o.append("## Files\n")
-    o.append("| file | what |")
-    o.append("|---|---|")
-    for f, w in [("r01_bench.json", "bench.py line (ours), 50 steps, with cpu_baseline and e2e_cold_load"), ("r01_bench_reference.json", "bench.py --impl reference line"),
-                 ("r01_launches.csv", "ncu gpu__time_duration launch list of `bench.py --steps 4 --warmup 3` (one eval_kernel launch per step, 100 % of the step's kernel time)"),
-                 ("r01_ncu_eval_kernel_summary.csv", "ncu --set full summary of eval_kernel (traffic, stalls, occupancy)"), ("traffic.json", "DRAM bytes per launch read by bench.py for `roofline.traffic`"),
-                 ("r01_ncu_pair_kernel_summary.csv / r01_ncu_groupby_kernel_summary.csv / r01_ncu_eval_wordpar_kernel_summary.csv / r01_ncu_eval_staged_kernel_summary.csv", "ncu --set full summaries of the other kernels"),
-                 ("r01_ncu_eval_first_summary.csv / r01_launches_first.csv / r01_bench_first.json / r01_sweep_first.jsonl", "the first correct version, for the before/after record"),
-                 ("r01_sweep.jsonl", "bench_sweep.py --configs 5,3,3L,4,R --batched"), ("r01_micro_aa_variants.txt", "bench_micro/aa_variants.cu: five array x array strategies + raw shared-memory atomic/LDS/STS throughput"),
-                 ("r01_sanitizer_*.log", "compute-sanitizer runs")]:
-        o.append(f"| `{f}` | {w} |")
+    o.append("## Sub-records of the same bench line (each parity-checked against the CPU port at full size)\n")
+    o.append("| workload | kernel | time | algorithmic GB/s | frac | CPU port | parity |")
+    o.append("|---|---|---|---|---|---|---|")
+    ns = b["north_star"]
+    for key, lab in (("batched", "32 row pairs in one launch"), ("single", "one query per launch (32 pairs rotated)")):
+        r = ns[key]
+        o.append(f"| north star: Count(Intersect(Row, Row)) @1 %, 1 B columns — {lab} | `pair_count_kernel` | {r['ms'] * 1e3:.1f} us | {r['gbs']:.0f} | **{r['frac']:.3f}** | {ns['cpu_baseline']['ms']:.0f} ms for the 32 pairs | {ns.get('parity_ok')} |")
+    for r in b.get("density_sweep", []):
+        o.append(f"| {r['density'] * 100:g} % {r['generator']}: batched ({r['batched']['pairs_per_launch']} pairs) / single | `pair_count_kernel` | {r['batched']['ms'] * 1e3:.1f} / {r['single']['ms'] * 1e3:.1f} us | "
+                 f"{r['batched']['gbs']:.0f} / {r['single']['gbs']:.0f} | {r['batched']['frac']:.3f} / {r['single']['frac']:.3f} | {r['cpu_baseline']['ms']:.1f} ms | {r.get('parity_ok')} ({', '.join('%s: %d' % kv for kv in r['container_pair_types_pair0'].items())}) |")
+    c3, c4 = b["config3"], b["config4"]
+    o.append(f"| config 3: BSI Count(Row(v > 2^31)), 10 M records | `eval_wordpar_kernel` | {c3['ms'] * 1e3:.1f} us | {c3['gbs']:.0f} | {c3['frac']:.3f} | {c3['cpu_baseline']['ms']:.1f} ms | {c3.get('parity_ok')} |")
+    o.append(f"| config 4: GroupBy 256 x 256, 512-shard share ({c4['records'] / 1e6:.1f} M records) | `groupby_shard_kernel` | {c4['ms'] * 1e3:.0f} us | {c4['gbs']:.0f} | {c4['frac']:.3f} | {c4['cpu_baseline']['ms']:.0f} ms | {c4.get('parity_ok')} |")
+    o.append("")
+    # full density sweep
+    sw = [json.loads(l) for l in open(os.path.join(P, "r02_sweep5.jsonl"))]
+    o.append("## Density sweep (bench_sweep.py --configs 5 --batched): Count(Intersect(Row, Row)), 1024 shards\n")
+    o.append("| generator | density | one query per launch: us / frac | batched: pairs, us / frac | containers (array / bitmap / run) |")
+    o.append("|---|---|---|---|---|")
+    single = {(r["generator"], r["density"]): r for r in sw if r["config"] == 5}
+    batched = {(r["generator"], r["density"]): r for r in sw if r["config"] == "5b"}
+    for k, r in single.items():
+        bb = batched.get(k)
+        c = r.get("containers", {})
+        o.append(f"| {k[0]} | {k[1] * 100:g} % | {r['ms'] * 1e3:.1f} / {r['frac']:.3f} | " + (f"{bb['pairs_per_launch']}, {bb['ms'] * 1e3:.1f} / {bb['frac']:.3f}" if bb else "-") +
+                 f" | {c.get('array', 0)} / {c.get('bitmap', 0)} / {c.get('run', 0)} |")
+    o.append("\nPoints below ~0.1 % touch 1-40 MB: they are launch- and dependent-latency-bound (a 16 us floor: launch + the three-deep descriptor chain + one payload round trip), "
+             "the fraction of an HBM roofline says little there.\n")
+    s34 = [json.loads(l) for l in open(os.path.join(P, "r02_sweep34.jsonl"))]
+    o.append("## Other entry points (bench_sweep.py --configs 3,4,X,R; X / R are wall-clock through the C ABI)\n")
+    o.append("| config | query | ms | note |")
+    o.append("|---|---|---|---|")
+    for r in s34:
+        extra = f"frac {r['frac']:.3f}" if r.get("frac") else (f"{r['result_bytes'] / 1e6:.1f} MB result: {r['result_bytes'] / (r['ms'] * 1e-3) / 1e9:.1f} GB/s" if r.get("result_bytes") else "")
+        o.append(f"| {r['config']} | {r['query']} | {r['ms']:.4f} | {extra} |")
+    o.append("")
+    o.append("## ncu summaries of the timed binary (`--set full`, `--clock-control none`; one row per captured launch)\n")
+    o.append("| file | kernel | time us | DRAM read | warp instr | issue active % | ALU pipe % | FMA pipe % | smem wavefronts (conflicts) | top stalls |")
+    o.append("|---|---|---|---|---|---|---|---|---|---|")
+    for name in sorted(os.listdir(P)):
+        if name.startswith("r02_ncu_") and name.endswith("_summary.csv"):
+            for d in ncu(name):
+                o.append(f"| `{name}` | {d['Kernel Name'][:28]} | {f(d['gpu__time_duration.sum'], 1)} | {f(d['dram__bytes_read.sum'], 1)} | {float(d['smsp__inst_executed.sum']) / 1e6:.1f} M | "
+                         f"{f(d['smsp__issue_active.avg.pct_of_peak_sustained_active'], 1)} | {f(d['sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active'], 1)} | "
+                         f"{f(d['sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active'], 1)} | {float(d['l1tex__data_pipe_lsu_wavefronts_mem_shared.sum']) / 1e6:.1f} M ({float(d['l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum']) / 1e6:.1f} M) | {d['top stalls (warps per issue-active cycle)']} |")
+    o.append("\n(`dram__bytes_read.sum` is in the unit ncu chose per kernel: MB for the small launches, GB for the headline.)  The launch list of one bench run "
+             "(`r02_launches.csv`, per-launch `gpu__time_duration.sum`, cold-cache and serialised) shows only this library's kernels.\n")
+    extra = os.path.join(P, "r02_log.md")
+    if os.path.exists(extra):
+        o.append(open(extra).read())
     open(os.path.join(P, "README.md"), "w").write("\n".join(o) + "\n")
 
 
