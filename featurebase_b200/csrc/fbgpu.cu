@@ -1493,9 +1493,11 @@ extern "C" int fbgpu_row_counts(fbgpu_ctx* c, uint32_t index, uint32_t field, ui
     std::vector<size_t> order;
     for (size_t i = 0; i < rows.size(); i++) if (counts[i]) order.push_back(i);
     std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return counts[a] != counts[b] ? counts[a] > counts[b] : rows[a] < rows[b]; });
-    int32_t n = (int32_t)std::min<size_t>(order.size(), (size_t)std::max(cap, 0));
-    for (int32_t i = 0; i < n; i++) { if (out_row_ids) out_row_ids[i] = rows[order[i]]; out_counts[i] = counts[order[i]]; }
-    if (out_n) *out_n = n;
+    // all rows with a non-zero count, or none: a silently truncated list would make Rows() / the TopN candidate set incomplete
+    // (ADVICE r1).  *out_n always receives the number of rows there are, so the caller can size its buffers and call again.
+    if (out_n) *out_n = (int32_t)std::min<size_t>(order.size(), (size_t)INT32_MAX);
+    if (order.size() > (size_t)std::max(cap, 0)) return fail(FBGPU_E_NOSPACE, "%zu rows have a non-zero count, cap is %d", order.size(), cap);
+    for (size_t i = 0; i < order.size(); i++) { if (out_row_ids) out_row_ids[i] = rows[order[i]]; out_counts[i] = counts[order[i]]; }
     return FBGPU_OK;
 } FBGPU_CATCH
 

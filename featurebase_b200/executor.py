@@ -551,8 +551,8 @@ class Executor:
             pairs = self._topn_cutoffs(idx, f, filt, ids, thr, tan, shards)
         elif ids is not None:
             src = c.children[0] if c.children else None
-            src_key = [k for k in src.args if not k.startswith("_")] if src is not None and src.name == "Row" else []
-            if src_key and not isinstance(src.args[src_key[0]], pql.Condition) and self._field(idx, src_key[0]).type != "int":
+            src_key = [k for k in src.args if not k.startswith("_") and k not in ("from", "to")] if src is not None and src.name == "Row" else []
+            if len(src_key) == 1 and "from" not in src.args and "to" not in src.args and not isinstance(src.args[src_key[0]], pql.Condition) and self._field(idx, src_key[0]).type != "int":
                 # Src is a plain Row: count = Src.intersectionCount(row) per candidate (fragment.go:1367-1372), fused
                 sf = self._field(idx, src_key[0])
                 counts = self.ctx.count_pairs(idx.id, f.id, VIEW_STANDARD, ids, sf.id, VIEW_STANDARD, [int(src.args[src_key[0]])] * len(ids), shards)

@@ -355,10 +355,16 @@ class Context:
             self._check(self.L.fbgpu_row_counts(self.h, index, field, view, ids.ctypes.data, len(ids), f, nf, sh.ctypes.data, len(sh),
                                                 None, out.ctypes.data, len(ids), C.byref(n)))
             return out
-        rid, out = np.zeros(cap, dtype=np.uint64), np.zeros(cap, dtype=np.uint64)
-        self._check(self.L.fbgpu_row_counts(self.h, index, field, view, None, 0, f, nf, sh.ctypes.data, len(sh),
-                                            rid.ctypes.data, out.ctypes.data, cap, C.byref(n)))
-        return rid[: n.value], out[: n.value]
+        cap = min(cap, 1 << 16)
+        while True:                                  # the library reports how many rows there are when the buffers are too small
+            rid, out = np.zeros(cap, dtype=np.uint64), np.zeros(cap, dtype=np.uint64)
+            rc = self.L.fbgpu_row_counts(self.h, index, field, view, None, 0, f, nf, sh.ctypes.data, len(sh),
+                                         rid.ctypes.data, out.ctypes.data, cap, C.byref(n))
+            if rc == E_NOSPACE and n.value > cap:
+                cap = n.value
+                continue
+            self._check(rc)
+            return rid[: n.value], out[: n.value]
 
     def row_counts_per_shard(self, index, field, view, shards, row_ids, filter_ops=None):
         """[len(shards), len(row_ids)] matrix of per-shard counts (fbgpu_row_counts_per_shard)"""

@@ -198,8 +198,11 @@ int fbgpu_bsi_sum(fbgpu_ctx *ctx, uint32_t index, const fbgpu_op *ops, int32_t n
 /* Per-row counts of one field, optionally intersected with a filter program: the exact part of TopN
  * (fragment.top with explicit ids, fragment.go:1317-1437) and TopK (doTopK executor.go:2705-2746).
  * row_ids != NULL: counts for exactly those rows (out_counts[i] for row_ids[i]).
- * row_ids == NULL: all rows present in the field over the shards; writes up to cap (row id, count) pairs with
+ * row_ids == NULL: all rows present in the field over the shards; writes every (row id, count) pair with
  * count > 0 sorted by (count desc, row id asc) — the reference's tie order is unspecified (cache.go:464-482).
+ * *out_n receives the number of such rows; when it exceeds cap nothing is written and the call returns
+ * FBGPU_E_NOSPACE (never a truncated list: Rows() and the TopN candidate set must be complete) — call again
+ * with buffers of *out_n entries.
  * Counts are all-reduced over the communicator in the row_ids form. */
 int fbgpu_row_counts(fbgpu_ctx *ctx, uint32_t index, uint32_t field, uint32_t view,
                      const uint64_t *row_ids, int32_t n_rows,

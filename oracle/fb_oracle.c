@@ -766,16 +766,18 @@ uint64_t fbo_b_write(fbo_bitmap *b, uint8_t *out, uint64_t cap, int optimize) {
 }
 
 /* pilosaRoaringIterator roaring.go:2124-2178 ; officialRoaringIterator :2194-2260, header parse :6943-7006 */
-fbo_bitmap *fbo_b_read(const uint8_t *buf, uint64_t len) {
+static fbo_bitmap *b_read_containers(const uint8_t *buf, uint64_t len, uint64_t *end_out) {
     if (len < 8) return NULL;
     uint32_t magic = get16(buf);
     fbo_bitmap *o = fbo_b_new();
+    *end_out = 0; /* lastDataOffset == 0: Remaining() has nothing (roaring.go:2103-2108) */
     if (magic == 12348) {
         if (buf[2] != 0) { fbo_b_free(o); return NULL; } /* storageVersion 0 */
         uint64_t keys = get32(buf + 4);
         if (8 + keys * 16 > len) { fbo_b_free(o); return NULL; }
         const uint8_t *hdr = buf + 8, *offs = buf + 8 + keys * 12;
         uint64_t chunk = 0; uint32_t prev = 0;
+        *end_out = keys ? 8 + keys * 16 : (len > 8 ? 8 : 0); /* roaring.go:1994-2001, 2016-2017 */
         for (uint64_t i = 0; i < keys; i++) {
             uint64_t key = get64(hdr + i * 12); uint16_t typ = get16(hdr + i * 12 + 8); int32_t n = (int32_t)get16(hdr + i * 12 + 10) + 1;
             uint32_t o32 = get32(offs + i * 4); if (o32 < prev) chunk += 1ull << 32; prev = o32;
@@ -783,22 +785,27 @@ fbo_bitmap *fbo_b_read(const uint8_t *buf, uint64_t len) {
             if (typ == FBO_ARRAY) {
                 if (off + (uint64_t)n * 2 > len) goto bad;
                 c = c_alloc(FBO_ARRAY, n); for (int k = 0; k < n; k++) ARR(c)[k] = get16(buf + off + 2 * k); c->n = n;
+                *end_out = off + (uint64_t)n * 2;
             } else if (typ == FBO_BITMAP) {
                 if (off + 8192 > len) goto bad;
                 c = c_alloc(FBO_BITMAP, 1024); for (int k = 0; k < 1024; k++) BMP(c)[k] = get64(buf + off + 8 * k); c->n = n;
+                *end_out = off + 8192;
             } else if (typ == FBO_RUN) {
                 if (off + 2 > len) goto bad;
                 int rc = get16(buf + off); if (off + 2 + (uint64_t)rc * 4 > len) goto bad;
                 c = c_alloc(FBO_RUN, rc); for (int k = 0; k < rc; k++) { RUN(c)[k].start = get16(buf + off + 2 + 4 * k); RUN(c)[k].last = get16(buf + off + 4 + 4 * k); } c->n = n;
+                *end_out = off + 2 + (uint64_t)rc * 4;
             } else goto bad;
-            b_append(o, key, c);
+            fbo_b_put(o, key, c); /* Containers.Put unmarshal_binary.go:58: a repeated key replaces, order does not matter */
         }
         return o;
     }
     if (magic == 12346 || magic == 12347) {
+        if (magic == 12346 && get32(buf) != 12346) goto bad; /* readOfficialHeader :6966: the no-run cookie is compared on 32 bits */
         uint64_t keys, pos; const uint8_t *runbits = NULL; int have_runs = magic == 12347;
-        if (have_runs) { keys = (uint64_t)get16(buf + 2) + 1; pos = 4; runbits = buf + pos; pos += (keys + 7) / 8; }
+        if (have_runs) { keys = (uint64_t)get16(buf + 2) + 1; pos = 4; runbits = buf + pos; pos += (keys + 7) / 8; if (pos > len) goto bad; }
         else { keys = get32(buf + 4); pos = 8; }
+        if (keys > (1u << 16)) goto bad; /* :6992 */
         if (pos + keys * 4 >= len) goto bad; /* readOfficialHeader roaring.go:7000: '>=' => zero containers is an error */
         const uint8_t *hdr = buf + pos; pos += keys * 4;
         const uint8_t *offs = NULL;
@@ -824,10 +831,53 @@ fbo_bitmap *fbo_b_read(const uint8_t *buf, uint64_t len) {
                 if (off + 8192 > len) goto bad;
                 c = c_alloc(FBO_BITMAP, 1024); for (int k = 0; k < 1024; k++) BMP(c)[k] = get64(buf + off + 8 * k); c->n = n; cur = off + 8192;
             }
-            b_append(o, key, c);
+            fbo_b_put(o, key, c);
         }
+        *end_out = cur;
         return o;
     }
+bad:
+    fbo_b_free(o);
+    return NULL;
+}
+
+static uint32_t fnv32a(uint32_t h, const uint8_t *p, uint64_t n) { for (uint64_t i = 0; i < n; i++) { h ^= p[i]; h *= 16777619u; } return h; }
+static fbo_bitmap *b_from_values(const uint8_t *p, uint64_t n) {
+    fbo_bitmap *x = fbo_b_new();
+    for (uint64_t i = 0; i < n; i++) fbo_b_add(x, get64(p + 8 * i));
+    return x;
+}
+
+/* Bitmap.UnmarshalBinary unmarshal_binary.go:17-95: the containers, then the ops log up to the end of the data — each op
+ * decoded and checksummed as op.UnmarshalBinary does (roaring.go:6375-6427) and applied as op.apply does (:6303-6322).
+ * Removal is written as a difference with the removed set, which is what remove() / DirectRemoveN / ImportRoaringBits(clear)
+ * leave in the bitmap. */
+fbo_bitmap *fbo_b_read(const uint8_t *buf, uint64_t len) {
+    uint64_t pos = 0;
+    fbo_bitmap *o = b_read_containers(buf, len, &pos);
+    if (!o || pos == 0) return o;
+    while (pos < len) {
+        const uint8_t *d = buf + pos; uint64_t left = len - pos, size;
+        if (left < 13) goto bad;
+        uint8_t typ = d[0]; uint64_t value = get64(d + 1);
+        uint32_t h = fnv32a(2166136261u, d, 9);
+        fbo_bitmap *arg = NULL;
+        if (typ <= 1) { size = 13; arg = b_from_values(d + 1, 1); }
+        else if (typ <= 3) {
+            if (value > (1ull << 59) || left < 13 + value * 8) goto bad;
+            size = 13 + value * 8; h = fnv32a(h, d + 13, value * 8); arg = b_from_values(d + 13, value);
+        } else if (typ <= 5) {
+            if (left < 17 || left - 17 < value) goto bad;
+            size = 17 + value; h = fnv32a(h, d + 13, 4 + value);
+            uint64_t ignored; arg = b_read_containers(d + 17, value, &ignored); /* ImportRoaringBits iterates the containers only */
+            if (!arg) goto bad;
+        } else goto bad;
+        if (get32(d + 9) != h) { fbo_b_free(arg); goto bad; }
+        fbo_bitmap *r = (typ & 1) ? fbo_b_difference(o, arg) : fbo_b_union(o, arg);
+        fbo_b_free(arg); fbo_b_free(o); o = r;
+        pos += size;
+    }
+    return o;
 bad:
     fbo_b_free(o);
     return NULL;

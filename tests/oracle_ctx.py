@@ -193,7 +193,7 @@ class OracleCtx:
                 tot[r] = tot.get(r, 0) + c
         if row_ids is not None:
             return np.array([tot.get(int(r), 0) for r in row_ids], dtype=np.uint64)
-        pairs = sorted(((r, c) for r, c in tot.items() if c), key=lambda kv: (-kv[1], kv[0]))[:cap]
+        pairs = sorted(((r, c) for r, c in tot.items() if c), key=lambda kv: (-kv[1], kv[0]))      # cap sizes buffers only: the list is never truncated
         return (np.array([p[0] for p in pairs], dtype=np.uint64), np.array([p[1] for p in pairs], dtype=np.uint64))
 
     def row_counts_per_shard(self, index, field, view, shards, row_ids, filter_ops=None):

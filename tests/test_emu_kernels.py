@@ -194,7 +194,7 @@ def test_bench_sweep_runs_against_interpreted_library():
                         "--generators", "uniform,clustered", "--batched"], cwd=ROOT, env=e, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=900)
     assert r.returncode == 0, r.stderr[-2000:]
     rows = [json.loads(l) for l in r.stdout.strip().splitlines()]
-    assert [str(d["config"]) for d in rows] == ["5", "5b", "5", "4", "X", "X", "X", "X", "X", "R", "R", "R"]
+    assert [str(d["config"]) for d in rows] == ["5", "5b", "5", "5b", "4", "X", "X", "X", "X", "X", "R", "R", "R"]
 
 
 def test_interpreter_reports_divergent_barriers():

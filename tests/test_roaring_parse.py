@@ -129,3 +129,97 @@ def test_truncated_and_corrupted_inputs_fail_cleanly(pc):
             continue
         for key, typ, n, cnt, official, payload in conts:  # accepted => every payload view lay inside the buffer
             assert len(payload) == (2 * n if typ == 1 else 8192 if typ == 2 else 4 * cnt)
+
+
+def _fnv32a(*parts):
+    h = 2166136261
+    for p in parts:
+        for b in p:
+            h = ((h ^ b) * 16777619) & 0xFFFFFFFF
+    return h
+
+
+def _op(typ, value=0, values=None, roaring=None, opn=0):
+    """op.WriteTo (roaring.go:6325-6366): type, value / length, fnv32a checksum, payload"""
+    if typ in (0, 1):
+        head, tail = struct.pack("<BQ", typ, value), b""
+    elif typ in (2, 3):
+        head, tail = struct.pack("<BQ", typ, len(values)), b"".join(struct.pack("<Q", v) for v in values)
+    else:
+        head, tail = struct.pack("<BQ", typ, len(roaring)), struct.pack("<I", opn) + roaring
+    return head + struct.pack("<I", _fnv32a(head, tail)) + tail
+
+
+def test_ops_log_is_replayed_by_the_oracle_and_refused_by_the_product(pc):
+    """Bytes after the last container are an ops log (unmarshal_binary.go:66-92).  The oracle replays it like the reference (the op
+    list of TestOpLogWriteUnmarshal, roaring_internal_test.go:4007-4060, plus the two roaring op types); the product's loader
+    refuses such an image instead of loading the containers without the log."""
+    base_vals = [1, 6, 28, 44, 70000, (5 << 16) + 3] + list(range(200000, 200000 + 5000))
+    base = O.Bitmap.from_values(base_vals)
+    add_r = O.Bitmap.from_values([9, 70001, (9 << 16) + 1]).to_bytes()
+    rem_r = O.Bitmap.from_values([70000, 200001, 999999]).to_bytes()
+    ops = [(0, 27), (1, 28), (2, [1, 2, 6, 19]), (3, [1, 2, 6, 19, 22, 44]), (2, [51234567890]), (3, [51234567890]), (0, 0), (1, 0),
+           (2, [0]), (3, [0]), (2, []), (3, []), (4, add_r), (5, rem_r), (0, 200001)]
+    def replay(start):
+        model, log = set(start), b""
+        for typ, arg in ops:
+            if typ in (0, 1):
+                log += _op(typ, value=arg)
+                (model.add if typ == 0 else model.discard)(arg)
+            elif typ in (2, 3):
+                log += _op(typ, values=arg)
+                model = model | set(arg) if typ == 2 else model - set(arg)
+            else:
+                log += _op(typ, roaring=arg, opn=3)
+                vals = set(O.Bitmap.from_bytes(arg).slice().tolist())
+                model = model | vals if typ == 4 else model - vals
+        return sorted(model), log
+    for start in (base_vals, []):                              # zero containers and a log: still replayed (roaring.go:1994-2001)
+        image = O.Bitmap.from_values(start).to_bytes()
+        model, log = replay(start)
+        assert O.Bitmap.from_bytes(image + log).slice().tolist() == model
+        with pytest.raises(ValueError, match="ops log"):
+            parse(pc, image + log)
+        assert values_of(parse(pc, image)).tolist() == sorted(start)
+    _, log = replay(base_vals)
+    data = base.to_bytes() + log
+    bad = bytearray(data); bad[len(base.to_bytes()) + 9] ^= 1      # checksum of the first op
+    with pytest.raises(ValueError):
+        O.Bitmap.from_bytes(bytes(bad))
+    with pytest.raises(ValueError):
+        O.Bitmap.from_bytes(data[:-3])                             # truncated op
+    with pytest.raises(ValueError):
+        O.Bitmap.from_bytes(base.to_bytes() + bytes([9]) + bytes(12))   # unknown op type
+
+
+def test_official_format_header_strictness(pc):
+    """readOfficialHeader (roaring.go:6960-6996): the no-run cookie is a 32-bit compare; more than 2^16 containers is refused.
+    The reference Put()s containers by key (a repeated key replaces, order is free): the oracle does the same, the product
+    refuses images whose keys are not strictly ascending (no writer emits them; the descriptor tables index by key rank)."""
+    # two array containers, no-run cookie: key 3 {1,2}, key 3 {7}  -> the second replaces the first in the reference
+    def norun(keys_cards_payloads):
+        n = len(keys_cards_payloads)
+        hdr = b"".join(struct.pack("<HH", k, len(v) - 1) for k, v in keys_cards_payloads)
+        off, offs, body = 8 + 8 * n, b"", b""
+        for _, v in keys_cards_payloads:
+            offs += struct.pack("<I", off + len(body)); body += b"".join(struct.pack("<H", x) for x in v)
+        return struct.pack("<II", 12346, n) + hdr + offs + body
+    ok = norun([(1, [5, 6]), (3, [1, 2])])
+    assert values_of(parse(pc, ok)).tolist() == [(1 << 16) + 5, (1 << 16) + 6, (3 << 16) + 1, (3 << 16) + 2]
+    assert O.Bitmap.from_bytes(ok).slice().tolist() == [(1 << 16) + 5, (1 << 16) + 6, (3 << 16) + 1, (3 << 16) + 2]
+    dup, unordered = norun([(3, [1, 2]), (3, [7])]), norun([(3, [1, 2]), (1, [7])])
+    assert O.Bitmap.from_bytes(dup).slice().tolist() == [(3 << 16) + 7]
+    assert O.Bitmap.from_bytes(unordered).slice().tolist() == [(1 << 16) + 7, (3 << 16) + 1, (3 << 16) + 2]
+    for img in (dup, unordered):
+        with pytest.raises(ValueError, match="ascending"):
+            parse(pc, img)
+    hi = bytearray(ok); hi[2] = 1                              # 0x0001303A: low 16 bits say no-run, the cookie does not
+    with pytest.raises(ValueError):
+        parse(pc, bytes(hi))
+    with pytest.raises(ValueError):
+        O.Bitmap.from_bytes(bytes(hi))
+    many = struct.pack("<II", 12346, (1 << 16) + 1) + bytes(8 * ((1 << 16) + 1) + 64)
+    with pytest.raises(ValueError):
+        parse(pc, many)
+    with pytest.raises(ValueError):
+        O.Bitmap.from_bytes(many)

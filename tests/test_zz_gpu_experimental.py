@@ -186,6 +186,13 @@ def test_time_quantum_rows():
         assert p.check_row("Row(f=1, from=2010-01-01T00:00, to=2011-01-01T00:00)").count == 0
         with pytest.raises(X.QueryError, match="not a time-field"):
             p.ex.execute("i", "Row(plain=1, from=2000-01-01T00:00)")
+        # TopN(ids=..) over a time-ranged Src: the Src is the union over the covering views, not the standard view's row
+        # (the fused pair path is for a plain Row only)
+        narrow = "Row(f=1, from=2000-01-01T00:00, to=2001-01-01T00:00)"
+        n_narrow, n_all = p.check_count(f"Count({narrow})"), p.check_count("Count(Row(f=1))")
+        assert 0 < n_narrow < n_all
+        assert p.ex.execute("i", f"TopN(f, {narrow}, ids=[1])")[0] == [(1, n_narrow)]
+        assert p.ex.execute("i", "TopN(f, Row(f=1), ids=[1])")[0] == [(1, n_all)]
 
 
 def test_kernel_table_goldens_on_device():
@@ -1377,6 +1384,18 @@ def test_row_counts_per_shard_entry_point():
         uniq = [0, 2, 3]
         total = ctx.row_counts(p.idx.id, mid, X.VIEW_STANDARD, uniq, row_ids=ids, filter_ops=ops)
         assert [int(x) for x in total] == [int(x) for x in ctx.row_counts_per_shard(p.idx.id, mid, X.VIEW_STANDARD, uniq, ids, filter_ops=ops).sum(axis=0)]
+    # the all-rows form never hands back a truncated list: buffers that are too small get FBGPU_E_NOSPACE and the number of rows
+    # there are, and the binding calls again with that many entries
+    full_ids, full_cnts = ctx.row_counts(p.idx.id, mid, X.VIEW_STANDARD, [0, 2, 3])
+    assert sorted(int(r) for r in full_ids) == [0, 1, 2, 5]
+    small_ids, small_cnts = ctx.row_counts(p.idx.id, mid, X.VIEW_STANDARD, [0, 2, 3], cap=1)
+    assert list(small_ids) == list(full_ids) and list(small_cnts) == list(full_cnts)
+    if hasattr(ctx, "L"):
+        import ctypes as C
+        sh = np.asarray([0, 2, 3], dtype=np.uint64)
+        rid, out, n = np.full(2, 99, dtype=np.uint64), np.full(2, 99, dtype=np.uint64), C.c_int32(-1)
+        rc = ctx.L.fbgpu_row_counts(ctx.h, p.idx.id, mid, X.VIEW_STANDARD, None, 0, None, 0, sh.ctypes.data, 3, rid.ctypes.data, out.ctypes.data, 2, C.byref(n))
+        assert rc == L.E_NOSPACE and n.value == 4 and list(rid) == [99, 99] and list(out) == [99, 99]
 
 
 def test_multi_batch_paths(monkeypatch):
