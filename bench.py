@@ -397,7 +397,7 @@ def config4(cpu, peak, steps, local, rank, world, dist, torch, uid_fn):
     pb, nb = h.ctx.rows_payload_bytes(idx.id, fb.id, 0, shards, None)
     algo = pa + pb + 16 * (na + nb) + 8 * 65536
     total = int(np.asarray(res[0]).sum())
-    rec = {"query": "GroupBy(Rows(a), Rows(b)) 256 x 256, %d shards per GPU (%d in all), ~24.4 k records per shard" % (S, S * world), "kernel": "groupby_kernel",
+    rec = {"query": "GroupBy(Rows(a), Rows(b)) 256 x 256, %d shards per GPU (%d in all), ~24.4 k records per shard" % (S, S * world), "kernel": ("groupby_shard_kernel" if os.environ.get("FBGPU_GROUPBY_HASH") else "groupby_direct_kernel"),
            "ms": ms, "ms_min": ms_min, "e2e_ms": wall, "records": total, "records_per_sec": total / (ms * 1e-3), "group_counts_per_sec": 65536 * S * world / (ms * 1e-3),
            "algorithmic_bytes_per_gpu": int(algo), "payload_bytes_per_gpu": int(pa + pb), "gbs": algo / (ms * 1e-3) / 1e9, "frac": algo / (ms * 1e-3) / 1e9 / peak,
            "count_merge": "ncclAllReduce(uint64, sum) of the 65536-entry tensor" if world > 1 else "none (one GPU)",

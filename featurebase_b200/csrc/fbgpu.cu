@@ -179,6 +179,7 @@ struct fbgpu_ctx {
     // points: 16384 units = 1024 shards = 128 MiB of workspace per lease.  FBGPU_UNIT_BATCH (a multiple of 16, fixed per
     // context) trades workspace for launches; the tests set it small to walk the multi-batch paths with a handful of shards.
     long long unit_batch = [] { const char* e = getenv("FBGPU_UNIT_BATCH"); const long long n = e ? atoll(e) : 0; return n >= 16 ? (n / 16) * 16 : 16384ll; }();
+    int gd_ctas_per_sm = 3;               // resident CTAs of groupby_direct_kernel per SM
     int pair_ctas_per_sm = 2;             // resident CTAs of pair_count_kernel per SM (occupancy query at init)
     std::atomic<uint64_t> counters_pair_launches{0};      // Count(Intersect(Row, Row)) queries that took the fused pair kernel
     DevBuf d_payload, d_views, d_shardmap, d_frags, d_rows, d_descs, d_rowtab;
@@ -236,6 +237,8 @@ extern "C" int fbgpu_init(int32_t device_ordinal, fbgpu_ctx** out) try {
     CUDA_TRY(cudaFuncSetAttribute(groupby_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGbSlots * 4 + 8192));
     CUDA_TRY(cudaFuncSetAttribute(groupby_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGbSlots * 4 + 8192));
     CUDA_TRY(cudaFuncSetAttribute(groupby_shard_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGhSmemBytes));
+    CUDA_TRY(cudaFuncSetAttribute(groupby_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGdSmemBytes));
+    { int nb = 0; if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, groupby_direct_kernel, kGdThreads, kGdSmemBytes) == cudaSuccess && nb > 0) c->gd_ctas_per_sm = nb; }
     { int nb = 0; if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, pair_count_kernel, kPcWarps * 32, kPcWarps * 8192) == cudaSuccess && nb > 0) c->pair_ctas_per_sm = nb; }
     guard.c = nullptr;
     *out = c;
@@ -1653,7 +1656,35 @@ static int groupby2(fbgpu_ctx* c, uint32_t index, uint32_t fvA, const uint64_t* 
         static const bool gb_cta_only = getenv("FBGPU_GROUPBY_CTA") != nullptr; // round-1 path only: one CTA per unit
         auto cta_kernel = gb_fast ? groupby_kernel<true> : groupby_kernel<false>;
         const int spg = gb_cta_only ? 0 : groupby_slots_per_group(c, fvA, fvB, shards + s0, ns);
-        if (spg > 0 && units < (1ll << 31)) {
+        const bool gb_hash = getenv("FBGPU_GROUPBY_HASH") != nullptr;           // groupby_shard_kernel (hash table per group of slots) instead of groupby_direct_kernel
+        if (spg > 0 && !gb_hash && units < (1ll << 31)) {
+            // array-dominated fields: groupby_direct_kernel, one CTA per (shard, slot), 256 a-rows per launch; what it declines is listed
+            // for the CTA kernel, launched only when the list is not empty (the 4-byte count is read back first, see below)
+            if (w->d_emit_units.ensure((size_t)(units + 1) * 4)) return FBGPU_E_NOMEM;
+            unsigned int* d_fb = (unsigned int*)w->d_emit_units.p;
+            unsigned int* h_fb = (unsigned int*)w->h_in.p;
+            const long long dgrid = std::min<long long>(units, (long long)c->sm_count * c->gd_ctas_per_sm);
+            for (int a0 = 0; a0 < nA; a0 += kGdThreads) {
+                const int na = std::min(kGdThreads, nA - a0);
+                const uint64_t* d_ra = (const uint64_t*)w->d_rows.p + a0;
+                unsigned long long* d_cnt = (unsigned long long*)w->d_counts.p + (size_t)a0 * nB;
+                CUDA_TRY(cudaMemsetAsync(d_fb, 0, 4, w->stream));
+                groupby_direct_kernel<<<(unsigned)dgrid, kGdThreads, kGdSmemBytes, w->stream>>>(store_ref(c), fvA, d_ra, na, fvB, (const uint64_t*)w->d_rows.p + nA, nB,
+                    d_shards + s0, units, have_filter ? (const uint4*)w->d_bitmaps.p : nullptr, d_cnt, d_fb);
+                CUDA_TRY(cudaGetLastError()); launches++;
+                CUDA_TRY(cudaEventRecord(w->ev1, w->stream));
+                CUDA_TRY(cudaMemcpyAsync(h_fb, d_fb, 4, cudaMemcpyDeviceToHost, w->stream));
+                CUDA_TRY(cudaStreamSynchronize(w->stream));
+                const unsigned int n_fb = *h_fb;
+                if (n_fb) {
+                    cta_kernel<<<(unsigned)std::min<long long>(n_fb, grid), kGbThreads, smem, w->stream>>>(store_ref(c), fvA, d_ra, na, fvB, (const uint64_t*)w->d_rows.p + nA, nB,
+                        d_shards + s0, units, have_filter ? (const uint4*)w->d_bitmaps.p : nullptr, d_cnt, d_fb);
+                    CUDA_TRY(cudaGetLastError()); launches++;
+                    CUDA_TRY(cudaEventRecord(w->ev1, w->stream));
+                }
+                fb_units += n_fb; all_units += (uint64_t)units;
+            }
+        } else if (spg > 0 && units < (1ll << 31)) {
             // one CTA per (shard, group of `spg` slots): contiguous descriptor / payload reads.  The units it declines are listed for
             // the CTA kernel, which is launched only when the list is not empty (its launch alone costs ~60 us on B200 next to a
             // kernel with another shared-memory carve-out: profiles/README.md) — the 4-byte count is read back first.

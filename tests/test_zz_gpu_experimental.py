@@ -484,6 +484,59 @@ def test_groupby_kernel_pass_shapes():
         assert int(exp.sum()) > 3000
 
 
+def test_groupby_direct_kernel_shapes():
+    """groupby_direct_kernel (byte table indexed by column, one CTA per (shard, slot)): more than 256 a-rows (the host launches it per
+    chunk of 256) and more than 256 b-rows (every b-row is vetted before anything is counted), run containers on both sides, columns
+    that sit in two a-rows (side list), a b-row whose container is a bitmap (that unit goes to groupby_kernel), a shard that lacks one
+    fragment, a filter — the dense count tensor against the oracle's nested loop"""
+    from oracle import oracle as O
+    from featurebase_b200 import roaring_io
+    SW = 1 << 20
+    rng = np.random.default_rng(23)
+    p = Pair(track_existence=False)
+    for n in ("a", "b", "f"):
+        p.field(n)
+    NA, NB = 300, 280
+    for s in (0, 2, 5):
+        cols = np.sort(rng.choice(SW, size=30000, replace=False)).astype(np.uint64)
+        ra, rb = rng.integers(0, NA, size=len(cols)).astype(np.uint64), rng.integers(0, NB, size=len(cols)).astype(np.uint64)
+        dup = rng.choice(len(cols), size=800, replace=False)                                      # 800 columns in two a-rows (~50 per slot: side list)
+        a_bits = [ra * np.uint64(SW) + cols, ((ra[dup] + np.uint64(1)) % np.uint64(NA)) * np.uint64(SW) + cols[dup]]
+        b_bits = [rb * np.uint64(SW) + cols]
+        a_bits.append(np.uint64(17 * SW) + np.arange(70000, 70400, dtype=np.uint64))            # runs: 400 adjacent columns in a-row 17 / b-row 9
+        b_bits.append(np.uint64(9 * SW) + np.arange(70100, 70700, dtype=np.uint64))
+        a_bits.append(np.uint64(299 * SW) + np.arange(5 * 65536 + 10, 5 * 65536 + 20, dtype=np.uint64))
+        if s == 0:
+            b_bits.append(np.uint64(7 * SW) + np.uint64(3 * 65536) + rng.choice(65536, size=6000, replace=False).astype(np.uint64))   # bitmap container: (shard 0, slot 3)
+        p.load("a", X.VIEW_STANDARD, s, roaring_io.encode(np.unique(np.concatenate(a_bits))))
+        if s != 5:
+            p.load("b", X.VIEW_STANDARD, s, roaring_io.encode(np.unique(np.concatenate(b_bits))))
+        p.load("f", X.VIEW_STANDARD, s, roaring_io.encode(np.uint64(1 * SW) + np.unique(np.concatenate([cols[cols % np.uint64(5) != 0], np.arange(70000, 70350, dtype=np.uint64)]))))
+    ids = [list(range(NA)), list(range(NB))]
+    shards = [0, 2, 5, 6]
+    for filt in (None, "Row(f=1)"):
+        call = pql.parse(filt)[0] if filt else None
+        exp = np.zeros(NA * NB, dtype=np.uint64)
+        for s in (0, 2):
+            O.groupby_shard([p.ora.frag(f, 0, s) for f in ("a", "b")], s, ids, p.ora.eval_shard(call, s) if call is not None else None, exp)
+        before = p.holder.ctx.counters()
+        got = p.holder.ctx.groupby(p.idx.id, [p.idx.fields["a"].id, p.idx.fields["b"].id], [X.VIEW_STANDARD] * 2, ids, shards,
+                                   filter_ops=p.ex._bitmap_call(p.idx, call) if call is not None else None)
+        assert np.array_equal(np.asarray(got).reshape(-1), exp), filt
+        assert int(exp.sum()) > 40000 and int(exp.reshape(NA, NB)[17, 9]) >= (300 if filt is None else 200)
+        after = p.holder.ctx.counters()
+        if "groupby_fallback_units" in after and not os.environ.get("FBGPU_GROUPBY_CTA") and not os.environ.get("FBGPU_GROUPBY_HASH"):
+            assert after["groupby_units"] - before["groupby_units"] == 2 * 16 * len(shards)            # two launches (256 + 44 a-rows) over 4 shards
+            assert after["groupby_fallback_units"] - before["groupby_fallback_units"] == 2, (filt, before, after)   # (shard 0, slot 3), once per launch
+
+
+def test_groupby_hash_kernel_still_selectable(monkeypatch):
+    """FBGPU_GROUPBY_HASH=1: groupby_shard_kernel (the hash table per group of slots) instead of groupby_direct_kernel, same results"""
+    monkeypatch.setenv("FBGPU_GROUPBY_HASH", "1")
+    test_groupby_slot_groups()
+    test_groupby_direct_kernel_shapes()
+
+
 def test_groupby_slot_groups():
     """groupby_shard_kernel with several slots per CTA (denser fields -> 2 slots per group instead of 16), one group whose columns
     overflow the shared-memory table (declined before anything is counted -> groupby_kernel takes its two (shard, slot) units), a

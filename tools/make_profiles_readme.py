@@ -62,7 +62,7 @@ def main():
                  f"{r['batched']['gbs']:.0f} / {r['single']['gbs']:.0f} | {r['batched']['frac']:.3f} / {r['single']['frac']:.3f} | {r['cpu_baseline']['ms']:.1f} ms | {r.get('parity_ok')} ({', '.join('%s: %d' % kv for kv in r['container_pair_types_pair0'].items())}) |")
     c3, c4 = b["config3"], b["config4"]
     o.append(f"| config 3: BSI Count(Row(v > 2^31)), 10 M records | `eval_wordpar_kernel` | {c3['ms'] * 1e3:.1f} us | {c3['gbs']:.0f} | {c3['frac']:.3f} | {c3['cpu_baseline']['ms']:.1f} ms | {c3.get('parity_ok')} |")
-    o.append(f"| config 4: GroupBy 256 x 256, 512-shard share ({c4['records'] / 1e6:.1f} M records) | `groupby_shard_kernel` | {c4['ms'] * 1e3:.0f} us | {c4['gbs']:.0f} | {c4['frac']:.3f} | {c4['cpu_baseline']['ms']:.0f} ms | {c4.get('parity_ok')} |")
+    o.append(f"| config 4: GroupBy 256 x 256, 512-shard share ({c4['records'] / 1e6:.1f} M records) | `{c4.get('kernel', 'groupby_shard_kernel')}` | {c4['ms'] * 1e3:.0f} us | {c4['gbs']:.0f} | {c4['frac']:.3f} | {c4['cpu_baseline']['ms']:.0f} ms | {c4.get('parity_ok')} |")
     o.append("")
     # full density sweep
     sw = [json.loads(l) for l in open(os.path.join(P, "r02_sweep5.jsonl"))]
