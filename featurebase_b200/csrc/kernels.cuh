@@ -2164,32 +2164,8 @@ constexpr uint32_t kGdOver = 256;                 // side-list entries ((column 
 constexpr uint32_t kGdMaxCard = 1024;
 constexpr size_t kGdSmemBytes = 65536 + 8192;
 
-// one thread walks an array or run container, eight columns at a time; `first` = its first 16 bytes, loaded earlier (all containers
-// start 16-byte aligned and are allocated in 16-byte units).  f(cols, n): cols[0..n) are columns of the container, cols[n..8) are
-// arbitrary 16-bit values (whatever follows the last element in its chunk) the callee may index its tables with but must not count.
-template <class F>
-__device__ __forceinline__ void thread_for_each_chunk(const Resolved& c, const uint4& first, F f) {
-    const uint4* p = reinterpret_cast<const uint4*>(c.ptr);
-    if (c.typ == kArray) {
-        for (uint32_t k0 = 0; k0 < c.card; k0 += 8) {
-            const uint4 v = k0 ? ldg_nc(p + (k0 >> 3)) : first;
-            const uint32_t cols[8] = { v.x & 0xffffu, v.x >> 16, v.y & 0xffffu, v.y >> 16, v.z & 0xffffu, v.z >> 16, v.w & 0xffffu, v.w >> 16 };
-            f(cols, min(8u, c.card - k0));
-        }
-    } else {                                      // run: cnt x (start, last); one column per call
-        for (uint32_t k0 = 0; k0 < c.cnt; k0 += 4) {
-            const uint4 v = k0 ? ldg_nc(p + (k0 >> 2)) : first;
-            const uint32_t w[4] = { v.x, v.y, v.z, v.w };
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-                if (k0 + q >= c.cnt) break;
-                for (uint32_t x = w[q] & 0xffffu, l = w[q] >> 16; x <= l; x++) { const uint32_t cols[8] = { x, x, x, x, x, x, x, x }; f(cols, 1u); }
-            }
-        }
-    }
-}
-
-// the same walk, one column per call
+// one thread walks an array or run container, one column per call; `first` = its first 16 bytes, loaded earlier (all containers start
+// 16-byte aligned and are allocated in 16-byte units)
 template <class F>
 __device__ __forceinline__ void thread_for_each_col(const Resolved& c, const uint4& first, F f) {
     const uint4* p = reinterpret_cast<const uint4*>(c.ptr);
@@ -2212,18 +2188,6 @@ __device__ __forceinline__ void thread_for_each_col(const Resolved& c, const uin
 
 #ifndef FBGPU_GD_PIPE
 #define FBGPU_GD_PIPE 1
-#endif
-#ifndef FBGPU_GD_CHUNK
-#define FBGPU_GD_CHUNK 0          // 1: eight columns per step with their shared-memory operations batched (measured slower: +40 % instructions)
-#endif
-#ifndef FBGPU_GD_SHPF
-#define FBGPU_GD_SHPF 0           // 1: shard ids loaded one unit further ahead than the directory entries they address
-#endif
-#ifndef FBGPU_GD_DESC12
-#define FBGPU_GD_DESC12 0         // 1: three 4-byte loads per descriptor instead of one 16-byte load (measured with FBGPU_GD_SHPF: 0.203 ms against 0.180)
-#endif
-#ifndef FBGPU_GD_TABLOAD
-#define FBGPU_GD_TABLOAD 0        // 1: the table byte of a probed column is loaded together with its bitmap word
 #endif
 
 __global__ void __launch_bounds__(kGdThreads, 3)
@@ -2253,28 +2217,6 @@ groupby_direct_kernel(StoreRef st, uint32_t fvA, const uint64_t* __restrict__ ro
         if (tid == 0) s_nover = 0;
         bool decline = __syncthreads_or(bad ? 1 : 0) != 0;
         if (!decline) {
-#if FBGPU_GD_CHUNK
-            // ---- a-rows: column -> row index.  The eight atomics of a chunk are issued before the first of their results is used.
-            if (ra.ptr) thread_for_each_chunk(ra, va, [&](const uint32_t (&col)[8], uint32_t n) {
-                uint32_t keep = (1u << n) - 1u, old[8];
-                if (flt) {
-                    uint32_t fw[8];
-#pragma unroll
-                    for (int q = 0; q < 8; q++) fw[q] = __ldg(flt + (col[q] >> 5));
-#pragma unroll
-                    for (int q = 0; q < 8; q++) if (!((fw[q] >> (col[q] & 31)) & 1u)) keep &= ~(1u << q);
-                }
-#pragma unroll
-                for (int q = 0; q < 8; q++) { old[q] = 0; if ((keep >> q) & 1u) old[q] = atomicOr(&bits[col[q] >> 5], 1u << (col[q] & 31)); }
-#pragma unroll
-                for (int q = 0; q < 8; q++) asm volatile("" : "+r"(old[q]));             // (all eight atomics in flight before the first result is looked at)
-#pragma unroll
-                for (int q = 0; q < 8; q++) if ((keep >> q) & 1u) {
-                    if (!((old[q] >> (col[q] & 31)) & 1u)) tab[col[q]] = (uint8_t)tid;
-                    else { const uint32_t k = atomicAdd(&s_nover, 1u); if (k < kGdOver) s_over[k] = (col[q] << 8) | (uint32_t)tid; }
-                }
-            });
-#else
             // ---- a-rows: column -> row index
             if (ra.ptr) thread_for_each_col(ra, va, [&](uint32_t col) {
                 if (flt && !((__ldg(flt + (col >> 5)) >> (col & 31)) & 1u)) return;
@@ -2282,7 +2224,6 @@ groupby_direct_kernel(StoreRef st, uint32_t fvA, const uint64_t* __restrict__ ro
                 if (!(atomicOr(&bits[col >> 5], m) & m)) tab[col] = (uint8_t)tid;
                 else { const uint32_t k = atomicAdd(&s_nover, 1u); if (k < kGdOver) s_over[k] = (col << 8) | (uint32_t)tid; }
             });
-#endif
             __syncthreads();
         }
         mid();
@@ -2295,35 +2236,10 @@ groupby_direct_kernel(StoreRef st, uint32_t fvA, const uint64_t* __restrict__ ro
                     if (multiB) { rb.ptr = nullptr; if (b0 + tid < nB) rb = resolve(st, fvB, shard, rowsB[b0 + tid], slot); if (rb.ptr) vb = ldg_nc(reinterpret_cast<const uint4*>(rb.ptr)); }
                     if (!rb.ptr) continue;
                     unsigned long long* cj = counts + (b0 + tid);
-#if FBGPU_GD_CHUNK
-                    // (the bitmap word and the table byte of all eight columns are loaded together: any 16-bit value indexes both)
-                    thread_for_each_chunk(rb, vb, [&](const uint32_t (&col)[8], uint32_t n) {
-                        uint32_t w[8], r[8];
-#pragma unroll
-                        for (int q = 0; q < 8; q++) { w[q] = bits[col[q] >> 5]; r[q] = tab[col[q]]; }
-#pragma unroll
-                        for (int q = 0; q < 8; q++) asm volatile("" : "+r"(r[q]));       // (keeps the byte loads up here, next to the word loads, instead of behind each bit test)
-#pragma unroll
-                        for (int q = 0; q < 8; q++) if ((uint32_t)q < n && ((w[q] >> (col[q] & 31)) & 1u)) atomicAdd(cj + r[q] * (uint32_t)nB, 1ull);
-                        if (nover)
-                            for (uint32_t k = 0; k < nover; k++) {
-                                const uint32_t e = s_over[k];
-#pragma unroll
-                                for (int q = 0; q < 8; q++) if ((uint32_t)q < n && (e >> 8) == col[q]) atomicAdd(cj + (e & 0xffu) * (uint32_t)nB, 1ull);
-                            }
-                    });
-#else
                     thread_for_each_col(rb, vb, [&](uint32_t col) {
-#if FBGPU_GD_TABLOAD
-                        const uint32_t w = bits[col >> 5]; uint32_t r = tab[col];
-                        asm volatile("" : "+r"(r));              // (keeps the byte load next to the word load instead of behind the bit test)
-                        if ((w >> (col & 31)) & 1u) atomicAdd(cj + r * (uint32_t)nB, 1ull);
-#else
                         if ((bits[col >> 5] >> (col & 31)) & 1u) atomicAdd(cj + (uint32_t)tab[col] * (uint32_t)nB, 1ull);
-#endif
                         for (uint32_t k = 0; k < nover; k++) { const uint32_t e = s_over[k]; if ((e >> 8) == col) atomicAdd(cj + (e & 0xffu) * (uint32_t)nB, 1ull); }
                     });
-#endif
                 }
         }
         if (decline && tid == 0) { const unsigned int k = atomicAdd(&fallback[0], 1u); fallback[1 + k] = (unsigned int)unit; }
@@ -2334,10 +2250,10 @@ groupby_direct_kernel(StoreRef st, uint32_t fvA, const uint64_t* __restrict__ ro
     if (FBGPU_GD_PIPE && !multiB && vA.rt_rows && vB.rt_rows) {
         // Both views have the dense (shard, row) directory: the three dependent loads of a unit — directory entry, descriptor, first
         // payload chunk — are issued one unit apart each, so that every level has a whole phase of another unit to arrive in:
-        //   iteration i:  shard id(i+3) | directory(i+2) | descriptor(i+1) <- directory(i+1) | insert(i) | payload(i+1) <- descriptor(i+1) | probe(i)
+        //   iteration i:  shard id(i+3), directory(i+2), descriptor(i+1) <- directory(i+1) | insert(i) | payload(i+1) <- descriptor(i+1) | probe(i)
         // (a shard without one of the fragments has empty directory entries on that side and counts nothing, like the explicit test)
         struct Ent { uint32_t fa, ma, fb, mb; };
-        struct D3 { uint32_t x, y, z; };
+        struct D3 { uint32_t x, y, z, w; };
         struct Dsc { D3 a, b; };                               // ContDesc images: x = off16, y = card (0: absent), z = typ | cnt << 16
         const uint64_t rowA = tid < nA ? rowsA[tid] : 0, rowB = tid < nB ? rowsB[tid] : 0;
         const bool inA = tid < nA && rowA >= vA.rmin && rowA - vA.rmin < vA.rt_rows, inB = tid < nB && rowB >= vB.rmin && rowB - vB.rmin < vB.rt_rows;
@@ -2352,20 +2268,19 @@ groupby_direct_kernel(StoreRef st, uint32_t fvA, const uint64_t* __restrict__ ro
         // (12 of the descriptor's 16 bytes: a 16-byte load would leave a dead fourth register that the allocator reuses at once, and the
         // next write to it then waits for the load — seen as a long-scoreboard stall at the top of the loop)
         auto load_desc = [&](uint32_t first, uint32_t mask, int slot) {
-            D3 d; d.x = d.y = d.z = 0;
+            D3 d; d.x = d.y = d.z = d.w = 0;
             if ((mask >> slot) & 1u) {
-#if FBGPU_GD_DESC12
-                const uint32_t* q = reinterpret_cast<const uint32_t*>(st.descs + first + __popc(mask & ((1u << slot) - 1u)));
-                d.x = __ldg(q); d.y = __ldg(q + 1); d.z = __ldg(q + 2);
-#else
                 const uint4 v = __ldg(reinterpret_cast<const uint4*>(st.descs + first + __popc(mask & ((1u << slot) - 1u))));
-                d.x = v.x; d.y = v.y; d.z = v.z;
-#endif
+                d.x = v.x; d.y = v.y; d.z = v.z; d.w = v.w;
             }
             return d;
         };
         auto load_dsc = [&](const Ent& e, int slot) { Dsc d; d.a = load_desc(e.fa, e.ma, slot); d.b = load_desc(e.fb, e.mb, slot); return d; };
-        auto located = [&](const D3& d) { Resolved r; r.ptr = d.y ? st.payload + (size_t)d.x * 16 : nullptr; r.card = d.y; r.typ = (uint16_t)(d.z & 0xffffu); r.cnt = (uint16_t)(d.z >> 16); return r; };
+        // (the descriptor's unused fourth word is kept live until the descriptor is consumed: a dead destination register of the
+        // 16-byte load is reused at once by the allocator, and the next write to it then waits for the load)
+        auto located = [&](D3 d) {
+            asm volatile("" : "+r"(d.w));
+            Resolved r; r.ptr = d.y ? st.payload + (size_t)d.x * 16 : nullptr; r.card = d.y; r.typ = (uint16_t)(d.z & 0xffffu); r.cnt = (uint16_t)(d.z >> 16); return r; };
         auto load_first = [&](const D3& d) { return d.y ? ldg_nc(reinterpret_cast<const uint4*>(st.payload + (size_t)d.x * 16)) : make_uint4(0, 0, 0, 0); };
         const long long step = gridDim.x;
         long long unit = blockIdx.x;
@@ -2375,11 +2290,7 @@ groupby_direct_kernel(StoreRef st, uint32_t fvA, const uint64_t* __restrict__ ro
         Dsc d0 = load_dsc(load_ent(shard_of(unit)), (int)(unit & 15));
         uint4 va = load_first(d0.a), vb = load_first(d0.b);
         for (; unit < n_units; unit += step) {
-#if FBGPU_GD_SHPF
             const uint64_t s3 = shard_of(unit + 3 * step);
-#else
-            s2 = shard_of(unit + 2 * step); const uint64_t s3 = 0;
-#endif
             const Ent e2 = load_ent(s2);
             const Dsc d1 = load_dsc(e1, (int)((unit + step) & 15));
             uint4 va1, vb1;

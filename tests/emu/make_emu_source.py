@@ -86,7 +86,7 @@ ASM = [
     (r'asm volatile\("red\.shared\.or\.b32 \[%0\], %1;" :: "r"\((\w+)\), "r"\(([^()]+)\) : "memory"\);', r"emu::red_or(\1, \2);"),
     (r'asm volatile\("red\.shared\.and\.b32 \[%0\], %1;" :: "r"\((\w+)\), "r"\(([^()]+)\) : "memory"\);', r"emu::red_and(\1, \2);"),
     (r'asm volatile\("red\.shared\.xor\.b32 \[%0\], %1;" :: "r"\((\w+)\), "r"\(([^()]+)\) : "memory"\);', r"emu::red_xor(\1, \2);"),
-    (r'asm volatile\("" : "\+r"\(([\w\[\]]+)\)\);', r"(void)\1;"),
+    (r'asm volatile\("" : "\+r"\(([\w\[\].]+)\)\);', r"(void)\1;"),
     (r'asm volatile\("" : "\+l"\((\w+)\)\);', r"(void)\1;"),
     (r'asm volatile\("cp\.async\.cg\.shared\.global \[%0\], \[%1\], 16;" :: "r"\(\(uint32_t\)__cvta_generic_to_shared\(dst_smem\)\), "l"\(src\) : "memory"\);', r"*dst_smem = *src;"),
     (r'asm volatile\("cp\.async\.commit_group;" ::: "memory"\);', r"(void)0;"),

@@ -4,11 +4,6 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from featurebase_b200 import build as B
 VARIANTS = {   # name -> -D defines; edit freely, outputs featurebase_b200/libfbgpu_<name>.so (select with FBGPU_LIB=...)
     "gd_nopipe": ["FBGPU_GD_PIPE=0"],
-    "gd_shpf": ["FBGPU_GD_SHPF=1"],             # shard ids one unit further ahead
-    "gd_desc12": ["FBGPU_GD_DESC12=1"],         # 12-byte descriptor loads (no dead fourth register)
-    "gd_shpf_desc12": ["FBGPU_GD_SHPF=1", "FBGPU_GD_DESC12=1"],   # both (call 15: 0.203 ms against 0.180 without)
-    "gd_tabload": ["FBGPU_GD_TABLOAD=1"],       # probe: table byte loaded with the bitmap word (call 15: 0.184 against 0.180)
-    "gd_chunk": ["FBGPU_GD_CHUNK=1"],           # eight columns per step, shared-memory operations batched (calls 14/15: 0.206 ms)
     "gh512": ["FBGPU_GH_THREADS=512"],          # groupby_shard_kernel: two CTAs of 512 threads per SM with 64 KiB tables
     "pair_nopf": ["FBGPU_PAIR_NO_PF"],          # pair kernel without the L2 prefetch of the next unit's payload lines
     "pair_bm4": ["FBGPU_PAIR_BM_UNROLL=4"],     # pair kernel: bitmap x bitmap loop unrolled 4 (default 8)
