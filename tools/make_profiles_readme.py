@@ -96,7 +96,7 @@ def main():
                          f"{f(d['smsp__issue_active.avg.pct_of_peak_sustained_active'], 1)} | {f(d['sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active'], 1)} | "
                          f"{f(d['sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active'], 1)} | {float(d['l1tex__data_pipe_lsu_wavefronts_mem_shared.sum']) / 1e6:.1f} M ({float(d['l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum']) / 1e6:.1f} M) | {d['top stalls (warps per issue-active cycle)']} |")
     o.append("\n(`dram__bytes_read.sum` is in the unit ncu chose per kernel: MB for the small launches, GB for the headline.)  The launch list of one bench run "
-             "(`r02_launches.csv`, per-launch `gpu__time_duration.sum`, cold-cache and serialised) shows only this library's kernels.\n")
+             "(`r02_launches.csv`, per-launch `gpu__time_duration.sum`, cold-cache and serialised) shows only this library's kernels.  The eval_kernel and groupby_direct_kernel rows, the bench lines, the config 3/4/X/R sweep, the gpu test log and the launch list are of the final kernel source (`tools/r2_final2.sh`, kernels.cuh sha1 b070fab3…); the pair_count / eval_wordpar / groupby_shard rows and the density sweep are of the source one commit earlier (`tools/r2_final.sh`, 906e406e…), in which those kernels are byte-identical — the only kernel change in between is the added `groupby_direct_kernel`.\n")
     extra = os.path.join(P, "r02_log.md")
     if os.path.exists(extra):
         o.append(open(extra).read())
