@@ -89,8 +89,10 @@ def test_sorted_array_order():
 def test_groupby_thread_per_row_variant():
     """FBGPU_GROUPBY_FAST=1 (groupby_kernel<true>): the GroupBy goldens and parity tests, and the shapes built for its passes
     (tiny arrays -> thread-per-row; a bitmap row / a 40-element row -> fallback inside the same kernel; two chunks per side; filter)"""
-    run_on_emulator(["tests/test_gpu_parity.py", "tests/test_zz_gpu_experimental.py", "-k", "(groupby or various_queries) and not sorted_order" + ("" if FULL else " and not full_size")],
-                    env={"FBGPU_GROUPBY_FAST": "1"})
+    sel = "(groupby or various_queries) and not sorted_order" + ("" if FULL else " and not full_size")
+    # FBGPU_GROUPBY_CTA=1: groupby_kernel for every unit (by default it only sees what groupby_direct_kernel declines)
+    run_on_emulator(["tests/test_gpu_parity.py", "tests/test_zz_gpu_experimental.py", "-k", sel], env={"FBGPU_GROUPBY_FAST": "1", "FBGPU_GROUPBY_CTA": "1"})
+    run_on_emulator(["tests/test_gpu_parity.py", "tests/test_zz_gpu_experimental.py", "-k", "groupby and not sorted_order and not full_size"], env={"FBGPU_GROUPBY_CTA": "1"})
 
 
 def test_wordpar_loop_variants():
