@@ -27,7 +27,7 @@ def main():
              "denominators are the driver-measured `MEASURED_PEAKS.json` (`hbm_gbs` = 6572 GB/s).  Algorithmic bytes = payload of every\n"
              "distinct input container + 16 B per descriptor + mandatory output (SURVEY §8d).  Round 1's files and log: `README_r01.md`, `r01_*`.\n"
              "Files named `r02_callN_*` are the A/B records of the round's GPU calls (scripts: `tools/r2_call*.sh`); `r02_*` without a call\n"
-             "number come from the final call (`tools/r2_final.sh`) on the committed source.\n")
+             "number come from the two final calls (`tools/r2_final.sh`, and `tools/r2_final2.sh` after `groupby_direct_kernel`: which file is of which call is said below the ncu table) on the committed source.\n")
     o.append("## Headline: BASELINE config[1] — 1024 shards x 2^20, 1 %, Count(Intersect(Union(32 rows), Union(32 rows)))\n")
     o.append("| arm | ms/step | set-ops/s | HBM GB/s (algorithmic) | frac of measured roofline |")
     o.append("|---|---|---|---|---|")
